@@ -1,0 +1,95 @@
+/* nb2.h — C ABI of the B200 batched differentiable-timestep engine (libnb2.so).
+ *
+ * Drop-in boundary for the reference's hot path.  What each entry point replaces:
+ *   nb2_step_forward   <- neural::forwardPass(world)            dart/neural/NeuralUtils.cpp:26-66
+ *                         = World::setState/setAction/step      dart/simulation/World.cpp:2024-2086, 221-254
+ *   nb2_step_backward  <- BackpropSnapshot::backpropState       dart/neural/BackpropSnapshot.cpp:382-420 (+ :121-194, :425-479)
+ *   nb2_model_create   <- the World/Skeleton object graph a loader builds (dart/simulation/World.cpp:749-793), flattened
+ *   nb2_rollout_*      <- trajectory::SingleShot::getSnapshots / backpropGradientWrt   dart/trajectory/SingleShot.cpp:635-686, 539-631
+ * The pointer-style precedent inside the reference is SimpleFeatherstone::forwardDynamics(s_t*,s_t*,s_t*,s_t*)
+ * (dart/dynamics/SimpleFeatherstone.hpp:61-65) and BoxedLcpSolver::solve(int, s_t*, ...) (dart/constraint/BoxedLcpSolver.hpp:125-135).
+ *
+ * Conventions: all batch buffers are row-major fp32, one row per world: state [B, 2*ndof] = [q ; qdot],
+ * action [B, na].  Device entry points take DEVICE pointers and are stream-ordered (no hidden sync); the *_host
+ * variants take HOST pointers and include the copies.  Every function returns 0 on success, a negative nb2_status
+ * otherwise; nb2_last_error() describes the last failure of the calling thread.  There is no CPU fallback.
+ */
+#ifndef NB2_H_
+#define NB2_H_
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct nb2_model nb2_model; /* opaque: device model + launch configuration */
+
+enum nb2_status {
+  NB2_OK = 0,
+  NB2_ERR_INVALID = -1,     /* bad argument / unsupported model */
+  NB2_ERR_CUDA = -2,        /* CUDA runtime error (see nb2_last_error) */
+  NB2_ERR_UNSUPPORTED = -3, /* model exceeds compiled limits */
+};
+
+enum nb2_precision { NB2_FP32 = 0, NB2_FP64 = 1 }; /* arithmetic type inside the kernels; I/O is always fp32 */
+
+/* Canonical model description (see nimblephysics_b200/modelspec.py::compile_model for the producer and
+ * nimblephysics_b200/csrc/nb2_model.h for the meaning of each field). All arrays are host memory, copied. */
+typedef struct nb2_model_desc {
+  int32_t nb, ndof, na, nslots;
+  const int32_t* parent;      /* [nb]  canonical parent or -1 */
+  const int32_t* jtype;       /* [nb]  1 revolute-z, 2 prismatic-z, 3 free */
+  const int32_t* dof_off;     /* [nb] */
+  const int32_t* flags;       /* [nb] */
+  const int32_t* slot_self;   /* [nb] */
+  const int32_t* slot_parent; /* [nb] */
+  const double* Xtree;        /* [nb*12] */
+  const double* inertia;      /* [nb*10] */
+  const double* damping;      /* [ndof] ... */
+  const double* spring;
+  const double* rest;
+  const double* pos_lo;
+  const double* pos_hi;
+  const double* vel_lo;
+  const double* vel_hi;
+  const double* force_lo;
+  const double* force_hi;
+  const int32_t* action_map;  /* [na] */
+  double gravity[3];
+  double dt;
+} nb2_model_desc;
+
+int nb2_model_create(const nb2_model_desc* desc, nb2_model** out);
+void nb2_model_destroy(nb2_model* m);
+int nb2_model_ndof(const nb2_model* m);
+int nb2_model_na(const nb2_model* m);
+
+/* fp32 words per world the forward pass streams out for the backward pass ([words][B] layout) */
+int nb2_saved_words_per_world(const nb2_model* m);
+
+/* One differentiable timestep for B independent worlds.  `saved` may be NULL (no backward will follow),
+ * otherwise it must hold nb2_saved_words_per_world(m)*B floats.  `stream` is a cudaStream_t (NULL = default). */
+int nb2_step_forward(const nb2_model* m, int B, const float* state, const float* action, float* next_state,
+                     float* saved, int precision, void* stream);
+
+/* Vector-Jacobian product of the same step: grad_next_state [B,2n] -> grad_state [B,2n], grad_action [B,na]. */
+int nb2_step_backward(const nb2_model* m, int B, const float* state, const float* action, const float* saved,
+                      const float* grad_next_state, float* grad_state, float* grad_action, int precision,
+                      void* stream);
+
+/* Same two calls with HOST buffers (pageable or pinned): H2D copies, kernels, D2H copies, synchronised on return. */
+int nb2_step_forward_host(nb2_model* m, int B, const float* state, const float* action, float* next_state,
+                          int keep_for_backward, int precision);
+int nb2_step_backward_host(nb2_model* m, int B, const float* grad_next_state, float* grad_state, float* grad_action,
+                           int precision);
+
+/* number of kernels this library has launched since load (bench.py reports it as gpu_launches) */
+long long nb2_launch_count(void);
+const char* nb2_last_error(void);
+const char* nb2_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NB2_H_ */

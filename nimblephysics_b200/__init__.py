@@ -1,0 +1,9 @@
+"""nimblephysics_b200 — B200-native batched differentiable timestep behind the
+Nimble ``timestep(world, state, action)`` surface.  See DESIGN.md."""
+from . import world as _world
+from .world import (World, Skeleton, BodyNode, Joint, Isometry3, BoxShape, SphereShape, CapsuleShape)
+from .loader import loadWorld, load_skeleton
+from .modelspec import RawModel, CanonModel, flatten_world, compile_model
+
+__all__ = ["World", "Skeleton", "BodyNode", "Joint", "Isometry3", "BoxShape", "SphereShape", "CapsuleShape",
+           "loadWorld", "load_skeleton", "RawModel", "CanonModel", "flatten_world", "compile_model"]

@@ -1,0 +1,101 @@
+"""ctypes binding of the C ABI declared in include/nb2.h (libnb2.so, built in-tree by __graft_entry__.build()).
+
+There is no CPU fallback: if the CUDA library is missing or fails to load, importing the compute path raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from typing import Optional
+
+import numpy as np
+
+from .modelspec import CanonModel
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libnb2.so")
+
+_I32P = ctypes.POINTER(ctypes.c_int32)
+_F64P = ctypes.POINTER(ctypes.c_double)
+_F32P = ctypes.POINTER(ctypes.c_float)
+
+
+class Nb2ModelDesc(ctypes.Structure):
+    _fields_ = [
+        ("nb", ctypes.c_int32), ("ndof", ctypes.c_int32), ("na", ctypes.c_int32), ("nslots", ctypes.c_int32),
+        ("parent", _I32P), ("jtype", _I32P), ("dof_off", _I32P), ("flags", _I32P), ("slot_self", _I32P),
+        ("slot_parent", _I32P),
+        ("Xtree", _F64P), ("inertia", _F64P),
+        ("damping", _F64P), ("spring", _F64P), ("rest", _F64P),
+        ("pos_lo", _F64P), ("pos_hi", _F64P), ("vel_lo", _F64P), ("vel_hi", _F64P), ("force_lo", _F64P),
+        ("force_hi", _F64P),
+        ("action_map", _I32P),
+        ("gravity", ctypes.c_double * 3), ("dt", ctypes.c_double),
+    ]
+
+
+def make_desc(cm: CanonModel):
+    """-> (Nb2ModelDesc, keepalive list).  The arrays must outlive the descriptor."""
+    keep = []
+
+    def i32(a):
+        a = np.ascontiguousarray(a, dtype=np.int32)
+        keep.append(a)
+        return a.ctypes.data_as(_I32P)
+
+    def f64(a):
+        a = np.ascontiguousarray(a, dtype=np.float64)
+        keep.append(a)
+        return a.ctypes.data_as(_F64P)
+
+    d = Nb2ModelDesc()
+    d.nb, d.ndof, d.na, d.nslots = cm.nb, cm.ndof, len(cm.action_map), cm.nslots
+    d.parent, d.jtype, d.dof_off = i32(cm.parent), i32(cm.jtype), i32(cm.dof_off)
+    d.flags, d.slot_self, d.slot_parent = i32(cm.flags), i32(cm.slot_self), i32(cm.slot_parent)
+    d.Xtree, d.inertia = f64(cm.Xtree), f64(cm.inertia)
+    d.damping, d.spring, d.rest = f64(cm.damping), f64(cm.spring), f64(cm.rest)
+    d.pos_lo, d.pos_hi = f64(cm.pos_lo), f64(cm.pos_hi)
+    d.vel_lo, d.vel_hi = f64(cm.vel_lo), f64(cm.vel_hi)
+    d.force_lo, d.force_hi = f64(cm.force_lo), f64(cm.force_hi)
+    d.action_map = i32(cm.action_map)
+    for k in range(3):
+        d.gravity[k] = float(cm.gravity[k])
+    d.dt = float(cm.dt)
+    return d, keep
+
+
+_lib: Optional[ctypes.CDLL] = None
+
+
+class Nb2Error(RuntimeError):
+    pass
+
+
+def lib() -> ctypes.CDLL:
+    """Load libnb2.so; fail loudly when it is absent (no fallback path exists)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise Nb2Error(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                           "(nvcc, sm_100a). nimblephysics_b200 has no CPU fallback.")
+        L = ctypes.CDLL(LIB_PATH)
+        L.nb2_last_error.restype = ctypes.c_char_p
+        L.nb2_version.restype = ctypes.c_char_p
+        L.nb2_launch_count.restype = ctypes.c_longlong
+        L.nb2_model_create.argtypes = [ctypes.POINTER(Nb2ModelDesc), ctypes.POINTER(ctypes.c_void_p)]
+        L.nb2_model_destroy.argtypes = [ctypes.c_void_p]
+        L.nb2_model_ndof.argtypes = [ctypes.c_void_p]
+        L.nb2_model_na.argtypes = [ctypes.c_void_p]
+        L.nb2_saved_words_per_world.argtypes = [ctypes.c_void_p]
+        vp = ctypes.c_void_p
+        L.nb2_step_forward.argtypes = [vp, ctypes.c_int, vp, vp, vp, vp, ctypes.c_int, vp]
+        L.nb2_step_backward.argtypes = [vp, ctypes.c_int, vp, vp, vp, vp, vp, vp, ctypes.c_int, vp]
+        L.nb2_step_forward_host.argtypes = [vp, ctypes.c_int, vp, vp, vp, ctypes.c_int, ctypes.c_int]
+        L.nb2_step_backward_host.argtypes = [vp, ctypes.c_int, vp, vp, vp, ctypes.c_int]
+        _lib = L
+    return _lib
+
+
+def check(rc: int):
+    if rc != 0:
+        raise Nb2Error(f"nb2 error {rc}: {lib().nb2_last_error().decode()}")

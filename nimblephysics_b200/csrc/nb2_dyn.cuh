@@ -1,0 +1,525 @@
+// Per-world forward (ABA + semi-implicit Euler) and backward (adjoint) of one contact-free timestep.
+//
+// What it computes is the reference's World::step (dart/simulation/World.cpp:221-254, 307-333) and
+// BackpropSnapshot::backpropState (dart/neural/BackpropSnapshot.cpp:121-194, 382-479) for a world without
+// active constraints.  HOW is new:
+//   * canonical model (nb2_model.h): joint axes along +z, so S^T I S is one matrix entry and I S one column;
+//   * gravity enters as a fictitious base acceleration (same q-ddot as the reference's per-body gravity force);
+//   * the backward never materialises the five n x n Jacobians of the reference (BackpropSnapshot.cpp:159-178):
+//     with lambda = M^-1 g_v'  (one ABA-style solve reusing the forward's articulated inertias) it evaluates the
+//     vector-Jacobian products of inverse dynamics, (d ID/dq)^T lambda and (d ID/dv)^T lambda, by one reverse sweep
+//     of RNEA — O(nb) instead of O(nb * n) — which is exactly  posVel^T g, velVel^T g, forceVel^T g.
+//
+// One world is processed by ONE thread; per-world working storage `scr` is strided by ST (32 on the device:
+// [word][lane] interleaving in shared memory => bank-conflict free; 1 in the host build used by tests).
+// All control flow depends on the model only, i.e. is warp-uniform.
+#pragma once
+#include <stddef.h>
+
+#include "nb2_math.cuh"
+#include "nb2_model.h"
+
+namespace nb2 {
+
+struct FwdLayout {
+  int oQ, oV, oTau, oBody, oSlot, oFree, total;
+};
+NB2_HD FwdLayout fwd_layout(int nb, int n, int nslots, int nfree) {
+  FwdLayout L;
+  L.oQ = 0; L.oV = n; L.oTau = 2 * n; L.oBody = 3 * n;
+  L.oSlot = L.oBody + 22 * nb;
+  L.oFree = L.oSlot + 27 * nslots;
+  L.total = L.oFree + 18 * nfree;
+  return L;
+}
+struct BwdLayout {
+  int oGQ, oGV, oLam, oQb, oVb, oBody, oSlot, oFree, total;
+};
+NB2_HD BwdLayout bwd_layout(int nb, int n, int nslots, int nfree) {
+  BwdLayout L;
+  L.oGQ = 0; L.oGV = n; L.oLam = 2 * n; L.oQb = 3 * n; L.oVb = 4 * n; L.oBody = 5 * n;
+  L.oSlot = L.oBody + 7 * nb;
+  L.oFree = L.oSlot + 18 * nslots;
+  L.total = L.oFree + 6 * nfree;
+  return L;
+}
+
+template <class R, int ST> NB2_HD V6<R> ld6(const R* p) {
+  V6<R> v; v.a.x = p[0]; v.a.y = p[ST]; v.a.z = p[2 * ST]; v.l.x = p[3 * ST]; v.l.y = p[4 * ST]; v.l.z = p[5 * ST]; return v;
+}
+template <class R, int ST> NB2_HD void st6(R* p, const V6<R>& v) {
+  p[0] = v.a.x; p[ST] = v.a.y; p[2 * ST] = v.a.z; p[3 * ST] = v.l.x; p[4 * ST] = v.l.y; p[5 * ST] = v.l.z;
+}
+template <class R, int ST> NB2_HD void add6(R* p, const V6<R>& v) {
+  p[0] += v.a.x; p[ST] += v.a.y; p[2 * ST] += v.a.z; p[3 * ST] += v.l.x; p[4 * ST] += v.l.y; p[5 * ST] += v.l.z;
+}
+template <class R, int ST> NB2_HD SI<R> ldSI(const R* p) {
+  SI<R> I;
+  I.A.xx = p[0]; I.A.yy = p[ST]; I.A.zz = p[2 * ST]; I.A.xy = p[3 * ST]; I.A.xz = p[4 * ST]; I.A.yz = p[5 * ST];
+  I.B.m00 = p[6 * ST]; I.B.m01 = p[7 * ST]; I.B.m02 = p[8 * ST]; I.B.m10 = p[9 * ST]; I.B.m11 = p[10 * ST]; I.B.m12 = p[11 * ST];
+  I.B.m20 = p[12 * ST]; I.B.m21 = p[13 * ST]; I.B.m22 = p[14 * ST];
+  I.C.xx = p[15 * ST]; I.C.yy = p[16 * ST]; I.C.zz = p[17 * ST]; I.C.xy = p[18 * ST]; I.C.xz = p[19 * ST]; I.C.yz = p[20 * ST];
+  return I;
+}
+template <class R, int ST, bool ADD> NB2_HD void stSI(R* p, const SI<R>& I) {
+#define NB2_W(k, val) if (ADD) p[(k) * ST] += (val); else p[(k) * ST] = (val);
+  NB2_W(0, I.A.xx) NB2_W(1, I.A.yy) NB2_W(2, I.A.zz) NB2_W(3, I.A.xy) NB2_W(4, I.A.xz) NB2_W(5, I.A.yz)
+  NB2_W(6, I.B.m00) NB2_W(7, I.B.m01) NB2_W(8, I.B.m02) NB2_W(9, I.B.m10) NB2_W(10, I.B.m11) NB2_W(11, I.B.m12)
+  NB2_W(12, I.B.m20) NB2_W(13, I.B.m21) NB2_W(14, I.B.m22)
+  NB2_W(15, I.C.xx) NB2_W(16, I.C.yy) NB2_W(17, I.C.zz) NB2_W(18, I.C.xy) NB2_W(19, I.C.xz) NB2_W(20, I.C.yz)
+#undef NB2_W
+}
+// saved-for-backward stream: word k of world w lives at sv[k * B] (sv already offset by w) -> coalesced
+NB2_HD void sv_st6(float* sv, size_t B, int k, const V6<float>& v) {
+  sv[(size_t)k * B] = v.a.x; sv[(size_t)(k + 1) * B] = v.a.y; sv[(size_t)(k + 2) * B] = v.a.z;
+  sv[(size_t)(k + 3) * B] = v.l.x; sv[(size_t)(k + 4) * B] = v.l.y; sv[(size_t)(k + 5) * B] = v.l.z;
+}
+template <class R> NB2_HD V6<float> tof(const V6<R>& v) {
+  V6<float> o; o.a.x = (float)v.a.x; o.a.y = (float)v.a.y; o.a.z = (float)v.a.z; o.l.x = (float)v.l.x; o.l.y = (float)v.l.y; o.l.z = (float)v.l.z; return o;
+}
+template <class R> NB2_HD V6<R> sv_ld6(const float* sv, size_t B, int k) {
+  V6<R> v;
+  v.a.x = (R)sv[(size_t)k * B]; v.a.y = (R)sv[(size_t)(k + 1) * B]; v.a.z = (R)sv[(size_t)(k + 2) * B];
+  v.l.x = (R)sv[(size_t)(k + 3) * B]; v.l.y = (R)sv[(size_t)(k + 4) * B]; v.l.z = (R)sv[(size_t)(k + 5) * B];
+  return v;
+}
+
+template <class R> NB2_HD Xf<R> xtree(const Nb2ModelDev<R>& M, int i) {
+  Xf<R> T;
+  T.R_.m00 = M.Xtree[i][0]; T.R_.m01 = M.Xtree[i][1]; T.R_.m02 = M.Xtree[i][2];
+  T.R_.m10 = M.Xtree[i][3]; T.R_.m11 = M.Xtree[i][4]; T.R_.m12 = M.Xtree[i][5];
+  T.R_.m20 = M.Xtree[i][6]; T.R_.m21 = M.Xtree[i][7]; T.R_.m22 = M.Xtree[i][8];
+  T.p = mk3<R>(M.Xtree[i][9], M.Xtree[i][10], M.Xtree[i][11]);
+  return T;
+}
+// parent <- child transform of a revolute-z joint: Xtree * Rz(theta)
+template <class R> NB2_HD Xf<R> xf_rev(const Nb2ModelDev<R>& M, int i, R s, R c) {
+  Xf<R> X = xtree(M, i), T;
+  T.R_.m00 = c * X.R_.m00 + s * X.R_.m01; T.R_.m01 = c * X.R_.m01 - s * X.R_.m00; T.R_.m02 = X.R_.m02;
+  T.R_.m10 = c * X.R_.m10 + s * X.R_.m11; T.R_.m11 = c * X.R_.m11 - s * X.R_.m10; T.R_.m12 = X.R_.m12;
+  T.R_.m20 = c * X.R_.m20 + s * X.R_.m21; T.R_.m21 = c * X.R_.m21 - s * X.R_.m20; T.R_.m22 = X.R_.m22;
+  T.p = X.p;
+  return T;
+}
+template <class R> NB2_HD Xf<R> xf_pris(const Nb2ModelDev<R>& M, int i, R d) {
+  Xf<R> T = xtree(M, i);
+  T.p.x += T.R_.m02 * d; T.p.y += T.R_.m12 * d; T.p.z += T.R_.m22 * d;
+  return T;
+}
+template <class R> NB2_HD void inertia_of(const Nb2ModelDev<R>& M, int i, R* m, V3<R>* h, S3<R>* Ib) {
+  *m = M.inertia[i][0];
+  *h = mk3<R>(M.inertia[i][1], M.inertia[i][2], M.inertia[i][3]);
+  Ib->xx = M.inertia[i][4]; Ib->yy = M.inertia[i][5]; Ib->zz = M.inertia[i][6];
+  Ib->xy = M.inertia[i][7]; Ib->xz = M.inertia[i][8]; Ib->yz = M.inertia[i][9];
+}
+template <class R, int ST> NB2_HD Xf<R> ldXf(const R* p) {
+  Xf<R> T;
+  T.R_.m00 = p[0]; T.R_.m01 = p[ST]; T.R_.m02 = p[2 * ST]; T.R_.m10 = p[3 * ST]; T.R_.m11 = p[4 * ST]; T.R_.m12 = p[5 * ST];
+  T.R_.m20 = p[6 * ST]; T.R_.m21 = p[7 * ST]; T.R_.m22 = p[8 * ST];
+  T.p = mk3<R>(p[9 * ST], p[10 * ST], p[11 * ST]);
+  return T;
+}
+template <class R, int ST> NB2_HD void stXf(R* p, const Xf<R>& T) {
+  p[0] = T.R_.m00; p[ST] = T.R_.m01; p[2 * ST] = T.R_.m02; p[3 * ST] = T.R_.m10; p[4 * ST] = T.R_.m11; p[5 * ST] = T.R_.m12;
+  p[6 * ST] = T.R_.m20; p[7 * ST] = T.R_.m21; p[8 * ST] = T.R_.m22; p[9 * ST] = T.p.x; p[10 * ST] = T.p.y; p[11 * ST] = T.p.z;
+}
+// transform of body i during the sweeps that follow the kinematics pass (forward scratch layout)
+template <class R, int ST> NB2_HD Xf<R> body_xf_fwd(const Nb2ModelDev<R>& M, int i, const R* scr, const FwdLayout& L) {
+  const int jt = M.jtype[i];
+  if (jt == NB2_JT_REV) { const R* b = scr + (size_t)(L.oBody + 22 * i + 6) * ST; return xf_rev(M, i, b[0], b[ST]); }
+  if (jt == NB2_JT_PRIS) return xf_pris(M, i, scr[(size_t)(L.oQ + M.dof_off[i]) * ST]);
+  return ldXf<R, ST>(scr + (size_t)(L.oFree + 18 * M.free_idx[i]) * ST);
+}
+// S * x for 1-dof joints / eta = ad(V, S v)
+template <class R> NB2_HD V6<R> S_times(int jt, R x) {
+  V6<R> s = zero6<R>();
+  if (jt == NB2_JT_REV) s.a.z = x; else s.l.z = x;
+  return s;
+}
+template <class R> NB2_HD R S_dot(int jt, const V6<R>& f) { return (jt == NB2_JT_REV) ? f.a.z : f.l.z; }
+
+// =====================================================================================================
+// forward: state=[q;v] (fp32 row), action (fp32 row) -> next state row; optionally streams intermediates to `sv`
+// =====================================================================================================
+template <class R, int ST>
+NB2_HD void world_forward(const Nb2ModelDev<R>& M, R* scr, const float* st, const float* act, float* out, float* sv,
+                          size_t B, bool save) {
+  const int nb = M.nb, n = M.ndof;
+  const FwdLayout L = fwd_layout(nb, n, M.nslots, M.nfree);
+  const R dt = M.dt;
+  for (int d = 0; d < n; d++) {
+    scr[(size_t)(L.oQ + d) * ST] = (R)st[d];
+    scr[(size_t)(L.oV + d) * ST] = (R)st[n + d];
+    scr[(size_t)(L.oTau + d) * ST] = R(0);
+  }
+  for (int i = 0; i < M.na; i++) scr[(size_t)(L.oTau + M.action_map[i]) * ST] = (R)act[i];  // World.cpp:2061-2086
+
+  // ---------------- pass 1, root -> leaf: joint transforms and spatial velocities (Frame.cpp:144-160)
+  for (int i = 0; i < nb; i++) {
+    const int jt = M.jtype[i], p = M.parent[i], o = M.dof_off[i];
+    R* bs = scr + (size_t)(L.oBody + 22 * i) * ST;
+    V6<R> Vp = (p >= 0) ? ld6<R, ST>(scr + (size_t)(L.oBody + 22 * p) * ST) : zero6<R>();
+    V6<R> V;
+    if (jt == NB2_JT_REV) {
+      R s, c; nb2_sincos(scr[(size_t)(L.oQ + o) * ST], &s, &c);
+      bs[6 * ST] = s; bs[7 * ST] = c;
+      V = AdInvT(xf_rev(M, i, s, c), Vp);
+      V.a.z += scr[(size_t)(L.oV + o) * ST];
+    } else if (jt == NB2_JT_PRIS) {
+      V = AdInvT(xf_pris(M, i, scr[(size_t)(L.oQ + o) * ST]), Vp);
+      V.l.z += scr[(size_t)(L.oV + o) * ST];
+    } else {  // FREE (FreeJoint.cpp:74-81, 1027-1061)
+      const R* q = scr + (size_t)(L.oQ + o) * ST;
+      const R* v = scr + (size_t)(L.oV + o) * ST;
+      Xf<R> X = xtree(M, i), T;
+      M3<R> Rq = expmap(mk3<R>(q[0], q[ST], q[2 * ST]));
+      T.R_ = mul(X.R_, Rq);
+      T.p = mul(X.R_, mk3<R>(q[3 * ST], q[4 * ST], q[5 * ST])) + X.p;
+      stXf<R, ST>(scr + (size_t)(L.oFree + 18 * M.free_idx[i]) * ST, T);
+      V = AdInvT(T, Vp) + ld6<R, ST>(v);
+    }
+    st6<R, ST>(bs, V);
+  }
+
+  // ---------------- pass 2, leaf -> root: articulated inertia, bias force, total joint force
+  // (BodyNode.cpp:2046-2114, GenericJoint.hpp:2168-2185, 2276-2301, 2395-2421, 2554-2571)
+  SI<R> hI = zeroSI<R>();
+  V6<R> hp = zero6<R>();
+  bool hvalid = false;
+  for (int i = nb - 1; i >= 0; i--) {
+    const int jt = M.jtype[i], p = M.parent[i], o = M.dof_off[i], fl = M.flags[i];
+    R* bs = scr + (size_t)(L.oBody + 22 * i) * ST;
+    R m; V3<R> h; S3<R> Ib; inertia_of(M, i, &m, &h, &Ib);
+    const V6<R> V = ld6<R, ST>(bs);
+    SI<R> IA = rigidSI(m, h, Ib);
+    V6<R> pA = crf(V, mulG(m, h, Ib, V));
+    if (hvalid) { IA = IA + hI; pA = pA + hp; }
+    if (fl & NB2_F_HAS_SLOT) {
+      const R* sl = scr + (size_t)(L.oSlot + 27 * M.slot_self[i]) * ST;
+      IA = IA + ldSI<R, ST>(sl);
+      pA = pA + ld6<R, ST>(sl + 21 * ST);
+    }
+    SI<R> Pi; V6<R> beta;
+    if (jt != NB2_JT_FREE) {
+      const R vq = scr[(size_t)(L.oV + o) * ST];
+      V6<R> U, eta;
+      R D;
+      if (jt == NB2_JT_REV) {
+        U.a = mk3<R>(IA.A.xz, IA.A.yz, IA.A.zz); U.l = mk3<R>(IA.B.m20, IA.B.m21, IA.B.m22); D = IA.A.zz;
+        eta.a = mk3<R>(V.a.y * vq, -V.a.x * vq, R(0)); eta.l = mk3<R>(V.l.y * vq, -V.l.x * vq, R(0));
+      } else {
+        U.a = mk3<R>(IA.B.m02, IA.B.m12, IA.B.m22); U.l = mk3<R>(IA.C.xz, IA.C.yz, IA.C.zz); D = IA.C.zz;
+        eta.a = zero3<R>(); eta.l = mk3<R>(V.a.y * vq, -V.a.x * vq, R(0));
+      }
+      const R psi = R(1) / D;
+      const R qv = scr[(size_t)(L.oQ + o) * ST];
+      const R u = scr[(size_t)(L.oTau + o) * ST] - M.spring[o] * (qv - M.rest[o] + vq * dt) - M.damping[o] * vq
+                  - (dot(U, eta) + S_dot(jt, pA));
+      st6<R, ST>(bs + 8 * ST, U);
+      bs[14 * ST] = psi; bs[15 * ST] = u;
+      if (p >= 0) {
+        const R k = -psi;
+        Pi = IA;
+        Pi.A.xx += k * U.a.x * U.a.x; Pi.A.yy += k * U.a.y * U.a.y; Pi.A.zz += k * U.a.z * U.a.z;
+        Pi.A.xy += k * U.a.x * U.a.y; Pi.A.xz += k * U.a.x * U.a.z; Pi.A.yz += k * U.a.y * U.a.z;
+        Pi.C.xx += k * U.l.x * U.l.x; Pi.C.yy += k * U.l.y * U.l.y; Pi.C.zz += k * U.l.z * U.l.z;
+        Pi.C.xy += k * U.l.x * U.l.y; Pi.C.xz += k * U.l.x * U.l.z; Pi.C.yz += k * U.l.y * U.l.z;
+        Pi.B.m00 += k * U.a.x * U.l.x; Pi.B.m01 += k * U.a.x * U.l.y; Pi.B.m02 += k * U.a.x * U.l.z;
+        Pi.B.m10 += k * U.a.y * U.l.x; Pi.B.m11 += k * U.a.y * U.l.y; Pi.B.m12 += k * U.a.y * U.l.z;
+        Pi.B.m20 += k * U.a.z * U.l.x; Pi.B.m21 += k * U.a.z * U.l.y; Pi.B.m22 += k * U.a.z * U.l.z;
+        beta = pA + mul(IA, eta) + U * (psi * u);
+      }
+    } else {
+      const R* q = scr + (size_t)(L.oQ + o) * ST;
+      const R* v = scr + (size_t)(L.oV + o) * ST;
+      const R* t = scr + (size_t)(L.oTau + o) * ST;
+      const V6<R> Vj = ld6<R, ST>(v);
+      const V6<R> eta = ad(V, Vj);
+      const V6<R> bf = mul(IA, eta) + pA;
+      V6<R> u;
+      u.a.x = t[0] - M.spring[o] * (q[0] - M.rest[o] + Vj.a.x * dt) - M.damping[o] * Vj.a.x - bf.a.x;
+      u.a.y = t[ST] - M.spring[o + 1] * (q[ST] - M.rest[o + 1] + Vj.a.y * dt) - M.damping[o + 1] * Vj.a.y - bf.a.y;
+      u.a.z = t[2 * ST] - M.spring[o + 2] * (q[2 * ST] - M.rest[o + 2] + Vj.a.z * dt) - M.damping[o + 2] * Vj.a.z - bf.a.z;
+      u.l.x = t[3 * ST] - M.spring[o + 3] * (q[3 * ST] - M.rest[o + 3] + Vj.l.x * dt) - M.damping[o + 3] * Vj.l.x - bf.l.x;
+      u.l.y = t[4 * ST] - M.spring[o + 4] * (q[4 * ST] - M.rest[o + 4] + Vj.l.y * dt) - M.damping[o + 4] * Vj.l.y - bf.l.y;
+      u.l.z = t[5 * ST] - M.spring[o + 5] * (q[5 * ST] - M.rest[o + 5] + Vj.l.z * dt) - M.damping[o + 5] * Vj.l.z - bf.l.z;
+      const SI<R> Iinv = spd6_inverse(IA);
+      const V6<R> y = mul(Iinv, u);
+      st6<R, ST>(scr + (size_t)(L.oFree + 18 * M.free_idx[i] + 12) * ST, y);
+      if (save) {
+        const int k0 = nb * 21 + M.free_idx[i] * 33;
+        float* s = sv + (size_t)k0 * B;
+        s[0] = (float)Iinv.A.xx; s[B] = (float)Iinv.A.yy; s[2 * B] = (float)Iinv.A.zz; s[3 * B] = (float)Iinv.A.xy; s[4 * B] = (float)Iinv.A.xz; s[5 * B] = (float)Iinv.A.yz;
+        s[6 * B] = (float)Iinv.B.m00; s[7 * B] = (float)Iinv.B.m01; s[8 * B] = (float)Iinv.B.m02; s[9 * B] = (float)Iinv.B.m10; s[10 * B] = (float)Iinv.B.m11; s[11 * B] = (float)Iinv.B.m12;
+        s[12 * B] = (float)Iinv.B.m20; s[13 * B] = (float)Iinv.B.m21; s[14 * B] = (float)Iinv.B.m22;
+        s[15 * B] = (float)Iinv.C.xx; s[16 * B] = (float)Iinv.C.yy; s[17 * B] = (float)Iinv.C.zz; s[18 * B] = (float)Iinv.C.xy; s[19 * B] = (float)Iinv.C.xz; s[20 * B] = (float)Iinv.C.yz;
+      }
+      if (p >= 0) { Pi = zeroSI<R>(); beta = bf + u; }  // a 6-dof joint transmits only its own joint force
+    }
+    hvalid = false;
+    if (p >= 0) {
+      const Xf<R> T = body_xf_fwd<R, ST>(M, i, scr, L);
+      const SI<R> Ic = xform_inertia(T, Pi);
+      const V6<R> pc = dAdInvT(T, beta);
+      if (fl & NB2_F_HANDOFF) { hI = Ic; hp = pc; hvalid = true; }
+      else {
+        R* sl = scr + (size_t)(L.oSlot + 27 * M.slot_parent[i]) * ST;
+        if (fl & NB2_F_FIRST_DEPOSIT) { stSI<R, ST, false>(sl, Ic); st6<R, ST>(sl + 21 * ST, pc); }
+        else { stSI<R, ST, true>(sl, Ic); add6<R, ST>(sl + 21 * ST, pc); }
+      }
+    }
+  }
+
+  // ---------------- pass 3, root -> leaf: accelerations (BodyNode.cpp:2159-2185, GenericJoint.hpp:2656-2676),
+  // then integrate: v+ = v + dt qdd ; q+ = q (+) dt v  with the PRE-step velocity (World.cpp:307-322)
+  V6<R> A0; A0.a = zero3<R>(); A0.l = mk3<R>(-M.gravity[0], -M.gravity[1], -M.gravity[2]);
+  for (int i = 0; i < nb; i++) {
+    const int jt = M.jtype[i], p = M.parent[i], o = M.dof_off[i];
+    R* bs = scr + (size_t)(L.oBody + 22 * i) * ST;
+    const Xf<R> T = body_xf_fwd<R, ST>(M, i, scr, L);
+    const V6<R> Ap = AdInvT(T, (p >= 0) ? ld6<R, ST>(scr + (size_t)(L.oBody + 22 * p + 16) * ST) : A0);
+    const V6<R> V = ld6<R, ST>(bs);
+    V6<R> A;
+    if (jt != NB2_JT_FREE) {
+      const R vq = scr[(size_t)(L.oV + o) * ST], qv = scr[(size_t)(L.oQ + o) * ST];
+      const V6<R> U = ld6<R, ST>(bs + 8 * ST);
+      const R psi = bs[14 * ST], u = bs[15 * ST];
+      const R qdd = psi * (u - dot(U, Ap));
+      A = Ap;
+      if (jt == NB2_JT_REV) { A.a.z += qdd; A.a.x += V.a.y * vq; A.a.y -= V.a.x * vq; A.l.x += V.l.y * vq; A.l.y -= V.l.x * vq; }
+      else { A.l.z += qdd; A.l.x += V.a.y * vq; A.l.y -= V.a.x * vq; }
+      out[o] = (float)(qv + vq * dt);
+      out[n + o] = (float)(vq + qdd * dt);
+      if (save) {
+        float* s = sv + (size_t)(i * 21) * B;
+        sv_st6(s, B, 0, tof(V)); sv_st6(s, B, 6, tof(A)); sv_st6(s, B, 12, tof(U));
+        s[18 * B] = (float)psi; s[19 * B] = (float)bs[6 * ST]; s[20 * B] = (float)bs[7 * ST];
+        sv[(size_t)(nb * 21 + M.nfree * 33 + o) * B] = (float)qdd;
+      }
+    } else {
+      const R* q = scr + (size_t)(L.oQ + o) * ST;
+      const R* fr = scr + (size_t)(L.oFree + 18 * M.free_idx[i]) * ST;
+      const V6<R> Vj = ld6<R, ST>(scr + (size_t)(L.oV + o) * ST);
+      const V6<R> y = ld6<R, ST>(fr + 12 * ST);
+      const V6<R> qdd = y - Ap;
+      A = y + ad(V, Vj);
+      // FreeJoint::integratePositionsExplicit, identity-Jacobian branch (FreeJoint.cpp:922-929)
+      const V3<R> phi = mk3<R>(q[0], q[ST], q[2 * ST]);
+      const M3<R> Rq = expmap(phi);
+      const V3<R> phin = logmap(mul(Rq, expmap(Vj.a * dt)));
+      const V3<R> pn = mk3<R>(q[3 * ST], q[4 * ST], q[5 * ST]) + mul(Rq, Vj.l * dt);
+      out[o] = (float)phin.x; out[o + 1] = (float)phin.y; out[o + 2] = (float)phin.z;
+      out[o + 3] = (float)pn.x; out[o + 4] = (float)pn.y; out[o + 5] = (float)pn.z;
+      out[n + o] = (float)(Vj.a.x + qdd.a.x * dt); out[n + o + 1] = (float)(Vj.a.y + qdd.a.y * dt); out[n + o + 2] = (float)(Vj.a.z + qdd.a.z * dt);
+      out[n + o + 3] = (float)(Vj.l.x + qdd.l.x * dt); out[n + o + 4] = (float)(Vj.l.y + qdd.l.y * dt); out[n + o + 5] = (float)(Vj.l.z + qdd.l.z * dt);
+      if (save) {
+        float* s = sv + (size_t)(i * 21) * B;
+        sv_st6(s, B, 0, tof(V)); sv_st6(s, B, 6, tof(A));
+        for (int k = 12; k < 21; k++) s[(size_t)k * B] = 0.f;
+        float* sf = sv + (size_t)(nb * 21 + M.free_idx[i] * 33 + 21) * B;
+        for (int k = 0; k < 12; k++) sf[(size_t)k * B] = (float)fr[(size_t)k * ST];
+        float* sq = sv + (size_t)(nb * 21 + M.nfree * 33 + o) * B;
+        sq[0] = (float)qdd.a.x; sq[B] = (float)qdd.a.y; sq[2 * B] = (float)qdd.a.z; sq[3 * B] = (float)qdd.l.x; sq[4 * B] = (float)qdd.l.y; sq[5 * B] = (float)qdd.l.z;
+      }
+    }
+    st6<R, ST>(bs + 16 * ST, A);
+  }
+}
+
+// =====================================================================================================
+// backward: g_next = dL/d[q+;v+]  ->  g_state = dL/d[q;v], g_action = dL/d action
+// =====================================================================================================
+template <class R, int ST>
+NB2_HD void world_backward(const Nb2ModelDev<R>& M, R* scr, const float* st, const float* act, const float* gnext,
+                           const float* sv, size_t B, float* gstate, float* gaction) {
+  const int nb = M.nb, n = M.ndof;
+  const BwdLayout L = bwd_layout(nb, n, M.nslots, M.nfree);
+  const R dt = M.dt;
+  const int kFree = nb * 21, kQdd = nb * 21 + M.nfree * 33;
+  for (int d = 0; d < n; d++) {
+    scr[(size_t)(L.oGQ + d) * ST] = (R)gnext[d];
+    scr[(size_t)(L.oGV + d) * ST] = (R)gnext[n + d];
+  }
+
+  // ---------------- B1, leaf -> root: bias pass of lambda = M^-1 g_v'  (impulse-ABA form,
+  // BodyNode.cpp:2117-2138, GenericJoint.hpp:2482-2498, 2607-2613) reusing the forward's U, psi
+  V6<R> hp = zero6<R>();
+  bool hvalid = false;
+  for (int i = nb - 1; i >= 0; i--) {
+    const int jt = M.jtype[i], p = M.parent[i], o = M.dof_off[i], fl = M.flags[i];
+    const float* s = sv + (size_t)(i * 21) * B;
+    V6<R> pI = hvalid ? hp : zero6<R>();
+    if (fl & NB2_F_HAS_SLOT) pI = pI + ld6<R, ST>(scr + (size_t)(L.oSlot + 18 * M.slot_self[i]) * ST);
+    V6<R> beta;
+    if (jt != NB2_JT_FREE) {
+      const R up = scr[(size_t)(L.oGV + o) * ST] - S_dot(jt, pI);
+      scr[(size_t)(L.oBody + 7 * i) * ST] = up;
+      if (p >= 0) beta = pI + sv_ld6<R>(s, B, 12) * ((R)s[18 * B] * up);
+    } else {
+      const V6<R> up = ld6<R, ST>(scr + (size_t)(L.oGV + o) * ST) - pI;
+      st6<R, ST>(scr + (size_t)(L.oFree + 6 * M.free_idx[i]) * ST, up);
+      if (p >= 0) beta = pI + up;
+    }
+    hvalid = false;
+    if (p >= 0) {
+      Xf<R> T;
+      if (jt == NB2_JT_REV) T = xf_rev(M, i, (R)s[19 * B], (R)s[20 * B]);
+      else if (jt == NB2_JT_PRIS) T = xf_pris(M, i, (R)st[o]);
+      else { R t12[12]; for (int k = 0; k < 12; k++) t12[k] = (R)sv[(size_t)(kFree + M.free_idx[i] * 33 + 21 + k) * B]; T = ldXf<R, 1>(t12); }
+      const V6<R> pc = dAdInvT(T, beta);
+      if (fl & NB2_F_HANDOFF) { hp = pc; hvalid = true; }
+      else {
+        R* sl = scr + (size_t)(L.oSlot + 18 * M.slot_parent[i]) * ST;
+        if (fl & NB2_F_FIRST_DEPOSIT) st6<R, ST>(sl, pc); else add6<R, ST>(sl, pc);
+      }
+    }
+  }
+  // ---------------- B2, root -> leaf: lambda and the spatial "velocities" W it induces
+  // (BodyNode.cpp:2188-2215, GenericJoint.hpp:2713-2725)
+  for (int i = 0; i < nb; i++) {
+    const int jt = M.jtype[i], p = M.parent[i], o = M.dof_off[i];
+    const float* s = sv + (size_t)(i * 21) * B;
+    R* bs = scr + (size_t)(L.oBody + 7 * i) * ST;
+    V6<R> W;
+    if (jt != NB2_JT_FREE) {
+      Xf<R> T = (jt == NB2_JT_REV) ? xf_rev(M, i, (R)s[19 * B], (R)s[20 * B]) : xf_pris(M, i, (R)st[o]);
+      W = (p >= 0) ? AdInvT(T, ld6<R, ST>(scr + (size_t)(L.oBody + 7 * p + 1) * ST)) : zero6<R>();
+      const R lam = (R)s[18 * B] * (bs[0] - dot(sv_ld6<R>(s, B, 12), W));
+      scr[(size_t)(L.oLam + o) * ST] = lam;
+      if (jt == NB2_JT_REV) W.a.z += lam; else W.l.z += lam;
+    } else {
+      const float* sf = sv + (size_t)(kFree + M.free_idx[i] * 33) * B;
+      R t12[12]; for (int k = 0; k < 12; k++) t12[k] = (R)sf[(size_t)(21 + k) * B];
+      const Xf<R> T = ldXf<R, 1>(t12);
+      const V6<R> Wp = (p >= 0) ? AdInvT(T, ld6<R, ST>(scr + (size_t)(L.oBody + 7 * p + 1) * ST)) : zero6<R>();
+      R i21[21]; for (int k = 0; k < 21; k++) i21[k] = (R)sf[(size_t)k * B];
+      const SI<R> Iinv = ldSI<R, 1>(i21);
+      W = mul(Iinv, ld6<R, ST>(scr + (size_t)(L.oFree + 6 * M.free_idx[i]) * ST));
+      st6<R, ST>(scr + (size_t)(L.oLam + o) * ST, W - Wp);
+    }
+    st6<R, ST>(bs + ST, W);
+  }
+  // ---------------- B3, leaf -> root: reverse sweep of RNEA, seeded with lambda on the joint forces.
+  //   forward RNEA:  V_i = X^-1 V_p + S v ;  A_i = X^-1 A_p + S a + ad(V_i, S v) ;  F_i = G A_i + V_i x* G V_i ;
+  //                  f_i = F_i + sum_c X*_c f_c ; tau_i = S^T f_i
+  //   adjoints:      fbar_i = W_i (from B2) ;  Abar_i = G W_i + sum_c X*_c Abar_c ;
+  //                  Vbar_i = -W x* (G V) + G ad(W, V) + (S v) x* Abar_i + sum_c X*_c Vbar_c
+  //                  vbar_i = S^T (Vbar_i - V_i x* Abar_i)
+  //                  c_i    = -( (X^-1 A_p) x* Abar_i + (X^-1 V_p) x* Vbar_i + (X^-1 W_p) x* f_i ) ; qbar_i = B_i(q)^T c_i
+  V6<R> hA = zero6<R>(), hV = zero6<R>(), hf = zero6<R>();
+  hvalid = false;
+  for (int i = nb - 1; i >= 0; i--) {
+    const int jt = M.jtype[i], p = M.parent[i], o = M.dof_off[i], fl = M.flags[i];
+    const float* s = sv + (size_t)(i * 21) * B;
+    R m; V3<R> h; S3<R> Ib; inertia_of(M, i, &m, &h, &Ib);
+    const V6<R> V = sv_ld6<R>(s, B, 0), A = sv_ld6<R>(s, B, 6);
+    const V6<R> W = ld6<R, ST>(scr + (size_t)(L.oBody + 7 * i + 1) * ST);
+    const V6<R> GV = mulG(m, h, Ib, V);
+    V6<R> f = mulG(m, h, Ib, A) + crf(V, GV);
+    V6<R> Abar = mulG(m, h, Ib, W);
+    V6<R> Vbar = mulG(m, h, Ib, ad(W, V)) - crf(W, GV);
+    if (hvalid) { Abar = Abar + hA; Vbar = Vbar + hV; f = f + hf; }
+    if (fl & NB2_F_HAS_SLOT) {
+      const R* sl = scr + (size_t)(L.oSlot + 18 * M.slot_self[i]) * ST;
+      Abar = Abar + ld6<R, ST>(sl); Vbar = Vbar + ld6<R, ST>(sl + 6 * ST); f = f + ld6<R, ST>(sl + 12 * ST);
+    }
+    V6<R> Sv, Sa, Sl;
+    Xf<R> T;
+    if (jt != NB2_JT_FREE) {
+      Sv = S_times<R>(jt, (R)st[n + o]);
+      Sa = S_times<R>(jt, (R)sv[(size_t)(kQdd + o) * B]);
+      Sl = S_times<R>(jt, scr[(size_t)(L.oLam + o) * ST]);
+      T = (jt == NB2_JT_REV) ? xf_rev(M, i, (R)s[19 * B], (R)s[20 * B]) : xf_pris(M, i, (R)st[o]);
+    } else {
+      Sv.a = mk3<R>((R)st[n + o], (R)st[n + o + 1], (R)st[n + o + 2]); Sv.l = mk3<R>((R)st[n + o + 3], (R)st[n + o + 4], (R)st[n + o + 5]);
+      Sa = sv_ld6<R>(sv + (size_t)(kQdd + o) * B, B, 0);
+      Sl = ld6<R, ST>(scr + (size_t)(L.oLam + o) * ST);
+      R t12[12]; for (int k = 0; k < 12; k++) t12[k] = (R)sv[(size_t)(kFree + M.free_idx[i] * 33 + 21 + k) * B];
+      T = ldXf<R, 1>(t12);
+    }
+    Vbar = Vbar + crf(Sv, Abar);
+    const V6<R> vb6 = Vbar - crf(V, Abar);
+    const V6<R> Alam = A - Sa - ad(V, Sv), Vlam = V - Sv, Wlam = W - Sl;
+    const V6<R> c6 = zero6<R>() - (crf(Alam, Abar) + crf(Vlam, Vbar) + crf(Wlam, f));
+    if (jt != NB2_JT_FREE) {
+      scr[(size_t)(L.oVb + o) * ST] = S_dot(jt, vb6);
+      scr[(size_t)(L.oQb + o) * ST] = S_dot(jt, c6);
+    } else {
+      st6<R, ST>(scr + (size_t)(L.oVb + o) * ST, vb6);
+      const V3<R> phi = mk3<R>((R)st[o], (R)st[o + 1], (R)st[o + 2]);
+      V6<R> qb;
+      qb.a = mulT(so3_Jr(phi), c6.a);
+      qb.l = mul(expmap(phi), c6.l);
+      st6<R, ST>(scr + (size_t)(L.oQb + o) * ST, qb);
+    }
+    hvalid = false;
+    if (p >= 0) {
+      const V6<R> cA = dAdInvT(T, Abar), cV = dAdInvT(T, Vbar), cf = dAdInvT(T, f);
+      if (fl & NB2_F_HANDOFF) { hA = cA; hV = cV; hf = cf; hvalid = true; }
+      else {
+        R* sl = scr + (size_t)(L.oSlot + 18 * M.slot_parent[i]) * ST;
+        if (fl & NB2_F_FIRST_DEPOSIT) { st6<R, ST>(sl, cA); st6<R, ST>(sl + 6 * ST, cV); st6<R, ST>(sl + 12 * ST, cf); }
+        else { add6<R, ST>(sl, cA); add6<R, ST>(sl + 6 * ST, cV); add6<R, ST>(sl + 12 * ST, cf); }
+      }
+    }
+  }
+  // ---------------- assemble:  g_tau = dt lambda ;  g_q = Pqq^T g_q' - dt (qbar + K lambda) ;
+  //                             g_v = Pvq^T g_q' + g_v' - dt (vbar + (D + dt K) lambda)
+  for (int i = 0; i < nb; i++) {
+    const int jt = M.jtype[i], o = M.dof_off[i];
+    if (jt != NB2_JT_FREE) {
+      const R lam = scr[(size_t)(L.oLam + o) * ST];
+      const R gq = scr[(size_t)(L.oGQ + o) * ST], gv = scr[(size_t)(L.oGV + o) * ST];
+      scr[(size_t)(L.oQb + o) * ST] = gq - dt * (scr[(size_t)(L.oQb + o) * ST] + M.spring[o] * lam);
+      scr[(size_t)(L.oVb + o) * ST] = dt * gq + gv - dt * (scr[(size_t)(L.oVb + o) * ST] + (M.damping[o] + dt * M.spring[o]) * lam);
+    } else {
+      // free-joint position update q+ = [log(R(phi) exp(w dt)); p + R(phi) v dt] (the reference differentiates this by
+      // finite differences, FreeJoint.cpp:950-1007; closed form here)
+      const V3<R> phi = mk3<R>((R)st[o], (R)st[o + 1], (R)st[o + 2]);
+      const V3<R> w = mk3<R>((R)st[n + o], (R)st[n + o + 1], (R)st[n + o + 2]);
+      const V3<R> vl = mk3<R>((R)st[n + o + 3], (R)st[n + o + 4], (R)st[n + o + 5]);
+      const M3<R> Rq = expmap(phi), E = expmap(w * dt);
+      const V3<R> phin = logmap(mul(Rq, E));
+      const V6<R> g = ld6<R, ST>(scr + (size_t)(L.oGQ + o) * ST);
+      const V3<R> t = mulT(so3_Jr_inv(phin), g.a);                 // Jr^-T(phi+) g_phi+
+      V6<R> gq, gvp;
+      gq.a = mulT(so3_Jr(phi), mul(E, t) + cross(vl * dt, mulT(Rq, g.l)));
+      gq.l = g.l;
+      gvp.a = mulT(so3_Jr(w * dt), t) * dt;
+      gvp.l = mulT(Rq, g.l) * dt;
+      const V6<R> lam = ld6<R, ST>(scr + (size_t)(L.oLam + o) * ST);
+      const V6<R> qb = ld6<R, ST>(scr + (size_t)(L.oQb + o) * ST), vb = ld6<R, ST>(scr + (size_t)(L.oVb + o) * ST);
+      const V6<R> gv = ld6<R, ST>(scr + (size_t)(L.oGV + o) * ST);
+      R lamv[6] = {lam.a.x, lam.a.y, lam.a.z, lam.l.x, lam.l.y, lam.l.z};
+      R qbv[6] = {qb.a.x, qb.a.y, qb.a.z, qb.l.x, qb.l.y, qb.l.z}, vbv[6] = {vb.a.x, vb.a.y, vb.a.z, vb.l.x, vb.l.y, vb.l.z};
+      R gqv[6] = {gq.a.x, gq.a.y, gq.a.z, gq.l.x, gq.l.y, gq.l.z}, gvpv[6] = {gvp.a.x, gvp.a.y, gvp.a.z, gvp.l.x, gvp.l.y, gvp.l.z};
+      R gvv[6] = {gv.a.x, gv.a.y, gv.a.z, gv.l.x, gv.l.y, gv.l.z};
+#pragma unroll
+      for (int k = 0; k < 6; k++) {
+        scr[(size_t)(L.oQb + o + k) * ST] = gqv[k] - dt * (qbv[k] + M.spring[o + k] * lamv[k]);
+        scr[(size_t)(L.oVb + o + k) * ST] = gvpv[k] + gvv[k] - dt * (vbv[k] + (M.damping[o + k] + dt * M.spring[o + k]) * lamv[k]);
+      }
+    }
+  }
+  // clipLossGradientsToBounds (BackpropSnapshot.cpp:425-479): exact equality against the pre-step state, then
+  // scatter through the action map (:404-417)
+  for (int d = 0; d < n; d++) {
+    float gq = (float)scr[(size_t)(L.oQb + d) * ST], gv = (float)scr[(size_t)(L.oVb + d) * ST];
+    const float qd = st[d], vd = st[n + d];
+    if (qd == M.pos_lo[d] && gq > 0.f) gq = 0.f;
+    if (qd == M.pos_hi[d] && gq < 0.f) gq = 0.f;
+    if (vd == M.vel_lo[d] && gv > 0.f) gv = 0.f;
+    if (vd == M.vel_hi[d] && gv < 0.f) gv = 0.f;
+    gstate[d] = gq; gstate[n + d] = gv;
+  }
+  for (int i = 0; i < M.na; i++) {
+    const int d = M.action_map[i];
+    float gt = (float)(dt * scr[(size_t)(L.oLam + d) * ST]);
+    const float fd = act[i];
+    if (fd == M.force_lo[d] && gt > 0.f) gt = 0.f;
+    if (fd == M.force_hi[d] && gt < 0.f) gt = 0.f;
+    gaction[i] = gt;
+  }
+}
+
+}  // namespace nb2

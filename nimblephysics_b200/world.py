@@ -1,0 +1,458 @@
+"""Host-side World / Skeleton / Joint / BodyNode builder surface.
+
+This mirrors the small part of the reference's object model that training
+scripts touch before calling ``timestep`` (reference: pybind `World`
+python/_nimblephysics/simulation_and_neural/World.cpp, `Skeleton` builder
+calls used in python/new_examples/cartpole.py:12-46).  It holds *description*
+only; all arithmetic happens on the GPU through the C-ABI (csrc/) after
+``modelspec.flatten_world`` / ``modelspec.compile_model`` turn it into flat
+arrays.
+
+Conventions follow the reference: spatial quantities are [angular; linear],
+transforms are 4x4 homogeneous (``T_parent_child``), default gravity is
+(0, 0, -9.81) and default dt 1e-3 (dart/simulation/World.cpp:75-76).
+"""
+from __future__ import annotations
+
+import math
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+# joint type ids shared with oracle/ and csrc/ (include/nb2.h)
+WELD, REVOLUTE, PRISMATIC, FREE = 0, 1, 2, 3
+JOINT_NDOF = {WELD: 0, REVOLUTE: 1, PRISMATIC: 1, FREE: 6}
+
+# shape type ids (include/nb2.h)
+SHAPE_BOX, SHAPE_SPHERE, SHAPE_CAPSULE = 0, 1, 2
+
+INF = float("inf")
+
+
+def _eye4():
+    return np.eye(4, dtype=np.float64)
+
+
+class Isometry3:
+    """Tiny stand-in for nimble.math.Isometry3 (set_translation / set_rotation)."""
+
+    def __init__(self, m: Optional[np.ndarray] = None):
+        self._m = _eye4() if m is None else np.array(m, dtype=np.float64).reshape(4, 4)
+
+    def set_translation(self, t):
+        self._m[:3, 3] = np.asarray(t, dtype=np.float64)
+
+    def set_rotation(self, r):
+        self._m[:3, :3] = np.asarray(r, dtype=np.float64).reshape(3, 3)
+
+    def translation(self):
+        return self._m[:3, 3].copy()
+
+    def rotation(self):
+        return self._m[:3, :3].copy()
+
+    def matrix(self):
+        return self._m.copy()
+
+
+def _as_T(T) -> np.ndarray:
+    if isinstance(T, Isometry3):
+        return T.matrix()
+    return np.array(T, dtype=np.float64).reshape(4, 4)
+
+
+class Shape:
+    def __init__(self, kind: int, dims: Sequence[float]):
+        self.kind = kind
+        self.dims = np.zeros(3)
+        self.dims[: len(dims)] = dims
+
+    def compute_inertia(self, mass: float) -> np.ndarray:
+        """Moment about the shape's own centre, shape-frame axes.
+        reference: dart/dynamics/BoxShape.cpp:74-83, CapsuleShape.cpp:107-131,
+        SphereShape (2/5 m r^2)."""
+        if self.kind == SHAPE_BOX:
+            sx, sy, sz = self.dims
+            return np.diag([
+                mass / 12.0 * (sy * sy + sz * sz),
+                mass / 12.0 * (sx * sx + sz * sz),
+                mass / 12.0 * (sx * sx + sy * sy),
+            ])
+        if self.kind == SHAPE_SPHERE:
+            r = self.dims[0]
+            return np.eye(3) * (0.4 * mass * r * r)
+        if self.kind == SHAPE_CAPSULE:
+            r, h = self.dims[0], self.dims[1]
+            r2, h2 = r * r, h * h
+            vc = math.pi * r2 * h
+            vs = 4.0 / 3.0 * math.pi * r2 * r
+            dens = mass / (vc + vs)
+            mc, ms = dens * vc, dens * vs
+            ixx = mc * (h2 / 12.0 + r2 / 4.0) + ms * (h2 + 0.375 * h * r + 0.4 * r2)
+            izz = mc * (r2 / 2.0) + ms * (0.4 * r2)
+            return np.diag([ixx, ixx, izz])
+        raise ValueError("unknown shape kind")
+
+
+def BoxShape(size):
+    return Shape(SHAPE_BOX, list(size))
+
+
+def SphereShape(radius):
+    return Shape(SHAPE_SPHERE, [radius])
+
+
+def CapsuleShape(radius, height):
+    return Shape(SHAPE_CAPSULE, [radius, height])
+
+
+class ShapeNode:
+    def __init__(self, shape: Shape, T_local: Optional[np.ndarray] = None, collidable=True):
+        self.shape = shape
+        self.T_local = _eye4() if T_local is None else _as_T(T_local)
+        self.collidable = collidable
+        self.has_collision = False
+
+    # the reference's visual calls are accepted and ignored (no renderer here)
+    def createVisualAspect(self):
+        return self
+
+    def createCollisionAspect(self):
+        self.has_collision = True
+        return self
+
+    def setColor(self, *_):
+        return None
+
+    def setRelativeTransform(self, T):
+        self.T_local = _as_T(T)
+
+
+class BodyNode:
+    """reference defaults: mass 1, com 0, moment I (dart/dynamics/Inertia.hpp
+    default ctor); friction 1.0, restitution 0 (detail/BodyNodeAspect.hpp:47-48)."""
+
+    def __init__(self, name: str):
+        self.name = name
+        self.mass = 1.0
+        self.com = np.zeros(3)
+        self.moment = np.eye(3)  # about the COM, body-frame axes
+        self.shapes: List[ShapeNode] = []
+        self.friction = 1.0
+        self.restitution = 0.0
+        self.gravity_mode = True
+        self.parent_joint: Optional["Joint"] = None
+        self.parent_body: Optional["BodyNode"] = None
+        self.skeleton: Optional["Skeleton"] = None
+
+    def setMass(self, m):
+        self.mass = float(m)
+
+    def getMass(self):
+        return self.mass
+
+    def setLocalCOM(self, c):
+        self.com = np.asarray(c, dtype=np.float64).copy()
+
+    def setMomentOfInertia(self, ixx, iyy, izz, ixy=0.0, ixz=0.0, iyz=0.0):
+        self.moment = np.array([[ixx, ixy, ixz], [ixy, iyy, iyz], [ixz, iyz, izz]], dtype=np.float64)
+
+    def setFrictionCoeff(self, mu):
+        self.friction = float(mu)
+
+    def setRestitutionCoeff(self, e):
+        self.restitution = float(e)
+
+    def createShapeNode(self, shape: Shape) -> ShapeNode:
+        sn = ShapeNode(shape)
+        self.shapes.append(sn)
+        return sn
+
+    def getName(self):
+        return self.name
+
+
+class Joint:
+    def __init__(self, jtype: int, name: str):
+        self.jtype = jtype
+        self.name = name
+        self.axis = np.array([0.0, 0.0, 1.0]) if jtype == REVOLUTE else np.array([1.0, 0.0, 0.0])
+        self.T_pj = _eye4()  # parent body -> joint
+        self.T_cj = _eye4()  # child body -> joint
+        nd = JOINT_NDOF[jtype]
+        self.ndof = nd
+        self.damping = np.zeros(nd)
+        self.spring = np.zeros(nd)
+        self.rest = np.zeros(nd)
+        self.pos_lo = np.full(nd, -INF)
+        self.pos_hi = np.full(nd, INF)
+        self.vel_lo = np.full(nd, -INF)
+        self.vel_hi = np.full(nd, INF)
+        self.force_lo = np.full(nd, -INF)
+        self.force_hi = np.full(nd, INF)
+        self.init_pos = np.zeros(nd)
+
+    # --- subset of the reference Joint API used by example scripts ---
+    def setAxis(self, a):
+        a = np.asarray(a, dtype=np.float64)
+        self.axis = a / np.linalg.norm(a)  # reference normalises (RevoluteJoint.cpp setAxis)
+
+    def setTransformFromParentBodyNode(self, T):
+        self.T_pj = _as_T(T)
+
+    def setTransformFromChildBodyNode(self, T):
+        self.T_cj = _as_T(T)
+
+    def setPositionUpperLimit(self, i, v):
+        self.pos_hi[i] = v
+
+    def setPositionLowerLimit(self, i, v):
+        self.pos_lo[i] = v
+
+    def setVelocityUpperLimit(self, i, v):
+        self.vel_hi[i] = v
+
+    def setVelocityLowerLimit(self, i, v):
+        self.vel_lo[i] = v
+
+    def setControlForceUpperLimit(self, i, v):
+        self.force_hi[i] = v
+
+    def setControlForceLowerLimit(self, i, v):
+        self.force_lo[i] = v
+
+    def setDampingCoefficient(self, i, v):
+        self.damping[i] = v
+
+    def setSpringStiffness(self, i, v):
+        self.spring[i] = v
+
+    def setRestPosition(self, i, v):
+        self.rest[i] = v
+
+    def getNumDofs(self):
+        return self.ndof
+
+
+class Skeleton:
+    def __init__(self, name: str = "skeleton"):
+        self.name = name
+        self.bodies: List[BodyNode] = []
+        self.mobile = True
+
+    def setMobile(self, m: bool):
+        self.mobile = bool(m)
+
+    def isMobile(self):
+        return self.mobile
+
+    def _create(self, jtype: int, parent: Optional[BodyNode], jname=None, bname=None):
+        j = Joint(jtype, jname or f"joint_{len(self.bodies)}")
+        b = BodyNode(bname or f"body_{len(self.bodies)}")
+        b.parent_joint, b.parent_body, b.skeleton = j, parent, self
+        if parent is not None and parent.skeleton is not self:
+            raise ValueError("parent body belongs to a different skeleton")
+        self.bodies.append(b)
+        return j, b
+
+    def createRevoluteJointAndBodyNodePair(self, parent=None):
+        return self._create(REVOLUTE, parent)
+
+    def createPrismaticJointAndBodyNodePair(self, parent=None):
+        return self._create(PRISMATIC, parent)
+
+    def createFreeJointAndBodyNodePair(self, parent=None):
+        return self._create(FREE, parent)
+
+    def createWeldJointAndBodyNodePair(self, parent=None):
+        return self._create(WELD, parent)
+
+    def getNumDofs(self):
+        return sum(b.parent_joint.ndof for b in self.bodies)
+
+    def getNumBodyNodes(self):
+        return len(self.bodies)
+
+    def getBodyNode(self, key):
+        if isinstance(key, int):
+            return self.bodies[key]
+        for b in self.bodies:
+            if b.name == key:
+                return b
+        return None
+
+    def getJoint(self, key):
+        if isinstance(key, int):
+            return self.bodies[key].parent_joint
+        for b in self.bodies:
+            if b.parent_joint.name == key:
+                return b.parent_joint
+        return None
+
+    def _ordered_bodies(self) -> List[BodyNode]:
+        """Bodies in an order where every parent precedes its children and that
+        is otherwise creation order (the reference's tree/DoF order for
+        single-tree skeletons, dart/dynamics/Skeleton.cpp registerBodyNode)."""
+        done, out = set(), []
+        pending = list(self.bodies)
+        while pending:
+            progressed = False
+            rest = []
+            for b in pending:
+                if b.parent_body is None or id(b.parent_body) in done:
+                    out.append(b)
+                    done.add(id(b))
+                    progressed = True
+                else:
+                    rest.append(b)
+            if not progressed:
+                raise ValueError("skeleton has a body whose parent is missing")
+            pending = rest
+        return out
+
+    def getPositionLowerLimits(self):
+        return np.concatenate([b.parent_joint.pos_lo for b in self._ordered_bodies()] or [np.zeros(0)])
+
+    def getPositionUpperLimits(self):
+        return np.concatenate([b.parent_joint.pos_hi for b in self._ordered_bodies()] or [np.zeros(0)])
+
+
+class World:
+    """Description of one simulated world; batched state lives in tensors, not here.
+
+    reference: dart/simulation/World.cpp (defaults :75-87, addSkeleton :749-793,
+    state/action API :2016-2185).
+    """
+
+    def __init__(self):
+        self.skeletons: List[Skeleton] = []
+        self.gravity = np.array([0.0, 0.0, -9.81])
+        self.dt = 1e-3
+        self.action_space: List[int] = []
+        self.penetration_correction = False
+        self.contact_clipping_depth = 0.03
+        self.fallback_cfm = 1e-4
+        self._version = 0  # bumped on every structural edit -> device model rebuilt lazily
+        self._device_model = None
+        # legacy single-world state (reference World is stateful)
+        self._state = None
+        self._lcp_cache = None
+
+    # ----- structure -----
+    def _touch(self):
+        self._version += 1
+        self._device_model = None
+
+    def addSkeleton(self, skel: Skeleton):
+        base = self.getNumDofs()
+        self.skeletons.append(skel)
+        # reference appends *every* dof (mobile or not) to the action space, World.cpp:779-785
+        self.action_space.extend(range(base, base + skel.getNumDofs()))
+        self._touch()
+        return skel
+
+    def loadSkeleton(self, path: str, base_position=None, base_euler=None):
+        from .loader import load_skeleton
+
+        skel = load_skeleton(path)
+        if skel is None:
+            return None
+        if base_position is not None or base_euler is not None:
+            raise NotImplementedError("loadSkeleton(base pose) is not supported yet")
+        return self.addSkeleton(skel)
+
+    def getSkeleton(self, i):
+        return self.skeletons[i]
+
+    def getNumSkeletons(self):
+        return len(self.skeletons)
+
+    # ----- parameters -----
+    def setGravity(self, g):
+        self.gravity = np.asarray(g, dtype=np.float64).copy()
+        self._touch()
+
+    def getGravity(self):
+        return self.gravity.copy()
+
+    def setTimeStep(self, dt):
+        self.dt = float(dt)
+        self._touch()
+
+    def getTimeStep(self):
+        return self.dt
+
+    def setPenetrationCorrectionEnabled(self, v):
+        self.penetration_correction = bool(v)
+        self._touch()
+
+    def setContactClippingDepth(self, d):
+        self.contact_clipping_depth = float(d)
+        self._touch()
+
+    def setFallbackConstraintForceMixingConstant(self, c):
+        self.fallback_cfm = float(c)
+        self._touch()
+
+    # ----- sizes -----
+    def getNumDofs(self):
+        return sum(s.getNumDofs() for s in self.skeletons)
+
+    def getStateSize(self):
+        return 2 * self.getNumDofs()
+
+    def getActionSize(self):
+        return len(self.action_space)
+
+    def getActionSpace(self):
+        return list(self.action_space)
+
+    def setActionSpace(self, mapping):
+        self.action_space = [int(i) for i in mapping]
+        self._touch()
+
+    def removeDofFromActionSpace(self, dof):
+        if dof in self.action_space:
+            self.action_space.remove(dof)
+            self._touch()
+
+    def addDofToActionSpace(self, dof):
+        if dof not in self.action_space:
+            self.action_space.append(int(dof))
+            self._touch()
+
+    # ----- legacy stateful API (single world) -----
+    def setState(self, state):
+        state = np.asarray(state, dtype=np.float64).reshape(-1)
+        if state.size != self.getStateSize():
+            # reference prints to stderr and ignores the call (World.cpp:2027-2033);
+            # we raise instead (documented deviation)
+            raise ValueError(
+                f"World.setState() got size {state.size}, expected getStateSize()={self.getStateSize()}")
+        self._state = state.copy()
+
+    def getState(self):
+        if self._state is None:
+            self._state = np.zeros(self.getStateSize())
+            n = self.getNumDofs()
+            self._state[:n] = self.getInitialPositions()
+        return self._state.copy()
+
+    def getPositions(self):
+        return self.getState()[: self.getNumDofs()]
+
+    def getVelocities(self):
+        return self.getState()[self.getNumDofs():]
+
+    def getInitialPositions(self):
+        out = []
+        for s in self.skeletons:
+            for b in s._ordered_bodies():
+                out.append(b.parent_joint.init_pos)
+        return np.concatenate(out) if out else np.zeros(0)
+
+    def getPositionLowerLimits(self):
+        return np.concatenate([s.getPositionLowerLimits() for s in self.skeletons] or [np.zeros(0)])
+
+    def getPositionUpperLimits(self):
+        return np.concatenate([s.getPositionUpperLimits() for s in self.skeletons] or [np.zeros(0)])

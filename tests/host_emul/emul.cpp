@@ -1,0 +1,52 @@
+// DEVELOPMENT/TEST HARNESS ONLY — compiles the per-world device functions (csrc/nb2_dyn.cuh) as host code so that
+// the kernel math can be checked against the oracle in the GPU-less build container (tests/test_host_emul.py).
+// It is never loaded by the nimblephysics_b200 package: the product path has no CPU fallback.
+#include <string>
+#include <vector>
+
+#include "../../nimblephysics_b200/csrc/nb2_dyn.cuh"
+#include "../../nimblephysics_b200/csrc/nb2_host_model.h"
+
+template <class R>
+static int run_fwd(const nb2_model_desc* d, int B, const float* state, const float* action, float* next, float* saved) {
+  Nb2ModelDev<R> M; std::string err;
+  if (!nb2_fill_model(*d, M, err)) { fprintf(stderr, "emul: %s\n", err.c_str()); return -1; }
+  nb2::FwdLayout L = nb2::fwd_layout(M.nb, M.ndof, M.nslots, M.nfree);
+  std::vector<R> scr(L.total);
+  std::vector<float> dummy;
+  for (int w = 0; w < B; w++) {
+    for (auto& x : scr) x = R(1e30);  // poison: catches reads of never-written scratch
+    nb2::world_forward<R, 1>(M, scr.data(), state + (size_t)w * 2 * M.ndof, action + (size_t)w * M.na,
+                             next + (size_t)w * 2 * M.ndof, saved ? saved + w : nullptr, (size_t)B, saved != nullptr);
+  }
+  return 0;
+}
+template <class R>
+static int run_bwd(const nb2_model_desc* d, int B, const float* state, const float* action, const float* saved,
+                   const float* gnext, float* gstate, float* gaction) {
+  Nb2ModelDev<R> M; std::string err;
+  if (!nb2_fill_model(*d, M, err)) { fprintf(stderr, "emul: %s\n", err.c_str()); return -1; }
+  nb2::BwdLayout L = nb2::bwd_layout(M.nb, M.ndof, M.nslots, M.nfree);
+  std::vector<R> scr(L.total);
+  for (int w = 0; w < B; w++) {
+    for (auto& x : scr) x = R(1e30);
+    nb2::world_backward<R, 1>(M, scr.data(), state + (size_t)w * 2 * M.ndof, action + (size_t)w * M.na,
+                              gnext + (size_t)w * 2 * M.ndof, saved + w, (size_t)B, gstate + (size_t)w * 2 * M.ndof,
+                              gaction + (size_t)w * M.na);
+  }
+  return 0;
+}
+extern "C" {
+int emul_saved_words(const nb2_model_desc* d) {
+  int nfree = 0; for (int i = 0; i < d->nb; i++) nfree += d->jtype[i] == NB2_JT_FREE;
+  return nb2_saved_words(d->nb, d->ndof, nfree);
+}
+int emul_forward(const nb2_model_desc* d, int B, const float* state, const float* action, float* next, float* saved, int fp64) {
+  return fp64 ? run_fwd<double>(d, B, state, action, next, saved) : run_fwd<float>(d, B, state, action, next, saved);
+}
+int emul_backward(const nb2_model_desc* d, int B, const float* state, const float* action, const float* saved,
+                  const float* gnext, float* gstate, float* gaction, int fp64) {
+  return fp64 ? run_bwd<double>(d, B, state, action, saved, gnext, gstate, gaction)
+              : run_bwd<float>(d, B, state, action, saved, gnext, gstate, gaction);
+}
+}
