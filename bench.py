@@ -1,0 +1,331 @@
+#!/usr/bin/env python
+"""bench.py — differentiable world-steps/s (fwd+bwd) of the batched Atlas timestep.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--batch B]
+  torchrun --nproc-per-node N bench.py --gpus N ...         (one rank per GPU; batch shards, no data-path collective)
+
+Workload (BASELINE.json configs[1]): Atlas humanoid (33 DoF, 28 moving bodies), contact-free, batch 4096 per GPU,
+one step = forward kernel + backward kernel over the whole batch, synthetic seeded inputs.
+`value`   : worlds*steps / device time, inputs resident in HBM (rotating buffer sets larger than L2).
+`e2e`     : same metric through the C-ABI host entry points (host buffers, H2D/D2H inside the timed region).
+`roofline`: HBM roofline of the dominant kernel from the algorithmic bytes of SURVEY §8(d).
+`cpu_baseline`: the fp64 oracle port timed on this box's host cores on a bounded sample.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+ATLAS = os.path.join(ROOT, "tests", "golden", "models", "atlas.json")
+METRIC = "differentiable world-steps/sec (fwd+bwd), batched Atlas"
+UNIT = "world-steps/s"
+
+
+def make_inputs(raw, B, seed):
+    """root rot ~N(0,0.1), root pos ~U(-0.1,0.1), joints ~U(-pi/8,pi/8), qdot ~U(-pi/4,pi/4),
+    tau = 0 on the root, U(-50,50) elsewhere."""
+    rng = np.random.default_rng(seed)
+    n, na = raw.ndof, len(raw.action_map)
+    q = rng.uniform(-np.pi / 8, np.pi / 8, (B, n))
+    q[:, 0:3] = rng.normal(0, 0.1, (B, 3))
+    q[:, 3:6] = rng.uniform(-0.1, 0.1, (B, 3))
+    q = np.clip(q, np.maximum(raw.pos_lo, -10), np.minimum(raw.pos_hi, 10))
+    v = rng.uniform(-np.pi / 4, np.pi / 4, (B, n))
+    tau = rng.uniform(-50, 50, (B, n))
+    tau[:, :6] = 0.0
+    a = tau[:, raw.action_map]
+    g = rng.normal(size=(B, 2 * n))
+    return (np.concatenate([q, v], 1).astype(np.float32), a.astype(np.float32), g.astype(np.float32))
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, gpu_index):
+        super().__init__(daemon=True)
+        self.rows = []
+        self.stop_flag = False
+        self.gpu = gpu_index
+        self.proc = None
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                self.rows.append([x.strip() for x in line.split(",")])
+                if self.stop_flag:
+                    break
+        except Exception:
+            pass
+
+    def finish(self):
+        self.stop_flag = True
+        if self.proc:
+            try:
+                self.proc.terminate()
+            except Exception:
+                pass
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+                for k, nm in enumerate(names):
+                    if r[2 + k].lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                continue
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+_CPU_STATE = {}
+
+
+def _cpu_worker_init(raw_json):
+    from oracle.binding import OracleWorld
+    import nimblephysics_b200 as nb
+
+    raw = nb.RawModel.from_json(raw_json)
+    _CPU_STATE["raw"] = raw
+    _CPU_STATE["ow"] = OracleWorld(raw)  # one World per worker, like MultiShot.cpp:66-70
+
+
+def _cpu_worker_run(job):
+    seed, lo, hi, total = job
+    raw, ow = _CPU_STATE["raw"], _CPU_STATE["ow"]
+    s, a, g = make_inputs(raw, total, seed)
+    s64, a64, g64 = s.astype(np.float64), a.astype(np.float64), g.astype(np.float64)
+    t0 = time.perf_counter()
+    for w in range(lo, hi):
+        ow.step(s64[w], a64[w])
+        ow.backprop(s64[w], a64[w], g64[w])
+    return time.perf_counter() - t0
+
+
+class CpuReference:
+    """Times the fp64 oracle (forward + backprop per world) on `procs` host processes (one World each)."""
+
+    def __init__(self, raw, procs):
+        import multiprocessing as mp
+
+        self.procs = procs
+        self.pool = mp.get_context("fork").Pool(procs, initializer=_cpu_worker_init, initargs=(raw.to_json(),))
+        self.run(procs * 2)  # warm-up: library load, page faults
+
+    def run(self, n_worlds, seed=1234):
+        per = (n_worlds + self.procs - 1) // self.procs
+        jobs = [(seed, k * per, min(n_worlds, (k + 1) * per), n_worlds) for k in range(self.procs)]
+        t0 = time.perf_counter()
+        busy = self.pool.map(_cpu_worker_run, jobs)
+        wall = time.perf_counter() - t0
+        # input synthesis happens inside the workers before their timers start; the slowest worker bounds the step
+        dt = max(busy)
+        return n_worlds / dt, dt, wall
+
+    def close(self):
+        self.pool.close()
+        self.pool.join()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=4096, help="worlds per GPU")
+    ap.add_argument("--precision", default="fp32", choices=["fp32", "fp64"])
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world_size = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    import nimblephysics_b200 as nb
+
+    raw = nb.RawModel.load(ATLAS)
+    n, na = raw.ndof, len(raw.action_map)
+    bytes_fwd = 4 * (2 * n + na + 2 * n)           # read state+action, write next state
+    bytes_bwd = 4 * ((2 * n + na) + 2 * n + (2 * n + na))  # re-read inputs, read dL/dx', write grads
+    config = {"workload": "Atlas (atlas_v3 URDF, 33 DoF, 28 moving bodies) contact-free Featherstone step fwd+bwd, "
+                          f"batch={args.batch}/GPU, dt=1e-3, y-up gravity (BASELINE configs[1])",
+              "global_batch": args.batch * max(world_size, 1), "parallelism": f"batch-sharded x{max(world_size,1)} (no data-path collective)",
+              "l2_policy": "rotating buffer sets > L2 (126 MB)", "precision_inside_kernels": args.precision}
+
+    # ------------------------------------------------------------------ reference arm (CPU)
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        cores = os.cpu_count() or 1
+        sample = max(cores * 8, 64)
+        ref = CpuReference(raw, cores)
+        for _ in range(max(args.warmup, 1)):
+            ref.run(sample)
+        tot_t, tot_n = 0.0, 0
+        for _ in range(args.steps):
+            _, dt, _ = ref.run(sample)
+            tot_t += dt
+            tot_n += sample
+        ref.close()
+        v = tot_n / tot_t
+        print(json.dumps({
+            "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                             "sample": f"{sample} Atlas worlds per step (fwd + backprop each), {cores} host processes, one oracle World per process; "
+                                       "fp64 restatement of dart/{dynamics,neural}, NOT the reference binary (it cannot be built here)"},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return
+
+    # ------------------------------------------------------------------ our arm (GPU)
+    cpu_baseline = None
+    if world_size == 1:  # timed BEFORE CUDA is initialised so the forked workers never inherit a CUDA context
+        cores = os.cpu_count() or 1
+        sample = max(cores * 16, 128)
+        ref = CpuReference(raw, cores)
+        v, dt, _ = ref.run(sample)
+        ref.close()
+        cpu_baseline = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                        "sample": f"{sample} Atlas worlds (fwd + backprop each) in {dt:.2f} s on {cores} host processes; fp64 oracle "
+                                  "(restatement of dart/{dynamics,neural}, not the reference binary)"}
+    import torch
+
+    assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world_size > 1:
+        import torch.distributed as dist_mod
+
+        dist_mod.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        dist = dist_mod
+    dev = torch.device("cuda", local_rank)
+    from nimblephysics_b200 import _cabi
+    from nimblephysics_b200.engine import FP32, FP64
+
+    prec = FP64 if args.precision == "fp64" else FP32
+    B = args.batch
+    dm = nb.DeviceModel(nb.compile_model(raw))
+    per_set = 4 * B * (2 * n * 4 + 2 * na + dm.saved_words)
+    nsets = max(2, int(np.ceil(160e6 / per_set)))
+    sets = []
+    for k in range(nsets):
+        s, a, g = make_inputs(raw, B, 1234 + 1000 * rank + k)
+        sets.append(dict(s=torch.tensor(s, device=dev), a=torch.tensor(a, device=dev), g=torch.tensor(g, device=dev),
+                         nxt=torch.empty((B, 2 * n), device=dev), saved=torch.empty((dm.saved_words, B), device=dev),
+                         gs=torch.empty((B, 2 * n), device=dev), ga=torch.empty((B, na), device=dev)))
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def fwd(d):
+        dm.forward_device(B, d["s"].data_ptr(), d["a"].data_ptr(), d["nxt"].data_ptr(), d["saved"].data_ptr(), stream, prec)
+
+    def bwd(d):
+        dm.backward_device(B, d["s"].data_ptr(), d["a"].data_ptr(), d["saved"].data_ptr(), d["g"].data_ptr(),
+                           d["gs"].data_ptr(), d["ga"].data_ptr(), stream, prec)
+
+    def barrier():
+        if dist:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(args.warmup):
+        fwd(sets[i % nsets]); bwd(sets[i % nsets])
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    time.sleep(0.3)
+    l0 = _cabi.lib().nb2_launch_count()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2 * args.steps + 1)]
+    barrier()
+    ev[0].record()
+    for i in range(args.steps):
+        d = sets[(args.warmup + i) % nsets]
+        fwd(d); ev[2 * i + 1].record()
+        bwd(d); ev[2 * i + 2].record()
+    barrier()
+    launches = _cabi.lib().nb2_launch_count() - l0
+    total_ms = ev[0].elapsed_time(ev[-1])
+    fwd_ms = float(np.mean([ev[2 * i].elapsed_time(ev[2 * i + 1]) for i in range(args.steps)]))
+    bwd_ms = float(np.mean([ev[2 * i + 1].elapsed_time(ev[2 * i + 2]) for i in range(args.steps)]))
+    time.sleep(0.2)
+    clocks = sampler.finish()
+
+    # ---- e2e through the C-ABI host entry points (pinned host buffers; copies inside the timed region)
+    hs, ha, hg = make_inputs(raw, B, 99 + rank)
+    pin = lambda x: torch.from_numpy(x).pin_memory()
+    hs_t, ha_t, hg_t = pin(hs), pin(ha), pin(hg)
+    o_n, o_gs, o_ga = (torch.empty((B, 2 * n)).pin_memory(), torch.empty((B, 2 * n)).pin_memory(), torch.empty((B, na)).pin_memory())
+    e2e_steps = max(5, args.steps // 2)
+
+    def e2e_step():
+        dm.forward_host(hs_t.numpy(), ha_t.numpy(), True, prec, out=o_n.numpy())
+        dm.backward_host(hg_t.numpy(), prec, out_state=o_gs.numpy(), out_action=o_ga.numpy())
+
+    for _ in range(3):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    barrier()
+    e2e_ms = 1e3 * (time.perf_counter() - t0)
+
+    t_total = torch.tensor([total_ms, e2e_ms], device=dev, dtype=torch.float64)
+    if dist:
+        dist.all_reduce(t_total, op=dist.ReduceOp.MAX)
+    total_ms, e2e_ms = t_total.tolist()
+    value = B * world_size * args.steps / (total_ms * 1e-3)
+    e2e_value = B * world_size * e2e_steps / (e2e_ms * 1e-3)
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        dom, dom_ms, dom_bytes = ("k_step_bwd", bwd_ms, bytes_bwd) if bwd_ms >= fwd_ms else ("k_step_fwd", fwd_ms, bytes_fwd)
+        achieved = dom_bytes * B / (dom_ms * 1e-3) / 1e9
+        traffic = None
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "dram_traffic.json"))).get(dom)
+        except Exception:
+            pass
+        out = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world_size, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32" if prec == FP32 else "f64", "data": "synthetic", "config": config,
+            "kernel_ms": {"k_step_fwd": fwd_ms, "k_step_bwd": bwd_ms},
+            "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": traffic,
+                         "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s",
+                         "algorithmic_bytes_per_world": {"k_step_fwd": bytes_fwd, "k_step_bwd": bytes_bwd, "step": bytes_fwd + bytes_bwd},
+                         "note": "path is FP32-latency bound, not HBM bound (DESIGN.md §roofline): the HBM fraction is reported as asked"},
+            "e2e": {"value": e2e_value, "unit": UNIT,
+                    "h2d_bytes_per_step": int(4 * B * (2 * n + na + 2 * n)), "d2h_bytes_per_step": int(4 * B * (2 * n + 2 * n + na)),
+                    "steps": e2e_steps, "path": "nb2_step_forward_host + nb2_step_backward_host (pinned host buffers)"},
+            "gpu_launches": int(launches), "clocks": clocks,
+        }
+        if cpu_baseline is not None:
+            out["cpu_baseline"] = cpu_baseline
+        print(json.dumps(out))
+    if dist:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -4,6 +4,8 @@ from . import world as _world
 from .world import (World, Skeleton, BodyNode, Joint, Isometry3, BoxShape, SphereShape, CapsuleShape)
 from .loader import loadWorld, load_skeleton
 from .modelspec import RawModel, CanonModel, flatten_world, compile_model
+from .timestep import timestep, TimestepLayer
+from .engine import DeviceModel, device_model_for
 
 __all__ = ["World", "Skeleton", "BodyNode", "Joint", "Isometry3", "BoxShape", "SphereShape", "CapsuleShape",
-           "loadWorld", "load_skeleton", "RawModel", "CanonModel", "flatten_world", "compile_model"]
+           "loadWorld", "load_skeleton", "timestep", "TimestepLayer", "DeviceModel", "device_model_for", "RawModel", "CanonModel", "flatten_world", "compile_model"]

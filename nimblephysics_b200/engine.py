@@ -1,0 +1,87 @@
+"""Device-side handle of a World: builds the canonical model and owns the nb2_model created through the C ABI."""
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+
+from . import _cabi
+from .modelspec import CanonModel, RawModel, compile_model, flatten_world
+
+FP32, FP64 = 0, 1
+
+
+class DeviceModel:
+    """nb2_model wrapper (include/nb2.h).  One per (World version)."""
+
+    def __init__(self, cm: CanonModel):
+        self.cm = cm
+        self.ndof = cm.ndof
+        self.na = len(cm.action_map)
+        L = _cabi.lib()
+        self._desc, self._keep = _cabi.make_desc(cm)
+        h = ctypes.c_void_p()
+        _cabi.check(L.nb2_model_create(ctypes.byref(self._desc), ctypes.byref(h)))
+        self.handle = h
+        self.saved_words = L.nb2_saved_words_per_world(h)
+
+    def __del__(self):
+        try:
+            if getattr(self, "handle", None):
+                _cabi.lib().nb2_model_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+    # ---- device pointers (torch tensors on the current CUDA device) ----
+    def forward_device(self, B, state_ptr, action_ptr, next_ptr, saved_ptr, stream, precision=FP32):
+        _cabi.check(_cabi.lib().nb2_step_forward(self.handle, B, state_ptr, action_ptr, next_ptr, saved_ptr, precision, stream))
+
+    def backward_device(self, B, state_ptr, action_ptr, saved_ptr, gnext_ptr, gstate_ptr, gaction_ptr, stream,
+                        precision=FP32):
+        _cabi.check(_cabi.lib().nb2_step_backward(self.handle, B, state_ptr, action_ptr, saved_ptr, gnext_ptr,
+                                                  gstate_ptr, gaction_ptr, precision, stream))
+
+    # ---- host pointers (numpy / CPU tensors): copies included ----
+    def forward_host(self, state: np.ndarray, action: np.ndarray, keep_for_backward=True, precision=FP32,
+                     out: np.ndarray = None) -> np.ndarray:
+        B = state.shape[0]
+        if out is None:
+            out = np.empty_like(state)
+        _cabi.check(_cabi.lib().nb2_step_forward_host(self.handle, B, state.ctypes.data, action.ctypes.data,
+                                                      out.ctypes.data, int(keep_for_backward), precision))
+        return out
+
+    def backward_host(self, grad_next: np.ndarray, precision=FP32, out_state=None, out_action=None):
+        B = grad_next.shape[0]
+        gs = np.empty_like(grad_next) if out_state is None else out_state
+        ga = np.empty((B, self.na), np.float32) if out_action is None else out_action
+        _cabi.check(_cabi.lib().nb2_step_backward_host(self.handle, B, grad_next.ctypes.data, gs.ctypes.data,
+                                                       ga.ctypes.data, precision))
+        return gs, ga
+
+
+def _has_possible_contacts(raw: RawModel) -> bool:
+    """True when some collision-shape pair could ever generate a contact (shapes on two different skeletons;
+    self-collision is off by default in the reference, dart/dynamics/Skeleton.cpp mEnabledSelfCollisionCheck=false)."""
+    if raw.ns < 2:
+        return False
+    skels = set(int(raw.skel_id[b]) for b in raw.shape_body)
+    return len(skels) > 1
+
+
+def device_model_for(world) -> DeviceModel:
+    """Lazily (re)build the device model of a World; cached until the World is edited."""
+    dm = getattr(world, "_device_model", None)
+    if dm is not None:
+        return dm
+    raw = flatten_world(world)
+    if _has_possible_contacts(raw) and not getattr(world, "_contacts_disabled", False):
+        raise NotImplementedError(
+            "this world has collision shapes on several skeletons; the contact/LCP stage (SURVEY §8 rows a7-a12) "
+            "is not implemented in the device path yet. Remove the colliders or call world._contacts_disabled = True "
+            "to run the contact-free step.")
+    world._raw_model = raw
+    dm = DeviceModel(compile_model(raw))
+    world._device_model = dm
+    return dm

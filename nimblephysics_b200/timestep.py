@@ -1,0 +1,87 @@
+"""``timestep(world, state, action, mass=None)`` — the reference's autograd boundary, batched.
+
+reference: python/nimblephysics/timestep.py:13-69 (TimestepLayer).  Same call, same gradient outputs
+(None, d/dstate, d/daction, d/dmass); what changes:
+  * ``state`` / ``action`` may be 2-D ``[B, 2n]`` / ``[B, a]`` tensors: B independent worlds advance in one launch;
+  * tensors stay on the GPU (fp32); nothing goes through numpy;
+  * 1-D tensors keep the legacy single-world meaning, including the side effect that ``world`` is left at the
+    post-step state (NeuralUtils.cpp:46 idempotent=False) and the fp64 return dtype (timestep.py:40).
+The work is done by libnb2.so through the C ABI (include/nb2.h).  There is no CPU implementation.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import numpy as np
+import torch
+
+from .engine import FP32, device_model_for
+
+
+def _ptr(t: torch.Tensor) -> int:
+    return t.data_ptr()
+
+
+class TimestepLayer(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, world, state, action, mass):
+        if mass is not None:
+            raise NotImplementedError("timestep(..., mass) (WithRespectToMass, SURVEY §8f-4) is not implemented yet")
+        dm = device_model_for(world)
+        n2, na = 2 * dm.ndof, dm.na
+        legacy = state.dim() == 1
+        s2 = state.detach().reshape(-1, n2) if legacy else state.detach()
+        a2 = action.detach().reshape(-1, na) if legacy else action.detach()
+        if s2.dim() != 2 or s2.shape[1] != n2:
+            raise ValueError(f"timestep(): state has shape {tuple(state.shape)}, expected [..., {n2}] (= getStateSize())")
+        if a2.dim() != 2 or a2.shape[1] != na or a2.shape[0] != s2.shape[0]:
+            raise ValueError(f"timestep(): action has shape {tuple(action.shape)}, expected [{s2.shape[0]}, {na}] (= getActionSize())")
+        if not torch.cuda.is_available():
+            raise RuntimeError("nimblephysics_b200.timestep needs a CUDA device (B200); there is no CPU fallback")
+        dev = s2.device if s2.is_cuda else torch.device("cuda", torch.cuda.current_device())
+        sd = s2.to(device=dev, dtype=torch.float32, non_blocking=True).contiguous()
+        ad = a2.to(device=dev, dtype=torch.float32, non_blocking=True).contiguous()
+        B = sd.shape[0]
+        need_grad = any(ctx.needs_input_grad[1:3])
+        with torch.cuda.device(dev):
+            nxt = torch.empty_like(sd)
+            saved = torch.empty((dm.saved_words, B), dtype=torch.float32, device=dev) if need_grad else None
+            stream = torch.cuda.current_stream().cuda_stream
+            dm.forward_device(B, _ptr(sd), _ptr(ad), _ptr(nxt), _ptr(saved) if saved is not None else None, stream, FP32)
+        ctx.dm = dm
+        ctx.legacy = legacy
+        ctx.in_device = state.device
+        ctx.in_dtype = state.dtype
+        ctx.act_device = action.device
+        ctx.act_dtype = action.dtype
+        ctx.B = B
+        if need_grad:
+            ctx.save_for_backward(sd, ad, saved)
+        if legacy:
+            out = nxt[0].to(dtype=torch.float64).cpu() if not state.is_cuda else nxt[0].to(torch.float64)
+            world._state = out.detach().cpu().numpy().astype(np.float64)
+            return out
+        return nxt.to(device=state.device, dtype=state.dtype)
+
+    @staticmethod
+    def backward(ctx, grad_state):
+        dm = ctx.dm
+        sd, ad, saved = ctx.saved_tensors
+        dev = sd.device
+        g = grad_state.detach().reshape(ctx.B, 2 * dm.ndof).to(device=dev, dtype=torch.float32).contiguous()
+        with torch.cuda.device(dev):
+            gs = torch.empty_like(sd)
+            ga = torch.empty_like(ad)
+            stream = torch.cuda.current_stream().cuda_stream
+            dm.backward_device(ctx.B, _ptr(sd), _ptr(ad), _ptr(saved), _ptr(g), _ptr(gs), _ptr(ga), stream, FP32)
+        if ctx.legacy:
+            # reference returns fp64 grads (timestep.py:55-60)
+            gs = gs[0].to(device=ctx.in_device, dtype=torch.float64 if ctx.in_dtype == torch.float64 else ctx.in_dtype)
+            ga = ga[0].to(device=ctx.act_device, dtype=ctx.act_dtype)
+            return None, gs, ga, None
+        return None, gs.to(device=ctx.in_device, dtype=ctx.in_dtype), ga.to(device=ctx.act_device, dtype=ctx.act_dtype), None
+
+
+def timestep(world, state: torch.Tensor, action: torch.Tensor, mass: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """One differentiable step of every world in the batch (forward stores what backward needs)."""
+    return TimestepLayer.apply(world, state, action, mass)

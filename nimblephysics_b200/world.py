@@ -338,6 +338,54 @@ class World:
         self._state = None
         self._lcp_cache = None
 
+    # ----- (de)serialisation -----
+    @staticmethod
+    def from_raw(raw) -> "World":
+        """Rebuild a World from a flattened RawModel (inverse of modelspec.flatten_world); used to ship model
+        fixtures as JSON (tests/golden/models) without the original .urdf/.skel files."""
+        from .modelspec import T_from_12
+
+        w = World()
+        w.gravity = np.array(raw.gravity, dtype=np.float64)
+        w.dt = float(raw.dt)
+        w.penetration_correction = bool(raw.penetration_correction)
+        w.contact_clipping_depth = float(raw.contact_clipping_depth)
+        w.fallback_cfm = float(raw.fallback_cfm)
+        skels = {}
+        bodies = []
+        for i in range(raw.nb):
+            sid = int(raw.skel_id[i])
+            if sid not in skels:
+                skels[sid] = Skeleton(f"skeleton_{sid}")
+                skels[sid].mobile = bool(raw.mobile[i])
+            sk = skels[sid]
+            p = int(raw.parent[i])
+            name = raw.body_names[i] if i < len(raw.body_names) else None
+            j, b = sk._create(int(raw.jtype[i]), bodies[p] if p >= 0 else None, None, name)
+            j.axis = np.array(raw.axis[i], dtype=np.float64)
+            j.T_pj = T_from_12(raw.Tpj[i])
+            j.T_cj = T_from_12(raw.Tcj[i])
+            o = int(raw.dof_off[i])
+            for k in ("damping", "spring", "rest", "pos_lo", "pos_hi", "vel_lo", "vel_hi", "force_lo", "force_hi",
+                      "init_pos"):
+                getattr(j, k)[:] = getattr(raw, k)[o:o + j.ndof]
+            b.mass = float(raw.mass[i])
+            b.com = np.array(raw.com[i], dtype=np.float64)
+            m = raw.moment[i]
+            b.moment = np.array([[m[0], m[3], m[4]], [m[3], m[1], m[5]], [m[4], m[5], m[2]]], dtype=np.float64)
+            b.friction = float(raw.friction[i])
+            b.restitution = float(raw.restitution[i])
+            b.gravity_mode = bool(raw.gravity_mode[i])
+            bodies.append(b)
+        for s in range(raw.ns):
+            sn = ShapeNode(Shape(int(raw.shape_type[s]), list(raw.shape_dims[s])), T_from_12(raw.shape_T[s]))
+            sn.has_collision = True
+            bodies[int(raw.shape_body[s])].shapes.append(sn)
+        for sid in sorted(skels):
+            w.skeletons.append(skels[sid])
+        w.action_space = [int(a) for a in raw.action_map]
+        return w
+
     # ----- structure -----
     def _touch(self):
         self._version += 1

@@ -114,7 +114,9 @@ template <class S> static void free_integrate(const S* q, const S* v, double dt,
 template <class S>
 static void step_nocontact(const Model& M, const S* q, const S* v, const S* tau, S* qn, S* vn, S* qdd_out = nullptr) {
   const int nb = M.nb;
-  std::vector<BodyState<S>> B(nb);
+  // per-thread reusable workspace: a fresh ~1 MB vector per call would hit mmap/munmap and serialise threads
+  static thread_local std::vector<BodyState<S>> B;
+  if ((int)B.size() < nb) B.resize(nb);
   const double dt = M.dt;
   // ---- kinematics, root -> leaf (Frame.cpp:144-160, GenericJoint.hpp:1803-1823)
   for (int i = 0; i < nb; i++) {
@@ -156,7 +158,9 @@ static void step_nocontact(const Model& M, const S* q, const S* v, const S* tau,
     b.G = spatial_tensor<S>(M, i);
   }
   // ---- articulated inertia + bias force, leaf -> root (BodyNode.cpp:2046-2114)
-  std::vector<std::vector<int>> kids(nb);
+  static thread_local std::vector<std::vector<int>> kids;
+  if ((int)kids.size() < nb) kids.resize(nb);
+  for (int i = 0; i < nb; i++) kids[i].clear();
   for (int i = 0; i < nb; i++) if (M.parent[i] >= 0) kids[M.parent[i]].push_back(i);
   Vec3<S> g = v3<S>(S(M.gravity[0]), S(M.gravity[1]), S(M.gravity[2]));
   for (int i = nb - 1; i >= 0; i--) {

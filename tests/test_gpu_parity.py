@@ -1,0 +1,171 @@
+"""Parity tests proper: the CUDA path (through the C ABI / the autograd boundary) vs the fp64 oracle on the same
+seeded inputs, plus size-independent properties at BASELINE.json's full batch size.
+Tolerance (north_star): fp32 results within 1e-4 relative of the fp64 reference path."""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+
+import nimblephysics_b200 as nb
+from tests.util import load_raw, rel_err, sample_inputs
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+
+
+def _world(name):
+    raw = load_raw(name)
+    w = nb.World.from_raw(raw)
+    w._contacts_disabled = True  # contact-free step (the ground collider of half_cheetah is ignored here)
+    return raw, w
+
+
+@pytest.mark.parametrize("name", ["cartpole", "half_cheetah", "atlas"])
+def test_autograd_boundary_matches_oracle(oracle_mod, name):
+    raw, world = _world(name)
+    ow = oracle_mod.OracleWorld(raw)
+    B = 96
+    s, a, g = sample_inputs(raw, B, seed=31)
+    st = torch.tensor(s, device="cuda", requires_grad=True)
+    at = torch.tensor(a, device="cuda", requires_grad=True)
+    nxt = nb.timestep(world, st, at)
+    nxt.backward(torch.tensor(g, device="cuda"))
+    nxt, gs, ga = nxt.detach().cpu().numpy(), st.grad.cpu().numpy(), at.grad.cpu().numpy()
+    for w in range(0, B, 5):
+        s64, a64, g64 = s[w].astype(np.float64), a[w].astype(np.float64), g[w].astype(np.float64)
+        ref = ow.step(s64, a64)
+        rgs, rga = ow.backprop(s64, a64, g64)
+        assert rel_err(nxt[w], ref) < TOL
+        assert rel_err(gs[w], rgs) < TOL
+        assert rel_err(ga[w], rga) < TOL
+
+
+@pytest.mark.parametrize("precision", [0, 1])
+def test_c_abi_device_and_host_entry_points(oracle_mod, precision):
+    raw, world = _world("atlas")
+    dm = nb.device_model_for(world)
+    ow = oracle_mod.OracleWorld(raw)
+    B = 40
+    s, a, g = sample_inputs(raw, B, seed=32)
+    # host entry points (copies inside)
+    nxt_h = dm.forward_host(s, a, keep_for_backward=True, precision=precision)
+    gs_h, ga_h = dm.backward_host(g, precision=precision)
+    # device entry points
+    sd, ad, gd = (torch.tensor(x, device="cuda") for x in (s, a, g))
+    nxt = torch.empty_like(sd)
+    saved = torch.empty((dm.saved_words, B), device="cuda")
+    gs, ga = torch.empty_like(sd), torch.empty_like(ad)
+    stream = torch.cuda.current_stream().cuda_stream
+    dm.forward_device(B, sd.data_ptr(), ad.data_ptr(), nxt.data_ptr(), saved.data_ptr(), stream, precision)
+    dm.backward_device(B, sd.data_ptr(), ad.data_ptr(), saved.data_ptr(), gd.data_ptr(), gs.data_ptr(), ga.data_ptr(), stream, precision)
+    torch.cuda.synchronize()
+    assert np.array_equal(nxt.cpu().numpy(), nxt_h) and np.array_equal(gs.cpu().numpy(), gs_h) and np.array_equal(ga.cpu().numpy(), ga_h)
+    tol = TOL if precision == 0 else 2e-6  # fp64 arithmetic, fp32 I/O
+    for w in range(0, B, 7):
+        s64, a64, g64 = s[w].astype(np.float64), a[w].astype(np.float64), g[w].astype(np.float64)
+        rgs, rga = ow.backprop(s64, a64, g64)
+        assert rel_err(nxt_h[w], ow.step(s64, a64)) < tol and rel_err(gs_h[w], rgs) < tol and rel_err(ga_h[w], rga) < tol
+
+
+def test_full_batch_properties_atlas_4096(oracle_mod):
+    """BASELINE config 2 size.  Properties that do not need the oracle at every world:
+    (a) a world's result does not depend on its position in the batch or on the batch size (bit-exact);
+    (b) the backward is linear in the incoming gradient;  (c) M^-1 is symmetric: e_i . gtau(e_j) == e_j . gtau(e_i);
+    (d) oracle parity on a strided sample."""
+    raw, world = _world("atlas")
+    ow = oracle_mod.OracleWorld(raw)
+    n = raw.ndof
+    B = 4096
+    s, a, g = sample_inputs(raw, B, seed=33, tau_scale=30.0)
+    st = torch.tensor(s, device="cuda")
+    at = torch.tensor(a, device="cuda")
+
+    def run(sx, ax, gx):
+        sx = sx.clone().requires_grad_(True)
+        ax = ax.clone().requires_grad_(True)
+        out = nb.timestep(world, sx, ax)
+        out.backward(gx)
+        return out.detach(), sx.grad, ax.grad
+
+    gt = torch.tensor(g, device="cuda")
+    out, gs, ga = run(st, at, gt)
+    perm = torch.randperm(B, device="cuda")[:777]
+    out2, gs2, ga2 = run(st[perm], at[perm], gt[perm])
+    assert torch.equal(out[perm], out2) and torch.equal(gs[perm], gs2) and torch.equal(ga[perm], ga2)  # (a)
+    g2 = torch.randn_like(gt)
+    _, gsa, gaa = run(st, at, gt + g2)
+    _, gsb, gab = run(st, at, g2)
+    assert rel_err((gs + gsb).cpu().numpy(), gsa.cpu().numpy()) < 1e-5  # (b)
+    assert rel_err((ga + gab).cpu().numpy(), gaa.cpu().numpy()) < 1e-5
+    ei = torch.zeros_like(gt)
+    ej = torch.zeros_like(gt)
+    ei[:, n + 7] = 1.0
+    ej[:, n + 20] = 1.0
+    _, _, gai = run(st, at, ei)
+    _, _, gaj = run(st, at, ej)
+    assert torch.allclose(gai[:, 20], gaj[:, 7], rtol=2e-4, atol=1e-9)  # (c)
+    out, gs, ga = out.cpu().numpy(), gs.cpu().numpy(), ga.cpu().numpy()
+    assert np.isfinite(out).all() and np.isfinite(gs).all() and np.isfinite(ga).all()
+    for w in range(0, B, 257):  # (d)
+        s64, a64, g64 = s[w].astype(np.float64), a[w].astype(np.float64), g[w].astype(np.float64)
+        rgs, rga = ow.backprop(s64, a64, g64)
+        assert rel_err(out[w], ow.step(s64, a64)) < TOL and rel_err(gs[w], rgs) < TOL and rel_err(ga[w], rga) < TOL
+
+
+def test_edge_cases(oracle_mod):
+    raw, world = _world("cartpole")
+    ow = oracle_mod.OracleWorld(raw)
+    # ragged batch sizes around the warp size, B=1 and the legacy 1-D call
+    for B in (1, 31, 33, 100):
+        s, a, g = sample_inputs(raw, B, seed=B)
+        out = nb.timestep(world, torch.tensor(s, device="cuda"), torch.tensor(a, device="cuda")).cpu().numpy()
+        for w in (0, B - 1):
+            assert rel_err(out[w], ow.step(s[w].astype(np.float64), a[w].astype(np.float64))) < TOL
+    s, a, g = sample_inputs(raw, 1, seed=9)
+    st = torch.tensor(s[0].astype(np.float64), requires_grad=True)  # CPU fp64 1-D like the reference's scripts
+    at = torch.tensor(a[0].astype(np.float64), requires_grad=True)
+    out = nb.timestep(world, st, at)
+    assert out.dtype == torch.float64 and out.shape == (4,)
+    out.backward(torch.tensor(g[0].astype(np.float64)))
+    rgs, rga = ow.backprop(s[0].astype(np.float64), a[0].astype(np.float64), g[0].astype(np.float64))
+    assert rel_err(st.grad.numpy(), rgs) < TOL and rel_err(at.grad.numpy(), rga) < TOL
+    assert np.allclose(world.getState(), out.detach().numpy())  # world left at the post-step state
+    # wrong sizes raise (reference prints and ignores)
+    with pytest.raises(ValueError):
+        nb.timestep(world, torch.zeros(5, device="cuda"), torch.zeros(2, device="cuda"))
+    # gradient clipping decision at a bound is bit-exact
+    s, a, g = sample_inputs(raw, 8, seed=4)
+    s[:, 0] = np.float32(raw.pos_hi[0])
+    st = torch.tensor(s, device="cuda", requires_grad=True)
+    nb.timestep(world, st, torch.tensor(a, device="cuda")).backward(torch.tensor(g, device="cuda"))
+    for w in range(8):
+        rgs, _ = ow.backprop(s[w].astype(np.float64), a[w].astype(np.float64), g[w].astype(np.float64))
+        assert (st.grad[w, 0].item() == 0.0) == (rgs[0] == 0.0)
+
+
+def test_rollout_through_autograd_matches_oracle_chain(oracle_mod):
+    """8 chained steps, loss on the final state, backprop through the horizon (SingleShot.cpp:539-686 semantics)."""
+    raw, world = _world("half_cheetah")
+    ow = oracle_mod.OracleWorld(raw)
+    T, B = 8, 16
+    s, a, _ = sample_inputs(raw, B, seed=77, v_scale=0.3)
+    acts = [np.random.default_rng(100 + t).uniform(-3, 3, a.shape).astype(np.float32) for t in range(T)]
+    st = torch.tensor(s, device="cuda", requires_grad=True)
+    ats = [torch.tensor(x, device="cuda", requires_grad=True) for x in acts]
+    x = st
+    for t in range(T):
+        x = nb.timestep(world, x, ats[t])
+    loss = (x * x).sum()
+    loss.backward()
+    w = 3
+    xs = [s[w].astype(np.float64)]
+    for t in range(T):
+        xs.append(ow.step(xs[-1], acts[t][w].astype(np.float64)))
+    gq = 2 * xs[-1]
+    ga_ref = [None] * T
+    for t in reversed(range(T)):
+        gq, ga_ref[t] = ow.backprop(xs[t], acts[t][w].astype(np.float64), gq)
+    assert rel_err(x[w].detach().cpu().numpy(), xs[-1]) < TOL
+    assert rel_err(st.grad[w].cpu().numpy(), gq) < 5e-4
+    assert rel_err(ats[0].grad[w].cpu().numpy(), ga_ref[0]) < 5e-4

@@ -1,0 +1,78 @@
+"""Kernel math on the CPU: the per-world device functions (csrc/nb2_dyn.cuh) compiled as host code
+(tests/host_emul) vs the fp64 oracle, on the same seeded inputs.  This is a development harness — the product
+path never runs on the CPU — but it lets the GPU-less container check the exact code the kernels execute.
+Tolerance: fp32 within 1e-4 rel of the fp64 reference path (BASELINE.json north_star)."""
+import numpy as np
+import pytest
+
+import nimblephysics_b200 as nb
+from tests.host_emul.binding import EmulWorld
+from tests.util import load_raw, rel_err, sample_inputs
+
+TOL = 1e-4
+
+
+@pytest.mark.parametrize("name", ["cartpole", "half_cheetah", "atlas"])
+@pytest.mark.parametrize("fp64", [False, True])
+def test_forward_backward_parity(oracle_mod, name, fp64):
+    raw = load_raw(name)
+    cm = nb.compile_model(raw)
+    ow, ew = oracle_mod.OracleWorld(raw), EmulWorld(cm)
+    B = 6
+    s, a, g = sample_inputs(raw, B, seed=21)
+    nxt, saved = ew.forward(s, a, fp64)
+    gs, ga = ew.backward(s, a, saved, g, fp64)
+    for w in range(B):
+        s64, a64, g64 = s[w].astype(np.float64), a[w].astype(np.float64), g[w].astype(np.float64)
+        ref = ow.step(s64, a64)
+        rgs, rga = ow.backprop(s64, a64, g64)
+        assert rel_err(nxt[w], ref) < TOL
+        assert rel_err(gs[w], rgs) < TOL
+        assert rel_err(ga[w], rga) < TOL
+
+
+def test_weld_folding_and_canonical_frames_preserve_dynamics(oracle_mod):
+    """compile_model folds welds / re-frames bodies; the oracle keeps the reference parametrisation."""
+    from tests.test_oracle import _tree_world
+
+    raw = nb.flatten_world(_tree_world())
+    cm = nb.compile_model(raw)
+    assert cm.nb == raw.nb - 1  # one weld folded
+    ow, ew = oracle_mod.OracleWorld(raw), EmulWorld(cm)
+    s, a, g = sample_inputs(raw, 3, seed=2)
+    nxt, saved = ew.forward(s, a, True)
+    gs, ga = ew.backward(s, a, saved, g, True)
+    for w in range(3):
+        ref = ow.step(s[w].astype(np.float64), a[w].astype(np.float64))
+        rgs, rga = ow.backprop(s[w].astype(np.float64), a[w].astype(np.float64), g[w].astype(np.float64))
+        assert rel_err(nxt[w], ref) < 1e-6 and rel_err(gs[w], rgs) < 1e-6 and rel_err(ga[w], rga) < 1e-6
+
+
+def test_gradient_clipping_at_bounds(oracle_mod):
+    raw = load_raw("cartpole")
+    cm = nb.compile_model(raw)
+    ow, ew = oracle_mod.OracleWorld(raw), EmulWorld(cm)
+    s, a, g = sample_inputs(raw, 4, seed=3)
+    s[:, 0] = np.float32(raw.pos_hi[0])  # cart exactly on its upper position limit (15)
+    s[2:, 0] = np.float32(raw.pos_lo[0])
+    nxt, saved = ew.forward(s, a)
+    gs, ga = ew.backward(s, a, saved, g)
+    for w in range(4):
+        rgs, rga = ow.backprop(s[w].astype(np.float64), a[w].astype(np.float64), g[w].astype(np.float64))
+        assert (gs[w][0] == 0.0) == (rgs[0] == 0.0)  # bit-exact clipping decision
+        assert rel_err(gs[w], rgs) < TOL
+
+
+def test_action_map_subset(oracle_mod):
+    raw = load_raw("atlas")
+    raw.action_map = np.arange(6, raw.ndof, dtype=np.int32)  # root is unactuated
+    cm = nb.compile_model(raw)
+    ow, ew = oracle_mod.OracleWorld(raw), EmulWorld(cm)
+    s, a, g = sample_inputs(raw, 2, seed=5, tau_scale=30.0)
+    nxt, saved = ew.forward(s, a)
+    gs, ga = ew.backward(s, a, saved, g)
+    assert ga.shape[1] == raw.ndof - 6
+    for w in range(2):
+        ref = ow.step(s[w].astype(np.float64), a[w].astype(np.float64))
+        rgs, rga = ow.backprop(s[w].astype(np.float64), a[w].astype(np.float64), g[w].astype(np.float64))
+        assert rel_err(nxt[w], ref) < TOL and rel_err(gs[w], rgs) < TOL and rel_err(ga[w], rga) < TOL

@@ -1,0 +1,104 @@
+"""Host logic: loaders -> RawModel -> CanonModel invariants (no GPU)."""
+import os
+
+import numpy as np
+import pytest
+
+import nimblephysics_b200 as nb
+from nimblephysics_b200.modelspec import T_from_12
+from tests.util import load_raw
+
+
+def test_fixture_shapes():
+    atlas = load_raw("atlas")
+    assert atlas.ndof == 33 and atlas.nb == 34  # 28 moving links + 6 welded camera links (contact-free: no ground body)
+    hc = load_raw("half_cheetah")
+    assert hc.ndof == 9 and hc.dt == pytest.approx(0.002) and tuple(hc.gravity) == (0.0, -9.81, 0.0)
+    cp = load_raw("cartpole")
+    assert cp.ndof == 2 and cp.nb == 3
+
+
+def test_raw_json_roundtrip():
+    for name in ("cartpole", "half_cheetah", "atlas", "atlas_ground"):
+        raw = load_raw(name)
+        raw2 = nb.flatten_world(nb.World.from_raw(raw))
+        for k, v in raw.__dict__.items():
+            v2 = getattr(raw2, k)
+            if isinstance(v, np.ndarray):
+                assert np.array_equal(v, v2), (name, k)
+
+
+@pytest.mark.parametrize("name", ["cartpole", "half_cheetah", "atlas", "atlas_ground"])
+def test_canonical_model_invariants(name):
+    raw = load_raw(name)
+    cm = nb.compile_model(raw)
+    assert cm.ndof == raw.ndof
+    assert all(cm.parent[i] < i for i in range(cm.nb))  # parents first (DFS pre-order)
+    assert sorted(int(cm.dof_off[i]) + k for i in range(cm.nb) for k in range(6 if cm.jtype[i] == 3 else 1)) == list(range(cm.ndof))
+    # every Xtree is a rigid transform
+    for i in range(cm.nb):
+        R = T_from_12(cm.Xtree[i])[:3, :3]
+        assert np.allclose(R @ R.T, np.eye(3), atol=1e-12) and np.linalg.det(R) == pytest.approx(1.0)
+    # total mass is preserved by weld folding (static bodies excluded)
+    static = [i for i in range(raw.nb) if not raw.mobile[i]]
+    moving_mass = sum(raw.mass[i] for i in range(raw.nb) if i not in static)
+    # bodies welded to the world inside a mobile skeleton are static too
+    assert cm.inertia[:, 0].sum() <= moving_mass + 1e-9
+    # accumulator-slot discipline: a handoff body's parent is i-1; deposits target the parent's slot
+    for i in range(cm.nb):
+        if cm.flags[i] & 1:
+            assert cm.parent[i] == i - 1
+        elif cm.parent[i] >= 0:
+            assert cm.slot_parent[i] == cm.slot_self[cm.parent[i]] >= 0
+    # simulate the reverse sweep and check no slot is overwritten while live
+    live = {}
+    for i in range(cm.nb - 1, -1, -1):
+        if cm.slot_self[i] >= 0:
+            assert live.pop(int(cm.slot_self[i])) == i
+        p = cm.parent[i]
+        if p >= 0 and not (cm.flags[i] & 1):
+            sl = int(cm.slot_parent[i])
+            if cm.flags[i] & 2:
+                assert sl not in live
+                live[sl] = int(p)
+            else:
+                assert live[sl] == p
+    assert not live
+
+
+def test_builder_surface_matches_reference_example():
+    """python/new_examples/cartpole.py:12-46 builds its cartpole through these calls."""
+    world = nb.World()
+    world.setGravity([0, -9.81, 0])
+    cartpole = nb.Skeleton()
+    rail, cart = cartpole.createPrismaticJointAndBodyNodePair()
+    rail.setAxis([1, 0, 0])
+    cart.createShapeNode(nb.BoxShape([.5, .1, .1])).createVisualAspect().setColor([0.5, 0.5, 0.5])
+    rail.setPositionUpperLimit(0, 10)
+    rail.setPositionLowerLimit(0, -10)
+    rail.setControlForceUpperLimit(0, 10)
+    rail.setControlForceLowerLimit(0, -10)
+    pj, pole = cartpole.createRevoluteJointAndBodyNodePair(cart)
+    pj.setAxis([0, 0, 1])
+    pj.setControlForceUpperLimit(0, 0)
+    pj.setControlForceLowerLimit(0, 0)
+    off = nb.Isometry3()
+    off.set_translation([0, -0.5, 0])
+    pj.setTransformFromChildBodyNode(off)
+    world.addSkeleton(cartpole)
+    world.setTimeStep(world.getTimeStep() * 10)
+    assert world.getStateSize() == 4 and world.getActionSize() == 2 and world.getTimeStep() == pytest.approx(1e-2)
+    with pytest.raises(ValueError):
+        world.setState(np.zeros(3))  # reference prints + ignores (World.cpp:2027-2033); we raise (documented)
+    cm = nb.compile_model(nb.flatten_world(world))
+    assert cm.nb == 2 and list(cm.jtype) == [2, 1]
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/data"), reason="reference data only in the build container")
+def test_fixtures_are_current_with_reference_files():
+    import subprocess, sys, tempfile, json
+    from tests.util import MODELS, ROOT
+    w = nb.loadWorld("/root/reference/data/skel/half_cheetah.skel")
+    fresh = json.loads(nb.flatten_world(w).to_json())
+    stored = json.load(open(os.path.join(MODELS, "half_cheetah.json")))
+    assert fresh == stored
