@@ -30,6 +30,10 @@ class TimestepLayer(torch.autograd.Function):
         dm = device_model_for(world)
         n2, na = 2 * dm.ndof, dm.na
         legacy = state.dim() == 1
+        if legacy and (state.numel() != n2 or action.numel() != na):
+            # reference: message on stderr and the call is ignored (World.cpp:2027-2033, :2063-2070); we raise
+            raise ValueError(f"timestep(): got state of size {state.numel()} / action of size {action.numel()}, expected "
+                             f"getStateSize()={n2} / getActionSize()={na}")
         s2 = state.detach().reshape(-1, n2) if legacy else state.detach()
         a2 = action.detach().reshape(-1, na) if legacy else action.detach()
         if s2.dim() != 2 or s2.shape[1] != n2:
