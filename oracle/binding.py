@@ -89,3 +89,116 @@ class OracleWorld:
         ga = np.empty(self.na)
         lib().orc_backprop(self.h, _p(s), _p(a), _p(g), _p(gs), _p(ga))
         return gs, ga
+
+
+# ---------------------------------------------------------------------------------------------- contact stage
+def _pi(a):
+    return a.ctypes.data_as(ctypes.POINTER(ctypes.c_int))
+
+
+class OracleContactWorld(OracleWorld):
+    """OracleWorld + the contact / LCP stage (ConstraintSolver::solve)."""
+
+    MAXC, MAXR = 64, 192
+
+    def __init__(self, raw):
+        super().__init__(raw)
+        f = lambda a: np.ascontiguousarray(a, dtype=np.float64)
+        i = lambda a: np.ascontiguousarray(a, dtype=np.int32)
+        k = [i(raw.skel_id), i(raw.shape_body), i(raw.shape_type), f(raw.shape_dims), f(raw.shape_T), f(raw.friction),
+             f(raw.restitution)]
+        self._keep2 = k
+        lib().orc_model_set_contact(self.h, _pi(k[0]), ctypes.c_int(raw.ns), _pi(k[1]), _pi(k[2]), _p(k[3]), _p(k[4]), _p(k[5]),
+                                    _p(k[6]), ctypes.c_int(int(raw.penetration_correction)),
+                                    ctypes.c_double(raw.contact_clipping_depth), ctypes.c_double(raw.fallback_cfm))
+
+    def step_contact(self, state, action, x_warm=None):
+        """-> dict(next_state, nc, point, normal, depth, bodies, type, A, b, lo, hi, findex, x, mapping, status, vstar)"""
+        s = np.ascontiguousarray(state, np.float64)
+        a = np.ascontiguousarray(action, np.float64)
+        C, R = self.MAXC, self.MAXR
+        out = np.empty(2 * self.n)
+        nc = ctypes.c_int(0)
+        status = ctypes.c_int(0)
+        pt, nr, dp = np.zeros((C, 3)), np.zeros((C, 3)), np.zeros(C)
+        bod, typ = np.zeros((C, 2), np.int32), np.zeros(C, np.int32)
+        A, b, lo, hi, x = np.zeros(R * R), np.zeros(R), np.zeros(R), np.zeros(R), np.zeros(R)
+        fi, mp = np.zeros(R, np.int32), np.zeros(R, np.int32)
+        vstar = np.zeros(self.n)
+        if x_warm is None:
+            xw, mw = np.zeros(1), -1
+        else:
+            xw = np.ascontiguousarray(x_warm, np.float64)
+            mw = xw.size
+        m = lib().orc_step_contact(self.h, _p(s), _p(a), _p(xw), ctypes.c_int(mw), _p(out), ctypes.c_int(C), ctypes.c_int(R),
+                                   ctypes.byref(nc), _p(pt), _p(nr), _p(dp), _pi(bod), _pi(typ), _p(A), _p(b), _p(lo), _p(hi),
+                                   _pi(fi), _p(x), _pi(mp), ctypes.byref(status), _p(vstar))
+        if m < 0:
+            raise RuntimeError("oracle contact buffers too small")
+        k = nc.value
+        return dict(next_state=out, nc=k, point=pt[:k], normal=nr[:k], depth=dp[:k], bodies=bod[:k], type=typ[:k],
+                    A=A[:m * m].reshape(m, m), b=b[:m], lo=lo[:m], hi=hi[:m], findex=fi[:m], x=x[:m], mapping=mp[:m],
+                    status=status.value, vstar=vstar, m=m)
+
+
+def solve_chain(A, b, lo, hi, findex, x0=None, fallback_cfm=1e-4):
+    n = len(b)
+    A = np.ascontiguousarray(A, np.float64)
+    b, lo, hi = (np.ascontiguousarray(v, np.float64) for v in (b, lo, hi))
+    fi = np.ascontiguousarray(findex, np.int32)
+    x = np.zeros(n)
+    mp = np.zeros(n, np.int32)
+    x0a = np.zeros(n) if x0 is None else np.ascontiguousarray(x0, np.float64)
+    st = lib().orc_solve_chain(ctypes.c_int(n), _p(A), _p(b), _p(lo), _p(hi), _pi(fi), _p(x0a), ctypes.c_int(0 if x0 is None else 1),
+                               ctypes.c_double(fallback_cfm), _p(x), _pi(mp))
+    return x, mp, st
+
+
+def lcp_valid(A, x, b, hi, lo, findex):
+    n = len(b)
+    A, x, b, hi, lo = (np.ascontiguousarray(v, np.float64) for v in (A, x, b, hi, lo))
+    fi = np.ascontiguousarray(findex, np.int32)
+    return bool(lib().orc_lcp_valid(ctypes.c_int(n), _p(A), _p(x), _p(b), _p(hi), _p(lo), _pi(fi)))
+
+
+def dantzig(A, b, lo, hi, findex, early=False):
+    n = len(b)
+    A, b, lo, hi = (np.ascontiguousarray(v, np.float64) for v in (A, b, lo, hi))
+    fi = np.ascontiguousarray(findex, np.int32)
+    x = np.zeros(n)
+    ok = lib().orc_dantzig(ctypes.c_int(n), _p(A), _p(b), _p(lo), _p(hi), _pi(fi), ctypes.c_int(int(early)), _p(x))
+    return x, bool(ok)
+
+
+def pinv_solve(Q, b):
+    Q = np.ascontiguousarray(Q, np.float64)
+    b = np.ascontiguousarray(b, np.float64)
+    m, n = Q.shape
+    x = np.zeros(n)
+    lib().orc_pinv_solve(ctypes.c_int(m), ctypes.c_int(n), _p(Q), _p(b), _p(x))
+    return x
+
+
+_REF = None
+
+
+def ref_ode():
+    """The reference's own dSolveLCP (compiled from /root/reference by oracle/Makefile) or None."""
+    global _REF
+    if _REF is None:
+        path = os.path.join(_HERE, "_ref", "libodelcp.so")
+        _REF = ctypes.CDLL(path) if os.path.exists(path) else False
+    return _REF or None
+
+
+def ref_dsolve_lcp(A, b, lo, hi, findex, early=False):
+    L = ref_ode()
+    n = len(b)
+    pad = L.ref_dPAD(ctypes.c_int(n))
+    Ap = np.zeros((n, pad))
+    Ap[:, :n] = A
+    x, w = np.zeros(n), np.zeros(n)
+    bb, ll, hh = (np.array(v, np.float64).copy() for v in (b, lo, hi))
+    fi = np.array(findex, np.int32).copy()
+    ok = L.ref_dSolveLCP(ctypes.c_int(n), _p(Ap), _p(x), _p(bb), _p(w), ctypes.c_int(0), _p(ll), _p(hh), _pi(fi), ctypes.c_int(int(early)))
+    return x, bool(ok)

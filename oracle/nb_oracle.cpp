@@ -28,6 +28,8 @@
 #include <vector>
 
 #include "spatial.hpp"
+#include "contact.hpp"
+#include "lcp_chain.hpp"
 
 namespace orc {
 
@@ -41,6 +43,12 @@ struct Model {
   double gravity[3] = {0, 0, -9.81};
   double dt = 1e-3;
   std::vector<int> action_map;
+  // contact stage
+  std::vector<int> skel_id, shape_body, shape_type;
+  std::vector<double> shape_dims, shape_T, friction, restitution;
+  bool penetration_correction = false;
+  double clip_depth = 0.03, fallback_cfm = 1e-4;
+  std::vector<int> has_dofs_above;  // BodyNode::getNumDependentGenCoords() > 0
 };
 
 template <class S> static Iso<S> iso_from12(const double* t) {
@@ -111,12 +119,18 @@ template <class S> static void free_integrate(const S* q, const S* v, double dt,
 }
 
 // One contact-free World::step.  q,v,tau: [ndof] -> qn, vn.  (World.cpp:221-254,307-333)
-template <class S>
-static void step_nocontact(const Model& M, const S* q, const S* v, const S* tau, S* qn, S* vn, S* qdd_out = nullptr) {
-  const int nb = M.nb;
+template <class S> static std::vector<BodyState<S>>& workspace(int nb) {
   // per-thread reusable workspace: a fresh ~1 MB vector per call would hit mmap/munmap and serialise threads
   static thread_local std::vector<BodyState<S>> B;
   if ((int)B.size() < nb) B.resize(nb);
+  return B;
+}
+
+// Skeleton::computeForwardDynamics for every mobile skeleton: fills B (transforms, velocities, articulated
+// inertias, psi) and the joint accelerations qdd.
+template <class S>
+static void aba_pass(const Model& M, const S* q, const S* v, const S* tau, std::vector<BodyState<S>>& B, std::vector<S>& qdd) {
+  const int nb = M.nb;
   const double dt = M.dt;
   // ---- kinematics, root -> leaf (Frame.cpp:144-160, GenericJoint.hpp:1803-1823)
   for (int i = 0; i < nb; i++) {
@@ -208,7 +222,7 @@ static void step_nocontact(const Model& M, const S* q, const S* v, const S* tau,
     }
   }
   // ---- accelerations, root -> leaf (BodyNode.cpp:2159-2185, GenericJoint.hpp:2656-2676, Frame.cpp:254-271)
-  std::vector<S> qdd(M.ndof, S(0.0));
+  qdd.assign(M.ndof, S(0.0));
   for (int i = 0; i < nb; i++) {
     BodyState<S>& b = B[i];
     if (!M.mobile[i]) { b.A = zero6<S>(); continue; }
@@ -224,15 +238,257 @@ static void step_nocontact(const Model& M, const S* q, const S* v, const S* tau,
     }
     b.A = Ap + Sa + b.eta;
   }
-  // ---- integrate: v+ = v + dt qdd (GenericJoint.hpp:1410-1414); q+ uses the PRE-step velocity (World.cpp:307-322)
+}
+
+// v+ = v + dt qdd (GenericJoint.hpp:1410-1414); q+ = q (+) dt v with the PRE-step velocity (World.cpp:307-322)
+template <class S>
+static void integrate(const Model& M, const S* q, const S* v, const S* vnew_mobile, S* qn, S* vn) {
+  const int nb = M.nb;
+  const double dt = M.dt;
   for (int i = 0; i < nb; i++) {
     const int o = M.dof_off[i];
     const int k = (M.jtype[i] == FREE) ? 6 : (M.jtype[i] == WELD ? 0 : 1);
     if (M.jtype[i] == FREE) free_integrate(&q[o], &v[o], dt, &qn[o]);
     else for (int a = 0; a < k; a++) qn[o + a] = q[o + a] + v[o + a] * dt;
-    for (int a = 0; a < k; a++) vn[o + a] = M.mobile[i] ? v[o + a] + qdd[o + a] * dt : v[o + a];
+    for (int a = 0; a < k; a++) vn[o + a] = M.mobile[i] ? vnew_mobile[o + a] : v[o + a];
   }
+}
+
+// One contact-free World::step.  q,v,tau: [ndof] -> qn, vn.  (World.cpp:221-254,307-333)
+template <class S>
+static void step_nocontact(const Model& M, const S* q, const S* v, const S* tau, S* qn, S* vn, S* qdd_out = nullptr) {
+  std::vector<BodyState<S>>& B = workspace<S>(M.nb);
+  static thread_local std::vector<S> qdd, vstar;
+  aba_pass<S>(M, q, v, tau, B, qdd);
+  vstar.assign(M.ndof, S(0.0));
+  for (int i = 0; i < M.ndof; i++) vstar[i] = v[i] + qdd[i] * M.dt;
+  integrate<S>(M, q, v, vstar.data(), qn, vn);
   if (qdd_out) for (int i = 0; i < M.ndof; i++) qdd_out[i] = qdd[i];
+}
+
+// ====================================================================================
+// contact stage (double only): ConstraintSolver::solve + integrateVelocitiesFromImpulses
+// ====================================================================================
+struct ContactRows {
+  int nc = 0, m = 0;
+  std::vector<Contact<double>> contacts;
+  std::vector<int> row_contact, row_off;        // row -> contact index ; contact -> first row
+  std::vector<Vec6<double>> JA, JB;             // per row, body-frame wrench on body A / body B
+  std::vector<int> reactA, reactB;              // per contact
+  std::vector<double> b, lo, hi, restitution;   // per row
+  std::vector<int> findex;
+  int unsupported = 0;
+};
+
+static bool is_reactive(const Model& M, int body) { return M.mobile[body] && M.has_dofs_above[body]; }
+
+// impulse-ABA: body impulses imp[i] (body frame) -> joint velocity changes dqd (Skeleton.cpp:13421-13456, 13552-13556,
+// BodyNode.cpp:2117-2138, 2188-2215, GenericJoint.hpp:2482-2498, 2607-2613, 2713-2725)
+static void impulse_response(const Model& M, std::vector<BodyState<double>>& B, const std::vector<Vec6<double>>& imp,
+                             std::vector<double>& dqd, std::vector<Vec6<double>>& dV) {
+  const int nb = M.nb;
+  static thread_local std::vector<Vec6<double>> pI;
+  static thread_local std::vector<double> uI;
+  pI.assign(nb, zero6<double>()); uI.assign(M.ndof, 0.0);
+  dqd.assign(M.ndof, 0.0); dV.assign(nb, zero6<double>());
+  std::vector<std::vector<int>> kids(nb);
+  for (int i = 0; i < nb; i++) if (M.parent[i] >= 0) kids[M.parent[i]].push_back(i);
+  for (int i = nb - 1; i >= 0; i--) {
+    if (!M.mobile[i]) continue;
+    BodyState<double>& b = B[i];
+    pI[i] = zero6<double>() - imp[i];
+    for (int c : kids[i]) {
+      BodyState<double>& ch = B[c];
+      Vec6<double> beta = pI[c];
+      if (ch.k > 0) {
+        Vec6<double> Su = zero6<double>();
+        const int oc = M.dof_off[c];
+        for (int a = 0; a < ch.k; a++) { double sacc = 0; for (int e = 0; e < ch.k; e++) sacc += ch.psi[a * ch.k + e] * uI[oc + e]; Su = Su + ch.Scol[a] * sacc; }
+        beta = beta + mul(ch.AI, Su);
+      }
+      pI[i] = pI[i] + dAdInvT(ch.T, beta);
+    }
+    const int o = M.dof_off[i];
+    for (int a = 0; a < b.k; a++) uI[o + a] = -dot(b.Scol[a], pI[i]);
+  }
+  for (int i = 0; i < nb; i++) {
+    if (!M.mobile[i]) continue;
+    BodyState<double>& b = B[i];
+    const int p = M.parent[i], o = M.dof_off[i];
+    Vec6<double> Vp = (p >= 0) ? AdInvT(b.T, dV[p]) : zero6<double>();
+    Vec6<double> AIVp = mul(b.AI, Vp);
+    Vec6<double> Sd = zero6<double>();
+    for (int a = 0; a < b.k; a++) {
+      double acc = 0;
+      for (int e = 0; e < b.k; e++) acc += b.psi[a * b.k + e] * (uI[o + e] - dot(b.Scol[e], AIVp));
+      dqd[o + a] = acc;
+      Sd = Sd + b.Scol[a] * acc;
+    }
+    dV[i] = Vp + Sd;
+  }
+}
+
+static void tangent_basis(const Vec3<double>& n, Vec3<double>& t1, Vec3<double>& t2) {  // ContactConstraint.cpp:734-795
+  Vec3<double> z = v3(0.0, 0.0, 1.0), x = v3(1.0, 0.0, 0.0), y = v3(0.0, 1.0, 0.0);
+  Vec3<double> t = cross(z, n);
+  if (dot(t, t) < 1e-12) { t = cross(x, n); if (dot(t, t) < 1e-12) { t = cross(y, n); if (dot(t, t) < 1e-12) t = cross(z, n); } }
+  t1 = t * (1.0 / std::sqrt(dot(t, t)));
+  t2 = cross(n, t1);
+}
+
+static void collide_world(const Model& M, const std::vector<BodyState<double>>& B, ContactRows& R) {
+  const int ns = (int)M.shape_body.size();
+  const double clip = M.clip_depth;
+  std::vector<Iso<double>> Tw(ns);
+  for (int s = 0; s < ns; s++) Tw[s] = mul(B[M.shape_body[s]].W, iso_from12<double>(&M.shape_T[12 * s]));
+  std::vector<Contact<double>> raw;
+  for (int i = 0; i + 1 < ns; i++) for (int j = i + 1; j < ns; j++) {
+    const int bi = M.shape_body[i], bj = M.shape_body[j];
+    if (bi == bj) continue;                                   // CollisionFilter.cpp:128-129
+    if (!M.mobile[bi] && !M.mobile[bj]) continue;             // :137-138
+    if (M.skel_id[bi] == M.skel_id[bj]) continue;             // self-collision check is off by default (:140-150)
+    const int ti = M.shape_type[i], tj = M.shape_type[j];
+    Vec3<double> di = v3(M.shape_dims[3 * i], M.shape_dims[3 * i + 1], M.shape_dims[3 * i + 2]);
+    Vec3<double> dj = v3(M.shape_dims[3 * j], M.shape_dims[3 * j + 1], M.shape_dims[3 * j + 2]);
+    if (ti == SH_BOX && tj == SH_BOX) collide_box_box(di, Tw[i], dj, Tw[j], clip, bi, bj, i, j, raw);
+    else if (ti == SH_BOX && tj == SH_SPHERE) collide_box_sphere(di, Tw[i], dj[0], Tw[j], clip, CLIP_BOTH, bi, bj, i, j, raw);
+    else if (ti == SH_SPHERE && tj == SH_BOX) collide_sphere_box(di[0], Tw[i], dj, Tw[j], clip, bi, bj, i, j, raw);
+    else if ((ti == SH_BOX && tj == SH_CAPSULE) || (ti == SH_CAPSULE && tj == SH_BOX)) {
+      const bool boxFirst = (ti == SH_BOX);
+      const int cs = boxFirst ? j : i, bs = boxFirst ? i : j;
+      const double r = M.shape_dims[3 * cs], h = M.shape_dims[3 * cs + 1];
+      Vec3<double> bdim = boxFirst ? di : dj;
+      // which end sphere is deeper inside / closer to the box? (stands in for ccdMPRPenetration's `pos`, DARTCollide.cpp:4455-4491)
+      double depth_end[2];
+      Iso<double> Tend[2];
+      for (int e = 0; e < 2; e++) {
+        Iso<double> off = iso_identity<double>(); off.p = v3(0.0, 0.0, e == 0 ? h / 2 : -h / 2);
+        Tend[e] = mul(Tw[cs], off);
+        Vec3<double> pl = apply(inverse(Tw[bs]), Tend[e].p), q = pl;
+        bool inside = true;
+        for (int k = 0; k < 3; k++) { double hk = 0.5 * bdim[k]; if (q[k] < -hk) { q[k] = -hk; inside = false; } if (q[k] > hk) { q[k] = hk; inside = false; } }
+        if (inside) { double mn = 1e300; for (int k = 0; k < 3; k++) mn = std::min(mn, 0.5 * bdim[k] - std::fabs(pl[k])); depth_end[e] = mn + r; }
+        else { Vec3<double> dd = pl - q; depth_end[e] = r - std::sqrt(dot(dd, dd)); }
+      }
+      if (std::max(depth_end[0], depth_end[1]) < 0) continue;  // no overlap: MPR reports no intersection
+      if (std::fabs(depth_end[0] - depth_end[1]) < 1e-9) { R.unsupported++; continue; }  // side-on "pipe" contact: needs MPR + createCapsuleMeshContact
+      const int e = depth_end[0] > depth_end[1] ? 0 : 1;
+      const int half = (e == 0) ? CLIP_TOP : CLIP_BOTTOM;
+      if (boxFirst) collide_box_sphere(bdim, Tw[bs], r, Tend[e], clip, half, bi, bj, i, j, raw);
+      else collide_sphere_box(r, Tend[e], bdim, Tw[bs], clip, bi, bj, i, j, raw);
+    } else { R.unsupported++; }
+  }
+  // ConstraintSolver::updateConstraints filtering (:576-601)
+  for (auto& c : raw) {
+    if (dot(c.normal, c.normal) < 1e-12) continue;
+    if (c.depth < 0.0) continue;
+    if (c.depth > clip) continue;
+    if (!(is_reactive(M, c.bodyA) || is_reactive(M, c.bodyB))) continue;  // ContactConstraint::update / isActive
+    R.contacts.push_back(c);
+  }
+  R.nc = (int)R.contacts.size();
+}
+
+struct ContactStepInfo {
+  ContactRows rows;
+  orc::Mat A;
+  std::vector<double> x, vstar;
+  std::vector<int> mapping;
+  int status = 0;
+};
+
+static void step_contact(const Model& M, const double* q, const double* v, const double* tau, const double* x_warm, int m_warm,
+                         double* qn, double* vn, ContactStepInfo& info) {
+  const int nb = M.nb, n = M.ndof;
+  std::vector<BodyState<double>>& B = workspace<double>(nb);
+  std::vector<double> qdd;
+  aba_pass<double>(M, q, v, tau, B, qdd);
+  std::vector<double>& vs = info.vstar;
+  vs.assign(n, 0.0);
+  for (int i = 0; i < nb; i++) { const int o = M.dof_off[i]; for (int a = 0; a < B[i].k; a++) vs[o + a] = M.mobile[i] ? v[o + a] + qdd[o + a] * M.dt : v[o + a]; }
+  // body velocities at the unconstrained velocity v* (positions unchanged)
+  for (int i = 0; i < nb; i++) {
+    BodyState<double>& b = B[i];
+    Vec6<double> Sv = zero6<double>();
+    for (int c = 0; c < b.k; c++) Sv = Sv + b.Scol[c] * vs[M.dof_off[i] + c];
+    b.V = (M.parent[i] >= 0) ? AdInvT(b.T, B[M.parent[i]].V) + Sv : Sv;
+  }
+  ContactRows& R = info.rows;
+  collide_world(M, B, R);
+  // ---- rows (ContactConstraint ctor + getInformation)
+  for (int ci = 0; ci < R.nc; ci++) {
+    const Contact<double>& c = R.contacts[ci];
+    const double mu = std::min(M.friction[c.bodyA], M.friction[c.bodyB]);
+    const bool fric = mu > 1e-3;
+    const double e = M.restitution[c.bodyA] * M.restitution[c.bodyB];
+    const bool bounce = e > 1e-3;
+    Vec3<double> dirs[3]; dirs[0] = c.normal;
+    if (fric) tangent_basis(c.normal, dirs[1], dirs[2]);
+    const Iso<double>&WA = B[c.bodyA].W, &WB = B[c.bodyB].W;
+    Vec3<double> pA = apply(inverse(WA), c.point), pB = apply(inverse(WB), c.point);
+    const int dim = fric ? 3 : 1, off = R.m;
+    R.row_off.push_back(off);
+    R.reactA.push_back(is_reactive(M, c.bodyA)); R.reactB.push_back(is_reactive(M, c.bodyB));
+    for (int k = 0; k < dim; k++) {
+      Vec3<double> dA = mulT(WA.R, dirs[k]), dB = mulT(WB.R, neg(dirs[k]));
+      Vec6<double> JA = v6(cross(pA, dA), dA), JB = v6(cross(pB, dB), dB);
+      R.JA.push_back(JA); R.JB.push_back(JB); R.row_contact.push_back(ci);
+      double rel = -(dot(JA, B[c.bodyA].V) + dot(JB, B[c.bodyB].V));  // getRelVelocity (:687-695)
+      R.b.push_back(rel);
+      R.restitution.push_back(k == 0 && bounce ? e : 0.0);
+      if (k == 0) { R.lo.push_back(0.0); R.hi.push_back(HUGE_VAL); R.findex.push_back(-1); }
+      else { R.lo.push_back(-mu); R.hi.push_back(mu); R.findex.push_back(off); }
+    }
+    // bouncing velocity (ContactConstraint.cpp:395-442): ERP 0.01, max ERV 1e-3, allowance 0
+    double bv = c.depth - 0.0;
+    if (bv < 0) bv = 0; else { bv *= 0.01 * (1.0 / M.dt); if (bv > 1e-3) bv = 1e-3; }
+    if (!M.penetration_correction) bv = 0;
+    if (bounce) { double rv = R.b[off] * e; if (rv > 1e-1) { if (rv > bv) { bv = rv; if (bv > 1e2) bv = 1e2; } } }
+    R.b[off] += bv;
+    R.m += dim;
+  }
+  const int m = R.m;
+  if (m == 0) { integrate<double>(M, q, v, vs.data(), qn, vn); info.status = 0; return; }
+  // ---- A by impulse tests (BoxedLcpConstraintSolver.cpp:190-349): upper blocks measured, lower mirrored
+  orc::Mat A(m, m);
+  std::vector<Vec6<double>> imp(nb), dV;
+  std::vector<double> dqd;
+  for (int r = 0; r < m; r++) {
+    const int ci = R.row_contact[r];
+    const Contact<double>& c = R.contacts[ci];
+    for (auto& x : imp) x = zero6<double>();
+    if (R.reactA[ci]) imp[c.bodyA] = imp[c.bodyA] + R.JA[r];
+    if (R.reactB[ci]) imp[c.bodyB] = imp[c.bodyB] + R.JB[r];
+    impulse_response(M, B, imp, dqd, dV);
+    for (int s = 0; s < m; s++) {
+      const int cj = R.row_contact[s];
+      if (cj < ci) { A(r, s) = A(s, r); continue; }
+      const Contact<double>& d = R.contacts[cj];
+      double a = 0;
+      if (R.reactA[cj]) a += dot(R.JA[s], dV[d.bodyA]);
+      if (R.reactB[cj]) a += dot(R.JB[s], dV[d.bodyB]);
+      A(r, s) = a;
+    }
+  }
+  info.A = A;
+  // ---- warm start (:202-208, :334-337)
+  orc::Vec x0(m, 0.0);
+  if (m_warm == m && x_warm) for (int i = 0; i < m; i++) x0[i] = x_warm[i];
+  else x0 = orc::guess_solution(A, R.b, R.findex);
+  orc::ChainResult CR = orc::solve_chain(A, R.b, R.lo, R.hi, R.findex, x0, R.restitution, M.fallback_cfm);
+  info.x = CR.x; info.mapping = CR.mapping; info.status = CR.status | (R.unsupported ? 128 : 0);
+  // ---- apply impulses (ConstraintSolver.cpp:813-823, ContactConstraint.cpp:630-684) and update velocities
+  for (auto& x : imp) x = zero6<double>();
+  for (int r = 0; r < m; r++) {
+    const int ci = R.row_contact[r];
+    const Contact<double>& c = R.contacts[ci];
+    if (R.reactA[ci]) imp[c.bodyA] = imp[c.bodyA] + R.JA[r] * CR.x[r];
+    if (R.reactB[ci]) imp[c.bodyB] = imp[c.bodyB] + R.JB[r] * CR.x[r];
+  }
+  impulse_response(M, B, imp, dqd, dV);
+  std::vector<double> vplus(n);
+  for (int i = 0; i < n; i++) vplus[i] = vs[i] + dqd[i];
+  integrate<double>(M, q, v, vplus.data(), qn, vn);
 }
 
 // J = d[qn; vn] / d[q; v; tau]  row-major [2n x 3n]
@@ -339,6 +595,82 @@ void orc_backprop(void* h, const double* state, const double* action, const doub
   }
   for (int j = 0; j < 2 * n; j++) grad_state[j] = g[j];
   for (size_t i = 0; i < M.action_map.size(); i++) grad_action[i] = g[2 * n + M.action_map[i]];  // :404-417
+}
+
+// ---- contact stage -----------------------------------------------------------------
+void orc_model_set_contact(void* h, const int* skel_id, int ns, const int* shape_body, const int* shape_type,
+                           const double* shape_dims, const double* shape_T, const double* friction,
+                           const double* restitution, int penetration_correction, double clip_depth, double fallback_cfm) {
+  Model& M = *(Model*)h;
+  M.skel_id.assign(skel_id, skel_id + M.nb);
+  M.shape_body.assign(shape_body, shape_body + ns); M.shape_type.assign(shape_type, shape_type + ns);
+  M.shape_dims.assign(shape_dims, shape_dims + 3 * ns); M.shape_T.assign(shape_T, shape_T + 12 * ns);
+  M.friction.assign(friction, friction + M.nb); M.restitution.assign(restitution, restitution + M.nb);
+  M.penetration_correction = penetration_correction != 0; M.clip_depth = clip_depth; M.fallback_cfm = fallback_cfm;
+  M.has_dofs_above.assign(M.nb, 0);
+  for (int i = 0; i < M.nb; i++) {
+    int k = (M.jtype[i] == orc::FREE) ? 6 : (M.jtype[i] == orc::WELD ? 0 : 1);
+    M.has_dofs_above[i] = (k > 0) || (M.parent[i] >= 0 && M.has_dofs_above[M.parent[i]]);
+  }
+}
+
+// One World::step with the contact stage.  x_warm/m_warm: cached LCP solution (BoxedLcpConstraintSolver mX) or m_warm=-1.
+// Outputs (caller-sized with max_rows / max_contacts): returns the LCP dimension m, or -1 if buffers are too small.
+int orc_step_contact(void* h, const double* state, const double* action, const double* x_warm, int m_warm, double* next_state,
+                     int max_contacts, int max_rows, int* nc_out, double* contact_point, double* contact_normal,
+                     double* contact_depth, int* contact_bodies, int* contact_type, double* A_out, double* b_out, double* lo_out,
+                     double* hi_out, int* findex_out, double* x_out, int* mapping_out, int* status_out, double* vstar_out) {
+  const Model& M = *(Model*)h;
+  const int n = M.ndof;
+  std::vector<double> tau(n, 0.0);
+  for (size_t i = 0; i < M.action_map.size(); i++) tau[M.action_map[i]] = action[i];
+  orc::ContactStepInfo info;
+  orc::step_contact(M, state, state + n, tau.data(), x_warm, m_warm, next_state, next_state + n, info);
+  const orc::ContactRows& R = info.rows;
+  if (R.nc > max_contacts || R.m > max_rows) return -1;
+  *nc_out = R.nc;
+  for (int c = 0; c < R.nc; c++) {
+    for (int k = 0; k < 3; k++) { contact_point[3 * c + k] = R.contacts[c].point[k]; contact_normal[3 * c + k] = R.contacts[c].normal[k]; }
+    contact_depth[c] = R.contacts[c].depth; contact_bodies[2 * c] = R.contacts[c].bodyA; contact_bodies[2 * c + 1] = R.contacts[c].bodyB;
+    contact_type[c] = R.contacts[c].type;
+  }
+  for (int r = 0; r < R.m; r++) {
+    b_out[r] = R.b[r]; lo_out[r] = R.lo[r]; hi_out[r] = R.hi[r]; findex_out[r] = R.findex[r];
+    x_out[r] = info.x[r]; mapping_out[r] = info.mapping[r];
+    for (int c = 0; c < R.m; c++) A_out[(size_t)r * R.m + c] = info.A(r, c);
+  }
+  *status_out = info.status;
+  if (vstar_out) for (int i = 0; i < n; i++) vstar_out[i] = info.vstar[i];
+  return R.m;
+}
+
+// raw LCP chain on caller data (tests: literal instances of unittests/unit/test_LCPUtils.cpp, comparison with dSolveLCP)
+int orc_solve_chain(int n, const double* A, const double* b, const double* lo, const double* hi, const int* findex,
+                    const double* x0, int have_x0, double fallback_cfm, double* x_out, int* mapping_out) {
+  orc::Mat Am(n, n); orc::Vec bv(b, b + n), lov(lo, lo + n), hiv(hi, hi + n), rest(n, 0.0);
+  std::vector<int> fi(findex, findex + n);
+  for (int i = 0; i < n * n; i++) Am.a[i] = A[i];
+  orc::Vec x0v = have_x0 ? orc::Vec(x0, x0 + n) : orc::guess_solution(Am, bv, fi);
+  orc::ChainResult R = orc::solve_chain(Am, bv, lov, hiv, fi, x0v, rest, fallback_cfm);
+  for (int i = 0; i < n; i++) { x_out[i] = R.x[i]; mapping_out[i] = R.mapping[i]; }
+  return R.status;
+}
+int orc_lcp_valid(int n, const double* A, const double* x, const double* b, const double* hi, const double* lo, const int* findex) {
+  orc::Mat Am(n, n); for (int i = 0; i < n * n; i++) Am.a[i] = A[i];
+  return orc::lcp_valid(Am, orc::Vec(x, x + n), orc::Vec(b, b + n), orc::Vec(hi, hi + n), orc::Vec(lo, lo + n), std::vector<int>(findex, findex + n), false) ? 1 : 0;
+}
+// the Dantzig restatement alone (A row-major n x n, clobbers nothing of the caller's)
+int orc_dantzig(int n, const double* A, const double* b, const double* lo, const double* hi, const int* findex, int early, double* x_out) {
+  orc::Problem P; P.A = orc::Mat(n, n); for (int i = 0; i < n * n; i++) P.A.a[i] = A[i];
+  P.x.assign(n, 0.0); P.b.assign(b, b + n); P.lo.assign(lo, lo + n); P.hi.assign(hi, hi + n); P.fi.assign(findex, findex + n);
+  bool ok = orc::run_dantzig(P, early != 0);
+  for (int i = 0; i < n; i++) x_out[i] = P.x[i];
+  return ok ? 1 : 0;
+}
+void orc_pinv_solve(int m, int n, const double* Q, const double* b, double* x) {
+  orc::Mat Qm(m, n); for (int i = 0; i < m * n; i++) Qm.a[i] = Q[i];
+  orc::Vec r = orc::pinv_solve(Qm, orc::Vec(b, b + m));
+  for (int i = 0; i < n; i++) x[i] = r[i];
 }
 
 }  // extern "C"
