@@ -220,13 +220,13 @@ def main():
     prec = FP64 if args.precision == "fp64" else FP32
     B = args.batch
     dm = nb.DeviceModel(nb.compile_model(raw))
-    per_set = 4 * B * (2 * n * 4 + 2 * na + dm.saved_words)
+    per_set = 4 * B * (2 * n * 4 + 2 * na + dm.saved_words * (2 if prec == FP64 else 1))
     nsets = max(2, int(np.ceil(160e6 / per_set)))
     sets = []
     for k in range(nsets):
         s, a, g = make_inputs(raw, B, 1234 + 1000 * rank + k)
         sets.append(dict(s=torch.tensor(s, device=dev), a=torch.tensor(a, device=dev), g=torch.tensor(g, device=dev),
-                         nxt=torch.empty((B, 2 * n), device=dev), saved=torch.empty((dm.saved_words, B), device=dev),
+                         nxt=torch.empty((B, 2 * n), device=dev), saved=torch.empty((dm.saved_words, B), device=dev, dtype=torch.float64 if prec == FP64 else torch.float32),
                          gs=torch.empty((B, 2 * n), device=dev), ga=torch.empty((B, na), device=dev)))
     stream = torch.cuda.current_stream().cuda_stream
 
@@ -284,6 +284,38 @@ def main():
     barrier()
     e2e_ms = 1e3 * (time.perf_counter() - t0)
 
+    # ---- extra (not the headline metric): forward step WITH the contact / boxed-LCP stage, configs[2] and configs[3] shapes
+    extra = {}
+    if world_size == 1:
+        from tests.util import contact_inputs
+
+        for cname, label in (("atlas_ground", "atlas_ground_contact_fwd"), ("half_cheetah", "half_cheetah_contact_fwd")):
+            try:
+                craw = nb.RawModel.load(os.path.join(ROOT, "tests", "golden", "models", f"{cname}.json"))
+                cworld = nb.World.from_raw(craw)
+                cs, ca = contact_inputs(craw, cname, B, seed=7)
+                cst, cat = torch.tensor(cs, device=dev), torch.tensor(ca, device=dev)
+                with torch.no_grad():
+                    for _ in range(3):
+                        nb.timestep(cworld, cst, cat)
+                    torch.cuda.synchronize()
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    ksteps = 10
+                    e0.record()
+                    for _ in range(ksteps):
+                        nb.timestep(cworld, cst, cat)
+                    e1.record()
+                    torch.cuda.synchronize()
+                cc = nb.contact_cache(cworld, B, dev)
+                extra[label] = {"world_steps_per_s": B * ksteps / (e0.elapsed_time(e1) * 1e-3), "batch": B,
+                                "mean_contacts": float(cc["nc"].float().mean()), "mean_lcp_rows": float(cc["m"].float().mean()),
+                                "frac_shortcircuit": float(((cc["status"] & 1) > 0).float().mean()),
+                                "frac_dantzig": float(((cc["status"] & 2) > 0).float().mean()),
+                                "frac_pgs_fallback": float(((cc["status"] & 8) > 0).float().mean()),
+                                "note": "forward only (fp64 ABA + contact/LCP kernels); same state re-stepped, warm-started LCP cache"}
+            except Exception as ex:  # never let the extra leg break the headline line
+                extra[label] = {"error": repr(ex)}
+
     t_total = torch.tensor([total_ms, e2e_ms], device=dev, dtype=torch.float64)
     if dist:
         dist.all_reduce(t_total, op=dist.ReduceOp.MAX)
@@ -318,7 +350,7 @@ def main():
             "e2e": {"value": e2e_value, "unit": UNIT,
                     "h2d_bytes_per_step": int(4 * B * (2 * n + na + 2 * n)), "d2h_bytes_per_step": int(4 * B * (2 * n + 2 * n + na)),
                     "steps": e2e_steps, "path": "nb2_step_forward_host + nb2_step_backward_host (pinned host buffers)"},
-            "gpu_launches": int(launches), "clocks": clocks,
+            "gpu_launches": int(launches), "clocks": clocks, "extra": extra,
         }
         if cpu_baseline is not None:
             out["cpu_baseline"] = cpu_baseline

@@ -58,6 +58,19 @@ typedef struct nb2_model_desc {
   const int32_t* action_map;  /* [na] */
   double gravity[3];
   double dt;
+  /* ---- contact stage (nshapes == 0: contact-free world) ---- */
+  int32_t nshapes, npairs;
+  const int32_t* shape_body;      /* [nshapes] canonical body index, -1 = static (world-fixed) */
+  const int32_t* shape_type;      /* 0 box (dims = full size), 1 sphere (dims[0] = r), 2 capsule (dims[0] = r, dims[1] = height) */
+  const int32_t* shape_orig_body; /* reference BodyNode index, reported with the contacts */
+  const double* shape_dims;       /* [nshapes*3] */
+  const double* shape_T;          /* [nshapes*12] shape frame -> canonical body frame (or world) */
+  const double* shape_mu;         /* friction coefficient of the owning body */
+  const double* shape_rest;       /* restitution coefficient of the owning body */
+  const int32_t* pair_a;          /* [npairs] collision pairs (shape indices) in the reference's enumeration order */
+  const int32_t* pair_b;
+  int32_t penetration_correction;
+  double contact_clipping_depth, fallback_cfm;
 } nb2_model_desc;
 
 int nb2_model_create(const nb2_model_desc* desc, nb2_model** out);
@@ -65,16 +78,17 @@ void nb2_model_destroy(nb2_model* m);
 int nb2_model_ndof(const nb2_model* m);
 int nb2_model_na(const nb2_model* m);
 
-/* fp32 words per world the forward pass streams out for the backward pass ([words][B] layout) */
+/* words per world the forward pass streams out for the backward pass ([words][B] layout); a word is 4 bytes
+ * with NB2_FP32 and 8 bytes with NB2_FP64 (the stream is kept in the arithmetic type of the kernels) */
 int nb2_saved_words_per_world(const nb2_model* m);
 
 /* One differentiable timestep for B independent worlds.  `saved` may be NULL (no backward will follow),
- * otherwise it must hold nb2_saved_words_per_world(m)*B floats.  `stream` is a cudaStream_t (NULL = default). */
+ * otherwise it must hold nb2_saved_words_per_world(m)*B words.  `stream` is a cudaStream_t (NULL = default). */
 int nb2_step_forward(const nb2_model* m, int B, const float* state, const float* action, float* next_state,
-                     float* saved, int precision, void* stream);
+                     void* saved, int precision, void* stream);
 
 /* Vector-Jacobian product of the same step: grad_next_state [B,2n] -> grad_state [B,2n], grad_action [B,na]. */
-int nb2_step_backward(const nb2_model* m, int B, const float* state, const float* action, const float* saved,
+int nb2_step_backward(const nb2_model* m, int B, const float* state, const float* action, const void* saved,
                       const float* grad_next_state, float* grad_state, float* grad_action, int precision,
                       void* stream);
 
@@ -83,6 +97,25 @@ int nb2_step_forward_host(nb2_model* m, int B, const float* state, const float* 
                           int keep_for_backward, int precision);
 int nb2_step_backward_host(nb2_model* m, int B, const float* grad_next_state, float* grad_state, float* grad_action,
                            int precision);
+
+/* ---- contact / boxed-LCP stage -------------------------------------------------------------------------------
+ * Replaces ConstraintSolver::solve + World::integrateVelocitiesFromImpulses (dart/constraint/ConstraintSolver.cpp:376-823,
+ * dart/constraint/BoxedLcpConstraintSolver.cpp:190-789, dart/simulation/World.cpp:283-304) for worlds whose model has shapes.
+ * Arithmetic is fp64.  Buffers are device memory, one row per world:
+ *   x_lcp   [B, NB2_MAX_ROWS] double   in: cached LCP solution (BoxedLcpConstraintSolver::mX), out: this step's solution
+ *   m_lcp   [B] int32                  in: its size (-1: none), out: LCP dimension of this step
+ *   labels  [B, NB2_MAX_ROWS] int32    out: ConstraintMapping per row (-2 clamping, -1 not clamping, >=0 upper-bound -> normal row)
+ *   status  [B] int32                  out: NB2_ST_* bits (which solver branch ran, unsupported geometry, overflow)
+ *   ncontacts [B] int32                out
+ *   cinfo   [B, NB2_MAX_CONTACTS, 10] float (optional, may be NULL): point(3) normal(3) depth bodyA bodyB type            */
+#define NB2_MAX_CONTACTS 16
+#define NB2_MAX_ROWS 48
+size_t nb2_contact_workspace_bytes(const nb2_model* m, int B);
+int nb2_model_has_contacts(const nb2_model* m);
+/* forward step WITH the contact stage: runs the fp64 ABA kernel (saved stream required) followed by the contact kernel. */
+int nb2_step_forward_contact(const nb2_model* m, int B, const float* state, const float* action, float* next_state,
+                             void* saved_fp64, void* workspace, double* x_lcp, int32_t* m_lcp, int32_t* labels,
+                             int32_t* status, int32_t* ncontacts, float* cinfo, void* stream);
 
 /* number of kernels this library has launched since load (bench.py reports it as gpu_launches) */
 long long nb2_launch_count(void);

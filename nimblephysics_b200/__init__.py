@@ -4,7 +4,7 @@ from . import world as _world
 from .world import (World, Skeleton, BodyNode, Joint, Isometry3, BoxShape, SphereShape, CapsuleShape)
 from .loader import loadWorld, load_skeleton
 from .modelspec import RawModel, CanonModel, flatten_world, compile_model
-from .timestep import timestep, TimestepLayer
+from .timestep import timestep, TimestepLayer, contact_cache, reset_contact_cache
 from .engine import DeviceModel, device_model_for
 
 __all__ = ["World", "Skeleton", "BodyNode", "Joint", "Isometry3", "BoxShape", "SphereShape", "CapsuleShape",

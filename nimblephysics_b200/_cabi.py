@@ -31,10 +31,18 @@ class Nb2ModelDesc(ctypes.Structure):
         ("force_hi", _F64P),
         ("action_map", _I32P),
         ("gravity", ctypes.c_double * 3), ("dt", ctypes.c_double),
+        ("nshapes", ctypes.c_int32), ("npairs", ctypes.c_int32),
+        ("shape_body", _I32P), ("shape_type", _I32P), ("shape_orig_body", _I32P),
+        ("shape_dims", _F64P), ("shape_T", _F64P), ("shape_mu", _F64P), ("shape_rest", _F64P),
+        ("pair_a", _I32P), ("pair_b", _I32P),
+        ("penetration_correction", ctypes.c_int32),
+        ("contact_clipping_depth", ctypes.c_double), ("fallback_cfm", ctypes.c_double),
     ]
 
+MAX_CONTACTS, MAX_ROWS = 16, 48  # include/nb2.h
 
-def make_desc(cm: CanonModel):
+
+def make_desc(cm: CanonModel, with_contacts: bool = True):
     """-> (Nb2ModelDesc, keepalive list).  The arrays must outlive the descriptor."""
     keep = []
 
@@ -61,7 +69,35 @@ def make_desc(cm: CanonModel):
     for k in range(3):
         d.gravity[k] = float(cm.gravity[k])
     d.dt = float(cm.dt)
+    # contact stage: shapes + the collision pairs in the reference's enumeration order (objects i < j in insertion
+    # order, DARTCollisionDetector.cpp:150-175) after the static part of BodyNodeCollisionFilter (CollisionFilter.cpp:105-152)
+    pa, pb = collision_pairs(cm) if with_contacts else ([], [])
+    ns = len(cm.shape_body) if (with_contacts and pa) else 0
+    d.nshapes, d.npairs = ns, len(pa) if ns else 0
+    d.shape_body, d.shape_type, d.shape_orig_body = i32(cm.shape_body[:ns]), i32(cm.shape_type[:ns]), i32(cm.shape_orig_body[:ns])
+    d.shape_dims, d.shape_T = f64(cm.shape_dims[:ns]), f64(cm.shape_T[:ns])
+    d.shape_mu, d.shape_rest = f64(cm.shape_friction[:ns]), f64(cm.shape_restitution[:ns])
+    d.pair_a, d.pair_b = i32(pa), i32(pb)
+    d.penetration_correction = int(cm.penetration_correction)
+    d.contact_clipping_depth = float(cm.contact_clipping_depth)
+    d.fallback_cfm = float(cm.fallback_cfm)
     return d, keep
+
+
+def collision_pairs(cm: CanonModel):
+    pa, pb = [], []
+    ns = len(cm.shape_body)
+    for i in range(ns - 1):
+        for j in range(i + 1, ns):
+            if cm.shape_orig_body[i] == cm.shape_orig_body[j]:
+                continue  # same BodyNode
+            if cm.shape_body[i] < 0 and cm.shape_body[j] < 0:
+                continue  # neither can move
+            if cm.shape_skel[i] == cm.shape_skel[j]:
+                continue  # self-collision checking is off by default in the reference
+            pa.append(i)
+            pb.append(j)
+    return pa, pb
 
 
 _lib: Optional[ctypes.CDLL] = None
@@ -90,6 +126,10 @@ def lib() -> ctypes.CDLL:
         vp = ctypes.c_void_p
         L.nb2_step_forward.argtypes = [vp, ctypes.c_int, vp, vp, vp, vp, ctypes.c_int, vp]
         L.nb2_step_backward.argtypes = [vp, ctypes.c_int, vp, vp, vp, vp, vp, vp, ctypes.c_int, vp]
+        L.nb2_model_has_contacts.argtypes = [vp]
+        L.nb2_contact_workspace_bytes.argtypes = [vp, ctypes.c_int]
+        L.nb2_contact_workspace_bytes.restype = ctypes.c_size_t
+        L.nb2_step_forward_contact.argtypes = [vp, ctypes.c_int, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
         L.nb2_step_forward_host.argtypes = [vp, ctypes.c_int, vp, vp, vp, ctypes.c_int, ctypes.c_int]
         L.nb2_step_backward_host.argtypes = [vp, ctypes.c_int, vp, vp, vp, ctypes.c_int]
         _lib = L

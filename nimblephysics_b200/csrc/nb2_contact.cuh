@@ -1,0 +1,758 @@
+// Contact / boxed-LCP stage of one world, run by ONE thread in fp64 after the ABA kernel has produced the
+// unconstrained step (v* = v + dt qdd) and streamed U, psi, joint transforms to the saved stream.
+//
+// Restates, per world (reference file:line):
+//   contact generation vs static colliders   dart/collision/dart/DARTCollide.cpp:764-1450 (dBoxBox), :1482-1810 (box/sphere),
+//                                            :4422-4645 (capsule end spheres on a box face; see oracle/contact.hpp for the MPR note)
+//   contact filtering                        dart/constraint/ConstraintSolver.cpp:576-601
+//   rows, b, bounds                          dart/constraint/ContactConstraint.cpp:66-230, 361-514, 687-695, 734-795
+//   A by impulse tests                       dart/constraint/BoxedLcpConstraintSolver.cpp:190-349 (impulse-ABA: BodyNode.cpp:2117-2138,
+//                                            2188-2215, GenericJoint.hpp:2482-2498, 2607-2613, 2713-2725) — here reusing the forward's U, psi
+//   solve chain                              BoxedLcpConstraintSolver.cpp:352-789; LCPUtils.cpp:12-140; PgsBoxedLcpSolver.cpp:79-278
+//   classification / standardisation         dart/neural/ConstrainedGroupGradientMatrices.cpp:482-872, 218-339
+//   impulses, velocity update                ContactConstraint.cpp:630-684, Skeleton.cpp:13571-13595
+// New: the minimum-norm least-squares solves (Eigen completeOrthogonalDecomposition in the reference) are done with a
+// rank-revealing pivoted Cholesky (symmetric case) / normal equations (sliding-friction case) instead of a QR/SVD.
+// Not yet restated on the device: LCPUtils::reduce (duplicate-column merge) — instances that would merge are flagged.
+#pragma once
+#include "nb2_dantzig.cuh"
+#include "nb2_dyn.cuh"
+
+#include "../../include/nb2.h"  // NB2_MAX_CONTACTS, NB2_MAX_ROWS
+
+#define NB2_MAX_SHAPES 24
+#define NB2_MAX_PAIRS 64
+
+// status bits (per world)
+#define NB2_ST_SHORTCIRCUIT 1
+#define NB2_ST_DANTZIG 2
+#define NB2_ST_DANTZIG_FAILED 4
+#define NB2_ST_PGS 8
+#define NB2_ST_FRICTION_DROPPED 16
+#define NB2_ST_NAN 32
+#define NB2_ST_NOT_STANDARDIZED 64
+#define NB2_ST_UNSUPPORTED_GEOMETRY 128
+#define NB2_ST_CONTACT_OVERFLOW 256
+#define NB2_ST_WOULD_MERGE 512
+
+// ConstraintMapping (dart/neural/ConstrainedGroupGradientMatrices.hpp:33-39)
+#define NB2_MAP_NOT_CLAMPING (-1)
+#define NB2_MAP_CLAMPING (-2)
+#define NB2_MAP_ILLEGAL (-3)
+
+struct Nb2ContactDev {
+  int nshapes, npairs, pen_correction, pad;
+  double clip_depth, fallback_cfm;
+  int16_t shape_body[NB2_MAX_SHAPES];       // canonical body index, -1 = static (world-fixed)
+  int16_t shape_type[NB2_MAX_SHAPES];       // 0 box, 1 sphere, 2 capsule
+  int16_t shape_orig_body[NB2_MAX_SHAPES];  // reference BodyNode index (reported with the contacts)
+  int16_t pair_a[NB2_MAX_PAIRS], pair_b[NB2_MAX_PAIRS];  // collision pairs in the reference's enumeration order
+  double shape_dims[NB2_MAX_SHAPES][3];
+  double shape_T[NB2_MAX_SHAPES][12];       // shape frame -> canonical body frame (or world)
+  double shape_mu[NB2_MAX_SHAPES], shape_rest[NB2_MAX_SHAPES];
+};
+
+namespace nb2 {
+
+typedef double CR;
+
+struct ContactWs {  // per-world fp64 workspace carved out of one contiguous block
+  CR *W, *V, *pI, *uI, *dqd, *vstar;
+  CR *cpoint, *cnormal, *cdepth, *cmu, *crest;
+  int *cbodyA, *cbodyB, *ctype, *cshapeA, *cshapeB;
+  CR *JA, *JB, *b, *lo, *hi, *x, *x0, *rest, *colnorm;
+  int *findex, *mapping, *clampIdx, *ubIdx;
+  CR *A, *Aw, *L, *Q, *Q2;
+  CR *v1, *v2, *v3, *v4, *v5, *v6, *v7, *v8;
+  int *i1, *i2;
+  unsigned char* st8;
+};
+NB2_HD size_t contact_ws_doubles(int nb, int ndof) {
+  const int MC = NB2_MAX_CONTACTS, MR = NB2_MAX_ROWS;
+  return (size_t)nb * 12 + nb * 6 + nb * 6 + 3 * ndof + MC * 10 + MC * 3 /*ints as 5 int arrays -> 2.5 doubles each*/ + 2 * MR * 6 + 7 * MR
+         + 2 * MR /*int arrays*/ + 5 * (size_t)MR * MR + 8 * MR + MR /*i1,i2*/ + 2 * MR / 8 + 8;
+}
+NB2_HD ContactWs carve_ws(CR* base, int nb, int ndof) {
+  const int MC = NB2_MAX_CONTACTS, MR = NB2_MAX_ROWS;
+  ContactWs w; CR* p = base;
+  w.W = p; p += nb * 12; w.V = p; p += nb * 6; w.pI = p; p += nb * 6; w.uI = p; p += ndof; w.dqd = p; p += ndof; w.vstar = p; p += ndof;
+  w.cpoint = p; p += MC * 3; w.cnormal = p; p += MC * 3; w.cdepth = p; p += MC; w.cmu = p; p += MC; w.crest = p; p += MC;
+  int* ip = (int*)p; w.cbodyA = ip; ip += MC; w.cbodyB = ip; ip += MC; w.ctype = ip; ip += MC; w.cshapeA = ip; ip += MC; w.cshapeB = ip; ip += MC;
+  p += MC * 3;  // 5*MC ints = 2.5*MC doubles <= 3*MC
+  w.JA = p; p += MR * 6; w.JB = p; p += MR * 6; w.b = p; p += MR; w.lo = p; p += MR; w.hi = p; p += MR; w.x = p; p += MR; w.x0 = p; p += MR;
+  w.rest = p; p += MR; w.colnorm = p; p += MR;
+  ip = (int*)p; w.findex = ip; ip += MR; w.mapping = ip; ip += MR; w.clampIdx = ip; ip += MR; w.ubIdx = ip; ip += MR; p += 2 * MR;
+  w.A = p; p += MR * MR; w.Aw = p; p += MR * MR; w.L = p; p += MR * MR; w.Q = p; p += MR * MR; w.Q2 = p; p += MR * MR;
+  w.v1 = p; p += MR; w.v2 = p; p += MR; w.v3 = p; p += MR; w.v4 = p; p += MR; w.v5 = p; p += MR; w.v6 = p; p += MR; w.v7 = p; p += MR; w.v8 = p; p += MR;
+  ip = (int*)p; w.i1 = ip; ip += MR; w.i2 = ip; ip += MR; p += MR;
+  w.st8 = (unsigned char*)p;
+  return w;
+}
+
+// ------------------------------------------------------------------ small helpers on raw arrays
+NB2_HD Xf<CR> xf_from12(const CR* t) {
+  Xf<CR> T; T.R_.m00 = t[0]; T.R_.m01 = t[1]; T.R_.m02 = t[2]; T.R_.m10 = t[3]; T.R_.m11 = t[4]; T.R_.m12 = t[5];
+  T.R_.m20 = t[6]; T.R_.m21 = t[7]; T.R_.m22 = t[8]; T.p = mk3<CR>(t[9], t[10], t[11]); return T;
+}
+NB2_HD void xf_to12(CR* t, const Xf<CR>& T) {
+  t[0] = T.R_.m00; t[1] = T.R_.m01; t[2] = T.R_.m02; t[3] = T.R_.m10; t[4] = T.R_.m11; t[5] = T.R_.m12;
+  t[6] = T.R_.m20; t[7] = T.R_.m21; t[8] = T.R_.m22; t[9] = T.p.x; t[10] = T.p.y; t[11] = T.p.z;
+}
+NB2_HD Xf<CR> xf_mul(const Xf<CR>& A, const Xf<CR>& B) { Xf<CR> C; C.R_ = mul(A.R_, B.R_); C.p = mul(A.R_, B.p) + A.p; return C; }
+NB2_HD V3<CR> xf_apply(const Xf<CR>& A, const V3<CR>& x) { return mul(A.R_, x) + A.p; }
+NB2_HD V3<CR> xf_apply_inv(const Xf<CR>& A, const V3<CR>& x) { return mulT(A.R_, x - A.p); }
+NB2_HD V3<CR> col3(const M3<CR>& R, int j) { return j == 0 ? mk3<CR>(R.m00, R.m10, R.m20) : (j == 1 ? mk3<CR>(R.m01, R.m11, R.m21) : mk3<CR>(R.m02, R.m12, R.m22)); }
+NB2_HD CR get3(const V3<CR>& v, int k) { return k == 0 ? v.x : (k == 1 ? v.y : v.z); }
+NB2_HD void set3(V3<CR>& v, int k, CR x) { if (k == 0) v.x = x; else if (k == 1) v.y = x; else v.z = x; }
+NB2_HD V6<CR> ldv6(const CR* p) { V6<CR> v; v.a = mk3<CR>(p[0], p[1], p[2]); v.l = mk3<CR>(p[3], p[4], p[5]); return v; }
+NB2_HD void stv6(CR* p, const V6<CR>& v) { p[0] = v.a.x; p[1] = v.a.y; p[2] = v.a.z; p[3] = v.l.x; p[4] = v.l.y; p[5] = v.l.z; }
+
+struct ContactOut {  // one emitted contact
+  V3<CR> point, normal; CR depth; int type;
+};
+
+// ---- box (object 1) vs sphere (object 2) and sphere (1) vs box (2)
+NB2_HD int collide_box_sphere(const V3<CR>& size0, const Xf<CR>& T0, CR r1, const Xf<CR>& T1, CR clip, int halfspace, bool sphere_first, ContactOut* out) {
+  // sphere_first=false: DARTCollide.cpp:1482-1653 (normal = contact point - centre); true: :1655-1810 (normal = centre - contact point, no halfspace clip)
+  V3<CR> half = size0 * CR(0.5);
+  bool inside = true;
+  const V3<CR> c0 = T1.p;
+  V3<CR> p = xf_apply_inv(T0, c0);
+  for (int k = 0; k < 3; k++) {
+    CR pk = get3(p, k), hk = get3(half, k);
+    if (pk < -hk) { set3(p, k, -hk); inside = false; }
+    if (pk > hk) { set3(p, k, hk); inside = false; }
+  }
+  CR mn = half.x - nb2_abs(p.x); int idx = 0;
+  CR t = half.y - nb2_abs(p.y); if (t < mn) { mn = t; idx = 1; }
+  t = half.z - nb2_abs(p.z); if (t < mn) { mn = t; idx = 2; }
+  V3<CR> nloc = zero3<CR>();
+  const CR sgn = (get3(p, idx) > 0.0) ? 1.0 : -1.0;
+  set3(nloc, idx, sphere_first ? sgn : -sgn);
+  const V3<CR> nface = mul(T0.R_, nloc);
+  if (inside) {
+    CR pen = mn + r1;
+    if (pen > clip) return 0;
+    out->type = sphere_first ? 1 /*VERTEX_FACE*/ : 2 /*FACE_VERTEX*/; out->point = c0; out->normal = nface; out->depth = pen; return 1;
+  }
+  const V3<CR> cp = xf_apply(T0, p);
+  V3<CR> n = sphere_first ? (c0 - cp) : (cp - c0);
+  const CR mag = nb2_sqrt(dot(n, n));
+  const CR pen = r1 - mag;
+  if (pen > clip) return 0;
+  if (!sphere_first) {
+    const CR lz = xf_apply_inv(T1, cp).z;
+    if (halfspace == 2 /*BOTTOM*/ && lz >= 0) return 0;
+    if (halfspace == 1 /*TOP*/ && lz <= 0) return 0;
+  }
+  if (pen < 0.0) return 0;
+  out->type = sphere_first ? 4 : 5; out->point = cp; out->depth = pen;
+  out->normal = (mag > 1e-6) ? n * (CR(1) / mag) : nface;
+  return 1;
+}
+
+NB2_HD int intersect_rect_quad(const CR h[2], CR p[8], CR ret[16]) {  // DARTCollide.cpp:513-580
+  int nq = 4, nr = 0;
+  CR buffer[16];
+  CR* q = p; CR* r = ret;
+  for (int dir = 0; dir <= 1; dir++) {
+    for (int sign = -1; sign <= 1; sign += 2) {
+      CR* pq = q; CR* pr = r; nr = 0;
+      for (int i = nq; i > 0; i--) {
+        if (sign * pq[dir] < h[dir]) { pr[0] = pq[0]; pr[1] = pq[1]; pr += 2; nr++; if (nr & 8) { q = r; goto done; } }
+        CR* nextq = (i > 1) ? pq + 2 : q;
+        if ((sign * pq[dir] < h[dir]) ^ (sign * nextq[dir] < h[dir])) {
+          pr[1 - dir] = pq[1 - dir] + (nextq[1 - dir] - pq[1 - dir]) / (nextq[dir] - pq[dir]) * (sign * h[dir] - pq[dir]);
+          pr[dir] = sign * h[dir];
+          pr += 2; nr++;
+          if (nr & 8) { q = r; goto done; }
+        }
+        pq += 2;
+      }
+      q = r; r = (q == ret) ? buffer : ret; nq = nr;
+    }
+  }
+done:
+  if (q != ret) for (int i = 0; i < nr * 2; i++) ret[i] = q[i];
+  return nr;
+}
+
+// dBoxBox (DARTCollide.cpp:764-1450); returns the number of contacts written to out (<= 8)
+NB2_HD int collide_box_box(const V3<CR>& size0, const Xf<CR>& T0, const V3<CR>& size1, const Xf<CR>& T1, CR clip, ContactOut* out) {
+  const CR fudge = 1.05;
+  const M3<CR>&R1 = T0.R_, &R2 = T1.R_;
+  const V3<CR> p1 = T0.p, p2 = T1.p;
+  const CR A[3] = {size0.x * 0.5, size0.y * 0.5, size0.z * 0.5}, Bh[3] = {size1.x * 0.5, size1.y * 0.5, size1.z * 0.5};
+  const V3<CR> p = p2 - p1;
+  const V3<CR> ppv = mulT(R1, p);
+  const CR pp[3] = {ppv.x, ppv.y, ppv.z};
+  CR Rm[3][3], Q[3][3];
+  for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) { Rm[i][j] = dot(col3(R1, i), col3(R2, j)); Q[i][j] = nb2_abs(Rm[i][j]); }
+  CR s = -1e12, s2;
+  int invert_normal = 0, code = 0, nbox = 0, ncol = -1;
+  V3<CR> normalC = zero3<CR>();
+#define NB2_TST(expr1, expr2, box, colj, cc) { const CR e1 = (expr1); s2 = nb2_abs(e1) - (expr2); if (s2 > s) { s = s2; nbox = box; ncol = colj; invert_normal = (e1 < 0); code = (cc); } }
+  NB2_TST(pp[0], (A[0] + Bh[0] * Q[0][0] + Bh[1] * Q[0][1] + Bh[2] * Q[0][2]), 1, 0, 1)
+  NB2_TST(pp[1], (A[1] + Bh[0] * Q[1][0] + Bh[1] * Q[1][1] + Bh[2] * Q[1][2]), 1, 1, 2)
+  NB2_TST(pp[2], (A[2] + Bh[0] * Q[2][0] + Bh[1] * Q[2][1] + Bh[2] * Q[2][2]), 1, 2, 3)
+  NB2_TST(dot(col3(R2, 0), p), (A[0] * Q[0][0] + A[1] * Q[1][0] + A[2] * Q[2][0] + Bh[0]), 2, 0, 4)
+  NB2_TST(dot(col3(R2, 1), p), (A[0] * Q[0][1] + A[1] * Q[1][1] + A[2] * Q[2][1] + Bh[1]), 2, 1, 5)
+  NB2_TST(dot(col3(R2, 2), p), (A[0] * Q[0][2] + A[1] * Q[1][2] + A[2] * Q[2][2] + Bh[2]), 2, 2, 6)
+#undef NB2_TST
+#define NB2_TST2(expr1, expr2, n1, n2, n3, cc) { const CR e1 = (expr1); s2 = nb2_abs(e1) - (expr2); const CR N1 = (n1), N2 = (n2), N3 = (n3); const CR l = nb2_sqrt(N1 * N1 + N2 * N2 + N3 * N3); \
+    if (l > 0) { s2 /= l; if (s2 * fudge > s) { s = s2; ncol = -1; normalC = mk3<CR>(N1 / l, N2 / l, N3 / l); invert_normal = (e1 < 0); code = (cc); } } }
+  NB2_TST2(pp[2] * Rm[1][0] - pp[1] * Rm[2][0], (A[1] * Q[2][0] + A[2] * Q[1][0] + Bh[1] * Q[0][2] + Bh[2] * Q[0][1]), 0.0, -Rm[2][0], Rm[1][0], 7)
+  NB2_TST2(pp[2] * Rm[1][1] - pp[1] * Rm[2][1], (A[1] * Q[2][1] + A[2] * Q[1][1] + Bh[0] * Q[0][2] + Bh[2] * Q[0][0]), 0.0, -Rm[2][1], Rm[1][1], 8)
+  NB2_TST2(pp[2] * Rm[1][2] - pp[1] * Rm[2][2], (A[1] * Q[2][2] + A[2] * Q[1][2] + Bh[0] * Q[0][1] + Bh[1] * Q[0][0]), 0.0, -Rm[2][2], Rm[1][2], 9)
+  NB2_TST2(pp[0] * Rm[2][0] - pp[2] * Rm[0][0], (A[0] * Q[2][0] + A[2] * Q[0][0] + Bh[1] * Q[1][2] + Bh[2] * Q[1][1]), Rm[2][0], 0.0, -Rm[0][0], 10)
+  NB2_TST2(pp[0] * Rm[2][1] - pp[2] * Rm[0][1], (A[0] * Q[2][1] + A[2] * Q[0][1] + Bh[0] * Q[1][2] + Bh[2] * Q[1][0]), Rm[2][1], 0.0, -Rm[0][1], 11)
+  NB2_TST2(pp[0] * Rm[2][2] - pp[2] * Rm[0][2], (A[0] * Q[2][2] + A[2] * Q[0][2] + Bh[0] * Q[1][1] + Bh[1] * Q[1][0]), Rm[2][2], 0.0, -Rm[0][2], 12)
+  NB2_TST2(pp[1] * Rm[0][0] - pp[0] * Rm[1][0], (A[0] * Q[1][0] + A[1] * Q[0][0] + Bh[1] * Q[2][2] + Bh[2] * Q[2][1]), -Rm[1][0], Rm[0][0], 0.0, 13)
+  NB2_TST2(pp[1] * Rm[0][1] - pp[0] * Rm[1][1], (A[0] * Q[1][1] + A[1] * Q[0][1] + Bh[0] * Q[2][2] + Bh[2] * Q[2][0]), -Rm[1][1], Rm[0][1], 0.0, 14)
+  NB2_TST2(pp[1] * Rm[0][2] - pp[0] * Rm[1][2], (A[0] * Q[1][2] + A[1] * Q[0][2] + Bh[0] * Q[2][1] + Bh[1] * Q[2][0]), -Rm[1][2], Rm[0][2], 0.0, 15)
+#undef NB2_TST2
+  if (!code) return 0;
+  if (s > 0.0) return 0;
+  V3<CR> normal;
+  if (ncol >= 0) normal = col3(nbox == 1 ? R1 : R2, ncol);
+  else { normal = mul(R1, normalC); normal = normal * (CR(1) / nb2_sqrt(dot(normal, normal))); }
+  if (invert_normal) normal = -normal;
+  if (code > 6) {
+    V3<CR> pa = p1, pb = p2;
+    for (int j = 0; j < 3; j++) { const CR sg = (dot(normal, col3(R1, j)) > -1e-10) ? 1.0 : -1.0; pa = pa + col3(R1, j) * (A[j] * sg); }
+    for (int j = 0; j < 3; j++) { const CR sg = (dot(normal, col3(R2, j)) > -1e-3) ? -1.0 : 1.0; pb = pb + col3(R2, j) * (Bh[j] * sg); }
+    const V3<CR> ua = col3(R1, (code - 7) / 3), ub = col3(R2, (code - 7) % 3);
+    const V3<CR> dp = pb - pa;
+    const CR uaub = dot(ua, ub), q1 = dot(ua, dp), q2 = -dot(ub, dp);
+    CR d = 1.0 - uaub * uaub, alpha = 0.0, beta = 0.0;
+    if (d > 0.0) { d = 1.0 / d; alpha = (q1 + uaub * q2) * d; beta = (uaub * q1 + q2) * d; }
+    pa = pa + ua * alpha; pb = pb + ub * beta;
+    const CR pen = -s;
+    if (pen > clip) return 0;
+    out[0].point = (pa + pb) * CR(0.5); out[0].normal = -normal; out[0].depth = pen; out[0].type = 3;
+    return 1;
+  }
+  const M3<CR>*Ra, *Rb; V3<CR> pa, pb; const CR *Sa, *Sb; bool flip;
+  if (code <= 3) { Ra = &R1; Rb = &R2; pa = p1; pb = p2; Sa = A; Sb = Bh; flip = false; }
+  else { Ra = &R2; Rb = &R1; pa = p2; pb = p1; Sa = Bh; Sb = A; flip = true; }
+  const V3<CR> normal2 = (code <= 3) ? normal : -normal;
+  const V3<CR> nr = mulT(*Rb, normal2);
+  const CR anr[3] = {nb2_abs(nr.x), nb2_abs(nr.y), nb2_abs(nr.z)};
+  int lanr, a1, a2;
+  if (anr[1] > anr[0]) { if (anr[1] > anr[2]) { a1 = 0; lanr = 1; a2 = 2; } else { a1 = 0; a2 = 1; lanr = 2; } }
+  else { if (anr[0] > anr[2]) { lanr = 0; a1 = 1; a2 = 2; } else { a1 = 0; a2 = 1; lanr = 2; } }
+  const V3<CR> center = (get3(nr, lanr) < 0) ? (pb - pa + col3(*Rb, lanr) * Sb[lanr]) : (pb - pa - col3(*Rb, lanr) * Sb[lanr]);
+  const int codeN = (code <= 3) ? code - 1 : code - 4;
+  int code1, code2;
+  if (codeN == 0) { code1 = 1; code2 = 2; } else if (codeN == 1) { code1 = 0; code2 = 2; } else { code1 = 0; code2 = 1; }
+  CR quad[8];
+  const CR c1 = dot(center, col3(*Ra, code1)), c2 = dot(center, col3(*Ra, code2));
+  CR m11 = dot(col3(*Ra, code1), col3(*Rb, a1)), m12 = dot(col3(*Ra, code1), col3(*Rb, a2));
+  CR m21 = dot(col3(*Ra, code2), col3(*Rb, a1)), m22 = dot(col3(*Ra, code2), col3(*Rb, a2));
+  {
+    const CR k1 = m11 * Sb[a1], k2 = m21 * Sb[a1], k3 = m12 * Sb[a2], k4 = m22 * Sb[a2];
+    quad[0] = c1 - k1 - k3; quad[1] = c2 - k2 - k4; quad[2] = c1 - k1 + k3; quad[3] = c2 - k2 + k4;
+    quad[4] = c1 + k1 + k3; quad[5] = c2 + k2 + k4; quad[6] = c1 + k1 - k3; quad[7] = c2 + k2 - k4;
+  }
+  const CR rect[2] = {Sa[code1], Sa[code2]};
+  CR ret[16];
+  const int n = intersect_rect_quad(rect, quad, ret);
+  if (n < 1) return 0;
+  const CR det1 = 1.0 / (m11 * m22 - m12 * m21);
+  m11 *= det1; m12 *= det1; m21 *= det1; m22 *= det1;
+  int cnum = 0;
+  for (int j = 0; j < n; j++) {
+    const CR k1 = m22 * (ret[j * 2] - c1) - m12 * (ret[j * 2 + 1] - c2);
+    const CR k2 = -m21 * (ret[j * 2] - c1) + m11 * (ret[j * 2 + 1] - c2);
+    const V3<CR> pt = center + col3(*Rb, a1) * k1 + col3(*Rb, a2) * k2;
+    const CR dep = Sa[codeN] - dot(normal2, pt);
+    if (dep >= 0) {
+      ContactOut& c = out[cnum];
+      c.point = pt + pa; c.normal = -normal; c.depth = dep;
+      const bool onX = nb2_abs(ret[j * 2]) == rect[0], onY = nb2_abs(ret[j * 2 + 1]) == rect[1];
+      if (onX && onY) {
+        if (flip) { c.type = 2; c.point = c.point + c.normal * c.depth; } else { c.type = 1; c.point = c.point - c.normal * c.depth; }
+      } else if (!onX && !onY) c.type = flip ? 1 : 2;
+      else c.type = 3;
+      cnum++;
+    }
+  }
+  return cnum;
+}
+
+// ------------------------------------------------------------------ joint transform of body i from the saved stream
+NB2_HD Xf<CR> saved_xf(const Nb2ModelDev<CR>& M, int i, const float* st, const CR* sv, size_t B) {
+  const int jt = M.jtype[i];
+  const CR* s = sv + (size_t)(i * 21) * B;
+  if (jt == NB2_JT_REV) return xf_rev(M, i, s[19 * B], s[20 * B]);
+  if (jt == NB2_JT_PRIS) return xf_pris(M, i, (CR)st[M.dof_off[i]]);
+  CR t12[12];
+  for (int k = 0; k < 12; k++) t12[k] = sv[(size_t)(M.nb * 21 + M.free_idx[i] * 33 + 21 + k) * B];
+  return xf_from12(t12);
+}
+
+// impulse-ABA with the forward's U, psi: body impulses in ws.pI (input, consumed) -> ws.dqd (joint velocity changes)
+// and ws.V (spatial velocity changes of every body)
+NB2_HD void impulse_response(const Nb2ModelDev<CR>& M, const float* st, const CR* sv, size_t B, const ContactWs& ws) {
+  const int nb = M.nb;
+  // leaf -> root: pI_i = -imp_i + sum_c X*_c (pI_c + U_c psi_c uI_c) ; uI_i = -S^T pI_i    (ws.pI holds -imp on entry)
+  for (int i = nb - 1; i >= 0; i--) {
+    const int jt = M.jtype[i], p = M.parent[i], o = M.dof_off[i];
+    const CR* s = sv + (size_t)(i * 21) * B;
+    const V6<CR> pI = ldv6(ws.pI + 6 * i);
+    V6<CR> beta;
+    if (jt != NB2_JT_FREE) {
+      const CR u = -S_dot(jt, pI);
+      ws.uI[o] = u;
+      if (p >= 0) beta = pI + sv_ld6<CR>(s, B, 12) * (s[18 * B] * u);
+    } else {
+      const V6<CR> u = zero6<CR>() - pI;
+      stv6(ws.uI + o, u);
+      if (p >= 0) beta = zero6<CR>();  // pI + I (I^-1 u) = 0: a 6-dof joint absorbs the whole impulse
+    }
+    if (p >= 0) {
+      const V6<CR> pc = dAdInvT(saved_xf(M, i, st, sv, B), beta);
+      CR* pp = ws.pI + 6 * p;
+      pp[0] += pc.a.x; pp[1] += pc.a.y; pp[2] += pc.a.z; pp[3] += pc.l.x; pp[4] += pc.l.y; pp[5] += pc.l.z;
+    }
+  }
+  // root -> leaf
+  for (int i = 0; i < nb; i++) {
+    const int jt = M.jtype[i], p = M.parent[i], o = M.dof_off[i];
+    const CR* s = sv + (size_t)(i * 21) * B;
+    const Xf<CR> T = saved_xf(M, i, st, sv, B);
+    V6<CR> dV = (p >= 0) ? AdInvT(T, ldv6(ws.V + 6 * p)) : zero6<CR>();
+    if (jt != NB2_JT_FREE) {
+      const CR d = s[18 * B] * (ws.uI[o] - dot(sv_ld6<CR>(s, B, 12), dV));
+      ws.dqd[o] = d;
+      if (jt == NB2_JT_REV) dV.a.z += d; else dV.l.z += d;
+    } else {
+      CR i21[21];
+      for (int k = 0; k < 21; k++) i21[k] = sv[(size_t)(M.nb * 21 + M.free_idx[i] * 33 + k) * B];
+      const V6<CR> d = mul(ldSI<CR, 1>(i21), ldv6(ws.uI + o)) - dV;
+      stv6(ws.dqd + o, d);
+      dV = dV + d;
+    }
+    stv6(ws.V + 6 * i, dV);
+  }
+}
+
+// ------------------------------------------------------------------ dense helpers (m x m, stride m)
+NB2_HD bool lcp_valid(int m, const CR* A, const CR* x, const CR* b, const CR* hi, const CR* lo, const int* fi, bool ignoreFriction) {
+  for (int i = 0; i < m; i++) {
+    CR v = -b[i];
+    for (int j = 0; j < m; j++) v += A[i * m + j] * x[j];
+    CR up = hi[i], low = lo[i];
+    if (fi[i] != -1) { if (ignoreFriction) { if (x[i] != 0) return false; continue; } up *= x[fi[i]]; low *= x[fi[i]]; }
+    const CR tol = 1e-5;
+    if (nb2_abs(low) < tol && nb2_abs(up) < tol && nb2_abs(x[i]) < tol) {}
+    else if (nb2_abs(x[i] - low) < tol) { if (v < -tol) return false; }
+    else if (nb2_abs(x[i] - up) < tol) { if (v > tol) return false; }
+    else if (x[i] > low && x[i] < up) { if (nb2_abs(v) > tol) return false; }
+    else return false;
+  }
+  return true;
+}
+
+// minimum-norm least squares x = Q^+ rhs for an n x n matrix.  symmetric PSD Q: rank-revealing pivoted Cholesky
+// Q = P L L^T P^T (L: n x r) and Q^+ = L (L^T L)^-2 L^T ; general Q: x = (Q^T Q)^+ Q^T rhs through the same routine.
+// work: G (n*n, destroyed copy), Lf (n*n), t1..t3 (n), perm (n)
+NB2_HD void pinv_psd(int n, const CR* Qin, const CR* rhs, CR* x, CR* G, CR* Lf, CR* t1, CR* t2, int* perm) {
+  for (int i = 0; i < n * n; i++) G[i] = Qin[i];
+  for (int i = 0; i < n; i++) perm[i] = i;
+  CR dmax0 = 0;
+  for (int i = 0; i < n; i++) dmax0 = G[i * n + i] > dmax0 ? G[i * n + i] : dmax0;
+  const CR tol = dmax0 * 1e-12;
+  int r = 0;
+  // pivoted Cholesky with lazily updated diagonal; Lf[row * n + k]
+  for (int k = 0; k < n; k++) {
+    int piv = -1; CR best = tol;
+    for (int i = k; i < n; i++) { const int pi = perm[i]; CR d = G[pi * n + pi]; for (int j = 0; j < k; j++) d -= Lf[pi * n + j] * Lf[pi * n + j]; if (d > best) { best = d; piv = i; } }
+    if (piv < 0) break;
+    { const int t = perm[k]; perm[k] = perm[piv]; perm[piv] = t; }
+    const int pk = perm[k];
+    const CR lkk = nb2_sqrt(best);
+    Lf[pk * n + k] = lkk;
+    for (int i = k + 1; i < n; i++) {
+      const int pi = perm[i];
+      CR s = G[pi * n + pk];
+      for (int j = 0; j < k; j++) s -= Lf[pi * n + j] * Lf[pk * n + j];
+      Lf[pi * n + k] = s / lkk;
+    }
+    r++;
+  }
+  for (int i = 0; i < n; i++) x[i] = 0;
+  if (r == 0) return;
+  // rows of L for indices not yet pivoted at step k are valid for columns < r; rows of pivoted indices have zeros above: fill
+  for (int k = 0; k < r; k++) for (int j = k + 1; j < r; j++) Lf[perm[k] * n + j] = 0;
+  // M = L^T L (r x r) in G ; y = L^T rhs
+  for (int a = 0; a < r; a++) {
+    CR ya = 0;
+    for (int i = 0; i < n; i++) ya += Lf[i * n + a] * rhs[i];
+    t1[a] = ya;
+    for (int c = a; c < r; c++) { CR s = 0; for (int i = 0; i < n; i++) s += Lf[i * n + a] * Lf[i * n + c]; G[a * n + c] = s; G[c * n + a] = s; }
+  }
+  // z = M^-2 y  via Cholesky of M (SPD r x r), two solves
+  for (int j = 0; j < r; j++) {
+    CR d = G[j * n + j];
+    for (int k = 0; k < j; k++) d -= G[j * n + k] * G[j * n + k];
+    d = nb2_sqrt(d); G[j * n + j] = d;
+    for (int i = j + 1; i < r; i++) { CR s = G[i * n + j]; for (int k = 0; k < j; k++) s -= G[i * n + k] * G[j * n + k]; G[i * n + j] = s / d; }
+  }
+  for (int rep = 0; rep < 2; rep++) {
+    for (int i = 0; i < r; i++) { CR s = t1[i]; for (int k = 0; k < i; k++) s -= G[i * n + k] * t2[k]; t2[i] = s / G[i * n + i]; }
+    for (int i = r - 1; i >= 0; i--) { CR s = t2[i]; for (int k = i + 1; k < r; k++) s -= G[k * n + i] * t1[k]; t1[i] = s / G[i * n + i]; }
+  }
+  for (int i = 0; i < n; i++) { CR s = 0; for (int a = 0; a < r; a++) s += Lf[i * n + a] * t1[a]; x[i] = s; }
+}
+
+// classification (constructMatrices) + standardisation; x is updated in place when the standardised solution is valid.
+// returns true when the results are standardised.
+NB2_HD bool classify_once(int m, const CR* A, CR* x, const CR* b, const CR* lo, const CR* hi, const int* fi, const CR* colnorm,
+                          bool ignoreFriction, const ContactWs& ws, bool* again) {
+  *again = false;
+  int* mapping = ws.mapping; int* clampIdx = ws.clampIdx; int* ubIdx = ws.ubIdx;
+  int nCl = 0, nUb = 0;
+  for (int j = 0; j < m; j++) { mapping[j] = fi[j]; clampIdx[j] = -1; ubIdx[j] = -1; }
+  for (int j = 0; j < m; j++) {
+    if (colnorm[j] < 1e-9) { mapping[j] = NB2_MAP_NOT_CLAMPING; continue; }
+    CR up = hi[j], low = lo[j];
+    const int fp = fi[j];
+    if (fp != -1) { up *= x[fp]; low *= x[fp]; }
+    if (nb2_abs(x[j]) < 1e-6) {
+      if (fp != -1) {
+        if (nb2_abs(x[fp]) < 1e-6) mapping[j] = NB2_MAP_NOT_CLAMPING;
+        else if (ignoreFriction) mapping[j] = NB2_MAP_NOT_CLAMPING;
+        else { mapping[j] = NB2_MAP_CLAMPING; clampIdx[j] = nCl++; }
+      } else mapping[j] = NB2_MAP_NOT_CLAMPING;
+      continue;
+    }
+    const CR tie = 1e-5;
+    if ((x[j] > low + tie && x[j] < up - tie) || (low - x[j] > 1e-2 || x[j] - up > 1e-2)) { mapping[j] = NB2_MAP_CLAMPING; clampIdx[j] = nCl++; }
+    else if (fp != -1 && nb2_abs(x[fp]) > 1e-9 && colnorm[fp] > 1e-9 && ((fp > j) || mapping[fp] == NB2_MAP_CLAMPING)) { mapping[j] = fp; ubIdx[j] = nUb++; }
+    else mapping[j] = NB2_MAP_NOT_CLAMPING;
+  }
+  // ---- opportunisticallyStandardizeResults
+  if (nCl == 0) {
+    for (int i = 0; i < m; i++) ws.v1[i] = 0;
+    if (lcp_valid(m, A, ws.v1, b, hi, lo, fi, ignoreFriction)) { for (int i = 0; i < m; i++) x[i] = 0; return true; }
+    return false;
+  }
+  int* cl = ws.i1; int* ub = ws.i2;
+  for (int j = 0; j < m; j++) { if (clampIdx[j] >= 0) cl[clampIdx[j]] = j; if (ubIdx[j] >= 0) ub[ubIdx[j]] = j; }
+  // E(u, clampIdx[fp]) = hi or lo of the row; Q = A[cl,cl] + A[cl,ub] E
+  CR* Q = ws.Q; CR* bc = ws.v2; CR* orig = ws.v3; CR* fc = ws.v4;
+  for (int r = 0; r < nCl; r++) {
+    bc[r] = b[cl[r]]; orig[r] = x[cl[r]];
+    for (int c = 0; c < nCl; c++) Q[r * nCl + c] = A[cl[r] * m + cl[c]];
+  }
+  for (int u = 0; u < nUb; u++) {
+    const int j = ub[u], fp = mapping[j];
+    const CR up = x[fp] * hi[j], low = x[fp] * lo[j];
+    const CR e = (nb2_abs(x[j] - up) < nb2_abs(x[j] - low)) ? hi[j] : lo[j];
+    const int c = clampIdx[fp];
+    for (int r = 0; r < nCl; r++) Q[r * nCl + c] += A[cl[r] * m + j] * e;
+  }
+  if (nUb == 0) pinv_psd(nCl, Q, bc, fc, ws.Aw, ws.L, ws.v5, ws.v6, ws.i2);
+  else {
+    // general Q: x = (Q^T Q)^+ Q^T b
+    CR* QtQ = ws.Q2;
+    CR* Qtb = ws.v7;
+    for (int a = 0; a < nCl; a++) {
+      CR s = 0; for (int r = 0; r < nCl; r++) s += Q[r * nCl + a] * bc[r];
+      Qtb[a] = s;
+      for (int c = 0; c < nCl; c++) { CR t = 0; for (int r = 0; r < nCl; r++) t += Q[r * nCl + a] * Q[r * nCl + c]; QtQ[a * nCl + c] = t; }
+    }
+    pinv_psd(nCl, QtQ, Qtb, fc, ws.Aw, ws.L, ws.v5, ws.v6, ws.i2);
+    // ws.i2 (ub list) was clobbered by the permutation: rebuild
+    for (int j = 0; j < m; j++) if (ubIdx[j] >= 0) ub[ubIdx[j]] = j;
+  }
+  bool anyNewlyNotClamping = false;
+  CR* nx = ws.v8;
+  for (int i = 0; i < m; i++) {
+    nx[i] = 0;
+    if (clampIdx[i] != -1) {
+      nx[i] = fc[clampIdx[i]];
+      if (nb2_abs(fc[clampIdx[i]]) < 1e-6 && nb2_abs(x[i]) > 1e-6 && fi[i] == -1) anyNewlyNotClamping = true;
+    }
+    if (ubIdx[i] != -1) {
+      const int fp = fi[i];
+      const CR origMult = orig[clampIdx[fp]] / x[i];
+      const CR clean = (nb2_abs(origMult - hi[i]) < nb2_abs(origMult - lo[i])) ? hi[i] : lo[i];
+      nx[i] = fc[clampIdx[fp]] * clean;
+    }
+  }
+  if (lcp_valid(m, A, nx, b, hi, lo, fi, ignoreFriction)) {
+    for (int i = 0; i < m; i++) x[i] = nx[i];
+    *again = anyNewlyNotClamping;  // a previously clamping normal row dropped to ~0: re-classify (:283-331)
+    return true;
+  }
+  return false;
+}
+NB2_HD bool classify_and_standardize(int m, const CR* A, CR* x, const CR* b, const CR* lo, const CR* hi, const int* fi, const CR* colnorm,
+                                     bool ignoreFriction, const ContactWs& ws) {
+  bool ok = false, again = false;
+  for (int it = 0; it < 6; it++) {
+    ok = classify_once(m, A, x, b, lo, hi, fi, colnorm, ignoreFriction, ws, &again);
+    if (!ok || !again) break;
+  }
+  return ok;
+}
+
+// PgsBoxedLcpSolver::solve with Option(30, 1e-6, 1e-3, 1e-9, false); A (m x m) and b are clobbered
+NB2_HD bool pgs_solve(int m, CR* A, CR* x, CR* b, const CR* lo, const CR* hi, const int* fi, unsigned char* skip) {
+  const CR dxTol = 1e-6, relTol = 1e-3, epsDiv = 1e-9;
+  bool term = true;
+  for (int i = 0; i < m; i++) {
+    skip[i] = 0;
+    if (A[i * m + i] < epsDiv) { x[i] = 0.0; skip[i] = 1; continue; }
+    const CR old_x = x[i];
+    CR nx = b[i];
+    for (int j = 0; j < i; j++) nx -= A[i * m + j] * x[j];
+    for (int j = i + 1; j < m; j++) nx -= A[i * m + j] * x[j];
+    nx /= A[i * m + i];
+    CR hi_t = hi[i], lo_t = lo[i];
+    if (fi[i] >= 0) { hi_t = hi[i] * x[fi[i]]; lo_t = -hi_t; }
+    x[i] = nx > hi_t ? hi_t : (nx < lo_t ? lo_t : nx);
+    if (term && nb2_abs(x[i] - old_x) > dxTol) term = false;
+  }
+  if (term) return true;
+  for (int i = 0; i < m; i++) if (!skip[i]) { const CR dm = 1.0 / A[i * m + i]; b[i] *= dm; for (int j = 0; j < m; j++) A[i * m + j] *= dm; }
+  for (int iter = 1; iter < 30; iter++) {
+    term = true;
+    for (int i = 0; i < m; i++) {
+      if (skip[i]) continue;
+      CR nx = b[i];
+      const CR old_x = x[i];
+      for (int j = 0; j < i; j++) nx -= A[i * m + j] * x[j];
+      for (int j = i + 1; j < m; j++) nx -= A[i * m + j] * x[j];
+      CR hi_t = hi[i], lo_t = lo[i];
+      if (fi[i] >= 0) { hi_t = hi[i] * x[fi[i]]; lo_t = -hi_t; }
+      x[i] = nx > hi_t ? hi_t : (nx < lo_t ? lo_t : nx);
+      if (term && nb2_abs(x[i]) > epsDiv) { if (nb2_abs((x[i] - old_x) / x[i]) > relTol) term = false; }
+    }
+    if (term) break;
+  }
+  return term;
+}
+
+// =====================================================================================================
+// the contact stage of one world.  `out` holds [q+ ; v*] on entry (written by the ABA kernel) and [q+ ; v+] on exit.
+// x_io: cached LCP solution (NB2_MAX_ROWS doubles), m_io: its size (-1 none) -> new solution / size.
+// =====================================================================================================
+NB2_HD void world_contact(const Nb2ModelDev<CR>& M, const Nb2ContactDev& C, const float* st, float* out, const CR* sv, size_t B,
+                          CR* wsbase, CR* x_io, int* m_io, int* labels_out, int* status_out, int* nc_out, float* cinfo_out) {
+  const int nb = M.nb, n = M.ndof;
+  const ContactWs ws = carve_ws(wsbase, nb, n);
+  const int kQdd = nb * 21 + M.nfree * 33;
+  const CR dt = M.dt;
+  int status = 0;
+  // ---- world transforms and body velocities at v* = v + dt qdd
+  for (int i = 0; i < nb; i++) {
+    const int jt = M.jtype[i], p = M.parent[i], o = M.dof_off[i];
+    const Xf<CR> T = saved_xf(M, i, st, sv, B);
+    const Xf<CR> W = (p >= 0) ? xf_mul(xf_from12(ws.W + 12 * p), T) : T;
+    xf_to12(ws.W + 12 * i, W);
+    V6<CR> V = (p >= 0) ? AdInvT(T, ldv6(ws.V + 6 * p)) : zero6<CR>();
+    if (jt != NB2_JT_FREE) {
+      const CR vs = (CR)st[n + o] + dt * sv[(size_t)(kQdd + o) * B];
+      ws.uI[o] = vs;  // v* kept in uI until the impulse sweeps start
+      if (jt == NB2_JT_REV) V.a.z += vs; else V.l.z += vs;
+    } else {
+      V6<CR> vs;
+      vs.a = mk3<CR>((CR)st[n + o] + dt * sv[(size_t)(kQdd + o) * B], (CR)st[n + o + 1] + dt * sv[(size_t)(kQdd + o + 1) * B], (CR)st[n + o + 2] + dt * sv[(size_t)(kQdd + o + 2) * B]);
+      vs.l = mk3<CR>((CR)st[n + o + 3] + dt * sv[(size_t)(kQdd + o + 3) * B], (CR)st[n + o + 4] + dt * sv[(size_t)(kQdd + o + 4) * B], (CR)st[n + o + 5] + dt * sv[(size_t)(kQdd + o + 5) * B]);
+      stv6(ws.uI + o, vs);
+      V = V + vs;
+    }
+    stv6(ws.V + 6 * i, V);
+  }
+  for (int d = 0; d < n; d++) ws.vstar[d] = ws.uI[d];
+
+  // ---- contact generation over the precomputed pair list (reference order)
+  int nc = 0;
+  for (int pi = 0; pi < C.npairs; pi++) {
+    const int sa = C.pair_a[pi], sb = C.pair_b[pi];
+    const int ba = C.shape_body[sa], bb = C.shape_body[sb];
+    const Xf<CR> Ta = (ba >= 0) ? xf_mul(xf_from12(ws.W + 12 * ba), xf_from12(C.shape_T[sa])) : xf_from12(C.shape_T[sa]);
+    const Xf<CR> Tb = (bb >= 0) ? xf_mul(xf_from12(ws.W + 12 * bb), xf_from12(C.shape_T[sb])) : xf_from12(C.shape_T[sb]);
+    const int ta = C.shape_type[sa], tb = C.shape_type[sb];
+    const V3<CR> da = mk3<CR>(C.shape_dims[sa][0], C.shape_dims[sa][1], C.shape_dims[sa][2]);
+    const V3<CR> db = mk3<CR>(C.shape_dims[sb][0], C.shape_dims[sb][1], C.shape_dims[sb][2]);
+    ContactOut co[8];
+    int k = 0;
+    if (ta == 0 && tb == 0) k = collide_box_box(da, Ta, db, Tb, C.clip_depth, co);
+    else if (ta == 0 && tb == 1) k = collide_box_sphere(da, Ta, db.x, Tb, C.clip_depth, 0, false, co);
+    else if (ta == 1 && tb == 0) k = collide_box_sphere(db, Tb, da.x, Ta, C.clip_depth, 0, true, co);
+    else if ((ta == 0 && tb == 2) || (ta == 2 && tb == 0)) {
+      const bool boxFirst = (ta == 0);
+      const Xf<CR>& Tc = boxFirst ? Tb : Ta; const Xf<CR>& Tbx = boxFirst ? Ta : Tb;
+      const V3<CR> bdim = boxFirst ? da : db;
+      const CR r = boxFirst ? db.x : da.x, h = boxFirst ? db.y : da.y;
+      CR dep[2]; Xf<CR> Tend[2];
+      for (int e = 0; e < 2; e++) {
+        Tend[e] = Tc; Tend[e].p = xf_apply(Tc, mk3<CR>(0, 0, e == 0 ? h / 2 : -h / 2));
+        const V3<CR> pl = xf_apply_inv(Tbx, Tend[e].p);
+        V3<CR> q = pl; bool inside = true;
+        for (int kk = 0; kk < 3; kk++) { const CR hk = 0.5 * get3(bdim, kk), v = get3(q, kk); if (v < -hk) { set3(q, kk, -hk); inside = false; } if (v > hk) { set3(q, kk, hk); inside = false; } }
+        if (inside) { CR mn = 1e300; for (int kk = 0; kk < 3; kk++) { const CR v = 0.5 * get3(bdim, kk) - nb2_abs(get3(pl, kk)); mn = v < mn ? v : mn; } dep[e] = mn + r; }
+        else { const V3<CR> dd = pl - q; dep[e] = r - nb2_sqrt(dot(dd, dd)); }
+      }
+      if ((dep[0] > dep[1] ? dep[0] : dep[1]) >= 0) {
+        if (nb2_abs(dep[0] - dep[1]) < 1e-9) status |= NB2_ST_UNSUPPORTED_GEOMETRY;
+        else {
+          const int e = dep[0] > dep[1] ? 0 : 1;
+          k = collide_box_sphere(bdim, Tbx, r, Tend[e], C.clip_depth, e == 0 ? 1 : 2, !boxFirst, co);
+        }
+      }
+    } else status |= NB2_ST_UNSUPPORTED_GEOMETRY;
+    for (int c = 0; c < k; c++) {
+      if (dot(co[c].normal, co[c].normal) < 1e-12) continue;
+      if (co[c].depth < 0.0 || co[c].depth > C.clip_depth) continue;
+      if (ba < 0 && bb < 0) continue;
+      if (nc >= NB2_MAX_CONTACTS) { status |= NB2_ST_CONTACT_OVERFLOW; continue; }
+      ws.cpoint[3 * nc] = co[c].point.x; ws.cpoint[3 * nc + 1] = co[c].point.y; ws.cpoint[3 * nc + 2] = co[c].point.z;
+      ws.cnormal[3 * nc] = co[c].normal.x; ws.cnormal[3 * nc + 1] = co[c].normal.y; ws.cnormal[3 * nc + 2] = co[c].normal.z;
+      ws.cdepth[nc] = co[c].depth; ws.cbodyA[nc] = ba; ws.cbodyB[nc] = bb; ws.ctype[nc] = co[c].type; ws.cshapeA[nc] = sa; ws.cshapeB[nc] = sb;
+      ws.cmu[nc] = C.shape_mu[sa] < C.shape_mu[sb] ? C.shape_mu[sa] : C.shape_mu[sb];
+      ws.crest[nc] = C.shape_rest[sa] * C.shape_rest[sb];
+      nc++;
+    }
+  }
+  *nc_out = nc;
+  if (cinfo_out) for (int c = 0; c < nc; c++) {
+    float* o = cinfo_out + 10 * c;
+    o[0] = (float)ws.cpoint[3 * c]; o[1] = (float)ws.cpoint[3 * c + 1]; o[2] = (float)ws.cpoint[3 * c + 2];
+    o[3] = (float)ws.cnormal[3 * c]; o[4] = (float)ws.cnormal[3 * c + 1]; o[5] = (float)ws.cnormal[3 * c + 2];
+    o[6] = (float)ws.cdepth[c]; o[7] = (float)C.shape_orig_body[ws.cshapeA[c]]; o[8] = (float)C.shape_orig_body[ws.cshapeB[c]]; o[9] = (float)ws.ctype[c];
+  }
+  // ---- rows
+  int m = 0;
+  for (int c = 0; c < nc; c++) {
+    const CR mu = ws.cmu[c], e = ws.crest[c];
+    const bool fric = mu > 1e-3, bounce = e > 1e-3;
+    const V3<CR> nrm = mk3<CR>(ws.cnormal[3 * c], ws.cnormal[3 * c + 1], ws.cnormal[3 * c + 2]);
+    const V3<CR> pt = mk3<CR>(ws.cpoint[3 * c], ws.cpoint[3 * c + 1], ws.cpoint[3 * c + 2]);
+    V3<CR> dirs[3]; dirs[0] = nrm;
+    if (fric) {  // getTangentBasisMatrixODE with first frictional direction = UnitZ (ContactConstraint.cpp:734-795)
+      V3<CR> t = cross(mk3<CR>(0, 0, 1), nrm);
+      if (dot(t, t) < 1e-12) { t = cross(mk3<CR>(1, 0, 0), nrm); if (dot(t, t) < 1e-12) { t = cross(mk3<CR>(0, 1, 0), nrm); if (dot(t, t) < 1e-12) t = cross(mk3<CR>(0, 0, 1), nrm); } }
+      dirs[1] = t * (CR(1) / nb2_sqrt(dot(t, t)));
+      dirs[2] = cross(nrm, dirs[1]);
+    }
+    const int dim = fric ? 3 : 1, off = m;
+    const int ba = ws.cbodyA[c], bb = ws.cbodyB[c];
+    for (int k = 0; k < dim; k++) {
+      CR rel = 0;
+      V6<CR> JA = zero6<CR>(), JB = zero6<CR>();
+      if (ba >= 0) { const Xf<CR> W = xf_from12(ws.W + 12 * ba); const V3<CR> pA = xf_apply_inv(W, pt), dA = mulT(W.R_, dirs[k]); JA.a = cross(pA, dA); JA.l = dA; rel -= dot(JA, ldv6(ws.V + 6 * ba)); }
+      if (bb >= 0) { const Xf<CR> W = xf_from12(ws.W + 12 * bb); const V3<CR> pB = xf_apply_inv(W, pt), dB = mulT(W.R_, -dirs[k]); JB.a = cross(pB, dB); JB.l = dB; rel -= dot(JB, ldv6(ws.V + 6 * bb)); }
+      stv6(ws.JA + 6 * m, JA); stv6(ws.JB + 6 * m, JB);
+      ws.b[m] = rel; ws.rest[m] = (k == 0 && bounce) ? e : 0.0;
+      ws.i1[m] = c;  // row -> contact (i1 is free until classification)
+      if (k == 0) { ws.lo[m] = 0.0; ws.hi[m] = HUGE_VAL; ws.findex[m] = -1; } else { ws.lo[m] = -mu; ws.hi[m] = mu; ws.findex[m] = off; }
+      m++;
+    }
+    CR bv = ws.cdepth[c];
+    if (bv < 0) bv = 0; else { bv *= 0.01 * (1.0 / dt); if (bv > 1e-3) bv = 1e-3; }
+    if (!C.pen_correction) bv = 0;
+    if (bounce) { const CR rv = ws.b[off] * e; if (rv > 1e-1) { if (rv > bv) { bv = rv; if (bv > 1e2) bv = 1e2; } } }
+    ws.b[off] += bv;
+  }
+  if (m == 0) { *m_io = 0; *status_out = status; return; }  // out already holds v*
+  // row -> contact map must survive classification (which uses i1): copy to st8 region as bytes
+  unsigned char* rowc = ws.st8 + NB2_MAX_ROWS;
+  for (int r = 0; r < m; r++) rowc[r] = (unsigned char)ws.i1[r];
+  // ---- A by impulse tests (upper blocks measured, lower mirrored; BoxedLcpConstraintSolver.cpp:293-314)
+  CR* A = ws.A;
+  for (int r = 0; r < m; r++) {
+    const int c = rowc[r];
+    for (int i = 0; i < nb * 6; i++) ws.pI[i] = 0;
+    if (ws.cbodyA[c] >= 0) { const CR* J = ws.JA + 6 * r; CR* p = ws.pI + 6 * ws.cbodyA[c]; for (int k = 0; k < 6; k++) p[k] -= J[k]; }
+    if (ws.cbodyB[c] >= 0) { const CR* J = ws.JB + 6 * r; CR* p = ws.pI + 6 * ws.cbodyB[c]; for (int k = 0; k < 6; k++) p[k] -= J[k]; }
+    impulse_response(M, st, sv, B, ws);
+    for (int s2 = 0; s2 < m; s2++) {
+      const int cj = rowc[s2];
+      if (cj < c) { A[r * m + s2] = A[s2 * m + r]; continue; }
+      CR a = 0;
+      if (ws.cbodyA[cj] >= 0) a += dot(ldv6(ws.JA + 6 * s2), ldv6(ws.V + 6 * ws.cbodyA[cj]));
+      if (ws.cbodyB[cj] >= 0) a += dot(ldv6(ws.JB + 6 * s2), ldv6(ws.V + 6 * ws.cbodyB[cj]));
+      A[r * m + s2] = a;
+    }
+  }
+  for (int c = 0; c < m; c++) { CR sn = 0; for (int r = 0; r < m; r++) sn += A[r * m + c] * A[r * m + c]; ws.colnorm[c] = sn; }
+  CR* b = ws.b; CR* lo = ws.lo; CR* hi = ws.hi; int* fi = ws.findex; CR* x = ws.x; CR* x0 = ws.x0;
+  // ---- warm start: cached solution if it has the same size, else LCPUtils::guessSolution (LCPUtils.cpp:86-140)
+  if (*m_io == m) { for (int i = 0; i < m; i++) x0[i] = x_io[i]; }
+  else {
+    int ng = 0;
+    for (int i = 0; i < m; i++) { x0[i] = 0; if (fi[i] == -1) { if (b[i] > 0) ws.i1[ng++] = i; } else ws.i1[ng++] = i; }
+    if (ng > 0) {
+      for (int r = 0; r < ng; r++) { ws.v1[r] = b[ws.i1[r]]; for (int c = 0; c < ng; c++) ws.Q[r * ng + c] = A[ws.i1[r] * m + ws.i1[c]]; }
+      pinv_psd(ng, ws.Q, ws.v1, ws.v2, ws.Aw, ws.L, ws.v5, ws.v6, ws.i2);
+      for (int r = 0; r < ng; r++) x0[ws.i1[r]] = ws.v2[r];
+    }
+  }
+  for (int i = 0; i < m; i++) x[i] = x0[i];
+  // ---- solve chain (BoxedLcpConstraintSolver.cpp:352-789)
+  bool success = classify_and_standardize(m, A, x, b, lo, hi, fi, ws.colnorm, false, ws);
+  const bool shortCircuit = success;
+  bool ignoredFriction = false;
+  if (success) status |= NB2_ST_SHORTCIRCUIT;
+  else {
+    status |= NB2_ST_DANTZIG;
+    // LCPUtils::reduce would merge near-identical columns first; not restated on the device: flag such instances
+    for (int a = 0; a < m - 1; a++) for (int c = a + 1; c < m; c++) {
+      if (fi[a] != fi[c] || hi[a] != hi[c] || lo[a] != lo[c] || nb2_abs(b[a] - b[c]) >= 1e-4) continue;
+      CR d2 = 0; for (int r = 0; r < m; r++) { const CR d = A[r * m + a] - A[r * m + c]; d2 += d * d; }
+      if (d2 < 1e-4) status |= NB2_ST_WOULD_MERGE;
+    }
+    for (int i = 0; i < m * m; i++) ws.Aw[i] = A[i];
+    for (int i = 0; i < m; i++) { ws.v1[i] = b[i]; ws.v2[i] = lo[i]; ws.v3[i] = hi[i]; ws.i1[i] = fi[i]; }
+    DantzigWork W;
+    W.A = ws.Aw; W.x = ws.v4; W.b = ws.v1; W.w = ws.v5; W.lo = ws.v2; W.hi = ws.v3; W.L = ws.L; W.d = ws.v6; W.delta_x = ws.v7; W.delta_w = ws.v8;
+    W.Dell = ws.Q; W.ell = ws.Q + m; W.tmp = ws.Q + 2 * m; W.findex = ws.i1; W.p = ws.i2; W.C = ws.clampIdx; W.state = ws.st8;
+    const int rc = dantzig_solve(W, m, true);
+    success = (rc == 1);
+    if (success) { for (int i = 0; i < m; i++) x[i] = ws.v4[i]; if (!lcp_valid(m, A, x, b, hi, lo, fi, false)) success = false; }
+    if (!success) status |= NB2_ST_DANTZIG_FAILED;
+  }
+  { bool nan = false; for (int i = 0; i < m; i++) if (x[i] != x[i]) nan = true; if (nan) { success = false; for (int i = 0; i < m; i++) x[i] = 0; status |= NB2_ST_NAN; } }
+  if (!success) {
+    for (int i = 0; i < m; i++) A[i * m + i] += C.fallback_cfm;  // :539-547 (both backups get the cfm; colnorms were taken before)
+    status |= NB2_ST_PGS;
+    for (int i = 0; i < m * m; i++) ws.Aw[i] = A[i];
+    for (int i = 0; i < m; i++) { ws.v1[i] = b[i]; ws.v4[i] = x0[i]; }
+    success = pgs_solve(m, ws.Aw, ws.v4, ws.v1, lo, hi, fi, ws.st8);
+    if (success) { for (int i = 0; i < m; i++) x[i] = ws.v4[i]; if (!lcp_valid(m, A, x, b, hi, lo, fi, false)) success = false; }
+  }
+  if (!success) {
+    ignoredFriction = true;
+    status |= NB2_ST_FRICTION_DROPPED;
+    int k = 0;
+    for (int i = 0; i < m; i++) if (fi[i] == -1) ws.i1[k++] = i;
+    for (int r = 0; r < k; r++) { ws.v1[r] = b[ws.i1[r]]; ws.v2[r] = lo[ws.i1[r]]; ws.v3[r] = hi[ws.i1[r]]; ws.v4[r] = 0; ws.i2[r] = -1; for (int c = 0; c < k; c++) ws.Aw[r * k + c] = A[ws.i1[r] * m + ws.i1[c]]; }
+    pgs_solve(k, ws.Aw, ws.v4, ws.v1, ws.v2, ws.v3, ws.i2, ws.st8);
+    for (int i = 0; i < m; i++) x[i] = 0;
+    for (int r = 0; r < k; r++) x[ws.i1[r]] = ws.v4[r];
+  }
+  { bool nan = false; for (int i = 0; i < m; i++) if (x[i] != x[i]) nan = true; if (nan) { for (int i = 0; i < m; i++) x[i] = 0; status |= NB2_ST_NAN; } }
+  if (!shortCircuit) {
+    for (int i = 0; i < m; i++) ws.v7[i] = x[i];
+    // classify works on x in place and only keeps the standardised x when valid
+    if (!classify_and_standardize(m, A, x, b, lo, hi, fi, ws.colnorm, ignoredFriction, ws)) { status |= NB2_ST_NOT_STANDARDIZED; }
+  }
+  for (int i = 0; i < m; i++) { x_io[i] = x[i]; labels_out[i] = ws.mapping[i]; }
+  // ---- apply the impulses and update the velocities (ContactConstraint.cpp:630-684, Skeleton.cpp:13571-13595)
+  for (int i = 0; i < nb * 6; i++) ws.pI[i] = 0;
+  for (int r = 0; r < m; r++) {
+    const int c = rowc[r];
+    if (ws.cbodyA[c] >= 0) { const CR* J = ws.JA + 6 * r; CR* p = ws.pI + 6 * ws.cbodyA[c]; for (int k = 0; k < 6; k++) p[k] -= J[k] * x[r]; }
+    if (ws.cbodyB[c] >= 0) { const CR* J = ws.JB + 6 * r; CR* p = ws.pI + 6 * ws.cbodyB[c]; for (int k = 0; k < 6; k++) p[k] -= J[k] * x[r]; }
+  }
+  impulse_response(M, st, sv, B, ws);
+  for (int d = 0; d < n; d++) out[n + d] = (float)(ws.vstar[d] + ws.dqd[d]);
+  *m_io = m; *status_out = status;
+}
+
+}  // namespace nb2

@@ -69,15 +69,14 @@ template <class R, int ST, bool ADD> NB2_HD void stSI(R* p, const SI<R>& I) {
   NB2_W(15, I.C.xx) NB2_W(16, I.C.yy) NB2_W(17, I.C.zz) NB2_W(18, I.C.xy) NB2_W(19, I.C.xz) NB2_W(20, I.C.yz)
 #undef NB2_W
 }
-// saved-for-backward stream: word k of world w lives at sv[k * B] (sv already offset by w) -> coalesced
-NB2_HD void sv_st6(float* sv, size_t B, int k, const V6<float>& v) {
+// saved-for-backward stream (element type = the arithmetic type R): word k of world w lives at sv[k * B]
+// (sv already offset by w) -> coalesced
+template <class R> NB2_HD void sv_st6(R* sv, size_t B, int k, const V6<R>& v) {
   sv[(size_t)k * B] = v.a.x; sv[(size_t)(k + 1) * B] = v.a.y; sv[(size_t)(k + 2) * B] = v.a.z;
   sv[(size_t)(k + 3) * B] = v.l.x; sv[(size_t)(k + 4) * B] = v.l.y; sv[(size_t)(k + 5) * B] = v.l.z;
 }
-template <class R> NB2_HD V6<float> tof(const V6<R>& v) {
-  V6<float> o; o.a.x = (float)v.a.x; o.a.y = (float)v.a.y; o.a.z = (float)v.a.z; o.l.x = (float)v.l.x; o.l.y = (float)v.l.y; o.l.z = (float)v.l.z; return o;
-}
-template <class R> NB2_HD V6<R> sv_ld6(const float* sv, size_t B, int k) {
+template <class R> NB2_HD V6<R> tof(const V6<R>& v) { return v; }
+template <class R> NB2_HD V6<R> sv_ld6(const R* sv, size_t B, int k) {
   V6<R> v;
   v.a.x = (R)sv[(size_t)k * B]; v.a.y = (R)sv[(size_t)(k + 1) * B]; v.a.z = (R)sv[(size_t)(k + 2) * B];
   v.l.x = (R)sv[(size_t)(k + 3) * B]; v.l.y = (R)sv[(size_t)(k + 4) * B]; v.l.z = (R)sv[(size_t)(k + 5) * B];
@@ -142,7 +141,7 @@ template <class R> NB2_HD R S_dot(int jt, const V6<R>& f) { return (jt == NB2_JT
 // forward: state=[q;v] (fp32 row), action (fp32 row) -> next state row; optionally streams intermediates to `sv`
 // =====================================================================================================
 template <class R, int ST>
-NB2_HD void world_forward(const Nb2ModelDev<R>& M, R* scr, const float* st, const float* act, float* out, float* sv,
+NB2_HD void world_forward(const Nb2ModelDev<R>& M, R* scr, const float* st, const float* act, float* out, R* sv,
                           size_t B, bool save) {
   const int nb = M.nb, n = M.ndof;
   const FwdLayout L = fwd_layout(nb, n, M.nslots, M.nfree);
@@ -248,11 +247,11 @@ NB2_HD void world_forward(const Nb2ModelDev<R>& M, R* scr, const float* st, cons
       st6<R, ST>(scr + (size_t)(L.oFree + 18 * M.free_idx[i] + 12) * ST, y);
       if (save) {
         const int k0 = nb * 21 + M.free_idx[i] * 33;
-        float* s = sv + (size_t)k0 * B;
-        s[0] = (float)Iinv.A.xx; s[B] = (float)Iinv.A.yy; s[2 * B] = (float)Iinv.A.zz; s[3 * B] = (float)Iinv.A.xy; s[4 * B] = (float)Iinv.A.xz; s[5 * B] = (float)Iinv.A.yz;
-        s[6 * B] = (float)Iinv.B.m00; s[7 * B] = (float)Iinv.B.m01; s[8 * B] = (float)Iinv.B.m02; s[9 * B] = (float)Iinv.B.m10; s[10 * B] = (float)Iinv.B.m11; s[11 * B] = (float)Iinv.B.m12;
-        s[12 * B] = (float)Iinv.B.m20; s[13 * B] = (float)Iinv.B.m21; s[14 * B] = (float)Iinv.B.m22;
-        s[15 * B] = (float)Iinv.C.xx; s[16 * B] = (float)Iinv.C.yy; s[17 * B] = (float)Iinv.C.zz; s[18 * B] = (float)Iinv.C.xy; s[19 * B] = (float)Iinv.C.xz; s[20 * B] = (float)Iinv.C.yz;
+        R* s = sv + (size_t)k0 * B;
+        s[0] = (R)Iinv.A.xx; s[B] = (R)Iinv.A.yy; s[2 * B] = (R)Iinv.A.zz; s[3 * B] = (R)Iinv.A.xy; s[4 * B] = (R)Iinv.A.xz; s[5 * B] = (R)Iinv.A.yz;
+        s[6 * B] = (R)Iinv.B.m00; s[7 * B] = (R)Iinv.B.m01; s[8 * B] = (R)Iinv.B.m02; s[9 * B] = (R)Iinv.B.m10; s[10 * B] = (R)Iinv.B.m11; s[11 * B] = (R)Iinv.B.m12;
+        s[12 * B] = (R)Iinv.B.m20; s[13 * B] = (R)Iinv.B.m21; s[14 * B] = (R)Iinv.B.m22;
+        s[15 * B] = (R)Iinv.C.xx; s[16 * B] = (R)Iinv.C.yy; s[17 * B] = (R)Iinv.C.zz; s[18 * B] = (R)Iinv.C.xy; s[19 * B] = (R)Iinv.C.xz; s[20 * B] = (R)Iinv.C.yz;
       }
       if (p >= 0) { Pi = zeroSI<R>(); beta = bf + u; }  // a 6-dof joint transmits only its own joint force
     }
@@ -291,10 +290,10 @@ NB2_HD void world_forward(const Nb2ModelDev<R>& M, R* scr, const float* st, cons
       out[o] = (float)(qv + vq * dt);
       out[n + o] = (float)(vq + qdd * dt);
       if (save) {
-        float* s = sv + (size_t)(i * 21) * B;
+        R* s = sv + (size_t)(i * 21) * B;
         sv_st6(s, B, 0, tof(V)); sv_st6(s, B, 6, tof(A)); sv_st6(s, B, 12, tof(U));
-        s[18 * B] = (float)psi; s[19 * B] = (float)bs[6 * ST]; s[20 * B] = (float)bs[7 * ST];
-        sv[(size_t)(nb * 21 + M.nfree * 33 + o) * B] = (float)qdd;
+        s[18 * B] = (R)psi; s[19 * B] = (R)bs[6 * ST]; s[20 * B] = (R)bs[7 * ST];
+        sv[(size_t)(nb * 21 + M.nfree * 33 + o) * B] = qdd;
       }
     } else {
       const R* q = scr + (size_t)(L.oQ + o) * ST;
@@ -313,13 +312,13 @@ NB2_HD void world_forward(const Nb2ModelDev<R>& M, R* scr, const float* st, cons
       out[n + o] = (float)(Vj.a.x + qdd.a.x * dt); out[n + o + 1] = (float)(Vj.a.y + qdd.a.y * dt); out[n + o + 2] = (float)(Vj.a.z + qdd.a.z * dt);
       out[n + o + 3] = (float)(Vj.l.x + qdd.l.x * dt); out[n + o + 4] = (float)(Vj.l.y + qdd.l.y * dt); out[n + o + 5] = (float)(Vj.l.z + qdd.l.z * dt);
       if (save) {
-        float* s = sv + (size_t)(i * 21) * B;
+        R* s = sv + (size_t)(i * 21) * B;
         sv_st6(s, B, 0, tof(V)); sv_st6(s, B, 6, tof(A));
-        for (int k = 12; k < 21; k++) s[(size_t)k * B] = 0.f;
-        float* sf = sv + (size_t)(nb * 21 + M.free_idx[i] * 33 + 21) * B;
-        for (int k = 0; k < 12; k++) sf[(size_t)k * B] = (float)fr[(size_t)k * ST];
-        float* sq = sv + (size_t)(nb * 21 + M.nfree * 33 + o) * B;
-        sq[0] = (float)qdd.a.x; sq[B] = (float)qdd.a.y; sq[2 * B] = (float)qdd.a.z; sq[3 * B] = (float)qdd.l.x; sq[4 * B] = (float)qdd.l.y; sq[5 * B] = (float)qdd.l.z;
+        for (int k = 12; k < 21; k++) s[(size_t)k * B] = R(0);
+        R* sf = sv + (size_t)(nb * 21 + M.free_idx[i] * 33 + 21) * B;
+        for (int k = 0; k < 12; k++) sf[(size_t)k * B] = fr[(size_t)k * ST];
+        R* sq = sv + (size_t)(nb * 21 + M.nfree * 33 + o) * B;
+        sq[0] = qdd.a.x; sq[B] = qdd.a.y; sq[2 * B] = qdd.a.z; sq[3 * B] = qdd.l.x; sq[4 * B] = qdd.l.y; sq[5 * B] = qdd.l.z;
       }
     }
     st6<R, ST>(bs + 16 * ST, A);
@@ -331,7 +330,7 @@ NB2_HD void world_forward(const Nb2ModelDev<R>& M, R* scr, const float* st, cons
 // =====================================================================================================
 template <class R, int ST>
 NB2_HD void world_backward(const Nb2ModelDev<R>& M, R* scr, const float* st, const float* act, const float* gnext,
-                           const float* sv, size_t B, float* gstate, float* gaction) {
+                           const R* sv, size_t B, float* gstate, float* gaction) {
   const int nb = M.nb, n = M.ndof;
   const BwdLayout L = bwd_layout(nb, n, M.nslots, M.nfree);
   const R dt = M.dt;
@@ -347,7 +346,7 @@ NB2_HD void world_backward(const Nb2ModelDev<R>& M, R* scr, const float* st, con
   bool hvalid = false;
   for (int i = nb - 1; i >= 0; i--) {
     const int jt = M.jtype[i], p = M.parent[i], o = M.dof_off[i], fl = M.flags[i];
-    const float* s = sv + (size_t)(i * 21) * B;
+    const R* s = sv + (size_t)(i * 21) * B;
     V6<R> pI = hvalid ? hp : zero6<R>();
     if (fl & NB2_F_HAS_SLOT) pI = pI + ld6<R, ST>(scr + (size_t)(L.oSlot + 18 * M.slot_self[i]) * ST);
     V6<R> beta;
@@ -378,7 +377,7 @@ NB2_HD void world_backward(const Nb2ModelDev<R>& M, R* scr, const float* st, con
   // (BodyNode.cpp:2188-2215, GenericJoint.hpp:2713-2725)
   for (int i = 0; i < nb; i++) {
     const int jt = M.jtype[i], p = M.parent[i], o = M.dof_off[i];
-    const float* s = sv + (size_t)(i * 21) * B;
+    const R* s = sv + (size_t)(i * 21) * B;
     R* bs = scr + (size_t)(L.oBody + 7 * i) * ST;
     V6<R> W;
     if (jt != NB2_JT_FREE) {
@@ -388,7 +387,7 @@ NB2_HD void world_backward(const Nb2ModelDev<R>& M, R* scr, const float* st, con
       scr[(size_t)(L.oLam + o) * ST] = lam;
       if (jt == NB2_JT_REV) W.a.z += lam; else W.l.z += lam;
     } else {
-      const float* sf = sv + (size_t)(kFree + M.free_idx[i] * 33) * B;
+      const R* sf = sv + (size_t)(kFree + M.free_idx[i] * 33) * B;
       R t12[12]; for (int k = 0; k < 12; k++) t12[k] = (R)sf[(size_t)(21 + k) * B];
       const Xf<R> T = ldXf<R, 1>(t12);
       const V6<R> Wp = (p >= 0) ? AdInvT(T, ld6<R, ST>(scr + (size_t)(L.oBody + 7 * p + 1) * ST)) : zero6<R>();
@@ -410,7 +409,7 @@ NB2_HD void world_backward(const Nb2ModelDev<R>& M, R* scr, const float* st, con
   hvalid = false;
   for (int i = nb - 1; i >= 0; i--) {
     const int jt = M.jtype[i], p = M.parent[i], o = M.dof_off[i], fl = M.flags[i];
-    const float* s = sv + (size_t)(i * 21) * B;
+    const R* s = sv + (size_t)(i * 21) * B;
     R m; V3<R> h; S3<R> Ib; inertia_of(M, i, &m, &h, &Ib);
     const V6<R> V = sv_ld6<R>(s, B, 0), A = sv_ld6<R>(s, B, 6);
     const V6<R> W = ld6<R, ST>(scr + (size_t)(L.oBody + 7 * i + 1) * ST);

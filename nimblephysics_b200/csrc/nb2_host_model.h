@@ -4,6 +4,7 @@
 
 #include "../../include/nb2.h"
 #include "nb2_model.h"
+#include "nb2_contact.cuh"
 
 template <class R>
 static inline bool nb2_fill_model(const nb2_model_desc& d, Nb2ModelDev<R>& M, std::string& err) {
@@ -50,6 +51,32 @@ static inline bool nb2_fill_model(const nb2_model_desc& d, Nb2ModelDev<R>& M, st
   for (int i = 0; i < d.na; i++) {
     if (d.action_map[i] < 0 || d.action_map[i] >= d.ndof) { err = "action map entry out of range"; return false; }
     M.action_map[i] = (int16_t)d.action_map[i];
+  }
+  return true;
+}
+
+static inline bool nb2_fill_contact(const nb2_model_desc& d, Nb2ContactDev& C, std::string& err) {
+  if (d.nshapes < 0 || d.nshapes > NB2_MAX_SHAPES) { err = "model has " + std::to_string(d.nshapes) + " collision shapes; compiled limit is " + std::to_string(NB2_MAX_SHAPES); return false; }
+  if (d.npairs < 0 || d.npairs > NB2_MAX_PAIRS) { err = "model has " + std::to_string(d.npairs) + " collision pairs; compiled limit is " + std::to_string(NB2_MAX_PAIRS); return false; }
+  C.nshapes = d.nshapes; C.npairs = d.npairs; C.pen_correction = d.penetration_correction; C.pad = 0;
+  C.clip_depth = d.contact_clipping_depth; C.fallback_cfm = d.fallback_cfm;
+  for (int s = 0; s < NB2_MAX_SHAPES; s++) {
+    C.shape_body[s] = -1; C.shape_type[s] = 0; C.shape_orig_body[s] = -1; C.shape_mu[s] = 0; C.shape_rest[s] = 0;
+    for (int k = 0; k < 3; k++) C.shape_dims[s][k] = 0;
+    for (int k = 0; k < 12; k++) C.shape_T[s][k] = 0;
+  }
+  for (int s = 0; s < d.nshapes; s++) {
+    if (d.shape_body[s] >= d.nb) { err = "shape attached to a body that does not exist"; return false; }
+    if (d.shape_type[s] < 0 || d.shape_type[s] > 2) { err = "unsupported shape type"; return false; }
+    C.shape_body[s] = (int16_t)d.shape_body[s]; C.shape_type[s] = (int16_t)d.shape_type[s]; C.shape_orig_body[s] = (int16_t)d.shape_orig_body[s];
+    C.shape_mu[s] = d.shape_mu[s]; C.shape_rest[s] = d.shape_rest[s];
+    for (int k = 0; k < 3; k++) C.shape_dims[s][k] = d.shape_dims[3 * s + k];
+    for (int k = 0; k < 12; k++) C.shape_T[s][k] = d.shape_T[12 * s + k];
+  }
+  for (int p = 0; p < NB2_MAX_PAIRS; p++) { C.pair_a[p] = 0; C.pair_b[p] = 0; }
+  for (int p = 0; p < d.npairs; p++) {
+    if (d.pair_a[p] < 0 || d.pair_a[p] >= d.nshapes || d.pair_b[p] < 0 || d.pair_b[p] >= d.nshapes) { err = "collision pair references a missing shape"; return false; }
+    C.pair_a[p] = (int16_t)d.pair_a[p]; C.pair_b[p] = (int16_t)d.pair_b[p];
   }
   return true;
 }

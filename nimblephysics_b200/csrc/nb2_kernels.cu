@@ -14,6 +14,7 @@
 
 #include "../../include/nb2.h"
 #include "nb2_dyn.cuh"
+#include "nb2_contact.cuh"
 #include "nb2_host_model.h"
 
 static thread_local std::string g_err;
@@ -33,7 +34,7 @@ namespace {
 template <class R>
 __global__ void __launch_bounds__(128)
 k_step_fwd(const __grid_constant__ Nb2ModelDev<R> M, int B, const float* __restrict__ state,
-           const float* __restrict__ action, float* __restrict__ next, float* __restrict__ saved, int words) {
+           const float* __restrict__ action, float* __restrict__ next, R* __restrict__ saved, int words) {
   extern __shared__ __align__(16) unsigned char nb2_smem[];
   const int w = blockIdx.x * blockDim.x + threadIdx.x;
   if (w >= B) return;
@@ -45,7 +46,7 @@ k_step_fwd(const __grid_constant__ Nb2ModelDev<R> M, int B, const float* __restr
 template <class R>
 __global__ void __launch_bounds__(128)
 k_step_bwd(const __grid_constant__ Nb2ModelDev<R> M, int B, const float* __restrict__ state,
-           const float* __restrict__ action, const float* __restrict__ saved, const float* __restrict__ gnext,
+           const float* __restrict__ action, const R* __restrict__ saved, const float* __restrict__ gnext,
            float* __restrict__ gstate, float* __restrict__ gaction, int words) {
   extern __shared__ __align__(16) unsigned char nb2_smem[];
   const int w = blockIdx.x * blockDim.x + threadIdx.x;
@@ -54,6 +55,21 @@ k_step_bwd(const __grid_constant__ Nb2ModelDev<R> M, int B, const float* __restr
   nb2::world_backward<R, 32>(M, scr, state + (size_t)w * 2 * M.ndof, action + (size_t)w * M.na,
                              gnext + (size_t)w * 2 * M.ndof, saved + w, (size_t)B,
                              gstate + (size_t)w * 2 * M.ndof, gaction + (size_t)w * M.na);
+}
+
+// contact / boxed-LCP stage: one thread per world, fp64, per-world workspace in global memory (L1/L2 cached).
+// The pivoting LCP solve is data dependent, so lanes of a warp diverge here by construction.
+__global__ void __launch_bounds__(64)
+k_contact_fwd(const __grid_constant__ Nb2ModelDev<double> M, const __grid_constant__ Nb2ContactDev C, int B,
+              const float* __restrict__ state, float* __restrict__ next, const double* __restrict__ saved,
+              double* __restrict__ workspace, size_t ws_doubles, double* __restrict__ x_lcp, int* __restrict__ m_lcp,
+              int* __restrict__ labels, int* __restrict__ status, int* __restrict__ ncontacts, float* __restrict__ cinfo) {
+  const int w = blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= B) return;
+  nb2::world_contact(M, C, state + (size_t)w * 2 * M.ndof, next + (size_t)w * 2 * M.ndof, saved + w, (size_t)B,
+                     workspace + (size_t)w * ws_doubles, x_lcp + (size_t)w * NB2_MAX_ROWS, m_lcp + w,
+                     labels + (size_t)w * NB2_MAX_ROWS, status + w, ncontacts + w,
+                     cinfo ? cinfo + (size_t)w * NB2_MAX_CONTACTS * 10 : nullptr);
 }
 
 constexpr int kMaxSmem = 227 * 1024;
@@ -75,12 +91,15 @@ int pick_warps(int B, size_t bytes_per_warp, int sm_count) {
 struct nb2_model {
   Nb2ModelDev<float> mf;
   Nb2ModelDev<double> md;
+  Nb2ContactDev contact;
+  bool has_contacts = false;
   int fwd_words, bwd_words, saved_words;
   int sm_count;
   bool attr_set[4] = {false, false, false, false};
   // device buffers owned by the *_host entry points
-  float *d_state = nullptr, *d_action = nullptr, *d_next = nullptr, *d_saved = nullptr, *d_gnext = nullptr,
+  float *d_state = nullptr, *d_action = nullptr, *d_next = nullptr, *d_gnext = nullptr,
         *d_gstate = nullptr, *d_gaction = nullptr;
+  void* d_saved = nullptr;  // sized for fp64 words
   int host_cap = 0;
   int host_B = 0;  // batch of the last forward_host kept for backward
   cudaStream_t host_stream = nullptr;
@@ -89,7 +108,7 @@ struct nb2_model {
 
 template <class R>
 static int launch_fwd(nb2_model* m, const Nb2ModelDev<R>& M, int B, const float* state, const float* action,
-                      float* next, float* saved, cudaStream_t st, int attr_idx) {
+                      float* next, R* saved, cudaStream_t st, int attr_idx) {
   const size_t per_warp = (size_t)m->fwd_words * 32 * sizeof(R);
   const int warps = pick_warps(B, per_warp, m->sm_count);
   if (warps == 0) { g_err = "model needs " + std::to_string(per_warp) + " B of shared memory per warp (> 227 KB)"; return NB2_ERR_UNSUPPORTED; }
@@ -106,7 +125,7 @@ static int launch_fwd(nb2_model* m, const Nb2ModelDev<R>& M, int B, const float*
 }
 template <class R>
 static int launch_bwd(nb2_model* m, const Nb2ModelDev<R>& M, int B, const float* state, const float* action,
-                      const float* saved, const float* gnext, float* gstate, float* gaction, cudaStream_t st,
+                      const R* saved, const float* gnext, float* gstate, float* gaction, cudaStream_t st,
                       int attr_idx) {
   const size_t per_warp = (size_t)m->bwd_words * 32 * sizeof(R);
   const int warps = pick_warps(B, per_warp, m->sm_count);
@@ -137,6 +156,10 @@ int nb2_model_create(const nb2_model_desc* desc, nb2_model** out) {
     g_err = err; delete m;
     return (desc->nb > NB2_MAX_BODIES || desc->ndof > NB2_MAX_DOFS) ? NB2_ERR_UNSUPPORTED : NB2_ERR_INVALID;
   }
+  if (desc->nshapes > 0 && desc->npairs > 0) {
+    if (!nb2_fill_contact(*desc, m->contact, err)) { g_err = err; delete m; return NB2_ERR_UNSUPPORTED; }
+    m->has_contacts = true;
+  }
   m->fwd_words = nb2::fwd_layout(m->mf.nb, m->mf.ndof, m->mf.nslots, m->mf.nfree).total;
   m->bwd_words = nb2::bwd_layout(m->mf.nb, m->mf.ndof, m->mf.nslots, m->mf.nfree).total;
   m->saved_words = nb2_saved_words(m->mf.nb, m->mf.ndof, m->mf.nfree);
@@ -159,21 +182,46 @@ void nb2_model_destroy(nb2_model* m) {
   if (m->host_stream) cudaStreamDestroy(m->host_stream);
   delete m;
 }
+int nb2_model_has_contacts(const nb2_model* m) { return (m && m->has_contacts) ? 1 : 0; }
+size_t nb2_contact_workspace_bytes(const nb2_model* m, int B) {
+  if (!m || !m->has_contacts || B <= 0) return 0;
+  return nb2::contact_ws_doubles(m->mf.nb, m->mf.ndof) * sizeof(double) * (size_t)B;
+}
+int nb2_step_forward_contact(const nb2_model* cm, int B, const float* state, const float* action, float* next_state,
+                             void* saved_fp64, void* workspace, double* x_lcp, int32_t* m_lcp, int32_t* labels,
+                             int32_t* status, int32_t* ncontacts, float* cinfo, void* stream) {
+  nb2_model* m = const_cast<nb2_model*>(cm);
+  if (!m || B < 0 || !state || !action || !next_state || !saved_fp64 || !workspace || !x_lcp || !m_lcp || !labels || !status || !ncontacts) {
+    g_err = "nb2_step_forward_contact: bad argument"; return NB2_ERR_INVALID;
+  }
+  if (!m->has_contacts) { g_err = "nb2_step_forward_contact: the model has no collision pairs"; return NB2_ERR_INVALID; }
+  if (B == 0) return NB2_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc = launch_fwd<double>(m, m->md, B, state, action, next_state, (double*)saved_fp64, st, 1);
+  if (rc) return rc;
+  const int threads = 32;
+  k_contact_fwd<<<(B + threads - 1) / threads, threads, 0, st>>>(m->md, m->contact, B, state, next_state, (const double*)saved_fp64,
+                                                                 (double*)workspace, nb2::contact_ws_doubles(m->mf.nb, m->mf.ndof), x_lcp,
+                                                                 m_lcp, labels, status, ncontacts, cinfo);
+  g_launches++;
+  NB2_CUDA(cudaGetLastError());
+  return NB2_OK;
+}
 int nb2_model_ndof(const nb2_model* m) { return m ? m->mf.ndof : -1; }
 int nb2_model_na(const nb2_model* m) { return m ? m->mf.na : -1; }
 int nb2_saved_words_per_world(const nb2_model* m) { return m ? m->saved_words : -1; }
 
 int nb2_step_forward(const nb2_model* cm, int B, const float* state, const float* action, float* next_state,
-                     float* saved, int precision, void* stream) {
+                     void* saved, int precision, void* stream) {
   nb2_model* m = const_cast<nb2_model*>(cm);
   if (!m || B < 0 || !state || !action || !next_state) { g_err = "nb2_step_forward: bad argument"; return NB2_ERR_INVALID; }
   if (B == 0) return NB2_OK;
   cudaStream_t st = (cudaStream_t)stream;
-  if (precision == NB2_FP64) return launch_fwd<double>(m, m->md, B, state, action, next_state, saved, st, 1);
-  return launch_fwd<float>(m, m->mf, B, state, action, next_state, saved, st, 0);
+  if (precision == NB2_FP64) return launch_fwd<double>(m, m->md, B, state, action, next_state, (double*)saved, st, 1);
+  return launch_fwd<float>(m, m->mf, B, state, action, next_state, (float*)saved, st, 0);
 }
 
-int nb2_step_backward(const nb2_model* cm, int B, const float* state, const float* action, const float* saved,
+int nb2_step_backward(const nb2_model* cm, int B, const float* state, const float* action, const void* saved,
                       const float* grad_next_state, float* grad_state, float* grad_action, int precision,
                       void* stream) {
   nb2_model* m = const_cast<nb2_model*>(cm);
@@ -182,8 +230,8 @@ int nb2_step_backward(const nb2_model* cm, int B, const float* state, const floa
   }
   if (B == 0) return NB2_OK;
   cudaStream_t st = (cudaStream_t)stream;
-  if (precision == NB2_FP64) return launch_bwd<double>(m, m->md, B, state, action, saved, grad_next_state, grad_state, grad_action, st, 3);
-  return launch_bwd<float>(m, m->mf, B, state, action, saved, grad_next_state, grad_state, grad_action, st, 2);
+  if (precision == NB2_FP64) return launch_bwd<double>(m, m->md, B, state, action, (const double*)saved, grad_next_state, grad_state, grad_action, st, 3);
+  return launch_bwd<float>(m, m->mf, B, state, action, (const float*)saved, grad_next_state, grad_state, grad_action, st, 2);
 }
 
 static int ensure_host_buffers(nb2_model* m, int B) {
@@ -191,13 +239,14 @@ static int ensure_host_buffers(nb2_model* m, int B) {
   if (B <= m->host_cap) return NB2_OK;
   cudaFree(m->d_state); cudaFree(m->d_action); cudaFree(m->d_next); cudaFree(m->d_saved);
   cudaFree(m->d_gnext); cudaFree(m->d_gstate); cudaFree(m->d_gaction);
-  m->d_state = m->d_action = m->d_next = m->d_saved = m->d_gnext = m->d_gstate = m->d_gaction = nullptr;
+  m->d_state = m->d_action = m->d_next = m->d_gnext = m->d_gstate = m->d_gaction = nullptr;
+  m->d_saved = nullptr;
   m->host_cap = 0;
   const size_t n2 = (size_t)2 * m->mf.ndof, na = (size_t)(m->mf.na > 0 ? m->mf.na : 1);
   NB2_CUDA(cudaMalloc(&m->d_state, n2 * B * sizeof(float)));
   NB2_CUDA(cudaMalloc(&m->d_action, na * B * sizeof(float)));
   NB2_CUDA(cudaMalloc(&m->d_next, n2 * B * sizeof(float)));
-  NB2_CUDA(cudaMalloc(&m->d_saved, (size_t)m->saved_words * B * sizeof(float)));
+  NB2_CUDA(cudaMalloc(&m->d_saved, (size_t)m->saved_words * B * sizeof(double)));
   NB2_CUDA(cudaMalloc(&m->d_gnext, n2 * B * sizeof(float)));
   NB2_CUDA(cudaMalloc(&m->d_gstate, n2 * B * sizeof(float)));
   NB2_CUDA(cudaMalloc(&m->d_gaction, na * B * sizeof(float)));

@@ -19,11 +19,12 @@ class DeviceModel:
         self.ndof = cm.ndof
         self.na = len(cm.action_map)
         L = _cabi.lib()
-        self._desc, self._keep = _cabi.make_desc(cm)
+        self._desc, self._keep = _cabi.make_desc(cm, with_contacts=len(cm.shape_body) > 0)
         h = ctypes.c_void_p()
         _cabi.check(L.nb2_model_create(ctypes.byref(self._desc), ctypes.byref(h)))
         self.handle = h
         self.saved_words = L.nb2_saved_words_per_world(h)
+        self.has_contacts = bool(L.nb2_model_has_contacts(h))
 
     def __del__(self):
         try:
@@ -41,6 +42,15 @@ class DeviceModel:
                         precision=FP32):
         _cabi.check(_cabi.lib().nb2_step_backward(self.handle, B, state_ptr, action_ptr, saved_ptr, gnext_ptr,
                                                   gstate_ptr, gaction_ptr, precision, stream))
+
+    def contact_workspace_bytes(self, B):
+        return int(_cabi.lib().nb2_contact_workspace_bytes(self.handle, B))
+
+    def forward_contact_device(self, B, state_ptr, action_ptr, next_ptr, saved_ptr, ws_ptr, x_ptr, m_ptr, labels_ptr,
+                               status_ptr, nc_ptr, cinfo_ptr, stream):
+        """fp64 ABA kernel + contact/LCP kernel (include/nb2.h nb2_step_forward_contact)."""
+        _cabi.check(_cabi.lib().nb2_step_forward_contact(self.handle, B, state_ptr, action_ptr, next_ptr, saved_ptr, ws_ptr, x_ptr,
+                                                         m_ptr, labels_ptr, status_ptr, nc_ptr, cinfo_ptr, stream))
 
     # ---- host pointers (numpy / CPU tensors): copies included ----
     def forward_host(self, state: np.ndarray, action: np.ndarray, keep_for_backward=True, precision=FP32,
@@ -76,12 +86,10 @@ def device_model_for(world) -> DeviceModel:
     if dm is not None:
         return dm
     raw = flatten_world(world)
-    if _has_possible_contacts(raw) and not getattr(world, "_contacts_disabled", False):
-        raise NotImplementedError(
-            "this world has collision shapes on several skeletons; the contact/LCP stage (SURVEY §8 rows a7-a12) "
-            "is not implemented in the device path yet. Remove the colliders or call world._contacts_disabled = True "
-            "to run the contact-free step.")
     world._raw_model = raw
-    dm = DeviceModel(compile_model(raw))
+    cm = compile_model(raw)
+    if getattr(world, "_contacts_disabled", False):
+        cm.shape_body = cm.shape_body[:0]  # contact-free step requested explicitly
+    dm = DeviceModel(cm)
     world._device_model = dm
     return dm

@@ -15,7 +15,8 @@ from typing import Optional
 import numpy as np
 import torch
 
-from .engine import FP32, device_model_for
+from ._cabi import MAX_CONTACTS, MAX_ROWS
+from .engine import FP32, FP64, device_model_for
 
 
 def _ptr(t: torch.Tensor) -> int:
@@ -47,11 +48,22 @@ class TimestepLayer(torch.autograd.Function):
         ad = a2.to(device=dev, dtype=torch.float32, non_blocking=True).contiguous()
         B = sd.shape[0]
         need_grad = any(ctx.needs_input_grad[1:3])
+        ctx.contact = dm.has_contacts
         with torch.cuda.device(dev):
             nxt = torch.empty_like(sd)
-            saved = torch.empty((dm.saved_words, B), dtype=torch.float32, device=dev) if need_grad else None
             stream = torch.cuda.current_stream().cuda_stream
-            dm.forward_device(B, _ptr(sd), _ptr(ad), _ptr(nxt), _ptr(saved) if saved is not None else None, stream, FP32)
+            if dm.has_contacts:
+                # contact / boxed-LCP stage: fp64 kernels; the LCP cache (BoxedLcpConstraintSolver::mX in the reference)
+                # lives on the world and flows from step to step like the reference's solver state
+                cache = contact_cache(world, B, dev)
+                saved = torch.empty((dm.saved_words, B), dtype=torch.float64, device=dev)
+                dm.forward_contact_device(B, _ptr(sd), _ptr(ad), _ptr(nxt), _ptr(saved), _ptr(cache["ws"]), _ptr(cache["x"]),
+                                          _ptr(cache["m"]), _ptr(cache["labels"]), _ptr(cache["status"]), _ptr(cache["nc"]),
+                                          _ptr(cache["cinfo"]), stream)
+                ctx.any_rows = cache["m"]
+            else:
+                saved = torch.empty((dm.saved_words, B), dtype=torch.float32, device=dev) if need_grad else None
+                dm.forward_device(B, _ptr(sd), _ptr(ad), _ptr(nxt), _ptr(saved) if saved is not None else None, stream, FP32)
         ctx.dm = dm
         ctx.legacy = legacy
         ctx.in_device = state.device
@@ -73,17 +85,46 @@ class TimestepLayer(torch.autograd.Function):
         sd, ad, saved = ctx.saved_tensors
         dev = sd.device
         g = grad_state.detach().reshape(ctx.B, 2 * dm.ndof).to(device=dev, dtype=torch.float32).contiguous()
+        if ctx.contact and int(ctx.any_rows.max().item()) > 0:
+            raise NotImplementedError(
+                "backward through a step with active contact constraints (SURVEY §8 rows a13/a14/a16 with contacts: "
+                "constraint-force Jacobians) is not implemented yet; contact-free steps of this world differentiate fine")
         with torch.cuda.device(dev):
             gs = torch.empty_like(sd)
             ga = torch.empty_like(ad)
             stream = torch.cuda.current_stream().cuda_stream
-            dm.backward_device(ctx.B, _ptr(sd), _ptr(ad), _ptr(saved), _ptr(g), _ptr(gs), _ptr(ga), stream, FP32)
+            dm.backward_device(ctx.B, _ptr(sd), _ptr(ad), _ptr(saved), _ptr(g), _ptr(gs), _ptr(ga), stream,
+                               FP64 if ctx.contact else FP32)
         if ctx.legacy:
             # reference returns fp64 grads (timestep.py:55-60)
             gs = gs[0].to(device=ctx.in_device, dtype=torch.float64 if ctx.in_dtype == torch.float64 else ctx.in_dtype)
             ga = ga[0].to(device=ctx.act_device, dtype=ctx.act_dtype)
             return None, gs, ga, None
         return None, gs.to(device=ctx.in_device, dtype=ctx.in_dtype), ga.to(device=ctx.act_device, dtype=ctx.act_dtype), None
+
+
+def contact_cache(world, B: int, device) -> dict:
+    """Per-world, per-batch-size device buffers of the contact stage: the cached LCP solution x/m (the reference's
+    BoxedLcpConstraintSolver::mX, warm start of the next step), and this step's labels / status / contact list."""
+    key = (B, str(device), world._version)
+    c = getattr(world, "_lcp_cache", None)
+    if c is None or c.get("key") != key:
+        dm = device_model_for(world)
+        c = dict(key=key,
+                 x=torch.zeros((B, MAX_ROWS), dtype=torch.float64, device=device),
+                 m=torch.full((B,), -1, dtype=torch.int32, device=device),
+                 labels=torch.zeros((B, MAX_ROWS), dtype=torch.int32, device=device),
+                 status=torch.zeros((B,), dtype=torch.int32, device=device),
+                 nc=torch.zeros((B,), dtype=torch.int32, device=device),
+                 cinfo=torch.zeros((B, MAX_CONTACTS, 10), dtype=torch.float32, device=device),
+                 ws=torch.empty((dm.contact_workspace_bytes(B) // 8,), dtype=torch.float64, device=device))
+        world._lcp_cache = c
+    return c
+
+
+def reset_contact_cache(world):
+    """Forget the cached LCP solutions (the next step starts from LCPUtils::guessSolution like a fresh solver)."""
+    world._lcp_cache = None
 
 
 def timestep(world, state: torch.Tensor, action: torch.Tensor, mass: Optional[torch.Tensor] = None) -> torch.Tensor:

@@ -17,7 +17,7 @@ def lib():
     if _LIB is None:
         so = os.path.join(_HERE, "libemul.so")
         srcs = [os.path.join(_HERE, "emul.cpp")] + [os.path.join(_ROOT, "nimblephysics_b200", "csrc", f)
-                                                      for f in ("nb2_dyn.cuh", "nb2_math.cuh", "nb2_model.h", "nb2_host_model.h")]
+                                                      for f in ("nb2_dyn.cuh", "nb2_math.cuh", "nb2_model.h", "nb2_host_model.h", "nb2_contact.cuh", "nb2_dantzig.cuh")]
         if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(s) for s in srcs):
             subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-Wno-unknown-pragmas", "-o", so,
                                    os.path.join(_HERE, "emul.cpp")])
@@ -41,7 +41,7 @@ class EmulWorld:
         action = np.ascontiguousarray(action, np.float32)
         B = state.shape[0]
         nxt = np.empty_like(state)
-        saved = np.zeros((self.sw, B), np.float32)
+        saved = np.zeros((self.sw, B), np.float64 if fp64 else np.float32)
         rc = lib().emul_forward(ctypes.byref(self.desc), B, _p(state), _p(action), _p(nxt), _p(saved), int(fp64))
         assert rc == 0
         return nxt, saved
@@ -57,3 +57,23 @@ class EmulWorld:
                                  _p(ga), int(fp64))
         assert rc == 0
         return gs, ga
+
+    def forward_contact(self, state, action, x_lcp=None, m_lcp=None):
+        """fp64 ABA + contact stage.  -> dict(next, saved, x, m, labels, status, nc, cinfo)"""
+        from nimblephysics_b200._cabi import MAX_CONTACTS, MAX_ROWS
+
+        state = np.ascontiguousarray(state, np.float32)
+        action = np.ascontiguousarray(action, np.float32)
+        B = state.shape[0]
+        nxt = np.empty_like(state)
+        saved = np.zeros((self.sw, B), np.float64)
+        x = np.zeros((B, MAX_ROWS)) if x_lcp is None else np.ascontiguousarray(x_lcp, np.float64).copy()
+        m = np.full(B, -1, np.int32) if m_lcp is None else np.ascontiguousarray(m_lcp, np.int32).copy()
+        labels = np.zeros((B, MAX_ROWS), np.int32)
+        status = np.zeros(B, np.int32)
+        nc = np.zeros(B, np.int32)
+        cinfo = np.zeros((B, MAX_CONTACTS, 10), np.float32)
+        rc = lib().emul_forward_contact(ctypes.byref(self.desc), B, _p(state), _p(action), _p(nxt), _p(saved), _p(x), _p(m),
+                                        _p(labels), _p(status), _p(nc), _p(cinfo))
+        assert rc == 0
+        return dict(next=nxt, saved=saved, x=x, m=m, labels=labels, status=status, nc=nc, cinfo=cinfo)

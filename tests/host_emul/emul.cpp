@@ -8,7 +8,7 @@
 #include "../../nimblephysics_b200/csrc/nb2_host_model.h"
 
 template <class R>
-static int run_fwd(const nb2_model_desc* d, int B, const float* state, const float* action, float* next, float* saved) {
+static int run_fwd(const nb2_model_desc* d, int B, const float* state, const float* action, float* next, R* saved) {
   Nb2ModelDev<R> M; std::string err;
   if (!nb2_fill_model(*d, M, err)) { fprintf(stderr, "emul: %s\n", err.c_str()); return -1; }
   nb2::FwdLayout L = nb2::fwd_layout(M.nb, M.ndof, M.nslots, M.nfree);
@@ -22,7 +22,7 @@ static int run_fwd(const nb2_model_desc* d, int B, const float* state, const flo
   return 0;
 }
 template <class R>
-static int run_bwd(const nb2_model_desc* d, int B, const float* state, const float* action, const float* saved,
+static int run_bwd(const nb2_model_desc* d, int B, const float* state, const float* action, const R* saved,
                    const float* gnext, float* gstate, float* gaction) {
   Nb2ModelDev<R> M; std::string err;
   if (!nb2_fill_model(*d, M, err)) { fprintf(stderr, "emul: %s\n", err.c_str()); return -1; }
@@ -36,17 +36,39 @@ static int run_bwd(const nb2_model_desc* d, int B, const float* state, const flo
   }
   return 0;
 }
+// forward with the contact stage (fp64): ABA kernel body with the saved stream, then the contact kernel body
+static int run_fwd_contact(const nb2_model_desc* d, int B, const float* state, const float* action, float* next, double* saved,
+                           double* x_lcp, int* m_lcp, int* labels, int* status, int* nc, float* cinfo) {
+  Nb2ModelDev<double> M; Nb2ContactDev C; std::string err;
+  if (!nb2_fill_model(*d, M, err) || !nb2_fill_contact(*d, C, err)) { fprintf(stderr, "emul: %s\n", err.c_str()); return -1; }
+  nb2::FwdLayout L = nb2::fwd_layout(M.nb, M.ndof, M.nslots, M.nfree);
+  std::vector<double> scr(L.total), ws(nb2::contact_ws_doubles(M.nb, M.ndof));
+  for (int w = 0; w < B; w++) {
+    for (auto& x : scr) x = 1e30;
+    nb2::world_forward<double, 1>(M, scr.data(), state + (size_t)w * 2 * M.ndof, action + (size_t)w * M.na,
+                                  next + (size_t)w * 2 * M.ndof, saved + w, (size_t)B, true);
+    for (auto& x : ws) x = 1e30;
+    nb2::world_contact(M, C, state + (size_t)w * 2 * M.ndof, next + (size_t)w * 2 * M.ndof, saved + w, (size_t)B, ws.data(),
+                       x_lcp + (size_t)w * NB2_MAX_ROWS, m_lcp + w, labels + (size_t)w * NB2_MAX_ROWS, status + w, nc + w,
+                       cinfo ? cinfo + (size_t)w * NB2_MAX_CONTACTS * 10 : nullptr);
+  }
+  return 0;
+}
 extern "C" {
+int emul_forward_contact(const nb2_model_desc* d, int B, const float* state, const float* action, float* next, double* saved,
+                         double* x_lcp, int* m_lcp, int* labels, int* status, int* nc, float* cinfo) {
+  return run_fwd_contact(d, B, state, action, next, saved, x_lcp, m_lcp, labels, status, nc, cinfo);
+}
 int emul_saved_words(const nb2_model_desc* d) {
   int nfree = 0; for (int i = 0; i < d->nb; i++) nfree += d->jtype[i] == NB2_JT_FREE;
   return nb2_saved_words(d->nb, d->ndof, nfree);
 }
-int emul_forward(const nb2_model_desc* d, int B, const float* state, const float* action, float* next, float* saved, int fp64) {
-  return fp64 ? run_fwd<double>(d, B, state, action, next, saved) : run_fwd<float>(d, B, state, action, next, saved);
+int emul_forward(const nb2_model_desc* d, int B, const float* state, const float* action, float* next, void* saved, int fp64) {
+  return fp64 ? run_fwd<double>(d, B, state, action, next, (double*)saved) : run_fwd<float>(d, B, state, action, next, (float*)saved);
 }
-int emul_backward(const nb2_model_desc* d, int B, const float* state, const float* action, const float* saved,
+int emul_backward(const nb2_model_desc* d, int B, const float* state, const float* action, const void* saved,
                   const float* gnext, float* gstate, float* gaction, int fp64) {
-  return fp64 ? run_bwd<double>(d, B, state, action, saved, gnext, gstate, gaction)
-              : run_bwd<float>(d, B, state, action, saved, gnext, gstate, gaction);
+  return fp64 ? run_bwd<double>(d, B, state, action, (const double*)saved, gnext, gstate, gaction)
+              : run_bwd<float>(d, B, state, action, (const float*)saved, gnext, gstate, gaction);
 }
 }

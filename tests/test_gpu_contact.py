@@ -1,0 +1,82 @@
+"""Contact / boxed-LCP stage on the GPU (through the autograd boundary -> C ABI nb2_step_forward_contact) vs the oracle.
+Contact set, LCP size, labels, status: bit-exact; impulses / next state: 1e-4 relative."""
+import numpy as np
+import pytest
+import torch
+
+import nimblephysics_b200 as nb
+from oracle import binding as ob
+from tests.util import contact_inputs, load_raw, rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("name", ["half_cheetah", "atlas_ground"])
+def test_contact_forward_matches_oracle(oracle_mod, name):
+    raw = load_raw(name)
+    world = nb.World.from_raw(raw)
+    ow = ob.OracleContactWorld(raw)
+    B, T = 64, 4
+    s, a = contact_inputs(raw, name, B, seed=5)
+    at = torch.tensor(a, device="cuda")
+    x = torch.tensor(s, device="cuda")
+    so = s.astype(np.float64).copy()
+    xo = [None] * B
+    nb.reset_contact_cache(world)
+    total_rows = 0
+    for t in range(T):
+        with torch.no_grad():
+            nxt = nb.timestep(world, x, at)
+        c = nb.contact_cache(world, B, x.device)
+        got = {k: c[k].cpu().numpy() for k in ("x", "m", "labels", "status", "nc", "cinfo")}
+        nxt_h = nxt.cpu().numpy()
+        for w in range(0, B, 3):
+            ro = ow.step_contact(so[w], a[w].astype(np.float64), xo[w])
+            mo = ro["m"]
+            total_rows += mo
+            assert got["nc"][w] == ro["nc"] and got["m"][w] == mo
+            assert np.array_equal(got["labels"][w][:mo], ro["mapping"])
+            assert got["status"][w] == ro["status"]
+            if mo:
+                assert np.abs(got["x"][w][:mo] - ro["x"]).max() < 1e-5 * max(1.0, np.abs(ro["x"]).max())
+            assert rel_err(nxt_h[w], ro["next_state"]) < 1e-4
+            xo[w] = ro["x"] if mo else None
+        # continue both sides from the device's fp32 rows (avoids tie flips from accumulated rounding differences)
+        so = nxt_h.astype(np.float64)
+        x = torch.tensor(so.astype(np.float32), device="cuda")
+    assert total_rows > 0
+
+
+def test_full_batch_contact_properties_atlas_4096():
+    """Size-independent properties at the benchmark batch: results do not depend on the position in the batch
+    (bit-exact, including labels), contact counts are plausible, every status word is one of the restated branches."""
+    raw = load_raw("atlas_ground")
+    world = nb.World.from_raw(raw)
+    B = 4096
+    s, a = contact_inputs(raw, "atlas_ground", B, seed=11)
+    st, at = torch.tensor(s, device="cuda"), torch.tensor(a, device="cuda")
+    nb.reset_contact_cache(world)
+    with torch.no_grad():
+        nxt = nb.timestep(world, st, at)
+    c = nb.contact_cache(world, B, st.device)
+    labels, m, status, nc, xl = c["labels"].clone(), c["m"].clone(), c["status"].clone(), c["nc"].clone(), c["x"].clone()
+    perm = torch.randperm(B, device="cuda")[:1000]
+    world2 = nb.World.from_raw(raw)
+    with torch.no_grad():
+        nxt2 = nb.timestep(world2, st[perm], at[perm])
+    c2 = nb.contact_cache(world2, 1000, st.device)
+    assert torch.equal(nxt[perm], nxt2) and torch.equal(labels[perm], c2["labels"]) and torch.equal(m[perm], c2["m"])
+    assert torch.equal(status[perm], c2["status"]) and torch.equal(xl[perm], c2["x"])
+    assert int(nc.max()) <= 16 and int(nc.min()) >= 0 and float((nc > 0).float().mean()) > 0.5
+    assert int((status & ~0x3FF).max()) == 0 and int((status & 0x180).max()) == 0  # no overflow / unsupported geometry
+    assert torch.isfinite(nxt).all()
+
+
+def test_backward_with_active_contacts_is_refused_loudly():
+    raw = load_raw("half_cheetah")
+    world = nb.World.from_raw(raw)
+    s, a = contact_inputs(raw, "half_cheetah", 8, seed=1)
+    st = torch.tensor(s, device="cuda", requires_grad=True)
+    out = nb.timestep(world, st, torch.tensor(a, device="cuda"))
+    with pytest.raises(NotImplementedError):
+        out.sum().backward()

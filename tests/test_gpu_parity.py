@@ -54,7 +54,7 @@ def test_c_abi_device_and_host_entry_points(oracle_mod, precision):
     # device entry points
     sd, ad, gd = (torch.tensor(x, device="cuda") for x in (s, a, g))
     nxt = torch.empty_like(sd)
-    saved = torch.empty((dm.saved_words, B), device="cuda")
+    saved = torch.empty((dm.saved_words, B), device="cuda", dtype=torch.float64 if precision else torch.float32)
     gs, ga = torch.empty_like(sd), torch.empty_like(ad)
     stream = torch.cuda.current_stream().cuda_stream
     dm.forward_device(B, sd.data_ptr(), ad.data_ptr(), nxt.data_ptr(), saved.data_ptr(), stream, precision)

@@ -29,3 +29,29 @@ def rel_err(x, ref):
     return float(np.linalg.norm(x - ref) / max(np.linalg.norm(ref), 1e-30))
 
 
+
+
+def contact_inputs(raw, name, B, seed=0):
+    """Seeded contact-rich inputs: half-cheetah bench pose q[1]=-0.1, q[2]=0.03 + noise
+    (python/nimblephysics_benchmarks/half_cheetah_bench.py:19-20); Atlas q[0]=-pi/2, q[4] so the feet penetrate 6-10 mm
+    (unittests/unit/test_AtlasGradients.cpp:235-236) + joint noise."""
+    rng = np.random.default_rng(seed)
+    n, na = raw.ndof, len(raw.action_map)
+    s = np.zeros((B, 2 * n))
+    for w in range(B):
+        q = np.zeros(n)
+        if name == "half_cheetah":
+            q[1] = -0.1 + rng.normal(0, 0.01)
+            q[2] = 0.03
+            q[3:] = rng.normal(0, 0.02, n - 3)
+            v = rng.normal(0, 0.1, n)
+        else:
+            q[0] = -0.5 * np.pi
+            q[4] = -0.01 + rng.uniform(-0.004, 0.0)
+            q[6:] = rng.normal(0, 0.01, n - 6)
+            v = rng.normal(0, 0.05, n)
+        s[w, :n], s[w, n:] = q, v
+    a = rng.uniform(-2, 2, (B, na))
+    if name != "half_cheetah":
+        a[:, :6] = 0.0
+    return s.astype(np.float32), a.astype(np.float32)
