@@ -57,7 +57,7 @@ namespace nb2 {
 typedef double CR;
 
 struct ContactWs {  // per-world fp64 workspace carved out of one contiguous block
-  CR *W, *V, *pI, *uI, *dqd, *vstar;
+  CR *W, *T, *V, *pI, *uI, *dqd, *vstar;
   CR *cpoint, *cnormal, *cdepth, *cmu, *crest;
   int *cbodyA, *cbodyB, *ctype, *cshapeA, *cshapeB;
   CR *JA, *JB, *b, *lo, *hi, *x, *x0, *rest, *colnorm;
@@ -69,13 +69,13 @@ struct ContactWs {  // per-world fp64 workspace carved out of one contiguous blo
 };
 NB2_HD size_t contact_ws_doubles(int nb, int ndof) {
   const int MC = NB2_MAX_CONTACTS, MR = NB2_MAX_ROWS;
-  return (size_t)nb * 12 + nb * 6 + nb * 6 + 3 * ndof + MC * 10 + MC * 3 /*ints as 5 int arrays -> 2.5 doubles each*/ + 2 * MR * 6 + 7 * MR
+  return (size_t)nb * 24 + nb * 6 + nb * 6 + 3 * ndof + MC * 10 + MC * 3 /*ints as 5 int arrays -> 2.5 doubles each*/ + 2 * MR * 6 + 7 * MR
          + 2 * MR /*int arrays*/ + 5 * (size_t)MR * MR + 8 * MR + MR /*i1,i2*/ + 2 * MR / 8 + 8;
 }
 NB2_HD ContactWs carve_ws(CR* base, int nb, int ndof) {
   const int MC = NB2_MAX_CONTACTS, MR = NB2_MAX_ROWS;
   ContactWs w; CR* p = base;
-  w.W = p; p += nb * 12; w.V = p; p += nb * 6; w.pI = p; p += nb * 6; w.uI = p; p += ndof; w.dqd = p; p += ndof; w.vstar = p; p += ndof;
+  w.W = p; p += nb * 12; w.T = p; p += nb * 12; w.V = p; p += nb * 6; w.pI = p; p += nb * 6; w.uI = p; p += ndof; w.dqd = p; p += ndof; w.vstar = p; p += ndof;
   w.cpoint = p; p += MC * 3; w.cnormal = p; p += MC * 3; w.cdepth = p; p += MC; w.cmu = p; p += MC; w.crest = p; p += MC;
   int* ip = (int*)p; w.cbodyA = ip; ip += MC; w.cbodyB = ip; ip += MC; w.ctype = ip; ip += MC; w.cshapeA = ip; ip += MC; w.cshapeB = ip; ip += MC;
   p += MC * 3;  // 5*MC ints = 2.5*MC doubles <= 3*MC
@@ -291,12 +291,14 @@ NB2_HD Xf<CR> saved_xf(const Nb2ModelDev<CR>& M, int i, const float* st, const C
   return xf_from12(t12);
 }
 
-// impulse-ABA with the forward's U, psi: body impulses in ws.pI (input, consumed) -> ws.dqd (joint velocity changes)
-// and ws.V (spatial velocity changes of every body)
-NB2_HD void impulse_response(const Nb2ModelDev<CR>& M, const float* st, const CR* sv, size_t B, const ContactWs& ws) {
+// impulse-ABA with the forward's U, psi: body impulses in ws.pI (holding -imp on entry, consumed) -> ws.dqd (joint velocity
+// changes) and ws.V (spatial velocity changes).  Only bodies in `mask` are visited: for the impulse TESTS that build A the
+// mask holds the ancestors of the contact bodies (every other body has zero bias impulse and its velocity change is never
+// read); the final impulse application visits every body.
+NB2_HD void impulse_response(const Nb2ModelDev<CR>& M, const CR* sv, size_t B, const ContactWs& ws, unsigned long long mask) {
   const int nb = M.nb;
-  // leaf -> root: pI_i = -imp_i + sum_c X*_c (pI_c + U_c psi_c uI_c) ; uI_i = -S^T pI_i    (ws.pI holds -imp on entry)
   for (int i = nb - 1; i >= 0; i--) {
+    if (!((mask >> i) & 1ull)) continue;
     const int jt = M.jtype[i], p = M.parent[i], o = M.dof_off[i];
     const CR* s = sv + (size_t)(i * 21) * B;
     const V6<CR> pI = ldv6(ws.pI + 6 * i);
@@ -306,22 +308,20 @@ NB2_HD void impulse_response(const Nb2ModelDev<CR>& M, const float* st, const CR
       ws.uI[o] = u;
       if (p >= 0) beta = pI + sv_ld6<CR>(s, B, 12) * (s[18 * B] * u);
     } else {
-      const V6<CR> u = zero6<CR>() - pI;
-      stv6(ws.uI + o, u);
+      stv6(ws.uI + o, zero6<CR>() - pI);
       if (p >= 0) beta = zero6<CR>();  // pI + I (I^-1 u) = 0: a 6-dof joint absorbs the whole impulse
     }
     if (p >= 0) {
-      const V6<CR> pc = dAdInvT(saved_xf(M, i, st, sv, B), beta);
+      const V6<CR> pc = dAdInvT(xf_from12(ws.T + 12 * i), beta);
       CR* pp = ws.pI + 6 * p;
       pp[0] += pc.a.x; pp[1] += pc.a.y; pp[2] += pc.a.z; pp[3] += pc.l.x; pp[4] += pc.l.y; pp[5] += pc.l.z;
     }
   }
-  // root -> leaf
   for (int i = 0; i < nb; i++) {
+    if (!((mask >> i) & 1ull)) continue;
     const int jt = M.jtype[i], p = M.parent[i], o = M.dof_off[i];
     const CR* s = sv + (size_t)(i * 21) * B;
-    const Xf<CR> T = saved_xf(M, i, st, sv, B);
-    V6<CR> dV = (p >= 0) ? AdInvT(T, ldv6(ws.V + 6 * p)) : zero6<CR>();
+    V6<CR> dV = (p >= 0) ? AdInvT(xf_from12(ws.T + 12 * i), ldv6(ws.V + 6 * p)) : zero6<CR>();
     if (jt != NB2_JT_FREE) {
       const CR d = s[18 * B] * (ws.uI[o] - dot(sv_ld6<CR>(s, B, 12), dV));
       ws.dqd[o] = d;
@@ -553,6 +553,7 @@ NB2_HD void world_contact(const Nb2ModelDev<CR>& M, const Nb2ContactDev& C, cons
     const Xf<CR> T = saved_xf(M, i, st, sv, B);
     const Xf<CR> W = (p >= 0) ? xf_mul(xf_from12(ws.W + 12 * p), T) : T;
     xf_to12(ws.W + 12 * i, W);
+    xf_to12(ws.T + 12 * i, T);
     V6<CR> V = (p >= 0) ? AdInvT(T, ldv6(ws.V + 6 * p)) : zero6<CR>();
     if (jt != NB2_JT_FREE) {
       const CR vs = (CR)st[n + o] + dt * sv[(size_t)(kQdd + o) * B];
@@ -665,12 +666,17 @@ NB2_HD void world_contact(const Nb2ModelDev<CR>& M, const Nb2ContactDev& C, cons
   for (int r = 0; r < m; r++) rowc[r] = (unsigned char)ws.i1[r];
   // ---- A by impulse tests (upper blocks measured, lower mirrored; BoxedLcpConstraintSolver.cpp:293-314)
   CR* A = ws.A;
+  unsigned long long mask = 0ull;  // ancestors (and self) of every contact body
+  for (int c = 0; c < nc; c++) {
+    for (int bdy = ws.cbodyA[c]; bdy >= 0; bdy = M.parent[bdy]) mask |= (1ull << bdy);
+    for (int bdy = ws.cbodyB[c]; bdy >= 0; bdy = M.parent[bdy]) mask |= (1ull << bdy);
+  }
   for (int r = 0; r < m; r++) {
     const int c = rowc[r];
-    for (int i = 0; i < nb * 6; i++) ws.pI[i] = 0;
+    for (int i = 0; i < nb; i++) if ((mask >> i) & 1ull) for (int k = 0; k < 6; k++) ws.pI[6 * i + k] = 0;
     if (ws.cbodyA[c] >= 0) { const CR* J = ws.JA + 6 * r; CR* p = ws.pI + 6 * ws.cbodyA[c]; for (int k = 0; k < 6; k++) p[k] -= J[k]; }
     if (ws.cbodyB[c] >= 0) { const CR* J = ws.JB + 6 * r; CR* p = ws.pI + 6 * ws.cbodyB[c]; for (int k = 0; k < 6; k++) p[k] -= J[k]; }
-    impulse_response(M, st, sv, B, ws);
+    impulse_response(M, sv, B, ws, mask);
     for (int s2 = 0; s2 < m; s2++) {
       const int cj = rowc[s2];
       if (cj < c) { A[r * m + s2] = A[s2 * m + r]; continue; }
@@ -750,7 +756,7 @@ NB2_HD void world_contact(const Nb2ModelDev<CR>& M, const Nb2ContactDev& C, cons
     if (ws.cbodyA[c] >= 0) { const CR* J = ws.JA + 6 * r; CR* p = ws.pI + 6 * ws.cbodyA[c]; for (int k = 0; k < 6; k++) p[k] -= J[k] * x[r]; }
     if (ws.cbodyB[c] >= 0) { const CR* J = ws.JB + 6 * r; CR* p = ws.pI + 6 * ws.cbodyB[c]; for (int k = 0; k < 6; k++) p[k] -= J[k] * x[r]; }
   }
-  impulse_response(M, st, sv, B, ws);
+  impulse_response(M, sv, B, ws, ~0ull);
   for (int d = 0; d < n; d++) out[n + d] = (float)(ws.vstar[d] + ws.dqd[d]);
   *m_io = m; *status_out = status;
 }

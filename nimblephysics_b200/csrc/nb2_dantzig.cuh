@@ -6,8 +6,9 @@
 // What is restated is the ALGORITHM and its pivoting/tie-breaking order (same physical permutation of the
 // problem, same loop orders, same strict '<' comparisons), so that the same index sets are reached.  The dense
 // linear algebra is new: A is kept as a full symmetric matrix (the reference touches only one triangle through
-// row pointers) and the L D L^T factor of A[C,C] is rebuilt from scratch whenever C changes instead of ODE's
-// incremental dLDLTAddTL / dLDLTRemove — identical in exact arithmetic, agreeing to rounding in floating point.
+// row pointers); rows are appended to the L D L^T factor of A[C,C] incrementally (same recurrence as ODE), and the
+// factor is rebuilt from scratch when an index LEAVES C instead of ODE's dLDLTRemove rank-one downdate — identical in
+// exact arithmetic, agreeing to rounding in floating point.
 // This one header is compiled both into the CUDA library and into the test oracle; sharing it is safe because it is
 // pinned against the REAL reference code: tests/test_lcp.py compares it with dSolveLCP compiled from
 // /root/reference (oracle/_ref/libodelcp.so) on random and literal LCP instances.
@@ -67,6 +68,14 @@ NB2_HD void dz_factor(const DantzigWork& W, int n, int nC) {
       else W.d[i] = 1.0 / s;
     }
   }
+}
+
+// append index (physical slot i, about to be swapped into slot nC) to the factor using the ell/Dell of the latest
+// dz_solve1(.., i, ..) — exactly what transfer_i_to_C does (lcp.cpp:503-535); O(nC) instead of a refactorisation
+NB2_HD void dz_append_from_solve1(const DantzigWork& W, int n, int nC, int i) {
+  double s = W.A[(size_t)i * n + i];
+  for (int j = 0; j < nC; j++) { W.L[nC * n + j] = W.ell[j]; s -= W.ell[j] * W.Dell[j]; }
+  W.d[nC] = 1.0 / s;
 }
 
 // solve1 (lcp.cpp:703-753): Dell = L \ A[C,i] ; ell = Dell .* d ; a[C] = -dir * L^T \ ell
@@ -140,10 +149,10 @@ NB2_HD int dantzig_solve(const DantzigWork& W, int n, bool early_termination) {
     if (W.lo[i] == 0 && W.w[i] >= 0) { nN++; W.state[i] = 0; }
     else if (W.hi[i] == 0 && W.w[i] <= 0) { nN++; W.state[i] = 1; }
     else if (W.w[i] == 0) {
-      // transfer_i_to_C: physical slot nC
+      dz_solve1(W, n, nC, W.delta_x, i, 0, true);
+      dz_append_from_solve1(W, n, nC, i);
       dz_swap_problem(W, n, nC, i);
       W.C[nC] = nC; nC++;
-      dz_factor(W, n, nC);
     } else {
       for (;;) {
         if (--iter_cap < 0) return -1;
@@ -194,10 +203,15 @@ NB2_HD int dantzig_solve(const DantzigWork& W, int n, bool early_termination) {
         for (int k = 0; k < nN; k++) W.w[nC + k] += s * W.delta_w[nC + k];
         W.w[i] += s * W.delta_w[i];
         switch (cmd) {
-          case 1: W.w[i] = 0; dz_swap_problem(W, n, nC, i); W.C[nC] = nC; nC++; dz_factor(W, n, nC); break;
+          case 1: W.w[i] = 0; dz_append_from_solve1(W, n, nC, i); dz_swap_problem(W, n, nC, i); W.C[nC] = nC; nC++; break;
           case 2: W.x[i] = W.lo[i]; W.state[i] = 0; nN++; break;
           case 3: W.x[i] = W.hi[i]; W.state[i] = 1; nN++; break;
-          case 4: W.w[si] = 0; dz_swap_problem(W, n, nC, si); W.C[nC] = nC; nN--; nC++; dz_factor(W, n, nC); break;
+          case 4:  // transfer_i_from_N_to_C (lcp.cpp:538-590): its own forward solve, then append
+            W.w[si] = 0;
+            dz_solve1(W, n, nC, W.delta_x, si, 0, true);
+            dz_append_from_solve1(W, n, nC, si);
+            dz_swap_problem(W, n, nC, si); W.C[nC] = nC; nN--; nC++;
+            break;
           case 5:
           case 6: {
             if (cmd == 5) { W.x[si] = W.lo[si]; W.state[si] = 0; } else { W.x[si] = W.hi[si]; W.state[si] = 1; }
