@@ -306,8 +306,22 @@ def main():
                         nb.timestep(cworld, cst, cat)
                     e1.record()
                     torch.cuda.synchronize()
+                # fwd + bwd through the autograd boundary (contact adjoint)
+                csg, cag = cst.clone().requires_grad_(True), cat.clone().requires_grad_(True)
+                gg = torch.randn_like(cst)
+                for _ in range(2):
+                    nb.timestep(cworld, csg, cag).backward(gg)
+                torch.cuda.synchronize()
+                f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                kfb = 5
+                f0.record()
+                for _ in range(kfb):
+                    nb.timestep(cworld, csg, cag).backward(gg)
+                f1.record()
+                torch.cuda.synchronize()
                 cc = nb.contact_cache(cworld, B, dev)
                 extra[label] = {"world_steps_per_s": B * ksteps / (e0.elapsed_time(e1) * 1e-3), "batch": B,
+                                "fwd_bwd_world_steps_per_s": B * kfb / (f0.elapsed_time(f1) * 1e-3),
                                 "mean_contacts": float(cc["nc"].float().mean()), "mean_lcp_rows": float(cc["m"].float().mean()),
                                 "frac_shortcircuit": float(((cc["status"] & 1) > 0).float().mean()),
                                 "frac_dantzig": float(((cc["status"] & 2) > 0).float().mean()),

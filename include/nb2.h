@@ -98,6 +98,8 @@ int nb2_step_forward_host(nb2_model* m, int B, const float* state, const float* 
 int nb2_step_backward_host(nb2_model* m, int B, const float* grad_next_state, float* grad_state, float* grad_action,
                            int precision);
 
+#define NB2_MAX_CONTACTS 16
+#define NB2_MAX_ROWS 48
 /* ---- contact / boxed-LCP stage -------------------------------------------------------------------------------
  * Replaces ConstraintSolver::solve + World::integrateVelocitiesFromImpulses (dart/constraint/ConstraintSolver.cpp:376-823,
  * dart/constraint/BoxedLcpConstraintSolver.cpp:190-789, dart/simulation/World.cpp:283-304) for worlds whose model has shapes.
@@ -107,15 +109,23 @@ int nb2_step_backward_host(nb2_model* m, int B, const float* grad_next_state, fl
  *   labels  [B, NB2_MAX_ROWS] int32    out: ConstraintMapping per row (-2 clamping, -1 not clamping, >=0 upper-bound -> normal row)
  *   status  [B] int32                  out: NB2_ST_* bits (which solver branch ran, unsupported geometry, overflow)
  *   ncontacts [B] int32                out
- *   cinfo   [B, NB2_MAX_CONTACTS, 10] float (optional, may be NULL): point(3) normal(3) depth bodyA bodyB type            */
-#define NB2_MAX_CONTACTS 16
-#define NB2_MAX_ROWS 48
+ *   cinfo   [B, NB2_MAX_CONTACTS, 10] float (optional, may be NULL): point(3) normal(3) depth bodyA bodyB type
+ *   contact_record [B, nb2_contact_record_bytes/B/8] double (optional): what nb2_step_backward_contact needs (labels, impulses,
+ *            LCP matrix), the batched counterpart of the ConstrainedGroupGradientMatrices a BackpropSnapshot holds.
+ */
 size_t nb2_contact_workspace_bytes(const nb2_model* m, int B);
 int nb2_model_has_contacts(const nb2_model* m);
 /* forward step WITH the contact stage: runs the fp64 ABA kernel (saved stream required) followed by the contact kernel. */
 int nb2_step_forward_contact(const nb2_model* m, int B, const float* state, const float* action, float* next_state,
                              void* saved_fp64, void* workspace, double* x_lcp, int32_t* m_lcp, int32_t* labels,
-                             int32_t* status, int32_t* ncontacts, float* cinfo, void* stream);
+                             int32_t* status, int32_t* ncontacts, float* cinfo, double* contact_record, void* stream);
+size_t nb2_contact_record_bytes(const nb2_model* m, int B);
+/* VJP of a step taken with nb2_step_forward_contact (classification frozen at the forward solution), replaces
+ * BackpropSnapshot::backpropState for steps with active contact constraints (dart/neural/BackpropSnapshot.cpp:980-1107,
+ * 2723-3146).  Unsupported configurations (contact between two moving bodies) yield NaN gradients, never silent garbage. */
+int nb2_step_backward_contact(const nb2_model* m, int B, const float* state, const float* action, const void* saved_fp64,
+                              const double* contact_record, void* workspace, const float* grad_next_state, float* grad_state,
+                              float* grad_action, void* stream);
 
 /* number of kernels this library has launched since load (bench.py reports it as gpu_launches) */
 long long nb2_launch_count(void);

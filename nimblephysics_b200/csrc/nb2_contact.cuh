@@ -17,6 +17,7 @@
 #pragma once
 #include "nb2_dantzig.cuh"
 #include "nb2_dyn.cuh"
+#include "nb2_geom.cuh"
 
 #include "../../include/nb2.h"  // NB2_MAX_CONTACTS, NB2_MAX_ROWS
 
@@ -54,8 +55,6 @@ struct Nb2ContactDev {
 
 namespace nb2 {
 
-typedef double CR;
-
 struct ContactWs {  // per-world fp64 workspace carved out of one contiguous block
   CR *W, *T, *V, *pI, *uI, *dqd, *vstar;
   CR *cpoint, *cnormal, *cdepth, *cmu, *crest;
@@ -67,6 +66,7 @@ struct ContactWs {  // per-world fp64 workspace carved out of one contiguous blo
   int *i1, *i2;
   unsigned char* st8;
 };
+NB2_HD size_t contact_rec_doubles(int ndof) { return 2 + 2 * (size_t)NB2_MAX_ROWS + ndof + (size_t)NB2_MAX_ROWS * NB2_MAX_ROWS; }
 NB2_HD size_t contact_ws_doubles(int nb, int ndof) {
   const int MC = NB2_MAX_CONTACTS, MR = NB2_MAX_ROWS;
   return (size_t)nb * 24 + nb * 6 + nb * 6 + 3 * ndof + MC * 10 + MC * 3 /*ints as 5 int arrays -> 2.5 doubles each*/ + 2 * MR * 6 + 7 * MR
@@ -107,178 +107,7 @@ NB2_HD void set3(V3<CR>& v, int k, CR x) { if (k == 0) v.x = x; else if (k == 1)
 NB2_HD V6<CR> ldv6(const CR* p) { V6<CR> v; v.a = mk3<CR>(p[0], p[1], p[2]); v.l = mk3<CR>(p[3], p[4], p[5]); return v; }
 NB2_HD void stv6(CR* p, const V6<CR>& v) { p[0] = v.a.x; p[1] = v.a.y; p[2] = v.a.z; p[3] = v.l.x; p[4] = v.l.y; p[5] = v.l.z; }
 
-struct ContactOut {  // one emitted contact
-  V3<CR> point, normal; CR depth; int type;
-};
-
-// ---- box (object 1) vs sphere (object 2) and sphere (1) vs box (2)
-NB2_HD int collide_box_sphere(const V3<CR>& size0, const Xf<CR>& T0, CR r1, const Xf<CR>& T1, CR clip, int halfspace, bool sphere_first, ContactOut* out) {
-  // sphere_first=false: DARTCollide.cpp:1482-1653 (normal = contact point - centre); true: :1655-1810 (normal = centre - contact point, no halfspace clip)
-  V3<CR> half = size0 * CR(0.5);
-  bool inside = true;
-  const V3<CR> c0 = T1.p;
-  V3<CR> p = xf_apply_inv(T0, c0);
-  for (int k = 0; k < 3; k++) {
-    CR pk = get3(p, k), hk = get3(half, k);
-    if (pk < -hk) { set3(p, k, -hk); inside = false; }
-    if (pk > hk) { set3(p, k, hk); inside = false; }
-  }
-  CR mn = half.x - nb2_abs(p.x); int idx = 0;
-  CR t = half.y - nb2_abs(p.y); if (t < mn) { mn = t; idx = 1; }
-  t = half.z - nb2_abs(p.z); if (t < mn) { mn = t; idx = 2; }
-  V3<CR> nloc = zero3<CR>();
-  const CR sgn = (get3(p, idx) > 0.0) ? 1.0 : -1.0;
-  set3(nloc, idx, sphere_first ? sgn : -sgn);
-  const V3<CR> nface = mul(T0.R_, nloc);
-  if (inside) {
-    CR pen = mn + r1;
-    if (pen > clip) return 0;
-    out->type = sphere_first ? 1 /*VERTEX_FACE*/ : 2 /*FACE_VERTEX*/; out->point = c0; out->normal = nface; out->depth = pen; return 1;
-  }
-  const V3<CR> cp = xf_apply(T0, p);
-  V3<CR> n = sphere_first ? (c0 - cp) : (cp - c0);
-  const CR mag = nb2_sqrt(dot(n, n));
-  const CR pen = r1 - mag;
-  if (pen > clip) return 0;
-  if (!sphere_first) {
-    const CR lz = xf_apply_inv(T1, cp).z;
-    if (halfspace == 2 /*BOTTOM*/ && lz >= 0) return 0;
-    if (halfspace == 1 /*TOP*/ && lz <= 0) return 0;
-  }
-  if (pen < 0.0) return 0;
-  out->type = sphere_first ? 4 : 5; out->point = cp; out->depth = pen;
-  out->normal = (mag > 1e-6) ? n * (CR(1) / mag) : nface;
-  return 1;
-}
-
-NB2_HD int intersect_rect_quad(const CR h[2], CR p[8], CR ret[16]) {  // DARTCollide.cpp:513-580
-  int nq = 4, nr = 0;
-  CR buffer[16];
-  CR* q = p; CR* r = ret;
-  for (int dir = 0; dir <= 1; dir++) {
-    for (int sign = -1; sign <= 1; sign += 2) {
-      CR* pq = q; CR* pr = r; nr = 0;
-      for (int i = nq; i > 0; i--) {
-        if (sign * pq[dir] < h[dir]) { pr[0] = pq[0]; pr[1] = pq[1]; pr += 2; nr++; if (nr & 8) { q = r; goto done; } }
-        CR* nextq = (i > 1) ? pq + 2 : q;
-        if ((sign * pq[dir] < h[dir]) ^ (sign * nextq[dir] < h[dir])) {
-          pr[1 - dir] = pq[1 - dir] + (nextq[1 - dir] - pq[1 - dir]) / (nextq[dir] - pq[dir]) * (sign * h[dir] - pq[dir]);
-          pr[dir] = sign * h[dir];
-          pr += 2; nr++;
-          if (nr & 8) { q = r; goto done; }
-        }
-        pq += 2;
-      }
-      q = r; r = (q == ret) ? buffer : ret; nq = nr;
-    }
-  }
-done:
-  if (q != ret) for (int i = 0; i < nr * 2; i++) ret[i] = q[i];
-  return nr;
-}
-
-// dBoxBox (DARTCollide.cpp:764-1450); returns the number of contacts written to out (<= 8)
-NB2_HD int collide_box_box(const V3<CR>& size0, const Xf<CR>& T0, const V3<CR>& size1, const Xf<CR>& T1, CR clip, ContactOut* out) {
-  const CR fudge = 1.05;
-  const M3<CR>&R1 = T0.R_, &R2 = T1.R_;
-  const V3<CR> p1 = T0.p, p2 = T1.p;
-  const CR A[3] = {size0.x * 0.5, size0.y * 0.5, size0.z * 0.5}, Bh[3] = {size1.x * 0.5, size1.y * 0.5, size1.z * 0.5};
-  const V3<CR> p = p2 - p1;
-  const V3<CR> ppv = mulT(R1, p);
-  const CR pp[3] = {ppv.x, ppv.y, ppv.z};
-  CR Rm[3][3], Q[3][3];
-  for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) { Rm[i][j] = dot(col3(R1, i), col3(R2, j)); Q[i][j] = nb2_abs(Rm[i][j]); }
-  CR s = -1e12, s2;
-  int invert_normal = 0, code = 0, nbox = 0, ncol = -1;
-  V3<CR> normalC = zero3<CR>();
-#define NB2_TST(expr1, expr2, box, colj, cc) { const CR e1 = (expr1); s2 = nb2_abs(e1) - (expr2); if (s2 > s) { s = s2; nbox = box; ncol = colj; invert_normal = (e1 < 0); code = (cc); } }
-  NB2_TST(pp[0], (A[0] + Bh[0] * Q[0][0] + Bh[1] * Q[0][1] + Bh[2] * Q[0][2]), 1, 0, 1)
-  NB2_TST(pp[1], (A[1] + Bh[0] * Q[1][0] + Bh[1] * Q[1][1] + Bh[2] * Q[1][2]), 1, 1, 2)
-  NB2_TST(pp[2], (A[2] + Bh[0] * Q[2][0] + Bh[1] * Q[2][1] + Bh[2] * Q[2][2]), 1, 2, 3)
-  NB2_TST(dot(col3(R2, 0), p), (A[0] * Q[0][0] + A[1] * Q[1][0] + A[2] * Q[2][0] + Bh[0]), 2, 0, 4)
-  NB2_TST(dot(col3(R2, 1), p), (A[0] * Q[0][1] + A[1] * Q[1][1] + A[2] * Q[2][1] + Bh[1]), 2, 1, 5)
-  NB2_TST(dot(col3(R2, 2), p), (A[0] * Q[0][2] + A[1] * Q[1][2] + A[2] * Q[2][2] + Bh[2]), 2, 2, 6)
-#undef NB2_TST
-#define NB2_TST2(expr1, expr2, n1, n2, n3, cc) { const CR e1 = (expr1); s2 = nb2_abs(e1) - (expr2); const CR N1 = (n1), N2 = (n2), N3 = (n3); const CR l = nb2_sqrt(N1 * N1 + N2 * N2 + N3 * N3); \
-    if (l > 0) { s2 /= l; if (s2 * fudge > s) { s = s2; ncol = -1; normalC = mk3<CR>(N1 / l, N2 / l, N3 / l); invert_normal = (e1 < 0); code = (cc); } } }
-  NB2_TST2(pp[2] * Rm[1][0] - pp[1] * Rm[2][0], (A[1] * Q[2][0] + A[2] * Q[1][0] + Bh[1] * Q[0][2] + Bh[2] * Q[0][1]), 0.0, -Rm[2][0], Rm[1][0], 7)
-  NB2_TST2(pp[2] * Rm[1][1] - pp[1] * Rm[2][1], (A[1] * Q[2][1] + A[2] * Q[1][1] + Bh[0] * Q[0][2] + Bh[2] * Q[0][0]), 0.0, -Rm[2][1], Rm[1][1], 8)
-  NB2_TST2(pp[2] * Rm[1][2] - pp[1] * Rm[2][2], (A[1] * Q[2][2] + A[2] * Q[1][2] + Bh[0] * Q[0][1] + Bh[1] * Q[0][0]), 0.0, -Rm[2][2], Rm[1][2], 9)
-  NB2_TST2(pp[0] * Rm[2][0] - pp[2] * Rm[0][0], (A[0] * Q[2][0] + A[2] * Q[0][0] + Bh[1] * Q[1][2] + Bh[2] * Q[1][1]), Rm[2][0], 0.0, -Rm[0][0], 10)
-  NB2_TST2(pp[0] * Rm[2][1] - pp[2] * Rm[0][1], (A[0] * Q[2][1] + A[2] * Q[0][1] + Bh[0] * Q[1][2] + Bh[2] * Q[1][0]), Rm[2][1], 0.0, -Rm[0][1], 11)
-  NB2_TST2(pp[0] * Rm[2][2] - pp[2] * Rm[0][2], (A[0] * Q[2][2] + A[2] * Q[0][2] + Bh[0] * Q[1][1] + Bh[1] * Q[1][0]), Rm[2][2], 0.0, -Rm[0][2], 12)
-  NB2_TST2(pp[1] * Rm[0][0] - pp[0] * Rm[1][0], (A[0] * Q[1][0] + A[1] * Q[0][0] + Bh[1] * Q[2][2] + Bh[2] * Q[2][1]), -Rm[1][0], Rm[0][0], 0.0, 13)
-  NB2_TST2(pp[1] * Rm[0][1] - pp[0] * Rm[1][1], (A[0] * Q[1][1] + A[1] * Q[0][1] + Bh[0] * Q[2][2] + Bh[2] * Q[2][0]), -Rm[1][1], Rm[0][1], 0.0, 14)
-  NB2_TST2(pp[1] * Rm[0][2] - pp[0] * Rm[1][2], (A[0] * Q[1][2] + A[1] * Q[0][2] + Bh[0] * Q[2][1] + Bh[1] * Q[2][0]), -Rm[1][2], Rm[0][2], 0.0, 15)
-#undef NB2_TST2
-  if (!code) return 0;
-  if (s > 0.0) return 0;
-  V3<CR> normal;
-  if (ncol >= 0) normal = col3(nbox == 1 ? R1 : R2, ncol);
-  else { normal = mul(R1, normalC); normal = normal * (CR(1) / nb2_sqrt(dot(normal, normal))); }
-  if (invert_normal) normal = -normal;
-  if (code > 6) {
-    V3<CR> pa = p1, pb = p2;
-    for (int j = 0; j < 3; j++) { const CR sg = (dot(normal, col3(R1, j)) > -1e-10) ? 1.0 : -1.0; pa = pa + col3(R1, j) * (A[j] * sg); }
-    for (int j = 0; j < 3; j++) { const CR sg = (dot(normal, col3(R2, j)) > -1e-3) ? -1.0 : 1.0; pb = pb + col3(R2, j) * (Bh[j] * sg); }
-    const V3<CR> ua = col3(R1, (code - 7) / 3), ub = col3(R2, (code - 7) % 3);
-    const V3<CR> dp = pb - pa;
-    const CR uaub = dot(ua, ub), q1 = dot(ua, dp), q2 = -dot(ub, dp);
-    CR d = 1.0 - uaub * uaub, alpha = 0.0, beta = 0.0;
-    if (d > 0.0) { d = 1.0 / d; alpha = (q1 + uaub * q2) * d; beta = (uaub * q1 + q2) * d; }
-    pa = pa + ua * alpha; pb = pb + ub * beta;
-    const CR pen = -s;
-    if (pen > clip) return 0;
-    out[0].point = (pa + pb) * CR(0.5); out[0].normal = -normal; out[0].depth = pen; out[0].type = 3;
-    return 1;
-  }
-  const M3<CR>*Ra, *Rb; V3<CR> pa, pb; const CR *Sa, *Sb; bool flip;
-  if (code <= 3) { Ra = &R1; Rb = &R2; pa = p1; pb = p2; Sa = A; Sb = Bh; flip = false; }
-  else { Ra = &R2; Rb = &R1; pa = p2; pb = p1; Sa = Bh; Sb = A; flip = true; }
-  const V3<CR> normal2 = (code <= 3) ? normal : -normal;
-  const V3<CR> nr = mulT(*Rb, normal2);
-  const CR anr[3] = {nb2_abs(nr.x), nb2_abs(nr.y), nb2_abs(nr.z)};
-  int lanr, a1, a2;
-  if (anr[1] > anr[0]) { if (anr[1] > anr[2]) { a1 = 0; lanr = 1; a2 = 2; } else { a1 = 0; a2 = 1; lanr = 2; } }
-  else { if (anr[0] > anr[2]) { lanr = 0; a1 = 1; a2 = 2; } else { a1 = 0; a2 = 1; lanr = 2; } }
-  const V3<CR> center = (get3(nr, lanr) < 0) ? (pb - pa + col3(*Rb, lanr) * Sb[lanr]) : (pb - pa - col3(*Rb, lanr) * Sb[lanr]);
-  const int codeN = (code <= 3) ? code - 1 : code - 4;
-  int code1, code2;
-  if (codeN == 0) { code1 = 1; code2 = 2; } else if (codeN == 1) { code1 = 0; code2 = 2; } else { code1 = 0; code2 = 1; }
-  CR quad[8];
-  const CR c1 = dot(center, col3(*Ra, code1)), c2 = dot(center, col3(*Ra, code2));
-  CR m11 = dot(col3(*Ra, code1), col3(*Rb, a1)), m12 = dot(col3(*Ra, code1), col3(*Rb, a2));
-  CR m21 = dot(col3(*Ra, code2), col3(*Rb, a1)), m22 = dot(col3(*Ra, code2), col3(*Rb, a2));
-  {
-    const CR k1 = m11 * Sb[a1], k2 = m21 * Sb[a1], k3 = m12 * Sb[a2], k4 = m22 * Sb[a2];
-    quad[0] = c1 - k1 - k3; quad[1] = c2 - k2 - k4; quad[2] = c1 - k1 + k3; quad[3] = c2 - k2 + k4;
-    quad[4] = c1 + k1 + k3; quad[5] = c2 + k2 + k4; quad[6] = c1 + k1 - k3; quad[7] = c2 + k2 - k4;
-  }
-  const CR rect[2] = {Sa[code1], Sa[code2]};
-  CR ret[16];
-  const int n = intersect_rect_quad(rect, quad, ret);
-  if (n < 1) return 0;
-  const CR det1 = 1.0 / (m11 * m22 - m12 * m21);
-  m11 *= det1; m12 *= det1; m21 *= det1; m22 *= det1;
-  int cnum = 0;
-  for (int j = 0; j < n; j++) {
-    const CR k1 = m22 * (ret[j * 2] - c1) - m12 * (ret[j * 2 + 1] - c2);
-    const CR k2 = -m21 * (ret[j * 2] - c1) + m11 * (ret[j * 2 + 1] - c2);
-    const V3<CR> pt = center + col3(*Rb, a1) * k1 + col3(*Rb, a2) * k2;
-    const CR dep = Sa[codeN] - dot(normal2, pt);
-    if (dep >= 0) {
-      ContactOut& c = out[cnum];
-      c.point = pt + pa; c.normal = -normal; c.depth = dep;
-      const bool onX = nb2_abs(ret[j * 2]) == rect[0], onY = nb2_abs(ret[j * 2 + 1]) == rect[1];
-      if (onX && onY) {
-        if (flip) { c.type = 2; c.point = c.point + c.normal * c.depth; } else { c.type = 1; c.point = c.point - c.normal * c.depth; }
-      } else if (!onX && !onY) c.type = flip ? 1 : 2;
-      else c.type = 3;
-      cnum++;
-    }
-  }
-  return cnum;
-}
+typedef ContactOutT<CR> ContactOut;
 
 // ------------------------------------------------------------------ joint transform of body i from the saved stream
 NB2_HD Xf<CR> saved_xf(const Nb2ModelDev<CR>& M, int i, const float* st, const CR* sv, size_t B) {
@@ -541,7 +370,8 @@ NB2_HD bool pgs_solve(int m, CR* A, CR* x, CR* b, const CR* lo, const CR* hi, co
 // x_io: cached LCP solution (NB2_MAX_ROWS doubles), m_io: its size (-1 none) -> new solution / size.
 // =====================================================================================================
 NB2_HD void world_contact(const Nb2ModelDev<CR>& M, const Nb2ContactDev& C, const float* st, float* out, const CR* sv, size_t B,
-                          CR* wsbase, CR* x_io, int* m_io, int* labels_out, int* status_out, int* nc_out, float* cinfo_out) {
+                          CR* wsbase, CR* x_io, int* m_io, int* labels_out, int* status_out, int* nc_out, float* cinfo_out,
+                          CR* crec) {
   const int nb = M.nb, n = M.ndof;
   const ContactWs ws = carve_ws(wsbase, nb, n);
   const int kQdd = nb * 21 + M.nfree * 33;
@@ -660,7 +490,7 @@ NB2_HD void world_contact(const Nb2ModelDev<CR>& M, const Nb2ContactDev& C, cons
     if (bounce) { const CR rv = ws.b[off] * e; if (rv > 1e-1) { if (rv > bv) { bv = rv; if (bv > 1e2) bv = 1e2; } } }
     ws.b[off] += bv;
   }
-  if (m == 0) { *m_io = 0; *status_out = status; return; }  // out already holds v*
+  if (m == 0) { *m_io = 0; *status_out = status; if (crec) crec[0] = 0; return; }  // out already holds v*
   // row -> contact map must survive classification (which uses i1): copy to st8 region as bytes
   unsigned char* rowc = ws.st8 + NB2_MAX_ROWS;
   for (int r = 0; r < m; r++) rowc[r] = (unsigned char)ws.i1[r];
@@ -759,6 +589,244 @@ NB2_HD void world_contact(const Nb2ModelDev<CR>& M, const Nb2ContactDev& C, cons
   impulse_response(M, sv, B, ws, ~0ull);
   for (int d = 0; d < n; d++) out[n + d] = (float)(ws.vstar[d] + ws.dqd[d]);
   *m_io = m; *status_out = status;
+  if (crec) {  // what the backward pass needs: sizes, labels, impulses, the velocity change they caused, the LCP matrix
+    crec[0] = (CR)m; crec[1] = (CR)status;
+    for (int i = 0; i < m; i++) { crec[2 + i] = (CR)ws.mapping[i]; crec[2 + NB2_MAX_ROWS + i] = x[i]; }
+    CR* cd = crec + 2 + 2 * NB2_MAX_ROWS;
+    for (int d = 0; d < n; d++) cd[d] = ws.dqd[d];
+    CR* cA = cd + n;
+    for (int i = 0; i < m * m; i++) cA[i] = A[i];
+  }
+}
+
+// =====================================================================================================
+// backward through the contact stage (classification frozen at the forward solution), adjoint form.
+// With  P = A_c + A_ub E,  f = Q^+ b_c,  v+ = v* + M^-1 P f  (BackpropSnapshot.cpp:980-1107 materialises the Jacobians of
+// this map); for an incoming g = dL/dv+ :
+//     lambda = M^-1 g ;  fbar = P^T lambda ;  mu = Q^-T fbar ;  nu = M^-1 A_c mu ;  w = lambda - nu
+//     dL/dv* = g - A_c mu  (so the ABA part is back-propagated with w in place of lambda and the REALISED acceleration
+//     (v+ - v)/dt in place of the unconstrained one) ;  dL/dtau = dt w
+//     contact-Jacobian part:  d/dq of  Phi(q) = sum_r  f_r J_r(q) w  -  mu_r J_r(q) v+   at fixed w, v+  (upper-bound rows: f_r := x_r, mu_r := 0),
+//     split into (i) the motion of the contact frame with the pose of the moving body — the contact generator re-run on
+//     dual numbers for the 6 pose directions, any contact type — and (ii) the kinematic chain (reverse velocity recursion).
+// This function runs between the lambda sweeps (B1/B2) and the reverse RNEA sweep (B3) of world_backward and prepares:
+//     scr: lambda -> w, W_i -> W_i(w);   ws: per-body injections, realised accelerations, v+ fields.
+// =====================================================================================================
+struct BwdContactView {  // views into the contact workspace used by world_backward<double, ST, true>
+  const CR* Aacc;   // [nb][6] spatial accelerations for the realised joint accelerations
+  const CR* Uplus;  // [nb][6] spatial velocities for v+
+  const CR* aeff;   // [n]
+  const CR* vplus;  // [n]
+  const CR* inj;    // [nb][24]  Uw_bar(6) Up_bar(6) G(6) H(6), already scaled by -1/dt except H
+  CR* JcTmu;        // [n] out
+  int active;       // 0: this world had no contact rows (plain contact-free backward)
+  int error;        // structure mismatch / unsupported pair
+};
+
+template <int ST>
+NB2_HD BwdContactView contact_backward_prepare(const Nb2ModelDev<CR>& M, const Nb2ContactDev& C, const float* st, const CR* sv, size_t B,
+                                               CR* wsbase, const CR* crec, CR* scr, int oLam, int oBody) {
+  const int nb = M.nb, n = M.ndof;
+  const ContactWs ws = carve_ws(wsbase, nb, n);
+  BwdContactView cv;
+  cv.Aacc = ws.W; cv.Uplus = ws.W + 6 * nb; cv.aeff = ws.uI; cv.vplus = ws.vstar; cv.inj = ws.Q2; cv.JcTmu = ws.dqd; cv.active = 0; cv.error = 0;
+  const int m = (int)crec[0];
+  if (m <= 0) return cv;
+  cv.active = 1;
+  const CR dt = M.dt;
+  const int kQdd = nb * 21 + M.nfree * 33;
+  const CR* mapping = crec + 2; const CR* xr = crec + 2 + NB2_MAX_ROWS; const CR* dqd_imp = crec + 2 + 2 * NB2_MAX_ROWS; const CR* Arec = dqd_imp + n;
+  // ---- transforms
+  for (int i = 0; i < nb; i++) {
+    const int p = M.parent[i];
+    const Xf<CR> T = saved_xf(M, i, st, sv, B);
+    xf_to12(ws.T + 12 * i, T);
+    xf_to12(ws.W + 12 * i, (p >= 0) ? xf_mul(xf_from12(ws.W + 12 * p), T) : T);
+  }
+  // ---- contact rows re-generated on dual numbers: F_r and dF_r/dxi (xi = body twist [angular; linear] of the moving body)
+  typedef DualT<6> D6;
+  CR* rowF = ws.JA; CR* rowdF = ws.A; int* rowbody = ws.i1; CR* rowmu = ws.v1;
+  int m2 = 0;
+  for (int pi = 0; pi < C.npairs && !cv.error; pi++) {
+    const int sa = C.pair_a[pi], sb = C.pair_b[pi];
+    const int ba = C.shape_body[sa], bb = C.shape_body[sb];
+    if (ba >= 0 && bb >= 0) { cv.error = 1; break; }  // two moving bodies: not supported by the backward yet
+    const int dyn = ba >= 0 ? ba : bb;
+    const bool dynIsA = ba >= 0;
+    // dual world transform of the moving body:  W (I + [xi_w]x , xi_v)
+    const Xf<CR> Wd = xf_from12(ws.W + 12 * dyn);
+    Xf<D6> WD;
+    {
+      const CR* r = &Wd.R_.m00; D6* o = &WD.R_.m00;
+      for (int i = 0; i < 9; i++) o[i] = D6(r[i]);
+      // dR/dxi_w[k] = R skew(e_k):  columns: R[:,a] x ... ; (R [e_k]x)[:,j] = R (e_k x e_j)
+      // k=0: e0 x e1 = e2, e0 x e2 = -e1 ; k=1: e1 x e0 = -e2, e1 x e2 = e0 ; k=2: e2 x e0 = e1, e2 x e1 = -e0
+      const V3<CR> c0 = col3(Wd.R_, 0), c1 = col3(Wd.R_, 1), c2 = col3(Wd.R_, 2);
+      // column 1 gets +c2 for k=0 ; column 2 gets -c1 for k=0
+      WD.R_.m01.d[0] = c2.x; WD.R_.m11.d[0] = c2.y; WD.R_.m21.d[0] = c2.z;
+      WD.R_.m02.d[0] = -c1.x; WD.R_.m12.d[0] = -c1.y; WD.R_.m22.d[0] = -c1.z;
+      WD.R_.m00.d[1] = -c2.x; WD.R_.m10.d[1] = -c2.y; WD.R_.m20.d[1] = -c2.z;
+      WD.R_.m02.d[1] = c0.x; WD.R_.m12.d[1] = c0.y; WD.R_.m22.d[1] = c0.z;
+      WD.R_.m00.d[2] = c1.x; WD.R_.m10.d[2] = c1.y; WD.R_.m20.d[2] = c1.z;
+      WD.R_.m01.d[2] = -c0.x; WD.R_.m11.d[2] = -c0.y; WD.R_.m21.d[2] = -c0.z;
+      WD.p.x = D6(Wd.p.x); WD.p.y = D6(Wd.p.y); WD.p.z = D6(Wd.p.z);
+      WD.p.x.d[3] = c0.x; WD.p.y.d[3] = c0.y; WD.p.z.d[3] = c0.z;
+      WD.p.x.d[4] = c1.x; WD.p.y.d[4] = c1.y; WD.p.z.d[4] = c1.z;
+      WD.p.x.d[5] = c2.x; WD.p.y.d[5] = c2.y; WD.p.z.d[5] = c2.z;
+    }
+    auto lift = [](const Xf<CR>& X) { Xf<D6> o; const CR* r = &X.R_.m00; D6* q = &o.R_.m00; for (int i = 0; i < 9; i++) q[i] = D6(r[i]); o.p.x = D6(X.p.x); o.p.y = D6(X.p.y); o.p.z = D6(X.p.z); return o; };
+    const Xf<D6> Ta = dynIsA ? gxf_mul(WD, lift(xf_from12(C.shape_T[sa]))) : lift(xf_from12(C.shape_T[sa]));
+    const Xf<D6> Tb = dynIsA ? lift(xf_from12(C.shape_T[sb])) : gxf_mul(WD, lift(xf_from12(C.shape_T[sb])));
+    const int ta = C.shape_type[sa], tb = C.shape_type[sb];
+    const V3<D6> da = mk3<D6>(D6(C.shape_dims[sa][0]), D6(C.shape_dims[sa][1]), D6(C.shape_dims[sa][2]));
+    const V3<D6> db = mk3<D6>(D6(C.shape_dims[sb][0]), D6(C.shape_dims[sb][1]), D6(C.shape_dims[sb][2]));
+    ContactOutT<D6> co[8];
+    int k = 0;
+    if (ta == 0 && tb == 0) k = collide_box_box(da, Ta, db, Tb, C.clip_depth, co);
+    else if (ta == 0 && tb == 1) k = collide_box_sphere(da, Ta, db.x, Tb, C.clip_depth, 0, false, co);
+    else if (ta == 1 && tb == 0) k = collide_box_sphere(db, Tb, da.x, Ta, C.clip_depth, 0, true, co);
+    else if ((ta == 0 && tb == 2) || (ta == 2 && tb == 0)) {
+      const bool boxFirst = (ta == 0);
+      const Xf<D6>& Tc = boxFirst ? Tb : Ta; const Xf<D6>& Tbx = boxFirst ? Ta : Tb;
+      const V3<D6> bdim = boxFirst ? da : db;
+      const D6 r = boxFirst ? db.x : da.x; const CR h = boxFirst ? C.shape_dims[sb][1] : C.shape_dims[sa][1];
+      CR dep[2]; Xf<D6> Tend[2];
+      for (int e = 0; e < 2; e++) {
+        Tend[e] = Tc; Tend[e].p = gxf_apply(Tc, mk3<D6>(D6(0.0), D6(0.0), D6(e == 0 ? h / 2 : -h / 2)));
+        const V3<D6> pld = gxf_apply_inv(Tbx, Tend[e].p);
+        const V3<CR> pl = mk3<CR>(pld.x.v, pld.y.v, pld.z.v);
+        V3<CR> q = pl; bool inside = true;
+        for (int kk = 0; kk < 3; kk++) { const CR hk = 0.5 * gget3(bdim, kk).v, v = get3(q, kk); if (v < -hk) { set3(q, kk, -hk); inside = false; } if (v > hk) { set3(q, kk, hk); inside = false; } }
+        if (inside) { CR mn = 1e300; for (int kk = 0; kk < 3; kk++) { const CR v = 0.5 * gget3(bdim, kk).v - nb2_abs(get3(pl, kk)); mn = v < mn ? v : mn; } dep[e] = mn + r.v; }
+        else { const V3<CR> dd = pl - q; dep[e] = r.v - nb2_sqrt(dot(dd, dd)); }
+      }
+      if ((dep[0] > dep[1] ? dep[0] : dep[1]) >= 0 && nb2_abs(dep[0] - dep[1]) >= 1e-9) {
+        const int e = dep[0] > dep[1] ? 0 : 1;
+        k = collide_box_sphere(bdim, Tbx, r, Tend[e], C.clip_depth, e == 0 ? 1 : 2, !boxFirst, co);
+      }
+    }
+    for (int c = 0; c < k; c++) {
+      const V3<CR> nv = mk3<CR>(co[c].normal.x.v, co[c].normal.y.v, co[c].normal.z.v);
+      if (dot(nv, nv) < 1e-12) continue;
+      if (co[c].depth.v < 0.0 || co[c].depth.v > C.clip_depth) continue;
+      const CR mu = C.shape_mu[sa] < C.shape_mu[sb] ? C.shape_mu[sa] : C.shape_mu[sb];
+      const bool fric = mu > 1e-3;
+      V3<D6> dirs[3]; dirs[0] = co[c].normal;
+      if (fric) tangent_basis<D6>(co[c].normal, &dirs[1], &dirs[2]);
+      const int dim = fric ? 3 : 1;
+      const V3<D6> pD = gxf_apply_inv(WD, co[c].point);
+      for (int kk = 0; kk < dim; kk++) {
+        if (m2 >= NB2_MAX_ROWS) { cv.error = 2; break; }
+        const V3<D6> dD = dynIsA ? mulT(WD.R_, dirs[kk]) : mulT(WD.R_, -dirs[kk]);
+        const V3<D6> mom = cross(pD, dD);
+        const D6 F[6] = {mom.x, mom.y, mom.z, dD.x, dD.y, dD.z};
+        for (int j = 0; j < 6; j++) { rowF[6 * m2 + j] = F[j].v; for (int q = 0; q < 6; q++) rowdF[36 * m2 + 6 * j + q] = F[j].d[q]; }
+        rowbody[m2] = dyn; rowmu[m2] = mu;
+        m2++;
+      }
+    }
+  }
+  if (m2 != m) cv.error = cv.error ? cv.error : 3;
+  if (cv.error) return cv;
+  // ---- clamping / upper-bound sets from the saved labels
+  int* clampIdx = ws.clampIdx; int* cl = ws.i2; int* ubl = ws.ubIdx;  // ubl: list of ub rows
+  int nCl = 0, nUb = 0;
+  for (int j = 0; j < m; j++) { clampIdx[j] = -1; if ((int)mapping[j] == NB2_MAP_CLAMPING) { clampIdx[j] = nCl; cl[nCl++] = j; } }
+  for (int j = 0; j < m; j++) if ((int)mapping[j] >= 0) ubl[nUb++] = j;
+  CR* fbar = ws.v2; CR* mu_c = ws.v3; CR* Eu = ws.v4;
+  // W_body(lambda) read from the strided scratch
+  auto ldW = [&](int body) { return ld6<CR, ST>(scr + (size_t)(oBody + 7 * body + 1) * ST); };
+  for (int r = 0; r < nCl; r++) fbar[r] = dot(ldv6(rowF + 6 * cl[r]), ldW(rowbody[cl[r]]));
+  for (int u = 0; u < nUb; u++) {
+    const int j = ubl[u], fp = (int)mapping[j];
+    const CR up = xr[fp] * rowmu[j], low = -xr[fp] * rowmu[j];
+    Eu[u] = (nb2_abs(xr[j] - up) < nb2_abs(xr[j] - low)) ? rowmu[j] : -rowmu[j];
+    fbar[clampIdx[fp]] += Eu[u] * dot(ldv6(rowF + 6 * j), ldW(rowbody[j]));
+  }
+  for (int r = 0; r < nCl; r++) mu_c[r] = 0;
+  if (nCl > 0) {
+    CR* Q = ws.Q;
+    for (int r = 0; r < nCl; r++) for (int c = 0; c < nCl; c++) Q[r * nCl + c] = Arec[cl[r] * m + cl[c]];
+    for (int u = 0; u < nUb; u++) { const int j = ubl[u], c = clampIdx[(int)mapping[j]]; for (int r = 0; r < nCl; r++) Q[r * nCl + c] += Arec[cl[r] * m + j] * Eu[u]; }
+    if (nUb == 0) pinv_psd(nCl, Q, fbar, mu_c, ws.Aw, ws.L, ws.v5, ws.v6, ws.mapping);
+    else {  // Q^T mu = fbar  ->  mu = (Q Q^T)^+ Q fbar
+      CR* QQt = ws.Aw + (size_t)NB2_MAX_ROWS * NB2_MAX_ROWS / 2;  // nCl <= 33 guaranteed below
+      if (2 * nCl * nCl > NB2_MAX_ROWS * NB2_MAX_ROWS / 2 * 2) { cv.error = 4; return cv; }
+      CR* Qf = ws.v7;
+      for (int a = 0; a < nCl; a++) {
+        CR sacc = 0; for (int c = 0; c < nCl; c++) sacc += Q[a * nCl + c] * fbar[c];
+        Qf[a] = sacc;
+        for (int c = 0; c < nCl; c++) { CR t = 0; for (int kx = 0; kx < nCl; kx++) t += Q[a * nCl + kx] * Q[c * nCl + kx]; QQt[a * nCl + c] = t; }
+      }
+      pinv_psd(nCl, QQt, Qf, mu_c, ws.Aw, ws.L, ws.v5, ws.v6, ws.mapping);
+    }
+  }
+  // ---- nu = M^-1 A_c mu  (one impulse sweep) ; w = lambda - nu ; W_i(w)
+  for (int i = 0; i < nb * 6; i++) ws.pI[i] = 0;
+  for (int r = 0; r < nCl; r++) { const CR* F = rowF + 6 * cl[r]; CR* p = ws.pI + 6 * rowbody[cl[r]]; for (int kx = 0; kx < 6; kx++) p[kx] -= F[kx] * mu_c[r]; }
+  impulse_response(M, sv, B, ws, ~0ull);
+  for (int d = 0; d < n; d++) scr[(size_t)(oLam + d) * ST] -= ws.dqd[d];
+  for (int i = 0; i < nb; i++) {
+    const V6<CR> Wn = ld6<CR, ST>(scr + (size_t)(oBody + 7 * i + 1) * ST) - ldv6(ws.V + 6 * i);
+    st6<CR, ST>(scr + (size_t)(oBody + 7 * i + 1) * ST, Wn);
+  }
+  // ---- realised accelerations, v+, and the fields they induce (ws.W is free now: Aacc | Uplus)
+  CR* aeff = ws.uI; CR* vplus = ws.vstar;
+  for (int d = 0; d < n; d++) { aeff[d] = sv[(size_t)(kQdd + d) * B] + dqd_imp[d] / dt; vplus[d] = (CR)st[n + d] + dt * aeff[d]; }
+  CR* Aacc = ws.W; CR* Uplus = ws.W + 6 * nb;
+  V6<CR> A0; A0.a = zero3<CR>(); A0.l = mk3<CR>(-M.gravity[0], -M.gravity[1], -M.gravity[2]);
+  for (int i = 0; i < nb; i++) {
+    const int jt = M.jtype[i], p = M.parent[i], o = M.dof_off[i];
+    const Xf<CR> T = xf_from12(ws.T + 12 * i);
+    const V6<CR> V = sv_ld6<CR>(sv + (size_t)(i * 21) * B, B, 0);
+    V6<CR> Ai = AdInvT(T, (p >= 0) ? ldv6(Aacc + 6 * p) : A0);
+    V6<CR> Ui = (p >= 0) ? AdInvT(T, ldv6(Uplus + 6 * p)) : zero6<CR>();
+    if (jt != NB2_JT_FREE) {
+      const V6<CR> Sv = S_times<CR>(jt, (CR)st[n + o]);
+      Ai = Ai + S_times<CR>(jt, aeff[o]) + ad(V, Sv);
+      Ui = Ui + S_times<CR>(jt, vplus[o]);
+    } else {
+      V6<CR> Sv; Sv.a = mk3<CR>((CR)st[n + o], (CR)st[n + o + 1], (CR)st[n + o + 2]); Sv.l = mk3<CR>((CR)st[n + o + 3], (CR)st[n + o + 4], (CR)st[n + o + 5]);
+      Ai = Ai + ldv6(aeff + o) + ad(V, Sv);
+      Ui = Ui + ldv6(vplus + o);
+    }
+    stv6(Aacc + 6 * i, Ai); stv6(Uplus + 6 * i, Ui);
+  }
+  // ---- per-body injections for the reverse sweep: Uw_bar, Up_bar, G (all scaled by -1/dt: they join the (dID/dq)^T w
+  // accumulator that is multiplied by -dt at the end) and H (plain: A_c mu propagated to joint space)
+  CR* inj = ws.Q2;
+  for (int i = 0; i < nb * 24; i++) inj[i] = 0;
+  const CR kap = -1.0 / dt;
+  for (int j = 0; j < m; j++) {
+    CR coefW = 0, coefV = 0, coefH = 0;
+    if (clampIdx[j] >= 0) { coefW = xr[j]; coefV = -mu_c[clampIdx[j]]; coefH = mu_c[clampIdx[j]]; }
+    else if ((int)mapping[j] >= 0) coefW = xr[j];
+    else continue;
+    const int body = rowbody[j];
+    const CR* F = rowF + 6 * j; const CR* dF = rowdF + 36 * j;
+    CR* bj = inj + 24 * body;
+    const V6<CR> Ww = ld6<CR, ST>(scr + (size_t)(oBody + 7 * body + 1) * ST);  // field of w
+    const V6<CR> Up = ldv6(Uplus + 6 * body);
+    const CR fw[6] = {Ww.a.x, Ww.a.y, Ww.a.z, Ww.l.x, Ww.l.y, Ww.l.z}, fu[6] = {Up.a.x, Up.a.y, Up.a.z, Up.l.x, Up.l.y, Up.l.z};
+    for (int kx = 0; kx < 6; kx++) {
+      bj[kx] += kap * coefW * F[kx];
+      bj[6 + kx] += kap * coefV * F[kx];
+      bj[18 + kx] += coefH * F[kx];
+      CR g = 0;
+      for (int jx = 0; jx < 6; jx++) g += dF[6 * jx + kx] * (coefW * fw[jx] + coefV * fu[jx]);
+      bj[12 + kx] += kap * g;
+    }
+  }
+  return cv;
+}
+
+template <int ST>
+NB2_HD BwdContactData contact_backward_hook(const Nb2ModelDev<double>& M, const BwdContactHook& H, const float* st, const double* sv, size_t B,
+                                            double* scr, int oLam, int oBody) {
+  const BwdContactView v = contact_backward_prepare<ST>(M, *(const Nb2ContactDev*)H.model_contact, st, sv, B, H.ws, H.crec, scr, oLam, oBody);
+  BwdContactData d;
+  d.Aacc = v.Aacc; d.Uplus = v.Uplus; d.aeff = v.aeff; d.vplus = v.vplus; d.inj = v.inj; d.JcTmu = v.JcTmu; d.active = v.active; d.error = v.error;
+  return d;
 }
 
 }  // namespace nb2

@@ -35,11 +35,11 @@ NB2_HD FwdLayout fwd_layout(int nb, int n, int nslots, int nfree) {
 struct BwdLayout {
   int oGQ, oGV, oLam, oQb, oVb, oBody, oSlot, oFree, total;
 };
-NB2_HD BwdLayout bwd_layout(int nb, int n, int nslots, int nfree) {
+NB2_HD BwdLayout bwd_layout(int nb, int n, int nslots, int nfree, int slotw = 18) {
   BwdLayout L;
   L.oGQ = 0; L.oGV = n; L.oLam = 2 * n; L.oQb = 3 * n; L.oVb = 4 * n; L.oBody = 5 * n;
   L.oSlot = L.oBody + 7 * nb;
-  L.oFree = L.oSlot + 18 * nslots;
+  L.oFree = L.oSlot + slotw * nslots;
   L.total = L.oFree + 6 * nfree;
   return L;
 }
@@ -325,14 +325,28 @@ NB2_HD void world_forward(const Nb2ModelDev<R>& M, R* scr, const float* st, cons
   }
 }
 
+// hook implemented in nb2_contact.cuh: turns lambda / W into w / W(w) and prepares the contact injections
+struct BwdContactHook {
+  const void* model_contact;  // const Nb2ContactDev*
+  double* ws;                 // per-world contact workspace
+  const double* crec;         // per-world contact record written by the forward pass
+};
+struct BwdContactData {  // filled by the hook (all double, unit stride)
+  const double* Aacc; const double* Uplus; const double* aeff; const double* vplus; const double* inj; double* JcTmu; int active; int error;
+};
+template <int ST>
+NB2_HD BwdContactData contact_backward_hook(const Nb2ModelDev<double>& M, const BwdContactHook& H, const float* st, const double* sv, size_t B,
+                                            double* scr, int oLam, int oBody);
+
 // =====================================================================================================
 // backward: g_next = dL/d[q+;v+]  ->  g_state = dL/d[q;v], g_action = dL/d action
 // =====================================================================================================
-template <class R, int ST>
+template <class R, int ST, bool CONTACT = false>
 NB2_HD void world_backward(const Nb2ModelDev<R>& M, R* scr, const float* st, const float* act, const float* gnext,
-                           const R* sv, size_t B, float* gstate, float* gaction) {
+                           const R* sv, size_t B, float* gstate, float* gaction, const BwdContactHook* hook = nullptr) {
   const int nb = M.nb, n = M.ndof;
-  const BwdLayout L = bwd_layout(nb, n, M.nslots, M.nfree);
+  constexpr int SLOTW = CONTACT ? 42 : 18;
+  const BwdLayout L = bwd_layout(nb, n, M.nslots, M.nfree, SLOTW);
   const R dt = M.dt;
   const int kFree = nb * 21, kQdd = nb * 21 + M.nfree * 33;
   for (int d = 0; d < n; d++) {
@@ -348,7 +362,7 @@ NB2_HD void world_backward(const Nb2ModelDev<R>& M, R* scr, const float* st, con
     const int jt = M.jtype[i], p = M.parent[i], o = M.dof_off[i], fl = M.flags[i];
     const R* s = sv + (size_t)(i * 21) * B;
     V6<R> pI = hvalid ? hp : zero6<R>();
-    if (fl & NB2_F_HAS_SLOT) pI = pI + ld6<R, ST>(scr + (size_t)(L.oSlot + 18 * M.slot_self[i]) * ST);
+    if (fl & NB2_F_HAS_SLOT) pI = pI + ld6<R, ST>(scr + (size_t)(L.oSlot + SLOTW * M.slot_self[i]) * ST);
     V6<R> beta;
     if (jt != NB2_JT_FREE) {
       const R up = scr[(size_t)(L.oGV + o) * ST] - S_dot(jt, pI);
@@ -368,7 +382,7 @@ NB2_HD void world_backward(const Nb2ModelDev<R>& M, R* scr, const float* st, con
       const V6<R> pc = dAdInvT(T, beta);
       if (fl & NB2_F_HANDOFF) { hp = pc; hvalid = true; }
       else {
-        R* sl = scr + (size_t)(L.oSlot + 18 * M.slot_parent[i]) * ST;
+        R* sl = scr + (size_t)(L.oSlot + SLOTW * M.slot_parent[i]) * ST;
         if (fl & NB2_F_FIRST_DEPOSIT) st6<R, ST>(sl, pc); else add6<R, ST>(sl, pc);
       }
     }
@@ -398,6 +412,11 @@ NB2_HD void world_backward(const Nb2ModelDev<R>& M, R* scr, const float* st, con
     }
     st6<R, ST>(bs + ST, W);
   }
+  // ---------------- contact stage adjoint (nb2_contact.cuh): lambda -> w, W -> W(w), injections for B3
+  BwdContactData cd; cd.active = 0; cd.error = 0;
+  if constexpr (CONTACT) {
+    cd = contact_backward_hook<ST>(M, *hook, st, sv, B, scr, L.oLam, L.oBody);
+  }
   // ---------------- B3, leaf -> root: reverse sweep of RNEA, seeded with lambda on the joint forces.
   //   forward RNEA:  V_i = X^-1 V_p + S v ;  A_i = X^-1 A_p + S a + ad(V_i, S v) ;  F_i = G A_i + V_i x* G V_i ;
   //                  f_i = F_i + sum_c X*_c f_c ; tau_i = S^T f_i
@@ -406,32 +425,46 @@ NB2_HD void world_backward(const Nb2ModelDev<R>& M, R* scr, const float* st, con
   //                  vbar_i = S^T (Vbar_i - V_i x* Abar_i)
   //                  c_i    = -( (X^-1 A_p) x* Abar_i + (X^-1 V_p) x* Vbar_i + (X^-1 W_p) x* f_i ) ; qbar_i = B_i(q)^T c_i
   V6<R> hA = zero6<R>(), hV = zero6<R>(), hf = zero6<R>();
+  V6<R> hUw = zero6<R>(), hUp = zero6<R>(), hG = zero6<R>(), hH = zero6<R>();
   hvalid = false;
   for (int i = nb - 1; i >= 0; i--) {
     const int jt = M.jtype[i], p = M.parent[i], o = M.dof_off[i], fl = M.flags[i];
     const R* s = sv + (size_t)(i * 21) * B;
     R m; V3<R> h; S3<R> Ib; inertia_of(M, i, &m, &h, &Ib);
-    const V6<R> V = sv_ld6<R>(s, B, 0), A = sv_ld6<R>(s, B, 6);
+    const V6<R> V = sv_ld6<R>(s, B, 0);
+    V6<R> A = sv_ld6<R>(s, B, 6);
+    if (CONTACT && cd.active) { const double* a6 = cd.Aacc + 6 * i; A.a = mk3<R>((R)a6[0], (R)a6[1], (R)a6[2]); A.l = mk3<R>((R)a6[3], (R)a6[4], (R)a6[5]); }
     const V6<R> W = ld6<R, ST>(scr + (size_t)(L.oBody + 7 * i + 1) * ST);
     const V6<R> GV = mulG(m, h, Ib, V);
     V6<R> f = mulG(m, h, Ib, A) + crf(V, GV);
     V6<R> Abar = mulG(m, h, Ib, W);
     V6<R> Vbar = mulG(m, h, Ib, ad(W, V)) - crf(W, GV);
     if (hvalid) { Abar = Abar + hA; Vbar = Vbar + hV; f = f + hf; }
+    V6<R> Uw = zero6<R>(), Up = zero6<R>(), Gc = zero6<R>(), Hc = zero6<R>();  // contact adjoints (CONTACT only)
+    if (CONTACT && cd.active) {
+      const double* b24 = cd.inj + 24 * i;
+      Uw.a = mk3<R>((R)b24[0], (R)b24[1], (R)b24[2]); Uw.l = mk3<R>((R)b24[3], (R)b24[4], (R)b24[5]);
+      Up.a = mk3<R>((R)b24[6], (R)b24[7], (R)b24[8]); Up.l = mk3<R>((R)b24[9], (R)b24[10], (R)b24[11]);
+      Gc.a = mk3<R>((R)b24[12], (R)b24[13], (R)b24[14]); Gc.l = mk3<R>((R)b24[15], (R)b24[16], (R)b24[17]);
+      Hc.a = mk3<R>((R)b24[18], (R)b24[19], (R)b24[20]); Hc.l = mk3<R>((R)b24[21], (R)b24[22], (R)b24[23]);
+      if (hvalid) { Uw = Uw + hUw; Up = Up + hUp; Gc = Gc + hG; Hc = Hc + hH; }
+    }
     if (fl & NB2_F_HAS_SLOT) {
-      const R* sl = scr + (size_t)(L.oSlot + 18 * M.slot_self[i]) * ST;
+      const R* sl = scr + (size_t)(L.oSlot + SLOTW * M.slot_self[i]) * ST;
       Abar = Abar + ld6<R, ST>(sl); Vbar = Vbar + ld6<R, ST>(sl + 6 * ST); f = f + ld6<R, ST>(sl + 12 * ST);
+      if (CONTACT && cd.active) { Uw = Uw + ld6<R, ST>(sl + 18 * ST); Up = Up + ld6<R, ST>(sl + 24 * ST); Gc = Gc + ld6<R, ST>(sl + 30 * ST); Hc = Hc + ld6<R, ST>(sl + 36 * ST); }
     }
     V6<R> Sv, Sa, Sl;
     Xf<R> T;
     if (jt != NB2_JT_FREE) {
       Sv = S_times<R>(jt, (R)st[n + o]);
-      Sa = S_times<R>(jt, (R)sv[(size_t)(kQdd + o) * B]);
+      Sa = S_times<R>(jt, (CONTACT && cd.active) ? (R)cd.aeff[o] : (R)sv[(size_t)(kQdd + o) * B]);
       Sl = S_times<R>(jt, scr[(size_t)(L.oLam + o) * ST]);
       T = (jt == NB2_JT_REV) ? xf_rev(M, i, (R)s[19 * B], (R)s[20 * B]) : xf_pris(M, i, (R)st[o]);
     } else {
       Sv.a = mk3<R>((R)st[n + o], (R)st[n + o + 1], (R)st[n + o + 2]); Sv.l = mk3<R>((R)st[n + o + 3], (R)st[n + o + 4], (R)st[n + o + 5]);
       Sa = sv_ld6<R>(sv + (size_t)(kQdd + o) * B, B, 0);
+      if (CONTACT && cd.active) { const double* a6 = cd.aeff + o; Sa.a = mk3<R>((R)a6[0], (R)a6[1], (R)a6[2]); Sa.l = mk3<R>((R)a6[3], (R)a6[4], (R)a6[5]); }
       Sl = ld6<R, ST>(scr + (size_t)(L.oLam + o) * ST);
       R t12[12]; for (int k = 0; k < 12; k++) t12[k] = (R)sv[(size_t)(kFree + M.free_idx[i] * 33 + 21 + k) * B];
       T = ldXf<R, 1>(t12);
@@ -439,7 +472,17 @@ NB2_HD void world_backward(const Nb2ModelDev<R>& M, R* scr, const float* st, con
     Vbar = Vbar + crf(Sv, Abar);
     const V6<R> vb6 = Vbar - crf(V, Abar);
     const V6<R> Alam = A - Sa - ad(V, Sv), Vlam = V - Sv, Wlam = W - Sl;
-    const V6<R> c6 = zero6<R>() - (crf(Alam, Abar) + crf(Vlam, Vbar) + crf(Wlam, f));
+    V6<R> c6 = zero6<R>() - (crf(Alam, Abar) + crf(Vlam, Vbar) + crf(Wlam, f));
+    if (CONTACT && cd.active) {
+      // kinematic-chain part of d/dq [J_r(q) w] and [J_r(q) v+], and the contact-frame part (wrench Gc), see nb2_contact.cuh
+      V6<R> Upl; { const double* u6 = cd.Uplus + 6 * i; Upl.a = mk3<R>((R)u6[0], (R)u6[1], (R)u6[2]); Upl.l = mk3<R>((R)u6[3], (R)u6[4], (R)u6[5]); }
+      V6<R> Svp;
+      if (jt != NB2_JT_FREE) Svp = S_times<R>(jt, (R)cd.vplus[o]);
+      else { const double* v6p = cd.vplus + o; Svp.a = mk3<R>((R)v6p[0], (R)v6p[1], (R)v6p[2]); Svp.l = mk3<R>((R)v6p[3], (R)v6p[4], (R)v6p[5]); }
+      c6 = c6 - crf(Wlam, Uw) - crf(Upl - Svp, Up) + Gc;
+      if (jt != NB2_JT_FREE) cd.JcTmu[o] = (double)S_dot(jt, Hc);
+      else { double* j6 = cd.JcTmu + o; j6[0] = (double)Hc.a.x; j6[1] = (double)Hc.a.y; j6[2] = (double)Hc.a.z; j6[3] = (double)Hc.l.x; j6[4] = (double)Hc.l.y; j6[5] = (double)Hc.l.z; }
+    }
     if (jt != NB2_JT_FREE) {
       scr[(size_t)(L.oVb + o) * ST] = S_dot(jt, vb6);
       scr[(size_t)(L.oQb + o) * ST] = S_dot(jt, c6);
@@ -454,11 +497,18 @@ NB2_HD void world_backward(const Nb2ModelDev<R>& M, R* scr, const float* st, con
     hvalid = false;
     if (p >= 0) {
       const V6<R> cA = dAdInvT(T, Abar), cV = dAdInvT(T, Vbar), cf = dAdInvT(T, f);
-      if (fl & NB2_F_HANDOFF) { hA = cA; hV = cV; hf = cf; hvalid = true; }
+      V6<R> cUw, cUp, cG, cH;
+      if (CONTACT && cd.active) { cUw = dAdInvT(T, Uw); cUp = dAdInvT(T, Up); cG = dAdInvT(T, Gc); cH = dAdInvT(T, Hc); }
+      if (fl & NB2_F_HANDOFF) { hA = cA; hV = cV; hf = cf; if (CONTACT && cd.active) { hUw = cUw; hUp = cUp; hG = cG; hH = cH; } hvalid = true; }
       else {
-        R* sl = scr + (size_t)(L.oSlot + 18 * M.slot_parent[i]) * ST;
-        if (fl & NB2_F_FIRST_DEPOSIT) { st6<R, ST>(sl, cA); st6<R, ST>(sl + 6 * ST, cV); st6<R, ST>(sl + 12 * ST, cf); }
-        else { add6<R, ST>(sl, cA); add6<R, ST>(sl + 6 * ST, cV); add6<R, ST>(sl + 12 * ST, cf); }
+        R* sl = scr + (size_t)(L.oSlot + SLOTW * M.slot_parent[i]) * ST;
+        if (fl & NB2_F_FIRST_DEPOSIT) {
+          st6<R, ST>(sl, cA); st6<R, ST>(sl + 6 * ST, cV); st6<R, ST>(sl + 12 * ST, cf);
+          if (CONTACT && cd.active) { st6<R, ST>(sl + 18 * ST, cUw); st6<R, ST>(sl + 24 * ST, cUp); st6<R, ST>(sl + 30 * ST, cG); st6<R, ST>(sl + 36 * ST, cH); }
+        } else {
+          add6<R, ST>(sl, cA); add6<R, ST>(sl + 6 * ST, cV); add6<R, ST>(sl + 12 * ST, cf);
+          if (CONTACT && cd.active) { add6<R, ST>(sl + 18 * ST, cUw); add6<R, ST>(sl + 24 * ST, cUp); add6<R, ST>(sl + 30 * ST, cG); add6<R, ST>(sl + 36 * ST, cH); }
+        }
       }
     }
   }
@@ -468,7 +518,9 @@ NB2_HD void world_backward(const Nb2ModelDev<R>& M, R* scr, const float* st, con
     const int jt = M.jtype[i], o = M.dof_off[i];
     if (jt != NB2_JT_FREE) {
       const R lam = scr[(size_t)(L.oLam + o) * ST];
-      const R gq = scr[(size_t)(L.oGQ + o) * ST], gv = scr[(size_t)(L.oGV + o) * ST];
+      const R gq = scr[(size_t)(L.oGQ + o) * ST];
+      R gv = scr[(size_t)(L.oGV + o) * ST];
+      if (CONTACT && cd.active) gv -= (R)cd.JcTmu[o];  // dL/dv* = g - A_c mu
       scr[(size_t)(L.oQb + o) * ST] = gq - dt * (scr[(size_t)(L.oQb + o) * ST] + M.spring[o] * lam);
       scr[(size_t)(L.oVb + o) * ST] = dt * gq + gv - dt * (scr[(size_t)(L.oVb + o) * ST] + (M.damping[o] + dt * M.spring[o]) * lam);
     } else {
@@ -488,7 +540,8 @@ NB2_HD void world_backward(const Nb2ModelDev<R>& M, R* scr, const float* st, con
       gvp.l = mulT(Rq, g.l) * dt;
       const V6<R> lam = ld6<R, ST>(scr + (size_t)(L.oLam + o) * ST);
       const V6<R> qb = ld6<R, ST>(scr + (size_t)(L.oQb + o) * ST), vb = ld6<R, ST>(scr + (size_t)(L.oVb + o) * ST);
-      const V6<R> gv = ld6<R, ST>(scr + (size_t)(L.oGV + o) * ST);
+      V6<R> gv = ld6<R, ST>(scr + (size_t)(L.oGV + o) * ST);
+      if (CONTACT && cd.active) { const double* j6 = cd.JcTmu + o; gv.a = gv.a - mk3<R>((R)j6[0], (R)j6[1], (R)j6[2]); gv.l = gv.l - mk3<R>((R)j6[3], (R)j6[4], (R)j6[5]); }
       R lamv[6] = {lam.a.x, lam.a.y, lam.a.z, lam.l.x, lam.l.y, lam.l.z};
       R qbv[6] = {qb.a.x, qb.a.y, qb.a.z, qb.l.x, qb.l.y, qb.l.z}, vbv[6] = {vb.a.x, vb.a.y, vb.a.z, vb.l.x, vb.l.y, vb.l.z};
       R gqv[6] = {gq.a.x, gq.a.y, gq.a.z, gq.l.x, gq.l.y, gq.l.z}, gvpv[6] = {gvp.a.x, gvp.a.y, gvp.a.z, gvp.l.x, gvp.l.y, gvp.l.z};
@@ -499,6 +552,11 @@ NB2_HD void world_backward(const Nb2ModelDev<R>& M, R* scr, const float* st, con
         scr[(size_t)(L.oVb + o + k) * ST] = gvpv[k] + gvv[k] - dt * (vbv[k] + (M.damping[o + k] + dt * M.spring[o + k]) * lamv[k]);
       }
     }
+  }
+  if (CONTACT && cd.error) {  // unsupported contact configuration for the backward: fail loudly, never silently wrong
+    for (int d = 0; d < 2 * n; d++) gstate[d] = nanf("");
+    for (int i = 0; i < M.na; i++) gaction[i] = nanf("");
+    return;
   }
   // clipLossGradientsToBounds (BackpropSnapshot.cpp:425-479): exact equality against the pre-step state, then
   // scatter through the action map (:404-417)

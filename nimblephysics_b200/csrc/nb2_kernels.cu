@@ -63,13 +63,31 @@ __global__ void __launch_bounds__(64)
 k_contact_fwd(const __grid_constant__ Nb2ModelDev<double> M, const __grid_constant__ Nb2ContactDev C, int B,
               const float* __restrict__ state, float* __restrict__ next, const double* __restrict__ saved,
               double* __restrict__ workspace, size_t ws_doubles, double* __restrict__ x_lcp, int* __restrict__ m_lcp,
-              int* __restrict__ labels, int* __restrict__ status, int* __restrict__ ncontacts, float* __restrict__ cinfo) {
+              int* __restrict__ labels, int* __restrict__ status, int* __restrict__ ncontacts, float* __restrict__ cinfo,
+              double* __restrict__ crec, size_t rec_doubles) {
   const int w = blockIdx.x * blockDim.x + threadIdx.x;
   if (w >= B) return;
   nb2::world_contact(M, C, state + (size_t)w * 2 * M.ndof, next + (size_t)w * 2 * M.ndof, saved + w, (size_t)B,
                      workspace + (size_t)w * ws_doubles, x_lcp + (size_t)w * NB2_MAX_ROWS, m_lcp + w,
                      labels + (size_t)w * NB2_MAX_ROWS, status + w, ncontacts + w,
-                     cinfo ? cinfo + (size_t)w * NB2_MAX_CONTACTS * 10 : nullptr);
+                     cinfo ? cinfo + (size_t)w * NB2_MAX_CONTACTS * 10 : nullptr, crec ? crec + (size_t)w * rec_doubles : nullptr);
+}
+
+// backward of a step with the contact stage (fp64): world_backward<double, 32, CONTACT=true>
+__global__ void __launch_bounds__(32)
+k_step_bwd_contact(const __grid_constant__ Nb2ModelDev<double> M, const __grid_constant__ Nb2ContactDev C, int B,
+                   const float* __restrict__ state, const float* __restrict__ action, const double* __restrict__ saved,
+                   const double* __restrict__ crec, size_t rec_doubles, double* __restrict__ workspace, size_t ws_doubles,
+                   const float* __restrict__ gnext, float* __restrict__ gstate, float* __restrict__ gaction, int words) {
+  extern __shared__ __align__(16) unsigned char nb2_smem[];
+  const int w = blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= B) return;
+  double* scr = reinterpret_cast<double*>(nb2_smem) + (size_t)(threadIdx.x >> 5) * words * 32 + (threadIdx.x & 31);
+  nb2::BwdContactHook H;
+  H.model_contact = &C; H.ws = workspace + (size_t)w * ws_doubles; H.crec = crec + (size_t)w * rec_doubles;
+  nb2::world_backward<double, 32, true>(M, scr, state + (size_t)w * 2 * M.ndof, action + (size_t)w * M.na,
+                                        gnext + (size_t)w * 2 * M.ndof, saved + w, (size_t)B,
+                                        gstate + (size_t)w * 2 * M.ndof, gaction + (size_t)w * M.na, &H);
 }
 
 constexpr int kMaxSmem = 227 * 1024;
@@ -189,7 +207,7 @@ size_t nb2_contact_workspace_bytes(const nb2_model* m, int B) {
 }
 int nb2_step_forward_contact(const nb2_model* cm, int B, const float* state, const float* action, float* next_state,
                              void* saved_fp64, void* workspace, double* x_lcp, int32_t* m_lcp, int32_t* labels,
-                             int32_t* status, int32_t* ncontacts, float* cinfo, void* stream) {
+                             int32_t* status, int32_t* ncontacts, float* cinfo, double* contact_record, void* stream) {
   nb2_model* m = const_cast<nb2_model*>(cm);
   if (!m || B < 0 || !state || !action || !next_state || !saved_fp64 || !workspace || !x_lcp || !m_lcp || !labels || !status || !ncontacts) {
     g_err = "nb2_step_forward_contact: bad argument"; return NB2_ERR_INVALID;
@@ -202,7 +220,34 @@ int nb2_step_forward_contact(const nb2_model* cm, int B, const float* state, con
   const int threads = 32;
   k_contact_fwd<<<(B + threads - 1) / threads, threads, 0, st>>>(m->md, m->contact, B, state, next_state, (const double*)saved_fp64,
                                                                  (double*)workspace, nb2::contact_ws_doubles(m->mf.nb, m->mf.ndof), x_lcp,
-                                                                 m_lcp, labels, status, ncontacts, cinfo);
+                                                                 m_lcp, labels, status, ncontacts, cinfo, contact_record,
+                                                                 nb2::contact_rec_doubles(m->mf.ndof));
+  g_launches++;
+  NB2_CUDA(cudaGetLastError());
+  return NB2_OK;
+}
+size_t nb2_contact_record_bytes(const nb2_model* m, int B) {
+  if (!m || !m->has_contacts || B <= 0) return 0;
+  return nb2::contact_rec_doubles(m->mf.ndof) * sizeof(double) * (size_t)B;
+}
+int nb2_step_backward_contact(const nb2_model* cm, int B, const float* state, const float* action, const void* saved_fp64,
+                              const double* contact_record, void* workspace, const float* grad_next_state, float* grad_state,
+                              float* grad_action, void* stream) {
+  nb2_model* m = const_cast<nb2_model*>(cm);
+  if (!m || B < 0 || !state || !action || !saved_fp64 || !contact_record || !workspace || !grad_next_state || !grad_state || !grad_action) {
+    g_err = "nb2_step_backward_contact: bad argument"; return NB2_ERR_INVALID;
+  }
+  if (!m->has_contacts) { g_err = "nb2_step_backward_contact: the model has no collision pairs"; return NB2_ERR_INVALID; }
+  if (B == 0) return NB2_OK;
+  const int words = nb2::bwd_layout(m->mf.nb, m->mf.ndof, m->mf.nslots, m->mf.nfree, 42).total;
+  const size_t smem = (size_t)words * 32 * sizeof(double);
+  if (smem > (size_t)kMaxSmem) { g_err = "model needs " + std::to_string(smem) + " B of shared memory per warp (> 227 KB)"; return NB2_ERR_UNSUPPORTED; }
+  static bool attr_done = false;
+  if (!attr_done) { NB2_CUDA(cudaFuncSetAttribute(k_step_bwd_contact, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem)); attr_done = true; }
+  k_step_bwd_contact<<<(B + 31) / 32, 32, smem, (cudaStream_t)stream>>>(m->md, m->contact, B, state, action, (const double*)saved_fp64,
+                                                                         contact_record, nb2::contact_rec_doubles(m->mf.ndof), (double*)workspace,
+                                                                         nb2::contact_ws_doubles(m->mf.nb, m->mf.ndof), grad_next_state,
+                                                                         grad_state, grad_action, words);
   g_launches++;
   NB2_CUDA(cudaGetLastError());
   return NB2_OK;

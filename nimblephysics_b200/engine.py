@@ -46,11 +46,19 @@ class DeviceModel:
     def contact_workspace_bytes(self, B):
         return int(_cabi.lib().nb2_contact_workspace_bytes(self.handle, B))
 
+    def contact_record_bytes(self, B):
+        return int(_cabi.lib().nb2_contact_record_bytes(self.handle, B))
+
     def forward_contact_device(self, B, state_ptr, action_ptr, next_ptr, saved_ptr, ws_ptr, x_ptr, m_ptr, labels_ptr,
-                               status_ptr, nc_ptr, cinfo_ptr, stream):
+                               status_ptr, nc_ptr, cinfo_ptr, crec_ptr, stream):
         """fp64 ABA kernel + contact/LCP kernel (include/nb2.h nb2_step_forward_contact)."""
         _cabi.check(_cabi.lib().nb2_step_forward_contact(self.handle, B, state_ptr, action_ptr, next_ptr, saved_ptr, ws_ptr, x_ptr,
-                                                         m_ptr, labels_ptr, status_ptr, nc_ptr, cinfo_ptr, stream))
+                                                         m_ptr, labels_ptr, status_ptr, nc_ptr, cinfo_ptr, crec_ptr, stream))
+
+    def backward_contact_device(self, B, state_ptr, action_ptr, saved_ptr, crec_ptr, ws_ptr, gnext_ptr, gstate_ptr, gaction_ptr,
+                                stream):
+        _cabi.check(_cabi.lib().nb2_step_backward_contact(self.handle, B, state_ptr, action_ptr, saved_ptr, crec_ptr, ws_ptr,
+                                                          gnext_ptr, gstate_ptr, gaction_ptr, stream))
 
     # ---- host pointers (numpy / CPU tensors): copies included ----
     def forward_host(self, state: np.ndarray, action: np.ndarray, keep_for_backward=True, precision=FP32,

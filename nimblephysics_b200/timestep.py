@@ -57,10 +57,12 @@ class TimestepLayer(torch.autograd.Function):
                 # lives on the world and flows from step to step like the reference's solver state
                 cache = contact_cache(world, B, dev)
                 saved = torch.empty((dm.saved_words, B), dtype=torch.float64, device=dev)
+                crec = torch.empty((B, dm.contact_record_bytes(B) // (8 * B)), dtype=torch.float64, device=dev) if need_grad else None
                 dm.forward_contact_device(B, _ptr(sd), _ptr(ad), _ptr(nxt), _ptr(saved), _ptr(cache["ws"]), _ptr(cache["x"]),
                                           _ptr(cache["m"]), _ptr(cache["labels"]), _ptr(cache["status"]), _ptr(cache["nc"]),
-                                          _ptr(cache["cinfo"]), stream)
-                ctx.any_rows = cache["m"]
+                                          _ptr(cache["cinfo"]), _ptr(crec) if crec is not None else None, stream)
+                ctx.crec = crec
+                ctx.ws = cache["ws"]
             else:
                 saved = torch.empty((dm.saved_words, B), dtype=torch.float32, device=dev) if need_grad else None
                 dm.forward_device(B, _ptr(sd), _ptr(ad), _ptr(nxt), _ptr(saved) if saved is not None else None, stream, FP32)
@@ -85,16 +87,20 @@ class TimestepLayer(torch.autograd.Function):
         sd, ad, saved = ctx.saved_tensors
         dev = sd.device
         g = grad_state.detach().reshape(ctx.B, 2 * dm.ndof).to(device=dev, dtype=torch.float32).contiguous()
-        if ctx.contact and int(ctx.any_rows.max().item()) > 0:
-            raise NotImplementedError(
-                "backward through a step with active contact constraints (SURVEY §8 rows a13/a14/a16 with contacts: "
-                "constraint-force Jacobians) is not implemented yet; contact-free steps of this world differentiate fine")
         with torch.cuda.device(dev):
             gs = torch.empty_like(sd)
             ga = torch.empty_like(ad)
             stream = torch.cuda.current_stream().cuda_stream
-            dm.backward_device(ctx.B, _ptr(sd), _ptr(ad), _ptr(saved), _ptr(g), _ptr(gs), _ptr(ga), stream,
-                               FP64 if ctx.contact else FP32)
+            if ctx.contact:
+                # adjoint of the contact stage with the classification frozen at the forward solution (csrc/nb2_contact.cuh)
+                dm.backward_contact_device(ctx.B, _ptr(sd), _ptr(ad), _ptr(saved), _ptr(ctx.crec), _ptr(ctx.ws), _ptr(g), _ptr(gs),
+                                           _ptr(ga), stream)
+                if bool(torch.isnan(gs).any()):
+                    raise NotImplementedError(
+                        "backward through a contact between two MOVING bodies is not implemented (the kernel marked those "
+                        "worlds with NaN gradients); contacts against static geometry are supported")
+            else:
+                dm.backward_device(ctx.B, _ptr(sd), _ptr(ad), _ptr(saved), _ptr(g), _ptr(gs), _ptr(ga), stream, FP32)
         if ctx.legacy:
             # reference returns fp64 grads (timestep.py:55-60)
             gs = gs[0].to(device=ctx.in_device, dtype=torch.float64 if ctx.in_dtype == torch.float64 else ctx.in_dtype)

@@ -202,3 +202,26 @@ def ref_dsolve_lcp(A, b, lo, hi, findex, early=False):
     fi = np.array(findex, np.int32).copy()
     ok = L.ref_dSolveLCP(ctypes.c_int(n), _p(Ap), _p(x), _p(bb), _p(w), ctypes.c_int(0), _p(ll), _p(hh), _pi(fi), ctypes.c_int(int(early)))
     return x, bool(ok)
+
+
+def _jc(self, state, action, x_warm=None):
+    s = np.ascontiguousarray(state, np.float64)
+    a = np.ascontiguousarray(action, np.float64)
+    J = np.empty((2 * self.n, 3 * self.n))
+    xw = np.zeros(1) if x_warm is None else np.ascontiguousarray(x_warm, np.float64)
+    rc = lib().orc_jacobian_contact(self.h, _p(s), _p(a), _p(xw), ctypes.c_int(-1 if x_warm is None else xw.size), _p(J))
+    return J, rc
+
+
+def _bc(self, state, action, grad_next, x_warm=None):
+    s = np.ascontiguousarray(state, np.float64)
+    a = np.ascontiguousarray(action, np.float64)
+    g = np.ascontiguousarray(grad_next, np.float64)
+    gs, ga = np.empty(2 * self.n), np.empty(self.na)
+    xw = np.zeros(1) if x_warm is None else np.ascontiguousarray(x_warm, np.float64)
+    rc = lib().orc_backprop_contact(self.h, _p(s), _p(a), _p(xw), ctypes.c_int(-1 if x_warm is None else xw.size), _p(g), _p(gs), _p(ga))
+    return gs, ga, rc
+
+
+OracleContactWorld.jacobian_contact = _jc
+OracleContactWorld.backprop_contact = _bc

@@ -23,6 +23,7 @@
 //
 // Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may load this library.
 // =====================================================================================
+#include <algorithm>
 #include <cstdint>
 #include <cstdio>
 #include <vector>
@@ -284,26 +285,27 @@ static bool is_reactive(const Model& M, int body) { return M.mobile[body] && M.h
 
 // impulse-ABA: body impulses imp[i] (body frame) -> joint velocity changes dqd (Skeleton.cpp:13421-13456, 13552-13556,
 // BodyNode.cpp:2117-2138, 2188-2215, GenericJoint.hpp:2482-2498, 2607-2613, 2713-2725)
-static void impulse_response(const Model& M, std::vector<BodyState<double>>& B, const std::vector<Vec6<double>>& imp,
-                             std::vector<double>& dqd, std::vector<Vec6<double>>& dV) {
+template <class S>
+static void impulse_response(const Model& M, std::vector<BodyState<S>>& B, const std::vector<Vec6<S>>& imp,
+                             std::vector<S>& dqd, std::vector<Vec6<S>>& dV) {
   const int nb = M.nb;
-  static thread_local std::vector<Vec6<double>> pI;
-  static thread_local std::vector<double> uI;
-  pI.assign(nb, zero6<double>()); uI.assign(M.ndof, 0.0);
-  dqd.assign(M.ndof, 0.0); dV.assign(nb, zero6<double>());
+  static thread_local std::vector<Vec6<S>> pI;
+  static thread_local std::vector<S> uI;
+  pI.assign(nb, zero6<S>()); uI.assign(M.ndof, S(0.0));
+  dqd.assign(M.ndof, S(0.0)); dV.assign(nb, zero6<S>());
   std::vector<std::vector<int>> kids(nb);
   for (int i = 0; i < nb; i++) if (M.parent[i] >= 0) kids[M.parent[i]].push_back(i);
   for (int i = nb - 1; i >= 0; i--) {
     if (!M.mobile[i]) continue;
-    BodyState<double>& b = B[i];
-    pI[i] = zero6<double>() - imp[i];
+    BodyState<S>& b = B[i];
+    pI[i] = zero6<S>() - imp[i];
     for (int c : kids[i]) {
-      BodyState<double>& ch = B[c];
-      Vec6<double> beta = pI[c];
+      BodyState<S>& ch = B[c];
+      Vec6<S> beta = pI[c];
       if (ch.k > 0) {
-        Vec6<double> Su = zero6<double>();
+        Vec6<S> Su = zero6<S>();
         const int oc = M.dof_off[c];
-        for (int a = 0; a < ch.k; a++) { double sacc = 0; for (int e = 0; e < ch.k; e++) sacc += ch.psi[a * ch.k + e] * uI[oc + e]; Su = Su + ch.Scol[a] * sacc; }
+        for (int a = 0; a < ch.k; a++) { S sacc = S(0.0); for (int e = 0; e < ch.k; e++) sacc = sacc + ch.psi[a * ch.k + e] * uI[oc + e]; Su = Su + ch.Scol[a] * sacc; }
         beta = beta + mul(ch.AI, Su);
       }
       pI[i] = pI[i] + dAdInvT(ch.T, beta);
@@ -313,14 +315,14 @@ static void impulse_response(const Model& M, std::vector<BodyState<double>>& B, 
   }
   for (int i = 0; i < nb; i++) {
     if (!M.mobile[i]) continue;
-    BodyState<double>& b = B[i];
+    BodyState<S>& b = B[i];
     const int p = M.parent[i], o = M.dof_off[i];
-    Vec6<double> Vp = (p >= 0) ? AdInvT(b.T, dV[p]) : zero6<double>();
-    Vec6<double> AIVp = mul(b.AI, Vp);
-    Vec6<double> Sd = zero6<double>();
+    Vec6<S> Vp = (p >= 0) ? AdInvT(b.T, dV[p]) : zero6<S>();
+    Vec6<S> AIVp = mul(b.AI, Vp);
+    Vec6<S> Sd = zero6<S>();
     for (int a = 0; a < b.k; a++) {
-      double acc = 0;
-      for (int e = 0; e < b.k; e++) acc += b.psi[a * b.k + e] * (uI[o + e] - dot(b.Scol[e], AIVp));
+      S acc = S(0.0);
+      for (int e = 0; e < b.k; e++) acc = acc + b.psi[a * b.k + e] * (uI[o + e] - dot(b.Scol[e], AIVp));
       dqd[o + a] = acc;
       Sd = Sd + b.Scol[a] * acc;
     }
@@ -328,28 +330,28 @@ static void impulse_response(const Model& M, std::vector<BodyState<double>>& B, 
   }
 }
 
-static void tangent_basis(const Vec3<double>& n, Vec3<double>& t1, Vec3<double>& t2) {  // ContactConstraint.cpp:734-795
-  Vec3<double> z = v3(0.0, 0.0, 1.0), x = v3(1.0, 0.0, 0.0), y = v3(0.0, 1.0, 0.0);
-  Vec3<double> t = cross(z, n);
-  if (dot(t, t) < 1e-12) { t = cross(x, n); if (dot(t, t) < 1e-12) { t = cross(y, n); if (dot(t, t) < 1e-12) t = cross(z, n); } }
-  t1 = t * (1.0 / std::sqrt(dot(t, t)));
+template <class S> static void tangent_basis(const Vec3<S>& n, Vec3<S>& t1, Vec3<S>& t2) {  // ContactConstraint.cpp:734-795
+  Vec3<S> z = v3<S>(S(0.0), S(0.0), S(1.0)), x = v3<S>(S(1.0), S(0.0), S(0.0)), y = v3<S>(S(0.0), S(1.0), S(0.0));
+  Vec3<S> t = cross(z, n);
+  if (val(dot(t, t)) < 1e-12) { t = cross(x, n); if (val(dot(t, t)) < 1e-12) { t = cross(y, n); if (val(dot(t, t)) < 1e-12) t = cross(z, n); } }
+  t1 = t * (S(1.0) / sqrt(dot(t, t)));
   t2 = cross(n, t1);
 }
 
-static void collide_world(const Model& M, const std::vector<BodyState<double>>& B, ContactRows& R) {
+template <class S>
+static void collide_raw(const Model& M, const std::vector<BodyState<S>>& B, std::vector<Contact<S>>& raw, int& unsupported) {
   const int ns = (int)M.shape_body.size();
   const double clip = M.clip_depth;
-  std::vector<Iso<double>> Tw(ns);
-  for (int s = 0; s < ns; s++) Tw[s] = mul(B[M.shape_body[s]].W, iso_from12<double>(&M.shape_T[12 * s]));
-  std::vector<Contact<double>> raw;
+  std::vector<Iso<S>> Tw(ns);
+  for (int s = 0; s < ns; s++) Tw[s] = mul(B[M.shape_body[s]].W, iso_from12<S>(&M.shape_T[12 * s]));
   for (int i = 0; i + 1 < ns; i++) for (int j = i + 1; j < ns; j++) {
     const int bi = M.shape_body[i], bj = M.shape_body[j];
     if (bi == bj) continue;                                   // CollisionFilter.cpp:128-129
     if (!M.mobile[bi] && !M.mobile[bj]) continue;             // :137-138
     if (M.skel_id[bi] == M.skel_id[bj]) continue;             // self-collision check is off by default (:140-150)
     const int ti = M.shape_type[i], tj = M.shape_type[j];
-    Vec3<double> di = v3(M.shape_dims[3 * i], M.shape_dims[3 * i + 1], M.shape_dims[3 * i + 2]);
-    Vec3<double> dj = v3(M.shape_dims[3 * j], M.shape_dims[3 * j + 1], M.shape_dims[3 * j + 2]);
+    Vec3<S> di = v3<S>(S(M.shape_dims[3 * i]), S(M.shape_dims[3 * i + 1]), S(M.shape_dims[3 * i + 2]));
+    Vec3<S> dj = v3<S>(S(M.shape_dims[3 * j]), S(M.shape_dims[3 * j + 1]), S(M.shape_dims[3 * j + 2]));
     if (ti == SH_BOX && tj == SH_BOX) collide_box_box(di, Tw[i], dj, Tw[j], clip, bi, bj, i, j, raw);
     else if (ti == SH_BOX && tj == SH_SPHERE) collide_box_sphere(di, Tw[i], dj[0], Tw[j], clip, CLIP_BOTH, bi, bj, i, j, raw);
     else if (ti == SH_SPHERE && tj == SH_BOX) collide_sphere_box(di[0], Tw[i], dj, Tw[j], clip, bi, bj, i, j, raw);
@@ -357,27 +359,34 @@ static void collide_world(const Model& M, const std::vector<BodyState<double>>& 
       const bool boxFirst = (ti == SH_BOX);
       const int cs = boxFirst ? j : i, bs = boxFirst ? i : j;
       const double r = M.shape_dims[3 * cs], h = M.shape_dims[3 * cs + 1];
-      Vec3<double> bdim = boxFirst ? di : dj;
+      Vec3<S> bdim = boxFirst ? di : dj;
       // which end sphere is deeper inside / closer to the box? (stands in for ccdMPRPenetration's `pos`, DARTCollide.cpp:4455-4491)
       double depth_end[2];
-      Iso<double> Tend[2];
+      Iso<S> Tend[2];
       for (int e = 0; e < 2; e++) {
-        Iso<double> off = iso_identity<double>(); off.p = v3(0.0, 0.0, e == 0 ? h / 2 : -h / 2);
+        Iso<S> off = iso_identity<S>(); off.p = v3<S>(S(0.0), S(0.0), S(e == 0 ? h / 2 : -h / 2));
         Tend[e] = mul(Tw[cs], off);
-        Vec3<double> pl = apply(inverse(Tw[bs]), Tend[e].p), q = pl;
+        Vec3<S> pl = apply(inverse(Tw[bs]), Tend[e].p);
+        double q[3] = {val(pl[0]), val(pl[1]), val(pl[2])}, plv[3] = {q[0], q[1], q[2]};
         bool inside = true;
-        for (int k = 0; k < 3; k++) { double hk = 0.5 * bdim[k]; if (q[k] < -hk) { q[k] = -hk; inside = false; } if (q[k] > hk) { q[k] = hk; inside = false; } }
-        if (inside) { double mn = 1e300; for (int k = 0; k < 3; k++) mn = std::min(mn, 0.5 * bdim[k] - std::fabs(pl[k])); depth_end[e] = mn + r; }
-        else { Vec3<double> dd = pl - q; depth_end[e] = r - std::sqrt(dot(dd, dd)); }
+        for (int k = 0; k < 3; k++) { double hk = 0.5 * val(bdim[k]); if (q[k] < -hk) { q[k] = -hk; inside = false; } if (q[k] > hk) { q[k] = hk; inside = false; } }
+        if (inside) { double mn = 1e300; for (int k = 0; k < 3; k++) mn = std::min(mn, 0.5 * val(bdim[k]) - std::fabs(plv[k])); depth_end[e] = mn + r; }
+        else { double d2 = 0; for (int k = 0; k < 3; k++) d2 += (plv[k] - q[k]) * (plv[k] - q[k]); depth_end[e] = r - std::sqrt(d2); }
       }
       if (std::max(depth_end[0], depth_end[1]) < 0) continue;  // no overlap: MPR reports no intersection
-      if (std::fabs(depth_end[0] - depth_end[1]) < 1e-9) { R.unsupported++; continue; }  // side-on "pipe" contact: needs MPR + createCapsuleMeshContact
+      if (std::fabs(depth_end[0] - depth_end[1]) < 1e-9) { unsupported++; continue; }  // side-on "pipe" contact: needs MPR + createCapsuleMeshContact
       const int e = depth_end[0] > depth_end[1] ? 0 : 1;
       const int half = (e == 0) ? CLIP_TOP : CLIP_BOTTOM;
-      if (boxFirst) collide_box_sphere(bdim, Tw[bs], r, Tend[e], clip, half, bi, bj, i, j, raw);
-      else collide_sphere_box(r, Tend[e], bdim, Tw[bs], clip, bi, bj, i, j, raw);
-    } else { R.unsupported++; }
+      if (boxFirst) collide_box_sphere(bdim, Tw[bs], S(r), Tend[e], clip, half, bi, bj, i, j, raw);
+      else collide_sphere_box(S(r), Tend[e], bdim, Tw[bs], clip, bi, bj, i, j, raw);
+    } else { unsupported++; }
   }
+}
+
+static void collide_world(const Model& M, const std::vector<BodyState<double>>& B, ContactRows& R) {
+  const double clip = M.clip_depth;
+  std::vector<Contact<double>> raw;
+  collide_raw<double>(M, B, raw, R.unsupported);
   // ConstraintSolver::updateConstraints filtering (:576-601)
   for (auto& c : raw) {
     if (dot(c.normal, c.normal) < 1e-12) continue;
@@ -423,7 +432,7 @@ static void step_contact(const Model& M, const double* q, const double* v, const
     const double e = M.restitution[c.bodyA] * M.restitution[c.bodyB];
     const bool bounce = e > 1e-3;
     Vec3<double> dirs[3]; dirs[0] = c.normal;
-    if (fric) tangent_basis(c.normal, dirs[1], dirs[2]);
+    if (fric) tangent_basis<double>(c.normal, dirs[1], dirs[2]);
     const Iso<double>&WA = B[c.bodyA].W, &WB = B[c.bodyB].W;
     Vec3<double> pA = apply(inverse(WA), c.point), pB = apply(inverse(WB), c.point);
     const int dim = fric ? 3 : 1, off = R.m;
@@ -459,7 +468,7 @@ static void step_contact(const Model& M, const double* q, const double* v, const
     for (auto& x : imp) x = zero6<double>();
     if (R.reactA[ci]) imp[c.bodyA] = imp[c.bodyA] + R.JA[r];
     if (R.reactB[ci]) imp[c.bodyB] = imp[c.bodyB] + R.JB[r];
-    impulse_response(M, B, imp, dqd, dV);
+    impulse_response<double>(M, B, imp, dqd, dV);
     for (int s = 0; s < m; s++) {
       const int cj = R.row_contact[s];
       if (cj < ci) { A(r, s) = A(s, r); continue; }
@@ -485,10 +494,228 @@ static void step_contact(const Model& M, const double* q, const double* v, const
     if (R.reactA[ci]) imp[c.bodyA] = imp[c.bodyA] + R.JA[r] * CR.x[r];
     if (R.reactB[ci]) imp[c.bodyB] = imp[c.bodyB] + R.JB[r] * CR.x[r];
   }
-  impulse_response(M, B, imp, dqd, dV);
+  impulse_response<double>(M, B, imp, dqd, dV);
   std::vector<double> vplus(n);
   for (int i = 0; i < n; i++) vplus[i] = vs[i] + dqd[i];
   integrate<double>(M, q, v, vplus.data(), qn, vn);
+}
+
+// ====================================================================================
+// contact stage with a FIXED classification, scalar-generic: what BackpropSnapshot differentiates
+// (dart/neural/BackpropSnapshot.cpp:980-1107): v+ = v* + M^-1 (A_c + A_ub E) f_c ,  f_c = Q^+ b_c ,
+// Q = A_c^T M^-1 (A_c + A_ub E) + cfm I , with the clamping / upper-bound sets and E taken from the forward pass.
+// Rank-deficient Q (redundant contacts on one rigid body): the velocity update only depends on the generalized impulse,
+// which is the same for every solution of Q f = b when Q is symmetric (no upper-bound rows), so the derivative is taken
+// through a maximal independent subset of clamping rows chosen on the primal values.
+// ====================================================================================
+template <class S> static bool solve_dense(int n, std::vector<S>& A, std::vector<S>& b) {  // Gaussian elimination, partial pivoting on values
+  for (int c = 0; c < n; c++) {
+    int piv = c; double best = std::fabs(val(A[c * n + c]));
+    for (int r = c + 1; r < n; r++) if (std::fabs(val(A[r * n + c])) > best) { best = std::fabs(val(A[r * n + c])); piv = r; }
+    if (best == 0) return false;
+    if (piv != c) { for (int j = 0; j < n; j++) std::swap(A[c * n + j], A[piv * n + j]); std::swap(b[c], b[piv]); }
+    S inv = S(1.0) / A[c * n + c];
+    for (int r = c + 1; r < n; r++) {
+      S f = A[r * n + c] * inv;
+      for (int j = c; j < n; j++) A[r * n + j] = A[r * n + j] - f * A[c * n + j];
+      b[r] = b[r] - f * b[c];
+    }
+  }
+  for (int r = n - 1; r >= 0; r--) { S acc = b[r]; for (int j = r + 1; j < n; j++) acc = acc - A[r * n + j] * b[j]; b[r] = acc / A[r * n + r]; }
+  return true;
+}
+
+struct FixedSets {  // from the primal (double) forward pass
+  int nc_expected = 0, m = 0;
+  std::vector<int> cl, ub, ub_normal_pos;  // row indices; for each ub row the position (in cl) of its normal row
+  std::vector<double> ub_E;                // +-mu
+  std::vector<int> keep;                   // independent subset of cl (positions in cl)
+  double cfm = 0;
+  bool ok = true;
+};
+
+static FixedSets make_fixed_sets(const ContactStepInfo& info) {
+  FixedSets F;
+  const ContactRows& R = info.rows;
+  F.nc_expected = R.nc; F.m = R.m;
+  if (R.m == 0) return F;
+  std::vector<int> clpos(R.m, -1);
+  for (int j = 0; j < R.m; j++) if (info.mapping[j] == orc::CLAMPING) { clpos[j] = (int)F.cl.size(); F.cl.push_back(j); }
+  for (int j = 0; j < R.m; j++) if (info.mapping[j] >= 0) {
+    const int fp = info.mapping[j];
+    F.ub.push_back(j); F.ub_normal_pos.push_back(clpos[fp]);
+    const double up = info.x[fp] * R.hi[j], low = info.x[fp] * R.lo[j];
+    F.ub_E.push_back((std::fabs(info.x[j] - up) < std::fabs(info.x[j] - low)) ? R.hi[j] : R.lo[j]);
+  }
+  for (int j = 0; j < R.m; j++) if (info.mapping[j] == orc::ILLEGAL) F.ok = false;
+  F.cfm = (info.status & 8) ? -1.0 : 0.0;  // resolved by the caller (model's fallback cfm)
+  const int nCl = (int)F.cl.size();
+  // independent subset: pivoted Cholesky on the primal clamping block (symmetric, un-regularised case only; with the
+  // fallback cfm on the diagonal Q is non-singular and every clamping row takes part, as in the reference)
+  if (F.ub.empty() && !(info.status & 8)) {
+    std::vector<double> G((size_t)nCl * nCl), L((size_t)nCl * nCl, 0.0);
+    for (int r = 0; r < nCl; r++) for (int c = 0; c < nCl; c++) G[r * nCl + c] = info.A(F.cl[r], F.cl[c]);
+    std::vector<int> perm(nCl); for (int i = 0; i < nCl; i++) perm[i] = i;
+    double dmax = 0; for (int i = 0; i < nCl; i++) dmax = std::max(dmax, G[i * nCl + i]);
+    for (int k = 0; k < nCl; k++) {
+      int piv = -1; double best = dmax * 1e-10;
+      for (int i = k; i < nCl; i++) { int pi = perm[i]; double d = G[pi * nCl + pi]; for (int j = 0; j < k; j++) d -= L[pi * nCl + j] * L[pi * nCl + j]; if (d > best) { best = d; piv = i; } }
+      if (piv < 0) break;
+      std::swap(perm[k], perm[piv]);
+      const int pk = perm[k]; const double lkk = std::sqrt(best);
+      L[pk * nCl + k] = lkk;
+      for (int i = k + 1; i < nCl; i++) { int pi = perm[i]; double sacc = G[pi * nCl + pk]; for (int j = 0; j < k; j++) sacc -= L[pi * nCl + j] * L[pk * nCl + j]; L[pi * nCl + k] = sacc / lkk; }
+      F.keep.push_back(pk);
+    }
+    std::sort(F.keep.begin(), F.keep.end());
+  } else {
+    for (int i = 0; i < nCl; i++) F.keep.push_back(i);
+  }
+  return F;
+}
+
+// v* -> v+ through the contact stage with the sets of F.  B must come from aba_pass<S> at (q, v, tau); vs = v*.
+template <class S>
+static bool contact_velocity_fixed(const Model& M, std::vector<BodyState<S>>& B, const std::vector<S>& vs, const FixedSets& F,
+                                   double cfm, std::vector<S>& vplus) {
+  const int nb = M.nb, n = M.ndof;
+  vplus = vs;
+  if (F.m == 0 || F.cl.empty()) return true;
+  for (int i = 0; i < nb; i++) {
+    BodyState<S>& b = B[i];
+    Vec6<S> Sv = zero6<S>();
+    for (int c = 0; c < b.k; c++) Sv = Sv + b.Scol[c] * vs[M.dof_off[i] + c];
+    b.V = (M.parent[i] >= 0) ? AdInvT(b.T, B[M.parent[i]].V) + Sv : Sv;
+  }
+  std::vector<Contact<S>> raw, cs;
+  int unsupported = 0;
+  collide_raw<S>(M, B, raw, unsupported);
+  for (auto& c : raw) {
+    if (val(dot(c.normal, c.normal)) < 1e-12) continue;
+    if (val(c.depth) < 0.0 || val(c.depth) > M.clip_depth) continue;
+    if (!(is_reactive(M, c.bodyA) || is_reactive(M, c.bodyB))) continue;
+    cs.push_back(c);
+  }
+  if ((int)cs.size() != F.nc_expected) return false;  // the perturbation-free structure must be reproduced
+  // rows of every contact (same construction as step_contact)
+  std::vector<Vec6<S>> JA, JB; std::vector<S> bvec; std::vector<int> rowc;
+  for (int ci = 0; ci < (int)cs.size(); ci++) {
+    const Contact<S>& c = cs[ci];
+    const double mu = std::min(M.friction[c.bodyA], M.friction[c.bodyB]);
+    const bool fric = mu > 1e-3;
+    const double e = M.restitution[c.bodyA] * M.restitution[c.bodyB];
+    const bool bounce = e > 1e-3;
+    Vec3<S> dirs[3]; dirs[0] = c.normal;
+    if (fric) tangent_basis<S>(c.normal, dirs[1], dirs[2]);
+    const Iso<S>&WA = B[c.bodyA].W, &WB = B[c.bodyB].W;
+    Vec3<S> pA = apply(inverse(WA), c.point), pB = apply(inverse(WB), c.point);
+    const int dim = fric ? 3 : 1, off = (int)bvec.size();
+    for (int k = 0; k < dim; k++) {
+      Vec3<S> dA = mulT(WA.R, dirs[k]), dB = mulT(WB.R, neg(dirs[k]));
+      Vec6<S> ja = v6(cross(pA, dA), dA), jb = v6(cross(pB, dB), dB);
+      JA.push_back(ja); JB.push_back(jb); rowc.push_back(ci);
+      bvec.push_back(zero6<S>()[0] - (dot(ja, B[c.bodyA].V) + dot(jb, B[c.bodyB].V)));
+    }
+    S bv = c.depth;
+    if (val(bv) < 0) bv = S(0.0); else { bv = bv * (0.01 * (1.0 / M.dt)); if (val(bv) > 1e-3) bv = S(1e-3); }
+    if (!M.penetration_correction) bv = S(0.0);
+    if (bounce) { S rv = bvec[off] * e; if (val(rv) > 1e-1) { if (val(rv) > val(bv)) { bv = rv; if (val(bv) > 1e2) bv = S(1e2); } } }
+    bvec[off] = bvec[off] + bv;
+  }
+  if ((int)bvec.size() != F.m) return false;
+  auto response = [&](int r, std::vector<S>& dqd, std::vector<Vec6<S>>& dV) {
+    std::vector<Vec6<S>> imp(nb, zero6<S>());
+    const Contact<S>& c = cs[rowc[r]];
+    if (is_reactive(M, c.bodyA)) imp[c.bodyA] = imp[c.bodyA] + JA[r];
+    if (is_reactive(M, c.bodyB)) imp[c.bodyB] = imp[c.bodyB] + JB[r];
+    impulse_response<S>(M, B, imp, dqd, dV);
+  };
+  auto measure = [&](int s2, const std::vector<Vec6<S>>& dV) {
+    const Contact<S>& d = cs[rowc[s2]];
+    S a = S(0.0);
+    if (is_reactive(M, d.bodyA)) a = a + dot(JA[s2], dV[d.bodyA]);
+    if (is_reactive(M, d.bodyB)) a = a + dot(JB[s2], dV[d.bodyB]);
+    return a;
+  };
+  const int nk = (int)F.keep.size(), nUb = (int)F.ub.size();
+  // Q[r, c] = A(cl_r, cl_c) + sum_u A(cl_r, ub_u) E(u, c)   restricted to the kept rows / columns
+  std::vector<S> Q((size_t)nk * nk, S(0.0)), rhs(nk);
+  std::vector<S> dqd; std::vector<Vec6<S>> dV;
+  for (int c = 0; c < nk; c++) {
+    // column c: impulse along P e_c = J_cl[c]^T + sum_{u: normal(u) == c} E_u J_ub[u]^T
+    std::vector<Vec6<S>> imp(nb, zero6<S>());
+    auto add_row = [&](int r, const S& coef) {
+      const Contact<S>& cc = cs[rowc[r]];
+      if (is_reactive(M, cc.bodyA)) imp[cc.bodyA] = imp[cc.bodyA] + JA[r] * coef;
+      if (is_reactive(M, cc.bodyB)) imp[cc.bodyB] = imp[cc.bodyB] + JB[r] * coef;
+    };
+    add_row(F.cl[F.keep[c]], S(1.0));
+    for (int u = 0; u < nUb; u++) if (F.ub_normal_pos[u] == F.keep[c]) add_row(F.ub[u], S(F.ub_E[u]));
+    impulse_response<S>(M, B, imp, dqd, dV);
+    for (int r = 0; r < nk; r++) Q[(size_t)r * nk + c] = measure(F.cl[F.keep[r]], dV);
+    Q[(size_t)c * nk + c] = Q[(size_t)c * nk + c] + S(cfm);
+  }
+  for (int r = 0; r < nk; r++) rhs[r] = bvec[F.cl[F.keep[r]]];
+  if (!solve_dense<S>(nk, Q, rhs)) return false;
+  std::vector<Vec6<S>> imp(nb, zero6<S>());
+  for (int c = 0; c < nk; c++) {
+    auto add_row = [&](int r, const S& coef) {
+      const Contact<S>& cc = cs[rowc[r]];
+      if (is_reactive(M, cc.bodyA)) imp[cc.bodyA] = imp[cc.bodyA] + JA[r] * coef;
+      if (is_reactive(M, cc.bodyB)) imp[cc.bodyB] = imp[cc.bodyB] + JB[r] * coef;
+    };
+    add_row(F.cl[F.keep[c]], rhs[c]);
+    for (int u = 0; u < nUb; u++) if (F.ub_normal_pos[u] == F.keep[c]) add_row(F.ub[u], rhs[c] * F.ub_E[u]);
+  }
+  impulse_response<S>(M, B, imp, dqd, dV);
+  for (int i = 0; i < n; i++) vplus[i] = vs[i] + dqd[i];
+  return true;
+}
+
+template <class S>
+static bool step_contact_fixed(const Model& M, const S* q, const S* v, const S* tau, const FixedSets& F, double cfm, S* qn, S* vn) {
+  std::vector<BodyState<S>>& B = workspace<S>(M.nb);
+  static thread_local std::vector<S> qdd;
+  aba_pass<S>(M, q, v, tau, B, qdd);
+  std::vector<S> vs(M.ndof, S(0.0)), vplus;
+  for (int i = 0; i < M.nb; i++) { const int o = M.dof_off[i]; for (int a = 0; a < B[i].k; a++) vs[o + a] = M.mobile[i] ? v[o + a] + qdd[o + a] * M.dt : v[o + a]; }
+  if (!contact_velocity_fixed<S>(M, B, vs, F, cfm, vplus)) return false;
+  integrate<S>(M, q, v, vplus.data(), qn, vn);
+  return true;
+}
+
+// Jacobian of the contact step for the classification found by the forward pass at (q, v, tau, x_warm)
+static int step_jacobian_contact(const Model& M, const double* q, const double* v, const double* tau, const double* x_warm, int m_warm, double* J) {
+  const int n = M.ndof, cols = 3 * n;
+  ContactStepInfo info;
+  std::vector<double> qn0(n), vn0(n);
+  step_contact(M, q, v, tau, x_warm, m_warm, qn0.data(), vn0.data(), info);
+  FixedSets F = make_fixed_sets(info);
+  const double cfm = (info.status & 8) ? M.fallback_cfm : 0.0;
+  if (!F.ok) return -2;
+  // consistency: the fixed-set recomputation must reproduce the forward result
+  {
+    std::vector<double> qn1(n), vn1(n);
+    if (!step_contact_fixed<double>(M, q, v, tau, F, cfm, qn1.data(), vn1.data())) return -3;
+    double err = 0, ref = 0; for (int i = 0; i < n; i++) { err = std::max(err, std::fabs(vn1[i] - vn0[i])); ref = std::max(ref, std::fabs(vn0[i])); }
+    if (err > 1e-7 * std::max(1.0, ref) && !(info.status & 16)) return -4;
+  }
+  constexpr int N = 12;
+  typedef Dual<N> D;
+  std::vector<D> dq(n), dv(n), dtau(n), qn(n), vn(n);
+  for (int c0 = 0; c0 < cols; c0 += N) {
+    for (int i = 0; i < n; i++) { dq[i] = D(q[i]); dv[i] = D(v[i]); dtau[i] = D(tau[i]); }
+    for (int k = 0; k < N && c0 + k < cols; k++) {
+      int c = c0 + k;
+      if (c < n) dq[c].d[k] = 1.0; else if (c < 2 * n) dv[c - n].d[k] = 1.0; else dtau[c - 2 * n].d[k] = 1.0;
+    }
+    if (!step_contact_fixed<D>(M, dq.data(), dv.data(), dtau.data(), F, cfm, qn.data(), vn.data())) return -5;
+    for (int k = 0; k < N && c0 + k < cols; k++) {
+      int c = c0 + k;
+      for (int r = 0; r < n; r++) { J[(size_t)r * cols + c] = qn[r].d[k]; J[(size_t)(n + r) * cols + c] = vn[r].d[k]; }
+    }
+  }
+  return info.status;
 }
 
 // J = d[qn; vn] / d[q; v; tau]  row-major [2n x 3n]
@@ -671,6 +898,40 @@ void orc_pinv_solve(int m, int n, const double* Q, const double* b, double* x) {
   orc::Mat Qm(m, n); for (int i = 0; i < m * n; i++) Qm.a[i] = Q[i];
   orc::Vec r = orc::pinv_solve(Qm, orc::Vec(b, b + m));
   for (int i = 0; i < n; i++) x[i] = r[i];
+}
+
+// Jacobian / VJP of the contact step (classification frozen at the forward solution).  Returns the forward status (>=0)
+// or a negative error (-2 illegal rows, -3/-5 structure changed, -4 fixed-set recomputation disagrees with the forward).
+int orc_jacobian_contact(void* h, const double* state, const double* action, const double* x_warm, int m_warm, double* J) {
+  const Model& M = *(Model*)h;
+  const int n = M.ndof;
+  std::vector<double> tau(n, 0.0);
+  for (size_t i = 0; i < M.action_map.size(); i++) tau[M.action_map[i]] = action[i];
+  return orc::step_jacobian_contact(M, state, state + n, tau.data(), x_warm, m_warm, J);
+}
+int orc_backprop_contact(void* h, const double* state, const double* action, const double* x_warm, int m_warm, const double* grad_next,
+                         double* grad_state, double* grad_action) {
+  const Model& M = *(Model*)h;
+  const int n = M.ndof, cols = 3 * n;
+  std::vector<double> tau(n, 0.0);
+  for (size_t i = 0; i < M.action_map.size(); i++) tau[M.action_map[i]] = action[i];
+  std::vector<double> J((size_t)2 * n * cols);
+  int rc = orc::step_jacobian_contact(M, state, state + n, tau.data(), x_warm, m_warm, J.data());
+  if (rc < 0) return rc;
+  std::vector<double> g(cols, 0.0);
+  for (int r = 0; r < 2 * n; r++) for (int c = 0; c < cols; c++) g[c] += J[(size_t)r * cols + c] * grad_next[r];
+  for (int j = 0; j < n; j++) {
+    double qj = state[j], vj = state[n + j], fj = tau[j];
+    if (qj == M.pos_lo[j] && g[j] > 0) g[j] = 0;
+    if (qj == M.pos_hi[j] && g[j] < 0) g[j] = 0;
+    if (vj == M.vel_lo[j] && g[n + j] > 0) g[n + j] = 0;
+    if (vj == M.vel_hi[j] && g[n + j] < 0) g[n + j] = 0;
+    if (fj == M.force_lo[j] && g[2 * n + j] > 0) g[2 * n + j] = 0;
+    if (fj == M.force_hi[j] && g[2 * n + j] < 0) g[2 * n + j] = 0;
+  }
+  for (int j = 0; j < 2 * n; j++) grad_state[j] = g[j];
+  for (size_t i = 0; i < M.action_map.size(); i++) grad_action[i] = g[2 * n + M.action_map[i]];
+  return rc;
 }
 
 }  // extern "C"

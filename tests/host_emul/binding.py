@@ -73,7 +73,18 @@ class EmulWorld:
         status = np.zeros(B, np.int32)
         nc = np.zeros(B, np.int32)
         cinfo = np.zeros((B, MAX_CONTACTS, 10), np.float32)
+        crec = np.zeros((B, lib().emul_contact_rec_doubles(ctypes.byref(self.desc))), np.float64)
         rc = lib().emul_forward_contact(ctypes.byref(self.desc), B, _p(state), _p(action), _p(nxt), _p(saved), _p(x), _p(m),
-                                        _p(labels), _p(status), _p(nc), _p(cinfo))
+                                        _p(labels), _p(status), _p(nc), _p(cinfo), _p(crec))
         assert rc == 0
-        return dict(next=nxt, saved=saved, x=x, m=m, labels=labels, status=status, nc=nc, cinfo=cinfo)
+        return dict(next=nxt, saved=saved, x=x, m=m, labels=labels, status=status, nc=nc, cinfo=cinfo, crec=crec)
+
+    def backward_contact(self, state, action, saved, crec, gnext):
+        state = np.ascontiguousarray(state, np.float32)
+        action = np.ascontiguousarray(action, np.float32)
+        gnext = np.ascontiguousarray(gnext, np.float32)
+        gs, ga = np.empty_like(state), np.empty_like(action)
+        rc = lib().emul_backward_contact(ctypes.byref(self.desc), state.shape[0], _p(state), _p(action), _p(saved), _p(crec),
+                                         _p(gnext), _p(gs), _p(ga))
+        assert rc == 0
+        return gs, ga

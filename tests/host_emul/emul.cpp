@@ -38,7 +38,7 @@ static int run_bwd(const nb2_model_desc* d, int B, const float* state, const flo
 }
 // forward with the contact stage (fp64): ABA kernel body with the saved stream, then the contact kernel body
 static int run_fwd_contact(const nb2_model_desc* d, int B, const float* state, const float* action, float* next, double* saved,
-                           double* x_lcp, int* m_lcp, int* labels, int* status, int* nc, float* cinfo) {
+                           double* x_lcp, int* m_lcp, int* labels, int* status, int* nc, float* cinfo, double* crec) {
   Nb2ModelDev<double> M; Nb2ContactDev C; std::string err;
   if (!nb2_fill_model(*d, M, err) || !nb2_fill_contact(*d, C, err)) { fprintf(stderr, "emul: %s\n", err.c_str()); return -1; }
   nb2::FwdLayout L = nb2::fwd_layout(M.nb, M.ndof, M.nslots, M.nfree);
@@ -50,14 +50,36 @@ static int run_fwd_contact(const nb2_model_desc* d, int B, const float* state, c
     for (auto& x : ws) x = 1e30;
     nb2::world_contact(M, C, state + (size_t)w * 2 * M.ndof, next + (size_t)w * 2 * M.ndof, saved + w, (size_t)B, ws.data(),
                        x_lcp + (size_t)w * NB2_MAX_ROWS, m_lcp + w, labels + (size_t)w * NB2_MAX_ROWS, status + w, nc + w,
-                       cinfo ? cinfo + (size_t)w * NB2_MAX_CONTACTS * 10 : nullptr);
+                       cinfo ? cinfo + (size_t)w * NB2_MAX_CONTACTS * 10 : nullptr,
+                       crec ? crec + (size_t)w * nb2::contact_rec_doubles(M.ndof) : nullptr);
+  }
+  return 0;
+}
+static int run_bwd_contact(const nb2_model_desc* d, int B, const float* state, const float* action, const double* saved,
+                           const double* crec, const float* gnext, float* gstate, float* gaction) {
+  Nb2ModelDev<double> M; Nb2ContactDev C; std::string err;
+  if (!nb2_fill_model(*d, M, err) || !nb2_fill_contact(*d, C, err)) { fprintf(stderr, "emul: %s\n", err.c_str()); return -1; }
+  nb2::BwdLayout L = nb2::bwd_layout(M.nb, M.ndof, M.nslots, M.nfree, 42);
+  std::vector<double> scr(L.total), ws(nb2::contact_ws_doubles(M.nb, M.ndof));
+  for (int w = 0; w < B; w++) {
+    for (auto& x : scr) x = 1e30;
+    for (auto& x : ws) x = 1e30;
+    nb2::BwdContactHook H; H.model_contact = &C; H.ws = ws.data(); H.crec = crec + (size_t)w * nb2::contact_rec_doubles(M.ndof);
+    nb2::world_backward<double, 1, true>(M, scr.data(), state + (size_t)w * 2 * M.ndof, action + (size_t)w * M.na,
+                                         gnext + (size_t)w * 2 * M.ndof, saved + w, (size_t)B, gstate + (size_t)w * 2 * M.ndof,
+                                         gaction + (size_t)w * M.na, &H);
   }
   return 0;
 }
 extern "C" {
 int emul_forward_contact(const nb2_model_desc* d, int B, const float* state, const float* action, float* next, double* saved,
-                         double* x_lcp, int* m_lcp, int* labels, int* status, int* nc, float* cinfo) {
-  return run_fwd_contact(d, B, state, action, next, saved, x_lcp, m_lcp, labels, status, nc, cinfo);
+                         double* x_lcp, int* m_lcp, int* labels, int* status, int* nc, float* cinfo, double* crec) {
+  return run_fwd_contact(d, B, state, action, next, saved, x_lcp, m_lcp, labels, status, nc, cinfo, crec);
+}
+int emul_contact_rec_doubles(const nb2_model_desc* d) { return (int)nb2::contact_rec_doubles(d->ndof); }
+int emul_backward_contact(const nb2_model_desc* d, int B, const float* state, const float* action, const double* saved,
+                          const double* crec, const float* gnext, float* gstate, float* gaction) {
+  return run_bwd_contact(d, B, state, action, saved, crec, gnext, gstate, gaction);
 }
 int emul_saved_words(const nb2_model_desc* d) {
   int nfree = 0; for (int i = 0; i < d->nb; i++) nfree += d->jtype[i] == NB2_JT_FREE;

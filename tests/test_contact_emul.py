@@ -74,3 +74,77 @@ def test_oracle_contact_step_invariants(oracle_mod):
             idx = [d for d in range(n) if not (name == "atlas_ground" and d < 6)]
             assert np.allclose(r["next_state"][:n][idx], (q + raw.dt * v)[idx], atol=1e-12)
         assert total_contacts > 0
+
+
+def _check_backward(ob, raw, S, A_, tol=1e-5):
+    cm = nb.compile_model(raw)
+    ow, ew = ob.OracleContactWorld(raw), EmulWorld(cm)
+    n = raw.ndof
+    B = S.shape[0]
+    g = np.random.default_rng(1).normal(size=(B, 2 * n)).astype(np.float32)
+    r = ew.forward_contact(S, A_)
+    gs, ga = ew.backward_contact(S, A_, r["saved"], r["crec"], g)
+    kinds = []
+    for w in range(B):
+        rgs, rga, rc = ow.backprop_contact(S[w].astype(np.float64), A_[w].astype(np.float64), g[w].astype(np.float64))
+        assert rc >= 0
+        lab = r["labels"][w][: r["m"][w]]
+        kinds.append((int((lab == -2).sum()), int((lab >= 0).sum()), int(r["status"][w])))
+        assert rel_err(gs[w], rgs) < tol and rel_err(ga[w], rga) < tol, (w, kinds[-1])
+    return kinds
+
+
+def test_contact_backward_adjoint_matches_oracle_jacobian(oracle_mod):
+    """The device backward through the contact stage (adjoint form + dual-number contact geometry, csrc/nb2_contact.cuh)
+    vs J^T g with the oracle's forward-mode Jacobian of the same frozen-classification step.  Covers: clamping rows only,
+    rank-deficient Q (24 clamping rows of a standing Atlas, rank 12), fallback-cfm solutions, sliding (upper-bound) rows."""
+    # seeded contact-rich batches
+    for name in ("half_cheetah", "atlas_ground"):
+        raw = load_raw(name)
+        s, a = contact_inputs(raw, name, 6, seed=4)
+        _check_backward(ob, raw, s, a)
+    # standing Atlas: every row clamping, Q rank-deficient
+    raw = load_raw("atlas_ground")
+    n = raw.ndof
+    S = np.zeros((2, 2 * n), np.float32)
+    S[:, 0] = -0.5 * np.pi
+    S[:, 4] = [-0.01, -0.012]
+    S[1, n + 3] = 0.01
+    kinds = _check_backward(ob, raw, S, np.zeros((2, n), np.float32))
+    assert any(k[0] == 24 for k in kinds)
+    # low friction + tangential velocity: sliding friction rows (UPPER_BOUND labels, non-symmetric Q)
+    raw = load_raw("half_cheetah")
+    raw.friction[:] = 0.2
+    n = raw.ndof
+    S = np.zeros((3, 2 * n), np.float32)
+    S[:, 1], S[:, 2] = -0.1, 0.03
+    S[:, n] = [0.5, 2.0, -1.5]
+    kinds = _check_backward(ob, raw, S, np.zeros((3, n), np.float32))
+    assert any(k[1] > 0 for k in kinds)
+
+
+def test_oracle_contact_jacobian_matches_finite_differences(oracle_mod):
+    """Reference-style pin of the oracle itself (GradientTestUtils.hpp verifyVelGradients): when the forward solution is an
+    exact LCP solution (short-circuit or Dantzig), the frozen-classification Jacobian equals central differences of the full
+    step wherever the perturbation does not flip a label."""
+    raw = load_raw("half_cheetah")
+    ow = ob.OracleContactWorld(raw)
+    n = raw.ndof
+    s, a = contact_inputs(raw, "half_cheetah", 3, seed=4)
+    for w in range(3):
+        s64, a64 = s[w].astype(np.float64), a[w].astype(np.float64)
+        r0 = ow.step_contact(s64, a64)
+        if r0["status"] & 24:
+            continue  # PGS / friction-drop answers are approximate: the analytic map is not their derivative
+        J, rc = ow.jacobian_contact(s64, a64)
+        assert rc >= 0
+        eps = 1e-7
+        for c in range(2 * n):
+            sp, sm = s64.copy(), s64.copy()
+            sp[c] += eps
+            sm[c] -= eps
+            rp, rm = ow.step_contact(sp, a64), ow.step_contact(sm, a64)
+            if not (np.array_equal(rp["mapping"], r0["mapping"]) and np.array_equal(rm["mapping"], r0["mapping"])):
+                continue
+            fd = (rp["next_state"] - rm["next_state"]) / (2 * eps)
+            assert np.abs(fd - J[:, c]).max() < 2e-6 * max(1.0, np.abs(J).max())

@@ -72,11 +72,41 @@ def test_full_batch_contact_properties_atlas_4096():
     assert torch.isfinite(nxt).all()
 
 
-def test_backward_with_active_contacts_is_refused_loudly():
+@pytest.mark.parametrize("name", ["half_cheetah", "atlas_ground"])
+def test_contact_backward_matches_oracle(oracle_mod, name):
+    """VJP of a step with active contact constraints (classification frozen at the forward solution) vs the oracle's
+    dual-number Jacobian of the same fixed-classification map (oracle/nb_oracle.cpp step_jacobian_contact)."""
+    raw = load_raw(name)
+    world = nb.World.from_raw(raw)
+    ow = ob.OracleContactWorld(raw)
+    B = 48
+    s, a = contact_inputs(raw, name, B, seed=8)
+    g = np.random.default_rng(2).normal(size=(B, 2 * raw.ndof)).astype(np.float32)
+    st = torch.tensor(s, device="cuda", requires_grad=True)
+    at = torch.tensor(a, device="cuda", requires_grad=True)
+    nb.reset_contact_cache(world)
+    out = nb.timestep(world, st, at)
+    out.backward(torch.tensor(g, device="cuda"))
+    gs, ga = st.grad.cpu().numpy(), at.grad.cpu().numpy()
+    checked = with_rows = 0
+    for w in range(0, B, 2):
+        rgs, rga, rc = ow.backprop_contact(s[w].astype(np.float64), a[w].astype(np.float64), g[w].astype(np.float64))
+        assert rc >= 0
+        assert rel_err(gs[w], rgs) < 1e-4 and rel_err(ga[w], rga) < 1e-4
+        checked += 1
+        with_rows += int(rc != 0)
+    assert checked > 10 and with_rows > 3
+
+
+def test_contact_rollout_backward_runs_and_is_finite():
     raw = load_raw("half_cheetah")
     world = nb.World.from_raw(raw)
-    s, a = contact_inputs(raw, "half_cheetah", 8, seed=1)
+    s, a = contact_inputs(raw, "half_cheetah", 32, seed=1)
     st = torch.tensor(s, device="cuda", requires_grad=True)
-    out = nb.timestep(world, st, torch.tensor(a, device="cuda"))
-    with pytest.raises(NotImplementedError):
-        out.sum().backward()
+    acts = [torch.tensor(a, device="cuda", requires_grad=True) for _ in range(6)]
+    nb.reset_contact_cache(world)
+    x = st
+    for t in range(6):
+        x = nb.timestep(world, x, acts[t])
+    (x * x).sum().backward()
+    assert torch.isfinite(st.grad).all() and all(torch.isfinite(u.grad).all() for u in acts)
