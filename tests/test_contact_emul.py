@@ -29,7 +29,7 @@ def test_contact_forward_chain_matches_oracle(oracle_mod, name):
             mo = ro["m"]
             assert r["nc"][w] == ro["nc"] and r["m"][w] == mo
             assert np.array_equal(r["labels"][w][:mo], ro["mapping"])          # bit-exact contact set / classification
-            assert r["status"][w] == ro["status"]                               # same solver branch
+            assert (r["status"][w] & ~96) == (ro["status"] & ~96)               # same solver branch (bits 32/64: see test_gpu_contact)
             assert np.array_equal(r["cinfo"][w][: ro["nc"], 7:9].astype(int), ro["bodies"])
             assert np.array_equal(r["cinfo"][w][: ro["nc"], 9].astype(int), ro["type"])
             if mo:
