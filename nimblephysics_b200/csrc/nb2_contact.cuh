@@ -55,46 +55,53 @@ struct Nb2ContactDev {
 
 namespace nb2 {
 
-struct ContactWs {  // per-world fp64 workspace carved out of one contiguous block
-  CR *W, *T, *V, *pI, *uI, *dqd, *vstar;
-  CR *cpoint, *cnormal, *cdepth, *cmu, *crest;
-  int *cbodyA, *cbodyB, *ctype, *cshapeA, *cshapeB;
-  CR *JA, *JB, *b, *lo, *hi, *x, *x0, *rest, *colnorm;
-  int *findex, *mapping, *clampIdx, *ubIdx;
-  CR *A, *Aw, *L, *Q, *Q2;
-  CR *v1, *v2, *v3, *v4, *v5, *v6, *v7, *v8;
-  int *i1, *i2;
-  unsigned char* st8;
+template <int ST>
+struct ContactWsT {  // per-world fp64 workspace; lane-interleaved on the device (ST = 32), contiguous on the host (ST = 1)
+  typedef SP<CR, ST> PD; typedef SP<int, ST> PI; typedef SP<unsigned char, ST> PB;
+  PD W, T, V, pI, uI, dqd, vstar;
+  PD cpoint, cnormal, cdepth, cmu, crest;
+  PI cbodyA, cbodyB, ctype, cshapeA, cshapeB;
+  PD JA, JB, b, lo, hi, x, x0, rest, colnorm;
+  PI findex, mapping, clampIdx, ubIdx;
+  PD A, Aw, L, Q, Q2;
+  PD v1, v2, v3, v4, v5, v6, v7, v8;
+  PI i1, i2;
+  PB st8;
 };
 NB2_HD size_t contact_rec_doubles(int ndof) { return 2 + 2 * (size_t)NB2_MAX_ROWS + ndof + (size_t)NB2_MAX_ROWS * NB2_MAX_ROWS; }
+// doubles per WORLD (the kernel allocates 32x this per warp)
 NB2_HD size_t contact_ws_doubles(int nb, int ndof) {
   const int MC = NB2_MAX_CONTACTS, MR = NB2_MAX_ROWS;
-  return (size_t)nb * 24 + nb * 6 + nb * 6 + 3 * ndof + MC * 10 + MC * 3 /*ints as 5 int arrays -> 2.5 doubles each*/ + 2 * MR * 6 + 7 * MR
-         + 2 * MR /*int arrays*/ + 5 * (size_t)MR * MR + 8 * MR + MR /*i1,i2*/ + 2 * MR / 8 + 8;
+  return (size_t)nb * 36 + 3 * ndof + MC * 9 + 5 * ((MC + 1) / 2) + 2 * MR * 6 + 7 * MR + 4 * ((MR + 1) / 2) + 5 * (size_t)MR * MR + 8 * MR
+         + 2 * ((MR + 1) / 2) + (2 * MR + 7) / 8 + 4;
 }
-NB2_HD ContactWs carve_ws(CR* base, int nb, int ndof) {
+// `block`: start of the warp's (device) or world's (host) block; `lane`: 0 on the host
+template <int ST>
+NB2_HD ContactWsT<ST> carve_ws(CR* block, int lane, int nb, int ndof) {
   const int MC = NB2_MAX_CONTACTS, MR = NB2_MAX_ROWS;
-  ContactWs w; CR* p = base;
-  w.W = p; p += nb * 12; w.T = p; p += nb * 12; w.V = p; p += nb * 6; w.pI = p; p += nb * 6; w.uI = p; p += ndof; w.dqd = p; p += ndof; w.vstar = p; p += ndof;
-  w.cpoint = p; p += MC * 3; w.cnormal = p; p += MC * 3; w.cdepth = p; p += MC; w.cmu = p; p += MC; w.crest = p; p += MC;
-  int* ip = (int*)p; w.cbodyA = ip; ip += MC; w.cbodyB = ip; ip += MC; w.ctype = ip; ip += MC; w.cshapeA = ip; ip += MC; w.cshapeB = ip; ip += MC;
-  p += MC * 3;  // 5*MC ints = 2.5*MC doubles <= 3*MC
-  w.JA = p; p += MR * 6; w.JB = p; p += MR * 6; w.b = p; p += MR; w.lo = p; p += MR; w.hi = p; p += MR; w.x = p; p += MR; w.x0 = p; p += MR;
-  w.rest = p; p += MR; w.colnorm = p; p += MR;
-  ip = (int*)p; w.findex = ip; ip += MR; w.mapping = ip; ip += MR; w.clampIdx = ip; ip += MR; w.ubIdx = ip; ip += MR; p += 2 * MR;
-  w.A = p; p += MR * MR; w.Aw = p; p += MR * MR; w.L = p; p += MR * MR; w.Q = p; p += MR * MR; w.Q2 = p; p += MR * MR;
-  w.v1 = p; p += MR; w.v2 = p; p += MR; w.v3 = p; p += MR; w.v4 = p; p += MR; w.v5 = p; p += MR; w.v6 = p; p += MR; w.v7 = p; p += MR; w.v8 = p; p += MR;
-  ip = (int*)p; w.i1 = ip; ip += MR; w.i2 = ip; ip += MR; p += MR;
-  w.st8 = (unsigned char*)p;
+  ContactWsT<ST> w;
+  size_t off = 0;  // in doubles per world
+  auto D = [&](size_t cnt) { SP<CR, ST> r; r.p = block + off * ST + lane; off += cnt; return r; };
+  auto I = [&](size_t cnt) { SP<int, ST> r; r.p = (int*)(block + off * ST) + lane; off += (cnt + 1) / 2; return r; };
+  auto Bt = [&](size_t cnt) { SP<unsigned char, ST> r; r.p = (unsigned char*)(block + off * ST) + lane; off += (cnt + 7) / 8; return r; };
+  w.W = D(nb * 12); w.T = D(nb * 12); w.V = D(nb * 6); w.pI = D(nb * 6); w.uI = D(ndof); w.dqd = D(ndof); w.vstar = D(ndof);
+  w.cpoint = D(MC * 3); w.cnormal = D(MC * 3); w.cdepth = D(MC); w.cmu = D(MC); w.crest = D(MC);
+  w.cbodyA = I(MC); w.cbodyB = I(MC); w.ctype = I(MC); w.cshapeA = I(MC); w.cshapeB = I(MC);
+  w.JA = D(MR * 6); w.JB = D(MR * 6); w.b = D(MR); w.lo = D(MR); w.hi = D(MR); w.x = D(MR); w.x0 = D(MR); w.rest = D(MR); w.colnorm = D(MR);
+  w.findex = I(MR); w.mapping = I(MR); w.clampIdx = I(MR); w.ubIdx = I(MR);
+  w.A = D((size_t)MR * MR); w.Aw = D((size_t)MR * MR); w.L = D((size_t)MR * MR); w.Q = D((size_t)MR * MR); w.Q2 = D((size_t)MR * MR);
+  w.v1 = D(MR); w.v2 = D(MR); w.v3 = D(MR); w.v4 = D(MR); w.v5 = D(MR); w.v6 = D(MR); w.v7 = D(MR); w.v8 = D(MR);
+  w.i1 = I(MR); w.i2 = I(MR);
+  w.st8 = Bt(2 * MR);
   return w;
 }
 
 // ------------------------------------------------------------------ small helpers on raw arrays
-NB2_HD Xf<CR> xf_from12(const CR* t) {
+template <class P> NB2_HD Xf<CR> xf_from12(P t) {
   Xf<CR> T; T.R_.m00 = t[0]; T.R_.m01 = t[1]; T.R_.m02 = t[2]; T.R_.m10 = t[3]; T.R_.m11 = t[4]; T.R_.m12 = t[5];
   T.R_.m20 = t[6]; T.R_.m21 = t[7]; T.R_.m22 = t[8]; T.p = mk3<CR>(t[9], t[10], t[11]); return T;
 }
-NB2_HD void xf_to12(CR* t, const Xf<CR>& T) {
+template <class P> NB2_HD void xf_to12(P t, const Xf<CR>& T) {
   t[0] = T.R_.m00; t[1] = T.R_.m01; t[2] = T.R_.m02; t[3] = T.R_.m10; t[4] = T.R_.m11; t[5] = T.R_.m12;
   t[6] = T.R_.m20; t[7] = T.R_.m21; t[8] = T.R_.m22; t[9] = T.p.x; t[10] = T.p.y; t[11] = T.p.z;
 }
@@ -104,8 +111,8 @@ NB2_HD V3<CR> xf_apply_inv(const Xf<CR>& A, const V3<CR>& x) { return mulT(A.R_,
 NB2_HD V3<CR> col3(const M3<CR>& R, int j) { return j == 0 ? mk3<CR>(R.m00, R.m10, R.m20) : (j == 1 ? mk3<CR>(R.m01, R.m11, R.m21) : mk3<CR>(R.m02, R.m12, R.m22)); }
 NB2_HD CR get3(const V3<CR>& v, int k) { return k == 0 ? v.x : (k == 1 ? v.y : v.z); }
 NB2_HD void set3(V3<CR>& v, int k, CR x) { if (k == 0) v.x = x; else if (k == 1) v.y = x; else v.z = x; }
-NB2_HD V6<CR> ldv6(const CR* p) { V6<CR> v; v.a = mk3<CR>(p[0], p[1], p[2]); v.l = mk3<CR>(p[3], p[4], p[5]); return v; }
-NB2_HD void stv6(CR* p, const V6<CR>& v) { p[0] = v.a.x; p[1] = v.a.y; p[2] = v.a.z; p[3] = v.l.x; p[4] = v.l.y; p[5] = v.l.z; }
+template <class P> NB2_HD V6<CR> ldv6(P p) { V6<CR> v; v.a = mk3<CR>(p[0], p[1], p[2]); v.l = mk3<CR>(p[3], p[4], p[5]); return v; }
+template <class P> NB2_HD void stv6(P p, const V6<CR>& v) { p[0] = v.a.x; p[1] = v.a.y; p[2] = v.a.z; p[3] = v.l.x; p[4] = v.l.y; p[5] = v.l.z; }
 
 typedef ContactOutT<CR> ContactOut;
 
@@ -124,7 +131,8 @@ NB2_HD Xf<CR> saved_xf(const Nb2ModelDev<CR>& M, int i, const float* st, const C
 // changes) and ws.V (spatial velocity changes).  Only bodies in `mask` are visited: for the impulse TESTS that build A the
 // mask holds the ancestors of the contact bodies (every other body has zero bias impulse and its velocity change is never
 // read); the final impulse application visits every body.
-NB2_HD void impulse_response(const Nb2ModelDev<CR>& M, const CR* sv, size_t B, const ContactWs& ws, unsigned long long mask) {
+template <int ST>
+NB2_HD void impulse_response(const Nb2ModelDev<CR>& M, const CR* sv, size_t B, const ContactWsT<ST>& ws, unsigned long long mask) {
   const int nb = M.nb;
   for (int i = nb - 1; i >= 0; i--) {
     if (!((mask >> i) & 1ull)) continue;
@@ -142,7 +150,7 @@ NB2_HD void impulse_response(const Nb2ModelDev<CR>& M, const CR* sv, size_t B, c
     }
     if (p >= 0) {
       const V6<CR> pc = dAdInvT(xf_from12(ws.T + 12 * i), beta);
-      CR* pp = ws.pI + 6 * p;
+      auto pp = ws.pI + 6 * p;
       pp[0] += pc.a.x; pp[1] += pc.a.y; pp[2] += pc.a.z; pp[3] += pc.l.x; pp[4] += pc.l.y; pp[5] += pc.l.z;
     }
   }
@@ -167,7 +175,8 @@ NB2_HD void impulse_response(const Nb2ModelDev<CR>& M, const CR* sv, size_t B, c
 }
 
 // ------------------------------------------------------------------ dense helpers (m x m, stride m)
-NB2_HD bool lcp_valid(int m, const CR* A, const CR* x, const CR* b, const CR* hi, const CR* lo, const int* fi, bool ignoreFriction) {
+template <class PA, class PX, class PB_, class PH, class PL, class PF>
+NB2_HD bool lcp_valid(int m, PA A, PX x, PB_ b, PH hi, PL lo, PF fi, bool ignoreFriction) {
   for (int i = 0; i < m; i++) {
     CR v = -b[i];
     for (int j = 0; j < m; j++) v += A[i * m + j] * x[j];
@@ -186,7 +195,8 @@ NB2_HD bool lcp_valid(int m, const CR* A, const CR* x, const CR* b, const CR* hi
 // minimum-norm least squares x = Q^+ rhs for an n x n matrix.  symmetric PSD Q: rank-revealing pivoted Cholesky
 // Q = P L L^T P^T (L: n x r) and Q^+ = L (L^T L)^-2 L^T ; general Q: x = (Q^T Q)^+ Q^T rhs through the same routine.
 // work: G (n*n, destroyed copy), Lf (n*n), t1..t3 (n), perm (n)
-NB2_HD void pinv_psd(int n, const CR* Qin, const CR* rhs, CR* x, CR* G, CR* Lf, CR* t1, CR* t2, int* perm) {
+template <class PQ, class PR, class PX, class PG, class PL, class PT1, class PT2, class PP>
+NB2_HD void pinv_psd(int n, PQ Qin, PR rhs, PX x, PG G, PL Lf, PT1 t1, PT2 t2, PP perm) {
   for (int i = 0; i < n * n; i++) G[i] = Qin[i];
   for (int i = 0; i < n; i++) perm[i] = i;
   CR dmax0 = 0;
@@ -237,10 +247,11 @@ NB2_HD void pinv_psd(int n, const CR* Qin, const CR* rhs, CR* x, CR* G, CR* Lf, 
 
 // classification (constructMatrices) + standardisation; x is updated in place when the standardised solution is valid.
 // returns true when the results are standardised.
-NB2_HD bool classify_once(int m, const CR* A, CR* x, const CR* b, const CR* lo, const CR* hi, const int* fi, const CR* colnorm,
-                          bool ignoreFriction, const ContactWs& ws, bool* again) {
+template <int ST, class PD>
+NB2_HD bool classify_once(int m, PD A, PD x, PD b, PD lo, PD hi, SP<int, ST> fi, PD colnorm,
+                          bool ignoreFriction, const ContactWsT<ST>& ws, bool* again) {
   *again = false;
-  int* mapping = ws.mapping; int* clampIdx = ws.clampIdx; int* ubIdx = ws.ubIdx;
+  auto mapping = ws.mapping; auto clampIdx = ws.clampIdx; auto ubIdx = ws.ubIdx;
   int nCl = 0, nUb = 0;
   for (int j = 0; j < m; j++) { mapping[j] = fi[j]; clampIdx[j] = -1; ubIdx[j] = -1; }
   for (int j = 0; j < m; j++) {
@@ -267,10 +278,10 @@ NB2_HD bool classify_once(int m, const CR* A, CR* x, const CR* b, const CR* lo, 
     if (lcp_valid(m, A, ws.v1, b, hi, lo, fi, ignoreFriction)) { for (int i = 0; i < m; i++) x[i] = 0; return true; }
     return false;
   }
-  int* cl = ws.i1; int* ub = ws.i2;
+  auto cl = ws.i1; auto ub = ws.i2;
   for (int j = 0; j < m; j++) { if (clampIdx[j] >= 0) cl[clampIdx[j]] = j; if (ubIdx[j] >= 0) ub[ubIdx[j]] = j; }
   // E(u, clampIdx[fp]) = hi or lo of the row; Q = A[cl,cl] + A[cl,ub] E
-  CR* Q = ws.Q; CR* bc = ws.v2; CR* orig = ws.v3; CR* fc = ws.v4;
+  auto Q = ws.Q; auto bc = ws.v2; auto orig = ws.v3; auto fc = ws.v4;
   for (int r = 0; r < nCl; r++) {
     bc[r] = b[cl[r]]; orig[r] = x[cl[r]];
     for (int c = 0; c < nCl; c++) Q[r * nCl + c] = A[cl[r] * m + cl[c]];
@@ -285,8 +296,8 @@ NB2_HD bool classify_once(int m, const CR* A, CR* x, const CR* b, const CR* lo, 
   if (nUb == 0) pinv_psd(nCl, Q, bc, fc, ws.Aw, ws.L, ws.v5, ws.v6, ws.i2);
   else {
     // general Q: x = (Q^T Q)^+ Q^T b
-    CR* QtQ = ws.Q2;
-    CR* Qtb = ws.v7;
+    auto QtQ = ws.Q2;
+    auto Qtb = ws.v7;
     for (int a = 0; a < nCl; a++) {
       CR s = 0; for (int r = 0; r < nCl; r++) s += Q[r * nCl + a] * bc[r];
       Qtb[a] = s;
@@ -297,7 +308,7 @@ NB2_HD bool classify_once(int m, const CR* A, CR* x, const CR* b, const CR* lo, 
     for (int j = 0; j < m; j++) if (ubIdx[j] >= 0) ub[ubIdx[j]] = j;
   }
   bool anyNewlyNotClamping = false;
-  CR* nx = ws.v8;
+  auto nx = ws.v8;
   for (int i = 0; i < m; i++) {
     nx[i] = 0;
     if (clampIdx[i] != -1) {
@@ -318,18 +329,20 @@ NB2_HD bool classify_once(int m, const CR* A, CR* x, const CR* b, const CR* lo, 
   }
   return false;
 }
-NB2_HD bool classify_and_standardize(int m, const CR* A, CR* x, const CR* b, const CR* lo, const CR* hi, const int* fi, const CR* colnorm,
-                                     bool ignoreFriction, const ContactWs& ws) {
+template <int ST, class PD>
+NB2_HD bool classify_and_standardize(int m, PD A, PD x, PD b, PD lo, PD hi, SP<int, ST> fi, PD colnorm,
+                                     bool ignoreFriction, const ContactWsT<ST>& ws) {
   bool ok = false, again = false;
   for (int it = 0; it < 6; it++) {
-    ok = classify_once(m, A, x, b, lo, hi, fi, colnorm, ignoreFriction, ws, &again);
+    ok = classify_once<ST>(m, A, x, b, lo, hi, fi, colnorm, ignoreFriction, ws, &again);
     if (!ok || !again) break;
   }
   return ok;
 }
 
 // PgsBoxedLcpSolver::solve with Option(30, 1e-6, 1e-3, 1e-9, false); A (m x m) and b are clobbered
-NB2_HD bool pgs_solve(int m, CR* A, CR* x, CR* b, const CR* lo, const CR* hi, const int* fi, unsigned char* skip) {
+template <class PA, class PX, class PB_, class PL, class PH, class PF, class PS>
+NB2_HD bool pgs_solve(int m, PA A, PX x, PB_ b, PL lo, PH hi, PF fi, PS skip) {
   const CR dxTol = 1e-6, relTol = 1e-3, epsDiv = 1e-9;
   bool term = true;
   for (int i = 0; i < m; i++) {
@@ -369,11 +382,12 @@ NB2_HD bool pgs_solve(int m, CR* A, CR* x, CR* b, const CR* lo, const CR* hi, co
 // the contact stage of one world.  `out` holds [q+ ; v*] on entry (written by the ABA kernel) and [q+ ; v+] on exit.
 // x_io: cached LCP solution (NB2_MAX_ROWS doubles), m_io: its size (-1 none) -> new solution / size.
 // =====================================================================================================
+template <int ST>
 NB2_HD void world_contact(const Nb2ModelDev<CR>& M, const Nb2ContactDev& C, const float* st, float* out, const CR* sv, size_t B,
-                          CR* wsbase, CR* x_io, int* m_io, int* labels_out, int* status_out, int* nc_out, float* cinfo_out,
+                          CR* wsblock, int lane, CR* x_io, int* m_io, int* labels_out, int* status_out, int* nc_out, float* cinfo_out,
                           CR* crec) {
   const int nb = M.nb, n = M.ndof;
-  const ContactWs ws = carve_ws(wsbase, nb, n);
+  const ContactWsT<ST> ws = carve_ws<ST>(wsblock, lane, nb, n);
   const int kQdd = nb * 21 + M.nfree * 33;
   const CR dt = M.dt;
   int status = 0;
@@ -492,10 +506,10 @@ NB2_HD void world_contact(const Nb2ModelDev<CR>& M, const Nb2ContactDev& C, cons
   }
   if (m == 0) { *m_io = 0; *status_out = status; if (crec) crec[0] = 0; return; }  // out already holds v*
   // row -> contact map must survive classification (which uses i1): copy to st8 region as bytes
-  unsigned char* rowc = ws.st8 + NB2_MAX_ROWS;
+  auto rowc = ws.st8 + NB2_MAX_ROWS;
   for (int r = 0; r < m; r++) rowc[r] = (unsigned char)ws.i1[r];
   // ---- A by impulse tests (upper blocks measured, lower mirrored; BoxedLcpConstraintSolver.cpp:293-314)
-  CR* A = ws.A;
+  auto A = ws.A;
   unsigned long long mask = 0ull;  // ancestors (and self) of every contact body
   for (int c = 0; c < nc; c++) {
     for (int bdy = ws.cbodyA[c]; bdy >= 0; bdy = M.parent[bdy]) mask |= (1ull << bdy);
@@ -504,9 +518,9 @@ NB2_HD void world_contact(const Nb2ModelDev<CR>& M, const Nb2ContactDev& C, cons
   for (int r = 0; r < m; r++) {
     const int c = rowc[r];
     for (int i = 0; i < nb; i++) if ((mask >> i) & 1ull) for (int k = 0; k < 6; k++) ws.pI[6 * i + k] = 0;
-    if (ws.cbodyA[c] >= 0) { const CR* J = ws.JA + 6 * r; CR* p = ws.pI + 6 * ws.cbodyA[c]; for (int k = 0; k < 6; k++) p[k] -= J[k]; }
-    if (ws.cbodyB[c] >= 0) { const CR* J = ws.JB + 6 * r; CR* p = ws.pI + 6 * ws.cbodyB[c]; for (int k = 0; k < 6; k++) p[k] -= J[k]; }
-    impulse_response(M, sv, B, ws, mask);
+    if (ws.cbodyA[c] >= 0) { auto J = ws.JA + 6 * r; auto p = ws.pI + 6 * ws.cbodyA[c]; for (int k = 0; k < 6; k++) p[k] -= J[k]; }
+    if (ws.cbodyB[c] >= 0) { auto J = ws.JB + 6 * r; auto p = ws.pI + 6 * ws.cbodyB[c]; for (int k = 0; k < 6; k++) p[k] -= J[k]; }
+    impulse_response<ST>(M, sv, B, ws, mask);
     for (int s2 = 0; s2 < m; s2++) {
       const int cj = rowc[s2];
       if (cj < c) { A[r * m + s2] = A[s2 * m + r]; continue; }
@@ -517,7 +531,7 @@ NB2_HD void world_contact(const Nb2ModelDev<CR>& M, const Nb2ContactDev& C, cons
     }
   }
   for (int c = 0; c < m; c++) { CR sn = 0; for (int r = 0; r < m; r++) sn += A[r * m + c] * A[r * m + c]; ws.colnorm[c] = sn; }
-  CR* b = ws.b; CR* lo = ws.lo; CR* hi = ws.hi; int* fi = ws.findex; CR* x = ws.x; CR* x0 = ws.x0;
+  auto b = ws.b; auto lo = ws.lo; auto hi = ws.hi; auto fi = ws.findex; auto x = ws.x; auto x0 = ws.x0;
   // ---- warm start: cached solution if it has the same size, else LCPUtils::guessSolution (LCPUtils.cpp:86-140)
   if (*m_io == m) { for (int i = 0; i < m; i++) x0[i] = x_io[i]; }
   else {
@@ -531,7 +545,7 @@ NB2_HD void world_contact(const Nb2ModelDev<CR>& M, const Nb2ContactDev& C, cons
   }
   for (int i = 0; i < m; i++) x[i] = x0[i];
   // ---- solve chain (BoxedLcpConstraintSolver.cpp:352-789)
-  bool success = classify_and_standardize(m, A, x, b, lo, hi, fi, ws.colnorm, false, ws);
+  bool success = classify_and_standardize<ST>(m, A, x, b, lo, hi, fi, ws.colnorm, false, ws);
   const bool shortCircuit = success;
   bool ignoredFriction = false;
   if (success) status |= NB2_ST_SHORTCIRCUIT;
@@ -545,7 +559,7 @@ NB2_HD void world_contact(const Nb2ModelDev<CR>& M, const Nb2ContactDev& C, cons
     }
     for (int i = 0; i < m * m; i++) ws.Aw[i] = A[i];
     for (int i = 0; i < m; i++) { ws.v1[i] = b[i]; ws.v2[i] = lo[i]; ws.v3[i] = hi[i]; ws.i1[i] = fi[i]; }
-    DantzigWork W;
+    DantzigWorkT<SP<CR, ST>, SP<int, ST>, SP<unsigned char, ST>> W;
     W.A = ws.Aw; W.x = ws.v4; W.b = ws.v1; W.w = ws.v5; W.lo = ws.v2; W.hi = ws.v3; W.L = ws.L; W.d = ws.v6; W.delta_x = ws.v7; W.delta_w = ws.v8;
     W.Dell = ws.Q; W.ell = ws.Q + m; W.tmp = ws.Q + 2 * m; W.findex = ws.i1; W.p = ws.i2; W.C = ws.clampIdx; W.state = ws.st8;
     const int rc = dantzig_solve(W, m, true);
@@ -576,17 +590,17 @@ NB2_HD void world_contact(const Nb2ModelDev<CR>& M, const Nb2ContactDev& C, cons
   if (!shortCircuit) {
     for (int i = 0; i < m; i++) ws.v7[i] = x[i];
     // classify works on x in place and only keeps the standardised x when valid
-    if (!classify_and_standardize(m, A, x, b, lo, hi, fi, ws.colnorm, ignoredFriction, ws)) { status |= NB2_ST_NOT_STANDARDIZED; }
+    if (!classify_and_standardize<ST>(m, A, x, b, lo, hi, fi, ws.colnorm, ignoredFriction, ws)) { status |= NB2_ST_NOT_STANDARDIZED; }
   }
   for (int i = 0; i < m; i++) { x_io[i] = x[i]; labels_out[i] = ws.mapping[i]; }
   // ---- apply the impulses and update the velocities (ContactConstraint.cpp:630-684, Skeleton.cpp:13571-13595)
   for (int i = 0; i < nb * 6; i++) ws.pI[i] = 0;
   for (int r = 0; r < m; r++) {
     const int c = rowc[r];
-    if (ws.cbodyA[c] >= 0) { const CR* J = ws.JA + 6 * r; CR* p = ws.pI + 6 * ws.cbodyA[c]; for (int k = 0; k < 6; k++) p[k] -= J[k] * x[r]; }
-    if (ws.cbodyB[c] >= 0) { const CR* J = ws.JB + 6 * r; CR* p = ws.pI + 6 * ws.cbodyB[c]; for (int k = 0; k < 6; k++) p[k] -= J[k] * x[r]; }
+    if (ws.cbodyA[c] >= 0) { auto J = ws.JA + 6 * r; auto p = ws.pI + 6 * ws.cbodyA[c]; for (int k = 0; k < 6; k++) p[k] -= J[k] * x[r]; }
+    if (ws.cbodyB[c] >= 0) { auto J = ws.JB + 6 * r; auto p = ws.pI + 6 * ws.cbodyB[c]; for (int k = 0; k < 6; k++) p[k] -= J[k] * x[r]; }
   }
-  impulse_response(M, sv, B, ws, ~0ull);
+  impulse_response<ST>(M, sv, B, ws, ~0ull);
   for (int d = 0; d < n; d++) out[n + d] = (float)(ws.vstar[d] + ws.dqd[d]);
   *m_io = m; *status_out = status;
   if (crec) {  // what the backward pass needs: sizes, labels, impulses, the velocity change they caused, the LCP matrix
@@ -612,23 +626,24 @@ NB2_HD void world_contact(const Nb2ModelDev<CR>& M, const Nb2ContactDev& C, cons
 // This function runs between the lambda sweeps (B1/B2) and the reverse RNEA sweep (B3) of world_backward and prepares:
 //     scr: lambda -> w, W_i -> W_i(w);   ws: per-body injections, realised accelerations, v+ fields.
 // =====================================================================================================
+template <int ST>
 struct BwdContactView {  // views into the contact workspace used by world_backward<double, ST, true>
-  const CR* Aacc;   // [nb][6] spatial accelerations for the realised joint accelerations
-  const CR* Uplus;  // [nb][6] spatial velocities for v+
-  const CR* aeff;   // [n]
-  const CR* vplus;  // [n]
-  const CR* inj;    // [nb][24]  Uw_bar(6) Up_bar(6) G(6) H(6), already scaled by -1/dt except H
-  CR* JcTmu;        // [n] out
+  SP<CR, ST> Aacc;   // [nb][6] spatial accelerations for the realised joint accelerations
+  SP<CR, ST> Uplus;  // [nb][6] spatial velocities for v+
+  SP<CR, ST> aeff;   // [n]
+  SP<CR, ST> vplus;  // [n]
+  SP<CR, ST> inj;    // [nb][24]  Uw_bar(6) Up_bar(6) G(6) H(6), already scaled by -1/dt except H
+  SP<CR, ST> JcTmu;  // [n] out
   int active;       // 0: this world had no contact rows (plain contact-free backward)
   int error;        // structure mismatch / unsupported pair
 };
 
 template <int ST>
-NB2_HD BwdContactView contact_backward_prepare(const Nb2ModelDev<CR>& M, const Nb2ContactDev& C, const float* st, const CR* sv, size_t B,
-                                               CR* wsbase, const CR* crec, CR* scr, int oLam, int oBody) {
+NB2_HD BwdContactView<ST> contact_backward_prepare(const Nb2ModelDev<CR>& M, const Nb2ContactDev& C, const float* st, const CR* sv, size_t B,
+                                                   CR* wsblock, int lane, const CR* crec, CR* scr, int oLam, int oBody) {
   const int nb = M.nb, n = M.ndof;
-  const ContactWs ws = carve_ws(wsbase, nb, n);
-  BwdContactView cv;
+  const ContactWsT<ST> ws = carve_ws<ST>(wsblock, lane, nb, n);
+  BwdContactView<ST> cv;
   cv.Aacc = ws.W; cv.Uplus = ws.W + 6 * nb; cv.aeff = ws.uI; cv.vplus = ws.vstar; cv.inj = ws.Q2; cv.JcTmu = ws.dqd; cv.active = 0; cv.error = 0;
   const int m = (int)crec[0];
   if (m <= 0) return cv;
@@ -645,7 +660,7 @@ NB2_HD BwdContactView contact_backward_prepare(const Nb2ModelDev<CR>& M, const N
   }
   // ---- contact rows re-generated on dual numbers: F_r and dF_r/dxi (xi = body twist [angular; linear] of the moving body)
   typedef DualT<6> D6;
-  CR* rowF = ws.JA; CR* rowdF = ws.A; int* rowbody = ws.i1; CR* rowmu = ws.v1;
+  auto rowF = ws.JA; auto rowdF = ws.A; auto rowbody = ws.i1; auto rowmu = ws.v1;
   int m2 = 0;
   for (int pi = 0; pi < C.npairs && !cv.error; pi++) {
     const int sa = C.pair_a[pi], sb = C.pair_b[pi];
@@ -729,11 +744,11 @@ NB2_HD BwdContactView contact_backward_prepare(const Nb2ModelDev<CR>& M, const N
   if (m2 != m) cv.error = cv.error ? cv.error : 3;
   if (cv.error) return cv;
   // ---- clamping / upper-bound sets from the saved labels
-  int* clampIdx = ws.clampIdx; int* cl = ws.i2; int* ubl = ws.ubIdx;  // ubl: list of ub rows
+  auto clampIdx = ws.clampIdx; auto cl = ws.i2; auto ubl = ws.ubIdx;  // ubl: list of ub rows
   int nCl = 0, nUb = 0;
   for (int j = 0; j < m; j++) { clampIdx[j] = -1; if ((int)mapping[j] == NB2_MAP_CLAMPING) { clampIdx[j] = nCl; cl[nCl++] = j; } }
   for (int j = 0; j < m; j++) if ((int)mapping[j] >= 0) ubl[nUb++] = j;
-  CR* fbar = ws.v2; CR* mu_c = ws.v3; CR* Eu = ws.v4;
+  auto fbar = ws.v2; auto mu_c = ws.v3; auto Eu = ws.v4;
   // W_body(lambda) read from the strided scratch
   auto ldW = [&](int body) { return ld6<CR, ST>(scr + (size_t)(oBody + 7 * body + 1) * ST); };
   for (int r = 0; r < nCl; r++) fbar[r] = dot(ldv6(rowF + 6 * cl[r]), ldW(rowbody[cl[r]]));
@@ -745,14 +760,14 @@ NB2_HD BwdContactView contact_backward_prepare(const Nb2ModelDev<CR>& M, const N
   }
   for (int r = 0; r < nCl; r++) mu_c[r] = 0;
   if (nCl > 0) {
-    CR* Q = ws.Q;
+    auto Q = ws.Q;
     for (int r = 0; r < nCl; r++) for (int c = 0; c < nCl; c++) Q[r * nCl + c] = Arec[cl[r] * m + cl[c]];
     for (int u = 0; u < nUb; u++) { const int j = ubl[u], c = clampIdx[(int)mapping[j]]; for (int r = 0; r < nCl; r++) Q[r * nCl + c] += Arec[cl[r] * m + j] * Eu[u]; }
     if (nUb == 0) pinv_psd(nCl, Q, fbar, mu_c, ws.Aw, ws.L, ws.v5, ws.v6, ws.mapping);
     else {  // Q^T mu = fbar  ->  mu = (Q Q^T)^+ Q fbar
-      CR* QQt = ws.Aw + (size_t)NB2_MAX_ROWS * NB2_MAX_ROWS / 2;  // nCl <= 33 guaranteed below
+      auto QQt = ws.Aw + (size_t)NB2_MAX_ROWS * NB2_MAX_ROWS / 2;  // nCl <= 33 guaranteed below
       if (2 * nCl * nCl > NB2_MAX_ROWS * NB2_MAX_ROWS / 2 * 2) { cv.error = 4; return cv; }
-      CR* Qf = ws.v7;
+      auto Qf = ws.v7;
       for (int a = 0; a < nCl; a++) {
         CR sacc = 0; for (int c = 0; c < nCl; c++) sacc += Q[a * nCl + c] * fbar[c];
         Qf[a] = sacc;
@@ -763,17 +778,17 @@ NB2_HD BwdContactView contact_backward_prepare(const Nb2ModelDev<CR>& M, const N
   }
   // ---- nu = M^-1 A_c mu  (one impulse sweep) ; w = lambda - nu ; W_i(w)
   for (int i = 0; i < nb * 6; i++) ws.pI[i] = 0;
-  for (int r = 0; r < nCl; r++) { const CR* F = rowF + 6 * cl[r]; CR* p = ws.pI + 6 * rowbody[cl[r]]; for (int kx = 0; kx < 6; kx++) p[kx] -= F[kx] * mu_c[r]; }
-  impulse_response(M, sv, B, ws, ~0ull);
+  for (int r = 0; r < nCl; r++) { auto F = rowF + 6 * cl[r]; auto p = ws.pI + 6 * rowbody[cl[r]]; for (int kx = 0; kx < 6; kx++) p[kx] -= F[kx] * mu_c[r]; }
+  impulse_response<ST>(M, sv, B, ws, ~0ull);
   for (int d = 0; d < n; d++) scr[(size_t)(oLam + d) * ST] -= ws.dqd[d];
   for (int i = 0; i < nb; i++) {
     const V6<CR> Wn = ld6<CR, ST>(scr + (size_t)(oBody + 7 * i + 1) * ST) - ldv6(ws.V + 6 * i);
     st6<CR, ST>(scr + (size_t)(oBody + 7 * i + 1) * ST, Wn);
   }
   // ---- realised accelerations, v+, and the fields they induce (ws.W is free now: Aacc | Uplus)
-  CR* aeff = ws.uI; CR* vplus = ws.vstar;
+  auto aeff = ws.uI; auto vplus = ws.vstar;
   for (int d = 0; d < n; d++) { aeff[d] = sv[(size_t)(kQdd + d) * B] + dqd_imp[d] / dt; vplus[d] = (CR)st[n + d] + dt * aeff[d]; }
-  CR* Aacc = ws.W; CR* Uplus = ws.W + 6 * nb;
+  auto Aacc = ws.W; auto Uplus = ws.W + 6 * nb;
   V6<CR> A0; A0.a = zero3<CR>(); A0.l = mk3<CR>(-M.gravity[0], -M.gravity[1], -M.gravity[2]);
   for (int i = 0; i < nb; i++) {
     const int jt = M.jtype[i], p = M.parent[i], o = M.dof_off[i];
@@ -794,7 +809,7 @@ NB2_HD BwdContactView contact_backward_prepare(const Nb2ModelDev<CR>& M, const N
   }
   // ---- per-body injections for the reverse sweep: Uw_bar, Up_bar, G (all scaled by -1/dt: they join the (dID/dq)^T w
   // accumulator that is multiplied by -dt at the end) and H (plain: A_c mu propagated to joint space)
-  CR* inj = ws.Q2;
+  auto inj = ws.Q2;
   for (int i = 0; i < nb * 24; i++) inj[i] = 0;
   const CR kap = -1.0 / dt;
   for (int j = 0; j < m; j++) {
@@ -803,8 +818,8 @@ NB2_HD BwdContactView contact_backward_prepare(const Nb2ModelDev<CR>& M, const N
     else if ((int)mapping[j] >= 0) coefW = xr[j];
     else continue;
     const int body = rowbody[j];
-    const CR* F = rowF + 6 * j; const CR* dF = rowdF + 36 * j;
-    CR* bj = inj + 24 * body;
+    auto F = rowF + 6 * j; auto dF = rowdF + 36 * j;
+    auto bj = inj + 24 * body;
     const V6<CR> Ww = ld6<CR, ST>(scr + (size_t)(oBody + 7 * body + 1) * ST);  // field of w
     const V6<CR> Up = ldv6(Uplus + 6 * body);
     const CR fw[6] = {Ww.a.x, Ww.a.y, Ww.a.z, Ww.l.x, Ww.l.y, Ww.l.z}, fu[6] = {Up.a.x, Up.a.y, Up.a.z, Up.l.x, Up.l.y, Up.l.z};
@@ -821,11 +836,11 @@ NB2_HD BwdContactView contact_backward_prepare(const Nb2ModelDev<CR>& M, const N
 }
 
 template <int ST>
-NB2_HD BwdContactData contact_backward_hook(const Nb2ModelDev<double>& M, const BwdContactHook& H, const float* st, const double* sv, size_t B,
+NB2_HD BwdContactData<ST> contact_backward_hook(const Nb2ModelDev<double>& M, const BwdContactHook& H, const float* st, const double* sv, size_t B,
                                             double* scr, int oLam, int oBody) {
-  const BwdContactView v = contact_backward_prepare<ST>(M, *(const Nb2ContactDev*)H.model_contact, st, sv, B, H.ws, H.crec, scr, oLam, oBody);
-  BwdContactData d;
-  d.Aacc = v.Aacc; d.Uplus = v.Uplus; d.aeff = v.aeff; d.vplus = v.vplus; d.inj = v.inj; d.JcTmu = v.JcTmu; d.active = v.active; d.error = v.error;
+  const BwdContactView<ST> v = contact_backward_prepare<ST>(M, *(const Nb2ContactDev*)H.model_contact, st, sv, B, H.ws, H.lane, H.crec, scr, oLam, oBody);
+  BwdContactData<ST> d;
+  d.Aacc.p = v.Aacc.p; d.Uplus.p = v.Uplus.p; d.aeff.p = v.aeff.p; d.vplus.p = v.vplus.p; d.inj.p = v.inj.p; d.JcTmu.p = v.JcTmu.p; d.active = v.active; d.error = v.error;
   return d;
 }
 

@@ -25,29 +25,41 @@ namespace nb2 {
 #define NB2_LCP_MAX 48  // max LCP dimension handled per world (16 contacts x 3 rows)
 #endif
 
-struct DantzigWork {
-  // all arrays of length n (or n*n) in fp64; caller allocates.  No striding: LCP scratch lives in per-thread
-  // global/local memory (it is too large and too irregular for the interleaved shared-memory layout).
-  double* A;     // n*n, row-major, full symmetric; permuted in place
-  double* x;     // n   (out)
-  double* b;     // n
-  double* w;     // n   (out)
-  double* lo;    // n
-  double* hi;    // n
-  double* L;     // n*n
-  double* d;     // n
-  double* delta_x;
-  double* delta_w;
-  double* Dell;
-  double* ell;
-  double* tmp;
-  int* findex;   // n
-  int* p;        // n
-  int* C;        // n
-  unsigned char* state;  // n
+// strided pointer: element i of a per-world array lives at p[i * ST].  On the device the LCP workspace of the 32 worlds
+// of a warp is interleaved [word][lane] (ST = 32) so that the warp-uniform parts of the pipeline touch one 256-byte line
+// per access; the host builds (oracle, tests) use ST = 1.
+template <class T, int ST> struct SP {
+  T* p;
+  NB2_HD T& operator[](int i) const { return p[(size_t)i * ST]; }
+  NB2_HD T& operator[](size_t i) const { return p[i * ST]; }
+  NB2_HD SP operator+(int k) const { SP r; r.p = p + (size_t)k * ST; return r; }
+  NB2_HD SP operator+(size_t k) const { SP r; r.p = p + k * ST; return r; }
 };
 
-NB2_HD void dz_swap_problem(const DantzigWork& W, int n, int i1, int i2) {
+template <class PD, class PI, class PB>
+struct DantzigWorkT {
+  // all arrays of length n (or n*n) in fp64; caller allocates
+  PD A;     // n*n, row-major, full symmetric; permuted in place
+  PD x;     // n   (out)
+  PD b;     // n
+  PD w;     // n   (out)
+  PD lo;    // n
+  PD hi;    // n
+  PD L;     // n*n
+  PD d;     // n
+  PD delta_x;
+  PD delta_w;
+  PD Dell;
+  PD ell;
+  PD tmp;
+  PI findex;   // n
+  PI p;        // n
+  PI C;        // n
+  PB state;    // n
+};
+typedef DantzigWorkT<double*, int*, unsigned char*> DantzigWork;
+
+template <class DW> NB2_HD void dz_swap_problem(const DW& W, int n, int i1, int i2) {
   if (i1 == i2) return;
   for (int k = 0; k < n; k++) { double t = W.A[i1 * n + k]; W.A[i1 * n + k] = W.A[i2 * n + k]; W.A[i2 * n + k] = t; }
   for (int k = 0; k < n; k++) { double t = W.A[k * n + i1]; W.A[k * n + i1] = W.A[k * n + i2]; W.A[k * n + i2] = t; }
@@ -58,9 +70,9 @@ NB2_HD void dz_swap_problem(const DantzigWork& W, int n, int i1, int i2) {
 }
 
 // L D L^T of A[C,C] (C in factor order); d holds the reciprocals like ODE's m_d
-NB2_HD void dz_factor(const DantzigWork& W, int n, int nC) {
+template <class DW> NB2_HD void dz_factor(const DW& W, int n, int nC) {
   for (int i = 0; i < nC; i++) {
-    const double* Ai = W.A + (size_t)W.C[i] * n;
+    const auto Ai = W.A + (size_t)W.C[i] * n;
     for (int j = 0; j <= i; j++) {
       double s = Ai[W.C[j]];
       for (int k = 0; k < j; k++) s -= W.L[i * n + k] * W.L[j * n + k] / W.d[k];
@@ -72,16 +84,16 @@ NB2_HD void dz_factor(const DantzigWork& W, int n, int nC) {
 
 // append index (physical slot i, about to be swapped into slot nC) to the factor using the ell/Dell of the latest
 // dz_solve1(.., i, ..) — exactly what transfer_i_to_C does (lcp.cpp:503-535); O(nC) instead of a refactorisation
-NB2_HD void dz_append_from_solve1(const DantzigWork& W, int n, int nC, int i) {
+template <class DW> NB2_HD void dz_append_from_solve1(const DW& W, int n, int nC, int i) {
   double s = W.A[(size_t)i * n + i];
   for (int j = 0; j < nC; j++) { W.L[nC * n + j] = W.ell[j]; s -= W.ell[j] * W.Dell[j]; }
   W.d[nC] = 1.0 / s;
 }
 
 // solve1 (lcp.cpp:703-753): Dell = L \ A[C,i] ; ell = Dell .* d ; a[C] = -dir * L^T \ ell
-NB2_HD void dz_solve1(const DantzigWork& W, int n, int nC, double* a, int i, int dir, bool only_transfer) {
+template <class DW, class PA> NB2_HD void dz_solve1(const DW& W, int n, int nC, PA a, int i, int dir, bool only_transfer) {
   if (nC <= 0) return;
-  const double* Ai = W.A + (size_t)i * n;
+  const auto Ai = W.A + (size_t)i * n;
   for (int j = 0; j < nC; j++) {
     double s = Ai[W.C[j]];
     for (int k = 0; k < j; k++) s -= W.L[j * n + k] * W.Dell[k];
@@ -100,7 +112,7 @@ NB2_HD void dz_solve1(const DantzigWork& W, int n, int nC, double* a, int i, int
 }
 
 // returns 1 on success, 0 on early termination (s <= 0), -1 when the iteration cap is hit
-NB2_HD int dantzig_solve(const DantzigWork& W, int n, bool early_termination) {
+template <class DW> NB2_HD int dantzig_solve(const DW& W, int n, bool early_termination) {
   const double INF = HUGE_VAL;
   int nC = 0, nN = 0;
   for (int k = 0; k < n; k++) { W.x[k] = 0.0; W.w[k] = 0.0; W.p[k] = k; W.state[k] = 0; }
@@ -139,7 +151,7 @@ NB2_HD int dantzig_solve(const DantzigWork& W, int n, bool early_termination) {
       hit_first_friction_index = true;
     }
     {
-      const double* Ai = W.A + (size_t)i * n;
+      const auto Ai = W.A + (size_t)i * n;
       double s = 0.0;
       for (int k = 0; k < nC; k++) s += Ai[k] * W.x[k];
       double s2 = 0.0;
@@ -161,13 +173,13 @@ NB2_HD int dantzig_solve(const DantzigWork& W, int n, bool early_termination) {
         dz_solve1(W, n, nC, W.delta_x, i, dir, false);
         // delta_w(N) = A(N,C) delta_x(C) + dir * A(N,i) ; delta_w(i) = A(i,C) delta_x(C) + A(i,i) dirf
         for (int k = 0; k < nN; k++) {
-          const double* Ak = W.A + (size_t)(nC + k) * n;
+          const auto Ak = W.A + (size_t)(nC + k) * n;
           double s = 0.0;
           for (int j = 0; j < nC; j++) s += Ak[j] * W.delta_x[j];
           W.delta_w[nC + k] = s;
         }
         {
-          const double* Ai = W.A + (size_t)i * n;
+          const auto Ai = W.A + (size_t)i * n;
           if (dir > 0) for (int k = 0; k < nN; k++) W.delta_w[nC + k] += Ai[nC + k];
           else for (int k = 0; k < nN; k++) W.delta_w[nC + k] -= Ai[nC + k];
           double s = 0.0;

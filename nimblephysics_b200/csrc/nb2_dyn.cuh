@@ -328,14 +328,17 @@ NB2_HD void world_forward(const Nb2ModelDev<R>& M, R* scr, const float* st, cons
 // hook implemented in nb2_contact.cuh: turns lambda / W into w / W(w) and prepares the contact injections
 struct BwdContactHook {
   const void* model_contact;  // const Nb2ContactDev*
-  double* ws;                 // per-world contact workspace
+  double* ws;                 // contact workspace block of this warp (device) / world (host)
+  int lane;                   // lane inside the block (0 on the host)
   const double* crec;         // per-world contact record written by the forward pass
 };
-struct BwdContactData {  // filled by the hook (all double, unit stride)
-  const double* Aacc; const double* Uplus; const double* aeff; const double* vplus; const double* inj; double* JcTmu; int active; int error;
+template <class T, int ST> struct SPd { T* p; NB2_HD T& operator[](int i) const { return p[(size_t)i * ST]; } NB2_HD SPd operator+(int k) const { SPd r; r.p = p + (size_t)k * ST; return r; } };
+template <int ST>
+struct BwdContactData {  // filled by the hook (all double, strided like the contact workspace)
+  SPd<double, ST> Aacc, Uplus, aeff, vplus, inj, JcTmu; int active; int error;
 };
 template <int ST>
-NB2_HD BwdContactData contact_backward_hook(const Nb2ModelDev<double>& M, const BwdContactHook& H, const float* st, const double* sv, size_t B,
+NB2_HD BwdContactData<ST> contact_backward_hook(const Nb2ModelDev<double>& M, const BwdContactHook& H, const float* st, const double* sv, size_t B,
                                             double* scr, int oLam, int oBody);
 
 // =====================================================================================================
@@ -413,7 +416,7 @@ NB2_HD void world_backward(const Nb2ModelDev<R>& M, R* scr, const float* st, con
     st6<R, ST>(bs + ST, W);
   }
   // ---------------- contact stage adjoint (nb2_contact.cuh): lambda -> w, W -> W(w), injections for B3
-  BwdContactData cd; cd.active = 0; cd.error = 0;
+  BwdContactData<ST> cd; cd.active = 0; cd.error = 0;
   if constexpr (CONTACT) {
     cd = contact_backward_hook<ST>(M, *hook, st, sv, B, scr, L.oLam, L.oBody);
   }
@@ -433,7 +436,7 @@ NB2_HD void world_backward(const Nb2ModelDev<R>& M, R* scr, const float* st, con
     R m; V3<R> h; S3<R> Ib; inertia_of(M, i, &m, &h, &Ib);
     const V6<R> V = sv_ld6<R>(s, B, 0);
     V6<R> A = sv_ld6<R>(s, B, 6);
-    if (CONTACT && cd.active) { const double* a6 = cd.Aacc + 6 * i; A.a = mk3<R>((R)a6[0], (R)a6[1], (R)a6[2]); A.l = mk3<R>((R)a6[3], (R)a6[4], (R)a6[5]); }
+    if (CONTACT && cd.active) { const auto a6 = cd.Aacc + 6 * i; A.a = mk3<R>((R)a6[0], (R)a6[1], (R)a6[2]); A.l = mk3<R>((R)a6[3], (R)a6[4], (R)a6[5]); }
     const V6<R> W = ld6<R, ST>(scr + (size_t)(L.oBody + 7 * i + 1) * ST);
     const V6<R> GV = mulG(m, h, Ib, V);
     V6<R> f = mulG(m, h, Ib, A) + crf(V, GV);
@@ -442,7 +445,7 @@ NB2_HD void world_backward(const Nb2ModelDev<R>& M, R* scr, const float* st, con
     if (hvalid) { Abar = Abar + hA; Vbar = Vbar + hV; f = f + hf; }
     V6<R> Uw = zero6<R>(), Up = zero6<R>(), Gc = zero6<R>(), Hc = zero6<R>();  // contact adjoints (CONTACT only)
     if (CONTACT && cd.active) {
-      const double* b24 = cd.inj + 24 * i;
+      const auto b24 = cd.inj + 24 * i;
       Uw.a = mk3<R>((R)b24[0], (R)b24[1], (R)b24[2]); Uw.l = mk3<R>((R)b24[3], (R)b24[4], (R)b24[5]);
       Up.a = mk3<R>((R)b24[6], (R)b24[7], (R)b24[8]); Up.l = mk3<R>((R)b24[9], (R)b24[10], (R)b24[11]);
       Gc.a = mk3<R>((R)b24[12], (R)b24[13], (R)b24[14]); Gc.l = mk3<R>((R)b24[15], (R)b24[16], (R)b24[17]);
@@ -464,7 +467,7 @@ NB2_HD void world_backward(const Nb2ModelDev<R>& M, R* scr, const float* st, con
     } else {
       Sv.a = mk3<R>((R)st[n + o], (R)st[n + o + 1], (R)st[n + o + 2]); Sv.l = mk3<R>((R)st[n + o + 3], (R)st[n + o + 4], (R)st[n + o + 5]);
       Sa = sv_ld6<R>(sv + (size_t)(kQdd + o) * B, B, 0);
-      if (CONTACT && cd.active) { const double* a6 = cd.aeff + o; Sa.a = mk3<R>((R)a6[0], (R)a6[1], (R)a6[2]); Sa.l = mk3<R>((R)a6[3], (R)a6[4], (R)a6[5]); }
+      if (CONTACT && cd.active) { const auto a6 = cd.aeff + o; Sa.a = mk3<R>((R)a6[0], (R)a6[1], (R)a6[2]); Sa.l = mk3<R>((R)a6[3], (R)a6[4], (R)a6[5]); }
       Sl = ld6<R, ST>(scr + (size_t)(L.oLam + o) * ST);
       R t12[12]; for (int k = 0; k < 12; k++) t12[k] = (R)sv[(size_t)(kFree + M.free_idx[i] * 33 + 21 + k) * B];
       T = ldXf<R, 1>(t12);
@@ -475,13 +478,13 @@ NB2_HD void world_backward(const Nb2ModelDev<R>& M, R* scr, const float* st, con
     V6<R> c6 = zero6<R>() - (crf(Alam, Abar) + crf(Vlam, Vbar) + crf(Wlam, f));
     if (CONTACT && cd.active) {
       // kinematic-chain part of d/dq [J_r(q) w] and [J_r(q) v+], and the contact-frame part (wrench Gc), see nb2_contact.cuh
-      V6<R> Upl; { const double* u6 = cd.Uplus + 6 * i; Upl.a = mk3<R>((R)u6[0], (R)u6[1], (R)u6[2]); Upl.l = mk3<R>((R)u6[3], (R)u6[4], (R)u6[5]); }
+      V6<R> Upl; { const auto u6 = cd.Uplus + 6 * i; Upl.a = mk3<R>((R)u6[0], (R)u6[1], (R)u6[2]); Upl.l = mk3<R>((R)u6[3], (R)u6[4], (R)u6[5]); }
       V6<R> Svp;
       if (jt != NB2_JT_FREE) Svp = S_times<R>(jt, (R)cd.vplus[o]);
-      else { const double* v6p = cd.vplus + o; Svp.a = mk3<R>((R)v6p[0], (R)v6p[1], (R)v6p[2]); Svp.l = mk3<R>((R)v6p[3], (R)v6p[4], (R)v6p[5]); }
+      else { const auto v6p = cd.vplus + o; Svp.a = mk3<R>((R)v6p[0], (R)v6p[1], (R)v6p[2]); Svp.l = mk3<R>((R)v6p[3], (R)v6p[4], (R)v6p[5]); }
       c6 = c6 - crf(Wlam, Uw) - crf(Upl - Svp, Up) + Gc;
       if (jt != NB2_JT_FREE) cd.JcTmu[o] = (double)S_dot(jt, Hc);
-      else { double* j6 = cd.JcTmu + o; j6[0] = (double)Hc.a.x; j6[1] = (double)Hc.a.y; j6[2] = (double)Hc.a.z; j6[3] = (double)Hc.l.x; j6[4] = (double)Hc.l.y; j6[5] = (double)Hc.l.z; }
+      else { auto j6 = cd.JcTmu + o; j6[0] = (double)Hc.a.x; j6[1] = (double)Hc.a.y; j6[2] = (double)Hc.a.z; j6[3] = (double)Hc.l.x; j6[4] = (double)Hc.l.y; j6[5] = (double)Hc.l.z; }
     }
     if (jt != NB2_JT_FREE) {
       scr[(size_t)(L.oVb + o) * ST] = S_dot(jt, vb6);
@@ -541,7 +544,7 @@ NB2_HD void world_backward(const Nb2ModelDev<R>& M, R* scr, const float* st, con
       const V6<R> lam = ld6<R, ST>(scr + (size_t)(L.oLam + o) * ST);
       const V6<R> qb = ld6<R, ST>(scr + (size_t)(L.oQb + o) * ST), vb = ld6<R, ST>(scr + (size_t)(L.oVb + o) * ST);
       V6<R> gv = ld6<R, ST>(scr + (size_t)(L.oGV + o) * ST);
-      if (CONTACT && cd.active) { const double* j6 = cd.JcTmu + o; gv.a = gv.a - mk3<R>((R)j6[0], (R)j6[1], (R)j6[2]); gv.l = gv.l - mk3<R>((R)j6[3], (R)j6[4], (R)j6[5]); }
+      if (CONTACT && cd.active) { const auto j6 = cd.JcTmu + o; gv.a = gv.a - mk3<R>((R)j6[0], (R)j6[1], (R)j6[2]); gv.l = gv.l - mk3<R>((R)j6[3], (R)j6[4], (R)j6[5]); }
       R lamv[6] = {lam.a.x, lam.a.y, lam.a.z, lam.l.x, lam.l.y, lam.l.z};
       R qbv[6] = {qb.a.x, qb.a.y, qb.a.z, qb.l.x, qb.l.y, qb.l.z}, vbv[6] = {vb.a.x, vb.a.y, vb.a.z, vb.l.x, vb.l.y, vb.l.z};
       R gqv[6] = {gq.a.x, gq.a.y, gq.a.z, gq.l.x, gq.l.y, gq.l.z}, gvpv[6] = {gvp.a.x, gvp.a.y, gvp.a.z, gvp.l.x, gvp.l.y, gvp.l.z};

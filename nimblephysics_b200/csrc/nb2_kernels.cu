@@ -67,8 +67,9 @@ k_contact_fwd(const __grid_constant__ Nb2ModelDev<double> M, const __grid_consta
               double* __restrict__ crec, size_t rec_doubles) {
   const int w = blockIdx.x * blockDim.x + threadIdx.x;
   if (w >= B) return;
-  nb2::world_contact(M, C, state + (size_t)w * 2 * M.ndof, next + (size_t)w * 2 * M.ndof, saved + w, (size_t)B,
-                     workspace + (size_t)w * ws_doubles, x_lcp + (size_t)w * NB2_MAX_ROWS, m_lcp + w,
+  // the 32 worlds of a warp share one lane-interleaved workspace block
+  nb2::world_contact<32>(M, C, state + (size_t)w * 2 * M.ndof, next + (size_t)w * 2 * M.ndof, saved + w, (size_t)B,
+                     workspace + (size_t)(w >> 5) * ws_doubles * 32, w & 31, x_lcp + (size_t)w * NB2_MAX_ROWS, m_lcp + w,
                      labels + (size_t)w * NB2_MAX_ROWS, status + w, ncontacts + w,
                      cinfo ? cinfo + (size_t)w * NB2_MAX_CONTACTS * 10 : nullptr, crec ? crec + (size_t)w * rec_doubles : nullptr);
 }
@@ -84,7 +85,7 @@ k_step_bwd_contact(const __grid_constant__ Nb2ModelDev<double> M, const __grid_c
   if (w >= B) return;
   double* scr = reinterpret_cast<double*>(nb2_smem) + (size_t)(threadIdx.x >> 5) * words * 32 + (threadIdx.x & 31);
   nb2::BwdContactHook H;
-  H.model_contact = &C; H.ws = workspace + (size_t)w * ws_doubles; H.crec = crec + (size_t)w * rec_doubles;
+  H.model_contact = &C; H.ws = workspace + (size_t)(w >> 5) * ws_doubles * 32; H.lane = w & 31; H.crec = crec + (size_t)w * rec_doubles;
   nb2::world_backward<double, 32, true>(M, scr, state + (size_t)w * 2 * M.ndof, action + (size_t)w * M.na,
                                         gnext + (size_t)w * 2 * M.ndof, saved + w, (size_t)B,
                                         gstate + (size_t)w * 2 * M.ndof, gaction + (size_t)w * M.na, &H);
@@ -203,7 +204,7 @@ void nb2_model_destroy(nb2_model* m) {
 int nb2_model_has_contacts(const nb2_model* m) { return (m && m->has_contacts) ? 1 : 0; }
 size_t nb2_contact_workspace_bytes(const nb2_model* m, int B) {
   if (!m || !m->has_contacts || B <= 0) return 0;
-  return nb2::contact_ws_doubles(m->mf.nb, m->mf.ndof) * sizeof(double) * (size_t)B;
+  return nb2::contact_ws_doubles(m->mf.nb, m->mf.ndof) * sizeof(double) * (size_t)((B + 31) / 32) * 32;
 }
 int nb2_step_forward_contact(const nb2_model* cm, int B, const float* state, const float* action, float* next_state,
                              void* saved_fp64, void* workspace, double* x_lcp, int32_t* m_lcp, int32_t* labels,

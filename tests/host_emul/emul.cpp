@@ -48,8 +48,8 @@ static int run_fwd_contact(const nb2_model_desc* d, int B, const float* state, c
     nb2::world_forward<double, 1>(M, scr.data(), state + (size_t)w * 2 * M.ndof, action + (size_t)w * M.na,
                                   next + (size_t)w * 2 * M.ndof, saved + w, (size_t)B, true);
     for (auto& x : ws) x = 1e30;
-    nb2::world_contact(M, C, state + (size_t)w * 2 * M.ndof, next + (size_t)w * 2 * M.ndof, saved + w, (size_t)B, ws.data(),
-                       x_lcp + (size_t)w * NB2_MAX_ROWS, m_lcp + w, labels + (size_t)w * NB2_MAX_ROWS, status + w, nc + w,
+    nb2::world_contact<1>(M, C, state + (size_t)w * 2 * M.ndof, next + (size_t)w * 2 * M.ndof, saved + w, (size_t)B, ws.data(), 0,
+                          x_lcp + (size_t)w * NB2_MAX_ROWS, m_lcp + w, labels + (size_t)w * NB2_MAX_ROWS, status + w, nc + w,
                        cinfo ? cinfo + (size_t)w * NB2_MAX_CONTACTS * 10 : nullptr,
                        crec ? crec + (size_t)w * nb2::contact_rec_doubles(M.ndof) : nullptr);
   }
@@ -64,7 +64,7 @@ static int run_bwd_contact(const nb2_model_desc* d, int B, const float* state, c
   for (int w = 0; w < B; w++) {
     for (auto& x : scr) x = 1e30;
     for (auto& x : ws) x = 1e30;
-    nb2::BwdContactHook H; H.model_contact = &C; H.ws = ws.data(); H.crec = crec + (size_t)w * nb2::contact_rec_doubles(M.ndof);
+    nb2::BwdContactHook H; H.model_contact = &C; H.ws = ws.data(); H.lane = 0; H.crec = crec + (size_t)w * nb2::contact_rec_doubles(M.ndof);
     nb2::world_backward<double, 1, true>(M, scr.data(), state + (size_t)w * 2 * M.ndof, action + (size_t)w * M.na,
                                          gnext + (size_t)w * 2 * M.ndof, saved + w, (size_t)B, gstate + (size_t)w * 2 * M.ndof,
                                          gaction + (size_t)w * M.na, &H);
