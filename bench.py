@@ -149,6 +149,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=4096, help="worlds per GPU")
     ap.add_argument("--precision", default="fp32", choices=["fp32", "fp64"])
+    ap.add_argument("--lanes", type=int, default=0, help="threads cooperating on one world (0 = library picks from the batch size)")
+    ap.add_argument("--no-extra", action="store_true", help="skip the cpu_baseline / e2e-independent extra contact legs")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -194,7 +196,7 @@ def main():
 
     # ------------------------------------------------------------------ our arm (GPU)
     cpu_baseline = None
-    if world_size == 1:  # timed BEFORE CUDA is initialised so the forked workers never inherit a CUDA context
+    if world_size == 1 and not args.no_extra:  # timed BEFORE CUDA is initialised so the forked workers never inherit a CUDA context
         cores = os.cpu_count() or 1
         sample = max(cores * 16, 128)
         ref = CpuReference(raw, cores)
@@ -219,7 +221,10 @@ def main():
 
     prec = FP64 if args.precision == "fp64" else FP32
     B = args.batch
-    dm = nb.DeviceModel(nb.compile_model(raw))
+    dm = nb.DeviceModel.from_raw(raw)
+    if args.lanes:
+        dm.set_lanes(args.lanes)
+    lanes_used = dm.lanes_for(B)
     per_set = 4 * B * (2 * n * 4 + 2 * na + dm.saved_words * (2 if prec == FP64 else 1))
     nsets = max(2, int(np.ceil(160e6 / per_set)))
     sets = []
@@ -286,7 +291,7 @@ def main():
 
     # ---- extra (not the headline metric): forward step WITH the contact / boxed-LCP stage, configs[2] and configs[3] shapes
     extra = {}
-    if world_size == 1:
+    if world_size == 1 and not args.no_extra:
         from tests.util import contact_inputs
 
         for cname, label in (("atlas_ground", "atlas_ground_contact_fwd"), ("half_cheetah", "half_cheetah_contact_fwd")):
@@ -355,7 +360,7 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world_size, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32" if prec == FP32 else "f64", "data": "synthetic", "config": config,
-            "kernel_ms": {"k_step_fwd": fwd_ms, "k_step_bwd": bwd_ms},
+            "kernel_ms": {"k_step_fwd": fwd_ms, "k_step_bwd": bwd_ms}, "lanes_per_world": lanes_used,
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic,
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s",

@@ -42,8 +42,9 @@ typedef struct nb2_model_desc {
   const int32_t* jtype;       /* [nb]  1 revolute-z, 2 prismatic-z, 3 free */
   const int32_t* dof_off;     /* [nb] */
   const int32_t* flags;       /* [nb] */
-  const int32_t* slot_self;   /* [nb] */
-  const int32_t* slot_parent; /* [nb] */
+  const int32_t* slot_self;   /* [nb] first accumulator slot owned by the body (or -1) */
+  const int32_t* slot_parent; /* [nb] slot the body deposits into (or -1) */
+  const int32_t* slot_count;  /* [nb] number of slots owned */
   const double* Xtree;        /* [nb*12] */
   const double* inertia;      /* [nb*10] */
   const double* damping;      /* [ndof] ... */
@@ -71,9 +72,20 @@ typedef struct nb2_model_desc {
   const int32_t* pair_b;
   int32_t penetration_correction;
   double contact_clipping_depth, fallback_cfm;
+  /* ---- cooperative schedule: `lanes` threads share one world (contact worlds must use 1). sched is
+   * [trunk_n, lo, hi, ...,  then for each lane: limb_n, lo, hi, ...] with half-open canonical body ranges. */
+  int32_t lanes, nsched;
+  const int32_t* sched;
 } nb2_model_desc;
 
 int nb2_model_create(const nb2_model_desc* desc, nb2_model** out);
+/* Register one more sweep schedule of the SAME model (desc identical except lanes / flags / slot_* / nslots / sched).
+ * The step entry points then pick, per launch, the widest schedule the batch leaves room for (small batches are
+ * latency bound: several threads cooperate on one world; large batches are throughput bound: one thread per world).
+ * nb2_model_set_lanes pins the choice (0 = automatic); nb2_model_lanes_for reports it for a batch size. */
+int nb2_model_add_schedule(nb2_model* m, const nb2_model_desc* desc);
+int nb2_model_set_lanes(nb2_model* m, int lanes);
+int nb2_model_lanes_for(const nb2_model* m, int B);
 void nb2_model_destroy(nb2_model* m);
 int nb2_model_ndof(const nb2_model* m);
 int nb2_model_na(const nb2_model* m);

@@ -24,7 +24,7 @@ class Nb2ModelDesc(ctypes.Structure):
     _fields_ = [
         ("nb", ctypes.c_int32), ("ndof", ctypes.c_int32), ("na", ctypes.c_int32), ("nslots", ctypes.c_int32),
         ("parent", _I32P), ("jtype", _I32P), ("dof_off", _I32P), ("flags", _I32P), ("slot_self", _I32P),
-        ("slot_parent", _I32P),
+        ("slot_parent", _I32P), ("slot_count", _I32P),
         ("Xtree", _F64P), ("inertia", _F64P),
         ("damping", _F64P), ("spring", _F64P), ("rest", _F64P),
         ("pos_lo", _F64P), ("pos_hi", _F64P), ("vel_lo", _F64P), ("vel_hi", _F64P), ("force_lo", _F64P),
@@ -37,6 +37,7 @@ class Nb2ModelDesc(ctypes.Structure):
         ("pair_a", _I32P), ("pair_b", _I32P),
         ("penetration_correction", ctypes.c_int32),
         ("contact_clipping_depth", ctypes.c_double), ("fallback_cfm", ctypes.c_double),
+        ("lanes", ctypes.c_int32), ("nsched", ctypes.c_int32), ("sched", _I32P),
     ]
 
 MAX_CONTACTS, MAX_ROWS = 16, 48  # include/nb2.h
@@ -60,6 +61,11 @@ def make_desc(cm: CanonModel, with_contacts: bool = True):
     d.nb, d.ndof, d.na, d.nslots = cm.nb, cm.ndof, len(cm.action_map), cm.nslots
     d.parent, d.jtype, d.dof_off = i32(cm.parent), i32(cm.jtype), i32(cm.dof_off)
     d.flags, d.slot_self, d.slot_parent = i32(cm.flags), i32(cm.slot_self), i32(cm.slot_parent)
+    d.slot_count = i32(cm.slot_count)
+    sched = [len(cm.trunk_ranges)] + [x for r in cm.trunk_ranges for x in r]
+    for lr in cm.limb_ranges:
+        sched += [len(lr)] + [x for r in lr for x in r]
+    d.lanes, d.nsched, d.sched = int(cm.lanes), len(sched), i32(sched)
     d.Xtree, d.inertia = f64(cm.Xtree), f64(cm.inertia)
     d.damping, d.spring, d.rest = f64(cm.damping), f64(cm.spring), f64(cm.rest)
     d.pos_lo, d.pos_hi = f64(cm.pos_lo), f64(cm.pos_hi)
@@ -120,6 +126,9 @@ def lib() -> ctypes.CDLL:
         L.nb2_launch_count.restype = ctypes.c_longlong
         L.nb2_model_create.argtypes = [ctypes.POINTER(Nb2ModelDesc), ctypes.POINTER(ctypes.c_void_p)]
         L.nb2_model_destroy.argtypes = [ctypes.c_void_p]
+        L.nb2_model_add_schedule.argtypes = [ctypes.c_void_p, ctypes.POINTER(Nb2ModelDesc)]
+        L.nb2_model_set_lanes.argtypes = [ctypes.c_void_p, ctypes.c_int]
+        L.nb2_model_lanes_for.argtypes = [ctypes.c_void_p, ctypes.c_int]
         L.nb2_model_ndof.argtypes = [ctypes.c_void_p]
         L.nb2_model_na.argtypes = [ctypes.c_void_p]
         L.nb2_saved_words_per_world.argtypes = [ctypes.c_void_p]

@@ -141,20 +141,13 @@ template <class R> NB2_HD R S_dot(int jt, const V6<R>& f) { return (jt == NB2_JT
 // forward: state=[q;v] (fp32 row), action (fp32 row) -> next state row; optionally streams intermediates to `sv`
 // =====================================================================================================
 template <class R, int ST>
-NB2_HD void world_forward(const Nb2ModelDev<R>& M, R* scr, const float* st, const float* act, float* out, R* sv,
-                          size_t B, bool save) {
+NB2_HD void fwd_pass1(const Nb2ModelDev<R>& M, R* scr, int lo, int hi) {
   const int nb = M.nb, n = M.ndof;
   const FwdLayout L = fwd_layout(nb, n, M.nslots, M.nfree);
   const R dt = M.dt;
-  for (int d = 0; d < n; d++) {
-    scr[(size_t)(L.oQ + d) * ST] = (R)st[d];
-    scr[(size_t)(L.oV + d) * ST] = (R)st[n + d];
-    scr[(size_t)(L.oTau + d) * ST] = R(0);
-  }
-  for (int i = 0; i < M.na; i++) scr[(size_t)(L.oTau + M.action_map[i]) * ST] = (R)act[i];  // World.cpp:2061-2086
-
+  (void)nb; (void)n; (void)dt;
   // ---------------- pass 1, root -> leaf: joint transforms and spatial velocities (Frame.cpp:144-160)
-  for (int i = 0; i < nb; i++) {
+  for (int i = lo; i < hi; i++) {
     const int jt = M.jtype[i], p = M.parent[i], o = M.dof_off[i];
     R* bs = scr + (size_t)(L.oBody + 22 * i) * ST;
     V6<R> Vp = (p >= 0) ? ld6<R, ST>(scr + (size_t)(L.oBody + 22 * p) * ST) : zero6<R>();
@@ -180,12 +173,20 @@ NB2_HD void world_forward(const Nb2ModelDev<R>& M, R* scr, const float* st, cons
     st6<R, ST>(bs, V);
   }
 
+}
+
+template <class R, int ST>
+NB2_HD void fwd_pass2(const Nb2ModelDev<R>& M, R* scr, R* sv, size_t B, bool save, int lo, int hi) {
+  const int nb = M.nb, n = M.ndof;
+  const FwdLayout L = fwd_layout(nb, n, M.nslots, M.nfree);
+  const R dt = M.dt;
+  (void)nb; (void)n; (void)dt;
   // ---------------- pass 2, leaf -> root: articulated inertia, bias force, total joint force
   // (BodyNode.cpp:2046-2114, GenericJoint.hpp:2168-2185, 2276-2301, 2395-2421, 2554-2571)
   SI<R> hI = zeroSI<R>();
   V6<R> hp = zero6<R>();
   bool hvalid = false;
-  for (int i = nb - 1; i >= 0; i--) {
+  for (int i = hi - 1; i >= lo; i--) {
     const int jt = M.jtype[i], p = M.parent[i], o = M.dof_off[i], fl = M.flags[i];
     R* bs = scr + (size_t)(L.oBody + 22 * i) * ST;
     R m; V3<R> h; S3<R> Ib; inertia_of(M, i, &m, &h, &Ib);
@@ -194,9 +195,11 @@ NB2_HD void world_forward(const Nb2ModelDev<R>& M, R* scr, const float* st, cons
     V6<R> pA = crf(V, mulG(m, h, Ib, V));
     if (hvalid) { IA = IA + hI; pA = pA + hp; }
     if (fl & NB2_F_HAS_SLOT) {
-      const R* sl = scr + (size_t)(L.oSlot + 27 * M.slot_self[i]) * ST;
-      IA = IA + ldSI<R, ST>(sl);
-      pA = pA + ld6<R, ST>(sl + 21 * ST);
+      for (int k = 0; k < M.slot_count[i]; k++) {  // contributions of the children that could not hand off in registers
+        const R* sl = scr + (size_t)(L.oSlot + 27 * (M.slot_self[i] + k)) * ST;
+        IA = IA + ldSI<R, ST>(sl);
+        pA = pA + ld6<R, ST>(sl + 21 * ST);
+      }
     }
     SI<R> Pi; V6<R> beta;
     if (jt != NB2_JT_FREE) {
@@ -262,17 +265,24 @@ NB2_HD void world_forward(const Nb2ModelDev<R>& M, R* scr, const float* st, cons
       const V6<R> pc = dAdInvT(T, beta);
       if (fl & NB2_F_HANDOFF) { hI = Ic; hp = pc; hvalid = true; }
       else {
-        R* sl = scr + (size_t)(L.oSlot + 27 * M.slot_parent[i]) * ST;
-        if (fl & NB2_F_FIRST_DEPOSIT) { stSI<R, ST, false>(sl, Ic); st6<R, ST>(sl + 21 * ST, pc); }
-        else { stSI<R, ST, true>(sl, Ic); add6<R, ST>(sl + 21 * ST, pc); }
+        R* sl = scr + (size_t)(L.oSlot + 27 * M.slot_parent[i]) * ST;  // this child's own slot: plain store
+        stSI<R, ST, false>(sl, Ic); st6<R, ST>(sl + 21 * ST, pc);
       }
     }
   }
 
+}
+
+template <class R, int ST>
+NB2_HD void fwd_pass3(const Nb2ModelDev<R>& M, R* scr, float* out, R* sv, size_t B, bool save, int lo, int hi) {
+  const int nb = M.nb, n = M.ndof;
+  const FwdLayout L = fwd_layout(nb, n, M.nslots, M.nfree);
+  const R dt = M.dt;
+  (void)nb; (void)n; (void)dt;
   // ---------------- pass 3, root -> leaf: accelerations (BodyNode.cpp:2159-2185, GenericJoint.hpp:2656-2676),
   // then integrate: v+ = v + dt qdd ; q+ = q (+) dt v  with the PRE-step velocity (World.cpp:307-322)
   V6<R> A0; A0.a = zero3<R>(); A0.l = mk3<R>(-M.gravity[0], -M.gravity[1], -M.gravity[2]);
-  for (int i = 0; i < nb; i++) {
+  for (int i = lo; i < hi; i++) {
     const int jt = M.jtype[i], p = M.parent[i], o = M.dof_off[i];
     R* bs = scr + (size_t)(L.oBody + 22 * i) * ST;
     const Xf<R> T = body_xf_fwd<R, ST>(M, i, scr, L);
@@ -325,6 +335,57 @@ NB2_HD void world_forward(const Nb2ModelDev<R>& M, R* scr, const float* st, cons
   }
 }
 
+// The sweeps are cut into STAGES so that M.lanes threads can cooperate on one world: lane 0 owns the TRUNK (an
+// ancestor-closed set of bodies), every lane owns some LIMB subtrees (modelspec._partition_tree).  A warp barrier is
+// needed only where data crosses lanes (NB2_FWD_SYNC_MASK bit = "barrier after this stage"):
+//   0 load q, v, tau (dofs strided over the lanes)           | barrier
+//   1 kinematics of the trunk           (lane 0, root->leaf) | barrier
+//   2 kinematics of the limbs           (every lane)
+//   3 articulated inertias of the limbs (every lane, leaf->root) | barrier
+//   4 articulated inertias of the trunk (lane 0)
+//   5 accelerations + integration, trunk (lane 0)            | barrier
+//   6 accelerations + integration, limbs (every lane)
+// With lanes == 1 everything is trunk.  Each pass body is instantiated once (the stage index is a run-time value).
+#define NB2_FWD_STAGES 7
+#define NB2_FWD_SYNC_MASK 0x2Bu  /* after stages 0, 1, 3, 5 */
+template <class R, int ST>
+NB2_HD void world_forward_stage(const Nb2ModelDev<R>& M, R* scr, const float* st, const float* act, float* out, R* sv,
+                                size_t B, bool save, int lane, int stage) {
+  const int n = M.ndof, K = M.lanes;
+  if (stage == 0) {
+    const FwdLayout L = fwd_layout(M.nb, n, M.nslots, M.nfree);
+    for (int d = lane; d < n; d += K) {
+      scr[(size_t)(L.oQ + d) * ST] = (R)st[d];
+      scr[(size_t)(L.oV + d) * ST] = (R)st[n + d];
+      scr[(size_t)(L.oTau + d) * ST] = R(0);
+    }
+    for (int i = 0; i < M.na; i++) {  // World.cpp:2061-2086; the lane that zeroed a dof also scatters into it
+      const int d = M.action_map[i];
+      if (d % K == lane) scr[(size_t)(L.oTau + d) * ST] = (R)act[i];
+    }
+    return;
+  }
+  const int pass = (stage + 1) >> 1;                          // 1, 2, 3
+  const bool trunk = (stage == 1) | (stage == 4) | (stage == 5);
+  if (trunk && lane != 0) return;
+  const int nr = trunk ? M.trunk_n : M.limb_n[lane];
+  for (int rr = 0; rr < nr; rr++) {
+    const int r = (pass == 2) ? nr - 1 - rr : rr;
+    const int lo = trunk ? M.trunk_lo[r] : M.limb_lo[lane][r], hi = trunk ? M.trunk_hi[r] : M.limb_hi[lane][r];
+    if (pass == 1) fwd_pass1<R, ST>(M, scr, lo, hi);
+    else if (pass == 2) fwd_pass2<R, ST>(M, scr, sv, B, save, lo, hi);
+    else fwd_pass3<R, ST>(M, scr, out, sv, B, save, lo, hi);
+  }
+}
+
+// single-thread convenience (any model: one thread plays every lane in turn)
+template <class R, int ST>
+NB2_HD void world_forward(const Nb2ModelDev<R>& M, R* scr, const float* st, const float* act, float* out, R* sv,
+                          size_t B, bool save) {
+  for (int sg = 0; sg < NB2_FWD_STAGES; sg++)
+    for (int lane = 0; lane < M.lanes; lane++) world_forward_stage<R, ST>(M, scr, st, act, out, sv, B, save, lane, sg);
+}
+
 // hook implemented in nb2_contact.cuh: turns lambda / W into w / W(w) and prepares the contact injections
 struct BwdContactHook {
   const void* model_contact;  // const Nb2ContactDev*
@@ -344,28 +405,24 @@ NB2_HD BwdContactData<ST> contact_backward_hook(const Nb2ModelDev<double>& M, co
 // =====================================================================================================
 // backward: g_next = dL/d[q+;v+]  ->  g_state = dL/d[q;v], g_action = dL/d action
 // =====================================================================================================
-template <class R, int ST, bool CONTACT = false>
-NB2_HD void world_backward(const Nb2ModelDev<R>& M, R* scr, const float* st, const float* act, const float* gnext,
-                           const R* sv, size_t B, float* gstate, float* gaction, const BwdContactHook* hook = nullptr) {
+template <class R, int ST, bool CONTACT>
+NB2_HD void bwd_B1(const Nb2ModelDev<R>& M, R* scr, const float* st, const R* sv, size_t B, int lo, int hi) {
   const int nb = M.nb, n = M.ndof;
   constexpr int SLOTW = CONTACT ? 42 : 18;
   const BwdLayout L = bwd_layout(nb, n, M.nslots, M.nfree, SLOTW);
   const R dt = M.dt;
   const int kFree = nb * 21, kQdd = nb * 21 + M.nfree * 33;
-  for (int d = 0; d < n; d++) {
-    scr[(size_t)(L.oGQ + d) * ST] = (R)gnext[d];
-    scr[(size_t)(L.oGV + d) * ST] = (R)gnext[n + d];
-  }
-
+  (void)n; (void)dt; (void)kFree; (void)kQdd;
   // ---------------- B1, leaf -> root: bias pass of lambda = M^-1 g_v'  (impulse-ABA form,
   // BodyNode.cpp:2117-2138, GenericJoint.hpp:2482-2498, 2607-2613) reusing the forward's U, psi
   V6<R> hp = zero6<R>();
   bool hvalid = false;
-  for (int i = nb - 1; i >= 0; i--) {
+  for (int i = hi - 1; i >= lo; i--) {
     const int jt = M.jtype[i], p = M.parent[i], o = M.dof_off[i], fl = M.flags[i];
     const R* s = sv + (size_t)(i * 21) * B;
     V6<R> pI = hvalid ? hp : zero6<R>();
-    if (fl & NB2_F_HAS_SLOT) pI = pI + ld6<R, ST>(scr + (size_t)(L.oSlot + SLOTW * M.slot_self[i]) * ST);
+    if (fl & NB2_F_HAS_SLOT)
+      for (int k = 0; k < M.slot_count[i]; k++) pI = pI + ld6<R, ST>(scr + (size_t)(L.oSlot + SLOTW * (M.slot_self[i] + k)) * ST);
     V6<R> beta;
     if (jt != NB2_JT_FREE) {
       const R up = scr[(size_t)(L.oGV + o) * ST] - S_dot(jt, pI);
@@ -386,13 +443,23 @@ NB2_HD void world_backward(const Nb2ModelDev<R>& M, R* scr, const float* st, con
       if (fl & NB2_F_HANDOFF) { hp = pc; hvalid = true; }
       else {
         R* sl = scr + (size_t)(L.oSlot + SLOTW * M.slot_parent[i]) * ST;
-        if (fl & NB2_F_FIRST_DEPOSIT) st6<R, ST>(sl, pc); else add6<R, ST>(sl, pc);
+        st6<R, ST>(sl, pc);
       }
     }
   }
+}
+
+template <class R, int ST, bool CONTACT>
+NB2_HD void bwd_B2(const Nb2ModelDev<R>& M, R* scr, const float* st, const R* sv, size_t B, int lo, int hi) {
+  const int nb = M.nb, n = M.ndof;
+  constexpr int SLOTW = CONTACT ? 42 : 18;
+  const BwdLayout L = bwd_layout(nb, n, M.nslots, M.nfree, SLOTW);
+  const R dt = M.dt;
+  const int kFree = nb * 21, kQdd = nb * 21 + M.nfree * 33;
+  (void)n; (void)dt; (void)kFree; (void)kQdd;
   // ---------------- B2, root -> leaf: lambda and the spatial "velocities" W it induces
   // (BodyNode.cpp:2188-2215, GenericJoint.hpp:2713-2725)
-  for (int i = 0; i < nb; i++) {
+  for (int i = lo; i < hi; i++) {
     const int jt = M.jtype[i], p = M.parent[i], o = M.dof_off[i];
     const R* s = sv + (size_t)(i * 21) * B;
     R* bs = scr + (size_t)(L.oBody + 7 * i) * ST;
@@ -415,11 +482,16 @@ NB2_HD void world_backward(const Nb2ModelDev<R>& M, R* scr, const float* st, con
     }
     st6<R, ST>(bs + ST, W);
   }
-  // ---------------- contact stage adjoint (nb2_contact.cuh): lambda -> w, W -> W(w), injections for B3
-  BwdContactData<ST> cd; cd.active = 0; cd.error = 0;
-  if constexpr (CONTACT) {
-    cd = contact_backward_hook<ST>(M, *hook, st, sv, B, scr, L.oLam, L.oBody);
-  }
+}
+
+template <class R, int ST, bool CONTACT>
+NB2_HD void bwd_B3(const Nb2ModelDev<R>& M, R* scr, const float* st, const R* sv, size_t B, const BwdContactData<ST>& cd, int lo, int hi) {
+  const int nb = M.nb, n = M.ndof;
+  constexpr int SLOTW = CONTACT ? 42 : 18;
+  const BwdLayout L = bwd_layout(nb, n, M.nslots, M.nfree, SLOTW);
+  const R dt = M.dt;
+  const int kFree = nb * 21, kQdd = nb * 21 + M.nfree * 33;
+  (void)n; (void)dt; (void)kFree; (void)kQdd;
   // ---------------- B3, leaf -> root: reverse sweep of RNEA, seeded with lambda on the joint forces.
   //   forward RNEA:  V_i = X^-1 V_p + S v ;  A_i = X^-1 A_p + S a + ad(V_i, S v) ;  F_i = G A_i + V_i x* G V_i ;
   //                  f_i = F_i + sum_c X*_c f_c ; tau_i = S^T f_i
@@ -429,8 +501,8 @@ NB2_HD void world_backward(const Nb2ModelDev<R>& M, R* scr, const float* st, con
   //                  c_i    = -( (X^-1 A_p) x* Abar_i + (X^-1 V_p) x* Vbar_i + (X^-1 W_p) x* f_i ) ; qbar_i = B_i(q)^T c_i
   V6<R> hA = zero6<R>(), hV = zero6<R>(), hf = zero6<R>();
   V6<R> hUw = zero6<R>(), hUp = zero6<R>(), hG = zero6<R>(), hH = zero6<R>();
-  hvalid = false;
-  for (int i = nb - 1; i >= 0; i--) {
+  bool hvalid = false;
+  for (int i = hi - 1; i >= lo; i--) {
     const int jt = M.jtype[i], p = M.parent[i], o = M.dof_off[i], fl = M.flags[i];
     const R* s = sv + (size_t)(i * 21) * B;
     R m; V3<R> h; S3<R> Ib; inertia_of(M, i, &m, &h, &Ib);
@@ -453,9 +525,11 @@ NB2_HD void world_backward(const Nb2ModelDev<R>& M, R* scr, const float* st, con
       if (hvalid) { Uw = Uw + hUw; Up = Up + hUp; Gc = Gc + hG; Hc = Hc + hH; }
     }
     if (fl & NB2_F_HAS_SLOT) {
-      const R* sl = scr + (size_t)(L.oSlot + SLOTW * M.slot_self[i]) * ST;
-      Abar = Abar + ld6<R, ST>(sl); Vbar = Vbar + ld6<R, ST>(sl + 6 * ST); f = f + ld6<R, ST>(sl + 12 * ST);
-      if (CONTACT && cd.active) { Uw = Uw + ld6<R, ST>(sl + 18 * ST); Up = Up + ld6<R, ST>(sl + 24 * ST); Gc = Gc + ld6<R, ST>(sl + 30 * ST); Hc = Hc + ld6<R, ST>(sl + 36 * ST); }
+      for (int k = 0; k < M.slot_count[i]; k++) {
+        const R* sl = scr + (size_t)(L.oSlot + SLOTW * (M.slot_self[i] + k)) * ST;
+        Abar = Abar + ld6<R, ST>(sl); Vbar = Vbar + ld6<R, ST>(sl + 6 * ST); f = f + ld6<R, ST>(sl + 12 * ST);
+        if (CONTACT && cd.active) { Uw = Uw + ld6<R, ST>(sl + 18 * ST); Up = Up + ld6<R, ST>(sl + 24 * ST); Gc = Gc + ld6<R, ST>(sl + 30 * ST); Hc = Hc + ld6<R, ST>(sl + 36 * ST); }
+      }
     }
     V6<R> Sv, Sa, Sl;
     Xf<R> T;
@@ -505,19 +579,24 @@ NB2_HD void world_backward(const Nb2ModelDev<R>& M, R* scr, const float* st, con
       if (fl & NB2_F_HANDOFF) { hA = cA; hV = cV; hf = cf; if (CONTACT && cd.active) { hUw = cUw; hUp = cUp; hG = cG; hH = cH; } hvalid = true; }
       else {
         R* sl = scr + (size_t)(L.oSlot + SLOTW * M.slot_parent[i]) * ST;
-        if (fl & NB2_F_FIRST_DEPOSIT) {
-          st6<R, ST>(sl, cA); st6<R, ST>(sl + 6 * ST, cV); st6<R, ST>(sl + 12 * ST, cf);
-          if (CONTACT && cd.active) { st6<R, ST>(sl + 18 * ST, cUw); st6<R, ST>(sl + 24 * ST, cUp); st6<R, ST>(sl + 30 * ST, cG); st6<R, ST>(sl + 36 * ST, cH); }
-        } else {
-          add6<R, ST>(sl, cA); add6<R, ST>(sl + 6 * ST, cV); add6<R, ST>(sl + 12 * ST, cf);
-          if (CONTACT && cd.active) { add6<R, ST>(sl + 18 * ST, cUw); add6<R, ST>(sl + 24 * ST, cUp); add6<R, ST>(sl + 30 * ST, cG); add6<R, ST>(sl + 36 * ST, cH); }
-        }
+        st6<R, ST>(sl, cA); st6<R, ST>(sl + 6 * ST, cV); st6<R, ST>(sl + 12 * ST, cf);
+        if (CONTACT && cd.active) { st6<R, ST>(sl + 18 * ST, cUw); st6<R, ST>(sl + 24 * ST, cUp); st6<R, ST>(sl + 30 * ST, cG); st6<R, ST>(sl + 36 * ST, cH); }
       }
     }
   }
+}
+
+template <class R, int ST, bool CONTACT>
+NB2_HD void bwd_assemble(const Nb2ModelDev<R>& M, R* scr, const float* st, const BwdContactData<ST>& cd, int lo, int hi) {
+  const int nb = M.nb, n = M.ndof;
+  constexpr int SLOTW = CONTACT ? 42 : 18;
+  const BwdLayout L = bwd_layout(nb, n, M.nslots, M.nfree, SLOTW);
+  const R dt = M.dt;
+  const int kFree = nb * 21, kQdd = nb * 21 + M.nfree * 33;
+  (void)n; (void)dt; (void)kFree; (void)kQdd;
   // ---------------- assemble:  g_tau = dt lambda ;  g_q = Pqq^T g_q' - dt (qbar + K lambda) ;
   //                             g_v = Pvq^T g_q' + g_v' - dt (vbar + (D + dt K) lambda)
-  for (int i = 0; i < nb; i++) {
+  for (int i = lo; i < hi; i++) {
     const int jt = M.jtype[i], o = M.dof_off[i];
     if (jt != NB2_JT_FREE) {
       const R lam = scr[(size_t)(L.oLam + o) * ST];
@@ -556,14 +635,25 @@ NB2_HD void world_backward(const Nb2ModelDev<R>& M, R* scr, const float* st, con
       }
     }
   }
-  if (CONTACT && cd.error) {  // unsupported contact configuration for the backward: fail loudly, never silently wrong
-    for (int d = 0; d < 2 * n; d++) gstate[d] = nanf("");
-    for (int i = 0; i < M.na; i++) gaction[i] = nanf("");
+}
+
+template <class R, int ST, bool CONTACT>
+NB2_HD void bwd_store(const Nb2ModelDev<R>& M, const R* scr, const float* st, const float* act, float* gstate, float* gaction,
+                      bool cd_error, int lane, int K) {
+  const int nb = M.nb, n = M.ndof;
+  constexpr int SLOTW = CONTACT ? 42 : 18;
+  const BwdLayout L = bwd_layout(nb, n, M.nslots, M.nfree, SLOTW);
+  const R dt = M.dt;
+  const int kFree = nb * 21, kQdd = nb * 21 + M.nfree * 33;
+  (void)n; (void)dt; (void)kFree; (void)kQdd;
+  if (cd_error) {  // unsupported contact configuration for the backward: fail loudly, never silently wrong
+    for (int d = lane; d < 2 * n; d += K) gstate[d] = nanf("");
+    for (int i = lane; i < M.na; i += K) gaction[i] = nanf("");
     return;
   }
   // clipLossGradientsToBounds (BackpropSnapshot.cpp:425-479): exact equality against the pre-step state, then
   // scatter through the action map (:404-417)
-  for (int d = 0; d < n; d++) {
+  for (int d = lane; d < n; d += K) {
     float gq = (float)scr[(size_t)(L.oQb + d) * ST], gv = (float)scr[(size_t)(L.oVb + d) * ST];
     const float qd = st[d], vd = st[n + d];
     if (qd == M.pos_lo[d] && gq > 0.f) gq = 0.f;
@@ -572,7 +662,7 @@ NB2_HD void world_backward(const Nb2ModelDev<R>& M, R* scr, const float* st, con
     if (vd == M.vel_hi[d] && gv < 0.f) gv = 0.f;
     gstate[d] = gq; gstate[n + d] = gv;
   }
-  for (int i = 0; i < M.na; i++) {
+  for (int i = lane; i < M.na; i += K) {
     const int d = M.action_map[i];
     float gt = (float)(dt * scr[(size_t)(L.oLam + d) * ST]);
     const float fd = act[i];
@@ -580,6 +670,68 @@ NB2_HD void world_backward(const Nb2ModelDev<R>& M, R* scr, const float* st, con
     if (fd == M.force_hi[d] && gt < 0.f) gt = 0.f;
     gaction[i] = gt;
   }
+}
+
+// Stages of the cooperative backward (see world_forward_stage for the trunk/limb split):
+//   0 load g_next (strided)            | barrier
+//   1 B1 limbs (leaf->root)            | barrier
+//   2 B1 trunk      3 B2 trunk         | barrier (after 3)
+//   4 B2 limbs      5 B3 limbs      6 assemble limbs | barrier (after 6)
+//   7 B3 trunk      8 assemble trunk   | barrier
+//   9 clip + store (strided)
+#define NB2_BWD_STAGES 10
+#define NB2_BWD_SYNC_MASK 0x14Bu  /* after stages 0, 1, 3, 6, 8 */
+template <class R, int ST>
+NB2_HD void world_backward_stage(const Nb2ModelDev<R>& M, R* scr, const float* st, const float* act, const float* gnext,
+                                 const R* sv, size_t B, float* gstate, float* gaction, int lane, int stage) {
+  const int n = M.ndof, K = M.lanes;
+  if (stage == 0) {
+    const BwdLayout L = bwd_layout(M.nb, n, M.nslots, M.nfree, 18);
+    for (int d = lane; d < n; d += K) {
+      scr[(size_t)(L.oGQ + d) * ST] = (R)gnext[d];
+      scr[(size_t)(L.oGV + d) * ST] = (R)gnext[n + d];
+    }
+    return;
+  }
+  if (stage == 9) { bwd_store<R, ST, false>(M, scr, st, act, gstate, gaction, false, lane, K); return; }
+  BwdContactData<ST> cd; cd.active = 0; cd.error = 0;
+  // pass: 1 = B1, 2 = B2, 3 = B3, 4 = assemble
+  const int pass = (stage == 1 || stage == 2) ? 1 : (stage == 3 || stage == 4) ? 2 : (stage == 5 || stage == 7) ? 3 : 4;
+  const bool trunk = (stage == 2) | (stage == 3) | (stage == 7) | (stage == 8);
+  if (trunk && lane != 0) return;
+  const int nr = trunk ? M.trunk_n : M.limb_n[lane];
+  for (int rr = 0; rr < nr; rr++) {
+    const int r = (pass == 1 || pass == 3) ? nr - 1 - rr : rr;
+    const int lo = trunk ? M.trunk_lo[r] : M.limb_lo[lane][r], hi = trunk ? M.trunk_hi[r] : M.limb_hi[lane][r];
+    if (pass == 1) bwd_B1<R, ST, false>(M, scr, st, sv, B, lo, hi);
+    else if (pass == 2) bwd_B2<R, ST, false>(M, scr, st, sv, B, lo, hi);
+    else if (pass == 3) bwd_B3<R, ST, false>(M, scr, st, sv, B, cd, lo, hi);
+    else bwd_assemble<R, ST, false>(M, scr, st, cd, lo, hi);
+  }
+}
+
+// single-thread backward; the only form that carries the contact-stage adjoint (slots make any schedule valid
+// when one thread sweeps all bodies in order)
+template <class R, int ST, bool CONTACT = false>
+NB2_HD void world_backward(const Nb2ModelDev<R>& M, R* scr, const float* st, const float* act, const float* gnext,
+                           const R* sv, size_t B, float* gstate, float* gaction, const BwdContactHook* hook = nullptr) {
+  const int nb = M.nb, n = M.ndof;
+  constexpr int SLOTW = CONTACT ? 42 : 18;
+  const BwdLayout L = bwd_layout(nb, n, M.nslots, M.nfree, SLOTW);
+  for (int d = 0; d < n; d++) {
+    scr[(size_t)(L.oGQ + d) * ST] = (R)gnext[d];
+    scr[(size_t)(L.oGV + d) * ST] = (R)gnext[n + d];
+  }
+  bwd_B1<R, ST, CONTACT>(M, scr, st, sv, B, 0, nb);
+  bwd_B2<R, ST, CONTACT>(M, scr, st, sv, B, 0, nb);
+  // ---------------- contact stage adjoint (nb2_contact.cuh): lambda -> w, W -> W(w), injections for B3
+  BwdContactData<ST> cd; cd.active = 0; cd.error = 0;
+  if constexpr (CONTACT) {
+    cd = contact_backward_hook<ST>(M, *hook, st, sv, B, scr, L.oLam, L.oBody);
+  }
+  bwd_B3<R, ST, CONTACT>(M, scr, st, sv, B, cd, 0, nb);
+  bwd_assemble<R, ST, CONTACT>(M, scr, st, cd, 0, nb);
+  bwd_store<R, ST, CONTACT>(M, scr, st, act, gstate, gaction, CONTACT && cd.error, 0, 1);
 }
 
 }  // namespace nb2

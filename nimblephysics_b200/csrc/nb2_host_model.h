@@ -12,12 +12,12 @@ static inline bool nb2_fill_model(const nb2_model_desc& d, Nb2ModelDev<R>& M, st
   if (d.ndof <= 0 || d.ndof > NB2_MAX_DOFS) { err = "model has " + std::to_string(d.ndof) + " dofs; compiled limit is " + std::to_string(NB2_MAX_DOFS); return false; }
   if (d.na < 0 || d.na > d.ndof) { err = "bad action map size"; return false; }
   M.nb = d.nb; M.ndof = d.ndof; M.na = d.na; M.nslots = d.nslots;
-  M.pad0 = M.pad1 = M.pad2 = 0;
+  M.pad2 = 0;
   M.dt = (R)d.dt;
   for (int k = 0; k < 3; k++) M.gravity[k] = (R)d.gravity[k];
   int nfree = 0, ndof = 0;
   for (int i = 0; i < NB2_MAX_BODIES; i++) {
-    M.parent[i] = -1; M.jtype[i] = 0; M.dof_off[i] = 0; M.flags[i] = 0; M.slot_self[i] = -1; M.slot_parent[i] = -1; M.free_idx[i] = -1;
+    M.parent[i] = -1; M.jtype[i] = 0; M.dof_off[i] = 0; M.flags[i] = 0; M.slot_self[i] = -1; M.slot_parent[i] = -1; M.slot_count[i] = 0; M.free_idx[i] = -1;
     for (int k = 0; k < 12; k++) M.Xtree[i][k] = R(0);
     for (int k = 0; k < 10; k++) M.inertia[i][k] = R(0);
   }
@@ -28,6 +28,7 @@ static inline bool nb2_fill_model(const nb2_model_desc& d, Nb2ModelDev<R>& M, st
     if (d.dof_off[i] != ndof) { /* canonical order may permute bodies relative to dof order: allowed */ }
     M.parent[i] = (int16_t)d.parent[i]; M.jtype[i] = (int16_t)jt; M.dof_off[i] = (int16_t)d.dof_off[i];
     M.flags[i] = (int16_t)d.flags[i]; M.slot_self[i] = (int16_t)d.slot_self[i]; M.slot_parent[i] = (int16_t)d.slot_parent[i];
+    M.slot_count[i] = (int16_t)d.slot_count[i];
     if ((d.flags[i] & NB2_F_HANDOFF) && d.parent[i] != i - 1) { err = "handoff flag on a body whose parent is not i-1"; return false; }
     if (jt == NB2_JT_FREE) M.free_idx[i] = (int16_t)nfree++;
     ndof += (jt == NB2_JT_FREE) ? 6 : 1;
@@ -35,6 +36,48 @@ static inline bool nb2_fill_model(const nb2_model_desc& d, Nb2ModelDev<R>& M, st
     for (int k = 0; k < 10; k++) M.inertia[i][k] = (R)d.inertia[10 * i + k];
   }
   if (ndof != d.ndof) { err = "sum of joint dofs does not match ndof"; return false; }
+  // ---- schedule: parse and validate (a wrong schedule would be a silent data race on the device)
+  {
+    const int K = d.lanes;
+    if (K != 1 && K != 2 && K != 4 && K != 8) { err = "lanes must be 1, 2, 4 or 8"; return false; }
+    M.lanes = K;
+    for (int r = 0; r < NB2_MAX_RANGES; r++) M.trunk_lo[r] = M.trunk_hi[r] = 0;
+    for (int l = 0; l < NB2_MAX_LANES; l++) { M.limb_n[l] = 0; for (int r = 0; r < NB2_MAX_RANGES; r++) M.limb_lo[l][r] = M.limb_hi[l][r] = 0; }
+    int owner[NB2_MAX_BODIES], rng[NB2_MAX_BODIES];  // -1 trunk, else lane ; range id
+    for (int i = 0; i < d.nb; i++) { owner[i] = -2; rng[i] = -1; }
+    int pos = 0, rid = 0;
+    auto take = [&](int& v) { if (pos >= d.nsched) return false; v = d.sched[pos++]; return true; };
+    auto take_ranges = [&](int own, int16_t* lo, int16_t* hi, int& cnt) {
+      if (!take(cnt) || cnt < 0 || cnt > NB2_MAX_RANGES) return false;
+      int prev = 0;
+      for (int r = 0; r < cnt; r++) {
+        int a, b;
+        if (!take(a) || !take(b) || a < prev || b <= a || b > d.nb) return false;
+        lo[r] = (int16_t)a; hi[r] = (int16_t)b; prev = b;
+        for (int i = a; i < b; i++) { if (owner[i] != -2) return false; owner[i] = own; rng[i] = rid; }
+        rid++;
+      }
+      return true;
+    };
+    int tn = 0;
+    if (!take_ranges(-1, M.trunk_lo, M.trunk_hi, tn)) { err = "malformed trunk schedule"; return false; }
+    M.trunk_n = tn;
+    for (int l = 0; l < K; l++) {
+      int ln = 0;
+      if (!take_ranges(l, M.limb_lo[l], M.limb_hi[l], ln)) { err = "malformed limb schedule"; return false; }
+      M.limb_n[l] = (int16_t)ln;
+    }
+    for (int i = 0; i < d.nb; i++) {
+      if (owner[i] == -2) { err = "schedule does not cover every body"; return false; }
+      const int p = d.parent[i];
+      if (p >= 0 && owner[p] != -1 && owner[p] != owner[i]) { err = "schedule: parent of a body is swept by another lane"; return false; }
+      if ((d.flags[i] & NB2_F_HANDOFF) && rng[p] != rng[i]) { err = "handoff flag across schedule ranges"; return false; }
+      if (p >= 0 && !(d.flags[i] & NB2_F_HANDOFF)) {
+        const int sp = d.slot_parent[i];
+        if (sp < d.slot_self[p] || sp >= d.slot_self[p] + d.slot_count[p] || sp >= d.nslots) { err = "child slot outside its parent's slots"; return false; }
+      }
+    }
+  }
   M.nfree = nfree;
   for (int j = 0; j < NB2_MAX_DOFS; j++) {
     M.damping[j] = M.spring[j] = M.rest[j] = R(0);

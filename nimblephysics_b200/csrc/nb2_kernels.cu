@@ -11,6 +11,7 @@
 #include <atomic>
 #include <mutex>
 #include <string>
+#include <vector>
 
 #include "../../include/nb2.h"
 #include "nb2_dyn.cuh"
@@ -31,30 +32,56 @@ static std::atomic<long long> g_launches{0};
 
 namespace {
 
-template <class R>
+// K lanes cooperate on one world (K = M.lanes, compile-time here so that the scratch stride is a constant):
+// a warp holds 32/K worlds, thread t of the warp is lane t % K of world slot t / K.  Scratch is [word][slot] with an
+// odd stride (32/K + 1) so that the lanes of one world and the slots of one lane spread over the banks.
+template <int K> struct CoopShape {
+  static constexpr int WPW = 32 / K;                    // worlds per warp
+  static constexpr int ST = (K == 1) ? 32 : WPW + 1;    // scratch stride in words
+};
+
+template <class R, int K>
 __global__ void __launch_bounds__(128)
 k_step_fwd(const __grid_constant__ Nb2ModelDev<R> M, int B, const float* __restrict__ state,
            const float* __restrict__ action, float* __restrict__ next, R* __restrict__ saved, int words) {
   extern __shared__ __align__(16) unsigned char nb2_smem[];
-  const int w = blockIdx.x * blockDim.x + threadIdx.x;
-  if (w >= B) return;
-  R* scr = reinterpret_cast<R*>(nb2_smem) + (size_t)(threadIdx.x >> 5) * words * 32 + (threadIdx.x & 31);
-  nb2::world_forward<R, 32>(M, scr, state + (size_t)w * 2 * M.ndof, action + (size_t)w * M.na,
-                            next + (size_t)w * 2 * M.ndof, saved ? saved + w : nullptr, (size_t)B, saved != nullptr);
+  constexpr int WPW = CoopShape<K>::WPW, ST = CoopShape<K>::ST;
+  const int li = threadIdx.x & 31, slot = li / K, lane = li % K;
+  const int w = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * WPW + slot;
+  const bool valid = w < B;
+  const int wc = valid ? w : 0;
+  R* scr = reinterpret_cast<R*>(nb2_smem) + (size_t)(threadIdx.x >> 5) * words * ST + slot;
+  const float* st = state + (size_t)wc * 2 * M.ndof;
+  const float* ac = action + (size_t)wc * M.na;
+  float* out = next + (size_t)wc * 2 * M.ndof;
+  R* sv = saved ? saved + wc : nullptr;
+#pragma unroll 1
+  for (int sg = 0; sg < NB2_FWD_STAGES; sg++) {
+    if (valid) nb2::world_forward_stage<R, ST>(M, scr, st, ac, out, sv, (size_t)B, saved != nullptr, lane, sg);
+    if (K > 1 && ((NB2_FWD_SYNC_MASK >> sg) & 1u)) __syncwarp();
+  }
 }
 
-template <class R>
+template <class R, int K>
 __global__ void __launch_bounds__(128)
 k_step_bwd(const __grid_constant__ Nb2ModelDev<R> M, int B, const float* __restrict__ state,
            const float* __restrict__ action, const R* __restrict__ saved, const float* __restrict__ gnext,
            float* __restrict__ gstate, float* __restrict__ gaction, int words) {
   extern __shared__ __align__(16) unsigned char nb2_smem[];
-  const int w = blockIdx.x * blockDim.x + threadIdx.x;
-  if (w >= B) return;
-  R* scr = reinterpret_cast<R*>(nb2_smem) + (size_t)(threadIdx.x >> 5) * words * 32 + (threadIdx.x & 31);
-  nb2::world_backward<R, 32>(M, scr, state + (size_t)w * 2 * M.ndof, action + (size_t)w * M.na,
-                             gnext + (size_t)w * 2 * M.ndof, saved + w, (size_t)B,
-                             gstate + (size_t)w * 2 * M.ndof, gaction + (size_t)w * M.na);
+  constexpr int WPW = CoopShape<K>::WPW, ST = CoopShape<K>::ST;
+  const int li = threadIdx.x & 31, slot = li / K, lane = li % K;
+  const int w = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * WPW + slot;
+  const bool valid = w < B;
+  const int wc = valid ? w : 0;
+  R* scr = reinterpret_cast<R*>(nb2_smem) + (size_t)(threadIdx.x >> 5) * words * ST + slot;
+  const float* st = state + (size_t)wc * 2 * M.ndof;
+  const float* ac = action + (size_t)wc * M.na;
+#pragma unroll 1
+  for (int sg = 0; sg < NB2_BWD_STAGES; sg++) {
+    if (valid) nb2::world_backward_stage<R, ST>(M, scr, st, ac, gnext + (size_t)wc * 2 * M.ndof, saved + wc, (size_t)B,
+                                                gstate + (size_t)wc * 2 * M.ndof, gaction + (size_t)wc * M.na, lane, sg);
+    if (K > 1 && ((NB2_BWD_SYNC_MASK >> sg) & 1u)) __syncwarp();
+  }
 }
 
 // contact / boxed-LCP stage: one thread per world, fp64, per-world workspace in global memory (L1/L2 cached).
@@ -95,8 +122,7 @@ constexpr int kMaxSmem = 227 * 1024;
 
 // warps per block: spread small batches over all SMs first (1 warp per block), pack up to 4 warps per block
 // once there are more warps than SMs can hold singly; always bounded by the shared-memory budget.
-int pick_warps(int B, size_t bytes_per_warp, int sm_count) {
-  const int total_warps = (B + 31) / 32;
+int pick_warps(int total_warps, size_t bytes_per_warp, int sm_count) {
   int fit = (int)(kMaxSmem / bytes_per_warp);
   if (fit < 1) return 0;
   int want = (total_warps <= 2 * sm_count) ? 1 : 4;
@@ -107,14 +133,22 @@ int pick_warps(int B, size_t bytes_per_warp, int sm_count) {
 
 }  // namespace
 
-struct nb2_model {
+// one sweep schedule of the model (same bodies, different lane count / slot assignment)
+struct nb2_variant {
   Nb2ModelDev<float> mf;
+  Nb2ModelDev<double> md;
+  int fwd_words, bwd_words;
+};
+
+struct nb2_model {
+  Nb2ModelDev<float> mf;   // the variant given to nb2_model_create (also what the contact kernels use)
   Nb2ModelDev<double> md;
   Nb2ContactDev contact;
   bool has_contacts = false;
-  int fwd_words, bwd_words, saved_words;
+  int saved_words;
   int sm_count;
-  bool attr_set[4] = {false, false, false, false};
+  std::vector<nb2_variant> variants;  // [0] = the create-time schedule
+  int forced_lanes = 0;               // 0: pick per launch from the batch size
   // device buffers owned by the *_host entry points
   float *d_state = nullptr, *d_action = nullptr, *d_next = nullptr, *d_gnext = nullptr,
         *d_gstate = nullptr, *d_gaction = nullptr;
@@ -125,40 +159,93 @@ struct nb2_model {
   std::mutex mu;
 };
 
-template <class R>
-static int launch_fwd(nb2_model* m, const Nb2ModelDev<R>& M, int B, const float* state, const float* action,
-                      float* next, R* saved, cudaStream_t st, int attr_idx) {
-  const size_t per_warp = (size_t)m->fwd_words * 32 * sizeof(R);
-  const int warps = pick_warps(B, per_warp, m->sm_count);
-  if (warps == 0) { g_err = "model needs " + std::to_string(per_warp) + " B of shared memory per warp (> 227 KB)"; return NB2_ERR_UNSUPPORTED; }
-  if (!m->attr_set[attr_idx]) {
-    NB2_CUDA(cudaFuncSetAttribute(k_step_fwd<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
-    m->attr_set[attr_idx] = true;
+template <class R> static const Nb2ModelDev<R>& model_of(const nb2_variant& v);
+template <> const Nb2ModelDev<float>& model_of<float>(const nb2_variant& v) { return v.mf; }
+template <> const Nb2ModelDev<double>& model_of<double>(const nb2_variant& v) { return v.md; }
+
+// Lane count for a launch: cooperative lanes shorten the dependent chain of one world (latency) but idle during the
+// trunk stages (throughput).  Use the widest schedule while the GPU still has free issue slots, i.e. while the batch
+// needs fewer than kCoopWarpsPerSM warps per SM at that width; fall back to the narrowest otherwise.
+constexpr int kCoopWarpsPerSM = 16;
+static const nb2_variant& pick_variant(const nb2_model* m, int B) {
+  const nb2_variant* best = &m->variants[0];
+  if (m->forced_lanes) {
+    for (const auto& v : m->variants) if (v.mf.lanes == m->forced_lanes) return v;
+    return *best;
   }
-  const int threads = warps * 32;
-  const int blocks = (B + threads - 1) / threads;
-  k_step_fwd<R><<<blocks, threads, per_warp * warps, st>>>(M, B, state, action, next, saved, m->fwd_words);
+  int best_k = 0;
+  const nb2_variant* narrow = best;
+  for (const auto& v : m->variants) {
+    const int K = v.mf.lanes;
+    if (K < narrow->mf.lanes) narrow = &v;
+    const long long warps = ((long long)B * K + 31) / 32;
+    if (warps <= (long long)kCoopWarpsPerSM * m->sm_count && K > best_k) { best_k = K; best = &v; }
+  }
+  return best_k ? *best : *narrow;
+}
+
+template <class R, int K>
+static int launch_fwd_k(const nb2_variant& v, int sm_count, const Nb2ModelDev<R>& M, int B, const float* state, const float* action,
+                        float* next, R* saved, cudaStream_t st) {
+  constexpr int WPW = CoopShape<K>::WPW, ST = CoopShape<K>::ST;
+  const size_t per_warp = (size_t)v.fwd_words * ST * sizeof(R);
+  const int total_warps = (B + WPW - 1) / WPW;
+  const int warps = pick_warps(total_warps, per_warp, sm_count);
+  if (warps == 0) { g_err = "model needs " + std::to_string(per_warp) + " B of shared memory per warp (> 227 KB)"; return NB2_ERR_UNSUPPORTED; }
+  static bool attr_set = false;  // one flag per (R, K) instantiation
+  if (!attr_set) {
+    NB2_CUDA(cudaFuncSetAttribute(k_step_fwd<R, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+    attr_set = true;
+  }
+  const int blocks = (total_warps + warps - 1) / warps;
+  k_step_fwd<R, K><<<blocks, warps * 32, per_warp * warps, st>>>(M, B, state, action, next, saved, v.fwd_words);
   g_launches++;
   NB2_CUDA(cudaGetLastError());
   return NB2_OK;
 }
 template <class R>
-static int launch_bwd(nb2_model* m, const Nb2ModelDev<R>& M, int B, const float* state, const float* action,
-                      const R* saved, const float* gnext, float* gstate, float* gaction, cudaStream_t st,
-                      int attr_idx) {
-  const size_t per_warp = (size_t)m->bwd_words * 32 * sizeof(R);
-  const int warps = pick_warps(B, per_warp, m->sm_count);
-  if (warps == 0) { g_err = "model needs " + std::to_string(per_warp) + " B of shared memory per warp (> 227 KB)"; return NB2_ERR_UNSUPPORTED; }
-  if (!m->attr_set[attr_idx]) {
-    NB2_CUDA(cudaFuncSetAttribute(k_step_bwd<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
-    m->attr_set[attr_idx] = true;
+static int launch_fwd(nb2_model* m, int B, const float* state, const float* action, float* next, R* saved, cudaStream_t st) {
+  const nb2_variant& v = pick_variant(m, B);
+  const Nb2ModelDev<R>& M = model_of<R>(v);
+  switch (M.lanes) {
+    case 1: return launch_fwd_k<R, 1>(v, m->sm_count, M, B, state, action, next, saved, st);
+    case 2: return launch_fwd_k<R, 2>(v, m->sm_count, M, B, state, action, next, saved, st);
+    case 4: return launch_fwd_k<R, 4>(v, m->sm_count, M, B, state, action, next, saved, st);
+    case 8: return launch_fwd_k<R, 8>(v, m->sm_count, M, B, state, action, next, saved, st);
   }
-  const int threads = warps * 32;
-  const int blocks = (B + threads - 1) / threads;
-  k_step_bwd<R><<<blocks, threads, per_warp * warps, st>>>(M, B, state, action, saved, gnext, gstate, gaction, m->bwd_words);
+  g_err = "bad lane count"; return NB2_ERR_INVALID;
+}
+template <class R, int K>
+static int launch_bwd_k(const nb2_variant& v, int sm_count, const Nb2ModelDev<R>& M, int B, const float* state, const float* action,
+                        const R* saved, const float* gnext, float* gstate, float* gaction, cudaStream_t st) {
+  constexpr int WPW = CoopShape<K>::WPW, ST = CoopShape<K>::ST;
+  const size_t per_warp = (size_t)v.bwd_words * ST * sizeof(R);
+  const int total_warps = (B + WPW - 1) / WPW;
+  const int warps = pick_warps(total_warps, per_warp, sm_count);
+  if (warps == 0) { g_err = "model needs " + std::to_string(per_warp) + " B of shared memory per warp (> 227 KB)"; return NB2_ERR_UNSUPPORTED; }
+  static bool attr_set = false;
+  if (!attr_set) {
+    NB2_CUDA(cudaFuncSetAttribute(k_step_bwd<R, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+    attr_set = true;
+  }
+  const int blocks = (total_warps + warps - 1) / warps;
+  k_step_bwd<R, K><<<blocks, warps * 32, per_warp * warps, st>>>(M, B, state, action, saved, gnext, gstate, gaction, v.bwd_words);
   g_launches++;
   NB2_CUDA(cudaGetLastError());
   return NB2_OK;
+}
+template <class R>
+static int launch_bwd(nb2_model* m, int B, const float* state, const float* action,
+                      const R* saved, const float* gnext, float* gstate, float* gaction, cudaStream_t st) {
+  const nb2_variant& v = pick_variant(m, B);
+  const Nb2ModelDev<R>& M = model_of<R>(v);
+  switch (M.lanes) {
+    case 1: return launch_bwd_k<R, 1>(v, m->sm_count, M, B, state, action, saved, gnext, gstate, gaction, st);
+    case 2: return launch_bwd_k<R, 2>(v, m->sm_count, M, B, state, action, saved, gnext, gstate, gaction, st);
+    case 4: return launch_bwd_k<R, 4>(v, m->sm_count, M, B, state, action, saved, gnext, gstate, gaction, st);
+    case 8: return launch_bwd_k<R, 8>(v, m->sm_count, M, B, state, action, saved, gnext, gstate, gaction, st);
+  }
+  g_err = "bad lane count"; return NB2_ERR_INVALID;
 }
 
 extern "C" {
@@ -179,8 +266,13 @@ int nb2_model_create(const nb2_model_desc* desc, nb2_model** out) {
     if (!nb2_fill_contact(*desc, m->contact, err)) { g_err = err; delete m; return NB2_ERR_UNSUPPORTED; }
     m->has_contacts = true;
   }
-  m->fwd_words = nb2::fwd_layout(m->mf.nb, m->mf.ndof, m->mf.nslots, m->mf.nfree).total;
-  m->bwd_words = nb2::bwd_layout(m->mf.nb, m->mf.ndof, m->mf.nslots, m->mf.nfree).total;
+  {
+    nb2_variant v;
+    v.mf = m->mf; v.md = m->md;
+    v.fwd_words = nb2::fwd_layout(m->mf.nb, m->mf.ndof, m->mf.nslots, m->mf.nfree).total;
+    v.bwd_words = nb2::bwd_layout(m->mf.nb, m->mf.ndof, m->mf.nslots, m->mf.nfree).total;
+    m->variants.push_back(v);
+  }
   m->saved_words = nb2_saved_words(m->mf.nb, m->mf.ndof, m->mf.nfree);
   int dev = 0;
   cudaDeviceProp prop;
@@ -193,6 +285,38 @@ int nb2_model_create(const nb2_model_desc* desc, nb2_model** out) {
   *out = m;
   return NB2_OK;
 }
+
+int nb2_model_add_schedule(nb2_model* m, const nb2_model_desc* desc) {
+  if (!m || !desc) { g_err = "null argument"; return NB2_ERR_INVALID; }
+  nb2_variant v;
+  std::string err;
+  if (!nb2_fill_model(*desc, v.mf, err) || !nb2_fill_model(*desc, v.md, err)) { g_err = err; return NB2_ERR_INVALID; }
+  // same bodies, same numbering: only the sweep schedule (lanes, slots, handoff flags) may differ
+  bool same = v.md.nb == m->md.nb && v.md.ndof == m->md.ndof && v.md.na == m->md.na && v.md.nfree == m->md.nfree && v.md.dt == m->md.dt;
+  for (int i = 0; same && i < m->md.nb; i++) {
+    same = v.md.parent[i] == m->md.parent[i] && v.md.jtype[i] == m->md.jtype[i] && v.md.dof_off[i] == m->md.dof_off[i];
+    for (int k = 0; same && k < 12; k++) same = v.md.Xtree[i][k] == m->md.Xtree[i][k];
+    for (int k = 0; same && k < 10; k++) same = v.md.inertia[i][k] == m->md.inertia[i][k];
+  }
+  if (!same) { g_err = "nb2_model_add_schedule: the descriptor describes a different model"; return NB2_ERR_INVALID; }
+  for (const auto& o : m->variants) if (o.mf.lanes == v.mf.lanes) { g_err = "nb2_model_add_schedule: a schedule with this lane count exists"; return NB2_ERR_INVALID; }
+  v.fwd_words = nb2::fwd_layout(v.mf.nb, v.mf.ndof, v.mf.nslots, v.mf.nfree).total;
+  v.bwd_words = nb2::bwd_layout(v.mf.nb, v.mf.ndof, v.mf.nslots, v.mf.nfree).total;
+  std::lock_guard<std::mutex> lk(m->mu);
+  m->variants.push_back(v);
+  return NB2_OK;
+}
+int nb2_model_set_lanes(nb2_model* m, int lanes) {
+  if (!m) { g_err = "null argument"; return NB2_ERR_INVALID; }
+  if (lanes != 0) {
+    bool found = false;
+    for (const auto& o : m->variants) found = found || o.mf.lanes == lanes;
+    if (!found) { g_err = "nb2_model_set_lanes: no schedule with " + std::to_string(lanes) + " lanes was added"; return NB2_ERR_INVALID; }
+  }
+  m->forced_lanes = lanes;
+  return NB2_OK;
+}
+int nb2_model_lanes_for(const nb2_model* m, int B) { return (m && B > 0) ? pick_variant(m, B).mf.lanes : -1; }
 
 void nb2_model_destroy(nb2_model* m) {
   if (!m) return;
@@ -216,7 +340,7 @@ int nb2_step_forward_contact(const nb2_model* cm, int B, const float* state, con
   if (!m->has_contacts) { g_err = "nb2_step_forward_contact: the model has no collision pairs"; return NB2_ERR_INVALID; }
   if (B == 0) return NB2_OK;
   cudaStream_t st = (cudaStream_t)stream;
-  int rc = launch_fwd<double>(m, m->md, B, state, action, next_state, (double*)saved_fp64, st, 1);
+  int rc = launch_fwd<double>(m, B, state, action, next_state, (double*)saved_fp64, st);
   if (rc) return rc;
   const int threads = 32;
   k_contact_fwd<<<(B + threads - 1) / threads, threads, 0, st>>>(m->md, m->contact, B, state, next_state, (const double*)saved_fp64,
@@ -263,8 +387,8 @@ int nb2_step_forward(const nb2_model* cm, int B, const float* state, const float
   if (!m || B < 0 || !state || !action || !next_state) { g_err = "nb2_step_forward: bad argument"; return NB2_ERR_INVALID; }
   if (B == 0) return NB2_OK;
   cudaStream_t st = (cudaStream_t)stream;
-  if (precision == NB2_FP64) return launch_fwd<double>(m, m->md, B, state, action, next_state, (double*)saved, st, 1);
-  return launch_fwd<float>(m, m->mf, B, state, action, next_state, (float*)saved, st, 0);
+  if (precision == NB2_FP64) return launch_fwd<double>(m, B, state, action, next_state, (double*)saved, st);
+  return launch_fwd<float>(m, B, state, action, next_state, (float*)saved, st);
 }
 
 int nb2_step_backward(const nb2_model* cm, int B, const float* state, const float* action, const void* saved,
@@ -276,8 +400,8 @@ int nb2_step_backward(const nb2_model* cm, int B, const float* state, const floa
   }
   if (B == 0) return NB2_OK;
   cudaStream_t st = (cudaStream_t)stream;
-  if (precision == NB2_FP64) return launch_bwd<double>(m, m->md, B, state, action, (const double*)saved, grad_next_state, grad_state, grad_action, st, 3);
-  return launch_bwd<float>(m, m->mf, B, state, action, (const float*)saved, grad_next_state, grad_state, grad_action, st, 2);
+  if (precision == NB2_FP64) return launch_bwd<double>(m, B, state, action, (const double*)saved, grad_next_state, grad_state, grad_action, st);
+  return launch_bwd<float>(m, B, state, action, (const float*)saved, grad_next_state, grad_state, grad_action, st);
 }
 
 static int ensure_host_buffers(nb2_model* m, int B) {

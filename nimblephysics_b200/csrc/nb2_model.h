@@ -14,15 +14,19 @@
 #define NB2_JT_FREE 3  // q = [log R; p], qdot = body twist:        S = I6  (DART_USE_IDENTITY_JACOBIAN build)
 
 // flags
-#define NB2_F_HANDOFF 1      // parent == i-1: leaf->root sweeps hand the contribution to the parent in registers
-#define NB2_F_FIRST_DEPOSIT 2  // first deposit into the parent's accumulator slot: store instead of add
-#define NB2_F_HAS_SLOT 4     // body owns an accumulator slot
+#define NB2_F_HANDOFF 1   // parent == i-1 and swept by the same lane: leaf->root sweeps hand the contribution over in registers
+#define NB2_F_HAS_SLOT 4  // body owns slot_count[i] consecutive slots starting at slot_self[i], one per non-handoff child
+
+// cooperative lanes: up to NB2_MAX_LANES threads share one world; each owns up to NB2_MAX_RANGES contiguous body ranges
+#define NB2_MAX_LANES 8
+#define NB2_MAX_RANGES 8
 
 template <class R>
 struct Nb2ModelDev {
   int nb, ndof, na, nslots;
   int nfree;        // number of FREE bodies
-  int pad0, pad1, pad2;
+  int lanes;        // threads cooperating on one world (1, 2, 4 or 8)
+  int trunk_n, pad2;
   R dt;
   R gravity[3];
   int16_t parent[NB2_MAX_BODIES];
@@ -30,7 +34,12 @@ struct Nb2ModelDev {
   int16_t dof_off[NB2_MAX_BODIES];
   int16_t flags[NB2_MAX_BODIES];
   int16_t slot_self[NB2_MAX_BODIES];
-  int16_t slot_parent[NB2_MAX_BODIES];
+  int16_t slot_parent[NB2_MAX_BODIES];  // the slot THIS body writes its contribution to (-1: handoff or root)
+  int16_t slot_count[NB2_MAX_BODIES];
+  // schedule: lane 0 sweeps the trunk (ancestor-closed), every lane sweeps its limb subtrees (half-open body ranges)
+  int16_t trunk_lo[NB2_MAX_RANGES], trunk_hi[NB2_MAX_RANGES];
+  int16_t limb_n[NB2_MAX_LANES];
+  int16_t limb_lo[NB2_MAX_LANES][NB2_MAX_RANGES], limb_hi[NB2_MAX_LANES][NB2_MAX_RANGES];
   int16_t free_idx[NB2_MAX_BODIES];  // index among FREE bodies or -1
   R Xtree[NB2_MAX_BODIES][12];       // R row-major (9), p (3): x_parent = R x_child + p at q = 0
   R inertia[NB2_MAX_BODIES][10];     // m, h(3) = m c, Ibar(6: xx,yy,zz,xy,xz,yz) about the body origin

@@ -14,7 +14,10 @@ FP32, FP64 = 0, 1
 class DeviceModel:
     """nb2_model wrapper (include/nb2.h).  One per (World version)."""
 
-    def __init__(self, cm: CanonModel):
+    def __init__(self, cm: CanonModel, schedules=()):
+        """cm: the canonical model (its own schedule, normally lanes=1, is what the contact kernels sweep with);
+        schedules: further compilations of the SAME RawModel with other lane counts (modelspec.compile_model(raw, lanes=K));
+        the library picks one per launch from the batch size (include/nb2.h nb2_model_add_schedule)."""
         self.cm = cm
         self.ndof = cm.ndof
         self.na = len(cm.action_map)
@@ -25,6 +28,38 @@ class DeviceModel:
         self.handle = h
         self.saved_words = L.nb2_saved_words_per_world(h)
         self.has_contacts = bool(L.nb2_model_has_contacts(h))
+        self.schedules = [cm]
+        for c in schedules:
+            d, keep = _cabi.make_desc(c, with_contacts=False)
+            _cabi.check(L.nb2_model_add_schedule(h, ctypes.byref(d)))
+            self.schedules.append(c)
+
+    @classmethod
+    def from_raw(cls, raw: RawModel, lanes=(1, 2, 4, 8), contacts=True):
+        """Compile `raw` once per lane count that shortens the sequential depth of a sweep (trunk + longest limb set)."""
+        cms, best = [], None
+        for K in sorted(lanes):
+            try:
+                c = compile_model(raw, lanes=K)
+            except ValueError:
+                if K == 1:
+                    raise
+                continue
+            depth = sum(hi - lo for lo, hi in c.trunk_ranges) + max(sum(hi - lo for lo, hi in rs) for rs in c.limb_ranges)
+            if best is None or depth < best:
+                cms.append(c)
+                best = depth
+        if not contacts:
+            for c in cms:
+                c.shape_body = c.shape_body[:0]
+        return cls(cms[0], cms[1:])
+
+    def set_lanes(self, lanes: int):
+        """Pin the lane count (0 = automatic choice per launch)."""
+        _cabi.check(_cabi.lib().nb2_model_set_lanes(self.handle, int(lanes)))
+
+    def lanes_for(self, B: int) -> int:
+        return int(_cabi.lib().nb2_model_lanes_for(self.handle, int(B)))
 
     def __del__(self):
         try:
@@ -95,9 +130,7 @@ def device_model_for(world) -> DeviceModel:
         return dm
     raw = flatten_world(world)
     world._raw_model = raw
-    cm = compile_model(raw)
-    if getattr(world, "_contacts_disabled", False):
-        cm.shape_body = cm.shape_body[:0]  # contact-free step requested explicitly
-    dm = DeviceModel(cm)
+    # contact-free step requested explicitly -> contacts=False
+    dm = DeviceModel.from_raw(raw, contacts=not getattr(world, "_contacts_disabled", False))
     world._device_model = dm
     return dm

@@ -224,9 +224,15 @@ class CanonModel:
     flags: np.ndarray = None  # bit0: hand result to parent in registers (parent == i-1)
     #                            bit1: first deposit into the parent's accumulator slot (store, not add)
     #                            bit2: body owns an accumulator slot (has a non-handoff child)
-    slot_self: np.ndarray = None  # accumulator slot owned by this body or -1
-    slot_parent: np.ndarray = None  # slot of the parent to deposit into, or -1
+    slot_self: np.ndarray = None  # first incoming accumulator slot of this body (or -1); it owns slot_count consecutive slots
+    slot_count: np.ndarray = None  # number of incoming slots (= children that cannot hand off in registers)
+    slot_parent: np.ndarray = None  # slot this body deposits its contribution to the parent into, or -1 (register handoff / root)
     nslots: int = 0
+    # cooperative-lane schedule: `lanes` threads work on one world.  Phase "trunk" is run by lane 0 over trunk_ranges,
+    # phase "limbs" by every lane over its own limb_ranges; ranges are [lo, hi) in canonical (DFS pre-order) numbering.
+    lanes: int = 1
+    trunk_ranges: List = field(default_factory=list)
+    limb_ranges: List = field(default_factory=list)  # per lane: list of (lo, hi)
     orig_body: np.ndarray = None  # [nb] raw body index this canonical body stems from
     # per dof
     damping: np.ndarray = None
@@ -281,7 +287,58 @@ def _spatial_inertia_about_origin(mass, com, Ic):
     return mass, mass * c, Ibar
 
 
-def compile_model(raw: RawModel) -> CanonModel:
+def _ranges(idx):
+    """sorted indices -> list of contiguous [lo, hi) ranges"""
+    out = []
+    for i in idx:
+        if out and out[-1][1] == i:
+            out[-1][1] = i + 1
+        else:
+            out.append([i, i + 1])
+    return [(a, b) for a, b in out]
+
+
+def _partition_tree(parent, lanes):
+    """Split a forest (DFS pre-order numbering) into an ancestor-closed TRUNK and disjoint LIMB subtrees so that
+    |trunk| + max(load per lane) — the sequential depth of one sweep with `lanes` cooperating threads — is small."""
+    nb = len(parent)
+    if lanes <= 1 or nb == 0:
+        return list(range(nb)), []
+    kids = {i: [] for i in range(-1, nb)}
+    for i in range(nb):
+        kids[int(parent[i])].append(i)
+    size = [1] * nb
+    for i in range(nb - 1, -1, -1):
+        if parent[i] >= 0:
+            size[int(parent[i])] += size[i]
+
+    def subtree(r):
+        return list(range(r, r + size[r]))  # contiguous in pre-order
+
+    def cost(trunk_n, limb_roots):
+        loads = [0] * lanes
+        for sz in sorted((size[r] for r in limb_roots), reverse=True):
+            loads[loads.index(min(loads))] += sz
+        return trunk_n + max(loads) if limb_roots else trunk_n
+
+    trunk = set()
+    limb_roots = list(kids[-1])
+    best = (cost(0, limb_roots), set(trunk), list(limb_roots))
+    for _ in range(nb):
+        if not limb_roots:
+            break
+        r = max(limb_roots, key=lambda x: size[x])
+        limb_roots.remove(r)
+        trunk.add(r)
+        limb_roots.extend(kids[r])
+        c = cost(len(trunk), limb_roots)
+        if c < best[0]:
+            best = (c, set(trunk), list(limb_roots))
+    _, trunk, limb_roots = best
+    return sorted(trunk), [subtree(r) for r in limb_roots]
+
+
+def compile_model(raw: RawModel, lanes: int = 1) -> CanonModel:
     nb = raw.nb
     # world pose bookkeeping is done with 4x4s: for every raw body keep
     #   rel[i]  : constant transform parent-body-frame <- joint frame (T_pj)
@@ -394,33 +451,48 @@ def compile_model(raw: RawModel) -> CanonModel:
         inertia[k, 4:10] += [Ibar[0, 0], Ibar[1, 1], Ibar[2, 2], Ibar[0, 1], Ibar[0, 2], Ibar[1, 2]]
     cm.inertia = inertia
 
-    # accumulator slots for the leaf->root sweeps (processing order = reverse index order)
+    # ---- cooperative-lane schedule + accumulator slots for the leaf->root sweeps
+    trunk, limbs = _partition_tree(cm.parent, lanes)
+    cm.lanes = lanes
+    cm.trunk_ranges = _ranges(sorted(trunk))
+    lane_bodies = [[] for _ in range(lanes)]
+    for li, limb in enumerate(sorted(limbs, key=lambda l: -len(l))):
+        k = min(range(lanes), key=lambda kk: len(lane_bodies[kk]))  # greedy balance
+        lane_bodies[k].extend(limb)
+    cm.limb_ranges = [_ranges(sorted(bs)) for bs in lane_bodies]
+    if len(cm.trunk_ranges) > 8 or any(len(rs) > 8 for rs in cm.limb_ranges):  # NB2_MAX_RANGES (csrc/nb2_model.h)
+        raise ValueError(f"the {lanes}-lane schedule of this tree needs more than 8 body ranges per lane")
+    # which range does a body belong to?  register handoff (child -> parent = child-1) only inside one range
+    range_id = {}
+    rid = 0
+    for (lo, hi) in cm.trunk_ranges:
+        for i in range(lo, hi):
+            range_id[i] = rid
+        rid += 1
+    for rs in cm.limb_ranges:
+        for (lo, hi) in rs:
+            for i in range(lo, hi):
+                range_id[i] = rid
+            rid += 1
     flags = np.zeros(cm.nb, np.int32)
     slot_self = np.full(cm.nb, -1, np.int32)
+    slot_count = np.zeros(cm.nb, np.int32)
     slot_parent = np.full(cm.nb, -1, np.int32)
-    free_slots: List[int] = []
     nslots = 0
-    for i in range(cm.nb - 1, -1, -1):
-        if slot_self[i] >= 0:
-            flags[i] |= 4
-            free_slots.append(int(slot_self[i]))  # released once i has consumed it
-        p = cm.parent[i]
-        if p < 0:
-            continue
-        if p == i - 1:
-            flags[i] |= 1
-            continue
-        if slot_self[p] < 0:
-            if free_slots:
-                slot_self[p] = free_slots.pop()
-            else:
-                slot_self[p] = nslots
+    for p_ in range(cm.nb):
+        kids_ = [c for c in range(cm.nb) if cm.parent[c] == p_]
+        cross = [c for c in kids_ if not (c == p_ + 1 and range_id[c] == range_id[p_])]
+        for c in kids_:
+            if c not in cross:
+                flags[c] |= 1  # NB2_F_HANDOFF
+        if cross:
+            slot_self[p_] = nslots
+            slot_count[p_] = len(cross)
+            flags[p_] |= 4  # NB2_F_HAS_SLOT
+            for c in cross:
+                slot_parent[c] = nslots
                 nslots += 1
-            flags[i] |= 2
-        slot_parent[i] = slot_self[p]
-    # a slot released by body i may only be reused by deposits that happen after i is processed:
-    # the loop above hands out free slots strictly later in processing order, so this holds.
-    cm.flags, cm.slot_self, cm.slot_parent, cm.nslots = flags, slot_self, slot_parent, nslots
+    cm.flags, cm.slot_self, cm.slot_count, cm.slot_parent, cm.nslots = flags, slot_self, slot_count, slot_parent, nslots
 
     for k in ("damping", "spring", "rest", "pos_lo", "pos_hi", "vel_lo", "vel_hi", "force_lo", "force_hi"):
         setattr(cm, k, getattr(raw, k).copy())

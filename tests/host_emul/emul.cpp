@@ -16,8 +16,13 @@ static int run_fwd(const nb2_model_desc* d, int B, const float* state, const flo
   std::vector<float> dummy;
   for (int w = 0; w < B; w++) {
     for (auto& x : scr) x = R(1e30);  // poison: catches reads of never-written scratch
-    nb2::world_forward<R, 1>(M, scr.data(), state + (size_t)w * 2 * M.ndof, action + (size_t)w * M.na,
-                             next + (size_t)w * 2 * M.ndof, saved ? saved + w : nullptr, (size_t)B, saved != nullptr);
+    // cooperative lanes are emulated stage by stage; odd worlds run the lanes in reverse order so that a missing
+    // barrier (a cross-lane dependency inside one stage) shows up as a poisoned read / wrong result
+    for (int sg = 0; sg < NB2_FWD_STAGES; sg++)
+      for (int l = 0; l < M.lanes; l++)
+        nb2::world_forward_stage<R, 1>(M, scr.data(), state + (size_t)w * 2 * M.ndof, action + (size_t)w * M.na,
+                                       next + (size_t)w * 2 * M.ndof, saved ? saved + w : nullptr, (size_t)B, saved != nullptr,
+                                       (w & 1) ? M.lanes - 1 - l : l, sg);
   }
   return 0;
 }
@@ -30,9 +35,11 @@ static int run_bwd(const nb2_model_desc* d, int B, const float* state, const flo
   std::vector<R> scr(L.total);
   for (int w = 0; w < B; w++) {
     for (auto& x : scr) x = R(1e30);
-    nb2::world_backward<R, 1>(M, scr.data(), state + (size_t)w * 2 * M.ndof, action + (size_t)w * M.na,
-                              gnext + (size_t)w * 2 * M.ndof, saved + w, (size_t)B, gstate + (size_t)w * 2 * M.ndof,
-                              gaction + (size_t)w * M.na);
+    for (int sg = 0; sg < NB2_BWD_STAGES; sg++)
+      for (int l = 0; l < M.lanes; l++)
+        nb2::world_backward_stage<R, 1>(M, scr.data(), state + (size_t)w * 2 * M.ndof, action + (size_t)w * M.na,
+                                        gnext + (size_t)w * 2 * M.ndof, saved + w, (size_t)B, gstate + (size_t)w * 2 * M.ndof,
+                                        gaction + (size_t)w * M.na, (w & 1) ? M.lanes - 1 - l : l, sg);
   }
   return 0;
 }

@@ -169,3 +169,41 @@ def test_rollout_through_autograd_matches_oracle_chain(oracle_mod):
     assert rel_err(x[w].detach().cpu().numpy(), xs[-1]) < TOL
     assert rel_err(st.grad[w].cpu().numpy(), gq) < 5e-4
     assert rel_err(ats[0].grad[w].cpu().numpy(), ga_ref[0]) < 5e-4
+
+
+@pytest.mark.parametrize("name", ["half_cheetah", "atlas"])
+def test_cooperative_lane_schedules_agree(oracle_mod, name):
+    """The library sweeps a world with 1, 2, 4 or 8 cooperating threads depending on the batch size
+    (include/nb2.h nb2_model_add_schedule).  Every schedule must give the same numbers: children are accumulated in
+    the same order whichever lane produced them, so the results are expected to agree to the last bit."""
+    raw, world = _world(name)
+    dm = nb.device_model_for(world)
+    ow = oracle_mod.OracleWorld(raw)
+    B = 1000  # not a multiple of the worlds-per-warp of any schedule: exercises the partial last warp
+    s, a, g = sample_inputs(raw, B, seed=35)
+    sd, ad, gd = (torch.tensor(x, device="cuda") for x in (s, a, g))
+    stream = torch.cuda.current_stream().cuda_stream
+    res = {}
+    lanes = sorted(int(c.lanes) for c in dm.schedules)
+    assert lanes[0] == 1 and len(lanes) > 1
+    try:
+        for K in lanes:
+            dm.set_lanes(K)
+            assert dm.lanes_for(B) == K
+            nxt = torch.full_like(sd, float("nan"))
+            saved = torch.empty((dm.saved_words, B), device="cuda")
+            gs, ga = torch.full_like(sd, float("nan")), torch.full_like(ad, float("nan"))
+            dm.forward_device(B, sd.data_ptr(), ad.data_ptr(), nxt.data_ptr(), saved.data_ptr(), stream, 0)
+            dm.backward_device(B, sd.data_ptr(), ad.data_ptr(), saved.data_ptr(), gd.data_ptr(), gs.data_ptr(), ga.data_ptr(), stream, 0)
+            torch.cuda.synchronize()
+            res[K] = (nxt.cpu().numpy(), gs.cpu().numpy(), ga.cpu().numpy(), saved.cpu().numpy())
+    finally:
+        dm.set_lanes(0)
+    for K in lanes[1:]:
+        for x, y in zip(res[1], res[K]):
+            assert np.array_equal(x, y), f"schedule with {K} lanes differs from the single-thread sweep"
+    for w in range(0, B, 97):
+        s64, a64, g64 = s[w].astype(np.float64), a[w].astype(np.float64), g[w].astype(np.float64)
+        rgs, rga = ow.backprop(s64, a64, g64)
+        K = lanes[-1]
+        assert rel_err(res[K][0][w], ow.step(s64, a64)) < TOL and rel_err(res[K][1][w], rgs) < TOL and rel_err(res[K][2][w], rga) < TOL

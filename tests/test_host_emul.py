@@ -14,9 +14,12 @@ TOL = 1e-4
 
 @pytest.mark.parametrize("name", ["cartpole", "half_cheetah", "atlas"])
 @pytest.mark.parametrize("fp64", [False, True])
-def test_forward_backward_parity(oracle_mod, name, fp64):
+@pytest.mark.parametrize("lanes", [1, 2, 4, 8])
+def test_forward_backward_parity(oracle_mod, name, fp64, lanes):
+    """lanes > 1: several threads cooperate on one world (trunk/limb stages, emulated with the lanes of odd worlds
+    running in reverse order so that a cross-lane dependency inside one stage cannot hide)."""
     raw = load_raw(name)
-    cm = nb.compile_model(raw)
+    cm = nb.compile_model(raw, lanes=lanes)
     ow, ew = oracle_mod.OracleWorld(raw), EmulWorld(cm)
     B = 6
     s, a, g = sample_inputs(raw, B, seed=21)
@@ -36,7 +39,7 @@ def test_weld_folding_and_canonical_frames_preserve_dynamics(oracle_mod):
     from tests.test_oracle import _tree_world
 
     raw = nb.flatten_world(_tree_world())
-    cm = nb.compile_model(raw)
+    cm = nb.compile_model(raw, lanes=2)
     assert cm.nb == raw.nb - 1  # one weld folded
     ow, ew = oracle_mod.OracleWorld(raw), EmulWorld(cm)
     s, a, g = sample_inputs(raw, 3, seed=2)

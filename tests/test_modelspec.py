@@ -44,26 +44,56 @@ def test_canonical_model_invariants(name):
     moving_mass = sum(raw.mass[i] for i in range(raw.nb) if i not in static)
     # bodies welded to the world inside a mobile skeleton are static too
     assert cm.inertia[:, 0].sum() <= moving_mass + 1e-9
-    # accumulator-slot discipline: a handoff body's parent is i-1; deposits target the parent's slot
+    _check_slots_and_schedule(cm)
+
+
+def _check_slots_and_schedule(cm):
+    # accumulator-slot discipline: a handoff body's parent is i-1; every other child owns ONE private slot inside the
+    # parent's block [slot_self, slot_self + slot_count)
+    used = set()
     for i in range(cm.nb):
+        p = int(cm.parent[i])
         if cm.flags[i] & 1:
-            assert cm.parent[i] == i - 1
-        elif cm.parent[i] >= 0:
-            assert cm.slot_parent[i] == cm.slot_self[cm.parent[i]] >= 0
-    # simulate the reverse sweep and check no slot is overwritten while live
-    live = {}
-    for i in range(cm.nb - 1, -1, -1):
-        if cm.slot_self[i] >= 0:
-            assert live.pop(int(cm.slot_self[i])) == i
-        p = cm.parent[i]
-        if p >= 0 and not (cm.flags[i] & 1):
+            assert p == i - 1
+        elif p >= 0:
             sl = int(cm.slot_parent[i])
-            if cm.flags[i] & 2:
-                assert sl not in live
-                live[sl] = int(p)
-            else:
-                assert live[sl] == p
-    assert not live
+            assert cm.flags[p] & 4 and cm.slot_self[p] <= sl < cm.slot_self[p] + cm.slot_count[p]
+            assert sl not in used and 0 <= sl < cm.nslots
+            used.add(sl)
+    assert len(used) == cm.nslots == int(cm.slot_count.sum())
+    # schedule: trunk + limbs partition the bodies; the trunk is ancestor-closed; a limb body's parent is in the trunk
+    # or swept by the same lane; register handoff never crosses a range
+    owner, rng = {}, {}
+    rid = 0
+    for (lo, hi) in cm.trunk_ranges:
+        for i in range(lo, hi):
+            assert i not in owner
+            owner[i], rng[i] = -1, rid
+        rid += 1
+    assert len(cm.limb_ranges) == cm.lanes
+    for lane, rs in enumerate(cm.limb_ranges):
+        assert len(rs) <= 8
+        for (lo, hi) in rs:
+            for i in range(lo, hi):
+                assert i not in owner
+                owner[i], rng[i] = lane, rid
+            rid += 1
+    assert sorted(owner) == list(range(cm.nb)) and len(cm.trunk_ranges) <= 8
+    for i in range(cm.nb):
+        p = int(cm.parent[i])
+        if p >= 0:
+            assert owner[p] in (-1, owner[i])
+            if cm.flags[i] & 1:
+                assert rng[p] == rng[i]
+
+
+@pytest.mark.parametrize("name", ["cartpole", "half_cheetah", "atlas"])
+@pytest.mark.parametrize("lanes", [2, 4, 8])
+def test_cooperative_schedule(name, lanes):
+    cm = nb.compile_model(load_raw(name), lanes=lanes)
+    _check_slots_and_schedule(cm)
+    if name == "atlas" and lanes == 4:  # the four limbs run side by side: sequential depth 4 + 6 instead of 28 bodies
+        assert sum(hi - lo for lo, hi in cm.trunk_ranges) + max(sum(hi - lo for lo, hi in rs) for rs in cm.limb_ranges) <= 12
 
 
 def test_builder_surface_matches_reference_example():
