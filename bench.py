@@ -224,7 +224,7 @@ def main():
     dm = nb.DeviceModel.from_raw(raw)
     if args.lanes:
         dm.set_lanes(args.lanes)
-    lanes_used = dm.lanes_for(B)
+    lanes_used = {"fwd": dm.lanes_for(B, False, prec), "bwd": dm.lanes_for(B, True, prec)}
     per_set = 4 * B * (2 * n * 4 + 2 * na + dm.saved_words * (2 if prec == FP64 else 1))
     nsets = max(2, int(np.ceil(160e6 / per_set)))
     sets = []

@@ -80,12 +80,13 @@ typedef struct nb2_model_desc {
 
 int nb2_model_create(const nb2_model_desc* desc, nb2_model** out);
 /* Register one more sweep schedule of the SAME model (desc identical except lanes / flags / slot_* / nslots / sched).
- * The step entry points then pick, per launch, the widest schedule the batch leaves room for (small batches are
- * latency bound: several threads cooperate on one world; large batches are throughput bound: one thread per world).
- * nb2_model_set_lanes pins the choice (0 = automatic); nb2_model_lanes_for reports it for a batch size. */
+ * The step entry points then pick, per launch, the schedule with the lowest estimated cost
+ * (sequential depth of the schedule x waves the batch needs at that schedule's occupancy): small batches are latency
+ * bound and get several threads per world, large ones fewer.  Register schedules before the first step call.
+ * nb2_model_set_lanes pins the choice (0 = automatic); nb2_model_lanes_for reports it (backward: 0/1, precision: nb2_precision). */
 int nb2_model_add_schedule(nb2_model* m, const nb2_model_desc* desc);
 int nb2_model_set_lanes(nb2_model* m, int lanes);
-int nb2_model_lanes_for(const nb2_model* m, int B);
+int nb2_model_lanes_for(nb2_model* m, int B, int backward, int precision);
 void nb2_model_destroy(nb2_model* m);
 int nb2_model_ndof(const nb2_model* m);
 int nb2_model_na(const nb2_model* m);
@@ -99,10 +100,13 @@ int nb2_saved_words_per_world(const nb2_model* m);
 int nb2_step_forward(const nb2_model* m, int B, const float* state, const float* action, float* next_state,
                      void* saved, int precision, void* stream);
 
-/* Vector-Jacobian product of the same step: grad_next_state [B,2n] -> grad_state [B,2n], grad_action [B,na]. */
+/* Vector-Jacobian product of the same step: grad_next_state [B,2n] -> grad_state [B,2n], grad_action [B,na].
+ * grad_inertia (may be NULL): [10*nb][B] floats, dL/d(m, h=m*c (3), Ibar xx,yy,zz,xy,xz,yz about the body origin) of every
+ * canonical body and world — the raw material of lossWrtMass (BackpropSnapshot.cpp:167-178, WithRespectToMass.cpp);
+ * the host contracts it with d(canonical inertia)/d(mass vector) (modelspec.inertia_param_jacobian). Contact-free step only. */
 int nb2_step_backward(const nb2_model* m, int B, const float* state, const float* action, const void* saved,
-                      const float* grad_next_state, float* grad_state, float* grad_action, int precision,
-                      void* stream);
+                      const float* grad_next_state, float* grad_state, float* grad_action, float* grad_inertia,
+                      int precision, void* stream);
 
 /* Same two calls with HOST buffers (pageable or pinned): H2D copies, kernels, D2H copies, synchronised on return. */
 int nb2_step_forward_host(nb2_model* m, int B, const float* state, const float* action, float* next_state,

@@ -128,13 +128,13 @@ def lib() -> ctypes.CDLL:
         L.nb2_model_destroy.argtypes = [ctypes.c_void_p]
         L.nb2_model_add_schedule.argtypes = [ctypes.c_void_p, ctypes.POINTER(Nb2ModelDesc)]
         L.nb2_model_set_lanes.argtypes = [ctypes.c_void_p, ctypes.c_int]
-        L.nb2_model_lanes_for.argtypes = [ctypes.c_void_p, ctypes.c_int]
+        L.nb2_model_lanes_for.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int]
         L.nb2_model_ndof.argtypes = [ctypes.c_void_p]
         L.nb2_model_na.argtypes = [ctypes.c_void_p]
         L.nb2_saved_words_per_world.argtypes = [ctypes.c_void_p]
         vp = ctypes.c_void_p
         L.nb2_step_forward.argtypes = [vp, ctypes.c_int, vp, vp, vp, vp, ctypes.c_int, vp]
-        L.nb2_step_backward.argtypes = [vp, ctypes.c_int, vp, vp, vp, vp, vp, vp, ctypes.c_int, vp]
+        L.nb2_step_backward.argtypes = [vp, ctypes.c_int, vp, vp, vp, vp, vp, vp, vp, ctypes.c_int, vp]
         L.nb2_model_has_contacts.argtypes = [vp]
         L.nb2_contact_workspace_bytes.argtypes = [vp, ctypes.c_int]
         L.nb2_contact_workspace_bytes.restype = ctypes.c_size_t

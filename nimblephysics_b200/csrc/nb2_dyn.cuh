@@ -302,7 +302,8 @@ NB2_HD void fwd_pass3(const Nb2ModelDev<R>& M, R* scr, float* out, R* sv, size_t
       if (save) {
         R* s = sv + (size_t)(i * 21) * B;
         sv_st6(s, B, 0, tof(V)); sv_st6(s, B, 6, tof(A)); sv_st6(s, B, 12, tof(U));
-        s[18 * B] = (R)psi; s[19 * B] = (R)bs[6 * ST]; s[20 * B] = (R)bs[7 * ST];
+        s[18 * B] = (R)psi;
+        s[19 * B] = (jt == NB2_JT_REV) ? (R)bs[6 * ST] : R(0); s[20 * B] = (jt == NB2_JT_REV) ? (R)bs[7 * ST] : R(0);  // sin, cos (revolute only)
         sv[(size_t)(nb * 21 + M.nfree * 33 + o) * B] = qdd;
       }
     } else {
@@ -402,6 +403,15 @@ template <int ST>
 NB2_HD BwdContactData<ST> contact_backward_hook(const Nb2ModelDev<double>& M, const BwdContactHook& H, const float* st, const double* sv, size_t B,
                                             double* scr, int oLam, int oBody);
 
+// d(Y^T G X)/d(m, h(3), Ibar(xx,yy,zz,xy,xz,yz)) for G X = [Ibar w + h x v ; m v - h x w]
+template <class R> NB2_HD void inertia_param_form(const V6<R>& Y, const V6<R>& X, R* t) {
+  t[0] = dot(Y.l, X.l);
+  const V3<R> dh = cross(X.l, Y.a) + cross(Y.l, X.a);
+  t[1] = dh.x; t[2] = dh.y; t[3] = dh.z;
+  t[4] = Y.a.x * X.a.x; t[5] = Y.a.y * X.a.y; t[6] = Y.a.z * X.a.z;
+  t[7] = Y.a.x * X.a.y + Y.a.y * X.a.x; t[8] = Y.a.x * X.a.z + Y.a.z * X.a.x; t[9] = Y.a.y * X.a.z + Y.a.z * X.a.y;
+}
+
 // =====================================================================================================
 // backward: g_next = dL/d[q+;v+]  ->  g_state = dL/d[q;v], g_action = dL/d action
 // =====================================================================================================
@@ -485,7 +495,8 @@ NB2_HD void bwd_B2(const Nb2ModelDev<R>& M, R* scr, const float* st, const R* sv
 }
 
 template <class R, int ST, bool CONTACT>
-NB2_HD void bwd_B3(const Nb2ModelDev<R>& M, R* scr, const float* st, const R* sv, size_t B, const BwdContactData<ST>& cd, int lo, int hi) {
+NB2_HD void bwd_B3(const Nb2ModelDev<R>& M, R* scr, const float* st, const R* sv, size_t B, const BwdContactData<ST>& cd, int lo, int hi,
+                   float* gI = nullptr) {
   const int nb = M.nb, n = M.ndof;
   constexpr int SLOTW = CONTACT ? 42 : 18;
   const BwdLayout L = bwd_layout(nb, n, M.nslots, M.nfree, SLOTW);
@@ -512,6 +523,17 @@ NB2_HD void bwd_B3(const Nb2ModelDev<R>& M, R* scr, const float* st, const R* sv
     const V6<R> W = ld6<R, ST>(scr + (size_t)(L.oBody + 7 * i + 1) * ST);
     const V6<R> GV = mulG(m, h, Ib, V);
     V6<R> f = mulG(m, h, Ib, A) + crf(V, GV);
+    if (gI) {
+      // dL/d(inertia parameters of body i) = -dt * W . d(G A + V x* G V) = -dt * [ t(W, A) - t(ad(V, W), V) ] with
+      // t(Y, X) = d(Y^T G X)/d(m, h, Ibar)   (the mass-vel Jacobian of BackpropSnapshot.cpp:580-640 contracted with g_v')
+      const V6<R> Y2 = ad(V, W);
+      R t[10];
+      inertia_param_form(W, A, t);
+      R t2[10];
+      inertia_param_form(Y2, V, t2);
+#pragma unroll
+      for (int k = 0; k < 10; k++) gI[(size_t)(10 * i + k) * B] = (float)(-dt * (t[k] - t2[k]));
+    }
     V6<R> Abar = mulG(m, h, Ib, W);
     V6<R> Vbar = mulG(m, h, Ib, ad(W, V)) - crf(W, GV);
     if (hvalid) { Abar = Abar + hA; Vbar = Vbar + hV; f = f + hf; }
@@ -683,7 +705,7 @@ NB2_HD void bwd_store(const Nb2ModelDev<R>& M, const R* scr, const float* st, co
 #define NB2_BWD_SYNC_MASK 0x14Bu  /* after stages 0, 1, 3, 6, 8 */
 template <class R, int ST>
 NB2_HD void world_backward_stage(const Nb2ModelDev<R>& M, R* scr, const float* st, const float* act, const float* gnext,
-                                 const R* sv, size_t B, float* gstate, float* gaction, int lane, int stage) {
+                                 const R* sv, size_t B, float* gstate, float* gaction, int lane, int stage, float* gI = nullptr) {
   const int n = M.ndof, K = M.lanes;
   if (stage == 0) {
     const BwdLayout L = bwd_layout(M.nb, n, M.nslots, M.nfree, 18);
@@ -705,7 +727,7 @@ NB2_HD void world_backward_stage(const Nb2ModelDev<R>& M, R* scr, const float* s
     const int lo = trunk ? M.trunk_lo[r] : M.limb_lo[lane][r], hi = trunk ? M.trunk_hi[r] : M.limb_hi[lane][r];
     if (pass == 1) bwd_B1<R, ST, false>(M, scr, st, sv, B, lo, hi);
     else if (pass == 2) bwd_B2<R, ST, false>(M, scr, st, sv, B, lo, hi);
-    else if (pass == 3) bwd_B3<R, ST, false>(M, scr, st, sv, B, cd, lo, hi);
+    else if (pass == 3) bwd_B3<R, ST, false>(M, scr, st, sv, B, cd, lo, hi, gI);
     else bwd_assemble<R, ST, false>(M, scr, st, cd, lo, hi);
   }
 }

@@ -66,7 +66,7 @@ template <class R, int K>
 __global__ void __launch_bounds__(128)
 k_step_bwd(const __grid_constant__ Nb2ModelDev<R> M, int B, const float* __restrict__ state,
            const float* __restrict__ action, const R* __restrict__ saved, const float* __restrict__ gnext,
-           float* __restrict__ gstate, float* __restrict__ gaction, int words) {
+           float* __restrict__ gstate, float* __restrict__ gaction, float* __restrict__ ginertia, int words) {
   extern __shared__ __align__(16) unsigned char nb2_smem[];
   constexpr int WPW = CoopShape<K>::WPW, ST = CoopShape<K>::ST;
   const int li = threadIdx.x & 31, slot = li / K, lane = li % K;
@@ -79,7 +79,8 @@ k_step_bwd(const __grid_constant__ Nb2ModelDev<R> M, int B, const float* __restr
 #pragma unroll 1
   for (int sg = 0; sg < NB2_BWD_STAGES; sg++) {
     if (valid) nb2::world_backward_stage<R, ST>(M, scr, st, ac, gnext + (size_t)wc * 2 * M.ndof, saved + wc, (size_t)B,
-                                                gstate + (size_t)wc * 2 * M.ndof, gaction + (size_t)wc * M.na, lane, sg);
+                                                gstate + (size_t)wc * 2 * M.ndof, gaction + (size_t)wc * M.na, lane, sg,
+                                                ginertia ? ginertia + wc : nullptr);
     if (K > 1 && ((NB2_BWD_SYNC_MASK >> sg) & 1u)) __syncwarp();
   }
 }
@@ -120,28 +121,20 @@ k_step_bwd_contact(const __grid_constant__ Nb2ModelDev<double> M, const __grid_c
 
 constexpr int kMaxSmem = 227 * 1024;
 
-// warps per block: spread small batches over all SMs first (1 warp per block), pack up to 4 warps per block
-// once there are more warps than SMs can hold singly; always bounded by the shared-memory budget.
-int pick_warps(int total_warps, size_t bytes_per_warp, int sm_count) {
-  int fit = (int)(kMaxSmem / bytes_per_warp);
-  if (fit < 1) return 0;
-  int want = (total_warps <= 2 * sm_count) ? 1 : 4;
-  if (want > fit) want = fit;
-  if (want > 4) want = 4;
-  return want;
-}
-
 }  // namespace
 
 // one sweep schedule of the model (same bodies, different lane count / slot assignment)
+struct LaunchShape { int warps_per_block = 0; int resident_warps = 0; };  // filled lazily from the occupancy API
 struct nb2_variant {
   Nb2ModelDev<float> mf;
   Nb2ModelDev<double> md;
   int fwd_words, bwd_words;
+  int depth;                 // bodies on the sequential path of one sweep: |trunk| + longest lane
+  LaunchShape shape[2][2];   // [forward/backward][fp32/fp64]
 };
 
 struct nb2_model {
-  Nb2ModelDev<float> mf;   // the variant given to nb2_model_create (also what the contact kernels use)
+  Nb2ModelDev<float> mf;   // the schedule given to nb2_model_create (also what the contact kernels use)
   Nb2ModelDev<double> md;
   Nb2ContactDev contact;
   bool has_contacts = false;
@@ -163,87 +156,147 @@ template <class R> static const Nb2ModelDev<R>& model_of(const nb2_variant& v);
 template <> const Nb2ModelDev<float>& model_of<float>(const nb2_variant& v) { return v.mf; }
 template <> const Nb2ModelDev<double>& model_of<double>(const nb2_variant& v) { return v.md; }
 
-// Lane count for a launch: cooperative lanes shorten the dependent chain of one world (latency) but idle during the
-// trunk stages (throughput).  Use the widest schedule while the GPU still has free issue slots, i.e. while the batch
-// needs fewer than kCoopWarpsPerSM warps per SM at that width; fall back to the narrowest otherwise.
-constexpr int kCoopWarpsPerSM = 16;
-static const nb2_variant& pick_variant(const nb2_model* m, int B) {
-  const nb2_variant* best = &m->variants[0];
-  if (m->forced_lanes) {
-    for (const auto& v : m->variants) if (v.mf.lanes == m->forced_lanes) return v;
-    return *best;
+static void init_variant(nb2_variant& v) {
+  v.fwd_words = nb2::fwd_layout(v.mf.nb, v.mf.ndof, v.mf.nslots, v.mf.nfree).total;
+  v.bwd_words = nb2::bwd_layout(v.mf.nb, v.mf.ndof, v.mf.nslots, v.mf.nfree).total;
+  int trunk = 0, longest = 0;
+  for (int r = 0; r < v.mf.trunk_n; r++) trunk += v.mf.trunk_hi[r] - v.mf.trunk_lo[r];
+  for (int l = 0; l < v.mf.lanes; l++) {
+    int len = 0;
+    for (int r = 0; r < v.mf.limb_n[l]; r++) len += v.mf.limb_hi[l][r] - v.mf.limb_lo[l][r];
+    if (len > longest) longest = len;
   }
-  int best_k = 0;
-  const nb2_variant* narrow = best;
-  for (const auto& v : m->variants) {
-    const int K = v.mf.lanes;
-    if (K < narrow->mf.lanes) narrow = &v;
-    const long long warps = ((long long)B * K + 31) / 32;
-    if (warps <= (long long)kCoopWarpsPerSM * m->sm_count && K > best_k) { best_k = K; best = &v; }
+  v.depth = trunk + longest;
+}
+
+// ---- launch shape.  The kernels are latency bound (one dependent chain per world), so a launch costs about
+//   (sequential depth of the schedule) x (number of waves the batch needs at that schedule's occupancy).
+// Occupancy is limited by the per-warp scratch in shared memory; blocks of 1, 2 or 4 warps are tried and the shape
+// that keeps most warps resident wins.  Small batches use 1-warp blocks so that they spread over all SMs.
+template <class Kern>
+static LaunchShape occupancy_shape(Kern kern, size_t bytes_per_warp) {
+  LaunchShape best;
+  for (int w = 1; w <= 4; w *= 2) {
+    const size_t smem = bytes_per_warp * w;
+    if (smem > (size_t)kMaxSmem) break;
+    int blocks = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, kern, w * 32, smem) != cudaSuccess) { cudaGetLastError(); continue; }
+    if (blocks * w > best.resident_warps) { best.resident_warps = blocks * w; best.warps_per_block = w; }
   }
-  return best_k ? *best : *narrow;
+  return best;
+}
+
+// warps per block for one launch: a batch that fits in one wave is spread so that every SM gets about the same number of
+// warps in as few blocks as possible (measured: 4 warps in one block beat 4 one-warp blocks on the same SM); beyond one
+// wave the occupancy-optimal shape is used.
+static int block_warps(int total_warps, int sm_count, const LaunchShape& sh, size_t per_warp) {
+  if ((long long)total_warps > (long long)sm_count * sh.resident_warps) return sh.warps_per_block;
+  int w = 1;
+  while (w < 4 && total_warps > sm_count * w && (size_t)(2 * w) * per_warp <= (size_t)kMaxSmem) w *= 2;
+  return w;
+}
+
+template <class R, int K> struct StepKernels {
+  static constexpr int ST = CoopShape<K>::ST, WPW = CoopShape<K>::WPW;
+  static int prepare(nb2_variant& v, int dir) {  // dir 0 forward, 1 backward
+    LaunchShape& sh = v.shape[dir][sizeof(R) == 8];
+    if (sh.warps_per_block) return NB2_OK;
+    const size_t per_warp = (size_t)(dir ? v.bwd_words : v.fwd_words) * ST * sizeof(R);
+    if (per_warp > (size_t)kMaxSmem) { g_err = "model needs " + std::to_string(per_warp) + " B of shared memory per warp (> 227 KB)"; return NB2_ERR_UNSUPPORTED; }
+    if (dir == 0) {
+      NB2_CUDA(cudaFuncSetAttribute(k_step_fwd<R, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+      sh = occupancy_shape(k_step_fwd<R, K>, per_warp);
+    } else {
+      NB2_CUDA(cudaFuncSetAttribute(k_step_bwd<R, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+      sh = occupancy_shape(k_step_bwd<R, K>, per_warp);
+    }
+    if (!sh.warps_per_block) { g_err = "no launch shape fits this model"; return NB2_ERR_UNSUPPORTED; }
+    return NB2_OK;
+  }
+};
+template <class R>
+static int prepare_variant(nb2_variant& v, int dir) {
+  switch (v.mf.lanes) {
+    case 1: return StepKernels<R, 1>::prepare(v, dir);
+    case 2: return StepKernels<R, 2>::prepare(v, dir);
+    case 4: return StepKernels<R, 4>::prepare(v, dir);
+    case 8: return StepKernels<R, 8>::prepare(v, dir);
+  }
+  g_err = "bad lane count"; return NB2_ERR_INVALID;
+}
+
+template <class R>
+static int pick_variant(nb2_model* m, int B, int dir, nb2_variant** out) {
+  nb2_variant* best = nullptr;
+  double best_cost = 0;
+  for (auto& v : m->variants) {
+    if (m->forced_lanes && v.mf.lanes != m->forced_lanes) continue;
+    int rc = prepare_variant<R>(v, dir);
+    if (rc) { if (m->variants.size() == 1 || m->forced_lanes) return rc; continue; }
+    const LaunchShape& sh = v.shape[dir][sizeof(R) == 8];
+    const double warps = ((double)B * v.mf.lanes + 31) / 32;
+    double waves = warps / ((double)m->sm_count * sh.resident_warps);
+    if (waves < 1) waves = 1;
+    const double cost = (v.depth + 3) * waves;   // +3: per-sweep fixed part (loads, stores, barriers)
+    if (!best || cost < best_cost - 1e-9) { best = &v; best_cost = cost; }
+  }
+  if (!best) { g_err = "no usable schedule"; return NB2_ERR_UNSUPPORTED; }
+  *out = best;
+  return NB2_OK;
 }
 
 template <class R, int K>
-static int launch_fwd_k(const nb2_variant& v, int sm_count, const Nb2ModelDev<R>& M, int B, const float* state, const float* action,
+static int launch_fwd_k(const nb2_variant& v, int sm_count, int B, const float* state, const float* action,
                         float* next, R* saved, cudaStream_t st) {
   constexpr int WPW = CoopShape<K>::WPW, ST = CoopShape<K>::ST;
+  const LaunchShape& sh = v.shape[0][sizeof(R) == 8];
   const size_t per_warp = (size_t)v.fwd_words * ST * sizeof(R);
   const int total_warps = (B + WPW - 1) / WPW;
-  const int warps = pick_warps(total_warps, per_warp, sm_count);
-  if (warps == 0) { g_err = "model needs " + std::to_string(per_warp) + " B of shared memory per warp (> 227 KB)"; return NB2_ERR_UNSUPPORTED; }
-  static bool attr_set = false;  // one flag per (R, K) instantiation
-  if (!attr_set) {
-    NB2_CUDA(cudaFuncSetAttribute(k_step_fwd<R, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
-    attr_set = true;
-  }
+  const int warps = block_warps(total_warps, sm_count, sh, per_warp);
   const int blocks = (total_warps + warps - 1) / warps;
-  k_step_fwd<R, K><<<blocks, warps * 32, per_warp * warps, st>>>(M, B, state, action, next, saved, v.fwd_words);
+  k_step_fwd<R, K><<<blocks, warps * 32, per_warp * warps, st>>>(model_of<R>(v), B, state, action, next, saved, v.fwd_words);
   g_launches++;
   NB2_CUDA(cudaGetLastError());
   return NB2_OK;
 }
 template <class R>
 static int launch_fwd(nb2_model* m, int B, const float* state, const float* action, float* next, R* saved, cudaStream_t st) {
-  const nb2_variant& v = pick_variant(m, B);
-  const Nb2ModelDev<R>& M = model_of<R>(v);
-  switch (M.lanes) {
-    case 1: return launch_fwd_k<R, 1>(v, m->sm_count, M, B, state, action, next, saved, st);
-    case 2: return launch_fwd_k<R, 2>(v, m->sm_count, M, B, state, action, next, saved, st);
-    case 4: return launch_fwd_k<R, 4>(v, m->sm_count, M, B, state, action, next, saved, st);
-    case 8: return launch_fwd_k<R, 8>(v, m->sm_count, M, B, state, action, next, saved, st);
+  nb2_variant* pv = nullptr;
+  int rc = pick_variant<R>(m, B, 0, &pv);
+  if (rc) return rc;
+  switch (pv->mf.lanes) {
+    case 1: return launch_fwd_k<R, 1>(*pv, m->sm_count, B, state, action, next, saved, st);
+    case 2: return launch_fwd_k<R, 2>(*pv, m->sm_count, B, state, action, next, saved, st);
+    case 4: return launch_fwd_k<R, 4>(*pv, m->sm_count, B, state, action, next, saved, st);
+    case 8: return launch_fwd_k<R, 8>(*pv, m->sm_count, B, state, action, next, saved, st);
   }
   g_err = "bad lane count"; return NB2_ERR_INVALID;
 }
 template <class R, int K>
-static int launch_bwd_k(const nb2_variant& v, int sm_count, const Nb2ModelDev<R>& M, int B, const float* state, const float* action,
-                        const R* saved, const float* gnext, float* gstate, float* gaction, cudaStream_t st) {
+static int launch_bwd_k(const nb2_variant& v, int sm_count, int B, const float* state, const float* action,
+                        const R* saved, const float* gnext, float* gstate, float* gaction, float* ginertia, cudaStream_t st) {
   constexpr int WPW = CoopShape<K>::WPW, ST = CoopShape<K>::ST;
+  const LaunchShape& sh = v.shape[1][sizeof(R) == 8];
   const size_t per_warp = (size_t)v.bwd_words * ST * sizeof(R);
   const int total_warps = (B + WPW - 1) / WPW;
-  const int warps = pick_warps(total_warps, per_warp, sm_count);
-  if (warps == 0) { g_err = "model needs " + std::to_string(per_warp) + " B of shared memory per warp (> 227 KB)"; return NB2_ERR_UNSUPPORTED; }
-  static bool attr_set = false;
-  if (!attr_set) {
-    NB2_CUDA(cudaFuncSetAttribute(k_step_bwd<R, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
-    attr_set = true;
-  }
+  const int warps = block_warps(total_warps, sm_count, sh, per_warp);
   const int blocks = (total_warps + warps - 1) / warps;
-  k_step_bwd<R, K><<<blocks, warps * 32, per_warp * warps, st>>>(M, B, state, action, saved, gnext, gstate, gaction, v.bwd_words);
+  k_step_bwd<R, K><<<blocks, warps * 32, per_warp * warps, st>>>(model_of<R>(v), B, state, action, saved, gnext, gstate, gaction, ginertia, v.bwd_words);
   g_launches++;
   NB2_CUDA(cudaGetLastError());
   return NB2_OK;
 }
 template <class R>
 static int launch_bwd(nb2_model* m, int B, const float* state, const float* action,
-                      const R* saved, const float* gnext, float* gstate, float* gaction, cudaStream_t st) {
-  const nb2_variant& v = pick_variant(m, B);
-  const Nb2ModelDev<R>& M = model_of<R>(v);
-  switch (M.lanes) {
-    case 1: return launch_bwd_k<R, 1>(v, m->sm_count, M, B, state, action, saved, gnext, gstate, gaction, st);
-    case 2: return launch_bwd_k<R, 2>(v, m->sm_count, M, B, state, action, saved, gnext, gstate, gaction, st);
-    case 4: return launch_bwd_k<R, 4>(v, m->sm_count, M, B, state, action, saved, gnext, gstate, gaction, st);
-    case 8: return launch_bwd_k<R, 8>(v, m->sm_count, M, B, state, action, saved, gnext, gstate, gaction, st);
+                      const R* saved, const float* gnext, float* gstate, float* gaction, float* ginertia, cudaStream_t st) {
+  nb2_variant* pv = nullptr;
+  int rc = pick_variant<R>(m, B, 1, &pv);
+  if (rc) return rc;
+  switch (pv->mf.lanes) {
+    case 1: return launch_bwd_k<R, 1>(*pv, m->sm_count, B, state, action, saved, gnext, gstate, gaction, ginertia, st);
+    case 2: return launch_bwd_k<R, 2>(*pv, m->sm_count, B, state, action, saved, gnext, gstate, gaction, ginertia, st);
+    case 4: return launch_bwd_k<R, 4>(*pv, m->sm_count, B, state, action, saved, gnext, gstate, gaction, ginertia, st);
+    case 8: return launch_bwd_k<R, 8>(*pv, m->sm_count, B, state, action, saved, gnext, gstate, gaction, ginertia, st);
   }
   g_err = "bad lane count"; return NB2_ERR_INVALID;
 }
@@ -269,8 +322,7 @@ int nb2_model_create(const nb2_model_desc* desc, nb2_model** out) {
   {
     nb2_variant v;
     v.mf = m->mf; v.md = m->md;
-    v.fwd_words = nb2::fwd_layout(m->mf.nb, m->mf.ndof, m->mf.nslots, m->mf.nfree).total;
-    v.bwd_words = nb2::bwd_layout(m->mf.nb, m->mf.ndof, m->mf.nslots, m->mf.nfree).total;
+    init_variant(v);
     m->variants.push_back(v);
   }
   m->saved_words = nb2_saved_words(m->mf.nb, m->mf.ndof, m->mf.nfree);
@@ -300,8 +352,7 @@ int nb2_model_add_schedule(nb2_model* m, const nb2_model_desc* desc) {
   }
   if (!same) { g_err = "nb2_model_add_schedule: the descriptor describes a different model"; return NB2_ERR_INVALID; }
   for (const auto& o : m->variants) if (o.mf.lanes == v.mf.lanes) { g_err = "nb2_model_add_schedule: a schedule with this lane count exists"; return NB2_ERR_INVALID; }
-  v.fwd_words = nb2::fwd_layout(v.mf.nb, v.mf.ndof, v.mf.nslots, v.mf.nfree).total;
-  v.bwd_words = nb2::bwd_layout(v.mf.nb, v.mf.ndof, v.mf.nslots, v.mf.nfree).total;
+  init_variant(v);
   std::lock_guard<std::mutex> lk(m->mu);
   m->variants.push_back(v);
   return NB2_OK;
@@ -316,7 +367,12 @@ int nb2_model_set_lanes(nb2_model* m, int lanes) {
   m->forced_lanes = lanes;
   return NB2_OK;
 }
-int nb2_model_lanes_for(const nb2_model* m, int B) { return (m && B > 0) ? pick_variant(m, B).mf.lanes : -1; }
+int nb2_model_lanes_for(nb2_model* m, int B, int backward, int precision) {
+  if (!m || B <= 0) return -1;
+  nb2_variant* pv = nullptr;
+  const int rc = (precision == NB2_FP64) ? pick_variant<double>(m, B, backward ? 1 : 0, &pv) : pick_variant<float>(m, B, backward ? 1 : 0, &pv);
+  return rc ? -1 : pv->mf.lanes;
+}
 
 void nb2_model_destroy(nb2_model* m) {
   if (!m) return;
@@ -392,16 +448,16 @@ int nb2_step_forward(const nb2_model* cm, int B, const float* state, const float
 }
 
 int nb2_step_backward(const nb2_model* cm, int B, const float* state, const float* action, const void* saved,
-                      const float* grad_next_state, float* grad_state, float* grad_action, int precision,
-                      void* stream) {
+                      const float* grad_next_state, float* grad_state, float* grad_action, float* grad_inertia,
+                      int precision, void* stream) {
   nb2_model* m = const_cast<nb2_model*>(cm);
   if (!m || B < 0 || !state || !action || !saved || !grad_next_state || !grad_state || !grad_action) {
     g_err = "nb2_step_backward: bad argument"; return NB2_ERR_INVALID;
   }
   if (B == 0) return NB2_OK;
   cudaStream_t st = (cudaStream_t)stream;
-  if (precision == NB2_FP64) return launch_bwd<double>(m, B, state, action, (const double*)saved, grad_next_state, grad_state, grad_action, st);
-  return launch_bwd<float>(m, B, state, action, (const float*)saved, grad_next_state, grad_state, grad_action, st);
+  if (precision == NB2_FP64) return launch_bwd<double>(m, B, state, action, (const double*)saved, grad_next_state, grad_state, grad_action, grad_inertia, st);
+  return launch_bwd<float>(m, B, state, action, (const float*)saved, grad_next_state, grad_state, grad_action, grad_inertia, st);
 }
 
 static int ensure_host_buffers(nb2_model* m, int B) {
@@ -450,7 +506,7 @@ int nb2_step_backward_host(nb2_model* m, int B, const float* grad_next_state, fl
   const size_t n2 = (size_t)2 * m->mf.ndof, na = (size_t)m->mf.na;
   cudaStream_t st = m->host_stream;
   NB2_CUDA(cudaMemcpyAsync(m->d_gnext, grad_next_state, n2 * B * sizeof(float), cudaMemcpyHostToDevice, st));
-  int rc = nb2_step_backward(m, B, m->d_state, m->d_action, m->d_saved, m->d_gnext, m->d_gstate, m->d_gaction, precision, st);
+  int rc = nb2_step_backward(m, B, m->d_state, m->d_action, m->d_saved, m->d_gnext, m->d_gstate, m->d_gaction, nullptr, precision, st);
   if (rc) return rc;
   NB2_CUDA(cudaMemcpyAsync(grad_state, m->d_gstate, n2 * B * sizeof(float), cudaMemcpyDeviceToHost, st));
   NB2_CUDA(cudaMemcpyAsync(grad_action, m->d_gaction, na * B * sizeof(float), cudaMemcpyDeviceToHost, st));

@@ -58,8 +58,8 @@ class DeviceModel:
         """Pin the lane count (0 = automatic choice per launch)."""
         _cabi.check(_cabi.lib().nb2_model_set_lanes(self.handle, int(lanes)))
 
-    def lanes_for(self, B: int) -> int:
-        return int(_cabi.lib().nb2_model_lanes_for(self.handle, int(B)))
+    def lanes_for(self, B: int, backward: bool = False, precision: int = FP32) -> int:
+        return int(_cabi.lib().nb2_model_lanes_for(self.handle, int(B), int(backward), int(precision)))
 
     def __del__(self):
         try:
@@ -74,9 +74,10 @@ class DeviceModel:
         _cabi.check(_cabi.lib().nb2_step_forward(self.handle, B, state_ptr, action_ptr, next_ptr, saved_ptr, precision, stream))
 
     def backward_device(self, B, state_ptr, action_ptr, saved_ptr, gnext_ptr, gstate_ptr, gaction_ptr, stream,
-                        precision=FP32):
+                        precision=FP32, ginertia_ptr=None):
+        """ginertia_ptr: optional [10*nb, B] float32 buffer receiving dL/d(inertia parameters) per body and world."""
         _cabi.check(_cabi.lib().nb2_step_backward(self.handle, B, state_ptr, action_ptr, saved_ptr, gnext_ptr,
-                                                  gstate_ptr, gaction_ptr, precision, stream))
+                                                  gstate_ptr, gaction_ptr, ginertia_ptr, precision, stream))
 
     def contact_workspace_bytes(self, B):
         return int(_cabi.lib().nb2_contact_workspace_bytes(self.handle, B))

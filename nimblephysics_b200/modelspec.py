@@ -221,9 +221,8 @@ class CanonModel:
     dof_off: np.ndarray = None
     Xtree: np.ndarray = None  # [nb,12] parent frame <- child frame at q=0 (R row-major, p)
     inertia: np.ndarray = None  # [nb,10] m, h(3)=m*c, Ibar(6: xx,yy,zz,xy,xz,yz) about body origin
-    flags: np.ndarray = None  # bit0: hand result to parent in registers (parent == i-1)
-    #                            bit1: first deposit into the parent's accumulator slot (store, not add)
-    #                            bit2: body owns an accumulator slot (has a non-handoff child)
+    flags: np.ndarray = None  # bit0: hand result to parent in registers (parent == i-1, same lane range)
+    #                            bit2: body owns accumulator slots (has non-handoff children)
     slot_self: np.ndarray = None  # first incoming accumulator slot of this body (or -1); it owns slot_count consecutive slots
     slot_count: np.ndarray = None  # number of incoming slots (= children that cannot hand off in registers)
     slot_parent: np.ndarray = None  # slot this body deposits its contribution to the parent into, or -1 (register handoff / root)
@@ -234,6 +233,8 @@ class CanonModel:
     trunk_ranges: List = field(default_factory=list)
     limb_ranges: List = field(default_factory=list)  # per lane: list of (lo, hi)
     orig_body: np.ndarray = None  # [nb] raw body index this canonical body stems from
+    body_owner: np.ndarray = None  # [raw nb] canonical body a raw body is (rigidly) part of, -1 = static
+    body_T: np.ndarray = None  # [raw nb,4,4] canonical owner frame <- raw body frame
     # per dof
     damping: np.ndarray = None
     spring: np.ndarray = None
@@ -285,6 +286,77 @@ def _spatial_inertia_about_origin(mass, com, Ic):
     c = np.asarray(com)
     Ibar = Ic + mass * (np.dot(c, c) * np.eye(3) - np.outer(c, c))
     return mass, mass * c, Ibar
+
+
+def body_inertia_contribution(T, mass, com, mom6):
+    """(m, h, Ibar about the origin) of one rigid body expressed in frame `T <- body`; polynomial in (mass, com, mom6),
+    written so that complex arguments pass through unchanged (complex-step differentiation in inertia_param_jacobian)."""
+    R, p = T[:3, :3], T[:3, 3]
+    mom = mom6
+    Ic = np.array([[mom[0], mom[3], mom[4]], [mom[3], mom[1], mom[5]], [mom[4], mom[5], mom[2]]])
+    c = R @ np.asarray(com) + p
+    RIR = R @ Ic @ R.T
+    Ibar = RIR + mass * (np.sum(c * c) * np.eye(3) - np.outer(c, c))
+    h = mass * c
+    return np.array([mass, h[0], h[1], h[2], Ibar[0, 0], Ibar[1, 1], Ibar[2, 2], Ibar[0, 1], Ibar[0, 2], Ibar[1, 2]])
+
+
+# WrtMassBodyNodeEntryType (dart/neural/WithRespectToMass.hpp:19-27)
+INERTIA_MASS, INERTIA_COM, INERTIA_COM_MU, INERTIA_DIAGONAL, INERTIA_OFF_DIAGONAL, INERTIA_FULL = range(6)
+WRT_MASS_DIMS = {INERTIA_MASS: 1, INERTIA_COM: 3, INERTIA_COM_MU: 1, INERTIA_DIAGONAL: 3, INERTIA_OFF_DIAGONAL: 3, INERTIA_FULL: 10}
+
+
+def _apply_mass_entry(kind, value, mass, com, mom6):
+    """(mass, com, mom6) of a body after WrtMassBodyNodyEntry::set (WithRespectToMass.cpp:44-134).  INERTIA_MASS goes
+    through Inertia::setMass, which keeps the body's dimensions: the moment scales with the mass (Inertia.cpp:157-177)."""
+    if kind == INERTIA_MASS:
+        scale = (value[0] / mass) if (mass > 0 and np.any(np.asarray(mom6) != 0)) else 1.0
+        return value[0], com, np.asarray(mom6) * scale
+    if kind == INERTIA_COM:
+        return mass, value[0:3], mom6
+    if kind == INERTIA_DIAGONAL:
+        return mass, com, np.array([value[0], value[1], value[2], mom6[3], mom6[4], mom6[5]])
+    if kind == INERTIA_OFF_DIAGONAL:
+        return mass, com, np.array([mom6[0], mom6[1], mom6[2], value[0], value[1], value[2]])
+    if kind == INERTIA_FULL:
+        return value[0], value[1:4], value[4:10]
+    raise NotImplementedError("INERTIA_COM_MU needs BodyNode::getBeta(), which this builder surface does not carry")
+
+
+def _mass_entry_value(kind, mass, com, mom6):
+    """WrtMassBodyNodyEntry::get (WithRespectToMass.cpp:136-185)."""
+    if kind == INERTIA_MASS:
+        return np.array([mass])
+    if kind == INERTIA_COM:
+        return np.array(com, dtype=np.float64)
+    if kind == INERTIA_DIAGONAL:
+        return np.array(mom6[0:3], dtype=np.float64)
+    if kind == INERTIA_OFF_DIAGONAL:
+        return np.array(mom6[3:6], dtype=np.float64)
+    if kind == INERTIA_FULL:
+        return np.concatenate([[mass], com, mom6])
+    raise NotImplementedError("INERTIA_COM_MU needs BodyNode::getBeta(), which this builder surface does not carry")
+
+
+def inertia_param_jacobian(raw: RawModel, cm: "CanonModel", entries) -> np.ndarray:
+    """d(canonical inertia [nb*10]) / d(mass vector), shape [mass_dims, nb*10], at the current values.
+    entries: [(raw body index, WrtMassBodyNodeEntryType)] in registration order (WithRespectToMass::get order).
+    The map raw (mass, com, moment) -> canonical (m, h, Ibar) is polynomial, so a complex step gives its exact derivative."""
+    rows = []
+    eps = 1e-30
+    for (bi, kind) in entries:
+        k = int(cm.body_owner[bi])
+        x0 = _mass_entry_value(kind, raw.mass[bi], raw.com[bi], raw.moment[bi]).astype(np.complex128)
+        for j in range(len(x0)):
+            row = np.zeros(cm.nb * 10)
+            if k >= 0:
+                x = x0.copy()
+                x[j] += 1j * eps
+                m_, c_, mom_ = _apply_mass_entry(kind, x, raw.mass[bi], raw.com[bi], raw.moment[bi])
+                row[10 * k:10 * k + 10] = np.imag(body_inertia_contribution(cm.body_T[bi].astype(np.complex128), m_, np.asarray(c_, np.complex128),
+                                                                            np.asarray(mom_, np.complex128))) / eps
+            rows.append(row)
+    return np.array(rows).reshape(len(rows), cm.nb * 10)
 
 
 def _ranges(idx):
@@ -436,19 +508,16 @@ def compile_model(raw: RawModel, lanes: int = 1) -> CanonModel:
 
     # inertia: sum over every raw body attached to the owner, expressed in the owner's canonical frame
     inertia = np.zeros((cm.nb, 10))
+    cm.body_owner = np.full(nb, -1, np.int32)
+    cm.body_T = np.tile(np.eye(4), (nb, 1, 1))
     for i in range(nb):
         o, T_ob = attach[i]
         if o < 0:
             continue  # static body, no dynamics
         T = np.linalg.inv(C[o]) @ T_ob  # canonical(o) <- body i
-        R, p = T[:3, :3], T[:3, 3]
-        mom = raw.moment[i]
-        Ic = np.array([[mom[0], mom[3], mom[4]], [mom[3], mom[1], mom[5]], [mom[4], mom[5], mom[2]]])
-        m_, h, Ibar = _spatial_inertia_about_origin(raw.mass[i], R @ raw.com[i] + p, R @ Ic @ R.T)
         k = new_index[o]
-        inertia[k, 0] += m_
-        inertia[k, 1:4] += h
-        inertia[k, 4:10] += [Ibar[0, 0], Ibar[1, 1], Ibar[2, 2], Ibar[0, 1], Ibar[0, 2], Ibar[1, 2]]
+        cm.body_owner[i], cm.body_T[i] = k, T
+        inertia[k] += body_inertia_contribution(T, raw.mass[i], raw.com[i], raw.moment[i])
     cm.inertia = inertia
 
     # ---- cooperative-lane schedule + accumulator slots for the leaf->root sweeps

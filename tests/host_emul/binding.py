@@ -46,17 +46,18 @@ class EmulWorld:
         assert rc == 0
         return nxt, saved
 
-    def backward(self, state, action, saved, gnext, fp64=False):
+    def backward(self, state, action, saved, gnext, fp64=False, want_inertia_grad=False):
         state = np.ascontiguousarray(state, np.float32)
         action = np.ascontiguousarray(action, np.float32)
         gnext = np.ascontiguousarray(gnext, np.float32)
         B = state.shape[0]
         gs = np.empty_like(state)
         ga = np.empty_like(action)
+        gi = np.zeros((10 * self.cm.nb, B), np.float32) if want_inertia_grad else None
         rc = lib().emul_backward(ctypes.byref(self.desc), B, _p(state), _p(action), _p(saved), _p(gnext), _p(gs),
-                                 _p(ga), int(fp64))
+                                 _p(ga), int(fp64), _p(gi) if gi is not None else None)
         assert rc == 0
-        return gs, ga
+        return (gs, ga, gi) if want_inertia_grad else (gs, ga)
 
     def forward_contact(self, state, action, x_lcp=None, m_lcp=None):
         """fp64 ABA + contact stage.  -> dict(next, saved, x, m, labels, status, nc, cinfo)"""

@@ -28,7 +28,7 @@ static int run_fwd(const nb2_model_desc* d, int B, const float* state, const flo
 }
 template <class R>
 static int run_bwd(const nb2_model_desc* d, int B, const float* state, const float* action, const R* saved,
-                   const float* gnext, float* gstate, float* gaction) {
+                   const float* gnext, float* gstate, float* gaction, float* ginertia) {
   Nb2ModelDev<R> M; std::string err;
   if (!nb2_fill_model(*d, M, err)) { fprintf(stderr, "emul: %s\n", err.c_str()); return -1; }
   nb2::BwdLayout L = nb2::bwd_layout(M.nb, M.ndof, M.nslots, M.nfree);
@@ -39,7 +39,8 @@ static int run_bwd(const nb2_model_desc* d, int B, const float* state, const flo
       for (int l = 0; l < M.lanes; l++)
         nb2::world_backward_stage<R, 1>(M, scr.data(), state + (size_t)w * 2 * M.ndof, action + (size_t)w * M.na,
                                         gnext + (size_t)w * 2 * M.ndof, saved + w, (size_t)B, gstate + (size_t)w * 2 * M.ndof,
-                                        gaction + (size_t)w * M.na, (w & 1) ? M.lanes - 1 - l : l, sg);
+                                        gaction + (size_t)w * M.na, (w & 1) ? M.lanes - 1 - l : l, sg,
+                                        ginertia ? ginertia + w : nullptr);
   }
   return 0;
 }
@@ -96,8 +97,8 @@ int emul_forward(const nb2_model_desc* d, int B, const float* state, const float
   return fp64 ? run_fwd<double>(d, B, state, action, next, (double*)saved) : run_fwd<float>(d, B, state, action, next, (float*)saved);
 }
 int emul_backward(const nb2_model_desc* d, int B, const float* state, const float* action, const void* saved,
-                  const float* gnext, float* gstate, float* gaction, int fp64) {
-  return fp64 ? run_bwd<double>(d, B, state, action, (const double*)saved, gnext, gstate, gaction)
-              : run_bwd<float>(d, B, state, action, (const float*)saved, gnext, gstate, gaction);
+                  const float* gnext, float* gstate, float* gaction, int fp64, float* ginertia) {
+  return fp64 ? run_bwd<double>(d, B, state, action, (const double*)saved, gnext, gstate, gaction, ginertia)
+              : run_bwd<float>(d, B, state, action, (const float*)saved, gnext, gstate, gaction, ginertia);
 }
 }

