@@ -87,6 +87,10 @@ int nb2_model_create(const nb2_model_desc* desc, nb2_model** out);
 int nb2_model_add_schedule(nb2_model* m, const nb2_model_desc* desc);
 int nb2_model_set_lanes(nb2_model* m, int lanes);
 int nb2_model_lanes_for(nb2_model* m, int B, int backward, int precision);
+/* Replace the inertia parameters [nb*10] (m, h, Ibar as in nb2_model_desc.inertia) of every registered schedule:
+ * what World::setMasses (World.cpp:1821-1825) changes; tree, limits and schedules stay.  Takes effect for launches
+ * issued after the call (the model is a kernel parameter, copied at launch). */
+int nb2_model_set_inertia(nb2_model* m, const double* inertia);
 void nb2_model_destroy(nb2_model* m);
 int nb2_model_ndof(const nb2_model* m);
 int nb2_model_na(const nb2_model* m);

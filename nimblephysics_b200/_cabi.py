@@ -127,6 +127,7 @@ def lib() -> ctypes.CDLL:
         L.nb2_model_create.argtypes = [ctypes.POINTER(Nb2ModelDesc), ctypes.POINTER(ctypes.c_void_p)]
         L.nb2_model_destroy.argtypes = [ctypes.c_void_p]
         L.nb2_model_add_schedule.argtypes = [ctypes.c_void_p, ctypes.POINTER(Nb2ModelDesc)]
+        L.nb2_model_set_inertia.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
         L.nb2_model_set_lanes.argtypes = [ctypes.c_void_p, ctypes.c_int]
         L.nb2_model_lanes_for.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int]
         L.nb2_model_ndof.argtypes = [ctypes.c_void_p]

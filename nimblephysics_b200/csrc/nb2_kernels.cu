@@ -42,14 +42,16 @@ template <int K> struct CoopShape {
 
 template <class R, int K>
 __global__ void __launch_bounds__(128)
-k_step_fwd(const __grid_constant__ Nb2ModelDev<R> M, int B, const float* __restrict__ state,
+k_step_fwd(const __grid_constant__ Nb2ModelDev<R> M, int B, int w0, int count, const float* __restrict__ state,
            const float* __restrict__ action, float* __restrict__ next, R* __restrict__ saved, int words) {
+  // worlds [w0, w0 + count) of a batch of B (B is the stride of the saved stream; the host entry points launch chunks)
   extern __shared__ __align__(16) unsigned char nb2_smem[];
   constexpr int WPW = CoopShape<K>::WPW, ST = CoopShape<K>::ST;
   const int li = threadIdx.x & 31, slot = li / K, lane = li % K;
-  const int w = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * WPW + slot;
-  const bool valid = w < B;
-  const int wc = valid ? w : 0;
+  const int wl = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * WPW + slot;
+  const bool valid = wl < count;
+  const int w = w0 + wl;
+  const int wc = valid ? w : w0;
   R* scr = reinterpret_cast<R*>(nb2_smem) + (size_t)(threadIdx.x >> 5) * words * ST + slot;
   const float* st = state + (size_t)wc * 2 * M.ndof;
   const float* ac = action + (size_t)wc * M.na;
@@ -64,15 +66,16 @@ k_step_fwd(const __grid_constant__ Nb2ModelDev<R> M, int B, const float* __restr
 
 template <class R, int K>
 __global__ void __launch_bounds__(128)
-k_step_bwd(const __grid_constant__ Nb2ModelDev<R> M, int B, const float* __restrict__ state,
+k_step_bwd(const __grid_constant__ Nb2ModelDev<R> M, int B, int w0, int count, const float* __restrict__ state,
            const float* __restrict__ action, const R* __restrict__ saved, const float* __restrict__ gnext,
            float* __restrict__ gstate, float* __restrict__ gaction, float* __restrict__ ginertia, int words) {
   extern __shared__ __align__(16) unsigned char nb2_smem[];
   constexpr int WPW = CoopShape<K>::WPW, ST = CoopShape<K>::ST;
   const int li = threadIdx.x & 31, slot = li / K, lane = li % K;
-  const int w = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * WPW + slot;
-  const bool valid = w < B;
-  const int wc = valid ? w : 0;
+  const int wl = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * WPW + slot;
+  const bool valid = wl < count;
+  const int w = w0 + wl;
+  const int wc = valid ? w : w0;
   R* scr = reinterpret_cast<R*>(nb2_smem) + (size_t)(threadIdx.x >> 5) * words * ST + slot;
   const float* st = state + (size_t)wc * 2 * M.ndof;
   const float* ac = action + (size_t)wc * M.na;
@@ -148,7 +151,7 @@ struct nb2_model {
   void* d_saved = nullptr;  // sized for fp64 words
   int host_cap = 0;
   int host_B = 0;  // batch of the last forward_host kept for backward
-  cudaStream_t host_stream = nullptr;
+  cudaStream_t host_streams[4] = {nullptr, nullptr, nullptr, nullptr};
   std::mutex mu;
 };
 
@@ -246,7 +249,7 @@ static int pick_variant(nb2_model* m, int B, int dir, nb2_variant** out) {
 }
 
 template <class R, int K>
-static int launch_fwd_k(const nb2_variant& v, int sm_count, int B, const float* state, const float* action,
+static int launch_fwd_k(const nb2_variant& v, int sm_count, int Btot, int w0, int B, const float* state, const float* action,
                         float* next, R* saved, cudaStream_t st) {
   constexpr int WPW = CoopShape<K>::WPW, ST = CoopShape<K>::ST;
   const LaunchShape& sh = v.shape[0][sizeof(R) == 8];
@@ -254,26 +257,28 @@ static int launch_fwd_k(const nb2_variant& v, int sm_count, int B, const float* 
   const int total_warps = (B + WPW - 1) / WPW;
   const int warps = block_warps(total_warps, sm_count, sh, per_warp);
   const int blocks = (total_warps + warps - 1) / warps;
-  k_step_fwd<R, K><<<blocks, warps * 32, per_warp * warps, st>>>(model_of<R>(v), B, state, action, next, saved, v.fwd_words);
+  k_step_fwd<R, K><<<blocks, warps * 32, per_warp * warps, st>>>(model_of<R>(v), Btot, w0, B, state, action, next, saved, v.fwd_words);
   g_launches++;
   NB2_CUDA(cudaGetLastError());
   return NB2_OK;
 }
 template <class R>
-static int launch_fwd(nb2_model* m, int B, const float* state, const float* action, float* next, R* saved, cudaStream_t st) {
+static int launch_fwd(nb2_model* m, int B, const float* state, const float* action, float* next, R* saved, cudaStream_t st,
+                      int Btot = -1, int w0 = 0) {
+  if (Btot < 0) Btot = B;
   nb2_variant* pv = nullptr;
   int rc = pick_variant<R>(m, B, 0, &pv);
   if (rc) return rc;
   switch (pv->mf.lanes) {
-    case 1: return launch_fwd_k<R, 1>(*pv, m->sm_count, B, state, action, next, saved, st);
-    case 2: return launch_fwd_k<R, 2>(*pv, m->sm_count, B, state, action, next, saved, st);
-    case 4: return launch_fwd_k<R, 4>(*pv, m->sm_count, B, state, action, next, saved, st);
-    case 8: return launch_fwd_k<R, 8>(*pv, m->sm_count, B, state, action, next, saved, st);
+    case 1: return launch_fwd_k<R, 1>(*pv, m->sm_count, Btot, w0, B, state, action, next, saved, st);
+    case 2: return launch_fwd_k<R, 2>(*pv, m->sm_count, Btot, w0, B, state, action, next, saved, st);
+    case 4: return launch_fwd_k<R, 4>(*pv, m->sm_count, Btot, w0, B, state, action, next, saved, st);
+    case 8: return launch_fwd_k<R, 8>(*pv, m->sm_count, Btot, w0, B, state, action, next, saved, st);
   }
   g_err = "bad lane count"; return NB2_ERR_INVALID;
 }
 template <class R, int K>
-static int launch_bwd_k(const nb2_variant& v, int sm_count, int B, const float* state, const float* action,
+static int launch_bwd_k(const nb2_variant& v, int sm_count, int Btot, int w0, int B, const float* state, const float* action,
                         const R* saved, const float* gnext, float* gstate, float* gaction, float* ginertia, cudaStream_t st) {
   constexpr int WPW = CoopShape<K>::WPW, ST = CoopShape<K>::ST;
   const LaunchShape& sh = v.shape[1][sizeof(R) == 8];
@@ -281,22 +286,24 @@ static int launch_bwd_k(const nb2_variant& v, int sm_count, int B, const float* 
   const int total_warps = (B + WPW - 1) / WPW;
   const int warps = block_warps(total_warps, sm_count, sh, per_warp);
   const int blocks = (total_warps + warps - 1) / warps;
-  k_step_bwd<R, K><<<blocks, warps * 32, per_warp * warps, st>>>(model_of<R>(v), B, state, action, saved, gnext, gstate, gaction, ginertia, v.bwd_words);
+  k_step_bwd<R, K><<<blocks, warps * 32, per_warp * warps, st>>>(model_of<R>(v), Btot, w0, B, state, action, saved, gnext, gstate, gaction, ginertia, v.bwd_words);
   g_launches++;
   NB2_CUDA(cudaGetLastError());
   return NB2_OK;
 }
 template <class R>
 static int launch_bwd(nb2_model* m, int B, const float* state, const float* action,
-                      const R* saved, const float* gnext, float* gstate, float* gaction, float* ginertia, cudaStream_t st) {
+                      const R* saved, const float* gnext, float* gstate, float* gaction, float* ginertia, cudaStream_t st,
+                      int Btot = -1, int w0 = 0) {
+  if (Btot < 0) Btot = B;
   nb2_variant* pv = nullptr;
   int rc = pick_variant<R>(m, B, 1, &pv);
   if (rc) return rc;
   switch (pv->mf.lanes) {
-    case 1: return launch_bwd_k<R, 1>(*pv, m->sm_count, B, state, action, saved, gnext, gstate, gaction, ginertia, st);
-    case 2: return launch_bwd_k<R, 2>(*pv, m->sm_count, B, state, action, saved, gnext, gstate, gaction, ginertia, st);
-    case 4: return launch_bwd_k<R, 4>(*pv, m->sm_count, B, state, action, saved, gnext, gstate, gaction, ginertia, st);
-    case 8: return launch_bwd_k<R, 8>(*pv, m->sm_count, B, state, action, saved, gnext, gstate, gaction, ginertia, st);
+    case 1: return launch_bwd_k<R, 1>(*pv, m->sm_count, Btot, w0, B, state, action, saved, gnext, gstate, gaction, ginertia, st);
+    case 2: return launch_bwd_k<R, 2>(*pv, m->sm_count, Btot, w0, B, state, action, saved, gnext, gstate, gaction, ginertia, st);
+    case 4: return launch_bwd_k<R, 4>(*pv, m->sm_count, Btot, w0, B, state, action, saved, gnext, gstate, gaction, ginertia, st);
+    case 8: return launch_bwd_k<R, 8>(*pv, m->sm_count, Btot, w0, B, state, action, saved, gnext, gstate, gaction, ginertia, st);
   }
   g_err = "bad lane count"; return NB2_ERR_INVALID;
 }
@@ -357,6 +364,19 @@ int nb2_model_add_schedule(nb2_model* m, const nb2_model_desc* desc) {
   m->variants.push_back(v);
   return NB2_OK;
 }
+int nb2_model_set_inertia(nb2_model* m, const double* inertia) {
+  if (!m || !inertia) { g_err = "null argument"; return NB2_ERR_INVALID; }
+  for (int i = 0; i < m->md.nb; i++)
+    if (!(inertia[10 * i] > 0)) { g_err = "nb2_model_set_inertia: body " + std::to_string(i) + " has non-positive mass"; return NB2_ERR_INVALID; }
+  std::lock_guard<std::mutex> lk(m->mu);
+  auto put = [&](Nb2ModelDev<float>& mf, Nb2ModelDev<double>& md) {
+    for (int i = 0; i < md.nb; i++)
+      for (int k = 0; k < 10; k++) { md.inertia[i][k] = inertia[10 * i + k]; mf.inertia[i][k] = (float)inertia[10 * i + k]; }
+  };
+  put(m->mf, m->md);
+  for (auto& v : m->variants) put(v.mf, v.md);
+  return NB2_OK;
+}
 int nb2_model_set_lanes(nb2_model* m, int lanes) {
   if (!m) { g_err = "null argument"; return NB2_ERR_INVALID; }
   if (lanes != 0) {
@@ -378,7 +398,7 @@ void nb2_model_destroy(nb2_model* m) {
   if (!m) return;
   cudaFree(m->d_state); cudaFree(m->d_action); cudaFree(m->d_next); cudaFree(m->d_saved);
   cudaFree(m->d_gnext); cudaFree(m->d_gstate); cudaFree(m->d_gaction);
-  if (m->host_stream) cudaStreamDestroy(m->host_stream);
+  for (auto& hs : m->host_streams) if (hs) cudaStreamDestroy(hs);
   delete m;
 }
 int nb2_model_has_contacts(const nb2_model* m) { return (m && m->has_contacts) ? 1 : 0; }
@@ -461,7 +481,7 @@ int nb2_step_backward(const nb2_model* cm, int B, const float* state, const floa
 }
 
 static int ensure_host_buffers(nb2_model* m, int B) {
-  if (!m->host_stream) NB2_CUDA(cudaStreamCreateWithFlags(&m->host_stream, cudaStreamNonBlocking));
+  for (auto& hs : m->host_streams) if (!hs) NB2_CUDA(cudaStreamCreateWithFlags(&hs, cudaStreamNonBlocking));
   if (B <= m->host_cap) return NB2_OK;
   cudaFree(m->d_state); cudaFree(m->d_action); cudaFree(m->d_next); cudaFree(m->d_saved);
   cudaFree(m->d_gnext); cudaFree(m->d_gstate); cudaFree(m->d_gaction);
@@ -480,6 +500,11 @@ static int ensure_host_buffers(nb2_model* m, int B) {
   return NB2_OK;
 }
 
+// The host entry points pipeline the batch in chunks over a few streams: chunk c's upload overlaps chunk c-1's kernel
+// and chunk c-2's download (separate copy engines per direction); the kernels are latency bound, so the chunks'
+// kernels also run side by side on disjoint SMs.  Pageable host memory still works (the copies just serialise).
+static int host_chunks(int B) { return B >= 4096 ? 4 : (B >= 1024 ? 2 : 1); }
+
 int nb2_step_forward_host(nb2_model* m, int B, const float* state, const float* action, float* next_state,
                           int keep_for_backward, int precision) {
   if (!m || B <= 0 || !state || !action || !next_state) { g_err = "nb2_step_forward_host: bad argument"; return NB2_ERR_INVALID; }
@@ -487,13 +512,18 @@ int nb2_step_forward_host(nb2_model* m, int B, const float* state, const float* 
   int rc = ensure_host_buffers(m, B);
   if (rc) return rc;
   const size_t n2 = (size_t)2 * m->mf.ndof, na = (size_t)m->mf.na;
-  cudaStream_t st = m->host_stream;
-  NB2_CUDA(cudaMemcpyAsync(m->d_state, state, n2 * B * sizeof(float), cudaMemcpyHostToDevice, st));
-  NB2_CUDA(cudaMemcpyAsync(m->d_action, action, na * B * sizeof(float), cudaMemcpyHostToDevice, st));
-  rc = nb2_step_forward(m, B, m->d_state, m->d_action, m->d_next, keep_for_backward ? m->d_saved : nullptr, precision, st);
-  if (rc) return rc;
-  NB2_CUDA(cudaMemcpyAsync(next_state, m->d_next, n2 * B * sizeof(float), cudaMemcpyDeviceToHost, st));
-  NB2_CUDA(cudaStreamSynchronize(st));
+  const int C = host_chunks(B);
+  for (int c = 0; c < C; c++) {
+    const int lo = (int)((long long)B * c / C), cnt = (int)((long long)B * (c + 1) / C) - lo;
+    cudaStream_t st = m->host_streams[c];
+    NB2_CUDA(cudaMemcpyAsync(m->d_state + n2 * lo, state + n2 * lo, n2 * cnt * sizeof(float), cudaMemcpyHostToDevice, st));
+    NB2_CUDA(cudaMemcpyAsync(m->d_action + na * lo, action + na * lo, na * cnt * sizeof(float), cudaMemcpyHostToDevice, st));
+    if (precision == NB2_FP64) rc = launch_fwd<double>(m, cnt, m->d_state, m->d_action, m->d_next, keep_for_backward ? (double*)m->d_saved : nullptr, st, B, lo);
+    else rc = launch_fwd<float>(m, cnt, m->d_state, m->d_action, m->d_next, keep_for_backward ? (float*)m->d_saved : nullptr, st, B, lo);
+    if (rc) return rc;
+    NB2_CUDA(cudaMemcpyAsync(next_state + n2 * lo, m->d_next + n2 * lo, n2 * cnt * sizeof(float), cudaMemcpyDeviceToHost, st));
+  }
+  for (int c = 0; c < C; c++) NB2_CUDA(cudaStreamSynchronize(m->host_streams[c]));
   m->host_B = keep_for_backward ? B : 0;
   return NB2_OK;
 }
@@ -504,13 +534,19 @@ int nb2_step_backward_host(nb2_model* m, int B, const float* grad_next_state, fl
   std::lock_guard<std::mutex> lk(m->mu);
   if (B <= 0 || B != m->host_B) { g_err = "nb2_step_backward_host: no matching forward_host(keep_for_backward=1) precedes this call"; return NB2_ERR_INVALID; }
   const size_t n2 = (size_t)2 * m->mf.ndof, na = (size_t)m->mf.na;
-  cudaStream_t st = m->host_stream;
-  NB2_CUDA(cudaMemcpyAsync(m->d_gnext, grad_next_state, n2 * B * sizeof(float), cudaMemcpyHostToDevice, st));
-  int rc = nb2_step_backward(m, B, m->d_state, m->d_action, m->d_saved, m->d_gnext, m->d_gstate, m->d_gaction, nullptr, precision, st);
-  if (rc) return rc;
-  NB2_CUDA(cudaMemcpyAsync(grad_state, m->d_gstate, n2 * B * sizeof(float), cudaMemcpyDeviceToHost, st));
-  NB2_CUDA(cudaMemcpyAsync(grad_action, m->d_gaction, na * B * sizeof(float), cudaMemcpyDeviceToHost, st));
-  NB2_CUDA(cudaStreamSynchronize(st));
+  const int C = host_chunks(B);
+  for (int c = 0; c < C; c++) {
+    const int lo = (int)((long long)B * c / C), cnt = (int)((long long)B * (c + 1) / C) - lo;
+    cudaStream_t st = m->host_streams[c];
+    NB2_CUDA(cudaMemcpyAsync(m->d_gnext + n2 * lo, grad_next_state + n2 * lo, n2 * cnt * sizeof(float), cudaMemcpyHostToDevice, st));
+    int rc;
+    if (precision == NB2_FP64) rc = launch_bwd<double>(m, cnt, m->d_state, m->d_action, (const double*)m->d_saved, m->d_gnext, m->d_gstate, m->d_gaction, nullptr, st, B, lo);
+    else rc = launch_bwd<float>(m, cnt, m->d_state, m->d_action, (const float*)m->d_saved, m->d_gnext, m->d_gstate, m->d_gaction, nullptr, st, B, lo);
+    if (rc) return rc;
+    NB2_CUDA(cudaMemcpyAsync(grad_state + n2 * lo, m->d_gstate + n2 * lo, n2 * cnt * sizeof(float), cudaMemcpyDeviceToHost, st));
+    NB2_CUDA(cudaMemcpyAsync(grad_action + na * lo, m->d_gaction + na * lo, na * cnt * sizeof(float), cudaMemcpyDeviceToHost, st));
+  }
+  for (int c = 0; c < C; c++) NB2_CUDA(cudaStreamSynchronize(m->host_streams[c]));
   return NB2_OK;
 }
 

@@ -54,6 +54,36 @@ class DeviceModel:
                 c.shape_body = c.shape_body[:0]
         return cls(cms[0], cms[1:])
 
+    def refresh_inertia(self, world):
+        """The World's masses / COMs / moments changed (World.setMasses): recompute the canonical inertias (welded bodies
+        summed into their owner) and push them to the device model; the tree, schedules and slots are unchanged."""
+        from .modelspec import body_inertia_contribution
+
+        raw = world._raw_model
+        k = 0
+        for sk in world.skeletons:
+            for b in sk._ordered_bodies():
+                raw.mass[k], raw.com[k] = b.mass, b.com
+                I = b.moment
+                raw.moment[k] = [I[0, 0], I[1, 1], I[2, 2], I[0, 1], I[0, 2], I[1, 2]]
+                k += 1
+        cm = self.cm
+        inertia = np.zeros((cm.nb, 10))
+        for i in range(raw.nb):
+            o = int(cm.body_owner[i])
+            if o >= 0:
+                inertia[o] += body_inertia_contribution(cm.body_T[i], raw.mass[i], raw.com[i], raw.moment[i])
+        for c in self.schedules:
+            c.inertia = inertia.copy()
+        buf = np.ascontiguousarray(inertia, dtype=np.float64)
+        _cabi.check(_cabi.lib().nb2_model_set_inertia(self.handle, buf.ctypes.data))
+
+    def inertia_param_jacobian(self, world) -> np.ndarray:
+        """[getMassDims(), 10*nb] : d(canonical inertia parameters)/d(mass vector) at the world's current values."""
+        from .modelspec import inertia_param_jacobian
+
+        return inertia_param_jacobian(world._raw_model, self.cm, world._mass_entries())
+
     def set_lanes(self, lanes: int):
         """Pin the lane count (0 = automatic choice per launch)."""
         _cabi.check(_cabi.lib().nb2_model_set_lanes(self.handle, int(lanes)))

@@ -26,9 +26,14 @@ def _ptr(t: torch.Tensor) -> int:
 class TimestepLayer(torch.autograd.Function):
     @staticmethod
     def forward(ctx, world, state, action, mass):
-        if mass is not None:
-            raise NotImplementedError("timestep(..., mass) (WithRespectToMass, SURVEY §8f-4) is not implemented yet")
         dm = device_model_for(world)
+        if mass is not None:
+            # reference: world.setMasses(mass) before the step (timestep.py:33-35); the masses stay set afterwards.
+            # One mass vector per call: every world of the batch shares the model (the gradient sums over the batch).
+            if mass.dim() != 1 or mass.numel() != world.getMassDims():
+                raise ValueError(f"timestep(): mass has shape {tuple(mass.shape)}, expected [{world.getMassDims()}] (= getMassDims(); "
+                                 "register parameters with world.tuneMass)")
+            world.setMasses(mass.detach().cpu().numpy().astype(np.float64))
         n2, na = 2 * dm.ndof, dm.na
         legacy = state.dim() == 1
         if legacy and (state.numel() != n2 or action.numel() != na):
@@ -47,7 +52,13 @@ class TimestepLayer(torch.autograd.Function):
         sd = s2.to(device=dev, dtype=torch.float32, non_blocking=True).contiguous()
         ad = a2.to(device=dev, dtype=torch.float32, non_blocking=True).contiguous()
         B = sd.shape[0]
-        need_grad = any(ctx.needs_input_grad[1:3])
+        need_grad = any(ctx.needs_input_grad[1:4])
+        ctx.mass_grad = mass is not None and ctx.needs_input_grad[3]
+        if ctx.mass_grad:
+            if dm.has_contacts:
+                raise NotImplementedError("d/dmass through the contact stage is not implemented (contact-free steps only)")
+            ctx.mass_P = torch.from_numpy(dm.inertia_param_jacobian(world))  # [mass_dims, 10*nb], fp64
+            ctx.mass_like = mass
         ctx.contact = dm.has_contacts
         with torch.cuda.device(dev):
             nxt = torch.empty_like(sd)
@@ -100,13 +111,19 @@ class TimestepLayer(torch.autograd.Function):
                         "backward through a contact between two MOVING bodies is not implemented (the kernel marked those "
                         "worlds with NaN gradients); contacts against static geometry are supported")
             else:
-                dm.backward_device(ctx.B, _ptr(sd), _ptr(ad), _ptr(saved), _ptr(g), _ptr(gs), _ptr(ga), stream, FP32)
+                gi = torch.empty((10 * dm.cm.nb, ctx.B), dtype=torch.float32, device=dev) if ctx.mass_grad else None
+                dm.backward_device(ctx.B, _ptr(sd), _ptr(ad), _ptr(saved), _ptr(g), _ptr(gs), _ptr(ga), stream, FP32,
+                                   _ptr(gi) if gi is not None else None)
+        gm = None
+        if ctx.mass_grad:
+            # lossWrtMass = massVel^T g_v' (BackpropSnapshot.cpp:177-178), summed over the worlds that share the model
+            gm = (ctx.mass_P.to(dev) @ gi.to(torch.float64).sum(dim=1)).to(device=ctx.mass_like.device, dtype=ctx.mass_like.dtype)
         if ctx.legacy:
             # reference returns fp64 grads (timestep.py:55-60)
             gs = gs[0].to(device=ctx.in_device, dtype=torch.float64 if ctx.in_dtype == torch.float64 else ctx.in_dtype)
             ga = ga[0].to(device=ctx.act_device, dtype=ctx.act_dtype)
-            return None, gs, ga, None
-        return None, gs.to(device=ctx.in_device, dtype=ctx.in_dtype), ga.to(device=ctx.act_device, dtype=ctx.act_dtype), None
+            return None, gs, ga, gm
+        return None, gs.to(device=ctx.in_device, dtype=ctx.in_dtype), ga.to(device=ctx.act_device, dtype=ctx.act_dtype), gm
 
 
 def contact_cache(world, B: int, device) -> dict:

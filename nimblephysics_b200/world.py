@@ -146,7 +146,14 @@ class BodyNode:
         self.skeleton: Optional["Skeleton"] = None
 
     def setMass(self, m):
-        self.mass = float(m)
+        """Inertia::setMass with preserveDimsAndEuler=true (dart/dynamics/Inertia.cpp:157-177): the body keeps its
+        dimensions, so a non-zero moment scales with the mass."""
+        m = float(m)
+        if m == self.mass:
+            return
+        if self.mass > 0 and np.any(self.moment != 0):
+            self.moment = self.moment * (m / self.mass)
+        self.mass = m
 
     def getMass(self):
         return self.mass
@@ -468,6 +475,70 @@ class World:
         if dof not in self.action_space:
             self.action_space.append(int(dof))
             self._touch()
+
+    # ----- tunable inertial parameters (dart/neural/WithRespectToMass.cpp; World.cpp:1013-1053, 1821-1825) -----
+    def tuneMass(self, node, type, upperBound=None, lowerBound=None):
+        """Register `node`'s inertial parameters of kind `type` (WrtMassBodyNodeEntryType) as part of the mass vector."""
+        from .modelspec import WRT_MASS_DIMS
+
+        if type not in WRT_MASS_DIMS:
+            raise ValueError("unknown WrtMassBodyNodeEntryType")
+        d = WRT_MASS_DIMS[type]
+        ub = np.full(d, np.inf) if upperBound is None else np.asarray(upperBound, np.float64).reshape(d)
+        lb = np.full(d, -np.inf) if lowerBound is None else np.asarray(lowerBound, np.float64).reshape(d)
+        self._wrt_mass = [e for e in getattr(self, "_wrt_mass", []) if e[0] is not node] + [(node, int(type), ub, lb)]
+
+    def clearTunableMassThisInstance(self):
+        self._wrt_mass = []
+
+    def getMassDims(self):
+        from .modelspec import WRT_MASS_DIMS
+
+        return sum(WRT_MASS_DIMS[t] for _, t, _, _ in getattr(self, "_wrt_mass", []))
+
+    def getMassUpperLimits(self):
+        return np.concatenate([ub for _, _, ub, _ in getattr(self, "_wrt_mass", [])] or [np.zeros(0)])
+
+    def getMassLowerLimits(self):
+        return np.concatenate([lb for _, _, _, lb in getattr(self, "_wrt_mass", [])] or [np.zeros(0)])
+
+    @staticmethod
+    def _mom6(b):
+        I = b.moment
+        return np.array([I[0, 0], I[1, 1], I[2, 2], I[0, 1], I[0, 2], I[1, 2]])
+
+    def getMasses(self):
+        from .modelspec import _mass_entry_value
+
+        out = [_mass_entry_value(t, b.mass, b.com, self._mom6(b)) for b, t, _, _ in getattr(self, "_wrt_mass", [])]
+        return np.concatenate(out) if out else np.zeros(0)
+
+    def setMasses(self, masses):
+        from .modelspec import WRT_MASS_DIMS, _apply_mass_entry
+
+        masses = np.asarray(masses, dtype=np.float64).reshape(-1)
+        if masses.size != self.getMassDims():
+            raise ValueError(f"World.setMasses() got size {masses.size}, expected getMassDims()={self.getMassDims()}")
+        cur = 0
+        for b, t, _, _ in getattr(self, "_wrt_mass", []):
+            d = WRT_MASS_DIMS[t]
+            m_, c_, mom = _apply_mass_entry(t, masses[cur:cur + d], b.mass, b.com, self._mom6(b))
+            b.mass, b.com = float(m_), np.array(c_, dtype=np.float64)
+            b.moment = np.array([[mom[0], mom[3], mom[4]], [mom[3], mom[1], mom[5]], [mom[4], mom[5], mom[2]]], dtype=np.float64)
+            cur += d
+        dm = self._device_model
+        if dm is not None:
+            dm.refresh_inertia(self)  # same tree, new inertias: no recompilation
+
+    def _mass_entries(self):
+        """[(raw body index, type)] in mass-vector order (raw bodies are numbered skeleton by skeleton, tree order)."""
+        index = {}
+        k = 0
+        for sk in self.skeletons:
+            for b in sk._ordered_bodies():
+                index[id(b)] = k
+                k += 1
+        return [(index[id(b)], t) for b, t, _, _ in getattr(self, "_wrt_mass", [])]
 
     # ----- legacy stateful API (single world) -----
     def setState(self, state):

@@ -208,3 +208,54 @@ def test_cooperative_lane_schedules_agree(oracle_mod, name):
         rgs, rga = ow.backprop(s64, a64, g64)
         K = lanes[-1]
         assert rel_err(res[K][0][w], ow.step(s64, a64)) < TOL and rel_err(res[K][1][w], rgs) < TOL and rel_err(res[K][2][w], rga) < TOL
+
+
+def test_timestep_mass_argument_and_gradient(oracle_mod):
+    """timestep(world, state, action, mass) (python/nimblephysics/timestep.py:28-35, 55-60): the masses registered with
+    world.tuneMass are set before the step and lossWrtMass comes back as the fourth gradient."""
+    import copy
+
+    from nimblephysics_b200 import modelspec as ms
+
+    raw, world = _world("atlas")
+    sk = world.getSkeleton(0)
+    bodies = sk._ordered_bodies()
+    picks = [(bodies[2], ms.INERTIA_MASS), (bodies[8], ms.INERTIA_COM), (bodies[15], ms.INERTIA_MASS)]
+    for b, kind in picks:
+        world.tuneMass(b, kind)
+    assert world.getMassDims() == 5
+    m0 = world.getMasses()
+    m1 = m0 * np.array([1.3, 1.0, 1.0, 1.0, 0.8]) + np.array([0, 0.01, -0.02, 0.005, 0])
+    B = 6
+    s, a, g = sample_inputs(raw, B, seed=41)
+    st, at = torch.tensor(s, device="cuda"), torch.tensor(a, device="cuda")
+    mt = torch.tensor(m1, dtype=torch.float64, requires_grad=True)
+    nxt = nb.timestep(world, st, at, mt)
+    assert np.allclose(world.getMasses(), m1)  # side effect of the reference: the masses stay set
+    (nxt * torch.tensor(g, device="cuda")).sum().backward()
+    gm = mt.grad.numpy()
+    assert mt.grad.dtype == torch.float64 and gm.shape == (5,)
+    # oracle at the new masses: forward parity and central differences of the loss
+    entries = world._mass_entries()
+
+    def raw_at(mvec):
+        r = copy.deepcopy(raw)
+        k = 0
+        for (bi, kind) in entries:
+            d = ms.WRT_MASS_DIMS[kind]
+            r.mass[bi], r.com[bi], r.moment[bi] = ms._apply_mass_entry(kind, mvec[k:k + d], r.mass[bi], r.com[bi], r.moment[bi])
+            k += d
+        return r
+
+    def loss(mvec):
+        ow = oracle_mod.OracleWorld(raw_at(mvec))
+        return sum(float(g[w].astype(np.float64) @ ow.step(s[w].astype(np.float64), a[w].astype(np.float64))) for w in range(B))
+
+    ow1 = oracle_mod.OracleWorld(raw_at(m1))
+    for w in range(B):
+        assert rel_err(nxt[w].detach().cpu().numpy(), ow1.step(s[w].astype(np.float64), a[w].astype(np.float64))) < TOL
+    fd = np.zeros(5)
+    for j in range(5):
+        e = np.zeros(5); e[j] = 1e-5
+        fd[j] = (loss(m1 + e) - loss(m1 - e)) / 2e-5
+    assert rel_err(gm, fd) < 1e-3, (gm, fd)  # fp32 kernels, sum over the batch

@@ -132,3 +132,27 @@ def test_fixtures_are_current_with_reference_files():
     fresh = json.loads(nb.flatten_world(w).to_json())
     stored = json.load(open(os.path.join(MODELS, "half_cheetah.json")))
     assert fresh == stored
+
+
+def test_world_mass_vector_api():
+    """World::tuneMass / getMasses / setMasses (World.cpp:1013-1053, 1821-1825; WithRespectToMass.cpp:44-185)."""
+    from nimblephysics_b200 import modelspec as ms
+
+    w = nb.World.from_raw(load_raw("half_cheetah"))
+    bodies = w.getSkeleton(0)._ordered_bodies() if w.getSkeleton(0).isMobile() else w.getSkeleton(1)._ordered_bodies()
+    b0, b1 = bodies[1], bodies[2]
+    assert w.getMassDims() == 0 and w.getMasses().shape == (0,)
+    w.tuneMass(b0, ms.INERTIA_MASS, [10.0], [0.1])
+    w.tuneMass(b1, ms.INERTIA_FULL)
+    assert w.getMassDims() == 11
+    v = w.getMasses()
+    assert v[0] == b0.mass and v[1] == b1.mass and np.allclose(v[2:5], b1.com)
+    mom_before = b0.moment.copy()
+    v2 = v.copy()
+    v2[0] *= 2.0
+    w.setMasses(v2)
+    assert b0.mass == v2[0] and np.allclose(b0.moment, 2.0 * mom_before)  # Inertia::setMass keeps the dimensions
+    assert np.allclose(w.getMasses(), v2)
+    assert w.getMassUpperLimits()[0] == 10.0 and w.getMassLowerLimits()[0] == 0.1
+    with pytest.raises(ValueError):
+        w.setMasses(np.zeros(3))
