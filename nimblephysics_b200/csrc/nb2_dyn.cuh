@@ -22,22 +22,22 @@
 namespace nb2 {
 
 struct FwdLayout {
-  int oQ, oV, oTau, oBody, oSlot, oFree, total;
+  int oQ, oV, oAct, oBody, oSlot, oFree, total;  // oAct: the raw action row (na <= n words)
 };
 NB2_HD FwdLayout fwd_layout(int nb, int n, int nslots, int nfree) {
   FwdLayout L;
-  L.oQ = 0; L.oV = n; L.oTau = 2 * n; L.oBody = 3 * n;
+  L.oQ = 0; L.oV = n; L.oAct = 2 * n; L.oBody = 3 * n;
   L.oSlot = L.oBody + 22 * nb;
   L.oFree = L.oSlot + 27 * nslots;
   L.total = L.oFree + 18 * nfree;
   return L;
 }
 struct BwdLayout {
-  int oGQ, oGV, oLam, oQb, oVb, oBody, oSlot, oFree, total;
+  int oGQ, oGV, oLam, oQb, oVb, oSt, oAct, oBody, oSlot, oFree, total;
 };
 NB2_HD BwdLayout bwd_layout(int nb, int n, int nslots, int nfree, int slotw = 18) {
   BwdLayout L;
-  L.oGQ = 0; L.oGV = n; L.oLam = 2 * n; L.oQb = 3 * n; L.oVb = 4 * n; L.oBody = 5 * n;
+  L.oGQ = 0; L.oGV = n; L.oLam = 2 * n; L.oQb = 3 * n; L.oVb = 4 * n; L.oSt = 5 * n; L.oAct = 7 * n; L.oBody = 8 * n;  // oSt: the step's input state [q; v]; oAct: action row in, dL/daction out
   L.oSlot = L.oBody + 7 * nb;
   L.oFree = L.oSlot + slotw * nslots;
   L.total = L.oFree + 6 * nfree;
@@ -83,34 +83,56 @@ template <class R> NB2_HD V6<R> sv_ld6(const R* sv, size_t B, int k) {
   return v;
 }
 
-template <class R> NB2_HD Xf<R> xtree(const Nb2ModelDev<R>& M, int i) {
+// Per-body constants (Xtree 12 + inertia 10 words).  `bt` is an optional copy of these tables in shared memory
+// ([body][NB2_BT_WORDS]): with several lanes per world the lanes of a warp sit on DIFFERENT bodies, and a constant-bank
+// load with a lane-varying index is replayed once per distinct address, while shared memory serves them in one pass.
+// bt == nullptr reads the kernel-parameter copy (one thread per world: the index is warp-uniform, constant bank is ideal).
+#define NB2_BT_WORDS 22
+template <class R> NB2_HD Xf<R> xtree(const Nb2ModelDev<R>& M, const R* bt, int i) {
   Xf<R> T;
+  if (bt) {
+    const R* t = bt + NB2_BT_WORDS * i;
+    T.R_.m00 = t[0]; T.R_.m01 = t[1]; T.R_.m02 = t[2]; T.R_.m10 = t[3]; T.R_.m11 = t[4]; T.R_.m12 = t[5];
+    T.R_.m20 = t[6]; T.R_.m21 = t[7]; T.R_.m22 = t[8];
+    T.p = mk3<R>(t[9], t[10], t[11]);
+    return T;
+  }
   T.R_.m00 = M.Xtree[i][0]; T.R_.m01 = M.Xtree[i][1]; T.R_.m02 = M.Xtree[i][2];
   T.R_.m10 = M.Xtree[i][3]; T.R_.m11 = M.Xtree[i][4]; T.R_.m12 = M.Xtree[i][5];
   T.R_.m20 = M.Xtree[i][6]; T.R_.m21 = M.Xtree[i][7]; T.R_.m22 = M.Xtree[i][8];
   T.p = mk3<R>(M.Xtree[i][9], M.Xtree[i][10], M.Xtree[i][11]);
   return T;
 }
+template <class R> NB2_HD Xf<R> xtree(const Nb2ModelDev<R>& M, int i) { return xtree<R>(M, (const R*)nullptr, i); }
 // parent <- child transform of a revolute-z joint: Xtree * Rz(theta)
-template <class R> NB2_HD Xf<R> xf_rev(const Nb2ModelDev<R>& M, int i, R s, R c) {
-  Xf<R> X = xtree(M, i), T;
+template <class R> NB2_HD Xf<R> xf_rev(const Nb2ModelDev<R>& M, const R* bt, int i, R s, R c) {
+  Xf<R> X = xtree(M, bt, i), T;
   T.R_.m00 = c * X.R_.m00 + s * X.R_.m01; T.R_.m01 = c * X.R_.m01 - s * X.R_.m00; T.R_.m02 = X.R_.m02;
   T.R_.m10 = c * X.R_.m10 + s * X.R_.m11; T.R_.m11 = c * X.R_.m11 - s * X.R_.m10; T.R_.m12 = X.R_.m12;
   T.R_.m20 = c * X.R_.m20 + s * X.R_.m21; T.R_.m21 = c * X.R_.m21 - s * X.R_.m20; T.R_.m22 = X.R_.m22;
   T.p = X.p;
   return T;
 }
-template <class R> NB2_HD Xf<R> xf_pris(const Nb2ModelDev<R>& M, int i, R d) {
-  Xf<R> T = xtree(M, i);
+template <class R> NB2_HD Xf<R> xf_rev(const Nb2ModelDev<R>& M, int i, R s, R c) { return xf_rev<R>(M, (const R*)nullptr, i, s, c); }
+template <class R> NB2_HD Xf<R> xf_pris(const Nb2ModelDev<R>& M, const R* bt, int i, R d) {
+  Xf<R> T = xtree(M, bt, i);
   T.p.x += T.R_.m02 * d; T.p.y += T.R_.m12 * d; T.p.z += T.R_.m22 * d;
   return T;
 }
-template <class R> NB2_HD void inertia_of(const Nb2ModelDev<R>& M, int i, R* m, V3<R>* h, S3<R>* Ib) {
+template <class R> NB2_HD Xf<R> xf_pris(const Nb2ModelDev<R>& M, int i, R d) { return xf_pris<R>(M, (const R*)nullptr, i, d); }
+template <class R> NB2_HD void inertia_of(const Nb2ModelDev<R>& M, const R* bt, int i, R* m, V3<R>* h, S3<R>* Ib) {
+  if (bt) {
+    const R* t = bt + NB2_BT_WORDS * i + 12;
+    *m = t[0]; *h = mk3<R>(t[1], t[2], t[3]);
+    Ib->xx = t[4]; Ib->yy = t[5]; Ib->zz = t[6]; Ib->xy = t[7]; Ib->xz = t[8]; Ib->yz = t[9];
+    return;
+  }
   *m = M.inertia[i][0];
   *h = mk3<R>(M.inertia[i][1], M.inertia[i][2], M.inertia[i][3]);
   Ib->xx = M.inertia[i][4]; Ib->yy = M.inertia[i][5]; Ib->zz = M.inertia[i][6];
   Ib->xy = M.inertia[i][7]; Ib->xz = M.inertia[i][8]; Ib->yz = M.inertia[i][9];
 }
+template <class R> NB2_HD void inertia_of(const Nb2ModelDev<R>& M, int i, R* m, V3<R>* h, S3<R>* Ib) { inertia_of<R>(M, (const R*)nullptr, i, m, h, Ib); }
 template <class R, int ST> NB2_HD Xf<R> ldXf(const R* p) {
   Xf<R> T;
   T.R_.m00 = p[0]; T.R_.m01 = p[ST]; T.R_.m02 = p[2 * ST]; T.R_.m10 = p[3 * ST]; T.R_.m11 = p[4 * ST]; T.R_.m12 = p[5 * ST];
@@ -123,10 +145,10 @@ template <class R, int ST> NB2_HD void stXf(R* p, const Xf<R>& T) {
   p[6 * ST] = T.R_.m20; p[7 * ST] = T.R_.m21; p[8 * ST] = T.R_.m22; p[9 * ST] = T.p.x; p[10 * ST] = T.p.y; p[11 * ST] = T.p.z;
 }
 // transform of body i during the sweeps that follow the kinematics pass (forward scratch layout)
-template <class R, int ST> NB2_HD Xf<R> body_xf_fwd(const Nb2ModelDev<R>& M, int i, const R* scr, const FwdLayout& L) {
+template <class R, int ST> NB2_HD Xf<R> body_xf_fwd(const Nb2ModelDev<R>& M, const R* bt, int i, const R* scr, const FwdLayout& L) {
   const int jt = M.jtype[i];
-  if (jt == NB2_JT_REV) { const R* b = scr + (size_t)(L.oBody + 22 * i + 6) * ST; return xf_rev(M, i, b[0], b[ST]); }
-  if (jt == NB2_JT_PRIS) return xf_pris(M, i, scr[(size_t)(L.oQ + M.dof_off[i]) * ST]);
+  if (jt == NB2_JT_REV) { const R* b = scr + (size_t)(L.oBody + 22 * i + 6) * ST; return xf_rev(M, bt, i, b[0], b[ST]); }
+  if (jt == NB2_JT_PRIS) return xf_pris(M, bt, i, scr[(size_t)(L.oQ + M.dof_off[i]) * ST]);
   return ldXf<R, ST>(scr + (size_t)(L.oFree + 18 * M.free_idx[i]) * ST);
 }
 // S * x for 1-dof joints / eta = ad(V, S v)
@@ -137,11 +159,17 @@ template <class R> NB2_HD V6<R> S_times(int jt, R x) {
 }
 template <class R> NB2_HD R S_dot(int jt, const V6<R>& f) { return (jt == NB2_JT_REV) ? f.a.z : f.l.z; }
 
+// generalized force on dof d: World.cpp:2061-2086 scatters the action through the action map, unmapped dofs get 0
+template <class R, int ST> NB2_HD R tau_of(const Nb2ModelDev<R>& M, const R* scr, int oAct, int d) {
+  const int a = M.act_of_dof[d];
+  return (a >= 0) ? scr[(size_t)(oAct + a) * ST] : R(0);
+}
+
 // =====================================================================================================
 // forward: state=[q;v] (fp32 row), action (fp32 row) -> next state row; optionally streams intermediates to `sv`
 // =====================================================================================================
 template <class R, int ST>
-NB2_HD void fwd_pass1(const Nb2ModelDev<R>& M, R* scr, int lo, int hi) {
+NB2_HD void fwd_pass1(const Nb2ModelDev<R>& M, R* scr, int lo, int hi, const R* bt = nullptr) {
   const int nb = M.nb, n = M.ndof;
   const FwdLayout L = fwd_layout(nb, n, M.nslots, M.nfree);
   const R dt = M.dt;
@@ -155,15 +183,15 @@ NB2_HD void fwd_pass1(const Nb2ModelDev<R>& M, R* scr, int lo, int hi) {
     if (jt == NB2_JT_REV) {
       R s, c; nb2_sincos(scr[(size_t)(L.oQ + o) * ST], &s, &c);
       bs[6 * ST] = s; bs[7 * ST] = c;
-      V = AdInvT(xf_rev(M, i, s, c), Vp);
+      V = AdInvT(xf_rev(M, bt, i, s, c), Vp);
       V.a.z += scr[(size_t)(L.oV + o) * ST];
     } else if (jt == NB2_JT_PRIS) {
-      V = AdInvT(xf_pris(M, i, scr[(size_t)(L.oQ + o) * ST]), Vp);
+      V = AdInvT(xf_pris(M, bt, i, scr[(size_t)(L.oQ + o) * ST]), Vp);
       V.l.z += scr[(size_t)(L.oV + o) * ST];
     } else {  // FREE (FreeJoint.cpp:74-81, 1027-1061)
       const R* q = scr + (size_t)(L.oQ + o) * ST;
       const R* v = scr + (size_t)(L.oV + o) * ST;
-      Xf<R> X = xtree(M, i), T;
+      Xf<R> X = xtree(M, bt, i), T;
       M3<R> Rq = expmap(mk3<R>(q[0], q[ST], q[2 * ST]));
       T.R_ = mul(X.R_, Rq);
       T.p = mul(X.R_, mk3<R>(q[3 * ST], q[4 * ST], q[5 * ST])) + X.p;
@@ -176,7 +204,7 @@ NB2_HD void fwd_pass1(const Nb2ModelDev<R>& M, R* scr, int lo, int hi) {
 }
 
 template <class R, int ST>
-NB2_HD void fwd_pass2(const Nb2ModelDev<R>& M, R* scr, R* sv, size_t B, bool save, int lo, int hi) {
+NB2_HD void fwd_pass2(const Nb2ModelDev<R>& M, R* scr, R* sv, size_t B, bool save, int lo, int hi, const R* bt = nullptr) {
   const int nb = M.nb, n = M.ndof;
   const FwdLayout L = fwd_layout(nb, n, M.nslots, M.nfree);
   const R dt = M.dt;
@@ -189,7 +217,7 @@ NB2_HD void fwd_pass2(const Nb2ModelDev<R>& M, R* scr, R* sv, size_t B, bool sav
   for (int i = hi - 1; i >= lo; i--) {
     const int jt = M.jtype[i], p = M.parent[i], o = M.dof_off[i], fl = M.flags[i];
     R* bs = scr + (size_t)(L.oBody + 22 * i) * ST;
-    R m; V3<R> h; S3<R> Ib; inertia_of(M, i, &m, &h, &Ib);
+    R m; V3<R> h; S3<R> Ib; inertia_of(M, bt, i, &m, &h, &Ib);
     const V6<R> V = ld6<R, ST>(bs);
     SI<R> IA = rigidSI(m, h, Ib);
     V6<R> pA = crf(V, mulG(m, h, Ib, V));
@@ -215,7 +243,7 @@ NB2_HD void fwd_pass2(const Nb2ModelDev<R>& M, R* scr, R* sv, size_t B, bool sav
       }
       const R psi = R(1) / D;
       const R qv = scr[(size_t)(L.oQ + o) * ST];
-      const R u = scr[(size_t)(L.oTau + o) * ST] - M.spring[o] * (qv - M.rest[o] + vq * dt) - M.damping[o] * vq
+      const R u = tau_of<R, ST>(M, scr, L.oAct, o) - M.spring[o] * (qv - M.rest[o] + vq * dt) - M.damping[o] * vq
                   - (dot(U, eta) + S_dot(jt, pA));
       st6<R, ST>(bs + 8 * ST, U);
       bs[14 * ST] = psi; bs[15 * ST] = u;
@@ -234,17 +262,19 @@ NB2_HD void fwd_pass2(const Nb2ModelDev<R>& M, R* scr, R* sv, size_t B, bool sav
     } else {
       const R* q = scr + (size_t)(L.oQ + o) * ST;
       const R* v = scr + (size_t)(L.oV + o) * ST;
-      const R* t = scr + (size_t)(L.oTau + o) * ST;
+      R t[6];
+#pragma unroll
+      for (int k = 0; k < 6; k++) t[k] = tau_of<R, ST>(M, scr, L.oAct, o + k);
       const V6<R> Vj = ld6<R, ST>(v);
       const V6<R> eta = ad(V, Vj);
       const V6<R> bf = mul(IA, eta) + pA;
       V6<R> u;
       u.a.x = t[0] - M.spring[o] * (q[0] - M.rest[o] + Vj.a.x * dt) - M.damping[o] * Vj.a.x - bf.a.x;
-      u.a.y = t[ST] - M.spring[o + 1] * (q[ST] - M.rest[o + 1] + Vj.a.y * dt) - M.damping[o + 1] * Vj.a.y - bf.a.y;
-      u.a.z = t[2 * ST] - M.spring[o + 2] * (q[2 * ST] - M.rest[o + 2] + Vj.a.z * dt) - M.damping[o + 2] * Vj.a.z - bf.a.z;
-      u.l.x = t[3 * ST] - M.spring[o + 3] * (q[3 * ST] - M.rest[o + 3] + Vj.l.x * dt) - M.damping[o + 3] * Vj.l.x - bf.l.x;
-      u.l.y = t[4 * ST] - M.spring[o + 4] * (q[4 * ST] - M.rest[o + 4] + Vj.l.y * dt) - M.damping[o + 4] * Vj.l.y - bf.l.y;
-      u.l.z = t[5 * ST] - M.spring[o + 5] * (q[5 * ST] - M.rest[o + 5] + Vj.l.z * dt) - M.damping[o + 5] * Vj.l.z - bf.l.z;
+      u.a.y = t[1] - M.spring[o + 1] * (q[ST] - M.rest[o + 1] + Vj.a.y * dt) - M.damping[o + 1] * Vj.a.y - bf.a.y;
+      u.a.z = t[2] - M.spring[o + 2] * (q[2 * ST] - M.rest[o + 2] + Vj.a.z * dt) - M.damping[o + 2] * Vj.a.z - bf.a.z;
+      u.l.x = t[3] - M.spring[o + 3] * (q[3 * ST] - M.rest[o + 3] + Vj.l.x * dt) - M.damping[o + 3] * Vj.l.x - bf.l.x;
+      u.l.y = t[4] - M.spring[o + 4] * (q[4 * ST] - M.rest[o + 4] + Vj.l.y * dt) - M.damping[o + 4] * Vj.l.y - bf.l.y;
+      u.l.z = t[5] - M.spring[o + 5] * (q[5 * ST] - M.rest[o + 5] + Vj.l.z * dt) - M.damping[o + 5] * Vj.l.z - bf.l.z;
       const SI<R> Iinv = spd6_inverse(IA);
       const V6<R> y = mul(Iinv, u);
       st6<R, ST>(scr + (size_t)(L.oFree + 18 * M.free_idx[i] + 12) * ST, y);
@@ -260,7 +290,7 @@ NB2_HD void fwd_pass2(const Nb2ModelDev<R>& M, R* scr, R* sv, size_t B, bool sav
     }
     hvalid = false;
     if (p >= 0) {
-      const Xf<R> T = body_xf_fwd<R, ST>(M, i, scr, L);
+      const Xf<R> T = body_xf_fwd<R, ST>(M, bt, i, scr, L);
       const SI<R> Ic = xform_inertia(T, Pi);
       const V6<R> pc = dAdInvT(T, beta);
       if (fl & NB2_F_HANDOFF) { hI = Ic; hp = pc; hvalid = true; }
@@ -274,7 +304,7 @@ NB2_HD void fwd_pass2(const Nb2ModelDev<R>& M, R* scr, R* sv, size_t B, bool sav
 }
 
 template <class R, int ST>
-NB2_HD void fwd_pass3(const Nb2ModelDev<R>& M, R* scr, float* out, R* sv, size_t B, bool save, int lo, int hi) {
+NB2_HD void fwd_pass3(const Nb2ModelDev<R>& M, R* scr, R* sv, size_t B, bool save, int lo, int hi, const R* bt = nullptr) {
   const int nb = M.nb, n = M.ndof;
   const FwdLayout L = fwd_layout(nb, n, M.nslots, M.nfree);
   const R dt = M.dt;
@@ -285,7 +315,7 @@ NB2_HD void fwd_pass3(const Nb2ModelDev<R>& M, R* scr, float* out, R* sv, size_t
   for (int i = lo; i < hi; i++) {
     const int jt = M.jtype[i], p = M.parent[i], o = M.dof_off[i];
     R* bs = scr + (size_t)(L.oBody + 22 * i) * ST;
-    const Xf<R> T = body_xf_fwd<R, ST>(M, i, scr, L);
+    const Xf<R> T = body_xf_fwd<R, ST>(M, bt, i, scr, L);
     const V6<R> Ap = AdInvT(T, (p >= 0) ? ld6<R, ST>(scr + (size_t)(L.oBody + 22 * p + 16) * ST) : A0);
     const V6<R> V = ld6<R, ST>(bs);
     V6<R> A;
@@ -297,8 +327,8 @@ NB2_HD void fwd_pass3(const Nb2ModelDev<R>& M, R* scr, float* out, R* sv, size_t
       A = Ap;
       if (jt == NB2_JT_REV) { A.a.z += qdd; A.a.x += V.a.y * vq; A.a.y -= V.a.x * vq; A.l.x += V.l.y * vq; A.l.y -= V.l.x * vq; }
       else { A.l.z += qdd; A.l.x += V.a.y * vq; A.l.y -= V.a.x * vq; }
-      out[o] = (float)(qv + vq * dt);
-      out[n + o] = (float)(vq + qdd * dt);
+      scr[(size_t)(L.oQ + o) * ST] = qv + vq * dt;   // q+, v+ replace q, v in the scratch (nothing reads this body's q, v again);
+      scr[(size_t)(L.oV + o) * ST] = vq + qdd * dt;  // fwd_store writes them out coalesced
       if (save) {
         R* s = sv + (size_t)(i * 21) * B;
         sv_st6(s, B, 0, tof(V)); sv_st6(s, B, 6, tof(A)); sv_st6(s, B, 12, tof(U));
@@ -318,10 +348,11 @@ NB2_HD void fwd_pass3(const Nb2ModelDev<R>& M, R* scr, float* out, R* sv, size_t
       const M3<R> Rq = expmap(phi);
       const V3<R> phin = logmap(mul(Rq, expmap(Vj.a * dt)));
       const V3<R> pn = mk3<R>(q[3 * ST], q[4 * ST], q[5 * ST]) + mul(Rq, Vj.l * dt);
-      out[o] = (float)phin.x; out[o + 1] = (float)phin.y; out[o + 2] = (float)phin.z;
-      out[o + 3] = (float)pn.x; out[o + 4] = (float)pn.y; out[o + 5] = (float)pn.z;
-      out[n + o] = (float)(Vj.a.x + qdd.a.x * dt); out[n + o + 1] = (float)(Vj.a.y + qdd.a.y * dt); out[n + o + 2] = (float)(Vj.a.z + qdd.a.z * dt);
-      out[n + o + 3] = (float)(Vj.l.x + qdd.l.x * dt); out[n + o + 4] = (float)(Vj.l.y + qdd.l.y * dt); out[n + o + 5] = (float)(Vj.l.z + qdd.l.z * dt);
+      R* qo = scr + (size_t)(L.oQ + o) * ST;
+      R* vo = scr + (size_t)(L.oV + o) * ST;
+      qo[0] = phin.x; qo[ST] = phin.y; qo[2 * ST] = phin.z; qo[3 * ST] = pn.x; qo[4 * ST] = pn.y; qo[5 * ST] = pn.z;
+      vo[0] = Vj.a.x + qdd.a.x * dt; vo[ST] = Vj.a.y + qdd.a.y * dt; vo[2 * ST] = Vj.a.z + qdd.a.z * dt;
+      vo[3 * ST] = Vj.l.x + qdd.l.x * dt; vo[4 * ST] = Vj.l.y + qdd.l.y * dt; vo[5 * ST] = Vj.l.z + qdd.l.z * dt;
       if (save) {
         R* s = sv + (size_t)(i * 21) * B;
         sv_st6(s, B, 0, tof(V)); sv_st6(s, B, 6, tof(A));
@@ -336,46 +367,125 @@ NB2_HD void fwd_pass3(const Nb2ModelDev<R>& M, R* scr, float* out, R* sv, size_t
   }
 }
 
+// ---- group I/O.  A GROUP is the set of worlds one warp works on (32/lanes of them on the device, one in the host
+// emulation and in the single-thread paths); its worlds are consecutive, so their state / action / output rows form
+// one contiguous block of global memory that the group's threads copy cooperatively (fully coalesced, every byte
+// touched once — the entry points may hand in mapped host memory).  scr0 = scratch of the group's first world.
+// Copy loops of the group I/O: 16-byte vector accesses when the block is aligned (it is whenever the batch pointers are,
+// since a group starts at a multiple of 4 worlds), several independent loads in flight per thread (the source may be
+// host memory behind PCIe), index -> (world slot, dof) by multiply-high with the precomputed reciprocal.
+#define NB2_IO_UNROLL 4
+struct alignas(16) F4 { float x, y, z, w; };
+NB2_HD unsigned fast_div(unsigned idx, unsigned magic) {
+#ifdef __CUDA_ARCH__
+  return __umulhi(idx, magic);
+#else
+  return (unsigned)(((unsigned long long)idx * magic) >> 32);
+#endif
+}
+template <class F> NB2_HD void group_read(const float* src, int tot, int tid, int nthr, const F& f) {
+  if ((((size_t)src) & 15) == 0) {
+    const F4* s4 = reinterpret_cast<const F4*>(src);
+    const int tot4 = tot >> 2;
+    for (int base = tid; base < tot4; base += nthr * NB2_IO_UNROLL) {
+      F4 v[NB2_IO_UNROLL];
+#pragma unroll
+      for (int u = 0; u < NB2_IO_UNROLL; u++) { const int j = base + u * nthr; if (j < tot4) v[u] = s4[j]; }
+#pragma unroll
+      for (int u = 0; u < NB2_IO_UNROLL; u++) {
+        const int j = base + u * nthr;
+        if (j < tot4) { f(4 * j, v[u].x); f(4 * j + 1, v[u].y); f(4 * j + 2, v[u].z); f(4 * j + 3, v[u].w); }
+      }
+    }
+    for (int idx = 4 * tot4 + tid; idx < tot; idx += nthr) f(idx, src[idx]);
+  } else {
+    for (int base = tid; base < tot; base += nthr * NB2_IO_UNROLL) {
+      float v[NB2_IO_UNROLL];
+#pragma unroll
+      for (int u = 0; u < NB2_IO_UNROLL; u++) { const int idx = base + u * nthr; v[u] = (idx < tot) ? src[idx] : 0.f; }
+#pragma unroll
+      for (int u = 0; u < NB2_IO_UNROLL; u++) { const int idx = base + u * nthr; if (idx < tot) f(idx, v[u]); }
+    }
+  }
+}
+template <class F> NB2_HD void group_write(float* dst, int tot, int tid, int nthr, const F& f) {
+  if ((((size_t)dst) & 15) == 0) {
+    F4* d4 = reinterpret_cast<F4*>(dst);
+    const int tot4 = tot >> 2;
+    for (int j = tid; j < tot4; j += nthr) { F4 v; v.x = f(4 * j); v.y = f(4 * j + 1); v.z = f(4 * j + 2); v.w = f(4 * j + 3); d4[j] = v; }
+    for (int idx = 4 * tot4 + tid; idx < tot; idx += nthr) dst[idx] = f(idx);
+  } else {
+    for (int idx = tid; idx < tot; idx += nthr) dst[idx] = f(idx);
+  }
+}
+
+template <class R, int ST> struct WordScatter {  // element d of row `slot` of a [*, width] block -> scratch word (base + d) (+ device copy)
+  R* scr0; int width, base; unsigned magic; float* copy;
+  NB2_HD void operator()(int idx, float v) const {
+    const int slot = (int)fast_div((unsigned)idx, magic), d = idx - slot * width;
+    scr0[(size_t)(base + d) * ST + slot] = (R)v;
+    if (copy) copy[idx] = v;
+  }
+};
+template <class R, int ST> struct WordGather {
+  const R* scr0; int width, base; unsigned magic;
+  NB2_HD float operator()(int idx) const {
+    const int slot = (int)fast_div((unsigned)idx, magic), d = idx - slot * width;
+    return (float)scr0[(size_t)(base + d) * ST + slot];
+  }
+};
+
+// ---- group I/O.  A GROUP is the set of worlds one warp works on (32/lanes of them on the device, a few in the host
+// emulation, one in the single-thread paths); its worlds are consecutive, so their state / action / output rows form
+// one contiguous block of global memory that the group's threads copy cooperatively (fully coalesced, every byte
+// touched once — the entry points may hand in mapped host memory).  scr0 = scratch of the group's first world.
+// The copies are pure word moves (q, v and the raw action row are adjacent in the scratch); the action map and the
+// gradient clipping are applied per body inside the sweeps, where the model tables are indexed (almost) uniformly.
+template <class R, int ST>
+NB2_HD void fwd_load(const Nb2ModelDev<R>& M, R* scr0, const float* st0, const float* act0, int nworlds, int tid, int nthr,
+                     float* st_copy0 = nullptr, float* act_copy0 = nullptr) {
+  const int n2 = 2 * M.ndof, na = M.na;
+  const FwdLayout L = fwd_layout(M.nb, M.ndof, M.nslots, M.nfree);
+  WordScatter<R, ST> ss{scr0, n2, L.oQ, M.magic_n2, st_copy0};  // oV = oQ + n
+  group_read(st0, nworlds * n2, tid, nthr, ss);
+  WordScatter<R, ST> as{scr0, na, L.oAct, M.magic_na, act_copy0};
+  group_read(act0, nworlds * na, tid, nthr, as);
+}
+template <class R, int ST>
+NB2_HD void fwd_store(const Nb2ModelDev<R>& M, const R* scr0, float* out0, int nworlds, int tid, int nthr) {
+  const int n2 = 2 * M.ndof;
+  const FwdLayout L = fwd_layout(M.nb, M.ndof, M.nslots, M.nfree);
+  WordGather<R, ST> sg{scr0, n2, L.oQ, M.magic_n2};
+  group_write(out0, nworlds * n2, tid, nthr, sg);
+}
+
 // The sweeps are cut into STAGES so that M.lanes threads can cooperate on one world: lane 0 owns the TRUNK (an
 // ancestor-closed set of bodies), every lane owns some LIMB subtrees (modelspec._partition_tree).  A warp barrier is
-// needed only where data crosses lanes (NB2_FWD_SYNC_MASK bit = "barrier after this stage"):
-//   0 load q, v, tau (dofs strided over the lanes)           | barrier
+// needed only where data crosses threads (NB2_FWD_SYNC_MASK bit = "barrier after this stage"):
+//   0 group load of q, v, tau (fwd_load)                     | barrier
 //   1 kinematics of the trunk           (lane 0, root->leaf) | barrier
 //   2 kinematics of the limbs           (every lane)
 //   3 articulated inertias of the limbs (every lane, leaf->root) | barrier
 //   4 articulated inertias of the trunk (lane 0)
 //   5 accelerations + integration, trunk (lane 0)            | barrier
-//   6 accelerations + integration, limbs (every lane)
+//   6 accelerations + integration, limbs (every lane)        | barrier
+//   7 group store of q+, v+ (fwd_store)
 // With lanes == 1 everything is trunk.  Each pass body is instantiated once (the stage index is a run-time value).
-#define NB2_FWD_STAGES 7
-#define NB2_FWD_SYNC_MASK 0x2Bu  /* after stages 0, 1, 3, 5 */
+#define NB2_FWD_STAGES 8
+#define NB2_FWD_SYNC_MASK 0x6Bu       /* after stages 0, 1, 3, 5, 6 */
+#define NB2_FWD_SYNC_MASK_1LANE 0x41u /* lanes == 1: only the group load / store exchange data between threads */
 template <class R, int ST>
-NB2_HD void world_forward_stage(const Nb2ModelDev<R>& M, R* scr, const float* st, const float* act, float* out, R* sv,
-                                size_t B, bool save, int lane, int stage) {
-  const int n = M.ndof, K = M.lanes;
-  if (stage == 0) {
-    const FwdLayout L = fwd_layout(M.nb, n, M.nslots, M.nfree);
-    for (int d = lane; d < n; d += K) {
-      scr[(size_t)(L.oQ + d) * ST] = (R)st[d];
-      scr[(size_t)(L.oV + d) * ST] = (R)st[n + d];
-      scr[(size_t)(L.oTau + d) * ST] = R(0);
-    }
-    for (int i = 0; i < M.na; i++) {  // World.cpp:2061-2086; the lane that zeroed a dof also scatters into it
-      const int d = M.action_map[i];
-      if (d % K == lane) scr[(size_t)(L.oTau + d) * ST] = (R)act[i];
-    }
-    return;
-  }
-  const int pass = (stage + 1) >> 1;                          // 1, 2, 3
+NB2_HD void world_forward_stage(const Nb2ModelDev<R>& M, R* scr, R* sv, size_t B, bool save, int lane, int stage, const R* bt = nullptr) {
+  const int pass = (stage + 1) >> 1;                          // stages 1..6 -> passes 1, 2, 3
   const bool trunk = (stage == 1) | (stage == 4) | (stage == 5);
   if (trunk && lane != 0) return;
   const int nr = trunk ? M.trunk_n : M.limb_n[lane];
   for (int rr = 0; rr < nr; rr++) {
     const int r = (pass == 2) ? nr - 1 - rr : rr;
     const int lo = trunk ? M.trunk_lo[r] : M.limb_lo[lane][r], hi = trunk ? M.trunk_hi[r] : M.limb_hi[lane][r];
-    if (pass == 1) fwd_pass1<R, ST>(M, scr, lo, hi);
-    else if (pass == 2) fwd_pass2<R, ST>(M, scr, sv, B, save, lo, hi);
-    else fwd_pass3<R, ST>(M, scr, out, sv, B, save, lo, hi);
+    if (pass == 1) fwd_pass1<R, ST>(M, scr, lo, hi, bt);
+    else if (pass == 2) fwd_pass2<R, ST>(M, scr, sv, B, save, lo, hi, bt);
+    else fwd_pass3<R, ST>(M, scr, sv, B, save, lo, hi, bt);
   }
 }
 
@@ -383,8 +493,10 @@ NB2_HD void world_forward_stage(const Nb2ModelDev<R>& M, R* scr, const float* st
 template <class R, int ST>
 NB2_HD void world_forward(const Nb2ModelDev<R>& M, R* scr, const float* st, const float* act, float* out, R* sv,
                           size_t B, bool save) {
-  for (int sg = 0; sg < NB2_FWD_STAGES; sg++)
-    for (int lane = 0; lane < M.lanes; lane++) world_forward_stage<R, ST>(M, scr, st, act, out, sv, B, save, lane, sg);
+  fwd_load<R, ST>(M, scr, st, act, 1, 0, 1);
+  for (int sg = 1; sg < NB2_FWD_STAGES - 1; sg++)
+    for (int lane = 0; lane < M.lanes; lane++) world_forward_stage<R, ST>(M, scr, sv, B, save, lane, sg);
+  fwd_store<R, ST>(M, scr, out, 1, 0, 1);
 }
 
 // hook implemented in nb2_contact.cuh: turns lambda / W into w / W(w) and prepares the contact injections
@@ -416,7 +528,7 @@ template <class R> NB2_HD void inertia_param_form(const V6<R>& Y, const V6<R>& X
 // backward: g_next = dL/d[q+;v+]  ->  g_state = dL/d[q;v], g_action = dL/d action
 // =====================================================================================================
 template <class R, int ST, bool CONTACT>
-NB2_HD void bwd_B1(const Nb2ModelDev<R>& M, R* scr, const float* st, const R* sv, size_t B, int lo, int hi) {
+NB2_HD void bwd_B1(const Nb2ModelDev<R>& M, R* scr, const float* st, const R* sv, size_t B, int lo, int hi, const R* bt = nullptr) {
   const int nb = M.nb, n = M.ndof;
   constexpr int SLOTW = CONTACT ? 42 : 18;
   const BwdLayout L = bwd_layout(nb, n, M.nslots, M.nfree, SLOTW);
@@ -446,8 +558,8 @@ NB2_HD void bwd_B1(const Nb2ModelDev<R>& M, R* scr, const float* st, const R* sv
     hvalid = false;
     if (p >= 0) {
       Xf<R> T;
-      if (jt == NB2_JT_REV) T = xf_rev(M, i, (R)s[19 * B], (R)s[20 * B]);
-      else if (jt == NB2_JT_PRIS) T = xf_pris(M, i, (R)st[o]);
+      if (jt == NB2_JT_REV) T = xf_rev(M, bt, i, (R)s[19 * B], (R)s[20 * B]);
+      else if (jt == NB2_JT_PRIS) T = xf_pris(M, bt, i, scr[(size_t)(L.oSt + o) * ST]);
       else { R t12[12]; for (int k = 0; k < 12; k++) t12[k] = (R)sv[(size_t)(kFree + M.free_idx[i] * 33 + 21 + k) * B]; T = ldXf<R, 1>(t12); }
       const V6<R> pc = dAdInvT(T, beta);
       if (fl & NB2_F_HANDOFF) { hp = pc; hvalid = true; }
@@ -460,7 +572,7 @@ NB2_HD void bwd_B1(const Nb2ModelDev<R>& M, R* scr, const float* st, const R* sv
 }
 
 template <class R, int ST, bool CONTACT>
-NB2_HD void bwd_B2(const Nb2ModelDev<R>& M, R* scr, const float* st, const R* sv, size_t B, int lo, int hi) {
+NB2_HD void bwd_B2(const Nb2ModelDev<R>& M, R* scr, const float* st, const R* sv, size_t B, int lo, int hi, const R* bt = nullptr) {
   const int nb = M.nb, n = M.ndof;
   constexpr int SLOTW = CONTACT ? 42 : 18;
   const BwdLayout L = bwd_layout(nb, n, M.nslots, M.nfree, SLOTW);
@@ -475,7 +587,7 @@ NB2_HD void bwd_B2(const Nb2ModelDev<R>& M, R* scr, const float* st, const R* sv
     R* bs = scr + (size_t)(L.oBody + 7 * i) * ST;
     V6<R> W;
     if (jt != NB2_JT_FREE) {
-      Xf<R> T = (jt == NB2_JT_REV) ? xf_rev(M, i, (R)s[19 * B], (R)s[20 * B]) : xf_pris(M, i, (R)st[o]);
+      Xf<R> T = (jt == NB2_JT_REV) ? xf_rev(M, bt, i, (R)s[19 * B], (R)s[20 * B]) : xf_pris(M, bt, i, scr[(size_t)(L.oSt + o) * ST]);
       W = (p >= 0) ? AdInvT(T, ld6<R, ST>(scr + (size_t)(L.oBody + 7 * p + 1) * ST)) : zero6<R>();
       const R lam = (R)s[18 * B] * (bs[0] - dot(sv_ld6<R>(s, B, 12), W));
       scr[(size_t)(L.oLam + o) * ST] = lam;
@@ -496,7 +608,7 @@ NB2_HD void bwd_B2(const Nb2ModelDev<R>& M, R* scr, const float* st, const R* sv
 
 template <class R, int ST, bool CONTACT>
 NB2_HD void bwd_B3(const Nb2ModelDev<R>& M, R* scr, const float* st, const R* sv, size_t B, const BwdContactData<ST>& cd, int lo, int hi,
-                   float* gI = nullptr) {
+                   float* gI = nullptr, const R* bt = nullptr) {
   const int nb = M.nb, n = M.ndof;
   constexpr int SLOTW = CONTACT ? 42 : 18;
   const BwdLayout L = bwd_layout(nb, n, M.nslots, M.nfree, SLOTW);
@@ -516,7 +628,7 @@ NB2_HD void bwd_B3(const Nb2ModelDev<R>& M, R* scr, const float* st, const R* sv
   for (int i = hi - 1; i >= lo; i--) {
     const int jt = M.jtype[i], p = M.parent[i], o = M.dof_off[i], fl = M.flags[i];
     const R* s = sv + (size_t)(i * 21) * B;
-    R m; V3<R> h; S3<R> Ib; inertia_of(M, i, &m, &h, &Ib);
+    R m; V3<R> h; S3<R> Ib; inertia_of(M, bt, i, &m, &h, &Ib);
     const V6<R> V = sv_ld6<R>(s, B, 0);
     V6<R> A = sv_ld6<R>(s, B, 6);
     if (CONTACT && cd.active) { const auto a6 = cd.Aacc + 6 * i; A.a = mk3<R>((R)a6[0], (R)a6[1], (R)a6[2]); A.l = mk3<R>((R)a6[3], (R)a6[4], (R)a6[5]); }
@@ -556,12 +668,12 @@ NB2_HD void bwd_B3(const Nb2ModelDev<R>& M, R* scr, const float* st, const R* sv
     V6<R> Sv, Sa, Sl;
     Xf<R> T;
     if (jt != NB2_JT_FREE) {
-      Sv = S_times<R>(jt, (R)st[n + o]);
+      Sv = S_times<R>(jt, scr[(size_t)(L.oSt + n + o) * ST]);
       Sa = S_times<R>(jt, (CONTACT && cd.active) ? (R)cd.aeff[o] : (R)sv[(size_t)(kQdd + o) * B]);
       Sl = S_times<R>(jt, scr[(size_t)(L.oLam + o) * ST]);
-      T = (jt == NB2_JT_REV) ? xf_rev(M, i, (R)s[19 * B], (R)s[20 * B]) : xf_pris(M, i, (R)st[o]);
+      T = (jt == NB2_JT_REV) ? xf_rev(M, bt, i, (R)s[19 * B], (R)s[20 * B]) : xf_pris(M, bt, i, scr[(size_t)(L.oSt + o) * ST]);
     } else {
-      Sv.a = mk3<R>((R)st[n + o], (R)st[n + o + 1], (R)st[n + o + 2]); Sv.l = mk3<R>((R)st[n + o + 3], (R)st[n + o + 4], (R)st[n + o + 5]);
+      Sv.a = mk3<R>(scr[(size_t)(L.oSt + n + o) * ST], scr[(size_t)(L.oSt + n + o + 1) * ST], scr[(size_t)(L.oSt + n + o + 2) * ST]); Sv.l = mk3<R>(scr[(size_t)(L.oSt + n + o + 3) * ST], scr[(size_t)(L.oSt + n + o + 4) * ST], scr[(size_t)(L.oSt + n + o + 5) * ST]);
       Sa = sv_ld6<R>(sv + (size_t)(kQdd + o) * B, B, 0);
       if (CONTACT && cd.active) { const auto a6 = cd.aeff + o; Sa.a = mk3<R>((R)a6[0], (R)a6[1], (R)a6[2]); Sa.l = mk3<R>((R)a6[3], (R)a6[4], (R)a6[5]); }
       Sl = ld6<R, ST>(scr + (size_t)(L.oLam + o) * ST);
@@ -587,7 +699,7 @@ NB2_HD void bwd_B3(const Nb2ModelDev<R>& M, R* scr, const float* st, const R* sv
       scr[(size_t)(L.oQb + o) * ST] = S_dot(jt, c6);
     } else {
       st6<R, ST>(scr + (size_t)(L.oVb + o) * ST, vb6);
-      const V3<R> phi = mk3<R>((R)st[o], (R)st[o + 1], (R)st[o + 2]);
+      const V3<R> phi = mk3<R>(scr[(size_t)(L.oSt + o) * ST], scr[(size_t)(L.oSt + o + 1) * ST], scr[(size_t)(L.oSt + o + 2) * ST]);
       V6<R> qb;
       qb.a = mulT(so3_Jr(phi), c6.a);
       qb.l = mul(expmap(phi), c6.l);
@@ -608,6 +720,30 @@ NB2_HD void bwd_B3(const Nb2ModelDev<R>& M, R* scr, const float* st, const R* sv
   }
 }
 
+// last step of the backward for one dof: clipLossGradientsToBounds (BackpropSnapshot.cpp:425-479; exact equality against
+// the pre-step state / action) and the scatter of dL/dtau through the action map (:404-417).  Results replace qbar / vbar
+// and the action value in the scratch; bwd_store copies them out.
+template <class R, int ST>
+NB2_HD void finish_dof(const Nb2ModelDev<R>& M, R* scr, const BwdLayout& L, int d, R gq_, R gv_, R lam) {
+  const int n = M.ndof;
+  float gq = (float)gq_, gv = (float)gv_;
+  const float qd = (float)scr[(size_t)(L.oSt + d) * ST], vd = (float)scr[(size_t)(L.oSt + n + d) * ST];  // exact: fp32 inputs widened
+  if (qd == M.pos_lo[d] && gq > 0.f) gq = 0.f;
+  if (qd == M.pos_hi[d] && gq < 0.f) gq = 0.f;
+  if (vd == M.vel_lo[d] && gv > 0.f) gv = 0.f;
+  if (vd == M.vel_hi[d] && gv < 0.f) gv = 0.f;
+  scr[(size_t)(L.oQb + d) * ST] = (R)gq;
+  scr[(size_t)(L.oVb + d) * ST] = (R)gv;
+  const int a = M.act_of_dof[d];
+  if (a >= 0) {
+    float gt = (float)(M.dt * lam);
+    const float fd = (float)scr[(size_t)(L.oAct + a) * ST];
+    if (fd == M.force_lo[d] && gt > 0.f) gt = 0.f;
+    if (fd == M.force_hi[d] && gt < 0.f) gt = 0.f;
+    scr[(size_t)(L.oAct + a) * ST] = (R)gt;
+  }
+}
+
 template <class R, int ST, bool CONTACT>
 NB2_HD void bwd_assemble(const Nb2ModelDev<R>& M, R* scr, const float* st, const BwdContactData<ST>& cd, int lo, int hi) {
   const int nb = M.nb, n = M.ndof;
@@ -625,14 +761,14 @@ NB2_HD void bwd_assemble(const Nb2ModelDev<R>& M, R* scr, const float* st, const
       const R gq = scr[(size_t)(L.oGQ + o) * ST];
       R gv = scr[(size_t)(L.oGV + o) * ST];
       if (CONTACT && cd.active) gv -= (R)cd.JcTmu[o];  // dL/dv* = g - A_c mu
-      scr[(size_t)(L.oQb + o) * ST] = gq - dt * (scr[(size_t)(L.oQb + o) * ST] + M.spring[o] * lam);
-      scr[(size_t)(L.oVb + o) * ST] = dt * gq + gv - dt * (scr[(size_t)(L.oVb + o) * ST] + (M.damping[o] + dt * M.spring[o]) * lam);
+      finish_dof<R, ST>(M, scr, L, o, gq - dt * (scr[(size_t)(L.oQb + o) * ST] + M.spring[o] * lam),
+                        dt * gq + gv - dt * (scr[(size_t)(L.oVb + o) * ST] + (M.damping[o] + dt * M.spring[o]) * lam), lam);
     } else {
       // free-joint position update q+ = [log(R(phi) exp(w dt)); p + R(phi) v dt] (the reference differentiates this by
       // finite differences, FreeJoint.cpp:950-1007; closed form here)
-      const V3<R> phi = mk3<R>((R)st[o], (R)st[o + 1], (R)st[o + 2]);
-      const V3<R> w = mk3<R>((R)st[n + o], (R)st[n + o + 1], (R)st[n + o + 2]);
-      const V3<R> vl = mk3<R>((R)st[n + o + 3], (R)st[n + o + 4], (R)st[n + o + 5]);
+      const V3<R> phi = mk3<R>(scr[(size_t)(L.oSt + o) * ST], scr[(size_t)(L.oSt + o + 1) * ST], scr[(size_t)(L.oSt + o + 2) * ST]);
+      const V3<R> w = mk3<R>(scr[(size_t)(L.oSt + n + o) * ST], scr[(size_t)(L.oSt + n + o + 1) * ST], scr[(size_t)(L.oSt + n + o + 2) * ST]);
+      const V3<R> vl = mk3<R>(scr[(size_t)(L.oSt + n + o + 3) * ST], scr[(size_t)(L.oSt + n + o + 4) * ST], scr[(size_t)(L.oSt + n + o + 5) * ST]);
       const M3<R> Rq = expmap(phi), E = expmap(w * dt);
       const V3<R> phin = logmap(mul(Rq, E));
       const V6<R> g = ld6<R, ST>(scr + (size_t)(L.oGQ + o) * ST);
@@ -652,72 +788,60 @@ NB2_HD void bwd_assemble(const Nb2ModelDev<R>& M, R* scr, const float* st, const
       R gvv[6] = {gv.a.x, gv.a.y, gv.a.z, gv.l.x, gv.l.y, gv.l.z};
 #pragma unroll
       for (int k = 0; k < 6; k++) {
-        scr[(size_t)(L.oQb + o + k) * ST] = gqv[k] - dt * (qbv[k] + M.spring[o + k] * lamv[k]);
-        scr[(size_t)(L.oVb + o + k) * ST] = gvpv[k] + gvv[k] - dt * (vbv[k] + (M.damping[o + k] + dt * M.spring[o + k]) * lamv[k]);
+        finish_dof<R, ST>(M, scr, L, o + k, gqv[k] - dt * (qbv[k] + M.spring[o + k] * lamv[k]),
+                          gvpv[k] + gvv[k] - dt * (vbv[k] + (M.damping[o + k] + dt * M.spring[o + k]) * lamv[k]), lamv[k]);
       }
     }
   }
 }
 
+// group load of dL/dx', the step's input state and action (B1..B3 and the clipping read them from the scratch)
 template <class R, int ST, bool CONTACT>
-NB2_HD void bwd_store(const Nb2ModelDev<R>& M, const R* scr, const float* st, const float* act, float* gstate, float* gaction,
-                      bool cd_error, int lane, int K) {
-  const int nb = M.nb, n = M.ndof;
+NB2_HD void bwd_load(const Nb2ModelDev<R>& M, R* scr0, const float* st0, const float* act0, const float* gnext0, int nworlds, int tid, int nthr) {
+  const int n = M.ndof, n2 = 2 * n;
   constexpr int SLOTW = CONTACT ? 42 : 18;
-  const BwdLayout L = bwd_layout(nb, n, M.nslots, M.nfree, SLOTW);
-  const R dt = M.dt;
-  const int kFree = nb * 21, kQdd = nb * 21 + M.nfree * 33;
-  (void)n; (void)dt; (void)kFree; (void)kQdd;
+  const BwdLayout L = bwd_layout(M.nb, n, M.nslots, M.nfree, SLOTW);
+  WordScatter<R, ST> sg{scr0, n2, L.oGQ, M.magic_n2, nullptr};  // oGV = oGQ + n
+  group_read(gnext0, nworlds * n2, tid, nthr, sg);
+  WordScatter<R, ST> sx{scr0, n2, L.oSt, M.magic_n2, nullptr};
+  group_read(st0, nworlds * n2, tid, nthr, sx);
+  WordScatter<R, ST> sa{scr0, M.na, L.oAct, M.magic_na, nullptr};
+  group_read(act0, nworlds * M.na, tid, nthr, sa);
+}
+struct NanGather { NB2_HD float operator()(int) const { return nanf(""); } };
+// group store of the (already clipped) gradients: [oQb, oVb] are adjacent, dL/daction sits in oAct
+template <class R, int ST, bool CONTACT>
+NB2_HD void bwd_store(const Nb2ModelDev<R>& M, const R* scr0, float* gstate0, float* gaction0,
+                      bool cd_error, int nworlds, int tid, int nthr) {
+  const int n = M.ndof, n2 = 2 * n, na = M.na;
+  constexpr int SLOTW = CONTACT ? 42 : 18;
+  const BwdLayout L = bwd_layout(M.nb, n, M.nslots, M.nfree, SLOTW);
   if (cd_error) {  // unsupported contact configuration for the backward: fail loudly, never silently wrong
-    for (int d = lane; d < 2 * n; d += K) gstate[d] = nanf("");
-    for (int i = lane; i < M.na; i += K) gaction[i] = nanf("");
+    group_write(gstate0, nworlds * n2, tid, nthr, NanGather());
+    group_write(gaction0, nworlds * na, tid, nthr, NanGather());
     return;
   }
-  // clipLossGradientsToBounds (BackpropSnapshot.cpp:425-479): exact equality against the pre-step state, then
-  // scatter through the action map (:404-417)
-  for (int d = lane; d < n; d += K) {
-    float gq = (float)scr[(size_t)(L.oQb + d) * ST], gv = (float)scr[(size_t)(L.oVb + d) * ST];
-    const float qd = st[d], vd = st[n + d];
-    if (qd == M.pos_lo[d] && gq > 0.f) gq = 0.f;
-    if (qd == M.pos_hi[d] && gq < 0.f) gq = 0.f;
-    if (vd == M.vel_lo[d] && gv > 0.f) gv = 0.f;
-    if (vd == M.vel_hi[d] && gv < 0.f) gv = 0.f;
-    gstate[d] = gq; gstate[n + d] = gv;
-  }
-  for (int i = lane; i < M.na; i += K) {
-    const int d = M.action_map[i];
-    float gt = (float)(dt * scr[(size_t)(L.oLam + d) * ST]);
-    const float fd = act[i];
-    if (fd == M.force_lo[d] && gt > 0.f) gt = 0.f;
-    if (fd == M.force_hi[d] && gt < 0.f) gt = 0.f;
-    gaction[i] = gt;
-  }
+  WordGather<R, ST> gs{scr0, n2, L.oQb, M.magic_n2};  // oVb = oQb + n
+  group_write(gstate0, nworlds * n2, tid, nthr, gs);
+  WordGather<R, ST> ga{scr0, na, L.oAct, M.magic_na};
+  group_write(gaction0, nworlds * na, tid, nthr, ga);
 }
 
 // Stages of the cooperative backward (see world_forward_stage for the trunk/limb split):
-//   0 load g_next (strided)            | barrier
+//   0 group load of g_next and the input state (bwd_load) | barrier
 //   1 B1 limbs (leaf->root)            | barrier
 //   2 B1 trunk      3 B2 trunk         | barrier (after 3)
 //   4 B2 limbs      5 B3 limbs      6 assemble limbs | barrier (after 6)
 //   7 B3 trunk      8 assemble trunk   | barrier
-//   9 clip + store (strided)
+//   9 clip + group store (bwd_store)
 #define NB2_BWD_STAGES 10
-#define NB2_BWD_SYNC_MASK 0x14Bu  /* after stages 0, 1, 3, 6, 8 */
+#define NB2_BWD_SYNC_MASK 0x14Bu        /* after stages 0, 1, 3, 6, 8 */
+#define NB2_BWD_SYNC_MASK_1LANE 0x101u  /* lanes == 1: after the group load and before the group store */
 template <class R, int ST>
-NB2_HD void world_backward_stage(const Nb2ModelDev<R>& M, R* scr, const float* st, const float* act, const float* gnext,
-                                 const R* sv, size_t B, float* gstate, float* gaction, int lane, int stage, float* gI = nullptr) {
-  const int n = M.ndof, K = M.lanes;
-  if (stage == 0) {
-    const BwdLayout L = bwd_layout(M.nb, n, M.nslots, M.nfree, 18);
-    for (int d = lane; d < n; d += K) {
-      scr[(size_t)(L.oGQ + d) * ST] = (R)gnext[d];
-      scr[(size_t)(L.oGV + d) * ST] = (R)gnext[n + d];
-    }
-    return;
-  }
-  if (stage == 9) { bwd_store<R, ST, false>(M, scr, st, act, gstate, gaction, false, lane, K); return; }
+NB2_HD void world_backward_stage(const Nb2ModelDev<R>& M, R* scr, const R* sv, size_t B, int lane, int stage, float* gI = nullptr, const R* bt = nullptr) {
+  const float* st = nullptr;  // the passes read the state from the scratch (oSt)
   BwdContactData<ST> cd; cd.active = 0; cd.error = 0;
-  // pass: 1 = B1, 2 = B2, 3 = B3, 4 = assemble
+  // stages 1..8; pass: 1 = B1, 2 = B2, 3 = B3, 4 = assemble
   const int pass = (stage == 1 || stage == 2) ? 1 : (stage == 3 || stage == 4) ? 2 : (stage == 5 || stage == 7) ? 3 : 4;
   const bool trunk = (stage == 2) | (stage == 3) | (stage == 7) | (stage == 8);
   if (trunk && lane != 0) return;
@@ -725,9 +849,9 @@ NB2_HD void world_backward_stage(const Nb2ModelDev<R>& M, R* scr, const float* s
   for (int rr = 0; rr < nr; rr++) {
     const int r = (pass == 1 || pass == 3) ? nr - 1 - rr : rr;
     const int lo = trunk ? M.trunk_lo[r] : M.limb_lo[lane][r], hi = trunk ? M.trunk_hi[r] : M.limb_hi[lane][r];
-    if (pass == 1) bwd_B1<R, ST, false>(M, scr, st, sv, B, lo, hi);
-    else if (pass == 2) bwd_B2<R, ST, false>(M, scr, st, sv, B, lo, hi);
-    else if (pass == 3) bwd_B3<R, ST, false>(M, scr, st, sv, B, cd, lo, hi, gI);
+    if (pass == 1) bwd_B1<R, ST, false>(M, scr, st, sv, B, lo, hi, bt);
+    else if (pass == 2) bwd_B2<R, ST, false>(M, scr, st, sv, B, lo, hi, bt);
+    else if (pass == 3) bwd_B3<R, ST, false>(M, scr, st, sv, B, cd, lo, hi, gI, bt);
     else bwd_assemble<R, ST, false>(M, scr, st, cd, lo, hi);
   }
 }
@@ -737,13 +861,10 @@ NB2_HD void world_backward_stage(const Nb2ModelDev<R>& M, R* scr, const float* s
 template <class R, int ST, bool CONTACT = false>
 NB2_HD void world_backward(const Nb2ModelDev<R>& M, R* scr, const float* st, const float* act, const float* gnext,
                            const R* sv, size_t B, float* gstate, float* gaction, const BwdContactHook* hook = nullptr) {
-  const int nb = M.nb, n = M.ndof;
+  const int nb = M.nb;
   constexpr int SLOTW = CONTACT ? 42 : 18;
-  const BwdLayout L = bwd_layout(nb, n, M.nslots, M.nfree, SLOTW);
-  for (int d = 0; d < n; d++) {
-    scr[(size_t)(L.oGQ + d) * ST] = (R)gnext[d];
-    scr[(size_t)(L.oGV + d) * ST] = (R)gnext[n + d];
-  }
+  const BwdLayout L = bwd_layout(nb, M.ndof, M.nslots, M.nfree, SLOTW);
+  bwd_load<R, ST, CONTACT>(M, scr, st, act, gnext, 1, 0, 1);
   bwd_B1<R, ST, CONTACT>(M, scr, st, sv, B, 0, nb);
   bwd_B2<R, ST, CONTACT>(M, scr, st, sv, B, 0, nb);
   // ---------------- contact stage adjoint (nb2_contact.cuh): lambda -> w, W -> W(w), injections for B3
@@ -753,7 +874,7 @@ NB2_HD void world_backward(const Nb2ModelDev<R>& M, R* scr, const float* st, con
   }
   bwd_B3<R, ST, CONTACT>(M, scr, st, sv, B, cd, 0, nb);
   bwd_assemble<R, ST, CONTACT>(M, scr, st, cd, 0, nb);
-  bwd_store<R, ST, CONTACT>(M, scr, st, act, gstate, gaction, CONTACT && cd.error, 0, 1);
+  bwd_store<R, ST, CONTACT>(M, scr, gstate, gaction, CONTACT && cd.error, 1, 0, 1);
 }
 
 }  // namespace nb2

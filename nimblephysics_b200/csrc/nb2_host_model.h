@@ -12,7 +12,9 @@ static inline bool nb2_fill_model(const nb2_model_desc& d, Nb2ModelDev<R>& M, st
   if (d.ndof <= 0 || d.ndof > NB2_MAX_DOFS) { err = "model has " + std::to_string(d.ndof) + " dofs; compiled limit is " + std::to_string(NB2_MAX_DOFS); return false; }
   if (d.na < 0 || d.na > d.ndof) { err = "bad action map size"; return false; }
   M.nb = d.nb; M.ndof = d.ndof; M.na = d.na; M.nslots = d.nslots;
-  M.pad2 = 0;
+  M.pad2 = 0; M.pad3 = 0;
+  auto magic = [](int x) { return x > 0 ? (unsigned)((0x100000000ull + (unsigned)x - 1) / (unsigned)x) : 0u; };
+  M.magic_n2 = magic(2 * d.ndof); M.magic_n = magic(d.ndof); M.magic_na = magic(d.na);
   M.dt = (R)d.dt;
   for (int k = 0; k < 3; k++) M.gravity[k] = (R)d.gravity[k];
   int nfree = 0, ndof = 0;
@@ -83,7 +85,7 @@ static inline bool nb2_fill_model(const nb2_model_desc& d, Nb2ModelDev<R>& M, st
     M.damping[j] = M.spring[j] = M.rest[j] = R(0);
     M.pos_lo[j] = M.vel_lo[j] = M.force_lo[j] = -__builtin_inff();
     M.pos_hi[j] = M.vel_hi[j] = M.force_hi[j] = __builtin_inff();
-    M.action_map[j] = 0;
+    M.action_map[j] = 0; M.act_of_dof[j] = -1;
   }
   for (int j = 0; j < d.ndof; j++) {
     M.damping[j] = (R)d.damping[j]; M.spring[j] = (R)d.spring[j]; M.rest[j] = (R)d.rest[j];
@@ -94,6 +96,8 @@ static inline bool nb2_fill_model(const nb2_model_desc& d, Nb2ModelDev<R>& M, st
   for (int i = 0; i < d.na; i++) {
     if (d.action_map[i] < 0 || d.action_map[i] >= d.ndof) { err = "action map entry out of range"; return false; }
     M.action_map[i] = (int16_t)d.action_map[i];
+    if (M.act_of_dof[d.action_map[i]] >= 0) { err = "the action map lists dof " + std::to_string(d.action_map[i]) + " twice"; return false; }
+    M.act_of_dof[d.action_map[i]] = (int16_t)i;
   }
   return true;
 }

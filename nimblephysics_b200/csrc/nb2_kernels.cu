@@ -7,6 +7,7 @@
 // only, so warps never diverge.  See DESIGN.md for the roofline discussion (the path is FP32-latency bound).
 #include <cuda_runtime.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include <atomic>
 #include <mutex>
@@ -40,27 +41,49 @@ template <int K> struct CoopShape {
   static constexpr int ST = (K == 1) ? 32 : WPW + 1;    // scratch stride in words
 };
 
+// With several lanes per world the per-body constants are staged once per block in shared memory (see nb2_dyn.cuh xtree):
+// lanes of a warp sit on different bodies, which a constant-bank load would serialise.
+template <int K> __host__ __device__ constexpr int body_table_words(int nb) { return (K > 1) ? ((nb * NB2_BT_WORDS + 3) & ~3) : 0; }
+template <class R, int K>
+__device__ __forceinline__ const R* stage_body_table(const Nb2ModelDev<R>& M, R* tab) {
+  if constexpr (K == 1) return nullptr;
+  else {
+  for (int k = threadIdx.x; k < M.nb * NB2_BT_WORDS; k += blockDim.x) {
+    const int i = k / NB2_BT_WORDS, j = k - i * NB2_BT_WORDS;
+    tab[k] = (j < 12) ? M.Xtree[i][j] : M.inertia[i][j - 12];
+  }
+  __syncthreads();
+  return tab;
+  }
+}
+
 template <class R, int K>
 __global__ void __launch_bounds__(128)
 k_step_fwd(const __grid_constant__ Nb2ModelDev<R> M, int B, int w0, int count, const float* __restrict__ state,
-           const float* __restrict__ action, float* __restrict__ next, R* __restrict__ saved, int words) {
+           const float* __restrict__ action, float* __restrict__ next, R* __restrict__ saved, int words,
+           float* __restrict__ state_copy, float* __restrict__ action_copy) {
   // worlds [w0, w0 + count) of a batch of B (B is the stride of the saved stream; the host entry points launch chunks)
   extern __shared__ __align__(16) unsigned char nb2_smem[];
   constexpr int WPW = CoopShape<K>::WPW, ST = CoopShape<K>::ST;
   const int li = threadIdx.x & 31, slot = li / K, lane = li % K;
-  const int wl = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * WPW + slot;
-  const bool valid = wl < count;
-  const int w = w0 + wl;
-  const int wc = valid ? w : w0;
-  R* scr = reinterpret_cast<R*>(nb2_smem) + (size_t)(threadIdx.x >> 5) * words * ST + slot;
-  const float* st = state + (size_t)wc * 2 * M.ndof;
-  const float* ac = action + (size_t)wc * M.na;
-  float* out = next + (size_t)wc * 2 * M.ndof;
-  R* sv = saved ? saved + wc : nullptr;
+  const int g0 = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * WPW;  // first world of this warp's group
+  const int nworlds = min(WPW, count - g0);                                      // <= 0: idle warp (grid tail)
+  const bool valid = slot < nworlds;
+  const size_t wg = (size_t)w0 + (nworlds > 0 ? g0 : 0);
+  const R* bt = stage_body_table<R, K>(M, reinterpret_cast<R*>(nb2_smem));
+  R* scr0 = reinterpret_cast<R*>(nb2_smem) + body_table_words<K>(M.nb) + (size_t)(threadIdx.x >> 5) * words * ST;
+  R* scr = scr0 + slot;
+  R* sv = saved ? saved + wg + (valid ? slot : 0) : nullptr;
+  constexpr unsigned sync_mask = (K > 1) ? NB2_FWD_SYNC_MASK : NB2_FWD_SYNC_MASK_1LANE;
 #pragma unroll 1
   for (int sg = 0; sg < NB2_FWD_STAGES; sg++) {
-    if (valid) nb2::world_forward_stage<R, ST>(M, scr, st, ac, out, sv, (size_t)B, saved != nullptr, lane, sg);
-    if (K > 1 && ((NB2_FWD_SYNC_MASK >> sg) & 1u)) __syncwarp();
+    if (sg == 0) {
+      if (nworlds > 0) nb2::fwd_load<R, ST>(M, scr0, state + wg * 2 * M.ndof, action + wg * M.na, nworlds, li, 32,
+                                            state_copy ? state_copy + wg * 2 * M.ndof : nullptr, action_copy ? action_copy + wg * M.na : nullptr);
+    }
+    else if (sg == NB2_FWD_STAGES - 1) { if (nworlds > 0) nb2::fwd_store<R, ST>(M, scr0, next + wg * 2 * M.ndof, nworlds, li, 32); }
+    else if (valid) nb2::world_forward_stage<R, ST>(M, scr, sv, (size_t)B, saved != nullptr, lane, sg, bt);
+    if ((sync_mask >> sg) & 1u) __syncwarp();
   }
 }
 
@@ -72,19 +95,22 @@ k_step_bwd(const __grid_constant__ Nb2ModelDev<R> M, int B, int w0, int count, c
   extern __shared__ __align__(16) unsigned char nb2_smem[];
   constexpr int WPW = CoopShape<K>::WPW, ST = CoopShape<K>::ST;
   const int li = threadIdx.x & 31, slot = li / K, lane = li % K;
-  const int wl = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * WPW + slot;
-  const bool valid = wl < count;
-  const int w = w0 + wl;
-  const int wc = valid ? w : w0;
-  R* scr = reinterpret_cast<R*>(nb2_smem) + (size_t)(threadIdx.x >> 5) * words * ST + slot;
-  const float* st = state + (size_t)wc * 2 * M.ndof;
-  const float* ac = action + (size_t)wc * M.na;
+  const int g0 = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * WPW;
+  const int nworlds = min(WPW, count - g0);
+  const bool valid = slot < nworlds;
+  const size_t wg = (size_t)w0 + (nworlds > 0 ? g0 : 0);
+  const size_t w = wg + (valid ? slot : 0);
+  const R* bt = stage_body_table<R, K>(M, reinterpret_cast<R*>(nb2_smem));
+  R* scr0 = reinterpret_cast<R*>(nb2_smem) + body_table_words<K>(M.nb) + (size_t)(threadIdx.x >> 5) * words * ST;
+  R* scr = scr0 + slot;
+  constexpr unsigned sync_mask = (K > 1) ? NB2_BWD_SYNC_MASK : NB2_BWD_SYNC_MASK_1LANE;
 #pragma unroll 1
   for (int sg = 0; sg < NB2_BWD_STAGES; sg++) {
-    if (valid) nb2::world_backward_stage<R, ST>(M, scr, st, ac, gnext + (size_t)wc * 2 * M.ndof, saved + wc, (size_t)B,
-                                                gstate + (size_t)wc * 2 * M.ndof, gaction + (size_t)wc * M.na, lane, sg,
-                                                ginertia ? ginertia + wc : nullptr);
-    if (K > 1 && ((NB2_BWD_SYNC_MASK >> sg) & 1u)) __syncwarp();
+    if (sg == 0) { if (nworlds > 0) nb2::bwd_load<R, ST, false>(M, scr0, state + wg * 2 * M.ndof, action + wg * M.na, gnext + wg * 2 * M.ndof, nworlds, li, 32); }
+    else if (sg == NB2_BWD_STAGES - 1) {
+      if (nworlds > 0) nb2::bwd_store<R, ST, false>(M, scr0, gstate + wg * 2 * M.ndof, gaction + wg * M.na, false, nworlds, li, 32);
+    } else if (valid) nb2::world_backward_stage<R, ST>(M, scr, saved + w, (size_t)B, lane, sg, ginertia ? ginertia + w : nullptr, bt);
+    if ((sync_mask >> sg) & 1u) __syncwarp();
   }
 }
 
@@ -177,10 +203,10 @@ static void init_variant(nb2_variant& v) {
 // Occupancy is limited by the per-warp scratch in shared memory; blocks of 1, 2 or 4 warps are tried and the shape
 // that keeps most warps resident wins.  Small batches use 1-warp blocks so that they spread over all SMs.
 template <class Kern>
-static LaunchShape occupancy_shape(Kern kern, size_t bytes_per_warp) {
+static LaunchShape occupancy_shape(Kern kern, size_t bytes_per_warp, size_t bytes_per_block) {
   LaunchShape best;
   for (int w = 1; w <= 4; w *= 2) {
-    const size_t smem = bytes_per_warp * w;
+    const size_t smem = bytes_per_warp * w + bytes_per_block;
     if (smem > (size_t)kMaxSmem) break;
     int blocks = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, kern, w * 32, smem) != cudaSuccess) { cudaGetLastError(); continue; }
@@ -205,13 +231,14 @@ template <class R, int K> struct StepKernels {
     LaunchShape& sh = v.shape[dir][sizeof(R) == 8];
     if (sh.warps_per_block) return NB2_OK;
     const size_t per_warp = (size_t)(dir ? v.bwd_words : v.fwd_words) * ST * sizeof(R);
-    if (per_warp > (size_t)kMaxSmem) { g_err = "model needs " + std::to_string(per_warp) + " B of shared memory per warp (> 227 KB)"; return NB2_ERR_UNSUPPORTED; }
+    const size_t per_block = (size_t)body_table_words<K>(v.mf.nb) * sizeof(R);
+    if (per_warp + per_block > (size_t)kMaxSmem) { g_err = "model needs " + std::to_string(per_warp) + " B of shared memory per warp (> 227 KB)"; return NB2_ERR_UNSUPPORTED; }
     if (dir == 0) {
       NB2_CUDA(cudaFuncSetAttribute(k_step_fwd<R, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
-      sh = occupancy_shape(k_step_fwd<R, K>, per_warp);
+      sh = occupancy_shape(k_step_fwd<R, K>, per_warp, per_block);
     } else {
       NB2_CUDA(cudaFuncSetAttribute(k_step_bwd<R, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
-      sh = occupancy_shape(k_step_bwd<R, K>, per_warp);
+      sh = occupancy_shape(k_step_bwd<R, K>, per_warp, per_block);
     }
     if (!sh.warps_per_block) { g_err = "no launch shape fits this model"; return NB2_ERR_UNSUPPORTED; }
     return NB2_OK;
@@ -250,30 +277,30 @@ static int pick_variant(nb2_model* m, int B, int dir, nb2_variant** out) {
 
 template <class R, int K>
 static int launch_fwd_k(const nb2_variant& v, int sm_count, int Btot, int w0, int B, const float* state, const float* action,
-                        float* next, R* saved, cudaStream_t st) {
+                        float* next, R* saved, cudaStream_t st, float* state_copy, float* action_copy) {
   constexpr int WPW = CoopShape<K>::WPW, ST = CoopShape<K>::ST;
   const LaunchShape& sh = v.shape[0][sizeof(R) == 8];
   const size_t per_warp = (size_t)v.fwd_words * ST * sizeof(R);
   const int total_warps = (B + WPW - 1) / WPW;
   const int warps = block_warps(total_warps, sm_count, sh, per_warp);
   const int blocks = (total_warps + warps - 1) / warps;
-  k_step_fwd<R, K><<<blocks, warps * 32, per_warp * warps, st>>>(model_of<R>(v), Btot, w0, B, state, action, next, saved, v.fwd_words);
+  k_step_fwd<R, K><<<blocks, warps * 32, per_warp * warps + (size_t)body_table_words<K>(v.mf.nb) * sizeof(R), st>>>(model_of<R>(v), Btot, w0, B, state, action, next, saved, v.fwd_words, state_copy, action_copy);
   g_launches++;
   NB2_CUDA(cudaGetLastError());
   return NB2_OK;
 }
 template <class R>
 static int launch_fwd(nb2_model* m, int B, const float* state, const float* action, float* next, R* saved, cudaStream_t st,
-                      int Btot = -1, int w0 = 0) {
+                      int Btot = -1, int w0 = 0, float* state_copy = nullptr, float* action_copy = nullptr) {
   if (Btot < 0) Btot = B;
   nb2_variant* pv = nullptr;
   int rc = pick_variant<R>(m, B, 0, &pv);
   if (rc) return rc;
   switch (pv->mf.lanes) {
-    case 1: return launch_fwd_k<R, 1>(*pv, m->sm_count, Btot, w0, B, state, action, next, saved, st);
-    case 2: return launch_fwd_k<R, 2>(*pv, m->sm_count, Btot, w0, B, state, action, next, saved, st);
-    case 4: return launch_fwd_k<R, 4>(*pv, m->sm_count, Btot, w0, B, state, action, next, saved, st);
-    case 8: return launch_fwd_k<R, 8>(*pv, m->sm_count, Btot, w0, B, state, action, next, saved, st);
+    case 1: return launch_fwd_k<R, 1>(*pv, m->sm_count, Btot, w0, B, state, action, next, saved, st, state_copy, action_copy);
+    case 2: return launch_fwd_k<R, 2>(*pv, m->sm_count, Btot, w0, B, state, action, next, saved, st, state_copy, action_copy);
+    case 4: return launch_fwd_k<R, 4>(*pv, m->sm_count, Btot, w0, B, state, action, next, saved, st, state_copy, action_copy);
+    case 8: return launch_fwd_k<R, 8>(*pv, m->sm_count, Btot, w0, B, state, action, next, saved, st, state_copy, action_copy);
   }
   g_err = "bad lane count"; return NB2_ERR_INVALID;
 }
@@ -286,7 +313,7 @@ static int launch_bwd_k(const nb2_variant& v, int sm_count, int Btot, int w0, in
   const int total_warps = (B + WPW - 1) / WPW;
   const int warps = block_warps(total_warps, sm_count, sh, per_warp);
   const int blocks = (total_warps + warps - 1) / warps;
-  k_step_bwd<R, K><<<blocks, warps * 32, per_warp * warps, st>>>(model_of<R>(v), Btot, w0, B, state, action, saved, gnext, gstate, gaction, ginertia, v.bwd_words);
+  k_step_bwd<R, K><<<blocks, warps * 32, per_warp * warps + (size_t)body_table_words<K>(v.mf.nb) * sizeof(R), st>>>(model_of<R>(v), Btot, w0, B, state, action, saved, gnext, gstate, gaction, ginertia, v.bwd_words);
   g_launches++;
   NB2_CUDA(cudaGetLastError());
   return NB2_OK;
@@ -306,6 +333,27 @@ static int launch_bwd(nb2_model* m, int B, const float* state, const float* acti
     case 8: return launch_bwd_k<R, 8>(*pv, m->sm_count, Btot, w0, B, state, action, saved, gnext, gstate, gaction, ginertia, st);
   }
   g_err = "bad lane count"; return NB2_ERR_INVALID;
+}
+
+// The host entry points take host buffers.  When every buffer of a call is page-locked memory visible to the device
+// (cudaHostAlloc / cudaHostRegister, e.g. torch pin_memory()), the kernels read and write it DIRECTLY: the group load /
+// store of every warp is a coalesced, deeply pipelined stream over PCIe, so the transfer overlaps the sweeps warp by warp
+// and no copy is ever queued (the forward kernel also leaves a device copy of state / action for the backward pass).
+// Pageable buffers go through staged cudaMemcpyAsync on up to NB2_HOST_CHUNKS streams (default 1).
+static int host_chunks(int B) {
+  static const int forced = [] { const char* e = getenv("NB2_HOST_CHUNKS"); return e ? atoi(e) : 1; }();
+  return (forced >= 1 && forced <= 4 && forced <= B) ? forced : 1;
+}
+static bool zero_copy_enabled() {
+  static const bool on = [] { const char* e = getenv("NB2_NO_ZEROCOPY"); return !(e && atoi(e)); }();
+  return on;
+}
+// device-side alias of a page-locked host buffer, or nullptr when the buffer is pageable
+template <class T> static T* mapped_alias(const T* host) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, host) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  if (a.type != cudaMemoryTypeHost || !a.devicePointer) return nullptr;
+  return (T*)a.devicePointer;
 }
 
 extern "C" {
@@ -500,11 +548,6 @@ static int ensure_host_buffers(nb2_model* m, int B) {
   return NB2_OK;
 }
 
-// The host entry points pipeline the batch in chunks over a few streams: chunk c's upload overlaps chunk c-1's kernel
-// and chunk c-2's download (separate copy engines per direction); the kernels are latency bound, so the chunks'
-// kernels also run side by side on disjoint SMs.  Pageable host memory still works (the copies just serialise).
-static int host_chunks(int B) { return B >= 4096 ? 4 : (B >= 1024 ? 2 : 1); }
-
 int nb2_step_forward_host(nb2_model* m, int B, const float* state, const float* action, float* next_state,
                           int keep_for_backward, int precision) {
   if (!m || B <= 0 || !state || !action || !next_state) { g_err = "nb2_step_forward_host: bad argument"; return NB2_ERR_INVALID; }
@@ -512,6 +555,18 @@ int nb2_step_forward_host(nb2_model* m, int B, const float* state, const float* 
   int rc = ensure_host_buffers(m, B);
   if (rc) return rc;
   const size_t n2 = (size_t)2 * m->mf.ndof, na = (size_t)m->mf.na;
+  if (zero_copy_enabled()) {
+    const float* zs = mapped_alias(state); const float* za = mapped_alias(action); float* zn = mapped_alias(next_state);
+    if (zs && za && zn) {
+      cudaStream_t st = m->host_streams[0];
+      if (precision == NB2_FP64) rc = launch_fwd<double>(m, B, zs, za, zn, keep_for_backward ? (double*)m->d_saved : nullptr, st, B, 0, m->d_state, m->d_action);
+      else rc = launch_fwd<float>(m, B, zs, za, zn, keep_for_backward ? (float*)m->d_saved : nullptr, st, B, 0, m->d_state, m->d_action);
+      if (rc) return rc;
+      NB2_CUDA(cudaStreamSynchronize(st));
+      m->host_B = keep_for_backward ? B : 0;
+      return NB2_OK;
+    }
+  }
   const int C = host_chunks(B);
   for (int c = 0; c < C; c++) {
     const int lo = (int)((long long)B * c / C), cnt = (int)((long long)B * (c + 1) / C) - lo;
@@ -534,6 +589,18 @@ int nb2_step_backward_host(nb2_model* m, int B, const float* grad_next_state, fl
   std::lock_guard<std::mutex> lk(m->mu);
   if (B <= 0 || B != m->host_B) { g_err = "nb2_step_backward_host: no matching forward_host(keep_for_backward=1) precedes this call"; return NB2_ERR_INVALID; }
   const size_t n2 = (size_t)2 * m->mf.ndof, na = (size_t)m->mf.na;
+  if (zero_copy_enabled()) {
+    const float* zg = mapped_alias(grad_next_state); float* zgs = mapped_alias(grad_state); float* zga = mapped_alias(grad_action);
+    if (zg && zgs && zga) {
+      cudaStream_t st = m->host_streams[0];
+      int rc;
+      if (precision == NB2_FP64) rc = launch_bwd<double>(m, B, m->d_state, m->d_action, (const double*)m->d_saved, zg, zgs, zga, nullptr, st);
+      else rc = launch_bwd<float>(m, B, m->d_state, m->d_action, (const float*)m->d_saved, zg, zgs, zga, nullptr, st);
+      if (rc) return rc;
+      NB2_CUDA(cudaStreamSynchronize(st));
+      return NB2_OK;
+    }
+  }
   const int C = host_chunks(B);
   for (int c = 0; c < C; c++) {
     const int lo = (int)((long long)B * c / C), cnt = (int)((long long)B * (c + 1) / C) - lo;

@@ -27,6 +27,7 @@ struct Nb2ModelDev {
   int nfree;        // number of FREE bodies
   int lanes;        // threads cooperating on one world (1, 2, 4 or 8)
   int trunk_n, pad2;
+  unsigned magic_n2, magic_n, magic_na, pad3;  // ceil(2^32 / x): idx / x == umulhi(idx, magic) for idx < 65536 (group I/O index math)
   R dt;
   R gravity[3];
   int16_t parent[NB2_MAX_BODIES];
@@ -50,6 +51,7 @@ struct Nb2ModelDev {
   float vel_lo[NB2_MAX_DOFS], vel_hi[NB2_MAX_DOFS];
   float force_lo[NB2_MAX_DOFS], force_hi[NB2_MAX_DOFS];
   int16_t action_map[NB2_MAX_DOFS];
+  int16_t act_of_dof[NB2_MAX_DOFS];  // inverse of action_map: action index driving a dof, -1 = unactuated
 };
 
 // number of fp32 words the forward pass saves per world for the backward pass

@@ -7,22 +7,28 @@
 #include "../../nimblephysics_b200/csrc/nb2_dyn.cuh"
 #include "../../nimblephysics_b200/csrc/nb2_host_model.h"
 
+// The emulated "warp" holds a GROUP of up to G worlds (scratch stride G, like the device's 32/lanes worlds per warp) and
+// NT virtual threads for the group load / store; the sweep stages run per (world slot, lane).  Lanes of odd worlds run in
+// reverse order so that a missing barrier (a cross-lane dependency inside one stage) shows up as a poisoned read.
+constexpr int G = 3, NT = 5;
 template <class R>
 static int run_fwd(const nb2_model_desc* d, int B, const float* state, const float* action, float* next, R* saved) {
   Nb2ModelDev<R> M; std::string err;
   if (!nb2_fill_model(*d, M, err)) { fprintf(stderr, "emul: %s\n", err.c_str()); return -1; }
   nb2::FwdLayout L = nb2::fwd_layout(M.nb, M.ndof, M.nslots, M.nfree);
-  std::vector<R> scr(L.total);
-  std::vector<float> dummy;
-  for (int w = 0; w < B; w++) {
+  std::vector<R> scr((size_t)L.total * G);
+  for (int g0 = 0; g0 < B; g0 += G) {
+    const int nw = (B - g0 < G) ? B - g0 : G;
     for (auto& x : scr) x = R(1e30);  // poison: catches reads of never-written scratch
-    // cooperative lanes are emulated stage by stage; odd worlds run the lanes in reverse order so that a missing
-    // barrier (a cross-lane dependency inside one stage) shows up as a poisoned read / wrong result
-    for (int sg = 0; sg < NB2_FWD_STAGES; sg++)
-      for (int l = 0; l < M.lanes; l++)
-        nb2::world_forward_stage<R, 1>(M, scr.data(), state + (size_t)w * 2 * M.ndof, action + (size_t)w * M.na,
-                                       next + (size_t)w * 2 * M.ndof, saved ? saved + w : nullptr, (size_t)B, saved != nullptr,
-                                       (w & 1) ? M.lanes - 1 - l : l, sg);
+    for (int sg = 0; sg < NB2_FWD_STAGES; sg++) {
+      if (sg == 0) { for (int t = NT - 1; t >= 0; t--) nb2::fwd_load<R, G>(M, scr.data(), state + (size_t)g0 * 2 * M.ndof, action + (size_t)g0 * M.na, nw, t, NT); continue; }
+      if (sg == NB2_FWD_STAGES - 1) { for (int t = 0; t < NT; t++) nb2::fwd_store<R, G>(M, scr.data(), next + (size_t)g0 * 2 * M.ndof, nw, t, NT); continue; }
+      for (int slot = 0; slot < nw; slot++)
+        for (int l = 0; l < M.lanes; l++) {
+          const int w = g0 + slot, lane = (w & 1) ? M.lanes - 1 - l : l;
+          nb2::world_forward_stage<R, G>(M, scr.data() + slot, saved ? saved + w : nullptr, (size_t)B, saved != nullptr, lane, sg);
+        }
+    }
   }
   return 0;
 }
@@ -32,15 +38,23 @@ static int run_bwd(const nb2_model_desc* d, int B, const float* state, const flo
   Nb2ModelDev<R> M; std::string err;
   if (!nb2_fill_model(*d, M, err)) { fprintf(stderr, "emul: %s\n", err.c_str()); return -1; }
   nb2::BwdLayout L = nb2::bwd_layout(M.nb, M.ndof, M.nslots, M.nfree);
-  std::vector<R> scr(L.total);
-  for (int w = 0; w < B; w++) {
+  std::vector<R> scr((size_t)L.total * G);
+  for (int g0 = 0; g0 < B; g0 += G) {
+    const int nw = (B - g0 < G) ? B - g0 : G;
     for (auto& x : scr) x = R(1e30);
-    for (int sg = 0; sg < NB2_BWD_STAGES; sg++)
-      for (int l = 0; l < M.lanes; l++)
-        nb2::world_backward_stage<R, 1>(M, scr.data(), state + (size_t)w * 2 * M.ndof, action + (size_t)w * M.na,
-                                        gnext + (size_t)w * 2 * M.ndof, saved + w, (size_t)B, gstate + (size_t)w * 2 * M.ndof,
-                                        gaction + (size_t)w * M.na, (w & 1) ? M.lanes - 1 - l : l, sg,
-                                        ginertia ? ginertia + w : nullptr);
+    for (int sg = 0; sg < NB2_BWD_STAGES; sg++) {
+      if (sg == 0) { for (int t = NT - 1; t >= 0; t--) nb2::bwd_load<R, G, false>(M, scr.data(), state + (size_t)g0 * 2 * M.ndof, action + (size_t)g0 * M.na, gnext + (size_t)g0 * 2 * M.ndof, nw, t, NT); continue; }
+      if (sg == NB2_BWD_STAGES - 1) {
+        for (int t = 0; t < NT; t++)
+          nb2::bwd_store<R, G, false>(M, scr.data(), gstate + (size_t)g0 * 2 * M.ndof, gaction + (size_t)g0 * M.na, false, nw, t, NT);
+        continue;
+      }
+      for (int slot = 0; slot < nw; slot++)
+        for (int l = 0; l < M.lanes; l++) {
+          const int w = g0 + slot, lane = (w & 1) ? M.lanes - 1 - l : l;
+          nb2::world_backward_stage<R, G>(M, scr.data() + slot, saved + w, (size_t)B, lane, sg, ginertia ? ginertia + w : nullptr);
+        }
+    }
   }
   return 0;
 }
