@@ -91,7 +91,8 @@ template <class R, int K>
 __global__ void __launch_bounds__(128)
 k_step_bwd(const __grid_constant__ Nb2ModelDev<R> M, int B, int w0, int count, const float* __restrict__ state,
            const float* __restrict__ action, const R* __restrict__ saved, const float* __restrict__ gnext,
-           float* __restrict__ gstate, float* __restrict__ gaction, float* __restrict__ ginertia, int words) {
+           float* __restrict__ gstate, float* __restrict__ gaction, float* __restrict__ ginertia, int words,
+           int stage_saved) {
   extern __shared__ __align__(16) unsigned char nb2_smem[];
   constexpr int WPW = CoopShape<K>::WPW, ST = CoopShape<K>::ST;
   const int li = threadIdx.x & 31, slot = li / K, lane = li % K;
@@ -103,14 +104,37 @@ k_step_bwd(const __grid_constant__ Nb2ModelDev<R> M, int B, int w0, int count, c
   const R* bt = stage_body_table<R, K>(M, reinterpret_cast<R*>(nb2_smem));
   R* scr0 = reinterpret_cast<R*>(nb2_smem) + body_table_words<K>(M.nb) + (size_t)(threadIdx.x >> 5) * words * ST;
   R* scr = scr0 + slot;
+  // The sweeps walk the saved stream body by body, every access a dependent DRAM round trip.  When the launch leaves room
+  // (small batches: the regime where latency is all that matters) each warp first pulls its group's rows of the stream
+  // into shared memory with one burst of asynchronous 16-byte copies ([word][B] layout: the group's worlds are adjacent),
+  // and the sweeps then read `svp` with stride `svB` = WPW instead of the global stream with stride B.
+  const R* svp = saved + wg + (valid ? slot : 0);
+  size_t svB = (size_t)B;
+  if (stage_saved && nworlds == WPW) {
+    const int sw = nb2_saved_words(M.nb, M.ndof, M.nfree);
+    R* svs = reinterpret_cast<R*>(nb2_smem) + ((body_table_words<K>(M.nb) + (size_t)(blockDim.x >> 5) * words * ST + 3) & ~(size_t)3)  // 16-byte aligned
+             + (size_t)(threadIdx.x >> 5) * sw * WPW;
+    constexpr int CH = (WPW * (int)sizeof(R)) / 16;  // 16-byte chunks per row of the group
+    const unsigned dst0 = (unsigned)__cvta_generic_to_shared(svs);
+    const char* src0 = reinterpret_cast<const char*>(saved + wg);
+    for (int idx = li; idx < sw * CH; idx += 32) {
+      const int k = idx / CH, c = idx - k * CH;
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst0 + (unsigned)(k * WPW * (int)sizeof(R) + c * 16)),
+                   "l"(src0 + (size_t)k * B * sizeof(R) + c * 16));
+    }
+    asm volatile("cp.async.commit_group;");
+    svp = svs + slot;
+    svB = WPW;
+  }
   constexpr unsigned sync_mask = (K > 1) ? NB2_BWD_SYNC_MASK : NB2_BWD_SYNC_MASK_1LANE;
 #pragma unroll 1
   for (int sg = 0; sg < NB2_BWD_STAGES; sg++) {
     if (sg == 0) { if (nworlds > 0) nb2::bwd_load<R, ST, false>(M, scr0, state + wg * 2 * M.ndof, action + wg * M.na, gnext + wg * 2 * M.ndof, nworlds, li, 32); }
     else if (sg == NB2_BWD_STAGES - 1) {
       if (nworlds > 0) nb2::bwd_store<R, ST, false>(M, scr0, gstate + wg * 2 * M.ndof, gaction + wg * M.na, false, nworlds, li, 32);
-    } else if (valid) nb2::world_backward_stage<R, ST>(M, scr, saved + w, (size_t)B, lane, sg, ginertia ? ginertia + w : nullptr, bt);
-    if ((sync_mask >> sg) & 1u) __syncwarp();
+    } else if (valid) nb2::world_backward_stage<R, ST>(M, scr, svp, svB, lane, sg, ginertia ? ginertia + w : nullptr, bt);
+    if (sg == 0 && stage_saved) asm volatile("cp.async.wait_group 0;" ::: "memory");
+    if (((sync_mask >> sg) & 1u) || (sg == 0 && stage_saved)) __syncwarp();
   }
 }
 
@@ -304,6 +328,10 @@ static int launch_fwd(nb2_model* m, int B, const float* state, const float* acti
   }
   g_err = "bad lane count"; return NB2_ERR_INVALID;
 }
+static bool no_stage_saved() {
+  static const bool off = [] { const char* e = getenv("NB2_NO_STAGE_SAVED"); return e && atoi(e); }();
+  return off;
+}
 template <class R, int K>
 static int launch_bwd_k(const nb2_variant& v, int sm_count, int Btot, int w0, int B, const float* state, const float* action,
                         const R* saved, const float* gnext, float* gstate, float* gaction, float* ginertia, cudaStream_t st) {
@@ -313,7 +341,16 @@ static int launch_bwd_k(const nb2_variant& v, int sm_count, int Btot, int w0, in
   const int total_warps = (B + WPW - 1) / WPW;
   const int warps = block_warps(total_warps, sm_count, sh, per_warp);
   const int blocks = (total_warps + warps - 1) / warps;
-  k_step_bwd<R, K><<<blocks, warps * 32, per_warp * warps + (size_t)body_table_words<K>(v.mf.nb) * sizeof(R), st>>>(model_of<R>(v), Btot, w0, B, state, action, saved, gnext, gstate, gaction, ginertia, v.bwd_words);
+  const size_t tab = (size_t)body_table_words<K>(v.mf.nb) * sizeof(R);
+  // stage the saved stream in shared memory when the whole batch is resident at once anyway (see the kernel)
+  const size_t stage_per_warp = (size_t)nb2_saved_words(v.mf.nb, v.mf.ndof, v.mf.nfree) * WPW * sizeof(R);
+  const bool aligned = (((size_t)Btot * sizeof(R)) % 16 == 0) && (((size_t)w0 * sizeof(R)) % 16 == 0) && ((reinterpret_cast<size_t>(saved) & 15) == 0) &&
+                       ((WPW * sizeof(R)) % 16 == 0);
+  const size_t smem_staged = (per_warp + stage_per_warp) * warps + tab + 16;
+  const int blocks_per_sm = (blocks + sm_count - 1) / sm_count;
+  const bool stage = aligned && smem_staged * blocks_per_sm + 1024 * blocks_per_sm <= (size_t)kMaxSmem && !no_stage_saved();
+  k_step_bwd<R, K><<<blocks, warps * 32, stage ? smem_staged : per_warp * warps + tab, st>>>(model_of<R>(v), Btot, w0, B, state, action, saved, gnext, gstate,
+                                                                                            gaction, ginertia, v.bwd_words, stage ? 1 : 0);
   g_launches++;
   NB2_CUDA(cudaGetLastError());
   return NB2_OK;

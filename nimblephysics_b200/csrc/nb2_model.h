@@ -57,4 +57,7 @@ struct Nb2ModelDev {
 // number of fp32 words the forward pass saves per world for the backward pass
 //   per body: V(6) A(6) U(6) psi(1) sc(2) = 21 ; per FREE body: inverse articulated inertia (21) + joint R,p (12)
 //   per dof : qdd
+#ifdef __CUDACC__
+__host__ __device__
+#endif
 static inline int nb2_saved_words(int nb, int ndof, int nfree) { return nb * 21 + nfree * 33 + ndof; }
