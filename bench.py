@@ -141,7 +141,25 @@ class CpuReference:
         self.pool.join()
 
 
+_REAL_STDOUT = None
+
+
+def emit(obj):
+    """The ONE JSON line of the contract goes to the process's original stdout; everything else any library prints
+    (NCCL's version banner, torch warnings) was routed to stderr at start-up."""
+    line = (json.dumps(obj) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(line.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, line)
+
+
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)  # fd-level: also catches output of native libraries
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=50)
@@ -184,7 +202,7 @@ def main():
             tot_n += sample
         ref.close()
         v = tot_n / tot_t
-        print(json.dumps({
+        emit(({
             "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
@@ -373,7 +391,7 @@ def main():
         }
         if cpu_baseline is not None:
             out["cpu_baseline"] = cpu_baseline
-        print(json.dumps(out))
+        emit(out)
     if dist:
         dist.destroy_process_group()
 

@@ -55,6 +55,7 @@ struct Nb2ContactDev {
 
 namespace nb2 {
 
+#define NB2_CONTACT_LANES 8  // threads that may cooperate on one world in the contact kernel
 template <int ST>
 struct ContactWsT {  // per-world fp64 workspace; lane-interleaved on the device (ST = 32), contiguous on the host (ST = 1)
   typedef SP<CR, ST> PD; typedef SP<int, ST> PI; typedef SP<unsigned char, ST> PB;
@@ -67,13 +68,15 @@ struct ContactWsT {  // per-world fp64 workspace; lane-interleaved on the device
   PD v1, v2, v3, v4, v5, v6, v7, v8;
   PI i1, i2;
   PB st8;
+  PD lbuf;  // NB2_CONTACT_LANES private sweep buffers (pI, V: 6 nb each; uI, dqd: ndof each) for the parallel impulse tests
+  PI meta;  // m, nc, status carried between the phases of world_contact
 };
 NB2_HD size_t contact_rec_doubles(int ndof) { return 2 + 2 * (size_t)NB2_MAX_ROWS + ndof + (size_t)NB2_MAX_ROWS * NB2_MAX_ROWS; }
 // doubles per WORLD (the kernel allocates 32x this per warp)
 NB2_HD size_t contact_ws_doubles(int nb, int ndof) {
   const int MC = NB2_MAX_CONTACTS, MR = NB2_MAX_ROWS;
   return (size_t)nb * 36 + 3 * ndof + MC * 9 + 5 * ((MC + 1) / 2) + 2 * MR * 6 + 7 * MR + 4 * ((MR + 1) / 2) + 5 * (size_t)MR * MR + 8 * MR
-         + 2 * ((MR + 1) / 2) + (2 * MR + 7) / 8 + 4;
+         + 2 * ((MR + 1) / 2) + (2 * MR + 7) / 8 + 4 + (size_t)NB2_CONTACT_LANES * (12 * nb + 2 * ndof) + 2;
 }
 // `block`: start of the warp's (device) or world's (host) block; `lane`: 0 on the host
 template <int ST>
@@ -93,6 +96,8 @@ NB2_HD ContactWsT<ST> carve_ws(CR* block, int lane, int nb, int ndof) {
   w.v1 = D(MR); w.v2 = D(MR); w.v3 = D(MR); w.v4 = D(MR); w.v5 = D(MR); w.v6 = D(MR); w.v7 = D(MR); w.v8 = D(MR);
   w.i1 = I(MR); w.i2 = I(MR);
   w.st8 = Bt(2 * MR);
+  w.lbuf = D((size_t)NB2_CONTACT_LANES * (12 * nb + 2 * ndof));
+  w.meta = I(4);
   return w;
 }
 
@@ -174,12 +179,27 @@ NB2_HD void impulse_response(const Nb2ModelDev<CR>& M, const CR* sv, size_t B, c
   }
 }
 
+// sum_{j != skip} row[j] * x[j] with four independent partial sums: the Gauss-Seidel row update is a chain of dependent
+// fp64 FMAs otherwise (the reference sums left to right, PgsBoxedLcpSolver.cpp:126-140; the difference is rounding only)
+template <class PA, class PX>
+NB2_HD CR row_dot_skip(int m, PA row, PX x, int skip) {
+  CR a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+  int j = 0;
+  for (; j + 3 < m; j += 4) {
+    a0 += (j == skip) ? CR(0) : row[j] * x[j];
+    a1 += (j + 1 == skip) ? CR(0) : row[j + 1] * x[j + 1];
+    a2 += (j + 2 == skip) ? CR(0) : row[j + 2] * x[j + 2];
+    a3 += (j + 3 == skip) ? CR(0) : row[j + 3] * x[j + 3];
+  }
+  for (; j < m; j++) a0 += (j == skip) ? CR(0) : row[j] * x[j];
+  return (a0 + a1) + (a2 + a3);
+}
+
 // ------------------------------------------------------------------ dense helpers (m x m, stride m)
 template <class PA, class PX, class PB_, class PH, class PL, class PF>
 NB2_HD bool lcp_valid(int m, PA A, PX x, PB_ b, PH hi, PL lo, PF fi, bool ignoreFriction) {
   for (int i = 0; i < m; i++) {
-    CR v = -b[i];
-    for (int j = 0; j < m; j++) v += A[i * m + j] * x[j];
+    const CR v = row_dot_skip(m, A + i * m, x, -1) - b[i];
     CR up = hi[i], low = lo[i];
     if (fi[i] != -1) { if (ignoreFriction) { if (x[i] != 0) return false; continue; } up *= x[fi[i]]; low *= x[fi[i]]; }
     const CR tol = 1e-5;
@@ -349,9 +369,7 @@ NB2_HD bool pgs_solve(int m, PA A, PX x, PB_ b, PL lo, PH hi, PF fi, PS skip) {
     skip[i] = 0;
     if (A[i * m + i] < epsDiv) { x[i] = 0.0; skip[i] = 1; continue; }
     const CR old_x = x[i];
-    CR nx = b[i];
-    for (int j = 0; j < i; j++) nx -= A[i * m + j] * x[j];
-    for (int j = i + 1; j < m; j++) nx -= A[i * m + j] * x[j];
+    CR nx = b[i] - row_dot_skip(m, A + i * m, x, i);
     nx /= A[i * m + i];
     CR hi_t = hi[i], lo_t = lo[i];
     if (fi[i] >= 0) { hi_t = hi[i] * x[fi[i]]; lo_t = -hi_t; }
@@ -364,10 +382,8 @@ NB2_HD bool pgs_solve(int m, PA A, PX x, PB_ b, PL lo, PH hi, PF fi, PS skip) {
     term = true;
     for (int i = 0; i < m; i++) {
       if (skip[i]) continue;
-      CR nx = b[i];
       const CR old_x = x[i];
-      for (int j = 0; j < i; j++) nx -= A[i * m + j] * x[j];
-      for (int j = i + 1; j < m; j++) nx -= A[i * m + j] * x[j];
+      const CR nx = b[i] - row_dot_skip(m, A + i * m, x, i);
       CR hi_t = hi[i], lo_t = lo[i];
       if (fi[i] >= 0) { hi_t = hi[i] * x[fi[i]]; lo_t = -hi_t; }
       x[i] = nx > hi_t ? hi_t : (nx < lo_t ? lo_t : nx);
@@ -383,9 +399,9 @@ NB2_HD bool pgs_solve(int m, PA A, PX x, PB_ b, PL lo, PH hi, PF fi, PS skip) {
 // x_io: cached LCP solution (NB2_MAX_ROWS doubles), m_io: its size (-1 none) -> new solution / size.
 // =====================================================================================================
 template <int ST>
-NB2_HD void world_contact(const Nb2ModelDev<CR>& M, const Nb2ContactDev& C, const float* st, float* out, const CR* sv, size_t B,
-                          CR* wsblock, int lane, CR* x_io, int* m_io, int* labels_out, int* status_out, int* nc_out, float* cinfo_out,
-                          CR* crec) {
+NB2_HD void contact_phase0(const Nb2ModelDev<CR>& M, const Nb2ContactDev& C, const float* st, float* out, const CR* sv, size_t B,
+                           CR* wsblock, int lane, CR* x_io, int* m_io, int* labels_out, int* status_out, int* nc_out, float* cinfo_out,
+                           CR* crec) {
   const int nb = M.nb, n = M.ndof;
   const ContactWsT<ST> ws = carve_ws<ST>(wsblock, lane, nb, n);
   const int kQdd = nb * 21 + M.nfree * 33;
@@ -504,32 +520,63 @@ NB2_HD void world_contact(const Nb2ModelDev<CR>& M, const Nb2ContactDev& C, cons
     if (bounce) { const CR rv = ws.b[off] * e; if (rv > 1e-1) { if (rv > bv) { bv = rv; if (bv > 1e2) bv = 1e2; } } }
     ws.b[off] += bv;
   }
+  ws.meta[0] = m; ws.meta[1] = nc; ws.meta[2] = status;
   if (m == 0) { *m_io = 0; *status_out = status; if (crec) crec[0] = 0; return; }  // out already holds v*
   // row -> contact map must survive classification (which uses i1): copy to st8 region as bytes
   auto rowc = ws.st8 + NB2_MAX_ROWS;
   for (int r = 0; r < m; r++) rowc[r] = (unsigned char)ws.i1[r];
-  // ---- A by impulse tests (upper blocks measured, lower mirrored; BoxedLcpConstraintSolver.cpp:293-314)
+}
+
+// phase 1 — A by impulse tests (upper blocks measured, lower mirrored in phase 2; BoxedLcpConstraintSolver.cpp:293-314).
+// The m impulse tests are independent: lane `cl` of `nl` cooperating threads takes rows cl, cl + nl, ... with private
+// sweep buffers; every lane writes only its own rows of A.
+template <int ST>
+NB2_HD void contact_phase1(const Nb2ModelDev<CR>& M, const CR* sv, size_t B, CR* wsblock, int lane, int cl, int nl) {
+  const int nb = M.nb, n = M.ndof;
+  const ContactWsT<ST> ws = carve_ws<ST>(wsblock, lane, nb, n);
+  const int m = ws.meta[0], nc = ws.meta[1];
+  if (m == 0) return;
+  auto rowc = ws.st8 + NB2_MAX_ROWS;
   auto A = ws.A;
   unsigned long long mask = 0ull;  // ancestors (and self) of every contact body
   for (int c = 0; c < nc; c++) {
     for (int bdy = ws.cbodyA[c]; bdy >= 0; bdy = M.parent[bdy]) mask |= (1ull << bdy);
     for (int bdy = ws.cbodyB[c]; bdy >= 0; bdy = M.parent[bdy]) mask |= (1ull << bdy);
   }
-  for (int r = 0; r < m; r++) {
+  ContactWsT<ST> wl = ws;  // same world, this lane's sweep buffers
+  {
+    auto base = ws.lbuf + (cl % NB2_CONTACT_LANES) * (12 * nb + 2 * n);
+    wl.pI = base; wl.V = base + 6 * nb; wl.uI = base + 12 * nb; wl.dqd = base + 12 * nb + n;
+  }
+  for (int r = cl; r < m; r += nl) {
     const int c = rowc[r];
-    for (int i = 0; i < nb; i++) if ((mask >> i) & 1ull) for (int k = 0; k < 6; k++) ws.pI[6 * i + k] = 0;
-    if (ws.cbodyA[c] >= 0) { auto J = ws.JA + 6 * r; auto p = ws.pI + 6 * ws.cbodyA[c]; for (int k = 0; k < 6; k++) p[k] -= J[k]; }
-    if (ws.cbodyB[c] >= 0) { auto J = ws.JB + 6 * r; auto p = ws.pI + 6 * ws.cbodyB[c]; for (int k = 0; k < 6; k++) p[k] -= J[k]; }
-    impulse_response<ST>(M, sv, B, ws, mask);
+    for (int i = 0; i < nb; i++) if ((mask >> i) & 1ull) for (int k = 0; k < 6; k++) wl.pI[6 * i + k] = 0;
+    if (ws.cbodyA[c] >= 0) { auto J = ws.JA + 6 * r; auto p = wl.pI + 6 * ws.cbodyA[c]; for (int k = 0; k < 6; k++) p[k] -= J[k]; }
+    if (ws.cbodyB[c] >= 0) { auto J = ws.JB + 6 * r; auto p = wl.pI + 6 * ws.cbodyB[c]; for (int k = 0; k < 6; k++) p[k] -= J[k]; }
+    impulse_response<ST>(M, sv, B, wl, mask);
     for (int s2 = 0; s2 < m; s2++) {
       const int cj = rowc[s2];
-      if (cj < c) { A[r * m + s2] = A[s2 * m + r]; continue; }
+      if (cj < c) continue;  // mirrored from row s2 in phase 2
       CR a = 0;
-      if (ws.cbodyA[cj] >= 0) a += dot(ldv6(ws.JA + 6 * s2), ldv6(ws.V + 6 * ws.cbodyA[cj]));
-      if (ws.cbodyB[cj] >= 0) a += dot(ldv6(ws.JB + 6 * s2), ldv6(ws.V + 6 * ws.cbodyB[cj]));
+      if (ws.cbodyA[cj] >= 0) a += dot(ldv6(ws.JA + 6 * s2), ldv6(wl.V + 6 * ws.cbodyA[cj]));
+      if (ws.cbodyB[cj] >= 0) a += dot(ldv6(ws.JB + 6 * s2), ldv6(wl.V + 6 * ws.cbodyB[cj]));
       A[r * m + s2] = a;
     }
   }
+}
+
+// phase 2 — mirror A, warm start, solve chain, classification, impulse application (one thread)
+template <int ST>
+NB2_HD void contact_phase2(const Nb2ModelDev<CR>& M, const Nb2ContactDev& C, const float* st, float* out, const CR* sv, size_t B,
+                           CR* wsblock, int lane, CR* x_io, int* m_io, int* labels_out, int* status_out, CR* crec) {
+  const int nb = M.nb, n = M.ndof;
+  const ContactWsT<ST> ws = carve_ws<ST>(wsblock, lane, nb, n);
+  const int m = ws.meta[0];
+  int status = ws.meta[2];
+  if (m == 0) return;
+  auto rowc = ws.st8 + NB2_MAX_ROWS;
+  auto A = ws.A;
+  for (int r = 0; r < m; r++) { const int cr = rowc[r]; for (int s2 = 0; s2 < r; s2++) if (rowc[s2] < cr) A[r * m + s2] = A[s2 * m + r]; }
   for (int c = 0; c < m; c++) { CR sn = 0; for (int r = 0; r < m; r++) sn += A[r * m + c] * A[r * m + c]; ws.colnorm[c] = sn; }
   auto b = ws.b; auto lo = ws.lo; auto hi = ws.hi; auto fi = ws.findex; auto x = ws.x; auto x0 = ws.x0;
   // ---- warm start: cached solution if it has the same size, else LCPUtils::guessSolution (LCPUtils.cpp:86-140)
@@ -611,6 +658,17 @@ NB2_HD void world_contact(const Nb2ModelDev<CR>& M, const Nb2ContactDev& C, cons
     CR* cA = cd + n;
     for (int i = 0; i < m * m; i++) cA[i] = A[i];
   }
+}
+
+
+// single-thread form (host emulation, tests): the three phases back to back
+template <int ST>
+NB2_HD void world_contact(const Nb2ModelDev<CR>& M, const Nb2ContactDev& C, const float* st, float* out, const CR* sv, size_t B,
+                          CR* wsblock, int lane, CR* x_io, int* m_io, int* labels_out, int* status_out, int* nc_out, float* cinfo_out,
+                          CR* crec, int emulate_lanes = 1) {
+  contact_phase0<ST>(M, C, st, out, sv, B, wsblock, lane, x_io, m_io, labels_out, status_out, nc_out, cinfo_out, crec);
+  for (int cl = emulate_lanes - 1; cl >= 0; cl--) contact_phase1<ST>(M, sv, B, wsblock, lane, cl, emulate_lanes);
+  contact_phase2<ST>(M, C, st, out, sv, B, wsblock, lane, x_io, m_io, labels_out, status_out, crec);
 }
 
 // =====================================================================================================

@@ -138,21 +138,37 @@ k_step_bwd(const __grid_constant__ Nb2ModelDev<R> M, int B, int w0, int count, c
   }
 }
 
-// contact / boxed-LCP stage: one thread per world, fp64, per-world workspace in global memory (L1/L2 cached).
-// The pivoting LCP solve is data dependent, so lanes of a warp diverge here by construction.
+// contact / boxed-LCP stage, fp64, per-world workspace in global memory (L1/L2 cached), KC threads per world:
+// one thread runs the data-dependent parts (collision, LCP pivoting, classification), all KC share the m impulse tests
+// that assemble A = J M^-1 J^T (the dominant cost: m leaf->root->leaf sweeps).  A warp holds 32/KC worlds; with KC = 8 a
+// batch of 4096 worlds fills 1024 warps instead of 128, which is what hides the latency of the serial parts.
+template <int KC>
 __global__ void __launch_bounds__(64)
 k_contact_fwd(const __grid_constant__ Nb2ModelDev<double> M, const __grid_constant__ Nb2ContactDev C, int B,
               const float* __restrict__ state, float* __restrict__ next, const double* __restrict__ saved,
               double* __restrict__ workspace, size_t ws_doubles, double* __restrict__ x_lcp, int* __restrict__ m_lcp,
               int* __restrict__ labels, int* __restrict__ status, int* __restrict__ ncontacts, float* __restrict__ cinfo,
               double* __restrict__ crec, size_t rec_doubles) {
-  const int w = blockIdx.x * blockDim.x + threadIdx.x;
-  if (w >= B) return;
-  // the 32 worlds of a warp share one lane-interleaved workspace block
-  nb2::world_contact<32>(M, C, state + (size_t)w * 2 * M.ndof, next + (size_t)w * 2 * M.ndof, saved + w, (size_t)B,
-                     workspace + (size_t)(w >> 5) * ws_doubles * 32, w & 31, x_lcp + (size_t)w * NB2_MAX_ROWS, m_lcp + w,
-                     labels + (size_t)w * NB2_MAX_ROWS, status + w, ncontacts + w,
-                     cinfo ? cinfo + (size_t)w * NB2_MAX_CONTACTS * 10 : nullptr, crec ? crec + (size_t)w * rec_doubles : nullptr);
+  constexpr int WPW = 32 / KC;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int li = threadIdx.x & 31, slot = li / KC, cl = li % KC;
+  const int w = (t >> 5) * WPW + slot;
+  const bool valid = w < B;
+  const int wc = valid ? w : 0;
+  // the WPW worlds of a warp share one slot-interleaved workspace block
+  double* wsb = workspace + (size_t)(t >> 5) * ws_doubles * WPW;
+  const float* st = state + (size_t)wc * 2 * M.ndof;
+  float* out = next + (size_t)wc * 2 * M.ndof;
+  if (valid && cl == 0)
+    nb2::contact_phase0<WPW>(M, C, st, out, saved + wc, (size_t)B, wsb, slot, x_lcp + (size_t)wc * NB2_MAX_ROWS, m_lcp + wc,
+                             labels + (size_t)wc * NB2_MAX_ROWS, status + wc, ncontacts + wc,
+                             cinfo ? cinfo + (size_t)wc * NB2_MAX_CONTACTS * 10 : nullptr, crec ? crec + (size_t)wc * rec_doubles : nullptr);
+  __syncwarp();
+  if (valid) nb2::contact_phase1<WPW>(M, saved + wc, (size_t)B, wsb, slot, cl, KC);
+  __syncwarp();
+  if (valid && cl == 0)
+    nb2::contact_phase2<WPW>(M, C, st, out, saved + wc, (size_t)B, wsb, slot, x_lcp + (size_t)wc * NB2_MAX_ROWS, m_lcp + wc,
+                             labels + (size_t)wc * NB2_MAX_ROWS, status + wc, crec ? crec + (size_t)wc * rec_doubles : nullptr);
 }
 
 // backward of a step with the contact stage (fp64): world_backward<double, 32, CONTACT=true>
@@ -503,11 +519,19 @@ int nb2_step_forward_contact(const nb2_model* cm, int B, const float* state, con
   cudaStream_t st = (cudaStream_t)stream;
   int rc = launch_fwd<double>(m, B, state, action, next_state, (double*)saved_fp64, st);
   if (rc) return rc;
-  const int threads = 32;
-  k_contact_fwd<<<(B + threads - 1) / threads, threads, 0, st>>>(m->md, m->contact, B, state, next_state, (const double*)saved_fp64,
-                                                                 (double*)workspace, nb2::contact_ws_doubles(m->mf.nb, m->mf.ndof), x_lcp,
-                                                                 m_lcp, labels, status, ncontacts, cinfo, contact_record,
-                                                                 nb2::contact_rec_doubles(m->mf.ndof));
+  // 8 threads per world while that still leaves the GPU short of warps, one thread per world for huge batches
+  const size_t wsd = nb2::contact_ws_doubles(m->mf.nb, m->mf.ndof), recd = nb2::contact_rec_doubles(m->mf.ndof);
+  if ((long long)B * 8 / 32 <= (long long)m->sm_count * 48) {
+    const int threads = 32, worlds_per_block = 4;
+    k_contact_fwd<8><<<(B + worlds_per_block - 1) / worlds_per_block, threads, 0, st>>>(m->md, m->contact, B, state, next_state, (const double*)saved_fp64,
+                                                                                     (double*)workspace, wsd, x_lcp, m_lcp, labels, status, ncontacts, cinfo,
+                                                                                     contact_record, recd);
+  } else {
+    const int threads = 32;
+    k_contact_fwd<1><<<(B + threads - 1) / threads, threads, 0, st>>>(m->md, m->contact, B, state, next_state, (const double*)saved_fp64,
+                                                                   (double*)workspace, wsd, x_lcp, m_lcp, labels, status, ncontacts, cinfo,
+                                                                   contact_record, recd);
+  }
   g_launches++;
   NB2_CUDA(cudaGetLastError());
   return NB2_OK;

@@ -73,7 +73,8 @@ static int run_fwd_contact(const nb2_model_desc* d, int B, const float* state, c
     nb2::world_contact<1>(M, C, state + (size_t)w * 2 * M.ndof, next + (size_t)w * 2 * M.ndof, saved + w, (size_t)B, ws.data(), 0,
                           x_lcp + (size_t)w * NB2_MAX_ROWS, m_lcp + w, labels + (size_t)w * NB2_MAX_ROWS, status + w, nc + w,
                        cinfo ? cinfo + (size_t)w * NB2_MAX_CONTACTS * 10 : nullptr,
-                       crec ? crec + (size_t)w * nb2::contact_rec_doubles(M.ndof) : nullptr);
+                       crec ? crec + (size_t)w * nb2::contact_rec_doubles(M.ndof) : nullptr,
+                       1 + (w % 4) /* lanes sharing the impulse tests: 1..4, so every split of the rows is exercised */);
   }
   return 0;
 }
