@@ -13,7 +13,6 @@
 //   impulses, velocity update                ContactConstraint.cpp:630-684, Skeleton.cpp:13571-13595
 // New: the minimum-norm least-squares solves (Eigen completeOrthogonalDecomposition in the reference) are done with a
 // rank-revealing pivoted Cholesky (symmetric case) / normal equations (sliding-friction case) instead of a QR/SVD.
-// Not yet restated on the device: LCPUtils::reduce (duplicate-column merge) — instances that would merge are flagged.
 #pragma once
 #include "nb2_dantzig.cuh"
 #include "nb2_dyn.cuh"
@@ -34,7 +33,7 @@
 #define NB2_ST_NOT_STANDARDIZED 64
 #define NB2_ST_UNSUPPORTED_GEOMETRY 128
 #define NB2_ST_CONTACT_OVERFLOW 256
-#define NB2_ST_WOULD_MERGE 512
+#define NB2_ST_MERGED 512  // LCPUtils::reduce merged near-identical columns before a solver ran
 
 // ConstraintMapping (dart/neural/ConstrainedGroupGradientMatrices.hpp:33-39)
 #define NB2_MAP_NOT_CLAMPING (-1)
@@ -394,6 +393,122 @@ NB2_HD bool pgs_solve(int m, PA A, PX x, PB_ b, PL lo, PH hi, PF fi, PS skip) {
   return term;
 }
 
+// LCPUtils::reduce (LCPUtils.cpp:144-201) + mergeLCPColumns (:346-444): near-identical columns (same bounds, findex,
+// |b_a - b_b| < 1e-4, ||A_a - A_b||^2 < 1e-4) are merged one pair at a time — column a doubled, row/column b dropped —
+// until none is left; `map` (n0 x n, row-major with the CURRENT n as stride) accumulates the un-merge map x = map * x_r.
+// Everything is compacted in place (destination index <= source index in row-major order). Returns the reduced size.
+template <class PD, class PI>
+NB2_HD int lcp_reduce(int n0, PD A, PD x, PD b, PD lo, PD hi, PI fi, PD map) {
+  int n = n0;
+  for (int i = 0; i < n0; i++) for (int j = 0; j < n0; j++) map[i * n0 + j] = (i == j) ? 1.0 : 0.0;
+  while (true) {
+    int ca = -1, cb = -1;
+    for (int a = 0; a < n - 1 && ca < 0; a++) for (int c = a + 1; c < n; c++) {
+      if (fi[a] != fi[c] || hi[a] != hi[c] || lo[a] != lo[c] || !(nb2_abs(b[a] - b[c]) < 1e-4)) continue;
+      CR d2 = 0;
+      for (int r = 0; r < n; r++) { const CR d = A[r * n + a] - A[r * n + c]; d2 += d * d; }
+      if (d2 < 1e-4) { ca = a; cb = c; break; }
+    }
+    if (ca < 0) break;
+    for (int r = 0, ri = 0; r < n; r++) {
+      if (r == cb) continue;
+      for (int i = 0, ci = 0; i < n; i++) { if (i == cb) continue; A[ri * (n - 1) + ci] = A[r * n + i] * (i == ca ? 2.0 : 1.0); ci++; }
+      ri++;
+    }
+    for (int i = 0, ni = 0; i < n; i++) {
+      if (i == cb) continue;
+      x[ni] = x[i]; b[ni] = b[i]; lo[ni] = lo[i]; hi[ni] = hi[i];
+      const int f = fi[i];
+      fi[ni] = (f < cb) ? f : (f == cb ? ca : f - 1);
+      ni++;
+    }
+    for (int r = 0; r < n0; r++) {
+      const CR vb = map[r * n + cb];
+      for (int i = 0, ni = 0; i < n; i++) { if (i == cb) continue; map[r * (n - 1) + ni] = map[r * n + i]; ni++; }
+      map[r * (n - 1) + ca] += vb;
+    }
+    n--;
+  }
+  return n;
+}
+
+// The solve chain of BoxedLcpConstraintSolver::solveLcp (:352-789) on the problem held in the workspace (A, b, lo, hi,
+// findex of size m): warm start -> short-circuit classification -> [reduce] Dantzig -> cfm + [reduce] PGS -> friction drop
+// -> classification / standardisation.  x_cached: last step's solution when it has the same size, else nullptr
+// (LCPUtils::guessSolution).  Leaves x in ws.x and the labels in ws.mapping; returns the status bits.
+template <int ST>
+NB2_HD int lcp_chain_ws(int m, const ContactWsT<ST>& ws, CR fallback_cfm, const CR* x_cached) {
+  int status = 0;
+  auto A = ws.A;
+  for (int c = 0; c < m; c++) { CR sn = 0; for (int r = 0; r < m; r++) sn += A[r * m + c] * A[r * m + c]; ws.colnorm[c] = sn; }
+  auto b = ws.b; auto lo = ws.lo; auto hi = ws.hi; auto fi = ws.findex; auto x = ws.x; auto x0 = ws.x0;
+  // ---- warm start: cached solution if it has the same size, else LCPUtils::guessSolution (LCPUtils.cpp:86-140)
+  if (x_cached) { for (int i = 0; i < m; i++) x0[i] = x_cached[i]; }
+  else {
+    int ng = 0;
+    for (int i = 0; i < m; i++) { x0[i] = 0; if (fi[i] == -1) { if (b[i] > 0) ws.i1[ng++] = i; } else ws.i1[ng++] = i; }
+    if (ng > 0) {
+      for (int r = 0; r < ng; r++) { ws.v1[r] = b[ws.i1[r]]; for (int c = 0; c < ng; c++) ws.Q[r * ng + c] = A[ws.i1[r] * m + ws.i1[c]]; }
+      pinv_psd(ng, ws.Q, ws.v1, ws.v2, ws.Aw, ws.L, ws.v5, ws.v6, ws.i2);
+      for (int r = 0; r < ng; r++) x0[ws.i1[r]] = ws.v2[r];
+    }
+  }
+  for (int i = 0; i < m; i++) x[i] = x0[i];
+  // ---- solve chain (BoxedLcpConstraintSolver.cpp:352-789)
+  bool success = classify_and_standardize<ST>(m, A, x, b, lo, hi, fi, ws.colnorm, false, ws);
+  const bool shortCircuit = success;
+  bool ignoredFriction = false;
+  if (success) status |= NB2_ST_SHORTCIRCUIT;
+  else {
+    status |= NB2_ST_DANTZIG;
+    for (int i = 0; i < m * m; i++) ws.Aw[i] = A[i];
+    for (int i = 0; i < m; i++) { ws.v1[i] = b[i]; ws.v2[i] = lo[i]; ws.v3[i] = hi[i]; ws.i1[i] = fi[i]; ws.v4[i] = x[i]; }
+    const int mr = lcp_reduce(m, ws.Aw, ws.v4, ws.v1, ws.v2, ws.v3, ws.i1, ws.Q2);  // :596 reduce before the Dantzig solve
+    if (mr < m) status |= NB2_ST_MERGED;
+    DantzigWorkT<SP<CR, ST>, SP<int, ST>, SP<unsigned char, ST>> W;
+    W.A = ws.Aw; W.x = ws.v4; W.b = ws.v1; W.w = ws.v5; W.lo = ws.v2; W.hi = ws.v3; W.L = ws.L; W.d = ws.v6; W.delta_x = ws.v7; W.delta_w = ws.v8;
+    W.Dell = ws.Q; W.ell = ws.Q + mr; W.tmp = ws.Q + 2 * mr; W.findex = ws.i1; W.p = ws.i2; W.C = ws.clampIdx; W.state = ws.st8;
+    const int rc = dantzig_solve(W, mr, true);
+    success = (rc == 1);
+    if (success) {
+      for (int i = 0; i < m; i++) { CR v = 0; for (int c = 0; c < mr; c++) v += ws.Q2[i * mr + c] * ws.v4[c]; x[i] = v; }  // x = mapOut * x_reduced
+      if (!lcp_valid(m, A, x, b, hi, lo, fi, false)) success = false;
+    }
+    if (!success) status |= NB2_ST_DANTZIG_FAILED;
+  }
+  { bool nan = false; for (int i = 0; i < m; i++) if (x[i] != x[i]) nan = true; if (nan) { success = false; for (int i = 0; i < m; i++) x[i] = 0; status |= NB2_ST_NAN; } }
+  if (!success) {
+    for (int i = 0; i < m; i++) A[i * m + i] += fallback_cfm;  // :539-547 (both backups get the cfm; colnorms were taken before)
+    status |= NB2_ST_PGS;
+    for (int i = 0; i < m * m; i++) ws.Aw[i] = A[i];
+    for (int i = 0; i < m; i++) { ws.v1[i] = b[i]; ws.v2[i] = lo[i]; ws.v3[i] = hi[i]; ws.i1[i] = fi[i]; ws.v4[i] = x0[i]; }
+    const int mr = lcp_reduce(m, ws.Aw, ws.v4, ws.v1, ws.v2, ws.v3, ws.i1, ws.Q2);  // :551-557 the backup problem is reduced too
+    if (mr < m) status |= NB2_ST_MERGED;
+    success = pgs_solve(mr, ws.Aw, ws.v4, ws.v1, ws.v2, ws.v3, ws.i1, ws.st8);
+    if (success) {
+      for (int i = 0; i < m; i++) { CR v = 0; for (int c = 0; c < mr; c++) v += ws.Q2[i * mr + c] * ws.v4[c]; x[i] = v; }
+      if (!lcp_valid(m, A, x, b, hi, lo, fi, false)) success = false;
+    }
+  }
+  if (!success) {
+    ignoredFriction = true;
+    status |= NB2_ST_FRICTION_DROPPED;
+    int k = 0;
+    for (int i = 0; i < m; i++) if (fi[i] == -1) ws.i1[k++] = i;
+    for (int r = 0; r < k; r++) { ws.v1[r] = b[ws.i1[r]]; ws.v2[r] = lo[ws.i1[r]]; ws.v3[r] = hi[ws.i1[r]]; ws.v4[r] = 0; ws.i2[r] = -1; for (int c = 0; c < k; c++) ws.Aw[r * k + c] = A[ws.i1[r] * m + ws.i1[c]]; }
+    pgs_solve(k, ws.Aw, ws.v4, ws.v1, ws.v2, ws.v3, ws.i2, ws.st8);
+    for (int i = 0; i < m; i++) x[i] = 0;
+    for (int r = 0; r < k; r++) x[ws.i1[r]] = ws.v4[r];
+  }
+  { bool nan = false; for (int i = 0; i < m; i++) if (x[i] != x[i]) nan = true; if (nan) { for (int i = 0; i < m; i++) x[i] = 0; status |= NB2_ST_NAN; } }
+  if (!shortCircuit) {
+    for (int i = 0; i < m; i++) ws.v7[i] = x[i];
+    // classify works on x in place and only keeps the standardised x when valid
+    if (!classify_and_standardize<ST>(m, A, x, b, lo, hi, fi, ws.colnorm, ignoredFriction, ws)) { status |= NB2_ST_NOT_STANDARDIZED; }
+  }
+  return status;
+}
+
 // =====================================================================================================
 // the contact stage of one world.  `out` holds [q+ ; v*] on entry (written by the ABA kernel) and [q+ ; v+] on exit.
 // x_io: cached LCP solution (NB2_MAX_ROWS doubles), m_io: its size (-1 none) -> new solution / size.
@@ -577,68 +692,8 @@ NB2_HD void contact_phase2(const Nb2ModelDev<CR>& M, const Nb2ContactDev& C, con
   auto rowc = ws.st8 + NB2_MAX_ROWS;
   auto A = ws.A;
   for (int r = 0; r < m; r++) { const int cr = rowc[r]; for (int s2 = 0; s2 < r; s2++) if (rowc[s2] < cr) A[r * m + s2] = A[s2 * m + r]; }
-  for (int c = 0; c < m; c++) { CR sn = 0; for (int r = 0; r < m; r++) sn += A[r * m + c] * A[r * m + c]; ws.colnorm[c] = sn; }
-  auto b = ws.b; auto lo = ws.lo; auto hi = ws.hi; auto fi = ws.findex; auto x = ws.x; auto x0 = ws.x0;
-  // ---- warm start: cached solution if it has the same size, else LCPUtils::guessSolution (LCPUtils.cpp:86-140)
-  if (*m_io == m) { for (int i = 0; i < m; i++) x0[i] = x_io[i]; }
-  else {
-    int ng = 0;
-    for (int i = 0; i < m; i++) { x0[i] = 0; if (fi[i] == -1) { if (b[i] > 0) ws.i1[ng++] = i; } else ws.i1[ng++] = i; }
-    if (ng > 0) {
-      for (int r = 0; r < ng; r++) { ws.v1[r] = b[ws.i1[r]]; for (int c = 0; c < ng; c++) ws.Q[r * ng + c] = A[ws.i1[r] * m + ws.i1[c]]; }
-      pinv_psd(ng, ws.Q, ws.v1, ws.v2, ws.Aw, ws.L, ws.v5, ws.v6, ws.i2);
-      for (int r = 0; r < ng; r++) x0[ws.i1[r]] = ws.v2[r];
-    }
-  }
-  for (int i = 0; i < m; i++) x[i] = x0[i];
-  // ---- solve chain (BoxedLcpConstraintSolver.cpp:352-789)
-  bool success = classify_and_standardize<ST>(m, A, x, b, lo, hi, fi, ws.colnorm, false, ws);
-  const bool shortCircuit = success;
-  bool ignoredFriction = false;
-  if (success) status |= NB2_ST_SHORTCIRCUIT;
-  else {
-    status |= NB2_ST_DANTZIG;
-    // LCPUtils::reduce would merge near-identical columns first; not restated on the device: flag such instances
-    for (int a = 0; a < m - 1; a++) for (int c = a + 1; c < m; c++) {
-      if (fi[a] != fi[c] || hi[a] != hi[c] || lo[a] != lo[c] || nb2_abs(b[a] - b[c]) >= 1e-4) continue;
-      CR d2 = 0; for (int r = 0; r < m; r++) { const CR d = A[r * m + a] - A[r * m + c]; d2 += d * d; }
-      if (d2 < 1e-4) status |= NB2_ST_WOULD_MERGE;
-    }
-    for (int i = 0; i < m * m; i++) ws.Aw[i] = A[i];
-    for (int i = 0; i < m; i++) { ws.v1[i] = b[i]; ws.v2[i] = lo[i]; ws.v3[i] = hi[i]; ws.i1[i] = fi[i]; }
-    DantzigWorkT<SP<CR, ST>, SP<int, ST>, SP<unsigned char, ST>> W;
-    W.A = ws.Aw; W.x = ws.v4; W.b = ws.v1; W.w = ws.v5; W.lo = ws.v2; W.hi = ws.v3; W.L = ws.L; W.d = ws.v6; W.delta_x = ws.v7; W.delta_w = ws.v8;
-    W.Dell = ws.Q; W.ell = ws.Q + m; W.tmp = ws.Q + 2 * m; W.findex = ws.i1; W.p = ws.i2; W.C = ws.clampIdx; W.state = ws.st8;
-    const int rc = dantzig_solve(W, m, true);
-    success = (rc == 1);
-    if (success) { for (int i = 0; i < m; i++) x[i] = ws.v4[i]; if (!lcp_valid(m, A, x, b, hi, lo, fi, false)) success = false; }
-    if (!success) status |= NB2_ST_DANTZIG_FAILED;
-  }
-  { bool nan = false; for (int i = 0; i < m; i++) if (x[i] != x[i]) nan = true; if (nan) { success = false; for (int i = 0; i < m; i++) x[i] = 0; status |= NB2_ST_NAN; } }
-  if (!success) {
-    for (int i = 0; i < m; i++) A[i * m + i] += C.fallback_cfm;  // :539-547 (both backups get the cfm; colnorms were taken before)
-    status |= NB2_ST_PGS;
-    for (int i = 0; i < m * m; i++) ws.Aw[i] = A[i];
-    for (int i = 0; i < m; i++) { ws.v1[i] = b[i]; ws.v4[i] = x0[i]; }
-    success = pgs_solve(m, ws.Aw, ws.v4, ws.v1, lo, hi, fi, ws.st8);
-    if (success) { for (int i = 0; i < m; i++) x[i] = ws.v4[i]; if (!lcp_valid(m, A, x, b, hi, lo, fi, false)) success = false; }
-  }
-  if (!success) {
-    ignoredFriction = true;
-    status |= NB2_ST_FRICTION_DROPPED;
-    int k = 0;
-    for (int i = 0; i < m; i++) if (fi[i] == -1) ws.i1[k++] = i;
-    for (int r = 0; r < k; r++) { ws.v1[r] = b[ws.i1[r]]; ws.v2[r] = lo[ws.i1[r]]; ws.v3[r] = hi[ws.i1[r]]; ws.v4[r] = 0; ws.i2[r] = -1; for (int c = 0; c < k; c++) ws.Aw[r * k + c] = A[ws.i1[r] * m + ws.i1[c]]; }
-    pgs_solve(k, ws.Aw, ws.v4, ws.v1, ws.v2, ws.v3, ws.i2, ws.st8);
-    for (int i = 0; i < m; i++) x[i] = 0;
-    for (int r = 0; r < k; r++) x[ws.i1[r]] = ws.v4[r];
-  }
-  { bool nan = false; for (int i = 0; i < m; i++) if (x[i] != x[i]) nan = true; if (nan) { for (int i = 0; i < m; i++) x[i] = 0; status |= NB2_ST_NAN; } }
-  if (!shortCircuit) {
-    for (int i = 0; i < m; i++) ws.v7[i] = x[i];
-    // classify works on x in place and only keeps the standardised x when valid
-    if (!classify_and_standardize<ST>(m, A, x, b, lo, hi, fi, ws.colnorm, ignoredFriction, ws)) { status |= NB2_ST_NOT_STANDARDIZED; }
-  }
+  status |= lcp_chain_ws<ST>(m, ws, C.fallback_cfm, (*m_io == m) ? x_io : nullptr);
+  auto x = ws.x;
   for (int i = 0; i < m; i++) { x_io[i] = x[i]; labels_out[i] = ws.mapping[i]; }
   // ---- apply the impulses and update the velocities (ContactConstraint.cpp:630-684, Skeleton.cpp:13571-13595)
   for (int i = 0; i < nb * 6; i++) ws.pI[i] = 0;

@@ -344,6 +344,7 @@ inline ChainResult solve_chain(const Mat& A_in, const Vec& b, const Vec& lo, con
     R.status |= 2;
     Problem P; P.A = A_in; P.x = x; P.b = b; P.hi = hi; P.lo = lo; P.fi = fi;
     reduce(P);
+    if (P.A.c < n) R.status |= 512;  // columns merged (informational)
     Problem Psolve = P;
     success = run_dantzig(Psolve, true);
     if (success) {
@@ -361,6 +362,7 @@ inline ChainResult solve_chain(const Mat& A_in, const Vec& b, const Vec& lo, con
     R.status |= 8;
     Problem P; P.A = Aback; P.x = x0; P.b = b; P.hi = hi; P.lo = lo; P.fi = fi;  // mXBackup = x at entry
     reduce(P);
+    if (P.A.c < n) R.status |= 512;
     Problem Psolve = P;
     success = run_pgs(Psolve);
     if (success) {

@@ -94,7 +94,23 @@ static int run_bwd_contact(const nb2_model_desc* d, int B, const float* state, c
   }
   return 0;
 }
+// LCP-level entry: the device solve chain on a caller-supplied boxed LCP (tests/test_lcp.py compares it with the oracle's chain)
+static int run_chain(int m, const double* A, const double* b, const double* lo, const double* hi, const int* fi, const double* x0, int have_x0,
+                     double cfm, double* x_out, int* mapping_out) {
+  const int nb = 1, ndof = 1;
+  std::vector<double> wsb(nb2::contact_ws_doubles(nb, ndof), 1e30);
+  const nb2::ContactWsT<1> ws = nb2::carve_ws<1>(wsb.data(), 0, nb, ndof);
+  for (int i = 0; i < m * m; i++) ws.A[i] = A[i];
+  for (int i = 0; i < m; i++) { ws.b[i] = b[i]; ws.lo[i] = lo[i]; ws.hi[i] = hi[i]; ws.findex[i] = fi[i]; ws.rest[i] = 0.0; }
+  const int status = nb2::lcp_chain_ws<1>(m, ws, cfm, have_x0 ? x0 : nullptr);
+  for (int i = 0; i < m; i++) { x_out[i] = ws.x[i]; mapping_out[i] = ws.mapping[i]; }
+  return status;
+}
 extern "C" {
+int emul_solve_chain(int m, const double* A, const double* b, const double* lo, const double* hi, const int* fi, const double* x0, int have_x0,
+                     double cfm, double* x_out, int* mapping_out) {
+  return run_chain(m, A, b, lo, hi, fi, x0, have_x0, cfm, x_out, mapping_out);
+}
 int emul_forward_contact(const nb2_model_desc* d, int B, const float* state, const float* action, float* next, double* saved,
                          double* x_lcp, int* m_lcp, int* labels, int* status, int* nc, float* cinfo, double* crec) {
   return run_fwd_contact(d, B, state, action, next, saved, x_lcp, m_lcp, labels, status, nc, cinfo, crec);
