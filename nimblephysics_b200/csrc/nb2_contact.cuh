@@ -757,7 +757,7 @@ NB2_HD BwdContactView<ST> contact_backward_prepare(const Nb2ModelDev<CR>& M, con
   const int nb = M.nb, n = M.ndof;
   const ContactWsT<ST> ws = carve_ws<ST>(wsblock, lane, nb, n);
   BwdContactView<ST> cv;
-  cv.Aacc = ws.W; cv.Uplus = ws.W + 6 * nb; cv.aeff = ws.uI; cv.vplus = ws.vstar; cv.inj = ws.Q2; cv.JcTmu = ws.dqd; cv.active = 0; cv.error = 0;
+  cv.Aacc = ws.pI; cv.Uplus = ws.V; cv.aeff = ws.uI; cv.vplus = ws.vstar; cv.inj = ws.Q2; cv.JcTmu = ws.dqd; cv.active = 0; cv.error = 0;
   const int m = (int)crec[0];
   if (m <= 0) return cv;
   cv.active = 1;
@@ -771,17 +771,17 @@ NB2_HD BwdContactView<ST> contact_backward_prepare(const Nb2ModelDev<CR>& M, con
     xf_to12(ws.T + 12 * i, T);
     xf_to12(ws.W + 12 * i, (p >= 0) ? xf_mul(xf_from12(ws.W + 12 * p), T) : T);
   }
-  // ---- contact rows re-generated on dual numbers: F_r and dF_r/dxi (xi = body twist [angular; linear] of the moving body)
+  // ---- contact rows re-generated on dual numbers.  Row r acts on up to two bodies: wrench F_A on the body of shape A and
+  // F_B on the body of shape B (ContactConstraint.cpp:66-230; a static side has no term).  The generator runs in two
+  // passes: pass 0 records the wrenches (needed for mu), pass 1 — after mu, w and v+ are known — differentiates them with
+  // respect to the pose of one moving body at a time (6 twist directions) and accumulates the contact-frame wrench G.
   typedef DualT<6> D6;
-  auto rowF = ws.JA; auto rowdF = ws.A; auto rowbody = ws.i1; auto rowmu = ws.v1;
-  int m2 = 0;
-  for (int pi = 0; pi < C.npairs && !cv.error; pi++) {
-    const int sa = C.pair_a[pi], sb = C.pair_b[pi];
-    const int ba = C.shape_body[sa], bb = C.shape_body[sb];
-    if (ba >= 0 && bb >= 0) { cv.error = 1; break; }  // two moving bodies: not supported by the backward yet
-    const int dyn = ba >= 0 ? ba : bb;
-    const bool dynIsA = ba >= 0;
-    // dual world transform of the moving body:  W (I + [xi_w]x , xi_v)
+  auto rowFA = ws.JA; auto rowFB = ws.JB; auto rowbA = ws.i1; auto rowbB = ws.findex; auto rowmu = ws.v1;
+  auto coefWr = ws.v7; auto coefVr = ws.v8;  // per-row weights of the w- and v+-fields (filled before pass 1)
+  auto inj = ws.Q2;
+  auto Aacc = ws.pI; auto Uplus = ws.V;      // valid in pass 1 (after the impulse sweep for nu released these buffers)
+  auto lift = [](const Xf<CR>& X) { Xf<D6> o; const CR* r = &X.R_.m00; D6* q = &o.R_.m00; for (int i = 0; i < 9; i++) q[i] = D6(r[i]); o.p.x = D6(X.p.x); o.p.y = D6(X.p.y); o.p.z = D6(X.p.z); return o; };
+  auto dual_pose = [&](int dyn) {  // world transform of body `dyn` perturbed by a body twist:  W (I + [xi_w]x , xi_v)
     const Xf<CR> Wd = xf_from12(ws.W + 12 * dyn);
     Xf<D6> WD;
     {
@@ -802,58 +802,96 @@ NB2_HD BwdContactView<ST> contact_backward_prepare(const Nb2ModelDev<CR>& M, con
       WD.p.x.d[4] = c1.x; WD.p.y.d[4] = c1.y; WD.p.z.d[4] = c1.z;
       WD.p.x.d[5] = c2.x; WD.p.y.d[5] = c2.y; WD.p.z.d[5] = c2.z;
     }
-    auto lift = [](const Xf<CR>& X) { Xf<D6> o; const CR* r = &X.R_.m00; D6* q = &o.R_.m00; for (int i = 0; i < 9; i++) q[i] = D6(r[i]); o.p.x = D6(X.p.x); o.p.y = D6(X.p.y); o.p.z = D6(X.p.z); return o; };
-    const Xf<D6> Ta = dynIsA ? gxf_mul(WD, lift(xf_from12(C.shape_T[sa]))) : lift(xf_from12(C.shape_T[sa]));
-    const Xf<D6> Tb = dynIsA ? lift(xf_from12(C.shape_T[sb])) : gxf_mul(WD, lift(xf_from12(C.shape_T[sb])));
-    const int ta = C.shape_type[sa], tb = C.shape_type[sb];
-    const V3<D6> da = mk3<D6>(D6(C.shape_dims[sa][0]), D6(C.shape_dims[sa][1]), D6(C.shape_dims[sa][2]));
-    const V3<D6> db = mk3<D6>(D6(C.shape_dims[sb][0]), D6(C.shape_dims[sb][1]), D6(C.shape_dims[sb][2]));
-    ContactOutT<D6> co[8];
-    int k = 0;
-    if (ta == 0 && tb == 0) k = collide_box_box(da, Ta, db, Tb, C.clip_depth, co);
-    else if (ta == 0 && tb == 1) k = collide_box_sphere(da, Ta, db.x, Tb, C.clip_depth, 0, false, co);
-    else if (ta == 1 && tb == 0) k = collide_box_sphere(db, Tb, da.x, Ta, C.clip_depth, 0, true, co);
-    else if ((ta == 0 && tb == 2) || (ta == 2 && tb == 0)) {
-      const bool boxFirst = (ta == 0);
-      const Xf<D6>& Tc = boxFirst ? Tb : Ta; const Xf<D6>& Tbx = boxFirst ? Ta : Tb;
-      const V3<D6> bdim = boxFirst ? da : db;
-      const D6 r = boxFirst ? db.x : da.x; const CR h = boxFirst ? C.shape_dims[sb][1] : C.shape_dims[sa][1];
-      CR dep[2]; Xf<D6> Tend[2];
-      for (int e = 0; e < 2; e++) {
-        Tend[e] = Tc; Tend[e].p = gxf_apply(Tc, mk3<D6>(D6(0.0), D6(0.0), D6(e == 0 ? h / 2 : -h / 2)));
-        const V3<D6> pld = gxf_apply_inv(Tbx, Tend[e].p);
-        const V3<CR> pl = mk3<CR>(pld.x.v, pld.y.v, pld.z.v);
-        V3<CR> q = pl; bool inside = true;
-        for (int kk = 0; kk < 3; kk++) { const CR hk = 0.5 * gget3(bdim, kk).v, v = get3(q, kk); if (v < -hk) { set3(q, kk, -hk); inside = false; } if (v > hk) { set3(q, kk, hk); inside = false; } }
-        if (inside) { CR mn = 1e300; for (int kk = 0; kk < 3; kk++) { const CR v = 0.5 * gget3(bdim, kk).v - nb2_abs(get3(pl, kk)); mn = v < mn ? v : mn; } dep[e] = mn + r.v; }
-        else { const V3<CR> dd = pl - q; dep[e] = r.v - nb2_sqrt(dot(dd, dd)); }
-      }
-      if ((dep[0] > dep[1] ? dep[0] : dep[1]) >= 0 && nb2_abs(dep[0] - dep[1]) >= 1e-9) {
-        const int e = dep[0] > dep[1] ? 0 : 1;
-        k = collide_box_sphere(bdim, Tbx, r, Tend[e], C.clip_depth, e == 0 ? 1 : 2, !boxFirst, co);
+    return WD;
+  };
+  auto rows_pass = [&](int pass) {
+    int m2 = 0;
+    for (int pi = 0; pi < C.npairs && !cv.error; pi++) {
+      const int sa = C.pair_a[pi], sb = C.pair_b[pi];
+      const int ba = C.shape_body[sa], bb = C.shape_body[sb];
+      const int nvary = (pass == 1 && ba >= 0 && bb >= 0) ? 2 : 1;
+      const int m2_pair = m2;
+      for (int v = 0; v < nvary; v++) {
+        m2 = m2_pair;
+        const bool varyA = (ba >= 0) && (v == 0);          // which body's pose carries the dual part in this run
+        const int dyn = varyA ? ba : bb;
+        const Xf<D6> WDa = (ba >= 0) ? (varyA ? dual_pose(ba) : lift(xf_from12(ws.W + 12 * ba))) : Xf<D6>();
+        const Xf<D6> WDb = (bb >= 0) ? (!varyA ? dual_pose(bb) : lift(xf_from12(ws.W + 12 * bb))) : Xf<D6>();
+        const Xf<D6> Ta = (ba >= 0) ? gxf_mul(WDa, lift(xf_from12(C.shape_T[sa]))) : lift(xf_from12(C.shape_T[sa]));
+        const Xf<D6> Tb = (bb >= 0) ? gxf_mul(WDb, lift(xf_from12(C.shape_T[sb]))) : lift(xf_from12(C.shape_T[sb]));
+        const int ta = C.shape_type[sa], tb = C.shape_type[sb];
+        const V3<D6> da = mk3<D6>(D6(C.shape_dims[sa][0]), D6(C.shape_dims[sa][1]), D6(C.shape_dims[sa][2]));
+        const V3<D6> db = mk3<D6>(D6(C.shape_dims[sb][0]), D6(C.shape_dims[sb][1]), D6(C.shape_dims[sb][2]));
+        ContactOutT<D6> co[8];
+        int k = 0;
+        if (ta == 0 && tb == 0) k = collide_box_box(da, Ta, db, Tb, C.clip_depth, co);
+        else if (ta == 0 && tb == 1) k = collide_box_sphere(da, Ta, db.x, Tb, C.clip_depth, 0, false, co);
+        else if (ta == 1 && tb == 0) k = collide_box_sphere(db, Tb, da.x, Ta, C.clip_depth, 0, true, co);
+        else if ((ta == 0 && tb == 2) || (ta == 2 && tb == 0)) {
+          const bool boxFirst = (ta == 0);
+          const Xf<D6>& Tc = boxFirst ? Tb : Ta; const Xf<D6>& Tbx = boxFirst ? Ta : Tb;
+          const V3<D6> bdim = boxFirst ? da : db;
+          const D6 r = boxFirst ? db.x : da.x; const CR h = boxFirst ? C.shape_dims[sb][1] : C.shape_dims[sa][1];
+          CR dep[2]; Xf<D6> Tend[2];
+          for (int e = 0; e < 2; e++) {
+            Tend[e] = Tc; Tend[e].p = gxf_apply(Tc, mk3<D6>(D6(0.0), D6(0.0), D6(e == 0 ? h / 2 : -h / 2)));
+            const V3<D6> pld = gxf_apply_inv(Tbx, Tend[e].p);
+            const V3<CR> pl = mk3<CR>(pld.x.v, pld.y.v, pld.z.v);
+            V3<CR> q = pl; bool inside = true;
+            for (int kk = 0; kk < 3; kk++) { const CR hk = 0.5 * gget3(bdim, kk).v, v = get3(q, kk); if (v < -hk) { set3(q, kk, -hk); inside = false; } if (v > hk) { set3(q, kk, hk); inside = false; } }
+            if (inside) { CR mn = 1e300; for (int kk = 0; kk < 3; kk++) { const CR v = 0.5 * gget3(bdim, kk).v - nb2_abs(get3(pl, kk)); mn = v < mn ? v : mn; } dep[e] = mn + r.v; }
+            else { const V3<CR> dd = pl - q; dep[e] = r.v - nb2_sqrt(dot(dd, dd)); }
+          }
+          if ((dep[0] > dep[1] ? dep[0] : dep[1]) >= 0 && nb2_abs(dep[0] - dep[1]) >= 1e-9) {
+            const int e = dep[0] > dep[1] ? 0 : 1;
+            k = collide_box_sphere(bdim, Tbx, r, Tend[e], C.clip_depth, e == 0 ? 1 : 2, !boxFirst, co);
+          }
+        }
+        for (int c = 0; c < k; c++) {
+          const V3<CR> nv = mk3<CR>(co[c].normal.x.v, co[c].normal.y.v, co[c].normal.z.v);
+          if (dot(nv, nv) < 1e-12) continue;
+          if (co[c].depth.v < 0.0 || co[c].depth.v > C.clip_depth) continue;
+          const CR mu = C.shape_mu[sa] < C.shape_mu[sb] ? C.shape_mu[sa] : C.shape_mu[sb];
+          const bool fric = mu > 1e-3;
+          V3<D6> dirs[3]; dirs[0] = co[c].normal;
+          if (fric) tangent_basis<D6>(co[c].normal, &dirs[1], &dirs[2]);
+          const int dim = fric ? 3 : 1;
+          V3<D6> pA, pB;
+          if (ba >= 0) pA = gxf_apply_inv(WDa, co[c].point);
+          if (bb >= 0) pB = gxf_apply_inv(WDb, co[c].point);
+          for (int kk = 0; kk < dim; kk++) {
+            if (m2 >= NB2_MAX_ROWS) { cv.error = 2; break; }
+            D6 FA[6], FB[6];
+            if (ba >= 0) { const V3<D6> dA = mulT(WDa.R_, dirs[kk]); const V3<D6> mo = cross(pA, dA); FA[0] = mo.x; FA[1] = mo.y; FA[2] = mo.z; FA[3] = dA.x; FA[4] = dA.y; FA[5] = dA.z; }
+            if (bb >= 0) { const V3<D6> dB = mulT(WDb.R_, -dirs[kk]); const V3<D6> mo = cross(pB, dB); FB[0] = mo.x; FB[1] = mo.y; FB[2] = mo.z; FB[3] = dB.x; FB[4] = dB.y; FB[5] = dB.z; }
+            if (pass == 0) {
+              for (int j = 0; j < 6; j++) { rowFA[6 * m2 + j] = (ba >= 0) ? FA[j].v : 0.0; rowFB[6 * m2 + j] = (bb >= 0) ? FB[j].v : 0.0; }
+              rowbA[m2] = ba; rowbB[m2] = bb; rowmu[m2] = mu;
+            } else if (coefWr[m2] != 0.0 || coefVr[m2] != 0.0) {
+              // G_dyn += sum_terms (dF_term/dxi_dyn)^T (coefW * field_w(body_term) + coefV * field_v+(body_term)), scaled by -1/dt
+              auto gj = inj + 24 * dyn + 12;
+              for (int side = 0; side < 2; side++) {
+                const int body = side == 0 ? ba : bb;
+                if (body < 0) continue;
+                const D6* F = side == 0 ? FA : FB;
+                const V6<CR> Ww = ld6<CR, ST>(scr + (size_t)(oBody + 7 * body + 1) * ST);
+                const V6<CR> Up = ldv6(Uplus + 6 * body);
+                const CR fw[6] = {Ww.a.x, Ww.a.y, Ww.a.z, Ww.l.x, Ww.l.y, Ww.l.z}, fu[6] = {Up.a.x, Up.a.y, Up.a.z, Up.l.x, Up.l.y, Up.l.z};
+                for (int kx = 0; kx < 6; kx++) {
+                  CR g = 0;
+                  for (int jx = 0; jx < 6; jx++) g += F[jx].d[kx] * (coefWr[m2] * fw[jx] + coefVr[m2] * fu[jx]);
+                  gj[kx] += (-1.0 / dt) * g;
+                }
+              }
+            }
+            m2++;
+          }
+        }
       }
     }
-    for (int c = 0; c < k; c++) {
-      const V3<CR> nv = mk3<CR>(co[c].normal.x.v, co[c].normal.y.v, co[c].normal.z.v);
-      if (dot(nv, nv) < 1e-12) continue;
-      if (co[c].depth.v < 0.0 || co[c].depth.v > C.clip_depth) continue;
-      const CR mu = C.shape_mu[sa] < C.shape_mu[sb] ? C.shape_mu[sa] : C.shape_mu[sb];
-      const bool fric = mu > 1e-3;
-      V3<D6> dirs[3]; dirs[0] = co[c].normal;
-      if (fric) tangent_basis<D6>(co[c].normal, &dirs[1], &dirs[2]);
-      const int dim = fric ? 3 : 1;
-      const V3<D6> pD = gxf_apply_inv(WD, co[c].point);
-      for (int kk = 0; kk < dim; kk++) {
-        if (m2 >= NB2_MAX_ROWS) { cv.error = 2; break; }
-        const V3<D6> dD = dynIsA ? mulT(WD.R_, dirs[kk]) : mulT(WD.R_, -dirs[kk]);
-        const V3<D6> mom = cross(pD, dD);
-        const D6 F[6] = {mom.x, mom.y, mom.z, dD.x, dD.y, dD.z};
-        for (int j = 0; j < 6; j++) { rowF[6 * m2 + j] = F[j].v; for (int q = 0; q < 6; q++) rowdF[36 * m2 + 6 * j + q] = F[j].d[q]; }
-        rowbody[m2] = dyn; rowmu[m2] = mu;
-        m2++;
-      }
-    }
-  }
+    return m2;
+  };
+  const int m2 = rows_pass(0);
   if (m2 != m) cv.error = cv.error ? cv.error : 3;
   if (cv.error) return cv;
   // ---- clamping / upper-bound sets from the saved labels
@@ -864,12 +902,18 @@ NB2_HD BwdContactView<ST> contact_backward_prepare(const Nb2ModelDev<CR>& M, con
   auto fbar = ws.v2; auto mu_c = ws.v3; auto Eu = ws.v4;
   // W_body(lambda) read from the strided scratch
   auto ldW = [&](int body) { return ld6<CR, ST>(scr + (size_t)(oBody + 7 * body + 1) * ST); };
-  for (int r = 0; r < nCl; r++) fbar[r] = dot(ldv6(rowF + 6 * cl[r]), ldW(rowbody[cl[r]]));
+  auto rowdot = [&](int j) {  // J_j lambda-field: wrench of row j against the field induced on its (one or two) bodies
+    CR a = 0;
+    if (rowbA[j] >= 0) a += dot(ldv6(rowFA + 6 * j), ldW(rowbA[j]));
+    if (rowbB[j] >= 0) a += dot(ldv6(rowFB + 6 * j), ldW(rowbB[j]));
+    return a;
+  };
+  for (int r = 0; r < nCl; r++) fbar[r] = rowdot(cl[r]);
   for (int u = 0; u < nUb; u++) {
     const int j = ubl[u], fp = (int)mapping[j];
     const CR up = xr[fp] * rowmu[j], low = -xr[fp] * rowmu[j];
     Eu[u] = (nb2_abs(xr[j] - up) < nb2_abs(xr[j] - low)) ? rowmu[j] : -rowmu[j];
-    fbar[clampIdx[fp]] += Eu[u] * dot(ldv6(rowF + 6 * j), ldW(rowbody[j]));
+    fbar[clampIdx[fp]] += Eu[u] * rowdot(j);
   }
   for (int r = 0; r < nCl; r++) mu_c[r] = 0;
   if (nCl > 0) {
@@ -891,17 +935,21 @@ NB2_HD BwdContactView<ST> contact_backward_prepare(const Nb2ModelDev<CR>& M, con
   }
   // ---- nu = M^-1 A_c mu  (one impulse sweep) ; w = lambda - nu ; W_i(w)
   for (int i = 0; i < nb * 6; i++) ws.pI[i] = 0;
-  for (int r = 0; r < nCl; r++) { auto F = rowF + 6 * cl[r]; auto p = ws.pI + 6 * rowbody[cl[r]]; for (int kx = 0; kx < 6; kx++) p[kx] -= F[kx] * mu_c[r]; }
+  for (int r = 0; r < nCl; r++) {
+    const int j = cl[r];
+    if (rowbA[j] >= 0) { auto F = rowFA + 6 * j; auto p = ws.pI + 6 * rowbA[j]; for (int kx = 0; kx < 6; kx++) p[kx] -= F[kx] * mu_c[r]; }
+    if (rowbB[j] >= 0) { auto F = rowFB + 6 * j; auto p = ws.pI + 6 * rowbB[j]; for (int kx = 0; kx < 6; kx++) p[kx] -= F[kx] * mu_c[r]; }
+  }
   impulse_response<ST>(M, sv, B, ws, ~0ull);
   for (int d = 0; d < n; d++) scr[(size_t)(oLam + d) * ST] -= ws.dqd[d];
   for (int i = 0; i < nb; i++) {
     const V6<CR> Wn = ld6<CR, ST>(scr + (size_t)(oBody + 7 * i + 1) * ST) - ldv6(ws.V + 6 * i);
     st6<CR, ST>(scr + (size_t)(oBody + 7 * i + 1) * ST, Wn);
   }
-  // ---- realised accelerations, v+, and the fields they induce (ws.W is free now: Aacc | Uplus)
+  // ---- realised accelerations, v+, and the fields they induce (the sweep buffers pI / V are free now: Aacc | Uplus;
+  // ws.W keeps the world transforms for the second generator pass)
   auto aeff = ws.uI; auto vplus = ws.vstar;
   for (int d = 0; d < n; d++) { aeff[d] = sv[(size_t)(kQdd + d) * B] + dqd_imp[d] / dt; vplus[d] = (CR)st[n + d] + dt * aeff[d]; }
-  auto Aacc = ws.W; auto Uplus = ws.W + 6 * nb;
   V6<CR> A0; A0.a = zero3<CR>(); A0.l = mk3<CR>(-M.gravity[0], -M.gravity[1], -M.gravity[2]);
   for (int i = 0; i < nb; i++) {
     const int jt = M.jtype[i], p = M.parent[i], o = M.dof_off[i];
@@ -922,29 +970,27 @@ NB2_HD BwdContactView<ST> contact_backward_prepare(const Nb2ModelDev<CR>& M, con
   }
   // ---- per-body injections for the reverse sweep: Uw_bar, Up_bar, G (all scaled by -1/dt: they join the (dID/dq)^T w
   // accumulator that is multiplied by -dt at the end) and H (plain: A_c mu propagated to joint space)
-  auto inj = ws.Q2;
   for (int i = 0; i < nb * 24; i++) inj[i] = 0;
   const CR kap = -1.0 / dt;
   for (int j = 0; j < m; j++) {
     CR coefW = 0, coefV = 0, coefH = 0;
     if (clampIdx[j] >= 0) { coefW = xr[j]; coefV = -mu_c[clampIdx[j]]; coefH = mu_c[clampIdx[j]]; }
     else if ((int)mapping[j] >= 0) coefW = xr[j];
-    else continue;
-    const int body = rowbody[j];
-    auto F = rowF + 6 * j; auto dF = rowdF + 36 * j;
-    auto bj = inj + 24 * body;
-    const V6<CR> Ww = ld6<CR, ST>(scr + (size_t)(oBody + 7 * body + 1) * ST);  // field of w
-    const V6<CR> Up = ldv6(Uplus + 6 * body);
-    const CR fw[6] = {Ww.a.x, Ww.a.y, Ww.a.z, Ww.l.x, Ww.l.y, Ww.l.z}, fu[6] = {Up.a.x, Up.a.y, Up.a.z, Up.l.x, Up.l.y, Up.l.z};
-    for (int kx = 0; kx < 6; kx++) {
-      bj[kx] += kap * coefW * F[kx];
-      bj[6 + kx] += kap * coefV * F[kx];
-      bj[18 + kx] += coefH * F[kx];
-      CR g = 0;
-      for (int jx = 0; jx < 6; jx++) g += dF[6 * jx + kx] * (coefW * fw[jx] + coefV * fu[jx]);
-      bj[12 + kx] += kap * g;
+    coefWr[j] = coefW; coefVr[j] = coefV;
+    if (coefW == 0.0 && coefV == 0.0 && coefH == 0.0) continue;
+    for (int side = 0; side < 2; side++) {
+      const int body = side == 0 ? rowbA[j] : rowbB[j];
+      if (body < 0) continue;
+      auto F = (side == 0 ? rowFA : rowFB) + 6 * j;
+      auto bj = inj + 24 * body;
+      for (int kx = 0; kx < 6; kx++) {
+        bj[kx] += kap * coefW * F[kx];
+        bj[6 + kx] += kap * coefV * F[kx];
+        bj[18 + kx] += coefH * F[kx];
+      }
     }
   }
+  rows_pass(1);  // contact-frame part G: derivatives of every wrench w.r.t. the pose of each moving body
   return cv;
 }
 

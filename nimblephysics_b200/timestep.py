@@ -107,9 +107,10 @@ class TimestepLayer(torch.autograd.Function):
                 dm.backward_contact_device(ctx.B, _ptr(sd), _ptr(ad), _ptr(saved), _ptr(ctx.crec), _ptr(ctx.ws), _ptr(g), _ptr(gs),
                                            _ptr(ga), stream)
                 if bool(torch.isnan(gs).any()):
-                    raise NotImplementedError(
-                        "backward through a contact between two MOVING bodies is not implemented (the kernel marked those "
-                        "worlds with NaN gradients); contacts against static geometry are supported")
+                    raise RuntimeError(
+                        "backward through the contact stage failed for some worlds (the kernel marked them with NaN gradients): "
+                        "the contact rows regenerated in the backward pass did not match the forward's, or the clamping set "
+                        "exceeds the compiled limits")
             else:
                 gi = torch.empty((10 * dm.cm.nb, ctx.B), dtype=torch.float32, device=dev) if ctx.mass_grad else None
                 dm.backward_device(ctx.B, _ptr(sd), _ptr(ad), _ptr(saved), _ptr(g), _ptr(gs), _ptr(ga), stream, FP32,

@@ -127,24 +127,117 @@ def test_oracle_contact_jacobian_matches_finite_differences(oracle_mod):
     """Reference-style pin of the oracle itself (GradientTestUtils.hpp verifyVelGradients): when the forward solution is an
     exact LCP solution (short-circuit or Dantzig), the frozen-classification Jacobian equals central differences of the full
     step wherever the perturbation does not flip a label."""
+    cases = []
     raw = load_raw("half_cheetah")
-    ow = ob.OracleContactWorld(raw)
-    n = raw.ndof
     s, a = contact_inputs(raw, "half_cheetah", 3, seed=4)
-    for w in range(3):
-        s64, a64 = s[w].astype(np.float64), a[w].astype(np.float64)
-        r0 = ow.step_contact(s64, a64)
-        if r0["status"] & 24:
-            continue  # PGS / friction-drop answers are approximate: the analytic map is not their derivative
-        J, rc = ow.jacobian_contact(s64, a64)
-        assert rc >= 0
-        eps = 1e-7
-        for c in range(2 * n):
-            sp, sm = s64.copy(), s64.copy()
-            sp[c] += eps
-            sm[c] -= eps
-            rp, rm = ow.step_contact(sp, a64), ow.step_contact(sm, a64)
-            if not (np.array_equal(rp["mapping"], r0["mapping"]) and np.array_equal(rm["mapping"], r0["mapping"])):
-                continue
-            fd = (rp["next_state"] - rm["next_state"]) / (2 * eps)
-            assert np.abs(fd - J[:, c]).max() < 2e-6 * max(1.0, np.abs(J).max())
+    cases.append((raw, s, a))
+    raw2 = nb.flatten_world(_box_stack_world())  # rows acting on two moving bodies
+    s2, a2 = _box_stack_inputs(raw2, 12, seed=0)  # a few of these worlds get an exact (Dantzig) answer
+    cases.append((raw2, s2, a2))
+    checked = []
+    for raw, s, a in cases:
+        ow = ob.OracleContactWorld(raw)
+        n = raw.ndof
+        cols = 0
+        for w in range(s.shape[0]):
+            s64, a64 = s[w].astype(np.float64), a[w].astype(np.float64)
+            r0 = ow.step_contact(s64, a64)
+            if r0["status"] & 24:
+                continue  # PGS / friction-drop answers are approximate: the analytic map is not their derivative
+            J, rc = ow.jacobian_contact(s64, a64)
+            assert rc >= 0
+            eps = 1e-7
+            for c in range(2 * n):
+                sp, sm = s64.copy(), s64.copy()
+                sp[c] += eps
+                sm[c] -= eps
+                rp, rm = ow.step_contact(sp, a64), ow.step_contact(sm, a64)
+                if not (np.array_equal(rp["mapping"], r0["mapping"]) and np.array_equal(rm["mapping"], r0["mapping"])):
+                    continue
+                fd = (rp["next_state"] - rm["next_state"]) / (2 * eps)
+                assert np.abs(fd - J[:, c]).max() < 2e-6 * max(1.0, np.abs(J).max())
+                cols += 1
+        checked.append(cols)
+    assert all(c > 0 for c in checked), checked
+
+
+def _box_stack_world():
+    """static ground + a free box resting on it + a smaller free box resting on the first: ground-box contacts and
+    contacts between two MOVING bodies of different skeletons (ConstraintSolver.cpp:723-793 puts them in one group)."""
+    w = nb.World()
+    w.setGravity([0, -9.81, 0])
+    w.setTimeStep(1e-3)
+    g = nb.Skeleton("ground")
+    g.setMobile(False)
+    j, b = g.createWeldJointAndBodyNodePair()
+    b.createShapeNode(nb.BoxShape([4, 0.2, 4])).createCollisionAspect()
+    T = nb.Isometry3()
+    T.set_translation([0, -0.1, 0])
+    j.setTransformFromParentBodyNode(T)
+    w.addSkeleton(g)
+    for k, size in enumerate(([0.6, 0.4, 0.6], [0.3, 0.3, 0.3])):
+        s = nb.Skeleton(f"box{k}")
+        j, b = s.createFreeJointAndBodyNodePair()
+        b.setMass(2.0 - k)
+        b.createShapeNode(nb.BoxShape(size)).createCollisionAspect()
+        w.addSkeleton(s)
+    return w
+
+
+def test_contacts_between_two_moving_bodies_forward(oracle_mod):
+    raw = nb.flatten_world(_box_stack_world())
+    cm = nb.compile_model(raw)
+    n = raw.ndof
+    rng = np.random.default_rng(0)
+    B = 12
+    S = np.zeros((B, 2 * n), np.float32)
+    for w in range(B):
+        S[w, 0:3] = rng.normal(0, 0.01, 3)
+        S[w, 3:6] = [rng.normal(0, 0.01), 0.2 - 0.002, rng.normal(0, 0.01)]
+        S[w, 6:9] = rng.normal(0, 0.01, 3)
+        S[w, 9:12] = [rng.normal(0, 0.02), 0.55 - 0.004, rng.normal(0, 0.02)]
+        S[w, n:] = rng.normal(0, 0.05, n)
+    A = np.zeros((B, len(raw.action_map)), np.float32)
+    r = EmulWorld(cm).forward_contact(S, A)
+    ow = oracle_mod.OracleContactWorld(raw)
+    both = 0
+    for w in range(B):
+        ro = ow.step_contact(S[w].astype(np.float64), A[w].astype(np.float64))
+        m = int(r["m"][w])
+        assert r["nc"][w] == ro["nc"] and m == ro["m"]
+        assert (r["status"][w] & ~96) == (ro["status"] & ~96)
+        assert np.array_equal(r["labels"][w][:m], ro["mapping"][:m])  # contact set and labels bit-exact
+        assert rel_err(r["next"][w], ro["next_state"]) < 1e-6
+        both += int(any(a >= 1 and b_ >= 1 for a, b_ in ro["bodies"].tolist()))
+    assert both >= 6  # box-on-box contacts were really in play
+
+
+def _box_stack_inputs(raw, B, seed):
+    n = raw.ndof
+    rng = np.random.default_rng(seed)
+    S = np.zeros((B, 2 * n), np.float32)
+    for w in range(B):
+        S[w, 0:3] = rng.normal(0, 0.01, 3)
+        S[w, 3:6] = [rng.normal(0, 0.01), 0.2 - 0.002, rng.normal(0, 0.01)]
+        S[w, 6:9] = rng.normal(0, 0.01, 3)
+        S[w, 9:12] = [rng.normal(0, 0.02), 0.55 - 0.004, rng.normal(0, 0.02)]
+        S[w, n:] = rng.normal(0, 0.05, n)
+    return S, np.zeros((B, len(raw.action_map)), np.float32)
+
+
+def test_contacts_between_two_moving_bodies_backward(oracle_mod):
+    """Rows whose wrench acts on TWO moving bodies (box resting on a box): the adjoint differentiates each wrench with
+    respect to the pose of either body (csrc/nb2_contact.cuh contact_backward_prepare, rows_pass) — checked against
+    J^T g with the oracle's dual-number Jacobian of the frozen-classification step, and the oracle against central
+    differences where the forward answer is exact."""
+    raw = nb.flatten_world(_box_stack_world())
+    S, A_ = _box_stack_inputs(raw, 8, seed=3)
+    kinds = _check_backward(ob, raw, S, A_, tol=2e-5)
+    assert len(kinds) == 8
+    # low friction: sliding rows between the two boxes
+    raw.friction[:] = 0.15
+    S, A_ = _box_stack_inputs(raw, 6, seed=5)
+    n = raw.ndof
+    S[:, n + 9] += 0.8  # the upper box slides along x
+    kinds = _check_backward(ob, raw, S, A_, tol=2e-5)
+    assert any(k[1] > 0 for k in kinds)
