@@ -352,6 +352,42 @@ def main():
                                 "note": "forward only (fp64 ABA + contact/LCP kernels); same state re-stepped, warm-started LCP cache"}
             except Exception as ex:  # never let the extra leg break the headline line
                 extra[label] = {"error": repr(ex)}
+        # BASELINE configs[4] shape at reduced batch: 64-step rollout of Atlas + ground, backprop through the full horizon
+        try:
+            from nimblephysics_b200.rollout import rollout
+
+            craw = nb.RawModel.load(os.path.join(ROOT, "tests", "golden", "models", "atlas_ground.json"))
+            cworld = nb.World.from_raw(craw)
+            Br, T = 1024, 64
+            cs, _ = contact_inputs(craw, "atlas_ground", Br, seed=11)
+            rng = np.random.default_rng(12)
+            na_c = len(craw.action_map)
+            acts_np = rng.uniform(-20, 20, (T, Br, na_c)).astype(np.float32)
+            acts_np[:, :, :6] = 0.0
+            x0 = torch.tensor(cs, device=dev, requires_grad=True)
+            acts = [torch.tensor(acts_np[t], device=dev, requires_grad=True) for t in range(T)]
+
+            def run():
+                nb.reset_contact_cache(cworld)
+                xT = rollout(cworld, x0, acts)
+                loss = (xT * xT).sum()
+                loss.backward()
+                return loss
+
+            run()
+            torch.cuda.synchronize()
+            r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            r0.record()
+            loss = run()
+            r1.record()
+            torch.cuda.synchronize()
+            ms = r0.elapsed_time(r1)
+            extra["atlas_ground_rollout64"] = {"batch": Br, "horizon": T, "ms_per_rollout_fwd_bwd": ms,
+                                               "world_steps_per_s": Br * T / (ms * 1e-3), "loss_finite": bool(torch.isfinite(loss)),
+                                               "grad_finite": bool(torch.isfinite(x0.grad).all()),
+                                               "note": "Atlas + ground contact, loss = |x_T|^2, backprop to x_0 and every tau_t (configs[4] at 1024 worlds/GPU)"}
+        except Exception as ex:
+            extra["atlas_ground_rollout64"] = {"error": repr(ex)}
 
     t_total = torch.tensor([total_ms, e2e_ms], device=dev, dtype=torch.float64)
     if dist:

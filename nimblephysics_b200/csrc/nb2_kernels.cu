@@ -164,28 +164,34 @@ k_contact_fwd(const __grid_constant__ Nb2ModelDev<double> M, const __grid_consta
                              labels + (size_t)wc * NB2_MAX_ROWS, status + wc, ncontacts + wc,
                              cinfo ? cinfo + (size_t)wc * NB2_MAX_CONTACTS * 10 : nullptr, crec ? crec + (size_t)wc * rec_doubles : nullptr);
   __syncwarp();
-  if (valid) nb2::contact_phase1<WPW>(M, saved + wc, (size_t)B, wsb, slot, cl, KC);
+  constexpr int NL = KC < NB2_CONTACT_LANES ? KC : NB2_CONTACT_LANES;  // threads sharing the impulse tests
+  if (valid && cl < NL) nb2::contact_phase1<WPW>(M, saved + wc, (size_t)B, wsb, slot, cl, NL);
   __syncwarp();
   if (valid && cl == 0)
     nb2::contact_phase2<WPW>(M, C, st, out, saved + wc, (size_t)B, wsb, slot, x_lcp + (size_t)wc * NB2_MAX_ROWS, m_lcp + wc,
                              labels + (size_t)wc * NB2_MAX_ROWS, status + wc, crec ? crec + (size_t)wc * rec_doubles : nullptr);
 }
 
-// backward of a step with the contact stage (fp64): world_backward<double, 32, CONTACT=true>
+// backward of a step with the contact stage (fp64): world_backward<double, WPW, CONTACT=true>, one thread per world.
+// WPW = worlds per warp (32 by default; NB2_CONTACT_BWD_WPW=4|8 packs fewer worlds per warp — more warps, less divergence,
+// idle lanes — which measured no faster on B200: the kernel is bound by its per-thread local-memory traffic).
+template <int WPW>
 __global__ void __launch_bounds__(32)
 k_step_bwd_contact(const __grid_constant__ Nb2ModelDev<double> M, const __grid_constant__ Nb2ContactDev C, int B,
                    const float* __restrict__ state, const float* __restrict__ action, const double* __restrict__ saved,
                    const double* __restrict__ crec, size_t rec_doubles, double* __restrict__ workspace, size_t ws_doubles,
                    const float* __restrict__ gnext, float* __restrict__ gstate, float* __restrict__ gaction, int words) {
   extern __shared__ __align__(16) unsigned char nb2_smem[];
-  const int w = blockIdx.x * blockDim.x + threadIdx.x;
+  const int li = threadIdx.x & 31;
+  if (li >= WPW) return;
+  const int w = blockIdx.x * WPW + li;
   if (w >= B) return;
-  double* scr = reinterpret_cast<double*>(nb2_smem) + (size_t)(threadIdx.x >> 5) * words * 32 + (threadIdx.x & 31);
+  double* scr = reinterpret_cast<double*>(nb2_smem) + li;
   nb2::BwdContactHook H;
-  H.model_contact = &C; H.ws = workspace + (size_t)(w >> 5) * ws_doubles * 32; H.lane = w & 31; H.crec = crec + (size_t)w * rec_doubles;
-  nb2::world_backward<double, 32, true>(M, scr, state + (size_t)w * 2 * M.ndof, action + (size_t)w * M.na,
-                                        gnext + (size_t)w * 2 * M.ndof, saved + w, (size_t)B,
-                                        gstate + (size_t)w * 2 * M.ndof, gaction + (size_t)w * M.na, &H);
+  H.model_contact = &C; H.ws = workspace + (size_t)blockIdx.x * ws_doubles * WPW; H.lane = li; H.crec = crec + (size_t)w * rec_doubles;
+  nb2::world_backward<double, WPW, true>(M, scr, state + (size_t)w * 2 * M.ndof, action + (size_t)w * M.na,
+                                         gnext + (size_t)w * 2 * M.ndof, saved + w, (size_t)B,
+                                         gstate + (size_t)w * 2 * M.ndof, gaction + (size_t)w * M.na, &H);
 }
 
 constexpr int kMaxSmem = 227 * 1024;
@@ -521,17 +527,20 @@ int nb2_step_forward_contact(const nb2_model* cm, int B, const float* state, con
   if (rc) return rc;
   // 8 threads per world while that still leaves the GPU short of warps, one thread per world for huge batches
   const size_t wsd = nb2::contact_ws_doubles(m->mf.nb, m->mf.ndof), recd = nb2::contact_rec_doubles(m->mf.ndof);
-  if ((long long)B * 8 / 32 <= (long long)m->sm_count * 48) {
-    const int threads = 32, worlds_per_block = 4;
-    k_contact_fwd<8><<<(B + worlds_per_block - 1) / worlds_per_block, threads, 0, st>>>(m->md, m->contact, B, state, next_state, (const double*)saved_fp64,
-                                                                                     (double*)workspace, wsd, x_lcp, m_lcp, labels, status, ncontacts, cinfo,
-                                                                                     contact_record, recd);
-  } else {
-    const int threads = 32;
-    k_contact_fwd<1><<<(B + threads - 1) / threads, threads, 0, st>>>(m->md, m->contact, B, state, next_state, (const double*)saved_fp64,
-                                                                   (double*)workspace, wsd, x_lcp, m_lcp, labels, status, ncontacts, cinfo,
-                                                                   contact_record, recd);
+  static const int forced_kc = [] { const char* e = getenv("NB2_CONTACT_KC"); return e ? atoi(e) : 0; }();
+  int kc = forced_kc;
+  if (!kc) kc = ((long long)B * 8 / 32 <= (long long)m->sm_count * 48) ? 8 : 1;
+#define NB2_LAUNCH_CONTACT(KC_)                                                                                                  \
+  k_contact_fwd<KC_><<<(B + (32 / KC_) - 1) / (32 / KC_), 32, 0, st>>>(m->md, m->contact, B, state, next_state, (const double*)saved_fp64, \
+                                                                     (double*)workspace, wsd, x_lcp, m_lcp, labels, status, ncontacts,     \
+                                                                     cinfo, contact_record, recd)
+  switch (kc) {
+    case 32: NB2_LAUNCH_CONTACT(32); break;
+    case 16: NB2_LAUNCH_CONTACT(16); break;
+    case 8: NB2_LAUNCH_CONTACT(8); break;
+    default: NB2_LAUNCH_CONTACT(1); break;
   }
+#undef NB2_LAUNCH_CONTACT
   g_launches++;
   NB2_CUDA(cudaGetLastError());
   return NB2_OK;
@@ -550,14 +559,26 @@ int nb2_step_backward_contact(const nb2_model* cm, int B, const float* state, co
   if (!m->has_contacts) { g_err = "nb2_step_backward_contact: the model has no collision pairs"; return NB2_ERR_INVALID; }
   if (B == 0) return NB2_OK;
   const int words = nb2::bwd_layout(m->mf.nb, m->mf.ndof, m->mf.nslots, m->mf.nfree, 42).total;
-  const size_t smem = (size_t)words * 32 * sizeof(double);
+  static const int forced = [] { const char* e = getenv("NB2_CONTACT_BWD_WPW"); return e ? atoi(e) : 0; }();
+  int wpw = forced ? forced : 32;  // measured (B200, Atlas + ground, B = 1024 / 4096): 32 worlds per warp is never slower than 8 or 4
+  if ((size_t)words * wpw * sizeof(double) > (size_t)kMaxSmem) wpw = 4;
+  const size_t smem = (size_t)words * wpw * sizeof(double);
   if (smem > (size_t)kMaxSmem) { g_err = "model needs " + std::to_string(smem) + " B of shared memory per warp (> 227 KB)"; return NB2_ERR_UNSUPPORTED; }
-  static bool attr_done = false;
-  if (!attr_done) { NB2_CUDA(cudaFuncSetAttribute(k_step_bwd_contact, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem)); attr_done = true; }
-  k_step_bwd_contact<<<(B + 31) / 32, 32, smem, (cudaStream_t)stream>>>(m->md, m->contact, B, state, action, (const double*)saved_fp64,
-                                                                         contact_record, nb2::contact_rec_doubles(m->mf.ndof), (double*)workspace,
-                                                                         nb2::contact_ws_doubles(m->mf.nb, m->mf.ndof), grad_next_state,
-                                                                         grad_state, grad_action, words);
+#define NB2_LAUNCH_BWDC(W_)                                                                                                       \
+  do {                                                                                                                            \
+    static bool attr_done = false;                                                                                                \
+    if (!attr_done) { NB2_CUDA(cudaFuncSetAttribute(k_step_bwd_contact<W_>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem)); attr_done = true; } \
+    k_step_bwd_contact<W_><<<(B + W_ - 1) / W_, 32, smem, (cudaStream_t)stream>>>(m->md, m->contact, B, state, action, (const double*)saved_fp64,        \
+                                                                               contact_record, nb2::contact_rec_doubles(m->mf.ndof), (double*)workspace, \
+                                                                               nb2::contact_ws_doubles(m->mf.nb, m->mf.ndof), grad_next_state,           \
+                                                                               grad_state, grad_action, words);                                          \
+  } while (0)
+  switch (wpw) {
+    case 4: NB2_LAUNCH_BWDC(4); break;
+    case 8: NB2_LAUNCH_BWDC(8); break;
+    default: NB2_LAUNCH_BWDC(32); break;
+  }
+#undef NB2_LAUNCH_BWDC
   g_launches++;
   NB2_CUDA(cudaGetLastError());
   return NB2_OK;
