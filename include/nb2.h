@@ -142,10 +142,12 @@ int nb2_step_forward_contact(const nb2_model* m, int B, const float* state, cons
 size_t nb2_contact_record_bytes(const nb2_model* m, int B);
 /* VJP of a step taken with nb2_step_forward_contact (classification frozen at the forward solution), replaces
  * BackpropSnapshot::backpropState for steps with active contact constraints (dart/neural/BackpropSnapshot.cpp:980-1107,
- * 2723-3146).  Unsupported configurations (contact between two moving bodies) yield NaN gradients, never silent garbage. */
+ * 2723-3146).  Rows may act on one or two moving bodies.  If the rows regenerated in the backward pass do not match the
+ * forward's (or a compiled limit is exceeded) the world's gradients are NaN, never silent garbage.
+ * grad_inertia: optional [10*nb][B] floats as in nb2_step_backward (mass gradient through the contact stage). */
 int nb2_step_backward_contact(const nb2_model* m, int B, const float* state, const float* action, const void* saved_fp64,
                               const double* contact_record, void* workspace, const float* grad_next_state, float* grad_state,
-                              float* grad_action, void* stream);
+                              float* grad_action, float* grad_inertia, void* stream);
 
 /* number of kernels this library has launched since load (bench.py reports it as gpu_launches) */
 long long nb2_launch_count(void);

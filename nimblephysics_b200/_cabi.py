@@ -142,7 +142,7 @@ def lib() -> ctypes.CDLL:
         L.nb2_step_forward_contact.argtypes = [vp, ctypes.c_int, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
         L.nb2_contact_record_bytes.argtypes = [vp, ctypes.c_int]
         L.nb2_contact_record_bytes.restype = ctypes.c_size_t
-        L.nb2_step_backward_contact.argtypes = [vp, ctypes.c_int, vp, vp, vp, vp, vp, vp, vp, vp, vp]
+        L.nb2_step_backward_contact.argtypes = [vp, ctypes.c_int, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
         L.nb2_step_forward_host.argtypes = [vp, ctypes.c_int, vp, vp, vp, ctypes.c_int, ctypes.c_int]
         L.nb2_step_backward_host.argtypes = [vp, ctypes.c_int, vp, vp, vp, ctypes.c_int]
         _lib = L

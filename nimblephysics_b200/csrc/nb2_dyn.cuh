@@ -608,7 +608,7 @@ NB2_HD void bwd_B2(const Nb2ModelDev<R>& M, R* scr, const float* st, const R* sv
 
 template <class R, int ST, bool CONTACT>
 NB2_HD void bwd_B3(const Nb2ModelDev<R>& M, R* scr, const float* st, const R* sv, size_t B, const BwdContactData<ST>& cd, int lo, int hi,
-                   float* gI = nullptr, const R* bt = nullptr) {
+                   float* gI = nullptr, const R* bt = nullptr, size_t gIB = 0) {
   const int nb = M.nb, n = M.ndof;
   constexpr int SLOTW = CONTACT ? 42 : 18;
   const BwdLayout L = bwd_layout(nb, n, M.nslots, M.nfree, SLOTW);
@@ -637,14 +637,16 @@ NB2_HD void bwd_B3(const Nb2ModelDev<R>& M, R* scr, const float* st, const R* sv
     V6<R> f = mulG(m, h, Ib, A) + crf(V, GV);
     if (gI) {
       // dL/d(inertia parameters of body i) = -dt * W . d(G A + V x* G V) = -dt * [ t(W, A) - t(ad(V, W), V) ] with
-      // t(Y, X) = d(Y^T G X)/d(m, h, Ibar)   (the mass-vel Jacobian of BackpropSnapshot.cpp:580-640 contracted with g_v')
+      // t(Y, X) = d(Y^T G X)/d(m, h, Ibar)   (the mass-vel Jacobian of BackpropSnapshot.cpp:580-640 contracted with g_v').
+      // With active contacts W is the field of w = lambda - nu and A the REALISED acceleration: same identity (the
+      // constraint rows do not depend on the inertias).
       const V6<R> Y2 = ad(V, W);
       R t[10];
       inertia_param_form(W, A, t);
       R t2[10];
       inertia_param_form(Y2, V, t2);
 #pragma unroll
-      for (int k = 0; k < 10; k++) gI[(size_t)(10 * i + k) * B] = (float)(-dt * (t[k] - t2[k]));
+      for (int k = 0; k < 10; k++) gI[(size_t)(10 * i + k) * gIB] = (float)(-dt * (t[k] - t2[k]));
     }
     V6<R> Abar = mulG(m, h, Ib, W);
     V6<R> Vbar = mulG(m, h, Ib, ad(W, V)) - crf(W, GV);
@@ -838,7 +840,8 @@ NB2_HD void bwd_store(const Nb2ModelDev<R>& M, const R* scr0, float* gstate0, fl
 #define NB2_BWD_SYNC_MASK 0x14Bu        /* after stages 0, 1, 3, 6, 8 */
 #define NB2_BWD_SYNC_MASK_1LANE 0x101u  /* lanes == 1: after the group load and before the group store */
 template <class R, int ST>
-NB2_HD void world_backward_stage(const Nb2ModelDev<R>& M, R* scr, const R* sv, size_t B, int lane, int stage, float* gI = nullptr, const R* bt = nullptr) {
+NB2_HD void world_backward_stage(const Nb2ModelDev<R>& M, R* scr, const R* sv, size_t B, int lane, int stage, float* gI = nullptr, const R* bt = nullptr,
+                                 size_t gIB = 0) {
   const float* st = nullptr;  // the passes read the state from the scratch (oSt)
   BwdContactData<ST> cd; cd.active = 0; cd.error = 0;
   // stages 1..8; pass: 1 = B1, 2 = B2, 3 = B3, 4 = assemble
@@ -851,7 +854,7 @@ NB2_HD void world_backward_stage(const Nb2ModelDev<R>& M, R* scr, const R* sv, s
     const int lo = trunk ? M.trunk_lo[r] : M.limb_lo[lane][r], hi = trunk ? M.trunk_hi[r] : M.limb_hi[lane][r];
     if (pass == 1) bwd_B1<R, ST, false>(M, scr, st, sv, B, lo, hi, bt);
     else if (pass == 2) bwd_B2<R, ST, false>(M, scr, st, sv, B, lo, hi, bt);
-    else if (pass == 3) bwd_B3<R, ST, false>(M, scr, st, sv, B, cd, lo, hi, gI, bt);
+    else if (pass == 3) bwd_B3<R, ST, false>(M, scr, st, sv, B, cd, lo, hi, gI, bt, gIB ? gIB : B);
     else bwd_assemble<R, ST, false>(M, scr, st, cd, lo, hi);
   }
 }
@@ -860,7 +863,7 @@ NB2_HD void world_backward_stage(const Nb2ModelDev<R>& M, R* scr, const R* sv, s
 // when one thread sweeps all bodies in order)
 template <class R, int ST, bool CONTACT = false>
 NB2_HD void world_backward(const Nb2ModelDev<R>& M, R* scr, const float* st, const float* act, const float* gnext,
-                           const R* sv, size_t B, float* gstate, float* gaction, const BwdContactHook* hook = nullptr) {
+                           const R* sv, size_t B, float* gstate, float* gaction, const BwdContactHook* hook = nullptr, float* gI = nullptr) {
   const int nb = M.nb;
   constexpr int SLOTW = CONTACT ? 42 : 18;
   const BwdLayout L = bwd_layout(nb, M.ndof, M.nslots, M.nfree, SLOTW);
@@ -872,7 +875,7 @@ NB2_HD void world_backward(const Nb2ModelDev<R>& M, R* scr, const float* st, con
   if constexpr (CONTACT) {
     cd = contact_backward_hook<ST>(M, *hook, st, sv, B, scr, L.oLam, L.oBody);
   }
-  bwd_B3<R, ST, CONTACT>(M, scr, st, sv, B, cd, 0, nb);
+  bwd_B3<R, ST, CONTACT>(M, scr, st, sv, B, cd, 0, nb, gI, (const R*)nullptr, B);
   bwd_assemble<R, ST, CONTACT>(M, scr, st, cd, 0, nb);
   bwd_store<R, ST, CONTACT>(M, scr, gstate, gaction, CONTACT && cd.error, 1, 0, 1);
 }

@@ -132,7 +132,7 @@ k_step_bwd(const __grid_constant__ Nb2ModelDev<R> M, int B, int w0, int count, c
     if (sg == 0) { if (nworlds > 0) nb2::bwd_load<R, ST, false>(M, scr0, state + wg * 2 * M.ndof, action + wg * M.na, gnext + wg * 2 * M.ndof, nworlds, li, 32); }
     else if (sg == NB2_BWD_STAGES - 1) {
       if (nworlds > 0) nb2::bwd_store<R, ST, false>(M, scr0, gstate + wg * 2 * M.ndof, gaction + wg * M.na, false, nworlds, li, 32);
-    } else if (valid) nb2::world_backward_stage<R, ST>(M, scr, svp, svB, lane, sg, ginertia ? ginertia + w : nullptr, bt);
+    } else if (valid) nb2::world_backward_stage<R, ST>(M, scr, svp, svB, lane, sg, ginertia ? ginertia + w : nullptr, bt, (size_t)B);
     if (sg == 0 && stage_saved) asm volatile("cp.async.wait_group 0;" ::: "memory");
     if (((sync_mask >> sg) & 1u) || (sg == 0 && stage_saved)) __syncwarp();
   }
@@ -180,7 +180,8 @@ __global__ void __launch_bounds__(32)
 k_step_bwd_contact(const __grid_constant__ Nb2ModelDev<double> M, const __grid_constant__ Nb2ContactDev C, int B,
                    const float* __restrict__ state, const float* __restrict__ action, const double* __restrict__ saved,
                    const double* __restrict__ crec, size_t rec_doubles, double* __restrict__ workspace, size_t ws_doubles,
-                   const float* __restrict__ gnext, float* __restrict__ gstate, float* __restrict__ gaction, int words) {
+                   const float* __restrict__ gnext, float* __restrict__ gstate, float* __restrict__ gaction, float* __restrict__ ginertia,
+                   int words) {
   extern __shared__ __align__(16) unsigned char nb2_smem[];
   const int li = threadIdx.x & 31;
   if (li >= WPW) return;
@@ -191,7 +192,7 @@ k_step_bwd_contact(const __grid_constant__ Nb2ModelDev<double> M, const __grid_c
   H.model_contact = &C; H.ws = workspace + (size_t)blockIdx.x * ws_doubles * WPW; H.lane = li; H.crec = crec + (size_t)w * rec_doubles;
   nb2::world_backward<double, WPW, true>(M, scr, state + (size_t)w * 2 * M.ndof, action + (size_t)w * M.na,
                                          gnext + (size_t)w * 2 * M.ndof, saved + w, (size_t)B,
-                                         gstate + (size_t)w * 2 * M.ndof, gaction + (size_t)w * M.na, &H);
+                                         gstate + (size_t)w * 2 * M.ndof, gaction + (size_t)w * M.na, &H, ginertia ? ginertia + w : nullptr);
 }
 
 constexpr int kMaxSmem = 227 * 1024;
@@ -551,7 +552,7 @@ size_t nb2_contact_record_bytes(const nb2_model* m, int B) {
 }
 int nb2_step_backward_contact(const nb2_model* cm, int B, const float* state, const float* action, const void* saved_fp64,
                               const double* contact_record, void* workspace, const float* grad_next_state, float* grad_state,
-                              float* grad_action, void* stream) {
+                              float* grad_action, float* grad_inertia, void* stream) {
   nb2_model* m = const_cast<nb2_model*>(cm);
   if (!m || B < 0 || !state || !action || !saved_fp64 || !contact_record || !workspace || !grad_next_state || !grad_state || !grad_action) {
     g_err = "nb2_step_backward_contact: bad argument"; return NB2_ERR_INVALID;
@@ -571,7 +572,7 @@ int nb2_step_backward_contact(const nb2_model* cm, int B, const float* state, co
     k_step_bwd_contact<W_><<<(B + W_ - 1) / W_, 32, smem, (cudaStream_t)stream>>>(m->md, m->contact, B, state, action, (const double*)saved_fp64,        \
                                                                                contact_record, nb2::contact_rec_doubles(m->mf.ndof), (double*)workspace, \
                                                                                nb2::contact_ws_doubles(m->mf.nb, m->mf.ndof), grad_next_state,           \
-                                                                               grad_state, grad_action, words);                                          \
+                                                                               grad_state, grad_action, grad_inertia, words);                            \
   } while (0)
   switch (wpw) {
     case 4: NB2_LAUNCH_BWDC(4); break;

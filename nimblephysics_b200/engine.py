@@ -122,9 +122,9 @@ class DeviceModel:
                                                          m_ptr, labels_ptr, status_ptr, nc_ptr, cinfo_ptr, crec_ptr, stream))
 
     def backward_contact_device(self, B, state_ptr, action_ptr, saved_ptr, crec_ptr, ws_ptr, gnext_ptr, gstate_ptr, gaction_ptr,
-                                stream):
+                                stream, ginertia_ptr=None):
         _cabi.check(_cabi.lib().nb2_step_backward_contact(self.handle, B, state_ptr, action_ptr, saved_ptr, crec_ptr, ws_ptr,
-                                                          gnext_ptr, gstate_ptr, gaction_ptr, stream))
+                                                          gnext_ptr, gstate_ptr, gaction_ptr, ginertia_ptr, stream))
 
     # ---- host pointers (numpy / CPU tensors): copies included ----
     def forward_host(self, state: np.ndarray, action: np.ndarray, keep_for_backward=True, precision=FP32,

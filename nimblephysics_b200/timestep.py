@@ -55,8 +55,6 @@ class TimestepLayer(torch.autograd.Function):
         need_grad = any(ctx.needs_input_grad[1:4])
         ctx.mass_grad = mass is not None and ctx.needs_input_grad[3]
         if ctx.mass_grad:
-            if dm.has_contacts:
-                raise NotImplementedError("d/dmass through the contact stage is not implemented (contact-free steps only)")
             ctx.mass_P = torch.from_numpy(dm.inertia_param_jacobian(world))  # [mass_dims, 10*nb], fp64
             ctx.mass_like = mass
         ctx.contact = dm.has_contacts
@@ -104,8 +102,9 @@ class TimestepLayer(torch.autograd.Function):
             stream = torch.cuda.current_stream().cuda_stream
             if ctx.contact:
                 # adjoint of the contact stage with the classification frozen at the forward solution (csrc/nb2_contact.cuh)
+                gi = torch.empty((10 * dm.cm.nb, ctx.B), dtype=torch.float32, device=dev) if ctx.mass_grad else None
                 dm.backward_contact_device(ctx.B, _ptr(sd), _ptr(ad), _ptr(saved), _ptr(ctx.crec), _ptr(ctx.ws), _ptr(g), _ptr(gs),
-                                           _ptr(ga), stream)
+                                           _ptr(ga), stream, _ptr(gi) if gi is not None else None)
                 if bool(torch.isnan(gs).any()):
                     raise RuntimeError(
                         "backward through the contact stage failed for some worlds (the kernel marked them with NaN gradients): "

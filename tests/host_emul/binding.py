@@ -80,15 +80,16 @@ class EmulWorld:
         assert rc == 0
         return dict(next=nxt, saved=saved, x=x, m=m, labels=labels, status=status, nc=nc, cinfo=cinfo, crec=crec)
 
-    def backward_contact(self, state, action, saved, crec, gnext):
+    def backward_contact(self, state, action, saved, crec, gnext, want_inertia_grad=False):
         state = np.ascontiguousarray(state, np.float32)
         action = np.ascontiguousarray(action, np.float32)
         gnext = np.ascontiguousarray(gnext, np.float32)
         gs, ga = np.empty_like(state), np.empty_like(action)
+        gi = np.zeros((10 * self.cm.nb, state.shape[0]), np.float32) if want_inertia_grad else None
         rc = lib().emul_backward_contact(ctypes.byref(self.desc), state.shape[0], _p(state), _p(action), _p(saved), _p(crec),
-                                         _p(gnext), _p(gs), _p(ga))
+                                         _p(gnext), _p(gs), _p(ga), _p(gi) if gi is not None else None)
         assert rc == 0
-        return gs, ga
+        return (gs, ga, gi) if want_inertia_grad else (gs, ga)
 
 
 def solve_chain(A, b, lo, hi, findex, x0=None, fallback_cfm=1e-4):

@@ -79,7 +79,7 @@ static int run_fwd_contact(const nb2_model_desc* d, int B, const float* state, c
   return 0;
 }
 static int run_bwd_contact(const nb2_model_desc* d, int B, const float* state, const float* action, const double* saved,
-                           const double* crec, const float* gnext, float* gstate, float* gaction) {
+                           const double* crec, const float* gnext, float* gstate, float* gaction, float* ginertia) {
   Nb2ModelDev<double> M; Nb2ContactDev C; std::string err;
   if (!nb2_fill_model(*d, M, err) || !nb2_fill_contact(*d, C, err)) { fprintf(stderr, "emul: %s\n", err.c_str()); return -1; }
   nb2::BwdLayout L = nb2::bwd_layout(M.nb, M.ndof, M.nslots, M.nfree, 42);
@@ -90,7 +90,7 @@ static int run_bwd_contact(const nb2_model_desc* d, int B, const float* state, c
     nb2::BwdContactHook H; H.model_contact = &C; H.ws = ws.data(); H.lane = 0; H.crec = crec + (size_t)w * nb2::contact_rec_doubles(M.ndof);
     nb2::world_backward<double, 1, true>(M, scr.data(), state + (size_t)w * 2 * M.ndof, action + (size_t)w * M.na,
                                          gnext + (size_t)w * 2 * M.ndof, saved + w, (size_t)B, gstate + (size_t)w * 2 * M.ndof,
-                                         gaction + (size_t)w * M.na, &H);
+                                         gaction + (size_t)w * M.na, &H, ginertia ? ginertia + w : nullptr);
   }
   return 0;
 }
@@ -117,8 +117,8 @@ int emul_forward_contact(const nb2_model_desc* d, int B, const float* state, con
 }
 int emul_contact_rec_doubles(const nb2_model_desc* d) { return (int)nb2::contact_rec_doubles(d->ndof); }
 int emul_backward_contact(const nb2_model_desc* d, int B, const float* state, const float* action, const double* saved,
-                          const double* crec, const float* gnext, float* gstate, float* gaction) {
-  return run_bwd_contact(d, B, state, action, saved, crec, gnext, gstate, gaction);
+                          const double* crec, const float* gnext, float* gstate, float* gaction, float* ginertia) {
+  return run_bwd_contact(d, B, state, action, saved, crec, gnext, gstate, gaction, ginertia);
 }
 int emul_saved_words(const nb2_model_desc* d) {
   int nfree = 0; for (int i = 0; i < d->nb; i++) nfree += d->jtype[i] == NB2_JT_FREE;

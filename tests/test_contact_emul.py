@@ -241,3 +241,57 @@ def test_contacts_between_two_moving_bodies_backward(oracle_mod):
     S[:, n + 9] += 0.8  # the upper box slides along x
     kinds = _check_backward(ob, raw, S, A_, tol=2e-5)
     assert any(k[1] > 0 for k in kinds)
+
+
+def test_mass_gradient_through_the_contact_stage(oracle_mod):
+    """lossWrtMass with active contact constraints: the same inertia-parameter form as the contact-free step, evaluated with
+    the field of w = lambda - nu and the realised acceleration (the constraint rows do not depend on the inertias).
+    Checked against central differences of the oracle's full contact step on worlds whose forward answer is exact and whose
+    labels do not move under the perturbation."""
+    import copy
+
+    from nimblephysics_b200 import modelspec as ms
+
+    raw = load_raw("half_cheetah")
+    cm = nb.compile_model(raw)
+    ew = EmulWorld(cm)
+    mobile = [i for i in range(raw.nb) if cm.body_owner[i] >= 0]
+    entries = [(mobile[1], ms.INERTIA_MASS), (mobile[3], ms.INERTIA_COM), (mobile[5], ms.INERTIA_MASS), (mobile[2], ms.INERTIA_DIAGONAL)]
+    P = ms.inertia_param_jacobian(raw, cm, entries)
+    s, a = contact_inputs(raw, "half_cheetah", 10, seed=4)
+    g = np.random.default_rng(3).normal(size=s.shape).astype(np.float32)
+    g[:, :raw.ndof] = 0  # positions do not depend on the masses within one step
+    r = ew.forward_contact(s, a)
+    gs, ga, gi = ew.backward_contact(s, a, r["saved"], r["crec"], g, want_inertia_grad=True)
+    checked = 0
+    for w in range(s.shape[0]):
+        if r["status"][w] & (8 | 16 | 64) or r["m"][w] == 0:
+            continue  # approximate forward answers are not differentiable maps of their inputs
+        s64, a64, g64 = s[w].astype(np.float64), a[w].astype(np.float64), g[w].astype(np.float64)
+        lab0 = r["labels"][w][: r["m"][w]]
+
+        def at(row, h):
+            rr = copy.deepcopy(raw)
+            k = 0
+            for (bi, kind) in entries:
+                x = ms._mass_entry_value(kind, rr.mass[bi], rr.com[bi], rr.moment[bi]).astype(np.float64)
+                for j in range(len(x)):
+                    if k == row:
+                        x[j] += h
+                    k += 1
+                rr.mass[bi], rr.com[bi], rr.moment[bi] = ms._apply_mass_entry(kind, x, rr.mass[bi], rr.com[bi], rr.moment[bi])
+            ro = ob.OracleContactWorld(rr).step_contact(s64, a64)
+            return float(g64 @ ro["next_state"]), ro["mapping"]
+
+        gm = P @ gi[:, w].astype(np.float64)
+        ok = True
+        fd = np.zeros(P.shape[0])
+        for j in range(P.shape[0]):
+            (lp, mp), (lm, mm_) = at(j, 1e-5), at(j, -1e-5)
+            ok = ok and np.array_equal(mp, lab0) and np.array_equal(mm_, lab0)
+            fd[j] = (lp - lm) / 2e-5
+        if not ok:
+            continue
+        assert rel_err(gm, fd) < 1e-4, (w, gm, fd)
+        checked += 1
+    assert checked >= 2, checked

@@ -152,3 +152,35 @@ def test_box_stack_contacts_between_moving_bodies(oracle_mod):
             continue  # the forward could not standardise x (f_c != Q^+ b): the frozen-classification map is only approximate there
         assert rel_err(gs[w], rgs) < 1e-4 and rel_err(ga[w], rga) < 1e-4
     assert both >= B // 2
+
+
+def test_mass_gradient_through_contact_matches_host_build(oracle_mod):
+    """timestep(..., mass) on a world with active contacts: the GPU's lossWrtMass vs the same device code compiled for the
+    host (tests/host_emul), which tests/test_contact_emul.py pins against finite differences of the oracle."""
+    from nimblephysics_b200 import modelspec as ms
+    from tests.host_emul.binding import EmulWorld
+
+    raw = load_raw("half_cheetah")
+    world = nb.World.from_raw(raw)
+    bodies = [b for sk in world.skeletons for b in sk._ordered_bodies()]
+    cm = nb.compile_model(raw)
+    mobile = [i for i in range(raw.nb) if cm.body_owner[i] >= 0]
+    picks = [(mobile[1], ms.INERTIA_MASS), (mobile[3], ms.INERTIA_COM), (mobile[5], ms.INERTIA_MASS)]
+    for bi, kind in picks:
+        world.tuneMass(bodies[bi], kind)
+    B = 32
+    s, a = contact_inputs(raw, "half_cheetah", B, seed=6)
+    g = np.random.default_rng(4).normal(size=s.shape).astype(np.float32)
+    mt = torch.tensor(world.getMasses(), dtype=torch.float64, requires_grad=True)
+    st, at = torch.tensor(s, device="cuda"), torch.tensor(a, device="cuda")
+    nb.reset_contact_cache(world)
+    out = nb.timestep(world, st, at, mt)
+    (out * torch.tensor(g, device="cuda")).sum().backward()
+    gm = mt.grad.numpy()
+    ew = EmulWorld(cm)
+    r = ew.forward_contact(s, a)
+    _, _, gi = ew.backward_contact(s, a, r["saved"], r["crec"], g, want_inertia_grad=True)
+    P = ms.inertia_param_jacobian(raw, cm, picks)
+    ref = P @ gi.astype(np.float64).sum(axis=1)
+    assert int((r["m"] > 0).sum()) > B // 2
+    assert rel_err(gm, ref) < 1e-4, (gm, ref)
