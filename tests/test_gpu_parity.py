@@ -226,7 +226,7 @@ def test_timestep_mass_argument_and_gradient(oracle_mod):
     assert world.getMassDims() == 5
     m0 = world.getMasses()
     m1 = m0 * np.array([1.3, 1.0, 1.0, 1.0, 0.8]) + np.array([0, 0.01, -0.02, 0.005, 0])
-    B = 6
+    B = 16  # two full warp groups: the backward stages the saved stream in shared memory (its stride differs from the batch's)
     s, a, g = sample_inputs(raw, B, seed=41)
     st, at = torch.tensor(s, device="cuda"), torch.tensor(a, device="cuda")
     mt = torch.tensor(m1, dtype=torch.float64, requires_grad=True)
