@@ -352,6 +352,37 @@ def main():
                                 "note": "forward only (fp64 ABA + contact/LCP kernels); same state re-stepped, warm-started LCP cache"}
             except Exception as ex:  # never let the extra leg break the headline line
                 extra[label] = {"error": repr(ex)}
+        # contact-free 64-step rollout through the fused entry points (nb2_rollout_forward / nb2_rollout_backward)
+        try:
+            from nimblephysics_b200.rollout import rollout_fused
+
+            fworld = nb.World.from_raw(raw)
+            fworld._contacts_disabled = True
+            Tf = 64
+            rngf = np.random.default_rng(21)
+            uf = rngf.uniform(-20, 20, (Tf, B, na)).astype(np.float32)
+            uf[:, :, :6] = 0.0
+            xf0 = sets[0]["s"].clone().requires_grad_(True)
+            uft = torch.tensor(uf, device=dev, requires_grad=True)
+
+            def runf():
+                tr = rollout_fused(fworld, xf0, uft)
+                (tr[-1] * tr[-1]).sum().backward()
+
+            runf()
+            torch.cuda.synchronize()
+            q0, q1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            q0.record()
+            for _ in range(3):
+                runf()
+            q1.record()
+            torch.cuda.synchronize()
+            msf = q0.elapsed_time(q1) / 3
+            extra["atlas_rollout64_contact_free"] = {"batch": B, "horizon": Tf, "ms_per_rollout_fwd_bwd": msf,
+                                                     "world_steps_per_s": B * Tf / (msf * 1e-3),
+                                                     "note": "one C-ABI call per direction; trajectory and saved streams stay on the device"}
+        except Exception as ex:
+            extra["atlas_rollout64_contact_free"] = {"error": repr(ex)}
         # BASELINE configs[4] shape at reduced batch: 64-step rollout of Atlas + ground, backprop through the full horizon
         try:
             from nimblephysics_b200.rollout import rollout

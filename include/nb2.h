@@ -149,6 +149,18 @@ int nb2_step_backward_contact(const nb2_model* m, int B, const float* state, con
                               const double* contact_record, void* workspace, const float* grad_next_state, float* grad_state,
                               float* grad_action, float* grad_inertia, void* stream);
 
+/* T-step rollout of a contact-free world and its reverse sweep — SingleShot::getSnapshots (dart/trajectory/SingleShot.cpp:635-686)
+ * and SingleShot::backpropGradientWrt (:539-631).  All buffers are device memory, fp32, time-major:
+ *   states  [T+1, B, 2n]: states[0] = x_0 on entry, the forward fills states[1..T];  actions [T, B, na];
+ *   saved   T consecutive saved streams (nb2_saved_words_per_world * B words each); NULL = no backward will follow;
+ *   grad_states [T+1, B, 2n]: on entry the gradient of the loss with respect to EVERY state of the trajectory (zeros where the
+ *     loss does not look); on exit grad_states[t] holds the total dL/dx_t (grad_states[0] = dL/dx_0);
+ *   grad_actions [T, B, na] out.
+ * One call queues the 2T kernels on `stream`; nothing returns to the host in between. */
+int nb2_rollout_forward(const nb2_model* m, int B, int T, float* states, const float* actions, void* saved, int precision, void* stream);
+int nb2_rollout_backward(const nb2_model* m, int B, int T, const float* states, const float* actions, const void* saved,
+                         float* grad_states, float* grad_actions, int precision, void* stream);
+
 /* number of kernels this library has launched since load (bench.py reports it as gpu_launches) */
 long long nb2_launch_count(void);
 const char* nb2_last_error(void);

@@ -136,6 +136,8 @@ def lib() -> ctypes.CDLL:
         vp = ctypes.c_void_p
         L.nb2_step_forward.argtypes = [vp, ctypes.c_int, vp, vp, vp, vp, ctypes.c_int, vp]
         L.nb2_step_backward.argtypes = [vp, ctypes.c_int, vp, vp, vp, vp, vp, vp, vp, ctypes.c_int, vp]
+        L.nb2_rollout_forward.argtypes = [vp, ctypes.c_int, ctypes.c_int, vp, vp, vp, ctypes.c_int, vp]
+        L.nb2_rollout_backward.argtypes = [vp, ctypes.c_int, ctypes.c_int, vp, vp, vp, vp, vp, ctypes.c_int, vp]
         L.nb2_model_has_contacts.argtypes = [vp]
         L.nb2_contact_workspace_bytes.argtypes = [vp, ctypes.c_int]
         L.nb2_contact_workspace_bytes.restype = ctypes.c_size_t

@@ -811,10 +811,11 @@ NB2_HD void bwd_load(const Nb2ModelDev<R>& M, R* scr0, const float* st0, const f
   group_read(act0, nworlds * M.na, tid, nthr, sa);
 }
 struct NanGather { NB2_HD float operator()(int) const { return nanf(""); } };
+template <class F> struct AddTo { F f; const float* dst; NB2_HD float operator()(int idx) const { return dst[idx] + f(idx); } };
 // group store of the (already clipped) gradients: [oQb, oVb] are adjacent, dL/daction sits in oAct
 template <class R, int ST, bool CONTACT>
 NB2_HD void bwd_store(const Nb2ModelDev<R>& M, const R* scr0, float* gstate0, float* gaction0,
-                      bool cd_error, int nworlds, int tid, int nthr) {
+                      bool cd_error, int nworlds, int tid, int nthr, bool accumulate_state = false) {
   const int n = M.ndof, n2 = 2 * n, na = M.na;
   constexpr int SLOTW = CONTACT ? 42 : 18;
   const BwdLayout L = bwd_layout(M.nb, n, M.nslots, M.nfree, SLOTW);
@@ -824,7 +825,10 @@ NB2_HD void bwd_store(const Nb2ModelDev<R>& M, const R* scr0, float* gstate0, fl
     return;
   }
   WordGather<R, ST> gs{scr0, n2, L.oQb, M.magic_n2};  // oVb = oQb + n
-  group_write(gstate0, nworlds * n2, tid, nthr, gs);
+  if (accumulate_state) {  // rollouts: dL/dx_t = (loss gradient already in the buffer) + clipped back-propagated part
+    AddTo<WordGather<R, ST>> acc{gs, gstate0};
+    group_write(gstate0, nworlds * n2, tid, nthr, acc);
+  } else group_write(gstate0, nworlds * n2, tid, nthr, gs);
   WordGather<R, ST> ga{scr0, na, L.oAct, M.magic_na};
   group_write(gaction0, nworlds * na, tid, nthr, ga);
 }

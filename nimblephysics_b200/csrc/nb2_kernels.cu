@@ -92,7 +92,7 @@ __global__ void __launch_bounds__(128)
 k_step_bwd(const __grid_constant__ Nb2ModelDev<R> M, int B, int w0, int count, const float* __restrict__ state,
            const float* __restrict__ action, const R* __restrict__ saved, const float* __restrict__ gnext,
            float* __restrict__ gstate, float* __restrict__ gaction, float* __restrict__ ginertia, int words,
-           int stage_saved) {
+           int stage_saved, int accumulate_state) {
   extern __shared__ __align__(16) unsigned char nb2_smem[];
   constexpr int WPW = CoopShape<K>::WPW, ST = CoopShape<K>::ST;
   const int li = threadIdx.x & 31, slot = li / K, lane = li % K;
@@ -131,7 +131,7 @@ k_step_bwd(const __grid_constant__ Nb2ModelDev<R> M, int B, int w0, int count, c
   for (int sg = 0; sg < NB2_BWD_STAGES; sg++) {
     if (sg == 0) { if (nworlds > 0) nb2::bwd_load<R, ST, false>(M, scr0, state + wg * 2 * M.ndof, action + wg * M.na, gnext + wg * 2 * M.ndof, nworlds, li, 32); }
     else if (sg == NB2_BWD_STAGES - 1) {
-      if (nworlds > 0) nb2::bwd_store<R, ST, false>(M, scr0, gstate + wg * 2 * M.ndof, gaction + wg * M.na, false, nworlds, li, 32);
+      if (nworlds > 0) nb2::bwd_store<R, ST, false>(M, scr0, gstate + wg * 2 * M.ndof, gaction + wg * M.na, false, nworlds, li, 32, accumulate_state != 0);
     } else if (valid) nb2::world_backward_stage<R, ST>(M, scr, svp, svB, lane, sg, ginertia ? ginertia + w : nullptr, bt, (size_t)B);
     if (sg == 0 && stage_saved) asm volatile("cp.async.wait_group 0;" ::: "memory");
     if (((sync_mask >> sg) & 1u) || (sg == 0 && stage_saved)) __syncwarp();
@@ -357,7 +357,7 @@ static bool no_stage_saved() {
 }
 template <class R, int K>
 static int launch_bwd_k(const nb2_variant& v, int sm_count, int Btot, int w0, int B, const float* state, const float* action,
-                        const R* saved, const float* gnext, float* gstate, float* gaction, float* ginertia, cudaStream_t st) {
+                        const R* saved, const float* gnext, float* gstate, float* gaction, float* ginertia, cudaStream_t st, int accumulate) {
   constexpr int WPW = CoopShape<K>::WPW, ST = CoopShape<K>::ST;
   const LaunchShape& sh = v.shape[1][sizeof(R) == 8];
   const size_t per_warp = (size_t)v.bwd_words * ST * sizeof(R);
@@ -373,7 +373,7 @@ static int launch_bwd_k(const nb2_variant& v, int sm_count, int Btot, int w0, in
   const int blocks_per_sm = (blocks + sm_count - 1) / sm_count;
   const bool stage = aligned && smem_staged * blocks_per_sm + 1024 * blocks_per_sm <= (size_t)kMaxSmem && !no_stage_saved();
   k_step_bwd<R, K><<<blocks, warps * 32, stage ? smem_staged : per_warp * warps + tab, st>>>(model_of<R>(v), Btot, w0, B, state, action, saved, gnext, gstate,
-                                                                                            gaction, ginertia, v.bwd_words, stage ? 1 : 0);
+                                                                                            gaction, ginertia, v.bwd_words, stage ? 1 : 0, accumulate);
   g_launches++;
   NB2_CUDA(cudaGetLastError());
   return NB2_OK;
@@ -381,16 +381,16 @@ static int launch_bwd_k(const nb2_variant& v, int sm_count, int Btot, int w0, in
 template <class R>
 static int launch_bwd(nb2_model* m, int B, const float* state, const float* action,
                       const R* saved, const float* gnext, float* gstate, float* gaction, float* ginertia, cudaStream_t st,
-                      int Btot = -1, int w0 = 0) {
+                      int Btot = -1, int w0 = 0, int accumulate = 0) {
   if (Btot < 0) Btot = B;
   nb2_variant* pv = nullptr;
   int rc = pick_variant<R>(m, B, 1, &pv);
   if (rc) return rc;
   switch (pv->mf.lanes) {
-    case 1: return launch_bwd_k<R, 1>(*pv, m->sm_count, Btot, w0, B, state, action, saved, gnext, gstate, gaction, ginertia, st);
-    case 2: return launch_bwd_k<R, 2>(*pv, m->sm_count, Btot, w0, B, state, action, saved, gnext, gstate, gaction, ginertia, st);
-    case 4: return launch_bwd_k<R, 4>(*pv, m->sm_count, Btot, w0, B, state, action, saved, gnext, gstate, gaction, ginertia, st);
-    case 8: return launch_bwd_k<R, 8>(*pv, m->sm_count, Btot, w0, B, state, action, saved, gnext, gstate, gaction, ginertia, st);
+    case 1: return launch_bwd_k<R, 1>(*pv, m->sm_count, Btot, w0, B, state, action, saved, gnext, gstate, gaction, ginertia, st, accumulate);
+    case 2: return launch_bwd_k<R, 2>(*pv, m->sm_count, Btot, w0, B, state, action, saved, gnext, gstate, gaction, ginertia, st, accumulate);
+    case 4: return launch_bwd_k<R, 4>(*pv, m->sm_count, Btot, w0, B, state, action, saved, gnext, gstate, gaction, ginertia, st, accumulate);
+    case 8: return launch_bwd_k<R, 8>(*pv, m->sm_count, Btot, w0, B, state, action, saved, gnext, gstate, gaction, ginertia, st, accumulate);
   }
   g_err = "bad lane count"; return NB2_ERR_INVALID;
 }
@@ -609,6 +609,40 @@ int nb2_step_backward(const nb2_model* cm, int B, const float* state, const floa
   cudaStream_t st = (cudaStream_t)stream;
   if (precision == NB2_FP64) return launch_bwd<double>(m, B, state, action, (const double*)saved, grad_next_state, grad_state, grad_action, grad_inertia, st);
   return launch_bwd<float>(m, B, state, action, (const float*)saved, grad_next_state, grad_state, grad_action, grad_inertia, st);
+}
+
+int nb2_rollout_forward(const nb2_model* cm, int B, int T, float* states, const float* actions, void* saved, int precision, void* stream) {
+  nb2_model* m = const_cast<nb2_model*>(cm);
+  if (!m || B < 0 || T < 0 || !states || (!actions && T > 0)) { g_err = "nb2_rollout_forward: bad argument"; return NB2_ERR_INVALID; }
+  if (m->has_contacts) { g_err = "nb2_rollout_forward: contact worlds roll out through nb2_step_forward_contact (one call per step)"; return NB2_ERR_INVALID; }
+  if (B == 0) return NB2_OK;
+  const size_t n2 = (size_t)2 * m->mf.ndof, na = (size_t)m->mf.na;
+  const size_t sv_step = (size_t)m->saved_words * B * (precision == NB2_FP64 ? sizeof(double) : sizeof(float));
+  for (int t = 0; t < T; t++) {  // x_{t+1} = step(x_t, u_t): every launch reads the rows the previous one wrote (stream order)
+    void* sv = saved ? (char*)saved + sv_step * t : nullptr;
+    int rc = nb2_step_forward(m, B, states + n2 * B * t, actions + na * B * t, states + n2 * B * (t + 1), sv, precision, stream);
+    if (rc) return rc;
+  }
+  return NB2_OK;
+}
+
+int nb2_rollout_backward(const nb2_model* cm, int B, int T, const float* states, const float* actions, const void* saved,
+                         float* grad_states, float* grad_actions, int precision, void* stream) {
+  nb2_model* m = const_cast<nb2_model*>(cm);
+  if (!m || B < 0 || T < 0 || !states || !saved || !grad_states || (!actions && T > 0) || (!grad_actions && T > 0)) { g_err = "nb2_rollout_backward: bad argument"; return NB2_ERR_INVALID; }
+  if (m->has_contacts) { g_err = "nb2_rollout_backward: contact worlds back-propagate through nb2_step_backward_contact"; return NB2_ERR_INVALID; }
+  if (B == 0) return NB2_OK;
+  const size_t n2 = (size_t)2 * m->mf.ndof, na = (size_t)m->mf.na;
+  const size_t sv_step = (size_t)m->saved_words * B * (precision == NB2_FP64 ? sizeof(double) : sizeof(float));
+  cudaStream_t st = (cudaStream_t)stream;
+  for (int t = T - 1; t >= 0; t--) {  // grad_states[t] += clip(J_t^T grad_states[t+1]) ; grad_actions[t] = ...
+    const char* sv = (const char*)saved + sv_step * t;
+    int rc;
+    if (precision == NB2_FP64) rc = launch_bwd<double>(m, B, states + n2 * B * t, actions + na * B * t, (const double*)sv, grad_states + n2 * B * (t + 1), grad_states + n2 * B * t, grad_actions + na * B * t, nullptr, st, -1, 0, 1);
+    else rc = launch_bwd<float>(m, B, states + n2 * B * t, actions + na * B * t, (const float*)sv, grad_states + n2 * B * (t + 1), grad_states + n2 * B * t, grad_actions + na * B * t, nullptr, st, -1, 0, 1);
+    if (rc) return rc;
+  }
+  return NB2_OK;
 }
 
 static int ensure_host_buffers(nb2_model* m, int B) {

@@ -109,6 +109,13 @@ class DeviceModel:
         _cabi.check(_cabi.lib().nb2_step_backward(self.handle, B, state_ptr, action_ptr, saved_ptr, gnext_ptr,
                                                   gstate_ptr, gaction_ptr, ginertia_ptr, precision, stream))
 
+    def rollout_forward_device(self, B, T, states_ptr, actions_ptr, saved_ptr, stream, precision=FP32):
+        _cabi.check(_cabi.lib().nb2_rollout_forward(self.handle, B, T, states_ptr, actions_ptr, saved_ptr, precision, stream))
+
+    def rollout_backward_device(self, B, T, states_ptr, actions_ptr, saved_ptr, gstates_ptr, gactions_ptr, stream, precision=FP32):
+        _cabi.check(_cabi.lib().nb2_rollout_backward(self.handle, B, T, states_ptr, actions_ptr, saved_ptr, gstates_ptr,
+                                                     gactions_ptr, precision, stream))
+
     def contact_workspace_bytes(self, B):
         return int(_cabi.lib().nb2_contact_workspace_bytes(self.handle, B))
 

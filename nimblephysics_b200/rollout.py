@@ -28,6 +28,64 @@ def rollout(world, state0: torch.Tensor, actions: Sequence[torch.Tensor], keep_s
     return (x, states) if keep_states else x
 
 
+class _FusedRollout(torch.autograd.Function):
+    """Whole-horizon rollout behind ONE C-ABI call per direction (include/nb2.h nb2_rollout_forward / _backward): the 2T
+    kernels are queued back to back on the stream, the trajectory and the saved streams never leave the device, and
+    autograd sees a single node instead of T."""
+
+    @staticmethod
+    def forward(ctx, world, state0, actions):
+        from .engine import FP32, device_model_for
+
+        dm = device_model_for(world)
+        T, B = actions.shape[0], actions.shape[1]
+        n2, na = 2 * dm.ndof, dm.na
+        if state0.shape != (B, n2) or actions.shape[2] != na:
+            raise ValueError(f"rollout(): state0 {tuple(state0.shape)} / actions {tuple(actions.shape)} do not match [B,{n2}] / [T,B,{na}]")
+        dev = state0.device
+        states = torch.empty((T + 1, B, n2), dtype=torch.float32, device=dev)
+        states[0].copy_(state0.detach())
+        acts = actions.detach().to(dtype=torch.float32).contiguous()
+        need = any(ctx.needs_input_grad[1:3])
+        saved = torch.empty((T, dm.saved_words, B), dtype=torch.float32, device=dev) if need else None
+        with torch.cuda.device(dev):
+            dm.rollout_forward_device(B, T, states.data_ptr(), acts.data_ptr(), saved.data_ptr() if need else None,
+                                      torch.cuda.current_stream().cuda_stream, FP32)
+        ctx.dm, ctx.T, ctx.B = dm, T, B
+        ctx.dtypes = (state0.dtype, actions.dtype)
+        if need:
+            ctx.save_for_backward(states, acts, saved)
+        return states.to(state0.dtype)
+
+    @staticmethod
+    def backward(ctx, grad_states):
+        from .engine import FP32
+
+        states, acts, saved = ctx.saved_tensors
+        dm, T, B = ctx.dm, ctx.T, ctx.B
+        gs = grad_states.detach().to(dtype=torch.float32).contiguous().clone()  # in: loss gradient per state; out: total dL/dx_t
+        ga = torch.empty_like(acts)
+        with torch.cuda.device(states.device):
+            dm.rollout_backward_device(B, T, states.data_ptr(), acts.data_ptr(), saved.data_ptr(), gs.data_ptr(), ga.data_ptr(),
+                                       torch.cuda.current_stream().cuda_stream, FP32)
+        return None, gs[0].to(ctx.dtypes[0]), ga.to(ctx.dtypes[1])
+
+
+def rollout_fused(world, state0: torch.Tensor, actions: torch.Tensor) -> torch.Tensor:
+    """states[T+1, B, 2n] of the T-step rollout x_{t+1} = timestep(x_t, actions[t]) of a contact-free world
+    (SingleShot::getSnapshots, dart/trajectory/SingleShot.cpp:635-686), differentiable with respect to state0 and every
+    action (SingleShot::backpropGradientWrt, :539-631); losses may look at any state of the trajectory.
+    Worlds with collision pairs keep the per-step path (`rollout`), whose LCP cache flows from step to step."""
+    from .engine import device_model_for
+
+    if device_model_for(world).has_contacts:
+        xs = [state0]
+        for t in range(actions.shape[0]):
+            xs.append(timestep(world, xs[-1], actions[t]))
+        return torch.stack(xs, 0)
+    return _FusedRollout.apply(world, state0, actions)
+
+
 def shard_range(total: int, rank: int, world_size: int) -> Tuple[int, int]:
     """Contiguous slice [lo, hi) of a batch of `total` worlds owned by `rank` (sizes differ by at most one)."""
     if world_size <= 0 or not (0 <= rank < world_size):

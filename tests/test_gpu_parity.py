@@ -259,3 +259,34 @@ def test_timestep_mass_argument_and_gradient(oracle_mod):
         e = np.zeros(5); e[j] = 1e-5
         fd[j] = (loss(m1 + e) - loss(m1 - e)) / 2e-5
     assert rel_err(gm, fd) < 1e-3, (gm, fd)  # fp32 kernels, sum over the batch
+
+
+def test_fused_rollout_matches_step_by_step_rollout():
+    """nb2_rollout_forward / nb2_rollout_backward (one C-ABI call per direction) vs chaining `timestep` through autograd:
+    same kernels in the same order, so trajectories and gradients agree to the last bit; the loss looks at several states of
+    the trajectory (the reverse sweep adds per-step loss gradients like SingleShot::backpropGradientWrt)."""
+    raw, world = _world("atlas")
+    B, T = 200, 12
+    s, a, _ = sample_inputs(raw, B, seed=51)
+    rng = np.random.default_rng(52)
+    acts = rng.uniform(-10, 10, (T, B, len(raw.action_map))).astype(np.float32)
+    wts = torch.tensor(rng.normal(size=(T + 1, B, 2 * raw.ndof)).astype(np.float32), device="cuda")
+    wts[1:5] = 0  # some states carry no loss
+
+    x0 = torch.tensor(s, device="cuda", requires_grad=True)
+    u = torch.tensor(acts, device="cuda", requires_grad=True)
+    traj = nb.rollout_fused(world, x0, u)
+    assert traj.shape == (T + 1, B, 2 * raw.ndof)
+    (traj * wts).sum().backward()
+
+    x0r = torch.tensor(s, device="cuda", requires_grad=True)
+    ur = [torch.tensor(acts[t], device="cuda", requires_grad=True) for t in range(T)]
+    xs = [x0r]
+    for t in range(T):
+        xs.append(nb.timestep(world, xs[-1], ur[t]))
+    (torch.stack(xs, 0) * wts).sum().backward()
+
+    assert torch.equal(traj.detach(), torch.stack(xs, 0).detach())
+    assert rel_err(x0.grad.cpu().numpy(), x0r.grad.cpu().numpy()) < 1e-6
+    for t in range(T):
+        assert rel_err(u.grad[t].cpu().numpy(), ur[t].grad.cpu().numpy()) < 1e-6
