@@ -33,7 +33,8 @@
 #define NB2_ST_NOT_STANDARDIZED 64
 #define NB2_ST_UNSUPPORTED_GEOMETRY 128
 #define NB2_ST_CONTACT_OVERFLOW 256
-#define NB2_ST_MERGED 512  // LCPUtils::reduce merged near-identical columns before a solver ran
+#define NB2_ST_MERGED 512
+#define NB2_ST_BOUNCE 1024  // a restitution (bounce) term raised some b_i: the backward of such a step is not implemented (NaN, loud)  // LCPUtils::reduce merged near-identical columns before a solver ran
 
 // ConstraintMapping (dart/neural/ConstrainedGroupGradientMatrices.hpp:33-39)
 #define NB2_MAP_NOT_CLAMPING (-1)
@@ -632,7 +633,7 @@ NB2_HD void contact_phase0(const Nb2ModelDev<CR>& M, const Nb2ContactDev& C, con
     CR bv = ws.cdepth[c];
     if (bv < 0) bv = 0; else { bv *= 0.01 * (1.0 / dt); if (bv > 1e-3) bv = 1e-3; }
     if (!C.pen_correction) bv = 0;
-    if (bounce) { const CR rv = ws.b[off] * e; if (rv > 1e-1) { if (rv > bv) { bv = rv; if (bv > 1e2) bv = 1e2; } } }
+    if (bounce) { const CR rv = ws.b[off] * e; if (rv > 1e-1) { if (rv > bv) { bv = rv; if (bv > 1e2) bv = 1e2; status |= NB2_ST_BOUNCE; } } }
     ws.b[off] += bv;
   }
   ws.meta[0] = m; ws.meta[1] = nc; ws.meta[2] = status;
@@ -761,6 +762,9 @@ NB2_HD BwdContactView<ST> contact_backward_prepare(const Nb2ModelDev<CR>& M, con
   const int m = (int)crec[0];
   if (m <= 0) return cv;
   cv.active = 1;
+  // restitution: b depends on v* through (1 + e) J v*, which needs a second multiplier field in the reverse sweep
+  // (BackpropSnapshot::getBounceApproximationJacobian, BackpropSnapshot.cpp:1131-1226) — not implemented: fail loudly
+  if (((int)crec[1]) & NB2_ST_BOUNCE) { cv.error = 5; return cv; }
   const CR dt = M.dt;
   const int kQdd = nb * 21 + M.nfree * 33;
   const CR* mapping = crec + 2; const CR* xr = crec + 2 + NB2_MAX_ROWS; const CR* dqd_imp = crec + 2 + 2 * NB2_MAX_ROWS; const CR* Arec = dqd_imp + n;

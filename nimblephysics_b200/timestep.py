@@ -108,8 +108,9 @@ class TimestepLayer(torch.autograd.Function):
                 if bool(torch.isnan(gs).any()):
                     raise RuntimeError(
                         "backward through the contact stage failed for some worlds (the kernel marked them with NaN gradients): "
-                        "the contact rows regenerated in the backward pass did not match the forward's, or the clamping set "
-                        "exceeds the compiled limits")
+                        "a restitution (bounce) term was active in the forward step (status bit 1024; its backward is not implemented), "
+                        "the contact rows regenerated in the backward pass did not match the forward's, or the clamping set exceeds "
+                        "the compiled limits")
             else:
                 gi = torch.empty((10 * dm.cm.nb, ctx.B), dtype=torch.float32, device=dev) if ctx.mass_grad else None
                 dm.backward_device(ctx.B, _ptr(sd), _ptr(ad), _ptr(saved), _ptr(g), _ptr(gs), _ptr(ga), stream, FP32,

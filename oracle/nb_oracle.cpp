@@ -424,6 +424,7 @@ static void step_contact(const Model& M, const double* q, const double* v, const
   }
   ContactRows& R = info.rows;
   collide_world(M, B, R);
+  bool bounce_active = false;  // a restitution term raised some b_i (status bit 1024, informational)
   // ---- rows (ContactConstraint ctor + getInformation)
   for (int ci = 0; ci < R.nc; ci++) {
     const Contact<double>& c = R.contacts[ci];
@@ -452,7 +453,7 @@ static void step_contact(const Model& M, const double* q, const double* v, const
     double bv = c.depth - 0.0;
     if (bv < 0) bv = 0; else { bv *= 0.01 * (1.0 / M.dt); if (bv > 1e-3) bv = 1e-3; }
     if (!M.penetration_correction) bv = 0;
-    if (bounce) { double rv = R.b[off] * e; if (rv > 1e-1) { if (rv > bv) { bv = rv; if (bv > 1e2) bv = 1e2; } } }
+    if (bounce) { double rv = R.b[off] * e; if (rv > 1e-1) { if (rv > bv) { bv = rv; if (bv > 1e2) bv = 1e2; bounce_active = true; } } }
     R.b[off] += bv;
     R.m += dim;
   }
@@ -485,7 +486,7 @@ static void step_contact(const Model& M, const double* q, const double* v, const
   if (m_warm == m && x_warm) for (int i = 0; i < m; i++) x0[i] = x_warm[i];
   else x0 = orc::guess_solution(A, R.b, R.findex);
   orc::ChainResult CR = orc::solve_chain(A, R.b, R.lo, R.hi, R.findex, x0, R.restitution, M.fallback_cfm);
-  info.x = CR.x; info.mapping = CR.mapping; info.status = CR.status | (R.unsupported ? 128 : 0);
+  info.x = CR.x; info.mapping = CR.mapping; info.status = CR.status | (R.unsupported ? 128 : 0) | (bounce_active ? 1024 : 0);
   // ---- apply impulses (ConstraintSolver.cpp:813-823, ContactConstraint.cpp:630-684) and update velocities
   for (auto& x : imp) x = zero6<double>();
   for (int r = 0; r < m; r++) {

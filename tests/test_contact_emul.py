@@ -295,3 +295,27 @@ def test_mass_gradient_through_the_contact_stage(oracle_mod):
         assert rel_err(gm, fd) < 1e-4, (w, gm, fd)
         checked += 1
     assert checked >= 2, checked
+
+
+def test_restitution_forward_parity_and_loud_backward(oracle_mod):
+    """Bounce terms (ContactConstraint.cpp:395-442): the forward matches the oracle; the backward of such a step needs
+    BackpropSnapshot::getBounceApproximationJacobian (not implemented) and must fail loudly (NaN), never silently."""
+    raw = load_raw("half_cheetah")
+    raw.restitution[:] = 0.8
+    cm = nb.compile_model(raw)
+    ew, ow = EmulWorld(cm), ob.OracleContactWorld(raw)
+    s, a = contact_inputs(raw, "half_cheetah", 8, seed=4)
+    s[:, raw.ndof + 1] -= 1.5  # falling fast: e * (relative normal velocity) > 0.1 activates the bounce term
+    g = np.random.default_rng(1).normal(size=s.shape).astype(np.float32)
+    r = ew.forward_contact(s, a)
+    gs, ga = ew.backward_contact(s, a, r["saved"], r["crec"], g)
+    bounced = 0
+    for w in range(8):
+        ro = ow.step_contact(s[w].astype(np.float64), a[w].astype(np.float64))
+        assert (r["status"][w] & ~96) == (ro["status"] & ~96) and rel_err(r["next"][w], ro["next_state"]) < 1e-6
+        if r["status"][w] & 1024:
+            bounced += 1
+            assert np.isnan(gs[w]).all() and np.isnan(ga[w]).all()
+        else:
+            assert np.isfinite(gs[w]).all()
+    assert bounced >= 4
