@@ -34,7 +34,7 @@
 #define NB2_ST_UNSUPPORTED_GEOMETRY 128
 #define NB2_ST_CONTACT_OVERFLOW 256
 #define NB2_ST_MERGED 512
-#define NB2_ST_BOUNCE 1024  // a restitution (bounce) term raised some b_i: the backward of such a step is not implemented (NaN, loud)  // LCPUtils::reduce merged near-identical columns before a solver ran
+#define NB2_ST_BOUNCE 1024  // a restitution (bounce) or penetration-correction term raised some b_i: the backward of such a step is not implemented (NaN, loud)  // LCPUtils::reduce merged near-identical columns before a solver ran
 
 // ConstraintMapping (dart/neural/ConstrainedGroupGradientMatrices.hpp:33-39)
 #define NB2_MAP_NOT_CLAMPING (-1)
@@ -633,6 +633,7 @@ NB2_HD void contact_phase0(const Nb2ModelDev<CR>& M, const Nb2ContactDev& C, con
     CR bv = ws.cdepth[c];
     if (bv < 0) bv = 0; else { bv *= 0.01 * (1.0 / dt); if (bv > 1e-3) bv = 1e-3; }
     if (!C.pen_correction) bv = 0;
+    else if (bv > 0) status |= NB2_ST_BOUNCE;  // depth-dependent ERP velocity: not modelled by the backward either (loud)
     if (bounce) { const CR rv = ws.b[off] * e; if (rv > 1e-1) { if (rv > bv) { bv = rv; if (bv > 1e2) bv = 1e2; status |= NB2_ST_BOUNCE; } } }
     ws.b[off] += bv;
   }

@@ -453,6 +453,7 @@ static void step_contact(const Model& M, const double* q, const double* v, const
     double bv = c.depth - 0.0;
     if (bv < 0) bv = 0; else { bv *= 0.01 * (1.0 / M.dt); if (bv > 1e-3) bv = 1e-3; }
     if (!M.penetration_correction) bv = 0;
+    else if (bv > 0) bounce_active = true;
     if (bounce) { double rv = R.b[off] * e; if (rv > 1e-1) { if (rv > bv) { bv = rv; if (bv > 1e2) bv = 1e2; bounce_active = true; } } }
     R.b[off] += bv;
     R.m += dim;
