@@ -335,6 +335,145 @@ def load_skel_world(path: str) -> World:
     return world
 
 
+def _sdf_pose(el) -> np.ndarray:
+    """"x y z roll pitch yaw", extrinsic rotation = Rz(yaw) Ry(pitch) Rx(roll) (dart/utils/XmlHelpers.cpp:382-420)."""
+    if el is None or el.text is None:
+        return np.eye(4)
+    v = _floats(el.text)
+    return _T(_rpy_to_R(v[3:6]), v[0:3])
+
+
+def _sdf_shape(geom_el):
+    if geom_el is None:
+        return None
+    b = geom_el.find("box")
+    if b is not None:
+        return BoxShape(_floats(b.find("size").text))
+    sp = geom_el.find("sphere")
+    if sp is not None:
+        return SphereShape(float(sp.find("radius").text))
+    return None  # cylinders / meshes: no collider on the hot path (the reference meshes need assimp)
+
+
+def load_sdf_skeleton(path: str) -> Skeleton:
+    """dart/utils/sdf/SdfParser.cpp: link poses live in the model frame (:1117-1127); a joint's <pose> is child-link -> joint,
+    parent-to-joint = parentWorld^-1 childWorld childToJoint (:1608-1624); <axis><xyz> is in the joint frame unless
+    <use_parent_model_frame> (:1670-1690); links without a parent joint hang on a root FreeJoint placed at the link pose
+    (:858-871).  Bodies are created in the reference's order — alphabetical by link name, a missing parent first
+    (:843-880, std::map iteration) — because that order is the DoF order of the Skeleton."""
+    root = ET.parse(path).getroot()
+    model = root.find("model") if root.tag == "sdf" else root
+    if model is None:
+        w = root.find("world")
+        model = w.find("model") if w is not None else None
+    if model is None:
+        raise ValueError("no <model> in the SDF file")
+    skel = Skeleton(model.get("name", "skeleton"))
+    st = model.find("static")
+    if st is not None and st.text.strip().lower() in ("1", "true"):
+        skel.setMobile(False)
+    skel_frame = _sdf_pose(model.find("pose"))
+    links = {l.get("name"): l for l in model.findall("link")}
+    init_T = {name: skel_frame @ _sdf_pose(l.find("pose")) for name, l in links.items()}
+    joints = {}  # keyed by child link name (SdfParser.cpp:1498-1530)
+    for j in model.findall("joint"):
+        child = j.find("child").text.strip()
+        if child in joints:
+            continue
+        joints[child] = j
+    created: Dict[str, BodyNode] = {}
+
+    def fill_body(body: BodyNode, l):
+        g = l.find("gravity")
+        if g is not None:
+            body.gravity_mode = g.text.strip().lower() in ("1", "true")
+        ine = l.find("inertial")
+        if ine is not None:
+            m = ine.find("mass")
+            if m is not None:
+                body.setMass(float(m.text))          # Inertia::setMass first (scales the default moment) ...
+            if ine.find("pose") is not None:
+                body.com = _sdf_pose(ine.find("pose"))[:3, 3].copy()  # only the translation is used (:1143-1149)
+            moi = ine.find("inertia")
+            if moi is not None:                       # ... then the moment is set explicitly
+                gv = lambda k: float(moi.find(k).text) if moi.find(k) is not None else 0.0
+                body.setMomentOfInertia(gv("ixx"), gv("iyy"), gv("izz"), gv("ixy"), gv("ixz"), gv("iyz"))
+        for col in l.findall("collision"):
+            shape = _sdf_shape(col.find("geometry"))
+            if shape is None:
+                continue
+            sn = ShapeNode(shape, _sdf_pose(col.find("pose")))
+            sn.has_collision = True
+            body.shapes.append(sn)
+
+    def create(name: str):
+        l = links[name]
+        jel = joints.get(name)
+        if jel is None:  # root: FreeJoint at the link's pose
+            joint, body = skel._create(FREE, None, "root", name)
+            joint.T_pj = init_T[name].copy()
+            fill_body(body, l)
+            created[name] = body
+            return
+        pname = jel.find("parent").text.strip()
+        parent_body = created.get(pname)
+        jt = jel.get("type")
+        kind = {"revolute": REVOLUTE, "prismatic": PRISMATIC, "fixed": WELD}.get(jt)
+        if kind is None:
+            raise NotImplementedError(f"SDF joint type '{jt}' is outside the hot-path scope")
+        joint, body = skel._create(kind, parent_body, jel.get("name"), name)
+        child_world = init_T[name]
+        parent_world = init_T[pname] if pname in init_T else np.eye(4)
+        child_to_joint = _sdf_pose(jel.find("pose"))
+        joint.T_cj = child_to_joint
+        joint.T_pj = np.linalg.inv(parent_world) @ child_world @ child_to_joint
+        if kind in (REVOLUTE, PRISMATIC):
+            ax = jel.find("axis")
+            if ax is None:
+                raise ValueError(f"SDF joint {jel.get('name')} has no <axis>")
+            xyz = np.array(_floats(ax.find("xyz").text))
+            upf = ax.find("use_parent_model_frame")
+            if upf is not None and upf.text.strip().lower() in ("1", "true"):
+                parent_model_frame = np.linalg.inv(child_world @ child_to_joint) @ skel_frame
+                xyz = parent_model_frame[:3, :3] @ xyz
+            joint.setAxis(xyz)
+            dyn = ax.find("dynamics")
+            if dyn is not None and dyn.find("damping") is not None:
+                joint.damping[0] = float(dyn.find("damping").text)
+            lim = ax.find("limit")
+            lo, hi = -math.inf, math.inf
+            if lim is not None:
+                if lim.find("lower") is not None:
+                    lo = float(lim.find("lower").text)
+                if lim.find("upper") is not None:
+                    hi = float(lim.find("upper").text)
+            joint.pos_lo[0], joint.pos_hi[0] = lo, hi
+            if 0.0 < lo or hi < 0.0:  # zero outside the limits (:1722-1737)
+                init = 0.5 * (lo + hi) if (math.isfinite(lo) and math.isfinite(hi)) else (lo if math.isfinite(lo) else hi)
+                if math.isfinite(init):
+                    joint.init_pos[0] = init
+                    joint.rest[0] = init
+        fill_body(body, l)
+        created[name] = body
+
+    remaining = sorted(links)
+    cur = remaining[0] if remaining else None
+    while remaining:
+        name = cur if cur in remaining else remaining[0]
+        jel = joints.get(name)
+        if jel is not None:
+            pname = jel.find("parent").text.strip()
+            if pname not in created and pname != "world" and pname != "":
+                if pname not in links:
+                    raise ValueError(f"SDF joint {jel.get('name')} references the missing link {pname}")
+                cur = pname  # create the parent before the current joint
+                continue
+        create(name)
+        remaining.remove(name)
+        cur = remaining[0] if remaining else None
+    return skel
+
+
 def load_skeleton(path: str) -> Skeleton:
     ext = os.path.splitext(path)[1].lower()
     if ext == ".urdf":
@@ -344,7 +483,9 @@ def load_skeleton(path: str) -> Skeleton:
         if len(w.skeletons) != 1:
             raise ValueError(".skel file holds several skeletons; use loadWorld()")
         return w.skeletons[0]
-    raise NotImplementedError(f"unsupported model file type '{ext}' (urdf and skel only)")
+    if ext in (".sdf", ".world"):
+        return load_sdf_skeleton(path)
+    raise NotImplementedError(f"unsupported model file type '{ext}' (urdf, sdf and skel only)")
 
 
 def loadWorld(path: str) -> World:
@@ -355,5 +496,9 @@ def loadWorld(path: str) -> World:
     if ext == ".urdf":
         w = World()
         w.addSkeleton(load_urdf_skeleton(path))
+        return w
+    if ext in (".sdf", ".world"):
+        w = World()
+        w.addSkeleton(load_sdf_skeleton(path))
         return w
     raise NotImplementedError(f"unsupported world file type '{ext}'")

@@ -2,7 +2,7 @@
 Run in the build container only (needs /root/reference); the JSON fixtures travel to the GPU box.
   python tests/golden/make_models.py
 Sources (read-only inputs): data/urdf/cartpole.urdf, data/skel/half_cheetah.skel,
-data/sdf/atlas/atlas_v3_box_colliders.urdf, data/sdf/atlas/ground.urdf."""
+data/sdf/atlas/atlas_v3_box_colliders.urdf, data/sdf/atlas/ground.urdf, data/sdf/atlas/atlas_v3_no_head.sdf."""
 import os
 import sys
 
@@ -30,6 +30,11 @@ def main():
     # config 3: half-cheetah + ground
     w = nb.loadWorld(f"{REF}/skel/half_cheetah.skel")
     nb.flatten_world(w).save(f"{OUT}/half_cheetah.json")
+    # the SDF description of the same robot (28 links, no welded camera links): exercises the SDF loader
+    w = nb.World()
+    w.setGravity([0, -9.81, 0])
+    w.loadSkeleton(f"{REF}/sdf/atlas/atlas_v3_no_head.sdf")
+    nb.flatten_world(w).save(f"{OUT}/atlas_sdf.json")
     print("wrote", sorted(os.listdir(OUT)))
 
 

@@ -290,3 +290,31 @@ def test_fused_rollout_matches_step_by_step_rollout():
     assert rel_err(x0.grad.cpu().numpy(), x0r.grad.cpu().numpy()) < 1e-6
     for t in range(T):
         assert rel_err(u.grad[t].cpu().numpy(), ur[t].grad.cpu().numpy()) < 1e-6
+
+
+@pytest.mark.parametrize("name", ["half_cheetah", "atlas"])
+def test_host_entry_points_with_page_locked_buffers(name):
+    """nb2_step_forward_host / nb2_step_backward_host on page-locked buffers: the kernels read and write the host memory
+    directly (zero-copy, include/nb2.h).  Results must equal the device entry points bit for bit; B is not a multiple of
+    the group size so the partial last group and the unaligned (scalar) tail of the vector copies are exercised."""
+    raw, world = _world(name)
+    dm = nb.device_model_for(world)
+    B = 1003
+    s, a, g = sample_inputs(raw, B, seed=61)
+    pin = lambda x: torch.from_numpy(np.ascontiguousarray(x)).pin_memory()
+    hs, ha, hg = pin(s), pin(a), pin(g)
+    o_n, o_gs, o_ga = torch.empty_like(hs).pin_memory(), torch.empty_like(hs).pin_memory(), torch.empty_like(ha).pin_memory()
+    dm.forward_host(hs.numpy(), ha.numpy(), True, 0, out=o_n.numpy())
+    dm.backward_host(hg.numpy(), 0, out_state=o_gs.numpy(), out_action=o_ga.numpy())
+    sd, ad, gd = hs.cuda(), ha.cuda(), hg.cuda()
+    nxt, gs, ga = torch.empty_like(sd), torch.empty_like(sd), torch.empty_like(ad)
+    saved = torch.empty((dm.saved_words, B), device="cuda")
+    stream = torch.cuda.current_stream().cuda_stream
+    dm.forward_device(B, sd.data_ptr(), ad.data_ptr(), nxt.data_ptr(), saved.data_ptr(), stream, 0)
+    dm.backward_device(B, sd.data_ptr(), ad.data_ptr(), saved.data_ptr(), gd.data_ptr(), gs.data_ptr(), ga.data_ptr(), stream, 0)
+    torch.cuda.synchronize()
+    assert torch.equal(o_n, nxt.cpu()) and torch.equal(o_gs, gs.cpu()) and torch.equal(o_ga, ga.cpu())
+    # pageable buffers take the staged-copy path: same numbers
+    n2 = dm.forward_host(s, a, True, 0)
+    g2s, g2a = dm.backward_host(g, 0)
+    assert np.array_equal(n2, o_n.numpy()) and np.array_equal(g2s, o_gs.numpy()) and np.array_equal(g2a, o_ga.numpy())

@@ -123,3 +123,19 @@ def test_mass_gradient_matches_finite_differences_of_the_oracle(oracle_mod):
 
             fd = np.array([(loss_at(j, 1e-5) - loss_at(j, -1e-5)) / 2e-5 for j in range(P.shape[0])])
             assert rel_err(gm, fd) < 2e-5, (gm, fd)
+
+
+def test_sdf_loaded_atlas_parity(oracle_mod):
+    """Atlas from its SDF description (loader.load_sdf_skeleton, creation order of SdfParser.cpp:843-880): kernels vs oracle."""
+    raw = load_raw("atlas_sdf")
+    assert raw.nb == 28 and raw.ndof == 33
+    assert raw.body_names[:5] == ["pelvis", "ltorso", "mtorso", "utorso", "l_clav"]  # alphabetical, missing parents first
+    cm = nb.compile_model(raw, lanes=4)
+    ow, ew = oracle_mod.OracleWorld(raw), EmulWorld(cm)
+    s, a, g = sample_inputs(raw, 4, seed=23)
+    nxt, saved = ew.forward(s, a)
+    gs, ga = ew.backward(s, a, saved, g)
+    for w in range(4):
+        s64, a64, g64 = s[w].astype(np.float64), a[w].astype(np.float64), g[w].astype(np.float64)
+        rgs, rga = ow.backprop(s64, a64, g64)
+        assert rel_err(nxt[w], ow.step(s64, a64)) < TOL and rel_err(gs[w], rgs) < TOL and rel_err(ga[w], rga) < TOL

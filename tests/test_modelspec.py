@@ -28,7 +28,7 @@ def test_raw_json_roundtrip():
                 assert np.array_equal(v, v2), (name, k)
 
 
-@pytest.mark.parametrize("name", ["cartpole", "half_cheetah", "atlas", "atlas_ground"])
+@pytest.mark.parametrize("name", ["cartpole", "half_cheetah", "atlas", "atlas_ground", "atlas_sdf"])
 def test_canonical_model_invariants(name):
     raw = load_raw(name)
     cm = nb.compile_model(raw)

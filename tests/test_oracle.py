@@ -220,10 +220,13 @@ def test_free_rigid_body_newton_euler(oracle_mod):
     assert np.allclose(qdd[:3], wdot, atol=1e-10) and np.allclose(qdd[3:], vdot, atol=1e-10)
 
 
-def test_atlas_centre_of_mass_accelerates_with_gravity(oracle_mod):
+@pytest.mark.parametrize("name", ["atlas", "atlas_sdf"])
+def test_atlas_centre_of_mass_accelerates_with_gravity(oracle_mod, name):
+    """URDF- and SDF-loaded Atlas: whatever the internal torques, the centre of mass of a floating robot accelerates with g —
+    a check of the loaders' frames (joint poses, axes, inertial offsets) together with the dynamics."""
     from scipy.spatial.transform import Rotation
 
-    raw = load_raw("atlas")
+    raw = load_raw(name)
     ow = oracle_mod.OracleWorld(raw)
     s, a, _ = sample_inputs(raw, 1, seed=11)
     s, a = s[0].astype(np.float64), a[0].astype(np.float64)
