@@ -1,6 +1,6 @@
 #!/bin/bash
 # A/B of prebuilt libnb2 variants (dev only): copies each over the in-tree library and runs the bench
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 cp nimblephysics_b200/csrc/libnb2.so /tmp/libnb2_orig.so
 for v in build_variants/*.so; do
   cp $v nimblephysics_b200/csrc/libnb2.so

@@ -1,5 +1,5 @@
 import sys, time, numpy as np, torch
-sys.path.insert(0, ".")
+sys.path.insert(0, ".")  # run from the repo root
 import nimblephysics_b200 as nb
 from bench import make_inputs, ATLAS
 raw = nb.RawModel.load(ATLAS)

@@ -1,5 +1,5 @@
 import sys, numpy as np, torch
-sys.path.insert(0, ".")
+sys.path.insert(0, ".")  # run from the repo root
 import nimblephysics_b200 as nb
 from tests.util import load_raw, sample_inputs
 name = sys.argv[1] if len(sys.argv) > 1 else "half_cheetah"
