@@ -238,14 +238,14 @@ template <class R> NB2_HD SI<R> spd6_inverse(const SI<R>& I) {
   for (int i = 0; i < 3; i++)
 #pragma unroll
     for (int j = 0; j < 3; j++) { a[i][j] = Ap[3 * i + j]; a[i][3 + j] = Bp[3 * i + j]; a[3 + j][i] = Bp[3 * i + j]; a[3 + i][3 + j] = Cp[3 * i + j]; }
-  R L[6][6];
+  R L[6][6], invd[6];  // invd[j] = 1 / L[j][j]: every later division by a diagonal entry becomes a multiplication
 #pragma unroll
   for (int j = 0; j < 6; j++) {
     R d = a[j][j];
 #pragma unroll
     for (int k = 0; k < 6; k++) if (k < j) d -= L[j][k] * L[j][k];
     R ljj = nb2_sqrt(d), inv = R(1) / ljj;
-    L[j][j] = ljj;
+    L[j][j] = ljj; invd[j] = inv;
 #pragma unroll
     for (int i = 0; i < 6; i++) if (i > j) {
       R s = a[i][j];
@@ -258,13 +258,13 @@ template <class R> NB2_HD SI<R> spd6_inverse(const SI<R>& I) {
   R Li[6][6];
 #pragma unroll
   for (int j = 0; j < 6; j++) {
-    Li[j][j] = R(1) / L[j][j];
+    Li[j][j] = invd[j];
 #pragma unroll
     for (int i = 0; i < 6; i++) if (i > j) {
       R s = R(0);
 #pragma unroll
       for (int k = 0; k < 6; k++) if (k >= j && k < i) s -= L[i][k] * Li[k][j];
-      Li[i][j] = s / L[i][i];
+      Li[i][j] = s * invd[i];
     }
   }
   // inv = Li^T Li
