@@ -567,8 +567,9 @@ int nb2_step_backward_contact(const nb2_model* cm, int B, const float* state, co
   if (smem > (size_t)kMaxSmem) { g_err = "model needs " + std::to_string(smem) + " B of shared memory per warp (> 227 KB)"; return NB2_ERR_UNSUPPORTED; }
 #define NB2_LAUNCH_BWDC(W_)                                                                                                       \
   do {                                                                                                                            \
-    static bool attr_done = false;                                                                                                \
-    if (!attr_done) { NB2_CUDA(cudaFuncSetAttribute(k_step_bwd_contact<W_>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem)); attr_done = true; } \
+    static bool attr_done[64] = {};  /* function attributes are per device */                                                     \
+    int dev_ = 0; NB2_CUDA(cudaGetDevice(&dev_));                                                                                 \
+    if (!attr_done[dev_ & 63]) { NB2_CUDA(cudaFuncSetAttribute(k_step_bwd_contact<W_>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem)); attr_done[dev_ & 63] = true; } \
     k_step_bwd_contact<W_><<<(B + W_ - 1) / W_, 32, smem, (cudaStream_t)stream>>>(m->md, m->contact, B, state, action, (const double*)saved_fp64,        \
                                                                                contact_record, nb2::contact_rec_doubles(m->mf.ndof), (double*)workspace, \
                                                                                nb2::contact_ws_doubles(m->mf.nb, m->mf.ndof), grad_next_state,           \
