@@ -55,6 +55,22 @@ struct Nb2ContactDev {
 
 namespace nb2 {
 
+// The threads that cooperate on one world (the GROUP: `nl` adjacent lanes of a warp, this one is number `cl`).  The serial
+// parts of the contact stage are executed REDUNDANTLY by every thread of the group — in SIMT a warp instruction costs the
+// same whether one or eight lanes are active, and identical inputs keep the group in lock step — so that the dense inner
+// products can be split across the lanes and summed with a butterfly of shuffles (every lane receives the same bits,
+// which keeps all data-dependent branches uniform).  Host builds and one-thread-per-world launches use the default (1 lane).
+struct Grp {
+  int cl = 0, nl = 1;
+  unsigned mask = 0;
+  NB2_HD CR sum(CR v) const {
+#ifdef __CUDA_ARCH__
+    for (int off = nl >> 1; off > 0; off >>= 1) v += __shfl_xor_sync(mask, v, off);
+#endif
+    return v;
+  }
+};
+
 #define NB2_CONTACT_LANES 8  // threads that may cooperate on one world in the contact kernel
 template <int ST>
 struct ContactWsT {  // per-world fp64 workspace; lane-interleaved on the device (ST = 32), contiguous on the host (ST = 1)
@@ -68,6 +84,7 @@ struct ContactWsT {  // per-world fp64 workspace; lane-interleaved on the device
   PD v1, v2, v3, v4, v5, v6, v7, v8;
   PI i1, i2;
   PB st8;
+  Grp grp;  // the threads cooperating on this world (set by the kernel; default: one)
   PD lbuf;  // NB2_CONTACT_LANES private sweep buffers (pI, V: 6 nb each; uI, dqd: ndof each) for the parallel impulse tests
   PI meta;  // m, nc, status carried between the phases of world_contact
 };
@@ -179,10 +196,16 @@ NB2_HD void impulse_response(const Nb2ModelDev<CR>& M, const CR* sv, size_t B, c
   }
 }
 
-// sum_{j != skip} row[j] * x[j] with four independent partial sums: the Gauss-Seidel row update is a chain of dependent
-// fp64 FMAs otherwise (the reference sums left to right, PgsBoxedLcpSolver.cpp:126-140; the difference is rounding only)
+// sum_{j != skip} row[j] * x[j].  One thread: four independent partial sums (the Gauss-Seidel row update is a chain of
+// dependent fp64 FMAs otherwise).  A group: lane l takes the columns j = l (mod nl).  The reference sums left to right
+// (PgsBoxedLcpSolver.cpp:126-140); the difference is rounding only.
 template <class PA, class PX>
-NB2_HD CR row_dot_skip(int m, PA row, PX x, int skip) {
+NB2_HD CR row_dot_skip(int m, PA row, PX x, int skip, const Grp& g = Grp()) {
+  if (g.nl > 1) {
+    CR a = 0;
+    for (int j = g.cl; j < m; j += g.nl) a += (j == skip) ? CR(0) : row[j] * x[j];
+    return g.sum(a);
+  }
   CR a0 = 0, a1 = 0, a2 = 0, a3 = 0;
   int j = 0;
   for (; j + 3 < m; j += 4) {
@@ -197,9 +220,9 @@ NB2_HD CR row_dot_skip(int m, PA row, PX x, int skip) {
 
 // ------------------------------------------------------------------ dense helpers (m x m, stride m)
 template <class PA, class PX, class PB_, class PH, class PL, class PF>
-NB2_HD bool lcp_valid(int m, PA A, PX x, PB_ b, PH hi, PL lo, PF fi, bool ignoreFriction) {
+NB2_HD bool lcp_valid(int m, PA A, PX x, PB_ b, PH hi, PL lo, PF fi, bool ignoreFriction, const Grp& g = Grp()) {
   for (int i = 0; i < m; i++) {
-    const CR v = row_dot_skip(m, A + i * m, x, -1) - b[i];
+    const CR v = row_dot_skip(m, A + i * m, x, -1, g) - b[i];
     CR up = hi[i], low = lo[i];
     if (fi[i] != -1) { if (ignoreFriction) { if (x[i] != 0) return false; continue; } up *= x[fi[i]]; low *= x[fi[i]]; }
     const CR tol = 1e-5;
@@ -295,7 +318,7 @@ NB2_HD bool classify_once(int m, PD A, PD x, PD b, PD lo, PD hi, SP<int, ST> fi,
   // ---- opportunisticallyStandardizeResults
   if (nCl == 0) {
     for (int i = 0; i < m; i++) ws.v1[i] = 0;
-    if (lcp_valid(m, A, ws.v1, b, hi, lo, fi, ignoreFriction)) { for (int i = 0; i < m; i++) x[i] = 0; return true; }
+    if (lcp_valid(m, A, ws.v1, b, hi, lo, fi, ignoreFriction, ws.grp)) { for (int i = 0; i < m; i++) x[i] = 0; return true; }
     return false;
   }
   auto cl = ws.i1; auto ub = ws.i2;
@@ -342,7 +365,7 @@ NB2_HD bool classify_once(int m, PD A, PD x, PD b, PD lo, PD hi, SP<int, ST> fi,
       nx[i] = fc[clampIdx[fp]] * clean;
     }
   }
-  if (lcp_valid(m, A, nx, b, hi, lo, fi, ignoreFriction)) {
+  if (lcp_valid(m, A, nx, b, hi, lo, fi, ignoreFriction, ws.grp)) {
     for (int i = 0; i < m; i++) x[i] = nx[i];
     *again = anyNewlyNotClamping;  // a previously clamping normal row dropped to ~0: re-classify (:283-331)
     return true;
@@ -362,14 +385,14 @@ NB2_HD bool classify_and_standardize(int m, PD A, PD x, PD b, PD lo, PD hi, SP<i
 
 // PgsBoxedLcpSolver::solve with Option(30, 1e-6, 1e-3, 1e-9, false); A (m x m) and b are clobbered
 template <class PA, class PX, class PB_, class PL, class PH, class PF, class PS>
-NB2_HD bool pgs_solve(int m, PA A, PX x, PB_ b, PL lo, PH hi, PF fi, PS skip) {
+NB2_HD bool pgs_solve(int m, PA A, PX x, PB_ b, PL lo, PH hi, PF fi, PS skip, const Grp& g = Grp()) {
   const CR dxTol = 1e-6, relTol = 1e-3, epsDiv = 1e-9;
   bool term = true;
   for (int i = 0; i < m; i++) {
     skip[i] = 0;
     if (A[i * m + i] < epsDiv) { x[i] = 0.0; skip[i] = 1; continue; }
     const CR old_x = x[i];
-    CR nx = b[i] - row_dot_skip(m, A + i * m, x, i);
+    CR nx = b[i] - row_dot_skip(m, A + i * m, x, i, g);
     nx /= A[i * m + i];
     CR hi_t = hi[i], lo_t = lo[i];
     if (fi[i] >= 0) { hi_t = hi[i] * x[fi[i]]; lo_t = -hi_t; }
@@ -383,7 +406,7 @@ NB2_HD bool pgs_solve(int m, PA A, PX x, PB_ b, PL lo, PH hi, PF fi, PS skip) {
     for (int i = 0; i < m; i++) {
       if (skip[i]) continue;
       const CR old_x = x[i];
-      const CR nx = b[i] - row_dot_skip(m, A + i * m, x, i);
+      const CR nx = b[i] - row_dot_skip(m, A + i * m, x, i, g);
       CR hi_t = hi[i], lo_t = lo[i];
       if (fi[i] >= 0) { hi_t = hi[i] * x[fi[i]]; lo_t = -hi_t; }
       x[i] = nx > hi_t ? hi_t : (nx < lo_t ? lo_t : nx);
@@ -473,7 +496,7 @@ NB2_HD int lcp_chain_ws(int m, const ContactWsT<ST>& ws, CR fallback_cfm, const 
     success = (rc == 1);
     if (success) {
       for (int i = 0; i < m; i++) { CR v = 0; for (int c = 0; c < mr; c++) v += ws.Q2[i * mr + c] * ws.v4[c]; x[i] = v; }  // x = mapOut * x_reduced
-      if (!lcp_valid(m, A, x, b, hi, lo, fi, false)) success = false;
+      if (!lcp_valid(m, A, x, b, hi, lo, fi, false, ws.grp)) success = false;
     }
     if (!success) status |= NB2_ST_DANTZIG_FAILED;
   }
@@ -485,10 +508,10 @@ NB2_HD int lcp_chain_ws(int m, const ContactWsT<ST>& ws, CR fallback_cfm, const 
     for (int i = 0; i < m; i++) { ws.v1[i] = b[i]; ws.v2[i] = lo[i]; ws.v3[i] = hi[i]; ws.i1[i] = fi[i]; ws.v4[i] = x0[i]; }
     const int mr = lcp_reduce(m, ws.Aw, ws.v4, ws.v1, ws.v2, ws.v3, ws.i1, ws.Q2);  // :551-557 the backup problem is reduced too
     if (mr < m) status |= NB2_ST_MERGED;
-    success = pgs_solve(mr, ws.Aw, ws.v4, ws.v1, ws.v2, ws.v3, ws.i1, ws.st8);
+    success = pgs_solve(mr, ws.Aw, ws.v4, ws.v1, ws.v2, ws.v3, ws.i1, ws.st8, ws.grp);
     if (success) {
       for (int i = 0; i < m; i++) { CR v = 0; for (int c = 0; c < mr; c++) v += ws.Q2[i * mr + c] * ws.v4[c]; x[i] = v; }
-      if (!lcp_valid(m, A, x, b, hi, lo, fi, false)) success = false;
+      if (!lcp_valid(m, A, x, b, hi, lo, fi, false, ws.grp)) success = false;
     }
   }
   if (!success) {
@@ -497,7 +520,7 @@ NB2_HD int lcp_chain_ws(int m, const ContactWsT<ST>& ws, CR fallback_cfm, const 
     int k = 0;
     for (int i = 0; i < m; i++) if (fi[i] == -1) ws.i1[k++] = i;
     for (int r = 0; r < k; r++) { ws.v1[r] = b[ws.i1[r]]; ws.v2[r] = lo[ws.i1[r]]; ws.v3[r] = hi[ws.i1[r]]; ws.v4[r] = 0; ws.i2[r] = -1; for (int c = 0; c < k; c++) ws.Aw[r * k + c] = A[ws.i1[r] * m + ws.i1[c]]; }
-    pgs_solve(k, ws.Aw, ws.v4, ws.v1, ws.v2, ws.v3, ws.i2, ws.st8);
+    pgs_solve(k, ws.Aw, ws.v4, ws.v1, ws.v2, ws.v3, ws.i2, ws.st8, ws.grp);
     for (int i = 0; i < m; i++) x[i] = 0;
     for (int r = 0; r < k; r++) x[ws.i1[r]] = ws.v4[r];
   }
@@ -685,9 +708,10 @@ NB2_HD void contact_phase1(const Nb2ModelDev<CR>& M, const CR* sv, size_t B, CR*
 // phase 2 — mirror A, warm start, solve chain, classification, impulse application (one thread)
 template <int ST>
 NB2_HD void contact_phase2(const Nb2ModelDev<CR>& M, const Nb2ContactDev& C, const float* st, float* out, const CR* sv, size_t B,
-                           CR* wsblock, int lane, CR* x_io, int* m_io, int* labels_out, int* status_out, CR* crec) {
+                           CR* wsblock, int lane, CR* x_io, int* m_io, int* labels_out, int* status_out, CR* crec, const Grp& grp = Grp()) {
   const int nb = M.nb, n = M.ndof;
-  const ContactWsT<ST> ws = carve_ws<ST>(wsblock, lane, nb, n);
+  ContactWsT<ST> ws = carve_ws<ST>(wsblock, lane, nb, n);
+  ws.grp = grp;
   const int m = ws.meta[0];
   int status = ws.meta[2];
   if (m == 0) return;

@@ -159,7 +159,9 @@ k_contact_fwd(const __grid_constant__ Nb2ModelDev<double> M, const __grid_consta
   double* wsb = workspace + (size_t)(t >> 5) * ws_doubles * WPW;
   const float* st = state + (size_t)wc * 2 * M.ndof;
   float* out = next + (size_t)wc * 2 * M.ndof;
-  if (valid && cl == 0)
+  // phases 0 and 2 are executed redundantly by all KC threads of the world (see nb2::Grp): same instructions, same data,
+  // identical writes — and the inner products of the solver chain are shared among them
+  if (valid)
     nb2::contact_phase0<WPW>(M, C, st, out, saved + wc, (size_t)B, wsb, slot, x_lcp + (size_t)wc * NB2_MAX_ROWS, m_lcp + wc,
                              labels + (size_t)wc * NB2_MAX_ROWS, status + wc, ncontacts + wc,
                              cinfo ? cinfo + (size_t)wc * NB2_MAX_CONTACTS * 10 : nullptr, crec ? crec + (size_t)wc * rec_doubles : nullptr);
@@ -167,9 +169,13 @@ k_contact_fwd(const __grid_constant__ Nb2ModelDev<double> M, const __grid_consta
   constexpr int NL = KC < NB2_CONTACT_LANES ? KC : NB2_CONTACT_LANES;  // threads sharing the impulse tests
   if (valid && cl < NL) nb2::contact_phase1<WPW>(M, saved + wc, (size_t)B, wsb, slot, cl, NL);
   __syncwarp();
-  if (valid && cl == 0)
+  if (valid) {
+    nb2::Grp grp;
+    grp.cl = cl; grp.nl = KC;
+    grp.mask = (KC >= 32) ? 0xFFFFFFFFu : (((1u << KC) - 1u) << (slot * KC));
     nb2::contact_phase2<WPW>(M, C, st, out, saved + wc, (size_t)B, wsb, slot, x_lcp + (size_t)wc * NB2_MAX_ROWS, m_lcp + wc,
-                             labels + (size_t)wc * NB2_MAX_ROWS, status + wc, crec ? crec + (size_t)wc * rec_doubles : nullptr);
+                             labels + (size_t)wc * NB2_MAX_ROWS, status + wc, crec ? crec + (size_t)wc * rec_doubles : nullptr, grp);
+  }
 }
 
 // backward of a step with the contact stage (fp64): world_backward<double, WPW, CONTACT=true>, one thread per world.
