@@ -235,21 +235,37 @@ NB2_HD bool lcp_valid(int m, PA A, PX x, PB_ b, PH hi, PL lo, PF fi, bool ignore
   return true;
 }
 
+// dst[i] = src[i], i < n.  The GPU issues in order: a copy loop "load, store, load, store" keeps ONE load in flight (each store
+// waits for its load), so the loads of a batch are issued before its stores.  dst and src must not overlap.
+template <class PDst, class PSrc>
+NB2_HD void copy_n(PDst dst, PSrc src, int n) {
+  int i = 0;
+  for (; i + 7 < n; i += 8) {
+    CR t[8];
+#pragma unroll
+    for (int u = 0; u < 8; u++) t[u] = src[i + u];
+#pragma unroll
+    for (int u = 0; u < 8; u++) dst[i + u] = t[u];
+  }
+  for (; i < n; i++) dst[i] = src[i];
+}
+
 // minimum-norm least squares x = Q^+ rhs for an n x n matrix.  symmetric PSD Q: rank-revealing pivoted Cholesky
 // Q = P L L^T P^T (L: n x r) and Q^+ = L (L^T L)^-2 L^T ; general Q: x = (Q^T Q)^+ Q^T rhs through the same routine.
 // work: G (n*n, destroyed copy), Lf (n*n), t1..t3 (n), perm (n)
 template <class PQ, class PR, class PX, class PG, class PL, class PT1, class PT2, class PP>
 NB2_HD void pinv_psd(int n, PQ Qin, PR rhs, PX x, PG G, PL Lf, PT1 t1, PT2 t2, PP perm) {
-  for (int i = 0; i < n * n; i++) G[i] = Qin[i];
+  copy_n(G, Qin, n * n);
   for (int i = 0; i < n; i++) perm[i] = i;
   CR dmax0 = 0;
-  for (int i = 0; i < n; i++) dmax0 = G[i * n + i] > dmax0 ? G[i * n + i] : dmax0;
+  auto dg = t2;  // running diagonal of the Schur complement: dg[i] = G[i][i] - sum_{j<k} Lf[i][j]^2 (same subtraction order as a fresh sum)
+  for (int i = 0; i < n; i++) { const CR d = G[i * n + i]; dg[i] = d; dmax0 = d > dmax0 ? d : dmax0; }
   const CR tol = dmax0 * 1e-12;
   int r = 0;
-  // pivoted Cholesky with lazily updated diagonal; Lf[row * n + k]
+  // pivoted Cholesky; Lf[row * n + k]
   for (int k = 0; k < n; k++) {
     int piv = -1; CR best = tol;
-    for (int i = k; i < n; i++) { const int pi = perm[i]; CR d = G[pi * n + pi]; for (int j = 0; j < k; j++) d -= Lf[pi * n + j] * Lf[pi * n + j]; if (d > best) { best = d; piv = i; } }
+    for (int i = k; i < n; i++) { const CR d = dg[perm[i]]; if (d > best) { best = d; piv = i; } }
     if (piv < 0) break;
     { const int t = perm[k]; perm[k] = perm[piv]; perm[piv] = t; }
     const int pk = perm[k];
@@ -258,8 +274,11 @@ NB2_HD void pinv_psd(int n, PQ Qin, PR rhs, PX x, PG G, PL Lf, PT1 t1, PT2 t2, P
     for (int i = k + 1; i < n; i++) {
       const int pi = perm[i];
       CR s = G[pi * n + pk];
+#pragma unroll 4
       for (int j = 0; j < k; j++) s -= Lf[pi * n + j] * Lf[pk * n + j];
-      Lf[pi * n + k] = s / lkk;
+      const CR l = s / lkk;
+      Lf[pi * n + k] = l;
+      dg[pi] -= l * l;
     }
     r++;
   }
@@ -270,22 +289,49 @@ NB2_HD void pinv_psd(int n, PQ Qin, PR rhs, PX x, PG G, PL Lf, PT1 t1, PT2 t2, P
   // M = L^T L (r x r) in G ; y = L^T rhs
   for (int a = 0; a < r; a++) {
     CR ya = 0;
+#pragma unroll 4
     for (int i = 0; i < n; i++) ya += Lf[i * n + a] * rhs[i];
     t1[a] = ya;
-    for (int c = a; c < r; c++) { CR s = 0; for (int i = 0; i < n; i++) s += Lf[i * n + a] * Lf[i * n + c]; G[a * n + c] = s; G[c * n + a] = s; }
+    for (int c = a; c < r; c++) {
+      CR s = 0;
+#pragma unroll 4
+      for (int i = 0; i < n; i++) s += Lf[i * n + a] * Lf[i * n + c];
+      G[a * n + c] = s; G[c * n + a] = s;
+    }
   }
   // z = M^-2 y  via Cholesky of M (SPD r x r), two solves
   for (int j = 0; j < r; j++) {
     CR d = G[j * n + j];
+#pragma unroll 4
     for (int k = 0; k < j; k++) d -= G[j * n + k] * G[j * n + k];
     d = nb2_sqrt(d); G[j * n + j] = d;
-    for (int i = j + 1; i < r; i++) { CR s = G[i * n + j]; for (int k = 0; k < j; k++) s -= G[i * n + k] * G[j * n + k]; G[i * n + j] = s / d; }
+    for (int i = j + 1; i < r; i++) {
+      CR s = G[i * n + j];
+#pragma unroll 4
+      for (int k = 0; k < j; k++) s -= G[i * n + k] * G[j * n + k];
+      G[i * n + j] = s / d;
+    }
   }
   for (int rep = 0; rep < 2; rep++) {
-    for (int i = 0; i < r; i++) { CR s = t1[i]; for (int k = 0; k < i; k++) s -= G[i * n + k] * t2[k]; t2[i] = s / G[i * n + i]; }
-    for (int i = r - 1; i >= 0; i--) { CR s = t2[i]; for (int k = i + 1; k < r; k++) s -= G[k * n + i] * t1[k]; t1[i] = s / G[i * n + i]; }
+    for (int i = 0; i < r; i++) {
+      CR s = t1[i];
+#pragma unroll 4
+      for (int k = 0; k < i; k++) s -= G[i * n + k] * t2[k];
+      t2[i] = s / G[i * n + i];
+    }
+    for (int i = r - 1; i >= 0; i--) {
+      CR s = t2[i];
+#pragma unroll 4
+      for (int k = i + 1; k < r; k++) s -= G[k * n + i] * t1[k];
+      t1[i] = s / G[i * n + i];
+    }
   }
-  for (int i = 0; i < n; i++) { CR s = 0; for (int a = 0; a < r; a++) s += Lf[i * n + a] * t1[a]; x[i] = s; }
+  for (int i = 0; i < n; i++) {
+    CR s = 0;
+#pragma unroll 4
+    for (int a = 0; a < r; a++) s += Lf[i * n + a] * t1[a];
+    x[i] = s;
+  }
 }
 
 // classification (constructMatrices) + standardisation; x is updated in place when the standardised solution is valid.
@@ -327,7 +373,14 @@ NB2_HD bool classify_once(int m, PD A, PD x, PD b, PD lo, PD hi, SP<int, ST> fi,
   auto Q = ws.Q; auto bc = ws.v2; auto orig = ws.v3; auto fc = ws.v4;
   for (int r = 0; r < nCl; r++) {
     bc[r] = b[cl[r]]; orig[r] = x[cl[r]];
-    for (int c = 0; c < nCl; c++) Q[r * nCl + c] = A[cl[r] * m + cl[c]];
+    const int rowr = cl[r] * m;
+    for (int c0 = 0; c0 < nCl; c0 += 4) {  // batched gathers (see copy_n)
+      CR t[4];
+#pragma unroll
+      for (int u = 0; u < 4; u++) if (c0 + u < nCl) t[u] = A[rowr + cl[c0 + u]];
+#pragma unroll
+      for (int u = 0; u < 4; u++) if (c0 + u < nCl) Q[r * nCl + c0 + u] = t[u];
+    }
   }
   for (int u = 0; u < nUb; u++) {
     const int j = ub[u], fp = mapping[j];
@@ -383,9 +436,90 @@ NB2_HD bool classify_and_standardize(int m, PD A, PD x, PD b, PD lo, PD hi, SP<i
   return ok;
 }
 
+#ifdef __CUDA_ARCH__
+// pgs_solve for a group of 8 threads: lane l keeps x[l], x[l + 8], ... in registers and owns the same columns of A, so a
+// row update is <= 6 loads + FMAs per lane, one butterfly sum, and two broadcasts (old x_i, x of the friction row's normal);
+// nothing on the dependent chain goes through memory.  Same sweeps, tolerances and clamping as the one-thread version below.
+template <class PA, class PX, class PB_, class PL, class PH, class PF, class PS>
+__device__ bool pgs_solve_group8(int m, PA A, PX x, PB_ b, PL lo, PH hi, PF fi, PS skip, const Grp& g) {
+  constexpr int KX = NB2_MAX_ROWS / 8;
+  const CR dxTol = 1e-6, relTol = 1e-3, epsDiv = 1e-9;
+  const int base = __ffs(g.mask) - 1;
+  CR xr[KX];
+#pragma unroll
+  for (int k = 0; k < KX; k++) { const int j = g.cl + 8 * k; xr[k] = (j < m) ? x[j] : 0.0; }
+  auto xget = [&](int j) {
+    const int kk = j >> 3;
+    CR v = 0;
+#pragma unroll
+    for (int k = 0; k < KX; k++) if (k == kk) v = xr[k];
+    return __shfl_sync(g.mask, v, base + (j & 7));
+  };
+  auto xset = [&](int j, CR v) {
+    if ((j & 7) != g.cl) return;
+    const int kk = j >> 3;
+#pragma unroll
+    for (int k = 0; k < KX; k++) if (k == kk) xr[k] = v;
+  };
+  auto rowdot = [&](int i) {
+    CR a = 0;
+#pragma unroll
+    for (int k = 0; k < KX; k++) { const int j = g.cl + 8 * k; if (j < m && j != i) a += A[i * m + j] * xr[k]; }
+    return g.sum(a);
+  };
+  auto finish = [&](bool result) {
+#pragma unroll
+    for (int k = 0; k < KX; k++) { const int j = g.cl + 8 * k; if (j < m) x[j] = xr[k]; }
+    __syncwarp(g.mask);  // every lane wrote its own columns of x: make them visible to the whole group
+    return result;
+  };
+  bool term = true;
+  for (int i = 0; i < m; i++) {
+    const CR aii = A[i * m + i];
+    if (aii < epsDiv) { xset(i, 0.0); skip[i] = 1; continue; }
+    skip[i] = 0;
+    const CR old_x = xget(i);
+    const CR nx = (b[i] - rowdot(i)) / aii;
+    CR hi_t = hi[i], lo_t = lo[i];
+    const int f = fi[i];
+    if (f >= 0) { hi_t = hi[i] * xget(f); lo_t = -hi_t; }
+    const CR xi = nx > hi_t ? hi_t : (nx < lo_t ? lo_t : nx);
+    xset(i, xi);
+    if (term && nb2_abs(xi - old_x) > dxTol) term = false;
+  }
+  if (term) return finish(true);
+  for (int i = 0; i < m; i++) if (!skip[i]) {
+    const CR dm = 1.0 / A[i * m + i];
+    const CR bi = b[i] * dm;
+    __syncwarp(g.mask);            // every lane has read A[i][i] and b[i] before anyone rescales them
+    b[i] = bi;                      // (same value from every lane)
+    for (int j = g.cl; j < m; j += 8) A[i * m + j] *= dm;  // each lane rescales the columns it owns
+  }
+  for (int iter = 1; iter < 30; iter++) {
+    term = true;
+    for (int i = 0; i < m; i++) {
+      if (skip[i]) continue;
+      const CR old_x = xget(i);
+      const CR nx = b[i] - rowdot(i);
+      CR hi_t = hi[i], lo_t = lo[i];
+      const int f = fi[i];
+      if (f >= 0) { hi_t = hi[i] * xget(f); lo_t = -hi_t; }
+      const CR xi = nx > hi_t ? hi_t : (nx < lo_t ? lo_t : nx);
+      xset(i, xi);
+      if (term && nb2_abs(xi) > epsDiv) { if (nb2_abs((xi - old_x) / xi) > relTol) term = false; }
+    }
+    if (term) break;
+  }
+  return finish(term);
+}
+#endif
+
 // PgsBoxedLcpSolver::solve with Option(30, 1e-6, 1e-3, 1e-9, false); A (m x m) and b are clobbered
 template <class PA, class PX, class PB_, class PL, class PH, class PF, class PS>
 NB2_HD bool pgs_solve(int m, PA A, PX x, PB_ b, PL lo, PH hi, PF fi, PS skip, const Grp& g = Grp()) {
+#ifdef __CUDA_ARCH__
+  if (g.nl == 8) return pgs_solve_group8(m, A, x, b, lo, hi, fi, skip, g);
+#endif
   const CR dxTol = 1e-6, relTol = 1e-3, epsDiv = 1e-9;
   bool term = true;
   for (int i = 0; i < m; i++) {
@@ -485,7 +619,7 @@ NB2_HD int lcp_chain_ws(int m, const ContactWsT<ST>& ws, CR fallback_cfm, const 
   if (success) status |= NB2_ST_SHORTCIRCUIT;
   else {
     status |= NB2_ST_DANTZIG;
-    for (int i = 0; i < m * m; i++) ws.Aw[i] = A[i];
+    copy_n(ws.Aw, A, m * m);
     for (int i = 0; i < m; i++) { ws.v1[i] = b[i]; ws.v2[i] = lo[i]; ws.v3[i] = hi[i]; ws.i1[i] = fi[i]; ws.v4[i] = x[i]; }
     const int mr = lcp_reduce(m, ws.Aw, ws.v4, ws.v1, ws.v2, ws.v3, ws.i1, ws.Q2);  // :596 reduce before the Dantzig solve
     if (mr < m) status |= NB2_ST_MERGED;
@@ -504,7 +638,7 @@ NB2_HD int lcp_chain_ws(int m, const ContactWsT<ST>& ws, CR fallback_cfm, const 
   if (!success) {
     for (int i = 0; i < m; i++) A[i * m + i] += fallback_cfm;  // :539-547 (both backups get the cfm; colnorms were taken before)
     status |= NB2_ST_PGS;
-    for (int i = 0; i < m * m; i++) ws.Aw[i] = A[i];
+    copy_n(ws.Aw, A, m * m);
     for (int i = 0; i < m; i++) { ws.v1[i] = b[i]; ws.v2[i] = lo[i]; ws.v3[i] = hi[i]; ws.i1[i] = fi[i]; ws.v4[i] = x0[i]; }
     const int mr = lcp_reduce(m, ws.Aw, ws.v4, ws.v1, ws.v2, ws.v3, ws.i1, ws.Q2);  // :551-557 the backup problem is reduced too
     if (mr < m) status |= NB2_ST_MERGED;
@@ -737,7 +871,7 @@ NB2_HD void contact_phase2(const Nb2ModelDev<CR>& M, const Nb2ContactDev& C, con
     CR* cd = crec + 2 + 2 * NB2_MAX_ROWS;
     for (int d = 0; d < n; d++) cd[d] = ws.dqd[d];
     CR* cA = cd + n;
-    for (int i = 0; i < m * m; i++) cA[i] = A[i];
+    copy_n(cA, A, m * m);
   }
 }
 
@@ -947,7 +1081,16 @@ NB2_HD BwdContactView<ST> contact_backward_prepare(const Nb2ModelDev<CR>& M, con
   for (int r = 0; r < nCl; r++) mu_c[r] = 0;
   if (nCl > 0) {
     auto Q = ws.Q;
-    for (int r = 0; r < nCl; r++) for (int c = 0; c < nCl; c++) Q[r * nCl + c] = Arec[cl[r] * m + cl[c]];
+    for (int r = 0; r < nCl; r++) {
+      const int rowr = cl[r] * m;
+      for (int c0 = 0; c0 < nCl; c0 += 4) {  // batched: the gathers of four entries are issued before their stores
+        CR t[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) if (c0 + u < nCl) t[u] = Arec[rowr + cl[c0 + u]];
+#pragma unroll
+        for (int u = 0; u < 4; u++) if (c0 + u < nCl) Q[r * nCl + c0 + u] = t[u];
+      }
+    }
     for (int u = 0; u < nUb; u++) { const int j = ubl[u], c = clampIdx[(int)mapping[j]]; for (int r = 0; r < nCl; r++) Q[r * nCl + c] += Arec[cl[r] * m + j] * Eu[u]; }
     if (nUb == 0) pinv_psd(nCl, Q, fbar, mu_c, ws.Aw, ws.L, ws.v5, ws.v6, ws.mapping);
     else {  // Q^T mu = fbar  ->  mu = (Q Q^T)^+ Q fbar
@@ -957,7 +1100,12 @@ NB2_HD BwdContactView<ST> contact_backward_prepare(const Nb2ModelDev<CR>& M, con
       for (int a = 0; a < nCl; a++) {
         CR sacc = 0; for (int c = 0; c < nCl; c++) sacc += Q[a * nCl + c] * fbar[c];
         Qf[a] = sacc;
-        for (int c = 0; c < nCl; c++) { CR t = 0; for (int kx = 0; kx < nCl; kx++) t += Q[a * nCl + kx] * Q[c * nCl + kx]; QQt[a * nCl + c] = t; }
+        for (int c = 0; c < nCl; c++) {
+          CR t = 0;
+#pragma unroll 4
+          for (int kx = 0; kx < nCl; kx++) t += Q[a * nCl + kx] * Q[c * nCl + kx];
+          QQt[a * nCl + c] = t;
+        }
       }
       pinv_psd(nCl, QQt, Qf, mu_c, ws.Aw, ws.L, ws.v5, ws.v6, ws.mapping);
     }

@@ -61,8 +61,22 @@ typedef DantzigWorkT<double*, int*, unsigned char*> DantzigWork;
 
 template <class DW> NB2_HD void dz_swap_problem(const DW& W, int n, int i1, int i2) {
   if (i1 == i2) return;
-  for (int k = 0; k < n; k++) { double t = W.A[i1 * n + k]; W.A[i1 * n + k] = W.A[i2 * n + k]; W.A[i2 * n + k] = t; }
-  for (int k = 0; k < n; k++) { double t = W.A[k * n + i1]; W.A[k * n + i1] = W.A[k * n + i2]; W.A[k * n + i2] = t; }
+  // rows then columns; four elements per batch with all loads issued before the stores (in-order issue: "load, store,
+  // load, store" would keep a single load in flight)
+  for (int k0 = 0; k0 < n; k0 += 4) {
+    double ta[4], tb[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) if (k0 + u < n) { ta[u] = W.A[i1 * n + k0 + u]; tb[u] = W.A[i2 * n + k0 + u]; }
+#pragma unroll
+    for (int u = 0; u < 4; u++) if (k0 + u < n) { W.A[i1 * n + k0 + u] = tb[u]; W.A[i2 * n + k0 + u] = ta[u]; }
+  }
+  for (int k0 = 0; k0 < n; k0 += 4) {
+    double ta[4], tb[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) if (k0 + u < n) { ta[u] = W.A[(k0 + u) * n + i1]; tb[u] = W.A[(k0 + u) * n + i2]; }
+#pragma unroll
+    for (int u = 0; u < 4; u++) if (k0 + u < n) { W.A[(k0 + u) * n + i1] = tb[u]; W.A[(k0 + u) * n + i2] = ta[u]; }
+  }
 #define NB2_SW(arr, T) { T t = W.arr[i1]; W.arr[i1] = W.arr[i2]; W.arr[i2] = t; }
   NB2_SW(x, double) NB2_SW(b, double) NB2_SW(w, double) NB2_SW(lo, double) NB2_SW(hi, double)
   NB2_SW(p, int) NB2_SW(state, unsigned char) NB2_SW(findex, int)
@@ -75,6 +89,7 @@ template <class DW> NB2_HD void dz_factor(const DW& W, int n, int nC) {
     const auto Ai = W.A + (size_t)W.C[i] * n;
     for (int j = 0; j <= i; j++) {
       double s = Ai[W.C[j]];
+#pragma unroll 4
       for (int k = 0; k < j; k++) s -= W.L[i * n + k] * W.L[j * n + k] / W.d[k];
       if (j < i) W.L[i * n + j] = s * W.d[j];
       else W.d[i] = 1.0 / s;
@@ -96,6 +111,7 @@ template <class DW, class PA> NB2_HD void dz_solve1(const DW& W, int n, int nC, 
   const auto Ai = W.A + (size_t)i * n;
   for (int j = 0; j < nC; j++) {
     double s = Ai[W.C[j]];
+#pragma unroll 4
     for (int k = 0; k < j; k++) s -= W.L[j * n + k] * W.Dell[k];
     W.Dell[j] = s;
   }
@@ -104,6 +120,7 @@ template <class DW, class PA> NB2_HD void dz_solve1(const DW& W, int n, int nC, 
   for (int j = 0; j < nC; j++) W.tmp[j] = W.ell[j];
   for (int j = nC - 1; j >= 0; j--) {
     double s = W.tmp[j];
+#pragma unroll 4
     for (int k = j + 1; k < nC; k++) s -= W.L[k * n + j] * W.tmp[k];
     W.tmp[j] = s;
   }
@@ -153,8 +170,10 @@ template <class DW> NB2_HD int dantzig_solve(const DW& W, int n, bool early_term
     {
       const auto Ai = W.A + (size_t)i * n;
       double s = 0.0;
+#pragma unroll 4
       for (int k = 0; k < nC; k++) s += Ai[k] * W.x[k];
       double s2 = 0.0;
+#pragma unroll 4
       for (int k = 0; k < nN; k++) s2 += Ai[nC + k] * W.x[nC + k];
       W.w[i] = s + s2 - W.b[i];
     }
@@ -175,6 +194,7 @@ template <class DW> NB2_HD int dantzig_solve(const DW& W, int n, bool early_term
         for (int k = 0; k < nN; k++) {
           const auto Ak = W.A + (size_t)(nC + k) * n;
           double s = 0.0;
+#pragma unroll 4
           for (int j = 0; j < nC; j++) s += Ak[j] * W.delta_x[j];
           W.delta_w[nC + k] = s;
         }
@@ -183,6 +203,7 @@ template <class DW> NB2_HD int dantzig_solve(const DW& W, int n, bool early_term
           if (dir > 0) for (int k = 0; k < nN; k++) W.delta_w[nC + k] += Ai[nC + k];
           else for (int k = 0; k < nN; k++) W.delta_w[nC + k] -= Ai[nC + k];
           double s = 0.0;
+#pragma unroll 4
           for (int j = 0; j < nC; j++) s += Ai[j] * W.delta_x[j];
           W.delta_w[i] = s + Ai[i] * dirf;
         }
