@@ -14,6 +14,7 @@
 // New: the minimum-norm least-squares solves (Eigen completeOrthogonalDecomposition in the reference) are done with a
 // rank-revealing pivoted Cholesky (symmetric case) / normal equations (sliding-friction case) instead of a QR/SVD.
 #pragma once
+#include <type_traits>
 #include "nb2_dantzig.cuh"
 #include "nb2_dyn.cuh"
 #include "nb2_geom.cuh"
@@ -967,9 +968,20 @@ NB2_HD BwdContactView<ST> contact_backward_prepare(const Nb2ModelDev<CR>& M, con
     }
     return WD;
   };
-  auto rows_pass = [&](int pass) {
+  unsigned long long pairs_with_rows = 0ull;  // NB2_MAX_PAIRS <= 64
+  // S = CR: values only (pass 0) ; S = D6: derivatives with respect to one moving body's pose at a time (pass 1)
+  auto rows_pass = [&](auto tag) {
+    typedef decltype(tag) S;
+    constexpr bool DUALS = !std::is_same<S, CR>::value;
+    constexpr int pass = DUALS ? 1 : 0;
+    auto liftS = [](const Xf<CR>& X) { Xf<S> o; const CR* r = &X.R_.m00; S* q = &o.R_.m00; for (int i = 0; i < 9; i++) q[i] = S(r[i]); o.p.x = S(X.p.x); o.p.y = S(X.p.y); o.p.z = S(X.p.z); return o; };
+    auto poseS = [&](int body, bool vary) {
+      if constexpr (DUALS) { if (vary) return dual_pose(body); }
+      return liftS(xf_from12(ws.W + 12 * body));
+    };
     int m2 = 0;
     for (int pi = 0; pi < C.npairs && !cv.error; pi++) {
+      if (DUALS && !((pairs_with_rows >> pi) & 1ull)) continue;  // the plain pass found no contact row for this pair
       const int sa = C.pair_a[pi], sb = C.pair_b[pi];
       const int ba = C.shape_body[sa], bb = C.shape_body[sb];
       const int nvary = (pass == 1 && ba >= 0 && bb >= 0) ? 2 : 1;
@@ -978,32 +990,32 @@ NB2_HD BwdContactView<ST> contact_backward_prepare(const Nb2ModelDev<CR>& M, con
         m2 = m2_pair;
         const bool varyA = (ba >= 0) && (v == 0);          // which body's pose carries the dual part in this run
         const int dyn = varyA ? ba : bb;
-        const Xf<D6> WDa = (ba >= 0) ? (varyA ? dual_pose(ba) : lift(xf_from12(ws.W + 12 * ba))) : Xf<D6>();
-        const Xf<D6> WDb = (bb >= 0) ? (!varyA ? dual_pose(bb) : lift(xf_from12(ws.W + 12 * bb))) : Xf<D6>();
-        const Xf<D6> Ta = (ba >= 0) ? gxf_mul(WDa, lift(xf_from12(C.shape_T[sa]))) : lift(xf_from12(C.shape_T[sa]));
-        const Xf<D6> Tb = (bb >= 0) ? gxf_mul(WDb, lift(xf_from12(C.shape_T[sb]))) : lift(xf_from12(C.shape_T[sb]));
+        const Xf<S> WDa = (ba >= 0) ? poseS(ba, varyA) : Xf<S>();
+        const Xf<S> WDb = (bb >= 0) ? poseS(bb, !varyA) : Xf<S>();
+        const Xf<S> Ta = (ba >= 0) ? gxf_mul(WDa, liftS(xf_from12(C.shape_T[sa]))) : liftS(xf_from12(C.shape_T[sa]));
+        const Xf<S> Tb = (bb >= 0) ? gxf_mul(WDb, liftS(xf_from12(C.shape_T[sb]))) : liftS(xf_from12(C.shape_T[sb]));
         const int ta = C.shape_type[sa], tb = C.shape_type[sb];
-        const V3<D6> da = mk3<D6>(D6(C.shape_dims[sa][0]), D6(C.shape_dims[sa][1]), D6(C.shape_dims[sa][2]));
-        const V3<D6> db = mk3<D6>(D6(C.shape_dims[sb][0]), D6(C.shape_dims[sb][1]), D6(C.shape_dims[sb][2]));
-        ContactOutT<D6> co[8];
+        const V3<S> da = mk3<S>(S(C.shape_dims[sa][0]), S(C.shape_dims[sa][1]), S(C.shape_dims[sa][2]));
+        const V3<S> db = mk3<S>(S(C.shape_dims[sb][0]), S(C.shape_dims[sb][1]), S(C.shape_dims[sb][2]));
+        ContactOutT<S> co[8];
         int k = 0;
         if (ta == 0 && tb == 0) k = collide_box_box(da, Ta, db, Tb, C.clip_depth, co);
         else if (ta == 0 && tb == 1) k = collide_box_sphere(da, Ta, db.x, Tb, C.clip_depth, 0, false, co);
         else if (ta == 1 && tb == 0) k = collide_box_sphere(db, Tb, da.x, Ta, C.clip_depth, 0, true, co);
         else if ((ta == 0 && tb == 2) || (ta == 2 && tb == 0)) {
           const bool boxFirst = (ta == 0);
-          const Xf<D6>& Tc = boxFirst ? Tb : Ta; const Xf<D6>& Tbx = boxFirst ? Ta : Tb;
-          const V3<D6> bdim = boxFirst ? da : db;
-          const D6 r = boxFirst ? db.x : da.x; const CR h = boxFirst ? C.shape_dims[sb][1] : C.shape_dims[sa][1];
-          CR dep[2]; Xf<D6> Tend[2];
+          const Xf<S>& Tc = boxFirst ? Tb : Ta; const Xf<S>& Tbx = boxFirst ? Ta : Tb;
+          const V3<S> bdim = boxFirst ? da : db;
+          const S r = boxFirst ? db.x : da.x; const CR h = boxFirst ? C.shape_dims[sb][1] : C.shape_dims[sa][1];
+          CR dep[2]; Xf<S> Tend[2];
           for (int e = 0; e < 2; e++) {
-            Tend[e] = Tc; Tend[e].p = gxf_apply(Tc, mk3<D6>(D6(0.0), D6(0.0), D6(e == 0 ? h / 2 : -h / 2)));
-            const V3<D6> pld = gxf_apply_inv(Tbx, Tend[e].p);
-            const V3<CR> pl = mk3<CR>(pld.x.v, pld.y.v, pld.z.v);
+            Tend[e] = Tc; Tend[e].p = gxf_apply(Tc, mk3<S>(S(0.0), S(0.0), S(e == 0 ? h / 2 : -h / 2)));
+            const V3<S> pld = gxf_apply_inv(Tbx, Tend[e].p);
+            const V3<CR> pl = mk3<CR>(gval(pld.x), gval(pld.y), gval(pld.z));
             V3<CR> q = pl; bool inside = true;
-            for (int kk = 0; kk < 3; kk++) { const CR hk = 0.5 * gget3(bdim, kk).v, v = get3(q, kk); if (v < -hk) { set3(q, kk, -hk); inside = false; } if (v > hk) { set3(q, kk, hk); inside = false; } }
-            if (inside) { CR mn = 1e300; for (int kk = 0; kk < 3; kk++) { const CR v = 0.5 * gget3(bdim, kk).v - nb2_abs(get3(pl, kk)); mn = v < mn ? v : mn; } dep[e] = mn + r.v; }
-            else { const V3<CR> dd = pl - q; dep[e] = r.v - nb2_sqrt(dot(dd, dd)); }
+            for (int kk = 0; kk < 3; kk++) { const CR hk = 0.5 * gval(gget3(bdim, kk)), v = get3(q, kk); if (v < -hk) { set3(q, kk, -hk); inside = false; } if (v > hk) { set3(q, kk, hk); inside = false; } }
+            if (inside) { CR mn = 1e300; for (int kk = 0; kk < 3; kk++) { const CR v = 0.5 * gval(gget3(bdim, kk)) - nb2_abs(get3(pl, kk)); mn = v < mn ? v : mn; } dep[e] = mn + gval(r); }
+            else { const V3<CR> dd = pl - q; dep[e] = gval(r) - nb2_sqrt(dot(dd, dd)); }
           }
           if ((dep[0] > dep[1] ? dep[0] : dep[1]) >= 0 && nb2_abs(dep[0] - dep[1]) >= 1e-9) {
             const int e = dep[0] > dep[1] ? 0 : 1;
@@ -1011,32 +1023,33 @@ NB2_HD BwdContactView<ST> contact_backward_prepare(const Nb2ModelDev<CR>& M, con
           }
         }
         for (int c = 0; c < k; c++) {
-          const V3<CR> nv = mk3<CR>(co[c].normal.x.v, co[c].normal.y.v, co[c].normal.z.v);
+          const V3<CR> nv = mk3<CR>(gval(co[c].normal.x), gval(co[c].normal.y), gval(co[c].normal.z));
           if (dot(nv, nv) < 1e-12) continue;
-          if (co[c].depth.v < 0.0 || co[c].depth.v > C.clip_depth) continue;
+          if (gval(co[c].depth) < 0.0 || gval(co[c].depth) > C.clip_depth) continue;
           const CR mu = C.shape_mu[sa] < C.shape_mu[sb] ? C.shape_mu[sa] : C.shape_mu[sb];
           const bool fric = mu > 1e-3;
-          V3<D6> dirs[3]; dirs[0] = co[c].normal;
-          if (fric) tangent_basis<D6>(co[c].normal, &dirs[1], &dirs[2]);
+          V3<S> dirs[3]; dirs[0] = co[c].normal;
+          if (fric) tangent_basis<S>(co[c].normal, &dirs[1], &dirs[2]);
           const int dim = fric ? 3 : 1;
-          V3<D6> pA, pB;
+          V3<S> pA, pB;
           if (ba >= 0) pA = gxf_apply_inv(WDa, co[c].point);
           if (bb >= 0) pB = gxf_apply_inv(WDb, co[c].point);
           for (int kk = 0; kk < dim; kk++) {
             if (m2 >= NB2_MAX_ROWS) { cv.error = 2; break; }
-            D6 FA[6], FB[6];
-            if (ba >= 0) { const V3<D6> dA = mulT(WDa.R_, dirs[kk]); const V3<D6> mo = cross(pA, dA); FA[0] = mo.x; FA[1] = mo.y; FA[2] = mo.z; FA[3] = dA.x; FA[4] = dA.y; FA[5] = dA.z; }
-            if (bb >= 0) { const V3<D6> dB = mulT(WDb.R_, -dirs[kk]); const V3<D6> mo = cross(pB, dB); FB[0] = mo.x; FB[1] = mo.y; FB[2] = mo.z; FB[3] = dB.x; FB[4] = dB.y; FB[5] = dB.z; }
-            if (pass == 0) {
-              for (int j = 0; j < 6; j++) { rowFA[6 * m2 + j] = (ba >= 0) ? FA[j].v : 0.0; rowFB[6 * m2 + j] = (bb >= 0) ? FB[j].v : 0.0; }
+            S FA[6], FB[6];
+            if (ba >= 0) { const V3<S> dA = mulT(WDa.R_, dirs[kk]); const V3<S> mo = cross(pA, dA); FA[0] = mo.x; FA[1] = mo.y; FA[2] = mo.z; FA[3] = dA.x; FA[4] = dA.y; FA[5] = dA.z; }
+            if (bb >= 0) { const V3<S> dB = mulT(WDb.R_, -dirs[kk]); const V3<S> mo = cross(pB, dB); FB[0] = mo.x; FB[1] = mo.y; FB[2] = mo.z; FB[3] = dB.x; FB[4] = dB.y; FB[5] = dB.z; }
+            if constexpr (!DUALS) {
+              for (int j = 0; j < 6; j++) { rowFA[6 * m2 + j] = (ba >= 0) ? gval(FA[j]) : 0.0; rowFB[6 * m2 + j] = (bb >= 0) ? gval(FB[j]) : 0.0; }
               rowbA[m2] = ba; rowbB[m2] = bb; rowmu[m2] = mu;
+              pairs_with_rows |= (1ull << pi);
             } else if (coefWr[m2] != 0.0 || coefVr[m2] != 0.0) {
               // G_dyn += sum_terms (dF_term/dxi_dyn)^T (coefW * field_w(body_term) + coefV * field_v+(body_term)), scaled by -1/dt
               auto gj = inj + 24 * dyn + 12;
               for (int side = 0; side < 2; side++) {
                 const int body = side == 0 ? ba : bb;
                 if (body < 0) continue;
-                const D6* F = side == 0 ? FA : FB;
+                const S* F = side == 0 ? FA : FB;
                 const V6<CR> Ww = ld6<CR, ST>(scr + (size_t)(oBody + 7 * body + 1) * ST);
                 const V6<CR> Up = ldv6(Uplus + 6 * body);
                 const CR fw[6] = {Ww.a.x, Ww.a.y, Ww.a.z, Ww.l.x, Ww.l.y, Ww.l.z}, fu[6] = {Up.a.x, Up.a.y, Up.a.z, Up.l.x, Up.l.y, Up.l.z};
@@ -1054,7 +1067,7 @@ NB2_HD BwdContactView<ST> contact_backward_prepare(const Nb2ModelDev<CR>& M, con
     }
     return m2;
   };
-  const int m2 = rows_pass(0);
+  const int m2 = rows_pass(CR());
   if (m2 != m) cv.error = cv.error ? cv.error : 3;
   if (cv.error) return cv;
   // ---- clamping / upper-bound sets from the saved labels
@@ -1167,7 +1180,7 @@ NB2_HD BwdContactView<ST> contact_backward_prepare(const Nb2ModelDev<CR>& M, con
       }
     }
   }
-  rows_pass(1);  // contact-frame part G: derivatives of every wrench w.r.t. the pose of each moving body
+  rows_pass(D6());  // contact-frame part G: derivatives of every wrench w.r.t. the pose of each moving body
   return cv;
 }
 
