@@ -336,7 +336,7 @@ def main():
                     nb.timestep(cworld, csg, cag).backward(gg)
                 torch.cuda.synchronize()
                 f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                kfb = 5
+                kfb = 15
                 f0.record()
                 for _ in range(kfb):
                     nb.timestep(cworld, csg, cag).backward(gg)

@@ -285,6 +285,23 @@ NB2_HD void pinv_psd(int n, PQ Qin, PR rhs, PX x, PG G, PL Lf, PT1 t1, PT2 t2, P
   }
   for (int i = 0; i < n; i++) x[i] = 0;
   if (r == 0) return;
+  if (r == n) {  // full rank: Q^+ = Q^-1 = P L^-T L^-1 P^T, two triangular solves (rows of L in pivot order)
+    for (int i = 0; i < n; i++) {
+      const int pi = perm[i];
+      CR s = rhs[pi];
+#pragma unroll 4
+      for (int k = 0; k < i; k++) s -= Lf[pi * n + k] * t1[k];
+      t1[i] = s / Lf[pi * n + i];
+    }
+    for (int i = n - 1; i >= 0; i--) {
+      CR s = t1[i];
+#pragma unroll 4
+      for (int k = i + 1; k < n; k++) s -= Lf[perm[k] * n + i] * t2[k];
+      t2[i] = s / Lf[perm[i] * n + i];
+    }
+    for (int i = 0; i < n; i++) x[perm[i]] = t2[i];
+    return;
+  }
   // rows of L for indices not yet pivoted at step k are valid for columns < r; rows of pivoted indices have zeros above: fill
   for (int k = 0; k < r; k++) for (int j = k + 1; j < r; j++) Lf[perm[k] * n + j] = 0;
   // M = L^T L (r x r) in G ; y = L^T rhs
