@@ -57,6 +57,38 @@ __device__ __forceinline__ const R* stage_body_table(const Nb2ModelDev<R>& M, R*
   }
 }
 
+// ---- bulk (TMA) staging of a group's input rows.  The rows of the worlds of one warp are contiguous in global memory, so
+// ONE thread hands each block of rows to the copy engine of the SM (cp.async.bulk, completion counted on an mbarrier) instead
+// of 32 threads looping over vector loads: the requests are as wide as they can be — which is what matters when `src` is
+// mapped host memory behind PCIe — and cost two instructions.  The scatter into the [word][slot] scratch then reads shared
+// memory.  Needs 16-byte aligned sources and sizes; otherwise the vector-load path is used.
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(bar)));
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(__cvta_generic_to_global(src)), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+  for (int it = 0; it < (1 << 20); it++) {  // bounded: a copy that never lands must not hang the GPU
+    unsigned ok;
+    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    if (ok) return;
+  }
+  __trap();
+}
+__device__ __forceinline__ bool bulk_ok(const void* p, size_t bytes) { return ((reinterpret_cast<size_t>(p) | bytes) & 15) == 0 && bytes > 0; }
+// bytes of staging per warp: rows of `nrows` floats per world, rounded to 16 + the mbarrier
+template <int K> __host__ __device__ constexpr size_t staging_bytes(int floats_per_world) {
+  return (((size_t)floats_per_world * CoopShape<K>::WPW * sizeof(float) + 15) & ~(size_t)15) + 16;
+}
+
 template <class R, int K>
 __global__ void __launch_bounds__(128)
 k_step_fwd(const __grid_constant__ Nb2ModelDev<R> M, int B, int w0, int count, const float* __restrict__ state,
@@ -75,10 +107,31 @@ k_step_fwd(const __grid_constant__ Nb2ModelDev<R> M, int B, int w0, int count, c
   R* scr = scr0 + slot;
   R* sv = saved ? saved + wg + (valid ? slot : 0) : nullptr;
   constexpr unsigned sync_mask = (K > 1) ? NB2_FWD_SYNC_MASK : NB2_FWD_SYNC_MASK_1LANE;
+  // input rows of the group: through the bulk-copy staging buffer when they qualify, else read in place
+  const float* st_src = state + wg * 2 * M.ndof;
+  const float* act_src = action + wg * M.na;
+  if (nworlds > 0) {
+    const size_t sb = (size_t)nworlds * 2 * M.ndof * sizeof(float), ab = (size_t)nworlds * M.na * sizeof(float);
+    if (bulk_ok(st_src, sb) && bulk_ok(act_src, ab)) {
+      unsigned char* stg = nb2_smem + (((size_t)body_table_words<K>(M.nb) + (size_t)(blockDim.x >> 5) * words * ST) * sizeof(R) + 15 & ~(size_t)15) +
+                           (size_t)(threadIdx.x >> 5) * staging_bytes<K>(2 * M.ndof + M.na);
+      unsigned long long* bar = reinterpret_cast<unsigned long long*>(stg + staging_bytes<K>(2 * M.ndof + M.na) - 16);
+      if (li == 0) {
+        mbar_init(bar);
+        mbar_expect_tx(bar, (unsigned)(sb + ab));
+        bulk_g2s(stg, st_src, (unsigned)sb, bar);
+        bulk_g2s(stg + sb, act_src, (unsigned)ab, bar);
+      }
+      __syncwarp();
+      mbar_wait(bar, 0);
+      st_src = reinterpret_cast<const float*>(stg);
+      act_src = reinterpret_cast<const float*>(stg + sb);
+    }
+  }
 #pragma unroll 1
   for (int sg = 0; sg < NB2_FWD_STAGES; sg++) {
     if (sg == 0) {
-      if (nworlds > 0) nb2::fwd_load<R, ST>(M, scr0, state + wg * 2 * M.ndof, action + wg * M.na, nworlds, li, 32,
+      if (nworlds > 0) nb2::fwd_load<R, ST>(M, scr0, st_src, act_src, nworlds, li, 32,
                                             state_copy ? state_copy + wg * 2 * M.ndof : nullptr, action_copy ? action_copy + wg * M.na : nullptr);
     }
     else if (sg == NB2_FWD_STAGES - 1) { if (nworlds > 0) nb2::fwd_store<R, ST>(M, scr0, next + wg * 2 * M.ndof, nworlds, li, 32); }
@@ -92,7 +145,7 @@ __global__ void __launch_bounds__(128)
 k_step_bwd(const __grid_constant__ Nb2ModelDev<R> M, int B, int w0, int count, const float* __restrict__ state,
            const float* __restrict__ action, const R* __restrict__ saved, const float* __restrict__ gnext,
            float* __restrict__ gstate, float* __restrict__ gaction, float* __restrict__ ginertia, int words,
-           int stage_saved, int accumulate_state) {
+           int stage_saved, int accumulate_state, unsigned in_stage_off) {
   extern __shared__ __align__(16) unsigned char nb2_smem[];
   constexpr int WPW = CoopShape<K>::WPW, ST = CoopShape<K>::ST;
   const int li = threadIdx.x & 31, slot = li / K, lane = li % K;
@@ -127,9 +180,32 @@ k_step_bwd(const __grid_constant__ Nb2ModelDev<R> M, int B, int w0, int count, c
     svB = WPW;
   }
   constexpr unsigned sync_mask = (K > 1) ? NB2_BWD_SYNC_MASK : NB2_BWD_SYNC_MASK_1LANE;
+  // input rows (dL/dx', x, u) of the group through the bulk-copy staging buffer when they qualify (see k_step_fwd)
+  const float* g_src = gnext + wg * 2 * M.ndof;
+  const float* st_src = state + wg * 2 * M.ndof;
+  const float* act_src = action + wg * M.na;
+  if (nworlds > 0 && in_stage_off) {
+    const size_t sb = (size_t)nworlds * 2 * M.ndof * sizeof(float), ab = (size_t)nworlds * M.na * sizeof(float);
+    if (bulk_ok(g_src, sb) && bulk_ok(st_src, sb) && bulk_ok(act_src, ab)) {
+      unsigned char* stg = nb2_smem + in_stage_off + (size_t)(threadIdx.x >> 5) * staging_bytes<K>(4 * M.ndof + M.na);
+      unsigned long long* bar = reinterpret_cast<unsigned long long*>(stg + staging_bytes<K>(4 * M.ndof + M.na) - 16);
+      if (li == 0) {
+        mbar_init(bar);
+        mbar_expect_tx(bar, (unsigned)(2 * sb + ab));
+        bulk_g2s(stg, g_src, (unsigned)sb, bar);
+        bulk_g2s(stg + sb, st_src, (unsigned)sb, bar);
+        bulk_g2s(stg + 2 * sb, act_src, (unsigned)ab, bar);
+      }
+      __syncwarp();
+      mbar_wait(bar, 0);
+      g_src = reinterpret_cast<const float*>(stg);
+      st_src = reinterpret_cast<const float*>(stg + sb);
+      act_src = reinterpret_cast<const float*>(stg + 2 * sb);
+    }
+  }
 #pragma unroll 1
   for (int sg = 0; sg < NB2_BWD_STAGES; sg++) {
-    if (sg == 0) { if (nworlds > 0) nb2::bwd_load<R, ST, false>(M, scr0, state + wg * 2 * M.ndof, action + wg * M.na, gnext + wg * 2 * M.ndof, nworlds, li, 32); }
+    if (sg == 0) { if (nworlds > 0) nb2::bwd_load<R, ST, false>(M, scr0, st_src, act_src, g_src, nworlds, li, 32); }
     else if (sg == NB2_BWD_STAGES - 1) {
       if (nworlds > 0) nb2::bwd_store<R, ST, false>(M, scr0, gstate + wg * 2 * M.ndof, gaction + wg * M.na, false, nworlds, li, 32, accumulate_state != 0);
     } else if (valid) nb2::world_backward_stage<R, ST>(M, scr, svp, svB, lane, sg, ginertia ? ginertia + w : nullptr, bt, (size_t)B);
@@ -283,8 +359,8 @@ template <class R, int K> struct StepKernels {
   static int prepare(nb2_variant& v, int dir) {  // dir 0 forward, 1 backward
     LaunchShape& sh = v.shape[dir][sizeof(R) == 8];
     if (sh.warps_per_block) return NB2_OK;
-    const size_t per_warp = (size_t)(dir ? v.bwd_words : v.fwd_words) * ST * sizeof(R);
-    const size_t per_block = (size_t)body_table_words<K>(v.mf.nb) * sizeof(R);
+    const size_t per_warp = (size_t)(dir ? v.bwd_words : v.fwd_words) * ST * sizeof(R) + (dir ? staging_bytes<K>(4 * v.mf.ndof + v.mf.na) : staging_bytes<K>(2 * v.mf.ndof + v.mf.na));
+    const size_t per_block = (size_t)body_table_words<K>(v.mf.nb) * sizeof(R) + 16;
     if (per_warp + per_block > (size_t)kMaxSmem) { g_err = "model needs " + std::to_string(per_warp) + " B of shared memory per warp (> 227 KB)"; return NB2_ERR_UNSUPPORTED; }
     if (dir == 0) {
       NB2_CUDA(cudaFuncSetAttribute(k_step_fwd<R, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
@@ -333,11 +409,11 @@ static int launch_fwd_k(const nb2_variant& v, int sm_count, int Btot, int w0, in
                         float* next, R* saved, cudaStream_t st, float* state_copy, float* action_copy) {
   constexpr int WPW = CoopShape<K>::WPW, ST = CoopShape<K>::ST;
   const LaunchShape& sh = v.shape[0][sizeof(R) == 8];
-  const size_t per_warp = (size_t)v.fwd_words * ST * sizeof(R);
+  const size_t per_warp = (size_t)v.fwd_words * ST * sizeof(R) + staging_bytes<K>(2 * v.mf.ndof + v.mf.na);  // scratch + input staging
   const int total_warps = (B + WPW - 1) / WPW;
   const int warps = block_warps(total_warps, sm_count, sh, per_warp);
   const int blocks = (total_warps + warps - 1) / warps;
-  k_step_fwd<R, K><<<blocks, warps * 32, per_warp * warps + (size_t)body_table_words<K>(v.mf.nb) * sizeof(R), st>>>(model_of<R>(v), Btot, w0, B, state, action, next, saved, v.fwd_words, state_copy, action_copy);
+  k_step_fwd<R, K><<<blocks, warps * 32, per_warp * warps + (size_t)body_table_words<K>(v.mf.nb) * sizeof(R) + 16, st>>>(model_of<R>(v), Btot, w0, B, state, action, next, saved, v.fwd_words, state_copy, action_copy);
   g_launches++;
   NB2_CUDA(cudaGetLastError());
   return NB2_OK;
@@ -375,11 +451,15 @@ static int launch_bwd_k(const nb2_variant& v, int sm_count, int Btot, int w0, in
   const size_t stage_per_warp = (size_t)nb2_saved_words(v.mf.nb, v.mf.ndof, v.mf.nfree) * WPW * sizeof(R);
   const bool aligned = (((size_t)Btot * sizeof(R)) % 16 == 0) && (((size_t)w0 * sizeof(R)) % 16 == 0) && ((reinterpret_cast<size_t>(saved) & 15) == 0) &&
                        ((WPW * sizeof(R)) % 16 == 0);
+  const size_t in_per_warp = staging_bytes<K>(4 * v.mf.ndof + v.mf.na);  // bulk-copy staging of dL/dx', x, u rows
   const size_t smem_staged = (per_warp + stage_per_warp) * warps + tab + 16;
   const int blocks_per_sm = (blocks + sm_count - 1) / sm_count;
-  const bool stage = aligned && smem_staged * blocks_per_sm + 1024 * blocks_per_sm <= (size_t)kMaxSmem && !no_stage_saved();
-  k_step_bwd<R, K><<<blocks, warps * 32, stage ? smem_staged : per_warp * warps + tab, st>>>(model_of<R>(v), Btot, w0, B, state, action, saved, gnext, gstate,
-                                                                                            gaction, ginertia, v.bwd_words, stage ? 1 : 0, accumulate);
+  const bool stage = aligned && (smem_staged + in_per_warp * warps) * blocks_per_sm + 1024 * blocks_per_sm <= (size_t)kMaxSmem && !no_stage_saved();
+  const size_t base = ((stage ? smem_staged : per_warp * warps + tab) + 15) & ~(size_t)15;
+  const bool in_stage = base + in_per_warp * warps <= (size_t)kMaxSmem;
+  k_step_bwd<R, K><<<blocks, warps * 32, in_stage ? base + in_per_warp * warps : base, st>>>(model_of<R>(v), Btot, w0, B, state, action, saved, gnext, gstate,
+                                                                                         gaction, ginertia, v.bwd_words, stage ? 1 : 0, accumulate,
+                                                                                         in_stage ? (unsigned)base : 0u);
   g_launches++;
   NB2_CUDA(cudaGetLastError());
   return NB2_OK;
