@@ -21,7 +21,19 @@ template <class R> struct Xf { M3<R> R_; V3<R> p; };
 // symmetric 6x6 in blocks [[A, B], [B^T, C]] (A rotational, C translational)
 template <class R> struct SI { S3<R> A; M3<R> B; S3<R> C; };
 
-NB2_HD void nb2_sincos(float x, float* s, float* c) { sincosf(x, s, c); }
+NB2_HD void nb2_sincos(float x, float* s, float* c) {
+#ifdef __CUDA_ARCH__
+  // the library is built with --use_fast_math (fp32 division / sqrt / sincos are the special-function unit's): the hardware
+  // sine is accurate to ~5e-7 absolute on [-pi, pi] only, so the argument is reduced first (two-term 2 pi, exact to ~1e-7
+  // relative for |x| up to ~1e4 rad — an unbounded revolute joint may have wound up many turns)
+  const float k = rintf(x * 0.15915494309189535f);
+  float r = fmaf(-k, 6.2831854820251465f, x);   // 2 pi rounded to fp32
+  r = fmaf(-k, -1.7484555e-07f, r);             // 2 pi - fp32(2 pi)
+  __sincosf(r, s, c);
+#else
+  sincosf(x, s, c);
+#endif
+}
 NB2_HD void nb2_sincos(double x, double* s, double* c) { sincos(x, s, c); }
 NB2_HD float nb2_sqrt(float x) { return sqrtf(x); }
 NB2_HD double nb2_sqrt(double x) { return sqrt(x); }

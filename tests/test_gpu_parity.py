@@ -318,3 +318,26 @@ def test_host_entry_points_with_page_locked_buffers(name):
     n2 = dm.forward_host(s, a, True, 0)
     g2s, g2a = dm.backward_host(g, 0)
     assert np.array_equal(n2, o_n.numpy()) and np.array_equal(g2s, o_gs.numpy()) and np.array_equal(g2a, o_ga.numpy())
+
+
+def test_wound_up_joint_angles_keep_parity(oracle_mod):
+    """The fp32 kernels use the special-function unit's sine / cosine after an explicit 2*pi range reduction
+    (csrc/nb2_math.cuh nb2_sincos): revolute joints that have wound up many turns must stay inside the 1e-4 tolerance."""
+    raw, world = _world("atlas")
+    ow = oracle_mod.OracleWorld(raw)
+    B = 64
+    s, a, g = sample_inputs(raw, B, seed=71)
+    rng = np.random.default_rng(72)
+    n = raw.ndof
+    s[:, 6:n] = rng.uniform(-300.0, 300.0, (B, n - 6)).astype(np.float32)  # up to ~50 turns
+    st = torch.tensor(s, device="cuda", requires_grad=True)
+    at = torch.tensor(a, device="cuda", requires_grad=True)
+    nxt = nb.timestep(world, st, at)
+    nxt.backward(torch.tensor(g, device="cuda"))
+    nxt, gs, ga = nxt.detach().cpu().numpy(), st.grad.cpu().numpy(), at.grad.cpu().numpy()
+    worst = 0.0
+    for w in range(0, B, 4):
+        s64, a64, g64 = s[w].astype(np.float64), a[w].astype(np.float64), g[w].astype(np.float64)
+        rgs, rga = ow.backprop(s64, a64, g64)
+        worst = max(worst, rel_err(nxt[w], ow.step(s64, a64)), rel_err(gs[w], rgs), rel_err(ga[w], rga))
+    assert worst < TOL, worst
