@@ -405,14 +405,16 @@ def main():
                 loss.backward()
                 return loss
 
-            run()
+            run(); run()  # warm-up: the second run already finds its 1.3 GB of per-step records in torch's allocator cache
             torch.cuda.synchronize()
-            r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            r0.record()
-            loss = run()
-            r1.record()
-            torch.cuda.synchronize()
-            ms = r0.elapsed_time(r1)
+            ms = float("inf")
+            for _ in range(2):
+                r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                r0.record()
+                loss = run()
+                r1.record()
+                torch.cuda.synchronize()
+                ms = min(ms, r0.elapsed_time(r1))
             extra["atlas_ground_rollout64"] = {"batch": Br, "horizon": T, "ms_per_rollout_fwd_bwd": ms,
                                                "world_steps_per_s": Br * T / (ms * 1e-3), "loss_finite": bool(torch.isfinite(loss)),
                                                "grad_finite": bool(torch.isfinite(x0.grad).all()),
