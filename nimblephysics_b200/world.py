@@ -296,6 +296,70 @@ class Skeleton:
                 return b.parent_joint
         return None
 
+    # ----- per-dof access in the skeleton's own dof order (dart/dynamics/MetaSkeleton.hpp) -----
+    def _dof_slots(self):
+        """[(joint, local index)] in dof order."""
+        out = []
+        for b in self._ordered_bodies():
+            out.extend((b.parent_joint, k) for k in range(b.parent_joint.ndof))
+        return out
+
+    def _dof_offset_in_world(self):
+        w = getattr(self, "_world", None)
+        if w is None:
+            return None, 0
+        off = 0
+        for sk in w.skeletons:
+            if sk is self:
+                return w, off
+            off += sk.getNumDofs()
+        return None, 0
+
+    def setPosition(self, i, v):
+        """Skeleton::setPosition: the pose the world starts from (and its current legacy state, if it has one)."""
+        j, k = self._dof_slots()[i]
+        j.init_pos[k] = float(v)
+        w, off = self._dof_offset_in_world()
+        if w is not None and w._state is not None:
+            w._state[off + i] = float(v)
+
+    def setPositions(self, q):
+        for i, v in enumerate(np.asarray(q, dtype=np.float64).reshape(-1)):
+            self.setPosition(i, v)
+
+    def getPositions(self):
+        w, off = self._dof_offset_in_world()
+        if w is not None and w._state is not None:
+            return w._state[off:off + self.getNumDofs()].copy()
+        return np.array([j.init_pos[k] for j, k in self._dof_slots()])
+
+    def setVelocity(self, i, v):
+        w, off = self._dof_offset_in_world()
+        if w is None:
+            raise ValueError("setVelocity(): add the skeleton to a World first (velocities live in the world state)")
+        st = w.getState()
+        st[w.getNumDofs() + off + i] = float(v)
+        w.setState(st)
+
+    def setVelocities(self, v):
+        for i, x in enumerate(np.asarray(v, dtype=np.float64).reshape(-1)):
+            self.setVelocity(i, x)
+
+    def setControlForceUpperLimits(self, limits):
+        for (j, k), v in zip(self._dof_slots(), np.asarray(limits, dtype=np.float64).reshape(-1)):
+            j.force_hi[k] = v
+        self._touch_world()
+
+    def setControlForceLowerLimits(self, limits):
+        for (j, k), v in zip(self._dof_slots(), np.asarray(limits, dtype=np.float64).reshape(-1)):
+            j.force_lo[k] = v
+        self._touch_world()
+
+    def _touch_world(self):
+        w = getattr(self, "_world", None)
+        if w is not None:
+            w._touch()
+
     def _ordered_bodies(self) -> List[BodyNode]:
         """Bodies in an order where every parent precedes its children and that
         is otherwise creation order (the reference's tree/DoF order for
@@ -390,6 +454,7 @@ class World:
             bodies[int(raw.shape_body[s])].shapes.append(sn)
         for sid in sorted(skels):
             w.skeletons.append(skels[sid])
+            skels[sid]._world = w
         w.action_space = [int(a) for a in raw.action_map]
         return w
 
@@ -401,6 +466,7 @@ class World:
     def addSkeleton(self, skel: Skeleton):
         base = self.getNumDofs()
         self.skeletons.append(skel)
+        skel._world = self
         # reference appends *every* dof (mobile or not) to the action space, World.cpp:779-785
         self.action_space.extend(range(base, base + skel.getNumDofs()))
         self._touch()
@@ -540,7 +606,39 @@ class World:
                 k += 1
         return [(index[id(b)], t) for b, t, _, _ in getattr(self, "_wrt_mass", [])]
 
+    def getNumBodyNodes(self):
+        return sum(s.getNumBodyNodes() for s in self.skeletons)
+
+    def getBodyNodeByIndex(self, index):
+        """World::getBodyNodeByIndex (World.cpp): bodies numbered skeleton by skeleton."""
+        for s in self.skeletons:
+            if index < s.getNumBodyNodes():
+                return s._ordered_bodies()[index]
+            index -= s.getNumBodyNodes()
+        return None
+
     # ----- legacy stateful API (single world) -----
+    def setAction(self, action):
+        action = np.asarray(action, dtype=np.float64).reshape(-1)
+        if action.size != self.getActionSize():
+            raise ValueError(f"World.setAction() got size {action.size}, expected getActionSize()={self.getActionSize()}")
+        self._action = action.copy()
+
+    def getAction(self):
+        a = getattr(self, "_action", None)
+        return np.zeros(self.getActionSize()) if a is None else a.copy()
+
+    def step(self):
+        """World::step (World.cpp:221-254) of the single legacy world: advances the stored state with the stored action on
+        the GPU, then clears the control forces like the reference (World.cpp:297-302).  Returns nothing."""
+        import torch
+
+        from .timestep import timestep
+
+        with torch.no_grad():
+            timestep(self, torch.tensor(self.getState(), dtype=torch.float64), torch.tensor(self.getAction(), dtype=torch.float64))
+        self._action = None
+
     def setState(self, state):
         state = np.asarray(state, dtype=np.float64).reshape(-1)
         if state.size != self.getStateSize():

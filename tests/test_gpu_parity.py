@@ -341,3 +341,20 @@ def test_wound_up_joint_angles_keep_parity(oracle_mod):
         rgs, rga = ow.backprop(s64, a64, g64)
         worst = max(worst, rel_err(nxt[w], ow.step(s64, a64)), rel_err(gs[w], rgs), rel_err(ga[w], rga))
     assert worst < TOL, worst
+
+
+def test_legacy_world_step(oracle_mod):
+    """world.setAction(...); world.step() — the stateful single-world loop of the reference's examples (World.cpp:221-254):
+    the stored state advances, the control forces are cleared after the step (World.cpp:297-302)."""
+    raw, world = _world("cartpole")
+    ow = oracle_mod.OracleWorld(raw)
+    x = np.array([0.1, 0.3, -0.2, 0.4])
+    world.setState(x)
+    for k in range(3):
+        a = np.array([0.5 * (k + 1), 0.0])
+        world.setAction(a)
+        world.step()
+        x = ow.step(x.astype(np.float32).astype(np.float64), a)
+        assert rel_err(world.getState(), x) < TOL
+        assert np.all(world.getAction() == 0.0)
+        x = world.getState()

@@ -156,3 +156,31 @@ def test_world_mass_vector_api():
     assert w.getMassUpperLimits()[0] == 10.0 and w.getMassLowerLimits()[0] == 0.1
     with pytest.raises(ValueError):
         w.setMasses(np.zeros(3))
+
+
+def test_legacy_world_and_skeleton_accessors():
+    """Calls the reference's examples make on World / Skeleton (python/new_examples/atlas.py:14-36, cartpole.py):
+    setPosition before stepping, control-force limit vectors, body lookup by world index, setAction / getAction."""
+    w = nb.World.from_raw(load_raw("atlas"))
+    atlas = w.getSkeleton(0)
+    n = w.getNumDofs()
+    assert atlas.getNumDofs() == n and w.getNumBodyNodes() == atlas.getNumBodyNodes()
+    assert w.getBodyNodeByIndex(0) is atlas._ordered_bodies()[0] and w.getBodyNodeByIndex(10 ** 6) is None
+    atlas.setPosition(0, -0.5 * np.pi)          # before any state exists: becomes the initial pose
+    atlas.setPosition(4, -0.01)
+    st = w.getState()
+    assert st[0] == pytest.approx(-0.5 * np.pi) and st[4] == pytest.approx(-0.01) and np.all(st[n:] == 0)
+    atlas.setPosition(7, 0.25)                   # with a state: edits it in place
+    assert w.getState()[7] == 0.25 and atlas.getPositions()[7] == 0.25
+    atlas.setVelocity(3, 1.5)
+    assert w.getVelocities()[3] == 1.5
+    v0 = w._version
+    atlas.setControlForceUpperLimits(np.full(n, 7.0))
+    atlas.setControlForceLowerLimits(np.full(n, -7.0))
+    assert w._version > v0                       # limits are part of the device model: it is rebuilt lazily
+    raw = nb.flatten_world(w)
+    assert np.all(raw.force_hi == 7.0) and np.all(raw.force_lo == -7.0)
+    w.setAction(np.arange(w.getActionSize(), dtype=float))
+    assert w.getAction()[3] == 3.0
+    with pytest.raises(ValueError):
+        w.setAction(np.zeros(3))
