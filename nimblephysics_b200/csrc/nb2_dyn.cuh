@@ -21,13 +21,16 @@
 
 namespace nb2 {
 
+// per-body record of the forward scratch: V(6) [overwritten by A in pass 3: nothing reads a body's V after its own
+// pass-3 step, and its children only need its A], sin/cos(2), U(6), psi, u
+#define NB2_FWD_BODY_WORDS 16
 struct FwdLayout {
   int oQ, oV, oAct, oBody, oSlot, oFree, total;  // oAct: the raw action row (na <= n words)
 };
 NB2_HD FwdLayout fwd_layout(int nb, int n, int nslots, int nfree) {
   FwdLayout L;
   L.oQ = 0; L.oV = n; L.oAct = 2 * n; L.oBody = 3 * n;
-  L.oSlot = L.oBody + 22 * nb;
+  L.oSlot = L.oBody + NB2_FWD_BODY_WORDS * nb;
   L.oFree = L.oSlot + 27 * nslots;
   L.total = L.oFree + 18 * nfree;
   return L;
@@ -147,7 +150,7 @@ template <class R, int ST> NB2_HD void stXf(R* p, const Xf<R>& T) {
 // transform of body i during the sweeps that follow the kinematics pass (forward scratch layout)
 template <class R, int ST> NB2_HD Xf<R> body_xf_fwd(const Nb2ModelDev<R>& M, const R* bt, int i, const R* scr, const FwdLayout& L) {
   const int jt = M.jtype[i];
-  if (jt == NB2_JT_REV) { const R* b = scr + (size_t)(L.oBody + 22 * i + 6) * ST; return xf_rev(M, bt, i, b[0], b[ST]); }
+  if (jt == NB2_JT_REV) { const R* b = scr + (size_t)(L.oBody + NB2_FWD_BODY_WORDS * i + 6) * ST; return xf_rev(M, bt, i, b[0], b[ST]); }
   if (jt == NB2_JT_PRIS) return xf_pris(M, bt, i, scr[(size_t)(L.oQ + M.dof_off[i]) * ST]);
   return ldXf<R, ST>(scr + (size_t)(L.oFree + 18 * M.free_idx[i]) * ST);
 }
@@ -177,8 +180,8 @@ NB2_HD void fwd_pass1(const Nb2ModelDev<R>& M, R* scr, int lo, int hi, const R* 
   // ---------------- pass 1, root -> leaf: joint transforms and spatial velocities (Frame.cpp:144-160)
   for (int i = lo; i < hi; i++) {
     const int jt = M.jtype[i], p = M.parent[i], o = M.dof_off[i];
-    R* bs = scr + (size_t)(L.oBody + 22 * i) * ST;
-    V6<R> Vp = (p >= 0) ? ld6<R, ST>(scr + (size_t)(L.oBody + 22 * p) * ST) : zero6<R>();
+    R* bs = scr + (size_t)(L.oBody + NB2_FWD_BODY_WORDS * i) * ST;
+    V6<R> Vp = (p >= 0) ? ld6<R, ST>(scr + (size_t)(L.oBody + NB2_FWD_BODY_WORDS * p) * ST) : zero6<R>();
     V6<R> V;
     if (jt == NB2_JT_REV) {
       R s, c; nb2_sincos(scr[(size_t)(L.oQ + o) * ST], &s, &c);
@@ -216,7 +219,7 @@ NB2_HD void fwd_pass2(const Nb2ModelDev<R>& M, R* scr, R* sv, size_t B, bool sav
   bool hvalid = false;
   for (int i = hi - 1; i >= lo; i--) {
     const int jt = M.jtype[i], p = M.parent[i], o = M.dof_off[i], fl = M.flags[i];
-    R* bs = scr + (size_t)(L.oBody + 22 * i) * ST;
+    R* bs = scr + (size_t)(L.oBody + NB2_FWD_BODY_WORDS * i) * ST;
     R m; V3<R> h; S3<R> Ib; inertia_of(M, bt, i, &m, &h, &Ib);
     const V6<R> V = ld6<R, ST>(bs);
     SI<R> IA = rigidSI(m, h, Ib);
@@ -314,9 +317,9 @@ NB2_HD void fwd_pass3(const Nb2ModelDev<R>& M, R* scr, R* sv, size_t B, bool sav
   V6<R> A0; A0.a = zero3<R>(); A0.l = mk3<R>(-M.gravity[0], -M.gravity[1], -M.gravity[2]);
   for (int i = lo; i < hi; i++) {
     const int jt = M.jtype[i], p = M.parent[i], o = M.dof_off[i];
-    R* bs = scr + (size_t)(L.oBody + 22 * i) * ST;
+    R* bs = scr + (size_t)(L.oBody + NB2_FWD_BODY_WORDS * i) * ST;
     const Xf<R> T = body_xf_fwd<R, ST>(M, bt, i, scr, L);
-    const V6<R> Ap = AdInvT(T, (p >= 0) ? ld6<R, ST>(scr + (size_t)(L.oBody + 22 * p + 16) * ST) : A0);
+    const V6<R> Ap = AdInvT(T, (p >= 0) ? ld6<R, ST>(scr + (size_t)(L.oBody + NB2_FWD_BODY_WORDS * p) * ST) : A0);  // the parent's V slot holds its A by now
     const V6<R> V = ld6<R, ST>(bs);
     V6<R> A;
     if (jt != NB2_JT_FREE) {
@@ -363,7 +366,7 @@ NB2_HD void fwd_pass3(const Nb2ModelDev<R>& M, R* scr, R* sv, size_t B, bool sav
         sq[0] = qdd.a.x; sq[B] = qdd.a.y; sq[2 * B] = qdd.a.z; sq[3 * B] = qdd.l.x; sq[4 * B] = qdd.l.y; sq[5 * B] = qdd.l.z;
       }
     }
-    st6<R, ST>(bs + 16 * ST, A);
+    st6<R, ST>(bs, A);  // A replaces V (see NB2_FWD_BODY_WORDS)
   }
 }
 
