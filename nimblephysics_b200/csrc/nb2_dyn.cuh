@@ -207,7 +207,7 @@ NB2_HD void fwd_pass1(const Nb2ModelDev<R>& M, R* scr, int lo, int hi, const R* 
 }
 
 template <class R, int ST>
-NB2_HD void fwd_pass2(const Nb2ModelDev<R>& M, R* scr, R* sv, size_t B, bool save, int lo, int hi, const R* bt = nullptr) {
+NB2_HD void fwd_pass2(const Nb2ModelDev<R>& M, R* scr, R* sv, size_t B, bool save, int lo, int hi, const R* bt = nullptr, R* iinv_out = nullptr) {
   const int nb = M.nb, n = M.ndof;
   const FwdLayout L = fwd_layout(nb, n, M.nslots, M.nfree);
   const R dt = M.dt;
@@ -281,6 +281,7 @@ NB2_HD void fwd_pass2(const Nb2ModelDev<R>& M, R* scr, R* sv, size_t B, bool sav
       const SI<R> Iinv = spd6_inverse(IA);
       const V6<R> y = mul(Iinv, u);
       st6<R, ST>(scr + (size_t)(L.oFree + 18 * M.free_idx[i] + 12) * ST, y);
+      if (iinv_out) stSI<R, 1, false>(iinv_out + 21 * M.free_idx[i], Iinv);  // fused contact kernel: the contact stage needs it (per-world array, stride 1)
       if (save) {
         const int k0 = nb * 21 + M.free_idx[i] * 33;
         R* s = sv + (size_t)k0 * B;
@@ -478,7 +479,7 @@ NB2_HD void fwd_store(const Nb2ModelDev<R>& M, const R* scr0, float* out0, int n
 #define NB2_FWD_SYNC_MASK 0x6Bu       /* after stages 0, 1, 3, 5, 6 */
 #define NB2_FWD_SYNC_MASK_1LANE 0x41u /* lanes == 1: only the group load / store exchange data between threads */
 template <class R, int ST>
-NB2_HD void world_forward_stage(const Nb2ModelDev<R>& M, R* scr, R* sv, size_t B, bool save, int lane, int stage, const R* bt = nullptr) {
+NB2_HD void world_forward_stage(const Nb2ModelDev<R>& M, R* scr, R* sv, size_t B, bool save, int lane, int stage, const R* bt = nullptr, R* iinv_out = nullptr) {
   const int pass = (stage + 1) >> 1;                          // stages 1..6 -> passes 1, 2, 3
   const bool trunk = (stage == 1) | (stage == 4) | (stage == 5);
   if (trunk && lane != 0) return;
@@ -487,7 +488,7 @@ NB2_HD void world_forward_stage(const Nb2ModelDev<R>& M, R* scr, R* sv, size_t B
     const int r = (pass == 2) ? nr - 1 - rr : rr;
     const int lo = trunk ? M.trunk_lo[r] : M.limb_lo[lane][r], hi = trunk ? M.trunk_hi[r] : M.limb_hi[lane][r];
     if (pass == 1) fwd_pass1<R, ST>(M, scr, lo, hi, bt);
-    else if (pass == 2) fwd_pass2<R, ST>(M, scr, sv, B, save, lo, hi, bt);
+    else if (pass == 2) fwd_pass2<R, ST>(M, scr, sv, B, save, lo, hi, bt, iinv_out);
     else fwd_pass3<R, ST>(M, scr, sv, B, save, lo, hi, bt);
   }
 }

@@ -2,7 +2,8 @@
 // numbers carrying d/d(xi) for the 6 directions of a body-pose perturbation (backward: derivative of the contact
 // point / normal with respect to the pose of the moving body, whatever the contact type).
 // Restates  collideBoxSphere / collideSphereBox   dart/collision/dart/DARTCollide.cpp:1482-1653, 1655-1810
-//           dBoxBox + intersectRectQuad             DARTCollide.cpp:764-1450, 513-580, dLineClosestApproach :270-298
+//           dBoxBox (ODE, Russell Smith; OBB test after Gottschalk) DARTCollide.cpp:764-1450, its rectangle clipper :513-580,
+//           closest points of two lines :270-298
 #pragma once
 #include "nb2_math.cuh"
 
@@ -84,37 +85,99 @@ NB2_HD int collide_box_sphere(const V3<T>& size0, const Xf<T>& T0, const T& r1, 
   return 1;
 }
 
+// ---- box vs box (the algorithm of ODE's dBoxBox as used by the reference, DARTCollide.cpp:764-1450, after Gottschalk's OBB
+// separating-axis test).  Three steps, written here as three functions:
+//   sat_pick_axis      the 15 candidate axes (3 faces of each box, 9 edge x edge), smallest penetration wins; edge axes must
+//                      beat the best face axis by the factor `fudge` (face contacts are preferred)
+//   edge_edge_contact  closest points of the two touching edges
+//   face_contact       the incident face of the other box, projected into the reference face and clipped against its rectangle
+//                      (clip_quad_to_rect); every clip vertex that lies below the reference face becomes a contact
+// The ORDER in which axes are tested and clip vertices are emitted fixes the order of the contacts and therefore the LCP row
+// order, so it follows the reference; expressions keep the reference's operand order where a comparison depends on them.
+template <class T> struct SatAxis {
+  T depth_neg;        // s: largest separation (<= 0 when the boxes overlap)
+  int code;           // 0 none, 1..3 face of box 1, 4..6 face of box 2, 7..15 edge i of box 1 x edge j of box 2 (7 + 3 i + j)
+  bool invert;        // the axis points from box 2 to box 1: flip it
+  V3<T> edge_normal;  // unit axis in box-1 coordinates (edge codes only)
+};
+
+// Sutherland-Hodgman: clip the quadrilateral quad[0..8) = (x0, y0, ..., x3, y3) against |x| <= h[0], |y| <= h[1], one half-plane at
+// a time in the order -x, +x, -y, +y; vertices are emitted in traversal order, a crossing edge emits its intersection after the
+// vertex it leaves from; at most 8 vertices (the walk stops when the 8th is written).  Returns the vertex count.
 template <class T>
-NB2_HD int intersect_rect_quad(const T h[2], T p[8], T ret[16]) {
-  int nq = 4, nr = 0;
-  T buffer[16];
-  T* q = p; T* r = ret;
-  for (int dir = 0; dir <= 1; dir++) {
-    for (int sign = -1; sign <= 1; sign += 2) {
-      T* pq = q; T* pr = r; nr = 0;
-      for (int i = nq; i > 0; i--) {
-        if (sign * gval(pq[dir]) < gval(h[dir])) { pr[0] = pq[0]; pr[1] = pq[1]; pr += 2; nr++; if (nr & 8) { q = r; goto done; } }
-        T* nextq = (i > 1) ? pq + 2 : q;
-        if ((sign * gval(pq[dir]) < gval(h[dir])) ^ (sign * gval(nextq[dir]) < gval(h[dir]))) {
-          pr[1 - dir] = pq[1 - dir] + (nextq[1 - dir] - pq[1 - dir]) / (nextq[dir] - pq[dir]) * (T((double)sign) * h[dir] - pq[dir]);
-          pr[dir] = T((double)sign) * h[dir];
-          pr += 2; nr++;
-          if (nr & 8) { q = r; goto done; }
-        }
-        pq += 2;
+NB2_HD int clip_quad_to_rect(const T h[2], const T quad[8], T out[16]) {
+  T bufA[16], bufB[16];
+  for (int i = 0; i < 8; i++) bufA[i] = quad[i];
+  T* src = bufA; T* dst = bufB;
+  int n = 4;
+  for (int plane = 0; plane < 4; plane++) {
+    const int axis = plane >> 1, other = 1 - axis;
+    const double sg = (plane & 1) ? 1.0 : -1.0;
+    const T bound = T(sg) * h[axis];
+    int k = 0;
+    bool full = false;
+    for (int i = 0; i < n && !full; i++) {
+      const T* a = src + 2 * i;
+      const T* nx = src + 2 * ((i + 1 == n) ? 0 : i + 1);
+      const bool in_a = sg * gval(a[axis]) < gval(h[axis]), in_n = sg * gval(nx[axis]) < gval(h[axis]);
+      if (in_a) { dst[2 * k] = a[0]; dst[2 * k + 1] = a[1]; k++; if (k == 8) { full = true; break; } }
+      if (in_a != in_n) {
+        dst[2 * k + other] = a[other] + (nx[other] - a[other]) / (nx[axis] - a[axis]) * (bound - a[axis]);
+        dst[2 * k + axis] = bound;
+        k++;
+        if (k == 8) full = true;
       }
-      q = r; r = (q == ret) ? buffer : ret; nq = nr;
+    }
+    T* t = src; src = dst; dst = t;
+    n = k;
+    if (full) break;
+  }
+  for (int i = 0; i < 2 * n; i++) out[i] = src[i];
+  return n;
+}
+
+template <class T>
+NB2_HD SatAxis<T> sat_pick_axis(const T A[3], const T Bh[3], const T pp[3], const V3<T>& p, const M3<T>& R2, const T Rm[3][3], const T Q[3][3]) {
+  const double fudge = 1.05;
+  SatAxis<T> ax;
+  ax.depth_neg = T(-1e12); ax.code = 0; ax.invert = false; ax.edge_normal = mk3<T>(T(0.0), T(0.0), T(0.0));
+  // faces of box 1 (axes of box 1), then faces of box 2
+  for (int i = 0; i < 3; i++) {
+    const T e1 = pp[i];
+    const T s2 = nb2_abs(e1) - (A[i] + Bh[0] * Q[i][0] + Bh[1] * Q[i][1] + Bh[2] * Q[i][2]);
+    if (gval(s2) > gval(ax.depth_neg)) { ax.depth_neg = s2; ax.invert = gval(e1) < 0; ax.code = 1 + i; }
+  }
+  for (int j = 0; j < 3; j++) {
+    const T e1 = dot(gcol3(R2, j), p);
+    const T s2 = nb2_abs(e1) - (A[0] * Q[0][j] + A[1] * Q[1][j] + A[2] * Q[2][j] + Bh[j]);
+    if (gval(s2) > gval(ax.depth_neg)) { ax.depth_neg = s2; ax.invert = gval(e1) < 0; ax.code = 4 + j; }
+  }
+  // edge i of box 1 x edge j of box 2: axis = e_i x R2[:, j] in box-1 coordinates, i.e. components (0, -R[i2][j], R[i1][j]) rotated
+  // into place (i1 = i + 1, i2 = i + 2 mod 3); a1 < a2 / b1 < b2 are the two axes other than i / j in ascending order
+  for (int i = 0; i < 3; i++) {
+    const int i1 = (i + 1) % 3, i2 = (i + 2) % 3, a1 = i1 < i2 ? i1 : i2, a2 = i1 < i2 ? i2 : i1;
+    for (int j = 0; j < 3; j++) {
+      const int j1 = (j + 1) % 3, j2 = (j + 2) % 3, b1 = j1 < j2 ? j1 : j2, b2 = j1 < j2 ? j2 : j1;
+      const T e1 = pp[i2] * Rm[i1][j] - pp[i1] * Rm[i2][j];
+      T s2 = nb2_abs(e1) - (A[a1] * Q[a2][j] + A[a2] * Q[a1][j] + Bh[b1] * Q[i][b2] + Bh[b2] * Q[i][b1]);
+      T nc[3];
+      nc[i] = T(0.0); nc[i1] = -Rm[i2][j]; nc[i2] = Rm[i1][j];
+      const T l = nb2_sqrt(nc[0] * nc[0] + nc[1] * nc[1] + nc[2] * nc[2]);
+      if (gval(l) > 0) {
+        s2 = s2 / l;
+        if (gval(s2) * fudge > gval(ax.depth_neg)) {
+          ax.depth_neg = s2; ax.invert = gval(e1) < 0; ax.code = 7 + 3 * i + j;
+          ax.edge_normal = mk3<T>(nc[0] / l, nc[1] / l, nc[2] / l);
+        }
+      }
     }
   }
-done:
-  if (q != ret) for (int i = 0; i < nr * 2; i++) ret[i] = q[i];
-  return nr;
+  return ax;
 }
 
 // dBoxBox; returns the number of contacts written to out (<= 8)
 template <class T>
 NB2_HD int collide_box_box(const V3<T>& size0, const Xf<T>& T0, const V3<T>& size1, const Xf<T>& T1, CR clip, ContactOutT<T>* out) {
-  const double fudge = 1.05;
   const M3<T>&R1 = T0.R_, &R2 = T1.R_;
   const V3<T> p1 = T0.p, p2 = T1.p;
   const T A[3] = {size0.x * T(0.5), size0.y * T(0.5), size0.z * T(0.5)}, Bh[3] = {size1.x * T(0.5), size1.y * T(0.5), size1.z * T(0.5)};
@@ -123,37 +186,17 @@ NB2_HD int collide_box_box(const V3<T>& size0, const Xf<T>& T0, const V3<T>& siz
   const T pp[3] = {ppv.x, ppv.y, ppv.z};
   T Rm[3][3], Q[3][3];
   for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) { Rm[i][j] = dot(gcol3(R1, i), gcol3(R2, j)); Q[i][j] = nb2_abs(Rm[i][j]); }
-  T s = T(-1e12), s2;
-  int invert_normal = 0, code = 0, nbox = 0, ncol = -1;
-  V3<T> normalC = mk3<T>(T(0.0), T(0.0), T(0.0));
-#define NB2_TST(expr1, expr2, box, colj, cc) { const T e1 = (expr1); s2 = nb2_abs(e1) - (expr2); if (gval(s2) > gval(s)) { s = s2; nbox = box; ncol = colj; invert_normal = (gval(e1) < 0); code = (cc); } }
-  NB2_TST(pp[0], (A[0] + Bh[0] * Q[0][0] + Bh[1] * Q[0][1] + Bh[2] * Q[0][2]), 1, 0, 1)
-  NB2_TST(pp[1], (A[1] + Bh[0] * Q[1][0] + Bh[1] * Q[1][1] + Bh[2] * Q[1][2]), 1, 1, 2)
-  NB2_TST(pp[2], (A[2] + Bh[0] * Q[2][0] + Bh[1] * Q[2][1] + Bh[2] * Q[2][2]), 1, 2, 3)
-  NB2_TST(dot(gcol3(R2, 0), p), (A[0] * Q[0][0] + A[1] * Q[1][0] + A[2] * Q[2][0] + Bh[0]), 2, 0, 4)
-  NB2_TST(dot(gcol3(R2, 1), p), (A[0] * Q[0][1] + A[1] * Q[1][1] + A[2] * Q[2][1] + Bh[1]), 2, 1, 5)
-  NB2_TST(dot(gcol3(R2, 2), p), (A[0] * Q[0][2] + A[1] * Q[1][2] + A[2] * Q[2][2] + Bh[2]), 2, 2, 6)
-#undef NB2_TST
-#define NB2_TST2(expr1, expr2, n1, n2, n3, cc) { const T e1 = (expr1); s2 = nb2_abs(e1) - (expr2); const T N1 = (n1), N2 = (n2), N3 = (n3); const T l = nb2_sqrt(N1 * N1 + N2 * N2 + N3 * N3); \
-    if (gval(l) > 0) { s2 = s2 / l; if (gval(s2) * fudge > gval(s)) { s = s2; ncol = -1; normalC = mk3<T>(N1 / l, N2 / l, N3 / l); invert_normal = (gval(e1) < 0); code = (cc); } } }
-  const T Z = T(0.0);
-  NB2_TST2(pp[2] * Rm[1][0] - pp[1] * Rm[2][0], (A[1] * Q[2][0] + A[2] * Q[1][0] + Bh[1] * Q[0][2] + Bh[2] * Q[0][1]), Z, -Rm[2][0], Rm[1][0], 7)
-  NB2_TST2(pp[2] * Rm[1][1] - pp[1] * Rm[2][1], (A[1] * Q[2][1] + A[2] * Q[1][1] + Bh[0] * Q[0][2] + Bh[2] * Q[0][0]), Z, -Rm[2][1], Rm[1][1], 8)
-  NB2_TST2(pp[2] * Rm[1][2] - pp[1] * Rm[2][2], (A[1] * Q[2][2] + A[2] * Q[1][2] + Bh[0] * Q[0][1] + Bh[1] * Q[0][0]), Z, -Rm[2][2], Rm[1][2], 9)
-  NB2_TST2(pp[0] * Rm[2][0] - pp[2] * Rm[0][0], (A[0] * Q[2][0] + A[2] * Q[0][0] + Bh[1] * Q[1][2] + Bh[2] * Q[1][1]), Rm[2][0], Z, -Rm[0][0], 10)
-  NB2_TST2(pp[0] * Rm[2][1] - pp[2] * Rm[0][1], (A[0] * Q[2][1] + A[2] * Q[0][1] + Bh[0] * Q[1][2] + Bh[2] * Q[1][0]), Rm[2][1], Z, -Rm[0][1], 11)
-  NB2_TST2(pp[0] * Rm[2][2] - pp[2] * Rm[0][2], (A[0] * Q[2][2] + A[2] * Q[0][2] + Bh[0] * Q[1][1] + Bh[1] * Q[1][0]), Rm[2][2], Z, -Rm[0][2], 12)
-  NB2_TST2(pp[1] * Rm[0][0] - pp[0] * Rm[1][0], (A[0] * Q[1][0] + A[1] * Q[0][0] + Bh[1] * Q[2][2] + Bh[2] * Q[2][1]), -Rm[1][0], Rm[0][0], Z, 13)
-  NB2_TST2(pp[1] * Rm[0][1] - pp[0] * Rm[1][1], (A[0] * Q[1][1] + A[1] * Q[0][1] + Bh[0] * Q[2][2] + Bh[2] * Q[2][0]), -Rm[1][1], Rm[0][1], Z, 14)
-  NB2_TST2(pp[1] * Rm[0][2] - pp[0] * Rm[1][2], (A[0] * Q[1][2] + A[1] * Q[0][2] + Bh[0] * Q[2][1] + Bh[1] * Q[2][0]), -Rm[1][2], Rm[0][2], Z, 15)
-#undef NB2_TST2
+  const SatAxis<T> ax = sat_pick_axis(A, Bh, pp, p, R2, Rm, Q);
+  const int code = ax.code;
   if (!code) return 0;
-  if (gval(s) > 0.0) return 0;
+  if (gval(ax.depth_neg) > 0.0) return 0;  // a separating axis exists
   V3<T> normal;
-  if (ncol >= 0) normal = gcol3(nbox == 1 ? R1 : R2, ncol);
-  else { normal = mul(R1, normalC); normal = normal * (T(1.0) / nb2_sqrt(dot(normal, normal))); }
-  if (invert_normal) normal = -normal;
+  if (code <= 3) normal = gcol3(R1, code - 1);
+  else if (code <= 6) normal = gcol3(R2, code - 4);
+  else { normal = mul(R1, ax.edge_normal); normal = normal * (T(1.0) / nb2_sqrt(dot(normal, normal))); }
+  if (ax.invert) normal = -normal;
   if (code > 6) {
+    // ---- edge x edge: walk from each box centre to the touching edge, then closest points of the two lines
     V3<T> pa = p1, pb = p2;
     for (int j = 0; j < 3; j++) { const double sg = (gval(dot(normal, gcol3(R1, j))) > -1e-10) ? 1.0 : -1.0; pa = pa + gcol3(R1, j) * (A[j] * T(sg)); }
     for (int j = 0; j < 3; j++) { const double sg = (gval(dot(normal, gcol3(R2, j))) > -1e-3) ? -1.0 : 1.0; pb = pb + gcol3(R2, j) * (Bh[j] * T(sg)); }
@@ -163,48 +206,54 @@ NB2_HD int collide_box_box(const V3<T>& size0, const Xf<T>& T0, const V3<T>& siz
     T d = T(1.0) - uaub * uaub, alpha = T(0.0), beta = T(0.0);
     if (gval(d) > 0.0) { d = T(1.0) / d; alpha = (q1 + uaub * q2) * d; beta = (uaub * q1 + q2) * d; }
     pa = pa + ua * alpha; pb = pb + ub * beta;
-    const T pen = -s;
+    const T pen = -ax.depth_neg;
     if (gval(pen) > clip) return 0;
     out[0].point = (pa + pb) * T(0.5); out[0].normal = -normal; out[0].depth = pen; out[0].type = 3;
     return 1;
   }
-  const M3<T>*Ra, *Rb; V3<T> pa, pb; const T *Sa, *Sb; bool flip;
-  if (code <= 3) { Ra = &R1; Rb = &R2; pa = p1; pb = p2; Sa = A; Sb = Bh; flip = false; }
-  else { Ra = &R2; Rb = &R1; pa = p2; pb = p1; Sa = Bh; Sb = A; flip = true; }
-  const V3<T> normal2 = (code <= 3) ? normal : -normal;
-  const V3<T> nr = mulT(*Rb, normal2);
+  // ---- face contact.  Reference box a = the box owning the face, incident box b = the other one
+  const bool flip = code > 3;
+  const M3<T>& Ra = flip ? R2 : R1; const M3<T>& Rb = flip ? R1 : R2;
+  const V3<T> pa = flip ? p2 : p1, pb = flip ? p1 : p2;
+  const T* Sa = flip ? Bh : A; const T* Sb = flip ? A : Bh;
+  const V3<T> normal2 = flip ? -normal : normal;
+  const int refAxis = flip ? code - 4 : code - 1;
+  // incident face of b: the one most anti-parallel to the reference normal
+  const V3<T> nr = mulT(Rb, normal2);
   const double anr[3] = {fabs(gval(nr.x)), fabs(gval(nr.y)), fabs(gval(nr.z))};
   int lanr, a1, a2;
   if (anr[1] > anr[0]) { if (anr[1] > anr[2]) { a1 = 0; lanr = 1; a2 = 2; } else { a1 = 0; a2 = 1; lanr = 2; } }
   else { if (anr[0] > anr[2]) { lanr = 0; a1 = 1; a2 = 2; } else { a1 = 0; a2 = 1; lanr = 2; } }
-  const V3<T> center = (gval(gget3(nr, lanr)) < 0) ? (pb - pa + gcol3(*Rb, lanr) * Sb[lanr]) : (pb - pa - gcol3(*Rb, lanr) * Sb[lanr]);
-  const int codeN = (code <= 3) ? code - 1 : code - 4;
-  int code1, code2;
-  if (codeN == 0) { code1 = 1; code2 = 2; } else if (codeN == 1) { code1 = 0; code2 = 2; } else { code1 = 0; code2 = 1; }
+  const V3<T> center = (gval(gget3(nr, lanr)) < 0) ? (pb - pa + gcol3(Rb, lanr) * Sb[lanr]) : (pb - pa - gcol3(Rb, lanr) * Sb[lanr]);
+  const int c1i = (refAxis == 0) ? 1 : 0, c2i = (refAxis == 2) ? 1 : 2;  // the two in-plane axes of the reference face
+  // incident face corners in the 2-D coordinates of the reference face
+  const T c1 = dot(center, gcol3(Ra, c1i)), c2 = dot(center, gcol3(Ra, c2i));
+  T m11 = dot(gcol3(Ra, c1i), gcol3(Rb, a1)), m12 = dot(gcol3(Ra, c1i), gcol3(Rb, a2));
+  T m21 = dot(gcol3(Ra, c2i), gcol3(Rb, a1)), m22 = dot(gcol3(Ra, c2i), gcol3(Rb, a2));
   T quad[8];
-  const T c1 = dot(center, gcol3(*Ra, code1)), c2 = dot(center, gcol3(*Ra, code2));
-  T m11 = dot(gcol3(*Ra, code1), gcol3(*Rb, a1)), m12 = dot(gcol3(*Ra, code1), gcol3(*Rb, a2));
-  T m21 = dot(gcol3(*Ra, code2), gcol3(*Rb, a1)), m22 = dot(gcol3(*Ra, code2), gcol3(*Rb, a2));
   {
     const T k1 = m11 * Sb[a1], k2 = m21 * Sb[a1], k3 = m12 * Sb[a2], k4 = m22 * Sb[a2];
     quad[0] = c1 - k1 - k3; quad[1] = c2 - k2 - k4; quad[2] = c1 - k1 + k3; quad[3] = c2 - k2 + k4;
     quad[4] = c1 + k1 + k3; quad[5] = c2 + k2 + k4; quad[6] = c1 + k1 - k3; quad[7] = c2 + k2 - k4;
   }
-  const T rect[2] = {Sa[code1], Sa[code2]};
+  const T rect[2] = {Sa[c1i], Sa[c2i]};
   T ret[16];
-  const int n = intersect_rect_quad(rect, quad, ret);
+  const int n = clip_quad_to_rect(rect, quad, ret);
   if (n < 1) return 0;
+  // back to 3-D: invert the 2x2 projection, keep the vertices below the reference face
   const T det1 = T(1.0) / (m11 * m22 - m12 * m21);
   m11 = m11 * det1; m12 = m12 * det1; m21 = m21 * det1; m22 = m22 * det1;
   int cnum = 0;
   for (int j = 0; j < n; j++) {
     const T k1 = m22 * (ret[j * 2] - c1) - m12 * (ret[j * 2 + 1] - c2);
     const T k2 = -m21 * (ret[j * 2] - c1) + m11 * (ret[j * 2 + 1] - c2);
-    const V3<T> pt = center + gcol3(*Rb, a1) * k1 + gcol3(*Rb, a2) * k2;
-    const T dep = Sa[codeN] - dot(normal2, pt);
+    const V3<T> pt = center + gcol3(Rb, a1) * k1 + gcol3(Rb, a2) * k2;
+    const T dep = Sa[refAxis] - dot(normal2, pt);
     if (gval(dep) >= 0) {
       ContactOutT<T>& c = out[cnum];
       c.point = pt + pa; c.normal = -normal; c.depth = dep;
+      // a clip vertex on a corner of the rectangle is a vertex of the reference box, one strictly inside is a vertex of the incident
+      // box, one on a single side is an edge-edge crossing (DARTCollide.cpp:1283-1379)
       const bool onX = fabs(gval(ret[j * 2])) == gval(rect[0]), onY = fabs(gval(ret[j * 2 + 1])) == gval(rect[1]);
       if (onX && onY) {
         if (flip) { c.type = 2; c.point = c.point + c.normal * c.depth; } else { c.type = 1; c.point = c.point - c.normal * c.depth; }

@@ -4,7 +4,7 @@
 
 #include "../../include/nb2.h"
 #include "nb2_model.h"
-#include "nb2_contact.cuh"
+#include "nb2_cw.cuh"
 
 template <class R>
 static inline bool nb2_fill_model(const nb2_model_desc& d, Nb2ModelDev<R>& M, std::string& err) {
@@ -105,10 +105,10 @@ static inline bool nb2_fill_model(const nb2_model_desc& d, Nb2ModelDev<R>& M, st
 static inline bool nb2_fill_contact(const nb2_model_desc& d, Nb2ContactDev& C, std::string& err) {
   if (d.nshapes < 0 || d.nshapes > NB2_MAX_SHAPES) { err = "model has " + std::to_string(d.nshapes) + " collision shapes; compiled limit is " + std::to_string(NB2_MAX_SHAPES); return false; }
   if (d.npairs < 0 || d.npairs > NB2_MAX_PAIRS) { err = "model has " + std::to_string(d.npairs) + " collision pairs; compiled limit is " + std::to_string(NB2_MAX_PAIRS); return false; }
-  C.nshapes = d.nshapes; C.npairs = d.npairs; C.pen_correction = d.penetration_correction; C.pad = 0;
+  C.nshapes = d.nshapes; C.npairs = d.npairs; C.pen_correction = d.penetration_correction; C.pad_ = 0;
   C.clip_depth = d.contact_clipping_depth; C.fallback_cfm = d.fallback_cfm;
   for (int s = 0; s < NB2_MAX_SHAPES; s++) {
-    C.shape_body[s] = -1; C.shape_type[s] = 0; C.shape_orig_body[s] = -1; C.shape_mu[s] = 0; C.shape_rest[s] = 0;
+    C.shape_body[s] = -1; C.shape_type[s] = 0; C.shape_orig_body[s] = -1; C.shape_mu[s] = 0; C.shape_rest[s] = 0; C.cb_body[s] = -1;
     for (int k = 0; k < 3; k++) C.shape_dims[s][k] = 0;
     for (int k = 0; k < 12; k++) C.shape_T[s][k] = 0;
   }
@@ -124,6 +124,29 @@ static inline bool nb2_fill_contact(const nb2_model_desc& d, Nb2ContactDev& C, s
   for (int p = 0; p < d.npairs; p++) {
     if (d.pair_a[p] < 0 || d.pair_a[p] >= d.nshapes || d.pair_b[p] < 0 || d.pair_b[p] >= d.nshapes) { err = "collision pair references a missing shape"; return false; }
     C.pair_a[p] = (int16_t)d.pair_a[p]; C.pair_b[p] = (int16_t)d.pair_b[p];
+  }
+  // tree tables of the warp-cooperative contact stage: ancestor sets (bit masks: bodies are numbered parents-first, nb <= 64),
+  // depths, and the list of collision bodies (moving bodies carrying at least one shape)
+  for (int i = 0; i < NB2_MAX_BODIES; i++) { C.cb_of_body[i] = -1; C.cdof0[i] = 0; C.anc_mask[i] = 0ull; }
+  for (int i = 0; i < d.nb; i++) {
+    const int p = d.parent[i];
+    C.anc_mask[i] = (1ull << i) | (p >= 0 ? C.anc_mask[p] : 0ull);
+    C.cdof0[i] = (int16_t)(p >= 0 ? C.cdof0[p] + (d.jtype[p] == NB2_JT_FREE ? 6 : 1) : 0);
+  }
+  C.ncb = 0; C.max_chain_dofs = 1;
+  for (int s = 0; s < d.nshapes; s++) {
+    const int bdy = d.shape_body[s];
+    if (bdy < 0 || C.cb_of_body[bdy] >= 0) continue;
+    C.cb_of_body[bdy] = (int16_t)C.ncb; C.cb_body[C.ncb] = (int16_t)bdy; C.ncb++;
+    const int cd = C.cdof0[bdy] + (d.jtype[bdy] == NB2_JT_FREE ? 6 : 1);
+    if (cd > C.max_chain_dofs) C.max_chain_dofs = cd;
+  }
+  // every pair this stage can generate contacts for must be of a supported shape combination: reject the others at model
+  // creation instead of flagging them world by world at run time
+  for (int p = 0; p < d.npairs; p++) {
+    const int ta = d.shape_type[d.pair_a[p]], tb = d.shape_type[d.pair_b[p]];
+    const bool ok = (ta == 0 && tb == 0) || (ta == 0 && tb == 1) || (ta == 1 && tb == 0) || (ta == 0 && tb == 2) || (ta == 2 && tb == 0);
+    if (!ok) { err = "collision pair " + std::to_string(p) + ": shape types (" + std::to_string(ta) + ", " + std::to_string(tb) + ") have no contact generator (supported: box-box, box-sphere, box-capsule)"; return false; }
   }
   return true;
 }

@@ -58,6 +58,7 @@ static int run_bwd(const nb2_model_desc* d, int B, const float* state, const flo
   }
   return 0;
 }
+#if 0  // OLD serial contact stage (being replaced)
 // forward with the contact stage (fp64): ABA kernel body with the saved stream, then the contact kernel body
 static int run_fwd_contact(const nb2_model_desc* d, int B, const float* state, const float* action, float* next, double* saved,
                            double* x_lcp, int* m_lcp, int* labels, int* status, int* nc, float* cinfo, double* crec) {
@@ -106,7 +107,64 @@ static int run_chain(int m, const double* A, const double* b, const double* lo, 
   for (int i = 0; i < m; i++) { x_out[i] = ws.x[i]; mapping_out[i] = ws.mapping[i]; }
   return status;
 }
+#endif
+// fused forward with the contact stage (fp64), as k_cstep_fwd runs it: ABA sweeps (every lane of the schedule), warp-cooperative
+// contact stage on the world's scratch, store.  The saved stream is WORLD-MAJOR (word k of world w at saved[w * words + k]).
+static nb2::cw::Dims contact_dims(const Nb2ModelDev<double>& M, const Nb2ContactDev& C, int MC, int MR) {
+  return nb2::cw::make_dims(M.nb, M.ndof, M.nfree, MC, MR, C.ncb, C.max_chain_dofs);
+}
+static int run_fwd_contact(const nb2_model_desc* d, int B, const float* state, const float* action, float* next, double* saved,
+                           double* x_lcp, int* m_lcp, int* labels, int* status, int* nc, float* cinfo, double* crec, int small_mc, int reverse) {
+  Nb2ModelDev<double> M; Nb2ContactDev C; std::string err;
+  if (!nb2_fill_model(*d, M, err) || !nb2_fill_contact(*d, C, err)) { fprintf(stderr, "emul: %s\n", err.c_str()); return -1; }
+  nb2::FwdLayout L = nb2::fwd_layout(M.nb, M.ndof, M.nslots, M.nfree);
+  const int words = nb2_saved_words(M.nb, M.ndof, M.nfree);
+  const nb2::cw::Dims ds = contact_dims(M, C, small_mc, 3 * small_mc), db = contact_dims(M, C, NB2_MAX_CONTACTS, NB2_MAX_ROWS);
+  std::vector<double> scr(L.total), wss(nb2::cw::ws_doubles(ds)), wsb(nb2::cw::ws_doubles(db));
+  const size_t recd = nb2::cw::record_doubles(M.ndof);
+  for (int w = 0; w < B; w++) {
+    nb2::cw::cw_host_reverse() = reverse && (w & 1);
+    for (auto& x : scr) x = 1e30;
+    for (auto& x : wss) x = 1e30;
+    for (auto& x : wsb) x = 1e30;
+    const float* st = state + (size_t)w * 2 * M.ndof;
+    const nb2::cw::Ws ws0 = nb2::cw::carve(wss.data(), ds);
+    nb2::fwd_load<double, 1>(M, scr.data(), st, action + (size_t)w * M.na, 1, 0, 1);
+    for (int sg = 1; sg < NB2_FWD_STAGES - 1; sg++)
+      for (int l = 0; l < M.lanes; l++) {
+        const int lane = (w & 1) ? M.lanes - 1 - l : l;
+        nb2::world_forward_stage<double, 1>(M, scr.data(), saved + (size_t)w * words, 1, true, lane, sg, nullptr, ws0.Iinv);
+      }
+    nb2::cw::FwdIO io;
+    io.x_io = x_lcp + (size_t)w * NB2_MAX_ROWS; io.m_io = m_lcp + w; io.labels = labels + (size_t)w * NB2_MAX_ROWS; io.status = status + w;
+    io.nc = nc + w; io.cinfo = cinfo ? cinfo + (size_t)w * NB2_MAX_CONTACTS * 10 : nullptr; io.rec = crec ? crec + (size_t)w * recd : nullptr;
+    nb2::cw::contact_forward(M, C, scr.data(), st, wss.data(), ds, wsb.data(), db, ws0.Iinv, io);
+    nb2::fwd_store<double, 1>(M, scr.data(), next + (size_t)w * 2 * M.ndof, 1, 0, 1);
+  }
+  nb2::cw::cw_host_reverse() = 0;
+  return 0;
+}
+// warp-cooperative solve chain (csrc/nb2_cw.cuh) on a caller-supplied boxed LCP; reverse != 0 runs every CW_FOR backwards
+static int run_cw_chain(int m, const double* A, const double* b, const double* lo, const double* hi, const int* fi, const double* x0, int have_x0,
+                        double cfm, double* x_out, int* mapping_out, int reverse) {
+  nb2::cw::cw_host_reverse() = reverse;
+  const nb2::cw::Dims d = nb2::cw::make_dims(1, 1, 0, (m + 2) / 3 + 1, m > 3 ? m : 3, 1, 1);
+  std::vector<double> wsb(nb2::cw::ws_doubles(d), 1e30);
+  const nb2::cw::Ws ws = nb2::cw::carve(wsb.data(), d);
+  const int ld = m | 1;
+  for (int i = 0; i < m; i++) for (int j = 0; j < m; j++) ws.A[i * ld + j] = A[i * m + j];
+  for (int i = 0; i < m; i++) { ws.b[i] = b[i]; ws.lo[i] = lo[i]; ws.hi[i] = hi[i]; ws.findex[i] = fi[i]; }
+  const int status = nb2::cw::lcp_chain(m, ws, cfm, have_x0 ? x0 : nullptr);
+  for (int i = 0; i < m; i++) { x_out[i] = ws.x[i]; mapping_out[i] = ws.mapping[i]; }
+  nb2::cw::cw_host_reverse() = 0;
+  return status;
+}
 extern "C" {
+int emul_cw_solve_chain(int m, const double* A, const double* b, const double* lo, const double* hi, const int* fi, const double* x0, int have_x0,
+                        double cfm, double* x_out, int* mapping_out, int reverse) {
+  return run_cw_chain(m, A, b, lo, hi, fi, x0, have_x0, cfm, x_out, mapping_out, reverse);
+}
+#if 0
 int emul_solve_chain(int m, const double* A, const double* b, const double* lo, const double* hi, const int* fi, const double* x0, int have_x0,
                      double cfm, double* x_out, int* mapping_out) {
   return run_chain(m, A, b, lo, hi, fi, x0, have_x0, cfm, x_out, mapping_out);
@@ -120,6 +178,12 @@ int emul_backward_contact(const nb2_model_desc* d, int B, const float* state, co
                           const double* crec, const float* gnext, float* gstate, float* gaction, float* ginertia) {
   return run_bwd_contact(d, B, state, action, saved, crec, gnext, gstate, gaction, ginertia);
 }
+#endif
+int emul_forward_contact(const nb2_model_desc* d, int B, const float* state, const float* action, float* next, double* saved,
+                         double* x_lcp, int* m_lcp, int* labels, int* status, int* nc, float* cinfo, double* crec, int small_mc, int reverse) {
+  return run_fwd_contact(d, B, state, action, next, saved, x_lcp, m_lcp, labels, status, nc, cinfo, crec, small_mc, reverse);
+}
+int emul_contact_rec_doubles(const nb2_model_desc* d) { return (int)nb2::cw::record_doubles(d->ndof); }
 int emul_saved_words(const nb2_model_desc* d) {
   int nfree = 0; for (int i = 0; i < d->nb; i++) nfree += d->jtype[i] == NB2_JT_FREE;
   return nb2_saved_words(d->nb, d->ndof, nfree);
