@@ -245,15 +245,15 @@ template <bool UNIT> NB2_HD void trsv_lower_T(int n, const double* Lp, int ld, c
 // ------------------------------------------------------------------------------------------------ workspace
 // Capacities of one world's workspace: MC contacts, MR LCP rows, LD = MR | 1 (odd leading dimension: row AND column walks of a
 // matrix are bank-conflict free).  Problems are stored with their own leading dimension ld = m | 1 <= LD.
-struct Dims { int nb, n, MC, MR, LD, ncb, cdofs, nfree; size_t mats; };
+struct Dims { int nb, n, MC, MR, LD, ncb, cdofs, nfree, bwd; size_t mats; };
 // bytes of one pair slot of the collision phase: count, status, 8 contacts x (point, normal, depth, type)
 #define NB2_CW_PAIR_SLOT 66
-NB2_HD Dims make_dims(int nb, int n, int nfree, int MC, int MR, int ncb, int cdofs) {
-  Dims d; d.nb = nb; d.n = n; d.nfree = nfree; d.MC = MC; d.MR = MR; d.LD = MR | 1; d.ncb = ncb; d.cdofs = cdofs;
+NB2_HD Dims make_dims(int nb, int n, int nfree, int MC, int MR, int ncb, int cdofs, int bwd = 0) {
+  Dims d; d.nb = nb; d.n = n; d.nfree = nfree; d.MC = MC; d.MR = MR; d.LD = MR | 1; d.ncb = ncb; d.cdofs = cdofs; d.bwd = bwd;
   // the two work matrices double as: private chain buffers of the impulse tests (one per row / collision body), spatial velocity
   // changes of all bodies (impulse application), pair slots of the collision phase (at least 4)
   size_t mats = 2 * (size_t)MR * d.LD;
-  const size_t priv = (size_t)MR * cdofs, dv = (size_t)ncb * cdofs + (size_t)nb * 6, slots = 4 * (size_t)NB2_CW_PAIR_SLOT;
+  const size_t priv = (size_t)MR * cdofs, dv = (size_t)ncb * cdofs + (size_t)nb * (bwd ? 18 : 6), slots = 4 * (size_t)NB2_CW_PAIR_SLOT;
   if (mats < priv) mats = priv;
   if (mats < dv) mats = dv;
   if (mats < slots) mats = slots;
@@ -264,6 +264,7 @@ struct Ws {
   double *Wcb, *Vcb, *Fcb;      // [ncb][12], [ncb][6], [ncb][6]: world transform / spatial velocity (at v*) / net impulse of the collision bodies
   double *uI, *dqd;             // [n]
   double *Iinv;                 // [nfree][21] inverse articulated inertia of the FREE bodies (forward: written by the ABA pass)
+  double *aeff, *vplus, *JcTmu, *inj;  // backward only: [n] [n] [n] [ncb][24]
   double *cpoint, *cnormal, *cdepth, *cmu, *crest;   // contacts
   int *cbodyA, *cbodyB, *ctype, *cshapeA, *cshapeB, *crow;  // crow: first LCP row of a contact
   double *JA, *JB;              // [MR][6] body-frame wrenches of a row on body A / B
@@ -278,7 +279,7 @@ struct Ws {
 NB2_HD size_t ws_doubles(const Dims& d) {
   const size_t MC = d.MC, MR = d.MR;
   const size_t mats = d.mats;
-  return (size_t)d.ncb * 24 + 2 * d.n + (size_t)d.nfree * 21 + MC * 9 + 6 * ((MC + 1) / 2) + 2 * MR * 6 + 6 * MR + 5 * ((MR + 1) / 2) + MR * d.LD + mats + 11 * MR +
+  return (size_t)d.ncb * 24 + 2 * d.n + (size_t)d.nfree * 21 + (d.bwd ? 3 * (size_t)d.n + 24 * (size_t)d.ncb : 0) + MC * 9 + 6 * ((MC + 1) / 2) + 2 * MR * 6 + 6 * MR + 5 * ((MR + 1) / 2) + MR * d.LD + mats + 11 * MR +
          4 * ((MR + 1) / 2) + ((size_t)d.ncb + 1) / 2 + 4;
 }
 NB2_HD Ws carve(double* base, const Dims& d) {
@@ -288,6 +289,7 @@ NB2_HD Ws carve(double* base, const Dims& d) {
   auto D = [&](size_t cnt) { double* r = base + off; off += cnt; return r; };
   auto I = [&](size_t cnt) { int* r = (int*)(base + off); off += (cnt + 1) / 2; return r; };
   w.Wcb = D((size_t)d.ncb * 12); w.Vcb = D((size_t)d.ncb * 6); w.Fcb = D((size_t)d.ncb * 6); w.uI = D(d.n); w.dqd = D(d.n); w.Iinv = D((size_t)d.nfree * 21);
+  if (d.bwd) { w.aeff = D(d.n); w.vplus = D(d.n); w.JcTmu = D(d.n); w.inj = D((size_t)d.ncb * 24); } else { w.aeff = w.vplus = w.JcTmu = w.inj = nullptr; }
   w.cpoint = D(MC * 3); w.cnormal = D(MC * 3); w.cdepth = D(MC); w.cmu = D(MC); w.crest = D(MC);
   w.cbodyA = I(MC); w.cbodyB = I(MC); w.ctype = I(MC); w.cshapeA = I(MC); w.cshapeB = I(MC); w.crow = I(MC);
   w.JA = D(MR * 6); w.JB = D(MR * 6);
@@ -1412,6 +1414,276 @@ NB2_HD void contact_forward(const Nb2ModelDev<double>& M, const Nb2ContactDev& C
   }
   CW_ONE { *io.m_io = m; *io.status = status; if (io.rec) { io.rec[0] = (double)m; io.rec[1] = (double)status; } }
   CW_SYNC();
+}
+
+// =====================================================================================================
+// backward through the contact stage (classification frozen at the forward solution), adjoint form.
+// With  P = A_c + A_ub E,  f = Q^+ b_c,  v+ = v* + M^-1 P f  (BackpropSnapshot.cpp:980-1107 materialises the Jacobians of
+// this map); for an incoming g = dL/dv+ :
+//     lambda = M^-1 g ;  fbar = P^T lambda ;  mu = Q^-T fbar ;  nu = M^-1 A_c mu ;  w = lambda - nu
+//     dL/dv* = g - A_c mu  (so the ABA part is back-propagated with w in place of lambda and the REALISED acceleration
+//     (v+ - v)/dt in place of the unconstrained one) ;  dL/dtau = dt w
+//     contact-Jacobian part:  d/dq of  Phi(q) = sum_r  f_r J_r(q) w  -  mu_r J_r(q) v+   at fixed w, v+  (upper-bound rows: f_r := x_r, mu_r := 0),
+//     split into (i) the motion of the contact frame with the pose of the moving body — the contact generator re-run on
+//     dual numbers, one pose direction per lane, any contact type — and (ii) the kinematic chain (reverse velocity recursion).
+// Runs between the lambda sweeps (B1/B2) and the reverse RNEA sweep (B3) of the backward kernel, all 32 lanes:
+//     scr: lambda -> w, W_i -> W_i(w);   returned views: per-body injections, realised accelerations, v+ fields.
+// Q is re-measured by impulse tests on the clamping / upper-bound rows (cheap here) instead of being stored by the forward.
+// =====================================================================================================
+typedef DualT<1> D1;
+// world transform W of a body perturbed by the body twist direction kx:  W (I + [xi_w]x , xi_v), derivative part only for kx
+NB2_HD Xf<D1> dual_pose1(const Xf<double>& Wd, int kx) {
+  Xf<D1> WD;
+  const double* r = &Wd.R_.m00; D1* o = &WD.R_.m00;
+  for (int i = 0; i < 9; i++) o[i] = D1(r[i]);
+  WD.p.x = D1(Wd.p.x); WD.p.y = D1(Wd.p.y); WD.p.z = D1(Wd.p.z);
+  const V3<double> c0 = mk3<double>(Wd.R_.m00, Wd.R_.m10, Wd.R_.m20), c1 = mk3<double>(Wd.R_.m01, Wd.R_.m11, Wd.R_.m21), c2 = mk3<double>(Wd.R_.m02, Wd.R_.m12, Wd.R_.m22);
+  // d(R [e_k]x)/d.: column j of R [e_k]x is R (e_k x e_j)
+  if (kx == 0) { WD.R_.m01.d[0] = c2.x; WD.R_.m11.d[0] = c2.y; WD.R_.m21.d[0] = c2.z; WD.R_.m02.d[0] = -c1.x; WD.R_.m12.d[0] = -c1.y; WD.R_.m22.d[0] = -c1.z; }
+  else if (kx == 1) { WD.R_.m00.d[0] = -c2.x; WD.R_.m10.d[0] = -c2.y; WD.R_.m20.d[0] = -c2.z; WD.R_.m02.d[0] = c0.x; WD.R_.m12.d[0] = c0.y; WD.R_.m22.d[0] = c0.z; }
+  else if (kx == 2) { WD.R_.m00.d[0] = c1.x; WD.R_.m10.d[0] = c1.y; WD.R_.m20.d[0] = c1.z; WD.R_.m01.d[0] = -c0.x; WD.R_.m11.d[0] = -c0.y; WD.R_.m21.d[0] = -c0.z; }
+  else { const V3<double> c = (kx == 3) ? c0 : (kx == 4 ? c1 : c2); WD.p.x.d[0] = c.x; WD.p.y.d[0] = c.y; WD.p.z.d[0] = c.z; }
+  return WD;
+}
+NB2_HD Xf<D1> lift1(const Xf<double>& X) {
+  Xf<D1> o; const double* r = &X.R_.m00; D1* q = &o.R_.m00;
+  for (int i = 0; i < 9; i++) q[i] = D1(r[i]);
+  o.p.x = D1(X.p.x); o.p.y = D1(X.p.y); o.p.z = D1(X.p.z);
+  return o;
+}
+
+NB2_HD BwdContactData<1> contact_backward(const Nb2ModelDev<double>& M, const Nb2ContactDev& C, const float* st, const double* sv, double* ws_small,
+                                          const Dims& d_s, double* ws_big, const Dims& d_b, const double* rec, double* scr, int oLam, int oBody) {
+  const int nb = M.nb, n = M.ndof;
+  BwdContactData<1> cd;
+  cd.Aacc.p = cd.Uplus.p = cd.aeff.p = cd.vplus.p = cd.inj.p = cd.JcTmu.p = nullptr;
+  cd.inj_of_body = C.cb_of_body; cd.active = 0; cd.error = 0;
+  const int m = (int)rec[0];
+  if (m <= 0) return cd;
+  cd.active = 1;
+  const int fstatus = (int)rec[1];
+  // restitution: b depends on v* through (1 + e) J v*, which needs a second multiplier field in the reverse sweep
+  // (BackpropSnapshot::getBounceApproximationJacobian, BackpropSnapshot.cpp:1131-1226) — not implemented: fail loudly
+  if (fstatus & NB2_ST_BOUNCE) { cd.error = 5; cd.active = 0; return cd; }
+  Ws ws = carve(ws_small, d_s);
+  Dims d = d_s;
+  TreeSrc S; S.scr = nullptr; S.Iinv = nullptr; S.sv = sv; S.st = st; S.nb = nb; S.nfree = M.nfree;
+  S.L = fwd_layout(nb, n, M.nslots, M.nfree);
+  const double dt = M.dt;
+  const int kQdd = nb * 21 + M.nfree * 33;
+  const double* mapping_r = rec + 2; const double* xr = rec + 2 + NB2_MAX_ROWS; const double* dqd_imp = rec + 2 + 2 * NB2_MAX_ROWS;
+  // ---- contacts and row wrenches re-generated from the saved transforms (same code as the forward => same rows)
+  fk_collision_bodies(M, C, S, nullptr, ws);
+  collide_and_filter(C, ws, d);
+  if (ws.meta[3] && ws_big) {
+    const Ws wb = carve(ws_big, d_b);
+    CW_FOR(e, C.ncb * 12) wb.Wcb[e] = ws.Wcb[e];
+    CW_SYNC();
+    ws = wb; d = d_b;
+    collide_and_filter(C, ws, d);
+  }
+  if (ws.meta[3] || ws.meta[0] != m) { cd.error = 3; cd.active = 0; return cd; }
+  const int nc = ws.meta[1];
+  build_rows(M, C, ws, m, false);
+  cd.aeff.p = ws.aeff; cd.vplus.p = ws.vplus; cd.JcTmu.p = ws.JcTmu; cd.inj.p = ws.inj;
+  double* dVb = ws.M1 + (size_t)C.ncb * C.max_chain_dofs;
+  double* Aacc = dVb + (size_t)nb * 6; double* Uplus = Aacc + (size_t)nb * 6;
+  cd.Aacc.p = Aacc; cd.Uplus.p = Uplus;
+  // ---- clamping / upper-bound sets from the saved labels
+  int* mapping = ws.mapping; int* clampIdx = ws.clampIdx; int* cl = ws.i1; int* ubl = ws.i2; int* rows = ws.i3;
+  CW_FOR(j, m) { mapping[j] = (int)mapping_r[j]; clampIdx[j] = -1; ws.x[j] = xr[j]; }
+  CW_SYNC();
+  const int nCl = cw_enumerate(m, [&](int j) { return mapping[j] == NB2_MAP_CLAMPING; }, [&](int j, int r) { cl[r] = j; clampIdx[j] = r; rows[r] = j; });
+  const int nUb = cw_enumerate(m, [&](int j) { return mapping[j] >= 0; }, [&](int j, int r) { ubl[r] = j; });
+  CW_SYNC();
+  CW_FOR(u, nUb) rows[nCl + u] = ubl[u];
+  double* rdot = ws.v1; double* fbar = ws.v2; double* mu_c = ws.v3; double* Eu = ws.v4; double* coefM = ws.v5; double* coefW = ws.v7; double* coefV = ws.v8;
+  auto Wfield = [&](int body) { return ld6<double, 1>(scr + oBody + 7 * body + 1); };
+  CW_FOR(j, m) {  // J_j lambda-field: wrench of row j against the field induced on its (one or two) bodies
+    const int c = ws.rowc[j];
+    double a = 0;
+    if (ws.cbodyA[c] >= 0) a += dot(ldv6(ws.JA + 6 * j), Wfield(ws.cbodyA[c]));
+    if (ws.cbodyB[c] >= 0) a += dot(ldv6(ws.JB + 6 * j), Wfield(ws.cbodyB[c]));
+    rdot[j] = a;
+  }
+  CW_FOR(u, nUb) {
+    const int j = ubl[u], fp = mapping[j];
+    const double rmu = ws.cmu[ws.rowc[j]];
+    const double up = xr[fp] * rmu, low = -xr[fp] * rmu;
+    Eu[u] = (fabs(xr[j] - up) < fabs(xr[j] - low)) ? rmu : -rmu;
+  }
+  CW_SYNC();
+  CW_FOR(r, nCl) {
+    double f = rdot[cl[r]];
+    for (int u = 0; u < nUb; u++) if (clampIdx[mapping[ubl[u]]] == r) f += Eu[u] * rdot[ubl[u]];
+    fbar[r] = f; mu_c[r] = 0;
+  }
+  CW_SYNC();
+  if (nCl > 0) {
+    const int ld = m | 1, lq = nCl | 1;
+    assemble_A(M, C, S, ws, m, ld, rows, nCl + nUb);  // rows cl and ub of A, measured
+    // Q = A[cl,cl] + A[cl,ub] E (+ cfm on the diagonal when the forward's fallback added it); as in the forward, an entry below the
+    // block diagonal is the mirror image of its measured partner
+    double* Q = ws.M1;
+    auto Aget = [&](int r, int c) { return (ws.rowc[c] < ws.rowc[r]) ? ws.A[(size_t)c * ld + r] : ws.A[(size_t)r * ld + c]; };
+    const double cfm = (fstatus & NB2_ST_PGS) ? C.fallback_cfm : 0.0;
+    CW_FOR(e, nCl * nCl) {
+      const int r = e / nCl, c = e - r * nCl;
+      double q = Aget(cl[r], cl[c]);
+      if (r == c) q += cfm;
+      for (int u = 0; u < nUb; u++) if (clampIdx[mapping[ubl[u]]] == c) q += Aget(cl[r], ubl[u]) * Eu[u];
+      ws.M2[(size_t)r * lq + c] = q;
+    }
+    CW_SYNC();  // (built in M2: M1 still holds the private buffers of assemble_A for lanes that are not done reading A ... they are: synced)
+    if (nUb == 0) pinv_psd(nCl, ws.M2, lq, fbar, mu_c, ws.M1, ws.v5, ws.v6, ws.v9, ws.i4);
+    else {  // Q^T mu = fbar  ->  mu = (Q Q^T)^+ Q fbar
+      double* Qm = ws.M2; double* QQt = ws.M1; double* Qf = ws.v10;
+      CW_FOR(e, nCl * nCl) {
+        const int a = e / nCl, c = e - a * nCl;
+        double t = 0; for (int kx = 0; kx < nCl; kx++) t += Qm[(size_t)a * lq + kx] * Qm[(size_t)c * lq + kx];
+        QQt[(size_t)a * lq + c] = t;
+      }
+      CW_FOR(a, nCl) { double sacc = 0; for (int c = 0; c < nCl; c++) sacc += Qm[(size_t)a * lq + c] * fbar[c]; Qf[a] = sacc; }
+      CW_SYNC();
+      pinv_psd(nCl, QQt, lq, Qf, mu_c, Qm /* Lf */, ws.v5, ws.v6, ws.v9, ws.i4);
+    }
+  }
+  // ---- nu = M^-1 A_c mu  (one impulse response) ; w = lambda - nu ; W_i(w)
+  CW_FOR(j, m) coefM[j] = (clampIdx[j] >= 0) ? mu_c[clampIdx[j]] : 0.0;
+  CW_SYNC();
+  net_wrenches(C, ws, m, coefM, ws.Fcb);
+  impulse_response_all(M, C, S, ws, ws.Fcb, dVb);
+  CW_FOR(dd, n) scr[oLam + dd] -= ws.dqd[dd];
+  CW_FOR(e, nb * 6) { const int i = e / 6, k = e - 6 * i; scr[oBody + 7 * i + 1 + k] -= dVb[e]; }
+  // ---- realised accelerations, v+, and the fields they induce
+  CW_FOR(dd, n) { const double ae = sv[kQdd + dd] + dqd_imp[dd] / dt; ws.aeff[dd] = ae; ws.vplus[dd] = (double)st[n + dd] + dt * ae; }
+  CW_SYNC();
+  {
+    V6<double> A0; A0.a = zero3<double>(); A0.l = mk3<double>(-M.gravity[0], -M.gravity[1], -M.gravity[2]);
+    auto sweep = [&](int lo, int hi) {
+      for (int i = lo; i < hi; i++) {
+        const int jt = M.jtype[i], p = M.parent[i], o = M.dof_off[i];
+        const Xf<double> T = ts_xf(M, S, i);
+        const V6<double> V = ldv6(sv + i * 21);
+        V6<double> Ai = AdInvT(T, (p >= 0) ? ldv6(Aacc + 6 * p) : A0);
+        V6<double> Ui = (p >= 0) ? AdInvT(T, ldv6(Uplus + 6 * p)) : zero6<double>();
+        if (jt != NB2_JT_FREE) {
+          const V6<double> Sv = S_times<double>(jt, (double)st[n + o]);
+          Ai = Ai + S_times<double>(jt, ws.aeff[o]) + ad(V, Sv);
+          Ui = Ui + S_times<double>(jt, ws.vplus[o]);
+        } else {
+          V6<double> Sv; Sv.a = mk3<double>((double)st[n + o], (double)st[n + o + 1], (double)st[n + o + 2]); Sv.l = mk3<double>((double)st[n + o + 3], (double)st[n + o + 4], (double)st[n + o + 5]);
+          Ai = Ai + ldv6(ws.aeff + o) + ad(V, Sv);
+          Ui = Ui + ldv6(ws.vplus + o);
+        }
+        stv6(Aacc + 6 * i, Ai); stv6(Uplus + 6 * i, Ui);
+      }
+    };
+    CW_FOR(l, 1) for (int r = 0; r < M.trunk_n; r++) sweep(M.trunk_lo[r], M.trunk_hi[r]);
+    CW_SYNC();
+    CW_FOR(l, M.lanes) for (int r = 0; r < M.limb_n[l]; r++) sweep(M.limb_lo[l][r], M.limb_hi[l][r]);
+    CW_SYNC();
+  }
+  // ---- per-body injections for the reverse sweep: Uw_bar, Up_bar, G (all scaled by -1/dt: they join the (dID/dq)^T w accumulator
+  // that is multiplied by -dt at the end) and H (plain: A_c mu propagated to joint space).  One collision body per lane.
+  const double kap = -1.0 / dt;
+  CW_FOR(j, m) {
+    double cW = 0, cV = 0;
+    if (clampIdx[j] >= 0) { cW = xr[j]; cV = -mu_c[clampIdx[j]]; }
+    else if (mapping[j] >= 0) cW = xr[j];
+    coefW[j] = cW; coefV[j] = cV;
+  }
+  CW_SYNC();
+  CW_FOR(k, C.ncb) {
+    const int t = C.cb_body[k];
+    double* bj = ws.inj + 24 * k;
+    for (int e = 0; e < 24; e++) bj[e] = 0;
+    for (int j = 0; j < m; j++) {
+      const double cW = coefW[j], cV = coefV[j], cH = coefM[j];
+      if (cW == 0.0 && cV == 0.0 && cH == 0.0) continue;
+      const int c = ws.rowc[j];
+      for (int side = 0; side < 2; side++) {
+        if ((side ? ws.cbodyB[c] : ws.cbodyA[c]) != t) continue;
+        const double* F = (side ? ws.JB : ws.JA) + 6 * j;
+        for (int kx = 0; kx < 6; kx++) { bj[kx] += kap * cW * F[kx]; bj[6 + kx] += kap * cV * F[kx]; bj[18 + kx] += cH * F[kx]; }
+      }
+    }
+  }
+  CW_SYNC();
+  // ---- contact-frame part G: derivatives of every wrench with respect to the pose of each moving body of its pair.  Work item =
+  // (pair that produced contacts, body whose pose varies); each item takes 6 lanes, one pose direction each: the contact
+  // generator runs on 1-direction dual numbers.  Contacts of a pair are consecutive: groups are found from the shape indices.
+  int* gfirst = ws.i1; int* it_g = ws.i2; int* it_dyn = ws.i4;  // cl / ubl are dead by now
+  const int ng = cw_enumerate(nc, [&](int c) { return c == 0 || ws.cshapeA[c] != ws.cshapeA[c - 1] || ws.cshapeB[c] != ws.cshapeB[c - 1]; },
+                              [&](int c, int r) { gfirst[r] = c; });
+  CW_SYNC();
+  CW_ONE {
+    int ni = 0;
+    for (int g = 0; g < ng; g++) {
+      const int c0 = gfirst[g];
+      if (ws.cbodyA[c0] >= 0) { it_g[ni] = g; it_dyn[ni] = ws.cbodyA[c0]; ni++; }
+      if (ws.cbodyB[c0] >= 0) { it_g[ni] = g; it_dyn[ni] = ws.cbodyB[c0]; ni++; }
+    }
+    ws.meta[5] = ni;
+  }
+  CW_SYNC();
+  const int nitems = ws.meta[5];
+  bool bad = false;
+  double* gpart = ws.M2;  // [5][6]
+  for (int it0 = 0; it0 < nitems; it0 += 5) {
+    const int cnt = (nitems - it0 < 5) ? nitems - it0 : 5;
+    CW_FOR(q, cnt * 6) {
+      const int it = it0 + q / 6, kx = q % 6;
+      const int g = it_g[it], dyn = it_dyn[it];
+      const int c0 = gfirst[g], c1 = (g + 1 < ng) ? gfirst[g + 1] : nc;
+      const int sa = ws.cshapeA[c0], sb = ws.cshapeB[c0], ba = ws.cbodyA[c0], bb = ws.cbodyB[c0];
+      Xf<D1> WDa, WDb;
+      if (ba >= 0) { const Xf<double> Wa = ldXf<double, 1>(ws.Wcb + 12 * C.cb_of_body[ba]); WDa = (ba == dyn) ? dual_pose1(Wa, kx) : lift1(Wa); }
+      if (bb >= 0) { const Xf<double> Wb = ldXf<double, 1>(ws.Wcb + 12 * C.cb_of_body[bb]); WDb = (bb == dyn) ? dual_pose1(Wb, kx) : lift1(Wb); }
+      const Xf<D1> TsA = lift1(ldXf<double, 1>(C.shape_T[sa])), TsB = lift1(ldXf<double, 1>(C.shape_T[sb]));
+      const Xf<D1> Ta = (ba >= 0) ? gxf_mul(WDa, TsA) : TsA;
+      const Xf<D1> Tb = (bb >= 0) ? gxf_mul(WDb, TsB) : TsB;
+      ContactOutT<D1> co[8];
+      int st2 = 0;
+      const int k = pair_contacts<D1>(C, sa, sb, Ta, Tb, co, &st2);
+      double gsum = 0;
+      int cc = c0;
+      for (int c = 0; c < k; c++) {
+        const double nx = co[c].normal.x.v, ny = co[c].normal.y.v, nz = co[c].normal.z.v;
+        if (nx * nx + ny * ny + nz * nz < 1e-12) continue;
+        if (co[c].depth.v < 0.0 || co[c].depth.v > C.clip_depth) continue;
+        if (cc >= c1) { bad = true; break; }
+        const bool fric = ws.cmu[cc] > 1e-3;
+        V3<D1> dirs[3]; dirs[0] = co[c].normal;
+        if (fric) tangent_basis<D1>(co[c].normal, &dirs[1], &dirs[2]);
+        V3<D1> pA, pB;
+        if (ba >= 0) pA = gxf_apply_inv(WDa, co[c].point);
+        if (bb >= 0) pB = gxf_apply_inv(WDb, co[c].point);
+        for (int kk = 0; kk < (fric ? 3 : 1); kk++) {
+          const int r = ws.crow[cc] + kk;
+          const double cW = coefW[r], cV = coefV[r];
+          if (cW == 0.0 && cV == 0.0) continue;
+          for (int side = 0; side < 2; side++) {
+            const int body = side ? bb : ba;
+            if (body < 0) continue;
+            const V3<D1> dd = side ? mulT(WDb.R_, -dirs[kk]) : mulT(WDa.R_, dirs[kk]);
+            const V3<D1> mo = cross(side ? pB : pA, dd);
+            const V6<double> Ww = Wfield(body), Up = ldv6(Uplus + 6 * body);
+            gsum += mo.x.d[0] * (cW * Ww.a.x + cV * Up.a.x) + mo.y.d[0] * (cW * Ww.a.y + cV * Up.a.y) + mo.z.d[0] * (cW * Ww.a.z + cV * Up.a.z)
+                  + dd.x.d[0] * (cW * Ww.l.x + cV * Up.l.x) + dd.y.d[0] * (cW * Ww.l.y + cV * Up.l.y) + dd.z.d[0] * (cW * Ww.l.z + cV * Up.l.z);
+          }
+        }
+        cc++;
+      }
+      if (cc != c1) bad = true;
+      gpart[q] = kap * gsum;
+    }
+    CW_SYNC();
+    CW_ONE { for (int q = 0; q < cnt * 6; q++) ws.inj[24 * C.cb_of_body[it_dyn[it0 + q / 6]] + 12 + q % 6] += gpart[q]; }
+    CW_SYNC();
+  }
+  if (cw_any(bad)) { cd.error = 3; cd.active = 0; }
+  return cd;
 }
 
 }  // namespace cw

@@ -503,21 +503,16 @@ NB2_HD void world_forward(const Nb2ModelDev<R>& M, R* scr, const float* st, cons
   fwd_store<R, ST>(M, scr, out, 1, 0, 1);
 }
 
-// hook implemented in nb2_contact.cuh: turns lambda / W into w / W(w) and prepares the contact injections
-struct BwdContactHook {
-  const void* model_contact;  // const Nb2ContactDev*
-  double* ws;                 // contact workspace block of this warp (device) / world (host)
-  int lane;                   // lane inside the block (0 on the host)
-  const double* crec;         // per-world contact record written by the forward pass
-};
+// what the contact-stage adjoint (nb2_cw.cuh, contact_backward) hands to the reverse sweep B3 / the assembly: per-world arrays
+// (stride ST like the scratch; the fused contact kernels use ST = 1).  inj is COMPACT: one record per collision body
+// (inj_of_body[i] = record index or -1), Uw_bar(6) Up_bar(6) G(6) H(6).
 template <class T, int ST> struct SPd { T* p; NB2_HD T& operator[](int i) const { return p[(size_t)i * ST]; } NB2_HD SPd operator+(int k) const { SPd r; r.p = p + (size_t)k * ST; return r; } };
 template <int ST>
-struct BwdContactData {  // filled by the hook (all double, strided like the contact workspace)
-  SPd<double, ST> Aacc, Uplus, aeff, vplus, inj, JcTmu; int active; int error;
+struct BwdContactData {
+  SPd<double, ST> Aacc, Uplus, aeff, vplus, inj, JcTmu;
+  const int16_t* inj_of_body;
+  int active; int error;
 };
-template <int ST>
-NB2_HD BwdContactData<ST> contact_backward_hook(const Nb2ModelDev<double>& M, const BwdContactHook& H, const float* st, const double* sv, size_t B,
-                                            double* scr, int oLam, int oBody);
 
 // d(Y^T G X)/d(m, h(3), Ibar(xx,yy,zz,xy,xz,yz)) for G X = [Ibar w + h x v ; m v - h x w]
 template <class R> NB2_HD void inertia_param_form(const V6<R>& Y, const V6<R>& X, R* t) {
@@ -657,11 +652,14 @@ NB2_HD void bwd_B3(const Nb2ModelDev<R>& M, R* scr, const float* st, const R* sv
     if (hvalid) { Abar = Abar + hA; Vbar = Vbar + hV; f = f + hf; }
     V6<R> Uw = zero6<R>(), Up = zero6<R>(), Gc = zero6<R>(), Hc = zero6<R>();  // contact adjoints (CONTACT only)
     if (CONTACT && cd.active) {
-      const auto b24 = cd.inj + 24 * i;
-      Uw.a = mk3<R>((R)b24[0], (R)b24[1], (R)b24[2]); Uw.l = mk3<R>((R)b24[3], (R)b24[4], (R)b24[5]);
-      Up.a = mk3<R>((R)b24[6], (R)b24[7], (R)b24[8]); Up.l = mk3<R>((R)b24[9], (R)b24[10], (R)b24[11]);
-      Gc.a = mk3<R>((R)b24[12], (R)b24[13], (R)b24[14]); Gc.l = mk3<R>((R)b24[15], (R)b24[16], (R)b24[17]);
-      Hc.a = mk3<R>((R)b24[18], (R)b24[19], (R)b24[20]); Hc.l = mk3<R>((R)b24[21], (R)b24[22], (R)b24[23]);
+      const int ci = cd.inj_of_body[i];
+      if (ci >= 0) {
+        const auto b24 = cd.inj + 24 * ci;
+        Uw.a = mk3<R>((R)b24[0], (R)b24[1], (R)b24[2]); Uw.l = mk3<R>((R)b24[3], (R)b24[4], (R)b24[5]);
+        Up.a = mk3<R>((R)b24[6], (R)b24[7], (R)b24[8]); Up.l = mk3<R>((R)b24[9], (R)b24[10], (R)b24[11]);
+        Gc.a = mk3<R>((R)b24[12], (R)b24[13], (R)b24[14]); Gc.l = mk3<R>((R)b24[15], (R)b24[16], (R)b24[17]);
+        Hc.a = mk3<R>((R)b24[18], (R)b24[19], (R)b24[20]); Hc.l = mk3<R>((R)b24[21], (R)b24[22], (R)b24[23]);
+      }
       if (hvalid) { Uw = Uw + hUw; Up = Up + hUp; Gc = Gc + hG; Hc = Hc + hH; }
     }
     if (fl & NB2_F_HAS_SLOT) {
@@ -847,11 +845,12 @@ NB2_HD void bwd_store(const Nb2ModelDev<R>& M, const R* scr0, float* gstate0, fl
 #define NB2_BWD_STAGES 10
 #define NB2_BWD_SYNC_MASK 0x14Bu        /* after stages 0, 1, 3, 6, 8 */
 #define NB2_BWD_SYNC_MASK_1LANE 0x101u  /* lanes == 1: after the group load and before the group store */
-template <class R, int ST>
+template <class R, int ST, bool CONTACT = false>
 NB2_HD void world_backward_stage(const Nb2ModelDev<R>& M, R* scr, const R* sv, size_t B, int lane, int stage, float* gI = nullptr, const R* bt = nullptr,
-                                 size_t gIB = 0) {
+                                 size_t gIB = 0, const BwdContactData<ST>* cdp = nullptr) {
   const float* st = nullptr;  // the passes read the state from the scratch (oSt)
-  BwdContactData<ST> cd; cd.active = 0; cd.error = 0;
+  BwdContactData<ST> cd;
+  if (CONTACT && cdp) cd = *cdp; else { cd.active = 0; cd.error = 0; cd.inj_of_body = nullptr; }
   // stages 1..8; pass: 1 = B1, 2 = B2, 3 = B3, 4 = assemble
   const int pass = (stage == 1 || stage == 2) ? 1 : (stage == 3 || stage == 4) ? 2 : (stage == 5 || stage == 7) ? 3 : 4;
   const bool trunk = (stage == 2) | (stage == 3) | (stage == 7) | (stage == 8);
@@ -860,32 +859,25 @@ NB2_HD void world_backward_stage(const Nb2ModelDev<R>& M, R* scr, const R* sv, s
   for (int rr = 0; rr < nr; rr++) {
     const int r = (pass == 1 || pass == 3) ? nr - 1 - rr : rr;
     const int lo = trunk ? M.trunk_lo[r] : M.limb_lo[lane][r], hi = trunk ? M.trunk_hi[r] : M.limb_hi[lane][r];
-    if (pass == 1) bwd_B1<R, ST, false>(M, scr, st, sv, B, lo, hi, bt);
-    else if (pass == 2) bwd_B2<R, ST, false>(M, scr, st, sv, B, lo, hi, bt);
-    else if (pass == 3) bwd_B3<R, ST, false>(M, scr, st, sv, B, cd, lo, hi, gI, bt, gIB ? gIB : B);
-    else bwd_assemble<R, ST, false>(M, scr, st, cd, lo, hi);
+    if (pass == 1) bwd_B1<R, ST, CONTACT>(M, scr, st, sv, B, lo, hi, bt);
+    else if (pass == 2) bwd_B2<R, ST, CONTACT>(M, scr, st, sv, B, lo, hi, bt);
+    else if (pass == 3) bwd_B3<R, ST, CONTACT>(M, scr, st, sv, B, cd, lo, hi, gI, bt, gIB ? gIB : B);
+    else bwd_assemble<R, ST, CONTACT>(M, scr, st, cd, lo, hi);
   }
 }
 
-// single-thread backward; the only form that carries the contact-stage adjoint (slots make any schedule valid
-// when one thread sweeps all bodies in order)
-template <class R, int ST, bool CONTACT = false>
+// single-thread backward of a contact-free step (any schedule: one thread sweeps all bodies in order)
+template <class R, int ST>
 NB2_HD void world_backward(const Nb2ModelDev<R>& M, R* scr, const float* st, const float* act, const float* gnext,
-                           const R* sv, size_t B, float* gstate, float* gaction, const BwdContactHook* hook = nullptr, float* gI = nullptr) {
+                           const R* sv, size_t B, float* gstate, float* gaction, float* gI = nullptr) {
   const int nb = M.nb;
-  constexpr int SLOTW = CONTACT ? 42 : 18;
-  const BwdLayout L = bwd_layout(nb, M.ndof, M.nslots, M.nfree, SLOTW);
-  bwd_load<R, ST, CONTACT>(M, scr, st, act, gnext, 1, 0, 1);
-  bwd_B1<R, ST, CONTACT>(M, scr, st, sv, B, 0, nb);
-  bwd_B2<R, ST, CONTACT>(M, scr, st, sv, B, 0, nb);
-  // ---------------- contact stage adjoint (nb2_contact.cuh): lambda -> w, W -> W(w), injections for B3
-  BwdContactData<ST> cd; cd.active = 0; cd.error = 0;
-  if constexpr (CONTACT) {
-    cd = contact_backward_hook<ST>(M, *hook, st, sv, B, scr, L.oLam, L.oBody);
-  }
-  bwd_B3<R, ST, CONTACT>(M, scr, st, sv, B, cd, 0, nb, gI, (const R*)nullptr, B);
-  bwd_assemble<R, ST, CONTACT>(M, scr, st, cd, 0, nb);
-  bwd_store<R, ST, CONTACT>(M, scr, gstate, gaction, CONTACT && cd.error, 1, 0, 1);
+  bwd_load<R, ST, false>(M, scr, st, act, gnext, 1, 0, 1);
+  bwd_B1<R, ST, false>(M, scr, st, sv, B, 0, nb);
+  bwd_B2<R, ST, false>(M, scr, st, sv, B, 0, nb);
+  BwdContactData<ST> cd; cd.active = 0; cd.error = 0; cd.inj_of_body = nullptr;
+  bwd_B3<R, ST, false>(M, scr, st, sv, B, cd, 0, nb, gI, (const R*)nullptr, B);
+  bwd_assemble<R, ST, false>(M, scr, st, cd, 0, nb);
+  bwd_store<R, ST, false>(M, scr, gstate, gaction, false, 1, 0, 1);
 }
 
 }  // namespace nb2

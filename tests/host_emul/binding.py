@@ -82,14 +82,16 @@ class EmulWorld:
         assert rc == 0
         return dict(next=nxt, saved=saved, x=x, m=m, labels=labels, status=status, nc=nc, cinfo=cinfo, crec=crec)
 
-    def backward_contact(self, state, action, saved, crec, gnext, want_inertia_grad=False):
+    def backward_contact(self, state, action, saved, crec, gnext, want_inertia_grad=False, small_mc=8, reverse=False):
         state = np.ascontiguousarray(state, np.float32)
         action = np.ascontiguousarray(action, np.float32)
         gnext = np.ascontiguousarray(gnext, np.float32)
         gs, ga = np.empty_like(state), np.empty_like(action)
         gi = np.zeros((10 * self.cm.nb, state.shape[0]), np.float32) if want_inertia_grad else None
+        self.bwd_status = np.zeros(state.shape[0], np.int32)
         rc = lib().emul_backward_contact(ctypes.byref(self.desc), state.shape[0], _p(state), _p(action), _p(saved), _p(crec),
-                                         _p(gnext), _p(gs), _p(ga), _p(gi) if gi is not None else None)
+                                         _p(gnext), _p(gs), _p(ga), _p(gi) if gi is not None else None, _p(self.bwd_status),
+                                         int(small_mc), int(reverse))
         assert rc == 0
         return (gs, ga, gi) if want_inertia_grad else (gs, ga)
 

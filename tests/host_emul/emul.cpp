@@ -58,56 +58,6 @@ static int run_bwd(const nb2_model_desc* d, int B, const float* state, const flo
   }
   return 0;
 }
-#if 0  // OLD serial contact stage (being replaced)
-// forward with the contact stage (fp64): ABA kernel body with the saved stream, then the contact kernel body
-static int run_fwd_contact(const nb2_model_desc* d, int B, const float* state, const float* action, float* next, double* saved,
-                           double* x_lcp, int* m_lcp, int* labels, int* status, int* nc, float* cinfo, double* crec) {
-  Nb2ModelDev<double> M; Nb2ContactDev C; std::string err;
-  if (!nb2_fill_model(*d, M, err) || !nb2_fill_contact(*d, C, err)) { fprintf(stderr, "emul: %s\n", err.c_str()); return -1; }
-  nb2::FwdLayout L = nb2::fwd_layout(M.nb, M.ndof, M.nslots, M.nfree);
-  std::vector<double> scr(L.total), ws(nb2::contact_ws_doubles(M.nb, M.ndof));
-  for (int w = 0; w < B; w++) {
-    for (auto& x : scr) x = 1e30;
-    nb2::world_forward<double, 1>(M, scr.data(), state + (size_t)w * 2 * M.ndof, action + (size_t)w * M.na,
-                                  next + (size_t)w * 2 * M.ndof, saved + w, (size_t)B, true);
-    for (auto& x : ws) x = 1e30;
-    nb2::world_contact<1>(M, C, state + (size_t)w * 2 * M.ndof, next + (size_t)w * 2 * M.ndof, saved + w, (size_t)B, ws.data(), 0,
-                          x_lcp + (size_t)w * NB2_MAX_ROWS, m_lcp + w, labels + (size_t)w * NB2_MAX_ROWS, status + w, nc + w,
-                       cinfo ? cinfo + (size_t)w * NB2_MAX_CONTACTS * 10 : nullptr,
-                       crec ? crec + (size_t)w * nb2::contact_rec_doubles(M.ndof) : nullptr,
-                       1 + (w % 4) /* lanes sharing the impulse tests: 1..4, so every split of the rows is exercised */);
-  }
-  return 0;
-}
-static int run_bwd_contact(const nb2_model_desc* d, int B, const float* state, const float* action, const double* saved,
-                           const double* crec, const float* gnext, float* gstate, float* gaction, float* ginertia) {
-  Nb2ModelDev<double> M; Nb2ContactDev C; std::string err;
-  if (!nb2_fill_model(*d, M, err) || !nb2_fill_contact(*d, C, err)) { fprintf(stderr, "emul: %s\n", err.c_str()); return -1; }
-  nb2::BwdLayout L = nb2::bwd_layout(M.nb, M.ndof, M.nslots, M.nfree, 42);
-  std::vector<double> scr(L.total), ws(nb2::contact_ws_doubles(M.nb, M.ndof));
-  for (int w = 0; w < B; w++) {
-    for (auto& x : scr) x = 1e30;
-    for (auto& x : ws) x = 1e30;
-    nb2::BwdContactHook H; H.model_contact = &C; H.ws = ws.data(); H.lane = 0; H.crec = crec + (size_t)w * nb2::contact_rec_doubles(M.ndof);
-    nb2::world_backward<double, 1, true>(M, scr.data(), state + (size_t)w * 2 * M.ndof, action + (size_t)w * M.na,
-                                         gnext + (size_t)w * 2 * M.ndof, saved + w, (size_t)B, gstate + (size_t)w * 2 * M.ndof,
-                                         gaction + (size_t)w * M.na, &H, ginertia ? ginertia + w : nullptr);
-  }
-  return 0;
-}
-// LCP-level entry: the device solve chain on a caller-supplied boxed LCP (tests/test_lcp.py compares it with the oracle's chain)
-static int run_chain(int m, const double* A, const double* b, const double* lo, const double* hi, const int* fi, const double* x0, int have_x0,
-                     double cfm, double* x_out, int* mapping_out) {
-  const int nb = 1, ndof = 1;
-  std::vector<double> wsb(nb2::contact_ws_doubles(nb, ndof), 1e30);
-  const nb2::ContactWsT<1> ws = nb2::carve_ws<1>(wsb.data(), 0, nb, ndof);
-  for (int i = 0; i < m * m; i++) ws.A[i] = A[i];
-  for (int i = 0; i < m; i++) { ws.b[i] = b[i]; ws.lo[i] = lo[i]; ws.hi[i] = hi[i]; ws.findex[i] = fi[i]; ws.rest[i] = 0.0; }
-  const int status = nb2::lcp_chain_ws<1>(m, ws, cfm, have_x0 ? x0 : nullptr);
-  for (int i = 0; i < m; i++) { x_out[i] = ws.x[i]; mapping_out[i] = ws.mapping[i]; }
-  return status;
-}
-#endif
 // fused forward with the contact stage (fp64), as k_cstep_fwd runs it: ABA sweeps (every lane of the schedule), warp-cooperative
 // contact stage on the world's scratch, store.  The saved stream is WORLD-MAJOR (word k of world w at saved[w * words + k]).
 static nb2::cw::Dims contact_dims(const Nb2ModelDev<double>& M, const Nb2ContactDev& C, int MC, int MR) {
@@ -144,6 +94,40 @@ static int run_fwd_contact(const nb2_model_desc* d, int B, const float* state, c
   nb2::cw::cw_host_reverse() = 0;
   return 0;
 }
+// fused backward with the contact stage, as k_cstep_bwd runs it: lambda sweeps (B1, B2) along the schedule, the warp-cooperative
+// contact adjoint, reverse RNEA sweep (B3) + assembly with the contact injections, store.
+static int run_bwd_contact(const nb2_model_desc* d, int B, const float* state, const float* action, const double* saved,
+                           const double* crec, const float* gnext, float* gstate, float* gaction, float* ginertia, int* bstatus, int small_mc, int reverse) {
+  Nb2ModelDev<double> M; Nb2ContactDev C; std::string err;
+  if (!nb2_fill_model(*d, M, err) || !nb2_fill_contact(*d, C, err)) { fprintf(stderr, "emul: %s\n", err.c_str()); return -1; }
+  nb2::BwdLayout L = nb2::bwd_layout(M.nb, M.ndof, M.nslots, M.nfree, 42);
+  const int words = nb2_saved_words(M.nb, M.ndof, M.nfree);
+  const nb2::cw::Dims ds = nb2::cw::make_dims(M.nb, M.ndof, M.nfree, small_mc, 3 * small_mc, C.ncb, C.max_chain_dofs, 1);
+  const nb2::cw::Dims db = nb2::cw::make_dims(M.nb, M.ndof, M.nfree, NB2_MAX_CONTACTS, NB2_MAX_ROWS, C.ncb, C.max_chain_dofs, 1);
+  std::vector<double> scr(L.total), wss(nb2::cw::ws_doubles(ds)), wsb(nb2::cw::ws_doubles(db));
+  const size_t recd = nb2::cw::record_doubles(M.ndof);
+  for (int w = 0; w < B; w++) {
+    nb2::cw::cw_host_reverse() = reverse && (w & 1);
+    for (auto& x : scr) x = 1e30;
+    for (auto& x : wss) x = 1e30;
+    for (auto& x : wsb) x = 1e30;
+    const float* st = state + (size_t)w * 2 * M.ndof;
+    const double* sv = saved + (size_t)w * words;
+    nb2::bwd_load<double, 1, true>(M, scr.data(), st, action + (size_t)w * M.na, gnext + (size_t)w * 2 * M.ndof, 1, 0, 1);
+    nb2::BwdContactData<1> cd; cd.active = 0; cd.error = 0; cd.inj_of_body = nullptr;
+    for (int sg = 1; sg < NB2_BWD_STAGES - 1; sg++) {
+      if (sg == 5) cd = nb2::cw::contact_backward(M, C, st, sv, wss.data(), ds, wsb.data(), db, crec + (size_t)w * recd, scr.data(), L.oLam, L.oBody);
+      for (int l = 0; l < M.lanes; l++) {
+        const int lane = (w & 1) ? M.lanes - 1 - l : l;
+        nb2::world_backward_stage<double, 1, true>(M, scr.data(), sv, 1, lane, sg, ginertia ? ginertia + w : nullptr, nullptr, (size_t)B, &cd);
+      }
+    }
+    nb2::bwd_store<double, 1, true>(M, scr.data(), gstate + (size_t)w * 2 * M.ndof, gaction + (size_t)w * M.na, cd.error != 0, 1, 0, 1);
+    if (bstatus) bstatus[w] = cd.error;
+  }
+  nb2::cw::cw_host_reverse() = 0;
+  return 0;
+}
 // warp-cooperative solve chain (csrc/nb2_cw.cuh) on a caller-supplied boxed LCP; reverse != 0 runs every CW_FOR backwards
 static int run_cw_chain(int m, const double* A, const double* b, const double* lo, const double* hi, const int* fi, const double* x0, int have_x0,
                         double cfm, double* x_out, int* mapping_out, int reverse) {
@@ -164,24 +148,13 @@ int emul_cw_solve_chain(int m, const double* A, const double* b, const double* l
                         double cfm, double* x_out, int* mapping_out, int reverse) {
   return run_cw_chain(m, A, b, lo, hi, fi, x0, have_x0, cfm, x_out, mapping_out, reverse);
 }
-#if 0
-int emul_solve_chain(int m, const double* A, const double* b, const double* lo, const double* hi, const int* fi, const double* x0, int have_x0,
-                     double cfm, double* x_out, int* mapping_out) {
-  return run_chain(m, A, b, lo, hi, fi, x0, have_x0, cfm, x_out, mapping_out);
-}
-int emul_forward_contact(const nb2_model_desc* d, int B, const float* state, const float* action, float* next, double* saved,
-                         double* x_lcp, int* m_lcp, int* labels, int* status, int* nc, float* cinfo, double* crec) {
-  return run_fwd_contact(d, B, state, action, next, saved, x_lcp, m_lcp, labels, status, nc, cinfo, crec);
-}
-int emul_contact_rec_doubles(const nb2_model_desc* d) { return (int)nb2::contact_rec_doubles(d->ndof); }
-int emul_backward_contact(const nb2_model_desc* d, int B, const float* state, const float* action, const double* saved,
-                          const double* crec, const float* gnext, float* gstate, float* gaction, float* ginertia) {
-  return run_bwd_contact(d, B, state, action, saved, crec, gnext, gstate, gaction, ginertia);
-}
-#endif
 int emul_forward_contact(const nb2_model_desc* d, int B, const float* state, const float* action, float* next, double* saved,
                          double* x_lcp, int* m_lcp, int* labels, int* status, int* nc, float* cinfo, double* crec, int small_mc, int reverse) {
   return run_fwd_contact(d, B, state, action, next, saved, x_lcp, m_lcp, labels, status, nc, cinfo, crec, small_mc, reverse);
+}
+int emul_backward_contact(const nb2_model_desc* d, int B, const float* state, const float* action, const double* saved,
+                          const double* crec, const float* gnext, float* gstate, float* gaction, float* ginertia, int* bstatus, int small_mc, int reverse) {
+  return run_bwd_contact(d, B, state, action, saved, crec, gnext, gstate, gaction, ginertia, bstatus, small_mc, reverse);
 }
 int emul_contact_rec_doubles(const nb2_model_desc* d) { return (int)nb2::cw::record_doubles(d->ndof); }
 int emul_saved_words(const nb2_model_desc* d) {
