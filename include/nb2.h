@@ -130,24 +130,35 @@ int nb2_step_backward_host(nb2_model* m, int B, const float* grad_next_state, fl
  *   status  [B] int32                  out: NB2_ST_* bits (which solver branch ran, unsupported geometry, overflow)
  *   ncontacts [B] int32                out
  *   cinfo   [B, NB2_MAX_CONTACTS, 10] float (optional, may be NULL): point(3) normal(3) depth bodyA bodyB type
- *   contact_record [B, nb2_contact_record_bytes/B/8] double (optional): what nb2_step_backward_contact needs (labels, impulses,
- *            LCP matrix), the batched counterpart of the ConstrainedGroupGradientMatrices a BackpropSnapshot holds.
+ *   contact_record [B, nb2_contact_record_bytes/B/8] double (optional): what nb2_step_backward_contact needs (LCP size, labels,
+ *            impulses, the velocity change they caused — ~1 KB per world; the clamping block of the LCP matrix is re-measured),
+ *            the batched counterpart of the ConstrainedGroupGradientMatrices a BackpropSnapshot holds.
  */
 size_t nb2_contact_workspace_bytes(const nb2_model* m, int B);
 int nb2_model_has_contacts(const nb2_model* m);
-/* forward step WITH the contact stage: runs the fp64 ABA kernel (saved stream required) followed by the contact kernel. */
+/* forward step WITH the contact stage: ONE fused kernel, one warp per world (fp64 ABA sweeps + contact / boxed-LCP stage in shared
+ * memory).  saved_fp64: nb2_saved_words_per_world(m) * B doubles (world-major; opaque), may be NULL when no backward will follow
+ * (then contact_record must be NULL too).  workspace: nb2_contact_workspace_bytes(m, B) bytes of device memory — a pool of large
+ * per-world workspaces for the rare worlds whose contact count exceeds the shared-memory capacity (nb2_model_set_contact_capacity).
+ * status_accum (optional, [B] int32): every step ORs its status word into it — a sticky copy the caller reads once per rollout. */
 int nb2_step_forward_contact(const nb2_model* m, int B, const float* state, const float* action, float* next_state,
                              void* saved_fp64, void* workspace, double* x_lcp, int32_t* m_lcp, int32_t* labels,
-                             int32_t* status, int32_t* ncontacts, float* cinfo, double* contact_record, void* stream);
+                             int32_t* status, int32_t* ncontacts, float* cinfo, double* contact_record, int32_t* status_accum, void* stream);
 size_t nb2_contact_record_bytes(const nb2_model* m, int B);
 /* VJP of a step taken with nb2_step_forward_contact (classification frozen at the forward solution), replaces
  * BackpropSnapshot::backpropState for steps with active contact constraints (dart/neural/BackpropSnapshot.cpp:980-1107,
- * 2723-3146).  Rows may act on one or two moving bodies.  If the rows regenerated in the backward pass do not match the
- * forward's (or a compiled limit is exceeded) the world's gradients are NaN, never silent garbage.
+ * 2723-3146).  Rows may act on one or two moving bodies.  If a world cannot be back-propagated (the rows regenerated in the backward
+ * pass do not match the forward's, a bounce term was active, a compiled limit is exceeded) its gradients are NaN — never silent
+ * garbage — and, when `status_accum` is given, bit NB2_ST_BWD_ERROR (2048) is OR-ed into status_accum[w]: callers check the array
+ * once per rollout instead of scanning gradients.
  * grad_inertia: optional [10*nb][B] floats as in nb2_step_backward (mass gradient through the contact stage). */
 int nb2_step_backward_contact(const nb2_model* m, int B, const float* state, const float* action, const void* saved_fp64,
                               const double* contact_record, void* workspace, const float* grad_next_state, float* grad_state,
-                              float* grad_action, float* grad_inertia, void* stream);
+                              float* grad_action, float* grad_inertia, int32_t* status_accum, void* stream);
+/* contacts per world the shared-memory workspace of the fused contact kernels is sized for (LCP rows: 3x).  Default: 4 per box-box
+ * pair + 1 per other pair, clamped to [2, NB2_MAX_CONTACTS].  Smaller = more resident worlds per SM, more worlds in the slow pool. */
+int nb2_model_set_contact_capacity(nb2_model* m, int max_contacts_in_shared_memory);
+int nb2_model_contact_capacity(const nb2_model* m);
 
 /* T-step rollout of a contact-free world and its reverse sweep — SingleShot::getSnapshots (dart/trajectory/SingleShot.cpp:635-686)
  * and SingleShot::backpropGradientWrt (:539-631).  All buffers are device memory, fp32, time-major:

@@ -4,7 +4,7 @@ from . import world as _world
 from .world import (World, Skeleton, BodyNode, Joint, Isometry3, BoxShape, SphereShape, CapsuleShape)
 from .loader import loadWorld, load_skeleton
 from .modelspec import RawModel, CanonModel, flatten_world, compile_model
-from .timestep import timestep, TimestepLayer, contact_cache, reset_contact_cache
+from .timestep import timestep, TimestepLayer, contact_cache, reset_contact_cache, check_contact_status
 from .engine import DeviceModel, device_model_for
 from .rollout import rollout, rollout_fused, shard_range, shard_batch, allreduce_sum_, sharded_trajectory_loss
 

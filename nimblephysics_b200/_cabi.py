@@ -13,7 +13,7 @@ import numpy as np
 from .modelspec import CanonModel
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libnb2.so")
+LIB_PATH = os.environ.get("NB2_LIB") or os.path.join(_HERE, "csrc", "libnb2.so")  # NB2_LIB: a dev build (e.g. with -DNB2_CW_PROFILE)
 
 _I32P = ctypes.POINTER(ctypes.c_int32)
 _F64P = ctypes.POINTER(ctypes.c_double)
@@ -141,10 +141,12 @@ def lib() -> ctypes.CDLL:
         L.nb2_model_has_contacts.argtypes = [vp]
         L.nb2_contact_workspace_bytes.argtypes = [vp, ctypes.c_int]
         L.nb2_contact_workspace_bytes.restype = ctypes.c_size_t
-        L.nb2_step_forward_contact.argtypes = [vp, ctypes.c_int, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
+        L.nb2_step_forward_contact.argtypes = [vp, ctypes.c_int, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
         L.nb2_contact_record_bytes.argtypes = [vp, ctypes.c_int]
         L.nb2_contact_record_bytes.restype = ctypes.c_size_t
-        L.nb2_step_backward_contact.argtypes = [vp, ctypes.c_int, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
+        L.nb2_step_backward_contact.argtypes = [vp, ctypes.c_int, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
+        L.nb2_model_set_contact_capacity.argtypes = [vp, ctypes.c_int]
+        L.nb2_model_contact_capacity.argtypes = [vp]
         L.nb2_step_forward_host.argtypes = [vp, ctypes.c_int, vp, vp, vp, ctypes.c_int, ctypes.c_int]
         L.nb2_step_backward_host.argtypes = [vp, ctypes.c_int, vp, vp, vp, ctypes.c_int]
         _lib = L

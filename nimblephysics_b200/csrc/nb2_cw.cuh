@@ -69,6 +69,15 @@ struct Nb2ContactDev {
   double shape_mu[NB2_MAX_SHAPES], shape_rest[NB2_MAX_SHAPES];
 };
 
+// big routines exist ONCE in the device code (real calls): the fused kernels are instruction-fetch bound when everything is inlined
+#if defined(__CUDACC__) && !defined(NB2_CW_INLINE_ALL)
+#define NB2_HDN __host__ __device__ __noinline__
+#elif defined(__CUDACC__)
+#define NB2_HDN __host__ __device__ __forceinline__
+#else
+#define NB2_HDN inline
+#endif
+
 namespace nb2 {
 namespace cw {
 
@@ -77,7 +86,17 @@ namespace cw {
 #define CW_DEV 1
 #define CW_LANE ((int)(threadIdx.x & 31))
 #define CW_SYNC() __syncwarp()
+// The loop over passes has a warp-UNIFORM trip count and only the body is predicated: a per-lane loop `for (i = lane; i < n; i += 32)`
+// makes the lanes leave at different points, and a divergent loop exit costs ~110 cycles on B200 (scripts/dev/ubench/br.cu) against
+// ~10 for a predicated region — with hundreds of such loops per world that was most of the run time.
+#ifdef NB2_CW_FOR_DIVERGENT
 #define CW_FOR(i, n) for (int i = (int)(threadIdx.x & 31); i < (n); i += 32)
+#else
+#define CW_FOR(i, n)                                                         \
+  for (int i##_b = 0, i##_n = (n); i##_b < i##_n; i##_b += 32)               \
+    for (int i = i##_b + (int)(threadIdx.x & 31), i##_1 = 1; i##_1; i##_1 = 0) \
+      if (i < i##_n)
+#endif
 #define CW_ONE if ((threadIdx.x & 31) == 0)
 #define CW_FULL 0xFFFFFFFFu
 #else
@@ -88,6 +107,39 @@ inline int& cw_host_reverse() { static int r = 0; return r; }
 inline int cw_host_idx(int it, int n) { return cw_host_reverse() ? n - 1 - it : it; }
 #define CW_FOR(i, n) for (int i##_it = 0, i##_n = (n), i = cw_host_idx(0, i##_n); i##_it < i##_n; i##_it++, i = cw_host_idx(i##_it, i##_n))
 #define CW_ONE
+#endif
+
+// 2-D index space nr x nc spread over the lanes in row-major order WITHOUT an integer division per element (a runtime divisor costs
+// ~25 instructions): every lane walks (r, c) by the lane count.
+struct It2 { int row, col, e, dr, dc, tot, nc; };
+NB2_HD It2 it2_begin(int nr, int nc, int lane, int stride) {
+  It2 t; t.nc = nc; t.tot = (nc > 0) ? nr * nc : 0; t.e = lane;
+  t.row = (nc > 0) ? lane / nc : 0; t.col = lane - t.row * nc;
+  t.dr = (nc > 0) ? stride / nc : 0; t.dc = stride - t.dr * nc;
+  return t;
+}
+NB2_HD void it2_next(It2& t, int stride) { t.e += stride; t.row += t.dr; t.col += t.dc; if (t.col >= t.nc) { t.col -= t.nc; t.row++; } }
+#if CW_DEV
+#define CW_FOR2(R_, C_, nr, nc)                                                                                                   \
+  for (nb2::cw::It2 R_##_t = nb2::cw::it2_begin((nr), (nc), (int)(threadIdx.x & 31), 32); R_##_t.e - (int)(threadIdx.x & 31) < R_##_t.tot; nb2::cw::it2_next(R_##_t, 32)) \
+    for (int R_ = R_##_t.row, C_ = R_##_t.col, R_##_1 = 1; R_##_1; R_##_1 = 0)                                                    \
+      if (R_##_t.e < R_##_t.tot)
+#else
+#define CW_FOR2(R_, C_, nr, nc)                                                                           \
+  for (nb2::cw::It2 R_##_t = nb2::cw::it2_begin((nr), (nc), 0, 1); R_##_t.e < R_##_t.tot; nb2::cw::it2_next(R_##_t, 1)) \
+    for (int R_ = R_##_t.row, C_ = R_##_t.col, R_##_1 = 1; R_##_1; R_##_1 = 0)
+#endif
+
+// ---- optional per-phase cycle counters (-DNB2_CW_PROFILE; dev builds only): lane 0 adds clock64() deltas to a global table
+#if defined(NB2_CW_PROFILE) && defined(__CUDACC__)
+__device__ unsigned long long nb2_cw_prof[64];
+#endif
+#if defined(NB2_CW_PROFILE) && CW_DEV
+#define CW_PROF_DECL long long cw_t0_ = clock64()
+#define CW_PROF(k) do { const long long cw_t1_ = clock64(); if (CW_LANE == 0) atomicAdd(&nb2_cw_prof[k], (unsigned long long)(cw_t1_ - cw_t0_)); cw_t0_ = clock64(); } while (0)
+#else
+#define CW_PROF_DECL
+#define CW_PROF(k)
 #endif
 
 // per-lane partial -> the same total in every lane (host: the loop before it already produced the total)
@@ -172,14 +224,14 @@ template <class P, class Wr> NB2_HD int cw_enumerate(int n, const P& pred, const
 // ---- triangular solves with the unknowns in registers (device) / plain loops (host).  L(r, k) = Lp[rm(r) * ld + k] for k < r,
 // rm = identity when rowmap == nullptr; UNIT: unit diagonal, else the diagonal sits in the matrix.  n <= 64.
 // Each y_r receives its subtractions in the order k = 0 .. r-1 (lower) / k = n-1 .. r+1 (upper): the serial order.
-template <bool UNIT> NB2_HD void trsv_lower(int n, const double* Lp, int ld, const int* rowmap, double* y) {
+template <bool UNIT> NB2_HDN void trsv_lower(int n, const double* Lp, int ld, const int* rowmap, double* y) {
 #if CW_DEV
   const int lane = CW_LANE, r0 = lane, r1 = lane + 32;
   const double* row0 = Lp + (size_t)((r0 < n) ? (rowmap ? rowmap[r0] : r0) : 0) * ld;
   const double* row1 = Lp + (size_t)((r1 < n) ? (rowmap ? rowmap[r1] : r1) : 0) * ld;
   double s0 = (r0 < n) ? y[r0] : 0.0, s1 = (r1 < n) ? y[r1] : 0.0;
   double id0 = 1.0, id1 = 1.0;
-  if (!UNIT) { if (r0 < n) id0 = 1.0 / row0[r0]; if (r1 < n) id1 = 1.0 / row1[r1]; }
+  if (!UNIT) { if (r0 < n) id0 = nb2_rcp(row0[r0]); if (r1 < n) id1 = nb2_rcp(row1[r1]); }
   const int n0 = n < 32 ? n : 32;
 #pragma unroll 4
   for (int k = 0; k < n0; k++) {
@@ -201,19 +253,19 @@ template <bool UNIT> NB2_HD void trsv_lower(int n, const double* Lp, int ld, con
     const double* row = Lp + (size_t)(rowmap ? rowmap[r] : r) * ld;
     double s = y[r];
     for (int k = 0; k < r; k++) s -= row[k] * y[k];
-    y[r] = UNIT ? s : s * (1.0 / row[r]);
+    y[r] = UNIT ? s : s * nb2_rcp(row[r]);
   }
 #endif
 }
 // L^T y = rhs (in place)
-template <bool UNIT> NB2_HD void trsv_lower_T(int n, const double* Lp, int ld, const int* rowmap, double* y) {
+template <bool UNIT> NB2_HDN void trsv_lower_T(int n, const double* Lp, int ld, const int* rowmap, double* y) {
 #if CW_DEV
   const int lane = CW_LANE, j0 = lane, j1 = lane + 32;
   double s0 = (j0 < n) ? y[j0] : 0.0, s1 = (j1 < n) ? y[j1] : 0.0;
   double id0 = 1.0, id1 = 1.0;
   if (!UNIT) {
-    if (j0 < n) id0 = 1.0 / Lp[(size_t)(rowmap ? rowmap[j0] : j0) * ld + j0];
-    if (j1 < n) id1 = 1.0 / Lp[(size_t)(rowmap ? rowmap[j1] : j1) * ld + j1];
+    if (j0 < n) id0 = nb2_rcp(Lp[(size_t)(rowmap ? rowmap[j0] : j0) * ld + j0]);
+    if (j1 < n) id1 = nb2_rcp(Lp[(size_t)(rowmap ? rowmap[j1] : j1) * ld + j1]);
   }
   for (int k = n - 1; k >= 32; k--) {
     if (!UNIT && lane == k - 32) s1 *= id1;
@@ -237,7 +289,7 @@ template <bool UNIT> NB2_HD void trsv_lower_T(int n, const double* Lp, int ld, c
   for (int j = n - 1; j >= 0; j--) {
     double s = y[j];
     for (int k = n - 1; k > j; k--) s -= Lp[(size_t)(rowmap ? rowmap[k] : k) * ld + j] * y[k];
-    y[j] = UNIT ? s : s * (1.0 / Lp[(size_t)(rowmap ? rowmap[j] : j) * ld + j]);
+    y[j] = UNIT ? s : s * nb2_rcp(Lp[(size_t)(rowmap ? rowmap[j] : j) * ld + j]);
   }
 #endif
 }
@@ -245,18 +297,19 @@ template <bool UNIT> NB2_HD void trsv_lower_T(int n, const double* Lp, int ld, c
 // ------------------------------------------------------------------------------------------------ workspace
 // Capacities of one world's workspace: MC contacts, MR LCP rows, LD = MR | 1 (odd leading dimension: row AND column walks of a
 // matrix are bank-conflict free).  Problems are stored with their own leading dimension ld = m | 1 <= LD.
-struct Dims { int nb, n, MC, MR, LD, ncb, cdofs, nfree, bwd; size_t mats; };
+struct Dims { int nb, n, MC, MR, LD, ncb, cdofs, nfree, bwd, mode; size_t mats; };
 // bytes of one pair slot of the collision phase: count, status, 8 contacts x (point, normal, depth, type)
 #define NB2_CW_PAIR_SLOT 66
-NB2_HD Dims make_dims(int nb, int n, int nfree, int MC, int MR, int ncb, int cdofs, int bwd = 0) {
-  Dims d; d.nb = nb; d.n = n; d.nfree = nfree; d.MC = MC; d.MR = MR; d.LD = MR | 1; d.ncb = ncb; d.cdofs = cdofs; d.bwd = bwd;
+NB2_HD Dims make_dims(int nb, int n, int nfree, int MC, int MR, int ncb, int cdofs, int bwd = 0, int mode = 0) {
+  Dims d; d.nb = nb; d.n = n; d.nfree = nfree; d.MC = MC; d.MR = MR; d.LD = MR | 1; d.ncb = ncb; d.cdofs = cdofs; d.bwd = bwd; d.mode = mode;
   // the two work matrices double as: private chain buffers of the impulse tests (one per row / collision body), spatial velocity
   // changes of all bodies (impulse application), pair slots of the collision phase (at least 4)
-  size_t mats = 2 * (size_t)MR * d.LD;
+  size_t mats = 0;
   const size_t priv = (size_t)MR * cdofs, dv = (size_t)ncb * cdofs + (size_t)nb * (bwd ? 18 : 6), slots = 4 * (size_t)NB2_CW_PAIR_SLOT;
-  if (mats < priv) mats = priv;
-  if (mats < dv) mats = dv;
-  if (mats < slots) mats = slots;
+  if (mode != 2) mats = 2 * (size_t)MR * d.LD;       // FULL / SOLVE: the two work matrices
+  if (mode == 0 && mats < priv) mats = priv;          // FULL: private chain buffers of the impulse tests
+  if (mode != 1 && mats < dv) mats = dv;              // FULL / APPLY: impulse application buffers
+  if (mode == 0 && mats < slots) mats = slots;        // FULL: pair slots of the collision phase
   d.mats = mats;
   return d;
 }
@@ -276,37 +329,45 @@ struct Ws {
   int *tbl;                     // [ncb] distinct bodies touched by this world's contacts
   int *meta;                    // [8]
 };
-NB2_HD size_t ws_doubles(const Dims& d) {
-  const size_t MC = d.MC, MR = d.MR;
-  const size_t mats = d.mats;
-  return (size_t)d.ncb * 24 + 2 * d.n + (size_t)d.nfree * 21 + (d.bwd ? 3 * (size_t)d.n + 24 * (size_t)d.ncb : 0) + MC * 9 + 6 * ((MC + 1) / 2) + 2 * MR * 6 + 6 * MR + 5 * ((MR + 1) / 2) + MR * d.LD + mats + 11 * MR +
-         4 * ((MR + 1) / 2) + ((size_t)d.ncb + 1) / 2 + 4;
-}
-NB2_HD Ws carve(double* base, const Dims& d) {
+// Which arrays a kernel needs.  The forward step is split into three kernels so that the expensive, register-light solver phase runs
+// at a higher occupancy than the register-hungry tree sweeps and collision code allow: BUILD (everything; contacts, rows, A), SOLVE
+// (the LCP and its work matrices only), APPLY (row wrenches, impulses, tree buffers).  Dims.mode selects the subset; absent arrays are
+// nullptr.  The layout is a pure function of Dims, computed by one routine (count == true: size only).
+#define NB2_WS_FULL 0
+#define NB2_WS_SOLVE 1
+#define NB2_WS_APPLY 2
+NB2_HD size_t ws_layout(double* base, const Dims& d, Ws* out) {
   Ws w;
   size_t off = 0;
   const size_t MC = d.MC, MR = d.MR;
-  auto D = [&](size_t cnt) { double* r = base + off; off += cnt; return r; };
-  auto I = [&](size_t cnt) { int* r = (int*)(base + off); off += (cnt + 1) / 2; return r; };
-  w.Wcb = D((size_t)d.ncb * 12); w.Vcb = D((size_t)d.ncb * 6); w.Fcb = D((size_t)d.ncb * 6); w.uI = D(d.n); w.dqd = D(d.n); w.Iinv = D((size_t)d.nfree * 21);
-  if (d.bwd) { w.aeff = D(d.n); w.vplus = D(d.n); w.JcTmu = D(d.n); w.inj = D((size_t)d.ncb * 24); } else { w.aeff = w.vplus = w.JcTmu = w.inj = nullptr; }
-  w.cpoint = D(MC * 3); w.cnormal = D(MC * 3); w.cdepth = D(MC); w.cmu = D(MC); w.crest = D(MC);
-  w.cbodyA = I(MC); w.cbodyB = I(MC); w.ctype = I(MC); w.cshapeA = I(MC); w.cshapeB = I(MC); w.crow = I(MC);
-  w.JA = D(MR * 6); w.JB = D(MR * 6);
-  w.b = D(MR); w.lo = D(MR); w.hi = D(MR); w.x = D(MR); w.x0 = D(MR); w.colnorm = D(MR);
-  w.findex = I(MR); w.mapping = I(MR); w.clampIdx = I(MR); w.ubIdx = I(MR); w.rowc = I(MR);
-  w.A = D(MR * d.LD);
-  w.M1 = D(d.mats); w.M2 = w.M1 + MR * d.LD;
-  w.v1 = D(MR); w.v2 = D(MR); w.v3 = D(MR); w.v4 = D(MR); w.v5 = D(MR); w.v6 = D(MR); w.v7 = D(MR); w.v8 = D(MR); w.v9 = D(MR); w.v10 = D(MR); w.v11 = D(MR);
-  w.i1 = I(MR); w.i2 = I(MR); w.i3 = I(MR); w.i4 = I(MR);
-  w.tbl = I(d.ncb);
-  w.meta = I(8);
-  return w;
+  const bool full = d.mode == NB2_WS_FULL, solve = d.mode != NB2_WS_APPLY, apply = d.mode != NB2_WS_SOLVE;
+  auto D = [&](bool need, size_t cnt) -> double* { if (!need) return nullptr; double* r = base ? base + off : nullptr; off += cnt; return r; };
+  auto I = [&](bool need, size_t cnt) -> int* { if (!need) return nullptr; int* r = base ? (int*)(base + off) : nullptr; off += (cnt + 1) / 2; return r; };
+  w.Wcb = D(full, (size_t)d.ncb * 12); w.Vcb = D(full, (size_t)d.ncb * 6); w.Fcb = D(apply, (size_t)d.ncb * 6);
+  w.uI = D(apply, d.n); w.dqd = D(apply, d.n); w.Iinv = D(full, (size_t)d.nfree * 21);
+  const bool bw = full && d.bwd;
+  w.aeff = D(bw, d.n); w.vplus = D(bw, d.n); w.JcTmu = D(bw, d.n); w.inj = D(bw, (size_t)d.ncb * 24);
+  w.cpoint = D(full, MC * 3); w.cnormal = D(full, MC * 3); w.cdepth = D(full, MC); w.cmu = D(full, MC); w.crest = D(full, MC);
+  w.cbodyA = I(apply, MC); w.cbodyB = I(apply, MC); w.ctype = I(full, MC); w.cshapeA = I(full, MC); w.cshapeB = I(full, MC); w.crow = I(full, MC);
+  w.JA = D(apply, MR * 6); w.JB = D(apply, MR * 6);
+  w.b = D(solve, MR); w.lo = D(solve, MR); w.hi = D(solve, MR); w.x = D(true, MR); w.x0 = D(solve, MR); w.colnorm = D(solve, MR);
+  w.findex = I(solve, MR); w.mapping = I(solve, MR); w.clampIdx = I(solve, MR); w.ubIdx = I(solve, MR); w.rowc = I(apply, MR);
+  w.A = D(solve, MR * d.LD);
+  w.M1 = D(true, d.mats); w.M2 = solve ? w.M1 + MR * d.LD : nullptr;
+  w.v1 = D(solve, MR); w.v2 = D(solve, MR); w.v3 = D(solve, MR); w.v4 = D(solve, MR); w.v5 = D(solve, MR); w.v6 = D(solve, MR); w.v7 = D(solve, MR);
+  w.v8 = D(solve, MR); w.v9 = D(solve, MR); w.v10 = D(solve, MR); w.v11 = D(solve, MR);
+  w.i1 = I(solve, MR); w.i2 = I(solve, MR); w.i3 = I(solve, MR); w.i4 = I(solve, MR);
+  w.tbl = I(full, d.ncb);
+  w.meta = I(true, 8);
+  if (out) *out = w;
+  return off;
 }
+NB2_HD size_t ws_doubles(const Dims& d) { return ws_layout(nullptr, d, nullptr); }
+NB2_HD Ws carve(double* base, const Dims& d) { Ws w; ws_layout(base, d, &w); return w; }
 
 // ------------------------------------------------------------------------------------------------ LCP validity
 // LCPUtils::isLCPSolutionValid (LCPUtils.cpp:12-80), tol 1e-5; one row per lane.  Uniform call, uniform result.
-NB2_HD bool lcp_valid(int m, const double* A, int ld, const double* x, const double* b, const double* hi, const double* lo, const int* fi,
+NB2_HDN bool lcp_valid(int m, const double* A, int ld, const double* x, const double* b, const double* hi, const double* lo, const int* fi,
                       bool ignoreFriction) {
   bool bad = false;
   CW_FOR(i, m) {
@@ -333,7 +394,7 @@ NB2_HD bool lcp_valid(int m, const double* A, int ld, const double* x, const dou
 // x = Q^+ rhs for a symmetric PSD n x n matrix G (leading dimension ld), DESTROYED.  Rank-revealing pivoted Cholesky
 // G = P L L^T P^T (L: n x r) and Q^+ = L (L^T L)^-2 L^T (replaces Eigen's completeOrthogonalDecomposition().solve,
 // third party).  Lf: n x ld work matrix; t1, t2, t3: n doubles; perm: n ints.  x may alias nothing else.
-NB2_HD void pinv_psd(int n, double* G, int ld, const double* rhs, double* x, double* Lf, double* t1, double* t2, double* dg, int* perm) {
+NB2_HDN void pinv_psd(int n, double* G, int ld, const double* rhs, double* x, double* Lf, double* t1, double* t2, double* dg, int* perm) {
   double dmax0 = 0;
   CW_FOR(i, n) { perm[i] = i; const double d = G[(size_t)i * ld + i]; dg[i] = d; dmax0 = d > dmax0 ? d : dmax0; x[i] = 0; }
   dmax0 = cw_max(dmax0);
@@ -349,7 +410,7 @@ NB2_HD void pinv_psd(int n, double* G, int ld, const double* rhs, double* x, dou
     CW_SYNC();  // everyone has read perm[] before it changes
     CW_ONE { perm[best.i] = pold; perm[k] = pk; }
     CW_SYNC();
-    const double lkk = sqrt(best.v);
+    const double rlkk = nb2_rsqrt(best.v), lkk = best.v * rlkk;
     const double* Lk = Lf + (size_t)pk * ld;
     CW_FOR(i, n) {
       if (i == k) Lf[(size_t)pk * ld + k] = lkk;
@@ -358,7 +419,7 @@ NB2_HD void pinv_psd(int n, double* G, int ld, const double* rhs, double* x, dou
         double* Li = Lf + (size_t)pi * ld;
         double s = G[(size_t)pi * ld + pk];
         for (int j = 0; j < k; j++) s -= Li[j] * Lk[j];
-        const double l = s / lkk;
+        const double l = s * rlkk;
         Li[k] = l;
         dg[pi] -= l * l;
       }
@@ -380,8 +441,7 @@ NB2_HD void pinv_psd(int n, double* G, int ld, const double* rhs, double* x, dou
   CW_FOR(k, r) for (int j = k + 1; j < r; j++) Lf[(size_t)perm[k] * ld + j] = 0;
   CW_SYNC();
   // Mm = L^T L (r x r) into G ; y = L^T rhs
-  CW_FOR(e, r * r) {
-    const int a = e / r, c = e - a * r;
+  CW_FOR2(a, c, r, r) {
     if (c >= a) {
       double s = 0;
       for (int i = 0; i < n; i++) s += Lf[(size_t)i * ld + a] * Lf[(size_t)i * ld + c];
@@ -394,14 +454,15 @@ NB2_HD void pinv_psd(int n, double* G, int ld, const double* rhs, double* x, dou
   for (int j = 0; j < r; j++) {
     double d = G[(size_t)j * ld + j];
     for (int k = 0; k < j; k++) d -= G[(size_t)j * ld + k] * G[(size_t)j * ld + k];
-    d = sqrt(d);
+    const double rd = nb2_rsqrt(d);
+    d = d * rd;
     CW_SYNC();
     CW_FOR(i, r) {
       if (i == j) G[(size_t)j * ld + j] = d;
       else if (i > j) {
         double s = G[(size_t)i * ld + j];
         for (int k = 0; k < j; k++) s -= G[(size_t)i * ld + k] * G[(size_t)j * ld + k];
-        G[(size_t)i * ld + j] = s / d;
+        G[(size_t)i * ld + j] = s * rd;
       }
     }
     CW_SYNC();
@@ -467,7 +528,7 @@ NB2_HD bool classify_once(int m, const double* A, int ld, double* x, const doubl
   }
   const int lq = nCl | 1;
   double* Q = ws.M1; double* bc = ws.v2; double* orig = ws.v3; double* fc = ws.v4;
-  CW_FOR(e, nCl * nCl) { const int r = e / nCl, c = e - r * nCl; Q[(size_t)r * lq + c] = A[(size_t)cl[r] * ld + cl[c]]; }
+  CW_FOR2(r, c, nCl, nCl) Q[(size_t)r * lq + c] = A[(size_t)cl[r] * ld + cl[c]];
   CW_FOR(r, nCl) { bc[r] = b[cl[r]]; orig[r] = x[cl[r]]; }
   CW_SYNC();
   if (nUb > 0) {
@@ -484,8 +545,7 @@ NB2_HD bool classify_once(int m, const double* A, int ld, double* x, const doubl
     CW_SYNC();
     // general Q: f = (Q^T Q)^+ Q^T b
     double* QtQ = ws.M2; double* Qtb = ws.v7;
-    CW_FOR(e, nCl * nCl) {
-      const int a = e / nCl, c = e - a * nCl;
+    CW_FOR2(a, c, nCl, nCl) {
       double t = 0; for (int r = 0; r < nCl; r++) t += Q[(size_t)r * lq + a] * Q[(size_t)r * lq + c];
       QtQ[(size_t)a * lq + c] = t;
     }
@@ -505,7 +565,7 @@ NB2_HD bool classify_once(int m, const double* A, int ld, double* x, const doubl
     }
     if (ubIdx[i] != -1) {
       const int fp = fi[i];
-      const double origMult = orig[clampIdx[fp]] / x[i];
+      const double origMult = nb2_div(orig[clampIdx[fp]], x[i]);
       const double clean = (fabs(origMult - hi[i]) < fabs(origMult - lo[i])) ? hi[i] : lo[i];
       v = fc[clampIdx[fp]] * clean;
     }
@@ -521,8 +581,9 @@ NB2_HD bool classify_once(int m, const double* A, int ld, double* x, const doubl
   }
   return false;
 }
-NB2_HD bool classify_and_standardize(int m, const double* A, int ld, double* x, const double* b, const double* lo, const double* hi,
-                                     const int* fi, const double* colnorm, bool ignoreFriction, const Ws& ws) {
+NB2_HDN bool classify_and_standardize(int m, const double* A, int ld, double* x, const double* b, const double* lo, const double* hi,
+                                      const int* fi, const double* colnorm, bool ignoreFriction, const Ws& ws_) {
+  const Ws ws = ws_;  // array pointers into registers (the descriptor itself lives in shared memory / the caller's frame)
   bool ok = false, again = false;
   for (int it = 0; it < 6; it++) {
     ok = classify_once(m, A, ld, x, b, lo, hi, fi, colnorm, ignoreFriction, ws, &again);
@@ -536,8 +597,78 @@ NB2_HD bool classify_and_standardize(int m, const double* A, int ld, double* x, 
 // clobbered.  Gauss-Seidel is sequential in the rows; what is spread over the lanes is the row residual: lane j keeps
 // r_j = sum_k A_jk x_k up to date (one FMA per accepted change of some x_i), so a row update costs O(1) on its dependent chain
 // instead of an m-term inner product.  r is recomputed from scratch at the start of every sweep (no drift).
-NB2_HD bool pgs_solve(int m, double* A, int ld, double* x, double* b, const double* lo, const double* hi, const int* fi, double* r, int* skip) {
+NB2_HDN bool pgs_solve(int m, double* A, int ld, double* x, double* b, const double* lo, const double* hi, const int* fi, double* r, int* skip) {
   const double dxTol = 1e-6, relTol = 1e-3, epsDiv = 1e-9;
+#if CW_DEV && !defined(NB2_CW_PGS_SMEM)
+  if (m <= 32) {
+    // register form: lane j owns row j (x_j, r_j, b_j, bounds, 1 / A_jj); per row step the owner lane updates x_i, the change is
+    // broadcast and every lane folds it into its residual with ONE multiply-add on the (scaled-on-the-fly) column entry A_ji.
+    // Same arithmetic, in the same order, as the shared-memory form below.
+    const int lane = CW_LANE;
+    const bool act = lane < m;
+    const double* rowj = A + (size_t)(act ? lane : 0) * ld;
+    double xj = act ? x[lane] : 0.0, bj = act ? b[lane] : 0.0;
+    const double hij = act ? hi[lane] : 0.0, loj = act ? lo[lane] : 0.0;
+    double ajj = act ? rowj[lane] : 1.0;
+    const int fj = act ? fi[lane] : -1;
+    double dmj = 1.0;  // row scale (1 during the first sweep)
+    bool skipj = false;
+    auto residual = [&]() {
+      double rr = 0;
+      for (int k = 0; k < m; k++) { const double xk = __shfl_sync(CW_FULL, xj, k); if (act) rr += (dmj == 1.0 ? rowj[k] : rowj[k] * dmj) * xk; }
+      return rr;
+    };
+    double rj = residual();
+    bool changed = false;
+    for (int i = 0; i < m; i++) {
+      const int f = __shfl_sync(CW_FULL, fj, i);
+      const double xf = __shfl_sync(CW_FULL, xj, f >= 0 ? f : 0);
+      double delta = 0.0;
+      if (lane == i) {
+        double xi;
+        if (ajj < epsDiv) { xi = 0.0; skipj = true; }
+        else {
+          const double nx = nb2_div(bj - (rj - ajj * xj), ajj);
+          double hi_t = hij, lo_t = loj;
+          if (f >= 0) { hi_t = hij * xf; lo_t = -hi_t; }
+          xi = nx > hi_t ? hi_t : (nx < lo_t ? lo_t : nx);
+          if (fabs(xi - xj) > dxTol) changed = true;
+        }
+        delta = xi - xj; xj = xi;
+      }
+      delta = __shfl_sync(CW_FULL, delta, i);
+      if (act) rj += A[(size_t)lane * ld + i] * delta;
+    }
+    bool term = !__any_sync(CW_FULL, changed);
+    if (!term) {
+      if (act && !skipj) { dmj = nb2_rcp(ajj); bj *= dmj; ajj = ajj * dmj; }
+      for (int iter = 1; iter < 30; iter++) {
+        rj = residual();
+        changed = false;
+        for (int i = 0; i < m; i++) {
+          const int f = __shfl_sync(CW_FULL, fj, i);
+          const double xf = __shfl_sync(CW_FULL, xj, f >= 0 ? f : 0);
+          double delta = 0.0;
+          if (lane == i && !skipj) {
+            const double nx = bj - (rj - ajj * xj);
+            double hi_t = hij, lo_t = loj;
+            if (f >= 0) { hi_t = hij * xf; lo_t = -hi_t; }
+            const double xi = nx > hi_t ? hi_t : (nx < lo_t ? lo_t : nx);
+            if (fabs(xi) > epsDiv) { if (fabs(xi - xj) > relTol * fabs(xi)) changed = true; }
+            delta = xi - xj; xj = xi;
+          }
+          delta = __shfl_sync(CW_FULL, delta, i);
+          if (act) rj += (A[(size_t)lane * ld + i] * dmj) * delta;
+        }
+        term = !__any_sync(CW_FULL, changed);
+        if (term) break;
+      }
+    }
+    if (act) x[lane] = xj;
+    __syncwarp();
+    return term;
+  }
+#endif
   auto residuals = [&]() {
     CW_FOR(j, m) { const double* row = A + (size_t)j * ld; double s = 0; for (int k = 0; k < m; k++) s += row[k] * x[k]; r[j] = s; }
     CW_SYNC();
@@ -550,7 +681,7 @@ NB2_HD bool pgs_solve(int m, double* A, int ld, double* x, double* b, const doub
     int sk = 0;
     if (aii < epsDiv) { xi = 0.0; sk = 1; }
     else {
-      const double nx = (b[i] - (r[i] - aii * old_x)) / aii;
+      const double nx = nb2_div(b[i] - (r[i] - aii * old_x), aii);
       double hi_t = hi[i], lo_t = lo[i];
       const int f = fi[i];
       if (f >= 0) { hi_t = hi[i] * x[f]; lo_t = -hi_t; }
@@ -566,7 +697,7 @@ NB2_HD bool pgs_solve(int m, double* A, int ld, double* x, double* b, const doub
   if (term) return true;
   CW_FOR(i, m) if (!skip[i]) {
     double* row = A + (size_t)i * ld;
-    const double dm = 1.0 / row[i];
+    const double dm = nb2_rcp(row[i]);
     b[i] *= dm;
     for (int j = 0; j < m; j++) row[j] *= dm;
   }
@@ -582,7 +713,7 @@ NB2_HD bool pgs_solve(int m, double* A, int ld, double* x, double* b, const doub
       const int f = fi[i];
       if (f >= 0) { hi_t = hi[i] * x[f]; lo_t = -hi_t; }
       const double xi = nx > hi_t ? hi_t : (nx < lo_t ? lo_t : nx);
-      if (term && fabs(xi) > epsDiv) { if (fabs((xi - old_x) / xi) > relTol) term = false; }
+      if (term && fabs(xi) > epsDiv) { if (fabs(xi - old_x) > relTol * fabs(xi)) term = false; }
       const double delta = xi - old_x;
       CW_SYNC();
       CW_FOR(j, m) r[j] += A[(size_t)j * ld + i] * delta;  // rows were rescaled: column i
@@ -601,15 +732,15 @@ NB2_HD bool pgs_solve(int m, double* A, int ld, double* x, double* b, const doub
 // indices: alive[i], mult[i] (2^merges of a kept column), target[i] (the kept column an index was merged into; the un-merge
 // map x = mapOut * x_r has exactly one 1 per row) and fcur[i] (findex with merged normals redirected).  The reduced problem is
 // gathered once at the end: Ar (ldr = mr | 1), xr, br, lor, hir, fir.  Returns mr; keep[] lists the kept indices.
-NB2_HD int lcp_reduce(int m, const double* A, int ld, const double* x, const double* b, const double* lo, const double* hi, const int* fi,
+NB2_HDN int lcp_reduce(int m, const double* A, int ld, const double* x, const double* b, const double* lo, const double* hi, const int* fi,
                       double* Ar, double* xr, double* br, double* lor, double* hir, int* fir,
                       double* mult, int* alive, int* target, int* fcur, int* keep) {
   CW_FOR(i, m) { mult[i] = 1.0; alive[i] = 1; target[i] = i; fcur[i] = fi[i]; }
   CW_SYNC();
   for (;;) {
     int first = 0x7fffffff;
-    CW_FOR(p, m * m) {
-      const int a = p / m, c = p - a * m;
+    CW_FOR2(a, c, m, m) {
+      const int p = a * m + c;
       if (c <= a || !alive[a] || !alive[c] || p > first) continue;
       if (fcur[a] != fcur[c] || hi[a] != hi[c] || lo[a] != lo[c] || !(fabs(b[a] - b[c]) < 1e-4)) continue;
       const double ma = mult[a], mc = mult[c];
@@ -635,7 +766,7 @@ NB2_HD int lcp_reduce(int m, const double* A, int ld, const double* x, const dou
   CW_FOR(r, mr) alive[keep[r]] = r + 1;
   CW_SYNC();
   const int ldr = mr | 1;
-  CW_FOR(e, mr * mr) { const int ri = e / mr, ci = e - ri * mr; Ar[(size_t)ri * ldr + ci] = A[(size_t)keep[ri] * ld + keep[ci]] * mult[keep[ci]]; }
+  CW_FOR2(ri, ci, mr, mr) { Ar[(size_t)ri * ldr + ci] = A[(size_t)keep[ri] * ld + keep[ci]] * mult[keep[ci]]; }
   CW_FOR(ri, mr) {
     const int i = keep[ri];
     xr[ri] = x[i]; br[ri] = b[i]; lor[ri] = lo[i]; hir[ri] = hi[i];
@@ -684,14 +815,17 @@ NB2_HD void dz_factor(const DzWork& W, int nC) {
   for (int j = 0; j < nC; j++) {
     const int cj = W.C[j];
     const double* Lj = W.L + (size_t)j * ld;
+    // row j scaled back by the pivots once (L_jk / d_k with d the RECIPROCAL pivots), instead of one division per lane and term
+    CW_FOR(k, j) W.Dell[k] = nb2_div(Lj[k], W.d[k]);
+    CW_SYNC();
     CW_FOR(i, nC) if (i >= j) {
       const double* Li = W.L + (size_t)i * ld;
       double s = W.A[(size_t)W.C[i] * ld + cj];
-      for (int k = 0; k < j; k++) s -= Li[k] * Lj[k] / W.d[k];
+      for (int k = 0; k < j; k++) s -= Li[k] * W.Dell[k];
       W.tmp[i] = s;
     }
     CW_SYNC();
-    const double dj = 1.0 / W.tmp[j];
+    const double dj = nb2_rcp(W.tmp[j]);
     CW_FOR(i, nC) { if (i > j) W.L[(size_t)i * ld + j] = W.tmp[i] * dj; else if (i == j) W.d[j] = dj; }
     CW_SYNC();
   }
@@ -715,12 +849,13 @@ NB2_HD void dz_append(const DzWork& W, int nC, int i) {
   double s = 0;
   CW_FOR(j, nC) { W.L[(size_t)nC * W.ld + j] = W.ell[j]; s += W.ell[j] * W.Dell[j]; }
   s = cw_sum(s);
-  const double dd = 1.0 / (W.A[(size_t)i * W.ld + i] - s);
+  const double dd = nb2_rcp(W.A[(size_t)i * W.ld + i] - s);
   CW_ONE W.d[nC] = dd;
   CW_SYNC();
 }
 // returns 1 on success, 0 on early termination (s <= 0), -1 when the iteration cap is hit
-NB2_HD int dantzig_solve(const DzWork& W, int n, bool early_termination) {
+NB2_HDN int dantzig_solve(const DzWork& W_, int n, bool early_termination) {
+  const DzWork W = W_;  // pointers into registers: the caller's copy sits in local memory
   const double INF = HUGE_VAL;
   const int ld = W.ld;
   int nC = 0, nN = 0;
@@ -808,7 +943,7 @@ NB2_HD int dantzig_solve(const DzWork& W, int n, bool early_termination) {
         }
         // ratio test.  positions: 0 driving row to w = 0 (cmd 1) | 1 driving row to its bound (cmd 2/3) | 2 + k: N row k (cmd 4) |
         // 2 + nN + 2k, +1: C row k to lo (cmd 5) / hi (cmd 6).  The serial code initialises with position 0 and replaces on strict '<'.
-        const double s_first = -W.w[i] / W.delta_w[i];
+        const double s_first = nb2_div(-W.w[i], W.delta_w[i]);
         VI best; best.v = s_first; best.i = 0;
         {
           VI loc; loc.v = INF; loc.i = -1;
@@ -821,14 +956,14 @@ NB2_HD int dantzig_solve(const DzWork& W, int n, bool early_termination) {
               const int ik = nC + q - 1;
               const double dw = W.delta_w[ik];
               if (!W.state[ik] ? dw < 0 : dw > 0) {
-                if (!(W.lo[ik] == 0 && W.hi[ik] == 0)) vi_min(loc, -W.w[ik] / dw, 1 + q);
+                if (!(W.lo[ik] == 0 && W.hi[ik] == 0)) vi_min(loc, nb2_div(-W.w[ik], dw), 1 + q);
               }
             } else {
               const int e = q - 1 - nN, k = e >> 1;
               const double dx = W.delta_x[k];
               if (k < nub) {}
-              else if (!(e & 1)) { if (dx < 0 && W.lo[k] > -INF) vi_min(loc, (W.lo[k] - W.x[k]) / dx, 2 + nN + e); }
-              else { if (dx > 0 && W.hi[k] < INF) vi_min(loc, (W.hi[k] - W.x[k]) / dx, 2 + nN + e); }
+              else if (!(e & 1)) { if (dx < 0 && W.lo[k] > -INF) vi_min(loc, nb2_div(W.lo[k] - W.x[k], dx), 2 + nN + e); }
+              else { if (dx > 0 && W.hi[k] < INF) vi_min(loc, nb2_div(W.hi[k] - W.x[k], dx), 2 + nN + e); }
             }
           }
           loc = cw_vi_min(loc);
@@ -910,8 +1045,11 @@ unpermute:
 // findex): warm start -> short-circuit classification -> [reduce] Dantzig -> cfm + [reduce] PGS -> friction drop ->
 // classification / standardisation.  x_cached: last step's solution when it has the same size, else nullptr
 // (LCPUtils::guessSolution).  Leaves x in ws.x and the labels in ws.mapping; returns the status bits.
-NB2_HD int lcp_chain(int m, const Ws& ws, double fallback_cfm, const double* x_cached) {
+// ws: the caller's (register) copy of the workspace descriptor; ws_mem: the same descriptor at a stable address (shared memory on the
+// device), handed to the non-inlined classification so that the register copy never has to be spilled for a call
+NB2_HD int lcp_chain(int m, const Ws& ws, const Ws& ws_mem, double fallback_cfm, const double* x_cached) {
   int status = 0;
+  CW_PROF_DECL;
   const int ld = m | 1;
   double* A = ws.A;
   double* b = ws.b; double* lo = ws.lo; double* hi = ws.hi; int* fi = ws.findex; double* x = ws.x; double* x0 = ws.x0;
@@ -925,7 +1063,7 @@ NB2_HD int lcp_chain(int m, const Ws& ws, double fallback_cfm, const double* x_c
     CW_SYNC();
     if (ng > 0) {
       const int lg = ng | 1;
-      CW_FOR(e, ng * ng) { const int r = e / ng, c = e - r * ng; ws.M1[(size_t)r * lg + c] = A[(size_t)gi[r] * ld + gi[c]]; }
+      CW_FOR2(r, c, ng, ng) { ws.M1[(size_t)r * lg + c] = A[(size_t)gi[r] * ld + gi[c]]; }
       CW_FOR(r, ng) ws.v1[r] = b[gi[r]];
       CW_SYNC();
       pinv_psd(ng, ws.M1, lg, ws.v1, ws.v2, ws.M2, ws.v5, ws.v6, ws.v9, ws.i3);
@@ -935,8 +1073,10 @@ NB2_HD int lcp_chain(int m, const Ws& ws, double fallback_cfm, const double* x_c
   }
   CW_FOR(i, m) x[i] = x0[i];
   CW_SYNC();
+  CW_PROF(10);
   // ---- solve chain
-  bool success = classify_and_standardize(m, A, ld, x, b, lo, hi, fi, ws.colnorm, false, ws);
+  bool success = classify_and_standardize(m, A, ld, x, b, lo, hi, fi, ws.colnorm, false, ws_mem);
+  CW_PROF(11);
   const bool shortCircuit = success;
   bool ignoredFriction = false;
   // reduced problem: matrix in M1, vectors v1 (b) v2 (lo) v3 (hi) v4 (x), findex i1; bookkeeping v9 (mult), i2 (alive -> rank + 1),
@@ -952,7 +1092,9 @@ NB2_HD int lcp_chain(int m, const Ws& ws, double fallback_cfm, const double* x_c
     W.A = Ar; W.ld = mr | 1; W.x = xr; W.b = br; W.w = ws.v5; W.lo = lor; W.hi = hir; W.L = ws.M2; W.d = ws.v6; W.delta_x = ws.v7; W.delta_w = ws.v8;
     W.Dell = ws.v9; W.ell = ws.v10; W.tmp = ws.v11;  // v9 (mult) is dead once the reduced problem is gathered
     W.findex = fir; W.p = ws.clampIdx; W.C = ws.ubIdx; W.state = ws.i4;
+    CW_PROF(12);
     const int rc = dantzig_solve(W, mr, true);
+    CW_PROF(13);
     success = (rc == 1);
     if (success) {
       lcp_unreduce(m, xr, ws.i2, ws.i3, x);  // x = mapOut * x_reduced
@@ -971,7 +1113,9 @@ NB2_HD int lcp_chain(int m, const Ws& ws, double fallback_cfm, const double* x_c
     status |= NB2_ST_PGS;
     const int mr = lcp_reduce(m, A, ld, x0, b, lo, hi, fi, Ar, xr, br, lor, hir, fir, ws.v9, ws.i2, ws.i3, ws.i4, ws.mapping);  // :551-557
     if (mr < m) status |= NB2_ST_MERGED;
+    CW_PROF(14);
     success = pgs_solve(mr, Ar, mr | 1, xr, br, lor, hir, fir, ws.v5, ws.clampIdx);
+    CW_PROF(15);
     if (success) {
       lcp_unreduce(m, xr, ws.i2, ws.i3, x);
       if (!lcp_valid(m, A, ld, x, b, hi, lo, fi, false)) success = false;
@@ -984,7 +1128,7 @@ NB2_HD int lcp_chain(int m, const Ws& ws, double fallback_cfm, const double* x_c
     const int k = cw_enumerate(m, [&](int i) { return fi[i] == -1; }, [&](int i, int r) { nl[r] = i; });
     CW_SYNC();
     const int lk = k | 1;
-    CW_FOR(e, k * k) { const int r = e / k, c = e - r * k; Ar[(size_t)r * lk + c] = A[(size_t)nl[r] * ld + nl[c]]; }
+    CW_FOR2(r, c, k, k) { Ar[(size_t)r * lk + c] = A[(size_t)nl[r] * ld + nl[c]]; }
     CW_FOR(r, k) { br[r] = b[nl[r]]; lor[r] = lo[nl[r]]; hir[r] = hi[nl[r]]; xr[r] = 0; ws.i4[r] = -1; }
     CW_SYNC();
     pgs_solve(k, Ar, lk, xr, br, lor, hir, ws.i4, ws.v5, ws.clampIdx);
@@ -998,10 +1142,12 @@ NB2_HD int lcp_chain(int m, const Ws& ws, double fallback_cfm, const double* x_c
     CW_FOR(i, m) if (x[i] != x[i]) nan = true;
     if (cw_any(nan)) { CW_SYNC(); CW_FOR(i, m) x[i] = 0; CW_SYNC(); status |= NB2_ST_NAN; }
   }
+  CW_PROF(16);
   if (!shortCircuit) {
     // classify works on x in place and only keeps the standardised x when valid
-    if (!classify_and_standardize(m, A, ld, x, b, lo, hi, fi, ws.colnorm, ignoredFriction, ws)) status |= NB2_ST_NOT_STANDARDIZED;
+    if (!classify_and_standardize(m, A, ld, x, b, lo, hi, fi, ws.colnorm, ignoredFriction, ws_mem)) status |= NB2_ST_NOT_STANDARDIZED;
   }
+  CW_PROF(17);
   return status;
 }
 
@@ -1287,7 +1433,7 @@ NB2_HD void assemble_A(const Nb2ModelDev<double>& M, const Nb2ContactDev& C, con
   }
   CW_SYNC();
   if (!rows) {
-    CW_FOR(e, m * m) { const int r = e / m, s2 = e - r * m; if (ws.rowc[s2] < ws.rowc[r]) ws.A[(size_t)r * ld + s2] = ws.A[(size_t)s2 * ld + r]; }
+    CW_FOR2(r, s2, m, m) { if (ws.rowc[s2] < ws.rowc[r]) ws.A[(size_t)r * ld + s2] = ws.A[(size_t)s2 * ld + r]; }
     CW_SYNC();
   }
 }
@@ -1350,6 +1496,22 @@ NB2_HD void net_wrenches(const Nb2ContactDev& C, const Ws& ws, int m, const doub
 // record of a step for the backward pass, per world: [0] m, [1] status, then mapping[NB2_MAX_ROWS], x[NB2_MAX_ROWS], dqd[n]
 NB2_HD size_t record_doubles(int ndof) { return 2 + 2 * (size_t)NB2_MAX_ROWS + ndof; }
 
+// pool of LARGE workspaces in global memory for the rare world whose contacts exceed the shared-memory capacity: slots are handed
+// out with an atomic counter (reset by the host before every launch); a world that finds the pool empty keeps the contacts that fit
+// and is flagged NB2_ST_CONTACT_OVERFLOW.
+struct BigPool { int* counter; double* base; size_t stride; int nslots; };
+NB2_HD double* pool_acquire(const BigPool& P) {
+  if (!P.base || P.nslots <= 0) return nullptr;
+#if CW_DEV
+  int slot = 0;
+  if (CW_LANE == 0) slot = atomicAdd(P.counter, 1);
+  slot = __shfl_sync(CW_FULL, slot, 0);
+#else
+  const int slot = (*P.counter)++;
+#endif
+  return (slot < P.nslots) ? P.base + (size_t)slot * P.stride : nullptr;
+}
+
 struct FwdIO {
   double* x_io;     // [NB2_MAX_ROWS] cached LCP solution in / this step's solution out
   int* m_io;        // its size (-1: none) in / LCP dimension out
@@ -1365,19 +1527,29 @@ struct FwdIO {
 // on exit oV holds v+.  ws_s / d_s: the shared-memory workspace; big: a global-memory block of ws_doubles(d_b) doubles for the rare
 // world whose contact count exceeds the shared capacity (may be nullptr: such worlds then drop contacts and are flagged).
 // =====================================================================================================
-NB2_HD void contact_forward(const Nb2ModelDev<double>& M, const Nb2ContactDev& C, double* scr, const float* st, double* ws_small, const Dims& d_s,
-                            double* ws_big, const Dims& d_b, const double* Iinv_fwd, const FwdIO& io) {
+// wsm: storage of the workspace descriptor, ALREADY carved for the small workspace by the caller (shared memory on the device: the
+// non-inlined routines read the array pointers from there instead of dragging ~60 pointers through registers / local memory).
+NB2_HD void contact_forward(const Nb2ModelDev<double>& M, const Nb2ContactDev& C, double* scr, const float* st, Ws* wsm, const Dims& d_s,
+                            const BigPool& pool, const Dims& d_b, const double* Iinv_fwd, const FwdIO& io) {
   const FwdLayout L = fwd_layout(M.nb, M.ndof, M.nslots, M.nfree);
   const int n = M.ndof;
-  Ws ws = carve(ws_small, d_s);
+  Ws ws = *wsm;  // register copy for the inlined code
   Dims d = d_s;
-  TreeSrc S; S.scr = scr; S.L = L; S.Iinv = Iinv_fwd; S.sv = nullptr; S.st = st; S.nb = M.nb; S.nfree = M.nfree;
+  TreeSrc S; S.scr = scr; S.L = L; S.Iinv = ws.Iinv; S.sv = nullptr; S.st = st; S.nb = M.nb; S.nfree = M.nfree;
+  (void)Iinv_fwd;
+  CW_PROF_DECL;
   fk_collision_bodies(M, C, S, scr + L.oV, ws);
+  CW_PROF(1);
   collide_and_filter(C, ws, d);
-  if (ws.meta[3] && ws_big) {  // more contacts than the shared workspace holds: redo the stage in the large global workspace
+  CW_PROF(2);
+  double* ws_big = ws.meta[3] ? pool_acquire(pool) : nullptr;
+  if (ws_big) {  // more contacts than the shared workspace holds: redo the stage in a large global workspace
     const Ws wb = carve(ws_big, d_b);
     CW_FOR(e, C.ncb * 12) wb.Wcb[e] = ws.Wcb[e];
     CW_FOR(e, C.ncb * 6) wb.Vcb[e] = ws.Vcb[e];
+    CW_FOR(e, M.nfree * 21) wb.Iinv[e] = ws.Iinv[e];
+    CW_SYNC();
+    CW_ONE *wsm = wb;
     CW_SYNC();
     ws = wb; d = d_b;
     collide_and_filter(C, ws, d);
@@ -1399,10 +1571,13 @@ NB2_HD void contact_forward(const Nb2ModelDev<double>& M, const Nb2ContactDev& C
     return;  // scr already holds v*
   }
   status |= build_rows(M, C, ws, m, true);
+  CW_PROF(3);
   const int ld = m | 1;
   assemble_A(M, C, S, ws, m, ld, nullptr, 0);
-  status |= lcp_chain(m, ws, C.fallback_cfm, (*io.m_io == m) ? io.x_io : nullptr);
+  CW_PROF(4);
+  status |= lcp_chain(m, ws, *wsm, C.fallback_cfm, (*io.m_io == m) ? io.x_io : nullptr);
   CW_SYNC();
+  CW_PROF(5);
   // ---- apply the impulses and update the velocities
   net_wrenches(C, ws, m, ws.x, ws.Fcb);
   impulse_response_all(M, C, S, ws, ws.Fcb, ws.M1 + (size_t)C.ncb * C.max_chain_dofs);
@@ -1413,6 +1588,152 @@ NB2_HD void contact_forward(const Nb2ModelDev<double>& M, const Nb2ContactDev& C
     CW_FOR(dd, n) io.rec[2 + 2 * NB2_MAX_ROWS + dd] = ws.dqd[dd];
   }
   CW_ONE { *io.m_io = m; *io.status = status; if (io.rec) { io.rec[0] = (double)m; io.rec[1] = (double)status; } }
+  CW_SYNC();
+  CW_PROF(6);
+}
+
+// =====================================================================================================
+// The forward contact stage as THREE kernels (build | solve | apply) that hand a world over through an exchange record in global
+// memory.  Why: the solver chain is ~3/4 of the stage, needs few registers and only the LCP in shared memory, while the tree
+// sweeps and the collision code need 255 registers — in one kernel every phase runs at the occupancy of the hungriest.
+// Exchange record of a world (doubles; capacities NB2_MAX_ROWS / NB2_MAX_CONTACTS, only the used part is touched):
+//   [0] m  [1] nc  [2] status so far  [3] -   then b, lo, hi, findex, rowc (MRX each), cbodyA, cbodyB (MCX each), JA, JB (6 MRX each),
+//   v* (n), A (m x (m | 1), packed with the problem's own leading dimension)
+// =====================================================================================================
+struct XLayout { int oB, oLo, oHi, oFi, oRowc, oCA, oCB, oJA, oJB, oV, oA; size_t total; };
+NB2_HD XLayout xlayout(int n) {
+  const int MRX = NB2_MAX_ROWS, MCX = NB2_MAX_CONTACTS;
+  XLayout x; x.oB = 4; x.oLo = x.oB + MRX; x.oHi = x.oLo + MRX; x.oFi = x.oHi + MRX; x.oRowc = x.oFi + MRX; x.oCA = x.oRowc + MRX; x.oCB = x.oCA + MCX;
+  x.oJA = x.oCB + MCX; x.oJB = x.oJA + 6 * MRX; x.oV = x.oJB + 6 * MRX; x.oA = x.oV + n;
+  x.total = ((size_t)x.oA + (size_t)MRX * (MRX | 1) + 1) & ~(size_t)1;
+  return x;
+}
+
+// ---- build: collision, rows, A; leaves the record.  `scr`: the world's ABA scratch (q+ in oQ, v* in oV).
+NB2_HD void contact_build(const Nb2ModelDev<double>& M, const Nb2ContactDev& C, double* scr, const float* st, Ws* wsm, const Dims& d_s,
+                          const BigPool& pool, const Dims& d_b, const FwdIO& io, double* X) {
+  const FwdLayout L = fwd_layout(M.nb, M.ndof, M.nslots, M.nfree);
+  const XLayout xl = xlayout(M.ndof);
+  Ws ws = *wsm;
+  Dims d = d_s;
+  TreeSrc S; S.scr = scr; S.L = L; S.Iinv = ws.Iinv; S.sv = nullptr; S.st = st; S.nb = M.nb; S.nfree = M.nfree;
+  CW_PROF_DECL;
+  fk_collision_bodies(M, C, S, scr + L.oV, ws);
+  CW_PROF(1);
+  collide_and_filter(C, ws, d);
+  double* ws_big = ws.meta[3] ? pool_acquire(pool) : nullptr;
+  if (ws_big) {
+    const Ws wb = carve(ws_big, d_b);
+    CW_FOR(e, C.ncb * 12) wb.Wcb[e] = ws.Wcb[e];
+    CW_FOR(e, C.ncb * 6) wb.Vcb[e] = ws.Vcb[e];
+    CW_FOR(e, M.nfree * 21) wb.Iinv[e] = ws.Iinv[e];
+    CW_SYNC();
+    CW_ONE *wsm = wb;
+    CW_SYNC();
+    ws = wb; d = d_b;
+    collide_and_filter(C, ws, d);
+  }
+  CW_PROF(2);
+  const int m = ws.meta[0], nc = ws.meta[1];
+  int status = ws.meta[2];
+  if (ws.meta[3]) status |= NB2_ST_CONTACT_OVERFLOW;
+  CW_ONE {
+    *io.nc = nc;
+    if (io.cinfo) for (int c = 0; c < nc; c++) {
+      float* o = io.cinfo + 10 * c;
+      for (int e = 0; e < 3; e++) { o[e] = (float)ws.cpoint[3 * c + e]; o[3 + e] = (float)ws.cnormal[3 * c + e]; }
+      o[6] = (float)ws.cdepth[c]; o[7] = (float)C.shape_orig_body[ws.cshapeA[c]]; o[8] = (float)C.shape_orig_body[ws.cshapeB[c]]; o[9] = (float)ws.ctype[c];
+    }
+  }
+  if (m == 0) {
+    CW_ONE { X[0] = 0; X[1] = (double)nc; X[2] = (double)status; *io.m_io = 0; *io.status = status; if (io.rec) { io.rec[0] = 0; io.rec[1] = (double)status; } }
+    CW_SYNC();
+    return;
+  }
+  status |= build_rows(M, C, ws, m, true);
+  CW_PROF(3);
+  const int ld = m | 1;
+  assemble_A(M, C, S, ws, m, ld, nullptr, 0);
+  CW_PROF(4);
+  CW_FOR(i, m) {
+    X[xl.oB + i] = ws.b[i]; X[xl.oLo + i] = ws.lo[i]; X[xl.oHi + i] = ws.hi[i]; X[xl.oFi + i] = (double)ws.findex[i]; X[xl.oRowc + i] = (double)ws.rowc[i];
+  }
+  CW_FOR(c, nc) { X[xl.oCA + c] = (double)ws.cbodyA[c]; X[xl.oCB + c] = (double)ws.cbodyB[c]; }
+  CW_FOR(e, m * 6) { X[xl.oJA + e] = ws.JA[e]; X[xl.oJB + e] = ws.JB[e]; }
+  CW_FOR(dd, M.ndof) X[xl.oV + dd] = scr[L.oV + dd];
+  CW_FOR(e, m * ld) X[xl.oA + e] = ws.A[e];
+  CW_ONE { X[0] = (double)m; X[1] = (double)nc; X[2] = (double)status; }
+  CW_SYNC();
+  CW_PROF(6);
+}
+
+// ---- solve: the chain on the record's LCP.  wsm: descriptor carved in NB2_WS_SOLVE mode (small; large from the pool when m > d_s.MR)
+NB2_HD void contact_solve(const Nb2ContactDev& C, int ndof, Ws* wsm, const Dims& d_s, const BigPool& pool, const Dims& d_b, const FwdIO& io, double* X,
+                          int* status_accum) {
+  const int m = (int)X[0];
+  if (m <= 0) { CW_ONE { if (status_accum) *status_accum |= (int)X[2]; } return; }
+  const XLayout xl = xlayout(ndof);
+  Ws ws = *wsm;
+  if (m > d_s.MR) {
+    double* big = pool_acquire(pool);
+    if (!big) {  // pool exhausted: this world cannot be solved here — flag it and leave v* (no contact impulse)
+      CW_ONE {
+        const int st = (int)X[2] | NB2_ST_CONTACT_OVERFLOW;
+        *io.m_io = 0; *io.status = st; if (status_accum) *status_accum |= st; X[0] = 0; if (io.rec) { io.rec[0] = 0; io.rec[1] = (double)st; }
+      }
+      CW_SYNC();
+      return;
+    }
+    const Ws wb = carve(big, d_b);
+    CW_SYNC();
+    CW_ONE *wsm = wb;
+    CW_SYNC();
+    ws = wb;
+  }
+  const int ld = m | 1;
+  CW_FOR(i, m) { ws.b[i] = X[xl.oB + i]; ws.lo[i] = X[xl.oLo + i]; ws.hi[i] = X[xl.oHi + i]; ws.findex[i] = (int)X[xl.oFi + i]; }
+  CW_FOR(e, m * ld) ws.A[e] = X[xl.oA + e];
+  CW_SYNC();
+  int status = (int)X[2];
+  status |= lcp_chain(m, ws, *wsm, C.fallback_cfm, (*io.m_io == m) ? io.x_io : nullptr);
+  CW_SYNC();
+  CW_FOR(i, m) { io.x_io[i] = ws.x[i]; io.labels[i] = ws.mapping[i]; }
+  CW_ONE { *io.m_io = m; *io.status = status; if (status_accum) *status_accum |= status; X[2] = (double)status; }
+  CW_SYNC();
+}
+
+// ---- apply: impulses -> joint velocity changes -> v+ (fp32 row `vnext`), and the record of the step for the backward pass.
+// wsm: descriptor carved in NB2_WS_APPLY mode.  sv: the world's saved stream (world-major).
+NB2_HD void contact_apply(const Nb2ModelDev<double>& M, const Nb2ContactDev& C, const float* st, const double* sv, Ws* wsm, const Dims& d_s,
+                          const BigPool& pool, const Dims& d_b, const FwdIO& io, const double* X, float* vnext) {
+  const int m = (int)X[0], nc = (int)X[1];
+  if (m <= 0) return;
+  const XLayout xl = xlayout(M.ndof);
+  const int n = M.ndof;
+  Ws ws = *wsm;
+  if (m > d_s.MR || nc > d_s.MC) {
+    double* big = pool_acquire(pool);
+    if (!big) return;  // (contact_solve already flagged the world when the pool ran dry: same pool size, same demand)
+    const Ws wb = carve(big, d_b);
+    CW_SYNC();
+    CW_ONE *wsm = wb;
+    CW_SYNC();
+    ws = wb;
+  }
+  CW_FOR(i, m) { ws.rowc[i] = (int)X[xl.oRowc + i]; ws.x[i] = io.x_io[i]; }
+  CW_FOR(c, nc) { ws.cbodyA[c] = (int)X[xl.oCA + c]; ws.cbodyB[c] = (int)X[xl.oCB + c]; }
+  CW_FOR(e, m * 6) { ws.JA[e] = X[xl.oJA + e]; ws.JB[e] = X[xl.oJB + e]; }
+  CW_SYNC();
+  TreeSrc S; S.scr = nullptr; S.Iinv = nullptr; S.sv = sv; S.st = st; S.nb = M.nb; S.nfree = M.nfree;
+  S.L = fwd_layout(M.nb, n, M.nslots, M.nfree);
+  net_wrenches(C, ws, m, ws.x, ws.Fcb);
+  impulse_response_all(M, C, S, ws, ws.Fcb, ws.M1 + (size_t)C.ncb * C.max_chain_dofs);
+  CW_FOR(dd, n) vnext[dd] = (float)(X[xl.oV + dd] + ws.dqd[dd]);
+  if (io.rec) {
+    CW_FOR(i, m) { io.rec[2 + i] = (double)io.labels[i]; io.rec[2 + NB2_MAX_ROWS + i] = ws.x[i]; }
+    CW_FOR(dd, n) io.rec[2 + 2 * NB2_MAX_ROWS + dd] = ws.dqd[dd];
+    CW_ONE { io.rec[0] = (double)m; io.rec[1] = X[2]; }
+  }
   CW_SYNC();
 }
 
@@ -1452,8 +1773,8 @@ NB2_HD Xf<D1> lift1(const Xf<double>& X) {
   return o;
 }
 
-NB2_HD BwdContactData<1> contact_backward(const Nb2ModelDev<double>& M, const Nb2ContactDev& C, const float* st, const double* sv, double* ws_small,
-                                          const Dims& d_s, double* ws_big, const Dims& d_b, const double* rec, double* scr, int oLam, int oBody) {
+NB2_HD BwdContactData<1> contact_backward(const Nb2ModelDev<double>& M, const Nb2ContactDev& C, const float* st, const double* sv, Ws* wsm,
+                                          const Dims& d_s, const BigPool& pool, const Dims& d_b, const double* rec, double* scr, int oLam, int oBody) {
   const int nb = M.nb, n = M.ndof;
   BwdContactData<1> cd;
   cd.Aacc.p = cd.Uplus.p = cd.aeff.p = cd.vplus.p = cd.inj.p = cd.JcTmu.p = nullptr;
@@ -1465,7 +1786,7 @@ NB2_HD BwdContactData<1> contact_backward(const Nb2ModelDev<double>& M, const Nb
   // restitution: b depends on v* through (1 + e) J v*, which needs a second multiplier field in the reverse sweep
   // (BackpropSnapshot::getBounceApproximationJacobian, BackpropSnapshot.cpp:1131-1226) — not implemented: fail loudly
   if (fstatus & NB2_ST_BOUNCE) { cd.error = 5; cd.active = 0; return cd; }
-  Ws ws = carve(ws_small, d_s);
+  Ws ws = *wsm;
   Dims d = d_s;
   TreeSrc S; S.scr = nullptr; S.Iinv = nullptr; S.sv = sv; S.st = st; S.nb = nb; S.nfree = M.nfree;
   S.L = fwd_layout(nb, n, M.nslots, M.nfree);
@@ -1473,11 +1794,17 @@ NB2_HD BwdContactData<1> contact_backward(const Nb2ModelDev<double>& M, const Nb
   const int kQdd = nb * 21 + M.nfree * 33;
   const double* mapping_r = rec + 2; const double* xr = rec + 2 + NB2_MAX_ROWS; const double* dqd_imp = rec + 2 + 2 * NB2_MAX_ROWS;
   // ---- contacts and row wrenches re-generated from the saved transforms (same code as the forward => same rows)
+  CW_PROF_DECL;
   fk_collision_bodies(M, C, S, nullptr, ws);
+  CW_PROF(21);
   collide_and_filter(C, ws, d);
-  if (ws.meta[3] && ws_big) {
+  CW_PROF(22);
+  double* ws_big = ws.meta[3] ? pool_acquire(pool) : nullptr;
+  if (ws_big) {
     const Ws wb = carve(ws_big, d_b);
     CW_FOR(e, C.ncb * 12) wb.Wcb[e] = ws.Wcb[e];
+    CW_SYNC();
+    CW_ONE *wsm = wb;
     CW_SYNC();
     ws = wb; d = d_b;
     collide_and_filter(C, ws, d);
@@ -1519,16 +1846,17 @@ NB2_HD BwdContactData<1> contact_backward(const Nb2ModelDev<double>& M, const Nb
     fbar[r] = f; mu_c[r] = 0;
   }
   CW_SYNC();
+  CW_PROF(23);
   if (nCl > 0) {
     const int ld = m | 1, lq = nCl | 1;
     assemble_A(M, C, S, ws, m, ld, rows, nCl + nUb);  // rows cl and ub of A, measured
+    CW_PROF(24);
     // Q = A[cl,cl] + A[cl,ub] E (+ cfm on the diagonal when the forward's fallback added it); as in the forward, an entry below the
     // block diagonal is the mirror image of its measured partner
     double* Q = ws.M1;
     auto Aget = [&](int r, int c) { return (ws.rowc[c] < ws.rowc[r]) ? ws.A[(size_t)c * ld + r] : ws.A[(size_t)r * ld + c]; };
     const double cfm = (fstatus & NB2_ST_PGS) ? C.fallback_cfm : 0.0;
-    CW_FOR(e, nCl * nCl) {
-      const int r = e / nCl, c = e - r * nCl;
+    CW_FOR2(r, c, nCl, nCl) {
       double q = Aget(cl[r], cl[c]);
       if (r == c) q += cfm;
       for (int u = 0; u < nUb; u++) if (clampIdx[mapping[ubl[u]]] == c) q += Aget(cl[r], ubl[u]) * Eu[u];
@@ -1538,8 +1866,7 @@ NB2_HD BwdContactData<1> contact_backward(const Nb2ModelDev<double>& M, const Nb
     if (nUb == 0) pinv_psd(nCl, ws.M2, lq, fbar, mu_c, ws.M1, ws.v5, ws.v6, ws.v9, ws.i4);
     else {  // Q^T mu = fbar  ->  mu = (Q Q^T)^+ Q fbar
       double* Qm = ws.M2; double* QQt = ws.M1; double* Qf = ws.v10;
-      CW_FOR(e, nCl * nCl) {
-        const int a = e / nCl, c = e - a * nCl;
+      CW_FOR2(a, c, nCl, nCl) {
         double t = 0; for (int kx = 0; kx < nCl; kx++) t += Qm[(size_t)a * lq + kx] * Qm[(size_t)c * lq + kx];
         QQt[(size_t)a * lq + c] = t;
       }
@@ -1548,6 +1875,7 @@ NB2_HD BwdContactData<1> contact_backward(const Nb2ModelDev<double>& M, const Nb
       pinv_psd(nCl, QQt, lq, Qf, mu_c, Qm /* Lf */, ws.v5, ws.v6, ws.v9, ws.i4);
     }
   }
+  CW_PROF(25);
   // ---- nu = M^-1 A_c mu  (one impulse response) ; w = lambda - nu ; W_i(w)
   CW_FOR(j, m) coefM[j] = (clampIdx[j] >= 0) ? mu_c[clampIdx[j]] : 0.0;
   CW_SYNC();
@@ -1584,6 +1912,7 @@ NB2_HD BwdContactData<1> contact_backward(const Nb2ModelDev<double>& M, const Nb
     CW_FOR(l, M.lanes) for (int r = 0; r < M.limb_n[l]; r++) sweep(M.limb_lo[l][r], M.limb_hi[l][r]);
     CW_SYNC();
   }
+  CW_PROF(26);
   // ---- per-body injections for the reverse sweep: Uw_bar, Up_bar, G (all scaled by -1/dt: they join the (dID/dq)^T w accumulator
   // that is multiplied by -dt at the end) and H (plain: A_c mu propagated to joint space).  One collision body per lane.
   const double kap = -1.0 / dt;
@@ -1613,6 +1942,7 @@ NB2_HD BwdContactData<1> contact_backward(const Nb2ModelDev<double>& M, const Nb
   // ---- contact-frame part G: derivatives of every wrench with respect to the pose of each moving body of its pair.  Work item =
   // (pair that produced contacts, body whose pose varies); each item takes 6 lanes, one pose direction each: the contact
   // generator runs on 1-direction dual numbers.  Contacts of a pair are consecutive: groups are found from the shape indices.
+  CW_PROF(27);
   int* gfirst = ws.i1; int* it_g = ws.i2; int* it_dyn = ws.i4;  // cl / ubl are dead by now
   const int ng = cw_enumerate(nc, [&](int c) { return c == 0 || ws.cshapeA[c] != ws.cshapeA[c - 1] || ws.cshapeB[c] != ws.cshapeB[c - 1]; },
                               [&](int c, int r) { gfirst[r] = c; });
@@ -1682,6 +2012,7 @@ NB2_HD BwdContactData<1> contact_backward(const Nb2ModelDev<double>& M, const Nb
     CW_ONE { for (int q = 0; q < cnt * 6; q++) ws.inj[24 * C.cb_of_body[it_dyn[it0 + q / 6]] + 12 + q % 6] += gpart[q]; }
     CW_SYNC();
   }
+  CW_PROF(28);
   if (cw_any(bad)) { cd.error = 3; cd.active = 0; }
   return cd;
 }

@@ -244,7 +244,7 @@ NB2_HD void fwd_pass2(const Nb2ModelDev<R>& M, R* scr, R* sv, size_t B, bool sav
         U.a = mk3<R>(IA.B.m02, IA.B.m12, IA.B.m22); U.l = mk3<R>(IA.C.xz, IA.C.yz, IA.C.zz); D = IA.C.zz;
         eta.a = zero3<R>(); eta.l = mk3<R>(V.a.y * vq, -V.a.x * vq, R(0));
       }
-      const R psi = R(1) / D;
+      const R psi = nb2_rcp(D);
       const R qv = scr[(size_t)(L.oQ + o) * ST];
       const R u = tau_of<R, ST>(M, scr, L.oAct, o) - M.spring[o] * (qv - M.rest[o] + vq * dt) - M.damping[o] * vq
                   - (dot(U, eta) + S_dot(jt, pA));

@@ -7,6 +7,14 @@
 #pragma once
 #include "nb2_math.cuh"
 
+#if defined(__CUDACC__) && defined(NB2_CW_INLINE_ALL)
+#define NB2_HDG __host__ __device__ __forceinline__
+#elif defined(__CUDACC__)
+#define NB2_HDG __host__ __device__ __noinline__
+#else
+#define NB2_HDG inline
+#endif
+
 namespace nb2 {
 
 typedef double CR;
@@ -21,14 +29,18 @@ template <int N> NB2_HD DualT<N> operator+(const DualT<N>& a, const DualT<N>& b)
 template <int N> NB2_HD DualT<N> operator-(const DualT<N>& a, const DualT<N>& b) { DualT<N> r; r.v = a.v - b.v; for (int i = 0; i < N; i++) r.d[i] = a.d[i] - b.d[i]; return r; }
 template <int N> NB2_HD DualT<N> operator-(const DualT<N>& a) { DualT<N> r; r.v = -a.v; for (int i = 0; i < N; i++) r.d[i] = -a.d[i]; return r; }
 template <int N> NB2_HD DualT<N> operator*(const DualT<N>& a, const DualT<N>& b) { DualT<N> r; r.v = a.v * b.v; for (int i = 0; i < N; i++) r.d[i] = a.d[i] * b.v + a.v * b.d[i]; return r; }
-template <int N> NB2_HD DualT<N> operator/(const DualT<N>& a, const DualT<N>& b) { DualT<N> r; const double ib = 1.0 / b.v; r.v = a.v * ib; for (int i = 0; i < N; i++) r.d[i] = (a.d[i] - r.v * b.d[i]) * ib; return r; }
+template <int N> NB2_HD DualT<N> operator/(const DualT<N>& a, const DualT<N>& b) { DualT<N> r; const double ib = nb2_rcp(b.v); r.v = a.v * ib; for (int i = 0; i < N; i++) r.d[i] = (a.d[i] - r.v * b.d[i]) * ib; return r; }
 template <int N> NB2_HD DualT<N>& operator+=(DualT<N>& a, const DualT<N>& b) { a = a + b; return a; }
 template <int N> NB2_HD DualT<N>& operator-=(DualT<N>& a, const DualT<N>& b) { a = a - b; return a; }
 template <int N> NB2_HD DualT<N>& operator*=(DualT<N>& a, const DualT<N>& b) { a = a * b; return a; }
+template <int N> NB2_HD DualT<N> gdiv(const DualT<N>& a, const DualT<N>& b) { return a / b; }
 template <int N> NB2_HD DualT<N>& operator/=(DualT<N>& a, const DualT<N>& b) { a = a / b; return a; }
-template <int N> NB2_HD DualT<N> nb2_sqrt(const DualT<N>& a) { DualT<N> r; r.v = sqrt(a.v); const double k = r.v > 0 ? 0.5 / r.v : 0.0; for (int i = 0; i < N; i++) r.d[i] = k * a.d[i]; return r; }
+template <int N> NB2_HD DualT<N> nb2_sqrt(const DualT<N>& a) { DualT<N> r; r.v = nb2_sqrt(a.v); const double k = r.v > 0 ? 0.5 * nb2_rcp(r.v) : 0.0; for (int i = 0; i < N; i++) r.d[i] = k * a.d[i]; return r; }
 template <int N> NB2_HD DualT<N> nb2_abs(const DualT<N>& a) { return a.v < 0 ? -a : a; }
 NB2_HD double gval(double x) { return x; }
+// a / b: fast division for plain doubles (nb2_math.cuh), the dual-number operator otherwise
+NB2_HD double gdiv(double a, double b) { return nb2_div(a, b); }
+template <int N> NB2_HD DualT<N> gdiv(const DualT<N>& a, const DualT<N>& b);
 template <int N> NB2_HD double gval(const DualT<N>& x) { return x.v; }
 
 template <class T> NB2_HD Xf<T> gxf_mul(const Xf<T>& A, const Xf<T>& B) { Xf<T> C; C.R_ = mul(A.R_, B.R_); C.p = mul(A.R_, B.p) + A.p; return C; }
@@ -46,7 +58,7 @@ template <class T> struct ContactOutT { V3<T> point, normal; T depth; int type; 
 // ---- box vs sphere.  sphere_first=false: object 1 = box, object 2 = sphere (DARTCollide.cpp:1482-1653, normal = contact
 // point - centre); sphere_first=true: object 1 = sphere (:1655-1810, normal = centre - contact point, halfspace ignored)
 template <class T>
-NB2_HD int collide_box_sphere(const V3<T>& size0, const Xf<T>& T0, const T& r1, const Xf<T>& T1, CR clip, int halfspace, bool sphere_first,
+NB2_HDG int collide_box_sphere(const V3<T>& size0, const Xf<T>& T0, const T& r1, const Xf<T>& T1, CR clip, int halfspace, bool sphere_first,
                               ContactOutT<T>* out) {
   const V3<T> half = size0 * T(0.5);
   bool inside = true;
@@ -81,7 +93,7 @@ NB2_HD int collide_box_sphere(const V3<T>& size0, const Xf<T>& T0, const T& r1, 
   }
   if (gval(pen) < 0.0) return 0;
   out->type = sphere_first ? 4 : 5; out->point = cp; out->depth = pen;
-  out->normal = (gval(mag) > 1e-6) ? n * (T(1.0) / mag) : nface;
+  out->normal = (gval(mag) > 1e-6) ? n * gdiv(T(1.0), mag) : nface;
   return 1;
 }
 
@@ -122,7 +134,7 @@ NB2_HD int clip_quad_to_rect(const T h[2], const T quad[8], T out[16]) {
       const bool in_a = sg * gval(a[axis]) < gval(h[axis]), in_n = sg * gval(nx[axis]) < gval(h[axis]);
       if (in_a) { dst[2 * k] = a[0]; dst[2 * k + 1] = a[1]; k++; if (k == 8) { full = true; break; } }
       if (in_a != in_n) {
-        dst[2 * k + other] = a[other] + (nx[other] - a[other]) / (nx[axis] - a[axis]) * (bound - a[axis]);
+        dst[2 * k + other] = a[other] + gdiv(nx[other] - a[other], nx[axis] - a[axis]) * (bound - a[axis]);
         dst[2 * k + axis] = bound;
         k++;
         if (k == 8) full = true;
@@ -164,10 +176,10 @@ NB2_HD SatAxis<T> sat_pick_axis(const T A[3], const T Bh[3], const T pp[3], cons
       nc[i] = T(0.0); nc[i1] = -Rm[i2][j]; nc[i2] = Rm[i1][j];
       const T l = nb2_sqrt(nc[0] * nc[0] + nc[1] * nc[1] + nc[2] * nc[2]);
       if (gval(l) > 0) {
-        s2 = s2 / l;
+        s2 = gdiv(s2, l);
         if (gval(s2) * fudge > gval(ax.depth_neg)) {
           ax.depth_neg = s2; ax.invert = gval(e1) < 0; ax.code = 7 + 3 * i + j;
-          ax.edge_normal = mk3<T>(nc[0] / l, nc[1] / l, nc[2] / l);
+          ax.edge_normal = mk3<T>(gdiv(nc[0], l), gdiv(nc[1], l), gdiv(nc[2], l));
         }
       }
     }
@@ -177,7 +189,7 @@ NB2_HD SatAxis<T> sat_pick_axis(const T A[3], const T Bh[3], const T pp[3], cons
 
 // dBoxBox; returns the number of contacts written to out (<= 8)
 template <class T>
-NB2_HD int collide_box_box(const V3<T>& size0, const Xf<T>& T0, const V3<T>& size1, const Xf<T>& T1, CR clip, ContactOutT<T>* out) {
+NB2_HDG int collide_box_box(const V3<T>& size0, const Xf<T>& T0, const V3<T>& size1, const Xf<T>& T1, CR clip, ContactOutT<T>* out) {
   const M3<T>&R1 = T0.R_, &R2 = T1.R_;
   const V3<T> p1 = T0.p, p2 = T1.p;
   const T A[3] = {size0.x * T(0.5), size0.y * T(0.5), size0.z * T(0.5)}, Bh[3] = {size1.x * T(0.5), size1.y * T(0.5), size1.z * T(0.5)};
@@ -193,7 +205,7 @@ NB2_HD int collide_box_box(const V3<T>& size0, const Xf<T>& T0, const V3<T>& siz
   V3<T> normal;
   if (code <= 3) normal = gcol3(R1, code - 1);
   else if (code <= 6) normal = gcol3(R2, code - 4);
-  else { normal = mul(R1, ax.edge_normal); normal = normal * (T(1.0) / nb2_sqrt(dot(normal, normal))); }
+  else { normal = mul(R1, ax.edge_normal); normal = normal * gdiv(T(1.0), nb2_sqrt(dot(normal, normal))); }
   if (ax.invert) normal = -normal;
   if (code > 6) {
     // ---- edge x edge: walk from each box centre to the touching edge, then closest points of the two lines
@@ -204,7 +216,7 @@ NB2_HD int collide_box_box(const V3<T>& size0, const Xf<T>& T0, const V3<T>& siz
     const V3<T> dp = pb - pa;
     const T uaub = dot(ua, ub), q1 = dot(ua, dp), q2 = -dot(ub, dp);
     T d = T(1.0) - uaub * uaub, alpha = T(0.0), beta = T(0.0);
-    if (gval(d) > 0.0) { d = T(1.0) / d; alpha = (q1 + uaub * q2) * d; beta = (uaub * q1 + q2) * d; }
+    if (gval(d) > 0.0) { d = gdiv(T(1.0), d); alpha = (q1 + uaub * q2) * d; beta = (uaub * q1 + q2) * d; }
     pa = pa + ua * alpha; pb = pb + ub * beta;
     const T pen = -ax.depth_neg;
     if (gval(pen) > clip) return 0;
@@ -241,7 +253,7 @@ NB2_HD int collide_box_box(const V3<T>& size0, const Xf<T>& T0, const V3<T>& siz
   const int n = clip_quad_to_rect(rect, quad, ret);
   if (n < 1) return 0;
   // back to 3-D: invert the 2x2 projection, keep the vertices below the reference face
-  const T det1 = T(1.0) / (m11 * m22 - m12 * m21);
+  const T det1 = gdiv(T(1.0), m11 * m22 - m12 * m21);
   m11 = m11 * det1; m12 = m12 * det1; m21 = m21 * det1; m22 = m22 * det1;
   int cnum = 0;
   for (int j = 0; j < n; j++) {
@@ -269,7 +281,7 @@ NB2_HD int collide_box_box(const V3<T>& size0, const Xf<T>& T0, const V3<T>& siz
 template <class T> NB2_HD void tangent_basis(const V3<T>& n, V3<T>* t1, V3<T>* t2) {
   V3<T> t = cross(mk3<T>(T(0.0), T(0.0), T(1.0)), n);
   if (gval(dot(t, t)) < 1e-12) { t = cross(mk3<T>(T(1.0), T(0.0), T(0.0)), n); if (gval(dot(t, t)) < 1e-12) { t = cross(mk3<T>(T(0.0), T(1.0), T(0.0)), n); if (gval(dot(t, t)) < 1e-12) t = cross(mk3<T>(T(0.0), T(0.0), T(1.0)), n); } }
-  *t1 = t * (T(1.0) / nb2_sqrt(dot(t, t)));
+  *t1 = t * gdiv(T(1.0), nb2_sqrt(dot(t, t)));
   *t2 = cross(n, *t1);
 }
 

@@ -16,7 +16,7 @@
 
 #include "../../include/nb2.h"
 #include "nb2_dyn.cuh"
-#include "nb2_contact.cuh"
+#include "nb2_cw.cuh"
 #include "nb2_host_model.h"
 
 static thread_local std::string g_err;
@@ -214,67 +214,175 @@ k_step_bwd(const __grid_constant__ Nb2ModelDev<R> M, int B, int w0, int count, c
   }
 }
 
-// contact / boxed-LCP stage, fp64, per-world workspace in global memory (L1/L2 cached), KC threads per world:
-// one thread runs the data-dependent parts (collision, LCP pivoting, classification), all KC share the m impulse tests
-// that assemble A = J M^-1 J^T (the dominant cost: m leaf->root->leaf sweeps).  A warp holds 32/KC worlds; with KC = 8 a
-// batch of 4096 worlds fills 1024 warps instead of 128, which is what hides the latency of the serial parts.
-template <int KC>
-__global__ void __launch_bounds__(64)
-k_contact_fwd(const __grid_constant__ Nb2ModelDev<double> M, const __grid_constant__ Nb2ContactDev C, int B,
-              const float* __restrict__ state, float* __restrict__ next, const double* __restrict__ saved,
-              double* __restrict__ workspace, size_t ws_doubles, double* __restrict__ x_lcp, int* __restrict__ m_lcp,
-              int* __restrict__ labels, int* __restrict__ status, int* __restrict__ ncontacts, float* __restrict__ cinfo,
-              double* __restrict__ crec, size_t rec_doubles) {
-  constexpr int WPW = 32 / KC;
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  const int li = threadIdx.x & 31, slot = li / KC, cl = li % KC;
-  const int w = (t >> 5) * WPW + slot;
-  const bool valid = w < B;
-  const int wc = valid ? w : 0;
-  // the WPW worlds of a warp share one slot-interleaved workspace block
-  double* wsb = workspace + (size_t)(t >> 5) * ws_doubles * WPW;
-  const float* st = state + (size_t)wc * 2 * M.ndof;
-  float* out = next + (size_t)wc * 2 * M.ndof;
-  // phases 0 and 2 are executed redundantly by all KC threads of the world (see nb2::Grp): same instructions, same data,
-  // identical writes — and the inner products of the solver chain are shared among them
-  if (valid)
-    nb2::contact_phase0<WPW>(M, C, st, out, saved + wc, (size_t)B, wsb, slot, x_lcp + (size_t)wc * NB2_MAX_ROWS, m_lcp + wc,
-                             labels + (size_t)wc * NB2_MAX_ROWS, status + wc, ncontacts + wc,
-                             cinfo ? cinfo + (size_t)wc * NB2_MAX_CONTACTS * 10 : nullptr, crec ? crec + (size_t)wc * rec_doubles : nullptr);
+// ---- fused step kernels of worlds WITH a contact stage (fp64): ONE WARP PER WORLD.
+// Forward: group load -> the three ABA sweeps on the first M.lanes lanes (trunk / limb schedule) -> the warp-cooperative contact /
+// boxed-LCP stage on all 32 lanes (nb2_cw.cuh) -> store.  Everything a world needs — ABA scratch, contact list, LCP matrix and its
+// factors — sits in that warp's slice of shared memory; HBM sees the fp32 rows, the LCP warm start and what the backward needs
+// (the saved stream, world-major, and a ~1 KB record).  Backward: the lambda sweeps, the contact adjoint, the reverse RNEA sweep.
+// Blocks are one warp: no block-level barrier exists in these kernels, and a warp whose world is out of range simply leaves.
+#define NB2_WS_DESC_DOUBLES ((int)((sizeof(nb2::cw::Ws) + 15) / 16 * 2))  // the workspace descriptor sits in front of the arrays
+#ifndef NB2_CSTEP_MINB
+#define NB2_CSTEP_MINB 1   // resident warps per SM the register allocation of the fused contact kernels aims at
+#endif
+struct CStepArgs {
+  int B, fwd_words, bwd_words, saved_words;
+  size_t ws_small_doubles;   // doubles of the shared contact workspace (after the scratch)
+  nb2::cw::Dims ds, db;
+  nb2::cw::BigPool pool;
+  size_t rec_doubles;
+  // three-kernel forward: exchange records and the workspace shapes of the solve / apply kernels
+  double* exch; size_t exch_stride;
+  nb2::cw::Dims ds_solve, db_solve, ds_apply, db_apply;
+  nb2::cw::BigPool pool_solve, pool_apply;
+};
+__global__ void __launch_bounds__(32, NB2_CSTEP_MINB)
+k_cstep_fwd(const __grid_constant__ Nb2ModelDev<double> M, const __grid_constant__ Nb2ContactDev C, const __grid_constant__ CStepArgs P,
+            const float* __restrict__ state, const float* __restrict__ action, float* __restrict__ next, double* __restrict__ saved,
+            double* __restrict__ x_lcp, int* __restrict__ m_lcp, int* __restrict__ labels, int* __restrict__ status,
+            int* __restrict__ ncontacts, float* __restrict__ cinfo, double* __restrict__ crec, int* __restrict__ status_accum) {
+  extern __shared__ __align__(16) unsigned char nb2_smem[];
+  const int w = blockIdx.x, lane = threadIdx.x & 31;
+  if (w >= P.B) return;
+  double* scr = reinterpret_cast<double*>(nb2_smem);
+  nb2::cw::Ws* wsm = reinterpret_cast<nb2::cw::Ws*>(scr + ((P.fwd_words + 1) & ~1));
+  double* wsb = reinterpret_cast<double*>(wsm) + NB2_WS_DESC_DOUBLES;
+  if (lane == 0) *wsm = nb2::cw::carve(wsb, P.ds);
   __syncwarp();
-  constexpr int NL = KC < NB2_CONTACT_LANES ? KC : NB2_CONTACT_LANES;  // threads sharing the impulse tests
-  if (valid && cl < NL) nb2::contact_phase1<WPW>(M, saved + wc, (size_t)B, wsb, slot, cl, NL);
+  const nb2::cw::Ws& ws0 = *wsm;
+  const float* st = state + (size_t)w * 2 * M.ndof;
+  double* sv = saved ? saved + (size_t)w * P.saved_words : nullptr;
+  using namespace nb2::cw;
+  CW_PROF_DECL;
+  nb2::fwd_load<double, 1>(M, scr, st, action + (size_t)w * M.na, 1, lane, 32);
   __syncwarp();
-  if (valid) {
-    nb2::Grp grp;
-    grp.cl = cl; grp.nl = KC;
-    grp.mask = (KC >= 32) ? 0xFFFFFFFFu : (((1u << KC) - 1u) << (slot * KC));
-    nb2::contact_phase2<WPW>(M, C, st, out, saved + wc, (size_t)B, wsb, slot, x_lcp + (size_t)wc * NB2_MAX_ROWS, m_lcp + wc,
-                             labels + (size_t)wc * NB2_MAX_ROWS, status + wc, crec ? crec + (size_t)wc * rec_doubles : nullptr, grp);
+#pragma unroll 1
+  for (int sg = 1; sg < NB2_FWD_STAGES - 1; sg++) {
+    if (lane < M.lanes) nb2::world_forward_stage<double, 1>(M, scr, sv, 1, sv != nullptr, lane, sg, nullptr, ws0.Iinv);
+    if ((NB2_FWD_SYNC_MASK >> sg) & 1u) __syncwarp();
   }
+  __syncwarp();
+  CW_PROF(0);
+  nb2::cw::FwdIO io;
+  io.x_io = x_lcp + (size_t)w * NB2_MAX_ROWS; io.m_io = m_lcp + w; io.labels = labels + (size_t)w * NB2_MAX_ROWS; io.status = status + w;
+  io.nc = ncontacts + w; io.cinfo = cinfo ? cinfo + (size_t)w * NB2_MAX_CONTACTS * 10 : nullptr; io.rec = crec ? crec + (size_t)w * P.rec_doubles : nullptr;
+  nb2::cw::contact_forward(M, C, scr, st, wsm, P.ds, P.pool, P.db, ws0.Iinv, io);
+  __syncwarp();
+  if (status_accum && lane == 0) status_accum[w] |= status[w];  // sticky copy: one word per world, owned by this warp
+  CW_PROF(7);
+  nb2::fwd_store<double, 1>(M, scr, next + (size_t)w * 2 * M.ndof, 1, lane, 32);
+  CW_PROF(8);
 }
 
-// backward of a step with the contact stage (fp64): world_backward<double, WPW, CONTACT=true>, one thread per world.
-// WPW = worlds per warp (32 by default; NB2_CONTACT_BWD_WPW=4|8 packs fewer worlds per warp — more warps, less divergence,
-// idle lanes — which measured no faster on B200: the kernel is bound by its per-thread local-memory traffic).
-template <int WPW>
-__global__ void __launch_bounds__(32)
-k_step_bwd_contact(const __grid_constant__ Nb2ModelDev<double> M, const __grid_constant__ Nb2ContactDev C, int B,
-                   const float* __restrict__ state, const float* __restrict__ action, const double* __restrict__ saved,
-                   const double* __restrict__ crec, size_t rec_doubles, double* __restrict__ workspace, size_t ws_doubles,
-                   const float* __restrict__ gnext, float* __restrict__ gstate, float* __restrict__ gaction, float* __restrict__ ginertia,
-                   int words) {
+// ---- the forward step as three kernels (nb2_cw.cuh: build | solve | apply): same arithmetic as k_cstep_fwd
+__global__ void __launch_bounds__(32, NB2_CSTEP_MINB)
+k_cbuild(const __grid_constant__ Nb2ModelDev<double> M, const __grid_constant__ Nb2ContactDev C, const __grid_constant__ CStepArgs P,
+         const float* __restrict__ state, const float* __restrict__ action, float* __restrict__ next, double* __restrict__ saved,
+         int* __restrict__ m_lcp, int* __restrict__ status, int* __restrict__ ncontacts, float* __restrict__ cinfo, double* __restrict__ crec) {
   extern __shared__ __align__(16) unsigned char nb2_smem[];
-  const int li = threadIdx.x & 31;
-  if (li >= WPW) return;
-  const int w = blockIdx.x * WPW + li;
-  if (w >= B) return;
-  double* scr = reinterpret_cast<double*>(nb2_smem) + li;
-  nb2::BwdContactHook H;
-  H.model_contact = &C; H.ws = workspace + (size_t)blockIdx.x * ws_doubles * WPW; H.lane = li; H.crec = crec + (size_t)w * rec_doubles;
-  nb2::world_backward<double, WPW, true>(M, scr, state + (size_t)w * 2 * M.ndof, action + (size_t)w * M.na,
-                                         gnext + (size_t)w * 2 * M.ndof, saved + w, (size_t)B,
-                                         gstate + (size_t)w * 2 * M.ndof, gaction + (size_t)w * M.na, &H, ginertia ? ginertia + w : nullptr);
+  const int w = blockIdx.x, lane = threadIdx.x & 31;
+  if (w >= P.B) return;
+  double* scr = reinterpret_cast<double*>(nb2_smem);
+  nb2::cw::Ws* wsm = reinterpret_cast<nb2::cw::Ws*>(scr + ((P.fwd_words + 1) & ~1));
+  double* wsb = reinterpret_cast<double*>(wsm) + NB2_WS_DESC_DOUBLES;
+  if (lane == 0) *wsm = nb2::cw::carve(wsb, P.ds);
+  __syncwarp();
+  const nb2::cw::Ws& ws0 = *wsm;
+  const float* st = state + (size_t)w * 2 * M.ndof;
+  double* sv = saved + (size_t)w * P.saved_words;
+  using namespace nb2::cw;
+  CW_PROF_DECL;
+  nb2::fwd_load<double, 1>(M, scr, st, action + (size_t)w * M.na, 1, lane, 32);
+  __syncwarp();
+#pragma unroll 1
+  for (int sg = 1; sg < NB2_FWD_STAGES - 1; sg++) {
+    if (lane < M.lanes) nb2::world_forward_stage<double, 1>(M, scr, sv, 1, true, lane, sg, nullptr, ws0.Iinv);
+    if ((NB2_FWD_SYNC_MASK >> sg) & 1u) __syncwarp();
+  }
+  __syncwarp();
+  CW_PROF(0);
+  nb2::cw::FwdIO io;
+  io.x_io = nullptr; io.m_io = m_lcp + w; io.labels = nullptr; io.status = status + w;
+  io.nc = ncontacts + w; io.cinfo = cinfo ? cinfo + (size_t)w * NB2_MAX_CONTACTS * 10 : nullptr; io.rec = crec ? crec + (size_t)w * P.rec_doubles : nullptr;
+  nb2::cw::contact_build(M, C, scr, st, wsm, P.ds, P.pool, P.db, io, P.exch + (size_t)w * P.exch_stride);
+  __syncwarp();
+  nb2::fwd_store<double, 1>(M, scr, next + (size_t)w * 2 * M.ndof, 1, lane, 32);  // [q+ ; v*]: the apply kernel replaces v* by v+ where there are contacts
+}
+#ifndef NB2_CSOLVE_MINB
+#define NB2_CSOLVE_MINB 16
+#endif
+__global__ void __launch_bounds__(32, NB2_CSOLVE_MINB)
+k_csolve(const __grid_constant__ Nb2ContactDev C, const __grid_constant__ CStepArgs P, int ndof, double* __restrict__ x_lcp, int* __restrict__ m_lcp,
+         int* __restrict__ labels, int* __restrict__ status, double* __restrict__ crec, int* __restrict__ status_accum) {
+  extern __shared__ __align__(16) unsigned char nb2_smem[];
+  const int w = blockIdx.x, lane = threadIdx.x & 31;
+  if (w >= P.B) return;
+  double* X = P.exch + (size_t)w * P.exch_stride;
+  if ((int)X[0] <= 0) { if (lane == 0 && status_accum) status_accum[w] |= (int)X[2]; return; }
+  nb2::cw::Ws* wsm = reinterpret_cast<nb2::cw::Ws*>(nb2_smem);
+  double* wsb = reinterpret_cast<double*>(wsm) + NB2_WS_DESC_DOUBLES;
+  if (lane == 0) *wsm = nb2::cw::carve(wsb, P.ds_solve);
+  __syncwarp();
+  nb2::cw::FwdIO io;
+  io.x_io = x_lcp + (size_t)w * NB2_MAX_ROWS; io.m_io = m_lcp + w; io.labels = labels + (size_t)w * NB2_MAX_ROWS; io.status = status + w;
+  io.nc = nullptr; io.cinfo = nullptr; io.rec = crec ? crec + (size_t)w * P.rec_doubles : nullptr;
+  nb2::cw::contact_solve(C, ndof, wsm, P.ds_solve, P.pool_solve, P.db_solve, io, X, status_accum ? status_accum + w : nullptr);
+}
+__global__ void __launch_bounds__(32, 8)
+k_capply(const __grid_constant__ Nb2ModelDev<double> M, const __grid_constant__ Nb2ContactDev C, const __grid_constant__ CStepArgs P,
+         const float* __restrict__ state, float* __restrict__ next, const double* __restrict__ saved, double* __restrict__ x_lcp,
+         int* __restrict__ labels, double* __restrict__ crec) {
+  extern __shared__ __align__(16) unsigned char nb2_smem[];
+  const int w = blockIdx.x, lane = threadIdx.x & 31;
+  if (w >= P.B) return;
+  const double* X = P.exch + (size_t)w * P.exch_stride;
+  if ((int)X[0] <= 0) return;
+  nb2::cw::Ws* wsm = reinterpret_cast<nb2::cw::Ws*>(nb2_smem);
+  double* wsb = reinterpret_cast<double*>(wsm) + NB2_WS_DESC_DOUBLES;
+  if (lane == 0) *wsm = nb2::cw::carve(wsb, P.ds_apply);
+  __syncwarp();
+  nb2::cw::FwdIO io;
+  io.x_io = x_lcp + (size_t)w * NB2_MAX_ROWS; io.m_io = nullptr; io.labels = labels + (size_t)w * NB2_MAX_ROWS; io.status = nullptr;
+  io.nc = nullptr; io.cinfo = nullptr; io.rec = crec ? crec + (size_t)w * P.rec_doubles : nullptr;
+  nb2::cw::contact_apply(M, C, state + (size_t)w * 2 * M.ndof, saved + (size_t)w * P.saved_words, wsm, P.ds_apply, P.pool_apply, P.db_apply, io, X,
+                         next + (size_t)w * 2 * M.ndof + M.ndof);
+}
+
+__global__ void __launch_bounds__(32, NB2_CSTEP_MINB)
+k_cstep_bwd(const __grid_constant__ Nb2ModelDev<double> M, const __grid_constant__ Nb2ContactDev C, const __grid_constant__ CStepArgs P,
+            const float* __restrict__ state, const float* __restrict__ action, const double* __restrict__ saved, const double* __restrict__ crec,
+            const float* __restrict__ gnext, float* __restrict__ gstate, float* __restrict__ gaction, float* __restrict__ ginertia,
+            int* __restrict__ status) {
+  extern __shared__ __align__(16) unsigned char nb2_smem[];
+  const int w = blockIdx.x, lane = threadIdx.x & 31;
+  if (w >= P.B) return;
+  double* scr = reinterpret_cast<double*>(nb2_smem);
+  nb2::cw::Ws* wsm = reinterpret_cast<nb2::cw::Ws*>(scr + ((P.bwd_words + 1) & ~1));
+  double* wsb = reinterpret_cast<double*>(wsm) + NB2_WS_DESC_DOUBLES;
+  if (lane == 0) *wsm = nb2::cw::carve(wsb, P.ds);
+  const float* st = state + (size_t)w * 2 * M.ndof;
+  const double* sv = saved + (size_t)w * P.saved_words;
+  const nb2::BwdLayout L = nb2::bwd_layout(M.nb, M.ndof, M.nslots, M.nfree, 42);
+  using namespace nb2::cw;
+  CW_PROF_DECL;
+  nb2::bwd_load<double, 1, true>(M, scr, st, action + (size_t)w * M.na, gnext + (size_t)w * 2 * M.ndof, 1, lane, 32);
+  __syncwarp();
+  nb2::BwdContactData<1> cd; cd.active = 0; cd.error = 0; cd.inj_of_body = nullptr;
+#pragma unroll 1
+  for (int sg = 1; sg < NB2_BWD_STAGES - 1; sg++) {
+    if (sg == 5) {  // lambda and its fields are complete: the contact adjoint turns them into w and prepares the injections
+      __syncwarp();
+      CW_PROF(20);
+      cd = nb2::cw::contact_backward(M, C, st, sv, wsm, P.ds, P.pool, P.db, crec + (size_t)w * P.rec_doubles, scr, L.oLam, L.oBody);
+      __syncwarp();
+      CW_PROF(29);
+    }
+    if (lane < M.lanes) nb2::world_backward_stage<double, 1, true>(M, scr, sv, 1, lane, sg, ginertia ? ginertia + w : nullptr, nullptr, (size_t)P.B, &cd);
+    if ((NB2_BWD_SYNC_MASK >> sg) & 1u) __syncwarp();
+  }
+  __syncwarp();
+  nb2::bwd_store<double, 1, true>(M, scr, gstate + (size_t)w * 2 * M.ndof, gaction + (size_t)w * M.na, cd.error != 0, 1, lane, 32);
+  if (cd.error && status && lane == 0) atomicOr(status + w, NB2_ST_BWD_ERROR);
+  CW_PROF(30);
 }
 
 constexpr int kMaxSmem = 227 * 1024;
@@ -296,6 +404,8 @@ struct nb2_model {
   Nb2ModelDev<double> md;
   Nb2ContactDev contact;
   bool has_contacts = false;
+  int contact_mc = 0;      // contact capacity of the shared-memory workspace of the fused contact kernels (rows: 3x)
+  int contact_variant = 0; // schedule the fused contact kernels sweep the tree with
   int saved_words;
   int sm_count;
   std::vector<nb2_variant> variants;  // [0] = the create-time schedule
@@ -358,7 +468,10 @@ template <class R, int K> struct StepKernels {
   static constexpr int ST = CoopShape<K>::ST, WPW = CoopShape<K>::WPW;
   static int prepare(nb2_variant& v, int dir) {  // dir 0 forward, 1 backward
     LaunchShape& sh = v.shape[dir][sizeof(R) == 8];
-    if (sh.warps_per_block) return NB2_OK;
+    static bool attr_done[2][64] = {};  // function attributes are per device: a model may be used from several GPUs of one process
+    int dev = 0; NB2_CUDA(cudaGetDevice(&dev));
+    if (sh.warps_per_block && attr_done[dir][dev & 63]) return NB2_OK;
+    attr_done[dir][dev & 63] = true;
     const size_t per_warp = (size_t)(dir ? v.bwd_words : v.fwd_words) * ST * sizeof(R) + (dir ? staging_bytes<K>(4 * v.mf.ndof + v.mf.na) : staging_bytes<K>(2 * v.mf.ndof + v.mf.na));
     const size_t per_block = (size_t)body_table_words<K>(v.mf.nb) * sizeof(R) + 16;
     if (per_warp + per_block > (size_t)kMaxSmem) { g_err = "model needs " + std::to_string(per_warp) + " B of shared memory per warp (> 227 KB)"; return NB2_ERR_UNSUPPORTED; }
@@ -502,10 +615,49 @@ template <class T> static T* mapped_alias(const T* host) {
   return (T*)a.devicePointer;
 }
 
+// ---- fused contact kernels: launch plumbing
+static nb2::cw::Dims cdims(const nb2_model* m, int MC, int bwd, int mode = NB2_WS_FULL) {
+  return nb2::cw::make_dims(m->md.nb, m->md.ndof, m->md.nfree, MC, 3 * MC, m->contact.ncb, m->contact.max_chain_dofs, bwd, mode);
+}
+static bool contact_fused() {
+  static const bool on = [] { const char* e = getenv("NB2_CONTACT_FUSED"); return e && atoi(e); }();
+  return on;
+}
+static int pool_slots(int B) { int s = B / 16; if (s < 32) s = 32; if (s > 4096) s = 4096; return s; }
+static size_t pool_stride(const nb2_model* m) { return (nb2::cw::ws_doubles(cdims(m, NB2_MAX_CONTACTS, 1)) + 1) & ~(size_t)1; }
+static CStepArgs cstep_args(const nb2_model* m, const nb2_variant& v, int B, void* workspace, int bwd) {
+  CStepArgs P;
+  P.B = B;
+  P.fwd_words = v.fwd_words;
+  P.bwd_words = nb2::bwd_layout(v.md.nb, v.md.ndof, v.md.nslots, v.md.nfree, 42).total;
+  P.saved_words = m->saved_words;
+  P.ds = cdims(m, m->contact_mc, bwd);
+  P.db = cdims(m, NB2_MAX_CONTACTS, bwd);
+  P.ws_small_doubles = nb2::cw::ws_doubles(P.ds);
+  P.pool.counter = (int*)workspace;
+  P.pool.base = (double*)((char*)workspace + 64);
+  P.pool.stride = pool_stride(m);
+  P.pool.nslots = pool_slots(B);
+  P.rec_doubles = nb2::cw::record_doubles(m->md.ndof);
+  P.exch = P.pool.base + (size_t)P.pool.nslots * P.pool.stride;
+  P.exch_stride = nb2::cw::xlayout(m->md.ndof).total;
+  P.ds_solve = cdims(m, m->contact_mc, 0, NB2_WS_SOLVE); P.db_solve = cdims(m, NB2_MAX_CONTACTS, 0, NB2_WS_SOLVE);
+  P.ds_apply = cdims(m, m->contact_mc, 0, NB2_WS_APPLY); P.db_apply = cdims(m, NB2_MAX_CONTACTS, 0, NB2_WS_APPLY);
+  P.pool_solve = P.pool; P.pool_solve.counter = (int*)workspace + 1;  // the kernels run one after the other: same slots, own counter
+  P.pool_apply = P.pool; P.pool_apply.counter = (int*)workspace + 2;
+  return P;
+}
+template <class Kern> static int cstep_smem_attr(Kern kern, size_t smem, bool* done) {
+  int dev = 0; NB2_CUDA(cudaGetDevice(&dev));
+  if (!done[dev & 63]) { NB2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem)); done[dev & 63] = true; }  // per device
+  if (smem > (size_t)kMaxSmem) { g_err = "the fused contact kernel needs " + std::to_string(smem) + " B of shared memory per world (> 227 KB)"; return NB2_ERR_UNSUPPORTED; }
+  return NB2_OK;
+}
+
 extern "C" {
 
 const char* nb2_last_error(void) { return g_err.c_str(); }
-const char* nb2_version(void) { return "nb2 0.1 (sm_100a, thread-per-world ABA + adjoint)"; }
+const char* nb2_version(void) { return "nb2 0.2 (sm_100a; cooperative-lane ABA + adjoint, warp-per-world contact / boxed-LCP stage)"; }
 long long nb2_launch_count(void) { return g_launches.load(); }
 
 int nb2_model_create(const nb2_model_desc* desc, nb2_model** out) {
@@ -519,6 +671,12 @@ int nb2_model_create(const nb2_model_desc* desc, nb2_model** out) {
   if (desc->nshapes > 0 && desc->npairs > 0) {
     if (!nb2_fill_contact(*desc, m->contact, err)) { g_err = err; delete m; return NB2_ERR_UNSUPPORTED; }
     m->has_contacts = true;
+    // contacts the shared-memory workspace is sized for: a box-box pair yields up to 4 in the common face-face case (8 at most), every
+    // other supported pair at most one; worlds that exceed it fall back to a global-memory workspace (nb2_cw.cuh BigPool)
+    int mc = 0;
+    for (int p = 0; p < desc->npairs; p++) mc += (desc->shape_type[desc->pair_a[p]] == 0 && desc->shape_type[desc->pair_b[p]] == 0) ? 4 : 1;
+    if (const char* e = getenv("NB2_CONTACT_MC")) mc = atoi(e);
+    m->contact_mc = mc < 2 ? 2 : (mc > NB2_MAX_CONTACTS ? NB2_MAX_CONTACTS : mc);
   }
   {
     nb2_variant v;
@@ -556,6 +714,8 @@ int nb2_model_add_schedule(nb2_model* m, const nb2_model_desc* desc) {
   init_variant(v);
   std::lock_guard<std::mutex> lk(m->mu);
   m->variants.push_back(v);
+  // the fused contact kernels have a whole warp per world: they sweep the tree with the shallowest schedule registered
+  for (size_t k = 0; k < m->variants.size(); k++) if (m->variants[k].depth < m->variants[m->contact_variant].depth) m->contact_variant = (int)k;
   return NB2_OK;
 }
 int nb2_model_set_inertia(nb2_model* m, const double* inertia) {
@@ -598,78 +758,89 @@ void nb2_model_destroy(nb2_model* m) {
 int nb2_model_has_contacts(const nb2_model* m) { return (m && m->has_contacts) ? 1 : 0; }
 size_t nb2_contact_workspace_bytes(const nb2_model* m, int B) {
   if (!m || !m->has_contacts || B <= 0) return 0;
-  return nb2::contact_ws_doubles(m->mf.nb, m->mf.ndof) * sizeof(double) * (size_t)((B + 31) / 32) * 32;
+  // [64 B: pool counters] [pool of large workspaces] [exchange records of the three-kernel forward, one per world]
+  return 64 + ((size_t)pool_slots(B) * pool_stride(m) + (size_t)B * nb2::cw::xlayout(m->md.ndof).total) * sizeof(double);
 }
 int nb2_step_forward_contact(const nb2_model* cm, int B, const float* state, const float* action, float* next_state,
                              void* saved_fp64, void* workspace, double* x_lcp, int32_t* m_lcp, int32_t* labels,
-                             int32_t* status, int32_t* ncontacts, float* cinfo, double* contact_record, void* stream) {
+                             int32_t* status, int32_t* ncontacts, float* cinfo, double* contact_record, int32_t* status_accum, void* stream) {
   nb2_model* m = const_cast<nb2_model*>(cm);
-  if (!m || B < 0 || !state || !action || !next_state || !saved_fp64 || !workspace || !x_lcp || !m_lcp || !labels || !status || !ncontacts) {
+  if (!m || B < 0 || !state || !action || !next_state || !workspace || !x_lcp || !m_lcp || !labels || !status || !ncontacts) {
     g_err = "nb2_step_forward_contact: bad argument"; return NB2_ERR_INVALID;
   }
   if (!m->has_contacts) { g_err = "nb2_step_forward_contact: the model has no collision pairs"; return NB2_ERR_INVALID; }
+  if (contact_record && !saved_fp64) { g_err = "nb2_step_forward_contact: a contact record without the saved stream cannot be back-propagated"; return NB2_ERR_INVALID; }
   if (B == 0) return NB2_OK;
   cudaStream_t st = (cudaStream_t)stream;
-  int rc = launch_fwd<double>(m, B, state, action, next_state, (double*)saved_fp64, st);
+  const nb2_variant& v = m->variants[m->contact_variant];
+  const CStepArgs P = cstep_args(m, v, B, workspace, 0);
+  const size_t smem = ((((size_t)P.fwd_words + 1) & ~(size_t)1) + NB2_WS_DESC_DOUBLES + P.ws_small_doubles) * sizeof(double);
+  static bool attr_done[64] = {};
+  int rc = cstep_smem_attr(k_cstep_fwd, smem, attr_done);
   if (rc) return rc;
-  // 8 threads per world while that still leaves the GPU short of warps, one thread per world for huge batches
-  const size_t wsd = nb2::contact_ws_doubles(m->mf.nb, m->mf.ndof), recd = nb2::contact_rec_doubles(m->mf.ndof);
-  static const int forced_kc = [] { const char* e = getenv("NB2_CONTACT_KC"); return e ? atoi(e) : 0; }();
-  int kc = forced_kc;
-  if (!kc) kc = ((long long)B * 8 / 32 <= (long long)m->sm_count * 48) ? 8 : 1;
-#define NB2_LAUNCH_CONTACT(KC_)                                                                                                  \
-  k_contact_fwd<KC_><<<(B + (32 / KC_) - 1) / (32 / KC_), 32, 0, st>>>(m->md, m->contact, B, state, next_state, (const double*)saved_fp64, \
-                                                                     (double*)workspace, wsd, x_lcp, m_lcp, labels, status, ncontacts,     \
-                                                                     cinfo, contact_record, recd)
-  switch (kc) {
-    case 32: NB2_LAUNCH_CONTACT(32); break;
-    case 16: NB2_LAUNCH_CONTACT(16); break;
-    case 8: NB2_LAUNCH_CONTACT(8); break;
-    default: NB2_LAUNCH_CONTACT(1); break;
+  NB2_CUDA(cudaMemsetAsync(workspace, 0, 64, st));  // pool counters
+  if (contact_fused() || !saved_fp64) {
+    // one kernel does everything (also the only form that runs without a saved stream: the apply kernel reads the tree data from it)
+    k_cstep_fwd<<<B, 32, smem, st>>>(v.md, m->contact, P, state, action, next_state, (double*)saved_fp64, x_lcp, m_lcp, labels, status, ncontacts, cinfo,
+                                     contact_record, status_accum);
+    g_launches++;
+    NB2_CUDA(cudaGetLastError());
+    return NB2_OK;
   }
-#undef NB2_LAUNCH_CONTACT
-  g_launches++;
+  static bool attr_b[64] = {}, attr_s[64] = {}, attr_a[64] = {};
+  const size_t smem_s = (NB2_WS_DESC_DOUBLES + nb2::cw::ws_doubles(P.ds_solve)) * sizeof(double);
+  const size_t smem_a = (NB2_WS_DESC_DOUBLES + nb2::cw::ws_doubles(P.ds_apply)) * sizeof(double);
+  if ((rc = cstep_smem_attr(k_cbuild, smem, attr_b)) || (rc = cstep_smem_attr(k_csolve, smem_s, attr_s)) || (rc = cstep_smem_attr(k_capply, smem_a, attr_a))) return rc;
+  k_cbuild<<<B, 32, smem, st>>>(v.md, m->contact, P, state, action, next_state, (double*)saved_fp64, m_lcp, status, ncontacts, cinfo, contact_record);
+  k_csolve<<<B, 32, smem_s, st>>>(m->contact, P, m->md.ndof, x_lcp, m_lcp, labels, status, contact_record, status_accum);
+  k_capply<<<B, 32, smem_a, st>>>(v.md, m->contact, P, state, next_state, (const double*)saved_fp64, x_lcp, labels, contact_record);
+  g_launches += 3;
   NB2_CUDA(cudaGetLastError());
   return NB2_OK;
 }
 size_t nb2_contact_record_bytes(const nb2_model* m, int B) {
   if (!m || !m->has_contacts || B <= 0) return 0;
-  return nb2::contact_rec_doubles(m->mf.ndof) * sizeof(double) * (size_t)B;
+  return nb2::cw::record_doubles(m->mf.ndof) * sizeof(double) * (size_t)B;
 }
 int nb2_step_backward_contact(const nb2_model* cm, int B, const float* state, const float* action, const void* saved_fp64,
                               const double* contact_record, void* workspace, const float* grad_next_state, float* grad_state,
-                              float* grad_action, float* grad_inertia, void* stream) {
+                              float* grad_action, float* grad_inertia, int32_t* status_accum, void* stream) {
   nb2_model* m = const_cast<nb2_model*>(cm);
   if (!m || B < 0 || !state || !action || !saved_fp64 || !contact_record || !workspace || !grad_next_state || !grad_state || !grad_action) {
     g_err = "nb2_step_backward_contact: bad argument"; return NB2_ERR_INVALID;
   }
   if (!m->has_contacts) { g_err = "nb2_step_backward_contact: the model has no collision pairs"; return NB2_ERR_INVALID; }
   if (B == 0) return NB2_OK;
-  const int words = nb2::bwd_layout(m->mf.nb, m->mf.ndof, m->mf.nslots, m->mf.nfree, 42).total;
-  static const int forced = [] { const char* e = getenv("NB2_CONTACT_BWD_WPW"); return e ? atoi(e) : 0; }();
-  int wpw = forced ? forced : 32;  // measured (B200, Atlas + ground, B = 1024 / 4096): 32 worlds per warp is never slower than 8 or 4
-  if ((size_t)words * wpw * sizeof(double) > (size_t)kMaxSmem) wpw = 4;
-  const size_t smem = (size_t)words * wpw * sizeof(double);
-  if (smem > (size_t)kMaxSmem) { g_err = "model needs " + std::to_string(smem) + " B of shared memory per warp (> 227 KB)"; return NB2_ERR_UNSUPPORTED; }
-#define NB2_LAUNCH_BWDC(W_)                                                                                                       \
-  do {                                                                                                                            \
-    static bool attr_done[64] = {};  /* function attributes are per device */                                                     \
-    int dev_ = 0; NB2_CUDA(cudaGetDevice(&dev_));                                                                                 \
-    if (!attr_done[dev_ & 63]) { NB2_CUDA(cudaFuncSetAttribute(k_step_bwd_contact<W_>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem)); attr_done[dev_ & 63] = true; } \
-    k_step_bwd_contact<W_><<<(B + W_ - 1) / W_, 32, smem, (cudaStream_t)stream>>>(m->md, m->contact, B, state, action, (const double*)saved_fp64,        \
-                                                                               contact_record, nb2::contact_rec_doubles(m->mf.ndof), (double*)workspace, \
-                                                                               nb2::contact_ws_doubles(m->mf.nb, m->mf.ndof), grad_next_state,           \
-                                                                               grad_state, grad_action, grad_inertia, words);                            \
-  } while (0)
-  switch (wpw) {
-    case 4: NB2_LAUNCH_BWDC(4); break;
-    case 8: NB2_LAUNCH_BWDC(8); break;
-    default: NB2_LAUNCH_BWDC(32); break;
-  }
-#undef NB2_LAUNCH_BWDC
+  cudaStream_t st = (cudaStream_t)stream;
+  const nb2_variant& v = m->variants[m->contact_variant];
+  const CStepArgs P = cstep_args(m, v, B, workspace, 1);
+  const size_t smem = ((((size_t)P.bwd_words + 1) & ~(size_t)1) + NB2_WS_DESC_DOUBLES + P.ws_small_doubles) * sizeof(double);
+  static bool attr_done[64] = {};
+  int rc = cstep_smem_attr(k_cstep_bwd, smem, attr_done);
+  if (rc) return rc;
+  NB2_CUDA(cudaMemsetAsync(workspace, 0, 64, st));
+  k_cstep_bwd<<<B, 32, smem, st>>>(v.md, m->contact, P, state, action, (const double*)saved_fp64, contact_record, grad_next_state, grad_state,
+                                   grad_action, grad_inertia, status_accum);
   g_launches++;
   NB2_CUDA(cudaGetLastError());
   return NB2_OK;
+}
+int nb2_model_set_contact_capacity(nb2_model* m, int max_contacts_in_shared_memory) {
+  if (!m || !m->has_contacts) { g_err = "nb2_model_set_contact_capacity: the model has no collision pairs"; return NB2_ERR_INVALID; }
+  if (max_contacts_in_shared_memory < 1 || max_contacts_in_shared_memory > NB2_MAX_CONTACTS) { g_err = "nb2_model_set_contact_capacity: capacity must be in [1, NB2_MAX_CONTACTS]"; return NB2_ERR_INVALID; }
+  m->contact_mc = max_contacts_in_shared_memory;
+  return NB2_OK;
+}
+int nb2_model_contact_capacity(const nb2_model* m) { return (m && m->has_contacts) ? m->contact_mc : 0; }
+/* dev builds (-DNB2_CW_PROFILE): per-phase cycle counters of the fused contact kernels; returns 0 when not compiled in */
+int nb2_cw_profile_read(unsigned long long* out64, int reset) {
+#ifdef NB2_CW_PROFILE
+  if (out64 && cudaMemcpyFromSymbol(out64, nb2::cw::nb2_cw_prof, 64 * sizeof(unsigned long long)) != cudaSuccess) return 0;
+  if (reset) { unsigned long long z[64] = {}; cudaMemcpyToSymbol(nb2::cw::nb2_cw_prof, z, sizeof(z)); }
+  return 1;
+#else
+  (void)out64; (void)reset; return 0;
+#endif
 }
 int nb2_model_ndof(const nb2_model* m) { return m ? m->mf.ndof : -1; }
 int nb2_model_na(const nb2_model* m) { return m ? m->mf.na : -1; }
@@ -679,6 +850,7 @@ int nb2_step_forward(const nb2_model* cm, int B, const float* state, const float
                      void* saved, int precision, void* stream) {
   nb2_model* m = const_cast<nb2_model*>(cm);
   if (!m || B < 0 || !state || !action || !next_state) { g_err = "nb2_step_forward: bad argument"; return NB2_ERR_INVALID; }
+  if (m->has_contacts) { g_err = "nb2_step_forward: the model has collision pairs: use nb2_step_forward_contact (or build the model without shapes for a contact-free step)"; return NB2_ERR_INVALID; }
   if (B == 0) return NB2_OK;
   cudaStream_t st = (cudaStream_t)stream;
   if (precision == NB2_FP64) return launch_fwd<double>(m, B, state, action, next_state, (double*)saved, st);
@@ -692,6 +864,7 @@ int nb2_step_backward(const nb2_model* cm, int B, const float* state, const floa
   if (!m || B < 0 || !state || !action || !saved || !grad_next_state || !grad_state || !grad_action) {
     g_err = "nb2_step_backward: bad argument"; return NB2_ERR_INVALID;
   }
+  if (m->has_contacts) { g_err = "nb2_step_backward: the model has collision pairs: use nb2_step_backward_contact"; return NB2_ERR_INVALID; }
   if (B == 0) return NB2_OK;
   cudaStream_t st = (cudaStream_t)stream;
   if (precision == NB2_FP64) return launch_bwd<double>(m, B, state, action, (const double*)saved, grad_next_state, grad_state, grad_action, grad_inertia, st);
@@ -755,6 +928,7 @@ static int ensure_host_buffers(nb2_model* m, int B) {
 int nb2_step_forward_host(nb2_model* m, int B, const float* state, const float* action, float* next_state,
                           int keep_for_backward, int precision) {
   if (!m || B <= 0 || !state || !action || !next_state) { g_err = "nb2_step_forward_host: bad argument"; return NB2_ERR_INVALID; }
+  if (m->has_contacts) { g_err = "nb2_step_forward_host: the model has collision pairs: use nb2_step_forward_contact_host"; return NB2_ERR_INVALID; }
   std::lock_guard<std::mutex> lk(m->mu);
   int rc = ensure_host_buffers(m, B);
   if (rc) return rc;

@@ -123,15 +123,22 @@ class DeviceModel:
         return int(_cabi.lib().nb2_contact_record_bytes(self.handle, B))
 
     def forward_contact_device(self, B, state_ptr, action_ptr, next_ptr, saved_ptr, ws_ptr, x_ptr, m_ptr, labels_ptr,
-                               status_ptr, nc_ptr, cinfo_ptr, crec_ptr, stream):
-        """fp64 ABA kernel + contact/LCP kernel (include/nb2.h nb2_step_forward_contact)."""
+                               status_ptr, nc_ptr, cinfo_ptr, crec_ptr, status_accum_ptr, stream):
+        """fused fp64 step with the contact / boxed-LCP stage, one warp per world (include/nb2.h nb2_step_forward_contact)."""
         _cabi.check(_cabi.lib().nb2_step_forward_contact(self.handle, B, state_ptr, action_ptr, next_ptr, saved_ptr, ws_ptr, x_ptr,
-                                                         m_ptr, labels_ptr, status_ptr, nc_ptr, cinfo_ptr, crec_ptr, stream))
+                                                         m_ptr, labels_ptr, status_ptr, nc_ptr, cinfo_ptr, crec_ptr, status_accum_ptr, stream))
 
     def backward_contact_device(self, B, state_ptr, action_ptr, saved_ptr, crec_ptr, ws_ptr, gnext_ptr, gstate_ptr, gaction_ptr,
-                                stream, ginertia_ptr=None):
+                                stream, ginertia_ptr=None, status_ptr=None):
+        """status_ptr: the forward's status array; worlds that cannot be back-propagated get bit 2048 (and NaN gradients)."""
         _cabi.check(_cabi.lib().nb2_step_backward_contact(self.handle, B, state_ptr, action_ptr, saved_ptr, crec_ptr, ws_ptr,
-                                                          gnext_ptr, gstate_ptr, gaction_ptr, ginertia_ptr, stream))
+                                                          gnext_ptr, gstate_ptr, gaction_ptr, ginertia_ptr, status_ptr, stream))
+
+    def set_contact_capacity(self, max_contacts: int):
+        _cabi.check(_cabi.lib().nb2_model_set_contact_capacity(self.handle, int(max_contacts)))
+
+    def contact_capacity(self) -> int:
+        return int(_cabi.lib().nb2_model_contact_capacity(self.handle))
 
     # ---- host pointers (numpy / CPU tensors): copies included ----
     def forward_host(self, state: np.ndarray, action: np.ndarray, keep_for_backward=True, precision=FP32,

@@ -52,11 +52,11 @@ class TimestepLayer(torch.autograd.Function):
         sd = s2.to(device=dev, dtype=torch.float32, non_blocking=True).contiguous()
         ad = a2.to(device=dev, dtype=torch.float32, non_blocking=True).contiguous()
         B = sd.shape[0]
-        need_grad = any(ctx.needs_input_grad[1:4])
         ctx.mass_grad = mass is not None and ctx.needs_input_grad[3]
         if ctx.mass_grad:
-            ctx.mass_P = torch.from_numpy(dm.inertia_param_jacobian(world))  # [mass_dims, 10*nb], fp64
+            ctx.mass_P = torch.from_numpy(dm.inertia_param_jacobian(world)).to(dev)  # [mass_dims, 10*nb], fp64
             ctx.mass_like = mass
+        need_grad = any(ctx.needs_input_grad[1:4])
         ctx.contact = dm.has_contacts
         with torch.cuda.device(dev):
             nxt = torch.empty_like(sd)
@@ -65,13 +65,18 @@ class TimestepLayer(torch.autograd.Function):
                 # contact / boxed-LCP stage: fp64 kernels; the LCP cache (BoxedLcpConstraintSolver::mX in the reference)
                 # lives on the world and flows from step to step like the reference's solver state
                 cache = contact_cache(world, B, dev)
-                saved = torch.empty((dm.saved_words, B), dtype=torch.float64, device=dev)
+                # saved stream (world-major): the apply kernel of the three-kernel forward reads the tree data back from it, the
+                # backward too; the ~1 KB/world record only when a backward will follow
+                saved = torch.empty((B, dm.saved_words), dtype=torch.float64, device=dev)
                 crec = torch.empty((B, dm.contact_record_bytes(B) // (8 * B)), dtype=torch.float64, device=dev) if need_grad else None
-                dm.forward_contact_device(B, _ptr(sd), _ptr(ad), _ptr(nxt), _ptr(saved), _ptr(cache["ws"]), _ptr(cache["x"]),
-                                          _ptr(cache["m"]), _ptr(cache["labels"]), _ptr(cache["status"]), _ptr(cache["nc"]),
-                                          _ptr(cache["cinfo"]), _ptr(crec) if crec is not None else None, stream)
+                dm.forward_contact_device(B, _ptr(sd), _ptr(ad), _ptr(nxt), _ptr(saved) if saved is not None else None, _ptr(cache["ws"]),
+                                          _ptr(cache["x"]), _ptr(cache["m"]), _ptr(cache["labels"]), _ptr(cache["status"]), _ptr(cache["nc"]),
+                                          _ptr(cache["cinfo"]), _ptr(crec) if crec is not None else None, _ptr(cache["sticky"]), stream)
                 ctx.crec = crec
                 ctx.ws = cache["ws"]
+                ctx.sticky = cache["sticky"]
+                if getattr(world, "_strict_contact_checks", False) or legacy:
+                    check_contact_status(world)  # host sync: off by default for batches (call it once per rollout instead)
             else:
                 saved = torch.empty((dm.saved_words, B), dtype=torch.float32, device=dev) if need_grad else None
                 dm.forward_device(B, _ptr(sd), _ptr(ad), _ptr(nxt), _ptr(saved) if saved is not None else None, stream, FP32)
@@ -103,14 +108,12 @@ class TimestepLayer(torch.autograd.Function):
             if ctx.contact:
                 # adjoint of the contact stage with the classification frozen at the forward solution (csrc/nb2_contact.cuh)
                 gi = torch.empty((10 * dm.cm.nb, ctx.B), dtype=torch.float32, device=dev) if ctx.mass_grad else None
+                # worlds that cannot be back-propagated get NaN gradients and bit 2048 in the world's sticky status word: no host
+                # sync here — check_contact_status(world) reports them (rollout() / sharded_trajectory_loss() call it once)
                 dm.backward_contact_device(ctx.B, _ptr(sd), _ptr(ad), _ptr(saved), _ptr(ctx.crec), _ptr(ctx.ws), _ptr(g), _ptr(gs),
-                                           _ptr(ga), stream, _ptr(gi) if gi is not None else None)
-                if bool(torch.isnan(gs).any()):
-                    raise RuntimeError(
-                        "backward through the contact stage failed for some worlds (the kernel marked them with NaN gradients): "
-                        "a restitution (bounce) term was active in the forward step (status bit 1024; its backward is not implemented), "
-                        "the contact rows regenerated in the backward pass did not match the forward's, or the clamping set exceeds "
-                        "the compiled limits")
+                                           _ptr(ga), stream, _ptr(gi) if gi is not None else None, _ptr(ctx.sticky))
+                if ctx.legacy:
+                    _raise_on_status(int(ctx.sticky[0].item()), [0], backward=True)
             else:
                 gi = torch.empty((10 * dm.cm.nb, ctx.B), dtype=torch.float32, device=dev) if ctx.mass_grad else None
                 dm.backward_device(ctx.B, _ptr(sd), _ptr(ad), _ptr(saved), _ptr(g), _ptr(gs), _ptr(ga), stream, FP32,
@@ -118,7 +121,7 @@ class TimestepLayer(torch.autograd.Function):
         gm = None
         if ctx.mass_grad:
             # lossWrtMass = massVel^T g_v' (BackpropSnapshot.cpp:177-178), summed over the worlds that share the model
-            gm = (ctx.mass_P.to(dev) @ gi.to(torch.float64).sum(dim=1)).to(device=ctx.mass_like.device, dtype=ctx.mass_like.dtype)
+            gm = (ctx.mass_P @ gi.to(torch.float64).sum(dim=1)).to(device=ctx.mass_like.device, dtype=ctx.mass_like.dtype)
         if ctx.legacy:
             # reference returns fp64 grads (timestep.py:55-60)
             gs = gs[0].to(device=ctx.in_device, dtype=torch.float64 if ctx.in_dtype == torch.float64 else ctx.in_dtype)
@@ -139,11 +142,46 @@ def contact_cache(world, B: int, device) -> dict:
                  m=torch.full((B,), -1, dtype=torch.int32, device=device),
                  labels=torch.zeros((B, MAX_ROWS), dtype=torch.int32, device=device),
                  status=torch.zeros((B,), dtype=torch.int32, device=device),
+                 sticky=torch.zeros((B,), dtype=torch.int32, device=device),  # OR of every step's problem bits since the last check
                  nc=torch.zeros((B,), dtype=torch.int32, device=device),
                  cinfo=torch.zeros((B, MAX_CONTACTS, 10), dtype=torch.float32, device=device),
                  ws=torch.empty((dm.contact_workspace_bytes(B) // 8,), dtype=torch.float64, device=device))
         world._lcp_cache = c
     return c
+
+
+ST_NAN, ST_UNSUPPORTED, ST_OVERFLOW, ST_BOUNCE, ST_BWD_ERROR = 32, 128, 256, 1024, 2048
+
+
+def _raise_on_status(bits: int, worlds, backward=False):
+    if bits & ST_BWD_ERROR:
+        raise RuntimeError(
+            f"backward through the contact stage failed for worlds {list(worlds)[:16]} (their gradients are NaN): a restitution (bounce) "
+            "or penetration-correction term was active in the forward step (status bit 1024; its backward is not implemented), or the "
+            "contact rows regenerated in the backward pass did not match the forward's")
+    if bits & ST_OVERFLOW:
+        raise RuntimeError(f"contact stage: worlds {list(worlds)[:16]} generated more than {MAX_CONTACTS} contacts / {MAX_ROWS} LCP rows "
+                           "(or the overflow pool was exhausted): the extra contacts were DROPPED — the step differs from the reference")
+    if bits & ST_UNSUPPORTED:
+        raise RuntimeError(f"contact stage: worlds {list(worlds)[:16]} hit a contact configuration without a generator (a capsule lying flat "
+                           "on a box: the reference asks libccd's MPR): those contacts were NOT generated")
+
+
+def check_contact_status(world, reset: bool = True) -> int:
+    """Read the world's sticky contact-stage status (ONE host sync) and raise if any world dropped contacts, met an unsupported
+    geometry or could not be back-propagated since the last check; otherwise return the OR of all status words.
+    timestep() itself never synchronises on batches: call this once per rollout / optimiser step."""
+    c = getattr(world, "_lcp_cache", None)
+    if c is None:
+        return 0
+    st = c["sticky"].cpu().numpy()
+    if reset:
+        c["sticky"].zero_()
+    bits = int(np.bitwise_or.reduce(st)) if st.size else 0
+    bad = np.nonzero(st & (ST_BWD_ERROR | ST_OVERFLOW | ST_UNSUPPORTED))[0]
+    if bad.size:
+        _raise_on_status(int(np.bitwise_or.reduce(st[bad])), bad.tolist())
+    return bits
 
 
 def reset_contact_cache(world):

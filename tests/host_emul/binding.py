@@ -96,20 +96,6 @@ class EmulWorld:
         return (gs, ga, gi) if want_inertia_grad else (gs, ga)
 
 
-def solve_chain(A, b, lo, hi, findex, x0=None, fallback_cfm=1e-4):
-    """The device solve chain (csrc/nb2_contact.cuh lcp_chain_ws) on one boxed LCP -> (x, mapping, status)."""
-    A = np.ascontiguousarray(A, np.float64); b = np.ascontiguousarray(b, np.float64)
-    lo = np.ascontiguousarray(lo, np.float64); hi = np.ascontiguousarray(hi, np.float64)
-    fi = np.ascontiguousarray(findex, np.int32)
-    m = len(b)
-    x = np.zeros(m); mp = np.zeros(m, np.int32)
-    x0a = np.ascontiguousarray(x0, np.float64) if x0 is not None else np.zeros(m)
-    L = lib()
-    L.emul_solve_chain.argtypes = [ctypes.c_int] + [ctypes.c_void_p] * 6 + [ctypes.c_int, ctypes.c_double, ctypes.c_void_p, ctypes.c_void_p]
-    st = L.emul_solve_chain(m, _p(A), _p(b), _p(lo), _p(hi), _p(fi), _p(x0a), int(x0 is not None), float(fallback_cfm), _p(x), _p(mp))
-    return x, mp, st
-
-
 def cw_solve_chain(A, b, lo, hi, findex, x0=None, fallback_cfm=1e-4, reverse=False):
     """The warp-cooperative solve chain (csrc/nb2_cw.cuh lcp_chain, host build: one lane) -> (x, mapping, status)."""
     A = np.ascontiguousarray(A, np.float64); b = np.ascontiguousarray(b, np.float64)

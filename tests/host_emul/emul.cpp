@@ -78,7 +78,7 @@ static int run_fwd_contact(const nb2_model_desc* d, int B, const float* state, c
     for (auto& x : wss) x = 1e30;
     for (auto& x : wsb) x = 1e30;
     const float* st = state + (size_t)w * 2 * M.ndof;
-    const nb2::cw::Ws ws0 = nb2::cw::carve(wss.data(), ds);
+    nb2::cw::Ws ws0 = nb2::cw::carve(wss.data(), ds);
     nb2::fwd_load<double, 1>(M, scr.data(), st, action + (size_t)w * M.na, 1, 0, 1);
     for (int sg = 1; sg < NB2_FWD_STAGES - 1; sg++)
       for (int l = 0; l < M.lanes; l++) {
@@ -88,7 +88,8 @@ static int run_fwd_contact(const nb2_model_desc* d, int B, const float* state, c
     nb2::cw::FwdIO io;
     io.x_io = x_lcp + (size_t)w * NB2_MAX_ROWS; io.m_io = m_lcp + w; io.labels = labels + (size_t)w * NB2_MAX_ROWS; io.status = status + w;
     io.nc = nc + w; io.cinfo = cinfo ? cinfo + (size_t)w * NB2_MAX_CONTACTS * 10 : nullptr; io.rec = crec ? crec + (size_t)w * recd : nullptr;
-    nb2::cw::contact_forward(M, C, scr.data(), st, wss.data(), ds, wsb.data(), db, ws0.Iinv, io);
+    int pc = 0; nb2::cw::BigPool pool{&pc, wsb.data(), wsb.size(), 1};
+    nb2::cw::contact_forward(M, C, scr.data(), st, &ws0, ds, pool, db, ws0.Iinv, io);
     nb2::fwd_store<double, 1>(M, scr.data(), next + (size_t)w * 2 * M.ndof, 1, 0, 1);
   }
   nb2::cw::cw_host_reverse() = 0;
@@ -116,7 +117,9 @@ static int run_bwd_contact(const nb2_model_desc* d, int B, const float* state, c
     nb2::bwd_load<double, 1, true>(M, scr.data(), st, action + (size_t)w * M.na, gnext + (size_t)w * 2 * M.ndof, 1, 0, 1);
     nb2::BwdContactData<1> cd; cd.active = 0; cd.error = 0; cd.inj_of_body = nullptr;
     for (int sg = 1; sg < NB2_BWD_STAGES - 1; sg++) {
-      if (sg == 5) cd = nb2::cw::contact_backward(M, C, st, sv, wss.data(), ds, wsb.data(), db, crec + (size_t)w * recd, scr.data(), L.oLam, L.oBody);
+      int pc = 0; nb2::cw::BigPool pool{&pc, wsb.data(), wsb.size(), 1};
+      nb2::cw::Ws wsd = nb2::cw::carve(wss.data(), ds);
+      if (sg == 5) cd = nb2::cw::contact_backward(M, C, st, sv, &wsd, ds, pool, db, crec + (size_t)w * recd, scr.data(), L.oLam, L.oBody);
       for (int l = 0; l < M.lanes; l++) {
         const int lane = (w & 1) ? M.lanes - 1 - l : l;
         nb2::world_backward_stage<double, 1, true>(M, scr.data(), sv, 1, lane, sg, ginertia ? ginertia + w : nullptr, nullptr, (size_t)B, &cd);
@@ -138,7 +141,7 @@ static int run_cw_chain(int m, const double* A, const double* b, const double* l
   const int ld = m | 1;
   for (int i = 0; i < m; i++) for (int j = 0; j < m; j++) ws.A[i * ld + j] = A[i * m + j];
   for (int i = 0; i < m; i++) { ws.b[i] = b[i]; ws.lo[i] = lo[i]; ws.hi[i] = hi[i]; ws.findex[i] = fi[i]; }
-  const int status = nb2::cw::lcp_chain(m, ws, cfm, have_x0 ? x0 : nullptr);
+  const int status = nb2::cw::lcp_chain(m, ws, ws, cfm, have_x0 ? x0 : nullptr);
   for (int i = 0; i < m; i++) { x_out[i] = ws.x[i]; mapping_out[i] = ws.mapping[i]; }
   nb2::cw::cw_host_reverse() = 0;
   return status;
