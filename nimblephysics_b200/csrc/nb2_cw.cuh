@@ -142,6 +142,16 @@ __device__ unsigned long long nb2_cw_prof[64];
 #define CW_PROF(k)
 #endif
 
+// Block-level phase barrier (solve kernel with several worlds per block, NB2_CW_LOCKSTEP): the warps of a block enter every phase of
+// the chain together, so that they fetch the same code at the same time (the kernels are instruction-fetch bound: each warp wandering
+// through its own part of a few hundred KB of code thrashes the instruction caches).  A warp that skips a phase just waits.
+#if CW_DEV
+#define CW_PHASE() __syncthreads()
+#else
+#define CW_PHASE() ((void)0)
+#endif
+#define NB2_CHAIN_PHASES 6
+
 // per-lane partial -> the same total in every lane (host: the loop before it already produced the total)
 NB2_HD double cw_sum(double a) {
 #if CW_DEV
@@ -1055,6 +1065,7 @@ NB2_HD int lcp_chain(int m, const Ws& ws, const Ws& ws_mem, double fallback_cfm,
   double* b = ws.b; double* lo = ws.lo; double* hi = ws.hi; int* fi = ws.findex; double* x = ws.x; double* x0 = ws.x0;
   CW_FOR(c, m) { double sn = 0; for (int r = 0; r < m; r++) { const double a = A[(size_t)r * ld + c]; sn += a * a; } ws.colnorm[c] = sn; }
   // ---- warm start: cached solution if it has the same size, else LCPUtils::guessSolution (LCPUtils.cpp:86-140)
+  CW_PHASE();  // 1
   if (x_cached) { CW_FOR(i, m) x0[i] = x_cached[i]; CW_SYNC(); }
   else {
     CW_FOR(i, m) x0[i] = 0;
@@ -1074,6 +1085,7 @@ NB2_HD int lcp_chain(int m, const Ws& ws, const Ws& ws_mem, double fallback_cfm,
   CW_FOR(i, m) x[i] = x0[i];
   CW_SYNC();
   CW_PROF(10);
+  CW_PHASE();  // 2
   // ---- solve chain
   bool success = classify_and_standardize(m, A, ld, x, b, lo, hi, fi, ws.colnorm, false, ws_mem);
   CW_PROF(11);
@@ -1083,6 +1095,7 @@ NB2_HD int lcp_chain(int m, const Ws& ws, const Ws& ws_mem, double fallback_cfm,
   // i3 (target), i4 (fcur), mapping (keep list: free until the final classification)
   double *Ar = ws.M1, *br = ws.v1, *lor = ws.v2, *hir = ws.v3, *xr = ws.v4;
   int* fir = ws.i1;
+  CW_PHASE();  // 3
   if (success) status |= NB2_ST_SHORTCIRCUIT;
   else {
     status |= NB2_ST_DANTZIG;
@@ -1107,6 +1120,7 @@ NB2_HD int lcp_chain(int m, const Ws& ws, const Ws& ws_mem, double fallback_cfm,
     CW_FOR(i, m) if (x[i] != x[i]) nan = true;
     if (cw_any(nan)) { success = false; CW_SYNC(); CW_FOR(i, m) x[i] = 0; CW_SYNC(); status |= NB2_ST_NAN; }
   }
+  CW_PHASE();  // 4
   if (!success) {
     CW_FOR(i, m) A[(size_t)i * ld + i] += fallback_cfm;  // :539-547 (both backups get the cfm; colnorms were taken before)
     CW_SYNC();
@@ -1121,6 +1135,7 @@ NB2_HD int lcp_chain(int m, const Ws& ws, const Ws& ws_mem, double fallback_cfm,
       if (!lcp_valid(m, A, ld, x, b, hi, lo, fi, false)) success = false;
     }
   }
+  CW_PHASE();  // 5
   if (!success) {
     ignoredFriction = true;
     status |= NB2_ST_FRICTION_DROPPED;
@@ -1143,6 +1158,7 @@ NB2_HD int lcp_chain(int m, const Ws& ws, const Ws& ws_mem, double fallback_cfm,
     if (cw_any(nan)) { CW_SYNC(); CW_FOR(i, m) x[i] = 0; CW_SYNC(); status |= NB2_ST_NAN; }
   }
   CW_PROF(16);
+  CW_PHASE();  // 6
   if (!shortCircuit) {
     // classify works on x in place and only keeps the standardised x when valid
     if (!classify_and_standardize(m, A, ld, x, b, lo, hi, fi, ws.colnorm, ignoredFriction, ws_mem)) status |= NB2_ST_NOT_STANDARDIZED;
@@ -1609,9 +1625,13 @@ NB2_HD XLayout xlayout(int n) {
   return x;
 }
 
-// ---- build: collision, rows, A; leaves the record.  `scr`: the world's ABA scratch (q+ in oQ, v* in oV).
+// ---- build: collision, rows, A; leaves the record.  `scr`: the world's ABA scratch (q+ in oQ, v* in oV).  X == nullptr: a warp
+// without a world (tail of the last block) — it only takes part in the phase barriers.
+#define NB2_BUILD_PHASES 4
 NB2_HD void contact_build(const Nb2ModelDev<double>& M, const Nb2ContactDev& C, double* scr, const float* st, Ws* wsm, const Dims& d_s,
                           const BigPool& pool, const Dims& d_b, const FwdIO& io, double* X) {
+  int ph = 0;
+  if (!X) { while (ph < NB2_BUILD_PHASES) { CW_PHASE(); ph++; } return; }
   const FwdLayout L = fwd_layout(M.nb, M.ndof, M.nslots, M.nfree);
   const XLayout xl = xlayout(M.ndof);
   Ws ws = *wsm;
@@ -1620,6 +1640,7 @@ NB2_HD void contact_build(const Nb2ModelDev<double>& M, const Nb2ContactDev& C, 
   CW_PROF_DECL;
   fk_collision_bodies(M, C, S, scr + L.oV, ws);
   CW_PROF(1);
+  CW_PHASE(); ph++;  // 1
   collide_and_filter(C, ws, d);
   double* ws_big = ws.meta[3] ? pool_acquire(pool) : nullptr;
   if (ws_big) {
@@ -1648,13 +1669,17 @@ NB2_HD void contact_build(const Nb2ModelDev<double>& M, const Nb2ContactDev& C, 
   if (m == 0) {
     CW_ONE { X[0] = 0; X[1] = (double)nc; X[2] = (double)status; *io.m_io = 0; *io.status = status; if (io.rec) { io.rec[0] = 0; io.rec[1] = (double)status; } }
     CW_SYNC();
+    while (ph < NB2_BUILD_PHASES) { CW_PHASE(); ph++; }
     return;
   }
+  CW_PHASE(); ph++;  // 2
   status |= build_rows(M, C, ws, m, true);
   CW_PROF(3);
+  CW_PHASE(); ph++;  // 3
   const int ld = m | 1;
   assemble_A(M, C, S, ws, m, ld, nullptr, 0);
   CW_PROF(4);
+  CW_PHASE(); ph++;  // 4
   CW_FOR(i, m) {
     X[xl.oB + i] = ws.b[i]; X[xl.oLo + i] = ws.lo[i]; X[xl.oHi + i] = ws.hi[i]; X[xl.oFi + i] = (double)ws.findex[i]; X[xl.oRowc + i] = (double)ws.rowc[i];
   }
@@ -1670,8 +1695,12 @@ NB2_HD void contact_build(const Nb2ModelDev<double>& M, const Nb2ContactDev& C, 
 // ---- solve: the chain on the record's LCP.  wsm: descriptor carved in NB2_WS_SOLVE mode (small; large from the pool when m > d_s.MR)
 NB2_HD void contact_solve(const Nb2ContactDev& C, int ndof, Ws* wsm, const Dims& d_s, const BigPool& pool, const Dims& d_b, const FwdIO& io, double* X,
                           int* status_accum) {
-  const int m = (int)X[0];
-  if (m <= 0) { CW_ONE { if (status_accum) *status_accum |= (int)X[2]; } return; }
+  const int m = X ? (int)X[0] : 0;
+  if (m <= 0) {
+    CW_ONE { if (X && status_accum) *status_accum |= (int)X[2]; }
+    for (int k = 0; k < NB2_CHAIN_PHASES; k++) CW_PHASE();
+    return;
+  }
   const XLayout xl = xlayout(ndof);
   Ws ws = *wsm;
   if (m > d_s.MR) {
@@ -1682,6 +1711,7 @@ NB2_HD void contact_solve(const Nb2ContactDev& C, int ndof, Ws* wsm, const Dims&
         *io.m_io = 0; *io.status = st; if (status_accum) *status_accum |= st; X[0] = 0; if (io.rec) { io.rec[0] = 0; io.rec[1] = (double)st; }
       }
       CW_SYNC();
+      for (int k = 0; k < NB2_CHAIN_PHASES; k++) CW_PHASE();
       return;
     }
     const Ws wb = carve(big, d_b);
@@ -1706,14 +1736,14 @@ NB2_HD void contact_solve(const Nb2ContactDev& C, int ndof, Ws* wsm, const Dims&
 // wsm: descriptor carved in NB2_WS_APPLY mode.  sv: the world's saved stream (world-major).
 NB2_HD void contact_apply(const Nb2ModelDev<double>& M, const Nb2ContactDev& C, const float* st, const double* sv, Ws* wsm, const Dims& d_s,
                           const BigPool& pool, const Dims& d_b, const FwdIO& io, const double* X, float* vnext) {
-  const int m = (int)X[0], nc = (int)X[1];
-  if (m <= 0) return;
+  const int m = X ? (int)X[0] : 0, nc = X ? (int)X[1] : 0;
+  if (m <= 0) { CW_PHASE(); CW_PHASE(); return; }
   const XLayout xl = xlayout(M.ndof);
   const int n = M.ndof;
   Ws ws = *wsm;
   if (m > d_s.MR || nc > d_s.MC) {
     double* big = pool_acquire(pool);
-    if (!big) return;  // (contact_solve already flagged the world when the pool ran dry: same pool size, same demand)
+    if (!big) { CW_PHASE(); CW_PHASE(); return; }  // (contact_solve already flagged the world when the pool ran dry: same pool size, same demand)
     const Ws wb = carve(big, d_b);
     CW_SYNC();
     CW_ONE *wsm = wb;
@@ -1724,10 +1754,12 @@ NB2_HD void contact_apply(const Nb2ModelDev<double>& M, const Nb2ContactDev& C, 
   CW_FOR(c, nc) { ws.cbodyA[c] = (int)X[xl.oCA + c]; ws.cbodyB[c] = (int)X[xl.oCB + c]; }
   CW_FOR(e, m * 6) { ws.JA[e] = X[xl.oJA + e]; ws.JB[e] = X[xl.oJB + e]; }
   CW_SYNC();
+  CW_PHASE();
   TreeSrc S; S.scr = nullptr; S.Iinv = nullptr; S.sv = sv; S.st = st; S.nb = M.nb; S.nfree = M.nfree;
   S.L = fwd_layout(M.nb, n, M.nslots, M.nfree);
   net_wrenches(C, ws, m, ws.x, ws.Fcb);
   impulse_response_all(M, C, S, ws, ws.Fcb, ws.M1 + (size_t)C.ncb * C.max_chain_dofs);
+  CW_PHASE();
   CW_FOR(dd, n) vnext[dd] = (float)(X[xl.oV + dd] + ws.dqd[dd]);
   if (io.rec) {
     CW_FOR(i, m) { io.rec[2 + i] = (double)io.labels[i]; io.rec[2 + NB2_MAX_ROWS + i] = ws.x[i]; }
@@ -1779,13 +1811,16 @@ NB2_HD BwdContactData<1> contact_backward(const Nb2ModelDev<double>& M, const Nb
   BwdContactData<1> cd;
   cd.Aacc.p = cd.Uplus.p = cd.aeff.p = cd.vplus.p = cd.inj.p = cd.JcTmu.p = nullptr;
   cd.inj_of_body = C.cb_of_body; cd.active = 0; cd.error = 0;
-  const int m = (int)rec[0];
-  if (m <= 0) return cd;
+  int ph = 0;
+#define NB2_BWD_PHASES 7
+#define NB2_BWD_DRAIN() do { while (ph < NB2_BWD_PHASES) { CW_PHASE(); ph++; } } while (0)
+  const int m = rec ? (int)rec[0] : 0;
+  if (m <= 0) { NB2_BWD_DRAIN(); return cd; }
   cd.active = 1;
   const int fstatus = (int)rec[1];
   // restitution: b depends on v* through (1 + e) J v*, which needs a second multiplier field in the reverse sweep
   // (BackpropSnapshot::getBounceApproximationJacobian, BackpropSnapshot.cpp:1131-1226) — not implemented: fail loudly
-  if (fstatus & NB2_ST_BOUNCE) { cd.error = 5; cd.active = 0; return cd; }
+  if (fstatus & NB2_ST_BOUNCE) { cd.error = 5; cd.active = 0; NB2_BWD_DRAIN(); return cd; }
   Ws ws = *wsm;
   Dims d = d_s;
   TreeSrc S; S.scr = nullptr; S.Iinv = nullptr; S.sv = sv; S.st = st; S.nb = nb; S.nfree = M.nfree;
@@ -1797,6 +1832,7 @@ NB2_HD BwdContactData<1> contact_backward(const Nb2ModelDev<double>& M, const Nb
   CW_PROF_DECL;
   fk_collision_bodies(M, C, S, nullptr, ws);
   CW_PROF(21);
+  CW_PHASE(); ph++;  // 1
   collide_and_filter(C, ws, d);
   CW_PROF(22);
   double* ws_big = ws.meta[3] ? pool_acquire(pool) : nullptr;
@@ -1809,7 +1845,8 @@ NB2_HD BwdContactData<1> contact_backward(const Nb2ModelDev<double>& M, const Nb
     ws = wb; d = d_b;
     collide_and_filter(C, ws, d);
   }
-  if (ws.meta[3] || ws.meta[0] != m) { cd.error = 3; cd.active = 0; return cd; }
+  if (ws.meta[3] || ws.meta[0] != m) { cd.error = 3; cd.active = 0; NB2_BWD_DRAIN(); return cd; }
+  CW_PHASE(); ph++;  // 2
   const int nc = ws.meta[1];
   build_rows(M, C, ws, m, false);
   cd.aeff.p = ws.aeff; cd.vplus.p = ws.vplus; cd.JcTmu.p = ws.JcTmu; cd.inj.p = ws.inj;
@@ -1847,10 +1884,15 @@ NB2_HD BwdContactData<1> contact_backward(const Nb2ModelDev<double>& M, const Nb
   }
   CW_SYNC();
   CW_PROF(23);
+  CW_PHASE(); ph++;  // 3
+  if (nCl > 0) {
+    const int ld = m | 1;
+    assemble_A(M, C, S, ws, m, ld, rows, nCl + nUb);  // rows cl and ub of A, measured
+  }
+  CW_PROF(24);
+  CW_PHASE(); ph++;  // 4
   if (nCl > 0) {
     const int ld = m | 1, lq = nCl | 1;
-    assemble_A(M, C, S, ws, m, ld, rows, nCl + nUb);  // rows cl and ub of A, measured
-    CW_PROF(24);
     // Q = A[cl,cl] + A[cl,ub] E (+ cfm on the diagonal when the forward's fallback added it); as in the forward, an entry below the
     // block diagonal is the mirror image of its measured partner
     double* Q = ws.M1;
@@ -1876,6 +1918,7 @@ NB2_HD BwdContactData<1> contact_backward(const Nb2ModelDev<double>& M, const Nb
     }
   }
   CW_PROF(25);
+  CW_PHASE(); ph++;  // 5
   // ---- nu = M^-1 A_c mu  (one impulse response) ; w = lambda - nu ; W_i(w)
   CW_FOR(j, m) coefM[j] = (clampIdx[j] >= 0) ? mu_c[clampIdx[j]] : 0.0;
   CW_SYNC();
@@ -1913,6 +1956,7 @@ NB2_HD BwdContactData<1> contact_backward(const Nb2ModelDev<double>& M, const Nb
     CW_SYNC();
   }
   CW_PROF(26);
+  CW_PHASE(); ph++;  // 6
   // ---- per-body injections for the reverse sweep: Uw_bar, Up_bar, G (all scaled by -1/dt: they join the (dID/dq)^T w accumulator
   // that is multiplied by -dt at the end) and H (plain: A_c mu propagated to joint space).  One collision body per lane.
   const double kap = -1.0 / dt;
@@ -1943,6 +1987,7 @@ NB2_HD BwdContactData<1> contact_backward(const Nb2ModelDev<double>& M, const Nb
   // (pair that produced contacts, body whose pose varies); each item takes 6 lanes, one pose direction each: the contact
   // generator runs on 1-direction dual numbers.  Contacts of a pair are consecutive: groups are found from the shape indices.
   CW_PROF(27);
+  CW_PHASE(); ph++;  // 7
   int* gfirst = ws.i1; int* it_g = ws.i2; int* it_dyn = ws.i4;  // cl / ubl are dead by now
   const int ng = cw_enumerate(nc, [&](int c) { return c == 0 || ws.cshapeA[c] != ws.cshapeA[c - 1] || ws.cshapeB[c] != ws.cshapeB[c - 1]; },
                               [&](int c, int r) { gfirst[r] = c; });
