@@ -1057,13 +1057,21 @@ unpermute:
 // (LCPUtils::guessSolution).  Leaves x in ws.x and the labels in ws.mapping; returns the status bits.
 // ws: the caller's (register) copy of the workspace descriptor; ws_mem: the same descriptor at a stable address (shared memory on the
 // device), handed to the non-inlined classification so that the register copy never has to be spilled for a call
-NB2_HD int lcp_chain(int m, const Ws& ws, const Ws& ws_mem, double fallback_cfm, const double* x_cached) {
-  int status = 0;
+#define NB2_HEAD_PHASES 2
+#define NB2_TAIL_PHASES 4
+NB2_HD void lcp_colnorms(int m, const Ws& ws) {
+  const int ld = m | 1;
+  CW_FOR(c, m) { double sn = 0; for (int r = 0; r < m; r++) { const double a = ws.A[(size_t)r * ld + c]; sn += a * a; } ws.colnorm[c] = sn; }
+  CW_SYNC();
+}
+// head of the chain: warm start + the short-circuit classification.  true: x / mapping hold the answer (status NB2_ST_SHORTCIRCUIT);
+// false: x == x0 (the warm start) and the tail has to run.
+NB2_HD bool lcp_chain_head(int m, const Ws& ws, const Ws& ws_mem, const double* x_cached) {
   CW_PROF_DECL;
   const int ld = m | 1;
   double* A = ws.A;
   double* b = ws.b; double* lo = ws.lo; double* hi = ws.hi; int* fi = ws.findex; double* x = ws.x; double* x0 = ws.x0;
-  CW_FOR(c, m) { double sn = 0; for (int r = 0; r < m; r++) { const double a = A[(size_t)r * ld + c]; sn += a * a; } ws.colnorm[c] = sn; }
+  lcp_colnorms(m, ws);
   // ---- warm start: cached solution if it has the same size, else LCPUtils::guessSolution (LCPUtils.cpp:86-140)
   CW_PHASE();  // 1
   if (x_cached) { CW_FOR(i, m) x0[i] = x_cached[i]; CW_SYNC(); }
@@ -1089,7 +1097,18 @@ NB2_HD int lcp_chain(int m, const Ws& ws, const Ws& ws_mem, double fallback_cfm,
   // ---- solve chain
   bool success = classify_and_standardize(m, A, ld, x, b, lo, hi, fi, ws.colnorm, false, ws_mem);
   CW_PROF(11);
-  const bool shortCircuit = success;
+  return success;
+}
+// tail of the chain (the short-circuit failed): [reduce] Dantzig -> cfm + [reduce] PGS -> friction drop -> classification.
+// Entry: x == x0, colnorm valid.  Returns the status bits.
+NB2_HD int lcp_chain_tail(int m, const Ws& ws, const Ws& ws_mem, double fallback_cfm) {
+  int status = 0;
+  CW_PROF_DECL;
+  const int ld = m | 1;
+  double* A = ws.A;
+  double* b = ws.b; double* lo = ws.lo; double* hi = ws.hi; int* fi = ws.findex; double* x = ws.x; double* x0 = ws.x0;
+  bool success = false;
+  const bool shortCircuit = false;
   bool ignoredFriction = false;
   // reduced problem: matrix in M1, vectors v1 (b) v2 (lo) v3 (hi) v4 (x), findex i1; bookkeeping v9 (mult), i2 (alive -> rank + 1),
   // i3 (target), i4 (fcur), mapping (keep list: free until the final classification)
@@ -1165,6 +1184,14 @@ NB2_HD int lcp_chain(int m, const Ws& ws, const Ws& ws_mem, double fallback_cfm,
   }
   CW_PROF(17);
   return status;
+}
+// the whole chain (fused kernels, host emulation): same phase barriers as the split form
+NB2_HD int lcp_chain(int m, const Ws& ws, const Ws& ws_mem, double fallback_cfm, const double* x_cached) {
+  if (lcp_chain_head(m, ws, ws_mem, x_cached)) {
+    for (int k = 0; k < NB2_TAIL_PHASES; k++) CW_PHASE();
+    return NB2_ST_SHORTCIRCUIT;
+  }
+  return lcp_chain_tail(m, ws, ws_mem, fallback_cfm);
 }
 
 // ------------------------------------------------------------------------------------------------ tree data
@@ -1614,13 +1641,14 @@ NB2_HD void contact_forward(const Nb2ModelDev<double>& M, const Nb2ContactDev& C
 // sweeps and the collision code need 255 registers — in one kernel every phase runs at the occupancy of the hungriest.
 // Exchange record of a world (doubles; capacities NB2_MAX_ROWS / NB2_MAX_CONTACTS, only the used part is touched):
 //   [0] m  [1] nc  [2] status so far  [3] -   then b, lo, hi, findex, rowc (MRX each), cbodyA, cbodyB (MCX each), JA, JB (6 MRX each),
-//   v* (n), A (m x (m | 1), packed with the problem's own leading dimension)
+//   x0 (MRX: the warm start, written by the first solve kernel for the worlds it hands on), v* (n), A (m x (m | 1), packed with the
+//   problem's own leading dimension)
 // =====================================================================================================
-struct XLayout { int oB, oLo, oHi, oFi, oRowc, oCA, oCB, oJA, oJB, oV, oA; size_t total; };
+struct XLayout { int oB, oLo, oHi, oFi, oRowc, oCA, oCB, oJA, oJB, oX0, oV, oA; size_t total; };
 NB2_HD XLayout xlayout(int n) {
   const int MRX = NB2_MAX_ROWS, MCX = NB2_MAX_CONTACTS;
   XLayout x; x.oB = 4; x.oLo = x.oB + MRX; x.oHi = x.oLo + MRX; x.oFi = x.oHi + MRX; x.oRowc = x.oFi + MRX; x.oCA = x.oRowc + MRX; x.oCB = x.oCA + MCX;
-  x.oJA = x.oCB + MCX; x.oJB = x.oJA + 6 * MRX; x.oV = x.oJB + 6 * MRX; x.oA = x.oV + n;
+  x.oJA = x.oCB + MCX; x.oJB = x.oJA + 6 * MRX; x.oX0 = x.oJB + 6 * MRX; x.oV = x.oX0 + MRX; x.oA = x.oV + n;
   x.total = ((size_t)x.oA + (size_t)MRX * (MRX | 1) + 1) & ~(size_t)1;
   return x;
 }
@@ -1692,40 +1720,81 @@ NB2_HD void contact_build(const Nb2ModelDev<double>& M, const Nb2ContactDev& C, 
   CW_PROF(6);
 }
 
-// ---- solve: the chain on the record's LCP.  wsm: descriptor carved in NB2_WS_SOLVE mode (small; large from the pool when m > d_s.MR)
-NB2_HD void contact_solve(const Nb2ContactDev& C, int ndof, Ws* wsm, const Dims& d_s, const BigPool& pool, const Dims& d_b, const FwdIO& io, double* X,
-                          int* status_accum) {
-  const int m = X ? (int)X[0] : 0;
-  if (m <= 0) {
-    CW_ONE { if (X && status_accum) *status_accum |= (int)X[2]; }
-    for (int k = 0; k < NB2_CHAIN_PHASES; k++) CW_PHASE();
-    return;
-  }
-  const XLayout xl = xlayout(ndof);
-  Ws ws = *wsm;
-  if (m > d_s.MR) {
-    double* big = pool_acquire(pool);
-    if (!big) {  // pool exhausted: this world cannot be solved here — flag it and leave v* (no contact impulse)
-      CW_ONE {
-        const int st = (int)X[2] | NB2_ST_CONTACT_OVERFLOW;
-        *io.m_io = 0; *io.status = st; if (status_accum) *status_accum |= st; X[0] = 0; if (io.rec) { io.rec[0] = 0; io.rec[1] = (double)st; }
-      }
-      CW_SYNC();
-      for (int k = 0; k < NB2_CHAIN_PHASES; k++) CW_PHASE();
-      return;
-    }
-    const Ws wb = carve(big, d_b);
-    CW_SYNC();
-    CW_ONE *wsm = wb;
-    CW_SYNC();
-    ws = wb;
-  }
+// ---- solve, in two kernels so that the worlds of a block do the same amount of work (they run in lockstep):
+//   A  warm start + short-circuit classification for every world; the worlds it does not settle are appended to `todo`
+//   B  Dantzig / PGS / friction drop / classification for the worlds of `todo`
+// wsm: descriptor carved in NB2_WS_SOLVE mode (small; large from the pool when m > d_s.MR).  X == nullptr: warp without a world.
+NB2_HD bool solve_workspace(Ws* wsm, Ws& ws, int m, const Dims& d_s, const BigPool& pool, const Dims& d_b) {
+  if (m <= d_s.MR) return true;
+  double* big = pool_acquire(pool);
+  if (!big) return false;
+  const Ws wb = carve(big, d_b);
+  CW_SYNC();
+  CW_ONE *wsm = wb;
+  CW_SYNC();
+  ws = wb;
+  return true;
+}
+NB2_HD void solve_load(const Ws& ws, int m, const double* X, const XLayout& xl) {
   const int ld = m | 1;
   CW_FOR(i, m) { ws.b[i] = X[xl.oB + i]; ws.lo[i] = X[xl.oLo + i]; ws.hi[i] = X[xl.oHi + i]; ws.findex[i] = (int)X[xl.oFi + i]; }
   CW_FOR(e, m * ld) ws.A[e] = X[xl.oA + e];
   CW_SYNC();
-  int status = (int)X[2];
-  status |= lcp_chain(m, ws, *wsm, C.fallback_cfm, (*io.m_io == m) ? io.x_io : nullptr);
+}
+NB2_HD void contact_solve_a(const Nb2ContactDev& C, int ndof, Ws* wsm, const Dims& d_s, const BigPool& pool, const Dims& d_b, const FwdIO& io, double* X,
+                            int* status_accum, int world, int* todo, int* todo_count) {
+  const int m = X ? (int)X[0] : 0;
+  if (m <= 0) {
+    CW_ONE { if (X && status_accum) *status_accum |= (int)X[2]; }
+    for (int k = 0; k < NB2_HEAD_PHASES; k++) CW_PHASE();
+    return;
+  }
+  const XLayout xl = xlayout(ndof);
+  Ws ws = *wsm;
+  if (!solve_workspace(wsm, ws, m, d_s, pool, d_b)) {  // pool exhausted: this world cannot be solved here — flag it and leave v*
+    CW_ONE {
+      const int st = (int)X[2] | NB2_ST_CONTACT_OVERFLOW;
+      *io.m_io = 0; *io.status = st; if (status_accum) *status_accum |= st; X[0] = 0; if (io.rec) { io.rec[0] = 0; io.rec[1] = (double)st; }
+    }
+    CW_SYNC();
+    for (int k = 0; k < NB2_HEAD_PHASES; k++) CW_PHASE();
+    return;
+  }
+  solve_load(ws, m, X, xl);
+  const bool done = lcp_chain_head(m, ws, *wsm, (*io.m_io == m) ? io.x_io : nullptr);
+  CW_SYNC();
+  if (done) {
+    const int status = (int)X[2] | NB2_ST_SHORTCIRCUIT;
+    CW_FOR(i, m) { io.x_io[i] = ws.x[i]; io.labels[i] = ws.mapping[i]; }
+    CW_ONE { *io.m_io = m; *io.status = status; if (status_accum) *status_accum |= status; X[2] = (double)status; }
+  } else {
+    CW_FOR(i, m) X[xl.oX0 + i] = ws.x0[i];
+    CW_ONE {
+#if CW_DEV
+      const int slot = atomicAdd(todo_count, 1);
+#else
+      const int slot = (*todo_count)++;
+#endif
+      todo[slot] = world;
+    }
+  }
+  CW_SYNC();
+}
+NB2_HD void contact_solve_b(const Nb2ContactDev& C, int ndof, Ws* wsm, const Dims& d_s, const BigPool& pool, const Dims& d_b, const FwdIO& io, double* X,
+                            int* status_accum) {
+  const int m = X ? (int)X[0] : 0;
+  if (m <= 0) { for (int k = 0; k < NB2_TAIL_PHASES; k++) CW_PHASE(); return; }
+  const XLayout xl = xlayout(ndof);
+  Ws ws = *wsm;
+  if (!solve_workspace(wsm, ws, m, d_s, pool, d_b)) {  // (cannot happen when kernel A got its slot: same pool, same demand)
+    for (int k = 0; k < NB2_TAIL_PHASES; k++) CW_PHASE();
+    return;
+  }
+  solve_load(ws, m, X, xl);
+  CW_FOR(i, m) { ws.x0[i] = X[xl.oX0 + i]; ws.x[i] = X[xl.oX0 + i]; }
+  CW_SYNC();
+  lcp_colnorms(m, ws);
+  const int status = (int)X[2] | lcp_chain_tail(m, ws, *wsm, C.fallback_cfm);
   CW_SYNC();
   CW_FOR(i, m) { io.x_io[i] = ws.x[i]; io.labels[i] = ws.mapping[i]; }
   CW_ONE { *io.m_io = m; *io.status = status; if (status_accum) *status_accum |= status; X[2] = (double)status; }

@@ -233,7 +233,8 @@ struct CStepArgs {
   // three-kernel forward: exchange records and the workspace shapes of the solve / apply kernels
   double* exch; size_t exch_stride;
   nb2::cw::Dims ds_solve, db_solve, ds_apply, db_apply;
-  nb2::cw::BigPool pool_solve, pool_apply;
+  nb2::cw::BigPool pool_solve, pool_solve_b, pool_apply;
+  int *todo, *todo_count;
 };
 __global__ void __launch_bounds__(32, NB2_CSTEP_MINB)
 k_cstep_fwd(const __grid_constant__ Nb2ModelDev<double> M, const __grid_constant__ Nb2ContactDev C, const __grid_constant__ CStepArgs P,
@@ -318,13 +319,23 @@ k_cbuild(const __grid_constant__ Nb2ModelDev<double> M, const __grid_constant__ 
 // SM fetches each piece of code once for all of them.  Measured on B200 (Atlas + ground, 8192 worlds): 6.6 -> 3.7 ms per forward step
 // going from 1 to 11 worlds per block.  The warp count per block is chosen at launch (shared memory, batch size).
 #define NB2_CSOLVE_MAXW 12
+// solve kernel A (every world: warm start + short-circuit classification) / B (the worlds A listed in `todo`: the rest of the chain)
+template <int PART>
 __global__ void __launch_bounds__(32 * NB2_CSOLVE_MAXW, 1)
 k_csolve(const __grid_constant__ Nb2ContactDev C, const __grid_constant__ CStepArgs P, int ndof, double* __restrict__ x_lcp, int* __restrict__ m_lcp,
-         int* __restrict__ labels, int* __restrict__ status, double* __restrict__ crec, int* __restrict__ status_accum, size_t smem_per_warp) {
+         int* __restrict__ labels, int* __restrict__ status, double* __restrict__ crec, int* __restrict__ status_accum, size_t smem_per_warp,
+         int* __restrict__ todo, int* __restrict__ todo_count) {
   extern __shared__ __align__(16) unsigned char nb2_smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
-  const int w = blockIdx.x * wpb + warp;
-  const bool live = w < P.B;
+  const int idx = blockIdx.x * wpb + warp;
+  int w = idx;
+  bool live = idx < P.B;
+  if (PART == 1) {
+    const int cnt = *todo_count;
+    if (blockIdx.x * wpb >= cnt) return;  // the whole block has nothing to do
+    live = idx < cnt;
+    w = live ? todo[idx] : 0;
+  }
   double* X = live ? P.exch + (size_t)w * P.exch_stride : nullptr;
   nb2::cw::Ws* wsm = reinterpret_cast<nb2::cw::Ws*>(nb2_smem + (size_t)warp * smem_per_warp);
   double* wsb = reinterpret_cast<double*>(wsm) + NB2_WS_DESC_DOUBLES;
@@ -334,7 +345,8 @@ k_csolve(const __grid_constant__ Nb2ContactDev C, const __grid_constant__ CStepA
   const int wc = live ? w : 0;
   io.x_io = x_lcp + (size_t)wc * NB2_MAX_ROWS; io.m_io = m_lcp + wc; io.labels = labels + (size_t)wc * NB2_MAX_ROWS; io.status = status + wc;
   io.nc = nullptr; io.cinfo = nullptr; io.rec = crec ? crec + (size_t)wc * P.rec_doubles : nullptr;
-  nb2::cw::contact_solve(C, ndof, wsm, P.ds_solve, P.pool_solve, P.db_solve, io, X, status_accum ? status_accum + wc : nullptr);
+  if (PART == 0) nb2::cw::contact_solve_a(C, ndof, wsm, P.ds_solve, P.pool_solve, P.db_solve, io, X, status_accum ? status_accum + wc : nullptr, w, todo, todo_count);
+  else nb2::cw::contact_solve_b(C, ndof, wsm, P.ds_solve, P.pool_solve_b, P.db_solve, io, X, status_accum ? status_accum + wc : nullptr);
 }
 #define NB2_CAPPLY_MAXW 16
 __global__ void __launch_bounds__(32 * NB2_CAPPLY_MAXW, 1)
@@ -671,6 +683,9 @@ static CStepArgs cstep_args(const nb2_model* m, const nb2_variant& v, int B, voi
   P.ds_apply = cdims(m, m->contact_mc, 0, NB2_WS_APPLY); P.db_apply = cdims(m, NB2_MAX_CONTACTS, 0, NB2_WS_APPLY);
   P.pool_solve = P.pool; P.pool_solve.counter = (int*)workspace + 1;  // the kernels run one after the other: same slots, own counter
   P.pool_apply = P.pool; P.pool_apply.counter = (int*)workspace + 2;
+  P.pool_solve_b = P.pool; P.pool_solve_b.counter = (int*)workspace + 3;
+  P.todo_count = (int*)workspace + 4;
+  P.todo = (int*)(P.exch + (size_t)B * P.exch_stride);  // list of the worlds the first solve kernel hands to the second
   return P;
 }
 template <class Kern> static int cstep_smem_attr(Kern kern, size_t smem, bool* done) {
@@ -785,7 +800,7 @@ int nb2_model_has_contacts(const nb2_model* m) { return (m && m->has_contacts) ?
 size_t nb2_contact_workspace_bytes(const nb2_model* m, int B) {
   if (!m || !m->has_contacts || B <= 0) return 0;
   // [64 B: pool counters] [pool of large workspaces] [exchange records of the three-kernel forward, one per world]
-  return 64 + ((size_t)pool_slots(B) * pool_stride(m) + (size_t)B * nb2::cw::xlayout(m->md.ndof).total) * sizeof(double);
+  return 64 + ((size_t)pool_slots(B) * pool_stride(m) + (size_t)B * nb2::cw::xlayout(m->md.ndof).total) * sizeof(double) + (size_t)B * sizeof(int);
 }
 int nb2_step_forward_contact(const nb2_model* cm, int B, const float* state, const float* action, float* next_state,
                              void* saved_fp64, void* workspace, double* x_lcp, int32_t* m_lcp, int32_t* labels,
@@ -813,18 +828,21 @@ int nb2_step_forward_contact(const nb2_model* cm, int B, const float* state, con
     NB2_CUDA(cudaGetLastError());
     return NB2_OK;
   }
-  static bool attr_b[64] = {}, attr_s[64] = {}, attr_a[64] = {};
+  static bool attr_b[64] = {}, attr_s[64] = {}, attr_s2[64] = {}, attr_a[64] = {};
   const size_t smem_s = (NB2_WS_DESC_DOUBLES + nb2::cw::ws_doubles(P.ds_solve)) * sizeof(double);
   const size_t smem_a = (NB2_WS_DESC_DOUBLES + nb2::cw::ws_doubles(P.ds_apply)) * sizeof(double);
-  if ((rc = cstep_smem_attr(k_cbuild, smem, attr_b)) || (rc = cstep_smem_attr(k_csolve, smem_s, attr_s)) || (rc = cstep_smem_attr(k_capply, smem_a, attr_a))) return rc;
+  if ((rc = cstep_smem_attr(k_cbuild, smem, attr_b)) || (rc = cstep_smem_attr(k_csolve<0>, smem_s, attr_s)) || (rc = cstep_smem_attr(k_csolve<1>, smem_s, attr_s2)) || (rc = cstep_smem_attr(k_capply, smem_a, attr_a))) return rc;
   const int wpb_b = pick_wpb(B, m->sm_count, smem, NB2_CBUILD_MAXW), wpb_s = pick_wpb(B, m->sm_count, smem_s, NB2_CSOLVE_MAXW),
             wpb_a = pick_wpb(B, m->sm_count, smem_a, NB2_CAPPLY_MAXW);
   k_cbuild<<<(B + wpb_b - 1) / wpb_b, 32 * wpb_b, smem * wpb_b, st>>>(v.md, m->contact, P, state, action, next_state, (double*)saved_fp64, m_lcp, status, ncontacts, cinfo,
                                                                       contact_record, smem);
-  k_csolve<<<(B + wpb_s - 1) / wpb_s, 32 * wpb_s, smem_s * wpb_s, st>>>(m->contact, P, m->md.ndof, x_lcp, m_lcp, labels, status, contact_record, status_accum, smem_s);
+  k_csolve<0><<<(B + wpb_s - 1) / wpb_s, 32 * wpb_s, smem_s * wpb_s, st>>>(m->contact, P, m->md.ndof, x_lcp, m_lcp, labels, status, contact_record, status_accum, smem_s,
+                                                                         P.todo, P.todo_count);
+  k_csolve<1><<<(B + wpb_s - 1) / wpb_s, 32 * wpb_s, smem_s * wpb_s, st>>>(m->contact, P, m->md.ndof, x_lcp, m_lcp, labels, status, contact_record, status_accum, smem_s,
+                                                                         P.todo, P.todo_count);
   k_capply<<<(B + wpb_a - 1) / wpb_a, 32 * wpb_a, smem_a * wpb_a, st>>>(v.md, m->contact, P, state, next_state, (const double*)saved_fp64, x_lcp, labels, contact_record,
                                                                         smem_a);
-  g_launches += 3;
+  g_launches += 4;
   NB2_CUDA(cudaGetLastError());
   return NB2_OK;
 }
