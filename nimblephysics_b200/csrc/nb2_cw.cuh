@@ -69,9 +69,9 @@ struct Nb2ContactDev {
   double shape_mu[NB2_MAX_SHAPES], shape_rest[NB2_MAX_SHAPES];
 };
 
-// big routines exist ONCE in the device code (real calls): the fused kernels are instruction-fetch bound when everything is inlined
-#if defined(__CUDACC__) && !defined(NB2_CW_INLINE_ALL)
-#define NB2_HDN __host__ __device__ __noinline__
+// the big routines of the solver chain; inlined by default (NB2_CW_NOINLINE: real calls)
+#if defined(__CUDACC__) && defined(NB2_CW_NOINLINE)
+#define NB2_HDN __host__ __device__ __noinline__   // experiment: -23 % static code, but slower (calls cost ~60 cycles each, see scripts/dev/ubench)
 #elif defined(__CUDACC__)
 #define NB2_HDN __host__ __device__ __forceinline__
 #else
@@ -86,10 +86,10 @@ namespace cw {
 #define CW_DEV 1
 #define CW_LANE ((int)(threadIdx.x & 31))
 #define CW_SYNC() __syncwarp()
-// The loop over passes has a warp-UNIFORM trip count and only the body is predicated: a per-lane loop `for (i = lane; i < n; i += 32)`
-// makes the lanes leave at different points, and a divergent loop exit costs ~110 cycles on B200 (scripts/dev/ubench/br.cu) against
-// ~10 for a predicated region — with hundreds of such loops per world that was most of the run time.
-#ifdef NB2_CW_FOR_DIVERGENT
+// NB2_CW_FOR_UNIFORM: the loop over passes gets a warp-uniform trip count and only the body is predicated.  In isolation a divergent loop
+// exit costs ~110 cycles on B200 against ~60 for this form (scripts/dev/ubench/br.cu); inside the real kernels the plain per-lane loop
+// measured 10 % FASTER (the compiler turns the guarded bodies into divergent branches anyway), so it is the default.
+#ifndef NB2_CW_FOR_UNIFORM
 #define CW_FOR(i, n) for (int i = (int)(threadIdx.x & 31); i < (n); i += 32)
 #else
 #define CW_FOR(i, n)                                                         \
@@ -611,64 +611,62 @@ NB2_HDN bool pgs_solve(int m, double* A, int ld, double* x, double* b, const dou
   const double dxTol = 1e-6, relTol = 1e-3, epsDiv = 1e-9;
 #if CW_DEV && !defined(NB2_CW_PGS_SMEM)
   if (m <= 32) {
-    // register form: lane j owns row j (x_j, r_j, b_j, bounds, 1 / A_jj); per row step the owner lane updates x_i, the change is
-    // broadcast and every lane folds it into its residual with ONE multiply-add on the (scaled-on-the-fly) column entry A_ji.
-    // Same arithmetic, in the same order, as the shared-memory form below.
+    // register form: lane j owns row j (x_j, its row residual r_j = sum_k A_jk x_k, b_j, bounds).  Per row step every lane evaluates the
+    // update of ITS row (branch-free; only the owner's result is kept), the owner's change is broadcast and every lane folds it into its
+    // residual with one multiply-add on the column entry A_ji.  Rows are rescaled in place after the first sweep like the reference
+    // (PgsBoxedLcpSolver.cpp:163-180).  Same arithmetic, in the same order, as the shared-memory form below.
     const int lane = CW_LANE;
     const bool act = lane < m;
-    const double* rowj = A + (size_t)(act ? lane : 0) * ld;
+    double* rowj = A + (size_t)(act ? lane : 0) * ld;
     double xj = act ? x[lane] : 0.0, bj = act ? b[lane] : 0.0;
     const double hij = act ? hi[lane] : 0.0, loj = act ? lo[lane] : 0.0;
     double ajj = act ? rowj[lane] : 1.0;
     const int fj = act ? fi[lane] : -1;
-    double dmj = 1.0;  // row scale (1 during the first sweep)
+    const int fsrc = fj >= 0 ? fj : 0;
     bool skipj = false;
     auto residual = [&]() {
       double rr = 0;
-      for (int k = 0; k < m; k++) { const double xk = __shfl_sync(CW_FULL, xj, k); if (act) rr += (dmj == 1.0 ? rowj[k] : rowj[k] * dmj) * xk; }
+      for (int k = 0; k < m; k++) { const double xk = __shfl_sync(CW_FULL, xj, k); if (act) rr += rowj[k] * xk; }
       return rr;
     };
     double rj = residual();
     bool changed = false;
+    // first sweep: unscaled rows, division by the diagonal, absolute change test
+#pragma unroll 2
     for (int i = 0; i < m; i++) {
-      const int f = __shfl_sync(CW_FULL, fj, i);
-      const double xf = __shfl_sync(CW_FULL, xj, f >= 0 ? f : 0);
-      double delta = 0.0;
-      if (lane == i) {
-        double xi;
-        if (ajj < epsDiv) { xi = 0.0; skipj = true; }
-        else {
-          const double nx = nb2_div(bj - (rj - ajj * xj), ajj);
-          double hi_t = hij, lo_t = loj;
-          if (f >= 0) { hi_t = hij * xf; lo_t = -hi_t; }
-          xi = nx > hi_t ? hi_t : (nx < lo_t ? lo_t : nx);
-          if (fabs(xi - xj) > dxTol) changed = true;
-        }
-        delta = xi - xj; xj = xi;
-      }
-      delta = __shfl_sync(CW_FULL, delta, i);
-      if (act) rj += A[(size_t)lane * ld + i] * delta;
+      const double xf = __shfl_sync(CW_FULL, xj, fsrc);            // x of this lane's own normal row
+      const bool own = lane == i;
+      const bool sk = ajj < epsDiv;
+      const double nx = nb2_div(bj - (rj - ajj * xj), sk ? 1.0 : ajj);
+      const double hi_t = fj >= 0 ? hij * xf : hij, lo_t = fj >= 0 ? -hi_t : loj;
+      double xi = nx > hi_t ? hi_t : (nx < lo_t ? lo_t : nx);
+      xi = sk ? 0.0 : xi;
+      const double dl = own ? xi - xj : 0.0;
+      changed = changed || (own && !sk && fabs(dl) > dxTol);
+      skipj = skipj || (own && sk);
+      xj = own ? xi : xj;
+      const double delta = __shfl_sync(CW_FULL, dl, i);
+      if (act) rj = fma(A[(size_t)lane * ld + i], delta, rj);
     }
     bool term = !__any_sync(CW_FULL, changed);
     if (!term) {
-      if (act && !skipj) { dmj = nb2_rcp(ajj); bj *= dmj; ajj = ajj * dmj; }
+      if (act && !skipj) { const double dm = nb2_rcp(ajj); bj *= dm; for (int k = 0; k < m; k++) rowj[k] *= dm; ajj = rowj[lane]; }
+      __syncwarp();
       for (int iter = 1; iter < 30; iter++) {
         rj = residual();
         changed = false;
+#pragma unroll 4
         for (int i = 0; i < m; i++) {
-          const int f = __shfl_sync(CW_FULL, fj, i);
-          const double xf = __shfl_sync(CW_FULL, xj, f >= 0 ? f : 0);
-          double delta = 0.0;
-          if (lane == i && !skipj) {
-            const double nx = bj - (rj - ajj * xj);
-            double hi_t = hij, lo_t = loj;
-            if (f >= 0) { hi_t = hij * xf; lo_t = -hi_t; }
-            const double xi = nx > hi_t ? hi_t : (nx < lo_t ? lo_t : nx);
-            if (fabs(xi) > epsDiv) { if (fabs(xi - xj) > relTol * fabs(xi)) changed = true; }
-            delta = xi - xj; xj = xi;
-          }
-          delta = __shfl_sync(CW_FULL, delta, i);
-          if (act) rj += (A[(size_t)lane * ld + i] * dmj) * delta;
+          const double xf = __shfl_sync(CW_FULL, xj, fsrc);
+          const bool own = (lane == i) && !skipj;
+          const double nx = bj - (rj - ajj * xj);
+          const double hi_t = fj >= 0 ? hij * xf : hij, lo_t = fj >= 0 ? -hi_t : loj;
+          const double xi = nx > hi_t ? hi_t : (nx < lo_t ? lo_t : nx);
+          const double dl = own ? xi - xj : 0.0;
+          changed = changed || (own && fabs(xi) > epsDiv && fabs(dl) > relTol * fabs(xi));
+          xj = own ? xi : xj;
+          const double delta = __shfl_sync(CW_FULL, dl, i);
+          if (act) rj = fma(A[(size_t)lane * ld + i], delta, rj);
         }
         term = !__any_sync(CW_FULL, changed);
         if (term) break;

@@ -7,7 +7,7 @@
 #pragma once
 #include "nb2_math.cuh"
 
-#if defined(__CUDACC__) && defined(NB2_CW_INLINE_ALL)
+#if defined(__CUDACC__) && !defined(NB2_CW_NOINLINE)
 #define NB2_HDG __host__ __device__ __forceinline__
 #elif defined(__CUDACC__)
 #define NB2_HDG __host__ __device__ __noinline__
