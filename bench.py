@@ -4,8 +4,11 @@
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--batch B]
   torchrun --nproc-per-node N bench.py --gpus N ...         (one rank per GPU; batch shards, no data-path collective)
 
-Workload (BASELINE.json configs[1]): Atlas humanoid (33 DoF, 28 moving bodies), contact-free, batch 4096 per GPU,
+Headline workload (BASELINE.json configs[1]): Atlas humanoid (33 DoF, 28 moving bodies), contact-free, batch 4096 per GPU,
 one step = forward kernel + backward kernel over the whole batch, synthetic seeded inputs.
+`extra.legs` (every world size; each with its own value / roofline / e2e): configs[2] half-cheetah + ground (4096/GPU), configs[3]
+Atlas + ground contact (8192/GPU), configs[4] 64-step Atlas + ground rollout with backprop through the horizon (1024/GPU, the
+scalar loss all-reduced over NCCL).  Contact legs step FRESH states: x_{t+1} is the engine's own x_t -> step, LCP cache flowing.
 `value`   : worlds*steps / device time, inputs resident in HBM (rotating buffer sets larger than L2).
 `e2e`     : same metric through the C-ABI host entry points (host buffers, H2D/D2H inside the timed region).
 `roofline`: HBM roofline of the dominant kernel from the algorithmic bytes of SURVEY §8(d).
@@ -116,6 +119,103 @@ def _cpu_worker_run(job):
     return time.perf_counter() - t0
 
 
+
+def bind_to_gpu_numa(local_rank):
+    """Pin this rank (and therefore the first-touch placement of its pinned host buffers) to the NUMA node its GPU hangs off:
+    the e2e path streams host memory over PCIe, and 8 unpinned ranks on a 2-socket box cross the inter-socket link."""
+    try:
+        out = subprocess.run(["nvidia-smi", f"--id={local_rank}", "--query-gpu=pci.bus_id", "--format=csv,noheader"],
+                             capture_output=True, text=True, timeout=10).stdout.strip()
+        bdf = out.lower()
+        if bdf.count(":") == 2 and len(bdf.split(":")[0]) == 8:
+            bdf = bdf[4:]  # 00000000:17:00.0 -> 0000:17:00.0
+        node = int(open(f"/sys/bus/pci/devices/{bdf}/numa_node").read().strip())
+        if node < 0:
+            return None
+        cpus = []
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus += list(range(int(lo), int(hi or lo) + 1))
+        os.sched_setaffinity(0, set(cpus))
+        return {"numa_node": node, "cpus": len(cpus)}
+    except Exception:
+        return None
+
+
+def probe_reference():
+    """is the real reference importable (a driver-provided install under baseline/_ref/ or site-packages)?
+    Returns the module or None.  It cannot be built in the authoring container (needs Eigen, ccd, assimp, boost, ...)."""
+    ref_dir = os.path.join(ROOT, "baseline", "_ref")
+    if os.path.isdir(ref_dir) and ref_dir not in sys.path:
+        sys.path.insert(0, ref_dir)
+    try:
+        import nimblephysics  # noqa: F401
+
+        return nimblephysics
+    except Exception:
+        return None
+
+
+def time_real_reference(nimble, seconds=3.0):
+    """forwardPass + backpropState of the real reference on Atlas (python/nimblephysics_benchmarks/atlas_bench.py:12-27), one
+    process; returns world-steps/s or None when its data files are missing."""
+    try:
+        world = nimble.simulation.World()
+        world.setGravity([0, -9.81, 0])
+        base = os.path.dirname(nimble.__file__)
+        atlas = world.loadSkeleton(os.path.join(base, "models", "atlas", "atlas_v3_no_head.urdf"))
+        world.setTimeStep(1e-3)
+        n = world.getNumDofs()
+        rng = np.random.default_rng(0)
+        g = rng.normal(size=2 * n)
+        t0 = time.perf_counter(); k = 0
+        while time.perf_counter() - t0 < seconds:
+            world.setPositions(rng.uniform(-0.3, 0.3, n)); world.setVelocities(rng.uniform(-1, 1, n))
+            snap = nimble.neural.forwardPass(world)
+            lw = nimble.neural.LossGradient(); lw.lossWrtPosition = g[:n]; lw.lossWrtVelocity = g[n:]
+            out = nimble.neural.LossGradient()
+            snap.backprop(world, out, lw)
+            k += 1
+        return k / (time.perf_counter() - t0)
+    except Exception:
+        return None
+
+def _cpu_worker_init_contact(raw_json, name):
+    from oracle.binding import OracleContactWorld
+    import nimblephysics_b200 as nb
+
+    raw = nb.RawModel.from_json(raw_json)
+    _CPU_STATE["craw"], _CPU_STATE["cname"] = raw, name
+    _CPU_STATE["cow"] = OracleContactWorld(raw)
+
+
+def _cpu_worker_run_contact(job):
+    from tests.util import contact_inputs
+
+    seed, lo, hi, total = job
+    raw, ow, name = _CPU_STATE["craw"], _CPU_STATE["cow"], _CPU_STATE["cname"]
+    s, a = contact_inputs(raw, name, total, seed=seed)
+    g = np.random.default_rng(seed).normal(size=s.shape)
+    t0 = time.perf_counter()
+    for w in range(lo, hi):
+        ow.step_contact(s[w].astype(np.float64), a[w].astype(np.float64))
+        ow.backprop_contact(s[w].astype(np.float64), a[w].astype(np.float64), g[w])
+    return time.perf_counter() - t0
+
+
+def cpu_contact_baseline(raw, name, procs, n_worlds):
+    """fp64 oracle port (step with the contact stage + backprop) on `procs` host processes -> world-steps/s"""
+    import multiprocessing as mp
+
+    pool = mp.get_context("fork").Pool(procs, initializer=_cpu_worker_init_contact, initargs=(raw.to_json(), name))
+    per = (n_worlds + procs - 1) // procs
+    jobs = [(77, k * per, min(n_worlds, (k + 1) * per), n_worlds) for k in range(procs) if k * per < n_worlds]
+    pool.map(_cpu_worker_run_contact, jobs[: max(1, len(jobs) // 4)])  # warm-up
+    busy = pool.map(_cpu_worker_run_contact, jobs)
+    pool.close(); pool.join()
+    return n_worlds / (sum(busy) / len(busy)) if busy else None
+
+
 class CpuReference:
     """Times the fp64 oracle (forward + backprop per world) on `procs` host processes (one World each)."""
 
@@ -132,14 +232,171 @@ class CpuReference:
         t0 = time.perf_counter()
         busy = self.pool.map(_cpu_worker_run, jobs)
         wall = time.perf_counter() - t0
-        # input synthesis happens inside the workers before their timers start; the slowest worker bounds the step
-        dt = max(busy)
+        # throughput of the pool = worlds / (sum of busy time / processes): the mean load per core.  (max(busy) measured the one
+        # straggler a fork()ed pool of 128 always has and moved 6x between boxes; the wall clock includes input synthesis.)
+        dt = sum(busy) / max(len(busy), 1)
         return n_worlds / dt, dt, wall
 
     def close(self):
         self.pool.close()
         self.pool.join()
 
+
+
+ALG_BYTES = {"atlas_ground": 4 * (10 * 33 + 3 * 33) + 12 * 24, "half_cheetah": 4 * (10 * 9 + 3 * 9) + 12 * 12}  # 52 n + 12 m_max
+
+
+def contact_leg(nb, torch, name, B, K, W, dev, dist, rank, world_size, peak, cpu_rate):
+    """fwd+bwd world-steps/s of a model with the contact / boxed-LCP stage, stepping FRESH states: x_{t+1} = step(x_t) with the LCP
+    cache flowing, every step back-propagated with a random upstream gradient (configs[2] / configs[3])."""
+    from nimblephysics_b200 import _cabi
+    from tests.util import contact_inputs
+
+    raw = nb.RawModel.load(os.path.join(ROOT, "tests", "golden", "models", f"{name}.json"))
+    world = nb.World.from_raw(raw)
+    s, a = contact_inputs(raw, name, B, seed=7 + rank)
+    x0 = torch.tensor(s, device=dev); at = torch.tensor(a, device=dev); g = torch.randn(B, 2 * raw.ndof, device=dev)
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+
+    def barrier():
+        if dist:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    fwd_ms, bwd_ms = [], []
+
+    def step(x, timed):
+        xi = x.detach().requires_grad_(True); ai = at.detach().requires_grad_(True)
+        if timed:
+            e0, e1, e2 = ev(), ev(), ev(); e0.record()
+        out = nb.timestep(world, xi, ai)
+        if timed:
+            e1.record()
+        out.backward(g)
+        if timed:
+            e2.record(); fwd_ms.append((e0, e1)); bwd_ms.append((e1, e2))
+        return out.detach()
+
+    nb.reset_contact_cache(world)
+    x = x0
+    for _ in range(W):
+        x = step(x, False)
+    barrier()
+    l0 = _cabi.lib().nb2_launch_count()
+    t0, t1 = ev(), ev()
+    t0.record()
+    for _ in range(K):
+        x = step(x, True)
+    t1.record()
+    barrier()
+    ms = t0.elapsed_time(t1)
+    launches = _cabi.lib().nb2_launch_count() - l0
+    c = world._lcp_cache
+    st, mm = c["status"], c["m"]
+    frac = lambda bit: float(((st & bit) > 0).float().mean())
+    stats = {"mean_lcp_rows": float(mm.float().mean()), "frac_shortcircuit": frac(1), "frac_dantzig": frac(2), "frac_pgs": frac(8), "frac_friction_dropped": frac(16)}
+    # sustained: >= 0.5 s of timed work, states re-seeded every 32 steps so that the robot does not leave the contact regime
+    n_sus = max(K, int(np.ceil(500.0 / max(ms / K, 1e-3))))
+    barrier()
+    u0, u1 = ev(), ev()
+    u0.record()
+    for i in range(n_sus):
+        if i % 32 == 0:
+            x = x0; nb.reset_contact_cache(world)
+        x = step(x, False)
+    u1.record()
+    barrier()
+    sus_ms = u0.elapsed_time(u1)
+    sticky = nb.check_contact_status(world)
+    # e2e: the public call with pinned HOST tensors (H2D of state / action, D2H of the next state and of the gradients inside)
+    hs = torch.tensor(s).pin_memory(); ha = torch.tensor(a).pin_memory(); hg = torch.randn(B, 2 * raw.ndof).pin_memory()
+    e2e_steps = max(3, K // 4)
+
+    xi = hs.requires_grad_(True); ai = ha.requires_grad_(True)   # pinned leaves, allocated once (cudaHostAlloc costs milliseconds)
+
+    def e2e_step():
+        xi.grad = None; ai.grad = None
+        nb.timestep(world, xi, ai).backward(hg)
+        return xi.grad
+
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    w0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    barrier()
+    e2e_ms = 1e3 * (time.perf_counter() - w0)
+    t = torch.tensor([ms, sus_ms, e2e_ms], device=dev, dtype=torch.float64)
+    if dist:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, sus_ms, e2e_ms = t.tolist()
+    value = B * world_size * K / (ms * 1e-3)
+    alg = ALG_BYTES[name]
+    achieved = (value / world_size) * alg / 1e9
+    n, na = raw.ndof, len(raw.action_map)
+    leg = {"workload": f"{name}: fwd+bwd step with the contact / boxed-LCP stage, batch={B}/GPU, fresh states (x_t+1 = step(x_t), LCP cache flowing)",
+           "value": value, "unit": UNIT, "n_gpus": world_size, "steps": K, "warmup": W, "ms_per_step": ms / K,
+           "sustained": {"value": B * world_size * n_sus / (sus_ms * 1e-3), "steps": n_sus, "timed_region_s": sus_ms * 1e-3},
+           "kernel_ms": {"forward (build + solve x2 + apply)": float(np.mean([a_.elapsed_time(b_) for a_, b_ in fwd_ms])),
+                         "backward (k_cstep_bwd)": float(np.mean([a_.elapsed_time(b_) for a_, b_ in bwd_ms]))},
+           "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                        "algorithmic_bytes_per_world_step": alg,
+                        "note": "latency / instruction-issue bound fp64 kernels (profiles/r02_*): the HBM fraction is reported as asked"},
+           "e2e": {"value": B * world_size * e2e_steps / (e2e_ms * 1e-3), "unit": UNIT, "steps": e2e_steps,
+                   "h2d_bytes_per_step": int(4 * B * (2 * n + na + 2 * n)), "d2h_bytes_per_step": int(4 * B * (2 * n + 2 * n + na)),
+                   "path": "nimblephysics_b200.timestep() with pinned host tensors (copies inside the timed region)"},
+           "gpu_launches": int(launches), "branch_stats_last_step": stats, "sticky_status": int(sticky)}
+    if cpu_rate is not None:
+        leg["cpu_baseline"] = cpu_rate
+    return leg
+
+
+def rollout_leg(nb, torch, B, T, reps, dev, dist, rank, world_size):
+    """configs[4]: T-step rollout of Atlas + ground, loss = sum |x_T|^2 over ALL worlds (all-reduced over NCCL), backprop to x_0 and
+    every tau_t through the whole horizon.  One host sync per rollout (the sticky contact status)."""
+    from nimblephysics_b200.rollout import sharded_trajectory_loss
+    from tests.util import contact_inputs
+
+    raw = nb.RawModel.load(os.path.join(ROOT, "tests", "golden", "models", "atlas_ground.json"))
+    world = nb.World.from_raw(raw)
+    Bg = B * world_size
+    s, _ = contact_inputs(raw, "atlas_ground", Bg, seed=11)
+    rng = np.random.default_rng(12)
+    na = len(raw.action_map)
+    acts_np = rng.uniform(-20, 20, (T, Bg, na)).astype(np.float32)
+    acts_np[:, :, :6] = 0.0
+    x0 = torch.tensor(s, device=dev)                                  # the GLOBAL batch: sharded_trajectory_loss takes this rank's slice
+    acts = [torch.tensor(acts_np[t], device=dev) for t in range(T)]
+    loss_fn = lambda xT: (xT * xT).sum()
+
+    def run():
+        nb.reset_contact_cache(world)
+        total, gx0, gacts = sharded_trajectory_loss(world, x0, acts, loss_fn, rank, world_size)  # all-reduces the scalar loss (NCCL)
+        return total, gx0
+
+    run(); run()
+    if dist:
+        dist.barrier()
+    torch.cuda.synchronize()
+    best = float("inf")
+    for _ in range(reps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        total, gx0 = run()
+        e1.record()
+        torch.cuda.synchronize()
+        best = min(best, e0.elapsed_time(e1))
+    sticky = nb.check_contact_status(world)
+    t = torch.tensor([best], device=dev, dtype=torch.float64)
+    if dist:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t[0])
+    return {"workload": f"64-step Atlas + ground rollout, backprop through the horizon, batch={B}/GPU (BASELINE configs[4])", "horizon": T,
+            "value": Bg * T / (ms * 1e-3), "unit": UNIT, "n_gpus": world_size, "ms_per_rollout_fwd_bwd": ms,
+            "loss": float(total), "loss_finite": bool(torch.isfinite(total)), "grad_finite": bool(torch.isfinite(gx0).all()),
+            "collective": "all_reduce(SUM) of the scalar loss over %d rank(s)" % world_size, "sticky_status": int(sticky),
+            "peak_memory_gb": torch.cuda.max_memory_allocated(dev) / 2 ** 30}
 
 _REAL_STDOUT = None
 
@@ -191,7 +448,20 @@ def main():
         if rank != 0:
             return
         cores = os.cpu_count() or 1
-        sample = max(cores * 8, 64)
+        sample = max(cores * 32, 256)
+        config = dict(config, precision_inside_kernels="fp64 (CPU)")
+        real = probe_reference()
+        if real is not None:
+            rv = time_real_reference(real, seconds=max(3.0, 0.2 * args.steps))
+            if rv is not None:
+                v = rv * cores
+                emit(({"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+                       "ms_per_step": 1e3 * args.batch / v, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+                       "data": "synthetic", "config": config,
+                       "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "reference",
+                                        "sample": f"nimblephysics forwardPass + backprop on Atlas: {rv:.1f} steps/s on one core x {cores} cores"},
+                       "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+                return
         ref = CpuReference(raw, cores)
         for _ in range(max(args.warmup, 1)):
             ref.run(sample)
@@ -214,6 +484,7 @@ def main():
 
     # ------------------------------------------------------------------ our arm (GPU)
     cpu_baseline = None
+    cpu_contact = {}
     if world_size == 1 and not args.no_extra:  # timed BEFORE CUDA is initialised so the forked workers never inherit a CUDA context
         cores = os.cpu_count() or 1
         sample = max(cores * 16, 128)
@@ -221,11 +492,28 @@ def main():
         v, dt, _ = ref.run(sample)
         ref.close()
         cpu_baseline = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                        "sample": f"{sample} Atlas worlds (fwd + backprop each) in {dt:.2f} s on {cores} host processes; fp64 oracle "
-                                  "(restatement of dart/{dynamics,neural}, not the reference binary)"}
+                        "sample": f"{sample} Atlas worlds (fwd + backprop each), mean busy time {dt:.2f} s per process on {cores} host processes; fp64 "
+                                  "oracle (restatement of dart/{dynamics,neural}, not the reference binary)"}
+        real = probe_reference()
+        if real is not None:
+            rv = time_real_reference(real)
+            if rv is not None:
+                cpu_baseline = {"value": rv * cores, "unit": UNIT, "cores": cores, "kind": "reference",
+                                "sample": f"nimblephysics forwardPass + backprop on Atlas, one process for 3 s ({rv:.1f} steps/s) x {cores} cores "
+                                          "(one World per core like MultiShot.cpp:66-70)", "port_value": v}
+        for cname in ("half_cheetah", "atlas_ground"):
+            try:
+                craw = nb.RawModel.load(os.path.join(ROOT, "tests", "golden", "models", f"{cname}.json"))
+                nw = max(cores * 2, 64)
+                cv = cpu_contact_baseline(craw, cname, cores, nw)
+                cpu_contact[cname] = {"value": cv, "unit": UNIT, "cores": cores, "kind": "port",
+                                      "sample": f"{nw} worlds, step with the contact stage + backprop (dual-number Jacobians), fp64 oracle on {cores} processes"}
+            except Exception as ex:
+                cpu_contact[cname] = {"error": repr(ex)}
     import torch
 
     assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback)"
+    numa = bind_to_gpu_numa(local_rank)  # before the pinned buffers are allocated: they are first-touched on this node
     torch.cuda.set_device(local_rank)
     dist = None
     if world_size > 1:
@@ -284,6 +572,17 @@ def main():
     total_ms = ev[0].elapsed_time(ev[-1])
     fwd_ms = float(np.mean([ev[2 * i].elapsed_time(ev[2 * i + 1]) for i in range(args.steps)]))
     bwd_ms = float(np.mean([ev[2 * i + 1].elapsed_time(ev[2 * i + 2]) for i in range(args.steps)]))
+    # sustained: the same loop for >= 0.5 s of timed work (the K-step region above is a few milliseconds long)
+    n_sus = max(args.steps, int(np.ceil(500.0 / max(total_ms / args.steps, 1e-3))))
+    barrier()
+    s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s0.record()
+    for i in range(n_sus):
+        d = sets[i % nsets]
+        fwd(d); bwd(d)
+    s1.record()
+    barrier()
+    sus_ms = s0.elapsed_time(s1)
     time.sleep(0.2)
     clocks = sampler.finish()
 
@@ -307,51 +606,26 @@ def main():
     barrier()
     e2e_ms = 1e3 * (time.perf_counter() - t0)
 
-    # ---- extra (not the headline metric): forward step WITH the contact / boxed-LCP stage, configs[2] and configs[3] shapes
-    extra = {}
-    if world_size == 1 and not args.no_extra:
-        from tests.util import contact_inputs
-
-        for cname, label in (("atlas_ground", "atlas_ground_contact_fwd"), ("half_cheetah", "half_cheetah_contact_fwd")):
+    # ---- the other BASELINE configs, at EVERY world size (the batch shards; the rollout leg all-reduces its loss over NCCL)
+    extra = {"legs": {}}
+    if numa is not None:
+        extra["numa_binding"] = numa
+    if not args.no_extra:
+        peak_hbm = 6650.0
+        try:
+            peak_hbm = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("hbm_gbs", peak_hbm))
+        except Exception:
+            pass
+        for cname, cB, label in (("half_cheetah", 4096, "half_cheetah_ground_fwd_bwd (configs[2])"), ("atlas_ground", 8192, "atlas_ground_fwd_bwd (configs[3])")):
             try:
-                craw = nb.RawModel.load(os.path.join(ROOT, "tests", "golden", "models", f"{cname}.json"))
-                cworld = nb.World.from_raw(craw)
-                cs, ca = contact_inputs(craw, cname, B, seed=7)
-                cst, cat = torch.tensor(cs, device=dev), torch.tensor(ca, device=dev)
-                with torch.no_grad():
-                    for _ in range(3):
-                        nb.timestep(cworld, cst, cat)
-                    torch.cuda.synchronize()
-                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                    ksteps = 10
-                    e0.record()
-                    for _ in range(ksteps):
-                        nb.timestep(cworld, cst, cat)
-                    e1.record()
-                    torch.cuda.synchronize()
-                # fwd + bwd through the autograd boundary (contact adjoint)
-                csg, cag = cst.clone().requires_grad_(True), cat.clone().requires_grad_(True)
-                gg = torch.randn_like(cst)
-                for _ in range(2):
-                    nb.timestep(cworld, csg, cag).backward(gg)
-                torch.cuda.synchronize()
-                f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                kfb = 15
-                f0.record()
-                for _ in range(kfb):
-                    nb.timestep(cworld, csg, cag).backward(gg)
-                f1.record()
-                torch.cuda.synchronize()
-                cc = nb.contact_cache(cworld, B, dev)
-                extra[label] = {"world_steps_per_s": B * ksteps / (e0.elapsed_time(e1) * 1e-3), "batch": B,
-                                "fwd_bwd_world_steps_per_s": B * kfb / (f0.elapsed_time(f1) * 1e-3),
-                                "mean_contacts": float(cc["nc"].float().mean()), "mean_lcp_rows": float(cc["m"].float().mean()),
-                                "frac_shortcircuit": float(((cc["status"] & 1) > 0).float().mean()),
-                                "frac_dantzig": float(((cc["status"] & 2) > 0).float().mean()),
-                                "frac_pgs_fallback": float(((cc["status"] & 8) > 0).float().mean()),
-                                "note": "forward only (fp64 ABA + contact/LCP kernels); same state re-stepped, warm-started LCP cache"}
-            except Exception as ex:  # never let the extra leg break the headline line
-                extra[label] = {"error": repr(ex)}
+                extra["legs"][label] = contact_leg(nb, torch, cname, cB, max(args.steps, 8), max(args.warmup, 3), dev, dist, rank, world_size, peak_hbm,
+                                                   cpu_contact.get(cname))
+            except Exception as ex:  # never let a leg break the headline line
+                extra["legs"][label] = {"error": repr(ex)}
+        try:
+            extra["legs"]["atlas_ground_rollout64 (configs[4])"] = rollout_leg(nb, torch, 1024, 64, 2, dev, dist, rank, world_size)
+        except Exception as ex:
+            extra["legs"]["atlas_ground_rollout64 (configs[4])"] = {"error": repr(ex)}
         # contact-free 64-step rollout through the fused entry points (nb2_rollout_forward / nb2_rollout_backward)
         try:
             from nimblephysics_b200.rollout import rollout_fused
@@ -359,7 +633,7 @@ def main():
             fworld = nb.World.from_raw(raw)
             fworld._contacts_disabled = True
             Tf = 64
-            rngf = np.random.default_rng(21)
+            rngf = np.random.default_rng(21 + rank)
             uf = rngf.uniform(-20, 20, (Tf, B, na)).astype(np.float32)
             uf[:, :, :6] = 0.0
             xf0 = sets[0]["s"].clone().requires_grad_(True)
@@ -370,62 +644,26 @@ def main():
                 (tr[-1] * tr[-1]).sum().backward()
 
             runf()
-            torch.cuda.synchronize()
+            barrier()
             q0, q1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             q0.record()
             for _ in range(3):
                 runf()
             q1.record()
-            torch.cuda.synchronize()
-            msf = q0.elapsed_time(q1) / 3
-            extra["atlas_rollout64_contact_free"] = {"batch": B, "horizon": Tf, "ms_per_rollout_fwd_bwd": msf,
-                                                     "world_steps_per_s": B * Tf / (msf * 1e-3),
-                                                     "note": "one C-ABI call per direction; trajectory and saved streams stay on the device"}
+            barrier()
+            tq = torch.tensor([q0.elapsed_time(q1) / 3], device=dev, dtype=torch.float64)
+            if dist:
+                dist.all_reduce(tq, op=dist.ReduceOp.MAX)
+            msf = float(tq[0])
+            extra["legs"]["atlas_rollout64_contact_free"] = {"batch_per_gpu": B, "horizon": Tf, "ms_per_rollout_fwd_bwd": msf, "n_gpus": world_size,
+                                                             "value": B * world_size * Tf / (msf * 1e-3), "unit": UNIT}
         except Exception as ex:
-            extra["atlas_rollout64_contact_free"] = {"error": repr(ex)}
-        # BASELINE configs[4] shape at reduced batch: 64-step rollout of Atlas + ground, backprop through the full horizon
-        try:
-            from nimblephysics_b200.rollout import rollout
+            extra["legs"]["atlas_rollout64_contact_free"] = {"error": repr(ex)}
 
-            craw = nb.RawModel.load(os.path.join(ROOT, "tests", "golden", "models", "atlas_ground.json"))
-            cworld = nb.World.from_raw(craw)
-            Br, T = 1024, 64
-            cs, _ = contact_inputs(craw, "atlas_ground", Br, seed=11)
-            rng = np.random.default_rng(12)
-            na_c = len(craw.action_map)
-            acts_np = rng.uniform(-20, 20, (T, Br, na_c)).astype(np.float32)
-            acts_np[:, :, :6] = 0.0
-            x0 = torch.tensor(cs, device=dev, requires_grad=True)
-            acts = [torch.tensor(acts_np[t], device=dev, requires_grad=True) for t in range(T)]
-
-            def run():
-                nb.reset_contact_cache(cworld)
-                xT = rollout(cworld, x0, acts)
-                loss = (xT * xT).sum()
-                loss.backward()
-                return loss
-
-            run(); run()  # warm-up: the second run already finds its 1.3 GB of per-step records in torch's allocator cache
-            torch.cuda.synchronize()
-            ms = float("inf")
-            for _ in range(2):
-                r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                r0.record()
-                loss = run()
-                r1.record()
-                torch.cuda.synchronize()
-                ms = min(ms, r0.elapsed_time(r1))
-            extra["atlas_ground_rollout64"] = {"batch": Br, "horizon": T, "ms_per_rollout_fwd_bwd": ms,
-                                               "world_steps_per_s": Br * T / (ms * 1e-3), "loss_finite": bool(torch.isfinite(loss)),
-                                               "grad_finite": bool(torch.isfinite(x0.grad).all()),
-                                               "note": "Atlas + ground contact, loss = |x_T|^2, backprop to x_0 and every tau_t (configs[4] at 1024 worlds/GPU)"}
-        except Exception as ex:
-            extra["atlas_ground_rollout64"] = {"error": repr(ex)}
-
-    t_total = torch.tensor([total_ms, e2e_ms], device=dev, dtype=torch.float64)
+    t_total = torch.tensor([total_ms, e2e_ms, sus_ms], device=dev, dtype=torch.float64)
     if dist:
         dist.all_reduce(t_total, op=dist.ReduceOp.MAX)
-    total_ms, e2e_ms = t_total.tolist()
+    total_ms, e2e_ms, sus_ms = t_total.tolist()
     value = B * world_size * args.steps / (total_ms * 1e-3)
     e2e_value = B * world_size * e2e_steps / (e2e_ms * 1e-3)
 
@@ -456,6 +694,7 @@ def main():
             "e2e": {"value": e2e_value, "unit": UNIT,
                     "h2d_bytes_per_step": int(4 * B * (2 * n + na + 2 * n)), "d2h_bytes_per_step": int(4 * B * (2 * n + 2 * n + na)),
                     "steps": e2e_steps, "path": "nb2_step_forward_host + nb2_step_backward_host (pinned host buffers)"},
+            "sustained": {"value": B * world_size * n_sus / (sus_ms * 1e-3), "steps": n_sus, "timed_region_s": sus_ms * 1e-3},
             "gpu_launches": int(launches), "clocks": clocks, "extra": extra,
         }
         if cpu_baseline is not None:

@@ -160,6 +160,24 @@ int nb2_step_backward_contact(const nb2_model* m, int B, const float* state, con
 int nb2_model_set_contact_capacity(nb2_model* m, int max_contacts_in_shared_memory);
 int nb2_model_contact_capacity(const nb2_model* m);
 
+/* Pointer-style forward dynamics q-ddot = FD(q, q-dot, tau) of B worlds (ABA, no integration, no contacts): the batched counterpart of
+ * SimpleFeatherstone::forwardDynamics(s_t* pos, s_t* vel, s_t* force, s_t* accel) (dart/dynamics/SimpleFeatherstone.hpp:61-65,
+ * SimpleFeatherstone.cpp:26-138) and of Skeleton::computeForwardDynamics + getAccelerations.  fp64 device arrays [B, ndof]; the model's
+ * gravity applies (the reference's test zeroes it, unittests/comprehensive/test_SimpleFeatherstone.cpp:34).  Requires the default action
+ * space (every dof). */
+int nb2_forward_dynamics(const nb2_model* m, int B, const double* pos, const double* vel, const double* force, double* accel, void* stream);
+
+/* Batched boxed-LCP solves on the device: B independent problems, one warp each — the reference's pointer-style lower boundary
+ * BoxedLcpSolver::solve(n, A, x, b, nub, lo, hi, findex, earlyTermination) (dart/constraint/BoxedLcpSolver.hpp:125-135) and the
+ * solve chain of BoxedLcpConstraintSolver::solveLcp (BoxedLcpConstraintSolver.cpp:352-789).  Device pointers; problem w has dimension
+ * m[w] <= mcap <= NB2_MAX_ROWS and sits at A[w][mcap][mcap] (row-major, symmetric), b / lo / hi / findex / x0 / x / labels [w][mcap].
+ *   mode 0: Dantzig only (dSolveLCP, dart/external/odelcpsolver/lcp.cpp:780-1114); status[w] = 1 solved, 0 early termination, -1 cap
+ *   mode 1: warm start (x0 or guessSolution) -> short-circuit -> Dantzig -> cfm + PGS -> friction drop -> classification;
+ *           status[w] = NB2_ST_* bits, labels = ConstraintMapping per row.   x0 may be NULL. */
+int nb2_lcp_solve_batch(int B, int mcap, int mode, int early_termination, double fallback_cfm, const int32_t* m, const double* A, const double* b,
+                        const double* lo, const double* hi, const int32_t* findex, const double* x0, double* x, int32_t* labels, int32_t* status,
+                        void* stream);
+
 /* T-step rollout of a contact-free world and its reverse sweep — SingleShot::getSnapshots (dart/trajectory/SingleShot.cpp:635-686)
  * and SingleShot::backpropGradientWrt (:539-631).  All buffers are device memory, fp32, time-major:
  *   states  [T+1, B, 2n]: states[0] = x_0 on entry, the forward fills states[1..T];  actions [T, B, na];

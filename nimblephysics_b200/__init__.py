@@ -10,3 +10,4 @@ from .rollout import rollout, rollout_fused, shard_range, shard_batch, allreduce
 
 __all__ = ["World", "Skeleton", "BodyNode", "Joint", "Isometry3", "BoxShape", "SphereShape", "CapsuleShape",
            "loadWorld", "load_skeleton", "timestep", "TimestepLayer", "rollout", "rollout_fused", "DeviceModel", "device_model_for", "RawModel", "CanonModel", "flatten_world", "compile_model"]
+from .lcp import solve_boxed_lcp_batch

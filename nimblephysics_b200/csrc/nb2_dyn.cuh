@@ -689,7 +689,7 @@ NB2_HD void bwd_B3(const Nb2ModelDev<R>& M, R* scr, const float* st, const R* sv
     const V6<R> Alam = A - Sa - ad(V, Sv), Vlam = V - Sv, Wlam = W - Sl;
     V6<R> c6 = zero6<R>() - (crf(Alam, Abar) + crf(Vlam, Vbar) + crf(Wlam, f));
     if (CONTACT && cd.active) {
-      // kinematic-chain part of d/dq [J_r(q) w] and [J_r(q) v+], and the contact-frame part (wrench Gc), see nb2_contact.cuh
+      // kinematic-chain part of d/dq [J_r(q) w] and [J_r(q) v+], and the contact-frame part (wrench Gc), see nb2_cw.cuh
       V6<R> Upl; { const auto u6 = cd.Uplus + 6 * i; Upl.a = mk3<R>((R)u6[0], (R)u6[1], (R)u6[2]); Upl.l = mk3<R>((R)u6[3], (R)u6[4], (R)u6[5]); }
       V6<R> Svp;
       if (jt != NB2_JT_FREE) Svp = S_times<R>(jt, (R)cd.vplus[o]);

@@ -414,6 +414,61 @@ k_cstep_bwd(const __grid_constant__ Nb2ModelDev<double> M, const __grid_constant
   CW_PROF(30);
 }
 
+// ---- pointer-style forward dynamics (row a5: SimpleFeatherstone::forwardDynamics(pos, vel, force, accel), dynamics/SimpleFeatherstone.hpp:61-65):
+// fp64 in, fp64 out, one thread per world with its scratch in global memory — a convenience / parity entry, not a hot path.
+__global__ void __launch_bounds__(64)
+k_forward_dynamics(const __grid_constant__ Nb2ModelDev<double> M, int B, int words, const double* __restrict__ pos, const double* __restrict__ vel,
+                   const double* __restrict__ force, double* __restrict__ accel, double* __restrict__ scratch) {
+  const int w = blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= B) return;
+  double* scr = scratch + (size_t)w * words;
+  const nb2::FwdLayout L = nb2::fwd_layout(M.nb, M.ndof, M.nslots, M.nfree);
+  const int n = M.ndof;
+  for (int d = 0; d < n; d++) { scr[L.oQ + d] = pos[(size_t)w * n + d]; scr[L.oV + d] = vel[(size_t)w * n + d]; }
+  for (int a = 0; a < M.na; a++) scr[L.oAct + a] = force[(size_t)w * n + M.action_map[a]];
+  for (int sg = 1; sg < NB2_FWD_STAGES - 1; sg++)
+    for (int lane = 0; lane < M.lanes; lane++) nb2::world_forward_stage<double, 1>(M, scr, nullptr, 1, false, lane, sg);
+  // pass 3 left v + dt * qdd in the velocity slots
+  for (int d = 0; d < n; d++) accel[(size_t)w * n + d] = (scr[L.oV + d] - vel[(size_t)w * n + d]) / M.dt;
+}
+
+// ---- batched boxed-LCP entry (the reference's pointer-style lower boundary: BoxedLcpSolver::solve, constraint/BoxedLcpSolver.hpp:125-135,
+// and BoxedLcpConstraintSolver::solveLcp): one warp per problem, the same device code the contact stage runs.
+//   mode 0: Dantzig only (DantzigBoxedLcpSolver::solve -> dSolveLCP);  mode 1: the whole solve chain with classification
+__global__ void __launch_bounds__(32)
+k_lcp_batch(nb2::cw::Dims d, int B, int mcap, double cfm, int mode, int early_termination, const int* __restrict__ ms, const double* __restrict__ A,
+            const double* __restrict__ b, const double* __restrict__ lo, const double* __restrict__ hi, const int* __restrict__ findex,
+            const double* __restrict__ x0, double* __restrict__ x, int* __restrict__ labels, int* __restrict__ status) {
+  extern __shared__ __align__(16) unsigned char nb2_smem[];
+  const int w = blockIdx.x, lane = threadIdx.x & 31;
+  if (w >= B) return;
+  nb2::cw::Ws* wsm = reinterpret_cast<nb2::cw::Ws*>(nb2_smem);
+  double* wsb = reinterpret_cast<double*>(wsm) + NB2_WS_DESC_DOUBLES;
+  if (lane == 0) *wsm = nb2::cw::carve(wsb, d);
+  __syncwarp();
+  const nb2::cw::Ws ws = *wsm;
+  const int m = ms[w], ld = m | 1;
+  const size_t ov = (size_t)w * mcap;
+  for (int e = lane; e < m * m; e += 32) { const int r = e / m, c = e - r * m; ws.A[(size_t)r * ld + c] = A[((size_t)w * mcap + r) * mcap + c]; }
+  for (int i = lane; i < m; i += 32) { ws.b[i] = b[ov + i]; ws.lo[i] = lo[ov + i]; ws.hi[i] = hi[ov + i]; ws.findex[i] = findex[ov + i]; }
+  __syncwarp();
+  int st;
+  if (mode == 0) {
+    nb2::cw::DzWork W;
+    for (int e = lane; e < m * ld; e += 32) ws.M1[e] = ws.A[e];
+    for (int i = lane; i < m; i += 32) { ws.v1[i] = ws.b[i]; ws.v2[i] = ws.lo[i]; ws.v3[i] = ws.hi[i]; ws.i1[i] = ws.findex[i]; }
+    __syncwarp();
+    W.A = ws.M1; W.ld = ld; W.x = ws.x; W.b = ws.v1; W.w = ws.v5; W.lo = ws.v2; W.hi = ws.v3; W.L = ws.M2; W.d = ws.v6; W.delta_x = ws.v7; W.delta_w = ws.v8;
+    W.Dell = ws.v9; W.ell = ws.v10; W.tmp = ws.v11; W.findex = ws.i1; W.p = ws.clampIdx; W.C = ws.ubIdx; W.state = ws.i4;
+    st = nb2::cw::dantzig_solve(W, m, early_termination != 0);
+  } else {
+    st = nb2::cw::lcp_chain(m, ws, *wsm, cfm, x0 ? x0 + ov : nullptr);
+  }
+  __syncwarp();
+  for (int i = lane; i < m; i += 32) { x[ov + i] = ws.x[i]; if (labels) labels[ov + i] = (mode == 1) ? ws.mapping[i] : 0; }
+  if (lane == 0) status[w] = st;
+}
+
 constexpr int kMaxSmem = 227 * 1024;
 
 }  // namespace
@@ -890,6 +945,38 @@ int nb2_cw_profile_read(unsigned long long* out64, int reset) {
 #else
   (void)out64; (void)reset; return 0;
 #endif
+}
+int nb2_forward_dynamics(const nb2_model* cm, int B, const double* pos, const double* vel, const double* force, double* accel, void* stream) {
+  nb2_model* m = const_cast<nb2_model*>(cm);
+  if (!m || B < 0 || !pos || !vel || !force || !accel) { g_err = "nb2_forward_dynamics: bad argument"; return NB2_ERR_INVALID; }
+  if (m->md.na != m->md.ndof) { g_err = "nb2_forward_dynamics: the action space must cover every dof (force is given per dof)"; return NB2_ERR_INVALID; }
+  if (B == 0) return NB2_OK;
+  const nb2_variant& v = m->variants[0];
+  double* scratch = nullptr;
+  cudaStream_t st = (cudaStream_t)stream;
+  NB2_CUDA(cudaMallocAsync((void**)&scratch, (size_t)B * v.fwd_words * sizeof(double), st));
+  k_forward_dynamics<<<(B + 63) / 64, 64, 0, st>>>(v.md, B, v.fwd_words, pos, vel, force, accel, scratch);
+  g_launches++;
+  NB2_CUDA(cudaGetLastError());
+  NB2_CUDA(cudaFreeAsync(scratch, st));
+  return NB2_OK;
+}
+int nb2_lcp_solve_batch(int B, int mcap, int mode, int early_termination, double fallback_cfm, const int32_t* m, const double* A, const double* b,
+                        const double* lo, const double* hi, const int32_t* findex, const double* x0, double* x, int32_t* labels, int32_t* status,
+                        void* stream) {
+  if (B < 0 || mcap < 1 || mcap > NB2_MAX_ROWS || !m || !A || !b || !lo || !hi || !findex || !x || !status || (mode != 0 && mode != 1)) {
+    g_err = "nb2_lcp_solve_batch: bad argument (1 <= mcap <= NB2_MAX_ROWS)"; return NB2_ERR_INVALID;
+  }
+  if (B == 0) return NB2_OK;
+  const nb2::cw::Dims d = nb2::cw::make_dims(1, 1, 0, (mcap + 2) / 3 + 1, mcap < 3 ? 3 : mcap, 1, 1, 0, NB2_WS_SOLVE);
+  const size_t smem = (NB2_WS_DESC_DOUBLES + nb2::cw::ws_doubles(d)) * sizeof(double);
+  static bool attr_done[64] = {};
+  int rc = cstep_smem_attr(k_lcp_batch, smem, attr_done);
+  if (rc) return rc;
+  k_lcp_batch<<<B, 32, smem, (cudaStream_t)stream>>>(d, B, mcap, fallback_cfm, mode, early_termination, m, A, b, lo, hi, findex, x0, x, labels, status);
+  g_launches++;
+  NB2_CUDA(cudaGetLastError());
+  return NB2_OK;
 }
 int nb2_model_ndof(const nb2_model* m) { return m ? m->mf.ndof : -1; }
 int nb2_model_na(const nb2_model* m) { return m ? m->mf.na : -1; }

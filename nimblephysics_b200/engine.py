@@ -116,6 +116,20 @@ class DeviceModel:
         _cabi.check(_cabi.lib().nb2_rollout_backward(self.handle, B, T, states_ptr, actions_ptr, saved_ptr, gstates_ptr,
                                                      gactions_ptr, precision, stream))
 
+    def forward_dynamics(self, pos, vel, force):
+        """q-ddot [B, n] (float64 CUDA tensors in and out): pointer-style ABA, no integration, no contact stage
+        (SimpleFeatherstone::forwardDynamics / Skeleton::computeForwardDynamics + getAccelerations)."""
+        import torch
+
+        dev = pos.device
+        f = lambda t: t.to(device=dev, dtype=torch.float64).contiguous()
+        pos, vel, force = f(pos), f(vel), f(force)
+        acc = torch.empty_like(pos)
+        with torch.cuda.device(dev):
+            _cabi.check(_cabi.lib().nb2_forward_dynamics(self.handle, pos.shape[0], pos.data_ptr(), vel.data_ptr(), force.data_ptr(), acc.data_ptr(),
+                                                         torch.cuda.current_stream().cuda_stream))
+        return acc
+
     def contact_workspace_bytes(self, B):
         return int(_cabi.lib().nb2_contact_workspace_bytes(self.handle, B))
 
@@ -169,13 +183,25 @@ def _has_possible_contacts(raw: RawModel) -> bool:
 
 
 def device_model_for(world) -> DeviceModel:
-    """Lazily (re)build the device model of a World; cached until the World is edited."""
+    """Lazily (re)build the device model of a World.  The cache is validated against the object graph: any setter of a BodyNode / Joint /
+    Skeleton / ShapeNode bumps a global edit epoch (world.py); a World whose model was built at an older epoch is re-flattened and,
+    when its description really changed, rebuilt (with its LCP cache dropped)."""
+    import hashlib
+
+    from .world import edit_epoch
+
     dm = getattr(world, "_device_model", None)
-    if dm is not None:
+    if dm is not None and getattr(world, "_dm_epoch", -1) == edit_epoch():
         return dm
     raw = flatten_world(world)
+    h = hashlib.sha1(raw.to_json().encode()).hexdigest() + ("|nc" if getattr(world, "_contacts_disabled", False) else "")
+    if dm is not None and getattr(world, "_dm_hash", None) == h:
+        world._dm_epoch = edit_epoch()
+        return dm
     world._raw_model = raw
     # contact-free step requested explicitly -> contacts=False
     dm = DeviceModel.from_raw(raw, contacts=not getattr(world, "_contacts_disabled", False))
     world._device_model = dm
+    world._dm_hash, world._dm_epoch = h, edit_epoch()
+    world._lcp_cache = None
     return dm

@@ -124,4 +124,8 @@ def sharded_trajectory_loss(world, state0: torch.Tensor, actions: Sequence[torch
     loss = loss_fn(x)
     loss.backward()
     total = allreduce_sum_(loss.detach().clone())
+    if step is timestep:
+        from .timestep import check_contact_status
+
+        check_contact_status(world)  # ONE host sync per rollout: worlds that dropped contacts / could not be back-propagated raise here
     return total, x0.grad, [a.grad for a in acts]

@@ -106,7 +106,7 @@ class TimestepLayer(torch.autograd.Function):
             ga = torch.empty_like(ad)
             stream = torch.cuda.current_stream().cuda_stream
             if ctx.contact:
-                # adjoint of the contact stage with the classification frozen at the forward solution (csrc/nb2_contact.cuh)
+                # adjoint of the contact stage with the classification frozen at the forward solution (csrc/nb2_cw.cuh contact_backward)
                 gi = torch.empty((10 * dm.cm.nb, ctx.B), dtype=torch.float32, device=dev) if ctx.mass_grad else None
                 # worlds that cannot be back-propagated get NaN gradients and bit 2048 in the world's sticky status word: no host
                 # sync here — check_contact_status(world) reports them (rollout() / sharded_trajectory_loss() call it once)

@@ -106,6 +106,20 @@ def CapsuleShape(radius, height):
     return Shape(SHAPE_CAPSULE, [radius, height])
 
 
+# Every setter of the object graph bumps this counter.  device_model_for() re-flattens a World whose cached device model was built at
+# an older epoch and rebuilds it when the flattened description really changed (domain randomisation / system identification edit
+# masses, damping, friction between rollouts: the GPU model must follow).
+_EDIT_EPOCH = [0]
+
+
+def _edited():
+    _EDIT_EPOCH[0] += 1
+
+
+def edit_epoch() -> int:
+    return _EDIT_EPOCH[0]
+
+
 class ShapeNode:
     def __init__(self, shape: Shape, T_local: Optional[np.ndarray] = None, collidable=True):
         self.shape = shape
@@ -118,6 +132,7 @@ class ShapeNode:
         return self
 
     def createCollisionAspect(self):
+        _edited()
         self.has_collision = True
         return self
 
@@ -125,6 +140,7 @@ class ShapeNode:
         return None
 
     def setRelativeTransform(self, T):
+        _edited()
         self.T_local = _as_T(T)
 
 
@@ -148,6 +164,7 @@ class BodyNode:
     def setMass(self, m):
         """Inertia::setMass with preserveDimsAndEuler=true (dart/dynamics/Inertia.cpp:157-177): the body keeps its
         dimensions, so a non-zero moment scales with the mass."""
+        _edited()
         m = float(m)
         if m == self.mass:
             return
@@ -159,18 +176,23 @@ class BodyNode:
         return self.mass
 
     def setLocalCOM(self, c):
+        _edited()
         self.com = np.asarray(c, dtype=np.float64).copy()
 
     def setMomentOfInertia(self, ixx, iyy, izz, ixy=0.0, ixz=0.0, iyz=0.0):
+        _edited()
         self.moment = np.array([[ixx, ixy, ixz], [ixy, iyy, iyz], [ixz, iyz, izz]], dtype=np.float64)
 
     def setFrictionCoeff(self, mu):
+        _edited()
         self.friction = float(mu)
 
     def setRestitutionCoeff(self, e):
+        _edited()
         self.restitution = float(e)
 
     def createShapeNode(self, shape: Shape) -> ShapeNode:
+        _edited()
         sn = ShapeNode(shape)
         self.shapes.append(sn)
         return sn
@@ -201,40 +223,52 @@ class Joint:
 
     # --- subset of the reference Joint API used by example scripts ---
     def setAxis(self, a):
+        _edited()
         a = np.asarray(a, dtype=np.float64)
         self.axis = a / np.linalg.norm(a)  # reference normalises (RevoluteJoint.cpp setAxis)
 
     def setTransformFromParentBodyNode(self, T):
+        _edited()
         self.T_pj = _as_T(T)
 
     def setTransformFromChildBodyNode(self, T):
+        _edited()
         self.T_cj = _as_T(T)
 
     def setPositionUpperLimit(self, i, v):
+        _edited()
         self.pos_hi[i] = v
 
     def setPositionLowerLimit(self, i, v):
+        _edited()
         self.pos_lo[i] = v
 
     def setVelocityUpperLimit(self, i, v):
+        _edited()
         self.vel_hi[i] = v
 
     def setVelocityLowerLimit(self, i, v):
+        _edited()
         self.vel_lo[i] = v
 
     def setControlForceUpperLimit(self, i, v):
+        _edited()
         self.force_hi[i] = v
 
     def setControlForceLowerLimit(self, i, v):
+        _edited()
         self.force_lo[i] = v
 
     def setDampingCoefficient(self, i, v):
+        _edited()
         self.damping[i] = v
 
     def setSpringStiffness(self, i, v):
+        _edited()
         self.spring[i] = v
 
     def setRestPosition(self, i, v):
+        _edited()
         self.rest[i] = v
 
     def getNumDofs(self):
@@ -248,12 +282,14 @@ class Skeleton:
         self.mobile = True
 
     def setMobile(self, m: bool):
+        _edited()
         self.mobile = bool(m)
 
     def isMobile(self):
         return self.mobile
 
     def _create(self, jtype: int, parent: Optional[BodyNode], jname=None, bname=None):
+        _edited()
         j = Joint(jtype, jname or f"joint_{len(self.bodies)}")
         b = BodyNode(bname or f"body_{len(self.bodies)}")
         b.parent_joint, b.parent_body, b.skeleton = j, parent, self
@@ -460,6 +496,7 @@ class World:
 
     # ----- structure -----
     def _touch(self):
+        _edited()
         self._version += 1
         self._device_model = None
 

@@ -1,23 +1,17 @@
-// Boxed Dantzig LCP pivoting solver — restatement of the reference's vendored ODE solver
+// TEST INFRASTRUCTURE ONLY — serial restatement of the reference's vendored ODE boxed Dantzig LCP solver, used by the oracle.
 //   dSolveLCP   dart/external/odelcpsolver/lcp.cpp:780-1114   (driver loop, ratio test, cmd 1..6)
-//   dLCP        lcp.cpp:362-775 (index sets C / N kept contiguous by physically permuting the problem,
-//               friction rows moved to the end :491-501, lo/hi of friction rows fixed when the first one is
-//               reached :856-873)
-// What is restated is the ALGORITHM and its pivoting/tie-breaking order (same physical permutation of the
-// problem, same loop orders, same strict '<' comparisons), so that the same index sets are reached.  The dense
-// linear algebra is new: A is kept as a full symmetric matrix (the reference touches only one triangle through
-// row pointers); rows are appended to the L D L^T factor of A[C,C] incrementally (same recurrence as ODE), and the
-// factor is rebuilt from scratch when an index LEAVES C instead of ODE's dLDLTRemove rank-one downdate — identical in
-// exact arithmetic, agreeing to rounding in floating point.
-// This one header is compiled both into the CUDA library and into the test oracle; sharing it is safe because it is
-// pinned against the REAL reference code: tests/test_lcp.py compares it with dSolveLCP compiled from
-// /root/reference (oracle/_ref/libodelcp.so) on random and literal LCP instances.
-//
-// One LCP is solved by one thread; all storage is caller-provided and strided (ST) like the rest of the kernels.
+//   dLCP        lcp.cpp:362-775 (index sets C / N kept contiguous by physically permuting the problem, friction rows moved to the
+//               end :491-501, lo/hi of friction rows fixed when the first one is reached :856-873)
+// Pinned against the REAL reference code: tests/test_lcp.py compares it with dSolveLCP compiled from /root/reference
+// (oracle/_ref/libodelcp.so) on random and literal LCP instances.  The product has its OWN, warp-cooperative implementation
+// (nimblephysics_b200/csrc/nb2_cw.cuh dantzig_solve) which is compared against this one through the solve chain — the two share
+// no code.  Dense linear algebra: full symmetric A, L D L^T of A[C,C] appended row by row, rebuilt when an index leaves C.
 #pragma once
 #include <math.h>
 
-#include "nb2_math.cuh"
+#ifndef NB2_HD
+#define NB2_HD inline
+#endif
 
 namespace nb2 {
 

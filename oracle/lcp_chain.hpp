@@ -5,7 +5,7 @@
 //   PgsBoxedLcpSolver::solve                  dart/constraint/PgsBoxedLcpSolver.cpp:79-278 (defaults PgsBoxedLcpSolver.hpp:55-60)
 //   ConstrainedGroupGradientMatrices::{constructMatrices, opportunisticallyStandardizeResults}
 //                                             dart/neural/ConstrainedGroupGradientMatrices.cpp:482-872, 218-339
-//   Dantzig: nimblephysics_b200/csrc/nb2_dantzig.cuh (pinned against the reference's own dSolveLCP, tests/test_lcp.py)
+//   Dantzig: oracle/dantzig_serial.hpp (serial restatement, pinned against the reference's own dSolveLCP, tests/test_lcp.py)
 // Eigen's completeOrthogonalDecomposition().solve (third-party, not under /root/reference) is restated as the
 // minimum-norm least-squares solution computed from a one-sided Jacobi SVD with Eigen's default rank threshold
 // (eps * max(rows, cols) relative to the largest singular value / pivot).
@@ -14,7 +14,7 @@
 #include <cmath>
 #include <vector>
 
-#include "../nimblephysics_b200/csrc/nb2_dantzig.cuh"
+#include "dantzig_serial.hpp"
 
 namespace orc {
 

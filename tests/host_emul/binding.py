@@ -17,7 +17,7 @@ def lib():
     if _LIB is None:
         so = os.path.join(_HERE, "libemul.so")
         srcs = [os.path.join(_HERE, "emul.cpp")] + [os.path.join(_ROOT, "nimblephysics_b200", "csrc", f)
-                                                      for f in ("nb2_dyn.cuh", "nb2_math.cuh", "nb2_model.h", "nb2_host_model.h", "nb2_contact.cuh", "nb2_dantzig.cuh", "nb2_cw.cuh", "nb2_geom.cuh")]
+                                                      for f in ("nb2_dyn.cuh", "nb2_math.cuh", "nb2_model.h", "nb2_host_model.h", "nb2_cw.cuh", "nb2_geom.cuh")]
         if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(s) for s in srcs):
             subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-Wno-unknown-pragmas", "-o", so,
                                    os.path.join(_HERE, "emul.cpp")])

@@ -1,4 +1,4 @@
-"""Contact / boxed-LCP stage: the device code (csrc/nb2_contact.cuh, compiled for the host by tests/host_emul) vs the
+"""Contact / boxed-LCP stage: the device code (csrc/nb2_cw.cuh, compiled for the host by tests/host_emul) vs the
 fp64 oracle over several chained steps with the LCP cache flowing from step to step.
 Bar: contact set, LCP dimension, per-row ConstraintMapping labels and the solver-branch status word are BIT-EXACT;
 impulses and next state within 1e-4 relative (inputs are fp32 rows on the device side)."""
@@ -95,7 +95,7 @@ def _check_backward(ob, raw, S, A_, tol=1e-5):
 
 
 def test_contact_backward_adjoint_matches_oracle_jacobian(oracle_mod):
-    """The device backward through the contact stage (adjoint form + dual-number contact geometry, csrc/nb2_contact.cuh)
+    """The device backward through the contact stage (adjoint form + dual-number contact geometry, csrc/nb2_cw.cuh)
     vs J^T g with the oracle's forward-mode Jacobian of the same frozen-classification step.  Covers: clamping rows only,
     rank-deficient Q (24 clamping rows of a standing Atlas, rank 12), fallback-cfm solutions, sliding (upper-bound) rows."""
     # seeded contact-rich batches
@@ -227,7 +227,7 @@ def _box_stack_inputs(raw, B, seed):
 
 def test_contacts_between_two_moving_bodies_backward(oracle_mod):
     """Rows whose wrench acts on TWO moving bodies (box resting on a box): the adjoint differentiates each wrench with
-    respect to the pose of either body (csrc/nb2_contact.cuh contact_backward_prepare, rows_pass) — checked against
+    respect to the pose of either body (csrc/nb2_cw.cuh contact_backward, dual pass) — checked against
     J^T g with the oracle's dual-number Jacobian of the frozen-classification step, and the oracle against central
     differences where the forward answer is exact."""
     raw = nb.flatten_world(_box_stack_world())

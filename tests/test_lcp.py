@@ -1,6 +1,8 @@
 """LCP stage of the oracle, pinned against the real reference code and the reference's literal instances.
-  * nb2_dantzig.cuh (the Dantzig restatement shared by the CUDA library and the oracle) vs the reference's own
-    dSolveLCP compiled from /root/reference/dart/external/odelcpsolver (oracle/_ref/libodelcp.so);
+  * oracle/dantzig_serial.hpp (the ORACLE's serial Dantzig restatement; the CUDA library has its own warp-cooperative one) vs the
+    reference's own dSolveLCP compiled from /root/reference/dart/external/odelcpsolver (oracle/_ref/libodelcp.so);
+  * the product's chain (csrc/nb2_cw.cuh, host build) vs the oracle's chain, and — on the GPU, tests/test_gpu_lcp.py — the DEVICE chain
+    directly vs the reference's dSolveLCP;
   * the literal (A, x, lo, hi, b, fIndex) instances of unittests/unit/test_LCPUtils.cpp (tests/golden/lcp_fixtures.json):
     the chain's answer must satisfy LCPUtils::isLCPSolutionValid, as the reference's tests assert;
   * pinv_solve vs numpy.linalg.lstsq/pinv (Eigen completeOrthogonalDecomposition semantics: min-norm least squares)."""
