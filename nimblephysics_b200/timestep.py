@@ -133,6 +133,9 @@ class TimestepLayer(torch.autograd.Function):
 def contact_cache(world, B: int, device) -> dict:
     """Per-world, per-batch-size device buffers of the contact stage: the cached LCP solution x/m (the reference's
     BoxedLcpConstraintSolver::mX, warm start of the next step), and this step's labels / status / contact list."""
+    device = torch.device(device)
+    if device.type == "cuda" and device.index is None:
+        device = torch.device("cuda", torch.cuda.current_device())  # "cuda" and "cuda:0" are the same cache
     key = (B, str(device), world._version)
     c = getattr(world, "_lcp_cache", None)
     if c is None or c.get("key") != key:
