@@ -296,7 +296,7 @@ def contact_leg(nb, torch, name, B, K, W, dev, dist, rank, world_size, peak, cpu
     frac = lambda bit: float(((st & bit) > 0).float().mean())
     stats = {"mean_lcp_rows": float(mm.float().mean()), "frac_shortcircuit": frac(1), "frac_dantzig": frac(2), "frac_pgs": frac(8), "frac_friction_dropped": frac(16)}
     # sustained: >= 0.5 s of timed work, states re-seeded every 32 steps so that the robot does not leave the contact regime
-    n_sus = max(K, int(np.ceil(500.0 / max(ms / K, 1e-3))))
+    n_sus = max(K, int(np.ceil(650.0 / max(ms / K, 1e-3))))
     barrier()
     u0, u1 = ev(), ev()
     u0.record()
@@ -573,7 +573,7 @@ def main():
     fwd_ms = float(np.mean([ev[2 * i].elapsed_time(ev[2 * i + 1]) for i in range(args.steps)]))
     bwd_ms = float(np.mean([ev[2 * i + 1].elapsed_time(ev[2 * i + 2]) for i in range(args.steps)]))
     # sustained: the same loop for >= 0.5 s of timed work (the K-step region above is a few milliseconds long)
-    n_sus = max(args.steps, int(np.ceil(500.0 / max(total_ms / args.steps, 1e-3))))
+    n_sus = max(args.steps, int(np.ceil(650.0 / max(total_ms / args.steps, 1e-3))))
     barrier()
     s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     s0.record()

@@ -190,6 +190,23 @@ int nb2_rollout_forward(const nb2_model* m, int B, int T, float* states, const f
 int nb2_rollout_backward(const nb2_model* m, int B, int T, const float* states, const float* actions, const void* saved,
                          float* grad_states, float* grad_actions, int precision, void* stream);
 
+/* T-step rollout of a world WITH collision pairs and its reverse sweep (SingleShot::getSnapshots / backpropGradientWrt as above; every step
+ * is World::step with the constraint solve, and the solver's cached LCP solution x_lcp / m_lcp flows from step to step on the device as
+ * BoxedLcpConstraintSolver::mX does, dart/constraint/BoxedLcpConstraintSolver.cpp:263-306).  One call queues all kernels of the horizon on
+ * `stream`; nothing returns to the host in between; failures surface through status_accum (read once per rollout).
+ *   states / actions / grad_states / grad_actions: as for nb2_rollout_forward / _backward (grad_states accumulates in place);
+ *   x_lcp [B, NB2_MAX_ROWS] double, m_lcp [B] int32: the solver cache (in: before step 0, out: after step T-1; the backward leaves it so);
+ *   tape: nb2_rollout_contact_tape_bytes(m, B, T, checkpoint_every) bytes of device memory shared by the two calls;
+ *   checkpoint_every k: 0 (or >= T) keeps the saved stream + contact record of every step (~(saved_words + record) * 8 B per world-step);
+ *     0 < k < T keeps only ONE segment of k steps plus an LCP-cache snapshot per segment: the reverse sweep re-runs each segment's forward
+ *     from states[t0] before back-propagating through it (one extra forward per step, memory / k) — results are bit-identical either way;
+ *   workspace: nb2_contact_workspace_bytes(m, B). */
+size_t nb2_rollout_contact_tape_bytes(const nb2_model* m, int B, int T, int checkpoint_every);
+int nb2_rollout_forward_contact(const nb2_model* m, int B, int T, float* states, const float* actions, double* x_lcp, int32_t* m_lcp, void* tape,
+                                int checkpoint_every, void* workspace, int32_t* status_accum, void* stream);
+int nb2_rollout_backward_contact(const nb2_model* m, int B, int T, const float* states, const float* actions, double* x_lcp, int32_t* m_lcp, void* tape,
+                                 int checkpoint_every, float* grad_states, float* grad_actions, void* workspace, int32_t* status_accum, void* stream);
+
 /* number of kernels this library has launched since load (bench.py reports it as gpu_launches) */
 long long nb2_launch_count(void);
 const char* nb2_last_error(void);

@@ -138,6 +138,10 @@ def lib() -> ctypes.CDLL:
         L.nb2_step_backward.argtypes = [vp, ctypes.c_int, vp, vp, vp, vp, vp, vp, vp, ctypes.c_int, vp]
         L.nb2_rollout_forward.argtypes = [vp, ctypes.c_int, ctypes.c_int, vp, vp, vp, ctypes.c_int, vp]
         L.nb2_rollout_backward.argtypes = [vp, ctypes.c_int, ctypes.c_int, vp, vp, vp, vp, vp, ctypes.c_int, vp]
+        L.nb2_rollout_contact_tape_bytes.argtypes = [vp, ctypes.c_int, ctypes.c_int, ctypes.c_int]
+        L.nb2_rollout_contact_tape_bytes.restype = ctypes.c_size_t
+        L.nb2_rollout_forward_contact.argtypes = [vp, ctypes.c_int, ctypes.c_int, vp, vp, vp, vp, vp, ctypes.c_int, vp, vp, vp]
+        L.nb2_rollout_backward_contact.argtypes = [vp, ctypes.c_int, ctypes.c_int, vp, vp, vp, vp, vp, ctypes.c_int, vp, vp, vp, vp, vp]
         L.nb2_model_has_contacts.argtypes = [vp]
         L.nb2_contact_workspace_bytes.argtypes = [vp, ctypes.c_int]
         L.nb2_contact_workspace_bytes.restype = ctypes.c_size_t

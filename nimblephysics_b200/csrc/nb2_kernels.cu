@@ -375,7 +375,7 @@ __global__ void __launch_bounds__(32 * NB2_CBWD_MAXW, 1)
 k_cstep_bwd(const __grid_constant__ Nb2ModelDev<double> M, const __grid_constant__ Nb2ContactDev C, const __grid_constant__ CStepArgs P,
             const float* __restrict__ state, const float* __restrict__ action, const double* __restrict__ saved, const double* __restrict__ crec,
             const float* __restrict__ gnext, float* __restrict__ gstate, float* __restrict__ gaction, float* __restrict__ ginertia,
-            int* __restrict__ status, size_t smem_per_warp, int stage_saved) {
+            int* __restrict__ status, size_t smem_per_warp, int stage_saved, int accumulate_state) {
   extern __shared__ __align__(16) unsigned char nb2_smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
   const int w = blockIdx.x * wpb + warp;
@@ -417,7 +417,7 @@ k_cstep_bwd(const __grid_constant__ Nb2ModelDev<double> M, const __grid_constant
   }
   __syncwarp();
   if (live) {
-    nb2::bwd_store<double, 1, true>(M, scr, gstate + (size_t)w * 2 * M.ndof, gaction + (size_t)w * M.na, cd.error != 0, 1, lane, 32);
+    nb2::bwd_store<double, 1, true>(M, scr, gstate + (size_t)w * 2 * M.ndof, gaction + (size_t)w * M.na, cd.error != 0, 1, lane, 32, accumulate_state != 0);
     if (cd.error && status && lane == 0) atomicOr(status + w, NB2_ST_BWD_ERROR);
   }
   CW_PROF(30);
@@ -914,16 +914,11 @@ size_t nb2_contact_record_bytes(const nb2_model* m, int B) {
   if (!m || !m->has_contacts || B <= 0) return 0;
   return nb2::cw::record_doubles(m->mf.ndof) * sizeof(double) * (size_t)B;
 }
-int nb2_step_backward_contact(const nb2_model* cm, int B, const float* state, const float* action, const void* saved_fp64,
-                              const double* contact_record, void* workspace, const float* grad_next_state, float* grad_state,
-                              float* grad_action, float* grad_inertia, int32_t* status_accum, void* stream) {
-  nb2_model* m = const_cast<nb2_model*>(cm);
-  if (!m || B < 0 || !state || !action || !saved_fp64 || !contact_record || !workspace || !grad_next_state || !grad_state || !grad_action) {
-    g_err = "nb2_step_backward_contact: bad argument"; return NB2_ERR_INVALID;
-  }
-  if (!m->has_contacts) { g_err = "nb2_step_backward_contact: the model has no collision pairs"; return NB2_ERR_INVALID; }
-  if (B == 0) return NB2_OK;
-  cudaStream_t st = (cudaStream_t)stream;
+}  // extern "C"
+// accumulate: grad_state += clip(J^T grad_next_state) instead of = (rollouts: the loss gradient of x_t is already in the buffer)
+static int cbwd_launch(nb2_model* m, int B, const float* state, const float* action, const void* saved_fp64, const double* contact_record, void* workspace,
+                       const float* grad_next_state, float* grad_state, float* grad_action, float* grad_inertia, int32_t* status_accum, cudaStream_t st,
+                       int accumulate) {
   const nb2_variant& v = m->variants[m->contact_variant];
   const CStepArgs P = cstep_args(m, v, B, workspace, 1);
   const size_t smem_base = ((((size_t)P.bwd_words + 1) & ~(size_t)1) + NB2_WS_DESC_DOUBLES + ((P.ws_small_doubles + 1) & ~(size_t)1)) * sizeof(double);
@@ -936,9 +931,135 @@ int nb2_step_backward_contact(const nb2_model* cm, int B, const float* state, co
   NB2_CUDA(cudaMemsetAsync(workspace, 0, 64, st));
   const int wpb = pick_wpb(B, m->sm_count, smem, NB2_CBWD_MAXW);
   k_cstep_bwd<<<(B + wpb - 1) / wpb, 32 * wpb, smem * wpb, st>>>(v.md, m->contact, P, state, action, (const double*)saved_fp64, contact_record, grad_next_state,
-                                                                 grad_state, grad_action, grad_inertia, status_accum, smem, stage);
+                                                                 grad_state, grad_action, grad_inertia, status_accum, smem, stage, accumulate);
   g_launches++;
   NB2_CUDA(cudaGetLastError());
+  return NB2_OK;
+}
+extern "C" {
+int nb2_step_backward_contact(const nb2_model* cm, int B, const float* state, const float* action, const void* saved_fp64,
+                              const double* contact_record, void* workspace, const float* grad_next_state, float* grad_state,
+                              float* grad_action, float* grad_inertia, int32_t* status_accum, void* stream) {
+  nb2_model* m = const_cast<nb2_model*>(cm);
+  if (!m || B < 0 || !state || !action || !saved_fp64 || !contact_record || !workspace || !grad_next_state || !grad_state || !grad_action) {
+    g_err = "nb2_step_backward_contact: bad argument"; return NB2_ERR_INVALID;
+  }
+  if (!m->has_contacts) { g_err = "nb2_step_backward_contact: the model has no collision pairs"; return NB2_ERR_INVALID; }
+  if (B == 0) return NB2_OK;
+  return cbwd_launch(m, B, state, action, saved_fp64, contact_record, workspace, grad_next_state, grad_state, grad_action, grad_inertia, status_accum,
+                     (cudaStream_t)stream, 0);
+}
+
+// ---- whole-horizon rollouts of contact worlds (row f1): the T steps are queued from C, the LCP cache flows on the device, and the tape of
+// saved streams / contact records is either complete (checkpoint_every <= 0 or >= T) or holds ONE segment of `checkpoint_every` steps that the
+// reverse sweep refills by re-running the segment's forward from the stored state and the LCP-cache snapshot taken at its start.
+struct RolloutTape {
+  int k, nseg, nslots;
+  size_t slot_doubles, saved_doubles, rec_doubles, snap_doubles, x_doubles;
+  size_t o_slots, o_snaps, o_next, o_labels, o_status, o_nc, total_doubles;
+};
+static RolloutTape rollout_tape(const nb2_model* m, int B, int T, int checkpoint_every) {
+  RolloutTape L;
+  L.k = (checkpoint_every <= 0 || checkpoint_every >= T) ? (T > 0 ? T : 1) : checkpoint_every;
+  L.nseg = T > 0 ? (T + L.k - 1) / L.k : 0;
+  L.nslots = L.k;
+  L.saved_doubles = (size_t)m->saved_words * B;
+  L.rec_doubles = (size_t)nb2::cw::record_doubles(m->mf.ndof) * B;
+  L.slot_doubles = L.saved_doubles + L.rec_doubles;
+  L.x_doubles = (size_t)NB2_MAX_ROWS * B;
+  L.snap_doubles = L.x_doubles + ((size_t)B + 1) / 2;
+  const bool ckpt = L.nseg > 1;
+  size_t o = 0;
+  L.o_slots = o; o += L.slot_doubles * L.nslots;
+  L.o_snaps = o; o += ckpt ? L.snap_doubles * (L.nseg + 1) : 0;   // one per segment start + the cache after the last step
+  L.o_next = o; o += ckpt ? ((size_t)2 * m->mf.ndof * B + 1) / 2 : 0;
+  L.o_labels = o; o += ((size_t)NB2_MAX_ROWS * B + 1) / 2;
+  L.o_status = o; o += ((size_t)B + 1) / 2;
+  L.o_nc = o; o += ((size_t)B + 1) / 2;
+  L.total_doubles = o;
+  return L;
+}
+size_t nb2_rollout_contact_tape_bytes(const nb2_model* m, int B, int T, int checkpoint_every) {
+  if (!m || !m->has_contacts || B <= 0 || T < 0) return 0;
+  return rollout_tape(m, B, T, checkpoint_every).total_doubles * sizeof(double);
+}
+static int snap_copy(double* tape, const RolloutTape& L, int idx, double* x_lcp, int32_t* m_lcp, int B, bool restore, cudaStream_t st) {
+  double* sx = tape + L.o_snaps + L.snap_doubles * idx;
+  int32_t* sm = reinterpret_cast<int32_t*>(sx + L.x_doubles);
+  if (restore) {
+    NB2_CUDA(cudaMemcpyAsync(x_lcp, sx, L.x_doubles * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    NB2_CUDA(cudaMemcpyAsync(m_lcp, sm, (size_t)B * sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
+  } else {
+    NB2_CUDA(cudaMemcpyAsync(sx, x_lcp, L.x_doubles * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    NB2_CUDA(cudaMemcpyAsync(sm, m_lcp, (size_t)B * sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
+  }
+  return NB2_OK;
+}
+int nb2_rollout_forward_contact(const nb2_model* cm, int B, int T, float* states, const float* actions, double* x_lcp, int32_t* m_lcp, void* tape_,
+                                int checkpoint_every, void* workspace, int32_t* status_accum, void* stream) {
+  nb2_model* m = const_cast<nb2_model*>(cm);
+  if (!m || B < 0 || T < 0 || !states || (!actions && T > 0) || !x_lcp || !m_lcp || !tape_ || !workspace) { g_err = "nb2_rollout_forward_contact: bad argument"; return NB2_ERR_INVALID; }
+  if (!m->has_contacts) { g_err = "nb2_rollout_forward_contact: the model has no collision pairs (use nb2_rollout_forward)"; return NB2_ERR_INVALID; }
+  if (B == 0 || T == 0) return NB2_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  double* tape = (double*)tape_;
+  const RolloutTape L = rollout_tape(m, B, T, checkpoint_every);
+  const size_t n2 = (size_t)2 * m->mf.ndof, na = (size_t)m->mf.na;
+  int32_t* labels = reinterpret_cast<int32_t*>(tape + L.o_labels);
+  int32_t* status = reinterpret_cast<int32_t*>(tape + L.o_status);
+  int32_t* nc = reinterpret_cast<int32_t*>(tape + L.o_nc);
+  const bool ckpt = L.nseg > 1;
+  for (int t = 0; t < T; t++) {
+    int rc;
+    if (ckpt && t % L.k == 0 && (rc = snap_copy(tape, L, t / L.k, x_lcp, m_lcp, B, false, st))) return rc;
+    double* slot = tape + L.o_slots + L.slot_doubles * (t % L.nslots);
+    // with checkpoints the forward's records are thrown away (the reverse sweep regenerates them): do not write them
+    rc = nb2_step_forward_contact(m, B, states + n2 * B * t, actions + na * B * t, states + n2 * B * (t + 1), slot, workspace, x_lcp, m_lcp, labels, status, nc,
+                                  nullptr, ckpt ? nullptr : slot + L.saved_doubles, status_accum, stream);
+    if (rc) return rc;
+  }
+  if (ckpt) return snap_copy(tape, L, L.nseg, x_lcp, m_lcp, B, false, st);
+  return NB2_OK;
+}
+int nb2_rollout_backward_contact(const nb2_model* cm, int B, int T, const float* states, const float* actions, double* x_lcp, int32_t* m_lcp, void* tape_,
+                                 int checkpoint_every, float* grad_states, float* grad_actions, void* workspace, int32_t* status_accum, void* stream) {
+  nb2_model* m = const_cast<nb2_model*>(cm);
+  if (!m || B < 0 || T < 0 || !states || (!actions && T > 0) || !x_lcp || !m_lcp || !tape_ || !grad_states || (!grad_actions && T > 0) || !workspace) {
+    g_err = "nb2_rollout_backward_contact: bad argument"; return NB2_ERR_INVALID;
+  }
+  if (!m->has_contacts) { g_err = "nb2_rollout_backward_contact: the model has no collision pairs (use nb2_rollout_backward)"; return NB2_ERR_INVALID; }
+  if (B == 0 || T == 0) return NB2_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  double* tape = (double*)tape_;
+  const RolloutTape L = rollout_tape(m, B, T, checkpoint_every);
+  const size_t n2 = (size_t)2 * m->mf.ndof, na = (size_t)m->mf.na;
+  int32_t* labels = reinterpret_cast<int32_t*>(tape + L.o_labels);
+  int32_t* status = reinterpret_cast<int32_t*>(tape + L.o_status);
+  int32_t* nc = reinterpret_cast<int32_t*>(tape + L.o_nc);
+  float* next_scratch = reinterpret_cast<float*>(tape + L.o_next);
+  const bool ckpt = L.nseg > 1;
+  for (int seg = L.nseg - 1; seg >= 0; seg--) {
+    const int t0 = seg * L.k, t1 = (t0 + L.k < T) ? t0 + L.k : T;
+    int rc;
+    if (ckpt) {
+      // refill the tape: the segment's forward again, from the stored states and the LCP cache as it was at the segment start.  The stored
+      // trajectory is NOT overwritten (the recomputed next states go to a scratch row; they are the same bits).
+      if ((rc = snap_copy(tape, L, seg, x_lcp, m_lcp, B, true, st))) return rc;
+      for (int t = t0; t < t1; t++) {
+        double* slot = tape + L.o_slots + L.slot_doubles * (t - t0);
+        rc = nb2_step_forward_contact(m, B, states + n2 * B * t, actions + na * B * t, next_scratch, slot, workspace, x_lcp, m_lcp, labels, status, nc, nullptr,
+                                      slot + L.saved_doubles, nullptr, stream);
+        if (rc) return rc;
+      }
+    }
+    for (int t = t1 - 1; t >= t0; t--) {
+      const double* slot = tape + L.o_slots + L.slot_doubles * (t - t0);
+      rc = cbwd_launch(m, B, states + n2 * B * t, actions + na * B * t, slot, slot + L.saved_doubles, workspace, grad_states + n2 * B * (t + 1),
+                       grad_states + n2 * B * t, grad_actions + na * B * t, nullptr, status_accum, st, 1);
+      if (rc) return rc;
+    }
+  }
+  if (ckpt) return snap_copy(tape, L, L.nseg, x_lcp, m_lcp, B, true, st);  // leave the solver cache as the forward left it
   return NB2_OK;
 }
 int nb2_model_set_contact_capacity(nb2_model* m, int max_contacts_in_shared_memory) {

@@ -116,6 +116,18 @@ class DeviceModel:
         _cabi.check(_cabi.lib().nb2_rollout_backward(self.handle, B, T, states_ptr, actions_ptr, saved_ptr, gstates_ptr,
                                                      gactions_ptr, precision, stream))
 
+    def rollout_contact_tape_bytes(self, B, T, checkpoint_every):
+        return int(_cabi.lib().nb2_rollout_contact_tape_bytes(self.handle, B, T, checkpoint_every))
+
+    def rollout_forward_contact_device(self, B, T, states_ptr, actions_ptr, x_ptr, m_ptr, tape_ptr, checkpoint_every, ws_ptr, sticky_ptr, stream):
+        _cabi.check(_cabi.lib().nb2_rollout_forward_contact(self.handle, B, T, states_ptr, actions_ptr, x_ptr, m_ptr, tape_ptr, checkpoint_every,
+                                                            ws_ptr, sticky_ptr, stream))
+
+    def rollout_backward_contact_device(self, B, T, states_ptr, actions_ptr, x_ptr, m_ptr, tape_ptr, checkpoint_every, gstates_ptr, gactions_ptr,
+                                        ws_ptr, sticky_ptr, stream):
+        _cabi.check(_cabi.lib().nb2_rollout_backward_contact(self.handle, B, T, states_ptr, actions_ptr, x_ptr, m_ptr, tape_ptr, checkpoint_every,
+                                                             gstates_ptr, gactions_ptr, ws_ptr, sticky_ptr, stream))
+
     def forward_dynamics(self, pos, vel, force):
         """q-ddot [B, n] (float64 CUDA tensors in and out): pointer-style ABA, no integration, no contact stage
         (SimpleFeatherstone::forwardDynamics / Skeleton::computeForwardDynamics + getAccelerations)."""

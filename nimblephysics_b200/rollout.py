@@ -71,19 +71,73 @@ class _FusedRollout(torch.autograd.Function):
         return None, gs[0].to(ctx.dtypes[0]), ga.to(ctx.dtypes[1])
 
 
-def rollout_fused(world, state0: torch.Tensor, actions: torch.Tensor) -> torch.Tensor:
-    """states[T+1, B, 2n] of the T-step rollout x_{t+1} = timestep(x_t, actions[t]) of a contact-free world
+class _ContactRollout(torch.autograd.Function):
+    """Whole-horizon rollout of a world with collision pairs behind ONE C-ABI call per direction (nb2_rollout_forward_contact /
+    nb2_rollout_backward_contact): every kernel of the horizon is queued from C, the solver's LCP cache flows on the device, the tape
+    (saved streams + contact records) is one device buffer, optionally checkpointed every k steps."""
+
+    @staticmethod
+    def forward(ctx, world, state0, actions, checkpoint_every):
+        from .engine import device_model_for
+        from .timestep import contact_cache
+
+        dm = device_model_for(world)
+        T, B = actions.shape[0], actions.shape[1]
+        n2, na = 2 * dm.ndof, dm.na
+        if state0.shape != (B, n2) or actions.shape[2] != na:
+            raise ValueError(f"rollout(): state0 {tuple(state0.shape)} / actions {tuple(actions.shape)} do not match [B,{n2}] / [T,B,{na}]")
+        if not state0.is_cuda:
+            raise RuntimeError("rollout_fused needs CUDA tensors (B200); there is no CPU fallback")
+        dev = state0.device
+        states = torch.empty((T + 1, B, n2), dtype=torch.float32, device=dev)
+        states[0].copy_(state0.detach())
+        acts = actions.detach().to(dtype=torch.float32).contiguous()
+        k = int(checkpoint_every or 0)
+        cache = contact_cache(world, B, dev)
+        tape = torch.empty((dm.rollout_contact_tape_bytes(B, T, k) // 8,), dtype=torch.float64, device=dev)
+        with torch.cuda.device(dev):
+            dm.rollout_forward_contact_device(B, T, states.data_ptr(), acts.data_ptr(), cache["x"].data_ptr(), cache["m"].data_ptr(), tape.data_ptr(), k,
+                                              cache["ws"].data_ptr(), cache["sticky"].data_ptr(), torch.cuda.current_stream().cuda_stream)
+        ctx.dm, ctx.T, ctx.B, ctx.k, ctx.cache = dm, T, B, k, cache
+        ctx.dtypes = (state0.dtype, actions.dtype)
+        ctx.peak_tape_bytes = tape.numel() * 8
+        if any(ctx.needs_input_grad[1:3]):
+            ctx.save_for_backward(states, acts, tape)
+        return states.to(state0.dtype)
+
+    @staticmethod
+    def backward(ctx, grad_states):
+        states, acts, tape = ctx.saved_tensors
+        dm, T, B, cache = ctx.dm, ctx.T, ctx.B, ctx.cache
+        gs = grad_states.detach().to(dtype=torch.float32).contiguous().clone()  # in: loss gradient per state; out: total dL/dx_t
+        ga = torch.empty_like(acts)
+        with torch.cuda.device(states.device):
+            dm.rollout_backward_contact_device(B, T, states.data_ptr(), acts.data_ptr(), cache["x"].data_ptr(), cache["m"].data_ptr(), tape.data_ptr(),
+                                               ctx.k, gs.data_ptr(), ga.data_ptr(), cache["ws"].data_ptr(), cache["sticky"].data_ptr(),
+                                               torch.cuda.current_stream().cuda_stream)
+        return None, gs[0].to(ctx.dtypes[0]), ga.to(ctx.dtypes[1]), None
+
+
+def rollout_fused(world, state0: torch.Tensor, actions: torch.Tensor, checkpoint_every: int = 0) -> torch.Tensor:
+    """states[T+1, B, 2n] of the T-step rollout x_{t+1} = timestep(x_t, actions[t])
     (SingleShot::getSnapshots, dart/trajectory/SingleShot.cpp:635-686), differentiable with respect to state0 and every
-    action (SingleShot::backpropGradientWrt, :539-631); losses may look at any state of the trajectory.
-    Worlds with collision pairs keep the per-step path (`rollout`), whose LCP cache flows from step to step."""
+    action (SingleShot::backpropGradientWrt, :539-631); losses may look at any state of the trajectory.  One C call per direction.
+    Worlds with collision pairs run the contact / boxed-LCP stage every step with the world's LCP cache flowing exactly as when
+    chaining timestep() (bit-identical states and gradients); `checkpoint_every=k` keeps the backward tape of k steps instead of T and
+    re-runs each segment's forward in the reverse sweep.  Problems (dropped contacts, worlds that cannot be back-propagated) are
+    reported by check_contact_status(world), one host sync per rollout."""
     from .engine import device_model_for
 
     if device_model_for(world).has_contacts:
-        xs = [state0]
-        for t in range(actions.shape[0]):
-            xs.append(timestep(world, xs[-1], actions[t]))
-        return torch.stack(xs, 0)
+        return _ContactRollout.apply(world, state0, actions, checkpoint_every)
     return _FusedRollout.apply(world, state0, actions)
+
+
+def rollout_tape_bytes(world, B: int, T: int, checkpoint_every: int = 0) -> int:
+    """Device bytes the backward tape of rollout_fused(world, ...) takes for a world with collision pairs."""
+    from .engine import device_model_for
+
+    return device_model_for(world).rollout_contact_tape_bytes(B, T, int(checkpoint_every or 0))
 
 
 def shard_range(total: int, rank: int, world_size: int) -> Tuple[int, int]:
@@ -111,21 +165,29 @@ def allreduce_sum_(t: torch.Tensor, group=None) -> torch.Tensor:
 
 def sharded_trajectory_loss(world, state0: torch.Tensor, actions: Sequence[torch.Tensor],
                             loss_fn: Callable[[torch.Tensor], torch.Tensor], rank: int, world_size: int,
-                            step_fn: Optional[Callable] = None):
+                            step_fn: Optional[Callable] = None, checkpoint_every: int = 0):
     """Each rank rolls out its slice of the batch, backpropagates its part of the loss, and the scalar loss is
-    all-reduced (config 5 of BASELINE.json).  Returns (global_loss, local_state0_grad, local_action_grads)."""
-    step = step_fn or timestep
+    all-reduced (config 5 of BASELINE.json).  Returns (global_loss, local_state0_grad, local_action_grads).
+    Without `step_fn` the horizon runs through rollout_fused (one C call per direction); with one, step by step."""
     lo, hi = shard_range(state0.shape[0], rank, world_size)
     x0 = state0[lo:hi].detach().clone().requires_grad_(True)
-    acts = [a[lo:hi].detach().clone().requires_grad_(True) for a in actions]
-    x = x0
-    for a in acts:
-        x = step(world, x, a)
-    loss = loss_fn(x)
-    loss.backward()
+    if step_fn is None:
+        acts = torch.stack([a[lo:hi].detach() for a in actions], 0).requires_grad_(True)
+        states = rollout_fused(world, x0, acts, checkpoint_every)
+        loss = loss_fn(states[-1])
+        loss.backward()
+        grads = list(acts.grad.unbind(0))
+    else:
+        alist = [a[lo:hi].detach().clone().requires_grad_(True) for a in actions]
+        x = x0
+        for a in alist:
+            x = step_fn(world, x, a)
+        loss = loss_fn(x)
+        loss.backward()
+        grads = [a.grad for a in alist]
     total = allreduce_sum_(loss.detach().clone())
-    if step is timestep:
+    if step_fn is None or step_fn is timestep:
         from .timestep import check_contact_status
 
         check_contact_status(world)  # ONE host sync per rollout: worlds that dropped contacts / could not be back-propagated raise here
-    return total, x0.grad, [a.grad for a in acts]
+    return total, x0.grad, grads
