@@ -370,33 +370,40 @@ def rollout_leg(nb, torch, B, T, reps, dev, dist, rank, world_size):
     acts = [torch.tensor(acts_np[t], device=dev) for t in range(T)]
     loss_fn = lambda xT: (xT * xT).sum()
 
-    def run():
+    def run(k=0):
         nb.reset_contact_cache(world)
-        total, gx0, gacts = sharded_trajectory_loss(world, x0, acts, loss_fn, rank, world_size)  # all-reduces the scalar loss (NCCL)
+        total, gx0, gacts = sharded_trajectory_loss(world, x0, acts, loss_fn, rank, world_size, checkpoint_every=k)  # all-reduces the scalar loss (NCCL)
         return total, gx0
 
-    run(); run()
-    if dist:
-        dist.barrier()
-    torch.cuda.synchronize()
-    best = float("inf")
-    for _ in range(reps):
+    def timed(k):
+        run(k); run(k)
+        if dist:
+            dist.barrier()
+        torch.cuda.synchronize()
+        torch.cuda.reset_peak_memory_stats(dev)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        total, gx0 = run()
+        for _ in range(reps):
+            total, gx0 = run(k)
         e1.record()
         torch.cuda.synchronize()
-        best = min(best, e0.elapsed_time(e1))
+        t = torch.tensor([e0.elapsed_time(e1) / reps], device=dev, dtype=torch.float64)
+        if dist:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t[0]), total, gx0, torch.cuda.max_memory_allocated(dev) / 2 ** 30
+
+    ms, total, gx0, peak_gb = timed(0)
+    ms_k, total_k, gx0_k, peak_gb_k = timed(8)
     sticky = nb.check_contact_status(world)
-    t = torch.tensor([best], device=dev, dtype=torch.float64)
-    if dist:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = float(t[0])
     return {"workload": f"64-step Atlas + ground rollout, backprop through the horizon, batch={B}/GPU (BASELINE configs[4])", "horizon": T,
-            "value": Bg * T / (ms * 1e-3), "unit": UNIT, "n_gpus": world_size, "ms_per_rollout_fwd_bwd": ms,
+            "value": Bg * T / (ms * 1e-3), "unit": UNIT, "n_gpus": world_size, "ms_per_rollout_fwd_bwd": ms, "rollouts_timed": reps,
+            "driver": "nb2_rollout_forward_contact + nb2_rollout_backward_contact (one C call per direction, no host sync inside the horizon)",
             "loss": float(total), "loss_finite": bool(torch.isfinite(total)), "grad_finite": bool(torch.isfinite(gx0).all()),
             "collective": "all_reduce(SUM) of the scalar loss over %d rank(s)" % world_size, "sticky_status": int(sticky),
-            "peak_memory_gb": torch.cuda.max_memory_allocated(dev) / 2 ** 30}
+            "peak_memory_gb": peak_gb, "tape_bytes_per_gpu": nb.rollout_tape_bytes(world, B, T, 0),
+            "checkpoint_every_8": {"value": Bg * T / (ms_k * 1e-3), "ms_per_rollout_fwd_bwd": ms_k, "peak_memory_gb": peak_gb_k,
+                                   "tape_bytes_per_gpu": nb.rollout_tape_bytes(world, B, T, 8),
+                                   "same_bits_as_full_tape": bool(torch.equal(gx0, gx0_k) and float(total) == float(total_k))}}
 
 _REAL_STDOUT = None
 
@@ -623,7 +630,7 @@ def main():
             except Exception as ex:  # never let a leg break the headline line
                 extra["legs"][label] = {"error": repr(ex)}
         try:
-            extra["legs"]["atlas_ground_rollout64 (configs[4])"] = rollout_leg(nb, torch, 1024, 64, 2, dev, dist, rank, world_size)
+            extra["legs"]["atlas_ground_rollout64 (configs[4])"] = rollout_leg(nb, torch, 1024, 64, 6, dev, dist, rank, world_size)
         except Exception as ex:
             extra["legs"]["atlas_ground_rollout64 (configs[4])"] = {"error": repr(ex)}
         # contact-free 64-step rollout through the fused entry points (nb2_rollout_forward / nb2_rollout_backward)
@@ -643,15 +650,15 @@ def main():
                 tr = rollout_fused(fworld, xf0, uft)
                 (tr[-1] * tr[-1]).sum().backward()
 
-            runf()
+            runf(); runf()
             barrier()
             q0, q1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             q0.record()
-            for _ in range(3):
+            for _ in range(8):
                 runf()
             q1.record()
             barrier()
-            tq = torch.tensor([q0.elapsed_time(q1) / 3], device=dev, dtype=torch.float64)
+            tq = torch.tensor([q0.elapsed_time(q1) / 8], device=dev, dtype=torch.float64)
             if dist:
                 dist.all_reduce(tq, op=dist.ReduceOp.MAX)
             msf = float(tq[0])

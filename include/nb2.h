@@ -207,6 +207,25 @@ int nb2_rollout_forward_contact(const nb2_model* m, int B, int T, float* states,
 int nb2_rollout_backward_contact(const nb2_model* m, int B, int T, const float* states, const float* actions, double* x_lcp, int32_t* m_lcp, void* tape,
                                  int checkpoint_every, float* grad_states, float* grad_actions, void* workspace, int32_t* status_accum, void* stream);
 
+/* IKMapping: task-space outputs of a state and their VJP, on the device (neural/IKMapping.cpp:146-237 getPositionsInPlace /
+ * getVelocitiesInPlace; :371-476 getPosJacobian / getVelJacobian; python/nimblephysics/mapping.py:23-114 map_to_pos / map_to_vel).
+ * An entry names a body node and what to report for it, in the order IKMapping::addSpatialBodyNode / addLinearBodyNode / addAngularBodyNode
+ * were called:   type 0 SPATIAL -> pos [log(R_world) ; p_world] (6), vel [omega_world ; v_world] (6)   (IKMapping.cpp:160-170, 197-205)
+ *                type 1 LINEAR  -> p_world (3), v_world (3);   type 2 ANGULAR -> log(R_world) (3), omega_world (3);
+ *                type 3 COM     -> Skeleton::getCOM / getCOMLinearVelocity of the tree whose root body is `body` (3, 3).
+ * body[e]: the moving body of the compiled model the node is (rigidly) part of, -1 for a static node; T_owner_from_body[e]: 12 doubles
+ * (R row-major, p) placing the node's frame in that body's frame (the world frame for static nodes).
+ *   mapped_pos [B, nb2_ik_pos_dim], mapped_vel [B, nb2_ik_vel_dim] float (either may be NULL);
+ *   nb2_ik_backward: grad_state [B, 2n] = [J_pos^T grad_pos ; J_vel^T grad_vel] — positions feed only d/dq and velocities only d/dqdot,
+ *   as MapToPosLayer / MapToVelLayer return them (mapping.py:36-47, 84-95); grad_pos / grad_vel may be NULL (= zeros). */
+typedef struct nb2_ik_map nb2_ik_map;
+int nb2_ik_create(const nb2_model* m, int nentries, const int32_t* type, const int32_t* body, const double* T_owner_from_body, nb2_ik_map** out);
+void nb2_ik_destroy(nb2_ik_map* ik);
+int nb2_ik_pos_dim(const nb2_ik_map* ik);
+int nb2_ik_vel_dim(const nb2_ik_map* ik);
+int nb2_ik_forward(const nb2_ik_map* ik, int B, const float* state, float* mapped_pos, float* mapped_vel, void* stream);
+int nb2_ik_backward(const nb2_ik_map* ik, int B, const float* state, const float* grad_pos, const float* grad_vel, float* grad_state, void* stream);
+
 /* number of kernels this library has launched since load (bench.py reports it as gpu_launches) */
 long long nb2_launch_count(void);
 const char* nb2_last_error(void);

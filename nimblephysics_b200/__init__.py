@@ -11,3 +11,5 @@ from .rollout import rollout, rollout_fused, rollout_tape_bytes, shard_range, sh
 __all__ = ["World", "Skeleton", "BodyNode", "Joint", "Isometry3", "BoxShape", "SphereShape", "CapsuleShape",
            "loadWorld", "load_skeleton", "timestep", "TimestepLayer", "rollout", "rollout_fused", "DeviceModel", "device_model_for", "RawModel", "CanonModel", "flatten_world", "compile_model"]
 from .lcp import solve_boxed_lcp_batch
+from .jacobians import step_jacobians, state_jacobian, action_jacobian
+from .mapping import IKMapping, map_to_pos, map_to_vel

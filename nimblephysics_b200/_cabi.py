@@ -138,6 +138,13 @@ def lib() -> ctypes.CDLL:
         L.nb2_step_backward.argtypes = [vp, ctypes.c_int, vp, vp, vp, vp, vp, vp, vp, ctypes.c_int, vp]
         L.nb2_rollout_forward.argtypes = [vp, ctypes.c_int, ctypes.c_int, vp, vp, vp, ctypes.c_int, vp]
         L.nb2_rollout_backward.argtypes = [vp, ctypes.c_int, ctypes.c_int, vp, vp, vp, vp, vp, ctypes.c_int, vp]
+        L.nb2_ik_create.argtypes = [vp, ctypes.c_int, vp, vp, vp, ctypes.POINTER(ctypes.c_void_p)]
+        L.nb2_ik_destroy.argtypes = [vp]
+        L.nb2_ik_destroy.restype = None
+        L.nb2_ik_pos_dim.argtypes = [vp]
+        L.nb2_ik_vel_dim.argtypes = [vp]
+        L.nb2_ik_forward.argtypes = [vp, ctypes.c_int, vp, vp, vp, vp]
+        L.nb2_ik_backward.argtypes = [vp, ctypes.c_int, vp, vp, vp, vp, vp]
         L.nb2_rollout_contact_tape_bytes.argtypes = [vp, ctypes.c_int, ctypes.c_int, ctypes.c_int]
         L.nb2_rollout_contact_tape_bytes.restype = ctypes.c_size_t
         L.nb2_rollout_forward_contact.argtypes = [vp, ctypes.c_int, ctypes.c_int, vp, vp, vp, vp, vp, ctypes.c_int, vp, vp, vp]

@@ -423,6 +423,173 @@ k_cstep_bwd(const __grid_constant__ Nb2ModelDev<double> M, const __grid_constant
   CW_PROF(30);
 }
 
+
+// =====================================================================================================
+// IKMapping (row f4): world poses / spatial velocities of chosen bodies as a function of the state, and the VJP.
+// reference: neural/IKMapping.cpp:146-237 (getPositionsInPlace / getVelocitiesInPlace), :371-476 (getPosJacobian / getVelJacobian built from
+// Skeleton::getWorldPositionJacobian / getWorldJacobian), python/nimblephysics/mapping.py:23-114 (map_to_pos / map_to_vel and their backward).
+// One thread per (world, entry) forward; one thread per world backward (it owns the gradient row: deterministic sums, no atomics).  Every
+// entry walks its own root -> body chain (depth ~10), so nothing but the state row is read and nothing is staged.
+// =====================================================================================================
+struct IkEntryDev { int type, body, pos_off, vel_off; double T[12]; };  // body: canonical owner (-1 = static); T: owner frame <- entry body frame
+#define NB2_IK_SPATIAL 0
+#define NB2_IK_LINEAR 1
+#define NB2_IK_ANGULAR 2
+#define NB2_IK_COM 3
+
+using nb2::V3; using nb2::V6; using nb2::Xf; using nb2::M3;
+// parent <- child transform of body j at generalized position q (fwd_pass1's three cases)
+__device__ __forceinline__ Xf<double> ik_joint_xf(const Nb2ModelDev<double>& M, int j, const float* q) {
+  const int jt = M.jtype[j], o = M.dof_off[j];
+  if (jt == NB2_JT_REV) { double s, c; sincos((double)q[o], &s, &c); return nb2::xf_rev<double>(M, j, s, c); }
+  if (jt == NB2_JT_PRIS) return nb2::xf_pris<double>(M, j, (double)q[o]);
+  Xf<double> X = nb2::xtree<double>(M, j), T;
+  T.R_ = nb2::mul(X.R_, nb2::expmap(nb2::mk3<double>(q[o], q[o + 1], q[o + 2])));
+  T.p = nb2::mul(X.R_, nb2::mk3<double>(q[o + 3], q[o + 4], q[o + 5])) + X.p;
+  return T;
+}
+__device__ __forceinline__ int ik_chain(const Nb2ModelDev<double>& M, int body, unsigned char* chain) {
+  int d = 0;
+  for (int j = body; j >= 0; j = M.parent[j]) chain[d++] = (unsigned char)j;
+  return d;  // chain[d-1] is the root
+}
+// world transform W and body-frame spatial velocity V of canonical body `body`
+__device__ __forceinline__ void ik_fk(const Nb2ModelDev<double>& M, int body, const float* q, const float* qd, Xf<double>* W, V6<double>* V) {
+  unsigned char chain[NB2_MAX_BODIES];
+  const int d = ik_chain(M, body, chain);
+  Xf<double> Wc; V6<double> Vc = nb2::zero6<double>();
+  for (int k = d - 1; k >= 0; k--) {
+    const int j = chain[k], jt = M.jtype[j], o = M.dof_off[j];
+    const Xf<double> T = ik_joint_xf(M, j, q);
+    Wc = (k == d - 1) ? T : nb2::gxf_mul(Wc, T);
+    Vc = (k == d - 1) ? nb2::zero6<double>() : nb2::AdInvT(T, Vc);
+    if (jt == NB2_JT_REV) Vc.a.z += (double)qd[o];
+    else if (jt == NB2_JT_PRIS) Vc.l.z += (double)qd[o];
+    else { Vc.a = Vc.a + nb2::mk3<double>(qd[o], qd[o + 1], qd[o + 2]); Vc.l = Vc.l + nb2::mk3<double>(qd[o + 3], qd[o + 4], qd[o + 5]); }
+  }
+  *W = Wc; *V = Vc;
+}
+// adjoint of ik_fk for one body: world wrenches about the WORLD ORIGIN (torque n, force f) paired with position perturbations (np, fp) and with
+// velocities (nv, fv) -> += into the gradient row g = [g_q ; g_qdot]
+__device__ __forceinline__ void ik_fk_vjp(const Nb2ModelDev<double>& M, int body, const float* q, const V3<double>& np, const V3<double>& fp,
+                                          const V3<double>& nv, const V3<double>& fv, float* g) {
+  unsigned char chain[NB2_MAX_BODIES];
+  const int d = ik_chain(M, body, chain), n = M.ndof;
+  Xf<double> Wc;
+  for (int k = d - 1; k >= 0; k--) {
+    const int j = chain[k], jt = M.jtype[j], o = M.dof_off[j];
+    const Xf<double> T = ik_joint_xf(M, j, q);
+    Wc = (k == d - 1) ? T : nb2::gxf_mul(Wc, T);
+    // wrench in the frame of body j: the generalized force on its dofs is S^T of it
+    const V3<double> cpa = nb2::mulT(Wc.R_, np - nb2::cross(Wc.p, fp)), cpl = nb2::mulT(Wc.R_, fp);
+    const V3<double> cva = nb2::mulT(Wc.R_, nv - nb2::cross(Wc.p, fv)), cvl = nb2::mulT(Wc.R_, fv);
+    if (jt == NB2_JT_REV) { g[o] += (float)cpa.z; g[n + o] += (float)cva.z; }
+    else if (jt == NB2_JT_PRIS) { g[o] += (float)cpl.z; g[n + o] += (float)cvl.z; }
+    else {
+      // positions: R = exp(phi), p in the parent frame: body-frame twist of (d phi, d p) is (Jr(phi) d phi, R^T d p) (cf. bwd_B3)
+      const V3<double> phi = nb2::mk3<double>(q[o], q[o + 1], q[o + 2]);
+      const V3<double> ga = nb2::mulT(nb2::so3_Jr(phi), cpa), gl = nb2::mul(nb2::expmap(phi), cpl);
+      g[o] += (float)ga.x; g[o + 1] += (float)ga.y; g[o + 2] += (float)ga.z; g[o + 3] += (float)gl.x; g[o + 4] += (float)gl.y; g[o + 5] += (float)gl.z;
+      g[n + o] += (float)cva.x; g[n + o + 1] += (float)cva.y; g[n + o + 2] += (float)cva.z;
+      g[n + o + 3] += (float)cvl.x; g[n + o + 4] += (float)cvl.y; g[n + o + 5] += (float)cvl.z;
+    }
+  }
+}
+__device__ __forceinline__ int ik_root(const Nb2ModelDev<double>& M, int j) { while (M.parent[j] >= 0) j = M.parent[j]; return j; }
+
+__global__ void __launch_bounds__(128)
+k_ik_forward(const __grid_constant__ Nb2ModelDev<double> M, int B, int nent, int pos_dim, int vel_dim, const IkEntryDev* __restrict__ ent,
+             const float* __restrict__ state, float* __restrict__ pos, float* __restrict__ vel) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= B * nent) return;
+  const int w = t / nent, e = t - w * nent;
+  const IkEntryDev E = ent[e];
+  const float* q = state + (size_t)w * 2 * M.ndof; const float* qd = q + M.ndof;
+  float* po = pos ? pos + (size_t)w * pos_dim + E.pos_off : nullptr;
+  float* vo = vel ? vel + (size_t)w * vel_dim + E.vel_off : nullptr;
+  if (E.type == NB2_IK_COM) {  // Skeleton::getCOM / getCOMLinearVelocity of the tree rooted at E.body
+    double mt = 0; V3<double> c = nb2::zero3<double>(), cv = nb2::zero3<double>();
+    for (int i = 0; i < M.nb; i++) {
+      if (ik_root(M, i) != E.body) continue;
+      Xf<double> W; V6<double> V; ik_fk(M, i, q, qd, &W, &V);
+      const double m = M.inertia[i][0];
+      const V3<double> h = nb2::mul(W.R_, nb2::mk3<double>(M.inertia[i][1], M.inertia[i][2], M.inertia[i][3]));  // m * (com - origin), world axes
+      mt += m; c = c + W.p * m + h;
+      cv = cv + nb2::mul(W.R_, V.l) * m + nb2::cross(nb2::mul(W.R_, V.a), h);
+    }
+    const double inv = mt > 0 ? 1.0 / mt : 0.0;
+    if (po) { po[0] = (float)(c.x * inv); po[1] = (float)(c.y * inv); po[2] = (float)(c.z * inv); }
+    if (vo) { vo[0] = (float)(cv.x * inv); vo[1] = (float)(cv.y * inv); vo[2] = (float)(cv.z * inv); }
+    return;
+  }
+  Xf<double> Toff = nb2::ldXf<double, 1>(E.T), We; V3<double> om = nb2::zero3<double>(), vl = nb2::zero3<double>();
+  if (E.body >= 0) {
+    Xf<double> W; V6<double> V; ik_fk(M, E.body, q, qd, &W, &V);
+    We = nb2::gxf_mul(W, Toff);
+    om = nb2::mul(W.R_, V.a);
+    vl = nb2::mul(W.R_, V.l) + nb2::cross(om, We.p - W.p);
+  } else We = Toff;
+  int k = 0;
+  if (po) {
+    if (E.type != NB2_IK_LINEAR) { const V3<double> phi = nb2::logmap(We.R_); po[0] = (float)phi.x; po[1] = (float)phi.y; po[2] = (float)phi.z; k = 3; }
+    if (E.type != NB2_IK_ANGULAR) { po[k] = (float)We.p.x; po[k + 1] = (float)We.p.y; po[k + 2] = (float)We.p.z; }
+  }
+  if (vo) {
+    k = 0;
+    if (E.type != NB2_IK_LINEAR) { vo[0] = (float)om.x; vo[1] = (float)om.y; vo[2] = (float)om.z; k = 3; }
+    if (E.type != NB2_IK_ANGULAR) { vo[k] = (float)vl.x; vo[k + 1] = (float)vl.y; vo[k + 2] = (float)vl.z; }
+  }
+}
+
+// grad_state[w] = J_pos^T grad_pos[w] (into the position half) and J_vel^T grad_vel[w] (into the velocity half): exactly what
+// MapToPosLayer.backward / MapToVelLayer.backward return (mapping.py:36-47, 84-95: positions feed only d/dq, velocities only d/dqdot).
+__global__ void __launch_bounds__(128)
+k_ik_backward(const __grid_constant__ Nb2ModelDev<double> M, int B, int nent, int pos_dim, int vel_dim, const IkEntryDev* __restrict__ ent,
+              const float* __restrict__ state, const float* __restrict__ gpos, const float* __restrict__ gvel, float* __restrict__ gstate) {
+  const int w = blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= B) return;
+  const float* q = state + (size_t)w * 2 * M.ndof; const float* qd = q + M.ndof;
+  float* g = gstate + (size_t)w * 2 * M.ndof;
+  for (int d = 0; d < 2 * M.ndof; d++) g[d] = 0.f;
+  const V3<double> z3 = nb2::zero3<double>();
+  for (int e = 0; e < nent; e++) {
+    const IkEntryDev E = ent[e];
+    const float* gp = gpos ? gpos + (size_t)w * pos_dim + E.pos_off : nullptr;
+    const float* gv = gvel ? gvel + (size_t)w * vel_dim + E.vel_off : nullptr;
+    if (E.type == NB2_IK_COM) {
+      double mt = 0;
+      for (int i = 0; i < M.nb; i++) if (ik_root(M, i) == E.body) mt += M.inertia[i][0];
+      const double inv = mt > 0 ? 1.0 / mt : 0.0;
+      const V3<double> fp = gp ? nb2::mk3<double>(gp[0], gp[1], gp[2]) * inv : z3, fv = gv ? nb2::mk3<double>(gv[0], gv[1], gv[2]) * inv : z3;
+      for (int i = 0; i < M.nb; i++) {
+        if (ik_root(M, i) != E.body) continue;
+        Xf<double> W; V6<double> V; ik_fk(M, i, q, qd, &W, &V);
+        const double m = M.inertia[i][0];
+        const V3<double> h = nb2::mul(W.R_, nb2::mk3<double>(M.inertia[i][1], M.inertia[i][2], M.inertia[i][3]));
+        // d(m p + R h) = m dp + dtheta x h  ->  force m f at the origin, torque h x f; about the world origin: + p x (m f)
+        ik_fk_vjp(M, i, q, nb2::cross(h, fp) + nb2::cross(W.p, fp * m), fp * m, nb2::cross(h, fv) + nb2::cross(W.p, fv * m), fv * m, g);
+      }
+      continue;
+    }
+    if (E.body < 0) continue;  // static body: constants
+    Xf<double> W; V6<double> V; ik_fk(M, E.body, q, qd, &W, &V);
+    const Xf<double> We = nb2::gxf_mul(W, nb2::ldXf<double, 1>(E.T));
+    V3<double> np = z3, fp = z3, nv = z3, fv = z3;
+    int k = 0;
+    if (E.type != NB2_IK_LINEAR) {
+      // log(exp(dtheta) R) = phi + Jl^-1(phi) dtheta, and Jl^-T = Jr^-1
+      if (gp) np = nb2::mul(nb2::so3_Jr_inv(nb2::logmap(We.R_)), nb2::mk3<double>(gp[0], gp[1], gp[2]));
+      if (gv) nv = nb2::mk3<double>(gv[0], gv[1], gv[2]);
+      k = 3;
+    }
+    if (E.type != NB2_IK_ANGULAR) {
+      if (gp) fp = nb2::mk3<double>(gp[k], gp[k + 1], gp[k + 2]);
+      if (gv) fv = nb2::mk3<double>(gv[k], gv[k + 1], gv[k + 2]);
+    }
+    ik_fk_vjp(M, E.body, q, np + nb2::cross(We.p, fp), fp, nv + nb2::cross(We.p, fv), fv, g);
+  }
+}
+
 // ---- pointer-style forward dynamics (row a5: SimpleFeatherstone::forwardDynamics(pos, vel, force, accel), dynamics/SimpleFeatherstone.hpp:61-65):
 // fp64 in, fp64 out, one thread per world with its scratch in global memory — a convenience / parity entry, not a hot path.
 __global__ void __launch_bounds__(64)
@@ -1079,6 +1246,50 @@ int nb2_cw_profile_read(unsigned long long* out64, int reset) {
   (void)out64; (void)reset; return 0;
 #endif
 }
+// ---- IKMapping entry points
+struct nb2_ik_map { const nb2_model* m; int n, pos_dim, vel_dim; IkEntryDev* d_ent; };
+int nb2_ik_create(const nb2_model* m, int nentries, const int32_t* type, const int32_t* body, const double* T_owner_from_body, nb2_ik_map** out) {
+  if (!m || nentries <= 0 || !type || !body || !T_owner_from_body || !out) { g_err = "nb2_ik_create: bad argument"; return NB2_ERR_INVALID; }
+  std::vector<IkEntryDev> ent(nentries);
+  int po = 0, vo = 0;
+  for (int e = 0; e < nentries; e++) {
+    if (type[e] < 0 || type[e] > NB2_IK_COM || body[e] >= m->md.nb || (type[e] == NB2_IK_COM && (body[e] < 0 || m->md.parent[body[e]] >= 0))) {
+      g_err = "nb2_ik_create: entry " + std::to_string(e) + " has a bad type / body (a COM entry names the root body of its tree)"; return NB2_ERR_INVALID;
+    }
+    ent[e].type = type[e]; ent[e].body = body[e]; ent[e].pos_off = po; ent[e].vel_off = vo;
+    for (int k = 0; k < 12; k++) ent[e].T[k] = T_owner_from_body[12 * e + k];
+    const int d = type[e] == NB2_IK_SPATIAL ? 6 : 3;
+    po += d; vo += d;
+  }
+  nb2_ik_map* ik = new nb2_ik_map{m, nentries, po, vo, nullptr};
+  if (cudaMalloc(&ik->d_ent, sizeof(IkEntryDev) * nentries) != cudaSuccess ||
+      cudaMemcpy(ik->d_ent, ent.data(), sizeof(IkEntryDev) * nentries, cudaMemcpyHostToDevice) != cudaSuccess) {
+    g_err = std::string("nb2_ik_create: ") + cudaGetErrorString(cudaGetLastError()); cudaFree(ik->d_ent); delete ik; return NB2_ERR_CUDA;
+  }
+  *out = ik;
+  return NB2_OK;
+}
+void nb2_ik_destroy(nb2_ik_map* ik) { if (ik) { cudaFree(ik->d_ent); delete ik; } }
+int nb2_ik_pos_dim(const nb2_ik_map* ik) { return ik ? ik->pos_dim : -1; }
+int nb2_ik_vel_dim(const nb2_ik_map* ik) { return ik ? ik->vel_dim : -1; }
+int nb2_ik_forward(const nb2_ik_map* ik, int B, const float* state, float* mapped_pos, float* mapped_vel, void* stream) {
+  if (!ik || B < 0 || !state || (!mapped_pos && !mapped_vel)) { g_err = "nb2_ik_forward: bad argument"; return NB2_ERR_INVALID; }
+  if (B == 0) return NB2_OK;
+  const long long threads = (long long)B * ik->n;
+  k_ik_forward<<<(unsigned)((threads + 127) / 128), 128, 0, (cudaStream_t)stream>>>(ik->m->md, B, ik->n, ik->pos_dim, ik->vel_dim, ik->d_ent, state, mapped_pos, mapped_vel);
+  g_launches++;
+  NB2_CUDA(cudaGetLastError());
+  return NB2_OK;
+}
+int nb2_ik_backward(const nb2_ik_map* ik, int B, const float* state, const float* grad_pos, const float* grad_vel, float* grad_state, void* stream) {
+  if (!ik || B < 0 || !state || !grad_state) { g_err = "nb2_ik_backward: bad argument"; return NB2_ERR_INVALID; }
+  if (B == 0) return NB2_OK;
+  k_ik_backward<<<(B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(ik->m->md, B, ik->n, ik->pos_dim, ik->vel_dim, ik->d_ent, state, grad_pos, grad_vel, grad_state);
+  g_launches++;
+  NB2_CUDA(cudaGetLastError());
+  return NB2_OK;
+}
+
 int nb2_forward_dynamics(const nb2_model* cm, int B, const double* pos, const double* vel, const double* force, double* accel, void* stream) {
   nb2_model* m = const_cast<nb2_model*>(cm);
   if (!m || B < 0 || !pos || !vel || !force || !accel) { g_err = "nb2_forward_dynamics: bad argument"; return NB2_ERR_INVALID; }

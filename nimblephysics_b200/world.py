@@ -676,6 +676,28 @@ class World:
             timestep(self, torch.tensor(self.getState(), dtype=torch.float64), torch.tensor(self.getAction(), dtype=torch.float64))
         self._action = None
 
+    def _legacy_jacobians(self):
+        import torch
+
+        from .jacobians import step_jacobians
+
+        dev = torch.device("cuda", torch.cuda.current_device())
+        s = torch.tensor(self.getState(), dtype=torch.float32, device=dev)[None]
+        a = torch.tensor(self.getAction(), dtype=torch.float32, device=dev)[None]
+        _, Js, Ja = step_jacobians(self, s, a)
+        return Js[0].double().cpu().numpy(), Ja[0].double().cpu().numpy()
+
+    def getStateJacobian(self):
+        """[2n, 2n] d state_{t+1} / d state_t at the world's current state and action (World::getStateJacobian,
+        BackpropSnapshot::getStateJacobian, dart/neural/BackpropSnapshot.cpp:1230-1241).  The world is not advanced."""
+        return self._legacy_jacobians()[0]
+
+    def getActionJacobian(self):
+        """[2n, a] d state_{t+1} / d action_t (BackpropSnapshot::getActionJacobian, :1245-1260): like the reference's assembly the
+        position rows are zero (lossWrtTorque = forceVel^T lossWrtVelocity, BackpropSnapshot.cpp:176) and the velocity rows hold the
+        force-vel block restricted to the action space."""
+        return self._legacy_jacobians()[1]
+
     def setState(self, state):
         state = np.asarray(state, dtype=np.float64).reshape(-1)
         if state.size != self.getStateSize():

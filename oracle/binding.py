@@ -90,6 +90,20 @@ class OracleWorld:
         lib().orc_backprop(self.h, _p(s), _p(a), _p(g), _p(gs), _p(ga))
         return gs, ga
 
+    def ik(self, state, types, bodies, want_jac=True):
+        """IKMapping outputs for raw body indices `bodies` (types: 0 spatial, 1 linear, 2 angular, 3 COM of that body's skeleton):
+        (pos, vel, d pos/d q, d vel/d qdot)."""
+        s = np.ascontiguousarray(state, np.float64)
+        t = np.ascontiguousarray(types, np.int32); b = np.ascontiguousarray(bodies, np.int32)
+        sk = np.ascontiguousarray(self.raw.skel_id, np.int32)
+        dim = int(sum(6 if k == 0 else 3 for k in t))
+        pos, vel = np.empty(dim), np.empty(dim)
+        Jp, Jv = np.zeros((dim, self.n)), np.zeros((dim, self.n))
+        I = ctypes.c_int
+        lib().orc_ik(self.h, _p(s), I(len(t)), _p(t, I), _p(b, I), _p(sk, I), I(dim), _p(pos), _p(vel),
+                     _p(Jp) if want_jac else None, _p(Jv) if want_jac else None)
+        return pos, vel, Jp, Jv
+
 
 # ---------------------------------------------------------------------------------------------- contact stage
 def _pi(a):

@@ -127,12 +127,10 @@ template <class S> static std::vector<BodyState<S>>& workspace(int nb) {
   return B;
 }
 
-// Skeleton::computeForwardDynamics for every mobile skeleton: fills B (transforms, velocities, articulated
-// inertias, psi) and the joint accelerations qdd.
+// kinematics, root -> leaf: joint transforms, world transforms, body-frame spatial velocities (Frame.cpp:144-160, GenericJoint.hpp:1803-1823)
 template <class S>
-static void aba_pass(const Model& M, const S* q, const S* v, const S* tau, std::vector<BodyState<S>>& B, std::vector<S>& qdd) {
+static void kinematics_pass(const Model& M, const S* q, const S* v, std::vector<BodyState<S>>& B) {
   const int nb = M.nb;
-  const double dt = M.dt;
   // ---- kinematics, root -> leaf (Frame.cpp:144-160, GenericJoint.hpp:1803-1823)
   for (int i = 0; i < nb; i++) {
     BodyState<S>& b = B[i];
@@ -172,6 +170,15 @@ static void aba_pass(const Model& M, const S* q, const S* v, const S* tau, std::
     b.eta = ad(b.V, Sv);  // dS = 0 for these joint types in this build
     b.G = spatial_tensor<S>(M, i);
   }
+}
+
+// Skeleton::computeForwardDynamics for every mobile skeleton: fills B (transforms, velocities, articulated
+// inertias, psi) and the joint accelerations qdd.
+template <class S>
+static void aba_pass(const Model& M, const S* q, const S* v, const S* tau, std::vector<BodyState<S>>& B, std::vector<S>& qdd) {
+  const int nb = M.nb;
+  const double dt = M.dt;
+  kinematics_pass<S>(M, q, v, B);
   // ---- articulated inertia + bias force, leaf -> root (BodyNode.cpp:2046-2114)
   static thread_local std::vector<std::vector<int>> kids;
   if ((int)kids.size() < nb) kids.resize(nb);
@@ -740,6 +747,39 @@ static void step_jacobian(const Model& M, const double* q, const double* v, cons
   }
 }
 
+
+// ---- IKMapping (neural/IKMapping.cpp:146-237): mapped positions / velocities of raw body nodes.  type 0 SPATIAL [log R; p | omega; v],
+// 1 LINEAR, 2 ANGULAR, 3 COM of the skeleton of body `body` (Skeleton::getCOM = sum m_i W_i c_i / sum m_i).
+template <class S> static Vec3<S> ang_of(const Vec6<S>& V) { return v3<S>(V[0], V[1], V[2]); }
+template <class S> static Vec3<S> lin_of(const Vec6<S>& V) { return v3<S>(V[3], V[4], V[5]); }
+template <class S>
+static void ik_map(const Model& M, const S* q, const S* v, int nent, const int* type, const int* body, const int* skel_of_body, S* pos, S* vel) {
+  std::vector<BodyState<S>> B(M.nb);
+  kinematics_pass<S>(M, q, v, B);
+  int cp = 0;
+  for (int e = 0; e < nent; e++) {
+    if (type[e] == 3) {
+      S mt = S(0.0); Vec3<S> c = v3<S>(S(0.0), S(0.0), S(0.0)), cv = c;
+      for (int i = 0; i < M.nb; i++) {
+        if (skel_of_body[i] != skel_of_body[body[e]]) continue;
+        Vec3<S> lc = v3<S>(S(M.com[3 * i]), S(M.com[3 * i + 1]), S(M.com[3 * i + 2]));
+        Vec3<S> wc = mul(B[i].W.R, lc) + B[i].W.p;
+        Vec3<S> om = mul(B[i].W.R, ang_of(B[i].V)), vl = mul(B[i].W.R, lin_of(B[i].V));
+        Vec3<S> vc = vl + cross(om, mul(B[i].W.R, lc));  // BodyNode::getCOMLinearVelocity
+        mt = mt + S(M.mass[i]);
+        c = c + wc * S(M.mass[i]); cv = cv + vc * S(M.mass[i]);
+      }
+      for (int k = 0; k < 3; k++) { pos[cp + k] = c[k] / mt; vel[cp + k] = cv[k] / mt; }
+      cp += 3;
+      continue;
+    }
+    const BodyState<S>& b = B[body[e]];
+    Vec3<S> phi = logMap(b.W.R), om = mul(b.W.R, ang_of(b.V)), vl = mul(b.W.R, lin_of(b.V));
+    if (type[e] != 1) { for (int k = 0; k < 3; k++) { pos[cp + k] = phi[k]; vel[cp + k] = om[k]; } cp += 3; }
+    if (type[e] != 2) { for (int k = 0; k < 3; k++) { pos[cp + k] = b.W.p[k]; vel[cp + k] = vl[k]; } cp += 3; }
+  }
+}
+
 }  // namespace orc
 
 // =====================================================================================
@@ -790,6 +830,29 @@ void orc_step_f32(void* h, const double* state, const double* action, double* ne
   for (size_t i = 0; i < M.action_map.size(); i++) tau[M.action_map[i]] = (float)action[i];
   orc::step_nocontact<float>(M, q.data(), v.data(), tau.data(), qn.data(), vn.data());
   for (int i = 0; i < n; i++) { next_state[i] = qn[i]; next_state[n + i] = vn[i]; }
+}
+
+// IKMapping: mapped pos / vel (dim each) and the Jacobians d pos/d q, d vel/d qdot (row-major [dim x n]) by dual numbers
+// (the reference builds them from Skeleton::getWorldPositionJacobian / getWorldJacobian, IKMapping.cpp:371-476)
+void orc_ik(void* h, const double* state, int nent, const int* type, const int* body, const int* skel_of_body, int dim, double* pos, double* vel,
+            double* Jpos, double* Jvel) {
+  const Model& M = *(Model*)h;
+  const int n = M.ndof;
+  orc::ik_map<double>(M, state, state + n, nent, type, body, skel_of_body, pos, vel);
+  if (!Jpos && !Jvel) return;
+  constexpr int N = 12;
+  typedef orc::Dual<N> D;
+  std::vector<D> q(n), v(n), p(dim), w(dim);
+  for (int pass = 0; pass < 2; pass++) {
+    double* J = pass ? Jvel : Jpos;
+    if (!J) continue;
+    for (int c0 = 0; c0 < n; c0 += N) {
+      for (int i = 0; i < n; i++) { q[i] = D(state[i]); v[i] = D(state[n + i]); }
+      for (int k = 0; k < N && c0 + k < n; k++) (pass ? v : q)[c0 + k].d[k] = 1.0;
+      orc::ik_map<D>(M, q.data(), v.data(), nent, type, body, skel_of_body, p.data(), w.data());
+      for (int k = 0; k < N && c0 + k < n; k++) for (int r = 0; r < dim; r++) J[(size_t)r * n + c0 + k] = (pass ? w : p)[r].d[k];
+    }
+  }
 }
 
 // Jacobians wrt full tau (n columns), row-major: J[2n x 3n] = d[q+;v+]/d[q;v;tau]

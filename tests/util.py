@@ -55,3 +55,27 @@ def contact_inputs(raw, name, B, seed=0):
     if name != "half_cheetah":
         a[:, :6] = 0.0
     return s.astype(np.float32), a.astype(np.float32)
+
+
+def multiarm_world(nlinks=5, length=0.2, gravity=(0.0, 0.0, 0.0)):
+    """createMultiarmRobot(nlinks, length) (unittests/TestHelpers.hpp): a chain of revolute joints with alternating axes."""
+    import nimblephysics_b200 as nb
+
+    w = nb.World()
+    w.setGravity(list(gravity))
+    w.setTimeStep(1e-3)
+    sk = nb.Skeleton("arm")
+    parent = None
+    axes = [[0, 0, 1], [0, 1, 0], [1, 0, 0]]
+    for k in range(nlinks):
+        j, b = sk.createRevoluteJointAndBodyNodePair(parent)
+        j.setAxis(axes[k % 3])
+        T = nb.Isometry3()
+        T.set_translation([0, 0, length if k else 0.0])
+        j.setTransformFromParentBodyNode(T)
+        b.setMass(1.0 + 0.1 * k)
+        b.setLocalCOM([0.01 * k, 0.0, length / 2])
+        b.setMomentOfInertia(0.02, 0.03, 0.01, 0.001, 0.0, 0.002)
+        parent = b
+    w.addSkeleton(sk)
+    return w
