@@ -6,7 +6,7 @@ from .loader import loadWorld, load_skeleton
 from .modelspec import RawModel, CanonModel, flatten_world, compile_model
 from .timestep import timestep, TimestepLayer, contact_cache, reset_contact_cache, check_contact_status
 from .engine import DeviceModel, device_model_for
-from .rollout import rollout, rollout_fused, rollout_tape_bytes, shard_range, shard_batch, allreduce_sum_, sharded_trajectory_loss
+from .rollout import rollout, rollout_fused, rollout_tape_bytes, multishot_rollout, shard_range, shard_batch, allreduce_sum_, sharded_trajectory_loss
 
 __all__ = ["World", "Skeleton", "BodyNode", "Joint", "Isometry3", "BoxShape", "SphereShape", "CapsuleShape",
            "loadWorld", "load_skeleton", "timestep", "TimestepLayer", "rollout", "rollout_fused", "DeviceModel", "device_model_for", "RawModel", "CanonModel", "flatten_world", "compile_model"]

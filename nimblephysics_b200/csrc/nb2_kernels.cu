@@ -881,8 +881,15 @@ static nb2::cw::Dims cdims(const nb2_model* m, int MC, int bwd, int mode = NB2_W
 }
 // worlds (warps) per block of a lockstep kernel: as many as shared memory allows (one block per SM), fewer for batches that would
 // otherwise leave SMs idle
-static int pick_wpb(int B, int sm_count, size_t smem_per_warp, int max_warps) {
+static int wpb_cap(int which) {  // dev knob: NB2_WPB="build,solve,apply,bwd" caps the worlds per block of the lockstep kernels (0 = default)
+  static int caps[4] = {0, 0, 0, 0};
+  static const bool init = [] { const char* e = getenv("NB2_WPB"); if (e) sscanf(e, "%d,%d,%d,%d", &caps[0], &caps[1], &caps[2], &caps[3]); return true; }();
+  (void)init;
+  return caps[which];
+}
+static int pick_wpb(int B, int sm_count, size_t smem_per_warp, int max_warps, int which = -1) {
   int w = (int)((size_t)kMaxSmem / (smem_per_warp ? smem_per_warp : 1));
+  if (which >= 0 && wpb_cap(which) > 0 && wpb_cap(which) < max_warps) max_warps = wpb_cap(which);
   if (w > max_warps) w = max_warps;
   const int spread = (B + sm_count - 1) / sm_count;
   if (w > spread) w = spread;
@@ -1063,8 +1070,8 @@ int nb2_step_forward_contact(const nb2_model* cm, int B, const float* state, con
   const size_t smem_s = (NB2_WS_DESC_DOUBLES + nb2::cw::ws_doubles(P.ds_solve)) * sizeof(double);
   const size_t smem_a = (NB2_WS_DESC_DOUBLES + nb2::cw::ws_doubles(P.ds_apply)) * sizeof(double);
   if ((rc = cstep_smem_attr(k_cbuild, smem, attr_b)) || (rc = cstep_smem_attr(k_csolve<0>, smem_s, attr_s)) || (rc = cstep_smem_attr(k_csolve<1>, smem_s, attr_s2)) || (rc = cstep_smem_attr(k_capply, smem_a, attr_a))) return rc;
-  const int wpb_b = pick_wpb(B, m->sm_count, smem, NB2_CBUILD_MAXW), wpb_s = pick_wpb(B, m->sm_count, smem_s, NB2_CSOLVE_MAXW),
-            wpb_a = pick_wpb(B, m->sm_count, smem_a, NB2_CAPPLY_MAXW);
+  const int wpb_b = pick_wpb(B, m->sm_count, smem, NB2_CBUILD_MAXW, 0), wpb_s = pick_wpb(B, m->sm_count, smem_s, NB2_CSOLVE_MAXW, 1),
+            wpb_a = pick_wpb(B, m->sm_count, smem_a, NB2_CAPPLY_MAXW, 2);
   k_cbuild<<<(B + wpb_b - 1) / wpb_b, 32 * wpb_b, smem * wpb_b, st>>>(v.md, m->contact, P, state, action, next_state, (double*)saved_fp64, m_lcp, status, ncontacts, cinfo,
                                                                       contact_record, smem);
   k_csolve<0><<<(B + wpb_s - 1) / wpb_s, 32 * wpb_s, smem_s * wpb_s, st>>>(m->contact, P, m->md.ndof, x_lcp, m_lcp, labels, status, contact_record, status_accum, smem_s,
@@ -1090,13 +1097,13 @@ static int cbwd_launch(nb2_model* m, int B, const float* state, const float* act
   const CStepArgs P = cstep_args(m, v, B, workspace, 1);
   const size_t smem_base = ((((size_t)P.bwd_words + 1) & ~(size_t)1) + NB2_WS_DESC_DOUBLES + ((P.ws_small_doubles + 1) & ~(size_t)1)) * sizeof(double);
   const size_t smem_staged = smem_base + ((((size_t)P.saved_words + 1) & ~(size_t)1) + 2) * sizeof(double);
-  const int stage = pick_wpb(B, m->sm_count, smem_staged, NB2_CBWD_MAXW) == pick_wpb(B, m->sm_count, smem_base, NB2_CBWD_MAXW);
+  const int stage = pick_wpb(B, m->sm_count, smem_staged, NB2_CBWD_MAXW, 3) == pick_wpb(B, m->sm_count, smem_base, NB2_CBWD_MAXW, 3);
   const size_t smem = stage ? smem_staged : smem_base;
   static bool attr_done[64] = {};
   int rc = cstep_smem_attr(k_cstep_bwd, smem, attr_done);
   if (rc) return rc;
   NB2_CUDA(cudaMemsetAsync(workspace, 0, 64, st));
-  const int wpb = pick_wpb(B, m->sm_count, smem, NB2_CBWD_MAXW);
+  const int wpb = pick_wpb(B, m->sm_count, smem, NB2_CBWD_MAXW, 3);
   k_cstep_bwd<<<(B + wpb - 1) / wpb, 32 * wpb, smem * wpb, st>>>(v.md, m->contact, P, state, action, (const double*)saved_fp64, contact_record, grad_next_state,
                                                                  grad_state, grad_action, grad_inertia, status_accum, smem, stage, accumulate);
   g_launches++;

@@ -140,6 +140,32 @@ def rollout_tape_bytes(world, B: int, T: int, checkpoint_every: int = 0) -> int:
     return device_model_for(world).rollout_contact_tape_bytes(B, T, int(checkpoint_every or 0))
 
 
+def multishot_rollout(world, start_states: torch.Tensor, actions: torch.Tensor, shot_length: int, rollout_fn: Optional[Callable] = None):
+    """MultiShot as a batch: the S = ceil(T / shot_length) shots of a T-step problem run as S*B independent worlds of ONE rollout
+    (the reference gives each shot a cloned World and a std::async thread, dart/trajectory/MultiShot.cpp:24-72, 1228-1334).
+      start_states [S, B, 2n]: the start state of every shot (knot points; start_states[0] is the trajectory's x_0);
+      actions      [T, B, a].
+    Returns (states [T, B, 2n], defects [S-1, B, 2n]):
+      states[t]  = the state after step t (MultiShot::getStates concatenates the shots' snapshots, MultiShot.cpp:902-975);
+      defects[i] = final state of shot i - start state of shot i+1, the knot-point constraints of MultiShot::computeConstraints
+                   (MultiShot.cpp:164-213).
+    Differentiable with respect to start_states and actions; a last shot shorter than shot_length is padded with zero actions whose
+    steps are discarded (they receive no gradient)."""
+    S, B, n2 = start_states.shape
+    T, na = actions.shape[0], actions.shape[2]
+    L = int(shot_length)
+    if L <= 0 or S != (T + L - 1) // L or actions.shape[1] != B:
+        raise ValueError(f"multishot_rollout(): {T} steps in shots of {L} need start_states [{(T + L - 1) // max(L, 1)}, {actions.shape[1]}, 2n], got {tuple(start_states.shape)}")
+    pad = S * L - T
+    acts = torch.cat([actions, actions.new_zeros((pad, B, na))], 0) if pad else actions
+    acts = acts.reshape(S, L, B, na).permute(1, 0, 2, 3).reshape(L, S * B, na)
+    traj = (rollout_fn or rollout_fused)(world, start_states.reshape(S * B, n2), acts)  # [L+1, S*B, 2n]
+    traj = traj.reshape(L + 1, S, B, n2)
+    states = traj[1:].permute(1, 0, 2, 3).reshape(S * L, B, n2)[:T]
+    defects = traj[L, : S - 1] - start_states[1:]
+    return states, defects
+
+
 def shard_range(total: int, rank: int, world_size: int) -> Tuple[int, int]:
     """Contiguous slice [lo, hi) of a batch of `total` worlds owned by `rank` (sizes differ by at most one)."""
     if world_size <= 0 or not (0 <= rank < world_size):

@@ -52,3 +52,29 @@ def test_contact_rollout_matches_chained_timestep(name, B, T, k):
     if 0 < k < T:
         assert nb.rollout_tape_bytes(world, B, T, k) < nb.rollout_tape_bytes(world, B, T, 0)
     nb.check_contact_status(world)
+
+
+def test_multishot_closed_knots_reproduce_the_single_shot():
+    """MultiShot as a batch (nimblephysics_b200.multishot_rollout; MultiShot.cpp:164-213, 902-975): with the knot points placed ON the
+    single-shot trajectory the shots reproduce it and every defect is zero; gradients reach the knots and the actions."""
+    import nimblephysics_b200 as nb
+    from tests.util import sample_inputs
+
+    raw = load_raw("atlas")
+    world = nb.World.from_raw(raw)
+    B, T, L = 16, 10, 4
+    s, a, _ = sample_inputs(raw, B, seed=5)
+    x0 = torch.tensor(s, device="cuda")
+    acts = torch.tensor(a, device="cuda")[None].repeat(T, 1, 1)
+    with torch.no_grad():
+        single = nb.rollout_fused(world, x0, acts)          # [T+1, B, 2n]
+    S = (T + L - 1) // L
+    starts = torch.stack([single[i * L] for i in range(S)], 0).clone().requires_grad_(True)
+    u = acts.clone().requires_grad_(True)
+    states, defects = nb.multishot_rollout(world, starts, u, L)
+    assert states.shape == (T, B, 2 * raw.ndof) and defects.shape == (S - 1, B, 2 * raw.ndof)
+    assert torch.allclose(states, single[1:], rtol=1e-5, atol=1e-5)
+    assert defects.abs().max().item() < 1e-5
+    (states[-1].pow(2).sum() + defects.pow(2).sum()).backward()
+    assert torch.isfinite(starts.grad).all() and torch.isfinite(u.grad).all()
+    assert starts.grad[-1].abs().max() > 0 and u.grad[-1].abs().max() > 0

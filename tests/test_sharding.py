@@ -72,3 +72,42 @@ def test_two_rank_gloo_rollout_matches_single_process():
     for t in range(T):
         ga = np.concatenate([r[3][t] for r in res])
         assert np.allclose(ga, acts[t].grad.numpy(), atol=1e-6)
+
+
+def test_multishot_layout_and_defects_cpu():
+    """MultiShot-as-batch bookkeeping (shots -> batch slices, getStates order, knot defects; MultiShot.cpp:164-213, 902-975) with a
+    stand-in integrator: x' = x + u broadcast over the state, so every number is predictable."""
+    import torch
+    import nimblephysics_b200 as nb
+
+    def fake_rollout(world, x0, acts):
+        xs = [x0]
+        for t in range(acts.shape[0]):
+            xs.append(xs[-1] + acts[t].sum(-1, keepdim=True))
+        return torch.stack(xs, 0)
+
+    T, L, B, n2, na = 7, 3, 2, 4, 2
+    S = 3
+    g = torch.Generator().manual_seed(0)
+    starts = torch.randn(S, B, n2, generator=g, requires_grad=True)
+    acts = torch.randn(T, B, na, generator=g, requires_grad=True)
+    states, defects = nb.multishot_rollout(None, starts, acts, L, rollout_fn=fake_rollout)
+    assert states.shape == (T, B, n2) and defects.shape == (S - 1, B, n2)
+    for t in range(T):
+        s, k = divmod(t, L)
+        ref = starts[s] + acts[s * L: s * L + k + 1].sum(0).sum(-1, keepdim=True)
+        assert torch.allclose(states[t], ref, atol=1e-6)
+    for i in range(S - 1):
+        assert torch.allclose(defects[i], states[(i + 1) * L - 1] - starts[i + 1], atol=1e-6)
+    (states[-1].sum() + defects.pow(2).sum()).backward()
+    assert torch.isfinite(starts.grad).all() and torch.isfinite(acts.grad).all()
+    # closing the knots (start of shot i+1 := end of shot i) reproduces the single-shot trajectory
+    with torch.no_grad():
+        x = starts[0]
+        single = []
+        for t in range(T):
+            x = x + acts[t].sum(-1, keepdim=True)
+            single.append(x)
+        closed = torch.stack([starts[0].detach(), single[L - 1], single[2 * L - 1]], 0)
+        st2, df2 = nb.multishot_rollout(None, closed, acts.detach(), L, rollout_fn=fake_rollout)
+        assert torch.allclose(st2, torch.stack(single, 0), atol=1e-6) and df2.abs().max() < 1e-6
