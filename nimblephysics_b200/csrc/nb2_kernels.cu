@@ -407,11 +407,16 @@ k_cstep_bwd(const __grid_constant__ Nb2ModelDev<double> M, const __grid_constant
     if (sg == 5) {  // lambda and its fields are complete: the contact adjoint turns them into w and prepares the injections
       __syncwarp();
       CW_PROF(20);
+#ifndef NB2_DEV_NO_CBWD
       cd = nb2::cw::contact_backward(M, C, st, sv, wsm, P.ds, P.pool, P.db, crec + (size_t)wc * P.rec_doubles, scr, L.oLam, L.oBody);
+#endif
       __syncwarp();
       CW_PROF(29);
     }
     __syncthreads();  // lockstep: every warp of the block sweeps the same stage (see k_csolve)
+#ifdef NB2_DEV_NO_B3
+    if (sg == 5 || sg == 7) continue;
+#endif
     if (lane < M.lanes) nb2::world_backward_stage<double, 1, true>(M, scr, sv, 1, lane, sg, (ginertia && live) ? ginertia + w : nullptr, nullptr, (size_t)P.B, &cd);
     if ((NB2_BWD_SYNC_MASK >> sg) & 1u) __syncwarp();
   }
