@@ -127,7 +127,9 @@ int nb2_step_backward_host(nb2_model* m, int B, const float* grad_next_state, fl
  *   x_lcp   [B, NB2_MAX_ROWS] double   in: cached LCP solution (BoxedLcpConstraintSolver::mX), out: this step's solution
  *   m_lcp   [B] int32                  in: its size (-1: none), out: LCP dimension of this step
  *   labels  [B, NB2_MAX_ROWS] int32    out: ConstraintMapping per row (-2 clamping, -1 not clamping, >=0 upper-bound -> normal row)
- *   status  [B] int32                  out: NB2_ST_* bits (which solver branch ran, unsupported geometry, overflow)
+ *   status  [B] int32                  out: bits 1 warm-start short-circuit, 2 Dantzig ran, 4 Dantzig failed, 8 PGS ran, 16 friction dropped,
+ *            32 NaN reset, 64 standardisation kept the raw x, 128 unsupported geometry (capsule side contact), 256 contacts dropped (overflow),
+ *            512 columns merged, 1024 restitution bounce active (no backward), 2048 backward failed (status_accum only), 4096 penetration correction
  *   ncontacts [B] int32                out
  *   cinfo   [B, NB2_MAX_CONTACTS, 10] float (optional, may be NULL): point(3) normal(3) depth bodyA bodyB type
  *   contact_record [B, nb2_contact_record_bytes/B/8] double (optional): what nb2_step_backward_contact needs (LCP size, labels,
@@ -136,8 +138,8 @@ int nb2_step_backward_host(nb2_model* m, int B, const float* grad_next_state, fl
  */
 size_t nb2_contact_workspace_bytes(const nb2_model* m, int B);
 int nb2_model_has_contacts(const nb2_model* m);
-/* forward step WITH the contact stage: ONE fused kernel, one warp per world (fp64 ABA sweeps + contact / boxed-LCP stage in shared
- * memory).  saved_fp64: nb2_saved_words_per_world(m) * B doubles (world-major; opaque), may be NULL when no backward will follow
+/* forward step WITH the contact stage: one warp per world, the problem in shared memory; with a saved stream four kernels in stream order
+ * (build -> solve head -> solve tail over the worlds that need the chain -> apply), without one a single fused kernel.  saved_fp64: nb2_saved_words_per_world(m) * B doubles (world-major; opaque), may be NULL when no backward will follow
  * (then contact_record must be NULL too).  workspace: nb2_contact_workspace_bytes(m, B) bytes of device memory — a pool of large
  * per-world workspaces for the rare worlds whose contact count exceeds the shared-memory capacity (nb2_model_set_contact_capacity).
  * status_accum (optional, [B] int32): every step ORs its status word into it — a sticky copy the caller reads once per rollout. */

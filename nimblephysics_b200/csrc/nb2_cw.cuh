@@ -44,7 +44,8 @@
 #define NB2_ST_UNSUPPORTED_GEOMETRY 128
 #define NB2_ST_CONTACT_OVERFLOW 256
 #define NB2_ST_MERGED 512    // LCPUtils::reduce merged near-identical columns before a solver ran
-#define NB2_ST_BOUNCE 1024   // a restitution (bounce) or penetration-correction term raised some b_i
+#define NB2_ST_BOUNCE 1024   // a restitution (bounce) term raised some b_i: the backward of such a step is not implemented
+#define NB2_ST_PENCORR 4096  // a penetration-correction velocity raised some b_i (informational: the backward handles it)
 #define NB2_ST_BWD_ERROR 2048  // set by the BACKWARD kernel: the step could not be back-propagated (gradients are NaN)
 
 // ConstraintMapping (dart/neural/ConstrainedGroupGradientMatrices.hpp:33-39)
@@ -1361,7 +1362,7 @@ NB2_HD void collide_and_filter(const Nb2ContactDev& C, const Ws& ws, const Dims&
 // rows of the LCP: wrenches, b = -J v*, bounds, findex (ContactConstraint.cpp:66-230, 361-514, 687-695, 734-795); one row per lane.
 // Returns the status bits raised here (bounce).  want_b = false (backward pass): wrenches only.
 NB2_HD int build_rows(const Nb2ModelDev<double>& M, const Nb2ContactDev& C, const Ws& ws, int m, bool want_b) {
-  bool bounced = false;
+  bool bounced = false, pencorr = false;
   CW_FOR(r, m) {
     const int c = ws.rowc[r], k = r - ws.crow[c];
     const double mu = ws.cmu[c], e = ws.crest[c];
@@ -1394,16 +1395,16 @@ NB2_HD int build_rows(const Nb2ModelDev<double>& M, const Nb2ContactDev& C, cons
         double bv = ws.cdepth[c];
         if (bv < 0) bv = 0; else { bv *= 0.01 * (1.0 / M.dt); if (bv > 1e-3) bv = 1e-3; }
         if (!C.pen_correction) bv = 0;
-        else if (bv > 0) bounced = true;
+        else if (bv > 0) pencorr = true;
         if (e > 1e-3) { const double rv = rel * e; if (rv > 1e-1) { if (rv > bv) { bv = rv; if (bv > 1e2) bv = 1e2; bounced = true; } } }
         rel += bv;
       } else { ws.lo[r] = -mu; ws.hi[r] = mu; ws.findex[r] = ws.crow[c]; }
       ws.b[r] = rel;
     }
   }
-  bounced = cw_any(bounced);
+  bounced = cw_any(bounced); pencorr = cw_any(pencorr);
   CW_SYNC();
-  return bounced ? NB2_ST_BOUNCE : 0;
+  return (bounced ? NB2_ST_BOUNCE : 0) | (pencorr ? NB2_ST_PENCORR : 0);
 }
 
 // ---- impulse response along one chain (impulse-ABA with the forward's U, psi; BodyNode.cpp:2117-2138, 2188-2215,
@@ -2114,6 +2115,12 @@ NB2_HD BwdContactData<1> contact_backward(const Nb2ModelDev<double>& M, const Nb
         V3<D1> pA, pB;
         if (ba >= 0) pA = gxf_apply_inv(WDa, co[c].point);
         if (bb >= 0) pB = gxf_apply_inv(WDb, co[c].point);
+        if (C.pen_correction && coefV[ws.crow[cc]] != 0.0) {
+          // b_normal carries the penetration-correction velocity kpen * depth while it is below its cap (ContactConstraint.cpp:395-408):
+          // dL/db = mu, so the pose gradient gains mu * kpen * d(depth)  (gsum is scaled by kap = -1/dt below and by -dt at the end: net +1)
+          const double bv = co[c].depth.v * 0.01 * (1.0 / dt);
+          if (bv > 0.0 && bv <= 1e-3) gsum -= coefV[ws.crow[cc]] * (0.01 * (1.0 / dt)) * co[c].depth.d[0];  // coefV = -mu
+        }
         for (int kk = 0; kk < (fric ? 3 : 1); kk++) {
           const int r = ws.crow[cc] + kk;
           const double cW = coefW[r], cV = coefV[r];

@@ -160,7 +160,7 @@ def _raise_on_status(bits: int, worlds, backward=False):
     if bits & ST_BWD_ERROR:
         raise RuntimeError(
             f"backward through the contact stage failed for worlds {list(worlds)[:16]} (their gradients are NaN): a restitution (bounce) "
-            "or penetration-correction term was active in the forward step (status bit 1024; its backward is not implemented), or the "
+            "term was active in the forward step (status bit 1024; its backward is not implemented), or the "
             "contact rows regenerated in the backward pass did not match the forward's")
     if bits & ST_OVERFLOW:
         raise RuntimeError(f"contact stage: worlds {list(worlds)[:16]} generated more than {MAX_CONTACTS} contacts / {MAX_ROWS} LCP rows "

@@ -319,3 +319,29 @@ def test_restitution_forward_parity_and_loud_backward(oracle_mod):
         else:
             assert np.isfinite(gs[w]).all()
     assert bounced >= 4
+
+
+def test_penetration_correction_forward_and_backward(oracle_mod):
+    """World::setPenetrationCorrectionEnabled(true): b_normal gains min((depth - allowance) * erp / dt, cap) (ContactConstraint.cpp:395-408).
+    Forward parity with the oracle, status bit 4096, and the backward — including the depth derivative of the uncapped correction, which
+    the dual pass of contact_backward adds — against the oracle's dual-number Jacobian of the same frozen-classification step."""
+    raw = load_raw("half_cheetah")
+    raw.penetration_correction = True
+    cm = nb.compile_model(raw)
+    ew, ow = EmulWorld(cm), ob.OracleContactWorld(raw)
+    s, a = contact_inputs(raw, "half_cheetah", 10, seed=6)
+    s[5:, 1] += 0.0099
+    s[5, 1] += 0.00585  # the first contact of world 5 becomes shallower than 1e-4: its correction stays UNDER the cap (depth * 10 < 1e-3)
+    r = ew.forward_contact(s, a)
+    d5 = r["cinfo"][5, : r["nc"][5], 6]
+    assert 0 < d5[0] < 1e-4 and r["labels"][5][0] == -2, (d5, r["labels"][5][:6])  # ... and its normal row is CLAMPING
+    seen = 0
+    for w in range(s.shape[0]):
+        ro = ow.step_contact(s[w].astype(np.float64), a[w].astype(np.float64))
+        assert rel_err(r["next"][w], ro["next_state"]) < 1e-6
+        if r["status"][w] & 4096:
+            seen += 1
+        assert not (r["status"][w] & 1024)
+    assert seen >= 3
+    kinds = _check_backward(ob, raw, s, a, tol=2e-5)
+    assert len(kinds) == s.shape[0]

@@ -184,3 +184,29 @@ def test_mass_gradient_through_contact_matches_host_build(oracle_mod):
     ref = P @ gi.astype(np.float64).sum(axis=1)
     assert int((r["m"] > 0).sum()) > B // 2
     assert rel_err(gm, ref) < 1e-4, (gm, ref)
+
+
+def test_penetration_correction_backward_matches_oracle(oracle_mod):
+    """World::setPenetrationCorrectionEnabled(true) (ContactConstraint.cpp:395-408): steps carry status bit 4096 and back-propagate —
+    including the depth derivative of an uncapped correction — like the oracle's dual-number Jacobian.  (Restitution still fails loudly.)"""
+    raw = load_raw("half_cheetah")
+    raw.penetration_correction = True
+    world = nb.World.from_raw(raw)
+    ow = ob.OracleContactWorld(raw)
+    B = 10
+    s, a = contact_inputs(raw, "half_cheetah", B, seed=6)
+    s[5:, 1] += 0.0099
+    s[5, 1] += 0.00585  # first contact of world 5 shallower than 1e-4: correction under its cap, normal row clamping
+    g = np.random.default_rng(2).normal(size=(B, 2 * raw.ndof)).astype(np.float32)
+    st = torch.tensor(s, device="cuda", requires_grad=True)
+    at = torch.tensor(a, device="cuda", requires_grad=True)
+    nb.reset_contact_cache(world)
+    out = nb.timestep(world, st, at)
+    out.backward(torch.tensor(g, device="cuda"))
+    bits = nb.check_contact_status(world)
+    assert bits & 4096 and not bits & (1024 | 2048)
+    gs, ga = st.grad.cpu().numpy(), at.grad.cpu().numpy()
+    for w in range(B):
+        rgs, rga, rc = ow.backprop_contact(s[w].astype(np.float64), a[w].astype(np.float64), g[w].astype(np.float64))
+        assert rc >= 0
+        assert rel_err(gs[w], rgs) < 1e-4 and rel_err(ga[w], rga) < 1e-4, w
