@@ -129,7 +129,7 @@ int nb2_step_backward_host(nb2_model* m, int B, const float* grad_next_state, fl
  *   labels  [B, NB2_MAX_ROWS] int32    out: ConstraintMapping per row (-2 clamping, -1 not clamping, >=0 upper-bound -> normal row)
  *   status  [B] int32                  out: bits 1 warm-start short-circuit, 2 Dantzig ran, 4 Dantzig failed, 8 PGS ran, 16 friction dropped,
  *            32 NaN reset, 64 standardisation kept the raw x, 128 unsupported geometry (capsule side contact), 256 contacts dropped (overflow),
- *            512 columns merged, 1024 restitution bounce active (no backward), 2048 backward failed (status_accum only), 4096 penetration correction
+ *            512 columns merged, 1024 restitution bounce active, 2048 backward failed (status_accum only), 4096 penetration correction
  *   ncontacts [B] int32                out
  *   cinfo   [B, NB2_MAX_CONTACTS, 10] float (optional, may be NULL): point(3) normal(3) depth bodyA bodyB type
  *   contact_record [B, nb2_contact_record_bytes/B/8] double (optional): what nb2_step_backward_contact needs (LCP size, labels,
@@ -149,8 +149,8 @@ int nb2_step_forward_contact(const nb2_model* m, int B, const float* state, cons
 size_t nb2_contact_record_bytes(const nb2_model* m, int B);
 /* VJP of a step taken with nb2_step_forward_contact (classification frozen at the forward solution), replaces
  * BackpropSnapshot::backpropState for steps with active contact constraints (dart/neural/BackpropSnapshot.cpp:980-1107,
- * 2723-3146).  Rows may act on one or two moving bodies.  If a world cannot be back-propagated (the rows regenerated in the backward
- * pass do not match the forward's, a bounce term was active, a compiled limit is exceeded) its gradients are NaN — never silent
+ * 2723-3146), including steps with restitution (bounce diagonals, :2624-2680) and penetration correction.  Rows may act on one or two moving
+ * bodies.  If a world cannot be back-propagated (the rows regenerated in the backward pass do not match the forward's, a compiled limit is exceeded) its gradients are NaN — never silent
  * garbage — and, when `status_accum` is given, bit NB2_ST_BWD_ERROR (2048) is OR-ed into status_accum[w]: callers check the array
  * once per rollout instead of scanning gradients.
  * grad_inertia: optional [10*nb][B] floats as in nb2_step_backward (mass gradient through the contact stage). */

@@ -44,7 +44,7 @@
 #define NB2_ST_UNSUPPORTED_GEOMETRY 128
 #define NB2_ST_CONTACT_OVERFLOW 256
 #define NB2_ST_MERGED 512    // LCPUtils::reduce merged near-identical columns before a solver ran
-#define NB2_ST_BOUNCE 1024   // a restitution (bounce) term raised some b_i: the backward of such a step is not implemented
+#define NB2_ST_BOUNCE 1024   // a restitution (bounce) term raised some b_i: the backward runs a second reverse sweep for such a world
 #define NB2_ST_PENCORR 4096  // a penetration-correction velocity raised some b_i (informational: the backward handles it)
 #define NB2_ST_BWD_ERROR 2048  // set by the BACKWARD kernel: the step could not be back-propagated (gradients are NaN)
 
@@ -316,7 +316,7 @@ NB2_HD Dims make_dims(int nb, int n, int nfree, int MC, int MR, int ncb, int cdo
   // the two work matrices double as: private chain buffers of the impulse tests (one per row / collision body), spatial velocity
   // changes of all bodies (impulse application), pair slots of the collision phase (at least 4)
   size_t mats = 0;
-  const size_t priv = (size_t)MR * cdofs, dv = (size_t)ncb * cdofs + (size_t)nb * (bwd ? 18 : 6), slots = 4 * (size_t)NB2_CW_PAIR_SLOT;
+  const size_t priv = (size_t)MR * cdofs, dv = (size_t)ncb * cdofs + (bwd ? (size_t)nb * 30 + 3 * (size_t)n + 32 : (size_t)nb * 6), slots = 4 * (size_t)NB2_CW_PAIR_SLOT;
   if (mode != 2) mats = 2 * (size_t)MR * d.LD;       // FULL / SOLVE: the two work matrices
   if (mode == 0 && mats < priv) mats = priv;          // FULL: private chain buffers of the impulse tests
   if (mode != 1 && mats < dv) mats = dv;              // FULL / APPLY: impulse application buffers
@@ -1361,7 +1361,9 @@ NB2_HD void collide_and_filter(const Nb2ContactDev& C, const Ws& ws, const Dims&
 
 // rows of the LCP: wrenches, b = -J v*, bounds, findex (ContactConstraint.cpp:66-230, 361-514, 687-695, 734-795); one row per lane.
 // Returns the status bits raised here (bounce).  want_b = false (backward pass): wrenches only.
-NB2_HD int build_rows(const Nb2ModelDev<double>& M, const Nb2ContactDev& C, const Ws& ws, int m, bool want_b) {
+// eeff (optional, [m]): per row the restitution coefficient the forward APPLIED — e when b = (1 + e)(-J v*), -1 when the bounce velocity hit its
+// cap (a constant was added), 0 otherwise; needs Vcb at v* like want_b.
+NB2_HD int build_rows(const Nb2ModelDev<double>& M, const Nb2ContactDev& C, const Ws& ws, int m, bool want_b, double* eeff = nullptr) {
   bool bounced = false, pencorr = false;
   CW_FOR(r, m) {
     const int c = ws.rowc[r], k = r - ws.crow[c];
@@ -1388,6 +1390,16 @@ NB2_HD int build_rows(const Nb2ModelDev<double>& M, const Nb2ContactDev& C, cons
       rel -= dot(JB, ldv6(ws.Vcb + 6 * kb));
     }
     stv6(ws.JA + 6 * r, JA); stv6(ws.JB + 6 * r, JB);
+    if (eeff) {  // the same decisions as below, on the same numbers
+      double ee = 0;
+      if (k == 0) {
+        double bv = ws.cdepth[c];
+        if (bv < 0) bv = 0; else { bv *= 0.01 * (1.0 / M.dt); if (bv > 1e-3) bv = 1e-3; }
+        if (!C.pen_correction) bv = 0;
+        if (e > 1e-3) { const double rv = rel * e; if (rv > 1e-1 && rv > bv) ee = (rv > 1e2) ? -1.0 : e; }
+      }
+      eeff[r] = ee;
+    }
     if (want_b) {
       if (k == 0) {
         ws.lo[r] = 0.0; ws.hi[r] = HUGE_VAL; ws.findex[r] = -1;
@@ -1886,6 +1898,8 @@ int pair_contacts_dual(const Nb2ContactDev& C, int sa, int sb, const Xf<D1>& Ta,
   return pair_contacts<D1>(C, sa, sb, Ta, Tb, co, status);
 }
 
+// BOUNCE = false compiles the restitution branch out (models whose bodies all have restitution 0 — the usual case — keep the leaner kernel)
+template <bool BOUNCE>
 NB2_HD BwdContactData<1> contact_backward(const Nb2ModelDev<double>& M, const Nb2ContactDev& C, const float* st, const double* sv, Ws* wsm,
                                           const Dims& d_s, const BigPool& pool, const Dims& d_b, const double* rec, double* scr, int oLam, int oBody) {
   const int nb = M.nb, n = M.ndof;
@@ -1899,9 +1913,14 @@ NB2_HD BwdContactData<1> contact_backward(const Nb2ModelDev<double>& M, const Nb
   if (m <= 0) { NB2_BWD_DRAIN(); return cd; }
   cd.active = 1;
   const int fstatus = (int)rec[1];
-  // restitution: b depends on v* through (1 + e) J v*, which needs a second multiplier field in the reverse sweep
-  // (BackpropSnapshot::getBounceApproximationJacobian, BackpropSnapshot.cpp:1131-1226) — not implemented: fail loudly
-  if (fstatus & NB2_ST_BOUNCE) { cd.error = 5; cd.active = 0; NB2_BWD_DRAIN(); return cd; }
+  // restitution: b_r = (1 + e_r)(-J_r v*) on the rows that bounced.  With B = diag(1 + e):  dL/dv* = g - A_c B mu (the tree part is driven by
+  // w_B = w - nu_e, nu_e = M^-1 A_c E mu) while the impulse part keeps w = lambda - M^-1 A_c mu, and the contact-Jacobian part gains a v* field:
+  //     Phi = sum_r f_r J_r w - mu_r J_r (v+ + e_r v*).
+  // Since the reverse sweep is bilinear in (multiplier field, acceleration field) this is the usual sweep with (w, realised acceleration) PLUS a
+  // second sweep with (-nu_e, UNCONSTRAINED acceleration) that also carries the injections of the v* term (bounce_pass2_*, run by the kernel
+  // after the first B3).  The reference reaches the same Jacobians through getBounceDiagonals (BackpropSnapshot.cpp:2624-2680, 3088-3146).
+  const bool bounce = BOUNCE && (fstatus & NB2_ST_BOUNCE) != 0;
+  if (!BOUNCE && (fstatus & NB2_ST_BOUNCE)) { cd.error = 5; cd.active = 0; NB2_BWD_DRAIN(); return cd; }  // (cannot happen: the launcher picks BOUNCE from the model)
   Ws ws = *wsm;
   Dims d = d_s;
   TreeSrc S; S.scr = nullptr; S.Iinv = nullptr; S.sv = sv; S.st = st; S.nb = nb; S.nfree = M.nfree;
@@ -1911,7 +1930,11 @@ NB2_HD BwdContactData<1> contact_backward(const Nb2ModelDev<double>& M, const Nb
   const double* mapping_r = rec + 2; const double* xr = rec + 2 + NB2_MAX_ROWS; const double* dqd_imp = rec + 2 + 2 * NB2_MAX_ROWS;
   // ---- contacts and row wrenches re-generated from the saved transforms (same code as the forward => same rows)
   CW_PROF_DECL;
-  fk_collision_bodies(M, C, S, nullptr, ws);
+  if (bounce) {  // body velocities at v* = v + dt qdd (unconstrained): the rows re-decide which of them bounced
+    CW_FOR(dd, n) ws.vplus[dd] = (double)st[n + dd] + dt * sv[kQdd + dd];
+    CW_SYNC();
+  }
+  fk_collision_bodies(M, C, S, bounce ? ws.vplus : nullptr, ws);
   CW_PROF(21);
   CW_PHASE(); ph++;  // 1
   collide_and_filter(C, ws, d);
@@ -1920,6 +1943,7 @@ NB2_HD BwdContactData<1> contact_backward(const Nb2ModelDev<double>& M, const Nb
   if (ws_big) {
     const Ws wb = carve(ws_big, d_b);
     CW_FOR(e, C.ncb * 12) wb.Wcb[e] = ws.Wcb[e];
+    if (bounce) { CW_FOR(e, C.ncb * 6) wb.Vcb[e] = ws.Vcb[e]; CW_FOR(dd, n) wb.vplus[dd] = ws.vplus[dd]; }
     CW_SYNC();
     CW_ONE *wsm = wb;
     CW_SYNC();
@@ -1929,10 +1953,14 @@ NB2_HD BwdContactData<1> contact_backward(const Nb2ModelDev<double>& M, const Nb
   if (ws.meta[3] || ws.meta[0] != m) { cd.error = 3; cd.active = 0; NB2_BWD_DRAIN(); return cd; }
   CW_PHASE(); ph++;  // 2
   const int nc = ws.meta[1];
-  build_rows(M, C, ws, m, false);
+  double* eeff = ws.v11;
+  build_rows(M, C, ws, m, false, bounce ? eeff : nullptr);
   cd.aeff.p = ws.aeff; cd.vplus.p = ws.vplus; cd.JcTmu.p = ws.JcTmu; cd.inj.p = ws.inj;
   double* dVb = ws.M1 + (size_t)C.ncb * C.max_chain_dofs;
   double* Aacc = dVb + (size_t)nb * 6; double* Uplus = Aacc + (size_t)nb * 6;
+  // bounce only: field of v*, field of nu_e, w before the swap, nu_e, v*; and the scratch of the dual pass (kept clear of them)
+  double* Ustar = Uplus + (size_t)nb * 6; double* dVbE = Ustar + (size_t)nb * 6;
+  double* wold = dVbE + (size_t)nb * 6; double* nue = wold + n; double* vstar = nue + n; double* gpart = vstar + n;
   cd.Aacc.p = Aacc; cd.Uplus.p = Uplus;
   // ---- clamping / upper-bound sets from the saved labels
   int* mapping = ws.mapping; int* clampIdx = ws.clampIdx; int* cl = ws.i1; int* ubl = ws.i2; int* rows = ws.i3;
@@ -1943,6 +1971,7 @@ NB2_HD BwdContactData<1> contact_backward(const Nb2ModelDev<double>& M, const Nb
   CW_SYNC();
   CW_FOR(u, nUb) rows[nCl + u] = ubl[u];
   double* rdot = ws.v1; double* fbar = ws.v2; double* mu_c = ws.v3; double* Eu = ws.v4; double* coefM = ws.v5; double* coefW = ws.v7; double* coefV = ws.v8;
+  double* coefH = ws.v9; double* coefE = ws.v6;  // (pinv_psd's temporaries until phase 5)
   auto Wfield = [&](int body) { return ld6<double, 1>(scr + oBody + 7 * body + 1); };
   CW_FOR(j, m) {  // J_j lambda-field: wrench of row j against the field induced on its (one or two) bodies
     const int c = ws.rowc[j];
@@ -2001,8 +2030,21 @@ NB2_HD BwdContactData<1> contact_backward(const Nb2ModelDev<double>& M, const Nb
   CW_PROF(25);
   CW_PHASE(); ph++;  // 5
   // ---- nu = M^-1 A_c mu  (one impulse response) ; w = lambda - nu ; W_i(w)
-  CW_FOR(j, m) coefM[j] = (clampIdx[j] >= 0) ? mu_c[clampIdx[j]] : 0.0;
+  CW_FOR(j, m) {
+    const double mu = (clampIdx[j] >= 0) ? mu_c[clampIdx[j]] : 0.0, ee = (bounce && eeff[j] > 0.0) ? eeff[j] : 0.0;
+    coefM[j] = mu; coefH[j] = (1.0 + ee) * mu; coefE[j] = -ee * mu;
+  }
   CW_SYNC();
+  if (bounce) {  // nu_e = M^-1 A_c E mu and its field, kept for the second sweep
+    CW_FOR(dd, n) vstar[dd] = ws.vplus[dd];
+    CW_FOR(j, m) rdot[j] = -coefE[j];
+    CW_SYNC();
+    net_wrenches(C, ws, m, rdot, ws.Fcb);
+    impulse_response_all(M, C, S, ws, ws.Fcb, dVb);
+    CW_FOR(dd, n) nue[dd] = ws.dqd[dd];
+    CW_FOR(e, nb * 6) dVbE[e] = dVb[e];
+    CW_SYNC();
+  }
   net_wrenches(C, ws, m, coefM, ws.Fcb);
   impulse_response_all(M, C, S, ws, ws.Fcb, dVb);
   CW_FOR(dd, n) scr[oLam + dd] -= ws.dqd[dd];
@@ -2019,16 +2061,20 @@ NB2_HD BwdContactData<1> contact_backward(const Nb2ModelDev<double>& M, const Nb
         const V6<double> V = ldv6(sv + i * 21);
         V6<double> Ai = AdInvT(T, (p >= 0) ? ldv6(Aacc + 6 * p) : A0);
         V6<double> Ui = (p >= 0) ? AdInvT(T, ldv6(Uplus + 6 * p)) : zero6<double>();
+        V6<double> Us = (bounce && p >= 0) ? AdInvT(T, ldv6(Ustar + 6 * p)) : zero6<double>();
         if (jt != NB2_JT_FREE) {
           const V6<double> Sv = S_times<double>(jt, (double)st[n + o]);
           Ai = Ai + S_times<double>(jt, ws.aeff[o]) + ad(V, Sv);
           Ui = Ui + S_times<double>(jt, ws.vplus[o]);
+          if (bounce) Us = Us + S_times<double>(jt, vstar[o]);
         } else {
           V6<double> Sv; Sv.a = mk3<double>((double)st[n + o], (double)st[n + o + 1], (double)st[n + o + 2]); Sv.l = mk3<double>((double)st[n + o + 3], (double)st[n + o + 4], (double)st[n + o + 5]);
           Ai = Ai + ldv6(ws.aeff + o) + ad(V, Sv);
           Ui = Ui + ldv6(ws.vplus + o);
+          if (bounce) Us = Us + ldv6(vstar + o);
         }
         stv6(Aacc + 6 * i, Ai); stv6(Uplus + 6 * i, Ui);
+        if (bounce) stv6(Ustar + 6 * i, Us);
       }
     };
     CW_FOR(l, 1) for (int r = 0; r < M.trunk_n; r++) sweep(M.trunk_lo[r], M.trunk_hi[r]);
@@ -2053,7 +2099,7 @@ NB2_HD BwdContactData<1> contact_backward(const Nb2ModelDev<double>& M, const Nb
     double* bj = ws.inj + 24 * k;
     for (int e = 0; e < 24; e++) bj[e] = 0;
     for (int j = 0; j < m; j++) {
-      const double cW = coefW[j], cV = coefV[j], cH = coefM[j];
+      const double cW = coefW[j], cV = coefV[j], cH = coefH[j];
       if (cW == 0.0 && cV == 0.0 && cH == 0.0) continue;
       const int c = ws.rowc[j];
       for (int side = 0; side < 2; side++) {
@@ -2085,7 +2131,6 @@ NB2_HD BwdContactData<1> contact_backward(const Nb2ModelDev<double>& M, const Nb
   CW_SYNC();
   const int nitems = ws.meta[5];
   bool bad = false;
-  double* gpart = ws.M2;  // [5][6]
   for (int it0 = 0; it0 < nitems; it0 += 5) {
     const int cnt = (nitems - it0 < 5) ? nitems - it0 : 5;
     CW_FOR(q, cnt * 6) {
@@ -2115,7 +2160,7 @@ NB2_HD BwdContactData<1> contact_backward(const Nb2ModelDev<double>& M, const Nb
         V3<D1> pA, pB;
         if (ba >= 0) pA = gxf_apply_inv(WDa, co[c].point);
         if (bb >= 0) pB = gxf_apply_inv(WDb, co[c].point);
-        if (C.pen_correction && coefV[ws.crow[cc]] != 0.0) {
+        if (C.pen_correction && coefV[ws.crow[cc]] != 0.0 && !(bounce && eeff[ws.crow[cc]] != 0.0)) {
           // b_normal carries the penetration-correction velocity kpen * depth while it is below its cap (ContactConstraint.cpp:395-408):
           // dL/db = mu, so the pose gradient gains mu * kpen * d(depth)  (gsum is scaled by kap = -1/dt below and by -dt at the end: net +1)
           const double bv = co[c].depth.v * 0.01 * (1.0 / dt);
@@ -2123,16 +2168,18 @@ NB2_HD BwdContactData<1> contact_backward(const Nb2ModelDev<double>& M, const Nb
         }
         for (int kk = 0; kk < (fric ? 3 : 1); kk++) {
           const int r = ws.crow[cc] + kk;
-          const double cW = coefW[r], cV = coefV[r];
+          const double cW = coefW[r], cV = coefV[r], cE = bounce ? coefE[r] : 0.0;
           if (cW == 0.0 && cV == 0.0) continue;
           for (int side = 0; side < 2; side++) {
             const int body = side ? bb : ba;
             if (body < 0) continue;
             const V3<D1> dd = side ? mulT(WDb.R_, -dirs[kk]) : mulT(WDa.R_, dirs[kk]);
             const V3<D1> mo = cross(side ? pB : pA, dd);
-            const V6<double> Ww = Wfield(body), Up = ldv6(Uplus + 6 * body);
-            gsum += mo.x.d[0] * (cW * Ww.a.x + cV * Up.a.x) + mo.y.d[0] * (cW * Ww.a.y + cV * Up.a.y) + mo.z.d[0] * (cW * Ww.a.z + cV * Up.a.z)
-                  + dd.x.d[0] * (cW * Ww.l.x + cV * Up.l.x) + dd.y.d[0] * (cW * Ww.l.y + cV * Up.l.y) + dd.z.d[0] * (cW * Ww.l.z + cV * Up.l.z);
+            const V6<double> Ww = Wfield(body);
+            V6<double> Up = ldv6(Uplus + 6 * body) * cV;
+            if (cE != 0.0) Up = Up + ldv6(Ustar + 6 * body) * cE;   // - mu_r J_r (v+ + e_r v*)
+            gsum += mo.x.d[0] * (cW * Ww.a.x + Up.a.x) + mo.y.d[0] * (cW * Ww.a.y + Up.a.y) + mo.z.d[0] * (cW * Ww.a.z + Up.a.z)
+                  + dd.x.d[0] * (cW * Ww.l.x + Up.l.x) + dd.y.d[0] * (cW * Ww.l.y + Up.l.y) + dd.z.d[0] * (cW * Ww.l.z + Up.l.z);
           }
         }
         cc++;
@@ -2146,7 +2193,54 @@ NB2_HD BwdContactData<1> contact_backward(const Nb2ModelDev<double>& M, const Nb
   }
   CW_PROF(28);
   if (cw_any(bad)) { cd.error = 3; cd.active = 0; }
+  else if (bounce) {
+    cd.bounce = 1;
+    CW_ONE { ws.meta[6] = m; ws.meta[7] = (int)(dVb - ws.M1); }  // for bounce_pass2_begin (which re-derives the array addresses)
+    CW_SYNC();
+  }
   return cd;
+}
+
+// Second reverse sweep of a bouncing world.  begin: all lanes, after the first B3 (trunk included) and before the assembly: the scratch takes
+// the field of -nu_e, the injections become those of the v* term, and the returned view makes bwd_B3 read the unconstrained accelerations
+// and ADD its results.  end: the multiplier of the assembly becomes w_B = w - nu_e.
+NB2_HD BwdContactData<1> bounce_pass2_begin(const Nb2ModelDev<double>& M, const Nb2ContactDev& C, const Ws& ws, const BwdContactData<1>& cd, double* scr,
+                                            int oLam, int oBody) {
+  const int nb = M.nb, n = M.ndof, m = ws.meta[6];
+  double* dVb = ws.M1 + ws.meta[7];
+  double* Ustar = dVb + (size_t)nb * 18; double* dVbE = Ustar + (size_t)nb * 6;
+  double* wold = dVbE + (size_t)nb * 6; double* nue = wold + n; double* vstar = nue + n;
+  const double* coefE = ws.v6;
+  const double kap = -1.0 / M.dt;
+  CW_FOR(dd, n) { wold[dd] = scr[oLam + dd]; scr[oLam + dd] = -nue[dd]; }
+  CW_FOR(e, nb * 6) { const int i = e / 6, k = e - 6 * i; scr[oBody + 7 * i + 1 + k] = -dVbE[e]; }
+  CW_FOR(k, C.ncb) {
+    const int t = C.cb_body[k];
+    double* bj = ws.inj + 24 * k;
+    for (int e = 0; e < 24; e++) bj[e] = 0;
+    for (int j = 0; j < m; j++) {
+      const double cE = coefE[j];
+      if (cE == 0.0) continue;
+      const int c = ws.rowc[j];
+      for (int side = 0; side < 2; side++) {
+        if ((side ? ws.cbodyB[c] : ws.cbodyA[c]) != t) continue;
+        const double* F = (side ? ws.JB : ws.JA) + 6 * j;
+        for (int kx = 0; kx < 6; kx++) bj[6 + kx] += kap * cE * F[kx];
+      }
+    }
+  }
+  CW_SYNC();
+  BwdContactData<1> c2 = cd;
+  c2.pass2 = 1; c2.Uplus.p = Ustar; c2.vplus.p = vstar;
+  return c2;
+}
+NB2_HD void bounce_pass2_end(const Nb2ModelDev<double>& M, const Ws& ws, double* scr, int oLam) {
+  const int nb = M.nb, n = M.ndof;
+  double* dVb = ws.M1 + ws.meta[7];
+  double* wold = dVb + (size_t)nb * 30; double* nue = wold + n;
+  CW_SYNC();
+  CW_FOR(dd, n) scr[oLam + dd] = wold[dd] - nue[dd];
+  CW_SYNC();
 }
 
 }  // namespace cw

@@ -512,6 +512,9 @@ struct BwdContactData {
   SPd<double, ST> Aacc, Uplus, aeff, vplus, inj, JcTmu;
   const int16_t* inj_of_body;
   int active; int error;
+  // restitution (nb2_cw.cuh, contact_backward): bounce != 0 asks for a SECOND reverse sweep B3 (pass2 = 1) with the field of -nu_e, the
+  // unconstrained accelerations of the saved stream and the v* injections; it ADDS to qbar / vbar and leaves JcTmu / the inertia gradient alone
+  int bounce = 0, pass2 = 0;
 };
 
 // d(Y^T G X)/d(m, h(3), Ibar(xx,yy,zz,xy,xz,yz)) for G X = [Ibar w + h x v ; m v - h x w]
@@ -630,7 +633,7 @@ NB2_HD void bwd_B3(const Nb2ModelDev<R>& M, R* scr, const float* st, const R* sv
     R m; V3<R> h; S3<R> Ib; inertia_of(M, bt, i, &m, &h, &Ib);
     const V6<R> V = sv_ld6<R>(s, B, 0);
     V6<R> A = sv_ld6<R>(s, B, 6);
-    if (CONTACT && cd.active) { const auto a6 = cd.Aacc + 6 * i; A.a = mk3<R>((R)a6[0], (R)a6[1], (R)a6[2]); A.l = mk3<R>((R)a6[3], (R)a6[4], (R)a6[5]); }
+    if (CONTACT && cd.active && !cd.pass2) { const auto a6 = cd.Aacc + 6 * i; A.a = mk3<R>((R)a6[0], (R)a6[1], (R)a6[2]); A.l = mk3<R>((R)a6[3], (R)a6[4], (R)a6[5]); }
     const V6<R> W = ld6<R, ST>(scr + (size_t)(L.oBody + 7 * i + 1) * ST);
     const V6<R> GV = mulG(m, h, Ib, V);
     V6<R> f = mulG(m, h, Ib, A) + crf(V, GV);
@@ -645,7 +648,10 @@ NB2_HD void bwd_B3(const Nb2ModelDev<R>& M, R* scr, const float* st, const R* sv
       R t2[10];
       inertia_param_form(Y2, V, t2);
 #pragma unroll
-      for (int k = 0; k < 10; k++) gI[(size_t)(10 * i + k) * gIB] = (float)(-dt * (t[k] - t2[k]));
+      for (int k = 0; k < 10; k++) {
+        const float gk = (float)(-dt * (t[k] - t2[k]));
+        if (CONTACT && cd.pass2) gI[(size_t)(10 * i + k) * gIB] += gk; else gI[(size_t)(10 * i + k) * gIB] = gk;
+      }
     }
     V6<R> Abar = mulG(m, h, Ib, W);
     V6<R> Vbar = mulG(m, h, Ib, ad(W, V)) - crf(W, GV);
@@ -673,13 +679,13 @@ NB2_HD void bwd_B3(const Nb2ModelDev<R>& M, R* scr, const float* st, const R* sv
     Xf<R> T;
     if (jt != NB2_JT_FREE) {
       Sv = S_times<R>(jt, scr[(size_t)(L.oSt + n + o) * ST]);
-      Sa = S_times<R>(jt, (CONTACT && cd.active) ? (R)cd.aeff[o] : (R)sv[(size_t)(kQdd + o) * B]);
+      Sa = S_times<R>(jt, (CONTACT && cd.active && !cd.pass2) ? (R)cd.aeff[o] : (R)sv[(size_t)(kQdd + o) * B]);
       Sl = S_times<R>(jt, scr[(size_t)(L.oLam + o) * ST]);
       T = (jt == NB2_JT_REV) ? xf_rev(M, bt, i, (R)s[19 * B], (R)s[20 * B]) : xf_pris(M, bt, i, scr[(size_t)(L.oSt + o) * ST]);
     } else {
       Sv.a = mk3<R>(scr[(size_t)(L.oSt + n + o) * ST], scr[(size_t)(L.oSt + n + o + 1) * ST], scr[(size_t)(L.oSt + n + o + 2) * ST]); Sv.l = mk3<R>(scr[(size_t)(L.oSt + n + o + 3) * ST], scr[(size_t)(L.oSt + n + o + 4) * ST], scr[(size_t)(L.oSt + n + o + 5) * ST]);
       Sa = sv_ld6<R>(sv + (size_t)(kQdd + o) * B, B, 0);
-      if (CONTACT && cd.active) { const auto a6 = cd.aeff + o; Sa.a = mk3<R>((R)a6[0], (R)a6[1], (R)a6[2]); Sa.l = mk3<R>((R)a6[3], (R)a6[4], (R)a6[5]); }
+      if (CONTACT && cd.active && !cd.pass2) { const auto a6 = cd.aeff + o; Sa.a = mk3<R>((R)a6[0], (R)a6[1], (R)a6[2]); Sa.l = mk3<R>((R)a6[3], (R)a6[4], (R)a6[5]); }
       Sl = ld6<R, ST>(scr + (size_t)(L.oLam + o) * ST);
       R t12[12]; for (int k = 0; k < 12; k++) t12[k] = (R)sv[(size_t)(kFree + M.free_idx[i] * 33 + 21 + k) * B];
       T = ldXf<R, 1>(t12);
@@ -695,18 +701,23 @@ NB2_HD void bwd_B3(const Nb2ModelDev<R>& M, R* scr, const float* st, const R* sv
       if (jt != NB2_JT_FREE) Svp = S_times<R>(jt, (R)cd.vplus[o]);
       else { const auto v6p = cd.vplus + o; Svp.a = mk3<R>((R)v6p[0], (R)v6p[1], (R)v6p[2]); Svp.l = mk3<R>((R)v6p[3], (R)v6p[4], (R)v6p[5]); }
       c6 = c6 - crf(Wlam, Uw) - crf(Upl - Svp, Up) + Gc;
-      if (jt != NB2_JT_FREE) cd.JcTmu[o] = (double)S_dot(jt, Hc);
-      else { auto j6 = cd.JcTmu + o; j6[0] = (double)Hc.a.x; j6[1] = (double)Hc.a.y; j6[2] = (double)Hc.a.z; j6[3] = (double)Hc.l.x; j6[4] = (double)Hc.l.y; j6[5] = (double)Hc.l.z; }
+      if (!cd.pass2) {
+        if (jt != NB2_JT_FREE) cd.JcTmu[o] = (double)S_dot(jt, Hc);
+        else { auto j6 = cd.JcTmu + o; j6[0] = (double)Hc.a.x; j6[1] = (double)Hc.a.y; j6[2] = (double)Hc.a.z; j6[3] = (double)Hc.l.x; j6[4] = (double)Hc.l.y; j6[5] = (double)Hc.l.z; }
+      }
     }
+    const bool add = CONTACT && cd.pass2;  // second sweep of a bouncing world: accumulate
     if (jt != NB2_JT_FREE) {
-      scr[(size_t)(L.oVb + o) * ST] = S_dot(jt, vb6);
-      scr[(size_t)(L.oQb + o) * ST] = S_dot(jt, c6);
+      const R vb = S_dot(jt, vb6), qb = S_dot(jt, c6);
+      scr[(size_t)(L.oVb + o) * ST] = add ? scr[(size_t)(L.oVb + o) * ST] + vb : vb;
+      scr[(size_t)(L.oQb + o) * ST] = add ? scr[(size_t)(L.oQb + o) * ST] + qb : qb;
     } else {
-      st6<R, ST>(scr + (size_t)(L.oVb + o) * ST, vb6);
       const V3<R> phi = mk3<R>(scr[(size_t)(L.oSt + o) * ST], scr[(size_t)(L.oSt + o + 1) * ST], scr[(size_t)(L.oSt + o + 2) * ST]);
-      V6<R> qb;
+      V6<R> qb, vb = vb6;
       qb.a = mulT(so3_Jr(phi), c6.a);
       qb.l = mul(expmap(phi), c6.l);
+      if (add) { vb = vb + ld6<R, ST>(scr + (size_t)(L.oVb + o) * ST); qb = qb + ld6<R, ST>(scr + (size_t)(L.oQb + o) * ST); }
+      st6<R, ST>(scr + (size_t)(L.oVb + o) * ST, vb);
       st6<R, ST>(scr + (size_t)(L.oQb + o) * ST, qb);
     }
     hvalid = false;

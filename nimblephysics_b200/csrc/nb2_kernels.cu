@@ -371,6 +371,7 @@ k_capply(const __grid_constant__ Nb2ModelDev<double> M, const __grid_constant__ 
 }
 
 #define NB2_CBWD_MAXW 8
+template <bool BOUNCE>
 __global__ void __launch_bounds__(32 * NB2_CBWD_MAXW, 1)
 k_cstep_bwd(const __grid_constant__ Nb2ModelDev<double> M, const __grid_constant__ Nb2ContactDev C, const __grid_constant__ CStepArgs P,
             const float* __restrict__ state, const float* __restrict__ action, const double* __restrict__ saved, const double* __restrict__ crec,
@@ -402,23 +403,36 @@ k_cstep_bwd(const __grid_constant__ Nb2ModelDev<double> M, const __grid_constant
   __syncwarp();
   if (staged) { mbar_wait(bar, 0); sv = svs; }
   nb2::BwdContactData<1> cd; cd.active = 0; cd.error = 0; cd.inj_of_body = nullptr;
+  nb2::BwdContactData<1> c2 = cd;
+  float* gI = (ginertia && live) ? ginertia + w : nullptr;
+  // stage order: B1 limbs, B1 trunk, B2 trunk, B2 limbs | contact adjoint | B3 limbs, B3 trunk | (worlds in which restitution was active: a
+  // SECOND B3 over limbs and trunk, see contact_backward) | assembly limbs, trunk.  One call site for all of them (code size), one block-wide
+  // barrier per entry (lockstep, see k_csolve): worlds without a bounce only wait at the two extra barriers.
 #pragma unroll 1
-  for (int sg = 1; sg < NB2_BWD_STAGES - 1; sg++) {
-    if (sg == 5) {  // lambda and its fields are complete: the contact adjoint turns them into w and prepares the injections
+  for (int it = 0; it < 10; it++) {
+    const bool second = (it == 6) | (it == 7);
+    if (!BOUNCE && second) continue;
+    const int sg = (it < 4) ? it + 1 : (it == 4 || it == 6) ? 5 : (it == 5 || it == 7) ? 7 : (it == 8) ? 6 : 8;
+    if (it == 4) {  // lambda and its fields are complete: the contact adjoint turns them into w and prepares the injections
       __syncwarp();
       CW_PROF(20);
 #ifndef NB2_DEV_NO_CBWD
-      cd = nb2::cw::contact_backward(M, C, st, sv, wsm, P.ds, P.pool, P.db, crec + (size_t)wc * P.rec_doubles, scr, L.oLam, L.oBody);
+      cd = nb2::cw::contact_backward<BOUNCE>(M, C, st, sv, wsm, P.ds, P.pool, P.db, crec + (size_t)wc * P.rec_doubles, scr, L.oLam, L.oBody);
 #endif
       __syncwarp();
       CW_PROF(29);
     }
-    __syncthreads();  // lockstep: every warp of the block sweeps the same stage (see k_csolve)
+    __syncthreads();
 #ifdef NB2_DEV_NO_B3
     if (sg == 5 || sg == 7) continue;
 #endif
-    if (lane < M.lanes) nb2::world_backward_stage<double, 1, true>(M, scr, sv, 1, lane, sg, (ginertia && live) ? ginertia + w : nullptr, nullptr, (size_t)P.B, &cd);
-    if ((NB2_BWD_SYNC_MASK >> sg) & 1u) __syncwarp();
+    if (BOUNCE) {
+      if (second && !cd.bounce) continue;
+      if (it == 6) c2 = nb2::cw::bounce_pass2_begin(M, C, *wsm, cd, scr, L.oLam, L.oBody);
+      if (it == 8 && cd.bounce) nb2::cw::bounce_pass2_end(M, *wsm, scr, L.oLam);
+    }
+    if (lane < M.lanes) nb2::world_backward_stage<double, 1, true>(M, scr, sv, 1, lane, sg, gI, nullptr, (size_t)P.B, (BOUNCE && second) ? &c2 : &cd);
+    __syncwarp();
   }
   __syncwarp();
   if (live) {
@@ -669,6 +683,7 @@ struct nb2_model {
   Nb2ModelDev<double> md;
   Nb2ContactDev contact;
   bool has_contacts = false;
+  bool contact_restitution = false;  // any shape-carrying body with a restitution coefficient > 0
   int contact_mc = 0;      // contact capacity of the shared-memory workspace of the fused contact kernels (rows: 3x)
   int contact_variant = 0; // schedule the fused contact kernels sweep the tree with
   int saved_words;
@@ -955,6 +970,8 @@ int nb2_model_create(const nb2_model_desc* desc, nb2_model** out) {
   if (desc->nshapes > 0 && desc->npairs > 0) {
     if (!nb2_fill_contact(*desc, m->contact, err)) { g_err = err; delete m; return NB2_ERR_UNSUPPORTED; }
     m->has_contacts = true;
+    for (int p = 0; p < desc->npairs; p++)  // a pair bounces when the product of its shapes' coefficients exceeds 1e-3 (ContactConstraint.cpp:112-123)
+      if (m->contact.shape_rest[desc->pair_a[p]] * m->contact.shape_rest[desc->pair_b[p]] > 1e-3) m->contact_restitution = true;
     // contacts the shared-memory workspace is sized for: a box-box pair yields up to 4 in the common face-face case (8 at most), every
     // other supported pair at most one; worlds that exceed it fall back to a global-memory workspace (nb2_cw.cuh BigPool)
     int mc = 0;
@@ -1104,13 +1121,18 @@ static int cbwd_launch(nb2_model* m, int B, const float* state, const float* act
   const size_t smem_staged = smem_base + ((((size_t)P.saved_words + 1) & ~(size_t)1) + 2) * sizeof(double);
   const int stage = pick_wpb(B, m->sm_count, smem_staged, NB2_CBWD_MAXW, 3) == pick_wpb(B, m->sm_count, smem_base, NB2_CBWD_MAXW, 3);
   const size_t smem = stage ? smem_staged : smem_base;
-  static bool attr_done[64] = {};
-  int rc = cstep_smem_attr(k_cstep_bwd, smem, attr_done);
+  static bool attr_done[64] = {}, attr_done_b[64] = {};
+  const bool bounce = m->contact_restitution;  // some body has a restitution coefficient: the kernel with the second reverse sweep
+  int rc = bounce ? cstep_smem_attr(k_cstep_bwd<true>, smem, attr_done_b) : cstep_smem_attr(k_cstep_bwd<false>, smem, attr_done);
   if (rc) return rc;
   NB2_CUDA(cudaMemsetAsync(workspace, 0, 64, st));
   const int wpb = pick_wpb(B, m->sm_count, smem, NB2_CBWD_MAXW, 3);
-  k_cstep_bwd<<<(B + wpb - 1) / wpb, 32 * wpb, smem * wpb, st>>>(v.md, m->contact, P, state, action, (const double*)saved_fp64, contact_record, grad_next_state,
-                                                                 grad_state, grad_action, grad_inertia, status_accum, smem, stage, accumulate);
+  if (bounce)
+    k_cstep_bwd<true><<<(B + wpb - 1) / wpb, 32 * wpb, smem * wpb, st>>>(v.md, m->contact, P, state, action, (const double*)saved_fp64, contact_record, grad_next_state,
+                                                                         grad_state, grad_action, grad_inertia, status_accum, smem, stage, accumulate);
+  else
+    k_cstep_bwd<false><<<(B + wpb - 1) / wpb, 32 * wpb, smem * wpb, st>>>(v.md, m->contact, P, state, action, (const double*)saved_fp64, contact_record, grad_next_state,
+                                                                          grad_state, grad_action, grad_inertia, status_accum, smem, stage, accumulate);
   g_launches++;
   NB2_CUDA(cudaGetLastError());
   return NB2_OK;

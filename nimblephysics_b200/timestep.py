@@ -159,9 +159,8 @@ ST_NAN, ST_UNSUPPORTED, ST_OVERFLOW, ST_BOUNCE, ST_BWD_ERROR = 32, 128, 256, 102
 def _raise_on_status(bits: int, worlds, backward=False):
     if bits & ST_BWD_ERROR:
         raise RuntimeError(
-            f"backward through the contact stage failed for worlds {list(worlds)[:16]} (their gradients are NaN): a restitution (bounce) "
-            "term was active in the forward step (status bit 1024; its backward is not implemented), or the "
-            "contact rows regenerated in the backward pass did not match the forward's")
+            f"backward through the contact stage failed for worlds {list(worlds)[:16]} (their gradients are NaN): the contact rows "
+            "regenerated in the backward pass did not match the forward's")
     if bits & ST_OVERFLOW:
         raise RuntimeError(f"contact stage: worlds {list(worlds)[:16]} generated more than {MAX_CONTACTS} contacts / {MAX_ROWS} LCP rows "
                            "(or the overflow pool was exhausted): the extra contacts were DROPPED — the step differs from the reference")

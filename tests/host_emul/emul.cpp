@@ -116,13 +116,22 @@ static int run_bwd_contact(const nb2_model_desc* d, int B, const float* state, c
     const double* sv = saved + (size_t)w * words;
     nb2::bwd_load<double, 1, true>(M, scr.data(), st, action + (size_t)w * M.na, gnext + (size_t)w * 2 * M.ndof, 1, 0, 1);
     nb2::BwdContactData<1> cd; cd.active = 0; cd.error = 0; cd.inj_of_body = nullptr;
-    for (int sg = 1; sg < NB2_BWD_STAGES - 1; sg++) {
-      int pc = 0; nb2::cw::BigPool pool{&pc, wsb.data(), wsb.size(), 1};
-      nb2::cw::Ws wsd = nb2::cw::carve(wss.data(), ds);
-      if (sg == 5) cd = nb2::cw::contact_backward(M, C, st, sv, &wsd, ds, pool, db, crec + (size_t)w * recd, scr.data(), L.oLam, L.oBody);
+    nb2::cw::Ws wsd = nb2::cw::carve(wss.data(), ds);
+    nb2::BwdContactData<1> c2 = cd;
+    float* gI = ginertia ? ginertia + w : nullptr;
+    for (int it = 0; it < 10; it++) {  // the stage order of k_cstep_bwd
+      const bool second = (it == 6) | (it == 7);
+      const int sg = (it < 4) ? it + 1 : (it == 4 || it == 6) ? 5 : (it == 5 || it == 7) ? 7 : (it == 8) ? 6 : 8;
+      if (it == 4) {
+        int pc = 0; nb2::cw::BigPool pool{&pc, wsb.data(), wsb.size(), 1};
+        cd = nb2::cw::contact_backward<true>(M, C, st, sv, &wsd, ds, pool, db, crec + (size_t)w * recd, scr.data(), L.oLam, L.oBody);
+      }
+      if (second && !cd.bounce) continue;
+      if (it == 6) c2 = nb2::cw::bounce_pass2_begin(M, C, wsd, cd, scr.data(), L.oLam, L.oBody);
+      if (it == 8 && cd.bounce) nb2::cw::bounce_pass2_end(M, wsd, scr.data(), L.oLam);
       for (int l = 0; l < M.lanes; l++) {
         const int lane = (w & 1) ? M.lanes - 1 - l : l;
-        nb2::world_backward_stage<double, 1, true>(M, scr.data(), sv, 1, lane, sg, ginertia ? ginertia + w : nullptr, nullptr, (size_t)B, &cd);
+        nb2::world_backward_stage<double, 1, true>(M, scr.data(), sv, 1, lane, sg, gI, nullptr, (size_t)B, second ? &c2 : &cd);
       }
     }
     nb2::bwd_store<double, 1, true>(M, scr.data(), gstate + (size_t)w * 2 * M.ndof, gaction + (size_t)w * M.na, cd.error != 0, 1, 0, 1);

@@ -297,28 +297,37 @@ def test_mass_gradient_through_the_contact_stage(oracle_mod):
     assert checked >= 2, checked
 
 
-def test_restitution_forward_parity_and_loud_backward(oracle_mod):
-    """Bounce terms (ContactConstraint.cpp:395-442): the forward matches the oracle; the backward of such a step needs
-    BackpropSnapshot::getBounceApproximationJacobian (not implemented) and must fail loudly (NaN), never silently."""
+def test_restitution_forward_and_backward(oracle_mod):
+    """Bounce terms (ContactConstraint.cpp:410-436): b_normal = (1 + e)(-J v*) on the rows that bounce.  Forward parity with the oracle, and
+    the backward — second reverse sweep with the field of -nu_e, v* injections (csrc/nb2_cw.cuh contact_backward / bounce_pass2_*) — against
+    the oracle's dual-number Jacobian of the frozen-classification step (the reference: getBounceDiagonals, BackpropSnapshot.cpp:2624-2680)."""
     raw = load_raw("half_cheetah")
     raw.restitution[:] = 0.8
     cm = nb.compile_model(raw)
     ew, ow = EmulWorld(cm), ob.OracleContactWorld(raw)
     s, a = contact_inputs(raw, "half_cheetah", 8, seed=4)
     s[:, raw.ndof + 1] -= 1.5  # falling fast: e * (relative normal velocity) > 0.1 activates the bounce term
-    g = np.random.default_rng(1).normal(size=s.shape).astype(np.float32)
     r = ew.forward_contact(s, a)
-    gs, ga = ew.backward_contact(s, a, r["saved"], r["crec"], g)
     bounced = 0
     for w in range(8):
         ro = ow.step_contact(s[w].astype(np.float64), a[w].astype(np.float64))
         assert (r["status"][w] & ~96) == (ro["status"] & ~96) and rel_err(r["next"][w], ro["next_state"]) < 1e-6
-        if r["status"][w] & 1024:
-            bounced += 1
-            assert np.isnan(gs[w]).all() and np.isnan(ga[w]).all()
-        else:
-            assert np.isfinite(gs[w]).all()
+        bounced += int(bool(r["status"][w] & 1024))
     assert bounced >= 4
+    kinds = _check_backward(ob, raw, s, a, tol=2e-5)
+    assert sum(1 for k in kinds if k[2] & 1024 and k[0] > 0) >= 3  # bouncing worlds with clamping rows went through the second sweep
+    # reversed lane order and the large-workspace retry give the same gradients
+    g = np.random.default_rng(1).normal(size=s.shape).astype(np.float32)
+    gs0, ga0 = ew.backward_contact(s, a, r["saved"], r["crec"], g)
+    gs1, ga1 = ew.backward_contact(s, a, r["saved"], r["crec"], g, small_mc=1, reverse=True)
+    assert np.allclose(gs0, gs1, rtol=1e-6, atol=1e-7) and np.allclose(ga0, ga1, rtol=1e-6, atol=1e-7)
+    # Atlas standing on restitutive ground, dropped: rank-deficient Q, two feet
+    raw = load_raw("atlas_ground")
+    raw.restitution[:] = 0.5
+    s, a = contact_inputs(raw, "atlas_ground", 4, seed=4)
+    s[:, raw.ndof + 5] -= 1.0  # the root's body-frame z is the world's vertical in this pose
+    kinds = _check_backward(ob, raw, s, a, tol=5e-5)
+    assert any(k[2] & 1024 for k in kinds)
 
 
 def test_penetration_correction_forward_and_backward(oracle_mod):

@@ -210,3 +210,32 @@ def test_penetration_correction_backward_matches_oracle(oracle_mod):
         rgs, rga, rc = ow.backprop_contact(s[w].astype(np.float64), a[w].astype(np.float64), g[w].astype(np.float64))
         assert rc >= 0
         assert rel_err(gs[w], rgs) < 1e-4 and rel_err(ga[w], rga) < 1e-4, w
+
+
+def test_restitution_backward_matches_oracle(oracle_mod):
+    """Restitution (ContactConstraint.cpp:410-436): bouncing worlds (status bit 1024) back-propagate through the second reverse sweep of
+    k_cstep_bwd and match the oracle's dual-number Jacobian; non-bouncing worlds of the same batch take the usual path."""
+    raw = load_raw("half_cheetah")
+    raw.restitution[:] = 0.8
+    world = nb.World.from_raw(raw)
+    ow = ob.OracleContactWorld(raw)
+    B = 16
+    s, a = contact_inputs(raw, "half_cheetah", B, seed=4)
+    s[::2, raw.ndof + 1] -= 1.5  # every other world falls fast enough to bounce
+    g = np.random.default_rng(2).normal(size=(B, 2 * raw.ndof)).astype(np.float32)
+    st = torch.tensor(s, device="cuda", requires_grad=True)
+    at = torch.tensor(a, device="cuda", requires_grad=True)
+    nb.reset_contact_cache(world)
+    out = nb.timestep(world, st, at)
+    status = world._lcp_cache["status"].cpu().numpy().copy()
+    out.backward(torch.tensor(g, device="cuda"))
+    bits = nb.check_contact_status(world)
+    assert bits & 1024 and not bits & 2048
+    assert int(((status & 1024) > 0).sum()) >= 4
+    gs, ga = st.grad.cpu().numpy(), at.grad.cpu().numpy()
+    for w in range(B):
+        ro = ow.step_contact(s[w].astype(np.float64), a[w].astype(np.float64))
+        assert rel_err(out[w].detach().cpu().numpy(), ro["next_state"]) < 1e-5
+        rgs, rga, rc = ow.backprop_contact(s[w].astype(np.float64), a[w].astype(np.float64), g[w].astype(np.float64))
+        assert rc >= 0
+        assert rel_err(gs[w], rgs) < 1e-4 and rel_err(ga[w], rga) < 1e-4, (w, hex(status[w]))
