@@ -159,6 +159,12 @@ int nb2_step_backward_contact(const nb2_model* m, int B, const float* state, con
                               float* grad_action, float* grad_inertia, int32_t* status_accum, void* stream);
 /* contacts per world the shared-memory workspace of the fused contact kernels is sized for (LCP rows: 3x).  Default: 4 per box-box
  * pair + 1 per other pair, clamped to [2, NB2_MAX_CONTACTS].  Smaller = more resident worlds per SM, more worlds in the slow pool. */
+/* The same two calls with HOST buffers (pageable or pinned): copies, kernels and a synchronise inside; the solver cache, the saved stream, the
+ * contact record and the sticky status live in the model between calls (reset_cache != 0 forgets the cached LCP solutions first).
+ * status_out (optional, [B]): this step's status words; sticky_out (optional, [B]): read-and-clear of the sticky word after the backward. */
+int nb2_step_forward_contact_host(nb2_model* m, int B, const float* state, const float* action, float* next_state, int keep_for_backward,
+                                  int reset_cache, int32_t* status_out);
+int nb2_step_backward_contact_host(nb2_model* m, int B, const float* grad_next_state, float* grad_state, float* grad_action, int32_t* sticky_out);
 int nb2_model_set_contact_capacity(nb2_model* m, int max_contacts_in_shared_memory);
 int nb2_model_contact_capacity(const nb2_model* m);
 

@@ -156,6 +156,8 @@ def lib() -> ctypes.CDLL:
         L.nb2_contact_record_bytes.argtypes = [vp, ctypes.c_int]
         L.nb2_contact_record_bytes.restype = ctypes.c_size_t
         L.nb2_step_backward_contact.argtypes = [vp, ctypes.c_int, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
+        L.nb2_step_forward_contact_host.argtypes = [vp, ctypes.c_int, vp, vp, vp, ctypes.c_int, ctypes.c_int, vp]
+        L.nb2_step_backward_contact_host.argtypes = [vp, ctypes.c_int, vp, vp, vp, vp]
         L.nb2_forward_dynamics.argtypes = [vp, ctypes.c_int, vp, vp, vp, vp, vp]
         L.nb2_lcp_solve_batch.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_double] + [vp] * 11
         L.nb2_model_set_contact_capacity.argtypes = [vp, ctypes.c_int]

@@ -696,6 +696,9 @@ struct nb2_model {
   void* d_saved = nullptr;  // sized for fp64 words
   int host_cap = 0;
   int host_B = 0;  // batch of the last forward_host kept for backward
+  // contact path of the *_host entry points: solver cache (flows from call to call), per-step outputs, record, workspace
+  void* hc_ws = nullptr; double *hc_x = nullptr, *hc_rec = nullptr; int32_t *hc_m = nullptr, *hc_labels = nullptr, *hc_status = nullptr, *hc_nc = nullptr, *hc_sticky = nullptr;
+  int hc_cap = 0;
   cudaStream_t host_streams[4] = {nullptr, nullptr, nullptr, nullptr};
   std::mutex mu;
 };
@@ -1053,6 +1056,7 @@ void nb2_model_destroy(nb2_model* m) {
   if (!m) return;
   cudaFree(m->d_state); cudaFree(m->d_action); cudaFree(m->d_next); cudaFree(m->d_saved);
   cudaFree(m->d_gnext); cudaFree(m->d_gstate); cudaFree(m->d_gaction);
+  cudaFree(m->hc_ws); cudaFree(m->hc_x); cudaFree(m->hc_rec); cudaFree(m->hc_m); cudaFree(m->hc_labels); cudaFree(m->hc_status); cudaFree(m->hc_nc); cudaFree(m->hc_sticky);
   for (auto& hs : m->host_streams) if (hs) cudaStreamDestroy(hs);
   delete m;
 }
@@ -1506,6 +1510,70 @@ int nb2_step_backward_host(nb2_model* m, int B, const float* grad_next_state, fl
     NB2_CUDA(cudaMemcpyAsync(grad_action + na * lo, m->d_gaction + na * lo, na * cnt * sizeof(float), cudaMemcpyDeviceToHost, st));
   }
   for (int c = 0; c < C; c++) NB2_CUDA(cudaStreamSynchronize(m->host_streams[c]));
+  return NB2_OK;
+}
+
+// ---- host entry points of the contact path (pageable or pinned host buffers; staged copies on one stream, synchronised on return).  The solver
+// cache, the saved stream, the contact record and the sticky status live in the model between the calls.
+static int ensure_host_contact_buffers(nb2_model* m, int B) {
+  int rc = ensure_host_buffers(m, B);
+  if (rc) return rc;
+  if (B <= m->hc_cap) return NB2_OK;
+  cudaFree(m->hc_ws); cudaFree(m->hc_x); cudaFree(m->hc_rec); cudaFree(m->hc_m); cudaFree(m->hc_labels); cudaFree(m->hc_status); cudaFree(m->hc_nc); cudaFree(m->hc_sticky);
+  m->hc_ws = nullptr; m->hc_x = m->hc_rec = nullptr; m->hc_m = m->hc_labels = m->hc_status = m->hc_nc = m->hc_sticky = nullptr; m->hc_cap = 0;
+  const int cap = m->host_cap;  // (ensure_host_buffers sized the state / saved buffers for this many worlds)
+  NB2_CUDA(cudaMalloc(&m->hc_ws, nb2_contact_workspace_bytes(m, cap)));
+  NB2_CUDA(cudaMalloc(&m->hc_x, (size_t)cap * NB2_MAX_ROWS * sizeof(double)));
+  NB2_CUDA(cudaMalloc(&m->hc_rec, nb2_contact_record_bytes(m, cap)));
+  NB2_CUDA(cudaMalloc(&m->hc_m, (size_t)cap * sizeof(int32_t)));
+  NB2_CUDA(cudaMalloc(&m->hc_labels, (size_t)cap * NB2_MAX_ROWS * sizeof(int32_t)));
+  NB2_CUDA(cudaMalloc(&m->hc_status, (size_t)cap * sizeof(int32_t)));
+  NB2_CUDA(cudaMalloc(&m->hc_nc, (size_t)cap * sizeof(int32_t)));
+  NB2_CUDA(cudaMalloc(&m->hc_sticky, (size_t)cap * sizeof(int32_t)));
+  NB2_CUDA(cudaMemset(m->hc_m, 0xff, (size_t)cap * sizeof(int32_t)));  // -1: no cached solution
+  NB2_CUDA(cudaMemset(m->hc_x, 0, (size_t)cap * NB2_MAX_ROWS * sizeof(double)));
+  NB2_CUDA(cudaMemset(m->hc_sticky, 0, (size_t)cap * sizeof(int32_t)));
+  m->hc_cap = cap;
+  return NB2_OK;
+}
+int nb2_step_forward_contact_host(nb2_model* m, int B, const float* state, const float* action, float* next_state, int keep_for_backward,
+                                  int reset_cache, int32_t* status_out) {
+  if (!m || B <= 0 || !state || !action || !next_state) { g_err = "nb2_step_forward_contact_host: bad argument"; return NB2_ERR_INVALID; }
+  if (!m->has_contacts) { g_err = "nb2_step_forward_contact_host: the model has no collision pairs (use nb2_step_forward_host)"; return NB2_ERR_INVALID; }
+  std::lock_guard<std::mutex> lk(m->mu);
+  int rc = ensure_host_contact_buffers(m, B);
+  if (rc) return rc;
+  const size_t n2 = (size_t)2 * m->mf.ndof, na = (size_t)m->mf.na;
+  cudaStream_t st = m->host_streams[0];
+  if (reset_cache) NB2_CUDA(cudaMemsetAsync(m->hc_m, 0xff, (size_t)B * sizeof(int32_t), st));
+  NB2_CUDA(cudaMemcpyAsync(m->d_state, state, n2 * B * sizeof(float), cudaMemcpyHostToDevice, st));
+  NB2_CUDA(cudaMemcpyAsync(m->d_action, action, na * B * sizeof(float), cudaMemcpyHostToDevice, st));
+  rc = nb2_step_forward_contact(m, B, m->d_state, m->d_action, m->d_next, m->d_saved, m->hc_ws, m->hc_x, m->hc_m, m->hc_labels, m->hc_status, m->hc_nc, nullptr,
+                                keep_for_backward ? m->hc_rec : nullptr, m->hc_sticky, st);
+  if (rc) return rc;
+  NB2_CUDA(cudaMemcpyAsync(next_state, m->d_next, n2 * B * sizeof(float), cudaMemcpyDeviceToHost, st));
+  if (status_out) NB2_CUDA(cudaMemcpyAsync(status_out, m->hc_status, (size_t)B * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  NB2_CUDA(cudaStreamSynchronize(st));
+  m->host_B = keep_for_backward ? B : 0;
+  return NB2_OK;
+}
+int nb2_step_backward_contact_host(nb2_model* m, int B, const float* grad_next_state, float* grad_state, float* grad_action, int32_t* sticky_out) {
+  if (!m || B <= 0 || !grad_next_state || !grad_state || !grad_action) { g_err = "nb2_step_backward_contact_host: bad argument"; return NB2_ERR_INVALID; }
+  if (!m->has_contacts) { g_err = "nb2_step_backward_contact_host: the model has no collision pairs"; return NB2_ERR_INVALID; }
+  std::lock_guard<std::mutex> lk(m->mu);
+  if (m->host_B != B) { g_err = "nb2_step_backward_contact_host: no forward of this batch size was kept (keep_for_backward)"; return NB2_ERR_INVALID; }
+  const size_t n2 = (size_t)2 * m->mf.ndof, na = (size_t)m->mf.na;
+  cudaStream_t st = m->host_streams[0];
+  NB2_CUDA(cudaMemcpyAsync(m->d_gnext, grad_next_state, n2 * B * sizeof(float), cudaMemcpyHostToDevice, st));
+  int rc = nb2_step_backward_contact(m, B, m->d_state, m->d_action, m->d_saved, m->hc_rec, m->hc_ws, m->d_gnext, m->d_gstate, m->d_gaction, nullptr, m->hc_sticky, st);
+  if (rc) return rc;
+  NB2_CUDA(cudaMemcpyAsync(grad_state, m->d_gstate, n2 * B * sizeof(float), cudaMemcpyDeviceToHost, st));
+  NB2_CUDA(cudaMemcpyAsync(grad_action, m->d_gaction, na * B * sizeof(float), cudaMemcpyDeviceToHost, st));
+  if (sticky_out) {  // read-and-clear: the OR of every step's status word since the last read
+    NB2_CUDA(cudaMemcpyAsync(sticky_out, m->hc_sticky, (size_t)B * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    NB2_CUDA(cudaMemsetAsync(m->hc_sticky, 0, (size_t)B * sizeof(int32_t), st));
+  }
+  NB2_CUDA(cudaStreamSynchronize(st));
   return NB2_OK;
 }
 

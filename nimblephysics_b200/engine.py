@@ -184,6 +184,24 @@ class DeviceModel:
                                                        ga.ctypes.data, precision))
         return gs, ga
 
+    def forward_contact_host(self, state: np.ndarray, action: np.ndarray, keep_for_backward=True, reset_cache=False, out=None, status_out=None):
+        """Contact step on HOST arrays (float32 [B, 2n] / [B, a]); the solver cache lives in the model between calls."""
+        B = state.shape[0]
+        if out is None:
+            out = np.empty_like(state)
+        _cabi.check(_cabi.lib().nb2_step_forward_contact_host(self.handle, B, state.ctypes.data, action.ctypes.data, out.ctypes.data,
+                                                              int(keep_for_backward), int(reset_cache),
+                                                              status_out.ctypes.data if status_out is not None else None))
+        return out
+
+    def backward_contact_host(self, grad_next: np.ndarray, out_state=None, out_action=None, sticky_out=None):
+        B = grad_next.shape[0]
+        gs = np.empty_like(grad_next) if out_state is None else out_state
+        ga = np.empty((B, self.na), np.float32) if out_action is None else out_action
+        _cabi.check(_cabi.lib().nb2_step_backward_contact_host(self.handle, B, grad_next.ctypes.data, gs.ctypes.data, ga.ctypes.data,
+                                                               sticky_out.ctypes.data if sticky_out is not None else None))
+        return gs, ga
+
 
 def _has_possible_contacts(raw: RawModel) -> bool:
     """True when some collision-shape pair could ever generate a contact (shapes on two different skeletons;

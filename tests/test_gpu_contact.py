@@ -239,3 +239,30 @@ def test_restitution_backward_matches_oracle(oracle_mod):
         rgs, rga, rc = ow.backprop_contact(s[w].astype(np.float64), a[w].astype(np.float64), g[w].astype(np.float64))
         assert rc >= 0
         assert rel_err(gs[w], rgs) < 1e-4 and rel_err(ga[w], rga) < 1e-4, (w, hex(status[w]))
+
+
+def test_contact_host_entry_points_match_device_path():
+    """nb2_step_forward_contact_host / nb2_step_backward_contact_host (host buffers, copies inside, solver cache in the model) give the bits of
+    the device entry points, with the cache flowing from call to call."""
+    raw = load_raw("half_cheetah")
+    world = nb.World.from_raw(raw)
+    dm = nb.device_model_for(world)
+    B = 64
+    s, a = contact_inputs(raw, "half_cheetah", B, seed=12)
+    g = np.random.default_rng(3).normal(size=(B, 2 * raw.ndof)).astype(np.float32)
+    # device path, two chained steps
+    nb.reset_contact_cache(world)
+    x0 = torch.tensor(s, device="cuda", requires_grad=True); u = torch.tensor(a, device="cuda")
+    x1 = nb.timestep(world, x0, u)
+    x1d = x1.detach().clone().requires_grad_(True)
+    x2 = nb.timestep(world, x1d, u)
+    x2.backward(torch.tensor(g, device="cuda"))
+    # host path
+    status = np.zeros(B, np.int32); sticky = np.zeros(B, np.int32)
+    h1 = dm.forward_contact_host(s, a, keep_for_backward=False, reset_cache=True)
+    h2 = dm.forward_contact_host(h1, a, keep_for_backward=True, status_out=status)
+    gs, ga = dm.backward_contact_host(g, sticky_out=sticky)
+    assert np.array_equal(h1, x1.detach().cpu().numpy()) and np.array_equal(h2, x2.detach().cpu().numpy())
+    assert np.array_equal(gs, x1d.grad.cpu().numpy())
+    assert np.array_equal(status, world._lcp_cache["status"].cpu().numpy())
+    assert (sticky & 2048).sum() == 0 and sticky.any()
