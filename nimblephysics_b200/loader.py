@@ -27,6 +27,8 @@ import os
 import xml.etree.ElementTree as ET
 from typing import Dict, List, Optional
 
+import warnings
+
 import numpy as np
 
 from .world import (FREE, PRISMATIC, REVOLUTE, WELD, BodyNode, BoxShape, CapsuleShape, Joint, ShapeNode,
@@ -64,6 +66,20 @@ def _T(R=None, p=None) -> np.ndarray:
     return T
 
 
+_SKIPPED_WARNED = set()
+
+
+def _warn_skipped_collider(geom_el, where: str):
+    """A collision geometry this path has no generator for (mesh, cylinder, ...): say so ONCE per kind and file instead of dropping it silently —
+    a robot standing on mesh feet in the reference would fall through the floor here."""
+    kinds = [c.tag for c in list(geom_el)] if geom_el is not None else []
+    key = (where, tuple(kinds))
+    if kinds and key not in _SKIPPED_WARNED:
+        _SKIPPED_WARNED.add(key)
+        warnings.warn(f"nimblephysics_b200 loader: collision geometry {kinds} in {where} has no contact generator on the GPU path and is "
+                      "SKIPPED (supported: box, sphere, capsule)", stacklevel=3)
+
+
 def _urdf_origin(el) -> np.ndarray:
     if el is None:
         return np.eye(4)
@@ -84,6 +100,7 @@ def _urdf_geometry(geom_el):
     cap = geom_el.find("capsule")
     if cap is not None:
         return CapsuleShape(float(cap.get("radius")), float(cap.get("length", cap.get("height", "0"))))
+    _warn_skipped_collider(geom_el, "a .urdf collision element")
     return None  # cylinder / mesh: not a supported collider
 
 
@@ -352,6 +369,7 @@ def _sdf_shape(geom_el):
     sp = geom_el.find("sphere")
     if sp is not None:
         return SphereShape(float(sp.find("radius").text))
+    _warn_skipped_collider(geom_el, "a .sdf collision element")
     return None  # cylinders / meshes: no collider on the hot path (the reference meshes need assimp)
 
 
