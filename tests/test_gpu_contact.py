@@ -266,3 +266,21 @@ def test_contact_host_entry_points_match_device_path():
     assert np.array_equal(gs, x1d.grad.cpu().numpy())
     assert np.array_equal(status, world._lcp_cache["status"].cpu().numpy())
     assert (sticky & 2048).sum() == 0 and sticky.any()
+
+
+def test_box_box_face_face_annotation_golden_on_device():
+    """unittests/unit/test_DARTCollide.cpp:554-592 (BOX_BOX_FACE_FACE_COLLISION_ANNOTATION), on the GPU: 4 contacts, (+-0.25, 0.5, 0) EDGE_EDGE,
+    (+-0.25, 0.25, 0) FACE_VERTEX (the CPU twin of this test pins the oracle and the host build: tests/test_golden_collide.py)."""
+    from tests.test_golden_collide import _two_body_world
+
+    world = _two_body_world(nb.BoxShape([1.0, 1.0, 1.0]), [0.0, 0.0, -0.5], nb.BoxShape([0.5, 0.5, 0.5]))
+    n = world.getNumDofs()
+    s = torch.zeros(3, 2 * n, device="cuda"); s[:, 3:6] = torch.tensor([0.0, 0.5, 0.25], device="cuda")
+    with torch.no_grad():
+        nb.timestep(world, s, torch.zeros(3, world.getActionSize(), device="cuda"))
+    c = world._lcp_cache
+    assert c["nc"].cpu().tolist() == [4, 4, 4]
+    ci = c["cinfo"][1, :4].cpu().numpy()
+    seen = {(round(float(r[0]), 6), round(float(r[1]), 6)): int(r[9]) for r in ci}
+    assert seen == {(0.25, 0.5): 3, (-0.25, 0.5): 3, (0.25, 0.25): 2, (-0.25, 0.25): 2}, seen
+    assert np.allclose(ci[:, 2], 0, atol=1e-6) and np.allclose(ci[:, 6], 0, atol=1e-6)
