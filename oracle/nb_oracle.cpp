@@ -16,10 +16,12 @@
 // i.e. they are the exact derivatives the reference's analytic formulas compute (the reference verifies its
 // formulas against finite differences of the same step at 1e-8, unittests/GradientTestUtils.hpp:637-680).
 //
-// Parity status: the reference cannot be built in this container (Eigen/ccd/assimp absent), and its test-suite
-// holds no golden numeric vectors for this path => value-level parity is UNPINNED; the oracle is pinned by the
-// reference's own property tests instead (analytic-vs-FD consistency, tests/test_oracle.py) and, for the LCP
-// stage, bit-comparison with the reference's ODE dSolveLCP compiled from /root/reference (oracle/Makefile).
+// Parity status: the reference cannot be built in this container (Eigen/ccd/assimp absent).  What its test-suite holds as literal
+// vectors for this path IS pinned: the 8 LCP instances of unittests/unit/test_LCPUtils.cpp (tests/test_lcp.py) and the contact sets of
+// unittests/unit/test_DARTCollide.cpp (box-box face-face annotation, sphere / capsule-end vs box: tests/test_golden_collide.py); the LCP
+// stage is bit-compared with the reference's ODE dSolveLCP compiled from /root/reference (oracle/Makefile -> oracle/_ref/libodelcp.so).
+// For the dynamics and the gradients the reference ships property tests only (analytic-vs-FD, unittests/GradientTestUtils.hpp): there
+// value-level parity is UNPINNED and the oracle is held by the same properties (tests/test_oracle.py).
 //
 // Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may load this library.
 // =====================================================================================
