@@ -1725,6 +1725,7 @@ NB2_HD void contact_build(const Nb2ModelDev<double>& M, const Nb2ContactDev& C, 
   CW_FOR(c, nc) { X[xl.oCA + c] = (double)ws.cbodyA[c]; X[xl.oCB + c] = (double)ws.cbodyB[c]; }
   CW_FOR(e, m * 6) { X[xl.oJA + e] = ws.JA[e]; X[xl.oJB + e] = ws.JB[e]; }
   CW_FOR(dd, M.ndof) X[xl.oV + dd] = scr[L.oV + dd];
+  if (ld > m) { CW_FOR(i, m) ws.A[(size_t)i * ld + m] = 0.0; CW_SYNC(); }  // the padding column travels with the matrix: keep it defined
   CW_FOR(e, m * ld) X[xl.oA + e] = ws.A[e];
   CW_ONE { X[0] = (double)m; X[1] = (double)nc; X[2] = (double)status; }
   CW_SYNC();
