@@ -1264,6 +1264,10 @@ NB2_HD int pair_contacts(const Nb2ContactDev& C, int sa, int sb, const Xf<S>& Ta
   if (ta == 0 && tb == 0) return collide_box_box(da, Ta, db, Tb, C.clip_depth, co);
   if (ta == 0 && tb == 1) return collide_box_sphere(da, Ta, db.x, Tb, C.clip_depth, 0, false, co);
   if (ta == 1 && tb == 0) return collide_box_sphere(db, Tb, da.x, Ta, C.clip_depth, 0, true, co);
+  if (ta == 1 && tb == 1) return round_contact(Ta.p, da.x, Tb.p, db.x, C.clip_depth, false, true, 6, co);
+  if (ta == 2 && tb == 2) return collide_capsule_capsule(C.shape_dims[sa][1], da.x, Ta, C.shape_dims[sb][1], db.x, Tb, C.clip_depth, co);
+  if (ta == 1 && tb == 2) return collide_sphere_capsule(da.x, Ta, C.shape_dims[sb][1], db.x, Tb, C.clip_depth, true, co);
+  if (ta == 2 && tb == 1) return collide_sphere_capsule(db.x, Tb, C.shape_dims[sa][1], da.x, Ta, C.clip_depth, false, co);
   if ((ta == 0 && tb == 2) || (ta == 2 && tb == 0)) {
     const bool boxFirst = (ta == 0);
     const Xf<S>& Tc = boxFirst ? Tb : Ta; const Xf<S>& Tbx = boxFirst ? Ta : Tb;

@@ -53,7 +53,7 @@ template <class T> NB2_HD void gset3(V3<T>& v, int k, const T& x) { if (k == 0) 
 template <class T> struct ContactOutT { V3<T> point, normal; T depth; int type; };
 
 // contact types emitted (subset of collision::ContactType, dart/collision/Contact.hpp:50-80)
-//   1 VERTEX_FACE  2 FACE_VERTEX  3 EDGE_EDGE  4 SPHERE_BOX  5 BOX_SPHERE
+//   1 VERTEX_FACE  2 FACE_VERTEX  3 EDGE_EDGE  4 SPHERE_BOX  5 BOX_SPHERE  6 SPHERE_SPHERE  13 PIPE_SPHERE  14 SPHERE_PIPE  15 PIPE_PIPE
 
 // ---- box vs sphere.  sphere_first=false: object 1 = box, object 2 = sphere (DARTCollide.cpp:1482-1653, normal = contact
 // point - centre); sphere_first=true: object 1 = sphere (:1655-1810, normal = centre - contact point, halfspace ignored)
@@ -95,6 +95,99 @@ NB2_HDG int collide_box_sphere(const V3<T>& size0, const Xf<T>& T0, const T& r1,
   out->type = sphere_first ? 4 : 5; out->point = cp; out->depth = pen;
   out->normal = (gval(mag) > 1e-6) ? n * gdiv(T(1.0), mag) : nface;
   return 1;
+}
+
+// ---- round shapes against each other: sphere-sphere (DARTCollide.cpp:1812-1882), capsule-capsule (:4183-4284), sphere-capsule /
+// capsule-sphere (:4286-4420).  A capsule is its axis segment (local z, length h) swept by a sphere of radius r; the contact sits on the line
+// between the two closest points, at the radius-weighted position; normal from object 2 towards object 1.
+//   types: 6 SPHERE_SPHERE  13 PIPE_SPHERE  14 SPHERE_PIPE  15 PIPE_PIPE  (an axis parameter within 1e-8 of an end counts as that end's sphere)
+template <class T> NB2_HDG int round_contact(const V3<T>& c0, const T& r0, const V3<T>& c1, const T& r1, CR clip, bool strict, bool centres_may_coincide,
+                                             int type, ContactOutT<T>* out) {
+  const V3<T> dv = c0 - c1;
+  const T d2 = dot(dv, dv), rsum = r0 + r1;
+  if (centres_may_coincide) {                                   // collideSphereSphere: squared test first, zero normal for coincident centres
+    if (gval(d2) > gval(rsum) * gval(rsum)) return 0;
+    out->point = (c0 * r1 + c1 * r0) * gdiv(T(1.0), rsum);
+    out->type = type;
+    if (gval(d2) < 1e-6) {                                      // DART_COLLISION_EPS
+      if (gval(rsum) > clip) return 0;
+      out->normal = mk3<T>(T(0.0), T(0.0), T(0.0)); out->depth = rsum; return 1;
+    }
+    const T dist = nb2_sqrt(d2);
+    const T pen = rsum - dist;
+    if (gval(pen) > clip) return 0;
+    out->normal = dv * gdiv(T(1.0), dist); out->depth = pen;
+    return 1;
+  }
+  const T dist = nb2_sqrt(d2);
+  if (strict ? !(gval(dist) < gval(rsum)) : !(gval(dist) <= gval(rsum))) return 0;
+  const T pen = rsum - dist;
+  if (gval(pen) > clip) return 0;
+  out->point = (c0 * r1 + c1 * r0) * gdiv(T(1.0), rsum);
+  out->normal = dv * gdiv(T(1.0), dist);
+  out->depth = pen; out->type = type;
+  return 1;
+}
+// parameter in [0, 1] of the point of segment a -> b closest to p (dDistPointToSegment, DARTCollide.cpp:384-410)
+template <class T> NB2_HDG T segment_param_of_point(const V3<T>& p, const V3<T>& a, const V3<T>& b) {
+  const V3<T> v = b - a, w = p - a;
+  const T c1 = dot(w, v);
+  if (gval(c1) <= 0) return T(0.0);
+  const T c2 = dot(v, v);
+  if (gval(c2) <= gval(c1)) return T(1.0);
+  return gdiv(c1, c2);
+}
+// parameters (alpha on p0 -> p1, beta on q0 -> q1) of the closest points of two segments (dSegmentsClosestApproach, DARTCollide.cpp:301-381),
+// then clamped to [0, 1] as collideCapsuleCapsule does
+template <class T> NB2_HDG void segment_segment_params(const V3<T>& p0, const V3<T>& p1, const V3<T>& q0, const V3<T>& q1, T* alpha, T* beta) {
+  const V3<T> u = p1 - p0, v = q1 - q0, w = p0 - q0;
+  const T a = dot(u, u), b = dot(u, v), c = dot(v, v), d = dot(u, w), e = dot(v, w);
+  const T D = a * c - b * b;
+  T sN, sD = D, tN, tD = D;
+  if (gval(D) < 1e-15) { sN = T(0.0); sD = T(1.0); tN = e; tD = c; }  // almost parallel: start of the first segment
+  else {
+    sN = b * e - c * d; tN = a * e - b * d;
+    if (gval(sN) < 0.0) { sN = T(0.0); tN = e; tD = c; }
+    else if (gval(sN) > gval(sD)) { sN = sD; tN = e + b; tD = c; }
+  }
+  if (gval(tN) < 0.0) {
+    tN = T(0.0);
+    if (-gval(d) < 0.0) sN = T(0.0);
+    else if (-gval(d) > gval(a)) sN = sD;
+    else { sN = -d; sD = a; }
+  } else if (gval(tN) > gval(tD)) {
+    tN = tD;
+    const T db = b - d;
+    if (gval(db) < 0.0) sN = T(0.0);
+    else if (gval(db) > gval(a)) sN = sD;
+    else { sN = db; sD = a; }
+  }
+  T al = (fabs(gval(sN)) < 1e-15) ? T(0.0) : gdiv(sN, sD);
+  T be = (fabs(gval(tN)) < 1e-15) ? T(0.0) : gdiv(tN, tD);
+  if (gval(al) < 0) al = T(0.0);
+  if (gval(al) > 1) al = T(1.0);
+  if (gval(be) < 0) be = T(0.0);
+  if (gval(be) > 1) be = T(1.0);
+  *alpha = al; *beta = be;
+}
+NB2_HDG bool at_segment_end(double t) { return fabs(t) < 1e-8 || fabs(1.0 - t) < 1e-8; }
+template <class T> NB2_HDG int collide_capsule_capsule(CR h0, const T& r0, const Xf<T>& T0, CR h1, const T& r1, const Xf<T>& T1, CR clip, ContactOutT<T>* out) {
+  const V3<T> pa = gxf_apply(T0, mk3<T>(T(0.0), T(0.0), T(-0.5 * h0))), pb = gxf_apply(T0, mk3<T>(T(0.0), T(0.0), T(0.5 * h0)));
+  const V3<T> ua = gxf_apply(T1, mk3<T>(T(0.0), T(0.0), T(-0.5 * h1))), ub = gxf_apply(T1, mk3<T>(T(0.0), T(0.0), T(0.5 * h1)));
+  T al, be;
+  segment_segment_params(pa, pb, ua, ub, &al, &be);
+  const V3<T> c0 = pa + (pb - pa) * al, c1 = ua + (ub - ua) * be;
+  const bool s0 = at_segment_end(gval(al)), s1 = at_segment_end(gval(be));
+  return round_contact(c0, r0, c1, r1, clip, false, false, (s0 && s1) ? 6 : (s0 ? 14 : (s1 ? 13 : 15)), out);
+}
+// sphere_first: object 1 = sphere (collideSphereCapsule), else object 1 = capsule (collideCapsuleSphere)
+template <class T> NB2_HDG int collide_sphere_capsule(const T& rs, const Xf<T>& Ts, CR h, const T& rc, const Xf<T>& Tc, CR clip, bool sphere_first, ContactOutT<T>* out) {
+  const V3<T> ua = gxf_apply(Tc, mk3<T>(T(0.0), T(0.0), T(-0.5 * h))), ub = gxf_apply(Tc, mk3<T>(T(0.0), T(0.0), T(0.5 * h)));
+  const T al = segment_param_of_point(Ts.p, ua, ub);
+  const V3<T> cc = ua + (ub - ua) * al;
+  const bool end = at_segment_end(gval(al));
+  if (sphere_first) return round_contact(Ts.p, rs, cc, rc, clip, true, false, end ? 6 : 14, out);
+  return round_contact(cc, rc, Ts.p, rs, clip, true, false, end ? 6 : 13, out);
 }
 
 // ---- box vs box (the algorithm of ODE's dBoxBox as used by the reference, DARTCollide.cpp:764-1450, after Gottschalk's OBB

@@ -145,8 +145,8 @@ static inline bool nb2_fill_contact(const nb2_model_desc& d, Nb2ContactDev& C, s
   // creation instead of flagging them world by world at run time
   for (int p = 0; p < d.npairs; p++) {
     const int ta = d.shape_type[d.pair_a[p]], tb = d.shape_type[d.pair_b[p]];
-    const bool ok = (ta == 0 && tb == 0) || (ta == 0 && tb == 1) || (ta == 1 && tb == 0) || (ta == 0 && tb == 2) || (ta == 2 && tb == 0);
-    if (!ok) { err = "collision pair " + std::to_string(p) + ": shape types (" + std::to_string(ta) + ", " + std::to_string(tb) + ") have no contact generator (supported: box-box, box-sphere, box-capsule)"; return false; }
+    const bool ok = ta >= 0 && ta <= 2 && tb >= 0 && tb <= 2;  // box, sphere, capsule in any combination
+    if (!ok) { err = "collision pair " + std::to_string(p) + ": shape types (" + std::to_string(ta) + ", " + std::to_string(tb) + ") have no contact generator (supported: box, sphere, capsule)"; return false; }
   }
   return true;
 }

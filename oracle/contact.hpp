@@ -3,6 +3,7 @@
 //   collide() pair loop / filter      dart/collision/dart/DARTCollisionDetector.cpp:150-175, dart/collision/CollisionFilter.cpp:105-152
 //   collideBoxSphere / collideSphereBox   dart/collision/dart/DARTCollide.cpp:1482-1653, 1655-1810
 //   collideBoxBox -> dBoxBox            DARTCollide.cpp:764-1450 (+ intersectRectQuad :513-580, dLineClosestApproach)
+//   collideSphereSphere :1812-1882, collideCapsuleCapsule :4183-4284, collideSphereCapsule / collideCapsuleSphere :4286-4420
 //   collideBoxCapsule / collideCapsuleBox DARTCollide.cpp:4422-4645 — the reference asks libccd's MPR (third-party, absent here)
 //        which part of the capsule touches; on a box FACE that is the deeper end sphere, tested with the functions above
 //        (:4462-4491).  This restatement picks the deeper end sphere geometrically and flags the "pipe" (side-on) case as
@@ -19,7 +20,8 @@ namespace orc {
 enum { SH_BOX = 0, SH_SPHERE = 1, SH_CAPSULE = 2 };
 enum { CLIP_BOTH = 0, CLIP_TOP = 1, CLIP_BOTTOM = 2 };
 // subset of collision::ContactType (dart/collision/Contact.hpp:50-80) that these generators emit
-enum { CT_UNSUPPORTED = 0, CT_VERTEX_FACE = 1, CT_FACE_VERTEX = 2, CT_EDGE_EDGE = 3, CT_SPHERE_BOX = 4, CT_BOX_SPHERE = 5 };
+enum { CT_UNSUPPORTED = 0, CT_VERTEX_FACE = 1, CT_FACE_VERTEX = 2, CT_EDGE_EDGE = 3, CT_SPHERE_BOX = 4, CT_BOX_SPHERE = 5, CT_SPHERE_SPHERE = 6,
+       CT_PIPE_SPHERE = 13, CT_SPHERE_PIPE = 14, CT_PIPE_PIPE = 15 };
 
 template <class S> struct Contact {
   Vec3<S> point, normal;
@@ -105,6 +107,111 @@ inline void collide_sphere_box(const S& r0, const Iso<S>& T0, const Vec3<S>& siz
   if (val(pen) < 0.0) return;
   if (val(mag) > 1e-6) { c.point = cp; c.normal = n * (S(1.0) / mag); c.depth = pen; out.push_back(c); }
   else { S mn; c.normal = nearest_face_normal(mn); c.point = cp; c.depth = pen; out.push_back(c); }
+}
+
+// ---- sphere vs sphere (collideSphereSphere, DARTCollide.cpp:1812-1882)
+template <class S>
+inline void collide_sphere_sphere(const S& r0in, const Iso<S>& T0, const S& r1in, const Iso<S>& T1, double clip, int bA, int bB, int sA, int sB,
+                                  std::vector<Contact<S>>& out) {
+  S r0 = r0in, r1 = r1in;
+  const S rsum = r0 + r1;
+  Vec3<S> normal = T0.p - T1.p;
+  S nsq = dot(normal, normal);
+  if (val(nsq) > val(rsum) * val(rsum)) return;
+  r0 = r0 / rsum; r1 = r1 / rsum;
+  Contact<S> c; c.bodyA = bA; c.bodyB = bB; c.shapeA = sA; c.shapeB = sB; c.type = CT_SPHERE_SPHERE;
+  c.point = T0.p * r1 + T1.p * r0;
+  if (val(nsq) < 1e-6) {  // DART_COLLISION_EPS: coincident centres, zero normal (the constraint filter drops it)
+    if (val(rsum) > clip) return;
+    c.normal = v3<S>(S(0.0), S(0.0), S(0.0)); c.depth = rsum; out.push_back(c); return;
+  }
+  const S len = sqrt(nsq);
+  const S pen = rsum - len;
+  if (val(pen) > clip) return;
+  c.normal = normal * (S(1.0) / len); c.depth = pen; out.push_back(c);
+}
+// dDistPointToSegment (DARTCollide.cpp:384-410): distance and segment parameter
+template <class S> inline S dist_point_segment(const Vec3<S>& p, const Vec3<S>& ua, const Vec3<S>& ub, S& alpha) {
+  const Vec3<S> v = ub - ua, w = p - ua;
+  const S c1 = dot(w, v);
+  if (val(c1) <= 0) { alpha = S(0.0); const Vec3<S> d = p - ua; return sqrt(dot(d, d)); }
+  const S c2 = dot(v, v);
+  if (val(c2) <= val(c1)) { alpha = S(1.0); const Vec3<S> d = p - ub; return sqrt(dot(d, d)); }
+  alpha = c1 / c2;
+  const Vec3<S> d = p - (ua + v * alpha);
+  return sqrt(dot(d, d));
+}
+// dSegmentsClosestApproach (DARTCollide.cpp:301-381): segment 1 = pa -> pb (alpha), segment 2 = ua -> ub (beta)
+template <class S> inline void segments_closest_approach(const Vec3<S>& pa, const Vec3<S>& ua, const Vec3<S>& pb, const Vec3<S>& ub, S& alpha, S& beta) {
+  const Vec3<S> u = pb - pa, v = ub - ua, w = pa - ua;
+  const S a = dot(u, u), b = dot(u, v), c = dot(v, v), d = dot(u, w), e = dot(v, w);
+  const S D = a * c - b * b;
+  S sN, sD = D, tN, tD = D;
+  const double SMALL = 1e-15;
+  if (val(D) < SMALL) { sN = S(0.0); sD = S(1.0); tN = e; tD = c; }
+  else {
+    sN = b * e - c * d; tN = a * e - b * d;
+    if (val(sN) < 0.0) { sN = S(0.0); tN = e; tD = c; }
+    else if (val(sN) > val(sD)) { sN = sD; tN = e + b; tD = c; }
+  }
+  if (val(tN) < 0.0) {
+    tN = S(0.0);
+    if (-val(d) < 0.0) sN = S(0.0);
+    else if (-val(d) > val(a)) sN = sD;
+    else { sN = -d; sD = a; }
+  } else if (val(tN) > val(tD)) {
+    tN = tD;
+    if ((-val(d) + val(b)) < 0.0) sN = S(0.0);
+    else if ((-val(d) + val(b)) > val(a)) sN = sD;
+    else { sN = b - d; sD = a; }
+  }
+  alpha = (std::fabs(val(sN)) < SMALL) ? S(0.0) : sN / sD;
+  beta = (std::fabs(val(tN)) < SMALL) ? S(0.0) : tN / tD;
+}
+template <class S> inline Vec3<S> capsule_end(const Iso<S>& T, double h, double sign) { return apply(T, v3<S>(S(0.0), S(0.0), S(sign * h / 2))); }
+inline bool near_end(double t) { return std::fabs(t) < 1e-8 || std::fabs(1.0 - t) < 1e-8; }
+// collideCapsuleCapsule (DARTCollide.cpp:4183-4284)
+template <class S>
+inline void collide_capsule_capsule(double h0, const S& r0in, const Iso<S>& T0, double h1, const S& r1in, const Iso<S>& T1, double clip,
+                                    int bA, int bB, int sA, int sB, std::vector<Contact<S>>& out) {
+  const Vec3<S> pa = capsule_end(T0, h0, -1.0), pb = capsule_end(T0, h0, 1.0), ua = capsule_end(T1, h1, -1.0), ub = capsule_end(T1, h1, 1.0);
+  S alpha, beta;
+  segments_closest_approach(pa, ua, pb, ub, alpha, beta);
+  if (val(alpha) < 0) alpha = S(0.0);
+  if (val(alpha) > 1) alpha = S(1.0);
+  if (val(beta) < 0) beta = S(0.0);
+  if (val(beta) > 1) beta = S(1.0);
+  const Vec3<S> c0 = pa + (pb - pa) * alpha, c1 = ua + (ub - ua) * beta;
+  const Vec3<S> dv = c0 - c1;
+  const S dist = sqrt(dot(dv, dv)), rsum = r0in + r1in;
+  if (!(val(dist) <= val(rsum))) return;
+  Contact<S> c; c.bodyA = bA; c.bodyB = bB; c.shapeA = sA; c.shapeB = sB;
+  c.depth = rsum - dist;
+  if (val(c.depth) > clip) return;
+  c.point = c0 * (r1in / rsum) + c1 * (r0in / rsum);
+  c.normal = dv * (S(1.0) / dist);
+  const bool s0 = near_end(val(alpha)), s1 = near_end(val(beta));
+  c.type = (s0 && s1) ? CT_SPHERE_SPHERE : (s0 ? CT_SPHERE_PIPE : (s1 ? CT_PIPE_SPHERE : CT_PIPE_PIPE));
+  out.push_back(c);
+}
+// collideSphereCapsule / collideCapsuleSphere (DARTCollide.cpp:4286-4420)
+template <class S>
+inline void collide_sphere_capsule(const S& rs, const Iso<S>& Ts, double h, const S& rc, const Iso<S>& Tc, double clip, bool sphere_first,
+                                   int bA, int bB, int sA, int sB, std::vector<Contact<S>>& out) {
+  const Vec3<S> ua = capsule_end(Tc, h, -1.0), ub = capsule_end(Tc, h, 1.0);
+  S alpha;
+  const S dist = dist_point_segment(Ts.p, ua, ub, alpha);
+  const S rsum = rs + rc;
+  if (!(val(dist) < val(rsum))) return;
+  const Vec3<S> cc = ua + (ub - ua) * alpha;
+  Contact<S> c; c.bodyA = bA; c.bodyB = bB; c.shapeA = sA; c.shapeB = sB;
+  c.depth = rsum - dist;
+  if (val(c.depth) > clip) return;
+  c.point = Ts.p * (rc / rsum) + cc * (rs / rsum);
+  const Vec3<S> dv = sphere_first ? Ts.p - cc : cc - Ts.p;
+  c.normal = dv * (S(1.0) / sqrt(dot(dv, dv)));
+  c.type = near_end(val(alpha)) ? CT_SPHERE_SPHERE : (sphere_first ? CT_SPHERE_PIPE : CT_PIPE_SPHERE);
+  out.push_back(c);
 }
 
 // ---- intersectRectQuad (DARTCollide.cpp:513-580): clip quad p[8] against rect +-h; returns #points in ret[16]

@@ -388,7 +388,11 @@ static void collide_raw(const Model& M, const std::vector<BodyState<S>>& B, std:
       const int half = (e == 0) ? CLIP_TOP : CLIP_BOTTOM;
       if (boxFirst) collide_box_sphere(bdim, Tw[bs], S(r), Tend[e], clip, half, bi, bj, i, j, raw);
       else collide_sphere_box(S(r), Tend[e], bdim, Tw[bs], clip, bi, bj, i, j, raw);
-    } else { unsupported++; }
+    } else if (ti == SH_SPHERE && tj == SH_SPHERE) collide_sphere_sphere(di[0], Tw[i], dj[0], Tw[j], clip, bi, bj, i, j, raw);
+    else if (ti == SH_CAPSULE && tj == SH_CAPSULE) collide_capsule_capsule(M.shape_dims[3 * i + 1], di[0], Tw[i], M.shape_dims[3 * j + 1], dj[0], Tw[j], clip, bi, bj, i, j, raw);
+    else if (ti == SH_SPHERE && tj == SH_CAPSULE) collide_sphere_capsule(di[0], Tw[i], M.shape_dims[3 * j + 1], dj[0], Tw[j], clip, true, bi, bj, i, j, raw);
+    else if (ti == SH_CAPSULE && tj == SH_SPHERE) collide_sphere_capsule(dj[0], Tw[j], M.shape_dims[3 * i + 1], di[0], Tw[i], clip, false, bi, bj, i, j, raw);
+    else { unsupported++; }
   }
 }
 

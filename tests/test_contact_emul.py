@@ -354,3 +354,57 @@ def test_penetration_correction_forward_and_backward(oracle_mod):
     assert seen >= 3
     kinds = _check_backward(ob, raw, s, a, tol=2e-5)
     assert len(kinds) == s.shape[0]
+
+
+def test_round_shape_contacts_forward_and_backward(oracle_mod):
+    """sphere-sphere, capsule-capsule and sphere-capsule pairs (DARTCollide.cpp:1812-1882, 4183-4420): forward against the oracle (contact set,
+    labels, next state) and the backward — the dual-number contact generator differentiates them like any other pair — against the oracle's
+    Jacobian.  World: a static capsule lying along x and a static sphere; a free capsule crosses the static one (pipe-pipe), a free sphere
+    sits on the static capsule's side (pipe-sphere) and touches the free capsule's end region, a second free sphere rests on the static sphere."""
+    from scipy.spatial.transform import Rotation
+
+    w = nb.World()
+    w.setGravity([0, 0, -9.81])
+    w.setTimeStep(1e-3)
+    g = nb.Skeleton("fixed"); g.setMobile(False)
+    j, b = g.createWeldJointAndBodyNodePair()
+    sn = b.createShapeNode(nb.CapsuleShape(0.2, 2.0)); sn.createCollisionAspect()
+    T = nb.Isometry3(); T.set_rotation(Rotation.from_rotvec([0, np.pi / 2, 0]).as_matrix()); sn.setRelativeTransform(T.matrix())
+    sn2 = b.createShapeNode(nb.SphereShape(0.3)); sn2.createCollisionAspect()
+    T2 = nb.Isometry3(); T2.set_translation([0.0, 2.0, 0.0]); sn2.setRelativeTransform(T2.matrix())
+    w.addSkeleton(g)
+    shapes = [nb.CapsuleShape(0.15, 1.0), nb.SphereShape(0.25), nb.SphereShape(0.2)]
+    for k, shp in enumerate(shapes):
+        s = nb.Skeleton(f"m{k}")
+        j, b = s.createFreeJointAndBodyNodePair(); b.setMass(1.0 + 0.3 * k)
+        b.setMomentOfInertia(0.05, 0.06, 0.04)
+        b.createShapeNode(shp).createCollisionAspect()
+        w.addSkeleton(s)
+    raw = nb.flatten_world(w)
+    n = raw.ndof
+    rng = np.random.default_rng(7)
+    B = 8
+    S = np.zeros((B, 2 * n), np.float32)
+    for k in range(B):
+        # free capsule: axis along y (rotated about x), crossing the static capsule from above
+        S[k, 0:3] = [np.pi / 2 + rng.normal(0, 0.02), rng.normal(0, 0.02), rng.normal(0, 0.02)]
+        S[k, 3:6] = [0.3 + rng.normal(0, 0.01), rng.normal(0, 0.01), 0.2 + 0.15 - 0.004 + rng.normal(0, 0.001)]
+        # free sphere on the static capsule's side
+        S[k, 9:12] = [-0.5 + rng.normal(0, 0.01), rng.normal(0, 0.005), 0.2 + 0.25 - 0.003 + rng.normal(0, 0.001)]
+        # free sphere on the static sphere
+        S[k, 15:18] = [rng.normal(0, 0.01), 2.0 + rng.normal(0, 0.01), 0.3 + 0.2 - 0.003 + rng.normal(0, 0.001)]
+        S[k, n:] = rng.normal(0, 0.05, n)
+    A = np.zeros((B, len(raw.action_map)), np.float32)
+    cm = nb.compile_model(raw)
+    r = EmulWorld(cm).forward_contact(S, A)
+    ow = oracle_mod.OracleContactWorld(raw)
+    types = set()
+    for k in range(B):
+        ro = ow.step_contact(S[k].astype(np.float64), A[k].astype(np.float64))
+        assert r["nc"][k] == ro["nc"] and r["nc"][k] >= 3, (k, r["nc"][k], ro["nc"])
+        assert np.array_equal(r["labels"][k][: r["m"][k]], ro["mapping"][: ro["m"]])
+        assert rel_err(r["next"][k], ro["next_state"]) < 1e-6
+        types |= set(int(t) for t in ro["type"])
+    assert {6, 15} <= types and (13 in types or 14 in types), types
+    kinds = _check_backward(ob, raw, S, A, tol=2e-5)
+    assert len(kinds) == B

@@ -91,3 +91,63 @@ def test_sphere_box_golden_cases(oracle_mod):
         p, nrm, depth, typ = cs[0]
         assert np.allclose(np.abs(nrm), [0, 0, 1], atol=1e-9) and abs(depth - 0.01) < 1e-6, (name, nrm, depth)
         assert np.allclose(p[:2], [0.1, -0.1], atol=1e-6) and abs(p[2] - 0.5) < 0.011, (name, p)
+
+
+def _one(cs, name):
+    assert len(cs) == 1, (name, cs)
+    return cs[0]
+
+
+def test_capsule_capsule_and_capsule_sphere_golden_cases(oracle_mod):
+    """unittests/unit/test_DARTCollide.cpp: CAPSULE_CAPSULE_T_SHAPED (:2167-2245), X_SHAPED (:2248-2326), CAPSULE_SPHERE_END (:2424-2495) and
+    CAPSULE_SPHERE_SIDE (:2498-2570), forward and "backwards" (objects swapped): expected point, normal (object 2 -> object 1), depth 0.01, type."""
+    h, r1, r2 = 1.0, 0.4, 0.3
+    px = r1 - 0.01 * r1 / (r1 + r2)
+    cap1, cap2, sph2 = nb.CapsuleShape(r1, h), nb.CapsuleShape(r2, h), nb.SphereShape(r2)
+    cases = [
+        # (static shape, moving shape, moving position, moving rotation vector, expected point, expected normal, expected type)
+        ("T", cap1, cap2, [r1 + r2 + h / 2 - 0.01, 0, 0], [0, np.pi / 2, 0], [px, 0, 0], [-1, 0, 0], 13),          # PIPE_SPHERE
+        ("X", cap1, cap2, [0, r1 + r2 - 0.01, 0], [0, np.pi / 2, 0], [0, px, 0], [0, -1, 0], 15),                    # PIPE_PIPE
+        ("sphere at the end", cap1, sph2, [0, 0, h / 2 + r1 + r2 - 0.01], [0, 0, 0], [0, 0, h / 2 + px], [0, 0, -1], 6),   # SPHERE_SPHERE
+        ("sphere at the side", cap1, sph2, [r1 + r2 - 0.01, 0, 0], [0, 0, 0], [px, 0, 0], [-1, 0, 0], 13),           # PIPE_SPHERE
+    ]
+    for label, s_static, s_moving, pos, rot, ep, en, et in cases:
+        world = _two_body_world(s_static, [0, 0, 0], s_moving)
+        for name, cs in zip(("oracle", "device code"), _contacts(oracle_mod, world, pos, rot)):
+            p, nrm, depth, typ = _one(cs, (label, name))
+            assert np.allclose(p, ep, atol=1e-6) and np.allclose(nrm, en, atol=1e-6) and abs(depth - 0.01) < 1e-6 and typ == et, (label, name, p, nrm, depth, typ)
+    # backwards: the small shape is object 1 (static, placed where it was), the big capsule moves but sits at the origin
+    back = [
+        ("T backwards", cap2, [r1 + r2 + h / 2 - 0.01, 0, 0], [0, np.pi / 2, 0], [px, 0, 0], [1, 0, 0], 14),        # SPHERE_PIPE
+        ("sphere at the side backwards", sph2, [r1 + r2 - 0.01, 0, 0], [0, 0, 0], [px, 0, 0], [1, 0, 0], 14),       # SPHERE_PIPE
+        ("sphere at the end backwards", sph2, [0, 0, h / 2 + r1 + r2 - 0.01], [0, 0, 0], [0, 0, h / 2 + px], [0, 0, 1], 6),
+    ]
+    for label, s_static, pos, rot, ep, en, et in back:
+        w = nb.World(); w.setGravity([0, 0, 0])
+        g = nb.Skeleton("fixed"); g.setMobile(False)
+        j, b = g.createWeldJointAndBodyNodePair()
+        b.createShapeNode(s_static).createCollisionAspect()
+        from scipy.spatial.transform import Rotation
+        T = nb.Isometry3(); T.set_translation(pos); T.set_rotation(Rotation.from_rotvec(rot).as_matrix())
+        j.setTransformFromParentBodyNode(T)
+        w.addSkeleton(g)
+        s = nb.Skeleton("moving")
+        j, b = s.createFreeJointAndBodyNodePair(); b.setMass(1.0)
+        b.createShapeNode(cap1).createCollisionAspect()
+        w.addSkeleton(s)
+        for name, cs in zip(("oracle", "device code"), _contacts(oracle_mod, w, [0, 0, 0])):
+            p, nrm, depth, typ = _one(cs, (label, name))
+            assert np.allclose(p, ep, atol=1e-6) and np.allclose(nrm, en, atol=1e-6) and abs(depth - 0.01) < 1e-6 and typ == et, (label, name, p, nrm, depth, typ)
+
+
+def test_sphere_sphere_contact(oracle_mod):
+    """collideSphereSphere (DARTCollide.cpp:1812-1882): point at the radius-weighted position between the centres, normal from object 2 to 1."""
+    r0, r1 = 0.4, 0.3
+    world = _two_body_world(nb.SphereShape(r0), [0, 0, 0], nb.SphereShape(r1))
+    d = np.array([1.0, 2.0, -2.0]) / 3.0
+    for name, cs in zip(("oracle", "device code"), _contacts(oracle_mod, world, list(d * (r0 + r1 - 0.02)))):
+        p, nrm, depth, typ = _one(cs, name)
+        assert np.allclose(nrm, -d, atol=1e-6) and abs(depth - 0.02) < 1e-6 and typ == 6, (name, nrm, depth, typ)
+        assert np.allclose(p, d * (r0 + r1 - 0.02) * r0 / (r0 + r1), atol=1e-6), (name, p)
+    for name, cs in zip(("oracle", "device code"), _contacts(oracle_mod, world, list(d * (r0 + r1 + 0.01)))):
+        assert len(cs) == 0, (name, cs)

@@ -284,3 +284,50 @@ def test_box_box_face_face_annotation_golden_on_device():
     seen = {(round(float(r[0]), 6), round(float(r[1]), 6)): int(r[9]) for r in ci}
     assert seen == {(0.25, 0.5): 3, (-0.25, 0.5): 3, (0.25, 0.25): 2, (-0.25, 0.25): 2}, seen
     assert np.allclose(ci[:, 2], 0, atol=1e-6) and np.allclose(ci[:, 6], 0, atol=1e-6)
+
+
+def test_round_shape_contacts_on_device(oracle_mod):
+    """sphere-sphere, capsule-capsule, sphere-capsule pairs on the GPU against the oracle: contact set, labels, next state, gradients (the CPU twin
+    with the world description: tests/test_contact_emul.py::test_round_shape_contacts_forward_and_backward)."""
+    from scipy.spatial.transform import Rotation
+
+    w = nb.World(); w.setGravity([0, 0, -9.81]); w.setTimeStep(1e-3)
+    g = nb.Skeleton("fixed"); g.setMobile(False)
+    j, b = g.createWeldJointAndBodyNodePair()
+    sn = b.createShapeNode(nb.CapsuleShape(0.2, 2.0)); sn.createCollisionAspect()
+    T = nb.Isometry3(); T.set_rotation(Rotation.from_rotvec([0, np.pi / 2, 0]).as_matrix()); sn.setRelativeTransform(T.matrix())
+    sn2 = b.createShapeNode(nb.SphereShape(0.3)); sn2.createCollisionAspect()
+    T2 = nb.Isometry3(); T2.set_translation([0.0, 2.0, 0.0]); sn2.setRelativeTransform(T2.matrix())
+    w.addSkeleton(g)
+    for k, shp in enumerate([nb.CapsuleShape(0.15, 1.0), nb.SphereShape(0.25), nb.SphereShape(0.2)]):
+        s = nb.Skeleton(f"m{k}")
+        j, b = s.createFreeJointAndBodyNodePair(); b.setMass(1.0 + 0.3 * k); b.setMomentOfInertia(0.05, 0.06, 0.04)
+        b.createShapeNode(shp).createCollisionAspect()
+        w.addSkeleton(s)
+    raw = nb.flatten_world(w)
+    n = raw.ndof
+    rng = np.random.default_rng(7)
+    B = 16
+    S = np.zeros((B, 2 * n), np.float32)
+    for k in range(B):
+        S[k, 0:3] = [np.pi / 2 + rng.normal(0, 0.02), rng.normal(0, 0.02), rng.normal(0, 0.02)]
+        S[k, 3:6] = [0.3 + rng.normal(0, 0.01), rng.normal(0, 0.01), 0.2 + 0.15 - 0.004 + rng.normal(0, 0.001)]
+        S[k, 9:12] = [-0.5 + rng.normal(0, 0.01), rng.normal(0, 0.005), 0.2 + 0.25 - 0.003 + rng.normal(0, 0.001)]
+        S[k, 15:18] = [rng.normal(0, 0.01), 2.0 + rng.normal(0, 0.01), 0.3 + 0.2 - 0.003 + rng.normal(0, 0.001)]
+        S[k, n:] = rng.normal(0, 0.05, n)
+    A = np.zeros((B, len(raw.action_map)), np.float32)
+    gr = rng.normal(size=(B, 2 * n)).astype(np.float32)
+    st = torch.tensor(S, device="cuda", requires_grad=True); at = torch.tensor(A, device="cuda", requires_grad=True)
+    out = nb.timestep(w, st, at)
+    c = w._lcp_cache
+    labels, mm, ncs = c["labels"].cpu().numpy(), c["m"].cpu().numpy(), c["nc"].cpu().numpy()
+    out.backward(torch.tensor(gr, device="cuda"))
+    nb.check_contact_status(w)
+    ow = ob.OracleContactWorld(raw)
+    for k in range(B):
+        ro = ow.step_contact(S[k].astype(np.float64), A[k].astype(np.float64))
+        assert ncs[k] == ro["nc"] and ncs[k] >= 3 and mm[k] == ro["m"]
+        assert np.array_equal(labels[k][: mm[k]], ro["mapping"][: ro["m"]])
+        assert rel_err(out[k].detach().cpu().numpy(), ro["next_state"]) < 1e-5
+        rgs, rga, rc = ow.backprop_contact(S[k].astype(np.float64), A[k].astype(np.float64), gr[k].astype(np.float64))
+        assert rc >= 0 and rel_err(st.grad[k].cpu().numpy(), rgs) < 1e-4
