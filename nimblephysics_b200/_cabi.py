@@ -91,16 +91,27 @@ def make_desc(cm: CanonModel, with_contacts: bool = True):
 
 
 def collision_pairs(cm: CanonModel):
+    """Shape pairs the narrow phase visits, in the reference's enumeration order (object i < object j), after the static part of
+    BodyNodeCollisionFilter::ignoresCollision (dart/collision/CollisionFilter.cpp:105-152): same BodyNode, two immobile skeletons, the same
+    skeleton unless it enabled self-collision checking — and then adjacent BodyNodes only when it also enabled the adjacent-body check.
+    One addition: two BodyNodes welded into the same moving body cannot move against each other; their pair is dropped."""
     pa, pb = [], []
     ns = len(cm.shape_body)
+    selfcol = getattr(cm, "shape_selfcol", None)
     for i in range(ns - 1):
         for j in range(i + 1, ns):
-            if cm.shape_orig_body[i] == cm.shape_orig_body[j]:
+            bi, bj = int(cm.shape_orig_body[i]), int(cm.shape_orig_body[j])
+            if bi == bj:
                 continue  # same BodyNode
             if cm.shape_body[i] < 0 and cm.shape_body[j] < 0:
                 continue  # neither can move
             if cm.shape_skel[i] == cm.shape_skel[j]:
-                continue  # self-collision checking is off by default in the reference
+                if selfcol is None or not selfcol[i]:
+                    continue  # self-collision checking is off by default in the reference
+                if not cm.shape_adjcheck[i] and (cm.orig_parent[bi] == bj or cm.orig_parent[bj] == bi):
+                    continue  # adjacent bodies (areAdjacentBodies, CollisionFilter.cpp:155-170)
+                if cm.shape_body[i] == cm.shape_body[j]:
+                    continue  # welded together
             pa.append(i)
             pb.append(j)
     return pa, pb

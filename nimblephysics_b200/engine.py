@@ -204,12 +204,14 @@ class DeviceModel:
 
 
 def _has_possible_contacts(raw: RawModel) -> bool:
-    """True when some collision-shape pair could ever generate a contact (shapes on two different skeletons;
-    self-collision is off by default in the reference, dart/dynamics/Skeleton.cpp mEnabledSelfCollisionCheck=false)."""
+    """True when some collision-shape pair could ever generate a contact: shapes on two different skeletons, or two shapes of a skeleton
+    that enabled self-collision checking (off by default in the reference, dart/dynamics/Skeleton.cpp mEnabledSelfCollisionCheck=false)."""
     if raw.ns < 2:
         return False
-    skels = set(int(raw.skel_id[b]) for b in raw.shape_body)
-    return len(skels) > 1
+    skels = [int(raw.skel_id[b]) for b in raw.shape_body]
+    if len(set(skels)) > 1:
+        return True
+    return any(raw.self_collision[b] for b in raw.shape_body)
 
 
 def device_model_for(world) -> DeviceModel:

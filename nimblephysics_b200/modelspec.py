@@ -33,7 +33,7 @@ _ARRAY_FIELDS_F = ["axis", "Tpj", "Tcj", "mass", "com", "moment", "friction", "r
                    "rest", "pos_lo", "pos_hi", "vel_lo", "vel_hi", "force_lo", "force_hi", "init_pos", "gravity",
                    "shape_dims", "shape_T"]
 _ARRAY_FIELDS_I = ["parent", "jtype", "dof_off", "mobile", "gravity_mode", "skel_id", "shape_body", "shape_type",
-                   "action_map"]
+                   "action_map", "self_collision", "adjacent_check"]
 
 
 def T_to_12(T: np.ndarray) -> np.ndarray:
@@ -64,6 +64,8 @@ class RawModel:
     mobile: np.ndarray = None
     gravity_mode: np.ndarray = None
     skel_id: np.ndarray = None
+    self_collision: np.ndarray = None   # [nb] 1 when the body's skeleton has self-collision checking enabled (Skeleton::enableSelfCollisionCheck)
+    adjacent_check: np.ndarray = None   # [nb] 1 when that skeleton also checks ADJACENT bodies (Skeleton::enableAdjacentBodyCheck)
     friction: np.ndarray = None
     restitution: np.ndarray = None
     damping: np.ndarray = None
@@ -114,6 +116,10 @@ class RawModel:
 
     def _fix_shapes(self):
         nb, n = self.nb, self.ndof
+        if self.self_collision is None:  # fixtures written before these fields existed: the reference's defaults (both off)
+            self.self_collision = np.zeros(nb, np.int32)
+        if self.adjacent_check is None:
+            self.adjacent_check = np.zeros(nb, np.int32)
         self.axis = self.axis.reshape(nb, 3)
         self.Tpj = self.Tpj.reshape(nb, 12)
         self.Tcj = self.Tcj.reshape(nb, 12)
@@ -154,6 +160,8 @@ def flatten_world(world: World) -> RawModel:
     m.mobile = np.zeros(nb, np.int32)
     m.gravity_mode = np.zeros(nb, np.int32)
     m.skel_id = np.zeros(nb, np.int32)
+    m.self_collision = np.zeros(nb, np.int32)
+    m.adjacent_check = np.zeros(nb, np.int32)
     m.friction = np.zeros(nb)
     m.restitution = np.zeros(nb)
     per_dof = {k: [] for k in ("damping", "spring", "rest", "pos_lo", "pos_hi", "vel_lo", "vel_hi", "force_lo",
@@ -176,6 +184,8 @@ def flatten_world(world: World) -> RawModel:
         m.mobile[i] = 1 if skel.mobile else 0
         m.gravity_mode[i] = 1 if b.gravity_mode else 0
         m.skel_id[i] = si
+        m.self_collision[i] = 1 if getattr(skel, "self_collision", False) else 0
+        m.adjacent_check[i] = 1 if getattr(skel, "adjacent_check", False) else 0
         m.friction[i] = b.friction
         m.restitution[i] = b.restitution
         for k in per_dof:
@@ -257,6 +267,9 @@ class CanonModel:
     shape_friction: np.ndarray = None
     shape_restitution: np.ndarray = None
     shape_skel: np.ndarray = None
+    shape_selfcol: np.ndarray = None   # per shape: its skeleton checks self-collisions / adjacent bodies too
+    shape_adjcheck: np.ndarray = None
+    orig_parent: np.ndarray = None     # [raw nb] parent BodyNode (adjacency test of the collision filter)
     penetration_correction: bool = False
     contact_clipping_depth: float = 0.03
     fallback_cfm: float = 1e-4
@@ -597,6 +610,9 @@ def compile_model(raw: RawModel, lanes: int = 1) -> CanonModel:
     cm.shape_friction = np.array(sf, np.float64)
     cm.shape_restitution = np.array(sr, np.float64)
     cm.shape_skel = np.array(ss, np.int32)
+    cm.shape_selfcol = np.array([int(raw.self_collision[i]) for i in so], np.int32)
+    cm.shape_adjcheck = np.array([int(raw.adjacent_check[i]) for i in so], np.int32)
+    cm.orig_parent = np.array(raw.parent, np.int32)
     cm.penetration_correction = raw.penetration_correction
     cm.contact_clipping_depth = raw.contact_clipping_depth
     cm.fallback_cfm = raw.fallback_cfm

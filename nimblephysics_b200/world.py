@@ -281,6 +281,36 @@ class Skeleton:
         self.bodies: List[BodyNode] = []
         self.mobile = True
 
+    # ----- self-collision (Skeleton::enableSelfCollisionCheck / enableAdjacentBodyCheck, dart/dynamics/Skeleton.cpp; both off by default)
+    def setSelfCollisionCheck(self, enable: bool):
+        self.self_collision = bool(enable)
+        self._touch_world()
+
+    def enableSelfCollisionCheck(self):
+        self.setSelfCollisionCheck(True)
+
+    def disableSelfCollisionCheck(self):
+        self.setSelfCollisionCheck(False)
+
+    def isEnabledSelfCollisionCheck(self) -> bool:
+        return bool(getattr(self, "self_collision", False))
+
+    def getSelfCollisionCheck(self) -> bool:
+        return self.isEnabledSelfCollisionCheck()
+
+    def setAdjacentBodyCheck(self, enable: bool):
+        self.adjacent_check = bool(enable)
+        self._touch_world()
+
+    def enableAdjacentBodyCheck(self):
+        self.setAdjacentBodyCheck(True)
+
+    def disableAdjacentBodyCheck(self):
+        self.setAdjacentBodyCheck(False)
+
+    def isEnabledAdjacentBodyCheck(self) -> bool:
+        return bool(getattr(self, "adjacent_check", False))
+
     def setMobile(self, m: bool):
         _edited()
         self.mobile = bool(m)
@@ -465,6 +495,8 @@ class World:
             if sid not in skels:
                 skels[sid] = Skeleton(f"skeleton_{sid}")
                 skels[sid].mobile = bool(raw.mobile[i])
+                skels[sid].self_collision = bool(raw.self_collision[i])
+                skels[sid].adjacent_check = bool(raw.adjacent_check[i])
             sk = skels[sid]
             p = int(raw.parent[i])
             name = raw.body_names[i] if i < len(raw.body_names) else None

@@ -125,6 +125,11 @@ class OracleContactWorld(OracleWorld):
         lib().orc_model_set_contact(self.h, _pi(k[0]), ctypes.c_int(raw.ns), _pi(k[1]), _pi(k[2]), _p(k[3]), _p(k[4]), _p(k[5]),
                                     _p(k[6]), ctypes.c_int(int(raw.penetration_correction)),
                                     ctypes.c_double(raw.contact_clipping_depth), ctypes.c_double(raw.fallback_cfm))
+        sc = getattr(raw, "self_collision", None)
+        if sc is not None and np.any(sc):
+            k2 = [i(raw.self_collision), i(raw.adjacent_check)]
+            self._keep3 = k2
+            lib().orc_model_set_self_collision(self.h, _pi(k2[0]), _pi(k2[1]))
 
     def step_contact(self, state, action, x_warm=None):
         """-> dict(next_state, nc, point, normal, depth, bodies, type, A, b, lo, hi, findex, x, mapping, status, vstar)"""

@@ -52,6 +52,8 @@ struct Model {
   bool penetration_correction = false;
   double clip_depth = 0.03, fallback_cfm = 1e-4;
   std::vector<int> has_dofs_above;  // BodyNode::getNumDependentGenCoords() > 0
+  std::vector<int> self_collision, adjacent_check;  // per body: Skeleton::isEnabledSelfCollisionCheck / isEnabledAdjacentBodyCheck of its skeleton
+  std::vector<int> rigid_root;      // first ancestor reached through weld joints only (bodies with the same one cannot move against each other)
 };
 
 template <class S> static Iso<S> iso_from12(const double* t) {
@@ -357,7 +359,11 @@ static void collide_raw(const Model& M, const std::vector<BodyState<S>>& B, std:
     const int bi = M.shape_body[i], bj = M.shape_body[j];
     if (bi == bj) continue;                                   // CollisionFilter.cpp:128-129
     if (!M.mobile[bi] && !M.mobile[bj]) continue;             // :137-138
-    if (M.skel_id[bi] == M.skel_id[bj]) continue;             // self-collision check is off by default (:140-150)
+    if (M.skel_id[bi] == M.skel_id[bj]) {                       // BodyNodeCollisionFilter::ignoresCollision (:140-150)
+      if (M.self_collision.empty() || !M.self_collision[bi]) continue;   // self-collision checking is off by default
+      if (!M.adjacent_check[bi] && (M.parent[bi] == bj || M.parent[bj] == bi)) continue;  // areAdjacentBodies (:155-170)
+      if (M.rigid_root[bi] == M.rigid_root[bj]) continue;       // welded together: no relative motion (dropped on the device side too)
+    }
     const int ti = M.shape_type[i], tj = M.shape_type[j];
     Vec3<S> di = v3<S>(S(M.shape_dims[3 * i]), S(M.shape_dims[3 * i + 1]), S(M.shape_dims[3 * i + 2]));
     Vec3<S> dj = v3<S>(S(M.shape_dims[3 * j]), S(M.shape_dims[3 * j + 1]), S(M.shape_dims[3 * j + 2]));
@@ -906,10 +912,17 @@ void orc_model_set_contact(void* h, const int* skel_id, int ns, const int* shape
   M.friction.assign(friction, friction + M.nb); M.restitution.assign(restitution, restitution + M.nb);
   M.penetration_correction = penetration_correction != 0; M.clip_depth = clip_depth; M.fallback_cfm = fallback_cfm;
   M.has_dofs_above.assign(M.nb, 0);
+  M.rigid_root.assign(M.nb, 0);
   for (int i = 0; i < M.nb; i++) {
     int k = (M.jtype[i] == orc::FREE) ? 6 : (M.jtype[i] == orc::WELD ? 0 : 1);
     M.has_dofs_above[i] = (k > 0) || (M.parent[i] >= 0 && M.has_dofs_above[M.parent[i]]);
+    M.rigid_root[i] = (M.jtype[i] == orc::WELD && M.parent[i] >= 0) ? M.rigid_root[M.parent[i]] : i;
   }
+}
+void orc_model_set_self_collision(void* h, const int* self_collision, const int* adjacent_check) {
+  Model& M = *(Model*)h;
+  M.self_collision.assign(self_collision, self_collision + M.nb);
+  M.adjacent_check.assign(adjacent_check, adjacent_check + M.nb);
 }
 
 // One World::step with the contact stage.  x_warm/m_warm: cached LCP solution (BoxedLcpConstraintSolver mX) or m_warm=-1.

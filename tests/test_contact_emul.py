@@ -408,3 +408,71 @@ def test_round_shape_contacts_forward_and_backward(oracle_mod):
     assert {6, 15} <= types and (13 in types or 14 in types), types
     kinds = _check_backward(ob, raw, S, A, tol=2e-5)
     assert len(kinds) == B
+
+
+def _folding_arm_world(adjacent=False):
+    """A free-floating 3-link chain with box links, folded so that link 3 presses on link 1 (same skeleton, not adjacent), above a ground box.
+    Skeleton::enableSelfCollisionCheck() (off by default in the reference) makes the link 1 - link 3 pair visible to the narrow phase.
+    (Floating base: a chain pinned to the world with parallel axes could not move out of its plane and Q would be singular by construction.)"""
+    w = nb.World()
+    w.setGravity([0, -9.81, 0])
+    w.setTimeStep(1e-3)
+    g = nb.Skeleton("ground"); g.setMobile(False)
+    j, b = g.createWeldJointAndBodyNodePair()
+    b.createShapeNode(nb.BoxShape([4, 0.2, 4])).createCollisionAspect()
+    T = nb.Isometry3(); T.set_translation([0, -1.1, 0]); j.setTransformFromParentBodyNode(T)
+    w.addSkeleton(g)
+    arm = nb.Skeleton("arm")
+    parent = None
+    L = 0.5
+    for k in range(3):
+        j, b = arm.createRevoluteJointAndBodyNodePair(parent) if k else arm.createFreeJointAndBodyNodePair()
+        if k:
+            j.setAxis([0, 0, 1])
+        if k:
+            T = nb.Isometry3(); T.set_translation([L, 0, 0]); j.setTransformFromParentBodyNode(T)
+        b.setMass(1.0); b.setLocalCOM([L / 2, 0, 0]); b.setMomentOfInertia(0.01, 0.02, 0.02)
+        sn = b.createShapeNode(nb.BoxShape([L, 0.08, 0.1])); sn.createCollisionAspect()
+        Ts = nb.Isometry3(); Ts.set_translation([L / 2, 0, 0]); sn.setRelativeTransform(Ts.matrix())
+        parent = b
+    arm.enableSelfCollisionCheck()
+    if adjacent:
+        arm.enableAdjacentBodyCheck()
+    w.addSkeleton(arm)
+    return w
+
+
+def test_self_collision_pairs_forward_and_backward(oracle_mod):
+    """Self-collision (BodyNodeCollisionFilter, CollisionFilter.cpp:105-152): rows whose two bodies sit in the SAME tree.  Pair list (default off,
+    non-adjacent only unless the adjacent-body check is enabled), forward against the oracle, backward against its Jacobian."""
+    from nimblephysics_b200._cabi import collision_pairs
+
+    w_off = _folding_arm_world(); w_off.getSkeleton(1).disableSelfCollisionCheck()
+    w_on, w_adj = _folding_arm_world(), _folding_arm_world(adjacent=True)
+    npairs = [len(collision_pairs(nb.compile_model(nb.flatten_world(w)))[0]) for w in (w_off, w_on, w_adj)]
+    assert npairs == [3, 4, 6], npairs  # ground x 3 links | + link 1 - link 3 | + the two adjacent pairs
+    raw = nb.flatten_world(w_on)
+    n = raw.ndof
+    rng = np.random.default_rng(3)
+    B = 6
+    S = np.zeros((B, 2 * n), np.float32)
+    for k in range(B):
+        # fold: joint 2 and joint 3 turn by ~ 2 pi / 3 each so that link 3 comes back onto link 1
+        S[k, 0:3] = rng.normal(0, 0.05, 3)
+        S[k, 6] = 2.0944 + rng.normal(0, 0.003)
+        S[k, 7] = 1.99 + rng.normal(0, 0.006)   # link 3's end edge 0.5 - 2 cm into link 1 (deeper contacts are clipped away)
+        S[k, n:] = rng.normal(0, 0.1, n)
+    A = rng.normal(0, 1.0, (B, len(raw.action_map))).astype(np.float32)
+    cm = nb.compile_model(raw)
+    r = EmulWorld(cm).forward_contact(S, A)
+    ow = oracle_mod.OracleContactWorld(raw)
+    with_self = 0
+    for k in range(B):
+        ro = ow.step_contact(S[k].astype(np.float64), A[k].astype(np.float64))
+        assert r["nc"][k] == ro["nc"], (k, r["nc"][k], ro["nc"])
+        assert np.array_equal(r["labels"][k][: r["m"][k]], ro["mapping"][: ro["m"]])
+        assert rel_err(r["next"][k], ro["next_state"]) < 1e-6
+        with_self += int(any(bb[0] >= 0 and bb[1] >= 0 and raw.skel_id[bb[0]] == raw.skel_id[bb[1]] for bb in ro["bodies"]))
+    assert with_self >= 3, with_self
+    kinds = _check_backward(ob, raw, S, A, tol=2e-5)
+    assert len(kinds) == B

@@ -331,3 +331,39 @@ def test_round_shape_contacts_on_device(oracle_mod):
         assert rel_err(out[k].detach().cpu().numpy(), ro["next_state"]) < 1e-5
         rgs, rga, rc = ow.backprop_contact(S[k].astype(np.float64), A[k].astype(np.float64), gr[k].astype(np.float64))
         assert rc >= 0 and rel_err(st.grad[k].cpu().numpy(), rgs) < 1e-4
+
+
+def test_self_collision_on_device(oracle_mod):
+    """Skeleton::enableSelfCollisionCheck(): rows between two bodies of the same tree, GPU against the oracle (world and the CPU twin:
+    tests/test_contact_emul.py::test_self_collision_pairs_forward_and_backward)."""
+    from tests.test_contact_emul import _folding_arm_world
+
+    w = _folding_arm_world()
+    raw = nb.flatten_world(w)
+    n = raw.ndof
+    rng = np.random.default_rng(3)
+    B = 12
+    S = np.zeros((B, 2 * n), np.float32)
+    for k in range(B):
+        S[k, 0:3] = rng.normal(0, 0.05, 3)
+        S[k, 6] = 2.0944 + rng.normal(0, 0.003)
+        S[k, 7] = 1.99 + rng.normal(0, 0.006)
+        S[k, n:] = rng.normal(0, 0.1, n)
+    A = rng.normal(0, 1.0, (B, len(raw.action_map))).astype(np.float32)
+    gr = rng.normal(size=(B, 2 * n)).astype(np.float32)
+    st = torch.tensor(S, device="cuda", requires_grad=True); at = torch.tensor(A, device="cuda", requires_grad=True)
+    out = nb.timestep(w, st, at)
+    c = w._lcp_cache
+    labels, mm, ncs = c["labels"].cpu().numpy(), c["m"].cpu().numpy(), c["nc"].cpu().numpy()
+    out.backward(torch.tensor(gr, device="cuda"))
+    nb.check_contact_status(w)
+    ow = ob.OracleContactWorld(raw)
+    with_rows = 0
+    for k in range(B):
+        ro = ow.step_contact(S[k].astype(np.float64), A[k].astype(np.float64))
+        assert ncs[k] == ro["nc"] and mm[k] == ro["m"] and np.array_equal(labels[k][: mm[k]], ro["mapping"][: ro["m"]])
+        assert rel_err(out[k].detach().cpu().numpy(), ro["next_state"]) < 1e-5
+        rgs, rga, rc = ow.backprop_contact(S[k].astype(np.float64), A[k].astype(np.float64), gr[k].astype(np.float64))
+        assert rc >= 0 and rel_err(st.grad[k].cpu().numpy(), rgs) < 1e-4 and rel_err(at.grad[k].cpu().numpy(), rga) < 1e-4
+        with_rows += int(ro["m"] > 0)
+    assert with_rows >= 6
