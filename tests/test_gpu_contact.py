@@ -347,7 +347,7 @@ def test_self_collision_on_device(oracle_mod):
     for k in range(B):
         S[k, 0:3] = rng.normal(0, 0.05, 3)
         S[k, 6] = 2.0944 + rng.normal(0, 0.003)
-        S[k, 7] = 1.99 + rng.normal(0, 0.006)
+        S[k, 7] = 1.955 + rng.normal(0, 0.004)   # an edge of link 3 pressed 0.3 - 1.4 cm into link 1 (deeper contacts are clipped away)
         S[k, n:] = rng.normal(0, 0.1, n)
     A = rng.normal(0, 1.0, (B, len(raw.action_map))).astype(np.float32)
     gr = rng.normal(size=(B, 2 * n)).astype(np.float32)
