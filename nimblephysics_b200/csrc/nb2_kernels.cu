@@ -1070,6 +1070,7 @@ int nb2_step_forward_contact(const nb2_model* cm, int B, const float* state, con
                              void* saved_fp64, void* workspace, double* x_lcp, int32_t* m_lcp, int32_t* labels,
                              int32_t* status, int32_t* ncontacts, float* cinfo, double* contact_record, int32_t* status_accum, void* stream) {
   nb2_model* m = const_cast<nb2_model*>(cm);
+  if (m && B == 0) return NB2_OK;  // an empty batch has no buffers to check
   if (!m || B < 0 || !state || !action || !next_state || !workspace || !x_lcp || !m_lcp || !labels || !status || !ncontacts) {
     g_err = "nb2_step_forward_contact: bad argument"; return NB2_ERR_INVALID;
   }
@@ -1146,6 +1147,7 @@ int nb2_step_backward_contact(const nb2_model* cm, int B, const float* state, co
                               const double* contact_record, void* workspace, const float* grad_next_state, float* grad_state,
                               float* grad_action, float* grad_inertia, int32_t* status_accum, void* stream) {
   nb2_model* m = const_cast<nb2_model*>(cm);
+  if (m && B == 0) return NB2_OK;
   if (!m || B < 0 || !state || !action || !saved_fp64 || !contact_record || !workspace || !grad_next_state || !grad_state || !grad_action) {
     g_err = "nb2_step_backward_contact: bad argument"; return NB2_ERR_INVALID;
   }
@@ -1203,6 +1205,7 @@ static int snap_copy(double* tape, const RolloutTape& L, int idx, double* x_lcp,
 int nb2_rollout_forward_contact(const nb2_model* cm, int B, int T, float* states, const float* actions, double* x_lcp, int32_t* m_lcp, void* tape_,
                                 int checkpoint_every, void* workspace, int32_t* status_accum, void* stream) {
   nb2_model* m = const_cast<nb2_model*>(cm);
+  if (m && (B == 0 || T == 0)) return NB2_OK;
   if (!m || B < 0 || T < 0 || !states || (!actions && T > 0) || !x_lcp || !m_lcp || !tape_ || !workspace) { g_err = "nb2_rollout_forward_contact: bad argument"; return NB2_ERR_INVALID; }
   if (!m->has_contacts) { g_err = "nb2_rollout_forward_contact: the model has no collision pairs (use nb2_rollout_forward)"; return NB2_ERR_INVALID; }
   if (B == 0 || T == 0) return NB2_OK;
@@ -1229,6 +1232,7 @@ int nb2_rollout_forward_contact(const nb2_model* cm, int B, int T, float* states
 int nb2_rollout_backward_contact(const nb2_model* cm, int B, int T, const float* states, const float* actions, double* x_lcp, int32_t* m_lcp, void* tape_,
                                  int checkpoint_every, float* grad_states, float* grad_actions, void* workspace, int32_t* status_accum, void* stream) {
   nb2_model* m = const_cast<nb2_model*>(cm);
+  if (m && (B == 0 || T == 0)) return NB2_OK;
   if (!m || B < 0 || T < 0 || !states || (!actions && T > 0) || !x_lcp || !m_lcp || !tape_ || !grad_states || (!grad_actions && T > 0) || !workspace) {
     g_err = "nb2_rollout_backward_contact: bad argument"; return NB2_ERR_INVALID;
   }

@@ -367,3 +367,59 @@ def test_self_collision_on_device(oracle_mod):
         assert rc >= 0 and rel_err(st.grad[k].cpu().numpy(), rgs) < 1e-4 and rel_err(at.grad[k].cpu().numpy(), rga) < 1e-4
         with_rows += int(ro["m"] > 0)
     assert with_rows >= 6
+
+
+def test_contact_path_edge_cases():
+    """Empty and ragged batches, the large-workspace retry (same bits as the shared-memory path), and the loud failure when a world
+    exceeds the compiled contact limit (the reference has no such limit: dropping contacts silently would not be parity)."""
+    raw = load_raw("half_cheetah")
+    world = nb.World.from_raw(raw)
+    n2, na = 2 * raw.ndof, len(raw.action_map)
+    # B = 0
+    out = nb.timestep(world, torch.zeros(0, n2, device="cuda"), torch.zeros(0, na, device="cuda"))
+    assert out.shape == (0, n2)
+    # ragged batches: B = 1, 33 (one warp + 1), 67 give the rows of a B = 67 run
+    s, a = contact_inputs(raw, "half_cheetah", 67, seed=21)
+    g = np.random.default_rng(4).normal(size=s.shape).astype(np.float32)
+
+    def run(B, cap=None):
+        w = nb.World.from_raw(raw)
+        if cap:
+            nb.device_model_for(w).set_contact_capacity(cap)
+        st = torch.tensor(s[:B], device="cuda", requires_grad=True); at = torch.tensor(a[:B], device="cuda", requires_grad=True)
+        o = nb.timestep(w, st, at)
+        o.backward(torch.tensor(g[:B], device="cuda"))
+        nb.check_contact_status(w)
+        return o.detach().cpu().numpy(), st.grad.cpu().numpy(), at.grad.cpu().numpy()
+
+    full = run(67)
+    for B in (1, 33):
+        part = run(B)
+        for x, y in zip(part, full):
+            assert np.array_equal(x, y[:B]), B
+    pool = run(30, cap=1)  # every world with more than one contact retries in the global pool (32 slots at this batch size)
+    for x, y in zip(pool, full):
+        assert np.array_equal(x, y[:30])
+    # ... and when the pool itself runs out (67 worlds, 32 slots) the step says so instead of dropping contacts silently
+    with pytest.raises(RuntimeError, match="DROPPED|backward through the contact stage failed"):
+        run(67, cap=1)
+    # more contacts than NB2_MAX_CONTACTS (16): five boxes on the ground = 20 -> status bit 256, check_contact_status raises
+    w = nb.World(); w.setGravity([0, -9.81, 0])
+    g0 = nb.Skeleton("ground"); g0.setMobile(False)
+    j, b = g0.createWeldJointAndBodyNodePair()
+    b.createShapeNode(nb.BoxShape([10, 0.2, 10])).createCollisionAspect()
+    T = nb.Isometry3(); T.set_translation([0, -0.1, 0]); j.setTransformFromParentBodyNode(T)
+    w.addSkeleton(g0)
+    for k in range(5):
+        sk = nb.Skeleton(f"box{k}")
+        j, b = sk.createFreeJointAndBodyNodePair(); b.setMass(1.0)
+        b.createShapeNode(nb.BoxShape([0.3, 0.3, 0.3])).createCollisionAspect()
+        w.addSkeleton(sk)
+    n = w.getNumDofs()
+    st = torch.zeros(2, 2 * n, device="cuda")
+    for k in range(5):
+        st[:, 6 * k + 3] = 1.0 * k; st[:, 6 * k + 4] = 0.15 - 0.002
+    with torch.no_grad():
+        nb.timestep(w, st, torch.zeros(2, w.getActionSize(), device="cuda"))
+    with pytest.raises(RuntimeError, match="DROPPED"):
+        nb.check_contact_status(w)
