@@ -76,6 +76,11 @@ typedef struct nb2_model_desc {
    * [trunk_n, lo, hi, ...,  then for each lane: limb_n, lo, hi, ...] with half-open canonical body ranges. */
   int32_t lanes, nsched;
   const int32_t* sched;
+  /* ---- joints whose position limits are enforced (Joint::setPositionLimitEnforced, constraint/JointLimitConstraint.cpp): the bodies whose
+   * parent joint (revolute / prismatic) it is, in the reference's joint order.  While q sits on or beyond pos_lo / pos_hi the contact stage
+   * adds one LCP row for the joint after the contact rows (ConstraintSolver.cpp:642-695).  nlimits = 0: none (the loaders' default). */
+  int32_t nlimits;
+  const int32_t* limit_body;
 } nb2_model_desc;
 
 int nb2_model_create(const nb2_model_desc* desc, nb2_model** out);

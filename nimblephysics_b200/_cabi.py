@@ -38,6 +38,7 @@ class Nb2ModelDesc(ctypes.Structure):
         ("penetration_correction", ctypes.c_int32),
         ("contact_clipping_depth", ctypes.c_double), ("fallback_cfm", ctypes.c_double),
         ("lanes", ctypes.c_int32), ("nsched", ctypes.c_int32), ("sched", _I32P),
+        ("nlimits", ctypes.c_int32), ("limit_body", _I32P),
     ]
 
 MAX_CONTACTS, MAX_ROWS = 16, 48  # include/nb2.h
@@ -84,6 +85,8 @@ def make_desc(cm: CanonModel, with_contacts: bool = True):
     d.shape_dims, d.shape_T = f64(cm.shape_dims[:ns]), f64(cm.shape_T[:ns])
     d.shape_mu, d.shape_rest = f64(cm.shape_friction[:ns]), f64(cm.shape_restitution[:ns])
     d.pair_a, d.pair_b = i32(pa), i32(pb)
+    lb = list(getattr(cm, "limit_bodies", [])) if with_contacts else []
+    d.nlimits, d.limit_body = len(lb), i32(lb)
     d.penetration_correction = int(cm.penetration_correction)
     d.contact_clipping_depth = float(cm.contact_clipping_depth)
     d.fallback_cfm = float(cm.fallback_cfm)

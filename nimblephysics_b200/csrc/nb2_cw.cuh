@@ -31,6 +31,10 @@
 #include "../../include/nb2.h"  // NB2_MAX_CONTACTS, NB2_MAX_ROWS
 
 #define NB2_MAX_SHAPES 24
+#define NB2_MAX_LIMITS 32   // joints whose position limits are enforced (JointLimitConstraint rows)
+#define NB2_MAX_CB 64       // collision bodies: moving bodies that carry a shape, plus child and parent of every limit joint
+#define NB2_CT_LIMIT_LOWER 100  // "contact" types of the pseudo contacts that carry joint-limit rows
+#define NB2_CT_LIMIT_UPPER 101
 #define NB2_MAX_PAIRS 64
 
 // status bits (per world)
@@ -60,7 +64,9 @@ struct Nb2ContactDev {
   int16_t shape_type[NB2_MAX_SHAPES];       // 0 box, 1 sphere, 2 capsule
   int16_t shape_orig_body[NB2_MAX_SHAPES];  // reference BodyNode index (reported with the contacts)
   int16_t pair_a[NB2_MAX_PAIRS], pair_b[NB2_MAX_PAIRS];  // collision pairs in the reference's enumeration order
-  int16_t cb_body[NB2_MAX_SHAPES];          // collision body k -> canonical body
+  int16_t cb_body[NB2_MAX_CB];              // collision body k -> canonical body
+  int nlim, pad2_;                          // joints with enforced position limits (1-dof joints)
+  int16_t lim_body[NB2_MAX_LIMITS];         // canonical body whose parent joint it is
   int16_t cb_of_body[NB2_MAX_BODIES];       // canonical body -> collision body index or -1
   int16_t cdof0[NB2_MAX_BODIES];            // number of dofs of the PROPER ancestors of a body (offset of its own dofs on its chain)
   int max_chain_dofs, pad_;                 // most dofs on the chain root .. collision body, over the collision bodies
@@ -1305,7 +1311,9 @@ NB2_HD Xf<double> shape_pose(const Nb2ContactDev& C, const Ws& ws, int sh) {
 // the reference's enumeration order, which fixes the LCP row order.  meta: [0] m, [1] nc, [2] status, [3] capacity overflow,
 // [4] number of distinct contact bodies.  max_contacts / max_rows: the ABSOLUTE limits (beyond them contacts are dropped and
 // flagged); d.MC / d.MR: the capacity of THIS workspace (beyond it meta[3] is set and the caller retries with the large one).
-NB2_HD void collide_and_filter(const Nb2ContactDev& C, const Ws& ws, const Dims& d) {
+// Afterwards the active joint limits (JointLimitConstraint::update, constraint/JointLimitConstraint.cpp:150-240) are appended as pseudo contacts
+// with one frictionless row each, in joint order (ConstraintSolver.cpp:642-695 adds them after the contacts): M / st give the positions.
+NB2_HD void collide_and_filter(const Nb2ContactDev& C, const Ws& ws, const Dims& d, const Nb2ModelDev<double>* Mp = nullptr, const float* st = nullptr) {
   const int slots = (int)(d.mats / NB2_CW_PAIR_SLOT);
   CW_ONE { ws.meta[0] = 0; ws.meta[1] = 0; ws.meta[2] = 0; ws.meta[3] = 0; ws.meta[4] = 0; }
   CW_SYNC();
@@ -1361,6 +1369,36 @@ NB2_HD void collide_and_filter(const Nb2ContactDev& C, const Ws& ws, const Dims&
     CW_SYNC();
     if (ws.meta[3]) return;
   }
+  if (C.nlim > 0 && Mp && st) {
+    const Nb2ModelDev<double>& M = *Mp;
+    CW_ONE {
+      int m = ws.meta[0], nc = ws.meta[1], status = ws.meta[2], ovf = ws.meta[3], ntb = ws.meta[4];
+      for (int l = 0; l < C.nlim && !ovf; l++) {
+        const int i = C.lim_body[l], dd = M.dof_off[i];
+        const double q = (double)st[dd];
+        int type = 0;
+        if (q - (double)M.pos_lo[dd] <= 0.0) type = NB2_CT_LIMIT_LOWER;
+        else if (q - (double)M.pos_hi[dd] >= 0.0) type = NB2_CT_LIMIT_UPPER;
+        if (!type) continue;
+        if (nc >= NB2_MAX_CONTACTS || m + 1 > NB2_MAX_ROWS) { status |= NB2_ST_CONTACT_OVERFLOW; continue; }
+        if (nc >= d.MC || m + 1 > d.MR) { ovf = 1; break; }
+        for (int e = 0; e < 3; e++) { ws.cpoint[3 * nc + e] = 0.0; ws.cnormal[3 * nc + e] = 0.0; }
+        ws.cdepth[nc] = 0.0; ws.ctype[nc] = type; ws.cbodyA[nc] = i; ws.cbodyB[nc] = M.parent[i]; ws.cshapeA[nc] = -1; ws.cshapeB[nc] = -1;
+        ws.cmu[nc] = 0.0; ws.crest[nc] = 0.0;
+        ws.crow[nc] = m; ws.rowc[m] = nc;
+        for (int side = 0; side < 2; side++) {
+          const int bdy = side ? M.parent[i] : i;
+          if (bdy < 0) continue;
+          bool seen = false;
+          for (int e = 0; e < ntb; e++) if (ws.tbl[e] == bdy) seen = true;
+          if (!seen) ws.tbl[ntb++] = bdy;
+        }
+        m += 1; nc++;
+      }
+      ws.meta[0] = m; ws.meta[1] = nc; ws.meta[2] = status; ws.meta[3] = ovf; ws.meta[4] = ntb;
+    }
+    CW_SYNC();
+  }
 }
 
 // rows of the LCP: wrenches, b = -J v*, bounds, findex (ContactConstraint.cpp:66-230, 361-514, 687-695, 734-795); one row per lane.
@@ -1379,6 +1417,26 @@ NB2_HD int build_rows(const Nb2ModelDev<double>& M, const Nb2ContactDev& C, cons
     const int ba = ws.cbodyA[c], bb = ws.cbodyB[c];
     double rel = 0;
     V6<double> JA = zero6<double>(), JB = zero6<double>();
+    if (ws.ctype[c] >= NB2_CT_LIMIT_LOWER) {
+      // joint-limit row: a unit impulse on the joint (JointLimitConstraint::applyUnitImpulse, :258-283) is S on the child and its reaction
+      // on the parent; b = -(JA.V_A + JB.V_B) = -qdot* (getInformation :243-256: the "bouncing velocity" is +-allowance * erp / dt, allowance 0)
+      JA = S_times<double>(M.jtype[ba], 1.0);
+      const Xf<double> Wc = ldXf<double, 1>(ws.Wcb + 12 * C.cb_of_body[ba]);
+      rel -= dot(JA, ldv6(ws.Vcb + 6 * C.cb_of_body[ba]));
+      if (bb >= 0) {
+        const Xf<double> Wp = ldXf<double, 1>(ws.Wcb + 12 * C.cb_of_body[bb]);
+        Xf<double> X; X.R_ = mul(transpose(Wp.R_), Wc.R_); X.p = mulT(Wp.R_, Wc.p - Wp.p);   // parent <- child
+        JB = zero6<double>() - dAdInvT(X, JA);
+        rel -= dot(JB, ldv6(ws.Vcb + 6 * C.cb_of_body[bb]));
+      }
+      stv6(ws.JA + 6 * r, JA); stv6(ws.JB + 6 * r, JB);
+      if (eeff) eeff[r] = 0;
+      if (want_b) {
+        if (ws.ctype[c] == NB2_CT_LIMIT_LOWER) { ws.lo[r] = 0.0; ws.hi[r] = HUGE_VAL; } else { ws.lo[r] = -HUGE_VAL; ws.hi[r] = 0.0; }
+        ws.findex[r] = -1; ws.b[r] = rel;
+      }
+      continue;
+    }
     if (ba >= 0) {
       const int kb = C.cb_of_body[ba];
       const Xf<double> W = ldXf<double, 1>(ws.Wcb + 12 * kb);
@@ -1598,7 +1656,7 @@ NB2_HD void contact_forward(const Nb2ModelDev<double>& M, const Nb2ContactDev& C
   CW_PROF_DECL;
   fk_collision_bodies(M, C, S, scr + L.oV, ws);
   CW_PROF(1);
-  collide_and_filter(C, ws, d);
+  collide_and_filter(C, ws, d, &M, st);
   CW_PROF(2);
   double* ws_big = ws.meta[3] ? pool_acquire(pool) : nullptr;
   if (ws_big) {  // more contacts than the shared workspace holds: redo the stage in a large global workspace
@@ -1610,7 +1668,7 @@ NB2_HD void contact_forward(const Nb2ModelDev<double>& M, const Nb2ContactDev& C
     CW_ONE *wsm = wb;
     CW_SYNC();
     ws = wb; d = d_b;
-    collide_and_filter(C, ws, d);
+    collide_and_filter(C, ws, d, &M, st);
   }
   const int m = ws.meta[0], nc = ws.meta[1];
   int status = ws.meta[2];
@@ -1684,7 +1742,7 @@ NB2_HD void contact_build(const Nb2ModelDev<double>& M, const Nb2ContactDev& C, 
   fk_collision_bodies(M, C, S, scr + L.oV, ws);
   CW_PROF(1);
   CW_PHASE(); ph++;  // 1
-  collide_and_filter(C, ws, d);
+  collide_and_filter(C, ws, d, &M, st);
   double* ws_big = ws.meta[3] ? pool_acquire(pool) : nullptr;
   if (ws_big) {
     const Ws wb = carve(ws_big, d_b);
@@ -1695,7 +1753,7 @@ NB2_HD void contact_build(const Nb2ModelDev<double>& M, const Nb2ContactDev& C, 
     CW_ONE *wsm = wb;
     CW_SYNC();
     ws = wb; d = d_b;
-    collide_and_filter(C, ws, d);
+    collide_and_filter(C, ws, d, &M, st);
   }
   CW_PROF(2);
   const int m = ws.meta[0], nc = ws.meta[1];
@@ -1942,7 +2000,7 @@ NB2_HD BwdContactData<1> contact_backward(const Nb2ModelDev<double>& M, const Nb
   fk_collision_bodies(M, C, S, bounce ? ws.vplus : nullptr, ws);
   CW_PROF(21);
   CW_PHASE(); ph++;  // 1
-  collide_and_filter(C, ws, d);
+  collide_and_filter(C, ws, d, &M, st);
   CW_PROF(22);
   double* ws_big = ws.meta[3] ? pool_acquire(pool) : nullptr;
   if (ws_big) {
@@ -1953,7 +2011,7 @@ NB2_HD BwdContactData<1> contact_backward(const Nb2ModelDev<double>& M, const Nb
     CW_ONE *wsm = wb;
     CW_SYNC();
     ws = wb; d = d_b;
-    collide_and_filter(C, ws, d);
+    collide_and_filter(C, ws, d, &M, st);
   }
   if (ws.meta[3] || ws.meta[0] != m) { cd.error = 3; cd.active = 0; NB2_BWD_DRAIN(); return cd; }
   CW_PHASE(); ph++;  // 2
@@ -2121,7 +2179,9 @@ NB2_HD BwdContactData<1> contact_backward(const Nb2ModelDev<double>& M, const Nb
   CW_PROF(27);
   CW_PHASE(); ph++;  // 7
   int* gfirst = ws.i1; int* it_g = ws.i2; int* it_dyn = ws.i4;  // cl / ubl are dead by now
-  const int ng = cw_enumerate(nc, [&](int c) { return c == 0 || ws.cshapeA[c] != ws.cshapeA[c - 1] || ws.cshapeB[c] != ws.cshapeB[c - 1]; },
+  int ncr = nc;  // real contacts: the joint-limit pseudo contacts come last and have no geometry to differentiate (their rows are constant in joint space)
+  while (ncr > 0 && ws.ctype[ncr - 1] >= NB2_CT_LIMIT_LOWER) ncr--;
+  const int ng = cw_enumerate(ncr, [&](int c) { return c == 0 || ws.cshapeA[c] != ws.cshapeA[c - 1] || ws.cshapeB[c] != ws.cshapeB[c - 1]; },
                               [&](int c, int r) { gfirst[r] = c; });
   CW_SYNC();
   CW_ONE {
@@ -2141,7 +2201,7 @@ NB2_HD BwdContactData<1> contact_backward(const Nb2ModelDev<double>& M, const Nb
     CW_FOR(q, cnt * 6) {
       const int it = it0 + q / 6, kx = q % 6;
       const int g = it_g[it], dyn = it_dyn[it];
-      const int c0 = gfirst[g], c1 = (g + 1 < ng) ? gfirst[g + 1] : nc;
+      const int c0 = gfirst[g], c1 = (g + 1 < ng) ? gfirst[g + 1] : ncr;
       const int sa = ws.cshapeA[c0], sb = ws.cshapeB[c0], ba = ws.cbodyA[c0], bb = ws.cbodyB[c0];
       Xf<D1> WDa, WDb;
       if (ba >= 0) { const Xf<double> Wa = ldXf<double, 1>(ws.Wcb + 12 * C.cb_of_body[ba]); WDa = (ba == dyn) ? dual_pose1(Wa, kx) : lift1(Wa); }

@@ -107,8 +107,9 @@ static inline bool nb2_fill_contact(const nb2_model_desc& d, Nb2ContactDev& C, s
   if (d.npairs < 0 || d.npairs > NB2_MAX_PAIRS) { err = "model has " + std::to_string(d.npairs) + " collision pairs; compiled limit is " + std::to_string(NB2_MAX_PAIRS); return false; }
   C.nshapes = d.nshapes; C.npairs = d.npairs; C.pen_correction = d.penetration_correction; C.pad_ = 0;
   C.clip_depth = d.contact_clipping_depth; C.fallback_cfm = d.fallback_cfm;
+  for (int k = 0; k < NB2_MAX_CB; k++) C.cb_body[k] = -1;
   for (int s = 0; s < NB2_MAX_SHAPES; s++) {
-    C.shape_body[s] = -1; C.shape_type[s] = 0; C.shape_orig_body[s] = -1; C.shape_mu[s] = 0; C.shape_rest[s] = 0; C.cb_body[s] = -1;
+    C.shape_body[s] = -1; C.shape_type[s] = 0; C.shape_orig_body[s] = -1; C.shape_mu[s] = 0; C.shape_rest[s] = 0;
     for (int k = 0; k < 3; k++) C.shape_dims[s][k] = 0;
     for (int k = 0; k < 12; k++) C.shape_T[s][k] = 0;
   }
@@ -140,6 +141,23 @@ static inline bool nb2_fill_contact(const nb2_model_desc& d, Nb2ContactDev& C, s
     C.cb_of_body[bdy] = (int16_t)C.ncb; C.cb_body[C.ncb] = (int16_t)bdy; C.ncb++;
     const int cd = C.cdof0[bdy] + (d.jtype[bdy] == NB2_JT_FREE ? 6 : 1);
     if (cd > C.max_chain_dofs) C.max_chain_dofs = cd;
+  }
+  // joints with enforced position limits: their rows load the child body and (reaction) the parent body, which therefore join the list
+  C.nlim = 0; C.pad2_ = 0;
+  for (int l = 0; l < NB2_MAX_LIMITS; l++) C.lim_body[l] = -1;
+  if (d.nlimits < 0 || d.nlimits > NB2_MAX_LIMITS) { err = "model has " + std::to_string(d.nlimits) + " joints with enforced limits; compiled limit is " + std::to_string(NB2_MAX_LIMITS); return false; }
+  for (int l = 0; l < d.nlimits; l++) {
+    const int i = d.limit_body ? d.limit_body[l] : -1;
+    if (i < 0 || i >= d.nb || (d.jtype[i] != NB2_JT_REV && d.jtype[i] != NB2_JT_PRIS)) { err = "limit_body[" + std::to_string(l) + "] is not a revolute / prismatic body"; return false; }
+    C.lim_body[C.nlim++] = (int16_t)i;
+    for (int side = 0; side < 2; side++) {
+      const int bdy = side ? d.parent[i] : i;
+      if (bdy < 0 || C.cb_of_body[bdy] >= 0) continue;
+      if (C.ncb >= NB2_MAX_CB) { err = "too many bodies take part in contacts / joint limits"; return false; }
+      C.cb_of_body[bdy] = (int16_t)C.ncb; C.cb_body[C.ncb] = (int16_t)bdy; C.ncb++;
+      const int cd = C.cdof0[bdy] + (d.jtype[bdy] == NB2_JT_FREE ? 6 : 1);
+      if (cd > C.max_chain_dofs) C.max_chain_dofs = cd;
+    }
   }
   // every pair this stage can generate contacts for must be of a supported shape combination: reject the others at model
   // creation instead of flagging them world by world at run time

@@ -970,7 +970,7 @@ int nb2_model_create(const nb2_model_desc* desc, nb2_model** out) {
     g_err = err; delete m;
     return (desc->nb > NB2_MAX_BODIES || desc->ndof > NB2_MAX_DOFS) ? NB2_ERR_UNSUPPORTED : NB2_ERR_INVALID;
   }
-  if (desc->nshapes > 0 && desc->npairs > 0) {
+  if ((desc->nshapes > 0 && desc->npairs > 0) || desc->nlimits > 0) {
     if (!nb2_fill_contact(*desc, m->contact, err)) { g_err = err; delete m; return NB2_ERR_UNSUPPORTED; }
     m->has_contacts = true;
     for (int p = 0; p < desc->npairs; p++)  // a pair bounces when the product of its shapes' coefficients exceeds 1e-3 (ContactConstraint.cpp:112-123)
@@ -979,6 +979,7 @@ int nb2_model_create(const nb2_model_desc* desc, nb2_model** out) {
     // other supported pair at most one; worlds that exceed it fall back to a global-memory workspace (nb2_cw.cuh BigPool)
     int mc = 0;
     for (int p = 0; p < desc->npairs; p++) mc += (desc->shape_type[desc->pair_a[p]] == 0 && desc->shape_type[desc->pair_b[p]] == 0) ? 4 : 1;
+    mc += desc->nlimits;  // an active joint limit takes the slot of one contact (one row)
     if (const char* e = getenv("NB2_CONTACT_MC")) mc = atoi(e);
     m->contact_mc = mc < 2 ? 2 : (mc > NB2_MAX_CONTACTS ? NB2_MAX_CONTACTS : mc);
   }

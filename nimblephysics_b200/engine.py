@@ -22,7 +22,7 @@ class DeviceModel:
         self.ndof = cm.ndof
         self.na = len(cm.action_map)
         L = _cabi.lib()
-        self._desc, self._keep = _cabi.make_desc(cm, with_contacts=len(cm.shape_body) > 0)
+        self._desc, self._keep = _cabi.make_desc(cm, with_contacts=len(cm.shape_body) > 0 or len(getattr(cm, "limit_bodies", [])) > 0)
         h = ctypes.c_void_p()
         _cabi.check(L.nb2_model_create(ctypes.byref(self._desc), ctypes.byref(h)))
         self.handle = h
@@ -206,12 +206,16 @@ class DeviceModel:
 def _has_possible_contacts(raw: RawModel) -> bool:
     """True when some collision-shape pair could ever generate a contact: shapes on two different skeletons, or two shapes of a skeleton
     that enabled self-collision checking (off by default in the reference, dart/dynamics/Skeleton.cpp mEnabledSelfCollisionCheck=false)."""
+    if any(raw.limit_enforced[i] and raw.mobile[i] and raw.jtype[i] in (1, 2) for i in range(raw.nb)):
+        return True  # joint-limit rows go through the constraint stage even without a single shape
     if raw.ns < 2:
         return False
     skels = [int(raw.skel_id[b]) for b in raw.shape_body]
     if len(set(skels)) > 1:
         return True
-    return any(raw.self_collision[b] for b in raw.shape_body)
+    if any(raw.self_collision[b] for b in raw.shape_body):
+        return True
+    return False
 
 
 def device_model_for(world) -> DeviceModel:

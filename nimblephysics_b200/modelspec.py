@@ -33,7 +33,7 @@ _ARRAY_FIELDS_F = ["axis", "Tpj", "Tcj", "mass", "com", "moment", "friction", "r
                    "rest", "pos_lo", "pos_hi", "vel_lo", "vel_hi", "force_lo", "force_hi", "init_pos", "gravity",
                    "shape_dims", "shape_T"]
 _ARRAY_FIELDS_I = ["parent", "jtype", "dof_off", "mobile", "gravity_mode", "skel_id", "shape_body", "shape_type",
-                   "action_map", "self_collision", "adjacent_check"]
+                   "action_map", "self_collision", "adjacent_check", "limit_enforced"]
 
 
 def T_to_12(T: np.ndarray) -> np.ndarray:
@@ -66,6 +66,7 @@ class RawModel:
     skel_id: np.ndarray = None
     self_collision: np.ndarray = None   # [nb] 1 when the body's skeleton has self-collision checking enabled (Skeleton::enableSelfCollisionCheck)
     adjacent_check: np.ndarray = None   # [nb] 1 when that skeleton also checks ADJACENT bodies (Skeleton::enableAdjacentBodyCheck)
+    limit_enforced: np.ndarray = None   # [nb] 1 when the body's parent joint enforces its position limits (Joint::setPositionLimitEnforced)
     friction: np.ndarray = None
     restitution: np.ndarray = None
     damping: np.ndarray = None
@@ -120,6 +121,8 @@ class RawModel:
             self.self_collision = np.zeros(nb, np.int32)
         if self.adjacent_check is None:
             self.adjacent_check = np.zeros(nb, np.int32)
+        if self.limit_enforced is None:
+            self.limit_enforced = np.zeros(nb, np.int32)
         self.axis = self.axis.reshape(nb, 3)
         self.Tpj = self.Tpj.reshape(nb, 12)
         self.Tcj = self.Tcj.reshape(nb, 12)
@@ -162,6 +165,7 @@ def flatten_world(world: World) -> RawModel:
     m.skel_id = np.zeros(nb, np.int32)
     m.self_collision = np.zeros(nb, np.int32)
     m.adjacent_check = np.zeros(nb, np.int32)
+    m.limit_enforced = np.zeros(nb, np.int32)
     m.friction = np.zeros(nb)
     m.restitution = np.zeros(nb)
     per_dof = {k: [] for k in ("damping", "spring", "rest", "pos_lo", "pos_hi", "vel_lo", "vel_hi", "force_lo",
@@ -186,6 +190,7 @@ def flatten_world(world: World) -> RawModel:
         m.skel_id[i] = si
         m.self_collision[i] = 1 if getattr(skel, "self_collision", False) else 0
         m.adjacent_check[i] = 1 if getattr(skel, "adjacent_check", False) else 0
+        m.limit_enforced[i] = 1 if getattr(j, "limit_enforced", False) else 0
         m.friction[i] = b.friction
         m.restitution[i] = b.restitution
         for k in per_dof:
@@ -270,6 +275,7 @@ class CanonModel:
     shape_selfcol: np.ndarray = None   # per shape: its skeleton checks self-collisions / adjacent bodies too
     shape_adjcheck: np.ndarray = None
     orig_parent: np.ndarray = None     # [raw nb] parent BodyNode (adjacency test of the collision filter)
+    limit_bodies: List[int] = field(default_factory=list)  # canonical bodies whose parent joint enforces its position limits
     penetration_correction: bool = False
     contact_clipping_depth: float = 0.03
     fallback_cfm: float = 1e-4
@@ -613,6 +619,10 @@ def compile_model(raw: RawModel, lanes: int = 1) -> CanonModel:
     cm.shape_selfcol = np.array([int(raw.self_collision[i]) for i in so], np.int32)
     cm.shape_adjcheck = np.array([int(raw.adjacent_check[i]) for i in so], np.int32)
     cm.orig_parent = np.array(raw.parent, np.int32)
+    # joints with enforced position limits (1-dof joints of mobile skeletons), in raw joint order: canonical body of each
+    canon_of_raw = {int(r): k for k, r in enumerate(cm.orig_body)}
+    cm.limit_bodies = [canon_of_raw[i] for i in range(raw.nb)
+                       if raw.limit_enforced[i] and raw.mobile[i] and raw.jtype[i] in (REVOLUTE, PRISMATIC) and i in canon_of_raw]
     cm.penetration_correction = raw.penetration_correction
     cm.contact_clipping_depth = raw.contact_clipping_depth
     cm.fallback_cfm = raw.fallback_cfm

@@ -259,6 +259,18 @@ class Joint:
         _edited()
         self.force_lo[i] = v
 
+    def setPositionLimitEnforced(self, enforced: bool = True):
+        """Joint::setPositionLimitEnforced (dart/dynamics/Joint.cpp:1366): the constraint solver adds a JointLimitConstraint row while the
+        position sits on or beyond a limit (off by default, like the reference's loaders leave it)."""
+        self.limit_enforced = bool(enforced)
+        _edited()
+
+    def setLimitEnforcement(self, enforced: bool = True):
+        self.setPositionLimitEnforced(enforced)
+
+    def isPositionLimitEnforced(self) -> bool:
+        return bool(getattr(self, "limit_enforced", False))
+
     def setDampingCoefficient(self, i, v):
         _edited()
         self.damping[i] = v
@@ -504,6 +516,7 @@ class World:
             j.axis = np.array(raw.axis[i], dtype=np.float64)
             j.T_pj = T_from_12(raw.Tpj[i])
             j.T_cj = T_from_12(raw.Tcj[i])
+            j.limit_enforced = bool(raw.limit_enforced[i])
             o = int(raw.dof_off[i])
             for k in ("damping", "spring", "rest", "pos_lo", "pos_hi", "vel_lo", "vel_hi", "force_lo", "force_hi",
                       "init_pos"):

@@ -125,6 +125,10 @@ class OracleContactWorld(OracleWorld):
         lib().orc_model_set_contact(self.h, _pi(k[0]), ctypes.c_int(raw.ns), _pi(k[1]), _pi(k[2]), _p(k[3]), _p(k[4]), _p(k[5]),
                                     _p(k[6]), ctypes.c_int(int(raw.penetration_correction)),
                                     ctypes.c_double(raw.contact_clipping_depth), ctypes.c_double(raw.fallback_cfm))
+        le = getattr(raw, "limit_enforced", None)
+        if le is not None and np.any(le):
+            self._keep4 = i(le)
+            lib().orc_model_set_limits(self.h, _pi(self._keep4))
         sc = getattr(raw, "self_collision", None)
         if sc is not None and np.any(sc):
             k2 = [i(raw.self_collision), i(raw.adjacent_check)]

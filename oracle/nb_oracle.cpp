@@ -53,6 +53,7 @@ struct Model {
   double clip_depth = 0.03, fallback_cfm = 1e-4;
   std::vector<int> has_dofs_above;  // BodyNode::getNumDependentGenCoords() > 0
   std::vector<int> self_collision, adjacent_check;  // per body: Skeleton::isEnabledSelfCollisionCheck / isEnabledAdjacentBodyCheck of its skeleton
+  std::vector<int> limit_enforced;  // per body: Joint::isPositionLimitEnforced of its parent joint (1-dof joints; constraint/JointLimitConstraint.cpp)
   std::vector<int> rigid_root;      // first ancestor reached through weld joints only (bodies with the same one cannot move against each other)
 };
 
@@ -290,9 +291,33 @@ struct ContactRows {
   std::vector<double> b, lo, hi, restitution;   // per row
   std::vector<int> findex;
   int unsupported = 0;
+  std::vector<int> limit_body, limit_side;      // active joint-limit rows appended after the contacts: body whose joint it is, +1 lower / -1 upper
 };
 
 static bool is_reactive(const Model& M, int body) { return M.mobile[body] && M.has_dofs_above[body]; }
+
+// active joint-limit rows (JointLimitConstraint::update, JointLimitConstraint.cpp:150-240): 1-dof joints of mobile skeletons whose position
+// sits on or beyond a limit; joints in skeleton / tree order as ConstraintSolver::updateConstraints visits them (:642-695)
+static void active_limits(const Model& M, const double* q, std::vector<int>& body, std::vector<int>& side) {
+  body.clear(); side.clear();
+  if (M.limit_enforced.empty()) return;
+  for (int i = 0; i < M.nb; i++) {
+    if (!M.limit_enforced[i] || !M.mobile[i] || (M.jtype[i] != REVOLUTE && M.jtype[i] != PRISMATIC)) continue;
+    const int d = M.dof_off[i];
+    if (q[d] - M.pos_lo[d] <= 0.0) { body.push_back(i); side.push_back(+1); }
+    else if (q[d] - M.pos_hi[d] >= 0.0) { body.push_back(i); side.push_back(-1); }
+  }
+}
+// the row of a joint-limit constraint as a pair of body-frame wrenches: a unit impulse on the joint (applyUnitImpulse, :258-283) is S on the
+// child and its reaction on the parent; with them the generic formulas give b = -(JA.V_A + JB.V_B) = -qdot (getInformation :243-256: the
+// "bouncing velocity" is +-allowance * erp / dt with allowance 0, i.e. zero), lo / hi = [0, inf) on a lower limit, (-inf, 0] on an upper one
+template <class S>
+static void limit_row_wrenches(const Model& M, const std::vector<BodyState<S>>& B, int i, Vec6<S>& JA, Vec6<S>& JB, int& bodyB, bool& reactB) {
+  JA = B[i].Scol[0];
+  const int p = M.parent[i];
+  if (p >= 0) { JB = zero6<S>() - dAdInvT(B[i].T, JA); bodyB = p; reactB = is_reactive(M, p); }
+  else { JB = zero6<S>(); bodyB = i; reactB = false; }
+}
 
 // impulse-ABA: body impulses imp[i] (body frame) -> joint velocity changes dqd (Skeleton.cpp:13421-13456, 13552-13556,
 // BodyNode.cpp:2117-2138, 2188-2215, GenericJoint.hpp:2482-2498, 2607-2613, 2713-2725)
@@ -477,6 +502,23 @@ static void step_contact(const Model& M, const double* q, const double* v, const
     R.b[off] += bv;
     R.m += dim;
   }
+  // ---- joint-limit rows after the contact rows (ConstraintSolver.cpp:642-695)
+  active_limits(M, q, R.limit_body, R.limit_side);
+  for (size_t l = 0; l < R.limit_body.size(); l++) {
+    const int i = R.limit_body[l];
+    Vec6<double> JA, JB; int bodyB; bool reactB;
+    limit_row_wrenches<double>(M, B, i, JA, JB, bodyB, reactB);
+    Contact<double> c; c.point = v3<double>(0.0, 0.0, 0.0); c.normal = c.point; c.depth = 0.0; c.bodyA = i; c.bodyB = bodyB; c.shapeA = c.shapeB = -1;
+    c.type = R.limit_side[l] > 0 ? 100 : 101;
+    R.contacts.push_back(c); R.nc++;
+    R.row_off.push_back(R.m); R.reactA.push_back(is_reactive(M, i)); R.reactB.push_back(reactB);
+    R.JA.push_back(JA); R.JB.push_back(JB); R.row_contact.push_back(R.nc - 1);
+    R.b.push_back(-(dot(JA, B[i].V) + (reactB ? dot(JB, B[bodyB].V) : 0.0)));
+    R.restitution.push_back(0.0);
+    if (R.limit_side[l] > 0) { R.lo.push_back(0.0); R.hi.push_back(HUGE_VAL); } else { R.lo.push_back(-HUGE_VAL); R.hi.push_back(0.0); }
+    R.findex.push_back(-1);
+    R.m += 1;
+  }
   const int m = R.m;
   if (m == 0) { integrate<double>(M, q, v, vs.data(), qn, vn); info.status = 0; return; }
   // ---- A by impulse tests (BoxedLcpConstraintSolver.cpp:190-349): upper blocks measured, lower mirrored
@@ -553,12 +595,14 @@ struct FixedSets {  // from the primal (double) forward pass
   std::vector<int> keep;                   // independent subset of cl (positions in cl)
   double cfm = 0;
   bool ok = true;
+  std::vector<int> limit_body, limit_side;  // the active joint-limit rows of the forward pass (frozen like the labels)
 };
 
 static FixedSets make_fixed_sets(const ContactStepInfo& info) {
   FixedSets F;
   const ContactRows& R = info.rows;
   F.nc_expected = R.nc; F.m = R.m;
+  F.limit_body = R.limit_body; F.limit_side = R.limit_side;
   if (R.m == 0) return F;
   std::vector<int> clpos(R.m, -1);
   for (int j = 0; j < R.m; j++) if (info.mapping[j] == orc::CLAMPING) { clpos[j] = (int)F.cl.size(); F.cl.push_back(j); }
@@ -617,7 +661,7 @@ static bool contact_velocity_fixed(const Model& M, std::vector<BodyState<S>>& B,
     if (!(is_reactive(M, c.bodyA) || is_reactive(M, c.bodyB))) continue;
     cs.push_back(c);
   }
-  if ((int)cs.size() != F.nc_expected) return false;  // the perturbation-free structure must be reproduced
+  if ((int)cs.size() + (int)F.limit_body.size() != F.nc_expected) return false;  // the perturbation-free structure must be reproduced
   // rows of every contact (same construction as step_contact)
   std::vector<Vec6<S>> JA, JB; std::vector<S> bvec; std::vector<int> rowc;
   for (int ci = 0; ci < (int)cs.size(); ci++) {
@@ -643,6 +687,22 @@ static bool contact_velocity_fixed(const Model& M, std::vector<BodyState<S>>& B,
     if (bounce) { S rv = bvec[off] * e; if (val(rv) > 1e-1) { if (val(rv) > val(bv)) { bv = rv; if (val(bv) > 1e2) bv = S(1e2); } } }
     bvec[off] = bvec[off] + bv;
   }
+  // joint-limit rows, frozen at the forward pass's active set
+  std::vector<int> lim_bodyB; std::vector<char> lim_reactB;
+  const int ncs_real = (int)cs.size();
+  for (size_t l = 0; l < F.limit_body.size(); l++) {
+    const int i = F.limit_body[l];
+    Vec6<S> ja, jb; int bodyB; bool reactB;
+    limit_row_wrenches<S>(M, B, i, ja, jb, bodyB, reactB);
+    Contact<S> c; c.bodyA = i; c.bodyB = bodyB; c.shapeA = c.shapeB = -1; c.type = 100; c.depth = S(0.0);
+    c.point = v3<S>(S(0.0), S(0.0), S(0.0)); c.normal = c.point;
+    cs.push_back(c);
+    JA.push_back(ja); JB.push_back(jb); rowc.push_back((int)cs.size() - 1);
+    S rel = zero6<S>()[0] - dot(ja, B[i].V);
+    if (reactB) rel = rel - dot(jb, B[bodyB].V);
+    bvec.push_back(rel);
+  }
+  (void)ncs_real;
   if ((int)bvec.size() != F.m) return false;
   auto response = [&](int r, std::vector<S>& dqd, std::vector<Vec6<S>>& dV) {
     std::vector<Vec6<S>> imp(nb, zero6<S>());
@@ -918,6 +978,10 @@ void orc_model_set_contact(void* h, const int* skel_id, int ns, const int* shape
     M.has_dofs_above[i] = (k > 0) || (M.parent[i] >= 0 && M.has_dofs_above[M.parent[i]]);
     M.rigid_root[i] = (M.jtype[i] == orc::WELD && M.parent[i] >= 0) ? M.rigid_root[M.parent[i]] : i;
   }
+}
+void orc_model_set_limits(void* h, const int* limit_enforced) {
+  Model& M = *(Model*)h;
+  M.limit_enforced.assign(limit_enforced, limit_enforced + M.nb);
 }
 void orc_model_set_self_collision(void* h, const int* self_collision, const int* adjacent_check) {
   Model& M = *(Model*)h;

@@ -480,3 +480,52 @@ def test_self_collision_pairs_forward_and_backward(oracle_mod):
     assert with_self >= 3, with_self
     kinds = _check_backward(ob, raw, S, A, tol=2e-5)
     assert len(kinds) == B
+
+
+def test_joint_limit_rows_forward_and_backward(oracle_mod):
+    """Joint::setPositionLimitEnforced (constraint/JointLimitConstraint.cpp): while a 1-dof joint sits on or beyond a position limit the LCP
+    gains one row for it after the contact rows (ConstraintSolver.cpp:642-695): b = -qdot*, [0, inf) on a lower limit, (-inf, 0] on an upper
+    one.  Forward against the oracle (row count, labels, next state) and backward against its Jacobian, with and without contacts."""
+    raw = load_raw("half_cheetah")
+    raw.limit_enforced[:] = 1
+    raw.spring[:] = 0.0   # (the model's joint springs, 60-240 N m / rad on links of ~0.01 kg m^2, would throw every joint back off its limit within the step)
+    n = raw.ndof
+    s, a = contact_inputs(raw, "half_cheetah", 10, seed=9)
+    rng = np.random.default_rng(2)
+    for k in range(10):
+        for d in rng.choice(np.arange(3, n), size=2, replace=False):   # two joints per world on / beyond a limit, moving into it or away
+            hi = rng.random() < 0.5
+            s[k, d] = (raw.pos_hi[d] + 0.01 * rng.random()) if hi else (raw.pos_lo[d] - 0.01 * rng.random())
+            s[k, n + d] = (1.0 if hi else -1.0) * rng.choice([8.0, -0.5])
+    a *= 0.0   # no torques: the light links would otherwise out-accelerate the velocities set above
+    cm = nb.compile_model(raw)
+    assert len(cm.limit_bodies) == n   # (the planar root is two prismatic joints and a revolute one with infinite limits: never active)
+    r = EmulWorld(cm).forward_contact(s, a)
+    ow = oracle_mod.OracleContactWorld(raw)
+    limit_rows = clamping_limits = 0
+    for k in range(10):
+        ro = ow.step_contact(s[k].astype(np.float64), a[k].astype(np.float64))
+        assert r["nc"][k] == ro["nc"] and r["m"][k] == ro["m"], (k, r["nc"][k], ro["nc"], r["m"][k], ro["m"])
+        assert np.array_equal(r["labels"][k][: r["m"][k]], ro["mapping"][: ro["m"]]), (k, r["labels"][k][: r["m"][k]], ro["mapping"])
+        assert rel_err(r["next"][k], ro["next_state"]) < 1e-6
+        lim = [i for i, t in enumerate(ro["type"]) if t >= 100]
+        limit_rows += len(lim)
+        clamping_limits += int(sum(ro["mapping"][ro["m"] - len(lim) + i] == -2 for i in range(len(lim))))   # the limit rows come last
+    assert limit_rows >= 15 and clamping_limits >= 4, (limit_rows, clamping_limits)
+    _check_backward(ob, raw, s, a, tol=2e-5)
+    # a model without a single shape: the cartpole with its rail limit enforced
+    raw2 = load_raw("cartpole")
+    raw2.limit_enforced[:] = 1
+    raw2.pos_lo[0], raw2.pos_hi[0] = -1.0, 1.0
+    s2 = np.zeros((4, 4), np.float32); a2 = np.zeros((4, len(raw2.action_map)), np.float32)
+    s2[:, 0] = [1.0, 1.02, -1.0, 0.5]; s2[:, 1] = 0.3; s2[:, 2] = [1.5, 0.7, -2.0, 1.0]; s2[:, 3] = 0.2
+    cm2 = nb.compile_model(raw2)
+    r2 = EmulWorld(cm2).forward_contact(s2, a2)
+    ow2 = oracle_mod.OracleContactWorld(raw2)
+    for k in range(4):
+        ro = ow2.step_contact(s2[k].astype(np.float64), a2[k].astype(np.float64))
+        assert r2["m"][k] == ro["m"] and np.array_equal(r2["labels"][k][: r2["m"][k]], ro["mapping"][: ro["m"]])
+        assert rel_err(r2["next"][k], ro["next_state"]) < 1e-6
+    assert list(r2["m"]) == [1, 1, 1, 0]
+    assert abs(r2["next"][0][2]) < 1e-9 and abs(r2["next"][2][2]) < 1e-9   # the rail stops at the limit
+    _check_backward(ob, raw2, s2, a2, tol=2e-5)

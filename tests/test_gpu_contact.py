@@ -423,3 +423,48 @@ def test_contact_path_edge_cases():
         nb.timestep(w, st, torch.zeros(2, w.getActionSize(), device="cuda"))
     with pytest.raises(RuntimeError, match="DROPPED"):
         nb.check_contact_status(w)
+
+
+def test_joint_limit_rows_on_device(oracle_mod):
+    """Joint limits enforced (constraint/JointLimitConstraint.cpp) on the GPU against the oracle: half-cheetah with contacts + limit rows, and the
+    shape-less cartpole whose rail stops at its limit (CPU twin: tests/test_contact_emul.py::test_joint_limit_rows_forward_and_backward)."""
+    raw = load_raw("half_cheetah")
+    raw.limit_enforced[:] = 1
+    raw.spring[:] = 0.0
+    n = raw.ndof
+    B = 16
+    s, a = contact_inputs(raw, "half_cheetah", B, seed=9)
+    rng = np.random.default_rng(2)
+    for k in range(B):
+        for d in rng.choice(np.arange(3, n), size=2, replace=False):
+            hi = rng.random() < 0.5
+            s[k, d] = (raw.pos_hi[d] + 0.01 * rng.random()) if hi else (raw.pos_lo[d] - 0.01 * rng.random())
+            s[k, n + d] = (1.0 if hi else -1.0) * rng.choice([8.0, -0.5])
+    a *= 0.0
+    world = nb.World.from_raw(raw)
+    assert all(j.isPositionLimitEnforced() for sk in world.skeletons for b in sk._ordered_bodies() for j in [b.parent_joint])
+    gr = rng.normal(size=(B, 2 * n)).astype(np.float32)
+    st = torch.tensor(s, device="cuda", requires_grad=True); at = torch.tensor(a, device="cuda", requires_grad=True)
+    out = nb.timestep(world, st, at)
+    c = world._lcp_cache
+    labels, mm = c["labels"].cpu().numpy(), c["m"].cpu().numpy()
+    out.backward(torch.tensor(gr, device="cuda"))
+    nb.check_contact_status(world)
+    ow = ob.OracleContactWorld(raw)
+    lim = 0
+    for k in range(B):
+        ro = ow.step_contact(s[k].astype(np.float64), a[k].astype(np.float64))
+        assert mm[k] == ro["m"] and np.array_equal(labels[k][: mm[k]], ro["mapping"][: ro["m"]]), k
+        assert rel_err(out[k].detach().cpu().numpy(), ro["next_state"]) < 1e-5
+        rgs, rga, rc = ow.backprop_contact(s[k].astype(np.float64), a[k].astype(np.float64), gr[k].astype(np.float64))
+        assert rc >= 0 and rel_err(st.grad[k].cpu().numpy(), rgs) < 1e-4 and rel_err(at.grad[k].cpu().numpy(), rga) < 1e-4
+        lim += int(sum(t >= 100 for t in ro["type"]))
+    assert lim >= 20
+    # cartpole: no shapes at all, the rail limit is the only constraint
+    w2 = nb.World.from_raw(load_raw("cartpole"))
+    rail = next(b.parent_joint for sk in w2.skeletons for b in sk._ordered_bodies() if b.parent_joint.getNumDofs() == 1)  # the prismatic rail
+    rail.setPositionLowerLimit(0, -1.0); rail.setPositionUpperLimit(0, 1.0); rail.setPositionLimitEnforced(True)
+    s2 = torch.tensor([[1.0, 0.3, 1.5, 0.2], [0.5, 0.3, 1.0, 0.2]], device="cuda")
+    with torch.no_grad():
+        o2 = nb.timestep(w2, s2, torch.zeros(2, w2.getActionSize(), device="cuda"))
+    assert abs(float(o2[0, 2])) < 1e-7 and float(o2[1, 2]) > 0.9   # stopped at the limit / free
