@@ -203,21 +203,6 @@ class DeviceModel:
         return gs, ga
 
 
-def _has_possible_contacts(raw: RawModel) -> bool:
-    """True when some collision-shape pair could ever generate a contact: shapes on two different skeletons, or two shapes of a skeleton
-    that enabled self-collision checking (off by default in the reference, dart/dynamics/Skeleton.cpp mEnabledSelfCollisionCheck=false)."""
-    if any(raw.limit_enforced[i] and raw.mobile[i] and raw.jtype[i] in (1, 2) for i in range(raw.nb)):
-        return True  # joint-limit rows go through the constraint stage even without a single shape
-    if raw.ns < 2:
-        return False
-    skels = [int(raw.skel_id[b]) for b in raw.shape_body]
-    if len(set(skels)) > 1:
-        return True
-    if any(raw.self_collision[b] for b in raw.shape_body):
-        return True
-    return False
-
-
 def device_model_for(world) -> DeviceModel:
     """Lazily (re)build the device model of a World.  The cache is validated against the object graph: any setter of a BodyNode / Joint /
     Skeleton / ShapeNode bumps a global edit epoch (world.py); a World whose model was built at an older epoch is re-flattened and,
