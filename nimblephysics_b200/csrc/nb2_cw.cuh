@@ -1678,7 +1678,8 @@ NB2_HD void contact_forward(const Nb2ModelDev<double>& M, const Nb2ContactDev& C
     if (io.cinfo) for (int c = 0; c < nc; c++) {
       float* o = io.cinfo + 10 * c;
       for (int e = 0; e < 3; e++) { o[e] = (float)ws.cpoint[3 * c + e]; o[3 + e] = (float)ws.cnormal[3 * c + e]; }
-      o[6] = (float)ws.cdepth[c]; o[7] = (float)C.shape_orig_body[ws.cshapeA[c]]; o[8] = (float)C.shape_orig_body[ws.cshapeB[c]]; o[9] = (float)ws.ctype[c];
+      o[6] = (float)ws.cdepth[c]; o[7] = (float)(ws.cshapeA[c] >= 0 ? C.shape_orig_body[ws.cshapeA[c]] : -1); o[8] = (float)(ws.cshapeB[c] >= 0 ? C.shape_orig_body[ws.cshapeB[c]] : -1);  // (joint-limit rows have no shapes)
+      o[9] = (float)ws.ctype[c];
     }
   }
   if (m == 0) {
@@ -1764,7 +1765,8 @@ NB2_HD void contact_build(const Nb2ModelDev<double>& M, const Nb2ContactDev& C, 
     if (io.cinfo) for (int c = 0; c < nc; c++) {
       float* o = io.cinfo + 10 * c;
       for (int e = 0; e < 3; e++) { o[e] = (float)ws.cpoint[3 * c + e]; o[3 + e] = (float)ws.cnormal[3 * c + e]; }
-      o[6] = (float)ws.cdepth[c]; o[7] = (float)C.shape_orig_body[ws.cshapeA[c]]; o[8] = (float)C.shape_orig_body[ws.cshapeB[c]]; o[9] = (float)ws.ctype[c];
+      o[6] = (float)ws.cdepth[c]; o[7] = (float)(ws.cshapeA[c] >= 0 ? C.shape_orig_body[ws.cshapeA[c]] : -1); o[8] = (float)(ws.cshapeB[c] >= 0 ? C.shape_orig_body[ws.cshapeB[c]] : -1);  // (joint-limit rows have no shapes)
+      o[9] = (float)ws.ctype[c];
     }
   }
   if (m == 0) {

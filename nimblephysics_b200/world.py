@@ -466,6 +466,37 @@ class Skeleton:
         return np.concatenate([b.parent_joint.pos_hi for b in self._ordered_bodies()] or [np.zeros(0)])
 
 
+class Contact:
+    """collision::Contact (dart/collision/Contact.hpp:82-230), the fields the Python binding exposes: point and normal in the world frame
+    (normal from object 2 towards object 1), penetrationDepth, type (collision::ContactType), names of the two BodyNodes."""
+
+    def __init__(self, point, normal, penetrationDepth, type, bodyNodeA, bodyNodeB):
+        self.point, self.normal, self.penetrationDepth, self.type = point, normal, penetrationDepth, type
+        self.bodyNodeA, self.bodyNodeB = bodyNodeA, bodyNodeB
+
+    def __repr__(self):
+        return f"Contact({self.bodyNodeA} / {self.bodyNodeB}, depth={self.penetrationDepth:.4g}, type={self.type})"
+
+
+class CollisionResult:
+    """collision::CollisionResult (pybind collision/CollisionResult.cpp:49-65)."""
+
+    def __init__(self, contacts):
+        self._contacts = list(contacts)
+
+    def getNumContacts(self) -> int:
+        return len(self._contacts)
+
+    def getContacts(self):
+        return list(self._contacts)
+
+    def getContact(self, i):
+        return self._contacts[i]
+
+    def isCollision(self) -> bool:
+        return bool(self._contacts)
+
+
 class World:
     """Description of one simulated world; batched state lives in tensors, not here.
 
@@ -720,6 +751,25 @@ class World:
         with torch.no_grad():
             timestep(self, torch.tensor(self.getState(), dtype=torch.float64), torch.tensor(self.getAction(), dtype=torch.float64))
         self._action = None
+
+    def getLastCollisionResult(self, world_index: int = 0) -> "CollisionResult":
+        """World::getLastCollisionResult (pybind World.cpp:247-251): the contacts the constraint stage of the LAST timestep() / step() generated
+        for one world of the batch (default: the first / the legacy single world), read back from the device cache.  Joint-limit rows are not
+        contacts and are left out."""
+        c = getattr(self, "_lcp_cache", None)
+        if c is None:
+            return CollisionResult([])
+        nc = int(c["nc"][world_index].item())
+        rows = c["cinfo"][world_index, :nc].cpu().numpy()
+        names = [b.name for sk in self.skeletons for b in sk._ordered_bodies()]
+        out = []
+        for r in rows:
+            if int(r[9]) >= 100:
+                continue
+            a, b = int(r[7]), int(r[8])
+            out.append(Contact(point=r[0:3].astype(np.float64), normal=r[3:6].astype(np.float64), penetrationDepth=float(r[6]), type=int(r[9]),
+                               bodyNodeA=names[a] if 0 <= a < len(names) else None, bodyNodeB=names[b] if 0 <= b < len(names) else None))
+        return CollisionResult(out)
 
     def _legacy_jacobians(self):
         import torch

@@ -284,6 +284,11 @@ def test_box_box_face_face_annotation_golden_on_device():
     seen = {(round(float(r[0]), 6), round(float(r[1]), 6)): int(r[9]) for r in ci}
     assert seen == {(0.25, 0.5): 3, (-0.25, 0.5): 3, (0.25, 0.25): 2, (-0.25, 0.25): 2}, seen
     assert np.allclose(ci[:, 2], 0, atol=1e-6) and np.allclose(ci[:, 6], 0, atol=1e-6)
+    # the reference-style accessor (World::getLastCollisionResult, pybind World.cpp:247-251)
+    res = world.getLastCollisionResult(1)
+    assert res.getNumContacts() == 4 and res.isCollision()
+    assert sorted(c.type for c in res.getContacts()) == [2, 2, 3, 3]
+    assert all(c.bodyNodeA is not None and c.bodyNodeB is not None and abs(c.penetrationDepth) < 1e-6 for c in res.getContacts())
 
 
 def test_round_shape_contacts_on_device(oracle_mod):
