@@ -319,7 +319,7 @@ def contact_leg(nb, torch, name, B, K, W, dev, dist, rank, world_size, peak, cpu
         nb.timestep(world, xi, ai).backward(hg)
         return xi.grad
 
-    for _ in range(2):
+    for _ in range(3):
         e2e_step()
     barrier()
     w0 = time.perf_counter()
