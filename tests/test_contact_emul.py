@@ -529,3 +529,34 @@ def test_joint_limit_rows_forward_and_backward(oracle_mod):
     assert list(r2["m"]) == [1, 1, 1, 0]
     assert abs(r2["next"][0][2]) < 1e-9 and abs(r2["next"][2][2]) < 1e-9   # the rail stops at the limit
     _check_backward(ob, raw2, s2, a2, tol=2e-5)
+
+
+def test_all_constraint_features_together(oracle_mod):
+    """Restitution + penetration correction + enforced joint limits in one model, both lane orders: contact set, labels and next state against the
+    oracle; gradients against its Jacobian (status bits 0x400 bounce, 0x1000 penetration correction, the solver-branch bits all occur)."""
+    raw = load_raw("half_cheetah")
+    raw.limit_enforced[:] = 1
+    raw.spring[:] = 0
+    raw.restitution[:] = 0.6
+    raw.penetration_correction = True
+    n = raw.ndof
+    s, a = contact_inputs(raw, "half_cheetah", 12, seed=31)
+    a *= 0.1
+    rng = np.random.default_rng(5)
+    s[::2, n + 1] -= 1.2
+    for k in range(12):
+        d = rng.integers(3, n); hi = rng.random() < 0.5
+        s[k, d] = (raw.pos_hi[d] + 0.004) if hi else (raw.pos_lo[d] - 0.004)
+        s[k, n + d] = 6.0 if hi else -6.0
+    cm = nb.compile_model(raw)
+    ow = oracle_mod.OracleContactWorld(raw)
+    for rev in (False, True):
+        r = EmulWorld(cm).forward_contact(s, a, reverse=rev)
+        bits = 0
+        for k in range(12):
+            ro = ow.step_contact(s[k].astype(np.float64), a[k].astype(np.float64))
+            assert r["m"][k] == ro["m"] and np.array_equal(r["labels"][k][: r["m"][k]], ro["mapping"][: ro["m"]]), (rev, k)
+            assert rel_err(r["next"][k], ro["next_state"]) < 1e-6
+            bits |= int(r["status"][k])
+        assert bits & 0x400 and bits & 0x1000
+    _check_backward(ob, raw, s, a, tol=3e-5)
