@@ -28,6 +28,22 @@ for name, B, rest in (("half_cheetah", 21, 0.0), ("atlas_ground", 9, 0.0), ("hal
     x0 = torch.tensor(s, device="cuda", requires_grad=True)
     nb.rollout_fused(w, x0, u, checkpoint_every=2).sum().backward()
     print(name, rest, "status", hex(nb.check_contact_status(w)), flush=True)
+# joint-limit rows (with and without shapes), self-collision rows inside one tree, round-shape pairs
+raw = load_raw("half_cheetah"); raw.limit_enforced[:] = 1; raw.spring[:] = 0
+w = nb.World.from_raw(raw)
+s, a = contact_inputs(raw, "half_cheetah", 9, seed=9); a *= 0
+for k in range(9):
+    d = 3 + k % (raw.ndof - 3)
+    s[k, d] = raw.pos_hi[d] + 0.004; s[k, raw.ndof + d] = 6.0
+st = torch.tensor(s, device="cuda", requires_grad=True); at = torch.tensor(a, device="cuda", requires_grad=True)
+nb.timestep(w, st, at).sum().backward()
+print("limits status", hex(nb.check_contact_status(w)), flush=True)
+from tests.test_contact_emul import _folding_arm_world
+w = _folding_arm_world(); n = w.getNumDofs()
+S = np.zeros((5, 2 * n), np.float32); S[:, 6] = 2.0944; S[:, 7] = 1.955; S[:, n:] = 0.05
+st = torch.tensor(S, device="cuda", requires_grad=True); at = torch.zeros(5, w.getActionSize(), device="cuda", requires_grad=True)
+nb.timestep(w, st, at).sum().backward()
+print("self-collision status", hex(nb.check_contact_status(w)), "nc", w._lcp_cache["nc"].cpu().tolist(), flush=True)
 # IKMapping + host entries + batched LCP
 raw = load_raw("half_cheetah"); w = nb.World.from_raw(raw)
 nodes = [b for sk in w.skeletons for b in sk._ordered_bodies()]
