@@ -1063,7 +1063,11 @@ unpermute:
 // ws: the caller's (register) copy of the workspace descriptor; ws_mem: the same descriptor at a stable address (shared memory on the
 // device), handed to the non-inlined classification so that the register copy never has to be spilled for a call
 #define NB2_HEAD_PHASES 2
+#ifdef NB2_TAIL_FREE
+#define NB2_TAIL_PHASES 2   /* experiment: Dantzig -> PGS -> friction drop without block-wide barriers in between */
+#else
 #define NB2_TAIL_PHASES 4
+#endif
 NB2_HD void lcp_colnorms(int m, const Ws& ws) {
   const int ld = m | 1;
   CW_FOR(c, m) { double sn = 0; for (int r = 0; r < m; r++) { const double a = ws.A[(size_t)r * ld + c]; sn += a * a; } ws.colnorm[c] = sn; }
@@ -1144,7 +1148,9 @@ NB2_HD int lcp_chain_tail(int m, const Ws& ws, const Ws& ws_mem, double fallback
     CW_FOR(i, m) if (x[i] != x[i]) nan = true;
     if (cw_any(nan)) { success = false; CW_SYNC(); CW_FOR(i, m) x[i] = 0; CW_SYNC(); status |= NB2_ST_NAN; }
   }
+#ifndef NB2_TAIL_FREE
   CW_PHASE();  // 4
+#endif
   if (!success) {
     CW_FOR(i, m) A[(size_t)i * ld + i] += fallback_cfm;  // :539-547 (both backups get the cfm; colnorms were taken before)
     CW_SYNC();
@@ -1159,7 +1165,9 @@ NB2_HD int lcp_chain_tail(int m, const Ws& ws, const Ws& ws_mem, double fallback
       if (!lcp_valid(m, A, ld, x, b, hi, lo, fi, false)) success = false;
     }
   }
+#ifndef NB2_TAIL_FREE
   CW_PHASE();  // 5
+#endif
   if (!success) {
     ignoredFriction = true;
     status |= NB2_ST_FRICTION_DROPPED;

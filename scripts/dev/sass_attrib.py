@@ -37,7 +37,8 @@ for l in open(dis):
         loc[int(m.group(1), 16)] = cur
 rows = list(csv.reader(open(sass_csv)))
 ends = [i for i, r in enumerate(rows) if r and r[0] == "Kernel Name"]
-sec = [i for i in ends if kern.rstrip("E") in rows[i][1]][0]
+cand = [i for i in ends if kern.rstrip("E") in rows[i][1]]
+sec = cand[0] if cand else ends[0]  # (the CSV holds demangled names, the disassembly mangled ones)
 nxt = [i for i in ends if i > sec]
 rows = rows[sec:(nxt[0] if nxt else len(rows))]
 hdr = rows[1]
