@@ -639,9 +639,12 @@ NB2_HDN bool pgs_solve(int m, double* A, int ld, double* x, double* b, const dou
     double rj = residual();
     bool changed = false;
     // first sweep: unscaled rows, division by the diagonal, absolute change test
+    // xf: x of this lane's own normal row, kept in a register and refreshed from the broadcast of row fsrc's new value (the two broadcasts of a
+    // step are independent of each other, so they overlap; reading x[fsrc] by a shuffle at the start of every step put two dependent
+    // shuffles on the critical path of each row.  Measured: no change in the step time — the sweep is bound elsewhere)
+    double xf = __shfl_sync(CW_FULL, xj, fsrc);
 #pragma unroll 2
     for (int i = 0; i < m; i++) {
-      const double xf = __shfl_sync(CW_FULL, xj, fsrc);            // x of this lane's own normal row
       const bool own = lane == i;
       const bool sk = ajj < epsDiv;
       const double nx = nb2_div(bj - (rj - ajj * xj), sk ? 1.0 : ajj);
@@ -653,6 +656,8 @@ NB2_HDN bool pgs_solve(int m, double* A, int ld, double* x, double* b, const dou
       skipj = skipj || (own && sk);
       xj = own ? xi : xj;
       const double delta = __shfl_sync(CW_FULL, dl, i);
+      const double xnew = __shfl_sync(CW_FULL, xj, i);
+      if (fsrc == i) xf = xnew;
       if (act) rj = fma(A[(size_t)lane * ld + i], delta, rj);
     }
     bool term = !__any_sync(CW_FULL, changed);
@@ -664,7 +669,6 @@ NB2_HDN bool pgs_solve(int m, double* A, int ld, double* x, double* b, const dou
         changed = false;
 #pragma unroll 4
         for (int i = 0; i < m; i++) {
-          const double xf = __shfl_sync(CW_FULL, xj, fsrc);
           const bool own = (lane == i) && !skipj;
           const double nx = bj - (rj - ajj * xj);
           const double hi_t = fj >= 0 ? hij * xf : hij, lo_t = fj >= 0 ? -hi_t : loj;
@@ -673,6 +677,8 @@ NB2_HDN bool pgs_solve(int m, double* A, int ld, double* x, double* b, const dou
           changed = changed || (own && fabs(xi) > epsDiv && fabs(dl) > relTol * fabs(xi));
           xj = own ? xi : xj;
           const double delta = __shfl_sync(CW_FULL, dl, i);
+          const double xnew = __shfl_sync(CW_FULL, xj, i);
+          if (fsrc == i) xf = xnew;
           if (act) rj = fma(A[(size_t)lane * ld + i], delta, rj);
         }
         term = !__any_sync(CW_FULL, changed);
