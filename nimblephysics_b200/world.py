@@ -752,6 +752,24 @@ class World:
             timestep(self, torch.tensor(self.getState(), dtype=torch.float64), torch.tensor(self.getAction(), dtype=torch.float64))
         self._action = None
 
+    def clone(self) -> "World":
+        """World::clone (dart/simulation/World.cpp:107-160; MultiShot gives every shot a clone, MultiShot.cpp:57-72): an independent copy of the
+        model, the current state and the action; device buffers and the solver cache are NOT shared (the copy builds its own on first use)."""
+        from .modelspec import flatten_world
+
+        w = World.from_raw(flatten_world(self))
+        w.action_space = list(self.action_space)
+        if self._state is not None:
+            w._state = self._state.copy()
+        if getattr(self, "_action", None) is not None:
+            w._action = self._action.copy()
+        # tunable-mass registrations refer to BodyNode objects: re-point them at the copy's nodes (same order)
+        mine = [b for sk in self.skeletons for b in sk._ordered_bodies()]
+        theirs = [b for sk in w.skeletons for b in sk._ordered_bodies()]
+        idx = {id(b): k for k, b in enumerate(mine)}
+        w._wrt_mass = [(theirs[idx[id(node)]], t, ub.copy(), lb.copy()) for node, t, ub, lb in getattr(self, "_wrt_mass", []) if id(node) in idx]
+        return w
+
     def getLastCollisionResult(self, world_index: int = 0) -> "CollisionResult":
         """World::getLastCollisionResult (pybind World.cpp:247-251): the contacts the constraint stage of the LAST timestep() / step() generated
         for one world of the batch (default: the first / the legacy single world), read back from the device cache.  Joint-limit rows are not

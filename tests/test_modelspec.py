@@ -184,3 +184,33 @@ def test_legacy_world_and_skeleton_accessors():
     assert w.getAction()[3] == 3.0
     with pytest.raises(ValueError):
         w.setAction(np.zeros(3))
+
+
+def test_world_clone_and_new_model_flags_roundtrip():
+    """World::clone gives an independent copy (model, state, action, tunable-mass registrations); the self-collision and limit-enforcement flags
+    survive flatten -> JSON -> from_raw."""
+    import json
+
+    w = nb.World.from_raw(load_raw("half_cheetah"))
+    arm = w.getSkeleton(1)
+    arm.enableSelfCollisionCheck()
+    j = next(b.parent_joint for b in arm._ordered_bodies() if b.parent_joint.getNumDofs() == 1)
+    j.setPositionLimitEnforced(True)
+    w.setState(np.linspace(-0.2, 0.3, w.getStateSize()))
+    w.setAction(np.ones(w.getActionSize()))
+    body = arm._ordered_bodies()[3]
+    w.tuneMass(body, 0, upperBound=[5.0], lowerBound=[0.1])
+    c = w.clone()
+    assert np.allclose(c.getState(), w.getState()) and np.allclose(c.getAction(), w.getAction())
+    assert c.getSkeleton(1).isEnabledSelfCollisionCheck() and not c.getSkeleton(1).isEnabledAdjacentBodyCheck()
+    assert sum(b.parent_joint.isPositionLimitEnforced() for b in c.getSkeleton(1)._ordered_bodies()) == 1
+    assert c.getMassDims() == 1 and np.allclose(c.getMasses(), w.getMasses())
+    c.setState(np.zeros(c.getStateSize()))
+    assert not np.allclose(c.getState(), w.getState())          # independent
+    c.setMasses([3.0])
+    assert not np.allclose(c.getMasses(), w.getMasses())
+    raw2 = nb.RawModel.from_json(nb.flatten_world(w).to_json())
+    assert raw2.self_collision.sum() > 0 and raw2.limit_enforced.sum() == 1
+    old = json.loads(nb.flatten_world(w).to_json()); old.pop("self_collision"); old.pop("adjacent_check"); old.pop("limit_enforced")
+    raw3 = nb.RawModel.from_json(json.dumps(old))                 # a fixture written before these fields existed
+    assert raw3.self_collision.sum() == 0 and raw3.limit_enforced.sum() == 0
