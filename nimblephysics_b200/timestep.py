@@ -33,7 +33,15 @@ class TimestepLayer(torch.autograd.Function):
             if mass.dim() != 1 or mass.numel() != world.getMassDims():
                 raise ValueError(f"timestep(): mass has shape {tuple(mass.shape)}, expected [{world.getMassDims()}] (= getMassDims(); "
                                  "register parameters with world.tuneMass)")
-            world.setMasses(mass.detach().cpu().numpy().astype(np.float64))
+            # (a device -> host copy, i.e. a sync: skipped when this very tensor, unchanged since the last call, is already what the world holds)
+            from .world import edit_epoch
+
+            mkey = (mass.data_ptr(), mass._version, tuple(mass.shape), str(mass.device), edit_epoch())
+            if getattr(world, "_mass_key", None) != mkey:
+                world.setMasses(mass.detach().cpu().numpy().astype(np.float64))
+                dm = device_model_for(world)   # setMasses edited the model: the device model follows (inertia refresh)
+                world._mass_key = mkey
+                world._mass_P = None
         n2, na = 2 * dm.ndof, dm.na
         legacy = state.dim() == 1
         if legacy and (state.numel() != n2 or action.numel() != na):
@@ -54,7 +62,9 @@ class TimestepLayer(torch.autograd.Function):
         B = sd.shape[0]
         ctx.mass_grad = mass is not None and ctx.needs_input_grad[3]
         if ctx.mass_grad:
-            ctx.mass_P = torch.from_numpy(dm.inertia_param_jacobian(world)).to(dev)  # [mass_dims, 10*nb], fp64
+            if getattr(world, "_mass_P", None) is None or world._mass_P.device != dev:
+                world._mass_P = torch.from_numpy(dm.inertia_param_jacobian(world)).to(dev)  # [mass_dims, 10*nb], fp64; cached with the mass key
+            ctx.mass_P = world._mass_P
             ctx.mass_like = mass
         need_grad = any(ctx.needs_input_grad[1:4])
         ctx.contact = dm.has_contacts

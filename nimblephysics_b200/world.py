@@ -696,6 +696,8 @@ class World:
         from .modelspec import WRT_MASS_DIMS, _apply_mass_entry
 
         masses = np.asarray(masses, dtype=np.float64).reshape(-1)
+        self._mass_key = None  # (timestep() remembers which mass tensor the world holds; any direct call invalidates that)
+        self._mass_P = None
         if masses.size != self.getMassDims():
             raise ValueError(f"World.setMasses() got size {masses.size}, expected getMassDims()={self.getMassDims()}")
         cur = 0
